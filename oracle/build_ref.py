@@ -1,0 +1,145 @@
+#!/usr/bin/env python3
+"""Build oracle/_ref/ : the reference's OWN liquid-dsp 1.5.0 binary, made runnable on Linux.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is shipped or measured as the product; only
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may use it.
+
+The arithmetic of CubicSDR's hot path lives in liquid-dsp 1.5.0, which the reference vendors only as
+a prebuilt MinGW static archive (/root/reference/external/liquid-dsp/gcc/64/libliquid.a, PE/COFF
+x86-64 objects, with symbols).  This script never copies reference sources; it reads that archive
+where it lies and writes only into oracle/_ref/ (git-ignored, but shipped to the GPU box):
+
+  1. `ar x` the archive into oracle/_ref/obj/
+  2. objcopy every COFF object to ELF64, dropping the SEH sections and renaming every libc/libm
+     import S to ms_S (the imports follow the Microsoft x64 calling convention)
+  3. repair RELA addends: objcopy keeps COFF's in-place addends and writes r_addend = 0, so for
+     PC32/PLT32 set r_addend = site - 4, for absolute relocs r_addend = site, and zero the site
+  4. compile ms_abi shims that forward ms_S to glibc (oracle/ms_shims.c)
+  5. compile the CubicSDR glue restatement (oracle/ref_chain.cpp) and link everything into
+     oracle/_ref/libsdr_ref.so
+
+If /root/reference is absent (GPU box) and oracle/_ref/libsdr_ref.so already exists, nothing is done.
+"""
+import os
+import struct
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_AR = "/root/reference/external/liquid-dsp/gcc/64/libliquid.a"
+OUT = os.path.join(HERE, "_ref")
+OBJ = os.path.join(OUT, "obj")
+LIB = os.path.join(OUT, "libsdr_ref.so")
+
+# archive-undefined minus archive-defined (functions); these become ms_<name> shims
+IMPORT_FUNCS = """___chkstk_ms __mingw_vfprintf __mingw_vfscanf __mingw_vsprintf atan2f calloc ccosf cos cosf
+coshf csinf csqrtf div erfcf erff exp expf fclose feof fopen free fwrite hypot lgamma lgammaf log log10 log10f
+logf malloc memcpy memmove memset pow qsort rand realloc sin sincosf sinf sinhf strcmp strlen tanf tanhf""".split()
+IMPORT_DATA = ["__imp___acrt_iob_func", "__imp__assert"]
+
+R_X86_64_64, R_X86_64_PC32, R_X86_64_PLT32, R_X86_64_32, R_X86_64_32S = 1, 2, 4, 10, 11
+
+
+def run(cmd, **kw):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, **kw)
+    if r.returncode != 0:
+        sys.stderr.write("FAILED: %s ...\n%s\n" % (" ".join(cmd)[:300], r.stdout[-4000:]))
+        raise SystemExit(1)
+    return r.stdout
+
+
+def fix_rela_addends(path):
+    """objcopy COFF->ELF leaves the addend in the relocated field; move it into r_addend."""
+    with open(path, "rb") as f:
+        b = bytearray(f.read())
+    assert b[:4] == b"\x7fELF" and b[4] == 2 and b[5] == 1, path
+    e_shoff = struct.unpack_from("<Q", b, 0x28)[0]
+    e_shentsize, e_shnum = struct.unpack_from("<HH", b, 0x3A)
+    secs = []
+    for i in range(e_shnum):
+        (name, typ, flags, addr, off, size, link, info, align, entsize) = struct.unpack_from(
+            "<IIQQQQIIQQ", b, e_shoff + i * e_shentsize)
+        secs.append(dict(type=typ, off=off, size=size, info=info, entsize=entsize))
+    nfix = 0
+    for s in secs:
+        if s["type"] != 4:  # SHT_RELA
+            continue
+        tgt = secs[s["info"]]
+        for k in range(s["size"] // 24):
+            ro = s["off"] + 24 * k
+            r_offset, r_info, r_addend = struct.unpack_from("<QQq", b, ro)
+            rtype = r_info & 0xFFFFFFFF
+            site = tgt["off"] + r_offset
+            if rtype in (R_X86_64_PC32, R_X86_64_PLT32):
+                v = struct.unpack_from("<i", b, site)[0]
+                struct.pack_into("<q", b, ro + 16, r_addend + v - 4)
+                struct.pack_into("<i", b, site, 0)
+            elif rtype == R_X86_64_64:
+                v = struct.unpack_from("<q", b, site)[0]
+                struct.pack_into("<q", b, ro + 16, r_addend + v)
+                struct.pack_into("<q", b, site, 0)
+            elif rtype in (R_X86_64_32, R_X86_64_32S):
+                v = struct.unpack_from("<i", b, site)[0]
+                struct.pack_into("<q", b, ro + 16, r_addend + v)
+                struct.pack_into("<i", b, site, 0)
+            else:
+                raise SystemExit("unexpected relocation type %d in %s" % (rtype, path))
+            nfix += 1
+    with open(path, "wb") as f:
+        f.write(b)
+    return nfix
+
+
+def transplant():
+    os.makedirs(OBJ, exist_ok=True)
+    run(["ar", "x", REF_AR], cwd=OBJ)
+    redef = []
+    for s in IMPORT_FUNCS:
+        redef += ["--redefine-sym", "%s=ms_%s" % (s, s)]
+    elf = []
+    for fn in sorted(os.listdir(OBJ)):
+        if not fn.endswith(".o") or fn.endswith(".elf.o"):
+            continue
+        src = os.path.join(OBJ, fn)
+        dst = os.path.join(OBJ, fn[:-2] + ".elf.o")
+        run(["objcopy", "-O", "elf64-x86-64", "--wildcard", "-R", ".pdata*", "-R", ".xdata*", "-R", ".rdata$zzz"]
+            + redef + [src, dst])
+        fix_rela_addends(dst)
+        os.remove(src)
+        elf.append(dst)
+    for fn in os.listdir(OBJ):  # stray non-object members (*.rdata)
+        p = os.path.join(OBJ, fn)
+        if not fn.endswith(".elf.o"):
+            os.remove(p)
+    return elf
+
+
+def build(force=False):
+    have_ref = os.path.exists(REF_AR)
+    if not have_ref:
+        if os.path.exists(LIB):
+            return LIB
+        raise SystemExit("oracle/_ref missing and /root/reference absent: cannot build the reference oracle")
+    srcs = [os.path.join(HERE, "ms_shims.c"), os.path.join(HERE, "ref_chain.cpp"), os.path.join(HERE, "liquid_ms.h"),
+            os.path.abspath(__file__)]
+    if (not force) and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
+        return LIB
+    os.makedirs(OUT, exist_ok=True)
+    objs = [os.path.join(OBJ, f) for f in sorted(os.listdir(OBJ))] if os.path.isdir(OBJ) else []
+    objs = [o for o in objs if o.endswith(".elf.o")]
+    if len(objs) < 160:
+        objs = transplant()
+    shim_o = os.path.join(OUT, "ms_shims.o")
+    chain_o = os.path.join(OUT, "ref_chain.o")
+    run(["gcc", "-O2", "-fPIC", "-c", os.path.join(HERE, "ms_shims.c"), "-o", shim_o])
+    run(["g++", "-O2", "-std=c++14", "-fPIC", "-pthread", "-I", HERE, "-c", os.path.join(HERE, "ref_chain.cpp"), "-o", chain_o])
+    run(["g++", "-shared", "-o", LIB, chain_o, shim_o] + objs +
+        ["-lm", "-pthread", "-Wl,-Bsymbolic", "-Wl,-z,notext", "-Wl,--allow-multiple-definition", "-Wl,-z,execstack"])
+    return LIB
+
+
+if __name__ == "__main__":
+    if "--clean" in sys.argv and os.path.exists(REF_AR) and os.path.isdir(OBJ):
+        import shutil
+        shutil.rmtree(OBJ)      # our own build products only; re-extracted from the reference archive below
+    print(build(force="--force" in sys.argv or "--clean" in sys.argv))

@@ -1,0 +1,514 @@
+// oracle/ref_chain.cpp -- TEST INFRASTRUCTURE ONLY (checker + CPU baseline; never on the product path).
+//
+// CubicSDR's hot-path GLUE restated on top of the reference's own liquid-dsp 1.5.0 binary (transplanted by
+// oracle/build_ref.py).  The arithmetic therefore IS the reference's; only the ~100 lines of C++ glue between
+// liquid calls are restated, each block citing the reference lines it follows (paths relative to
+// /root/reference/).  Exposed as a plain C API (SysV) for ctypes / bench.py.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "liquid_ms.h"
+
+#define API extern "C" __attribute__((visibility("default")))
+
+// ---------------------------------------------------------------------------------------------------------
+// thin SysV -> ms_abi pass-throughs used by unit tests to pin the restatement (oracle/liquid_port.c) and the
+// product's host-side filter design against the reference binary
+// ---------------------------------------------------------------------------------------------------------
+API const char *ref_libversion() { return liquid_libversion(); }
+API unsigned ref_estimate_req_filter_len(float df, float as) { return estimate_req_filter_len(df, as); }
+API float ref_estimate_req_filter_df(float as, unsigned n) { return estimate_req_filter_df(as, n); }
+API float ref_kaiser_beta_As(float as) { return kaiser_beta_As(as); }
+API int ref_firdespm_halfband_as(unsigned m, float as, float *h) { return liquid_firdespm_halfband_as(m, as, h); }
+API int ref_firdes_kaiser(unsigned n, float fc, float as, float mu, float *h) { return liquid_firdes_kaiser(n, fc, as, mu, h); }
+API float ref_besseli0f(float z) { return liquid_besseli0f(z); }
+API float ref_kaiser_window(unsigned i, unsigned n, float beta) { return liquid_kaiser(i, n, beta); }
+
+API void *ref_nco_create() { return nco_crcf_create(0 /*LIQUID_NCO*/); }
+API void ref_nco_destroy(void *q) { nco_crcf_destroy((nco_crcf)q); }
+API void ref_nco_set_frequency(void *q, float f) { nco_crcf_set_frequency((nco_crcf)q, f); }
+API float ref_nco_get_frequency(void *q) { return nco_crcf_get_frequency((nco_crcf)q); }
+API void ref_nco_set_phase(void *q, float p) { nco_crcf_set_phase((nco_crcf)q, p); }
+API float ref_nco_get_phase(void *q) { return nco_crcf_get_phase((nco_crcf)q); }
+// object layout {int type; float sintab[1024]; uint32 theta; uint32 d_theta; ...}
+API uint32_t ref_nco_raw_theta(void *q) { uint32_t v; memcpy(&v, (char *)q + 4 + 4096, 4); return v; }
+API uint32_t ref_nco_raw_dtheta(void *q) { uint32_t v; memcpy(&v, (char *)q + 4 + 4096 + 4, 4); return v; }
+API void ref_nco_sintab(void *q, float *tab) { memcpy(tab, (char *)q + 4, 4096); }
+API void ref_nco_mix_block(void *q, int up, lq_cf *x, lq_cf *y, unsigned n) {
+    if (up) nco_crcf_mix_block_up((nco_crcf)q, x, y, n); else nco_crcf_mix_block_down((nco_crcf)q, x, y, n);
+}
+
+API void *ref_resamp2_crcf_create(unsigned m, float f0, float as) { return resamp2_crcf_create(m, f0, as); }
+API void ref_resamp2_crcf_destroy(void *q) { resamp2_crcf_destroy((resamp2_crcf)q); }
+API void ref_resamp2_crcf_decim(void *q, lq_cf *x, unsigned n_pairs, lq_cf *y) {
+    for (unsigned i = 0; i < n_pairs; i++) resamp2_crcf_decim_execute((resamp2_crcf)q, x + 2 * i, y + i);
+}
+API void *ref_resamp_crcf_create(float r, unsigned m, float fc, float as, unsigned npfb) { return resamp_crcf_create(r, m, fc, as, npfb); }
+API void ref_resamp_crcf_destroy(void *q) { resamp_crcf_destroy((resamp_crcf)q); }
+API unsigned ref_resamp_crcf_execute_block(void *q, lq_cf *x, unsigned n, lq_cf *y) {
+    unsigned tot = 0, nw;
+    for (unsigned i = 0; i < n; i++) { resamp_crcf_execute((resamp_crcf)q, x[i], y + tot, &nw); tot += nw; }
+    return tot;
+}
+API void *ref_msresamp_crcf_create(float r, float as) { return msresamp_crcf_create(r, as); }
+API void ref_msresamp_crcf_destroy(void *q) { msresamp_crcf_destroy((msresamp_crcf)q); }
+API float ref_msresamp_crcf_get_delay(void *q) { return msresamp_crcf_get_delay((msresamp_crcf)q); }
+API unsigned ref_msresamp_crcf_execute(void *q, lq_cf *x, unsigned n, lq_cf *y) {
+    unsigned ny = 0; msresamp_crcf_execute((msresamp_crcf)q, x, n, y, &ny); return ny;
+}
+API void *ref_msresamp_rrrf_create(float r, float as) { return msresamp_rrrf_create(r, as); }
+API void ref_msresamp_rrrf_destroy(void *q) { msresamp_rrrf_destroy((msresamp_rrrf)q); }
+API float ref_msresamp_rrrf_get_delay(void *q) { return msresamp_rrrf_get_delay((msresamp_rrrf)q); }
+API unsigned ref_msresamp_rrrf_execute(void *q, float *x, unsigned n, float *y) {
+    unsigned ny = 0; msresamp_rrrf_execute((msresamp_rrrf)q, x, n, y, &ny); return ny;
+}
+API void *ref_freqdem_create(float kf) { return freqdem_create(kf); }
+API void ref_freqdem_destroy(void *q) { freqdem_destroy((freqdem)q); }
+API void ref_freqdem_block(void *q, lq_cf *x, unsigned n, float *y) { freqdem_demodulate_block((freqdem)q, x, n, y); }
+API void *ref_firfilt_dc_blocker_create(unsigned m, float as) { return firfilt_rrrf_create_dc_blocker(m, as); }
+API void ref_firfilt_destroy(void *q) { firfilt_rrrf_destroy((firfilt_rrrf)q); }
+API void ref_firfilt_block(void *q, float *x, unsigned n, float *y) {
+    for (unsigned i = 0; i < n; i++) { firfilt_rrrf_push((firfilt_rrrf)q, x[i]); firfilt_rrrf_execute((firfilt_rrrf)q, y + i); }
+}
+API void *ref_iirfilt_lowpass_create(unsigned order, float fc) { return iirfilt_crcf_create_lowpass(order, fc); }
+API void *ref_iirfilt_dc_blocker_create(float alpha) { return iirfilt_crcf_create_dc_blocker(alpha); }
+API void ref_iirfilt_destroy(void *q) { iirfilt_crcf_destroy((iirfilt_crcf)q); }
+API void ref_iirfilt_block(void *q, lq_cf *x, unsigned n, lq_cf *y) { iirfilt_crcf_execute_block((iirfilt_crcf)q, x, n, y); }
+API void *ref_firhilb_create(unsigned m, float as) { return firhilbf_create(m, as); }
+API void ref_firhilb_destroy(void *q) { firhilbf_destroy((firhilbf)q); }
+API void ref_firhilb_c2r_block(void *q, lq_cf *x, unsigned n, float *lsb, float *usb) {
+    for (unsigned i = 0; i < n; i++) firhilbf_c2r_execute((firhilbf)q, x[i], lsb + i, usb + i);
+}
+API void ref_fft_forward(lq_cf *x, lq_cf *y, unsigned n) {
+    fftplan p = fft_create_plan(n, x, y, +1 /*LIQUID_FFT_FORWARD*/, 0);
+    fft_execute(p);
+    fft_destroy_plan(p);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// SDRPostThread::runSingleCH DC blocker     src/sdr/SDRPostThread.cpp:29 (create), :284 (execute_block)
+// ---------------------------------------------------------------------------------------------------------
+struct RefIngress { iirfilt_crcf dc; };
+API void *ref_ingress_create() { auto *g = new RefIngress; g->dc = iirfilt_crcf_create_dc_blocker(0.0005f); return g; }
+API void ref_ingress_destroy(void *h) { auto *g = (RefIngress *)h; iirfilt_crcf_destroy(g->dc); delete g; }
+API void ref_ingress_block(void *h, lq_cf *in, unsigned n, lq_cf *out) {
+    iirfilt_crcf_execute_block(((RefIngress *)h)->dc, in, n, out);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// one demodulator channel: DemodulatorPreThread + Modem + DemodulatorThread metering
+// ---------------------------------------------------------------------------------------------------------
+enum { M_FM = 0, M_NBFM = 1, M_AM = 2, M_USB = 3, M_LSB = 4 };
+
+struct RefChan {
+    int modem;
+    long long sampleRate;      // wideband rate
+    int bandwidth;             // modem rate (after checkSampleRate)
+    int audioRate;
+    // DemodulatorPreThread members (src/demod/DemodulatorPreThread.cpp:22, DemodulatorWorkerThread.cpp:95-101)
+    nco_crcf freqShifter;
+    msresamp_crcf iqResampler;
+    double iqResampleRatio;
+    long long shiftFrequency;
+    // ModemAnalog (src/modules/modem/ModemAnalog.cpp:6, :21-33)
+    msresamp_rrrf audioResampler;
+    double audioResampleRatio;
+    float aOutputCeil, aOutputCeilMA, aOutputCeilMAA;
+    // modem objects (ModemFM.cpp:7, ModemAM.cpp:9, ModemUSB.cpp:8-11)
+    freqdem demodFM;
+    firfilt_rrrf mDCBlock;
+    iirfilt_crcf ssbFilt;
+    nco_crcf ssbShift;
+    firhilbf c2rFilt;
+    std::vector<lq_cf> in_buf, out_buf, resampled;
+    std::vector<float> demodOut, audioOut;
+};
+
+static int modem_from_name(const char *n) {
+    std::string s(n);
+    if (s == "FM") return M_FM;
+    if (s == "NBFM") return M_NBFM;
+    if (s == "AM") return M_AM;
+    if (s == "USB") return M_USB;
+    if (s == "LSB") return M_LSB;
+    return -1;
+}
+
+// Modem*::checkSampleRate: ModemAnalog.cpp:14-19 (MIN_BANDWIDTH = 500, src/CubicSDRDefs.h), ModemUSB.cpp:29-37
+API int ref_modem_check_sample_rate(const char *name, long long bw) {
+    int m = modem_from_name(name);
+    if (m < 0) return -1;
+    if (bw < 500) return 500;
+    if ((m == M_USB || m == M_LSB) && (bw % 2)) return (int)(bw + 1);
+    return (int)bw;
+}
+
+API void *ref_chan_create(const char *modem, long long sampleRate, long long bandwidth, int audioRate) {
+    int m = modem_from_name(modem);
+    if (m < 0) return nullptr;
+    auto *c = new RefChan();
+    c->modem = m;
+    c->sampleRate = sampleRate;
+    c->bandwidth = ref_modem_check_sample_rate(modem, bandwidth);
+    c->audioRate = audioRate;
+    c->freqShifter = nco_crcf_create(0);                                   // DemodulatorPreThread.cpp:22
+    c->shiftFrequency = 0;
+    // DemodulatorWorkerThread.cpp:95-101
+    float As = 60.0f;
+    c->iqResampleRatio = (double)c->bandwidth / (double)sampleRate;
+    c->iqResampler = msresamp_crcf_create((float)c->iqResampleRatio, As);
+    // ModemAnalog::buildKit ModemAnalog.cpp:21-33
+    c->audioResampleRatio = double(audioRate) / double(c->bandwidth);
+    c->audioResampler = msresamp_rrrf_create((float)c->audioResampleRatio, As);
+    c->aOutputCeil = c->aOutputCeilMA = c->aOutputCeilMAA = 1;             // ModemAnalog.cpp:6
+    c->demodFM = nullptr; c->mDCBlock = nullptr; c->ssbFilt = nullptr; c->ssbShift = nullptr; c->c2rFilt = nullptr;
+    if (m == M_FM || m == M_NBFM) c->demodFM = freqdem_create(0.5f);       // ModemFM.cpp:7
+    if (m == M_AM) c->mDCBlock = firfilt_rrrf_create_dc_blocker(25, 30.0f); // ModemAM.cpp:9
+    if (m == M_USB || m == M_LSB) {                                        // ModemUSB.cpp:8-11
+        c->ssbFilt = iirfilt_crcf_create_lowpass(6, 0.25);
+        c->ssbShift = nco_crcf_create(0);
+        nco_crcf_set_frequency(c->ssbShift, (float)((2.0 * M_PI) * 0.25));
+        c->c2rFilt = firhilbf_create(5, 90.0);
+    }
+    return c;
+}
+
+API void ref_chan_destroy(void *h) {
+    auto *c = (RefChan *)h;
+    nco_crcf_destroy(c->freqShifter);
+    msresamp_crcf_destroy(c->iqResampler);
+    msresamp_rrrf_destroy(c->audioResampler);
+    if (c->demodFM) freqdem_destroy(c->demodFM);
+    if (c->mDCBlock) firfilt_rrrf_destroy(c->mDCBlock);
+    if (c->ssbFilt) iirfilt_crcf_destroy(c->ssbFilt);
+    if (c->ssbShift) nco_crcf_destroy(c->ssbShift);
+    if (c->c2rFilt) firhilbf_destroy(c->c2rFilt);
+    delete c;
+}
+
+API int ref_chan_bandwidth(void *h) { return ((RefChan *)h)->bandwidth; }
+
+// One block through the channel.  shift = demod frequency - block centre frequency.
+// Returns 0, or 1 if the block was skipped by the |shift| > 0.75 fs rule.
+// Outputs (any may be null): decimated IQ, demodulated (pre-audio-resample, post-autogain) samples, audio,
+// level_db (DemodulatorThread.cpp:142-163), peak (:223-233).
+API int ref_chan_process(void *h, const lq_cf *block, unsigned n, long long shift,
+                         lq_cf *iq_out, unsigned *n_iq, float *demod_out, float *audio_out, unsigned *n_audio,
+                         double *level_db, float *peak) {
+    auto *c = (RefChan *)h;
+    if (n_iq) *n_iq = 0;
+    if (n_audio) *n_audio = 0;
+    // --- DemodulatorPreThread.cpp:154-163
+    if (shift != c->shiftFrequency) {
+        c->shiftFrequency = shift;
+        if (std::llabs(c->shiftFrequency) <= (int)((double)(c->sampleRate / 2) * 1.5)) {
+            nco_crcf_set_frequency(c->freqShifter, (2.0 * M_PI) * (((double)std::llabs(c->shiftFrequency)) / ((double)c->sampleRate)));
+        }
+    }
+    if (std::llabs(c->shiftFrequency) > (int)((double)(c->sampleRate / 2) * 1.5)) return 1;
+    if (n == 0) return 0;
+    // --- :166-195
+    c->in_buf.assign(block, block + n);
+    c->out_buf.resize(n);
+    lq_cf *in_buf = c->in_buf.data(), *out_buf = c->out_buf.data();
+    if (c->shiftFrequency != 0) {
+        if (c->shiftFrequency < 0) nco_crcf_mix_block_up(c->freqShifter, in_buf, out_buf, n);
+        else nco_crcf_mix_block_down(c->freqShifter, in_buf, out_buf, n);
+        std::swap(in_buf, out_buf);
+    }
+    // --- :199-211
+    size_t out_size = (size_t)ceil((double)n * c->iqResampleRatio) + 512;
+    c->resampled.resize(out_size);
+    unsigned numWritten = 0;
+    msresamp_crcf_execute(c->iqResampler, in_buf, n, c->resampled.data(), &numWritten);
+    if (iq_out) memcpy(iq_out, c->resampled.data(), numWritten * sizeof(lq_cf));
+    if (n_iq) *n_iq = numWritten;
+
+    // --- DemodulatorThread.cpp:120-140 -> Modem::demodulate
+    size_t bufSize = numWritten;                                            // ModemAnalog::initOutputBuffers :42-65
+    if (!bufSize) return 0;
+    size_t audio_out_size = (size_t)ceil((double)bufSize * c->audioResampleRatio) + 512;
+    c->demodOut.resize(bufSize);
+    c->audioOut.resize(audio_out_size);
+    lq_cf *d = c->resampled.data();
+    bool autoGain = false, useSignalOutput = false;
+    switch (c->modem) {
+    case M_FM: case M_NBFM:                                                 // ModemFM.cpp:26-39
+        freqdem_demodulate_block(c->demodFM, d, (unsigned)bufSize, c->demodOut.data());
+        break;
+    case M_AM:                                                              // ModemAM.cpp:29-50
+        for (size_t i = 0; i < bufSize; i++) {
+            float I = d[i].real, Q = d[i].imag;
+            firfilt_rrrf_push(c->mDCBlock, sqrt(I * I + Q * Q));
+            firfilt_rrrf_execute(c->mDCBlock, &c->demodOut[i]);
+        }
+        autoGain = true; useSignalOutput = true;
+        break;
+    case M_USB:                                                             // ModemUSB.cpp:43-64
+        for (size_t i = 0; i < bufSize; i++) {
+            lq_cf x, y; float discard;
+            nco_crcf_step(c->ssbShift);
+            nco_crcf_mix_down(c->ssbShift, d[i], &x);
+            iirfilt_crcf_execute(c->ssbFilt, x, &y);
+            nco_crcf_mix_up(c->ssbShift, y, &x);
+            firhilbf_c2r_execute(c->c2rFilt, x, &discard, &c->demodOut[i]);
+        }
+        autoGain = true; useSignalOutput = true;
+        break;
+    case M_LSB:                                                             // ModemLSB.cpp:43-64
+        for (size_t i = 0; i < bufSize; i++) {
+            lq_cf x, y; float discard;
+            nco_crcf_step(c->ssbShift);
+            nco_crcf_mix_up(c->ssbShift, d[i], &x);
+            iirfilt_crcf_execute(c->ssbFilt, x, &y);
+            nco_crcf_mix_down(c->ssbShift, y, &x);
+            firhilbf_c2r_execute(c->c2rFilt, x, &c->demodOut[i], &discard);
+        }
+        autoGain = true; useSignalOutput = true;
+        break;
+    }
+    // --- ModemAnalog::buildAudioOutput ModemAnalog.cpp:67-93
+    if (autoGain) {
+        c->aOutputCeilMA = c->aOutputCeilMA + (c->aOutputCeil - c->aOutputCeilMA) * 0.025f;
+        c->aOutputCeilMAA = c->aOutputCeilMAA + (c->aOutputCeilMA - c->aOutputCeilMAA) * 0.025f;
+        c->aOutputCeil = 0;
+        for (size_t i = 0; i < bufSize; i++) if (c->demodOut[i] > c->aOutputCeil) c->aOutputCeil = c->demodOut[i];
+        float gain = 0.5f / c->aOutputCeilMAA;
+        for (size_t i = 0; i < bufSize; i++) c->demodOut[i] *= gain;
+    }
+    unsigned numAudioWritten = 0;
+    msresamp_rrrf_execute(c->audioResampler, c->demodOut.data(), (unsigned)bufSize, c->audioOut.data(), &numAudioWritten);
+    if (demod_out) memcpy(demod_out, c->demodOut.data(), bufSize * sizeof(float));
+    if (audio_out) memcpy(audio_out, c->audioOut.data(), numAudioWritten * sizeof(float));
+    if (n_audio) *n_audio = numAudioWritten;
+
+    // --- DemodulatorThread.cpp:142-163 (level) and :223-233 (peak); abMagnitude :49-58, linearToDb :60-67
+    if (numAudioWritten) {
+        double accum = 0;
+        if (useSignalOutput) {
+            for (unsigned i = 0; i < numAudioWritten; i++) { double v = (double)c->audioOut[i]; accum += sqrt(v * v + 0.0); }
+            accum /= double(numAudioWritten);
+        } else {
+            for (size_t i = 0; i < bufSize; i++) { double a = d[i].real, b = d[i].imag; accum += sqrt(a * a + b * b); }
+            accum /= double(bufSize);
+        }
+        if (accum <= 1e-20) accum = 1e-20;
+        if (level_db) *level_db = 20.0 * log10(accum);
+    } else if (level_db) *level_db = 0;
+    if (peak) {
+        float p = 0;
+        for (unsigned i = 0; i < numAudioWritten; i++) { float a = fabs(c->audioOut[i]); if (a > p) p = a; }
+        *peak = p;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// FFTDataDistributor framing             src/process/FFTDataDistributor.cpp:28-144
+// ---------------------------------------------------------------------------------------------------------
+struct RefDistrib {
+    unsigned fftSize; unsigned linesPerSecond; double lineRateAccum;
+    std::vector<lq_cf> buf; size_t bufferMax, bufferOffset, bufferedItems; long long sampleRate;
+};
+API void *ref_distrib_create(unsigned fftSize, unsigned lps) {
+    auto *d = new RefDistrib(); d->fftSize = fftSize; d->linesPerSecond = lps; d->lineRateAccum = 0;
+    d->bufferMax = d->bufferOffset = d->bufferedItems = 0; d->sampleRate = 0; return d;
+}
+API void ref_distrib_destroy(void *h) { delete (RefDistrib *)h; }
+// returns number of frames written to frames_out (each fftSize samples)
+API unsigned ref_distrib_push(void *h, const lq_cf *in, unsigned n, long long sampleRate, lq_cf *frames_out, unsigned cap_frames) {
+    auto *d = (RefDistrib *)h;
+    unsigned nf = 0;
+    if (d->sampleRate != sampleRate) {                                      // :41-53
+        d->bufferMax = std::max((size_t)(sampleRate * 0.250), (size_t)(1.2 * d->fftSize));
+        d->bufferOffset = 0; d->bufferedItems = 0; d->sampleRate = sampleRate; d->buf.resize(d->bufferMax);
+    }
+    if (d->bufferMax < (size_t)(1.2 * d->fftSize)) { d->bufferMax = (size_t)(1.2 * d->fftSize); d->buf.resize(d->bufferMax); }
+    size_t add = n;
+    if (d->bufferOffset + d->bufferedItems + n > d->bufferMax) {            // :66-76
+        memmove(&d->buf[0], &d->buf[d->bufferOffset], d->bufferedItems * sizeof(lq_cf));
+        d->bufferOffset = 0;
+        if (d->bufferedItems + n > d->bufferMax) add = d->bufferMax - d->bufferedItems;
+    }
+    memcpy(&d->buf[d->bufferOffset + d->bufferedItems], in, add * sizeof(lq_cf));
+    d->bufferedItems += add;
+    double inputTime = (double)d->bufferedItems / (double)d->sampleRate;    // :89-97
+    double inputLines = (double)d->bufferedItems / (double)d->fftSize;
+    double lineRateStep = ((double)d->linesPerSecond * inputTime) / inputLines;
+    if (d->bufferedItems >= d->fftSize) {                                   // :100-142
+        size_t numProcessed = 0;
+        if (d->lineRateAccum + (lineRateStep * ((double)d->bufferedItems / (double)d->fftSize)) < 1.0) {
+            d->lineRateAccum += (lineRateStep * ((double)d->bufferedItems / (double)d->fftSize));
+            numProcessed = d->bufferedItems;
+        } else {
+            for (size_t i = 0, iMax = d->bufferedItems; i < iMax; i += d->fftSize) {
+                if ((i + d->fftSize) > iMax) break;
+                d->lineRateAccum += lineRateStep;
+                if (d->lineRateAccum >= 1.0) {
+                    if (nf < cap_frames) memcpy(frames_out + (size_t)nf * d->fftSize, &d->buf[d->bufferOffset + i], d->fftSize * sizeof(lq_cf));
+                    nf++;
+                    while (d->lineRateAccum >= 1.0) d->lineRateAccum -= 1.0;
+                }
+                numProcessed += d->fftSize;
+            }
+        }
+        if (numProcessed) { d->bufferedItems -= numProcessed; d->bufferOffset += numProcessed; }
+        if (d->bufferedItems <= 0) { d->bufferedItems = 0; d->bufferOffset = 0; }
+    }
+    return nf;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// SpectrumVisualProcessor, non-view branch   src/process/SpectrumVisualProcessor.cpp:10-45,140-178,388-452,494-576
+// + WaterfallPanel::step u8 rule             src/panel/WaterfallPanel.cpp:51-83
+// ---------------------------------------------------------------------------------------------------------
+struct RefSpectrum {
+    unsigned fftSize, fftSizeInternal;
+    std::vector<lq_cf> fftInput, fftOutput;
+    fftplan plan;
+    double fft_ceil_ma, fft_ceil_maa, fft_floor_ma, fft_floor_maa;
+    float fft_average_rate, scaleFactor;
+    std::vector<double> fft_result, fft_result_ma, fft_result_maa;
+};
+API void *ref_spectrum_create(unsigned fftSize) {
+    auto *s = new RefSpectrum();
+    s->fftSize = fftSize; s->fftSizeInternal = fftSize * 2;                 // :145 (SPECTRUM_VZM = 2)
+    s->fftInput.assign(s->fftSizeInternal, lq_cf{0, 0}); s->fftOutput.assign(s->fftSizeInternal, lq_cf{0, 0});
+    s->plan = fft_create_plan(s->fftSizeInternal, s->fftInput.data(), s->fftOutput.data(), +1, 0);  // :177
+    s->fft_ceil_ma = s->fft_ceil_maa = 100.0; s->fft_floor_ma = s->fft_floor_maa = 0.0;           // :32-33
+    s->fft_average_rate = 0.65f; s->scaleFactor = 1.0f;                                           // :36-37
+    s->fft_result.assign(s->fftSizeInternal, 0.0); s->fft_result_ma.assign(s->fftSizeInternal, 0.0);
+    s->fft_result_maa.assign(s->fftSizeInternal, 0.0);                                            // :252-264
+    return s;
+}
+API void ref_spectrum_destroy(void *h) { auto *s = (RefSpectrum *)h; fft_destroy_plan(s->plan); delete s; }
+API void ref_spectrum_set_average_rate(void *h, float r) { ((RefSpectrum *)h)->fft_average_rate = r; }
+
+// frame: >= fftSizeInternal samples (n given); outputs: points_y[fftSize], u8 line[fftSize], optional copies of
+// fft_result (linear magnitudes, fftshifted) and fft_result_maa, and the ceil/floor pair used for this frame.
+API void ref_spectrum_frame(void *h, const lq_cf *frame, unsigned n, float *points_y, unsigned char *wf_line,
+                            double *fft_result_out, double *fft_maa_out, double *ceil_floor_out) {
+    auto *s = (RefSpectrum *)h;
+    const unsigned N = s->fftSizeInternal;
+    // :388-403 (non-view): copy first N samples, zero-pad a short frame (priming path not modelled: n >= N expected)
+    if (n < N) { memcpy(s->fftInput.data(), frame, n * sizeof(lq_cf)); memset(&s->fftInput[n], 0, (N - n) * sizeof(lq_cf)); }
+    else memcpy(s->fftInput.data(), frame, N * sizeof(lq_cf));
+    float fft_ceil = 0, fft_floor = 1;                                      // :437
+    fft_execute(s->plan);                                                   // :439
+    for (int i = 0, iMax = N / 2; i < iMax; i++) {                          // :441-452
+        float a = s->fftOutput[i].real, b = s->fftOutput[i].imag;
+        float c = sqrt(a * a + b * b);
+        float x = s->fftOutput[N / 2 + i].real, y = s->fftOutput[N / 2 + i].imag;
+        float z = sqrt(x * x + y * y);
+        s->fft_result[i] = (z);
+        s->fft_result[N / 2 + i] = (c);
+    }
+    for (int i = 0, iMax = N; i < iMax; i++) {                              // :494-511
+        if (s->fft_result_maa[i] != s->fft_result_maa[i]) s->fft_result_maa[i] = s->fft_result[i];
+        s->fft_result_maa[i] += (s->fft_result_ma[i] - s->fft_result_maa[i]) * s->fft_average_rate;
+        if (s->fft_result_ma[i] != s->fft_result_ma[i]) s->fft_result_ma[i] = s->fft_result[i];
+        s->fft_result_ma[i] += (s->fft_result[i] - s->fft_result_ma[i]) * s->fft_average_rate;
+        if (s->fft_result_maa[i] > fft_ceil || fft_ceil != fft_ceil) fft_ceil = s->fft_result_maa[i];
+        if (s->fft_result_maa[i] < fft_floor || fft_floor != fft_floor) fft_floor = s->fft_result_maa[i];
+    }
+    if (s->fft_ceil_ma != s->fft_ceil_ma) s->fft_ceil_ma = fft_ceil;         // :513-521
+    s->fft_ceil_ma = s->fft_ceil_ma + (fft_ceil - s->fft_ceil_ma) * 0.05;
+    if (s->fft_ceil_maa != s->fft_ceil_maa) s->fft_ceil_maa = fft_ceil;
+    s->fft_ceil_maa = s->fft_ceil_maa + (s->fft_ceil_ma - s->fft_ceil_maa) * 0.05;
+    if (s->fft_floor_ma != s->fft_floor_ma) s->fft_floor_ma = fft_floor;
+    s->fft_floor_ma = s->fft_floor_ma + (fft_floor - s->fft_floor_ma) * 0.05;
+    if (s->fft_floor_maa != s->fft_floor_maa) s->fft_floor_maa = fft_floor;
+    s->fft_floor_maa = s->fft_floor_maa + (s->fft_floor_ma - s->fft_floor_maa) * 0.05;
+
+    float sf = s->scaleFactor;                                              // :532-576 with bandwidth == resampleBw
+    double visualRatio = 1.0;
+    double visualStart = (double(N) / 2.0) - (double(N) * (visualRatio / 2.0));
+    double visualAccum = 0, acc = 0, accCount = 0, i = 0;
+    double point_ceil = s->fft_ceil_maa, point_floor = s->fft_floor_maa;
+    for (int x = 0, xMax = s->fftSize; x < xMax; x++) {
+        visualAccum += visualRatio * double(2);
+        while (visualAccum >= 1.0) {
+            unsigned int idx = round(visualStart + i);
+            if (idx > 0 && idx < N) acc += s->fft_result_maa[idx]; else acc += s->fft_floor_maa;
+            accCount += 1.0; visualAccum -= 1.0; i++;
+        }
+        if (accCount) {
+            float yv = ((log10((acc / accCount) + 0.25 - (point_floor - 0.75)) / log10((point_ceil + 0.25) - (point_floor - 0.75)))) * sf;
+            if (points_y) points_y[x] = yv;
+            if (wf_line) {                                                  // WaterfallPanel.cpp:64-70
+                float v = yv;
+                float wv = v < 0 ? 0 : (v > 0.99 ? 0.99 : v);
+                wf_line[x] = (unsigned char)floor(wv * 255.0);
+            }
+            acc = 0.0; accCount = 0.0;
+        }
+    }
+    if (fft_result_out) memcpy(fft_result_out, s->fft_result.data(), N * sizeof(double));
+    if (fft_maa_out) memcpy(fft_maa_out, s->fft_result_maa.data(), N * sizeof(double));
+    if (ceil_floor_out) { ceil_floor_out[0] = point_ceil; ceil_floor_out[1] = point_floor; }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// CPU baseline: whole path, threaded the way the reference is (one ingress, one per channel, one spectrum;
+// here the channel work is spread over `threads` workers).  Returns seconds for `blocks` blocks of n samples.
+// ---------------------------------------------------------------------------------------------------------
+API double ref_bench_path(const lq_cf *iq, unsigned n, unsigned blocks, long long sampleRate,
+                          unsigned n_chan, const char *const *modem_names, const long long *bandwidths, const long long *shifts,
+                          int audioRate, unsigned fftSize /*0 = no spectrum*/, unsigned threads, double *audio_checksum) {
+    std::vector<void *> chans(n_chan);
+    for (unsigned c = 0; c < n_chan; c++) chans[c] = ref_chan_create(modem_names[c], sampleRate, bandwidths[c], audioRate);
+    void *ing = ref_ingress_create();
+    void *spec = fftSize ? ref_spectrum_create(fftSize) : nullptr;
+    void *dist = fftSize ? ref_distrib_create(fftSize * 2, 1000000) : nullptr;
+    std::vector<lq_cf> dc(n);
+    std::vector<lq_cf> frames;
+    unsigned cap_frames = fftSize ? (n / (fftSize * 2) + 2) : 0;
+    if (fftSize) frames.resize((size_t)cap_frames * fftSize * 2);
+    std::vector<float> pts(fftSize ? fftSize : 1);
+    std::vector<unsigned char> line(fftSize ? fftSize : 1);
+    if (threads < 1) threads = 1;
+    std::vector<double> sums(threads, 0.0);
+    auto t0 = std::chrono::steady_clock::now();
+    for (unsigned b = 0; b < blocks; b++) {
+        ref_ingress_block(ing, const_cast<lq_cf *>(iq), n, dc.data());
+        std::atomic<unsigned> next(0);
+        auto work = [&](unsigned tid) {
+            std::vector<float> audio(8192);
+            for (;;) {
+                unsigned c = next.fetch_add(1);
+                if (c >= n_chan) break;
+                auto *rc = (RefChan *)chans[c];
+                size_t need = (size_t)ceil((double)n * rc->iqResampleRatio * rc->audioResampleRatio) + 2048;
+                if (audio.size() < need) audio.resize(need);
+                unsigned na = 0;
+                ref_chan_process(chans[c], dc.data(), n, shifts[c], nullptr, nullptr, nullptr, audio.data(), &na, nullptr, nullptr);
+                double s = 0; for (unsigned i = 0; i < na; i++) s += audio[i];
+                sums[tid] += s;
+            }
+        };
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < threads; t++) pool.emplace_back(work, t);
+        if (spec) {   // the spectrum thread's work rides on the calling thread, then it joins the channel pool
+            unsigned nf = ref_distrib_push(dist, dc.data(), n, sampleRate, frames.data(), cap_frames);
+            for (unsigned f = 0; f < nf && f < cap_frames; f++)
+                ref_spectrum_frame(spec, frames.data() + (size_t)f * fftSize * 2, fftSize * 2, pts.data(), line.data(), nullptr, nullptr, nullptr);
+        }
+        work(0);
+        for (auto &t : pool) t.join();
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    double tot = 0; for (double s : sums) tot += s;
+    if (audio_checksum) *audio_checksum = tot;
+    for (auto c : chans) ref_chan_destroy(c);
+    ref_ingress_destroy(ing);
+    if (spec) { ref_spectrum_destroy(spec); ref_distrib_destroy(dist); }
+    return std::chrono::duration<double>(t1 - t0).count();
+}
