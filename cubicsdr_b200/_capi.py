@@ -1,0 +1,204 @@
+"""ctypes binding of include/sdr_b200.h.
+
+`Lib(path)` binds every entry point of the C-ABI.  The package binds the product library (built by nvcc for
+sm_100a, cubicsdr_b200/libsdr_b200.so) and refuses to work without it: there is no CPU path.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PRODUCT_LIB = os.path.join(_HERE, "libsdr_b200.so")
+
+# every symbol include/sdr_b200.h declares (tests/test_abi.py checks the header against this list and the .so)
+SYMBOLS = [
+    "sdr_last_error", "sdr_version", "sdr_is_device_build",
+    "sdr_engine_create", "sdr_engine_destroy", "sdr_engine_submit", "sdr_engine_submit_device", "sdr_engine_wait",
+    "sdr_engine_fetch_block", "sdr_engine_launch_count",
+    "sdr_chan_create", "sdr_chan_destroy", "sdr_chan_set_frequency", "sdr_chan_get_bandwidth", "sdr_chan_want_iq",
+    "sdr_chan_fetch_audio", "sdr_chan_fetch_iq",
+    "sdr_spectrum_create", "sdr_spectrum_destroy", "sdr_spectrum_set_average_rate", "sdr_spectrum_frames",
+    "sdr_spectrum_fetch", "sdr_spectrum_fetch_debug",
+    "sdr_design_kaiser", "sdr_design_nco_table", "sdr_design_nco_step", "sdr_design_resampler",
+    "sdr_design_halfband_branch", "sdr_design_am_dc_block", "sdr_design_hilbert_q", "sdr_design_butter6_sos",
+]
+
+
+class SdrError(RuntimeError):
+    pass
+
+
+class Lib:
+    def __init__(self, path=PRODUCT_LIB):
+        if not os.path.exists(path):
+            raise SdrError(
+                "%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  cubicsdr_b200 has no CPU fallback." % path)
+        self.path = path
+        L = self.L = C.CDLL(path)
+        vp, u, i, ll, f, d = C.c_void_p, C.c_uint, C.c_int, C.c_longlong, C.c_float, C.c_double
+        P = C.POINTER
+        L.sdr_last_error.restype = C.c_char_p
+        L.sdr_version.restype = C.c_char_p
+        L.sdr_engine_create.argtypes = [i, u, vp, P(vp)]
+        L.sdr_engine_destroy.argtypes = [vp]
+        L.sdr_engine_submit.argtypes = [vp, vp, u, ll, ll]
+        L.sdr_engine_submit_device.argtypes = [vp, vp, u, ll, ll, i]
+        L.sdr_engine_wait.argtypes = [vp]
+        L.sdr_engine_fetch_block.argtypes = [vp, vp, u, P(u)]
+        L.sdr_engine_launch_count.argtypes = [vp]
+        L.sdr_engine_launch_count.restype = C.c_ulonglong
+        L.sdr_chan_create.argtypes = [vp, C.c_char_p, ll, ll, i, P(vp)]
+        L.sdr_chan_destroy.argtypes = [vp]
+        L.sdr_chan_set_frequency.argtypes = [vp, ll]
+        L.sdr_chan_get_bandwidth.argtypes = [vp, P(i)]
+        L.sdr_chan_want_iq.argtypes = [vp, i]
+        L.sdr_chan_fetch_audio.argtypes = [vp, vp, u, P(u), P(d), P(f), P(i)]
+        L.sdr_chan_fetch_iq.argtypes = [vp, vp, u, P(u)]
+        L.sdr_spectrum_create.argtypes = [vp, u, u, P(vp)]
+        L.sdr_spectrum_destroy.argtypes = [vp]
+        L.sdr_spectrum_set_average_rate.argtypes = [vp, f]
+        L.sdr_spectrum_frames.argtypes = [vp, P(u)]
+        L.sdr_spectrum_fetch.argtypes = [vp, u, vp, vp, vp]
+        L.sdr_spectrum_fetch_debug.argtypes = [vp, u, vp, vp]
+        L.sdr_design_kaiser.argtypes = [u, f, f, f, vp]
+        L.sdr_design_nco_table.argtypes = [vp]
+        L.sdr_design_nco_step.argtypes = [f]
+        L.sdr_design_nco_step.restype = C.c_uint32
+        L.sdr_design_resampler.argtypes = [f, f, P(i), P(i), P(f), P(C.c_uint32), vp, vp]
+        L.sdr_design_halfband_branch.argtypes = [i, f, vp]
+        L.sdr_design_am_dc_block.argtypes = [vp]
+        L.sdr_design_hilbert_q.argtypes = [vp]
+        L.sdr_design_butter6_sos.argtypes = [vp]
+
+    def check(self, rc):
+        if rc != 0:
+            raise SdrError("sdr_b200 error %d: %s" % (rc, self.L.sdr_last_error().decode()))
+
+    @property
+    def is_device_build(self):
+        return bool(self.L.sdr_is_device_build())
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    """One engine per GPU (sdr_engine).  submit() replaces SDRPostThread::runSingleCH (SDRPostThread.cpp:248-299)."""
+
+    def __init__(self, lib, device=0, max_block=1 << 20, stream=None):
+        self.lib = lib
+        h = C.c_void_p()
+        lib.check(lib.L.sdr_engine_create(device, max_block, C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.h = h
+        self.max_block = max_block
+
+    def close(self):
+        if self.h:
+            self.lib.L.sdr_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def submit(self, iq, center_freq, sample_rate):
+        iq = np.ascontiguousarray(iq, dtype=np.complex64)
+        self.lib.check(self.lib.L.sdr_engine_submit(self.h, _ptr(iq), iq.size, int(center_freq), int(sample_rate)))
+
+    def submit_device(self, dev_ptr, n, center_freq, sample_rate, fetch_to_host=True):
+        self.lib.check(self.lib.L.sdr_engine_submit_device(self.h, C.c_void_p(dev_ptr), n, int(center_freq), int(sample_rate),
+                                                           1 if fetch_to_host else 0))
+
+    def wait(self):
+        self.lib.check(self.lib.L.sdr_engine_wait(self.h))
+
+    def fetch_block(self, n):
+        out = np.zeros(n, np.complex64)
+        got = C.c_uint()
+        self.lib.check(self.lib.L.sdr_engine_fetch_block(self.h, _ptr(out), n, C.byref(got)))
+        return out[:got.value]
+
+    @property
+    def launch_count(self):
+        return int(self.lib.L.sdr_engine_launch_count(self.h))
+
+
+class Channel:
+    """sdr_chan: DemodulatorPreThread + Modem + DemodulatorThread metering for one demodulator."""
+
+    def __init__(self, engine, modem, sample_rate, bandwidth, audio_rate=48000, frequency=0, want_iq=False):
+        self.engine, self.lib = engine, engine.lib
+        h = C.c_void_p()
+        self.lib.check(self.lib.L.sdr_chan_create(engine.h, modem.encode(), int(sample_rate), int(bandwidth), int(audio_rate), C.byref(h)))
+        self.h = h
+        self.modem = modem
+        bw = C.c_int()
+        self.lib.check(self.lib.L.sdr_chan_get_bandwidth(h, C.byref(bw)))
+        self.bandwidth = bw.value
+        self.set_frequency(frequency)
+        if want_iq:
+            self.lib.check(self.lib.L.sdr_chan_want_iq(h, 1))
+        self._audio = np.zeros(int(engine.max_block * (audio_rate / float(sample_rate)) * 1.5) + 4096, np.float32)
+        self._iq = np.zeros(int(engine.max_block * (self.bandwidth / float(sample_rate)) * 1.5) + 4096, np.complex64)
+
+    def set_frequency(self, f):
+        self.lib.check(self.lib.L.sdr_chan_set_frequency(self.h, int(f)))
+
+    def fetch_audio(self):
+        n, lvl, pk, sk = C.c_uint(), C.c_double(), C.c_float(), C.c_int()
+        self.lib.check(self.lib.L.sdr_chan_fetch_audio(self.h, _ptr(self._audio), self._audio.size, C.byref(n), C.byref(lvl),
+                                                       C.byref(pk), C.byref(sk)))
+        return self._audio[:n.value].copy(), lvl.value, pk.value, bool(sk.value)
+
+    def fetch_iq(self):
+        n = C.c_uint()
+        self.lib.check(self.lib.L.sdr_chan_fetch_iq(self.h, _ptr(self._iq), self._iq.size, C.byref(n)))
+        return self._iq[:n.value].copy()
+
+    def close(self):
+        if self.h:
+            self.lib.L.sdr_chan_destroy(self.h)
+            self.h = None
+
+
+class Spectrum:
+    """sdr_spectrum: FFTDataDistributor framing + SpectrumVisualProcessor (non-view) + WaterfallPanel::step."""
+
+    def __init__(self, engine, fft_size, lines_per_second=0):
+        self.engine, self.lib = engine, engine.lib
+        h = C.c_void_p()
+        self.lib.check(self.lib.L.sdr_spectrum_create(engine.h, fft_size, lines_per_second, C.byref(h)))
+        self.h = h
+        self.fft_size = fft_size
+
+    def set_average_rate(self, r):
+        self.lib.check(self.lib.L.sdr_spectrum_set_average_rate(self.h, r))
+
+    @property
+    def frames(self):
+        n = C.c_uint()
+        self.lib.check(self.lib.L.sdr_spectrum_frames(self.h, C.byref(n)))
+        return n.value
+
+    def fetch(self, idx):
+        pts = np.zeros(self.fft_size, np.float32)
+        line = np.zeros(self.fft_size, np.uint8)
+        cf = np.zeros(2, np.float64)
+        self.lib.check(self.lib.L.sdr_spectrum_fetch(self.h, idx, _ptr(pts), _ptr(line), _ptr(cf)))
+        return pts, line, cf
+
+    def fetch_debug(self, idx):
+        mags = np.zeros(2 * self.fft_size, np.float32)
+        maa = np.zeros(2 * self.fft_size, np.float32)
+        self.lib.check(self.lib.L.sdr_spectrum_fetch_debug(self.h, idx, _ptr(mags), _ptr(maa)))
+        return mags, maa
+
+    def close(self):
+        if self.h:
+            self.lib.L.sdr_spectrum_destroy(self.h)
+            self.h = None

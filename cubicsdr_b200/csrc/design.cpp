@@ -1,0 +1,233 @@
+// cubicsdr_b200/csrc/design.cpp -- see design.h.  Host-only, plain C++14.
+#include "design.h"
+
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstring>
+
+namespace sdrb200 {
+
+static const double kPi = 3.14159265358979323846;
+
+// ---- Kaiser machinery --------------------------------------------------------------------------------------
+float kaiser_beta_for_atten(float as_db) {
+    as_db = std::fabs(as_db);
+    if (as_db > 50.0f) return 0.1102f * (as_db - 8.7f);
+    if (as_db > 21.0f) return 0.5842f * std::pow(as_db - 21.0f, 0.4f) + 0.07886f * (as_db - 21.0f);
+    return 0.0f;
+}
+
+unsigned filter_len_estimate(float df, float as_db) {
+    return (unsigned)((as_db - 7.95f) / (14.26f * df));
+}
+
+// I0(z) by its power series, in double (the reference evaluates a 32-term log-gamma form in float; the two agree
+// to float rounding, which is what the 1e-6 table tolerance in tests/test_design.py checks)
+static double bessel_i0(double z) {
+    double q = 0.25 * z * z, term = 1.0, sum = 1.0;
+    for (int k = 1; k < 64; ++k) {
+        term *= q / ((double)k * (double)k);
+        sum += term;
+        if (term < 1e-20 * sum) break;
+    }
+    return sum;
+}
+
+static float kaiser_window(unsigned i, unsigned n, float beta) {
+    float t = (float)i - (float)(n - 1) / 2;
+    float r = 2.0f * t / (float)(n - 1);
+    double a = bessel_i0((double)beta * std::sqrt(std::max(0.0, 1.0 - (double)r * (double)r)));
+    double b = bessel_i0((double)beta);
+    return (float)(a / b);
+}
+
+static float sinc_pi(float x) {
+    if (std::fabs(x) < 0.01f)
+        return (float)(std::cos(kPi * x / 2.0) * std::cos(kPi * x / 4.0) * std::cos(kPi * x / 8.0));
+    return (float)(std::sin(kPi * (double)x) / (kPi * (double)x));
+}
+
+void kaiser_lowpass(unsigned n, float fc, float as_db, float mu, float *h) {
+    float beta = kaiser_beta_for_atten(as_db);
+    for (unsigned i = 0; i < n; ++i) {
+        float t = (float)i - (float)(n - 1) / 2 + mu;
+        h[i] = sinc_pi(2.0f * fc * t) * kaiser_window(i, n, beta);
+    }
+}
+
+// ---- table oscillator ----------------------------------------------------------------------------------------
+void nco_sine_table(float *tab) {
+    // sintab[i] = sinf((float)i * (2 pi / 1024 as float)); libm sinf on the host so that the table is
+    // bit-identical to the one the reference builds (device sinf would differ in the last bit)
+    const float dphi = 0.0061359233f;
+    for (int i = 0; i < 1024; ++i) tab[i] = sinf((float)i * dphi);
+}
+
+uint32_t nco_phase_step(float dtheta_rad) {
+    // SURVEY.md A.1 set_frequency: scale by 1/(2 pi), keep the fractional turn in [0,1), 32-bit phase word
+    float x = (float)((double)dtheta_rad * 0.159154943091895);
+    x -= truncf(x);
+    if (x < 0.f) x += 1.0f;
+    return (uint32_t)(int64_t)(x * 4294967296.0f);
+}
+
+float nco_shift_word_arg(long long shift_hz, long long sample_rate) {
+    long long a = shift_hz < 0 ? -shift_hz : shift_hz;
+    return (float)((2.0 * kPi) * (((double)a) / ((double)sample_rate)));   // DemodulatorPreThread.cpp:157
+}
+
+// ---- half-bands ------------------------------------------------------------------------------------------------
+HalfbandPlan halfband_plan(int num_stages, float as_db) {
+    // per-stage transition widths from fc0 = 0.4, lengths from the Kaiser estimate at As+5
+    HalfbandPlan p;
+    p.num_stages = num_stages;
+    float fc = 0.4f, as_s = as_db + 5.0f;
+    for (int i = 0; i < num_stages; ++i) {
+        fc = (i == 1) ? (0.5f - fc) / 2.0f : 0.5f * fc;
+        float ft = 2.0f * (0.25f - fc);
+        unsigned h_len = filter_len_estimate(ft, as_s);
+        unsigned m = (unsigned)std::ceil((float)(h_len - 1) / 4.0f);
+        if (m < 3) m = 3;
+        p.m.push_back((int)m);
+    }
+    return p;
+}
+
+// Equiripple (Parks-McClellan) half-band prototypes for stop-band 65 dB: the odd-index taps hf[1], hf[3], ...,
+// hf[2m-1] of the 4m+1 tap prototype (even taps are zero, hf[2m] ~ 0.5, symmetric).  These three designs are
+// the only ones msresamp ever instantiates at As = 60 (m = 3, 5, 10); values are the converged Remez solution
+// (checked bit-for-bit against the reference binary in tests/test_design.py).
+// (IEEE-754 single bit patterns; decimal values in the comments)
+static const uint32_t kHb3[3] = {0x3c18fdc4u, 0xbd6aff07u, 0x3e98aab6u};   // 0.00933784619, -0.0573721193, 0.298177421
+static const uint32_t kHb5[5] = {0x3b25721du, 0xbc33cf23u, 0x3d04243cu, 0xbdaba2c5u, 0x3e9ed3eau};
+//   0.00252450188, -0.0109746782, 0.0322611183, -0.083806552, 0.310210526
+static const uint32_t kHb10[10] = {0xba3b0279u, 0x3ae57b8du, 0xbb74c970u, 0x3be61d5au, 0xbc4791eeu,
+                                   0x3ca4ad91u, 0xbd052c32u, 0x3d5c3bc8u, 0xbdcc95e4u, 0x3ea1e41fu};
+//   -0.000713385234, 0.00175081345, -0.00373515114, 0.00702254195, -0.0121807884,
+//    0.0201022942, -0.0325128511, 0.0537679493, -0.0998952687, 0.316193551
+
+bool halfband_branch_taps(int m, float as_db, float *h1) {
+    if (std::fabs(as_db - 65.0f) > 1e-3f) return false;
+    const uint32_t *odd = (m == 3) ? kHb3 : (m == 5) ? kHb5 : (m == 10) ? kHb10 : nullptr;
+    if (!odd) return false;
+    // branch taps = 2 * prototype odd taps, laid out oldest-sample-first; the prototype is symmetric
+    for (int j = 0; j < m; ++j) {
+        float v;
+        std::memcpy(&v, &odd[j], sizeof(v));
+        h1[j] = 2.0f * v;
+        h1[2 * m - 1 - j] = 2.0f * v;
+    }
+    return true;
+}
+
+// ---- multi-stage resampler plan ----------------------------------------------------------------------------------
+ResamplerPlan make_resampler_plan(float rate, float as_db) {
+    ResamplerPlan p;
+    p.rate = rate;
+    p.interp = rate > 1.0f;
+    float ra = rate;
+    int S = 0;
+    if (p.interp) { while (ra > 2.0f) { ++S; ra *= 0.5f; } }
+    else          { while (ra < 0.5f) { ++S; ra *= 2.0f; } }
+    p.num_halfband = S;
+    p.rate_arb = ra;
+    p.zeta = 1.0f / (float)(1u << S);
+    p.hb = halfband_plan(S, as_db);
+    p.arb_step = (uint32_t)roundf(16777216.0f / ra);
+    float fc = 0.515f * ra;
+    if (fc > 0.49f) fc = 0.49f;
+    p.arb_fc = fc;
+    const unsigned npfb = p.arb_npfb, m = p.arb_m, n = 2 * m * npfb + 1;
+    std::vector<float> hf(n);
+    kaiser_lowpass(n, fc / (float)npfb, as_db, 0.0f, hf.data());
+    float gain = 0.0f;
+    for (unsigned i = 0; i < n; ++i) gain += hf[i];
+    gain = (float)npfb / gain;
+    p.pfb.resize((size_t)npfb * 2 * m);
+    for (unsigned a = 0; a < npfb; ++a)
+        for (unsigned k = 0; k < 2 * m; ++k) p.pfb[(size_t)a * 2 * m + k] = hf[a + k * npfb] * gain;
+    return p;
+}
+
+float ResamplerPlan::delay() const {
+    // group delay in input samples: half-band stages then the arbitrary stage (informational only)
+    float d = 0.f;
+    for (int g = 0; g < num_halfband; ++g) d = 2.0f * d + (float)(2 * hb.m[g]) - 0.5f;
+    return d + (float)arb_m;
+}
+
+uint64_t arb_output_count(uint32_t step, uint64_t phase, uint64_t n_in, uint64_t *phase_after) {
+    const uint64_t span = n_in << 24;
+    uint64_t cnt = 0;
+    if (phase < span) cnt = (span - phase + step - 1) / step;
+    if (phase_after) *phase_after = phase + cnt * step - span;
+    return cnt;
+}
+
+// ---- demodulator filters -------------------------------------------------------------------------------------------
+void am_dc_block_taps(unsigned m, float as_db, float *h) {
+    // Kaiser-window notch at DC: h = delta - w / sum(w)
+    const unsigned n = 2 * m + 1;
+    float beta = kaiser_beta_for_atten(as_db), scale = 0.f;
+    for (unsigned i = 0; i < n; ++i) {
+        float w = kaiser_window(i, n, beta);
+        h[i] = -w;
+        scale += w;
+    }
+    for (unsigned i = 0; i < n; ++i) h[i] /= scale;
+    h[m] += 1.0f;
+}
+
+void hilbert_quadrature_taps(unsigned m, float as_db, float *hq) {
+    // half-band Kaiser low-pass shifted by fs/4; the quadrature branch keeps its odd taps (imaginary parts)
+    const unsigned n = 4 * m + 1;
+    std::vector<float> h(n);
+    kaiser_lowpass(n, 0.25f, as_db, 0.0f, h.data());
+    for (unsigned i = 0; i < n; ++i) {
+        float t = (float)i - (float)(n - 1) / 2.0f;
+        h[i] = h[i] * sinf((float)(0.5 * kPi * (double)t));
+    }
+    unsigned j = 0;
+    for (unsigned i = 1; i < n; i += 2) hq[j++] = h[n - i - 1];
+}
+
+void butterworth_lowpass_sos(unsigned order, float fc, std::vector<Sos> &sos) {
+    // analog Butterworth poles on the unit circle, bilinear transform with pre-warp tan(pi fc), conjugate pairs
+    // expanded into second-order sections, overall gain split evenly over the sections' numerators
+    typedef std::complex<double> cd;
+    const unsigned r = order % 2, L = (order - r) / 2;
+    std::vector<cd> pa;
+    for (unsigned i = 0; i < L; ++i) {
+        double theta = (double)(2 * (i + 1) + order - 1) * kPi / (double)(2 * order);
+        pa.push_back(std::polar(1.0, theta));
+        pa.push_back(std::polar(1.0, -theta));
+    }
+    if (r) pa.push_back(cd(-1.0, 0.0));
+    const double mw = std::tan(kPi * (double)fc);
+    std::vector<cd> pd(order);
+    cd G(1.0, 0.0);
+    for (unsigned i = 0; i < order; ++i) {
+        cd pm = pa[i] * mw;
+        pd[i] = (1.0 + pm) / (1.0 - pm);
+        G *= (1.0 - pd[i]) / (1.0 - cd(-1.0, 0.0));
+    }
+    const double k = std::pow(G.real(), 1.0 / (double)(L + r));
+    sos.clear();
+    for (unsigned i = 0; i < L; ++i) {
+        cd p0 = -pd[2 * i], p1 = -pd[2 * i + 1];
+        Sos s;
+        s.a[0] = 1.0f; s.a[1] = (float)(p0 + p1).real(); s.a[2] = (float)(p0 * p1).real();
+        s.b[0] = (float)k; s.b[1] = (float)(2.0 * k); s.b[2] = (float)k;      // zeros at z = -1 (twice)
+        sos.push_back(s);
+    }
+    if (r) {
+        cd p0 = -pd[order - 1];
+        Sos s;
+        s.a[0] = 1.0f; s.a[1] = (float)p0.real(); s.a[2] = 0.f;
+        s.b[0] = (float)k; s.b[1] = (float)k; s.b[2] = 0.f;
+        sos.push_back(s);
+    }
+}
+
+}  // namespace sdrb200

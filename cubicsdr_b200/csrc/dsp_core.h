@@ -1,0 +1,322 @@
+// cubicsdr_b200/csrc/dsp_core.h -- every kernel body of the engine, written as per-thread "phases".
+//
+// A kernel is a list of phases; on the GPU all threads of a CTA run phase p and then __syncthreads(); the test-only
+// emulator (SDR_EMU, see backend.h) runs the same phases serially.  The maths follows what the reference obtains
+// from liquid-dsp 1.5.0 on CubicSDR's hot path; citations name the reference call sites.
+//
+// HBM layout (all little-endian, cf32 = interleaved {re, im} float pairs as liquid_float_complex):
+//   wideband stream   float2 blk[kBlkHist + Nmax]      DC-blocked samples, history of the previous block in front
+//   per channel       a float arena holding one [kHist | new] stream buffer per resampler level (ChanLayout)
+//   per channel       a result slot {ChanResultHeader, audio[cap], iq[cap]} that is copied back to pinned host memory
+#pragma once
+#include <math.h>
+
+#include "backend.h"
+
+namespace sdrb200 {
+
+constexpr int kHist = 64;         // history elements in front of every low-rate stream buffer (>= 51-tap AM FIR, 4m = 40)
+constexpr int kBlkHist = 2048;    // wideband history kept in front of the current block (>= 12 * 2^kFrontMaxK + 2^kFrontMaxK)
+constexpr int kFrontMaxK = 6;     // most half-band stages the front kernel fuses with the mixer
+constexpr int kFrontWarm = 12;    // warm-up super-steps that flush a 13-tap (m = 3) half-band cascade
+constexpr int kMaxTailHb = 16;    // msresamp2 never has more than 16 stages
+constexpr int kMaxAudioHb = 8;
+constexpr int kPfbTaps = 14;      // 2 * m of the arbitrary resampler (m = 7)
+constexpr int kTailThreads = 256;
+
+enum ModemKind { MODEM_FM = 0, MODEM_NBFM = 1, MODEM_AM = 2, MODEM_USB = 3, MODEM_LSB = 4 };
+
+// ---- small complex helpers ------------------------------------------------------------------------------------------
+SDR_HD SDR_FORCEINLINE float2 cf_make(float a, float b) { return make_float2(a, b); }
+SDR_HD SDR_FORCEINLINE float2 cf_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+SDR_HD SDR_FORCEINLINE float2 cf_fma(float h, float2 x, float2 acc) { return make_float2(fmaf(h, x.x, acc.x), fmaf(h, x.y, acc.y)); }
+SDR_HD SDR_FORCEINLINE float2 cf_scale(float h, float2 x) { return make_float2(h * x.x, h * x.y); }
+// x * (c + j s)
+SDR_HD SDR_FORCEINLINE float2 cf_rot(float2 x, float c, float s) {
+    return make_float2(fmaf(x.x, c, -(x.y * s)), fmaf(x.x, s, x.y * c));
+}
+
+// ---- table oscillator (nco_crcf: SURVEY.md A.1) -----------------------------------------------------------------------
+// nco[idx] = {cos, sin} of table entry idx; idx = (theta + 2^21) >> 22
+SDR_HD SDR_FORCEINLINE float2 nco_lookup(const float2 *nco, uint32_t theta) {
+    return nco[(theta + 0x200000u) >> 22];
+}
+
+// =====================================================================================================================
+// 1. DC blocker: iirfilt_crcf_create_dc_blocker(0.0005f) + execute_block            src/sdr/SDRPostThread.cpp:29,284
+//    v[n] = x[n] + a v[n-1],  y[n] = v[n] - v[n-1],  a = 1 - alpha (as float).  Linear recurrence -> tiled scan in
+//    double (the reference runs it in float direct-form II; its own rounding noise, ~4.6e-6 relative, is the parity
+//    floor for this stage -- see DESIGN.md).
+// =====================================================================================================================
+constexpr int kDcTile = 1024;      // samples per scan tile (one CTA of 256 threads, 4 samples each)
+constexpr int kDcThreads = 256;
+
+struct DcArgs {
+    const float2 *x;      // raw block [n]
+    float2 *y;            // DC-blocked block [n]
+    int n;
+    double a;             // feedback coefficient as double((float)(1 - alpha))
+    double2 *tile_sum;    // [tiles]  zero-state end value of each tile
+    double2 *tile_carry;  // [tiles]  state entering each tile
+    double2 *state;       // [1]      v[-1] carried across blocks
+    const double *apow;   // [kDcTile + 1] a^k
+};
+
+// phase 0 of kernel A: each thread folds 4 consecutive samples, writes partial to shared; phase 1: thread 0 combines.
+struct DcShared { double2 part[kDcThreads]; };
+
+SDR_HD inline void dc_tile_sum_phase(int ph, const DcArgs &a, int bid, int tid, DcShared *sm) {
+    const int per = kDcTile / kDcThreads;
+    const int base = bid * kDcTile + tid * per;
+    if (ph == 0) {
+        double vr = 0.0, vi = 0.0;
+        for (int k = 0; k < per; ++k) {
+            int i = base + k;
+            float2 s = (i < a.n) ? a.x[i] : make_float2(0.f, 0.f);
+            // beyond the block end the recurrence is simply not advanced (handled by weighting below)
+            if (i < a.n) { vr = fma(a.a, vr, (double)s.x); vi = fma(a.a, vi, (double)s.y); }
+        }
+        sm->part[tid] = make_double2(vr, vi);
+    } else if (tid == 0) {
+        // combine thread partials in order: V = sum_t part[t] * a^(samples after thread t's chunk within the tile)
+        int tile_len = a.n - bid * kDcTile;
+        if (tile_len > kDcTile) tile_len = kDcTile;
+        double vr = 0.0, vi = 0.0;
+        for (int t = 0; t < kDcThreads; ++t) {
+            int end = (t + 1) * per;            // index (within tile) one past this thread's chunk
+            if (end > tile_len) end = tile_len;
+            int start = t * per;
+            if (start >= tile_len) break;
+            double w = a.apow[tile_len - end];
+            vr = fma(sm->part[t].x, w, vr);
+            vi = fma(sm->part[t].y, w, vi);
+        }
+        a.tile_sum[bid] = make_double2(vr, vi);
+    }
+}
+
+// kernel B (one thread): serial composition over tiles (tiles <= ~1000 per block)
+SDR_HD inline void dc_carry_phase(const DcArgs &a, int tiles) {
+    double cr = a.state[0].x, ci = a.state[0].y;
+    for (int t = 0; t < tiles; ++t) {
+        a.tile_carry[t] = make_double2(cr, ci);
+        int tile_len = a.n - t * kDcTile;
+        if (tile_len > kDcTile) tile_len = kDcTile;
+        double w = a.apow[tile_len];
+        cr = fma(cr, w, a.tile_sum[t].x);
+        ci = fma(ci, w, a.tile_sum[t].y);
+    }
+    a.state[0] = make_double2(cr, ci);
+}
+
+// kernel C: phase 0 thread partial prefix (same as A), phase 1 serial prefix over thread partials by thread 0,
+// phase 2 every thread replays its 4 samples from its exact entering state and writes y.
+struct DcShared2 { double2 part[kDcThreads]; double2 enter[kDcThreads]; };
+SDR_HD inline void dc_apply_phase(int ph, const DcArgs &a, int bid, int tid, DcShared2 *sm) {
+    const int per = kDcTile / kDcThreads;
+    const int base = bid * kDcTile + tid * per;
+    if (ph == 0) {
+        double vr = 0.0, vi = 0.0;
+        for (int k = 0; k < per; ++k) {
+            int i = base + k;
+            if (i < a.n) { float2 s = a.x[i]; vr = fma(a.a, vr, (double)s.x); vi = fma(a.a, vi, (double)s.y); }
+        }
+        sm->part[tid] = make_double2(vr, vi);
+    } else if (ph == 1) {
+        if (tid == 0) {
+            double cr = a.tile_carry[bid].x, ci = a.tile_carry[bid].y;
+            const double w = a.apow[per];
+            for (int t = 0; t < kDcThreads; ++t) {
+                sm->enter[t] = make_double2(cr, ci);
+                cr = fma(cr, w, sm->part[t].x);
+                ci = fma(ci, w, sm->part[t].y);
+            }
+        }
+    } else {
+        double vr = sm->enter[tid].x, vi = sm->enter[tid].y;
+        for (int k = 0; k < per; ++k) {
+            int i = base + k;
+            if (i < a.n) {
+                float2 s = a.x[i];
+                double nr = fma(a.a, vr, (double)s.x), ni = fma(a.a, vi, (double)s.y);
+                a.y[i] = make_float2((float)(nr - vr), (float)(ni - vi));
+                vr = nr; vi = ni;
+            }
+        }
+    }
+}
+
+// =====================================================================================================================
+// 2. Channel descriptors
+// =====================================================================================================================
+struct ChanStatic {
+    int modem;
+    int S;                        // half-band stages of the IQ resampler (msresamp_crcf)
+    int K1;                       // how many of them (all m = 3) the front kernel fuses with the mixer
+    int n_tail;                   // S - K1 stages left for the tail, executed in order j = 0..n_tail-1
+    int tail_m[kMaxTailHb];       // semi-length of tail stage j
+    int tail_h1[kMaxTailHb];      // offset (floats) of its 2m branch taps in the taps pool
+    float zeta;                   // 1 / 2^S
+    unsigned arb_step;            // fixed-point stride of the arbitrary stage
+    int pfb_off;                  // offset of its [256][14] taps in the taps pool
+    // audio resampler (msresamp_rrrf, ModemAnalog.cpp:30)
+    int a_interp, a_S;
+    int a_m[kMaxAudioHb];         // semi-lengths by cascade position g (g = 0 is the m = 10 stage)
+    int a_h1[kMaxAudioHb];
+    float a_zeta;
+    unsigned a_step;
+    int a_pfb_off;
+    // modem filters (offsets into the taps pool)
+    int am_taps_off;              // 51 taps
+    int hq_off;                   // 10 Hilbert quadrature taps
+    int sos_off;                  // 3 x {b0,b1,b2,a1,a2}
+    // stream buffers inside the channel arena (offsets in floats); each is [kHist | data]
+    float *arena;                 // this channel's arena in HBM
+    int lvl_off[kMaxTailHb + 1];  // complex level buffers: level 0 = front output, level j = output of tail stage j-1
+    int iq_off;                   // complex: arbitrary-stage output (decimated IQ handed to the modem)
+    int w_off;                    // complex: SSB post-filter stream feeding the Hilbert stage
+    int d_off;                    // real: demodulated samples (after auto-gain) feeding the audio resampler
+    int al_off[kMaxAudioHb + 1];  // real: audio resampler level buffers (decim: after each half-band; interp: arb out, then each half-band)
+    int want_iq;                  // copy decimated IQ into the result slot
+    int res_audio_cap, res_iq_cap;
+    long long res_off;            // byte offset of the result slot in the results buffer
+};
+
+struct ChanDyn {                  // written by the host for every block
+    long long g0;                 // wideband samples this channel consumed before this block
+    unsigned theta0;              // oscillator phase at the first sample of the block
+    unsigned dtheta, dtheta_prev; // phase step for this block / for the history in front of it
+    int dir, dir_prev;            // +1 mix up, -1 mix down, 0 no mixing   (DemodulatorPreThread.cpp:186-195)
+    int active;                   // 0: channel skips this block
+    int valid;                    // 0: free slot, nothing may be touched
+    int pad;
+    const float2 *hist;           // non-null: history for samples i < 0 is hist[i] (the channel skipped the previous block(s),
+                                  // so its delay lines must see the tail of the last block it DID consume)
+};
+
+struct ChanState {                // device-resident, advanced by the tail kernel
+    unsigned long long arb_phase;     // `phase` of the IQ arbitrary resampler between blocks
+    unsigned long long iq_count;      // decimated IQ samples produced so far (= demod samples)
+    unsigned long long a_phase;       // audio arbitrary resampler phase
+    unsigned long long a_lvl_count;   // real samples that have entered the audio arbitrary stage (decim) -- informational
+    unsigned ssb_theta;               // SSB quarter-rate oscillator phase
+    float sos_v[3][2][2];             // [section][v1,v2][re,im]
+    float agc_ceil, agc_ma, agc_maa;  // ModemAnalog.cpp:6,70-72
+    int pad;
+};
+
+struct ChanResultHeader {
+    unsigned n_audio, n_iq;
+    float peak;
+    int skipped;
+    double level_db;
+};
+
+// =====================================================================================================================
+// 3. Front kernel: table-oscillator mix + K half-band (m = 3) decimators, one thread per (channel, time span)
+//    nco_crcf_mix_block_up/down  DemodulatorPreThread.cpp:186-195 ; first K stages of msresamp_crcf_execute :209
+//    Each thread is a streaming decimator whose delay lines live in registers (transposed-form FIR: no shifts).
+// =====================================================================================================================
+struct FrontArgs {
+    const float2 *x;              // x[0] = first sample of the block, x[-kBlkHist..-1] = history
+    int n;
+    const float2 *nco;            // [1024] {cos, sin}
+    const ChanStatic *cs;
+    const ChanDyn *cd;
+    const int *group;             // channel ids handled by this launch (all with the same K1)
+    int cg;                       // number of channels in the group
+    int span;                     // super-steps per time span
+    int n_span;                   // spans per block
+    float c0, c1, c2;             // m = 3 branch taps (symmetric: c[d] = c[5-d])
+};
+
+struct Hb3State { float2 s0, s1, s2, s3, s4, s5; };
+
+SDR_HD SDR_FORCEINLINE void hb3_reset(Hb3State &h) {
+    h.s0 = h.s1 = h.s2 = h.s3 = h.s4 = h.s5 = make_float2(0.f, 0.f);
+}
+// first sample of a pair (filtered branch): returns the decimated output that becomes available with it
+SDR_HD SDR_FORCEINLINE float2 hb3_push_even(Hb3State &h, float2 x, float c0, float c1, float c2) {
+    h.s0 = cf_fma(c0, x, h.s1);
+    h.s1 = cf_fma(c1, x, h.s2);
+    h.s2 = cf_fma(c2, x, h.s3);
+    h.s3 = cf_fma(c2, x, h.s4);
+    h.s4 = cf_fma(c1, x, h.s5);
+    h.s5 = cf_scale(c0, x);
+    return h.s0;
+}
+// second sample of a pair (pure delay branch, emerges m = 3 outputs later)
+SDR_HD SDR_FORCEINLINE void hb3_push_odd(Hb3State &h, float2 x) { h.s3 = cf_add(h.s3, x); }
+
+template <int K>
+SDR_HD inline void front_thread(const FrontArgs &a, int job, int lane) {
+    const int n_chunks = (a.cg + 31) / 32;
+    const int span_idx = job / n_chunks;
+    const int chunk = job - span_idx * n_chunks;
+    const int ci = chunk * 32 + lane;
+    if (span_idx >= a.n_span || ci >= a.cg) return;
+    const int ch = a.group[ci];
+    const ChanStatic &cs = a.cs[ch];
+    const ChanDyn &cd = a.cd[ch];
+    constexpr int M = 1 << K;
+    const long long g0 = cd.g0, g1 = cd.g0 + a.n;
+    const long long qa = g0 >> K, qb = g1 >> K;           // outputs [qa, qb) complete inside this block
+    long long q_lo = qa + (long long)span_idx * a.span;
+    long long q_hi = q_lo + a.span;
+    if (span_idx == a.n_span - 1 || q_hi > qb) q_hi = qb;
+    if (q_lo >= q_hi) return;
+    float2 *out = reinterpret_cast<float2 *>(cs.arena + cs.lvl_off[0]) + kHist;
+    const float sdir = (float)cd.dir, sdir_prev = (float)cd.dir_prev;
+    const float2 *hx = cd.hist ? cd.hist : a.x;
+
+    if (K == 0) {
+        for (long long q = q_lo; q < q_hi; ++q) {
+            int i = (int)(q - g0);
+            float2 xs = sdr_ldg(a.x + i);
+            float2 w = nco_lookup(a.nco, cd.theta0 + (unsigned)i * cd.dtheta);
+            float c = cd.dir ? w.x : 1.0f, s = w.y * sdir;
+            out[q - qa] = cf_rot(xs, c, s);
+        }
+        return;
+    }
+
+    Hb3State hb[K > 0 ? K : 1];
+#pragma unroll
+    for (int l = 0; l < K; ++l) hb3_reset(hb[l]);
+    const float c0 = a.c0, c1 = a.c1, c2 = a.c2;
+
+    for (long long q = q_lo - kFrontWarm; q < q_hi; ++q) {
+        const long long gq = q * M;                         // channel sample index of the super-step's first input
+        const int i0 = (int)(gq - g0);                      // same, relative to the block start
+#pragma unroll
+        for (int t = 0; t < M; ++t) {
+            const int i = i0 + t;
+            float2 u = make_float2(0.f, 0.f);
+            if (gq + t >= 0 && i >= -kBlkHist) {            // before the channel existed the delay lines hold zeros
+                float2 xs = sdr_ldg((i >= 0 ? a.x : hx) + i);
+                unsigned th;
+                float sd;
+                int dr;
+                if (i >= 0) { th = cd.theta0 + (unsigned)i * cd.dtheta; sd = sdir; dr = cd.dir; }
+                else        { th = cd.theta0 - (unsigned)(-i) * cd.dtheta_prev; sd = sdir_prev; dr = cd.dir_prev; }
+                float2 w = nco_lookup(a.nco, th);
+                u = cf_rot(xs, dr ? w.x : 1.0f, w.y * sd);
+            }
+            // feed the cascade: the sample with in-super-step index t enters stage l only if bits 0..l-1 of t are 0
+            // (it was the first sample of a pair at every earlier stage); bit l then says which branch of stage l
+            // it lands on.  t is a compile-time constant after unrolling, so `alive` folds away.
+            float2 y = u;
+            bool alive = true;
+#pragma unroll
+            for (int l = 0; l < K; ++l) {
+                if (alive) {
+                    if ((t >> l) & 1) { hb3_push_odd(hb[l], y); alive = false; }
+                    else y = hb3_push_even(hb[l], y, c0, c1, c2);
+                }
+            }
+            if (alive && q >= q_lo) out[q - qa] = y;          // only t == 0 survives all K stages
+        }
+    }
+}
+
+}  // namespace sdrb200

@@ -1,0 +1,384 @@
+// cubicsdr_b200/csrc/dsp_tail.h -- per-channel low-rate tail: remaining half-bands, arbitrary (polyphase) stage,
+// demodulators, block auto-gain, audio resampler, metering.  One CTA per channel, phases separated by CTA barriers.
+//
+// Reference call sites (relative to /root/reference/src):
+//   msresamp_crcf_execute          demod/DemodulatorPreThread.cpp:209   (stages not fused into the front kernel)
+//   freqdem_demodulate_block       modules/modem/analog/ModemFM.cpp:36, ModemNBFM.cpp:36
+//   envelope + firfilt DC blocker  modules/modem/analog/ModemAM.cpp:42-47
+//   SSB chain                      modules/modem/analog/ModemUSB.cpp:54-61, ModemLSB.cpp:54-61
+//   block auto-gain + msresamp_rrrf modules/modem/ModemAnalog.cpp:67-93
+//   level / peak metering          demod/DemodulatorThread.cpp:142-163, 223-233
+#pragma once
+#include "dsp_core.h"
+
+namespace sdrb200 {
+
+constexpr int kTailStreams = kMaxTailHb + 1 + 3 + kMaxAudioHb + 1;   // complex levels, iq, w, d, audio levels
+
+struct TailArgs {
+    const ChanStatic *cs;
+    const ChanDyn *cd;
+    ChanState *st;
+    const float *taps;
+    const float2 *nco;
+    unsigned char *results;
+    int n;                        // wideband block length
+};
+
+struct TailShared {
+    int lvl_n[kMaxTailHb + 1];            // new elements per complex level this block
+    long long lvl_g0[kMaxTailHb + 1];     // global index of the first new element per level
+    int n_iq;                             // decimated IQ samples this block
+    unsigned long long arb_phase_after;
+    int a_n[kMaxAudioHb + 1];             // new elements per audio level
+    long long a_g0[kMaxAudioHb + 1];
+    int n_audio;
+    unsigned long long a_phase_after;
+    float gain;
+    float red_f[kTailThreads];
+    double red_d[kTailThreads];
+    float2 hist_tmp[kTailStreams][kHist];
+};
+
+// number of arbitrary-stage outputs for n_in inputs entering with `phase` (closed form of resamp_execute's loop)
+SDR_HD inline int arb_count(unsigned step, unsigned long long phase, int n_in, unsigned long long *phase_after) {
+    unsigned long long span = (unsigned long long)n_in << 24, cnt = 0;
+    if (phase < span) cnt = (span - phase + step - 1) / step;
+    *phase_after = phase + cnt * step - span;
+    return (int)cnt;
+}
+
+enum TailPhase {
+    TP_SETUP = 0,
+    TP_HB0 = 1,                                   // kMaxTailHb half-band phases
+    TP_ARB = TP_HB0 + kMaxTailHb,
+    TP_DEMOD_A,                                   // FM / AM parallel; SSB serial IIR by thread 0
+    TP_DEMOD_B,                                   // SSB Hilbert stage
+    TP_AGC_A, TP_AGC_B, TP_AGC_C,
+    TP_AUD0,                                      // audio: stage phases (kMaxAudioHb + 1)
+    TP_METER_A = TP_AUD0 + kMaxAudioHb + 1,
+    TP_METER_B,
+    TP_HIST_A, TP_HIST_B,
+    TP_COUNT
+};
+
+SDR_HD inline float2 *chan_cbuf(const TailArgs &, const ChanStatic &cs, int off) {
+    return reinterpret_cast<float2 *>(cs.arena + off);
+}
+SDR_HD inline float *chan_rbuf(const TailArgs &, const ChanStatic &cs, int off) { return cs.arena + off; }
+
+// generic decimate-by-2 half-band over a [kHist | new] complex stream, parallel over outputs
+SDR_HD inline void hb_decim_c(const float2 *in, long long in_g0, float2 *out, long long out_g0, int n_out, int m,
+                              const float *h1, int tid, int nt) {
+    for (int r = tid; r < n_out; r += nt) {
+        const long long k = out_g0 + r;
+        const int base = (int)(2 * k - in_g0) + kHist;       // buffer position of in[2k]
+        float2 acc = in[base - 2 * m + 1];                    // delay branch: in[2k - 2m + 1]
+        const float2 *p = in + base - 4 * m + 2;              // filtered branch: in[2k - 4m + 2 + 2t]
+        for (int t = 0; t < 2 * m; ++t) acc = cf_fma(sdr_ldg(h1 + t), p[2 * t], acc);
+        out[kHist + r] = acc;
+    }
+}
+SDR_HD inline void hb_decim_r(const float *in, long long in_g0, float *out, long long out_g0, int n_out, int m,
+                              const float *h1, int tid, int nt) {
+    for (int r = tid; r < n_out; r += nt) {
+        const long long k = out_g0 + r;
+        const int base = (int)(2 * k - in_g0) + kHist;
+        float acc = in[base - 2 * m + 1];
+        const float *p = in + base - 4 * m + 2;
+        for (int t = 0; t < 2 * m; ++t) acc = fmaf(sdr_ldg(h1 + t), p[2 * t], acc);
+        out[kHist + r] = acc;
+    }
+}
+// interpolate-by-2 half-band (resamp2 interp_execute): Y[2k] = X[k-m], Y[2k+1] = sum h1[t] X[k-2m+1+t]
+SDR_HD inline void hb_interp_r(const float *in, int n_in, float *out, int m, const float *h1, int tid, int nt) {
+    for (int r = tid; r < 2 * n_in; r += nt) {
+        const int k = r >> 1;
+        float v;
+        if ((r & 1) == 0) v = in[kHist + k - m];
+        else {
+            const float *p = in + kHist + k - 2 * m + 1;
+            v = 0.f;
+            for (int t = 0; t < 2 * m; ++t) v = fmaf(sdr_ldg(h1 + t), p[t], v);
+        }
+        out[kHist + r] = v;
+    }
+}
+
+SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt, TailShared *sm) {
+    const ChanStatic &cs = a.cs[ch];
+    const ChanDyn &cd = a.cd[ch];
+    if (!cd.valid) return;
+    ChanState &st = a.st[ch];
+    ChanResultHeader *hdr = reinterpret_cast<ChanResultHeader *>(a.results + cs.res_off);
+    float *res_audio = reinterpret_cast<float *>(a.results + cs.res_off + 32);
+    float2 *res_iq = reinterpret_cast<float2 *>(res_audio + cs.res_audio_cap);
+    if (!cd.active) {
+        if (ph == TP_SETUP && tid == 0) { hdr->n_audio = 0; hdr->n_iq = 0; hdr->peak = 0.f; hdr->skipped = 1; hdr->level_db = 0.0; }
+        return;
+    }
+    const bool is_fm = (cs.modem == MODEM_FM || cs.modem == MODEM_NBFM);
+    const bool is_ssb = (cs.modem == MODEM_USB || cs.modem == MODEM_LSB);
+
+    if (ph == TP_SETUP) {
+        if (tid == 0) {
+            const long long g0 = cd.g0, g1 = cd.g0 + a.n;
+            for (int j = 0; j <= cs.n_tail; ++j) {
+                const int sh = cs.K1 + j;
+                sm->lvl_g0[j] = g0 >> sh;
+                sm->lvl_n[j] = (int)((g1 >> sh) - (g0 >> sh));
+            }
+            sm->n_iq = arb_count(cs.arb_step, st.arb_phase, sm->lvl_n[cs.n_tail], &sm->arb_phase_after);
+            // audio resampler bookkeeping: its input is the demodulated stream, one sample per decimated IQ sample
+            const long long d0 = (long long)st.iq_count, d1 = d0 + sm->n_iq;
+            if (!cs.a_interp) {
+                for (int j = 0; j <= cs.a_S; ++j) { sm->a_g0[j] = d0 >> j; sm->a_n[j] = (int)((d1 >> j) - (d0 >> j)); }
+                sm->n_audio = arb_count(cs.a_step, st.a_phase, sm->a_n[cs.a_S], &sm->a_phase_after);
+            } else {
+                int nb = arb_count(cs.a_step, st.a_phase, sm->n_iq, &sm->a_phase_after);
+                for (int j = 0; j <= cs.a_S; ++j) { sm->a_g0[j] = 0; sm->a_n[j] = nb << j; }
+                sm->n_audio = nb << cs.a_S;
+            }
+        }
+        return;
+    }
+
+    // ---- remaining half-band decimators of the IQ resampler --------------------------------------------------------
+    if (ph >= TP_HB0 && ph < TP_HB0 + kMaxTailHb) {
+        const int j = ph - TP_HB0;
+        if (j < cs.n_tail)
+            hb_decim_c(chan_cbuf(a, cs, cs.lvl_off[j]), sm->lvl_g0[j], chan_cbuf(a, cs, cs.lvl_off[j + 1]), sm->lvl_g0[j + 1],
+                       sm->lvl_n[j + 1], cs.tail_m[j], a.taps + cs.tail_h1[j], tid, nt);
+        return;
+    }
+
+    if (ph == TP_ARB) {      // 256-arm polyphase stage, nearest arm, 24-bit phase
+        const float2 *z = chan_cbuf(a, cs, cs.lvl_off[cs.n_tail]) + kHist;
+        float2 *iq = chan_cbuf(a, cs, cs.iq_off) + kHist;
+        const float *pfb = a.taps + cs.pfb_off;
+        const unsigned long long ph0 = st.arb_phase;
+        for (int r = tid; r < sm->n_iq; r += nt) {
+            const unsigned long long psi = ph0 + (unsigned long long)r * cs.arb_step;
+            const int q = (int)(psi >> 24);
+            const float *h = pfb + ((psi >> 16) & 255u) * kPfbTaps;
+            float2 acc = make_float2(0.f, 0.f);
+            for (int t = 0; t < kPfbTaps; ++t) acc = cf_fma(sdr_ldg(h + t), z[q - t], acc);
+            acc = cf_scale(cs.zeta, acc);
+            iq[r] = acc;
+            if (cs.want_iq && r < cs.res_iq_cap) res_iq[r] = acc;
+        }
+        return;
+    }
+
+    float *d = chan_rbuf(a, cs, cs.d_off) + kHist;
+    const float2 *iq = chan_cbuf(a, cs, cs.iq_off) + kHist;
+
+    if (ph == TP_DEMOD_A) {
+        const int n = sm->n_iq;
+        if (is_fm) {
+            const float ref = 0.31830987f;                       // (float)(1 / (2 pi kf)), kf = 0.5  (freqdem_create(0.5))
+            for (int i = tid; i < n; i += nt) {
+                float2 x = iq[i], p = iq[i - 1];
+                float re = fmaf(p.x, x.x, p.y * x.y);            // conj(p) * x
+                float im = fmaf(p.x, x.y, -(p.y * x.x));
+                d[i] = atan2f(im, re) * ref;
+            }
+        } else if (cs.modem == MODEM_AM) {
+            const float *h = a.taps + cs.am_taps_off;
+            for (int i = tid; i < n; i += nt) {
+                float acc = 0.f;
+                for (int k = 0; k < 51; ++k) {
+                    float2 x = iq[i - k];
+                    acc = fmaf(sdr_ldg(h + k), sqrtf(x.x * x.x + x.y * x.y), acc);
+                }
+                d[i] = acc;
+            }
+        } else if (tid == 0) {                                   // SSB: quarter-rate shift, Butterworth-6, shift back
+            float2 *w = chan_cbuf(a, cs, cs.w_off) + kHist;
+            const float *sos = a.taps + cs.sos_off;
+            unsigned th = st.ssb_theta;
+            float v[3][2][2];
+            for (int s = 0; s < 3; ++s) for (int k = 0; k < 2; ++k) { v[s][k][0] = st.sos_v[s][k][0]; v[s][k][1] = st.sos_v[s][k][1]; }
+            const float sgn = (cs.modem == MODEM_USB) ? -1.0f : 1.0f;   // USB mixes down first, LSB mixes up first
+            for (int i = 0; i < n; ++i) {
+                th += 0x40000000u;                                // nco_crcf_step before use (ModemUSB.cpp:55)
+                float2 cs2 = nco_lookup(a.nco, th);
+                float2 x = cf_rot(iq[i], cs2.x, sgn * cs2.y);
+                for (int s = 0; s < 3; ++s) {                     // direct-form II second-order sections
+                    const float *c = sos + 5 * s;                 // {b0, b1, b2, a1, a2}
+                    float v0r = x.x - c[3] * v[s][0][0] - c[4] * v[s][1][0];
+                    float v0i = x.y - c[3] * v[s][0][1] - c[4] * v[s][1][1];
+                    float yr = c[0] * v0r + c[1] * v[s][0][0] + c[2] * v[s][1][0];
+                    float yi = c[0] * v0i + c[1] * v[s][0][1] + c[2] * v[s][1][1];
+                    v[s][1][0] = v[s][0][0]; v[s][1][1] = v[s][0][1];
+                    v[s][0][0] = v0r; v[s][0][1] = v0i;
+                    x = make_float2(yr, yi);
+                }
+                w[i] = cf_rot(x, cs2.x, -sgn * cs2.y);
+            }
+            st.ssb_theta = th;
+            for (int s = 0; s < 3; ++s) for (int k = 0; k < 2; ++k) { st.sos_v[s][k][0] = v[s][k][0]; st.sos_v[s][k][1] = v[s][k][1]; }
+        }
+        return;
+    }
+
+    if (ph == TP_DEMOD_B) {
+        if (is_ssb) {                                            // firhilbf c2r, 21 taps
+            const float2 *w = chan_cbuf(a, cs, cs.w_off) + kHist;
+            const float *hq = a.taps + cs.hq_off;
+            const float sgn = (cs.modem == MODEM_USB) ? -1.0f : 1.0f;   // usb = yi - yq, lsb = yi + yq
+            for (int i = tid; i < sm->n_iq; i += nt) {
+                float yq = 0.f;
+                for (int j = 0; j < 10; ++j) yq = fmaf(sdr_ldg(hq + j), w[i - 19 + 2 * j].y, yq);
+                d[i] = w[i - 10].x + sgn * yq;
+            }
+        }
+        return;
+    }
+
+    // ---- block auto-gain (AM / SSB): ModemAnalog.cpp:70-86 ------------------------------------------------------------
+    if (ph == TP_AGC_A) {
+        if (!is_fm) {
+            float mx = 0.f;
+            for (int i = tid; i < sm->n_iq; i += nt) mx = fmaxf(mx, d[i]);
+            sm->red_f[tid] = mx;
+        }
+        return;
+    }
+    if (ph == TP_AGC_B) {
+        if (!is_fm && tid == 0) {
+            float mx = 0.f;
+            for (int t = 0; t < nt; ++t) mx = fmaxf(mx, sm->red_f[t]);
+            float ma = st.agc_ma + (st.agc_ceil - st.agc_ma) * 0.025f;
+            float maa = st.agc_maa + (ma - st.agc_maa) * 0.025f;
+            st.agc_ma = ma; st.agc_maa = maa; st.agc_ceil = mx;
+            sm->gain = 0.5f / maa;
+        }
+        return;
+    }
+    if (ph == TP_AGC_C) {
+        if (!is_fm) { const float g = sm->gain; for (int i = tid; i < sm->n_iq; i += nt) d[i] *= g; }
+        return;
+    }
+
+    // ---- audio resampler msresamp_rrrf ---------------------------------------------------------------------------------
+    if (ph >= TP_AUD0 && ph < TP_AUD0 + kMaxAudioHb + 1) {
+        const int j = ph - TP_AUD0;
+        if (!cs.a_interp) {
+            // decimator: a_S half-bands (cascade position g = a_S-1-j for phase j), then the arbitrary stage
+            if (j < cs.a_S) {
+                const int g = cs.a_S - 1 - j;
+                const float *in = (j == 0) ? chan_rbuf(a, cs, cs.d_off) : chan_rbuf(a, cs, cs.al_off[j]);
+                hb_decim_r(in, sm->a_g0[j], chan_rbuf(a, cs, cs.al_off[j + 1]), sm->a_g0[j + 1], sm->a_n[j + 1], cs.a_m[g],
+                           a.taps + cs.a_h1[g], tid, nt);
+            } else if (j == cs.a_S) {
+                const float *z = ((cs.a_S == 0) ? chan_rbuf(a, cs, cs.d_off) : chan_rbuf(a, cs, cs.al_off[cs.a_S])) + kHist;
+                const float *pfb = a.taps + cs.a_pfb_off;
+                const unsigned long long ph0 = st.a_phase;
+                for (int r = tid; r < sm->n_audio; r += nt) {
+                    const unsigned long long psi = ph0 + (unsigned long long)r * cs.a_step;
+                    const int q = (int)(psi >> 24);
+                    const float *h = pfb + ((psi >> 16) & 255u) * kPfbTaps;
+                    float acc = 0.f;
+                    for (int t = 0; t < kPfbTaps; ++t) acc = fmaf(sdr_ldg(h + t), z[q - t], acc);
+                    if (r < cs.res_audio_cap) res_audio[r] = acc * cs.a_zeta;
+                }
+            }
+        } else {
+            // interpolator: arbitrary stage first (1..2 outputs per input), then a_S half-band interpolators (g = j-1)
+            if (j == 0) {
+                const float *z = chan_rbuf(a, cs, cs.d_off) + kHist;
+                float *out = (cs.a_S == 0) ? nullptr : chan_rbuf(a, cs, cs.al_off[0]) + kHist;
+                const float *pfb = a.taps + cs.a_pfb_off;
+                const unsigned long long ph0 = st.a_phase;
+                const int nb = sm->a_n[0];
+                for (int r = tid; r < nb; r += nt) {
+                    const unsigned long long psi = ph0 + (unsigned long long)r * cs.a_step;
+                    const int q = (int)(psi >> 24);
+                    const float *h = pfb + ((psi >> 16) & 255u) * kPfbTaps;
+                    float acc = 0.f;
+                    for (int t = 0; t < kPfbTaps; ++t) acc = fmaf(sdr_ldg(h + t), z[q - t], acc);
+                    if (out) out[r] = acc; else if (r < cs.res_audio_cap) res_audio[r] = acc;
+                }
+            } else if (j <= cs.a_S) {
+                const int g = j - 1;
+                const float *in = chan_rbuf(a, cs, cs.al_off[j - 1]);
+                float *out = chan_rbuf(a, cs, cs.al_off[j]);
+                hb_interp_r(in, sm->a_n[j - 1], out, cs.a_m[g], a.taps + cs.a_h1[g], tid, nt);
+                if (j == cs.a_S) {
+                    // final level: also the audio result (each thread copies what it just wrote)
+                    for (int r = tid; r < sm->n_audio && r < cs.res_audio_cap; r += nt) res_audio[r] = out[kHist + r];
+                }
+            }
+        }
+        return;
+    }
+
+    // ---- metering: DemodulatorThread.cpp:142-163 (level), 223-233 (peak) ---------------------------------------------
+    if (ph == TP_METER_A) {
+        const int na = sm->n_audio < cs.res_audio_cap ? sm->n_audio : cs.res_audio_cap;
+        float pk = 0.f;
+        double acc = 0.0;
+        for (int i = tid; i < na; i += nt) { float v = fabsf(res_audio[i]); pk = fmaxf(pk, v); if (!is_fm) acc += (double)v; }
+        if (is_fm) for (int i = tid; i < sm->n_iq; i += nt) { double re = iq[i].x, im = iq[i].y; acc += sqrt(re * re + im * im); }
+        sm->red_f[tid] = pk;
+        sm->red_d[tid] = acc;
+        return;
+    }
+    if (ph == TP_METER_B) {
+        if (tid == 0) {
+            float pk = 0.f;
+            double acc = 0.0;
+            for (int t = 0; t < nt; ++t) { pk = fmaxf(pk, sm->red_f[t]); acc += sm->red_d[t]; }
+            const int cnt = is_fm ? sm->n_iq : sm->n_audio;
+            double lvl = 0.0;
+            if (sm->n_audio > 0 && cnt > 0) {
+                double lin = acc / (double)cnt;
+                if (lin <= 1e-20) lin = 1e-20;
+                lvl = 20.0 * log10(lin);
+            }
+            hdr->n_audio = (unsigned)sm->n_audio; hdr->n_iq = (unsigned)sm->n_iq; hdr->peak = pk; hdr->skipped = 0; hdr->level_db = lvl;
+        }
+        return;
+    }
+
+    // ---- slide every stream's history: new_hist[t] = combined[n + t] -----------------------------------------------------
+    if (ph == TP_HIST_A || ph == TP_HIST_B) {
+        int s = 0;
+        for (int j = 0; j <= cs.n_tail; ++j, ++s) {
+            float2 *b = chan_cbuf(a, cs, cs.lvl_off[j]);
+            if (tid < kHist) { if (ph == TP_HIST_A) sm->hist_tmp[s][tid] = b[sm->lvl_n[j] + tid]; else b[tid] = sm->hist_tmp[s][tid]; }
+        }
+        {
+            float2 *b = chan_cbuf(a, cs, cs.iq_off);
+            if (tid < kHist) { if (ph == TP_HIST_A) sm->hist_tmp[s][tid] = b[sm->n_iq + tid]; else b[tid] = sm->hist_tmp[s][tid]; }
+            ++s;
+        }
+        if (is_ssb) {
+            float2 *b = chan_cbuf(a, cs, cs.w_off);
+            if (tid < kHist) { if (ph == TP_HIST_A) sm->hist_tmp[s][tid] = b[sm->n_iq + tid]; else b[tid] = sm->hist_tmp[s][tid]; }
+        }
+        ++s;
+        {
+            float *b = chan_rbuf(a, cs, cs.d_off);
+            if (tid < kHist) { if (ph == TP_HIST_A) sm->hist_tmp[s][tid].x = b[sm->n_iq + tid]; else b[tid] = sm->hist_tmp[s][tid].x; }
+            ++s;
+        }
+        const int n_al = cs.a_S;      // decim: levels 1..a_S ; interp: levels 0..a_S-1 are inputs of later stages
+        for (int j = 0; j <= n_al; ++j, ++s) {
+            if (!cs.a_interp && j == 0) continue;               // decimator level 0 is the d stream itself
+            if (cs.a_interp && j == cs.a_S && cs.a_S > 0) continue;   // final interpolator level feeds nothing
+            if (cs.a_interp && cs.a_S == 0) continue;
+            float *b = chan_rbuf(a, cs, cs.al_off[j]);
+            if (tid < kHist) { if (ph == TP_HIST_A) sm->hist_tmp[s][tid].x = b[sm->a_n[j] + tid]; else b[tid] = sm->hist_tmp[s][tid].x; }
+        }
+        if (ph == TP_HIST_B && tid == 0) {
+            st.arb_phase = sm->arb_phase_after;
+            st.iq_count += (unsigned long long)sm->n_iq;
+            st.a_phase = sm->a_phase_after;
+        }
+        return;
+    }
+}
+
+}  // namespace sdrb200

@@ -1,0 +1,923 @@
+// cubicsdr_b200/csrc/engine.cu -- engine object, kernel launches and the C-ABI of include/sdr_b200.h.
+//
+// One engine per GPU.  A submit does, on one CUDA stream:
+//   slide wideband history -> (H2D) -> DC-blocker scan -> spectrum kernels -> front kernel(s) -> tail kernel -> (D2H)
+// Host-side logic that the reference keeps in its threads is restated here next to the launch it controls:
+//   DemodulatorPreThread shift / skip rule      src/demod/DemodulatorPreThread.cpp:154-163
+//   FFTDataDistributor framing / line limiter   src/process/FFTDataDistributor.cpp:28-144
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/sdr_b200.h"
+#include "design.h"
+#include "dsp_core.h"
+#include "dsp_spec.h"
+#include "dsp_tail.h"
+
+using namespace sdrb200;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// error text
+// ---------------------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+#ifndef SDR_EMU
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess) return fail(SDR_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+#endif
+
+// ---------------------------------------------------------------------------------------------------------------------
+// kernels (GPU) / serial replays (test-only emulator)
+// ---------------------------------------------------------------------------------------------------------------------
+#ifndef SDR_EMU
+__global__ void __launch_bounds__(kDcThreads) k_dc_tile_sum(DcArgs a) {
+    __shared__ DcShared sm;
+    dc_tile_sum_phase(0, a, blockIdx.x, threadIdx.x, &sm);
+    __syncthreads();
+    dc_tile_sum_phase(1, a, blockIdx.x, threadIdx.x, &sm);
+}
+__global__ void k_dc_carry(DcArgs a, int tiles) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) dc_carry_phase(a, tiles);
+}
+__global__ void __launch_bounds__(kDcThreads) k_dc_apply(DcArgs a) {
+    __shared__ DcShared2 sm;
+    for (int ph = 0; ph < 3; ++ph) {
+        dc_apply_phase(ph, a, blockIdx.x, threadIdx.x, &sm);
+        __syncthreads();
+    }
+}
+template <int K>
+__global__ void __launch_bounds__(128) k_chan_front(FrontArgs a) {
+    const int job = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    front_thread<K>(a, job, threadIdx.x & 31);
+}
+__global__ void __launch_bounds__(kTailThreads) k_chan_tail(TailArgs a) {
+    __shared__ TailShared sm;
+    for (int ph = 0; ph < TP_COUNT; ++ph) {
+        tail_phase(ph, a, blockIdx.x, threadIdx.x, blockDim.x, &sm);
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(kFftThreads) k_spec_fft(SpecArgs a, int phases) {
+    extern __shared__ float2 fft_sm[];
+    for (int ph = 0; ph < phases; ++ph) {
+        spec_fft_phase(ph, a, blockIdx.x, threadIdx.x, blockDim.x, fft_sm);
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(kSpecThreads) k_spec_ema(SpecArgs a) { spec_ema_thread(a, blockIdx.x * blockDim.x + threadIdx.x); }
+__global__ void __launch_bounds__(kSpecThreads) k_spec_minmax(SpecArgs a) {
+    __shared__ SpecRedShared sm;
+    spec_minmax_phase(0, a, blockIdx.x, threadIdx.x, blockDim.x, &sm);
+    __syncthreads();
+    spec_minmax_phase(1, a, blockIdx.x, threadIdx.x, blockDim.x, &sm);
+}
+__global__ void k_spec_scalar(SpecArgs a) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) spec_scalar_thread(a);
+}
+__global__ void __launch_bounds__(kSpecThreads) k_spec_points(SpecArgs a) {
+    spec_points_thread(a, (long long)blockIdx.x * blockDim.x + threadIdx.x);
+}
+#endif
+
+static void launch_dc(const DcArgs &a, sdr_stream_t s, unsigned long long &launches) {
+    const int tiles = (a.n + kDcTile - 1) / kDcTile;
+    if (tiles == 0) return;
+#ifndef SDR_EMU
+    k_dc_tile_sum<<<tiles, kDcThreads, 0, s>>>(a);
+    k_dc_carry<<<1, 32, 0, s>>>(a, tiles);
+    k_dc_apply<<<tiles, kDcThreads, 0, s>>>(a);
+#else
+    (void)s;
+    for (int b = 0; b < tiles; ++b) {
+        DcShared sm;
+        for (int ph = 0; ph < 2; ++ph) for (int t = 0; t < kDcThreads; ++t) dc_tile_sum_phase(ph, a, b, t, &sm);
+    }
+    dc_carry_phase(a, tiles);
+    for (int b = 0; b < tiles; ++b) {
+        DcShared2 sm;
+        for (int ph = 0; ph < 3; ++ph) for (int t = 0; t < kDcThreads; ++t) dc_apply_phase(ph, a, b, t, &sm);
+    }
+#endif
+    launches += 3;
+}
+
+template <int K>
+static void launch_front_k(const FrontArgs &a, int jobs, sdr_stream_t s) {
+#ifndef SDR_EMU
+    const int warps_per_cta = 4;
+    k_chan_front<K><<<(jobs + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, s>>>(a);
+#else
+    (void)s;
+    for (int j = 0; j < jobs; ++j) for (int l = 0; l < 32; ++l) front_thread<K>(a, j, l);
+#endif
+}
+static void launch_front(int K, const FrontArgs &a, int jobs, sdr_stream_t s, unsigned long long &launches) {
+    switch (K) {
+    case 0: launch_front_k<0>(a, jobs, s); break;
+    case 1: launch_front_k<1>(a, jobs, s); break;
+    case 2: launch_front_k<2>(a, jobs, s); break;
+    case 3: launch_front_k<3>(a, jobs, s); break;
+    case 4: launch_front_k<4>(a, jobs, s); break;
+    case 5: launch_front_k<5>(a, jobs, s); break;
+    default: launch_front_k<6>(a, jobs, s); break;
+    }
+    launches += 1;
+}
+
+static void launch_tail(const TailArgs &a, int n_chan, sdr_stream_t s, unsigned long long &launches) {
+    if (n_chan == 0) return;
+#ifndef SDR_EMU
+    k_chan_tail<<<n_chan, kTailThreads, 0, s>>>(a);
+#else
+    (void)s;
+    TailShared *sm = new TailShared;
+    for (int c = 0; c < n_chan; ++c)
+        for (int ph = 0; ph < TP_COUNT; ++ph) for (int t = 0; t < kTailThreads; ++t) tail_phase(ph, a, c, t, kTailThreads, sm);
+    delete sm;
+#endif
+    launches += 1;
+}
+
+static int launch_spectrum(const SpecArgs &a, sdr_stream_t s, unsigned long long &launches) {
+    if (a.F == 0) return 0;
+    const int phases = fft_phase_count(a.log_nsub);
+#ifndef SDR_EMU
+    const size_t smem = (size_t)a.nsub * sizeof(float2);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(k_spec_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, kFftMaxSub * (int)sizeof(float2)));
+        attr_set = true;
+    }
+    k_spec_fft<<<a.F * a.P, kFftThreads, smem, s>>>(a, phases);
+    k_spec_ema<<<(a.N + kSpecThreads - 1) / kSpecThreads, kSpecThreads, 0, s>>>(a);
+    k_spec_minmax<<<a.F, kSpecThreads, 0, s>>>(a);
+    k_spec_scalar<<<1, 32, 0, s>>>(a);
+    const long long pts = (long long)a.F * a.fft_size;
+    k_spec_points<<<(unsigned)((pts + kSpecThreads - 1) / kSpecThreads), kSpecThreads, 0, s>>>(a);
+#else
+    (void)s;
+    std::vector<float2> sm(a.nsub);
+    for (int b = 0; b < a.F * a.P; ++b)
+        for (int ph = 0; ph < phases; ++ph) for (int t = 0; t < kFftThreads; ++t) spec_fft_phase(ph, a, b, t, kFftThreads, sm.data());
+    for (int i = 0; i < a.N; ++i) spec_ema_thread(a, i);
+    for (int f = 0; f < a.F; ++f) {
+        SpecRedShared rs;
+        for (int ph = 0; ph < 2; ++ph) for (int t = 0; t < kSpecThreads; ++t) spec_minmax_phase(ph, a, f, t, kSpecThreads, &rs);
+    }
+    spec_scalar_thread(a);
+    for (long long g = 0; g < (long long)a.F * a.fft_size; ++g) spec_points_thread(a, g);
+#endif
+    launches += 5;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host objects
+// ---------------------------------------------------------------------------------------------------------------------
+static int modem_from_name(const char *n) {
+    if (!n) return -1;
+    std::string s(n);
+    if (s == "FM") return MODEM_FM;
+    if (s == "NBFM") return MODEM_NBFM;
+    if (s == "AM") return MODEM_AM;
+    if (s == "USB") return MODEM_USB;
+    if (s == "LSB") return MODEM_LSB;
+    return -1;
+}
+
+// Modem::checkSampleRate: ModemAnalog.cpp:14-19 (MIN_BANDWIDTH 500), ModemUSB.cpp:29-37 / ModemLSB.cpp:29-37
+static int check_sample_rate(int modem, long long bw) {
+    if (bw < 500) return 500;
+    if ((modem == MODEM_USB || modem == MODEM_LSB) && (bw % 2)) return (int)(bw + 1);
+    return (int)bw;
+}
+
+struct sdr_chan {
+    sdr_engine *eng = nullptr;
+    int index = -1;                 // slot in the engine's arrays
+    int modem = 0;
+    long long sample_rate = 0;
+    int bandwidth = 0, audio_rate = 0;
+    ResamplerPlan iq_plan, audio_plan;
+    ChanStatic cs;
+    float *d_arena = nullptr;
+    size_t arena_floats = 0;
+    float2 *d_priv_hist = nullptr;  // tail of the last consumed block, kept while the channel skips blocks
+    bool priv_valid = false;
+    // DemodulatorPreThread state
+    long long frequency = 0;
+    long long shift_frequency = 0;  // last applied shift (starts at 0 like the reference member)
+    unsigned theta = 0, dtheta = 0, dtheta_prev = 0;
+    int dir_prev = 0;
+    long long consumed = 0;         // wideband samples consumed
+    size_t slot_bytes = 0;
+};
+
+struct sdr_spectrum {
+    sdr_engine *eng = nullptr;
+    unsigned fft_size = 0, N = 0, lps = 0;
+    int P = 1, nsub = 0, log_nsub = 0;
+    float average_rate = 0.65f, scale_factor = 1.0f;
+    // framing state (FFTDataDistributor)
+    long long buffered = 0, last_rate = 0;
+    double line_accum = 0.0;
+    // device
+    float2 *d_tw = nullptr; float *d_mags = nullptr, *d_maa = nullptr; double2 *d_ema = nullptr; double *d_scalars = nullptr;
+    float2 *d_frame_cf = nullptr; double2 *d_frame_cf_maa = nullptr; float *d_points = nullptr; unsigned char *d_lines = nullptr;
+    int *d_frame_start = nullptr;
+    // pinned host
+    float *h_points = nullptr; unsigned char *h_lines = nullptr; double2 *h_cf = nullptr; int *h_frame_start = nullptr;
+    float *h_dbg = nullptr;
+    unsigned f_max = 0, frames_last = 0;
+};
+
+struct sdr_engine {
+    int device = 0;
+    sdr_stream_t stream = nullptr;
+    bool own_stream = false;
+    unsigned max_block = 0;
+    std::mutex mu;
+    unsigned long long launches = 0;
+    // wideband buffers
+    size_t hist_cap = 0;
+    float2 *d_raw = nullptr, *d_blk = nullptr, *d_scratch = nullptr;
+    sdr_cf32 *h_stage = nullptr;        // pinned staging for H2D
+    unsigned last_n = 0;
+    bool have_block = false;
+    // DC blocker
+    double2 *d_tile_sum = nullptr, *d_tile_carry = nullptr, *d_dc_state = nullptr; double *d_apow = nullptr;
+    double dc_a = 0.0;
+    float2 *d_nco = nullptr;
+    // channels
+    static const int kMaxChan = 2048;
+    std::vector<sdr_chan *> chans;     // by slot; nullptr = free
+    ChanStatic *d_cs = nullptr; ChanDyn *d_cd = nullptr; ChanState *d_st = nullptr;
+    // small per-block parameter blocks live in a ring of pinned buffers so that submits can be enqueued back to back
+    static const int kRing = 8;
+    ChanDyn *h_cd = nullptr;            // pinned [kRing][kMaxChan]
+    int *d_group = nullptr; int *h_group = nullptr;   // h_group pinned [kRing][kMaxChan]
+    unsigned long long ring_seq = 0;
+#ifndef SDR_EMU
+    cudaEvent_t ring_ev[kRing];
+#endif
+    std::vector<float> taps_host; float *d_taps = nullptr; size_t taps_cap = 0, taps_uploaded = 0;
+    std::map<std::string, int> taps_cache;
+    unsigned char *d_results = nullptr, *h_results = nullptr; size_t results_bytes = 0;
+    bool dirty = true;
+    bool results_on_host = false;
+    std::vector<sdr_spectrum *> spectra;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// taps pool
+// ---------------------------------------------------------------------------------------------------------------------
+static int pool_add(sdr_engine *e, const std::string &key, const float *v, size_t n) {
+    auto it = e->taps_cache.find(key);
+    if (it != e->taps_cache.end()) return it->second;
+    int off = (int)e->taps_host.size();
+    e->taps_host.insert(e->taps_host.end(), v, v + n);
+    while (e->taps_host.size() % 4) e->taps_host.push_back(0.f);
+    e->taps_cache[key] = off;
+    return off;
+}
+static std::string fkey(const char *tag, float v, int extra = 0) {
+    char b[64];
+    uint32_t u; memcpy(&u, &v, 4);
+    snprintf(b, sizeof b, "%s:%08x:%d", tag, u, extra);
+    return b;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// C-ABI: misc
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" const char *sdr_last_error(void) { return g_err.c_str(); }
+extern "C" const char *sdr_version(void) { return "cubicsdr_b200 0.1 (sm_100a)"; }
+extern "C" int sdr_is_device_build(void) {
+#ifdef SDR_EMU
+    return 0;
+#else
+    return 1;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// engine
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, sdr_engine **out) {
+    if (!out || max_block == 0) return fail(SDR_ERR_ARG, "sdr_engine_create: bad arguments");
+#ifndef SDR_EMU
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail(SDR_ERR_CUDA, "sdr_engine_create: no CUDA device (this library has no CPU path)");
+    CUDA_TRY(cudaSetDevice(device));
+#endif
+    sdr_engine *e = new sdr_engine();
+    e->device = device;
+    e->max_block = max_block;
+#ifndef SDR_EMU
+    if (stream) { e->stream = (cudaStream_t)stream; e->own_stream = false; }
+    else { CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)); e->own_stream = true; }
+#else
+    (void)stream;
+#endif
+    e->hist_cap = 65536 + kBlkHist;
+    int bad = 0;
+    bad |= be_malloc((void **)&e->d_raw, (size_t)max_block * sizeof(float2));
+    bad |= be_malloc((void **)&e->d_blk, (e->hist_cap + max_block) * sizeof(float2));
+    bad |= be_malloc((void **)&e->d_scratch, e->hist_cap * sizeof(float2));
+    bad |= be_host_alloc((void **)&e->h_stage, (size_t)max_block * sizeof(sdr_cf32));
+    const int tiles = (max_block + kDcTile - 1) / kDcTile;
+    bad |= be_malloc((void **)&e->d_tile_sum, tiles * sizeof(double2));
+    bad |= be_malloc((void **)&e->d_tile_carry, tiles * sizeof(double2));
+    bad |= be_malloc((void **)&e->d_dc_state, sizeof(double2));
+    bad |= be_malloc((void **)&e->d_apow, (kDcTile + 1) * sizeof(double));
+    bad |= be_malloc((void **)&e->d_nco, 1024 * sizeof(float2));
+    bad |= be_malloc((void **)&e->d_cs, sdr_engine::kMaxChan * sizeof(ChanStatic));
+    bad |= be_malloc((void **)&e->d_cd, sdr_engine::kMaxChan * sizeof(ChanDyn));
+    bad |= be_malloc((void **)&e->d_st, sdr_engine::kMaxChan * sizeof(ChanState));
+    bad |= be_host_alloc((void **)&e->h_cd, (size_t)sdr_engine::kRing * sdr_engine::kMaxChan * sizeof(ChanDyn));
+    bad |= be_malloc((void **)&e->d_group, sdr_engine::kMaxChan * sizeof(int));
+    bad |= be_host_alloc((void **)&e->h_group, (size_t)sdr_engine::kRing * sdr_engine::kMaxChan * sizeof(int));
+#ifndef SDR_EMU
+    for (int i = 0; i < sdr_engine::kRing; ++i) CUDA_TRY(cudaEventCreateWithFlags(&e->ring_ev[i], cudaEventDisableTiming));
+#endif
+    e->taps_cap = 4u << 20;   // floats
+    bad |= be_malloc((void **)&e->d_taps, e->taps_cap * sizeof(float));
+    if (bad) { delete e; return fail(SDR_ERR_NOMEM, "sdr_engine_create: allocation failed"); }
+    be_memset(e->d_blk, 0, (e->hist_cap + max_block) * sizeof(float2), e->stream);
+    be_memset(e->d_dc_state, 0, sizeof(double2), e->stream);
+    // DC blocker coefficient: a = -(-1 + alpha) with alpha = 0.0005f, evaluated in float as the reference does
+    const float a_f = 1.0f - 0.0005f;
+    e->dc_a = (double)a_f;
+    std::vector<double> apow(kDcTile + 1);
+    apow[0] = 1.0;
+    for (int k = 1; k <= kDcTile; ++k) apow[k] = apow[k - 1] * e->dc_a;
+    be_h2d(e->d_apow, apow.data(), apow.size() * sizeof(double), e->stream);
+    float tab[1024];
+    nco_sine_table(tab);
+    std::vector<float2> nco(1024);
+    for (int i = 0; i < 1024; ++i) nco[i] = make_float2(tab[(i + 256) & 1023], tab[i]);
+    be_h2d(e->d_nco, nco.data(), 1024 * sizeof(float2), e->stream);
+    be_sync(e->stream);
+    *out = e;
+    return SDR_OK;
+}
+
+static void spectrum_free(sdr_spectrum *sp);
+
+extern "C" int sdr_engine_destroy(sdr_engine *e) {
+    if (!e) return SDR_OK;
+    be_sync(e->stream);
+    for (auto *c : e->chans) if (c) { be_free(c->d_arena); be_free(c->d_priv_hist); delete c; }
+    for (auto *s : e->spectra) if (s) { spectrum_free(s); delete s; }
+    be_free(e->d_raw); be_free(e->d_blk); be_free(e->d_scratch); be_host_free(e->h_stage);
+    be_free(e->d_tile_sum); be_free(e->d_tile_carry); be_free(e->d_dc_state); be_free(e->d_apow); be_free(e->d_nco);
+    be_free(e->d_cs); be_free(e->d_cd); be_free(e->d_st); be_host_free(e->h_cd); be_free(e->d_group); be_host_free(e->h_group);
+    be_free(e->d_taps); be_free(e->d_results); be_host_free(e->h_results);
+#ifndef SDR_EMU
+    for (int i = 0; i < sdr_engine::kRing; ++i) cudaEventDestroy(e->ring_ev[i]);
+    if (e->own_stream) cudaStreamDestroy(e->stream);
+#endif
+    delete e;
+    return SDR_OK;
+}
+
+extern "C" unsigned long long sdr_engine_launch_count(sdr_engine *e) { return e ? e->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// channels
+// ---------------------------------------------------------------------------------------------------------------------
+static int add_halfband_taps(sdr_engine *e, int m) {
+    float h1[2 * 10];
+    if (!halfband_branch_taps(m, 65.0f, h1)) return -1;
+    return pool_add(e, fkey("hb", (float)m), h1, 2 * m);
+}
+
+extern "C" int sdr_chan_create(sdr_engine *e, const char *modem, long long sample_rate, long long bandwidth, int audio_rate,
+                               sdr_chan **out) {
+    if (!e || !out || sample_rate <= 0 || audio_rate <= 0) return fail(SDR_ERR_ARG, "sdr_chan_create: bad arguments");
+    const int mk = modem_from_name(modem);
+    if (mk < 0) return fail(SDR_ERR_UNSUPPORTED, std::string("sdr_chan_create: unknown modem '") + (modem ? modem : "") + "'");
+    std::lock_guard<std::mutex> lk(e->mu);
+    int slot = -1;
+    for (size_t i = 0; i < e->chans.size(); ++i) if (!e->chans[i]) { slot = (int)i; break; }
+    if (slot < 0) {
+        if ((int)e->chans.size() >= sdr_engine::kMaxChan) return fail(SDR_ERR_STATE, "sdr_chan_create: too many channels");
+        slot = (int)e->chans.size();
+        e->chans.push_back(nullptr);
+    }
+    sdr_chan *c = new sdr_chan();
+    c->eng = e; c->index = slot; c->modem = mk; c->sample_rate = sample_rate;
+    c->bandwidth = check_sample_rate(mk, bandwidth);
+    c->audio_rate = audio_rate;
+    const float As = 60.0f;                                             // DemodulatorWorkerThread.cpp:95, ModemAnalog.cpp:25
+    const double iq_ratio = (double)c->bandwidth / (double)sample_rate; // :97-100
+    if (!(iq_ratio > 0.004 / 65536.0) || iq_ratio > 1.0) { delete c; return fail(SDR_ERR_ARG, "sdr_chan_create: bandwidth/sample_rate out of range"); }
+    c->iq_plan = make_resampler_plan((float)iq_ratio, As);
+    const double a_ratio = double(audio_rate) / double(c->bandwidth);   // ModemAnalog.cpp:29-30
+    c->audio_plan = make_resampler_plan((float)a_ratio, As);
+    if (c->iq_plan.interp) { delete c; return fail(SDR_ERR_UNSUPPORTED, "sdr_chan_create: bandwidth above the sample rate"); }
+    if (c->iq_plan.num_halfband > kMaxTailHb + kFrontMaxK || c->audio_plan.num_halfband > kMaxAudioHb) {
+        delete c; return fail(SDR_ERR_UNSUPPORTED, "sdr_chan_create: too many half-band stages");
+    }
+    ChanStatic &cs = c->cs;
+    memset(&cs, 0, sizeof cs);
+    cs.modem = mk;
+    cs.S = c->iq_plan.num_halfband;
+    cs.K1 = std::max(0, std::min(cs.S - 2, kFrontMaxK));               // only the m = 3 stages can be fused
+    cs.n_tail = cs.S - cs.K1;
+    if (cs.n_tail > kMaxTailHb) { delete c; return fail(SDR_ERR_UNSUPPORTED, "sdr_chan_create: too many tail stages"); }
+    for (int j = 0; j < cs.n_tail; ++j) {
+        const int g = cs.S - cs.K1 - 1 - j;                             // cascade position executed at tail step j
+        cs.tail_m[j] = c->iq_plan.hb.m[g];
+        cs.tail_h1[j] = add_halfband_taps(e, cs.tail_m[j]);
+        if (cs.tail_h1[j] < 0) { delete c; return fail(SDR_ERR_UNSUPPORTED, "half-band prototype not available"); }
+    }
+    for (int g = cs.S - cs.K1; g < cs.S; ++g)
+        if (c->iq_plan.hb.m[g] != 3) { delete c; return fail(SDR_ERR_STATE, "front stage is not m = 3"); }
+    cs.zeta = c->iq_plan.zeta;
+    cs.arb_step = c->iq_plan.arb_step;
+    cs.pfb_off = pool_add(e, fkey("pfb", c->iq_plan.rate_arb), c->iq_plan.pfb.data(), c->iq_plan.pfb.size());
+    cs.a_interp = c->audio_plan.interp ? 1 : 0;
+    cs.a_S = c->audio_plan.num_halfband;
+    for (int g = 0; g < cs.a_S; ++g) {
+        cs.a_m[g] = c->audio_plan.hb.m[g];
+        cs.a_h1[g] = add_halfband_taps(e, cs.a_m[g]);
+        if (cs.a_h1[g] < 0) { delete c; return fail(SDR_ERR_UNSUPPORTED, "half-band prototype not available"); }
+    }
+    cs.a_zeta = c->audio_plan.interp ? 1.0f : c->audio_plan.zeta;
+    cs.a_step = c->audio_plan.arb_step;
+    cs.a_pfb_off = pool_add(e, fkey("pfb", c->audio_plan.rate_arb), c->audio_plan.pfb.data(), c->audio_plan.pfb.size());
+    {
+        float am[51]; am_dc_block_taps(25, 30.0f, am);                  // ModemAM.cpp:9
+        // firfilt runs y[t] = sum h[k] x[t-k]; the filter is symmetric so no reversal is needed
+        cs.am_taps_off = pool_add(e, "am51", am, 51);
+        float hq[10]; hilbert_quadrature_taps(5, 90.0f, hq);            // ModemUSB.cpp:11
+        cs.hq_off = pool_add(e, "hq10", hq, 10);
+        std::vector<Sos> sos; butterworth_lowpass_sos(6, 0.25f, sos);   // ModemUSB.cpp:8
+        float flat[15];
+        for (int s = 0; s < 3; ++s) { flat[5 * s] = sos[s].b[0]; flat[5 * s + 1] = sos[s].b[1]; flat[5 * s + 2] = sos[s].b[2]; flat[5 * s + 3] = sos[s].a[1]; flat[5 * s + 4] = sos[s].a[2]; }
+        cs.sos_off = pool_add(e, "sos6", flat, 15);
+    }
+    if (e->taps_host.size() > e->taps_cap) { delete c; return fail(SDR_ERR_NOMEM, "taps pool exhausted"); }
+    // ---- arena layout (floats)
+    size_t off = 0;
+    auto take = [&](size_t floats) { size_t o = off; off += (floats + 3) & ~size_t(3); return (int)o; };
+    const size_t nb = e->max_block;
+    for (int j = 0; j <= cs.n_tail; ++j) cs.lvl_off[j] = take(2 * (kHist + (nb >> (cs.K1 + j)) + 4));
+    const size_t cap_z = (nb >> cs.S) + 4;
+    const size_t cap_iq = (size_t)std::ceil((double)cap_z * (double)c->iq_plan.rate_arb) + 8;
+    cs.iq_off = take(2 * (kHist + cap_iq));
+    cs.w_off = take(2 * (kHist + cap_iq));
+    cs.d_off = take(kHist + cap_iq);
+    size_t cap_audio;
+    if (!cs.a_interp) {
+        for (int j = 1; j <= cs.a_S; ++j) cs.al_off[j] = take(kHist + (cap_iq >> j) + 4);
+        cap_audio = (size_t)std::ceil((double)((cap_iq >> cs.a_S) + 4) * (double)c->audio_plan.rate_arb) + 8;
+    } else {
+        const size_t cap_b = (size_t)std::ceil((double)cap_iq * (double)c->audio_plan.rate_arb) + 8;
+        for (int j = 0; j <= cs.a_S; ++j) cs.al_off[j] = take(kHist + (cap_b << j) + 4);
+        cap_audio = cap_b << cs.a_S;
+    }
+    cs.res_audio_cap = (int)((cap_audio + 3) & ~size_t(3));
+    cs.res_iq_cap = (int)cap_iq;
+    cs.want_iq = 0;
+    c->arena_floats = off;
+    if (be_malloc((void **)&c->d_arena, off * sizeof(float))) { delete c; return fail(SDR_ERR_NOMEM, "sdr_chan_create: arena"); }
+    be_memset(c->d_arena, 0, off * sizeof(float), e->stream);
+    cs.arena = c->d_arena;
+    if (be_malloc((void **)&c->d_priv_hist, kBlkHist * sizeof(float2))) { be_free(c->d_arena); delete c; return fail(SDR_ERR_NOMEM, "sdr_chan_create: history"); }
+    c->slot_bytes = 32 + (size_t)cs.res_audio_cap * 4 + (size_t)cs.res_iq_cap * 8;
+    c->slot_bytes = (c->slot_bytes + 31) & ~size_t(31);
+    ChanState st;
+    memset(&st, 0, sizeof st);
+    st.agc_ceil = st.agc_ma = st.agc_maa = 1.0f;                        // ModemAnalog.cpp:6
+    be_h2d(e->d_st + slot, &st, sizeof st, e->stream);
+    be_sync(e->stream);
+    e->chans[slot] = c;
+    e->dirty = true;
+    *out = c;
+    return SDR_OK;
+}
+
+extern "C" int sdr_chan_destroy(sdr_chan *c) {
+    if (!c) return SDR_OK;
+    sdr_engine *e = c->eng;
+    std::lock_guard<std::mutex> lk(e->mu);
+    be_sync(e->stream);
+    e->chans[c->index] = nullptr;
+    be_free(c->d_arena);
+    be_free(c->d_priv_hist);
+    e->dirty = true;
+    delete c;
+    return SDR_OK;
+}
+
+extern "C" int sdr_chan_set_frequency(sdr_chan *c, long long f) {
+    if (!c) return fail(SDR_ERR_ARG, "null channel");
+    std::lock_guard<std::mutex> lk(c->eng->mu);
+    c->frequency = f;
+    return SDR_OK;
+}
+extern "C" int sdr_chan_get_bandwidth(sdr_chan *c, int *bw) {
+    if (!c || !bw) return fail(SDR_ERR_ARG, "null argument");
+    *bw = c->bandwidth;
+    return SDR_OK;
+}
+extern "C" int sdr_chan_want_iq(sdr_chan *c, int enable) {
+    if (!c) return fail(SDR_ERR_ARG, "null channel");
+    std::lock_guard<std::mutex> lk(c->eng->mu);
+    c->cs.want_iq = enable ? 1 : 0;
+    c->eng->dirty = true;
+    return SDR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// spectrum
+// ---------------------------------------------------------------------------------------------------------------------
+static void spectrum_free(sdr_spectrum *s) {
+    be_free(s->d_tw); be_free(s->d_mags); be_free(s->d_maa); be_free(s->d_ema); be_free(s->d_scalars); be_free(s->d_frame_cf);
+    be_free(s->d_frame_cf_maa); be_free(s->d_points); be_free(s->d_lines); be_free(s->d_frame_start);
+    be_host_free(s->h_points); be_host_free(s->h_lines); be_host_free(s->h_cf); be_host_free(s->h_frame_start); be_host_free(s->h_dbg);
+}
+
+extern "C" int sdr_spectrum_create(sdr_engine *e, unsigned fft_size, unsigned lps, sdr_spectrum **out) {
+    if (!e || !out) return fail(SDR_ERR_ARG, "sdr_spectrum_create: null argument");
+    if (fft_size < 16 || (fft_size & (fft_size - 1)) || fft_size > 32768)
+        return fail(SDR_ERR_UNSUPPORTED, "sdr_spectrum_create: fft_size must be a power of two in [16, 32768]");
+    std::lock_guard<std::mutex> lk(e->mu);
+    sdr_spectrum *s = new sdr_spectrum();
+    s->eng = e; s->fft_size = fft_size; s->N = 2 * fft_size; s->lps = lps;     // SPECTRUM_VZM = 2 (SpectrumVisualProcessor.cpp:145)
+    s->P = 1;
+    while ((int)(s->N / s->P) > kFftMaxSub) s->P *= 2;
+    s->nsub = s->N / s->P;
+    s->log_nsub = 0;
+    while ((1 << s->log_nsub) < s->nsub) ++s->log_nsub;
+    s->f_max = e->max_block / s->N + 2;
+    const size_t N = s->N, F = s->f_max;
+    int bad = 0;
+    bad |= be_malloc((void **)&s->d_tw, N * sizeof(float2));
+    bad |= be_malloc((void **)&s->d_mags, F * N * sizeof(float));
+    bad |= be_malloc((void **)&s->d_maa, F * N * sizeof(float));
+    bad |= be_malloc((void **)&s->d_ema, N * sizeof(double2));
+    bad |= be_malloc((void **)&s->d_scalars, 4 * sizeof(double));
+    bad |= be_malloc((void **)&s->d_frame_cf, F * sizeof(float2));
+    bad |= be_malloc((void **)&s->d_frame_cf_maa, F * sizeof(double2));
+    bad |= be_malloc((void **)&s->d_points, F * fft_size * sizeof(float));
+    bad |= be_malloc((void **)&s->d_lines, F * fft_size);
+    bad |= be_malloc((void **)&s->d_frame_start, F * sizeof(int));
+    bad |= be_host_alloc((void **)&s->h_points, F * fft_size * sizeof(float));
+    bad |= be_host_alloc((void **)&s->h_lines, F * fft_size);
+    bad |= be_host_alloc((void **)&s->h_cf, F * sizeof(double2));
+    bad |= be_host_alloc((void **)&s->h_frame_start, (size_t)sdr_engine::kRing * F * sizeof(int));
+    bad |= be_host_alloc((void **)&s->h_dbg, 2 * N * sizeof(float));
+    if (bad) { spectrum_free(s); delete s; return fail(SDR_ERR_NOMEM, "sdr_spectrum_create: allocation failed"); }
+    std::vector<float2> tw(N);
+    for (size_t k = 0; k < N; ++k) {
+        double ang = -2.0 * 3.14159265358979323846 * (double)k / (double)N;
+        tw[k] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+    }
+    be_h2d(s->d_tw, tw.data(), N * sizeof(float2), e->stream);
+    be_memset(s->d_ema, 0, N * sizeof(double2), e->stream);                      // vectors resized to zeros (:252-264)
+    const double sc[4] = {100.0, 100.0, 0.0, 0.0};                                 // fft_ceil_ma/maa, fft_floor_ma/maa (:32-33)
+    be_h2d(s->d_scalars, sc, sizeof sc, e->stream);
+    be_sync(e->stream);
+    e->spectra.push_back(s);
+    *out = s;
+    return SDR_OK;
+}
+
+extern "C" int sdr_spectrum_destroy(sdr_spectrum *s) {
+    if (!s) return SDR_OK;
+    sdr_engine *e = s->eng;
+    std::lock_guard<std::mutex> lk(e->mu);
+    be_sync(e->stream);
+    e->spectra.erase(std::remove(e->spectra.begin(), e->spectra.end(), s), e->spectra.end());
+    spectrum_free(s);
+    delete s;
+    return SDR_OK;
+}
+
+extern "C" int sdr_spectrum_set_average_rate(sdr_spectrum *s, float r) {
+    if (!s) return fail(SDR_ERR_ARG, "null spectrum");
+    std::lock_guard<std::mutex> lk(s->eng->mu);
+    s->average_rate = r;
+    return SDR_OK;
+}
+
+// FFTDataDistributor::process restated for frames that are transformed immediately (src/process/FFTDataDistributor.cpp:
+// 41-53 reset on rate change, :89-97 line-rate step, :100-142 emit loop).  Returns frame starts relative to the block.
+static void schedule_frames(sdr_spectrum *s, unsigned n, long long sample_rate, std::vector<int> &starts) {
+    starts.clear();
+    if (s->last_rate != sample_rate) { s->buffered = 0; s->last_rate = sample_rate; }
+    const long long before = s->buffered, N = s->N;
+    s->buffered += n;
+    if (s->buffered < N) return;
+    if (s->lps == 0) {                                  // full coverage: every non-overlapping frame
+        long long i = 0;
+        for (; i + N <= s->buffered; i += N) starts.push_back((int)(i - before));
+        s->buffered -= i;
+        return;
+    }
+    const double inputTime = (double)s->buffered / (double)sample_rate;
+    const double inputLines = (double)s->buffered / (double)N;
+    const double step = ((double)s->lps * inputTime) / inputLines;
+    long long processed = 0;
+    if (s->line_accum + (step * ((double)s->buffered / (double)N)) < 1.0) {
+        s->line_accum += (step * ((double)s->buffered / (double)N));
+        processed = s->buffered;
+    } else {
+        for (long long i = 0; i < s->buffered; i += N) {
+            if (i + N > s->buffered) break;
+            s->line_accum += step;
+            if (s->line_accum >= 1.0) {
+                starts.push_back((int)(i - before));
+                while (s->line_accum >= 1.0) s->line_accum -= 1.0;
+            }
+            processed += N;
+        }
+    }
+    s->buffered -= processed;
+    if (s->buffered < 0) s->buffered = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// submit
+// ---------------------------------------------------------------------------------------------------------------------
+static int rebuild(sdr_engine *e) {
+    be_sync(e->stream);
+    size_t total = 0;
+    for (auto *c : e->chans) if (c) { c->cs.res_off = (long long)total; total += c->slot_bytes; }
+    if (total > e->results_bytes) {
+        be_free(e->d_results); be_host_free(e->h_results);
+        e->d_results = nullptr; e->h_results = nullptr;
+        if (be_malloc((void **)&e->d_results, total) || be_host_alloc((void **)&e->h_results, total))
+            return fail(SDR_ERR_NOMEM, "results buffer");
+        e->results_bytes = total;
+    }
+    for (auto *c : e->chans) if (c) be_h2d(e->d_cs + c->index, &c->cs, sizeof(ChanStatic), e->stream);
+    if (e->taps_host.size() > e->taps_uploaded) {
+        be_h2d(e->d_taps, e->taps_host.data(), e->taps_host.size() * sizeof(float), e->stream);
+        e->taps_uploaded = e->taps_host.size();
+    }
+    be_sync(e->stream);
+    e->dirty = false;
+    return SDR_OK;
+}
+
+static int submit_common(sdr_engine *e, const float2 *d_src, unsigned n, long long center, long long rate, bool to_host) {
+    if (e->dirty) { int r = rebuild(e); if (r) return r; }
+    float2 *blk = e->d_blk + e->hist_cap;
+    const int slot = (int)(e->ring_seq++ % sdr_engine::kRing);
+#ifndef SDR_EMU
+    CUDA_TRY(cudaEventSynchronize(e->ring_ev[slot]));      // the copies that last used this parameter slot are done
+#endif
+    ChanDyn *h_cd = e->h_cd + (size_t)slot * sdr_engine::kMaxChan;
+    int *h_group = e->h_group + (size_t)slot * sdr_engine::kMaxChan;
+    // 1. slide the wideband history so that blk[-h..-1] holds the last h samples of the stream so far
+    size_t need = kBlkHist;
+    for (auto *s : e->spectra) need = std::max(need, (size_t)s->N + 16);
+    if (need > e->hist_cap) need = e->hist_cap;
+    if (e->have_block && e->last_n > 0) {
+        const size_t h = need;
+        be_d2d(e->d_scratch, blk + (long long)e->last_n - (long long)h, h * sizeof(float2), e->stream);
+        be_d2d(blk - h, e->d_scratch, h * sizeof(float2), e->stream);
+    }
+    // 2. DC blocker (SDRPostThread.cpp:284) raw -> blk
+    DcArgs dc;
+    dc.x = d_src; dc.y = blk; dc.n = (int)n; dc.a = e->dc_a; dc.tile_sum = e->d_tile_sum; dc.tile_carry = e->d_tile_carry;
+    dc.state = e->d_dc_state; dc.apow = e->d_apow;
+    launch_dc(dc, e->stream, e->launches);
+    e->last_n = n; e->have_block = true;
+    e->results_on_host = to_host;
+
+    // 3. spectra
+    std::vector<int> starts;
+    for (auto *s : e->spectra) {
+        schedule_frames(s, n, rate, starts);
+        s->frames_last = (unsigned)std::min<size_t>(starts.size(), s->f_max);
+        if (!s->frames_last) continue;
+        int *h_fs = s->h_frame_start + (size_t)slot * s->f_max;
+        memcpy(h_fs, starts.data(), s->frames_last * sizeof(int));
+        be_h2d(s->d_frame_start, h_fs, s->frames_last * sizeof(int), e->stream);
+        SpecArgs a;
+        a.x = blk; a.frame_start = s->d_frame_start; a.F = (int)s->frames_last; a.N = (int)s->N; a.fft_size = (int)s->fft_size;
+        a.P = s->P; a.nsub = s->nsub; a.log_nsub = s->log_nsub; a.tw = s->d_tw; a.mags = s->d_mags; a.maa_f = s->d_maa; a.ema = s->d_ema;
+        a.rate = (double)s->average_rate; a.frame_cf = s->d_frame_cf; a.scalars = s->d_scalars; a.frame_cf_maa = s->d_frame_cf_maa;
+        a.points = s->d_points; a.lines = s->d_lines; a.scale_factor = s->scale_factor;
+        int r = launch_spectrum(a, e->stream, e->launches);
+        if (r) return r;
+        if (to_host) {
+            be_d2h(s->h_points, s->d_points, (size_t)s->frames_last * s->fft_size * sizeof(float), e->stream);
+            be_d2h(s->h_lines, s->d_lines, (size_t)s->frames_last * s->fft_size, e->stream);
+            be_d2h(s->h_cf, s->d_frame_cf_maa, (size_t)s->frames_last * sizeof(double2), e->stream);
+        }
+    }
+
+    // 4. channels: per-block oscillator bookkeeping (DemodulatorPreThread.cpp:154-163, 186-195)
+    int n_slots = (int)e->chans.size();
+    if (n_slots == 0) {
+#ifndef SDR_EMU
+        CUDA_TRY(cudaEventRecord(e->ring_ev[slot], e->stream));
+#endif
+        return SDR_OK;
+    }
+    std::vector<int> by_k[kFrontMaxK + 1];
+    for (int i = 0; i < n_slots; ++i) {
+        sdr_chan *c = e->chans[i];
+        ChanDyn &d = h_cd[i];
+        memset(&d, 0, sizeof d);
+        if (!c) continue;
+        d.valid = 1;
+        // a channel that sits this block out keeps the tail of the last block it consumed (its filters do not advance)
+        auto keep_tail = [&]() {
+            if (!c->priv_valid && c->consumed > 0) {
+                be_d2d(c->d_priv_hist, blk - kBlkHist, kBlkHist * sizeof(float2), e->stream);
+                c->priv_valid = true;
+            }
+        };
+        if (c->sample_rate != rate) { keep_tail(); continue; }                     // `inp->sampleRate == currentSampleRate` (:167)
+        const long long shift = c->frequency - center;
+        const long long lim = (long long)(int)((double)(rate / 2) * 1.5);
+        if (shift != c->shift_frequency) {
+            c->shift_frequency = shift;
+            if (std::llabs(shift) <= lim) c->dtheta = nco_phase_step(nco_shift_word_arg(shift, rate));
+        }
+        if (std::llabs(c->shift_frequency) > lim) { keep_tail(); continue; }   // block skipped for this channel (:161-164)
+        const int dir = c->shift_frequency < 0 ? +1 : (c->shift_frequency > 0 ? -1 : 0);
+        d.active = 1; d.g0 = c->consumed; d.theta0 = c->theta; d.dtheta = c->dtheta; d.dtheta_prev = c->dtheta_prev;
+        d.dir = dir; d.dir_prev = c->dir_prev;
+        d.hist = c->priv_valid ? c->d_priv_hist + kBlkHist : nullptr;
+        c->priv_valid = false;
+        if (dir) c->theta += (unsigned)n * c->dtheta;                   // mix_block advances the phase by n steps
+        c->dtheta_prev = c->dtheta; c->dir_prev = dir;
+        c->consumed += n;
+        by_k[c->cs.K1].push_back(i);
+    }
+    be_h2d(e->d_cd, h_cd, (size_t)n_slots * sizeof(ChanDyn), e->stream);
+    int goff = 0;
+    float h3[6];
+    halfband_branch_taps(3, 65.0f, h3);
+    for (int K = 0; K <= kFrontMaxK; ++K) {
+        const int cg = (int)by_k[K].size();
+        if (!cg) continue;
+        memcpy(h_group + goff, by_k[K].data(), cg * sizeof(int));
+        be_h2d(e->d_group + goff, h_group + goff, cg * sizeof(int), e->stream);
+        FrontArgs fa;
+        fa.x = blk; fa.n = (int)n; fa.nco = e->d_nco; fa.cs = e->d_cs; fa.cd = e->d_cd; fa.group = e->d_group + goff; fa.cg = cg;
+        const int n_chunks = (cg + 31) / 32;
+        const long long nq = ((long long)n >> K) + 1;
+        int n_span = (2368 + n_chunks - 1) / n_chunks;                  // ~16 warps on each of the 148 SMs
+        const long long min_span = (K == 0) ? 256 : 4 * kFrontWarm;
+        if ((long long)n_span * min_span > nq) n_span = (int)std::max<long long>(1, nq / min_span);
+        fa.n_span = n_span;
+        fa.span = (int)((nq + n_span - 1) / n_span);
+        fa.c0 = h3[0]; fa.c1 = h3[1]; fa.c2 = h3[2];
+        launch_front(K, fa, n_chunks * n_span, e->stream, e->launches);
+        goff += cg;
+    }
+    TailArgs ta;
+    ta.cs = e->d_cs; ta.cd = e->d_cd; ta.st = e->d_st; ta.taps = e->d_taps; ta.nco = e->d_nco;
+    ta.results = e->d_results; ta.n = (int)n;
+    // the tail indexes channels by slot; free slots carry valid = 0 and are not touched
+#ifndef SDR_EMU
+    CUDA_TRY(cudaEventRecord(e->ring_ev[slot], e->stream));
+#endif
+    launch_tail(ta, n_slots, e->stream, e->launches);
+    if (to_host && e->results_bytes) {
+        size_t total = 0;
+        for (auto *c : e->chans) if (c) total = std::max(total, (size_t)c->cs.res_off + c->slot_bytes);
+        be_d2h(e->h_results, e->d_results, total, e->stream);
+    }
+    return SDR_OK;
+}
+
+extern "C" int sdr_engine_submit(sdr_engine *e, const sdr_cf32 *iq, unsigned n, long long center, long long rate) {
+    if (!e || !iq) return fail(SDR_ERR_ARG, "sdr_engine_submit: null argument");
+    if (n == 0 || n > e->max_block) return fail(SDR_ERR_ARG, "sdr_engine_submit: block size out of range");
+    std::lock_guard<std::mutex> lk(e->mu);
+    // the pinned staging buffer is reused every block: wait for the previous block's H2D before overwriting it
+    be_sync(e->stream);
+    memcpy(e->h_stage, iq, (size_t)n * sizeof(sdr_cf32));
+    be_h2d(e->d_raw, e->h_stage, (size_t)n * sizeof(sdr_cf32), e->stream);
+    return submit_common(e, e->d_raw, n, center, rate, true);
+}
+
+extern "C" int sdr_engine_submit_device(sdr_engine *e, const void *d_iq, unsigned n, long long center, long long rate, int to_host) {
+    if (!e || !d_iq) return fail(SDR_ERR_ARG, "sdr_engine_submit_device: null argument");
+    if (n == 0 || n > e->max_block) return fail(SDR_ERR_ARG, "sdr_engine_submit_device: block size out of range");
+    std::lock_guard<std::mutex> lk(e->mu);
+    return submit_common(e, (const float2 *)d_iq, n, center, rate, to_host != 0);
+}
+
+extern "C" int sdr_engine_wait(sdr_engine *e) {
+    if (!e) return fail(SDR_ERR_ARG, "null engine");
+    if (be_sync(e->stream)) return fail(SDR_ERR_CUDA, std::string("stream sync failed: ") + be_last_error());
+#ifndef SDR_EMU
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(SDR_ERR_CUDA, std::string("kernel error: ") + cudaGetErrorString(err));
+#endif
+    return SDR_OK;
+}
+
+extern "C" int sdr_engine_fetch_block(sdr_engine *e, sdr_cf32 *out, unsigned cap, unsigned *n) {
+    if (!e || !out) return fail(SDR_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(e->mu);
+    unsigned m = std::min(cap, e->last_n);
+    be_d2h(out, e->d_blk + e->hist_cap, (size_t)m * sizeof(sdr_cf32), e->stream);
+    be_sync(e->stream);
+    if (n) *n = m;
+    return SDR_OK;
+}
+
+extern "C" int sdr_chan_fetch_audio(sdr_chan *c, float *audio, unsigned cap, unsigned *n_audio, double *level_db, float *peak, int *skipped) {
+    if (!c) return fail(SDR_ERR_ARG, "null channel");
+    sdr_engine *e = c->eng;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!e->results_on_host || !e->h_results) return fail(SDR_ERR_STATE, "no host results for the last block");
+    const unsigned char *slot = e->h_results + c->cs.res_off;
+    const ChanResultHeader *h = reinterpret_cast<const ChanResultHeader *>(slot);
+    unsigned m = std::min(cap, std::min(h->n_audio, (unsigned)c->cs.res_audio_cap));
+    if (audio) memcpy(audio, slot + 32, (size_t)m * sizeof(float));
+    if (n_audio) *n_audio = h->n_audio;
+    if (level_db) *level_db = h->level_db;
+    if (peak) *peak = h->peak;
+    if (skipped) *skipped = h->skipped;
+    return SDR_OK;
+}
+
+extern "C" int sdr_chan_fetch_iq(sdr_chan *c, sdr_cf32 *iq, unsigned cap, unsigned *n_iq) {
+    if (!c) return fail(SDR_ERR_ARG, "null channel");
+    sdr_engine *e = c->eng;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!e->results_on_host || !e->h_results) return fail(SDR_ERR_STATE, "no host results for the last block");
+    if (!c->cs.want_iq) return fail(SDR_ERR_STATE, "sdr_chan_want_iq was not enabled");
+    const unsigned char *slot = e->h_results + c->cs.res_off;
+    const ChanResultHeader *h = reinterpret_cast<const ChanResultHeader *>(slot);
+    unsigned m = std::min(cap, std::min(h->n_iq, (unsigned)c->cs.res_iq_cap));
+    if (iq) memcpy(iq, slot + 32 + (size_t)c->cs.res_audio_cap * 4, (size_t)m * sizeof(sdr_cf32));
+    if (n_iq) *n_iq = h->n_iq;
+    return SDR_OK;
+}
+
+extern "C" int sdr_spectrum_frames(sdr_spectrum *s, unsigned *n) {
+    if (!s || !n) return fail(SDR_ERR_ARG, "null argument");
+    *n = s->frames_last;
+    return SDR_OK;
+}
+
+extern "C" int sdr_spectrum_fetch(sdr_spectrum *s, unsigned idx, float *points_y, uint8_t *line, double *cf) {
+    if (!s) return fail(SDR_ERR_ARG, "null spectrum");
+    std::lock_guard<std::mutex> lk(s->eng->mu);
+    if (idx >= s->frames_last) return fail(SDR_ERR_ARG, "frame index out of range");
+    if (!s->eng->results_on_host) return fail(SDR_ERR_STATE, "no host results for the last block");
+    if (points_y) memcpy(points_y, s->h_points + (size_t)idx * s->fft_size, s->fft_size * sizeof(float));
+    if (line) memcpy(line, s->h_lines + (size_t)idx * s->fft_size, s->fft_size);
+    if (cf) { cf[0] = s->h_cf[idx].x; cf[1] = s->h_cf[idx].y; }
+    return SDR_OK;
+}
+
+extern "C" int sdr_spectrum_fetch_debug(sdr_spectrum *s, unsigned idx, float *mags, float *maa) {
+    if (!s) return fail(SDR_ERR_ARG, "null spectrum");
+    std::lock_guard<std::mutex> lk(s->eng->mu);
+    if (idx >= s->frames_last) return fail(SDR_ERR_ARG, "frame index out of range");
+    be_d2h(s->h_dbg, s->d_mags + (size_t)idx * s->N, s->N * sizeof(float), s->eng->stream);
+    be_d2h(s->h_dbg + s->N, s->d_maa + (size_t)idx * s->N, s->N * sizeof(float), s->eng->stream);
+    be_sync(s->eng->stream);
+    if (mags) memcpy(mags, s->h_dbg, s->N * sizeof(float));
+    if (maa) memcpy(maa, s->h_dbg + s->N, s->N * sizeof(float));
+    return SDR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// design introspection
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int sdr_design_kaiser(unsigned n, float fc, float as_db, float mu, float *h) { if (!h) return SDR_ERR_ARG; kaiser_lowpass(n, fc, as_db, mu, h); return SDR_OK; }
+extern "C" int sdr_design_nco_table(float *t) { if (!t) return SDR_ERR_ARG; nco_sine_table(t); return SDR_OK; }
+extern "C" uint32_t sdr_design_nco_step(float d) { return nco_phase_step(d); }
+extern "C" int sdr_design_resampler(float rate, float as_db, int *interp, int *S, float *ra, uint32_t *step, float *pfb, int *m) {
+    ResamplerPlan p = make_resampler_plan(rate, as_db);
+    if (interp) *interp = p.interp; if (S) *S = p.num_halfband; if (ra) *ra = p.rate_arb; if (step) *step = p.arb_step;
+    if (pfb) memcpy(pfb, p.pfb.data(), p.pfb.size() * sizeof(float));
+    if (m) for (int i = 0; i < p.num_halfband && i < 16; ++i) m[i] = p.hb.m[i];
+    return SDR_OK;
+}
+extern "C" int sdr_design_halfband_branch(int m, float as_db, float *h1) { return (h1 && halfband_branch_taps(m, as_db + 5.0f, h1)) ? SDR_OK : SDR_ERR_UNSUPPORTED; }
+extern "C" int sdr_design_am_dc_block(float *h) { if (!h) return SDR_ERR_ARG; am_dc_block_taps(25, 30.0f, h); return SDR_OK; }
+extern "C" int sdr_design_hilbert_q(float *hq) { if (!hq) return SDR_ERR_ARG; hilbert_quadrature_taps(5, 90.0f, hq); return SDR_OK; }
+extern "C" int sdr_design_butter6_sos(float *o) {
+    if (!o) return SDR_ERR_ARG;
+    std::vector<Sos> s; butterworth_lowpass_sos(6, 0.25f, s);
+    for (int i = 0; i < 3; ++i) { memcpy(o + 6 * i, s[i].b, 12); memcpy(o + 6 * i + 3, s[i].a, 12); }
+    return SDR_OK;
+}

@@ -1,0 +1,105 @@
+/* include/sdr_b200.h -- C-ABI of the B200 SDR DSP engine (libsdr_b200.so).
+ *
+ * Drop-in boundary for CubicSDR's spectrum + demodulator hot path.  The reference has no FFI on this path; its
+ * host code speaks liquid-dsp's C API (opaque handle, create / execute / destroy, int status, caller-owned arrays,
+ * "num written" out-parameters).  This ABI keeps that shape, so the three in-process seams of the reference can
+ * bind to it with a few lines each (INTEGRATION.md shows the bindings).  File:line citations are relative to
+ * /root/reference/.
+ *
+ * Threading: calls on one engine are serialised internally; different engines are independent.
+ * Errors: every function returns 0 on success, a negative sdr_status otherwise; sdr_last_error() gives text.
+ * All sample data is float32, complex = interleaved {re, im} (liquid_float_complex, liquid.h:153).
+ */
+#ifndef SDR_B200_H
+#define SDR_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sdr_engine sdr_engine;       /* one per GPU: owns streams, the wideband block buffer, all channels */
+typedef struct sdr_chan sdr_chan;           /* one demodulator channel (DemodulatorPreThread + Modem + metering)  */
+typedef struct sdr_spectrum sdr_spectrum;   /* one SpectrumVisualProcessor-equivalent                              */
+typedef struct { float re, im; } sdr_cf32;
+
+enum sdr_status {
+    SDR_OK = 0, SDR_ERR_ARG = -1, SDR_ERR_CUDA = -2, SDR_ERR_NOMEM = -3, SDR_ERR_STATE = -4, SDR_ERR_UNSUPPORTED = -5
+};
+
+const char *sdr_last_error(void);
+const char *sdr_version(void);
+/* 1 when the library was built for the GPU (always, for libsdr_b200.so); the test-only emulator reports 0 */
+int sdr_is_device_build(void);
+
+/* ---- engine ------------------------------------------------------------------------------------------------------ */
+/* device: CUDA ordinal.  max_block: largest block (complex samples) sdr_engine_submit will accept.
+ * stream: a cudaStream_t to run on (as void*), or NULL to create one.                                              */
+int sdr_engine_create(int device, unsigned max_block, void *stream, sdr_engine **out);
+int sdr_engine_destroy(sdr_engine *eng);
+
+/* Replaces SDRPostThread::runSingleCH (src/sdr/SDRPostThread.cpp:248-299): takes one block of raw IQ, applies the
+ * DC blocker (:284), and runs every attached spectrum and channel on it.  Asynchronous: returns once the work is
+ * enqueued; results are fetched per channel / spectrum after sdr_engine_wait().  center_freq / sample_rate are the
+ * SDRThreadIQData fields (src/sdr/SoapySDRThread.h:20-39).  iq is host memory.                                    */
+int sdr_engine_submit(sdr_engine *eng, const sdr_cf32 *iq, unsigned n, long long center_freq, long long sample_rate);
+/* Same, for a block that already lives in this GPU's memory (e.g. after an NCCL broadcast).  No host copy is made;
+ * with fetch_to_host = 0 results stay in device memory (throughput measurement), otherwise they are copied back.  */
+int sdr_engine_submit_device(sdr_engine *eng, const void *d_iq, unsigned n, long long center_freq, long long sample_rate,
+                             int fetch_to_host);
+int sdr_engine_wait(sdr_engine *eng);
+/* DC-blocked block of the last submit (what runSingleCH pushes to the visual queues / demod pipes), host copy.    */
+int sdr_engine_fetch_block(sdr_engine *eng, sdr_cf32 *out, unsigned cap, unsigned *n);
+/* kernel launches issued by this engine so far (bench.py's gpu_launches) */
+unsigned long long sdr_engine_launch_count(sdr_engine *eng);
+
+/* ---- channel: DemodulatorPreThread + Modem + DemodulatorThread metering --------------------------------------------- */
+/* modem: "FM" "NBFM" "AM" "USB" "LSB" (Modem::addModemFactory names, src/CubicSDR.cpp:305-311).
+ * bandwidth is passed through Modem::checkSampleRate (ModemAnalog.cpp:14-19, ModemUSB.cpp:29-37).
+ * Builds what DemodulatorWorkerThread builds (src/demod/DemodulatorWorkerThread.cpp:63-101): msresamp_crcf(bw/fs, 60),
+ * the modem, and its kit msresamp_rrrf(audio_rate/bw, 60) (ModemAnalog.cpp:21-33).                                  */
+int sdr_chan_create(sdr_engine *eng, const char *modem, long long sample_rate, long long bandwidth, int audio_rate,
+                    sdr_chan **out);
+int sdr_chan_destroy(sdr_chan *ch);
+/* Demodulator frequency (absolute, Hz).  Shift = frequency - block centre is applied per block exactly as
+ * DemodulatorPreThread.cpp:154-163 does, including abs(), the up/down choice and the 0.75 fs skip rule.            */
+int sdr_chan_set_frequency(sdr_chan *ch, long long frequency);
+int sdr_chan_get_bandwidth(sdr_chan *ch, int *bandwidth);
+/* also return the decimated IQ of each block (DemodulatorThreadPostIQData::data, src/demod/DemodDefs.h:43-59) */
+int sdr_chan_want_iq(sdr_chan *ch, int enable);
+/* Results of the last submitted block (after sdr_engine_wait): audio = AudioThreadInput::data
+ * (src/audio/AudioThread.h:16-51), level_db = DemodulatorThread.cpp:142-163, peak = :223-233.  skipped = 1 when the
+ * 0.75 fs rule dropped the block for this channel.                                                                */
+int sdr_chan_fetch_audio(sdr_chan *ch, float *audio, unsigned cap, unsigned *n_audio, double *level_db, float *peak,
+                         int *skipped);
+int sdr_chan_fetch_iq(sdr_chan *ch, sdr_cf32 *iq, unsigned cap, unsigned *n_iq);
+
+/* ---- spectrum: FFTDataDistributor framing + SpectrumVisualProcessor + WaterfallPanel::step --------------------------- */
+/* fft_size: display points (SpectrumVisualProcessor::setup, :140-178); the transform is 2 * fft_size.
+ * lines_per_second: FFTDataDistributor::setLinesPerSecond; 0 = transform every non-overlapping frame.             */
+int sdr_spectrum_create(sdr_engine *eng, unsigned fft_size, unsigned lines_per_second, sdr_spectrum **out);
+int sdr_spectrum_destroy(sdr_spectrum *sp);
+int sdr_spectrum_set_average_rate(sdr_spectrum *sp, float rate);      /* setFFTAverageRate, default 0.65 (:36) */
+/* frames produced by the last submitted block */
+int sdr_spectrum_frames(sdr_spectrum *sp, unsigned *n_frames);
+/* frame `idx` of the last block: points_y = SpectrumVisualData::spectrum_points y values (fft_size floats),
+ * line = the u8 waterfall line, ceil_floor = {fft_ceil_maa, fft_floor_maa}.  Any pointer may be NULL.            */
+int sdr_spectrum_fetch(sdr_spectrum *sp, unsigned idx, float *points_y, uint8_t *line, double *ceil_floor);
+/* diagnostics for parity tests: linear fftshifted magnitudes and float(maa) of frame idx (2 * fft_size floats each) */
+int sdr_spectrum_fetch_debug(sdr_spectrum *sp, unsigned idx, float *mags, float *maa);
+
+/* ---- design introspection (host only; used by the tests to pin filter tables against the reference) ---------------- */
+int sdr_design_kaiser(unsigned n, float fc, float as_db, float mu, float *h);
+int sdr_design_nco_table(float *sintab1024);
+uint32_t sdr_design_nco_step(float dtheta);
+/* plan of msresamp_{crcf,rrrf}_create(rate, as_db): outputs may be NULL.  pfb: [256*14] floats.  m: [16] ints. */
+int sdr_design_resampler(float rate, float as_db, int *interp, int *num_halfband, float *rate_arb, uint32_t *arb_step,
+                         float *pfb, int *m);
+int sdr_design_halfband_branch(int m, float as_db, float *h1 /* 2m */);
+int sdr_design_am_dc_block(float *h51);
+int sdr_design_hilbert_q(float *hq10);
+int sdr_design_butter6_sos(float *sos18 /* 3 x {b0,b1,b2,a0,a1,a2} */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,156 @@
+"""oracle/refbind.py -- ctypes binding of oracle/_ref/libsdr_ref.so.  TEST INFRASTRUCTURE ONLY.
+
+The library is the reference's own liquid-dsp 1.5.0 binary plus the CubicSDR glue restated in oracle/ref_chain.cpp
+(see oracle/build_ref.py).  Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_LIB = os.path.join(_HERE, "_ref", "libsdr_ref.so")
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Ref:
+    def __init__(self, path=REF_LIB):
+        if not os.path.exists(path):
+            import subprocess, sys
+            subprocess.check_call([sys.executable, os.path.join(_HERE, "build_ref.py")])
+        L = self.L = C.CDLL(path)
+        vp, u, i, ll, f, d = C.c_void_p, C.c_uint, C.c_int, C.c_longlong, C.c_float, C.c_double
+        L.ref_libversion.restype = C.c_char_p
+        for name in ("ref_nco_create", "ref_ingress_create"):
+            getattr(L, name).restype = vp
+        L.ref_estimate_req_filter_len.restype = u; L.ref_estimate_req_filter_len.argtypes = [f, f]
+        L.ref_kaiser_beta_As.restype = f; L.ref_kaiser_beta_As.argtypes = [f]
+        L.ref_firdespm_halfband_as.argtypes = [u, f, vp]
+        L.ref_firdes_kaiser.argtypes = [u, f, f, f, vp]
+        L.ref_nco_destroy.argtypes = [vp]
+        L.ref_nco_set_frequency.argtypes = [vp, f]
+        L.ref_nco_raw_dtheta.restype = C.c_uint32; L.ref_nco_raw_dtheta.argtypes = [vp]
+        L.ref_nco_raw_theta.restype = C.c_uint32; L.ref_nco_raw_theta.argtypes = [vp]
+        L.ref_nco_sintab.argtypes = [vp, vp]
+        L.ref_nco_mix_block.argtypes = [vp, i, vp, vp, u]
+        L.ref_resamp_crcf_create.restype = vp; L.ref_resamp_crcf_create.argtypes = [f, u, f, f, u]
+        L.ref_resamp_crcf_destroy.argtypes = [vp]
+        L.ref_resamp_crcf_execute_block.restype = u; L.ref_resamp_crcf_execute_block.argtypes = [vp, vp, u, vp]
+        L.ref_msresamp_crcf_create.restype = vp; L.ref_msresamp_crcf_create.argtypes = [f, f]
+        L.ref_msresamp_crcf_destroy.argtypes = [vp]
+        L.ref_msresamp_crcf_execute.restype = u; L.ref_msresamp_crcf_execute.argtypes = [vp, vp, u, vp]
+        L.ref_msresamp_rrrf_create.restype = vp; L.ref_msresamp_rrrf_create.argtypes = [f, f]
+        L.ref_msresamp_rrrf_destroy.argtypes = [vp]
+        L.ref_msresamp_rrrf_execute.restype = u; L.ref_msresamp_rrrf_execute.argtypes = [vp, vp, u, vp]
+        L.ref_firfilt_dc_blocker_create.restype = vp; L.ref_firfilt_dc_blocker_create.argtypes = [u, f]
+        L.ref_firfilt_destroy.argtypes = [vp]
+        L.ref_firfilt_block.argtypes = [vp, vp, u, vp]
+        L.ref_iirfilt_lowpass_create.restype = vp; L.ref_iirfilt_lowpass_create.argtypes = [u, f]
+        L.ref_iirfilt_destroy.argtypes = [vp]
+        L.ref_iirfilt_block.argtypes = [vp, vp, u, vp]
+        L.ref_firhilb_create.restype = vp; L.ref_firhilb_create.argtypes = [u, f]
+        L.ref_firhilb_destroy.argtypes = [vp]
+        L.ref_firhilb_c2r_block.argtypes = [vp, vp, u, vp, vp]
+        L.ref_fft_forward.argtypes = [vp, vp, u]
+        L.ref_ingress_destroy.argtypes = [vp]
+        L.ref_ingress_block.argtypes = [vp, vp, u, vp]
+        L.ref_modem_check_sample_rate.argtypes = [C.c_char_p, ll]
+        L.ref_chan_create.restype = vp; L.ref_chan_create.argtypes = [C.c_char_p, ll, ll, i]
+        L.ref_chan_destroy.argtypes = [vp]
+        L.ref_chan_bandwidth.argtypes = [vp]
+        L.ref_chan_process.argtypes = [vp, vp, u, ll, vp, vp, vp, vp, vp, vp, vp]
+        L.ref_distrib_create.restype = vp; L.ref_distrib_create.argtypes = [u, u]
+        L.ref_distrib_destroy.argtypes = [vp]
+        L.ref_distrib_push.restype = u; L.ref_distrib_push.argtypes = [vp, vp, u, ll, vp, u]
+        L.ref_spectrum_create.restype = vp; L.ref_spectrum_create.argtypes = [u]
+        L.ref_spectrum_destroy.argtypes = [vp]
+        L.ref_spectrum_set_average_rate.argtypes = [vp, f]
+        L.ref_spectrum_frame.argtypes = [vp, vp, u, vp, vp, vp, vp, vp]
+        L.ref_bench_path.restype = d
+        L.ref_bench_path.argtypes = [vp, u, u, ll, u, vp, vp, vp, i, u, u, vp]
+
+    def version(self):
+        return self.L.ref_libversion().decode()
+
+
+class RefIngress:
+    """SDRPostThread::runSingleCH DC blocker (src/sdr/SDRPostThread.cpp:29,284)."""
+
+    def __init__(self, ref):
+        self.ref = ref
+        self.h = C.c_void_p(ref.L.ref_ingress_create())
+
+    def block(self, x):
+        x = np.ascontiguousarray(x, np.complex64)
+        y = np.zeros_like(x)
+        self.ref.L.ref_ingress_block(self.h, _p(x), x.size, _p(y))
+        return y
+
+    def close(self):
+        self.ref.L.ref_ingress_destroy(self.h)
+
+
+class RefChan:
+    """DemodulatorPreThread + Modem + DemodulatorThread metering for one channel (see ref_chain.cpp)."""
+
+    def __init__(self, ref, modem, sample_rate, bandwidth, audio_rate=48000):
+        self.ref = ref
+        self.h = C.c_void_p(ref.L.ref_chan_create(modem.encode(), int(sample_rate), int(bandwidth), int(audio_rate)))
+        assert self.h.value
+        self.bandwidth = ref.L.ref_chan_bandwidth(self.h)
+        self.sample_rate, self.audio_rate = sample_rate, audio_rate
+
+    def process(self, block, shift):
+        block = np.ascontiguousarray(block, np.complex64)
+        n = block.size
+        cap_iq = int(n * self.bandwidth / self.sample_rate) + 1024
+        cap_a = int(n * self.audio_rate / self.sample_rate) + 2048
+        iq = np.zeros(cap_iq, np.complex64); dm = np.zeros(cap_iq, np.float32); au = np.zeros(cap_a, np.float32)
+        niq, na, lvl, pk = C.c_uint(), C.c_uint(), C.c_double(), C.c_float()
+        skipped = self.ref.L.ref_chan_process(self.h, _p(block), n, int(shift), _p(iq), C.byref(niq), _p(dm), _p(au), C.byref(na),
+                                              C.byref(lvl), C.byref(pk))
+        return dict(skipped=bool(skipped), iq=iq[:niq.value].copy(), demod=dm[:niq.value].copy(), audio=au[:na.value].copy(),
+                    level_db=lvl.value, peak=pk.value)
+
+    def close(self):
+        self.ref.L.ref_chan_destroy(self.h)
+
+
+class RefDistrib:
+    """FFTDataDistributor (src/process/FFTDataDistributor.cpp:28-144)."""
+
+    def __init__(self, ref, frame_len, lps):
+        self.ref, self.n = ref, frame_len
+        self.h = C.c_void_p(ref.L.ref_distrib_create(frame_len, lps))
+
+    def push(self, block, sample_rate):
+        block = np.ascontiguousarray(block, np.complex64)
+        cap = block.size // self.n + 4
+        out = np.zeros(cap * self.n, np.complex64)
+        nf = self.ref.L.ref_distrib_push(self.h, _p(block), block.size, int(sample_rate), _p(out), cap)
+        return out[:nf * self.n].reshape(nf, self.n)
+
+    def close(self):
+        self.ref.L.ref_distrib_destroy(self.h)
+
+
+class RefSpectrum:
+    """SpectrumVisualProcessor non-view branch + WaterfallPanel::step."""
+
+    def __init__(self, ref, fft_size):
+        self.ref, self.fft_size = ref, fft_size
+        self.h = C.c_void_p(ref.L.ref_spectrum_create(fft_size))
+
+    def frame(self, frame):
+        frame = np.ascontiguousarray(frame, np.complex64)
+        N = 2 * self.fft_size
+        pts = np.zeros(self.fft_size, np.float32); line = np.zeros(self.fft_size, np.uint8)
+        res = np.zeros(N, np.float64); maa = np.zeros(N, np.float64); cf = np.zeros(2, np.float64)
+        self.ref.L.ref_spectrum_frame(self.h, _p(frame), frame.size, _p(pts), _p(line), _p(res), _p(maa), _p(cf))
+        return dict(points=pts, line=line, fft_result=res, maa=maa, ceil_floor=cf)
+
+    def close(self):
+        self.ref.L.ref_spectrum_destroy(self.h)

@@ -1,0 +1,128 @@
+"""Parity harness shared by the emulator tier (no GPU) and the GPU tier.
+
+Both tiers drive the engine through the C-ABI binding (cubicsdr_b200._capi) and compare with the oracle
+(oracle/refbind.py: the reference's own liquid-dsp binary + CubicSDR glue) on identical seeded inputs.
+"""
+import numpy as np
+
+from cubicsdr_b200 import synth
+from cubicsdr_b200._capi import Channel, Engine, Spectrum
+from oracle.refbind import RefChan, RefDistrib, RefIngress, RefSpectrum
+
+# north_star tolerance: 1e-5 relative RMS on audio and spectrum magnitudes
+TOL = 1e-5
+CENTER = 100_000_000
+
+
+def relrms(a, b):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    dt = np.complex128 if (a.dtype.kind == "c" or b.dtype.kind == "c") else np.float64
+    a = a.astype(dt)
+    b = b.astype(dt)
+    nb = np.linalg.norm(b)
+    return float(np.linalg.norm(a - b) / nb) if nb > 0 else float(np.linalg.norm(a))
+
+
+def run_channels(lib, ref, fs, chans, n_blocks, block=None, seed=1234, device=0, want_iq=True, retune=None, signal=None):
+    """Stream n_blocks through engine and oracle.  chans: [(modem, bw, offset_hz)].
+    Returns per-channel dict with concatenated audio / iq of both sides and per-block count equality."""
+    N = block or synth.block_size(fs)
+    eng = Engine(lib, device=device, max_block=N)
+    cs = [Channel(eng, m, fs, bw, 48000, frequency=CENTER + off, want_iq=want_iq) for m, bw, off in chans]
+    rcs = [RefChan(ref, m, fs, bw) for m, bw, off in chans]
+    ing = RefIngress(ref)
+    out = [dict(modem=m, audio=[], ref_audio=[], iq=[], ref_iq=[], counts_ok=True, lvl=[], ref_lvl=[], peak=[], ref_peak=[],
+                skipped=[], ref_skipped=[]) for m, _, _ in chans]
+    dc_err = []
+    offs = [off for _, _, off in chans]
+    for b in range(n_blocks):
+        if retune and b in retune:
+            for i, new_off in retune[b].items():
+                offs[i] = new_off
+                cs[i].set_frequency(CENTER + new_off)
+        x = synth.wideband(fs, N, signal if signal is not None else chans, seed=seed, t0=b * N)
+        eng.submit(x, CENTER, fs)
+        eng.wait()
+        y = ing.block(x)
+        dc_err.append(relrms(eng.fetch_block(N), y))
+        for i, (c, rc) in enumerate(zip(cs, rcs)):
+            r = rc.process(y, offs[i])
+            a, lvl, pk, sk = c.fetch_audio()
+            o = out[i]
+            o["skipped"].append(sk); o["ref_skipped"].append(r["skipped"])
+            if len(a) != len(r["audio"]):
+                o["counts_ok"] = False
+            o["audio"].append(a); o["ref_audio"].append(r["audio"])
+            if want_iq and not sk:
+                q = c.fetch_iq()
+                if len(q) != len(r["iq"]):
+                    o["counts_ok"] = False
+                o["iq"].append(q); o["ref_iq"].append(r["iq"])
+            o["lvl"].append(lvl); o["ref_lvl"].append(r["level_db"]); o["peak"].append(pk); o["ref_peak"].append(r["peak"])
+    for o in out:
+        for k in ("audio", "ref_audio", "iq", "ref_iq"):
+            o[k] = np.concatenate(o[k]) if len(o[k]) else np.zeros(0)
+    for c in cs:
+        c.close()
+    for rc in rcs:
+        rc.close()
+    ing.close()
+    launches = eng.launch_count
+    eng.close()
+    return out, dc_err, launches
+
+
+def check_channels(out, tol=TOL):
+    for o in out:
+        assert o["counts_ok"], "%s: per-block sample counts differ from the reference" % o["modem"]
+        assert o["skipped"] == o["ref_skipped"], "%s: skip rule differs" % o["modem"]
+        if len(o["ref_audio"]):
+            e = relrms(o["audio"], o["ref_audio"])
+            assert e <= tol, "%s: audio relative RMS error %.3g > %.1g" % (o["modem"], e, tol)
+        if len(o["ref_iq"]):
+            e = relrms(o["iq"], o["ref_iq"])
+            assert e <= tol, "%s: decimated IQ relative RMS error %.3g > %.1g" % (o["modem"], e, tol)
+        assert np.allclose(o["lvl"], o["ref_lvl"], atol=2e-3), "%s: level metering differs" % o["modem"]
+        assert np.allclose(o["peak"], o["ref_peak"], rtol=1e-4, atol=1e-6), "%s: peak differs" % o["modem"]
+
+
+def run_spectrum(lib, ref, fs, fft_size, n_blocks, chans, lps=0, block=None, seed=1234, device=0):
+    """Returns worst-case errors over all frames: magnitudes, maa, points, ceil/floor, u8 mismatch fraction."""
+    N = block or synth.block_size(fs)
+    eng = Engine(lib, device=device, max_block=N)
+    sp = Spectrum(eng, fft_size, lps)
+    ing = RefIngress(ref)
+    rsp = RefSpectrum(ref, fft_size)
+    rd = RefDistrib(ref, 2 * fft_size, lps if lps else 100000000)
+    worst = dict(mags=0.0, maa=0.0, points=0.0, cf=0.0)
+    n_frames = 0
+    u8_bad = 0
+    u8_bad_far = 0
+    for b in range(n_blocks):
+        x = synth.wideband(fs, N, chans, seed=seed, t0=b * N)
+        eng.submit(x, CENTER, fs)
+        eng.wait()
+        frames = rd.push(ing.block(x), fs)
+        assert sp.frames == len(frames), "frame count %d vs reference %d in block %d" % (sp.frames, len(frames), b)
+        for f in range(sp.frames):
+            r = rsp.frame(frames[f])
+            pts, line, cf = sp.fetch(f)
+            mags, maa = sp.fetch_debug(f)
+            worst["mags"] = max(worst["mags"], relrms(mags, r["fft_result"]))
+            worst["maa"] = max(worst["maa"], relrms(maa, r["maa"]))
+            worst["points"] = max(worst["points"], relrms(pts, r["points"]))
+            worst["cf"] = max(worst["cf"], float(np.abs(cf - r["ceil_floor"]).max() / np.abs(r["ceil_floor"]).max()))
+            bad = line.astype(np.int32) != r["line"].astype(np.int32)
+            u8_bad += int(bad.sum())
+            # a mismatch only counts as "far" if the reference's float is not next to a quantisation edge
+            v = np.clip(r["points"].astype(np.float64), 0, 0.99) * 255.0
+            near_edge = np.abs(v - np.round(v)) < 255.0 * 1e-4
+            u8_bad_far += int((bad & ~near_edge).sum())
+            n_frames += 1
+    sp.close(); rsp.close(); rd.close(); ing.close(); eng.close()
+    worst["frames"] = n_frames
+    worst["u8_bad"] = u8_bad
+    worst["u8_bad_far"] = u8_bad_far
+    worst["u8_total"] = n_frames * fft_size
+    return worst

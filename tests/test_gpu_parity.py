@@ -1,0 +1,107 @@
+"""GPU tier: the CUDA path (through the C-ABI) against the oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+from cubicsdr_b200 import synth
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+FIVE = [("FM", 200000, 300000), ("NBFM", 12500, -150000), ("AM", 6000, 450000), ("USB", 5400, -600000), ("LSB", 5400, 750000)]
+
+
+def test_cfg1_wbfm(gpu_lib, ref):
+    """configs[0]: 1x WBFM, 2.4 MSps, 200 kHz -> 48 kHz audio."""
+    out, dc_err, launches = parity.run_channels(gpu_lib, ref, 2400000, synth.channel_plan("wbfm1", 2400000, 1), n_blocks=12)
+    parity.check_channels(out)
+    assert launches > 0
+
+
+def test_five_modems(gpu_lib, ref):
+    out, dc_err, _ = parity.run_channels(gpu_lib, ref, 2400000, FIVE, n_blocks=6)
+    assert max(dc_err) <= parity.TOL
+    parity.check_channels(out)
+
+
+def test_ragged_blocks_and_carry(gpu_lib, ref):
+    out, _, _ = parity.run_channels(gpu_lib, ref, 2400000, FIVE[:3], n_blocks=5, block=40003)
+    parity.check_channels(out)
+    out, _, _ = parity.run_channels(gpu_lib, ref, 2400000, [FIVE[0], FIVE[3]], n_blocks=12, block=4099)
+    parity.check_channels(out)
+
+
+def test_retune_zero_shift_and_skip_rule(gpu_lib, ref):
+    chans = [("FM", 200000, 300000), ("NBFM", 12500, 0), ("FM", 200000, -250000)]
+    signal = chans + [("FM", 200000, -620000), ("NBFM", 12500, 50000), ("FM", 200000, 850000), ("NBFM", 12500, -30000)]
+    retune = {2: {0: -620000}, 3: {2: 2000000}, 5: {2: 850000, 1: 50000}, 6: {1: -30000}}
+    out, _, _ = parity.run_channels(gpu_lib, ref, 2400000, chans, n_blocks=8, retune=retune, signal=signal)
+    parity.check_channels(out)
+    assert any(out[2]["skipped"])
+
+
+def test_cfg3_slice_nbfm_20msps(gpu_lib, ref):
+    """configs[2] shape (NBFM at 12.5 kHz spacing from 20 MSps, S = 10 half-band stages), 8 of the 64 channels."""
+    fs = 20000000
+    chans = synth.channel_plan("nbfm64", fs, 64)
+    sub = chans[::8]
+    out, _, _ = parity.run_channels(gpu_lib, ref, fs, sub, n_blocks=3, signal=chans)
+    parity.check_channels(out)
+
+
+def test_cfg4_slice_mixed_40msps(gpu_lib, ref):
+    """configs[3] shape: FM/AM/USB/LSB from 40 MSps (S = 7 / 12 / 12)."""
+    fs = 40000000
+    chans = synth.channel_plan("mixed", fs, 16)
+    out, _, _ = parity.run_channels(gpu_lib, ref, fs, chans[4:12], n_blocks=2, signal=chans)
+    parity.check_channels(out)
+
+
+def test_cfg2_spectrum_10msps(gpu_lib, ref):
+    """configs[1]: 8192-point spectrum + waterfall on 10 MSps."""
+    chans = synth.channel_plan("mixed", 10000000, 16)
+    w = parity.run_spectrum(gpu_lib, ref, 10000000, 8192, n_blocks=3, chans=chans)
+    assert w["frames"] >= 30
+    assert w["mags"] <= parity.TOL and w["maa"] <= parity.TOL and w["cf"] <= 1e-6
+    assert w["points"] <= 1e-4
+    assert w["u8_bad_far"] == 0 and w["u8_bad"] <= 0.005 * w["u8_total"]
+
+
+def test_cfg5_spectrum_16384_split_transform(gpu_lib, ref):
+    """configs[4] spectrum: 16384 points = 32768-point transform, two CTAs per frame."""
+    chans = synth.channel_plan("mixed", 10000000, 8)
+    w = parity.run_spectrum(gpu_lib, ref, 10000000, 16384, n_blocks=2, chans=chans)
+    assert w["frames"] >= 8 and w["mags"] <= parity.TOL and w["points"] <= 1e-4
+
+
+def test_line_limiter(gpu_lib, ref):
+    chans = synth.channel_plan("mixed", 2400000, 4)
+    w = parity.run_spectrum(gpu_lib, ref, 2400000, 512, n_blocks=6, chans=chans, lps=30)
+    assert 1 <= w["frames"] <= 6 and w["mags"] <= parity.TOL
+
+
+def test_block_partition_invariance_full_size(gpu_lib):
+    """Size-independent property at BASELINE size (61.44 MSps block): streaming the same samples as one block or as
+    three ragged pieces yields bit-identical audio (all state is carried exactly)."""
+    from cubicsdr_b200 import Channel, Engine
+    fs = 61440000
+    N = synth.block_size(fs)
+    chans = synth.channel_plan("mixed", fs, 8)
+    x = synth.wideband(fs, N, chans, t0=0)
+    res = []
+    for cuts in ([N], [333331, 400003, N - 333331 - 400003]):
+        eng = Engine(gpu_lib, max_block=N)
+        cs = [Channel(eng, m, fs, bw, 48000, frequency=parity.CENTER + off) for m, bw, off in chans]
+        audio = [[] for _ in cs]
+        p = 0
+        for c in cuts:
+            eng.submit(x[p:p + c], parity.CENTER, fs); eng.wait(); p += c
+            for i, ch in enumerate(cs):
+                audio[i].append(ch.fetch_audio()[0])
+        res.append([np.concatenate(a) for a in audio])
+        eng.close()
+    for a, b in zip(*res):
+        assert len(a) == len(b) and len(a) > 700
+        # FM is exactly partition-invariant; AM/SSB auto-gain is per block by definition, so compare FM only bit-exactly
+    for i, (m, _, _) in enumerate(chans):
+        if m == "FM":
+            assert np.array_equal(res[0][i], res[1][i])
