@@ -1,0 +1,361 @@
+#!/usr/bin/env python3
+"""bench.py -- IQ MSamples/s through the spectrum + demodulator chain (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg5|cfg3|cfg2] [--impl ours|reference]
+  N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A step = one reference-sized IQ block (fs/60 samples, SoapySDRThread.cpp:668-674) through the whole hot path:
+DC blocker -> spectrum FFT / EMA / waterfall line (rank 0) -> NCO mix + multi-stage decimation + demodulation + audio
+resampling for every channel of this rank.  Channels are sharded over the ranks (strong scaling: the job is fixed);
+when N > 1 the raw block is broadcast from rank 0 over NCCL inside the timed region.
+
+`value`   device-resident inputs (a ring of distinct blocks larger than L2), results left in HBM.
+`e2e`     the same through host buffers: pinned host block -> H2D -> (broadcast) -> kernels -> D2H -> batched audio fetch.
+`roofline` for the dominant kernel (channel front: oscillator mix + half-band cascade), timed with CUDA events on the
+           engine's stream inside the timed region.
+`cpu_baseline` / `--impl reference`: the reference's own liquid-dsp binary + CubicSDR glue (oracle/_ref) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+CENTER = 100_000_000
+WORKLOADS = {
+    # BASELINE.json configs[4] (the metric's own config: spectrum + demod chain), run as a fixed job sharded over N GPUs
+    "cfg5": dict(fs=61440000, plan="mixed", n_chan=512, fft=16384,
+                 desc="cfg5: 512 mixed FM/AM/USB/LSB demod channels + 16384-pt spectrum/waterfall on 61.44 MSps IQ"),
+    "cfg3": dict(fs=20000000, plan="nbfm64", n_chan=64, fft=0, desc="cfg3: 64 NBFM channels @12.5 kHz from 20 MSps IQ"),
+    "cfg2": dict(fs=10000000, plan="mixed", n_chan=0, fft=8192, desc="cfg2: 8192-pt spectrum FFT + waterfall on 10 MSps IQ"),
+}
+FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12    # non-tensor FP32 issue peak of a B200 at max clock
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+def torch_wideband(torch, fs, n, chans, t0, device, seed):
+    """GPU version of cubicsdr_b200.synth.wideband (same signal model, torch RNG): complex64 tensor [n]."""
+    t = (torch.arange(n, device=device, dtype=torch.float64) + float(t0)) / float(fs)
+    x = torch.zeros(n, device=device, dtype=torch.complex128)
+    amp = 0.5 / max(1.0, np.sqrt(len(chans)) * 1.5) if chans else 0.0
+    two_pi = 2.0 * np.pi
+    for k, (modem, bw, off) in enumerate(chans):
+        tone = 1000.0 + (400.0 if (k & 1) else 0.0)
+        if modem in ("FM", "NBFM"):
+            dev = 75000.0 if modem == "FM" else 2500.0
+            ph = two_pi * off * t + (dev / tone) * torch.sin(two_pi * tone * t)
+            x += amp * torch.polar(torch.ones_like(ph), ph)
+        elif modem == "AM":
+            env = 1.0 + 0.8 * torch.sin(two_pi * tone * t)
+            ph = two_pi * off * t
+            x += torch.polar(amp * 0.5 * env, ph)
+        else:
+            sgn = 1.0 if modem == "USB" else -1.0
+            x += amp * 0.5 * (torch.polar(torch.ones_like(t), two_pi * (off + sgn * 700.0) * t) +
+                              torch.polar(torch.ones_like(t), two_pi * (off + sgn * 1900.0) * t))
+    g = torch.Generator(device=device)
+    g.manual_seed(seed + t0 % 1000003)
+    sigma = 0.01 / np.sqrt(2.0)
+    x += sigma * torch.complex(torch.randn(n, device=device, dtype=torch.float64, generator=g),
+                               torch.randn(n, device=device, dtype=torch.float64, generator=g))
+    x += complex(0.01, -0.02)
+    return x.to(torch.complex64)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [c.strip() for c in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(wl, chans, iq_host, threads, blocks):
+    """Time the reference CPU path (oracle/_ref: reference liquid-dsp binary + CubicSDR glue) on `blocks` blocks."""
+    import ctypes as C
+    from oracle.refbind import Ref
+    ref = Ref()
+    n_chan = len(chans)
+    names = (C.c_char_p * max(1, n_chan))(*[m.encode() for m, _, _ in chans])
+    bws = (C.c_longlong * max(1, n_chan))(*[bw for _, bw, _ in chans])
+    shifts = (C.c_longlong * max(1, n_chan))(*[off for _, _, off in chans])
+    chk = C.c_double()
+    iq = np.ascontiguousarray(iq_host, np.complex64)
+    secs = ref.L.ref_bench_path(iq.ctypes.data_as(C.c_void_p), iq.size, blocks, wl["fs"], n_chan, names, bws, shifts, 48000,
+                                wl["fft"], threads, C.byref(chk))
+    return secs, ref.version()
+
+
+def run_reference(args, wl, chans, rank):
+    """--impl reference: the reference's own CPU implementation on the host cores, same config / metric / unit."""
+    from cubicsdr_b200 import synth
+    if rank != 0:
+        return
+    N = synth.block_size(wl["fs"])
+    iq = synth.wideband(wl["fs"], N, chans[:: max(1, len(chans) // 32)] if chans else [], t0=0)   # carriers: a 32-channel subset keeps generation quick
+    threads = os.cpu_count() or 1
+    for _ in range(max(0, args.warmup - 2)):       # the CPU path has no warm-up effects worth minutes of work
+        pass
+    t_tot = 0.0
+    for _ in range(args.steps):
+        secs, ver = cpu_reference_run(wl, chans, iq, threads, 1)
+        t_tot += secs
+    val = N * args.steps / t_tot / 1e6
+    line = {"impl": "reference", "metric": "IQ MSamples/s through spectrum+demod chain", "value": val, "unit": "MSamples/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "fs": wl["fs"], "block": N, "channels": len(chans), "fft_size": wl["fft"]},
+            "cpu_baseline": {"value": val, "unit": "MSamples/s", "cores": threads, "kind": "reference",
+                             "sample": "1 block (1/60 s of IQ) per step, all channels + spectrum, liquid-dsp %s" % ver},
+            "e2e": {"value": val, "unit": "MSamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ring", type=int, default=16, help="distinct input blocks rotated through (ring * block > L2)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = WORKLOADS[args.workload]
+    from cubicsdr_b200 import synth
+    fs = wl["fs"]
+    N = synth.block_size(fs)
+    chans = synth.channel_plan(wl["plan"], fs, wl["n_chan"]) if wl["n_chan"] else []
+
+    if args.impl == "reference":
+        run_reference(args, wl, chans, rank)
+        return
+
+    import torch
+    import cubicsdr_b200
+    from cubicsdr_b200 import Channel, Engine, Spectrum
+    if args.warmup < 3:
+        args.warmup = 3
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    lib = cubicsdr_b200.lib()
+    stream = torch.cuda.current_stream()
+    eng = Engine(lib, device=local_rank, max_block=N, stream=stream.cuda_stream)
+    mine = chans[rank::world]                                  # channel sharding
+    cobjs = [Channel(eng, m, fs, bw, 48000, frequency=CENTER + off) for m, bw, off in mine]
+    spec = Spectrum(eng, wl["fft"], 0) if (wl["fft"] and rank == 0) else None
+
+    # ---- inputs: ring of distinct blocks resident in HBM on rank 0 (ring * block bytes > 126 MB L2) -----------------
+    ring = []
+    carriers = chans if chans else synth.channel_plan("mixed", fs, 16)
+    if rank == 0:
+        for r in range(args.ring):
+            ring.append(torch_wideband(torch, fs, N, carriers, r * N, dev, 1234))
+    recv = torch.empty(N, dtype=torch.complex64, device=dev) if world > 1 else None
+    host_blocks = None
+    if rank == 0:
+        host_blocks = [torch.empty(N, dtype=torch.complex64).pin_memory() for _ in range(2)]
+        host_blocks[0].copy_(ring[0]); host_blocks[1].copy_(ring[1 % args.ring])
+    stage = torch.empty(N, dtype=torch.complex64, device=dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def step_device(i):
+        buf = ring[i % args.ring] if rank == 0 else recv
+        if world > 1:
+            dist.broadcast(buf, src=0)                            # the path's one exchange step (raw IQ over NVLink)
+        eng.submit_device(buf.data_ptr(), N, CENTER, fs, fetch_to_host=False)
+
+    def step_e2e(i):
+        if rank == 0:
+            stage.copy_(host_blocks[i & 1], non_blocking=True)   # H2D from pinned host memory, inside the timed region
+        if world > 1:
+            dist.broadcast(stage, src=0)
+        eng.submit_device(stage.data_ptr(), N, CENTER, fs, fetch_to_host=True)
+        eng.wait()
+        nbytes = 0
+        if cobjs:
+            audio, n_audio, _, _ = eng.fetch_audio_batch(cobjs, 1024)
+            nbytes += int(n_audio.sum()) * 4
+        if spec is not None:
+            for f in range(spec.frames):
+                pts, line, cf = spec.fetch(f)
+                nbytes += pts.nbytes + line.nbytes
+        return nbytes
+
+    # ---- warm-up ------------------------------------------------------------------------------------------------------
+    for i in range(args.warmup):
+        step_device(i)
+    eng.wait()
+    torch.cuda.synchronize()
+
+    # ---- timed: device-resident -----------------------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    eng.set_timing(True)
+    launches0 = eng.launch_count
+    barrier(); torch.cuda.synchronize()
+    sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        step_device(args.warmup + i)
+    e1.record(stream)
+    torch.cuda.synchronize(); barrier()
+    ms = e0.elapsed_time(e1)
+    eng.wait()
+    clocks = sampler.stop()
+    stage_ms, stage_blocks = eng.get_timing()
+    eng.set_timing(False)
+    launches = eng.launch_count - launches0
+    if dist is not None:
+        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    value = N * args.steps / (ms * 1e-3) / 1e6
+
+    # ---- timed: end to end through host buffers -------------------------------------------------------------------------
+    for i in range(3):
+        step_e2e(i)
+    barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    d2h = 0
+    for i in range(args.steps):
+        d2h = step_e2e(i)
+    torch.cuda.synchronize(); barrier()
+    t_e2e = time.perf_counter() - t0
+    if dist is not None:
+        tt = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_e2e = float(tt.item())
+        dd = torch.tensor([d2h], device=dev, dtype=torch.float64)
+        dist.all_reduce(dd, op=dist.ReduceOp.SUM)
+        d2h = int(dd.item())
+    e2e_value = N * args.steps / t_e2e / 1e6
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------------------------------
+    peak, peak_src = measured_peaks()
+    c_local = len(mine)
+    b_alg = 8.0 + c_local * 4.0 * 48000.0 / fs + (2.5 if spec is not None else 0.0)     # bytes / wideband sample / GPU
+    dom = "front" if c_local else "spectrum"
+    t_dom_ms = stage_ms[dom] / max(1, stage_blocks)
+    achieved = (N * b_alg / (t_dom_ms * 1e-3)) / 1e9 if t_dom_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(args.workload, {}).get(dom)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_chan_front (NCO mix + half-band cascade)" if c_local else "spectrum kernels",
+                "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "alg_bytes_per_sample": b_alg, "kernel_ms_per_block": t_dom_ms,
+                "stage_ms_per_block": {k: v / max(1, stage_blocks) for k, v in stage_ms.items()}}
+    if c_local:
+        flops = 30.0 * c_local * N / (t_dom_ms * 1e-3) / 1e12
+        roofline["fp32"] = {"note": "many-channel single-channel-mode is FP32-issue bound (SURVEY.md 8d): ~30 flop / sample / channel",
+                            "achieved_tflops": flops, "nominal_peak_tflops": FP32_NOMINAL_TFLOPS, "frac": flops / FP32_NOMINAL_TFLOPS}
+
+    # ---- CPU baseline (bounded sample: one block, all channels) -------------------------------------------------------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            threads = os.cpu_count() or 1
+            iq_host = ring[0].cpu().numpy()
+            secs, ver = cpu_reference_run(wl, chans, iq_host, threads, 1)
+            cpu = {"value": N / secs / 1e6, "unit": "MSamples/s", "cores": threads, "kind": "reference",
+                   "sample": "1 block (%d samples = 1/60 s), all %d channels%s, reference liquid-dsp %s binary + CubicSDR glue" % (
+                       N, len(chans), " + spectrum" if wl["fft"] else "", ver)}
+        except Exception as ex:        # the oracle is a checker; its absence must not hide the GPU number
+            cpu = {"value": None, "unit": "MSamples/s", "cores": 0, "kind": "reference", "sample": "unavailable: %r" % (ex,)}
+
+    line = {"metric": "IQ MSamples/s through spectrum+demod chain", "value": value, "unit": "MSamples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "fs": fs, "block": N, "channels": len(chans), "channels_per_gpu": c_local,
+                       "fft_size": wl["fft"], "l2": "%d distinct %.1f MB input blocks rotate (%.0f MB > 126 MB L2)" % (
+                           args.ring, N * 8 / 1e6, args.ring * N * 8 / 1e6),
+                       "realtime_factor": value * 1e6 / fs},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "MSamples/s", "h2d_bytes_per_step": N * 8, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

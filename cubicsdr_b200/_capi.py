@@ -15,9 +15,9 @@ PRODUCT_LIB = os.path.join(_HERE, "libsdr_b200.so")
 SYMBOLS = [
     "sdr_last_error", "sdr_version", "sdr_is_device_build",
     "sdr_engine_create", "sdr_engine_destroy", "sdr_engine_submit", "sdr_engine_submit_device", "sdr_engine_wait",
-    "sdr_engine_fetch_block", "sdr_engine_launch_count",
+    "sdr_engine_fetch_block", "sdr_engine_launch_count", "sdr_engine_set_timing", "sdr_engine_get_timing",
     "sdr_chan_create", "sdr_chan_destroy", "sdr_chan_set_frequency", "sdr_chan_get_bandwidth", "sdr_chan_want_iq",
-    "sdr_chan_fetch_audio", "sdr_chan_fetch_iq",
+    "sdr_chan_fetch_audio", "sdr_chan_fetch_iq", "sdr_engine_fetch_audio_batch",
     "sdr_spectrum_create", "sdr_spectrum_destroy", "sdr_spectrum_set_average_rate", "sdr_spectrum_frames",
     "sdr_spectrum_fetch", "sdr_spectrum_fetch_debug",
     "sdr_design_kaiser", "sdr_design_nco_table", "sdr_design_nco_step", "sdr_design_resampler",
@@ -49,6 +49,8 @@ class Lib:
         L.sdr_engine_fetch_block.argtypes = [vp, vp, u, P(u)]
         L.sdr_engine_launch_count.argtypes = [vp]
         L.sdr_engine_launch_count.restype = C.c_ulonglong
+        L.sdr_engine_set_timing.argtypes = [vp, i]
+        L.sdr_engine_get_timing.argtypes = [vp, vp, P(C.c_ulonglong)]
         L.sdr_chan_create.argtypes = [vp, C.c_char_p, ll, ll, i, P(vp)]
         L.sdr_chan_destroy.argtypes = [vp]
         L.sdr_chan_set_frequency.argtypes = [vp, ll]
@@ -56,6 +58,7 @@ class Lib:
         L.sdr_chan_want_iq.argtypes = [vp, i]
         L.sdr_chan_fetch_audio.argtypes = [vp, vp, u, P(u), P(d), P(f), P(i)]
         L.sdr_chan_fetch_iq.argtypes = [vp, vp, u, P(u)]
+        L.sdr_engine_fetch_audio_batch.argtypes = [vp, vp, u, vp, u, vp, vp, vp]
         L.sdr_spectrum_create.argtypes = [vp, u, u, P(vp)]
         L.sdr_spectrum_destroy.argtypes = [vp]
         L.sdr_spectrum_set_average_rate.argtypes = [vp, f]
@@ -126,6 +129,31 @@ class Engine:
     @property
     def launch_count(self):
         return int(self.lib.L.sdr_engine_launch_count(self.h))
+
+    def fetch_audio_batch(self, chans, stride=1024):
+        """(audio[n_chan, stride], n_audio[n_chan], level_db[n_chan], peak[n_chan]) for a list of Channel objects."""
+        n = len(chans)
+        key = (id(chans), n, stride)
+        if getattr(self, "_batch_key", None) != key:
+            self._batch_key = key
+            self._batch_h = (C.c_void_p * n)(*[c.h for c in chans])
+            self._batch_audio = np.zeros((n, stride), np.float32)
+            self._batch_n = np.zeros(n, np.uint32)
+            self._batch_lvl = np.zeros(n, np.float64)
+            self._batch_pk = np.zeros(n, np.float32)
+        self.lib.check(self.lib.L.sdr_engine_fetch_audio_batch(self.h, self._batch_h, n, _ptr(self._batch_audio), stride,
+                                                               _ptr(self._batch_n), _ptr(self._batch_lvl), _ptr(self._batch_pk)))
+        return self._batch_audio, self._batch_n, self._batch_lvl, self._batch_pk
+
+    def set_timing(self, on=True):
+        self.lib.check(self.lib.L.sdr_engine_set_timing(self.h, 1 if on else 0))
+
+    def get_timing(self):
+        """({'dc','spectrum','front','tail'} accumulated ms, blocks)"""
+        ms = np.zeros(4, np.float64)
+        nb = C.c_ulonglong()
+        self.lib.check(self.lib.L.sdr_engine_get_timing(self.h, _ptr(ms), C.byref(nb)))
+        return dict(dc=ms[0], spectrum=ms[1], front=ms[2], tail=ms[3]), int(nb.value)
 
 
 class Channel:

@@ -276,7 +276,37 @@ struct sdr_engine {
     bool dirty = true;
     bool results_on_host = false;
     std::vector<sdr_spectrum *> spectra;
+    // optional per-stage device timing (CUDA events on the engine stream): 0 dc, 1 spectrum, 2 front, 3 tail
+    bool timing = false;
+    static const int kTimeSets = 64;
+    int time_pending = 0;
+    double stage_ms[4] = {0, 0, 0, 0};
+    unsigned long long stage_count = 0;
+#ifndef SDR_EMU
+    cudaEvent_t tev[kTimeSets][5];
+    bool tev_made = false;
+#endif
 };
+
+static void time_mark(sdr_engine *e, int which) {
+#ifndef SDR_EMU
+    if (e->timing && e->time_pending < sdr_engine::kTimeSets) cudaEventRecord(e->tev[e->time_pending][which], e->stream);
+#else
+    (void)e; (void)which;
+#endif
+}
+static void time_collect(sdr_engine *e) {
+#ifndef SDR_EMU
+    for (int i = 0; i < e->time_pending; ++i) {
+        for (int k = 0; k < 4; ++k) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, e->tev[i][k], e->tev[i][k + 1]) == cudaSuccess) e->stage_ms[k] += ms;
+        }
+        e->stage_count++;
+    }
+#endif
+    e->time_pending = 0;
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // taps pool
@@ -393,6 +423,30 @@ extern "C" int sdr_engine_destroy(sdr_engine *e) {
 }
 
 extern "C" unsigned long long sdr_engine_launch_count(sdr_engine *e) { return e ? e->launches : 0; }
+
+extern "C" int sdr_engine_set_timing(sdr_engine *e, int enable) {
+    if (!e) return fail(SDR_ERR_ARG, "null engine");
+    std::lock_guard<std::mutex> lk(e->mu);
+#ifndef SDR_EMU
+    if (enable && !e->tev_made) {
+        for (int i = 0; i < sdr_engine::kTimeSets; ++i) for (int k = 0; k < 5; ++k) CUDA_TRY(cudaEventCreate(&e->tev[i][k]));
+        e->tev_made = true;
+    }
+#endif
+    e->timing = enable != 0;
+    e->time_pending = 0;
+    for (int k = 0; k < 4; ++k) e->stage_ms[k] = 0.0;
+    e->stage_count = 0;
+    return SDR_OK;
+}
+
+extern "C" int sdr_engine_get_timing(sdr_engine *e, double *stage_ms4, unsigned long long *blocks) {
+    if (!e) return fail(SDR_ERR_ARG, "null engine");
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (stage_ms4) for (int k = 0; k < 4; ++k) stage_ms4[k] = e->stage_ms[k];
+    if (blocks) *blocks = e->stage_count;
+    return SDR_OK;
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // channels
@@ -697,7 +751,9 @@ static int submit_common(sdr_engine *e, const float2 *d_src, unsigned n, long lo
     DcArgs dc;
     dc.x = d_src; dc.y = blk; dc.n = (int)n; dc.a = e->dc_a; dc.tile_sum = e->d_tile_sum; dc.tile_carry = e->d_tile_carry;
     dc.state = e->d_dc_state; dc.apow = e->d_apow;
+    time_mark(e, 0);
     launch_dc(dc, e->stream, e->launches);
+    time_mark(e, 1);
     e->last_n = n; e->have_block = true;
     e->results_on_host = to_host;
 
@@ -724,9 +780,12 @@ static int submit_common(sdr_engine *e, const float2 *d_src, unsigned n, long lo
         }
     }
 
+    time_mark(e, 2);
     // 4. channels: per-block oscillator bookkeeping (DemodulatorPreThread.cpp:154-163, 186-195)
     int n_slots = (int)e->chans.size();
     if (n_slots == 0) {
+        time_mark(e, 3); time_mark(e, 4);
+        if (e->timing && e->time_pending < sdr_engine::kTimeSets) e->time_pending++;
 #ifndef SDR_EMU
         CUDA_TRY(cudaEventRecord(e->ring_ev[slot], e->stream));
 #endif
@@ -793,7 +852,10 @@ static int submit_common(sdr_engine *e, const float2 *d_src, unsigned n, long lo
 #ifndef SDR_EMU
     CUDA_TRY(cudaEventRecord(e->ring_ev[slot], e->stream));
 #endif
+    time_mark(e, 3);
     launch_tail(ta, n_slots, e->stream, e->launches);
+    time_mark(e, 4);
+    if (e->timing && e->time_pending < sdr_engine::kTimeSets) e->time_pending++;
     if (to_host && e->results_bytes) {
         size_t total = 0;
         for (auto *c : e->chans) if (c) total = std::max(total, (size_t)c->cs.res_off + c->slot_bytes);
@@ -827,6 +889,10 @@ extern "C" int sdr_engine_wait(sdr_engine *e) {
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(SDR_ERR_CUDA, std::string("kernel error: ") + cudaGetErrorString(err));
 #endif
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        time_collect(e);
+    }
     return SDR_OK;
 }
 
@@ -853,6 +919,25 @@ extern "C" int sdr_chan_fetch_audio(sdr_chan *c, float *audio, unsigned cap, uns
     if (level_db) *level_db = h->level_db;
     if (peak) *peak = h->peak;
     if (skipped) *skipped = h->skipped;
+    return SDR_OK;
+}
+
+extern "C" int sdr_engine_fetch_audio_batch(sdr_engine *e, sdr_chan *const *chans, unsigned n_chan, float *audio, unsigned stride,
+                                            unsigned *n_audio, double *level_db, float *peak) {
+    if (!e || !chans) return fail(SDR_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!e->results_on_host || !e->h_results) return fail(SDR_ERR_STATE, "no host results for the last block");
+    for (unsigned i = 0; i < n_chan; ++i) {
+        const sdr_chan *c = chans[i];
+        if (!c || c->eng != e) return fail(SDR_ERR_ARG, "channel does not belong to this engine");
+        const unsigned char *slot = e->h_results + c->cs.res_off;
+        const ChanResultHeader *h = reinterpret_cast<const ChanResultHeader *>(slot);
+        unsigned m = std::min(stride, std::min(h->n_audio, (unsigned)c->cs.res_audio_cap));
+        if (audio) memcpy(audio + (size_t)i * stride, slot + 32, (size_t)m * sizeof(float));
+        if (n_audio) n_audio[i] = h->n_audio;
+        if (level_db) level_db[i] = h->level_db;
+        if (peak) peak[i] = h->peak;
+    }
     return SDR_OK;
 }
 

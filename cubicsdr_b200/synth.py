@@ -10,12 +10,16 @@ MODEM_DEFAULT_BW = {"FM": 200000, "NBFM": 12500, "AM": 6000, "USB": 5400, "LSB":
 
 
 def block_size(sample_rate):
-    """Reference block length: ceil(floor(fs/60)/nch)*nch, nch = even(ceil(fs/500000)) (SoapySDRThread.cpp:668-695)."""
-    nch = int(np.ceil(sample_rate / 500000.0))
-    if nch % 2:
-        nch += 1
-    if nch < 2:
-        nch = 2
+    """Reference block length (SDRThread::getOptimalElementCount / getOptimalChannelCount, SoapySDRThread.cpp:668-695):
+    ceil(floor(fs/60)/nch)*nch with nch = ceil(fs/500000) rounded DOWN to even, at least 2 (1 when fs <= 500 kHz)."""
+    if sample_rate <= 500000:
+        nch = 1
+    else:
+        nch = int(np.ceil(sample_rate / 500000.0))
+        if nch % 2:
+            nch -= 1
+        if nch < 2:
+            nch = 2
     n = int(sample_rate // 60)
     return int(np.ceil(n / nch) * nch)
 

@@ -51,6 +51,11 @@ int sdr_engine_wait(sdr_engine *eng);
 int sdr_engine_fetch_block(sdr_engine *eng, sdr_cf32 *out, unsigned cap, unsigned *n);
 /* kernel launches issued by this engine so far (bench.py's gpu_launches) */
 unsigned long long sdr_engine_launch_count(sdr_engine *eng);
+/* Per-stage device time, measured with CUDA events on the engine's stream around each stage of every submit while
+ * enabled (bench.py's roofline figure).  stage_ms4 = accumulated {DC blocker, spectrum, channel front kernel(s),
+ * channel tail kernel} milliseconds over `blocks` submits; collected at sdr_engine_wait (at most 64 submits per wait). */
+int sdr_engine_set_timing(sdr_engine *eng, int enable);
+int sdr_engine_get_timing(sdr_engine *eng, double *stage_ms4, unsigned long long *blocks);
 
 /* ---- channel: DemodulatorPreThread + Modem + DemodulatorThread metering --------------------------------------------- */
 /* modem: "FM" "NBFM" "AM" "USB" "LSB" (Modem::addModemFactory names, src/CubicSDR.cpp:305-311).
@@ -72,6 +77,10 @@ int sdr_chan_want_iq(sdr_chan *ch, int enable);
 int sdr_chan_fetch_audio(sdr_chan *ch, float *audio, unsigned cap, unsigned *n_audio, double *level_db, float *peak,
                          int *skipped);
 int sdr_chan_fetch_iq(sdr_chan *ch, sdr_cf32 *iq, unsigned cap, unsigned *n_iq);
+/* One call for many channels (what a host with hundreds of demodulators uses instead of n_chan fetches): audio of
+ * channel i lands at audio + i * stride (at most stride samples); the other arrays have n_chan entries and may be NULL. */
+int sdr_engine_fetch_audio_batch(sdr_engine *eng, sdr_chan *const *chans, unsigned n_chan, float *audio, unsigned stride,
+                                 unsigned *n_audio, double *level_db, float *peak);
 
 /* ---- spectrum: FFTDataDistributor framing + SpectrumVisualProcessor + WaterfallPanel::step --------------------------- */
 /* fft_size: display points (SpectrumVisualProcessor::setup, :140-178); the transform is 2 * fft_size.
