@@ -458,9 +458,10 @@ API void ref_spectrum_frame(void *h, const lq_cf *frame, unsigned n, float *poin
 
 // ---------------------------------------------------------------------------------------------------------
 // CPU baseline: whole path, threaded the way the reference is (one ingress, one per channel, one spectrum;
-// here the channel work is spread over `threads` workers).  Returns seconds for `blocks` blocks of n samples.
+// here the channel work is spread over `threads` workers).  Returns seconds for `blocks` blocks of n samples
+// after `warm_blocks` untimed ones.
 // ---------------------------------------------------------------------------------------------------------
-API double ref_bench_path(const lq_cf *iq, unsigned n, unsigned blocks, long long sampleRate,
+API double ref_bench_path(const lq_cf *iq, unsigned n, unsigned warm_blocks, unsigned blocks, long long sampleRate,
                           unsigned n_chan, const char *const *modem_names, const long long *bandwidths, const long long *shifts,
                           int audioRate, unsigned fftSize /*0 = no spectrum*/, unsigned threads, double *audio_checksum) {
     std::vector<void *> chans(n_chan);
@@ -477,7 +478,8 @@ API double ref_bench_path(const lq_cf *iq, unsigned n, unsigned blocks, long lon
     if (threads < 1) threads = 1;
     std::vector<double> sums(threads, 0.0);
     auto t0 = std::chrono::steady_clock::now();
-    for (unsigned b = 0; b < blocks; b++) {
+    for (unsigned b = 0; b < warm_blocks + blocks; b++) {
+        if (b == warm_blocks) t0 = std::chrono::steady_clock::now();   // first-touch page faults and cold filters stay outside
         ref_ingress_block(ing, const_cast<lq_cf *>(iq), n, dc.data());
         std::atomic<unsigned> next(0);
         auto work = [&](unsigned tid) {

@@ -70,7 +70,7 @@ class Ref:
         L.ref_spectrum_set_average_rate.argtypes = [vp, f]
         L.ref_spectrum_frame.argtypes = [vp, vp, u, vp, vp, vp, vp, vp]
         L.ref_bench_path.restype = d
-        L.ref_bench_path.argtypes = [vp, u, u, ll, u, vp, vp, vp, i, u, u, vp]
+        L.ref_bench_path.argtypes = [vp, u, u, u, ll, u, vp, vp, vp, i, u, u, vp]
 
     def version(self):
         return self.L.ref_libversion().decode()
