@@ -199,7 +199,10 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     lib = cubicsdr_b200.lib()
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream shared by torch and the engine: torch.cuda.Event timing then sees the kernels
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     eng = Engine(lib, device=local_rank, max_block=N, stream=stream.cuda_stream)
     mine = chans[rank::world]                                  # channel sharding
     cobjs = [Channel(eng, m, fs, bw, 48000, frequency=CENTER + off) for m, bw, off in mine]

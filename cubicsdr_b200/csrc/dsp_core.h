@@ -95,18 +95,44 @@ SDR_HD inline void dc_tile_sum_phase(int ph, const DcArgs &a, int bid, int tid, 
     }
 }
 
-// kernel B (one thread): serial composition over tiles (tiles <= ~1000 per block)
-SDR_HD inline void dc_carry_phase(const DcArgs &a, int tiles) {
-    double cr = a.state[0].x, ci = a.state[0].y;
-    for (int t = 0; t < tiles; ++t) {
-        a.tile_carry[t] = make_double2(cr, ci);
-        int tile_len = a.n - t * kDcTile;
-        if (tile_len > kDcTile) tile_len = kDcTile;
-        double w = a.apow[tile_len];
-        cr = fma(cr, w, a.tile_sum[t].x);
-        ci = fma(ci, w, a.tile_sum[t].y);
+// kernel B (one CTA): carry entering every tile.  Each thread composes the affine maps of its run of tiles, thread 0
+// chains the 256 thread-level maps, then every thread replays its run from its exact entering state.
+struct DcCarryShared { double ar[kDcThreads]; double2 b[kDcThreads]; double2 enter[kDcThreads]; };
+SDR_HD inline void dc_carry_phase(int ph, const DcArgs &a, int tiles, int tid, DcCarryShared *sm) {
+    const int per = (tiles + kDcThreads - 1) / kDcThreads;
+    const int t0 = tid * per, t1 = (t0 + per < tiles) ? t0 + per : tiles;
+    if (ph == 0) {
+        double A = 1.0, br = 0.0, bi = 0.0;
+        for (int t = t0; t < t1; ++t) {
+            int tile_len = a.n - t * kDcTile;
+            if (tile_len > kDcTile) tile_len = kDcTile;
+            const double w = a.apow[tile_len];
+            A *= w;
+            br = fma(br, w, a.tile_sum[t].x);
+            bi = fma(bi, w, a.tile_sum[t].y);
+        }
+        sm->ar[tid] = A; sm->b[tid] = make_double2(br, bi);
+    } else if (ph == 1) {
+        if (tid == 0) {
+            double cr = a.state[0].x, ci = a.state[0].y;
+            for (int t = 0; t < kDcThreads; ++t) {
+                sm->enter[t] = make_double2(cr, ci);
+                cr = fma(cr, sm->ar[t], sm->b[t].x);
+                ci = fma(ci, sm->ar[t], sm->b[t].y);
+            }
+            a.state[0] = make_double2(cr, ci);
+        }
+    } else {
+        double cr = sm->enter[tid].x, ci = sm->enter[tid].y;
+        for (int t = t0; t < t1; ++t) {
+            a.tile_carry[t] = make_double2(cr, ci);
+            int tile_len = a.n - t * kDcTile;
+            if (tile_len > kDcTile) tile_len = kDcTile;
+            const double w = a.apow[tile_len];
+            cr = fma(cr, w, a.tile_sum[t].x);
+            ci = fma(ci, w, a.tile_sum[t].y);
+        }
     }
-    a.state[0] = make_double2(cr, ci);
 }
 
 // kernel C: phase 0 thread partial prefix (same as A), phase 1 serial prefix over thread partials by thread 0,

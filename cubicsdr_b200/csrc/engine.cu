@@ -45,8 +45,12 @@ __global__ void __launch_bounds__(kDcThreads) k_dc_tile_sum(DcArgs a) {
     __syncthreads();
     dc_tile_sum_phase(1, a, blockIdx.x, threadIdx.x, &sm);
 }
-__global__ void k_dc_carry(DcArgs a, int tiles) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) dc_carry_phase(a, tiles);
+__global__ void __launch_bounds__(kDcThreads) k_dc_carry(DcArgs a, int tiles) {
+    __shared__ DcCarryShared sm;
+    for (int ph = 0; ph < 3; ++ph) {
+        dc_carry_phase(ph, a, tiles, threadIdx.x, &sm);
+        __syncthreads();
+    }
 }
 __global__ void __launch_bounds__(kDcThreads) k_dc_apply(DcArgs a) {
     __shared__ DcShared2 sm;
@@ -94,7 +98,7 @@ static void launch_dc(const DcArgs &a, sdr_stream_t s, unsigned long long &launc
     if (tiles == 0) return;
 #ifndef SDR_EMU
     k_dc_tile_sum<<<tiles, kDcThreads, 0, s>>>(a);
-    k_dc_carry<<<1, 32, 0, s>>>(a, tiles);
+    k_dc_carry<<<1, kDcThreads, 0, s>>>(a, tiles);
     k_dc_apply<<<tiles, kDcThreads, 0, s>>>(a);
 #else
     (void)s;
@@ -102,7 +106,10 @@ static void launch_dc(const DcArgs &a, sdr_stream_t s, unsigned long long &launc
         DcShared sm;
         for (int ph = 0; ph < 2; ++ph) for (int t = 0; t < kDcThreads; ++t) dc_tile_sum_phase(ph, a, b, t, &sm);
     }
-    dc_carry_phase(a, tiles);
+    {
+        DcCarryShared cs;
+        for (int ph = 0; ph < 3; ++ph) for (int t = 0; t < kDcThreads; ++t) dc_carry_phase(ph, a, tiles, t, &cs);
+    }
     for (int b = 0; b < tiles; ++b) {
         DcShared2 sm;
         for (int ph = 0; ph < 3; ++ph) for (int t = 0; t < kDcThreads; ++t) dc_apply_phase(ph, a, b, t, &sm);
