@@ -246,7 +246,8 @@ struct ChanResultHeader {
 struct FrontArgs {
     const float2 *x;              // x[0] = first sample of the block, x[-kBlkHist..-1] = history
     int n;
-    const float2 *nco;            // [1024] {cos, sin}
+ const float2 *nco;            // [1024] {cos, sin}
+    const float2 *nco_dn;         // [1024] {cos, -sin}
     const ChanStatic *cs;
     const ChanDyn *cd;
     const int *group;             // channel ids handled by this launch (all with the same K1)
@@ -274,34 +275,99 @@ SDR_HD SDR_FORCEINLINE float2 hb3_push_even(Hb3State &h, float2 x, float c0, flo
 // second sample of a pair (pure delay branch, emerges m = 3 outputs later)
 SDR_HD SDR_FORCEINLINE void hb3_push_odd(Hb3State &h, float2 x) { h.s3 = cf_add(h.s3, x); }
 
+// Feed one mixed sample into the cascade.  The sample with in-super-step index t enters stage l only if bits 0..l-1 of
+// t are 0 (it was the first sample of a pair at every earlier stage); bit l then says which branch of stage l it lands
+// on.  Returns the stage-(K-1) output, which exists only for t == 0.  With t a compile-time constant (unrolled caller)
+// everything folds to straight-line code.
 template <int K>
-SDR_HD inline void front_thread(const FrontArgs &a, int job, int lane) {
-    const int n_chunks = (a.cg + 31) / 32;
-    const int span_idx = job / n_chunks;
-    const int chunk = job - span_idx * n_chunks;
-    const int ci = chunk * 32 + lane;
-    if (span_idx >= a.n_span || ci >= a.cg) return;
-    const int ch = a.group[ci];
+SDR_HD SDR_FORCEINLINE float2 front_feed(Hb3State *hb, int t, float2 u, float c0, float c1, float c2) {
+    float2 y = u;
+    bool alive = true;
+#pragma unroll
+    for (int l = 0; l < K; ++l) {
+        if (alive) {
+            if ((t >> l) & 1) { hb3_push_odd(hb[l], y); alive = false; }
+            else y = hb3_push_even(hb[l], y, c0, c1, c2);
+        }
+    }
+    return y;
+}
+// Same with a run-time t (slow path: few super-steps per span, keeps the code small).  hb[] is indexed with compile-time
+// constants only, so it stays in registers.
+template <int K>
+SDR_HD inline float2 front_feed_dyn(Hb3State *hb, int t, float2 u, float c0, float c1, float c2) {
+    float2 y = u;
+    bool alive = true;
+#pragma unroll
+    for (int l = 0; l < K; ++l) {
+        if (alive) {
+            if ((t >> l) & 1) { hb3_push_odd(hb[l], y); alive = false; }
+            else y = hb3_push_even(hb[l], y, c0, c1, c2);
+        }
+    }
+    return y;
+}
+
+// Where the samples of a super-step that lies entirely inside the current block come from.
+// XDirect: straight from global memory (one address per warp -> a broadcast load); used by the emulator, by warps whose
+// channels are not in lock step, and for K < 4.
+struct XDirect {
+    const float2 *p;
+    SDR_HD SDR_FORCEINLINE void prefetch(const float2 *) {}
+    SDR_HD SDR_FORCEINLINE void commit(const float2 *src) { p = src; }
+    SDR_HD SDR_FORCEINLINE float2 get(int t) const { return sdr_ldg(p + t); }
+};
+#ifndef SDR_EMU
+// XWarpStage: the warp fetches the next super-step (M samples, M/2 lanes x one 16-byte pair each) while it computes the
+// current one, parks it in its private double-buffered shared-memory slot, and every lane then reads the samples back
+// as broadcast 16-byte loads.  No per-sample global load, no CTA barrier.
+template <int M>
+struct XWarpStage {
+    float4 *buf;          // [2][32] float4, private to this warp
+    int lane, cur;
+    float2 pa, pb;
+    __device__ __forceinline__ void prefetch(const float2 *src) {
+        if (lane < M / 2) { pa = __ldg(src + 2 * lane); pb = __ldg(src + 2 * lane + 1); }
+    }
+    __device__ __forceinline__ void commit(const float2 *) {
+        cur ^= 1;
+        if (lane < M / 2) buf[cur * 32 + lane] = make_float4(pa.x, pa.y, pb.x, pb.y);
+        __syncwarp();
+    }
+    __device__ __forceinline__ float2 get(int t) const {
+        const float4 v = buf[cur * 32 + (t >> 1)];
+        return (t & 1) ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
+    }
+};
+#endif
+
+// One thread = one channel over one time span.  `store` is false for padding lanes that only keep a warp converged.
+template <int K, class XS>
+SDR_HD inline void front_span(const FrontArgs &a, int ch, int span_idx, bool store, const float2 *tab_up, const float2 *tab_dn,
+                              XS &xs) {
     const ChanStatic &cs = a.cs[ch];
-    const ChanDyn &cd = a.cd[ch];
+    const ChanDyn cd = a.cd[ch];                           // by value: keep the per-block parameters in registers
     constexpr int M = 1 << K;
     const long long g0 = cd.g0, g1 = cd.g0 + a.n;
-    const long long qa = g0 >> K, qb = g1 >> K;           // outputs [qa, qb) complete inside this block
+    const long long qa = g0 >> K, qb = g1 >> K;            // outputs [qa, qb) complete inside this block
     long long q_lo = qa + (long long)span_idx * a.span;
     long long q_hi = q_lo + a.span;
     if (span_idx == a.n_span - 1 || q_hi > qb) q_hi = qb;
     if (q_lo >= q_hi) return;
     float2 *out = reinterpret_cast<float2 *>(cs.arena + cs.lvl_off[0]) + kHist;
-    const float sdir = (float)cd.dir, sdir_prev = (float)cd.dir_prev;
     const float2 *hx = cd.hist ? cd.hist : a.x;
+    // table oscillator: entry = (theta + 2^21) >> 22; the "down" table holds the conjugates; no mixing = entry 0 = (1, 0)
+    const float2 *tab = cd.dir < 0 ? tab_dn : tab_up;
+    const float2 *tab_prev = cd.dir_prev < 0 ? tab_dn : tab_up;
+    const unsigned dth = cd.dir ? cd.dtheta : 0u, dth_prev = cd.dir_prev ? cd.dtheta_prev : 0u;
+    const unsigned thb = (cd.dir ? cd.theta0 : 0u) + 0x200000u;          // biased phase at sample 0 of the block
+    const unsigned thb_prev = (cd.dir_prev ? cd.theta0 : 0u) + 0x200000u;
 
     if (K == 0) {
         for (long long q = q_lo; q < q_hi; ++q) {
-            int i = (int)(q - g0);
-            float2 xs = sdr_ldg(a.x + i);
-            float2 w = nco_lookup(a.nco, cd.theta0 + (unsigned)i * cd.dtheta);
-            float c = cd.dir ? w.x : 1.0f, s = w.y * sdir;
-            out[q - qa] = cf_rot(xs, c, s);
+            const int i = (int)(q - g0);
+            const float2 w = tab[(thb + (unsigned)i * dth) >> 22];
+            if (store) out[q - qa] = cf_rot(sdr_ldg(a.x + i), w.x, w.y);
         }
         return;
     }
@@ -310,39 +376,62 @@ SDR_HD inline void front_thread(const FrontArgs &a, int job, int lane) {
 #pragma unroll
     for (int l = 0; l < K; ++l) hb3_reset(hb[l]);
     const float c0 = a.c0, c1 = a.c1, c2 = a.c2;
+    bool prefetched = false;
 
     for (long long q = q_lo - kFrontWarm; q < q_hi; ++q) {
         const long long gq = q * M;                         // channel sample index of the super-step's first input
         const int i0 = (int)(gq - g0);                      // same, relative to the block start
+        const bool inside = (i0 >= 0) && (gq >= 0);         // whole super-step lies in the current block
+        if (inside) {
+            if (!prefetched) xs.prefetch(a.x + i0);
+            xs.commit(a.x + i0);
+            prefetched = (q + 1 < q_hi);
+            if (prefetched) xs.prefetch(a.x + i0 + M);
+        }
+        if (inside) {
+            // ---- fast super-step: every sample is in the current block; phase advances by one add per sample
+            unsigned th = thb + (unsigned)i0 * dth;
 #pragma unroll
-        for (int t = 0; t < M; ++t) {
-            const int i = i0 + t;
-            float2 u = make_float2(0.f, 0.f);
-            if (gq + t >= 0 && i >= -kBlkHist) {            // before the channel existed the delay lines hold zeros
-                float2 xs = sdr_ldg((i >= 0 ? a.x : hx) + i);
-                unsigned th;
-                float sd;
-                int dr;
-                if (i >= 0) { th = cd.theta0 + (unsigned)i * cd.dtheta; sd = sdir; dr = cd.dir; }
-                else        { th = cd.theta0 - (unsigned)(-i) * cd.dtheta_prev; sd = sdir_prev; dr = cd.dir_prev; }
-                float2 w = nco_lookup(a.nco, th);
-                u = cf_rot(xs, dr ? w.x : 1.0f, w.y * sd);
+            for (int t = 0; t < M; ++t) {
+                const float2 w = tab[th >> 22];
+                th += dth;
+                const float2 y = front_feed<K>(hb, t, cf_rot(xs.get(t), w.x, w.y), c0, c1, c2);
+                if (t == 0 && store && q >= q_lo) out[q - qa] = y;
             }
-            // feed the cascade: the sample with in-super-step index t enters stage l only if bits 0..l-1 of t are 0
-            // (it was the first sample of a pair at every earlier stage); bit l then says which branch of stage l
-            // it lands on.  t is a compile-time constant after unrolling, so `alive` folds away.
-            float2 y = u;
-            bool alive = true;
-#pragma unroll
-            for (int l = 0; l < K; ++l) {
-                if (alive) {
-                    if ((t >> l) & 1) { hb3_push_odd(hb[l], y); alive = false; }
-                    else y = hb3_push_even(hb[l], y, c0, c1, c2);
+        } else {
+            // ---- slow super-step: history in front of the block (mixed with the previous block's oscillator settings)
+            // or samples from before the channel existed (its delay lines then held zeros)
+#pragma unroll 2
+            for (int t = 0; t < M; ++t) {
+                const int i = i0 + t;
+                float2 u = make_float2(0.f, 0.f);
+                if (gq + t >= 0 && i >= -kBlkHist) {
+                    if (i >= 0) {
+                        const float2 w = tab[(thb + (unsigned)i * dth) >> 22];
+                        u = cf_rot(sdr_ldg(a.x + i), w.x, w.y);
+                    } else {
+                        const float2 w = tab_prev[(thb_prev - (unsigned)(-i) * dth_prev) >> 22];
+                        u = cf_rot(sdr_ldg(hx + i), w.x, w.y);
+                    }
                 }
+                const float2 y = front_feed_dyn<K>(hb, t, u, c0, c1, c2);
+                if (t == 0 && store && q >= q_lo) out[q - qa] = y;
             }
-            if (alive && q >= q_lo) out[q - qa] = y;          // only t == 0 survives all K stages
         }
     }
+}
+
+// generic entry (emulator; GPU warps whose lanes are not in lock step): every lane on its own, samples from global memory
+template <int K>
+SDR_HD inline void front_thread(const FrontArgs &a, int job, int lane) {
+    const int n_chunks = (a.cg + 31) / 32;
+    const int span_idx = job / n_chunks;
+    const int chunk = job - span_idx * n_chunks;
+    const int ci = chunk * 32 + lane;
+    if (span_idx >= a.n_span || ci >= a.cg) return;
+    XDirect xs;
+    xs.p = a.x;
+    front_span<K, XDirect>(a, a.group[ci], span_idx, true, a.nco, a.nco_dn, xs);
 }
 
 }  // namespace sdrb200

@@ -59,10 +59,35 @@ __global__ void __launch_bounds__(kDcThreads) k_dc_apply(DcArgs a) {
         __syncthreads();
     }
 }
+// Channel front: 4 warps per CTA, one warp = 32 channels over one time span.  The oscillator tables (up / conjugate)
+// sit in shared memory; lock-step warps stage the wideband samples through a private shared-memory slot (XWarpStage).
 template <int K>
-__global__ void __launch_bounds__(128) k_chan_front(FrontArgs a) {
-    const int job = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    front_thread<K>(a, job, threadIdx.x & 31);
+__global__ void __launch_bounds__(128, 4) k_chan_front(FrontArgs a) {
+    __shared__ float2 s_up[1024];
+    __shared__ float2 s_dn[1024];
+    __shared__ float4 s_x[4][2][32];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) { s_up[i] = a.nco[i]; s_dn[i] = a.nco_dn[i]; }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int job = blockIdx.x * 4 + warp;
+    const int n_chunks = (a.cg + 31) / 32;
+    const int span_idx = job / n_chunks;
+    if (span_idx >= a.n_span) return;
+    int ci = (job - span_idx * n_chunks) * 32 + lane;
+    const bool real = ci < a.cg;
+    if (!real) ci = a.cg - 1;                                  // padding lanes shadow the last channel, without stores
+    const int ch = a.group[ci];
+    const long long g0 = a.cd[ch].g0;
+    const bool lock_step = __all_sync(0xffffffffu, g0 == __shfl_sync(0xffffffffu, g0, 0));
+    if (K >= 4 && lock_step) {
+        XWarpStage<(1 << K)> xs;
+        xs.buf = &s_x[warp][0][0]; xs.lane = lane; xs.cur = 0;
+        front_span<K, XWarpStage<(1 << K)> >(a, ch, span_idx, real, s_up, s_dn, xs);
+    } else if (real) {
+        XDirect xs;
+        xs.p = a.x;
+        front_span<K, XDirect>(a, ch, span_idx, true, s_up, s_dn, xs);
+    }
 }
 __global__ void __launch_bounds__(kTailThreads) k_chan_tail(TailArgs a) {
     __shared__ TailShared sm;
@@ -264,7 +289,7 @@ struct sdr_engine {
     // DC blocker
     double2 *d_tile_sum = nullptr, *d_tile_carry = nullptr, *d_dc_state = nullptr; double *d_apow = nullptr;
     double dc_a = 0.0;
-    float2 *d_nco = nullptr;
+    float2 *d_nco = nullptr, *d_nco_dn = nullptr;
     // channels
     static const int kMaxChan = 2048;
     std::vector<sdr_chan *> chans;     // by slot; nullptr = free
@@ -379,6 +404,7 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
     bad |= be_malloc((void **)&e->d_dc_state, sizeof(double2));
     bad |= be_malloc((void **)&e->d_apow, (kDcTile + 1) * sizeof(double));
     bad |= be_malloc((void **)&e->d_nco, 1024 * sizeof(float2));
+    bad |= be_malloc((void **)&e->d_nco_dn, 1024 * sizeof(float2));
     bad |= be_malloc((void **)&e->d_cs, sdr_engine::kMaxChan * sizeof(ChanStatic));
     bad |= be_malloc((void **)&e->d_cd, sdr_engine::kMaxChan * sizeof(ChanDyn));
     bad |= be_malloc((void **)&e->d_st, sdr_engine::kMaxChan * sizeof(ChanState));
@@ -405,6 +431,11 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
     std::vector<float2> nco(1024);
     for (int i = 0; i < 1024; ++i) nco[i] = make_float2(tab[(i + 256) & 1023], tab[i]);
     be_h2d(e->d_nco, nco.data(), 1024 * sizeof(float2), e->stream);
+    // entry 0 must be exactly (1, 0): "no mixing" is expressed as a constant phase of 0 (front_span)
+    if (nco[0].x != 1.0f || nco[0].y != 0.0f) { delete e; return fail(SDR_ERR_STATE, "oscillator table entry 0 is not (1, 0)"); }
+    std::vector<float2> nco_dn(1024);
+    for (int i = 0; i < 1024; ++i) nco_dn[i] = make_float2(nco[i].x, -nco[i].y);
+    be_h2d(e->d_nco_dn, nco_dn.data(), 1024 * sizeof(float2), e->stream);
     be_sync(e->stream);
     *out = e;
     return SDR_OK;
@@ -418,7 +449,7 @@ extern "C" int sdr_engine_destroy(sdr_engine *e) {
     for (auto *c : e->chans) if (c) { be_free(c->d_arena); be_free(c->d_priv_hist); delete c; }
     for (auto *s : e->spectra) if (s) { spectrum_free(s); delete s; }
     be_free(e->d_raw); be_free(e->d_blk); be_free(e->d_scratch); be_host_free(e->h_stage);
-    be_free(e->d_tile_sum); be_free(e->d_tile_carry); be_free(e->d_dc_state); be_free(e->d_apow); be_free(e->d_nco);
+    be_free(e->d_tile_sum); be_free(e->d_tile_carry); be_free(e->d_dc_state); be_free(e->d_apow); be_free(e->d_nco); be_free(e->d_nco_dn);
     be_free(e->d_cs); be_free(e->d_cd); be_free(e->d_st); be_host_free(e->h_cd); be_free(e->d_group); be_host_free(e->h_group);
     be_free(e->d_taps); be_free(e->d_results); be_host_free(e->h_results);
 #ifndef SDR_EMU
@@ -840,7 +871,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, unsigned n, long lo
         memcpy(h_group + goff, by_k[K].data(), cg * sizeof(int));
         be_h2d(e->d_group + goff, h_group + goff, cg * sizeof(int), e->stream);
         FrontArgs fa;
-        fa.x = blk; fa.n = (int)n; fa.nco = e->d_nco; fa.cs = e->d_cs; fa.cd = e->d_cd; fa.group = e->d_group + goff; fa.cg = cg;
+        fa.x = blk; fa.n = (int)n; fa.nco = e->d_nco; fa.nco_dn = e->d_nco_dn; fa.cs = e->d_cs; fa.cd = e->d_cd; fa.group = e->d_group + goff; fa.cg = cg;
         const int n_chunks = (cg + 31) / 32;
         const long long nq = ((long long)n >> K) + 1;
         int n_span = (2368 + n_chunks - 1) / n_chunks;                  // ~16 warps on each of the 148 SMs
