@@ -126,3 +126,29 @@ def run_spectrum(lib, ref, fs, fft_size, n_blocks, chans, lps=0, block=None, see
     worst["u8_bad_far"] = u8_bad_far
     worst["u8_total"] = n_frames * fft_size
     return worst
+
+
+def check_against_golden(lib, device=0):
+    """Engine output against the committed golden vectors (tests/golden/chain_2p4msps.npz, produced by the reference binary)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "chain_2p4msps.npz"))
+    five = [("FM", 200000, 300000), ("NBFM", 12500, -150000), ("AM", 6000, 450000), ("USB", 5400, -600000), ("LSB", 5400, 750000)]
+    fs, N = 2400000, synth.block_size(2400000)
+    eng = Engine(lib, device=device, max_block=N)
+    cs = [Channel(eng, m, fs, bw, 48000, frequency=CENTER + off) for m, bw, off in five]
+    sp = Spectrum(eng, 256, 0)
+    worst = 0.0
+    for b in range(2):
+        eng.submit(synth.wideband(fs, N, five, seed=1234, t0=b * N), CENTER, fs)
+        eng.wait()
+        for i, c in enumerate(cs):
+            a = c.fetch_audio()[0]
+            ga = g["audio_%s_b%d" % (five[i][0], b)]
+            assert len(a) == len(ga), five[i][0]
+            worst = max(worst, relrms(a, ga))
+        for f in (0, sp.frames - 1):
+            pts, line, _ = sp.fetch(f)
+            assert relrms(pts, g["spec_points_b%d_f%d" % (b, f)]) <= 1e-4
+    eng.close()
+    assert worst <= TOL, worst
+    return worst

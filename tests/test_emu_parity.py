@@ -53,3 +53,7 @@ def test_spectrum_split_transform_and_line_limiter(emu_lib, ref):
     # FFTDataDistributor line limiter at 30 lines/s
     w = parity.run_spectrum(emu_lib, ref, 2400000, 512, n_blocks=6, chans=chans, lps=30)
     assert 1 <= w["frames"] <= 6 and w["mags"] <= parity.TOL
+
+
+def test_against_golden_vectors(emu_lib):
+    parity.check_against_golden(emu_lib)

@@ -105,3 +105,7 @@ def test_block_partition_invariance_full_size(gpu_lib):
     for i, (m, _, _) in enumerate(chans):
         if m == "FM":
             assert np.abs(res[0][i] - res[1][i]).max() < 1e-6
+
+
+def test_against_golden_vectors(gpu_lib):
+    parity.check_against_golden(gpu_lib)
