@@ -18,6 +18,7 @@ SYMBOLS = [
     "sdr_engine_fetch_block", "sdr_engine_launch_count", "sdr_engine_set_timing", "sdr_engine_get_timing",
     "sdr_chan_create", "sdr_chan_destroy", "sdr_chan_set_frequency", "sdr_chan_get_bandwidth", "sdr_chan_want_iq",
     "sdr_chan_fetch_audio", "sdr_chan_fetch_iq", "sdr_engine_fetch_audio_batch",
+    "sdr_modem_check_sample_rate", "sdr_modem_create", "sdr_modem_demodulate",
     "sdr_spectrum_create", "sdr_spectrum_destroy", "sdr_spectrum_set_average_rate", "sdr_spectrum_frames",
     "sdr_spectrum_fetch", "sdr_spectrum_fetch_debug",
     "sdr_design_kaiser", "sdr_design_nco_table", "sdr_design_nco_step", "sdr_design_resampler",
@@ -59,6 +60,9 @@ class Lib:
         L.sdr_chan_fetch_audio.argtypes = [vp, vp, u, P(u), P(d), P(f), P(i)]
         L.sdr_chan_fetch_iq.argtypes = [vp, vp, u, P(u)]
         L.sdr_engine_fetch_audio_batch.argtypes = [vp, vp, u, vp, u, vp, vp, vp]
+        L.sdr_modem_check_sample_rate.argtypes = [C.c_char_p, ll]
+        L.sdr_modem_create.argtypes = [vp, C.c_char_p, ll, i, u, P(vp)]
+        L.sdr_modem_demodulate.argtypes = [vp, vp, u, vp, u, P(u), P(d), P(f)]
         L.sdr_spectrum_create.argtypes = [vp, u, u, P(vp)]
         L.sdr_spectrum_destroy.argtypes = [vp]
         L.sdr_spectrum_set_average_rate.argtypes = [vp, f]

@@ -215,7 +215,8 @@ struct ChanDyn {                  // written by the host for every block
     int dir, dir_prev;            // +1 mix up, -1 mix down, 0 no mixing   (DemodulatorPreThread.cpp:186-195)
     int active;                   // 0: channel skips this block
     int valid;                    // 0: free slot, nothing may be touched
-    int pad;
+    int inject_n;                 // > 0: the decimated IQ of this call was uploaded by the host (Modem::demodulate seam):
+                                  //      skip the IQ resampler and demodulate inject_n samples
     const float2 *hist;           // non-null: history for samples i < 0 is hist[i] (the channel skipped the previous block(s),
                                   // so its delay lines must see the tail of the last block it DID consume)
 };

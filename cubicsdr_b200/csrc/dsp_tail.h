@@ -23,6 +23,7 @@ struct TailArgs {
     const float2 *nco;
     unsigned char *results;
     int n;                        // wideband block length
+    int first;                    // channel slot handled by CTA 0
 };
 
 struct TailShared {
@@ -129,6 +130,11 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
                 sm->lvl_n[j] = (int)((g1 >> sh) - (g0 >> sh));
             }
             sm->n_iq = arb_count(cs.arb_step, st.arb_phase, sm->lvl_n[cs.n_tail], &sm->arb_phase_after);
+            if (cd.inject_n > 0) {              // Modem::demodulate seam: IQ already at the modem rate
+                for (int j = 0; j <= cs.n_tail; ++j) sm->lvl_n[j] = 0;
+                sm->n_iq = cd.inject_n;
+                sm->arb_phase_after = st.arb_phase;
+            }
             // audio resampler bookkeeping: its input is the demodulated stream, one sample per decimated IQ sample
             const long long d0 = (long long)st.iq_count, d1 = d0 + sm->n_iq;
             if (!cs.a_interp) {
@@ -146,12 +152,13 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
     // ---- remaining half-band decimators of the IQ resampler --------------------------------------------------------
     if (ph >= TP_HB0 && ph < TP_HB0 + kMaxTailHb) {
         const int j = ph - TP_HB0;
-        if (j < cs.n_tail)
+        if (j < cs.n_tail && cd.inject_n <= 0)
             hb_decim_c(chan_cbuf(a, cs, cs.lvl_off[j]), sm->lvl_g0[j], chan_cbuf(a, cs, cs.lvl_off[j + 1]), sm->lvl_g0[j + 1],
                        sm->lvl_n[j + 1], cs.tail_m[j], a.taps + cs.tail_h1[j], tid, nt);
         return;
     }
 
+    if (ph == TP_ARB && cd.inject_n > 0) return;
     if (ph == TP_ARB) {      // 256-arm polyphase stage, nearest arm, 24-bit phase
         const float2 *z = chan_cbuf(a, cs, cs.lvl_off[cs.n_tail]) + kHist;
         float2 *iq = chan_cbuf(a, cs, cs.iq_off) + kHist;

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(128, 4) k_chan_front(FrontArgs a) {
 __global__ void __launch_bounds__(kTailThreads) k_chan_tail(TailArgs a) {
     __shared__ TailShared sm;
     for (int ph = 0; ph < TP_COUNT; ++ph) {
-        tail_phase(ph, a, blockIdx.x, threadIdx.x, blockDim.x, &sm);
+        tail_phase(ph, a, a.first + blockIdx.x, threadIdx.x, blockDim.x, &sm);
         __syncthreads();
     }
 }
@@ -174,7 +174,7 @@ static void launch_tail(const TailArgs &a, int n_chan, sdr_stream_t s, unsigned 
     (void)s;
     TailShared *sm = new TailShared;
     for (int c = 0; c < n_chan; ++c)
-        for (int ph = 0; ph < TP_COUNT; ++ph) for (int t = 0; t < kTailThreads; ++t) tail_phase(ph, a, c, t, kTailThreads, sm);
+        for (int ph = 0; ph < TP_COUNT; ++ph) for (int t = 0; t < kTailThreads; ++t) tail_phase(ph, a, a.first + c, t, kTailThreads, sm);
     delete sm;
 #endif
     launches += 1;
@@ -244,6 +244,10 @@ struct sdr_chan {
     ChanStatic cs;
     float *d_arena = nullptr;
     size_t arena_floats = 0;
+    bool standalone = false;        // sdr_modem: driven by sdr_modem_demodulate, ignored by sdr_engine_submit
+    unsigned inject_cap = 0;
+    ChanDyn *h_dyn = nullptr;       // pinned, standalone only
+    unsigned char *h_slot = nullptr; // pinned result slot, standalone only
     float2 *d_priv_hist = nullptr;  // tail of the last consumed block, kept while the channel skips blocks
     bool priv_valid = false;
     // DemodulatorPreThread state
@@ -446,7 +450,7 @@ static void spectrum_free(sdr_spectrum *sp);
 extern "C" int sdr_engine_destroy(sdr_engine *e) {
     if (!e) return SDR_OK;
     be_sync(e->stream);
-    for (auto *c : e->chans) if (c) { be_free(c->d_arena); be_free(c->d_priv_hist); delete c; }
+    for (auto *c : e->chans) if (c) { be_free(c->d_arena); be_free(c->d_priv_hist); be_host_free(c->h_dyn); be_host_free(c->h_slot); delete c; }
     for (auto *s : e->spectra) if (s) { spectrum_free(s); delete s; }
     be_free(e->d_raw); be_free(e->d_blk); be_free(e->d_scratch); be_host_free(e->h_stage);
     be_free(e->d_tile_sum); be_free(e->d_tile_carry); be_free(e->d_dc_state); be_free(e->d_apow); be_free(e->d_nco); be_free(e->d_nco_dn);
@@ -495,8 +499,10 @@ static int add_halfband_taps(sdr_engine *e, int m) {
     return pool_add(e, fkey("hb", (float)m), h1, 2 * m);
 }
 
-extern "C" int sdr_chan_create(sdr_engine *e, const char *modem, long long sample_rate, long long bandwidth, int audio_rate,
-                               sdr_chan **out) {
+static int rebuild(sdr_engine *e);
+
+static int chan_create_impl(sdr_engine *e, const char *modem, long long sample_rate, long long bandwidth, int audio_rate,
+                            unsigned inject_cap, sdr_chan **out) {
     if (!e || !out || sample_rate <= 0 || audio_rate <= 0) return fail(SDR_ERR_ARG, "sdr_chan_create: bad arguments");
     const int mk = modem_from_name(modem);
     if (mk < 0) return fail(SDR_ERR_UNSUPPORTED, std::string("sdr_chan_create: unknown modem '") + (modem ? modem : "") + "'");
@@ -565,7 +571,9 @@ extern "C" int sdr_chan_create(sdr_engine *e, const char *modem, long long sampl
     // ---- arena layout (floats)
     size_t off = 0;
     auto take = [&](size_t floats) { size_t o = off; off += (floats + 3) & ~size_t(3); return (int)o; };
-    const size_t nb = e->max_block;
+    const size_t nb = inject_cap ? inject_cap : e->max_block;
+    c->standalone = inject_cap != 0;
+    c->inject_cap = inject_cap;
     for (int j = 0; j <= cs.n_tail; ++j) cs.lvl_off[j] = take(2 * (kHist + (nb >> (cs.K1 + j)) + 4));
     const size_t cap_z = (nb >> cs.S) + 4;
     const size_t cap_iq = (size_t)std::ceil((double)cap_z * (double)c->iq_plan.rate_arb) + 8;
@@ -596,9 +604,67 @@ extern "C" int sdr_chan_create(sdr_engine *e, const char *modem, long long sampl
     st.agc_ceil = st.agc_ma = st.agc_maa = 1.0f;                        // ModemAnalog.cpp:6
     be_h2d(e->d_st + slot, &st, sizeof st, e->stream);
     be_sync(e->stream);
+    if (c->standalone) {
+        if (be_host_alloc((void **)&c->h_dyn, sizeof(ChanDyn)) || be_host_alloc((void **)&c->h_slot, c->slot_bytes)) {
+            be_free(c->d_arena); be_free(c->d_priv_hist); delete c;
+            return fail(SDR_ERR_NOMEM, "sdr_modem_create: host buffers");
+        }
+    }
     e->chans[slot] = c;
     e->dirty = true;
     *out = c;
+    return SDR_OK;
+}
+
+extern "C" int sdr_chan_create(sdr_engine *e, const char *modem, long long sample_rate, long long bandwidth, int audio_rate,
+                               sdr_chan **out) {
+    return chan_create_impl(e, modem, sample_rate, bandwidth, audio_rate, 0, out);
+}
+
+// ---- Modem plugin seam (S1): demodulate already-decimated IQ, one call = Modem::demodulate(kit, input, audioOut) ---------
+extern "C" int sdr_modem_check_sample_rate(const char *modem, long long sample_rate) {
+    const int mk = modem_from_name(modem);
+    if (mk < 0) return fail(SDR_ERR_UNSUPPORTED, "unknown modem");
+    return check_sample_rate(mk, sample_rate);
+}
+
+extern "C" int sdr_modem_create(sdr_engine *e, const char *modem, long long sample_rate, int audio_rate, unsigned max_samples,
+                                sdr_chan **out) {
+    if (max_samples == 0) return fail(SDR_ERR_ARG, "sdr_modem_create: max_samples must be > 0");
+    // the kit's input rate IS the modem rate: no IQ resampler in front (bandwidth == sample_rate after checkSampleRate)
+    const int mk = modem_from_name(modem);
+    if (mk < 0) return fail(SDR_ERR_UNSUPPORTED, "sdr_modem_create: unknown modem");
+    const long long rate = check_sample_rate(mk, sample_rate);
+    return chan_create_impl(e, modem, rate, rate, audio_rate, max_samples, out);
+}
+
+extern "C" int sdr_modem_demodulate(sdr_chan *c, const sdr_cf32 *iq, unsigned n, float *audio, unsigned cap, unsigned *n_audio,
+                                    double *level_db, float *peak) {
+    if (!c || !c->standalone) return fail(SDR_ERR_ARG, "sdr_modem_demodulate: not a modem handle");
+    if (n_audio) *n_audio = 0;
+    if (n == 0) return SDR_OK;                                          // ModemAnalog::initOutputBuffers: `if (!bufSize) return`
+    if (!iq || n > c->inject_cap) return fail(SDR_ERR_ARG, "sdr_modem_demodulate: bad buffer / too many samples");
+    sdr_engine *e = c->eng;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (e->dirty) { int r = rebuild(e); if (r) return r; }
+    be_sync(e->stream);                                                 // h_dyn / h_slot are reused call to call
+    float *d_iq = c->cs.arena + c->cs.iq_off + 2 * kHist;
+    be_h2d(d_iq, iq, (size_t)n * sizeof(sdr_cf32), e->stream);
+    memset(c->h_dyn, 0, sizeof(ChanDyn));
+    c->h_dyn->valid = 1; c->h_dyn->active = 1; c->h_dyn->inject_n = (int)n;
+    be_h2d(e->d_cd + c->index, c->h_dyn, sizeof(ChanDyn), e->stream);
+    TailArgs ta;
+    ta.cs = e->d_cs; ta.cd = e->d_cd; ta.st = e->d_st; ta.taps = e->d_taps; ta.nco = e->d_nco;
+    ta.results = e->d_results; ta.n = 0; ta.first = c->index;
+    launch_tail(ta, 1, e->stream, e->launches);
+    be_d2h(c->h_slot, e->d_results + c->cs.res_off, c->slot_bytes, e->stream);
+    if (be_sync(e->stream)) return fail(SDR_ERR_CUDA, std::string("sdr_modem_demodulate: ") + be_last_error());
+    const ChanResultHeader *h = reinterpret_cast<const ChanResultHeader *>(c->h_slot);
+    unsigned m = std::min(cap, std::min(h->n_audio, (unsigned)c->cs.res_audio_cap));
+    if (audio) memcpy(audio, c->h_slot + 32, (size_t)m * sizeof(float));
+    if (n_audio) *n_audio = h->n_audio;
+    if (level_db) *level_db = h->level_db;
+    if (peak) *peak = h->peak;
     return SDR_OK;
 }
 
@@ -610,6 +676,8 @@ extern "C" int sdr_chan_destroy(sdr_chan *c) {
     e->chans[c->index] = nullptr;
     be_free(c->d_arena);
     be_free(c->d_priv_hist);
+    be_host_free(c->h_dyn);
+    be_host_free(c->h_slot);
     e->dirty = true;
     delete c;
     return SDR_OK;
@@ -834,7 +902,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, unsigned n, long lo
         sdr_chan *c = e->chans[i];
         ChanDyn &d = h_cd[i];
         memset(&d, 0, sizeof d);
-        if (!c) continue;
+        if (!c || c->standalone) continue;
         d.valid = 1;
         // a channel that sits this block out keeps the tail of the last block it consumed (its filters do not advance)
         auto keep_tail = [&]() {
@@ -885,7 +953,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, unsigned n, long lo
     }
     TailArgs ta;
     ta.cs = e->d_cs; ta.cd = e->d_cd; ta.st = e->d_st; ta.taps = e->d_taps; ta.nco = e->d_nco;
-    ta.results = e->d_results; ta.n = (int)n;
+    ta.results = e->d_results; ta.n = (int)n; ta.first = 0;
     // the tail indexes channels by slot; free slots carry valid = 0 and are not touched
 #ifndef SDR_EMU
     CUDA_TRY(cudaEventRecord(e->ring_ev[slot], e->stream));

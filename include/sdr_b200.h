@@ -82,6 +82,18 @@ int sdr_chan_fetch_iq(sdr_chan *ch, sdr_cf32 *iq, unsigned cap, unsigned *n_iq);
 int sdr_engine_fetch_audio_batch(sdr_engine *eng, sdr_chan *const *chans, unsigned n_chan, float *audio, unsigned stride,
                                  unsigned *n_audio, double *level_db, float *peak);
 
+/* ---- Modem plugin seam: one call = Modem::demodulate(kit, input, audioOut) (src/modules/modem/Modem.h:148-153) -------- */
+/* Modem::checkSampleRate for `modem` (ModemAnalog.cpp:14-19, ModemUSB.cpp:29-37); negative on unknown modem.       */
+int sdr_modem_check_sample_rate(const char *modem, long long sample_rate);
+/* Modem factory + buildKit(sample_rate, audio_rate) (Modem.cpp:40-55, ModemAnalog.cpp:21-33).  The handle is an sdr_chan
+ * without the pre-demod stage: sdr_engine_submit ignores it; destroy it with sdr_chan_destroy (= disposeKit + delete). */
+int sdr_modem_create(sdr_engine *eng, const char *modem, long long sample_rate, int audio_rate, unsigned max_samples,
+                     sdr_chan **out);
+/* iq: n samples already at the modem rate (DemodulatorThreadPostIQData::data).  Synchronous.  Also returns what
+ * DemodulatorThread computes right after the call: level_db (:142-163) and peak (:223-233).  n == 0 is a no-op.   */
+int sdr_modem_demodulate(sdr_chan *modem, const sdr_cf32 *iq, unsigned n, float *audio, unsigned cap, unsigned *n_audio,
+                         double *level_db, float *peak);
+
 /* ---- spectrum: FFTDataDistributor framing + SpectrumVisualProcessor + WaterfallPanel::step --------------------------- */
 /* fft_size: display points (SpectrumVisualProcessor::setup, :140-178); the transform is 2 * fft_size.
  * lines_per_second: FFTDataDistributor::setLinesPerSecond; 0 = transform every non-overlapping frame.             */
