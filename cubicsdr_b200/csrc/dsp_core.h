@@ -36,6 +36,34 @@ SDR_HD SDR_FORCEINLINE float2 cf_rot(float2 x, float c, float s) {
     return make_float2(fmaf(x.x, c, -(x.y * s)), fmaf(x.x, s, x.y * c));
 }
 
+// ---- packed complex arithmetic: one Blackwell FFMA2 / FMUL2 / FADD2 (PTX fma/mul/add .f32x2, sm_100+) handles the real and
+//      imaginary parts together, halving the issue slots of the half-band cascade.  Bit-identical to two scalar ops.
+#if defined(__CUDA_ARCH__) && !defined(SDR_EMU)
+SDR_DEV SDR_FORCEINLINE float2 pk_fma(float2 h2, float2 x, float2 acc) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(h2.x), "f"(h2.y), "f"(x.x), "f"(x.y), "f"(acc.x), "f"(acc.y));
+    return d;
+}
+SDR_DEV SDR_FORCEINLINE float2 pk_mul(float2 h2, float2 x) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(h2.x), "f"(h2.y), "f"(x.x), "f"(x.y));
+    return d;
+}
+SDR_DEV SDR_FORCEINLINE float2 pk_add(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+#else
+SDR_HD SDR_FORCEINLINE float2 pk_fma(float2 h2, float2 x, float2 acc) { return make_float2(fmaf(h2.x, x.x, acc.x), fmaf(h2.y, x.y, acc.y)); }
+SDR_HD SDR_FORCEINLINE float2 pk_mul(float2 h2, float2 x) { return make_float2(h2.x * x.x, h2.y * x.y); }
+SDR_HD SDR_FORCEINLINE float2 pk_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+#endif
+
 // ---- table oscillator (nco_crcf: SURVEY.md A.1) -----------------------------------------------------------------------
 // nco[idx] = {cos, sin} of table entry idx; idx = (theta + 2^21) >> 22
 SDR_HD SDR_FORCEINLINE float2 nco_lookup(const float2 *nco, uint32_t theta) {
@@ -247,8 +275,7 @@ struct ChanResultHeader {
 struct FrontArgs {
     const float2 *x;              // x[0] = first sample of the block, x[-kBlkHist..-1] = history
     int n;
- const float2 *nco;            // [1024] {cos, sin}
-    const float2 *nco_dn;         // [1024] {cos, -sin}
+    const float2 *nco;            // [1024] {cos, sin}
     const ChanStatic *cs;
     const ChanDyn *cd;
     const int *group;             // channel ids handled by this launch (all with the same K1)
@@ -264,24 +291,25 @@ SDR_HD SDR_FORCEINLINE void hb3_reset(Hb3State &h) {
     h.s0 = h.s1 = h.s2 = h.s3 = h.s4 = h.s5 = make_float2(0.f, 0.f);
 }
 // first sample of a pair (filtered branch): returns the decimated output that becomes available with it
-SDR_HD SDR_FORCEINLINE float2 hb3_push_even(Hb3State &h, float2 x, float c0, float c1, float c2) {
-    h.s0 = cf_fma(c0, x, h.s1);
-    h.s1 = cf_fma(c1, x, h.s2);
-    h.s2 = cf_fma(c2, x, h.s3);
-    h.s3 = cf_fma(c2, x, h.s4);
-    h.s4 = cf_fma(c1, x, h.s5);
-    h.s5 = cf_scale(c0, x);
+// (c0, c1, c2 are the taps duplicated into both halves of a packed pair)
+SDR_HD SDR_FORCEINLINE float2 hb3_push_even(Hb3State &h, float2 x, float2 c0, float2 c1, float2 c2) {
+    h.s0 = pk_fma(c0, x, h.s1);
+    h.s1 = pk_fma(c1, x, h.s2);
+    h.s2 = pk_fma(c2, x, h.s3);
+    h.s3 = pk_fma(c2, x, h.s4);
+    h.s4 = pk_fma(c1, x, h.s5);
+    h.s5 = pk_mul(c0, x);
     return h.s0;
 }
 // second sample of a pair (pure delay branch, emerges m = 3 outputs later)
-SDR_HD SDR_FORCEINLINE void hb3_push_odd(Hb3State &h, float2 x) { h.s3 = cf_add(h.s3, x); }
+SDR_HD SDR_FORCEINLINE void hb3_push_odd(Hb3State &h, float2 x) { h.s3 = pk_add(h.s3, x); }
 
 // Feed one mixed sample into the cascade.  The sample with in-super-step index t enters stage l only if bits 0..l-1 of
 // t are 0 (it was the first sample of a pair at every earlier stage); bit l then says which branch of stage l it lands
 // on.  Returns the stage-(K-1) output, which exists only for t == 0.  With t a compile-time constant (unrolled caller)
 // everything folds to straight-line code.
 template <int K>
-SDR_HD SDR_FORCEINLINE float2 front_feed(Hb3State *hb, int t, float2 u, float c0, float c1, float c2) {
+SDR_HD SDR_FORCEINLINE float2 front_feed(Hb3State *hb, int t, float2 u, float2 c0, float2 c1, float2 c2) {
     float2 y = u;
     bool alive = true;
 #pragma unroll
@@ -296,7 +324,7 @@ SDR_HD SDR_FORCEINLINE float2 front_feed(Hb3State *hb, int t, float2 u, float c0
 // Same with a run-time t (slow path: few super-steps per span, keeps the code small).  hb[] is indexed with compile-time
 // constants only, so it stays in registers.
 template <int K>
-SDR_HD inline float2 front_feed_dyn(Hb3State *hb, int t, float2 u, float c0, float c1, float c2) {
+SDR_HD inline float2 front_feed_dyn(Hb3State *hb, int t, float2 u, float2 c0, float2 c1, float2 c2) {
     float2 y = u;
     bool alive = true;
 #pragma unroll
@@ -342,9 +370,28 @@ struct XWarpStage {
 };
 #endif
 
+// Oscillator table access.  TabPlain: the 8 KB {cos, sin} table as is.  TabRep16 (GPU): the table replicated 16 times
+// in shared memory, entry i copy r at ((i * 16 + r) * 8) bytes with r = lane & 15, so the 16 lanes of a half-warp always
+// hit 16 different bank pairs whatever their phases: 2 wavefronts per lookup instead of ~5.6 with random conflicts.
+struct TabPlain {
+    const float2 *t;
+    SDR_HD SDR_FORCEINLINE float2 get(unsigned th_biased) const { return t[th_biased >> 22]; }
+};
+#ifndef SDR_EMU
+struct TabRep16 {
+    const char *base;        // shared memory
+    unsigned lane_off;       // (lane & 15) * 8
+    __device__ __forceinline__ float2 get(unsigned th_biased) const {
+        return *reinterpret_cast<const float2 *>(base + (((th_biased >> 15) & 0x1FF80u) | lane_off));
+    }
+};
+#endif
+
 // One thread = one channel over one time span.  `store` is false for padding lanes that only keep a warp converged.
-template <int K, class XS>
-SDR_HD inline void front_span(const FrontArgs &a, int ch, int span_idx, bool store, const float2 *tab_up, const float2 *tab_dn,
+// DIR = +1: every channel of the launch mixes up (or not at all); DIR = -1: every channel mixes down.  Sorting the
+// channels by direction on the host keeps the conjugation out of the inner loop.
+template <int K, int DIR, class XS, class TAB>
+SDR_HD inline void front_span(const FrontArgs &a, int ch, int span_idx, bool store, const TAB &tabf, const float2 *tab_plain,
                               XS &xs) {
     const ChanStatic &cs = a.cs[ch];
     const ChanDyn cd = a.cd[ch];                           // by value: keep the per-block parameters in registers
@@ -357,9 +404,8 @@ SDR_HD inline void front_span(const FrontArgs &a, int ch, int span_idx, bool sto
     if (q_lo >= q_hi) return;
     float2 *out = reinterpret_cast<float2 *>(cs.arena + cs.lvl_off[0]) + kHist;
     const float2 *hx = cd.hist ? cd.hist : a.x;
-    // table oscillator: entry = (theta + 2^21) >> 22; the "down" table holds the conjugates; no mixing = entry 0 = (1, 0)
-    const float2 *tab = cd.dir < 0 ? tab_dn : tab_up;
-    const float2 *tab_prev = cd.dir_prev < 0 ? tab_dn : tab_up;
+    // table oscillator: entry = (theta + 2^21) >> 22; no mixing = constant entry 0 = (1, 0)
+    const float sgn_prev = cd.dir_prev < 0 ? -1.0f : 1.0f;
     const unsigned dth = cd.dir ? cd.dtheta : 0u, dth_prev = cd.dir_prev ? cd.dtheta_prev : 0u;
     const unsigned thb = (cd.dir ? cd.theta0 : 0u) + 0x200000u;          // biased phase at sample 0 of the block
     const unsigned thb_prev = (cd.dir_prev ? cd.theta0 : 0u) + 0x200000u;
@@ -367,8 +413,8 @@ SDR_HD inline void front_span(const FrontArgs &a, int ch, int span_idx, bool sto
     if (K == 0) {
         for (long long q = q_lo; q < q_hi; ++q) {
             const int i = (int)(q - g0);
-            const float2 w = tab[(thb + (unsigned)i * dth) >> 22];
-            if (store) out[q - qa] = cf_rot(sdr_ldg(a.x + i), w.x, w.y);
+            const float2 w = tabf.get(thb + (unsigned)i * dth);
+            if (store) out[q - qa] = cf_rot(sdr_ldg(a.x + i), w.x, DIR > 0 ? w.y : -w.y);
         }
         return;
     }
@@ -376,7 +422,7 @@ SDR_HD inline void front_span(const FrontArgs &a, int ch, int span_idx, bool sto
     Hb3State hb[K > 0 ? K : 1];
 #pragma unroll
     for (int l = 0; l < K; ++l) hb3_reset(hb[l]);
-    const float c0 = a.c0, c1 = a.c1, c2 = a.c2;
+    const float2 c0 = make_float2(a.c0, a.c0), c1 = make_float2(a.c1, a.c1), c2 = make_float2(a.c2, a.c2);
     bool prefetched = false;
 
     for (long long q = q_lo - kFrontWarm; q < q_hi; ++q) {
@@ -394,9 +440,13 @@ SDR_HD inline void front_span(const FrontArgs &a, int ch, int span_idx, bool sto
             unsigned th = thb + (unsigned)i0 * dth;
 #pragma unroll
             for (int t = 0; t < M; ++t) {
-                const float2 w = tab[th >> 22];
+                const float2 w = tabf.get(th);
                 th += dth;
-                const float2 y = front_feed<K>(hb, t, cf_rot(xs.get(t), w.x, w.y), c0, c1, c2);
+                const float2 xv = xs.get(t);
+                // x * (c + j s) when mixing up, x * (c - j s) when mixing down
+                const float2 u = DIR > 0 ? make_float2(fmaf(xv.x, w.x, -(xv.y * w.y)), fmaf(xv.x, w.y, xv.y * w.x))
+                                         : make_float2(fmaf(xv.x, w.x, xv.y * w.y), fmaf(xv.y, w.x, -(xv.x * w.y)));
+                const float2 y = front_feed<K>(hb, t, u, c0, c1, c2);
                 if (t == 0 && store && q >= q_lo) out[q - qa] = y;
             }
         } else {
@@ -408,11 +458,11 @@ SDR_HD inline void front_span(const FrontArgs &a, int ch, int span_idx, bool sto
                 float2 u = make_float2(0.f, 0.f);
                 if (gq + t >= 0 && i >= -kBlkHist) {
                     if (i >= 0) {
-                        const float2 w = tab[(thb + (unsigned)i * dth) >> 22];
-                        u = cf_rot(sdr_ldg(a.x + i), w.x, w.y);
+                        const float2 w = tab_plain[(thb + (unsigned)i * dth) >> 22];
+                        u = cf_rot(sdr_ldg(a.x + i), w.x, DIR > 0 ? w.y : -w.y);
                     } else {
-                        const float2 w = tab_prev[(thb_prev - (unsigned)(-i) * dth_prev) >> 22];
-                        u = cf_rot(sdr_ldg(hx + i), w.x, w.y);
+                        const float2 w = tab_plain[(thb_prev - (unsigned)(-i) * dth_prev) >> 22];
+                        u = cf_rot(sdr_ldg(hx + i), w.x, sgn_prev * w.y);
                     }
                 }
                 const float2 y = front_feed_dyn<K>(hb, t, u, c0, c1, c2);
@@ -423,7 +473,7 @@ SDR_HD inline void front_span(const FrontArgs &a, int ch, int span_idx, bool sto
 }
 
 // generic entry (emulator; GPU warps whose lanes are not in lock step): every lane on its own, samples from global memory
-template <int K>
+template <int K, int DIR>
 SDR_HD inline void front_thread(const FrontArgs &a, int job, int lane) {
     const int n_chunks = (a.cg + 31) / 32;
     const int span_idx = job / n_chunks;
@@ -432,7 +482,9 @@ SDR_HD inline void front_thread(const FrontArgs &a, int job, int lane) {
     if (span_idx >= a.n_span || ci >= a.cg) return;
     XDirect xs;
     xs.p = a.x;
-    front_span<K, XDirect>(a, a.group[ci], span_idx, true, a.nco, a.nco_dn, xs);
+    TabPlain tp;
+    tp.t = a.nco;
+    front_span<K, DIR, XDirect, TabPlain>(a, a.group[ci], span_idx, true, tp, a.nco, xs);
 }
 
 }  // namespace sdrb200

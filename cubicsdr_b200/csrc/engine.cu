@@ -59,17 +59,21 @@ __global__ void __launch_bounds__(kDcThreads) k_dc_apply(DcArgs a) {
         __syncthreads();
     }
 }
-// Channel front: 4 warps per CTA, one warp = 32 channels over one time span.  The oscillator tables (up / conjugate)
-// sit in shared memory; lock-step warps stage the wideband samples through a private shared-memory slot (XWarpStage).
-template <int K>
-__global__ void __launch_bounds__(128, 4) k_chan_front(FrontArgs a) {
-    __shared__ float2 s_up[1024];
-    __shared__ float2 s_dn[1024];
-    __shared__ float4 s_x[4][2][32];
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) { s_up[i] = a.nco[i]; s_dn[i] = a.nco_dn[i]; }
+// Channel front: 16 warps per CTA (one CTA per SM), one warp = 32 channels over one time span.  Dynamic shared memory:
+// the oscillator table replicated 16 times (128 KB, bank-conflict-free lookups for arbitrary phases) followed by each
+// warp's private double-buffered slot for the wideband samples of the super-step it is working on (XWarpStage).
+constexpr int kFrontWarps = 16;
+constexpr int kFrontSmemTab = 1024 * 16 * (int)sizeof(float2);                    // 131072
+constexpr int kFrontSmemBytes = kFrontSmemTab + kFrontWarps * 2 * 32 * (int)sizeof(float4);   // + 16384
+template <int K, int DIR>
+__global__ void __launch_bounds__(kFrontWarps * 32, 1) k_chan_front(FrontArgs a) {
+    extern __shared__ __align__(16) unsigned char front_sm[];
+    float2 *rep = reinterpret_cast<float2 *>(front_sm);
+    float4 *s_x = reinterpret_cast<float4 *>(front_sm + kFrontSmemTab);
+    for (int i = threadIdx.x; i < 1024 * 16; i += blockDim.x) rep[i] = __ldg(a.nco + (i >> 4));
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int job = blockIdx.x * 4 + warp;
+    const int job = blockIdx.x * kFrontWarps + warp;
     const int n_chunks = (a.cg + 31) / 32;
     const int span_idx = job / n_chunks;
     if (span_idx >= a.n_span) return;
@@ -79,14 +83,17 @@ __global__ void __launch_bounds__(128, 4) k_chan_front(FrontArgs a) {
     const int ch = a.group[ci];
     const long long g0 = a.cd[ch].g0;
     const bool lock_step = __all_sync(0xffffffffu, g0 == __shfl_sync(0xffffffffu, g0, 0));
+    TabRep16 tab;
+    tab.base = reinterpret_cast<const char *>(front_sm);
+    tab.lane_off = (unsigned)(lane & 15) * 8u;
     if (K >= 4 && lock_step) {
         XWarpStage<(1 << K)> xs;
-        xs.buf = &s_x[warp][0][0]; xs.lane = lane; xs.cur = 0;
-        front_span<K, XWarpStage<(1 << K)> >(a, ch, span_idx, real, s_up, s_dn, xs);
+        xs.buf = s_x + warp * 64; xs.lane = lane; xs.cur = 0;
+        front_span<K, DIR, XWarpStage<(1 << K)>, TabRep16>(a, ch, span_idx, real, tab, a.nco, xs);
     } else if (real) {
         XDirect xs;
         xs.p = a.x;
-        front_span<K, XDirect>(a, ch, span_idx, true, s_up, s_dn, xs);
+        front_span<K, DIR, XDirect, TabRep16>(a, ch, span_idx, true, tab, a.nco, xs);
     }
 }
 __global__ void __launch_bounds__(kTailThreads) k_chan_tail(TailArgs a) {
@@ -143,27 +150,36 @@ static void launch_dc(const DcArgs &a, sdr_stream_t s, unsigned long long &launc
     launches += 3;
 }
 
-template <int K>
-static void launch_front_k(const FrontArgs &a, int jobs, sdr_stream_t s) {
+template <int K, int DIR>
+static int launch_front_kd(const FrontArgs &a, int jobs, sdr_stream_t s) {
 #ifndef SDR_EMU
-    const int warps_per_cta = 4;
-    k_chan_front<K><<<(jobs + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, s>>>(a);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(k_chan_front<K, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrontSmemBytes));
+        attr_set = true;
+    }
+    k_chan_front<K, DIR><<<(jobs + kFrontWarps - 1) / kFrontWarps, kFrontWarps * 32, kFrontSmemBytes, s>>>(a);
 #else
     (void)s;
-    for (int j = 0; j < jobs; ++j) for (int l = 0; l < 32; ++l) front_thread<K>(a, j, l);
+    for (int j = 0; j < jobs; ++j) for (int l = 0; l < 32; ++l) front_thread<K, DIR>(a, j, l);
 #endif
+    return 0;
 }
-static void launch_front(int K, const FrontArgs &a, int jobs, sdr_stream_t s, unsigned long long &launches) {
+template <int DIR>
+static int launch_front_d(int K, const FrontArgs &a, int jobs, sdr_stream_t s) {
     switch (K) {
-    case 0: launch_front_k<0>(a, jobs, s); break;
-    case 1: launch_front_k<1>(a, jobs, s); break;
-    case 2: launch_front_k<2>(a, jobs, s); break;
-    case 3: launch_front_k<3>(a, jobs, s); break;
-    case 4: launch_front_k<4>(a, jobs, s); break;
-    case 5: launch_front_k<5>(a, jobs, s); break;
-    default: launch_front_k<6>(a, jobs, s); break;
+    case 0: return launch_front_kd<0, DIR>(a, jobs, s);
+    case 1: return launch_front_kd<1, DIR>(a, jobs, s);
+    case 2: return launch_front_kd<2, DIR>(a, jobs, s);
+    case 3: return launch_front_kd<3, DIR>(a, jobs, s);
+    case 4: return launch_front_kd<4, DIR>(a, jobs, s);
+    case 5: return launch_front_kd<5, DIR>(a, jobs, s);
+    default: return launch_front_kd<6, DIR>(a, jobs, s);
     }
+}
+static int launch_front(int K, int dir_class, const FrontArgs &a, int jobs, sdr_stream_t s, unsigned long long &launches) {
     launches += 1;
+    return dir_class >= 0 ? launch_front_d<1>(K, a, jobs, s) : launch_front_d<-1>(K, a, jobs, s);
 }
 
 static void launch_tail(const TailArgs &a, int n_chan, sdr_stream_t s, unsigned long long &launches) {
@@ -293,7 +309,7 @@ struct sdr_engine {
     // DC blocker
     double2 *d_tile_sum = nullptr, *d_tile_carry = nullptr, *d_dc_state = nullptr; double *d_apow = nullptr;
     double dc_a = 0.0;
-    float2 *d_nco = nullptr, *d_nco_dn = nullptr;
+    float2 *d_nco = nullptr;
     // channels
     static const int kMaxChan = 2048;
     std::vector<sdr_chan *> chans;     // by slot; nullptr = free
@@ -408,7 +424,7 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
     bad |= be_malloc((void **)&e->d_dc_state, sizeof(double2));
     bad |= be_malloc((void **)&e->d_apow, (kDcTile + 1) * sizeof(double));
     bad |= be_malloc((void **)&e->d_nco, 1024 * sizeof(float2));
-    bad |= be_malloc((void **)&e->d_nco_dn, 1024 * sizeof(float2));
+
     bad |= be_malloc((void **)&e->d_cs, sdr_engine::kMaxChan * sizeof(ChanStatic));
     bad |= be_malloc((void **)&e->d_cd, sdr_engine::kMaxChan * sizeof(ChanDyn));
     bad |= be_malloc((void **)&e->d_st, sdr_engine::kMaxChan * sizeof(ChanState));
@@ -437,9 +453,7 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
     be_h2d(e->d_nco, nco.data(), 1024 * sizeof(float2), e->stream);
     // entry 0 must be exactly (1, 0): "no mixing" is expressed as a constant phase of 0 (front_span)
     if (nco[0].x != 1.0f || nco[0].y != 0.0f) { delete e; return fail(SDR_ERR_STATE, "oscillator table entry 0 is not (1, 0)"); }
-    std::vector<float2> nco_dn(1024);
-    for (int i = 0; i < 1024; ++i) nco_dn[i] = make_float2(nco[i].x, -nco[i].y);
-    be_h2d(e->d_nco_dn, nco_dn.data(), 1024 * sizeof(float2), e->stream);
+
     be_sync(e->stream);
     *out = e;
     return SDR_OK;
@@ -453,7 +467,7 @@ extern "C" int sdr_engine_destroy(sdr_engine *e) {
     for (auto *c : e->chans) if (c) { be_free(c->d_arena); be_free(c->d_priv_hist); be_host_free(c->h_dyn); be_host_free(c->h_slot); delete c; }
     for (auto *s : e->spectra) if (s) { spectrum_free(s); delete s; }
     be_free(e->d_raw); be_free(e->d_blk); be_free(e->d_scratch); be_host_free(e->h_stage);
-    be_free(e->d_tile_sum); be_free(e->d_tile_carry); be_free(e->d_dc_state); be_free(e->d_apow); be_free(e->d_nco); be_free(e->d_nco_dn);
+    be_free(e->d_tile_sum); be_free(e->d_tile_carry); be_free(e->d_dc_state); be_free(e->d_apow); be_free(e->d_nco);
     be_free(e->d_cs); be_free(e->d_cd); be_free(e->d_st); be_host_free(e->h_cd); be_free(e->d_group); be_host_free(e->h_group);
     be_free(e->d_taps); be_free(e->d_results); be_host_free(e->h_results);
 #ifndef SDR_EMU
@@ -897,7 +911,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, unsigned n, long lo
 #endif
         return SDR_OK;
     }
-    std::vector<int> by_k[kFrontMaxK + 1];
+    std::vector<int> by_k[2 * (kFrontMaxK + 1)];          // [2 * K + (mixes down ? 1 : 0)]
     for (int i = 0; i < n_slots; ++i) {
         sdr_chan *c = e->chans[i];
         ChanDyn &d = h_cd[i];
@@ -927,19 +941,20 @@ static int submit_common(sdr_engine *e, const float2 *d_src, unsigned n, long lo
         if (dir) c->theta += (unsigned)n * c->dtheta;                   // mix_block advances the phase by n steps
         c->dtheta_prev = c->dtheta; c->dir_prev = dir;
         c->consumed += n;
-        by_k[c->cs.K1].push_back(i);
+        by_k[2 * c->cs.K1 + (dir < 0 ? 1 : 0)].push_back(i);
     }
     be_h2d(e->d_cd, h_cd, (size_t)n_slots * sizeof(ChanDyn), e->stream);
     int goff = 0;
     float h3[6];
     halfband_branch_taps(3, 65.0f, h3);
-    for (int K = 0; K <= kFrontMaxK; ++K) {
-        const int cg = (int)by_k[K].size();
+    for (int kd = 0; kd < 2 * (kFrontMaxK + 1); ++kd) {
+        const int K = kd >> 1, dir_class = (kd & 1) ? -1 : +1;
+        const int cg = (int)by_k[kd].size();
         if (!cg) continue;
-        memcpy(h_group + goff, by_k[K].data(), cg * sizeof(int));
+        memcpy(h_group + goff, by_k[kd].data(), cg * sizeof(int));
         be_h2d(e->d_group + goff, h_group + goff, cg * sizeof(int), e->stream);
         FrontArgs fa;
-        fa.x = blk; fa.n = (int)n; fa.nco = e->d_nco; fa.nco_dn = e->d_nco_dn; fa.cs = e->d_cs; fa.cd = e->d_cd; fa.group = e->d_group + goff; fa.cg = cg;
+        fa.x = blk; fa.n = (int)n; fa.nco = e->d_nco; fa.cs = e->d_cs; fa.cd = e->d_cd; fa.group = e->d_group + goff; fa.cg = cg;
         const int n_chunks = (cg + 31) / 32;
         const long long nq = ((long long)n >> K) + 1;
         int n_span = (2368 + n_chunks - 1) / n_chunks;                  // ~16 warps on each of the 148 SMs
@@ -948,7 +963,8 @@ static int submit_common(sdr_engine *e, const float2 *d_src, unsigned n, long lo
         fa.n_span = n_span;
         fa.span = (int)((nq + n_span - 1) / n_span);
         fa.c0 = h3[0]; fa.c1 = h3[1]; fa.c2 = h3[2];
-        launch_front(K, fa, n_chunks * n_span, e->stream, e->launches);
+        int fr = launch_front(K, dir_class, fa, n_chunks * n_span, e->stream, e->launches);
+        if (fr) return fr;
         goff += cg;
     }
     TailArgs ta;
