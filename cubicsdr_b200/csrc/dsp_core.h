@@ -283,6 +283,7 @@ struct FrontArgs {
     int span;                     // super-steps per time span
     int n_span;                   // spans per block
     float c0, c1, c2;             // m = 3 branch taps (symmetric: c[d] = c[5-d])
+    unsigned long long *dbg;      // optional [4 * CTAs]: {smid, t_start, t_after_table, t_end} in ns (globaltimer), else null
 };
 
 struct Hb3State { float2 s0, s1, s2, s3, s4, s5; };
@@ -388,11 +389,8 @@ struct TabRep16 {
 #endif
 
 // One thread = one channel over one time span.  `store` is false for padding lanes that only keep a warp converged.
-// DIR = +1: every channel of the launch mixes up (or not at all); DIR = -1: every channel mixes down.  Sorting the
-// channels by direction on the host keeps the conjugation out of the inner loop.
-template <int K, int DIR, class XS, class TAB>
-SDR_HD inline void front_span(const FrontArgs &a, int ch, int span_idx, bool store, const TAB &tabf, const float2 *tab_plain,
-                              XS &xs) {
+template <int K, class XS, class TAB>
+SDR_HD inline void front_span(const FrontArgs &a, int ch, int span_idx, bool store, const TAB &tabf, XS &xs) {
     const ChanStatic &cs = a.cs[ch];
     const ChanDyn cd = a.cd[ch];                           // by value: keep the per-block parameters in registers
     constexpr int M = 1 << K;
@@ -404,8 +402,9 @@ SDR_HD inline void front_span(const FrontArgs &a, int ch, int span_idx, bool sto
     if (q_lo >= q_hi) return;
     float2 *out = reinterpret_cast<float2 *>(cs.arena + cs.lvl_off[0]) + kHist;
     const float2 *hx = cd.hist ? cd.hist : a.x;
-    // table oscillator: entry = (theta + 2^21) >> 22; no mixing = constant entry 0 = (1, 0)
-    const float sgn_prev = cd.dir_prev < 0 ? -1.0f : 1.0f;
+    // table oscillator: entry = (theta + 2^21) >> 22; mixing down conjugates (sign on the sine); no mixing = constant
+    // entry 0 = (1, 0).  The *_prev values describe the block whose tail forms the history in front of this one.
+    const float sg = cd.dir < 0 ? -1.0f : 1.0f, sg_prev = cd.dir_prev < 0 ? -1.0f : 1.0f;
     const unsigned dth = cd.dir ? cd.dtheta : 0u, dth_prev = cd.dir_prev ? cd.dtheta_prev : 0u;
     const unsigned thb = (cd.dir ? cd.theta0 : 0u) + 0x200000u;          // biased phase at sample 0 of the block
     const unsigned thb_prev = (cd.dir_prev ? cd.theta0 : 0u) + 0x200000u;
@@ -414,7 +413,7 @@ SDR_HD inline void front_span(const FrontArgs &a, int ch, int span_idx, bool sto
         for (long long q = q_lo; q < q_hi; ++q) {
             const int i = (int)(q - g0);
             const float2 w = tabf.get(thb + (unsigned)i * dth);
-            if (store) out[q - qa] = cf_rot(sdr_ldg(a.x + i), w.x, DIR > 0 ? w.y : -w.y);
+            if (store) out[q - qa] = cf_rot(sdr_ldg(a.x + i), w.x, w.y * sg);
         }
         return;
     }
@@ -428,41 +427,41 @@ SDR_HD inline void front_span(const FrontArgs &a, int ch, int span_idx, bool sto
     for (long long q = q_lo - kFrontWarm; q < q_hi; ++q) {
         const long long gq = q * M;                         // channel sample index of the super-step's first input
         const int i0 = (int)(gq - g0);                      // same, relative to the block start
-        const bool inside = (i0 >= 0) && (gq >= 0);         // whole super-step lies in the current block
-        if (inside) {
-            if (!prefetched) xs.prefetch(a.x + i0);
-            xs.commit(a.x + i0);
-            prefetched = (q + 1 < q_hi);
-            if (prefetched) xs.prefetch(a.x + i0 + M);
-        }
-        if (inside) {
-            // ---- fast super-step: every sample is in the current block; phase advances by one add per sample
-            unsigned th = thb + (unsigned)i0 * dth;
+        // a super-step is "whole" when all its samples come from one place with one oscillator setting: the current
+        // block (i0 >= 0) or the history in front of it (i0 + M <= 0), and the channel already existed (gq >= 0)
+        const bool in_block = i0 >= 0, in_hist = (i0 + M <= 0) && (i0 >= -kBlkHist);
+        if ((in_block || in_hist) && gq >= 0) {
+            const float2 *src = (in_block ? a.x : hx) + i0;
+            if (!prefetched) xs.prefetch(src);
+            xs.commit(src);
+            // the next super-step can be prefetched only if it is whole and comes from the same buffer
+            prefetched = (q + 1 < q_hi) && (in_block || (i0 + 2 * M <= 0));
+            if (prefetched) xs.prefetch(src + M);
+            const unsigned step = in_block ? dth : dth_prev;
+            const float s_sign = in_block ? sg : sg_prev;
+            unsigned th = in_block ? thb + (unsigned)i0 * dth : thb_prev - (unsigned)(-i0) * dth_prev;
 #pragma unroll
             for (int t = 0; t < M; ++t) {
                 const float2 w = tabf.get(th);
-                th += dth;
-                const float2 xv = xs.get(t);
-                // x * (c + j s) when mixing up, x * (c - j s) when mixing down
-                const float2 u = DIR > 0 ? make_float2(fmaf(xv.x, w.x, -(xv.y * w.y)), fmaf(xv.x, w.y, xv.y * w.x))
-                                         : make_float2(fmaf(xv.x, w.x, xv.y * w.y), fmaf(xv.y, w.x, -(xv.x * w.y)));
-                const float2 y = front_feed<K>(hb, t, u, c0, c1, c2);
+                th += step;
+                const float2 y = front_feed<K>(hb, t, cf_rot(xs.get(t), w.x, w.y * s_sign), c0, c1, c2);
                 if (t == 0 && store && q >= q_lo) out[q - qa] = y;
             }
         } else {
-            // ---- slow super-step: history in front of the block (mixed with the previous block's oscillator settings)
-            // or samples from before the channel existed (its delay lines then held zeros)
+            // ---- rare: a super-step straddling the block start, or samples from before the channel existed (its delay
+            // lines then held zeros)
+            prefetched = false;
 #pragma unroll 2
             for (int t = 0; t < M; ++t) {
                 const int i = i0 + t;
                 float2 u = make_float2(0.f, 0.f);
                 if (gq + t >= 0 && i >= -kBlkHist) {
                     if (i >= 0) {
-                        const float2 w = tab_plain[(thb + (unsigned)i * dth) >> 22];
-                        u = cf_rot(sdr_ldg(a.x + i), w.x, DIR > 0 ? w.y : -w.y);
+                        const float2 w = tabf.get(thb + (unsigned)i * dth);
+                        u = cf_rot(sdr_ldg(a.x + i), w.x, w.y * sg);
                     } else {
-                        const float2 w = tab_plain[(thb_prev - (unsigned)(-i) * dth_prev) >> 22];
-                        u = cf_rot(sdr_ldg(hx + i), w.x, sgn_prev * w.y);
+                        const float2 w = tabf.get(thb_prev - (unsigned)(-i) * dth_prev);
+                        u = cf_rot(sdr_ldg(hx + i), w.x, w.y * sg_prev);
                     }
                 }
                 const float2 y = front_feed_dyn<K>(hb, t, u, c0, c1, c2);
@@ -472,19 +471,26 @@ SDR_HD inline void front_span(const FrontArgs &a, int ch, int span_idx, bool sto
     }
 }
 
-// generic entry (emulator; GPU warps whose lanes are not in lock step): every lane on its own, samples from global memory
-template <int K, int DIR>
-SDR_HD inline void front_thread(const FrontArgs &a, int job, int lane) {
+// job -> (span, channel chunk): jobs are dealt round-robin over the CTAs so that a small job count still lands on
+// every SM (job = cta + n_cta * warp_in_cta)
+SDR_HD SDR_FORCEINLINE void front_job(const FrontArgs &a, int job, int &span_idx, int &chunk) {
     const int n_chunks = (a.cg + 31) / 32;
-    const int span_idx = job / n_chunks;
-    const int chunk = job - span_idx * n_chunks;
+    span_idx = job / n_chunks;
+    chunk = job - span_idx * n_chunks;
+}
+
+// generic entry (emulator): every lane on its own, samples from global memory
+template <int K>
+SDR_HD inline void front_thread(const FrontArgs &a, int job, int lane) {
+    int span_idx, chunk;
+    front_job(a, job, span_idx, chunk);
     const int ci = chunk * 32 + lane;
     if (span_idx >= a.n_span || ci >= a.cg) return;
     XDirect xs;
     xs.p = a.x;
     TabPlain tp;
     tp.t = a.nco;
-    front_span<K, DIR, XDirect, TabPlain>(a, a.group[ci], span_idx, true, tp, a.nco, xs);
+    front_span<K, XDirect, TabPlain>(a, a.group[ci], span_idx, true, tp, xs);
 }
 
 }  // namespace sdrb200

@@ -38,6 +38,7 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 // ---------------------------------------------------------------------------------------------------------------------
 // kernels (GPU) / serial replays (test-only emulator)
 // ---------------------------------------------------------------------------------------------------------------------
+constexpr int kFrontWarps = 16;      // warps per CTA of the channel front kernel (one CTA per SM)
 #ifndef SDR_EMU
 __global__ void __launch_bounds__(kDcThreads) k_dc_tile_sum(DcArgs a) {
     __shared__ DcShared sm;
@@ -62,38 +63,51 @@ __global__ void __launch_bounds__(kDcThreads) k_dc_apply(DcArgs a) {
 // Channel front: 16 warps per CTA (one CTA per SM), one warp = 32 channels over one time span.  Dynamic shared memory:
 // the oscillator table replicated 16 times (128 KB, bank-conflict-free lookups for arbitrary phases) followed by each
 // warp's private double-buffered slot for the wideband samples of the super-step it is working on (XWarpStage).
-constexpr int kFrontWarps = 16;
 constexpr int kFrontSmemTab = 1024 * 16 * (int)sizeof(float2);                    // 131072
 constexpr int kFrontSmemBytes = kFrontSmemTab + kFrontWarps * 2 * 32 * (int)sizeof(float4);   // + 16384
-template <int K, int DIR>
-__global__ void __launch_bounds__(kFrontWarps * 32, 1) k_chan_front(FrontArgs a) {
+template <int K>
+__global__ void __launch_bounds__(kFrontWarps * 32, 1) k_chan_front(FrontArgs a, int jobs) {
     extern __shared__ __align__(16) unsigned char front_sm[];
     float2 *rep = reinterpret_cast<float2 *>(front_sm);
     float4 *s_x = reinterpret_cast<float4 *>(front_sm + kFrontSmemTab);
+    unsigned long long t_start = 0;
+    if (a.dbg && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
     for (int i = threadIdx.x; i < 1024 * 16; i += blockDim.x) rep[i] = __ldg(a.nco + (i >> 4));
     __syncthreads();
+    if (a.dbg && threadIdx.x == 0) {
+        unsigned smid; unsigned long long t1;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        a.dbg[4 * blockIdx.x] = smid; a.dbg[4 * blockIdx.x + 1] = t_start; a.dbg[4 * blockIdx.x + 2] = t1;
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int job = blockIdx.x * kFrontWarps + warp;
-    const int n_chunks = (a.cg + 31) / 32;
-    const int span_idx = job / n_chunks;
-    if (span_idx >= a.n_span) return;
-    int ci = (job - span_idx * n_chunks) * 32 + lane;
-    const bool real = ci < a.cg;
-    if (!real) ci = a.cg - 1;                                  // padding lanes shadow the last channel, without stores
-    const int ch = a.group[ci];
-    const long long g0 = a.cd[ch].g0;
-    const bool lock_step = __all_sync(0xffffffffu, g0 == __shfl_sync(0xffffffffu, g0, 0));
-    TabRep16 tab;
-    tab.base = reinterpret_cast<const char *>(front_sm);
-    tab.lane_off = (unsigned)(lane & 15) * 8u;
-    if (K >= 4 && lock_step) {
-        XWarpStage<(1 << K)> xs;
-        xs.buf = s_x + warp * 64; xs.lane = lane; xs.cur = 0;
-        front_span<K, DIR, XWarpStage<(1 << K)>, TabRep16>(a, ch, span_idx, real, tab, a.nco, xs);
-    } else if (real) {
-        XDirect xs;
-        xs.p = a.x;
-        front_span<K, DIR, XDirect, TabRep16>(a, ch, span_idx, true, tab, a.nco, xs);
+    const int job = blockIdx.x + gridDim.x * warp;
+    if (job < jobs) {
+        int span_idx, chunk;
+        front_job(a, job, span_idx, chunk);
+        int ci = chunk * 32 + lane;
+        const bool real = ci < a.cg;
+        if (!real) ci = a.cg - 1;                              // padding lanes shadow the last channel, without stores
+        const int ch = a.group[ci];
+        const long long g0 = a.cd[ch].g0;
+        const bool lock_step = __all_sync(0xffffffffu, g0 == __shfl_sync(0xffffffffu, g0, 0));
+        TabRep16 tab;
+        tab.base = reinterpret_cast<const char *>(front_sm);
+        tab.lane_off = (unsigned)(lane & 15) * 8u;
+        if (K >= 4 && lock_step) {
+            XWarpStage<(1 << K)> xs;
+            xs.buf = s_x + warp * 64; xs.lane = lane; xs.cur = 0;
+            front_span<K, XWarpStage<(1 << K)>, TabRep16>(a, ch, span_idx, real, tab, xs);
+        } else if (real) {
+            XDirect xs;
+            xs.p = a.x;
+            front_span<K, XDirect, TabRep16>(a, ch, span_idx, true, tab, xs);
+        }
+    }
+    if (a.dbg) {
+        unsigned long long t2;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t2));
+        atomicMax(a.dbg + 4 * blockIdx.x + 3, t2);
     }
 }
 __global__ void __launch_bounds__(kTailThreads) k_chan_tail(TailArgs a) {
@@ -150,36 +164,35 @@ static void launch_dc(const DcArgs &a, sdr_stream_t s, unsigned long long &launc
     launches += 3;
 }
 
-template <int K, int DIR>
-static int launch_front_kd(const FrontArgs &a, int jobs, sdr_stream_t s) {
+template <int K>
+static int launch_front_k(const FrontArgs &a, int jobs, sdr_stream_t s) {
 #ifndef SDR_EMU
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(k_chan_front<K, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrontSmemBytes));
+        CUDA_TRY(cudaFuncSetAttribute(k_chan_front<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrontSmemBytes));
         attr_set = true;
     }
-    k_chan_front<K, DIR><<<(jobs + kFrontWarps - 1) / kFrontWarps, kFrontWarps * 32, kFrontSmemBytes, s>>>(a);
+    // one CTA per SM while the jobs fit (148 x 16 warps); beyond that, more CTAs
+    int n_cta = (jobs + kFrontWarps - 1) / kFrontWarps;
+    if (jobs <= 148 * kFrontWarps) n_cta = jobs < 148 ? jobs : 148;
+    k_chan_front<K><<<n_cta, kFrontWarps * 32, kFrontSmemBytes, s>>>(a, jobs);
 #else
     (void)s;
-    for (int j = 0; j < jobs; ++j) for (int l = 0; l < 32; ++l) front_thread<K, DIR>(a, j, l);
+    for (int j = 0; j < jobs; ++j) for (int l = 0; l < 32; ++l) front_thread<K>(a, j, l);
 #endif
     return 0;
 }
-template <int DIR>
-static int launch_front_d(int K, const FrontArgs &a, int jobs, sdr_stream_t s) {
-    switch (K) {
-    case 0: return launch_front_kd<0, DIR>(a, jobs, s);
-    case 1: return launch_front_kd<1, DIR>(a, jobs, s);
-    case 2: return launch_front_kd<2, DIR>(a, jobs, s);
-    case 3: return launch_front_kd<3, DIR>(a, jobs, s);
-    case 4: return launch_front_kd<4, DIR>(a, jobs, s);
-    case 5: return launch_front_kd<5, DIR>(a, jobs, s);
-    default: return launch_front_kd<6, DIR>(a, jobs, s);
-    }
-}
-static int launch_front(int K, int dir_class, const FrontArgs &a, int jobs, sdr_stream_t s, unsigned long long &launches) {
+static int launch_front(int K, const FrontArgs &a, int jobs, sdr_stream_t s, unsigned long long &launches) {
     launches += 1;
-    return dir_class >= 0 ? launch_front_d<1>(K, a, jobs, s) : launch_front_d<-1>(K, a, jobs, s);
+    switch (K) {
+    case 0: return launch_front_k<0>(a, jobs, s);
+    case 1: return launch_front_k<1>(a, jobs, s);
+    case 2: return launch_front_k<2>(a, jobs, s);
+    case 3: return launch_front_k<3>(a, jobs, s);
+    case 4: return launch_front_k<4>(a, jobs, s);
+    case 5: return launch_front_k<5>(a, jobs, s);
+    default: return launch_front_k<6>(a, jobs, s);
+    }
 }
 
 static void launch_tail(const TailArgs &a, int n_chan, sdr_stream_t s, unsigned long long &launches) {
@@ -310,6 +323,7 @@ struct sdr_engine {
     double2 *d_tile_sum = nullptr, *d_tile_carry = nullptr, *d_dc_state = nullptr; double *d_apow = nullptr;
     double dc_a = 0.0;
     float2 *d_nco = nullptr;
+    unsigned long long *d_front_dbg = nullptr;   // diagnostics (sdr_engine_debug_front_timeline)
     // channels
     static const int kMaxChan = 2048;
     std::vector<sdr_chan *> chans;     // by slot; nullptr = free
@@ -479,6 +493,24 @@ extern "C" int sdr_engine_destroy(sdr_engine *e) {
 }
 
 extern "C" unsigned long long sdr_engine_launch_count(sdr_engine *e) { return e ? e->launches : 0; }
+
+// diagnostics: per-CTA {smid, t_start, t_after_table, t_end} of the LAST front-kernel launch (not part of the public header)
+extern "C" int sdr_engine_debug_front_timeline(sdr_engine *e, int enable, unsigned long long *out, unsigned max_ctas) {
+    if (!e) return SDR_ERR_ARG;
+    std::lock_guard<std::mutex> lk(e->mu);
+    be_sync(e->stream);
+    if (enable && !e->d_front_dbg) {
+        if (be_malloc((void **)&e->d_front_dbg, 4 * 1024 * sizeof(unsigned long long))) return SDR_ERR_NOMEM;
+        be_memset(e->d_front_dbg, 0, 4 * 1024 * sizeof(unsigned long long), e->stream);
+    }
+    if (out && e->d_front_dbg) {
+        be_d2h(out, e->d_front_dbg, (size_t)4 * std::min(max_ctas, 1024u) * sizeof(unsigned long long), e->stream);
+        be_sync(e->stream);
+        be_memset(e->d_front_dbg, 0, 4 * 1024 * sizeof(unsigned long long), e->stream);
+    }
+    if (!enable && e->d_front_dbg) { be_free(e->d_front_dbg); e->d_front_dbg = nullptr; }
+    return SDR_OK;
+}
 
 extern "C" int sdr_engine_set_timing(sdr_engine *e, int enable) {
     if (!e) return fail(SDR_ERR_ARG, "null engine");
@@ -911,7 +943,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, unsigned n, long lo
 #endif
         return SDR_OK;
     }
-    std::vector<int> by_k[2 * (kFrontMaxK + 1)];          // [2 * K + (mixes down ? 1 : 0)]
+    std::vector<int> by_k[kFrontMaxK + 1];
     for (int i = 0; i < n_slots; ++i) {
         sdr_chan *c = e->chans[i];
         ChanDyn &d = h_cd[i];
@@ -941,29 +973,30 @@ static int submit_common(sdr_engine *e, const float2 *d_src, unsigned n, long lo
         if (dir) c->theta += (unsigned)n * c->dtheta;                   // mix_block advances the phase by n steps
         c->dtheta_prev = c->dtheta; c->dir_prev = dir;
         c->consumed += n;
-        by_k[2 * c->cs.K1 + (dir < 0 ? 1 : 0)].push_back(i);
+        by_k[c->cs.K1].push_back(i);
     }
     be_h2d(e->d_cd, h_cd, (size_t)n_slots * sizeof(ChanDyn), e->stream);
     int goff = 0;
     float h3[6];
     halfband_branch_taps(3, 65.0f, h3);
-    for (int kd = 0; kd < 2 * (kFrontMaxK + 1); ++kd) {
-        const int K = kd >> 1, dir_class = (kd & 1) ? -1 : +1;
-        const int cg = (int)by_k[kd].size();
+    for (int K = 0; K <= kFrontMaxK; ++K) {
+        const int cg = (int)by_k[K].size();
         if (!cg) continue;
-        memcpy(h_group + goff, by_k[kd].data(), cg * sizeof(int));
+        memcpy(h_group + goff, by_k[K].data(), cg * sizeof(int));
         be_h2d(e->d_group + goff, h_group + goff, cg * sizeof(int), e->stream);
         FrontArgs fa;
         fa.x = blk; fa.n = (int)n; fa.nco = e->d_nco; fa.cs = e->d_cs; fa.cd = e->d_cd; fa.group = e->d_group + goff; fa.cg = cg;
         const int n_chunks = (cg + 31) / 32;
         const long long nq = ((long long)n >> K) + 1;
-        int n_span = (2368 + n_chunks - 1) / n_chunks;                  // ~16 warps on each of the 148 SMs
-        const long long min_span = (K == 0) ? 256 : 4 * kFrontWarm;
+        int n_span = std::max(1, (148 * kFrontWarps) / n_chunks);       // jobs <= 16 warps on each of the 148 SMs
+        // every span pays kFrontWarm warm-up super-steps; with few channels, parallelism is worth more than the overhead
+        const long long min_span = (K == 0) ? 256 : kFrontWarm;
         if ((long long)n_span * min_span > nq) n_span = (int)std::max<long long>(1, nq / min_span);
         fa.n_span = n_span;
         fa.span = (int)((nq + n_span - 1) / n_span);
         fa.c0 = h3[0]; fa.c1 = h3[1]; fa.c2 = h3[2];
-        int fr = launch_front(K, dir_class, fa, n_chunks * n_span, e->stream, e->launches);
+        fa.dbg = e->d_front_dbg;
+        int fr = launch_front(K, fa, n_chunks * n_span, e->stream, e->launches);
         if (fr) return fr;
         goff += cg;
     }
