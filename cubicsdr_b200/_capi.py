@@ -20,7 +20,7 @@ SYMBOLS = [
     "sdr_chan_fetch_audio", "sdr_chan_fetch_iq", "sdr_engine_fetch_audio_batch",
     "sdr_modem_check_sample_rate", "sdr_modem_create", "sdr_modem_demodulate",
     "sdr_spectrum_create", "sdr_spectrum_destroy", "sdr_spectrum_set_average_rate", "sdr_spectrum_frames",
-    "sdr_spectrum_fetch", "sdr_spectrum_fetch_debug",
+    "sdr_spectrum_fetch", "sdr_spectrum_fetch_all", "sdr_spectrum_fetch_debug",
     "sdr_design_kaiser", "sdr_design_nco_table", "sdr_design_nco_step", "sdr_design_resampler",
     "sdr_design_halfband_branch", "sdr_design_am_dc_block", "sdr_design_hilbert_q", "sdr_design_butter6_sos",
 ]
@@ -69,6 +69,7 @@ class Lib:
         L.sdr_spectrum_frames.argtypes = [vp, P(u)]
         L.sdr_spectrum_fetch.argtypes = [vp, u, vp, vp, vp]
         L.sdr_spectrum_fetch_debug.argtypes = [vp, u, vp, vp]
+        L.sdr_spectrum_fetch_all.argtypes = [vp, u, vp, vp, vp, P(u)]
         L.sdr_design_kaiser.argtypes = [u, f, f, f, vp]
         L.sdr_design_nco_table.argtypes = [vp]
         L.sdr_design_nco_step.argtypes = [f]
@@ -223,6 +224,19 @@ class Spectrum:
         cf = np.zeros(2, np.float64)
         self.lib.check(self.lib.L.sdr_spectrum_fetch(self.h, idx, _ptr(pts), _ptr(line), _ptr(cf)))
         return pts, line, cf
+
+    def fetch_all(self, cap_frames=64):
+        """(points[n, fft_size], lines[n, fft_size], ceil_floor[n, 2]) of the last block, one call."""
+        if getattr(self, "_all_cap", 0) != cap_frames:
+            self._all_cap = cap_frames
+            self._all_pts = np.zeros((cap_frames, self.fft_size), np.float32)
+            self._all_lines = np.zeros((cap_frames, self.fft_size), np.uint8)
+            self._all_cf = np.zeros((cap_frames, 2), np.float64)
+        n = C.c_uint()
+        self.lib.check(self.lib.L.sdr_spectrum_fetch_all(self.h, cap_frames, _ptr(self._all_pts), _ptr(self._all_lines),
+                                                         _ptr(self._all_cf), C.byref(n)))
+        m = min(n.value, cap_frames)
+        return self._all_pts[:m], self._all_lines[:m], self._all_cf[:m]
 
     def fetch_debug(self, idx):
         mags = np.zeros(2 * self.fft_size, np.float32)

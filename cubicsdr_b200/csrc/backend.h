@@ -15,7 +15,9 @@
 #define SDR_DEV
 #define SDR_FORCEINLINE inline
 struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
 struct double2 { double x, y; };
+static inline float4 make_float4(float a, float b, float c, float d) { float4 r; r.x = a; r.y = b; r.z = c; r.w = d; return r; }
 static inline float2 make_float2(float a, float b) { float2 r; r.x = a; r.y = b; return r; }
 static inline double2 make_double2(double a, double b) { double2 r; r.x = a; r.y = b; return r; }
 template <typename T> static inline T sdr_ldg(const T *p) { return *p; }

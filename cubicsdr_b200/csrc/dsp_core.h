@@ -93,17 +93,26 @@ struct DcArgs {
 // phase 0 of kernel A: each thread folds 4 consecutive samples, writes partial to shared; phase 1: thread 0 combines.
 struct DcShared { double2 part[kDcThreads]; };
 
+// a thread's 4 consecutive samples (32 contiguous bytes): two 16-byte loads when the block is 16-byte aligned
+SDR_HD SDR_FORCEINLINE void dc_load4(const float2 *x, int base, int n, float2 *s) {
+    if (base + 4 <= n && ((reinterpret_cast<size_t>(x + base) & 15) == 0)) {
+        const float4 *p = reinterpret_cast<const float4 *>(x + base);
+        const float4 u = sdr_ldg(p), v = sdr_ldg(p + 1);
+        s[0] = make_float2(u.x, u.y); s[1] = make_float2(u.z, u.w); s[2] = make_float2(v.x, v.y); s[3] = make_float2(v.z, v.w);
+    } else {
+        for (int k = 0; k < 4; ++k) s[k] = (base + k < n) ? x[base + k] : make_float2(0.f, 0.f);
+    }
+}
+
 SDR_HD inline void dc_tile_sum_phase(int ph, const DcArgs &a, int bid, int tid, DcShared *sm) {
     const int per = kDcTile / kDcThreads;
     const int base = bid * kDcTile + tid * per;
     if (ph == 0) {
         double vr = 0.0, vi = 0.0;
-        for (int k = 0; k < per; ++k) {
-            int i = base + k;
-            float2 s = (i < a.n) ? a.x[i] : make_float2(0.f, 0.f);
-            // beyond the block end the recurrence is simply not advanced (handled by weighting below)
-            if (i < a.n) { vr = fma(a.a, vr, (double)s.x); vi = fma(a.a, vi, (double)s.y); }
-        }
+        float2 s[4];
+        dc_load4(a.x, base, a.n, s);
+        for (int k = 0; k < per; ++k)      // beyond the block end the recurrence is simply not advanced
+            if (base + k < a.n) { vr = fma(a.a, vr, (double)s[k].x); vi = fma(a.a, vi, (double)s[k].y); }
         sm->part[tid] = make_double2(vr, vi);
     } else if (tid == 0) {
         // combine thread partials in order: V = sum_t part[t] * a^(samples after thread t's chunk within the tile)
@@ -171,10 +180,10 @@ SDR_HD inline void dc_apply_phase(int ph, const DcArgs &a, int bid, int tid, DcS
     const int base = bid * kDcTile + tid * per;
     if (ph == 0) {
         double vr = 0.0, vi = 0.0;
-        for (int k = 0; k < per; ++k) {
-            int i = base + k;
-            if (i < a.n) { float2 s = a.x[i]; vr = fma(a.a, vr, (double)s.x); vi = fma(a.a, vi, (double)s.y); }
-        }
+        float2 s[4];
+        dc_load4(a.x, base, a.n, s);
+        for (int k = 0; k < per; ++k)
+            if (base + k < a.n) { vr = fma(a.a, vr, (double)s[k].x); vi = fma(a.a, vi, (double)s[k].y); }
         sm->part[tid] = make_double2(vr, vi);
     } else if (ph == 1) {
         if (tid == 0) {
@@ -188,14 +197,19 @@ SDR_HD inline void dc_apply_phase(int ph, const DcArgs &a, int bid, int tid, DcS
         }
     } else {
         double vr = sm->enter[tid].x, vi = sm->enter[tid].y;
+        float2 s[4], o[4];
+        dc_load4(a.x, base, a.n, s);
         for (int k = 0; k < per; ++k) {
-            int i = base + k;
-            if (i < a.n) {
-                float2 s = a.x[i];
-                double nr = fma(a.a, vr, (double)s.x), ni = fma(a.a, vi, (double)s.y);
-                a.y[i] = make_float2((float)(nr - vr), (float)(ni - vi));
-                vr = nr; vi = ni;
-            }
+            const double nr = fma(a.a, vr, (double)s[k].x), ni = fma(a.a, vi, (double)s[k].y);
+            o[k] = make_float2((float)(nr - vr), (float)(ni - vi));
+            vr = nr; vi = ni;
+        }
+        if (base + 4 <= a.n && ((reinterpret_cast<size_t>(a.y + base) & 15) == 0)) {
+            float4 *p = reinterpret_cast<float4 *>(a.y + base);
+            p[0] = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+            p[1] = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
+        } else {
+            for (int k = 0; k < per; ++k) if (base + k < a.n) a.y[base + k] = o[k];
         }
     }
 }

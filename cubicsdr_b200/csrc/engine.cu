@@ -350,7 +350,11 @@ struct sdr_engine {
     unsigned long long stage_count = 0;
 #ifndef SDR_EMU
     cudaEvent_t tev[kTimeSets][5];
+    cudaEvent_t tev_spec[kTimeSets][2];
     bool tev_made = false;
+    // the spectrum kernels run on a side stream, concurrently with the channel kernels (both only read the block)
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 #endif
 };
 
@@ -366,7 +370,10 @@ static void time_collect(sdr_engine *e) {
     for (int i = 0; i < e->time_pending; ++i) {
         for (int k = 0; k < 4; ++k) {
             float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, e->tev[i][k], e->tev[i][k + 1]) == cudaSuccess) e->stage_ms[k] += ms;
+            if (k == 1) { if (cudaEventElapsedTime(&ms, e->tev_spec[i][0], e->tev_spec[i][1]) == cudaSuccess) e->stage_ms[k] += ms; continue; }
+            // the front segment starts where the DC blocker ended (the spectrum is on the side stream)
+            cudaEvent_t from = (k == 2) ? e->tev[i][1] : e->tev[i][k];
+            if (cudaEventElapsedTime(&ms, from, e->tev[i][k + 1]) == cudaSuccess) e->stage_ms[k] += ms;
         }
         e->stage_count++;
     }
@@ -447,6 +454,9 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
     bad |= be_host_alloc((void **)&e->h_group, (size_t)sdr_engine::kRing * sdr_engine::kMaxChan * sizeof(int));
 #ifndef SDR_EMU
     for (int i = 0; i < sdr_engine::kRing; ++i) CUDA_TRY(cudaEventCreateWithFlags(&e->ring_ev[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
 #endif
     e->taps_cap = 4u << 20;   // floats
     bad |= be_malloc((void **)&e->d_taps, e->taps_cap * sizeof(float));
@@ -486,6 +496,9 @@ extern "C" int sdr_engine_destroy(sdr_engine *e) {
     be_free(e->d_taps); be_free(e->d_results); be_host_free(e->h_results);
 #ifndef SDR_EMU
     for (int i = 0; i < sdr_engine::kRing; ++i) cudaEventDestroy(e->ring_ev[i]);
+    if (e->stream2) { cudaStreamSynchronize(e->stream2); cudaStreamDestroy(e->stream2); }
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
     if (e->own_stream) cudaStreamDestroy(e->stream);
 #endif
     delete e;
@@ -518,6 +531,7 @@ extern "C" int sdr_engine_set_timing(sdr_engine *e, int enable) {
 #ifndef SDR_EMU
     if (enable && !e->tev_made) {
         for (int i = 0; i < sdr_engine::kTimeSets; ++i) for (int k = 0; k < 5; ++k) CUDA_TRY(cudaEventCreate(&e->tev[i][k]));
+        for (int i = 0; i < sdr_engine::kTimeSets; ++i) for (int k = 0; k < 2; ++k) CUDA_TRY(cudaEventCreate(&e->tev_spec[i][k]));
         e->tev_made = true;
     }
 #endif
@@ -909,8 +923,10 @@ static int submit_common(sdr_engine *e, const float2 *d_src, unsigned n, long lo
     e->last_n = n; e->have_block = true;
     e->results_on_host = to_host;
 
-    // 3. spectra
+    // 3. spectra: on the side stream, concurrently with the channel kernels (both only read the DC-blocked block)
     std::vector<int> starts;
+    sdr_stream_t sps = e->stream;
+    bool forked = false;
     for (auto *s : e->spectra) {
         schedule_frames(s, n, rate, starts);
         s->frames_last = (unsigned)std::min<size_t>(starts.size(), s->f_max);
@@ -918,19 +934,45 @@ static int submit_common(sdr_engine *e, const float2 *d_src, unsigned n, long lo
         int *h_fs = s->h_frame_start + (size_t)slot * s->f_max;
         memcpy(h_fs, starts.data(), s->frames_last * sizeof(int));
         be_h2d(s->d_frame_start, h_fs, s->frames_last * sizeof(int), e->stream);
+#ifndef SDR_EMU
+        if (!forked) {
+            CUDA_TRY(cudaEventRecord(e->ev_fork, e->stream));
+            CUDA_TRY(cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
+            sps = e->stream2;
+            forked = true;
+            if (e->timing && e->time_pending < sdr_engine::kTimeSets) cudaEventRecord(e->tev_spec[e->time_pending][0], sps);
+        }
+#endif
         SpecArgs a;
         a.x = blk; a.frame_start = s->d_frame_start; a.F = (int)s->frames_last; a.N = (int)s->N; a.fft_size = (int)s->fft_size;
         a.P = s->P; a.nsub = s->nsub; a.log_nsub = s->log_nsub; a.tw = s->d_tw; a.mags = s->d_mags; a.maa_f = s->d_maa; a.ema = s->d_ema;
         a.rate = (double)s->average_rate; a.frame_cf = s->d_frame_cf; a.scalars = s->d_scalars; a.frame_cf_maa = s->d_frame_cf_maa;
         a.points = s->d_points; a.lines = s->d_lines; a.scale_factor = s->scale_factor;
-        int r = launch_spectrum(a, e->stream, e->launches);
+        int r = launch_spectrum(a, sps, e->launches);
         if (r) return r;
         if (to_host) {
-            be_d2h(s->h_points, s->d_points, (size_t)s->frames_last * s->fft_size * sizeof(float), e->stream);
-            be_d2h(s->h_lines, s->d_lines, (size_t)s->frames_last * s->fft_size, e->stream);
-            be_d2h(s->h_cf, s->d_frame_cf_maa, (size_t)s->frames_last * sizeof(double2), e->stream);
+            be_d2h(s->h_points, s->d_points, (size_t)s->frames_last * s->fft_size * sizeof(float), sps);
+            be_d2h(s->h_lines, s->d_lines, (size_t)s->frames_last * s->fft_size, sps);
+            be_d2h(s->h_cf, s->d_frame_cf_maa, (size_t)s->frames_last * sizeof(double2), sps);
         }
     }
+#ifndef SDR_EMU
+    if (forked) {
+        if (e->timing && e->time_pending < sdr_engine::kTimeSets) cudaEventRecord(e->tev_spec[e->time_pending][1], sps);
+        CUDA_TRY(cudaEventRecord(e->ev_join, e->stream2));
+    } else if (e->timing && e->time_pending < sdr_engine::kTimeSets) {
+        cudaEventRecord(e->tev_spec[e->time_pending][0], e->stream);
+        cudaEventRecord(e->tev_spec[e->time_pending][1], e->stream);
+    }
+#endif
+    // everything enqueued after this submit on the main stream (next block's history slide, DC blocker) waits for the
+    // side stream; join_side() is called on every return path below
+    auto join_side = [&]() -> int {
+#ifndef SDR_EMU
+        if (forked) CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
+#endif
+        return SDR_OK;
+    };
 
     time_mark(e, 2);
     // 4. channels: per-block oscillator bookkeeping (DemodulatorPreThread.cpp:154-163, 186-195)
@@ -941,7 +983,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, unsigned n, long lo
 #ifndef SDR_EMU
         CUDA_TRY(cudaEventRecord(e->ring_ev[slot], e->stream));
 #endif
-        return SDR_OK;
+        return join_side();
     }
     std::vector<int> by_k[kFrontMaxK + 1];
     for (int i = 0; i < n_slots; ++i) {
@@ -1016,7 +1058,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, unsigned n, long lo
         for (auto *c : e->chans) if (c) total = std::max(total, (size_t)c->cs.res_off + c->slot_bytes);
         be_d2h(e->h_results, e->d_results, total, e->stream);
     }
-    return SDR_OK;
+    return join_side();
 }
 
 extern "C" int sdr_engine_submit(sdr_engine *e, const sdr_cf32 *iq, unsigned n, long long center, long long rate) {
@@ -1124,6 +1166,18 @@ extern "C" int sdr_spectrum_fetch(sdr_spectrum *s, unsigned idx, float *points_y
     if (points_y) memcpy(points_y, s->h_points + (size_t)idx * s->fft_size, s->fft_size * sizeof(float));
     if (line) memcpy(line, s->h_lines + (size_t)idx * s->fft_size, s->fft_size);
     if (cf) { cf[0] = s->h_cf[idx].x; cf[1] = s->h_cf[idx].y; }
+    return SDR_OK;
+}
+
+extern "C" int sdr_spectrum_fetch_all(sdr_spectrum *s, unsigned cap_frames, float *points_y, uint8_t *lines, double *cf, unsigned *n_frames) {
+    if (!s) return fail(SDR_ERR_ARG, "null spectrum");
+    std::lock_guard<std::mutex> lk(s->eng->mu);
+    if (!s->eng->results_on_host) return fail(SDR_ERR_STATE, "no host results for the last block");
+    const unsigned m = std::min(cap_frames, s->frames_last);
+    if (points_y) memcpy(points_y, s->h_points, (size_t)m * s->fft_size * sizeof(float));
+    if (lines) memcpy(lines, s->h_lines, (size_t)m * s->fft_size);
+    if (cf) for (unsigned f = 0; f < m; ++f) { cf[2 * f] = s->h_cf[f].x; cf[2 * f + 1] = s->h_cf[f].y; }
+    if (n_frames) *n_frames = s->frames_last;
     return SDR_OK;
 }
 

@@ -105,6 +105,9 @@ int sdr_spectrum_frames(sdr_spectrum *sp, unsigned *n_frames);
 /* frame `idx` of the last block: points_y = SpectrumVisualData::spectrum_points y values (fft_size floats),
  * line = the u8 waterfall line, ceil_floor = {fft_ceil_maa, fft_floor_maa}.  Any pointer may be NULL.            */
 int sdr_spectrum_fetch(sdr_spectrum *sp, unsigned idx, float *points_y, uint8_t *line, double *ceil_floor);
+/* every frame of the last block in one call: points_y [cap_frames][fft_size], lines likewise, ceil_floor [cap_frames][2] */
+int sdr_spectrum_fetch_all(sdr_spectrum *sp, unsigned cap_frames, float *points_y, uint8_t *lines, double *ceil_floor,
+                           unsigned *n_frames);
 /* diagnostics for parity tests: linear fftshifted magnitudes and float(maa) of frame idx (2 * fft_size floats each) */
 int sdr_spectrum_fetch_debug(sdr_spectrum *sp, unsigned idx, float *mags, float *maa);
 
