@@ -167,7 +167,7 @@ def run_reference(args, wl, chans, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -270,11 +270,16 @@ def main():
     torch.cuda.synchronize()
 
     # ---- timed: device-resident -----------------------------------------------------------------------------------------
+    # clocks / throttle reasons are sampled from just before the timed region until the end of the e2e region
+    # (nvidia-smi cannot sample faster than ~10 Hz, and the device-resident region alone lasts a fraction of a second)
     sampler = ClockSampler(local_rank)
+    sampler.start()
+    for i in range(60):                                         # ~50 ms of the same work so the first samples see load
+        step_device(i)
+    eng.wait()
     eng.set_timing(True)
     launches0 = eng.launch_count
     barrier(); torch.cuda.synchronize()
-    sampler.start()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for i in range(args.steps):
@@ -283,7 +288,6 @@ def main():
     torch.cuda.synchronize(); barrier()
     ms = e0.elapsed_time(e1)
     eng.wait()
-    clocks = sampler.stop()
     stage_ms, stage_blocks = eng.get_timing()
     eng.set_timing(False)
     launches = eng.launch_count - launches0
@@ -312,6 +316,7 @@ def main():
         dist.all_reduce(dd, op=dist.ReduceOp.SUM)
         d2h = int(dd.item())
     e2e_value = N * args.steps / t_e2e / 1e6
+    clocks = sampler.stop()
 
     if rank != 0:
         if dist is not None:

@@ -115,18 +115,20 @@ SDR_HD inline void dc_tile_sum_phase(int ph, const DcArgs &a, int bid, int tid, 
             if (base + k < a.n) { vr = fma(a.a, vr, (double)s[k].x); vi = fma(a.a, vi, (double)s[k].y); }
         sm->part[tid] = make_double2(vr, vi);
     } else if (tid == 0) {
-        // combine thread partials in order: V = sum_t part[t] * a^(samples after thread t's chunk within the tile)
+        // combine the thread partials in order (Horner): V <- V * a^(samples in chunk t) + part[t]
         int tile_len = a.n - bid * kDcTile;
         if (tile_len > kDcTile) tile_len = kDcTile;
+        double pw[5];
+        pw[0] = 1.0;
+        for (int k = 1; k <= per; ++k) pw[k] = pw[k - 1] * a.a;
         double vr = 0.0, vi = 0.0;
         for (int t = 0; t < kDcThreads; ++t) {
-            int end = (t + 1) * per;            // index (within tile) one past this thread's chunk
-            if (end > tile_len) end = tile_len;
-            int start = t * per;
+            const int start = t * per;
             if (start >= tile_len) break;
-            double w = a.apow[tile_len - end];
-            vr = fma(sm->part[t].x, w, vr);
-            vi = fma(sm->part[t].y, w, vi);
+            const int len = (tile_len - start < per) ? tile_len - start : per;
+            const double w = pw[len];
+            vr = fma(vr, w, sm->part[t].x);
+            vi = fma(vi, w, sm->part[t].y);
         }
         a.tile_sum[bid] = make_double2(vr, vi);
     }
@@ -188,7 +190,7 @@ SDR_HD inline void dc_apply_phase(int ph, const DcArgs &a, int bid, int tid, DcS
     } else if (ph == 1) {
         if (tid == 0) {
             double cr = a.tile_carry[bid].x, ci = a.tile_carry[bid].y;
-            const double w = a.apow[per];
+            const double w = a.a * a.a * a.a * a.a;          // a^per, per = 4
             for (int t = 0; t < kDcThreads; ++t) {
                 sm->enter[t] = make_double2(cr, ci);
                 cr = fma(cr, w, sm->part[t].x);

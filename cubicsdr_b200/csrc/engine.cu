@@ -923,10 +923,11 @@ static int submit_common(sdr_engine *e, const float2 *d_src, unsigned n, long lo
     e->last_n = n; e->have_block = true;
     e->results_on_host = to_host;
 
-    // 3. spectra: on the side stream, concurrently with the channel kernels (both only read the DC-blocked block)
+    // 3. spectra.  Frame scheduling and the (tiny) frame-start upload happen here; the kernels are enqueued on the side
+    //    stream AFTER the channel front kernel has been launched (run_spectra below), so that the front kernel's single
+    //    wave of 148 CTAs gets the SMs first and the spectrum fills in underneath the channel tail.
     std::vector<int> starts;
-    sdr_stream_t sps = e->stream;
-    bool forked = false;
+    std::vector<std::pair<sdr_spectrum *, SpecArgs>> spec_jobs;
     for (auto *s : e->spectra) {
         schedule_frames(s, n, rate, starts);
         s->frames_last = (unsigned)std::min<size_t>(starts.size(), s->f_max);
@@ -934,39 +935,43 @@ static int submit_common(sdr_engine *e, const float2 *d_src, unsigned n, long lo
         int *h_fs = s->h_frame_start + (size_t)slot * s->f_max;
         memcpy(h_fs, starts.data(), s->frames_last * sizeof(int));
         be_h2d(s->d_frame_start, h_fs, s->frames_last * sizeof(int), e->stream);
-#ifndef SDR_EMU
-        if (!forked) {
-            CUDA_TRY(cudaEventRecord(e->ev_fork, e->stream));
-            CUDA_TRY(cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
-            sps = e->stream2;
-            forked = true;
-            if (e->timing && e->time_pending < sdr_engine::kTimeSets) cudaEventRecord(e->tev_spec[e->time_pending][0], sps);
-        }
-#endif
         SpecArgs a;
         a.x = blk; a.frame_start = s->d_frame_start; a.F = (int)s->frames_last; a.N = (int)s->N; a.fft_size = (int)s->fft_size;
         a.P = s->P; a.nsub = s->nsub; a.log_nsub = s->log_nsub; a.tw = s->d_tw; a.mags = s->d_mags; a.maa_f = s->d_maa; a.ema = s->d_ema;
         a.rate = (double)s->average_rate; a.frame_cf = s->d_frame_cf; a.scalars = s->d_scalars; a.frame_cf_maa = s->d_frame_cf_maa;
         a.points = s->d_points; a.lines = s->d_lines; a.scale_factor = s->scale_factor;
-        int r = launch_spectrum(a, sps, e->launches);
-        if (r) return r;
-        if (to_host) {
-            be_d2h(s->h_points, s->d_points, (size_t)s->frames_last * s->fft_size * sizeof(float), sps);
-            be_d2h(s->h_lines, s->d_lines, (size_t)s->frames_last * s->fft_size, sps);
-            be_d2h(s->h_cf, s->d_frame_cf_maa, (size_t)s->frames_last * sizeof(double2), sps);
-        }
+        spec_jobs.emplace_back(s, a);
     }
+    bool forked = false;
+    auto run_spectra = [&]() -> int {
+        sdr_stream_t sps = e->stream;
 #ifndef SDR_EMU
-    if (forked) {
-        if (e->timing && e->time_pending < sdr_engine::kTimeSets) cudaEventRecord(e->tev_spec[e->time_pending][1], sps);
-        CUDA_TRY(cudaEventRecord(e->ev_join, e->stream2));
-    } else if (e->timing && e->time_pending < sdr_engine::kTimeSets) {
-        cudaEventRecord(e->tev_spec[e->time_pending][0], e->stream);
-        cudaEventRecord(e->tev_spec[e->time_pending][1], e->stream);
-    }
+        if (!spec_jobs.empty()) {
+            CUDA_TRY(cudaEventRecord(e->ev_fork, e->stream));
+            CUDA_TRY(cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
+            sps = e->stream2;
+            forked = true;
+        }
+        if (e->timing && e->time_pending < sdr_engine::kTimeSets) cudaEventRecord(e->tev_spec[e->time_pending][0], sps);
 #endif
-    // everything enqueued after this submit on the main stream (next block's history slide, DC blocker) waits for the
-    // side stream; join_side() is called on every return path below
+        for (auto &job : spec_jobs) {
+            sdr_spectrum *s = job.first;
+            int r = launch_spectrum(job.second, sps, e->launches);
+            if (r) return r;
+            if (to_host) {
+                be_d2h(s->h_points, s->d_points, (size_t)s->frames_last * s->fft_size * sizeof(float), sps);
+                be_d2h(s->h_lines, s->d_lines, (size_t)s->frames_last * s->fft_size, sps);
+                be_d2h(s->h_cf, s->d_frame_cf_maa, (size_t)s->frames_last * sizeof(double2), sps);
+            }
+        }
+#ifndef SDR_EMU
+        if (e->timing && e->time_pending < sdr_engine::kTimeSets) cudaEventRecord(e->tev_spec[e->time_pending][1], sps);
+        if (forked) CUDA_TRY(cudaEventRecord(e->ev_join, e->stream2));
+#endif
+        return SDR_OK;
+    };
+    // everything enqueued after this submit on the main stream (next block's history slide, DC blocker) must wait for the
+    // side stream: join_side() is called on every successful return path below
     auto join_side = [&]() -> int {
 #ifndef SDR_EMU
         if (forked) CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
@@ -978,6 +983,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, unsigned n, long lo
     // 4. channels: per-block oscillator bookkeeping (DemodulatorPreThread.cpp:154-163, 186-195)
     int n_slots = (int)e->chans.size();
     if (n_slots == 0) {
+        { int r = run_spectra(); if (r) return r; }
         time_mark(e, 3); time_mark(e, 4);
         if (e->timing && e->time_pending < sdr_engine::kTimeSets) e->time_pending++;
 #ifndef SDR_EMU
@@ -1042,6 +1048,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, unsigned n, long lo
         if (fr) return fr;
         goff += cg;
     }
+    { int r = run_spectra(); if (r) return r; }                     // side stream, after the front kernel got the SMs
     TailArgs ta;
     ta.cs = e->d_cs; ta.cd = e->d_cd; ta.st = e->d_st; ta.taps = e->d_taps; ta.nco = e->d_nco;
     ta.results = e->d_results; ta.n = (int)n; ta.first = 0;
