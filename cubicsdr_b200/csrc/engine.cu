@@ -65,6 +65,58 @@ __global__ void __launch_bounds__(kDcThreads) k_dc_apply(DcArgs a) {
 // warp's private double-buffered slot for the wideband samples of the super-step it is working on (XWarpStage).
 constexpr int kFrontSmemTab = 1024 * 16 * (int)sizeof(float2);                    // 131072
 constexpr int kFrontSmemBytes = kFrontSmemTab + kFrontWarps * 2 * 32 * (int)sizeof(float4);   // + 16384
+// Bit-exact DC blocker: one warp per segment.  All lanes run the (strictly serial) chain redundantly; the warp as a whole
+// prefetches the raw samples three 32-sample batches ahead into shared memory and stores the outputs coalesced.
+__global__ void __launch_bounds__(32) k_dc_exact(DcExactArgs a) {
+    __shared__ float2 sx[4][32];
+    const int s = blockIdx.x, lane = threadIdx.x;
+    int i0;
+    float2 v;
+    dc_exact_plan(a, s, i0, v);
+    const int p0 = s * a.seg_len;
+    int p1 = p0 + a.seg_len;
+    if (p1 > a.n) p1 = a.n;
+    const int nb = (p1 - i0 + 31) / 32;
+    for (int k = 0; k < 3 && k < nb; ++k) {
+        const int idx = i0 + 32 * k + lane;
+        sx[k & 3][lane] = idx < p1 ? __ldg(a.xraw + idx) : make_float2(0.f, 0.f);
+    }
+    __syncwarp();
+    float2 v_in = v, y;
+    for (int k = 0; k < nb; ++k) {
+        const int base = i0 + 32 * k;
+        float2 nxt = make_float2(0.f, 0.f);
+        const bool has = k + 3 < nb;
+        if (has) { const int idx = base + 96 + lane; if (idx < p1) nxt = __ldg(a.xraw + idx); }
+        if (base + 32 <= p0) {
+            // pure warm-up batch: nothing but the chain
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dc_ref_step(a.c, sx[k & 3][j], v, y);
+            if (base + 32 == p0) v_in = v;
+        } else {
+            float2 mine = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int idx = base + j;
+                if (idx < p1) {
+                    if (idx == p0) v_in = v;
+                    dc_ref_step(a.c, sx[k & 3][j], v, y);
+                    if (lane == j) mine = y;
+                }
+            }
+            const int idx = base + lane;
+            if (idx >= p0 && idx < p1) a.y[idx] = mine;
+        }
+        __syncwarp();
+        if (has) sx[(k + 3) & 3][lane] = nxt;
+        __syncwarp();
+    }
+    if (lane == 0) { a.seg_in[s] = v_in; a.seg_out[s] = v; }
+}
+__global__ void k_dc_verify(DcExactArgs a) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) dc_exact_verify(a);
+}
+
 template <int K>
 __global__ void __launch_bounds__(kFrontWarps * 32, 1) k_chan_front(FrontArgs a, int jobs) {
     extern __shared__ __align__(16) unsigned char front_sm[];
@@ -139,13 +191,27 @@ __global__ void __launch_bounds__(kSpecThreads) k_spec_points(SpecArgs a) {
 }
 #endif
 
-static void launch_dc(const DcArgs &a, sdr_stream_t s, unsigned long long &launches) {
+static void launch_dc_exact(const DcExactArgs &a, sdr_stream_t s, unsigned long long &launches) {
+#ifndef SDR_EMU
+    k_dc_exact<<<a.n_seg, 32, 0, s>>>(a);
+    k_dc_verify<<<1, 32, 0, s>>>(a);
+#else
+    (void)s;
+    for (int g = 0; g < a.n_seg; ++g) dc_exact_segment_serial(a, g, false, make_float2(0.f, 0.f));
+    dc_exact_verify(a);
+#endif
+    launches += 2;
+}
+
+// double-precision scan of the recurrence: tile sums + carries always (they seed the bit-exact replay), and the direct
+// evaluation of y from them when `apply` is set (SDR_B200_DC=scan: the exact-arithmetic variant, not bit-exact)
+static void launch_dc(const DcArgs &a, bool apply, sdr_stream_t s, unsigned long long &launches) {
     const int tiles = (a.n + kDcTile - 1) / kDcTile;
     if (tiles == 0) return;
 #ifndef SDR_EMU
     k_dc_tile_sum<<<tiles, kDcThreads, 0, s>>>(a);
     k_dc_carry<<<1, kDcThreads, 0, s>>>(a, tiles);
-    k_dc_apply<<<tiles, kDcThreads, 0, s>>>(a);
+    if (apply) k_dc_apply<<<tiles, kDcThreads, 0, s>>>(a);
 #else
     (void)s;
     for (int b = 0; b < tiles; ++b) {
@@ -156,12 +222,12 @@ static void launch_dc(const DcArgs &a, sdr_stream_t s, unsigned long long &launc
         DcCarryShared cs;
         for (int ph = 0; ph < 3; ++ph) for (int t = 0; t < kDcThreads; ++t) dc_carry_phase(ph, a, tiles, t, &cs);
     }
-    for (int b = 0; b < tiles; ++b) {
+    if (apply) for (int b = 0; b < tiles; ++b) {
         DcShared2 sm;
         for (int ph = 0; ph < 3; ++ph) for (int t = 0; t < kDcThreads; ++t) dc_apply_phase(ph, a, b, t, &sm);
     }
 #endif
-    launches += 3;
+    launches += apply ? 3 : 2;
 }
 
 template <int K>
@@ -315,12 +381,19 @@ struct sdr_engine {
     unsigned long long launches = 0;
     // wideband buffers
     size_t hist_cap = 0;
-    float2 *d_raw = nullptr, *d_blk = nullptr, *d_scratch = nullptr;
+    float2 *d_raw = nullptr, *d_scratch = nullptr;
+    float2 *d_blkbuf[2] = {nullptr, nullptr};   // DC-blocked stream, double-buffered: [hist_cap | max_block] each
+    float2 *d_rawbuf = nullptr;                 // raw stream [hist_cap | max_block] (the bit-exact DC replay warms up on history)
+    int parity = 0;                             // buffer holding the block submitted last
+    bool exact_dc = true;                       // bit-exact replay of the reference's float DC blocker (SDR_B200_DC=scan disables)
+    double2 *d_tile_carry2[2] = {nullptr, nullptr};
+    float2 *d_seg_in = nullptr, *d_seg_out = nullptr, *d_fstate = nullptr;
+    unsigned *d_fixups = nullptr;
     sdr_cf32 *h_stage = nullptr;        // pinned staging for H2D
     unsigned last_n = 0;
     bool have_block = false;
     // DC blocker
-    double2 *d_tile_sum = nullptr, *d_tile_carry = nullptr, *d_dc_state = nullptr; double *d_apow = nullptr;
+    double2 *d_tile_sum = nullptr, *d_dc_state = nullptr; double *d_apow = nullptr;
     double dc_a = 0.0;
     float2 *d_nco = nullptr;
     unsigned long long *d_front_dbg = nullptr;   // diagnostics (sdr_engine_debug_front_timeline)
@@ -355,6 +428,10 @@ struct sdr_engine {
     // the spectrum kernels run on a side stream, concurrently with the channel kernels (both only read the block)
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // the DC blocker of block b+1 runs on its own stream underneath the channel kernels of block b
+    cudaStream_t stream_dc = nullptr;
+    cudaEvent_t ev_input = nullptr, ev_dc_done[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+    cudaEvent_t tev_dc[kTimeSets][2];
 #endif
 };
 
@@ -370,10 +447,9 @@ static void time_collect(sdr_engine *e) {
     for (int i = 0; i < e->time_pending; ++i) {
         for (int k = 0; k < 4; ++k) {
             float ms = 0.f;
+            if (k == 0) { if (cudaEventElapsedTime(&ms, e->tev_dc[i][0], e->tev_dc[i][1]) == cudaSuccess) e->stage_ms[k] += ms; continue; }
             if (k == 1) { if (cudaEventElapsedTime(&ms, e->tev_spec[i][0], e->tev_spec[i][1]) == cudaSuccess) e->stage_ms[k] += ms; continue; }
-            // the front segment starts where the DC blocker ended (the spectrum is on the side stream)
-            cudaEvent_t from = (k == 2) ? e->tev[i][1] : e->tev[i][k];
-            if (cudaEventElapsedTime(&ms, from, e->tev[i][k + 1]) == cudaSuccess) e->stage_ms[k] += ms;
+            if (cudaEventElapsedTime(&ms, e->tev[i][k], e->tev[i][k + 1]) == cudaSuccess) e->stage_ms[k] += ms;
         }
         e->stage_count++;
     }
@@ -436,12 +512,19 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
     e->hist_cap = 65536 + kBlkHist;
     int bad = 0;
     bad |= be_malloc((void **)&e->d_raw, (size_t)max_block * sizeof(float2));
-    bad |= be_malloc((void **)&e->d_blk, (e->hist_cap + max_block) * sizeof(float2));
+    for (int b = 0; b < 2; ++b) bad |= be_malloc((void **)&e->d_blkbuf[b], (e->hist_cap + max_block) * sizeof(float2));
+    bad |= be_malloc((void **)&e->d_rawbuf, (e->hist_cap + max_block) * sizeof(float2));
     bad |= be_malloc((void **)&e->d_scratch, e->hist_cap * sizeof(float2));
     bad |= be_host_alloc((void **)&e->h_stage, (size_t)max_block * sizeof(sdr_cf32));
     const int tiles = (max_block + kDcTile - 1) / kDcTile;
     bad |= be_malloc((void **)&e->d_tile_sum, tiles * sizeof(double2));
-    bad |= be_malloc((void **)&e->d_tile_carry, tiles * sizeof(double2));
+    for (int b = 0; b < 2; ++b) bad |= be_malloc((void **)&e->d_tile_carry2[b], tiles * sizeof(double2));
+    const int max_seg = (int)(max_block / kDcSegLen) + 2;
+    bad |= be_malloc((void **)&e->d_seg_in, max_seg * sizeof(float2));
+    bad |= be_malloc((void **)&e->d_seg_out, max_seg * sizeof(float2));
+    bad |= be_malloc((void **)&e->d_fstate, sizeof(float2));
+    bad |= be_malloc((void **)&e->d_fixups, sizeof(unsigned));
+    { const char *m = getenv("SDR_B200_DC"); if (m && std::string(m) == "scan") e->exact_dc = false; }
     bad |= be_malloc((void **)&e->d_dc_state, sizeof(double2));
     bad |= be_malloc((void **)&e->d_apow, (kDcTile + 1) * sizeof(double));
     bad |= be_malloc((void **)&e->d_nco, 1024 * sizeof(float2));
@@ -455,13 +538,22 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
 #ifndef SDR_EMU
     for (int i = 0; i < sdr_engine::kRing; ++i) CUDA_TRY(cudaEventCreateWithFlags(&e->ring_ev[i], cudaEventDisableTiming));
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_dc, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&e->ev_input, cudaEventDisableTiming));
+    for (int b = 0; b < 2; ++b) {
+        CUDA_TRY(cudaEventCreateWithFlags(&e->ev_dc_done[b], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&e->ev_consumed[b], cudaEventDisableTiming));
+    }
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
 #endif
     e->taps_cap = 4u << 20;   // floats
     bad |= be_malloc((void **)&e->d_taps, e->taps_cap * sizeof(float));
     if (bad) { delete e; return fail(SDR_ERR_NOMEM, "sdr_engine_create: allocation failed"); }
-    be_memset(e->d_blk, 0, (e->hist_cap + max_block) * sizeof(float2), e->stream);
+    for (int b = 0; b < 2; ++b) be_memset(e->d_blkbuf[b], 0, (e->hist_cap + max_block) * sizeof(float2), e->stream);
+    be_memset(e->d_rawbuf, 0, (e->hist_cap + max_block) * sizeof(float2), e->stream);
+    be_memset(e->d_fstate, 0, sizeof(float2), e->stream);
+    be_memset(e->d_fixups, 0, sizeof(unsigned), e->stream);
     be_memset(e->d_dc_state, 0, sizeof(double2), e->stream);
     // DC blocker coefficient: a = -(-1 + alpha) with alpha = 0.0005f, evaluated in float as the reference does
     const float a_f = 1.0f - 0.0005f;
@@ -490,13 +582,17 @@ extern "C" int sdr_engine_destroy(sdr_engine *e) {
     be_sync(e->stream);
     for (auto *c : e->chans) if (c) { be_free(c->d_arena); be_free(c->d_priv_hist); be_host_free(c->h_dyn); be_host_free(c->h_slot); delete c; }
     for (auto *s : e->spectra) if (s) { spectrum_free(s); delete s; }
-    be_free(e->d_raw); be_free(e->d_blk); be_free(e->d_scratch); be_host_free(e->h_stage);
-    be_free(e->d_tile_sum); be_free(e->d_tile_carry); be_free(e->d_dc_state); be_free(e->d_apow); be_free(e->d_nco);
+    be_free(e->d_raw); be_free(e->d_blkbuf[0]); be_free(e->d_blkbuf[1]); be_free(e->d_rawbuf); be_free(e->d_scratch); be_host_free(e->h_stage);
+    be_free(e->d_tile_sum); be_free(e->d_tile_carry2[0]); be_free(e->d_tile_carry2[1]); be_free(e->d_dc_state);
+    be_free(e->d_seg_in); be_free(e->d_seg_out); be_free(e->d_fstate); be_free(e->d_fixups); be_free(e->d_apow); be_free(e->d_nco);
     be_free(e->d_cs); be_free(e->d_cd); be_free(e->d_st); be_host_free(e->h_cd); be_free(e->d_group); be_host_free(e->h_group);
     be_free(e->d_taps); be_free(e->d_results); be_host_free(e->h_results);
 #ifndef SDR_EMU
     for (int i = 0; i < sdr_engine::kRing; ++i) cudaEventDestroy(e->ring_ev[i]);
     if (e->stream2) { cudaStreamSynchronize(e->stream2); cudaStreamDestroy(e->stream2); }
+    if (e->stream_dc) { cudaStreamSynchronize(e->stream_dc); cudaStreamDestroy(e->stream_dc); }
+    if (e->ev_input) cudaEventDestroy(e->ev_input);
+    for (int b = 0; b < 2; ++b) { if (e->ev_dc_done[b]) cudaEventDestroy(e->ev_dc_done[b]); if (e->ev_consumed[b]) cudaEventDestroy(e->ev_consumed[b]); }
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
     if (e->own_stream) cudaStreamDestroy(e->stream);
@@ -506,6 +602,19 @@ extern "C" int sdr_engine_destroy(sdr_engine *e) {
 }
 
 extern "C" unsigned long long sdr_engine_launch_count(sdr_engine *e) { return e ? e->launches : 0; }
+
+// diagnostics: number of segment junctions the bit-exact DC replay had to recompute serially so far
+extern "C" int sdr_engine_debug_dc_fixups(sdr_engine *e, unsigned *fixups, int *exact_mode) {
+    if (!e) return SDR_ERR_ARG;
+    std::lock_guard<std::mutex> lk(e->mu);
+    be_sync(e->stream);
+    unsigned v = 0;
+    be_d2h(&v, e->d_fixups, sizeof v, e->stream);
+    be_sync(e->stream);
+    if (fixups) *fixups = v;
+    if (exact_mode) *exact_mode = e->exact_dc ? 1 : 0;
+    return SDR_OK;
+}
 
 // diagnostics: per-CTA {smid, t_start, t_after_table, t_end} of the LAST front-kernel launch (not part of the public header)
 extern "C" int sdr_engine_debug_front_timeline(sdr_engine *e, int enable, unsigned long long *out, unsigned max_ctas) {
@@ -532,6 +641,7 @@ extern "C" int sdr_engine_set_timing(sdr_engine *e, int enable) {
     if (enable && !e->tev_made) {
         for (int i = 0; i < sdr_engine::kTimeSets; ++i) for (int k = 0; k < 5; ++k) CUDA_TRY(cudaEventCreate(&e->tev[i][k]));
         for (int i = 0; i < sdr_engine::kTimeSets; ++i) for (int k = 0; k < 2; ++k) CUDA_TRY(cudaEventCreate(&e->tev_spec[i][k]));
+        for (int i = 0; i < sdr_engine::kTimeSets; ++i) for (int k = 0; k < 2; ++k) CUDA_TRY(cudaEventCreate(&e->tev_dc[i][k]));
         e->tev_made = true;
     }
 #endif
@@ -897,29 +1007,66 @@ static int rebuild(sdr_engine *e) {
 
 static int submit_common(sdr_engine *e, const float2 *d_src, unsigned n, long long center, long long rate, bool to_host) {
     if (e->dirty) { int r = rebuild(e); if (r) return r; }
-    float2 *blk = e->d_blk + e->hist_cap;
+    const int p = e->parity ^ 1;                               // this block's buffer; the other one holds the previous block
+    float2 *blk = e->d_blkbuf[p] + e->hist_cap;
+    float2 *raw = e->d_rawbuf + e->hist_cap;
     const int slot = (int)(e->ring_seq++ % sdr_engine::kRing);
 #ifndef SDR_EMU
     CUDA_TRY(cudaEventSynchronize(e->ring_ev[slot]));      // the copies that last used this parameter slot are done
 #endif
     ChanDyn *h_cd = e->h_cd + (size_t)slot * sdr_engine::kMaxChan;
     int *h_group = e->h_group + (size_t)slot * sdr_engine::kMaxChan;
-    // 1. slide the wideband history so that blk[-h..-1] holds the last h samples of the stream so far
+
+    // 1+2. DC blocker (SDRPostThread.cpp:284) on its own stream, so that it runs underneath the channel kernels of the
+    //      previous block: raw history slide -> copy the block in -> double-precision scan -> bit-exact float replay
+    //      into blk -> history of blk from the other buffer.
+    sdr_stream_t dcs = e->stream;
+#ifndef SDR_EMU
+    dcs = e->stream_dc;
+    CUDA_TRY(cudaEventRecord(e->ev_input, e->stream));         // the input block is ready when the caller's stream gets here
+    CUDA_TRY(cudaStreamWaitEvent(dcs, e->ev_input, 0));
+    CUDA_TRY(cudaStreamWaitEvent(dcs, e->ev_consumed[p], 0));  // the kernels of two blocks ago are done with this buffer
+    if (e->timing && e->time_pending < sdr_engine::kTimeSets) cudaEventRecord(e->tev_dc[e->time_pending][0], dcs);
+#endif
+    const size_t need_raw = std::min(e->hist_cap, (size_t)kDcWarm + 2 * kDcTile);
+    if (e->have_block && e->last_n > 0) {
+        be_d2d(e->d_scratch, raw + (long long)e->last_n - (long long)need_raw, need_raw * sizeof(float2), dcs);
+        be_d2d(raw - need_raw, e->d_scratch, need_raw * sizeof(float2), dcs);
+    }
+    be_d2d(raw, d_src, (size_t)n * sizeof(float2), dcs);
+    DcArgs dc;
+    dc.x = raw; dc.y = blk; dc.n = (int)n; dc.a = e->dc_a; dc.tile_sum = e->d_tile_sum; dc.tile_carry = e->d_tile_carry2[p];
+    dc.state = e->d_dc_state; dc.apow = e->d_apow;
+    launch_dc(dc, !e->exact_dc, dcs, e->launches);
+    if (e->exact_dc) {
+        DcExactArgs xa;
+        xa.xraw = raw; xa.y = blk; xa.n = (int)n; xa.seg_len = kDcSegLen; xa.warm = kDcWarm;
+        xa.c = (float)e->dc_a;
+        xa.tile_carry = e->d_tile_carry2[p]; xa.prev_tile_carry = e->d_tile_carry2[p ^ 1];
+        xa.prev_n = e->have_block ? (int)e->last_n : 0;
+        xa.seg_in = e->d_seg_in; xa.seg_out = e->d_seg_out; xa.fstate = e->d_fstate; xa.fixups = e->d_fixups;
+        // speculate only when there is parallelism to gain and the warm-up region lies inside the data we hold
+        const bool spec = n >= 4u * kDcSegLen && (!e->have_block || e->last_n >= (unsigned)(kDcWarm + kDcTile));
+        xa.n_seg = spec ? (int)((n + kDcSegLen - 1) / kDcSegLen) : 1;
+        if (!spec) xa.seg_len = (int)n;
+        launch_dc_exact(xa, dcs, e->launches);
+    }
+    // history in front of the block: the tail of the previous block, which lives in the other buffer
     size_t need = kBlkHist;
     for (auto *s : e->spectra) need = std::max(need, (size_t)s->N + 16);
     if (need > e->hist_cap) need = e->hist_cap;
     if (e->have_block && e->last_n > 0) {
-        const size_t h = need;
-        be_d2d(e->d_scratch, blk + (long long)e->last_n - (long long)h, h * sizeof(float2), e->stream);
-        be_d2d(blk - h, e->d_scratch, h * sizeof(float2), e->stream);
+        const float2 *prev = e->d_blkbuf[p ^ 1] + e->hist_cap;
+        be_d2d(blk - need, prev + (long long)e->last_n - (long long)need, need * sizeof(float2), dcs);
     }
-    // 2. DC blocker (SDRPostThread.cpp:284) raw -> blk
-    DcArgs dc;
-    dc.x = d_src; dc.y = blk; dc.n = (int)n; dc.a = e->dc_a; dc.tile_sum = e->d_tile_sum; dc.tile_carry = e->d_tile_carry;
-    dc.state = e->d_dc_state; dc.apow = e->d_apow;
+#ifndef SDR_EMU
+    if (e->timing && e->time_pending < sdr_engine::kTimeSets) cudaEventRecord(e->tev_dc[e->time_pending][1], dcs);
+    CUDA_TRY(cudaEventRecord(e->ev_dc_done[p], dcs));
+    CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_dc_done[p], 0));
+#endif
     time_mark(e, 0);
-    launch_dc(dc, e->stream, e->launches);
     time_mark(e, 1);
+    e->parity = p;
     e->last_n = n; e->have_block = true;
     e->results_on_host = to_host;
 
@@ -975,6 +1122,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, unsigned n, long lo
     auto join_side = [&]() -> int {
 #ifndef SDR_EMU
         if (forked) CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
+        CUDA_TRY(cudaEventRecord(e->ev_consumed[p], e->stream));   // this block's readers are done once the stream gets here
 #endif
         return SDR_OK;
     };
@@ -1104,7 +1252,7 @@ extern "C" int sdr_engine_fetch_block(sdr_engine *e, sdr_cf32 *out, unsigned cap
     if (!e || !out) return fail(SDR_ERR_ARG, "null argument");
     std::lock_guard<std::mutex> lk(e->mu);
     unsigned m = std::min(cap, e->last_n);
-    be_d2h(out, e->d_blk + e->hist_cap, (size_t)m * sizeof(sdr_cf32), e->stream);
+    be_d2h(out, e->d_blkbuf[e->parity] + e->hist_cap, (size_t)m * sizeof(sdr_cf32), e->stream);
     be_sync(e->stream);
     if (n) *n = m;
     return SDR_OK;

@@ -18,7 +18,7 @@ def build(force=False):
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".h")] + [os.path.join(ROOT, "include", "sdr_b200.h")]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
         return OUT
-    cmd = ["g++", "-O2", "-std=c++14", "-DSDR_EMU", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"),
+    cmd = ["g++", "-O2", "-ffp-contract=off", "-std=c++14", "-DSDR_EMU", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"),
            "-x", "c++", srcs[0], srcs[1], "-o", OUT]
     subprocess.check_call(cmd)
     return OUT

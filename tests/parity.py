@@ -117,7 +117,7 @@ def run_spectrum(lib, ref, fs, fft_size, n_blocks, chans, lps=0, block=None, see
             u8_bad += int(bad.sum())
             # a mismatch only counts as "far" if the reference's float is not next to a quantisation edge
             v = np.clip(r["points"].astype(np.float64), 0, 0.99) * 255.0
-            near_edge = np.abs(v - np.round(v)) < 255.0 * 1e-4
+            near_edge = np.abs(v - np.round(v)) < 255.0 * 1e-5
             u8_bad_far += int((bad & ~near_edge).sum())
             n_frames += 1
     sp.close(); rsp.close(); rd.close(); ing.close(); eng.close()
@@ -148,7 +148,7 @@ def check_against_golden(lib, device=0):
             worst = max(worst, relrms(a, ga))
         for f in (0, sp.frames - 1):
             pts, line, _ = sp.fetch(f)
-            assert relrms(pts, g["spec_points_b%d_f%d" % (b, f)]) <= 1e-4
+            assert relrms(pts, g["spec_points_b%d_f%d" % (b, f)]) <= TOL
     eng.close()
     assert worst <= TOL, worst
     return worst

@@ -56,7 +56,7 @@ def _run(lib, ref, tmp):
     got = np.fromfile(os.path.join(tmp, "postiq_chan_FM.bin"), np.complex64)
     assert len(got) == sum(len(q) for q in fm_iq) and relrms(got, np.concatenate(fm_iq)) <= TOL
     pts = np.fromfile(os.path.join(tmp, "spec_last_points.bin"), np.float32)
-    assert len(pts) == 256 and relrms(pts, last_pts) <= 1e-4
+    assert len(pts) == 256 and relrms(pts, last_pts) <= TOL
 
 
 def test_host_adapters_on_emulator(emu_lib, ref, tmp_path):
