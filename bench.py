@@ -214,7 +214,7 @@ def main():
     if rank == 0:
         for r in range(args.ring):
             ring.append(torch_wideband(torch, fs, N, carriers, r * N, dev, 1234))
-    recv = torch.empty(N, dtype=torch.complex64, device=dev) if world > 1 else None
+    recvs = [torch.empty(N, dtype=torch.complex64, device=dev) for _ in range(4)] if world > 1 else None
     host_blocks = None
     if rank == 0:
         host_blocks = [torch.empty(N, dtype=torch.complex64).pin_memory() for _ in range(2)]
@@ -225,11 +225,19 @@ def main():
         if dist is not None:
             dist.barrier()
 
+    side = torch.cuda.Stream(device=dev)                       # input production (NCCL broadcast) off the engine's stream
+    bc_done = [torch.cuda.Event() for _ in range(4)]
+
     def step_device(i):
-        buf = ring[i % args.ring] if rank == 0 else recv
+        buf = ring[i % args.ring] if rank == 0 else recvs[i & 3]
+        ev = None
         if world > 1:
-            dist.broadcast(buf, src=0)                            # the path's one exchange step (raw IQ over NVLink)
-        eng.submit_device(buf.data_ptr(), N, CENTER, fs, fetch_to_host=False)
+            with torch.cuda.stream(side):
+                dist.broadcast(buf, src=0)                        # the path's one exchange step (raw IQ over NVLink)
+                bc_done[i & 3].record(side)
+            ev = bc_done[i & 3].cuda_event
+        # resident block (or ready at `ev`): the DC blocker of this block overlaps the previous block's channel kernels
+        eng.submit_device_async(buf.data_ptr(), N, CENTER, fs, fetch_to_host=False, ready_event=ev)
 
     # end to end: pinned host block -> H2D (copy stream, overlapped with the previous block's kernels) -> (broadcast) ->
     # kernels -> D2H of every result -> batched fetch into host arrays.  Public API only: submit_device / wait / fetch.
@@ -246,12 +254,16 @@ def main():
     def step_e2e(i, first):
         if first:
             h2d(i)
-        if rank == 0:
-            stream.wait_event(h2d_done[i & 1])
         buf = stages[i & 1]
+        ev = h2d_done[i & 1]
         if world > 1:
-            dist.broadcast(buf, src=0)
-        eng.submit_device(buf.data_ptr(), N, CENTER, fs, fetch_to_host=True)
+            with torch.cuda.stream(side):
+                if rank == 0:
+                    side.wait_event(h2d_done[i & 1])
+                dist.broadcast(buf, src=0)
+                bc_done[i & 3].record(side)
+            ev = bc_done[i & 3]
+        eng.submit_device_async(buf.data_ptr(), N, CENTER, fs, fetch_to_host=True, ready_event=ev.cuda_event if (rank == 0 or world > 1) else None)
         h2d(i + 1)                                             # next block's copy overlaps this block's kernels
         eng.wait()
         nbytes = 0

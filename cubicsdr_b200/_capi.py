@@ -14,7 +14,8 @@ PRODUCT_LIB = os.path.join(_HERE, "libsdr_b200.so")
 # every symbol include/sdr_b200.h declares (tests/test_abi.py checks the header against this list and the .so)
 SYMBOLS = [
     "sdr_last_error", "sdr_version", "sdr_is_device_build",
-    "sdr_engine_create", "sdr_engine_destroy", "sdr_engine_submit", "sdr_engine_submit_device", "sdr_engine_wait",
+    "sdr_engine_create", "sdr_engine_destroy", "sdr_engine_submit", "sdr_engine_submit_device", "sdr_engine_submit_device_async",
+    "sdr_engine_wait",
     "sdr_engine_fetch_block", "sdr_engine_launch_count", "sdr_engine_set_timing", "sdr_engine_get_timing",
     "sdr_chan_create", "sdr_chan_destroy", "sdr_chan_set_frequency", "sdr_chan_get_bandwidth", "sdr_chan_want_iq",
     "sdr_chan_fetch_audio", "sdr_chan_fetch_iq", "sdr_engine_fetch_audio_batch",
@@ -46,6 +47,7 @@ class Lib:
         L.sdr_engine_destroy.argtypes = [vp]
         L.sdr_engine_submit.argtypes = [vp, vp, u, ll, ll]
         L.sdr_engine_submit_device.argtypes = [vp, vp, u, ll, ll, i]
+        L.sdr_engine_submit_device_async.argtypes = [vp, vp, u, ll, ll, i, vp]
         L.sdr_engine_wait.argtypes = [vp]
         L.sdr_engine_fetch_block.argtypes = [vp, vp, u, P(u)]
         L.sdr_engine_launch_count.argtypes = [vp]
@@ -121,6 +123,12 @@ class Engine:
     def submit_device(self, dev_ptr, n, center_freq, sample_rate, fetch_to_host=True):
         self.lib.check(self.lib.L.sdr_engine_submit_device(self.h, C.c_void_p(dev_ptr), n, int(center_freq), int(sample_rate),
                                                            1 if fetch_to_host else 0))
+
+    def submit_device_async(self, dev_ptr, n, center_freq, sample_rate, fetch_to_host=True, ready_event=None):
+        """ready_event: a cudaEvent_t handle (int) after which the block is valid, or None if it already is."""
+        self.lib.check(self.lib.L.sdr_engine_submit_device_async(self.h, C.c_void_p(dev_ptr), n, int(center_freq), int(sample_rate),
+                                                                 1 if fetch_to_host else 0,
+                                                                 C.c_void_p(ready_event) if ready_event else None))
 
     def wait(self):
         self.lib.check(self.lib.L.sdr_engine_wait(self.h))

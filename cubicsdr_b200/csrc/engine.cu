@@ -1005,7 +1005,11 @@ static int rebuild(sdr_engine *e) {
     return SDR_OK;
 }
 
-static int submit_common(sdr_engine *e, const float2 *d_src, unsigned n, long long center, long long rate, bool to_host) {
+// ready: 0 = the block becomes ready when the engine's main stream reaches this point (conservative),
+//        1 = the block is ready now (resident data, or a host block that submit copies on the DC stream itself),
+//        2 = the block is ready when `ready_event` fires
+static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_src, unsigned n, long long center, long long rate,
+                         bool to_host, int ready, void *ready_event) {
     if (e->dirty) { int r = rebuild(e); if (r) return r; }
     const int p = e->parity ^ 1;                               // this block's buffer; the other one holds the previous block
     float2 *blk = e->d_blkbuf[p] + e->hist_cap;
@@ -1023,8 +1027,12 @@ static int submit_common(sdr_engine *e, const float2 *d_src, unsigned n, long lo
     sdr_stream_t dcs = e->stream;
 #ifndef SDR_EMU
     dcs = e->stream_dc;
-    CUDA_TRY(cudaEventRecord(e->ev_input, e->stream));         // the input block is ready when the caller's stream gets here
-    CUDA_TRY(cudaStreamWaitEvent(dcs, e->ev_input, 0));
+    if (ready == 0) {
+        CUDA_TRY(cudaEventRecord(e->ev_input, e->stream));     // the input block is ready when the caller's stream gets here
+        CUDA_TRY(cudaStreamWaitEvent(dcs, e->ev_input, 0));
+    } else if (ready == 2 && ready_event) {
+        CUDA_TRY(cudaStreamWaitEvent(dcs, (cudaEvent_t)ready_event, 0));
+    }
     CUDA_TRY(cudaStreamWaitEvent(dcs, e->ev_consumed[p], 0));  // the kernels of two blocks ago are done with this buffer
     if (e->timing && e->time_pending < sdr_engine::kTimeSets) cudaEventRecord(e->tev_dc[e->time_pending][0], dcs);
 #endif
@@ -1033,7 +1041,8 @@ static int submit_common(sdr_engine *e, const float2 *d_src, unsigned n, long lo
         be_d2d(e->d_scratch, raw + (long long)e->last_n - (long long)need_raw, need_raw * sizeof(float2), dcs);
         be_d2d(raw - need_raw, e->d_scratch, need_raw * sizeof(float2), dcs);
     }
-    be_d2d(raw, d_src, (size_t)n * sizeof(float2), dcs);
+    if (h_src) be_h2d(raw, h_src, (size_t)n * sizeof(float2), dcs);   // host block: straight into the raw stream buffer
+    else be_d2d(raw, d_src, (size_t)n * sizeof(float2), dcs);
     DcArgs dc;
     dc.x = raw; dc.y = blk; dc.n = (int)n; dc.a = e->dc_a; dc.tile_sum = e->d_tile_sum; dc.tile_carry = e->d_tile_carry2[p];
     dc.state = e->d_dc_state; dc.apow = e->d_apow;
@@ -1220,18 +1229,27 @@ extern "C" int sdr_engine_submit(sdr_engine *e, const sdr_cf32 *iq, unsigned n, 
     if (!e || !iq) return fail(SDR_ERR_ARG, "sdr_engine_submit: null argument");
     if (n == 0 || n > e->max_block) return fail(SDR_ERR_ARG, "sdr_engine_submit: block size out of range");
     std::lock_guard<std::mutex> lk(e->mu);
-    // the pinned staging buffer is reused every block: wait for the previous block's H2D before overwriting it
-    be_sync(e->stream);
+    // the pinned staging buffer is reused every block: wait for the previous block's H2D (on the DC stream) first
+#ifndef SDR_EMU
+    be_sync(e->stream_dc);
+#endif
     memcpy(e->h_stage, iq, (size_t)n * sizeof(sdr_cf32));
-    be_h2d(e->d_raw, e->h_stage, (size_t)n * sizeof(sdr_cf32), e->stream);
-    return submit_common(e, e->d_raw, n, center, rate, true);
+    return submit_common(e, nullptr, e->h_stage, n, center, rate, true, 1, nullptr);
 }
 
 extern "C" int sdr_engine_submit_device(sdr_engine *e, const void *d_iq, unsigned n, long long center, long long rate, int to_host) {
     if (!e || !d_iq) return fail(SDR_ERR_ARG, "sdr_engine_submit_device: null argument");
     if (n == 0 || n > e->max_block) return fail(SDR_ERR_ARG, "sdr_engine_submit_device: block size out of range");
     std::lock_guard<std::mutex> lk(e->mu);
-    return submit_common(e, (const float2 *)d_iq, n, center, rate, to_host != 0);
+    return submit_common(e, (const float2 *)d_iq, nullptr, n, center, rate, to_host != 0, 0, nullptr);
+}
+
+extern "C" int sdr_engine_submit_device_async(sdr_engine *e, const void *d_iq, unsigned n, long long center, long long rate,
+                                              int to_host, void *ready_event) {
+    if (!e || !d_iq) return fail(SDR_ERR_ARG, "sdr_engine_submit_device_async: null argument");
+    if (n == 0 || n > e->max_block) return fail(SDR_ERR_ARG, "sdr_engine_submit_device_async: block size out of range");
+    std::lock_guard<std::mutex> lk(e->mu);
+    return submit_common(e, (const float2 *)d_iq, nullptr, n, center, rate, to_host != 0, ready_event ? 2 : 1, ready_event);
 }
 
 extern "C" int sdr_engine_wait(sdr_engine *e) {

@@ -46,6 +46,11 @@ int sdr_engine_submit(sdr_engine *eng, const sdr_cf32 *iq, unsigned n, long long
  * with fetch_to_host = 0 results stay in device memory (throughput measurement), otherwise they are copied back.  */
 int sdr_engine_submit_device(sdr_engine *eng, const void *d_iq, unsigned n, long long center_freq, long long sample_rate,
                              int fetch_to_host);
+/* Pipelined form: the block is ready when `ready_event` (a cudaEvent_t, as void*) fires, or already is if it is NULL --
+ * independent of what is queued on the engine's stream.  This lets the DC blocker of block b+1 run underneath the
+ * channel kernels of block b.  The caller must not overwrite d_iq before a later sdr_engine_wait().              */
+int sdr_engine_submit_device_async(sdr_engine *eng, const void *d_iq, unsigned n, long long center_freq, long long sample_rate,
+                                   int fetch_to_host, void *ready_event);
 int sdr_engine_wait(sdr_engine *eng);
 /* DC-blocked block of the last submit (what runSingleCH pushes to the visual queues / demod pipes), host copy.    */
 int sdr_engine_fetch_block(sdr_engine *eng, sdr_cf32 *out, unsigned cap, unsigned *n);
