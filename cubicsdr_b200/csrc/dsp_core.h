@@ -223,7 +223,7 @@ SDR_HD inline void dc_apply_phase(int ph, const DcArgs &a, int bid, int tid, DcS
 //     noise (~5e-6 .. 2e-5 of the block RMS) would otherwise be the parity floor of everything downstream.
 //     The recurrence is strictly sequential, but it is a contraction on the float lattice: two trajectories that start a
 //     few ulps apart differ by an integer number of ulps that shrinks by one with probability ~|d|/2000 per step and
-//     never grows, so they coalesce (median ~4k steps, 1e-6 tail beyond ~32k) and are identical from then on.
+//     never grows, so they coalesce (median ~4k steps, exponential tail with a ~2k-step time constant) and are identical from then on.
 //     Hence: cut the block into segments of L samples, give each a warm-up of W samples started from the EXACT state
 //     (the double-precision scan above) rounded to float, run all segments in parallel, then check every junction
 //     (end state of segment s-1 == warmed-up state of segment s, bitwise).  Matching junctions prove, by induction
@@ -231,7 +231,7 @@ SDR_HD inline void dc_apply_phase(int ph, const DcArgs &a, int bid, int tid, DcS
 //     replayed serially by dc_exact_verify.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kDcSegLen = 4096;
-constexpr int kDcWarm = 32768;
+constexpr int kDcWarm = 24576;      // P(junction not coalesced) ~ 1.5e-4: a serial fix-up every dozen blocks at 61 MSps
 
 struct DcExactArgs {
     const float2 *xraw;              // raw stream: xraw[0] = first sample of the block, history at negative indices

@@ -68,7 +68,7 @@ constexpr int kFrontSmemBytes = kFrontSmemTab + kFrontWarps * 2 * 32 * (int)size
 // Bit-exact DC blocker: one warp per segment.  All lanes run the (strictly serial) chain redundantly; the warp as a whole
 // prefetches the raw samples three 32-sample batches ahead into shared memory and stores the outputs coalesced.
 __global__ void __launch_bounds__(32) k_dc_exact(DcExactArgs a) {
-    __shared__ float2 sx[4][32];
+    __shared__ __align__(16) float2 sx[4][32];
     const int s = blockIdx.x, lane = threadIdx.x;
     int i0;
     float2 v;
@@ -77,17 +77,23 @@ __global__ void __launch_bounds__(32) k_dc_exact(DcExactArgs a) {
     int p1 = p0 + a.seg_len;
     if (p1 > a.n) p1 = a.n;
     const int nb = (p1 - i0 + 31) / 32;
-    for (int k = 0; k < 3 && k < nb; ++k) {
+    // cp.async ring, three batches in flight: the global -> shared copy of batch k+3 is issued before batch k is consumed,
+    // so the serial chain never waits on memory
+    auto fetch = [&](int k) {
         const int idx = i0 + 32 * k + lane;
-        sx[k & 3][lane] = idx < p1 ? __ldg(a.xraw + idx) : make_float2(0.f, 0.f);
-    }
-    __syncwarp();
+        if (k < nb && idx < p1) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&sx[k & 3][lane]);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(a.xraw + idx));
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    fetch(0); fetch(1); fetch(2);
     float2 v_in = v, y;
     for (int k = 0; k < nb; ++k) {
+        asm volatile("cp.async.wait_group 2;" ::: "memory");   // batch k has landed (for this lane)
+        __syncwarp();                                          // ... and for every lane; batch k-1 is fully consumed
+        fetch(k + 3);
         const int base = i0 + 32 * k;
-        float2 nxt = make_float2(0.f, 0.f);
-        const bool has = k + 3 < nb;
-        if (has) { const int idx = base + 96 + lane; if (idx < p1) nxt = __ldg(a.xraw + idx); }
         if (base + 32 <= p0) {
             // pure warm-up batch: nothing but the chain
 #pragma unroll
@@ -107,10 +113,8 @@ __global__ void __launch_bounds__(32) k_dc_exact(DcExactArgs a) {
             const int idx = base + lane;
             if (idx >= p0 && idx < p1) a.y[idx] = mine;
         }
-        __syncwarp();
-        if (has) sx[(k + 3) & 3][lane] = nxt;
-        __syncwarp();
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (lane == 0) { a.seg_in[s] = v_in; a.seg_out[s] = v; }
 }
 __global__ void k_dc_verify(DcExactArgs a) {
@@ -538,7 +542,11 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
 #ifndef SDR_EMU
     for (int i = 0; i < sdr_engine::kRing; ++i) CUDA_TRY(cudaEventCreateWithFlags(&e->ring_ev[i], cudaEventDisableTiming));
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_dc, cudaStreamNonBlocking));
+    {   // highest priority: the DC blocker's one-warp CTAs should slot in the moment any SM has room
+        int lo = 0, hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&e->stream_dc, cudaStreamNonBlocking, hi));
+    }
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_input, cudaEventDisableTiming));
     for (int b = 0; b < 2; ++b) {
         CUDA_TRY(cudaEventCreateWithFlags(&e->ev_dc_done[b], cudaEventDisableTiming));
