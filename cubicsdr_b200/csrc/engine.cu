@@ -67,8 +67,10 @@ constexpr int kFrontSmemTab = 1024 * 16 * (int)sizeof(float2);                  
 constexpr int kFrontSmemBytes = kFrontSmemTab + kFrontWarps * 2 * 32 * (int)sizeof(float4);   // + 16384
 // Bit-exact DC blocker: one warp per segment.  All lanes run the (strictly serial) chain redundantly; the warp as a whole
 // prefetches the raw samples three 32-sample batches ahead into shared memory and stores the outputs coalesced.
+constexpr int kDcRing = 8;       // cp.async batches in flight (32 samples each): ~2000 cycles of lead over the serial chain
 __global__ void __launch_bounds__(32) k_dc_exact(DcExactArgs a) {
-    __shared__ __align__(16) float2 sx[4][32];
+    __shared__ __align__(16) float2 sx[kDcRing][32];
+    __shared__ float2 sy[32];
     const int s = blockIdx.x, lane = threadIdx.x;
     int i0;
     float2 v;
@@ -77,36 +79,48 @@ __global__ void __launch_bounds__(32) k_dc_exact(DcExactArgs a) {
     int p1 = p0 + a.seg_len;
     if (p1 > a.n) p1 = a.n;
     const int nb = (p1 - i0 + 31) / 32;
-    // cp.async ring, three batches in flight: the global -> shared copy of batch k+3 is issued before batch k is consumed,
-    // so the serial chain never waits on memory
+    // cp.async ring: the global -> shared copy of batch k + kDcRing - 1 is issued before batch k is consumed, so the
+    // serial chain never waits on memory
     auto fetch = [&](int k) {
         const int idx = i0 + 32 * k + lane;
         if (k < nb && idx < p1) {
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(&sx[k & 3][lane]);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&sx[k & (kDcRing - 1)][lane]);
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(a.xraw + idx));
         }
         asm volatile("cp.async.commit_group;");
     };
-    fetch(0); fetch(1); fetch(2);
+#pragma unroll
+    for (int k = 0; k < kDcRing - 1; ++k) fetch(k);
     float2 v_in = v, y;
     for (int k = 0; k < nb; ++k) {
-        asm volatile("cp.async.wait_group 2;" ::: "memory");   // batch k has landed (for this lane)
+        asm volatile("cp.async.wait_group %0;" ::"n"(kDcRing - 2) : "memory");   // batch k has landed (for this lane)
         __syncwarp();                                          // ... and for every lane; batch k-1 is fully consumed
-        fetch(k + 3);
+        fetch(k + kDcRing - 1);
+        const float2 *b = sx[k & (kDcRing - 1)];
         const int base = i0 + 32 * k;
         if (base + 32 <= p0) {
             // pure warm-up batch: nothing but the chain
 #pragma unroll
-            for (int j = 0; j < 32; ++j) dc_ref_step(a.c, sx[k & 3][j], v, y);
+            for (int j = 0; j < 32; ++j) dc_ref_step(a.c, b[j], v, y);
             if (base + 32 == p0) v_in = v;
+        } else if (base >= p0 && base + 32 <= p1) {
+            // pure output batch
+            if (base == p0) v_in = v;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                dc_ref_step(a.c, b[j], v, y);
+                if (lane == 0) sy[j] = y;
+            }
+            __syncwarp();
+            a.y[base + lane] = sy[lane];
         } else {
             float2 mine = make_float2(0.f, 0.f);
-#pragma unroll
+#pragma unroll 4
             for (int j = 0; j < 32; ++j) {
                 const int idx = base + j;
                 if (idx < p1) {
                     if (idx == p0) v_in = v;
-                    dc_ref_step(a.c, sx[k & 3][j], v, y);
+                    dc_ref_step(a.c, b[j], v, y);
                     if (lane == j) mine = y;
                 }
             }
