@@ -67,10 +67,11 @@ constexpr int kFrontSmemTab = 1024 * 16 * (int)sizeof(float2);                  
 constexpr int kFrontSmemBytes = kFrontSmemTab + kFrontWarps * 2 * 32 * (int)sizeof(float4);   // + 16384
 // Bit-exact DC blocker: one warp per segment.  All lanes run the (strictly serial) chain redundantly; the warp as a whole
 // prefetches the raw samples three 32-sample batches ahead into shared memory and stores the outputs coalesced.
-constexpr int kDcRing = 8;       // cp.async batches in flight (32 samples each): ~2000 cycles of lead over the serial chain
+constexpr int kDcBatch = 64;     // samples per cp.async batch (two 8-byte copies per lane)
+constexpr int kDcRing = 4;       // batches in flight: ~1700 cycles of lead over the serial chain
 __global__ void __launch_bounds__(32) k_dc_exact(DcExactArgs a) {
-    __shared__ __align__(16) float2 sx[kDcRing][32];
-    __shared__ float2 sy[32];
+    __shared__ __align__(16) float2 sx[kDcRing][kDcBatch];
+    __shared__ float2 sy[kDcBatch];
     const int s = blockIdx.x, lane = threadIdx.x;
     int i0;
     float2 v;
@@ -78,54 +79,57 @@ __global__ void __launch_bounds__(32) k_dc_exact(DcExactArgs a) {
     const int p0 = s * a.seg_len;
     int p1 = p0 + a.seg_len;
     if (p1 > a.n) p1 = a.n;
-    const int nb = (p1 - i0 + 31) / 32;
+    const int nb = (p1 - i0 + kDcBatch - 1) / kDcBatch;
+    const float c = a.c;
+    float2 *const y_out = a.y;
     // cp.async ring: the global -> shared copy of batch k + kDcRing - 1 is issued before batch k is consumed, so the
-    // serial chain never waits on memory
-    auto fetch = [&](int k) {
-        const int idx = i0 + 32 * k + lane;
-        if (k < nb && idx < p1) {
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(&sx[k & (kDcRing - 1)][lane]);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(a.xraw + idx));
-        }
+    // serial chain never waits on memory.  `src` / `fidx` walk ahead of the chain by kDcRing - 1 batches.
+    const float2 *src = a.xraw + i0 + lane;
+    int fidx = i0 + lane;
+    const unsigned sx_base = (unsigned)__cvta_generic_to_shared(&sx[0][0]) + (unsigned)lane * 8u;
+    int fk = 0;
+    auto fetch = [&]() {
+        const unsigned dst = sx_base + (unsigned)(fk & (kDcRing - 1)) * (kDcBatch * 8u);
+        if (fidx < p1) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src));
+        if (fidx + 32 < p1) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 256u), "l"(src + 32));
         asm volatile("cp.async.commit_group;");
+        src += kDcBatch; fidx += kDcBatch; ++fk;
     };
 #pragma unroll
-    for (int k = 0; k < kDcRing - 1; ++k) fetch(k);
+    for (int k = 0; k < kDcRing - 1; ++k) fetch();
     float2 v_in = v, y;
-    for (int k = 0; k < nb; ++k) {
+    int base = i0;
+    for (int k = 0; k < nb; ++k, base += kDcBatch) {
         asm volatile("cp.async.wait_group %0;" ::"n"(kDcRing - 2) : "memory");   // batch k has landed (for this lane)
         __syncwarp();                                          // ... and for every lane; batch k-1 is fully consumed
-        fetch(k + kDcRing - 1);
+        fetch();
         const float2 *b = sx[k & (kDcRing - 1)];
-        const int base = i0 + 32 * k;
-        if (base + 32 <= p0) {
+        if (base + kDcBatch <= p0) {
             // pure warm-up batch: nothing but the chain
 #pragma unroll
-            for (int j = 0; j < 32; ++j) dc_ref_step(a.c, b[j], v, y);
-            if (base + 32 == p0) v_in = v;
-        } else if (base >= p0 && base + 32 <= p1) {
+            for (int j = 0; j < kDcBatch; ++j) dc_ref_step(c, b[j], v, y);
+            if (base + kDcBatch == p0) v_in = v;
+        } else if (base >= p0 && base + kDcBatch <= p1) {
             // pure output batch
             if (base == p0) v_in = v;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                dc_ref_step(a.c, b[j], v, y);
+            for (int j = 0; j < kDcBatch; ++j) {
+                dc_ref_step(c, b[j], v, y);
                 if (lane == 0) sy[j] = y;
             }
             __syncwarp();
-            a.y[base + lane] = sy[lane];
+            y_out[base + lane] = sy[lane];
+            y_out[base + 32 + lane] = sy[32 + lane];
         } else {
-            float2 mine = make_float2(0.f, 0.f);
-#pragma unroll 4
-            for (int j = 0; j < 32; ++j) {
+            // boundary batch (segment start not aligned to the batch grid, or the end of the block)
+            for (int j = 0; j < kDcBatch; ++j) {
                 const int idx = base + j;
                 if (idx < p1) {
                     if (idx == p0) v_in = v;
-                    dc_ref_step(a.c, b[j], v, y);
-                    if (lane == j) mine = y;
+                    dc_ref_step(c, b[j], v, y);
+                    if (idx >= p0 && lane == 0) y_out[idx] = y;
                 }
             }
-            const int idx = base + lane;
-            if (idx >= p0 && idx < p1) a.y[idx] = mine;
         }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
