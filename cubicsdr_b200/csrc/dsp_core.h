@@ -76,8 +76,10 @@ SDR_HD SDR_FORCEINLINE float2 nco_lookup(const float2 *nco, uint32_t theta) {
 //    double (the reference runs it in float direct-form II; its own rounding noise, ~4.6e-6 relative, is the parity
 //    floor for this stage -- see DESIGN.md).
 // =====================================================================================================================
-constexpr int kDcTile = 1024;      // samples per scan tile (one CTA of 256 threads, 4 samples each)
-constexpr int kDcThreads = 256;
+constexpr int kDcTile = 1024;      // samples per scan tile (one CTA of 64 threads, 16 samples each)
+constexpr int kDcThreads = 64;     // small CTAs (64 x 32 registers): they fit on an SM next to a resident channel-front CTA,
+                                   // so the DC blocker of the next block really runs underneath the front kernel
+constexpr int kDcPer = kDcTile / kDcThreads;
 
 struct DcArgs {
     const float2 *x;      // raw block [n]
@@ -93,14 +95,17 @@ struct DcArgs {
 // phase 0 of kernel A: each thread folds 4 consecutive samples, writes partial to shared; phase 1: thread 0 combines.
 struct DcShared { double2 part[kDcThreads]; };
 
-// a thread's 4 consecutive samples (32 contiguous bytes): two 16-byte loads when the block is 16-byte aligned
-SDR_HD SDR_FORCEINLINE void dc_load4(const float2 *x, int base, int n, float2 *s) {
-    if (base + 4 <= n && ((reinterpret_cast<size_t>(x + base) & 15) == 0)) {
+// a thread's kDcPer consecutive samples (128 contiguous bytes): 16-byte loads when the block is 16-byte aligned
+SDR_HD SDR_FORCEINLINE void dc_load(const float2 *x, int base, int n, float2 *s) {
+    if (base + kDcPer <= n && ((reinterpret_cast<size_t>(x + base) & 15) == 0)) {
         const float4 *p = reinterpret_cast<const float4 *>(x + base);
-        const float4 u = sdr_ldg(p), v = sdr_ldg(p + 1);
-        s[0] = make_float2(u.x, u.y); s[1] = make_float2(u.z, u.w); s[2] = make_float2(v.x, v.y); s[3] = make_float2(v.z, v.w);
+#pragma unroll
+        for (int k = 0; k < kDcPer / 2; ++k) {
+            const float4 u = sdr_ldg(p + k);
+            s[2 * k] = make_float2(u.x, u.y); s[2 * k + 1] = make_float2(u.z, u.w);
+        }
     } else {
-        for (int k = 0; k < 4; ++k) s[k] = (base + k < n) ? x[base + k] : make_float2(0.f, 0.f);
+        for (int k = 0; k < kDcPer; ++k) s[k] = (base + k < n) ? x[base + k] : make_float2(0.f, 0.f);
     }
 }
 
@@ -109,8 +114,8 @@ SDR_HD inline void dc_tile_sum_phase(int ph, const DcArgs &a, int bid, int tid, 
     const int base = bid * kDcTile + tid * per;
     if (ph == 0) {
         double vr = 0.0, vi = 0.0;
-        float2 s[4];
-        dc_load4(a.x, base, a.n, s);
+        float2 s[kDcPer];
+        dc_load(a.x, base, a.n, s);
         for (int k = 0; k < per; ++k)      // beyond the block end the recurrence is simply not advanced
             if (base + k < a.n) { vr = fma(a.a, vr, (double)s[k].x); vi = fma(a.a, vi, (double)s[k].y); }
         sm->part[tid] = make_double2(vr, vi);
@@ -118,7 +123,7 @@ SDR_HD inline void dc_tile_sum_phase(int ph, const DcArgs &a, int bid, int tid, 
         // combine the thread partials in order (Horner): V <- V * a^(samples in chunk t) + part[t]
         int tile_len = a.n - bid * kDcTile;
         if (tile_len > kDcTile) tile_len = kDcTile;
-        double pw[5];
+        double pw[kDcPer + 1];
         pw[0] = 1.0;
         for (int k = 1; k <= per; ++k) pw[k] = pw[k - 1] * a.a;
         double vr = 0.0, vi = 0.0;
@@ -182,15 +187,15 @@ SDR_HD inline void dc_apply_phase(int ph, const DcArgs &a, int bid, int tid, DcS
     const int base = bid * kDcTile + tid * per;
     if (ph == 0) {
         double vr = 0.0, vi = 0.0;
-        float2 s[4];
-        dc_load4(a.x, base, a.n, s);
+        float2 s[kDcPer];
+        dc_load(a.x, base, a.n, s);
         for (int k = 0; k < per; ++k)
             if (base + k < a.n) { vr = fma(a.a, vr, (double)s[k].x); vi = fma(a.a, vi, (double)s[k].y); }
         sm->part[tid] = make_double2(vr, vi);
     } else if (ph == 1) {
         if (tid == 0) {
             double cr = a.tile_carry[bid].x, ci = a.tile_carry[bid].y;
-            const double w = a.a * a.a * a.a * a.a;          // a^per, per = 4
+            const double w = a.apow[per];
             for (int t = 0; t < kDcThreads; ++t) {
                 sm->enter[t] = make_double2(cr, ci);
                 cr = fma(cr, w, sm->part[t].x);
@@ -199,17 +204,17 @@ SDR_HD inline void dc_apply_phase(int ph, const DcArgs &a, int bid, int tid, DcS
         }
     } else {
         double vr = sm->enter[tid].x, vi = sm->enter[tid].y;
-        float2 s[4], o[4];
-        dc_load4(a.x, base, a.n, s);
+        float2 s[kDcPer], o[kDcPer];
+        dc_load(a.x, base, a.n, s);
         for (int k = 0; k < per; ++k) {
             const double nr = fma(a.a, vr, (double)s[k].x), ni = fma(a.a, vi, (double)s[k].y);
             o[k] = make_float2((float)(nr - vr), (float)(ni - vi));
             vr = nr; vi = ni;
         }
-        if (base + 4 <= a.n && ((reinterpret_cast<size_t>(a.y + base) & 15) == 0)) {
+        if (base + kDcPer <= a.n && ((reinterpret_cast<size_t>(a.y + base) & 15) == 0)) {
             float4 *p = reinterpret_cast<float4 *>(a.y + base);
-            p[0] = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
-            p[1] = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
+#pragma unroll
+            for (int k = 0; k < kDcPer / 2; ++k) p[k] = make_float4(o[2 * k].x, o[2 * k].y, o[2 * k + 1].x, o[2 * k + 1].y);
         } else {
             for (int k = 0; k < per; ++k) if (base + k < a.n) a.y[base + k] = o[k];
         }

@@ -38,7 +38,8 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 // ---------------------------------------------------------------------------------------------------------------------
 // kernels (GPU) / serial replays (test-only emulator)
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kFrontWarps = 16;      // warps per CTA of the channel front kernel (one CTA per SM)
+constexpr int kFrontWarps = 15;      // warps per CTA of the channel front kernel (one CTA per SM); 15 x 32 x 128 registers leave room for one
+                                     // warp of the bit-exact DC blocker on every SM, which then runs underneath the front kernel
 #ifndef SDR_EMU
 __global__ void __launch_bounds__(kDcThreads) k_dc_tile_sum(DcArgs a) {
     __shared__ DcShared sm;
@@ -442,6 +443,8 @@ struct sdr_engine {
     static const int kTimeSets = 64;
     int time_pending = 0;
     double stage_ms[4] = {0, 0, 0, 0};
+    float timeline[16][5];
+    int timeline_n = 0;
     unsigned long long stage_count = 0;
 #ifndef SDR_EMU
     cudaEvent_t tev[kTimeSets][5];
@@ -466,6 +469,18 @@ static void time_mark(sdr_engine *e, int which) {
 }
 static void time_collect(sdr_engine *e) {
 #ifndef SDR_EMU
+    // diagnostics: absolute timeline (ms since the first block's DC start) of the first 16 blocks of this batch
+    e->timeline_n = 0;
+    for (int i = 0; i < e->time_pending && i < 16; ++i) {
+        float t[5] = {0, 0, 0, 0, 0};
+        cudaEventElapsedTime(&t[0], e->tev_dc[0][0], e->tev_dc[i][0]);
+        cudaEventElapsedTime(&t[1], e->tev_dc[0][0], e->tev_dc[i][1]);
+        cudaEventElapsedTime(&t[2], e->tev_dc[0][0], e->tev[i][2]);
+        cudaEventElapsedTime(&t[3], e->tev_dc[0][0], e->tev[i][3]);
+        cudaEventElapsedTime(&t[4], e->tev_dc[0][0], e->tev[i][4]);
+        for (int k = 0; k < 5; ++k) e->timeline[i][k] = t[k];
+        e->timeline_n = i + 1;
+    }
     for (int i = 0; i < e->time_pending; ++i) {
         for (int k = 0; k < 4; ++k) {
             float ms = 0.f;
@@ -628,6 +643,15 @@ extern "C" int sdr_engine_destroy(sdr_engine *e) {
 }
 
 extern "C" unsigned long long sdr_engine_launch_count(sdr_engine *e) { return e ? e->launches : 0; }
+
+// diagnostics: {dc_start, dc_end, front_start, front_end, tail_end} in ms for up to 16 blocks of the last timed batch
+extern "C" int sdr_engine_debug_timeline(sdr_engine *e, float *out80, int *n_blocks) {
+    if (!e || !out80) return SDR_ERR_ARG;
+    std::lock_guard<std::mutex> lk(e->mu);
+    memcpy(out80, e->timeline, sizeof e->timeline);
+    if (n_blocks) *n_blocks = e->timeline_n;
+    return SDR_OK;
+}
 
 // diagnostics: number of segment junctions the bit-exact DC replay had to recompute serially so far
 extern "C" int sdr_engine_debug_dc_fixups(sdr_engine *e, unsigned *fixups, int *exact_mode) {
