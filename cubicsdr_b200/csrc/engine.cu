@@ -70,100 +70,71 @@ constexpr int kFrontSmemBytes = kFrontSmemTab + kFrontWarps * 2 * 32 * (int)size
 // prefetches the raw samples three 32-sample batches ahead into shared memory and stores the outputs coalesced.
 constexpr int kDcBatch = 64;     // samples per cp.async batch (two 8-byte copies per lane)
 constexpr int kDcRing = 4;       // batches in flight: ~1700 cycles of lead over the serial chain
-// One warp replays TWO segments (2 x {re, im} = four independent dependency chains): alone, a chain is latency-bound at
-// ~9 cycles per step; next to the channel-front warps it only gets a fraction of the issue slots, and four ready
-// instructions per slot instead of two keep it moving.  Both segments have the same number of warm-up + output steps
-// except at the end of the block, so they advance in lock step batch by batch.
-struct DcSeg {
-    int i0, p0, p1, nb, base, fk, fidx;
-    const float2 *src;
-    float2 v, v_in;
-};
 __global__ void __launch_bounds__(32) k_dc_exact(DcExactArgs a) {
-    __shared__ __align__(16) float2 sx[2][kDcRing][kDcBatch];
-    __shared__ float2 sy[2][kDcBatch];
-    const int lane = threadIdx.x;
+    __shared__ __align__(16) float2 sx[kDcRing][kDcBatch];
+    __shared__ float2 sy[kDcBatch];
+    const int s = blockIdx.x, lane = threadIdx.x;
+    int i0;
+    float2 v;
+    dc_exact_plan(a, s, i0, v);
+    const int p0 = s * a.seg_len;
+    int p1 = p0 + a.seg_len;
+    if (p1 > a.n) p1 = a.n;
+    const int nb = (p1 - i0 + kDcBatch - 1) / kDcBatch;
     const float c = a.c;
     float2 *const y_out = a.y;
-    DcSeg g[2];
-    int nb_max = 0;
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        const int s = 2 * blockIdx.x + u;
-        g[u].nb = 0; g[u].p0 = g[u].p1 = 0; g[u].i0 = 0; g[u].v = make_float2(0.f, 0.f);
-        if (s < a.n_seg) {
-            dc_exact_plan(a, s, g[u].i0, g[u].v);
-            g[u].p0 = s * a.seg_len;
-            g[u].p1 = g[u].p0 + a.seg_len;
-            if (g[u].p1 > a.n) g[u].p1 = a.n;
-            g[u].nb = (g[u].p1 - g[u].i0 + kDcBatch - 1) / kDcBatch;
-        }
-        g[u].v_in = g[u].v; g[u].base = g[u].i0; g[u].fk = 0; g[u].fidx = g[u].i0 + lane; g[u].src = a.xraw + g[u].i0 + lane;
-        if (g[u].nb > nb_max) nb_max = g[u].nb;
-    }
-    const unsigned sx_base = (unsigned)__cvta_generic_to_shared(&sx[0][0][0]) + (unsigned)lane * 8u;
-    auto fetch = [&](int u) {
-        DcSeg &q = g[u];
-        const unsigned dst = sx_base + (unsigned)(u * kDcRing + (q.fk & (kDcRing - 1))) * (kDcBatch * 8u);
-        if (q.fidx < q.p1) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(q.src));
-        if (q.fidx + 32 < q.p1) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 256u), "l"(q.src + 32));
-        q.src += kDcBatch; q.fidx += kDcBatch; ++q.fk;
+    // cp.async ring: the global -> shared copy of batch k + kDcRing - 1 is issued before batch k is consumed, so the
+    // serial chain never waits on memory.  `src` / `fidx` walk ahead of the chain by kDcRing - 1 batches.
+    const float2 *src = a.xraw + i0 + lane;
+    int fidx = i0 + lane;
+    const unsigned sx_base = (unsigned)__cvta_generic_to_shared(&sx[0][0]) + (unsigned)lane * 8u;
+    int fk = 0;
+    auto fetch = [&]() {
+        const unsigned dst = sx_base + (unsigned)(fk & (kDcRing - 1)) * (kDcBatch * 8u);
+        if (fidx < p1) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src));
+        if (fidx + 32 < p1) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 256u), "l"(src + 32));
+        asm volatile("cp.async.commit_group;");
+        src += kDcBatch; fidx += kDcBatch; ++fk;
     };
 #pragma unroll
-    for (int k = 0; k < kDcRing - 1; ++k) { fetch(0); fetch(1); asm volatile("cp.async.commit_group;"); }
-    float2 y0, y1;
-    for (int k = 0; k < nb_max; ++k) {
-        asm volatile("cp.async.wait_group %0;" ::"n"(kDcRing - 2) : "memory");   // batch k of both segments has landed
-        __syncwarp();
-        fetch(0); fetch(1);
-        asm volatile("cp.async.commit_group;");
-        const float2 *b0 = sx[0][k & (kDcRing - 1)], *b1 = sx[1][k & (kDcRing - 1)];
-        const bool warm0 = g[0].base + kDcBatch <= g[0].p0, warm1 = g[1].base + kDcBatch <= g[1].p0;
-        const bool out0 = g[0].base >= g[0].p0 && g[0].base + kDcBatch <= g[0].p1;
-        const bool out1 = g[1].base >= g[1].p0 && g[1].base + kDcBatch <= g[1].p1;
-        if (warm0 && warm1) {
-            // both segments warming up: four interleaved chains, nothing else
+    for (int k = 0; k < kDcRing - 1; ++k) fetch();
+    float2 v_in = v, y;
+    int base = i0;
+    for (int k = 0; k < nb; ++k, base += kDcBatch) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kDcRing - 2) : "memory");   // batch k has landed (for this lane)
+        __syncwarp();                                          // ... and for every lane; batch k-1 is fully consumed
+        fetch();
+        const float2 *b = sx[k & (kDcRing - 1)];
+        if (base + kDcBatch <= p0) {
+            // pure warm-up batch: nothing but the chain
 #pragma unroll
-            for (int j = 0; j < kDcBatch; ++j) { dc_ref_step(c, b0[j], g[0].v, y0); dc_ref_step(c, b1[j], g[1].v, y1); }
-            if (g[0].base + kDcBatch == g[0].p0) g[0].v_in = g[0].v;
-            if (g[1].base + kDcBatch == g[1].p0) g[1].v_in = g[1].v;
-        } else if (out0 && out1) {
-            if (g[0].base == g[0].p0) g[0].v_in = g[0].v;
-            if (g[1].base == g[1].p0) g[1].v_in = g[1].v;
+            for (int j = 0; j < kDcBatch; ++j) dc_ref_step(c, b[j], v, y);
+            if (base + kDcBatch == p0) v_in = v;
+        } else if (base >= p0 && base + kDcBatch <= p1) {
+            // pure output batch
+            if (base == p0) v_in = v;
 #pragma unroll
             for (int j = 0; j < kDcBatch; ++j) {
-                dc_ref_step(c, b0[j], g[0].v, y0); dc_ref_step(c, b1[j], g[1].v, y1);
-                if (lane == 0) { sy[0][j] = y0; sy[1][j] = y1; }
+                dc_ref_step(c, b[j], v, y);
+                if (lane == 0) sy[j] = y;
             }
             __syncwarp();
-            y_out[g[0].base + lane] = sy[0][lane]; y_out[g[0].base + 32 + lane] = sy[0][32 + lane];
-            y_out[g[1].base + lane] = sy[1][lane]; y_out[g[1].base + 32 + lane] = sy[1][32 + lane];
+            y_out[base + lane] = sy[lane];
+            y_out[base + 32 + lane] = sy[32 + lane];
         } else {
-            // boundary batches (segment start off the batch grid, end of the block, or only one segment left)
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                if (k >= g[u].nb) continue;
-                const float2 *b = u ? b1 : b0;
-                for (int j = 0; j < kDcBatch; ++j) {
-                    const int idx = g[u].base + j;
-                    if (idx < g[u].p1) {
-                        if (idx == g[u].p0) g[u].v_in = g[u].v;
-                        dc_ref_step(c, b[j], g[u].v, y0);
-                        if (idx >= g[u].p0 && lane == 0) y_out[idx] = y0;
-                    }
+            // boundary batch (segment start not aligned to the batch grid, or the end of the block)
+            for (int j = 0; j < kDcBatch; ++j) {
+                const int idx = base + j;
+                if (idx < p1) {
+                    if (idx == p0) v_in = v;
+                    dc_ref_step(c, b[j], v, y);
+                    if (idx >= p0 && lane == 0) y_out[idx] = y;
                 }
             }
         }
-        g[0].base += kDcBatch; g[1].base += kDcBatch;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    if (lane == 0) {
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int s = 2 * blockIdx.x + u;
-            if (s < a.n_seg) { a.seg_in[s] = g[u].v_in; a.seg_out[s] = g[u].v; }
-        }
-    }
+    if (lane == 0) { a.seg_in[s] = v_in; a.seg_out[s] = v; }
 }
 __global__ void k_dc_verify(DcExactArgs a) {
     if (threadIdx.x == 0 && blockIdx.x == 0) dc_exact_verify(a);
@@ -245,7 +216,7 @@ __global__ void __launch_bounds__(kSpecThreads) k_spec_points(SpecArgs a) {
 
 static void launch_dc_exact(const DcExactArgs &a, sdr_stream_t s, unsigned long long &launches) {
 #ifndef SDR_EMU
-    k_dc_exact<<<(a.n_seg + 1) / 2, 32, 0, s>>>(a);
+    k_dc_exact<<<a.n_seg, 32, 0, s>>>(a);
     k_dc_verify<<<1, 32, 0, s>>>(a);
 #else
     (void)s;
