@@ -343,6 +343,8 @@ struct ChanStatic {
     // stream buffers inside the channel arena (offsets in floats); each is [kHist | data]
     float *arena;                 // this channel's arena in HBM
     int lvl_off[kMaxTailHb + 1];  // complex level buffers: level 0 = front output, level j = output of tail stage j-1
+    int lvl0_alt_off;             // second level-0 buffer: the front kernel of block b+1 writes one while the tail of block b
+                                  // still reads the other (ChanDyn::lvl0_sel says which one a block uses)
     int iq_off;                   // complex: arbitrary-stage output (decimated IQ handed to the modem)
     int w_off;                    // complex: SSB post-filter stream feeding the Hilbert stage
     int d_off;                    // real: demodulated samples (after auto-gain) feeding the audio resampler
@@ -361,6 +363,8 @@ struct ChanDyn {                  // written by the host for every block
     int valid;                    // 0: free slot, nothing may be touched
     int inject_n;                 // > 0: the decimated IQ of this call was uploaded by the host (Modem::demodulate seam):
                                   //      skip the IQ resampler and demodulate inject_n samples
+    int lvl0_sel;                 // which level-0 buffer this block uses (0: lvl_off[0], 1: lvl0_alt_off)
+    int pad0;
     const float2 *hist;           // non-null: history for samples i < 0 is hist[i] (the channel skipped the previous block(s),
                                   // so its delay lines must see the tail of the last block it DID consume)
 };
@@ -516,7 +520,7 @@ SDR_HD inline void front_span(const FrontArgs &a, int ch, int span_idx, bool sto
     long long q_hi = q_lo + a.span;
     if (span_idx == a.n_span - 1 || q_hi > qb) q_hi = qb;
     if (q_lo >= q_hi) return;
-    float2 *out = reinterpret_cast<float2 *>(cs.arena + cs.lvl_off[0]) + kHist;
+    float2 *out = reinterpret_cast<float2 *>(cs.arena + (cd.lvl0_sel ? cs.lvl0_alt_off : cs.lvl_off[0])) + kHist;
     const float2 *hx = cd.hist ? cd.hist : a.x;
     // table oscillator: entry = (theta + 2^21) >> 22; mixing down conjugates (sign on the sine); no mixing = constant
     // entry 0 = (1, 0).  The *_prev values describe the block whose tail forms the history in front of this one.

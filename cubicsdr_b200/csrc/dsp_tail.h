@@ -67,6 +67,10 @@ SDR_HD inline float2 *chan_cbuf(const TailArgs &, const ChanStatic &cs, int off)
     return reinterpret_cast<float2 *>(cs.arena + off);
 }
 SDR_HD inline float *chan_rbuf(const TailArgs &, const ChanStatic &cs, int off) { return cs.arena + off; }
+// level j complex buffer of this block (level 0 is double-buffered against the next block's front kernel)
+SDR_HD inline float2 *chan_lvl(const TailArgs &a, const ChanStatic &cs, const ChanDyn &cd, int j) {
+    return chan_cbuf(a, cs, (j == 0 && cd.lvl0_sel) ? cs.lvl0_alt_off : cs.lvl_off[j]);
+}
 
 // generic decimate-by-2 half-band over a [kHist | new] complex stream, parallel over outputs
 SDR_HD inline void hb_decim_c(const float2 *in, long long in_g0, float2 *out, long long out_g0, int n_out, int m,
@@ -153,14 +157,14 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
     if (ph >= TP_HB0 && ph < TP_HB0 + kMaxTailHb) {
         const int j = ph - TP_HB0;
         if (j < cs.n_tail && cd.inject_n <= 0)
-            hb_decim_c(chan_cbuf(a, cs, cs.lvl_off[j]), sm->lvl_g0[j], chan_cbuf(a, cs, cs.lvl_off[j + 1]), sm->lvl_g0[j + 1],
+            hb_decim_c(chan_lvl(a, cs, cd, j), sm->lvl_g0[j], chan_cbuf(a, cs, cs.lvl_off[j + 1]), sm->lvl_g0[j + 1],
                        sm->lvl_n[j + 1], cs.tail_m[j], a.taps + cs.tail_h1[j], tid, nt);
         return;
     }
 
     if (ph == TP_ARB && cd.inject_n > 0) return;
     if (ph == TP_ARB) {      // 256-arm polyphase stage, nearest arm, 24-bit phase
-        const float2 *z = chan_cbuf(a, cs, cs.lvl_off[cs.n_tail]) + kHist;
+        const float2 *z = chan_lvl(a, cs, cd, cs.n_tail) + kHist;
         float2 *iq = chan_cbuf(a, cs, cs.iq_off) + kHist;
         const float *pfb = a.taps + cs.pfb_off;
         const unsigned long long ph0 = st.arb_phase;
@@ -353,8 +357,10 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
     if (ph == TP_HIST_A || ph == TP_HIST_B) {
         int s = 0;
         for (int j = 0; j <= cs.n_tail; ++j, ++s) {
-            float2 *b = chan_cbuf(a, cs, cs.lvl_off[j]);
-            if (tid < kHist) { if (ph == TP_HIST_A) sm->hist_tmp[s][tid] = b[sm->lvl_n[j] + tid]; else b[tid] = sm->hist_tmp[s][tid]; }
+            float2 *b = chan_lvl(a, cs, cd, j);
+            // level 0: the slid history goes in front of the OTHER buffer, where the next block's tail will look for it
+            float2 *dst = (j == 0) ? chan_cbuf(a, cs, cd.lvl0_sel ? cs.lvl_off[0] : cs.lvl0_alt_off) : b;
+            if (tid < kHist) { if (ph == TP_HIST_A) sm->hist_tmp[s][tid] = b[sm->lvl_n[j] + tid]; else dst[tid] = sm->hist_tmp[s][tid]; }
         }
         {
             float2 *b = chan_cbuf(a, cs, cs.iq_off);

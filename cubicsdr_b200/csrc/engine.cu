@@ -362,6 +362,7 @@ struct sdr_chan {
     ChanStatic cs;
     float *d_arena = nullptr;
     size_t arena_floats = 0;
+    int lvl0_sel = 0;               // level-0 buffer the channel's next processed block will use
     bool standalone = false;        // sdr_modem: driven by sdr_modem_demodulate, ignored by sdr_engine_submit
     unsigned inject_cap = 0;
     ChanDyn *h_dyn = nullptr;       // pinned, standalone only
@@ -423,7 +424,9 @@ struct sdr_engine {
     // channels
     static const int kMaxChan = 2048;
     std::vector<sdr_chan *> chans;     // by slot; nullptr = free
-    ChanStatic *d_cs = nullptr; ChanDyn *d_cd = nullptr; ChanState *d_st = nullptr;
+    ChanStatic *d_cs = nullptr; ChanState *d_st = nullptr;
+    ChanDyn *d_cd2[2] = {nullptr, nullptr};   // per-block parameters, double-buffered: the tail of block b reads its copy
+                                              // while the next submit already uploads block b+1's
     // small per-block parameter blocks live in a ring of pinned buffers so that submits can be enqueued back to back
     static const int kRing = 8;
     ChanDyn *h_cd = nullptr;            // pinned [kRing][kMaxChan]
@@ -454,6 +457,10 @@ struct sdr_engine {
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // the DC blocker of block b+1 runs on its own stream underneath the channel kernels of block b
+    // the channel tail of block b runs on its own stream underneath the front kernel of block b+1
+    cudaStream_t stream_tail = nullptr;
+    cudaEvent_t ev_front_done = nullptr, ev_tail_done[2] = {nullptr, nullptr};
+    cudaEvent_t tev_tail[kTimeSets][2];
     cudaStream_t stream_dc = nullptr;
     cudaEvent_t ev_input = nullptr, ev_dc_done[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     cudaEvent_t tev_dc[kTimeSets][2];
@@ -477,7 +484,7 @@ static void time_collect(sdr_engine *e) {
         cudaEventElapsedTime(&t[1], e->tev_dc[0][0], e->tev_dc[i][1]);
         cudaEventElapsedTime(&t[2], e->tev_dc[0][0], e->tev[i][2]);
         cudaEventElapsedTime(&t[3], e->tev_dc[0][0], e->tev[i][3]);
-        cudaEventElapsedTime(&t[4], e->tev_dc[0][0], e->tev[i][4]);
+        cudaEventElapsedTime(&t[4], e->tev_dc[0][0], e->tev_tail[i][1]);
         for (int k = 0; k < 5; ++k) e->timeline[i][k] = t[k];
         e->timeline_n = i + 1;
     }
@@ -486,6 +493,7 @@ static void time_collect(sdr_engine *e) {
             float ms = 0.f;
             if (k == 0) { if (cudaEventElapsedTime(&ms, e->tev_dc[i][0], e->tev_dc[i][1]) == cudaSuccess) e->stage_ms[k] += ms; continue; }
             if (k == 1) { if (cudaEventElapsedTime(&ms, e->tev_spec[i][0], e->tev_spec[i][1]) == cudaSuccess) e->stage_ms[k] += ms; continue; }
+            if (k == 3) { if (cudaEventElapsedTime(&ms, e->tev_tail[i][0], e->tev_tail[i][1]) == cudaSuccess) e->stage_ms[k] += ms; continue; }
             if (cudaEventElapsedTime(&ms, e->tev[i][k], e->tev[i][k + 1]) == cudaSuccess) e->stage_ms[k] += ms;
         }
         e->stage_count++;
@@ -567,7 +575,7 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
     bad |= be_malloc((void **)&e->d_nco, 1024 * sizeof(float2));
 
     bad |= be_malloc((void **)&e->d_cs, sdr_engine::kMaxChan * sizeof(ChanStatic));
-    bad |= be_malloc((void **)&e->d_cd, sdr_engine::kMaxChan * sizeof(ChanDyn));
+    for (int b = 0; b < 2; ++b) bad |= be_malloc((void **)&e->d_cd2[b], sdr_engine::kMaxChan * sizeof(ChanDyn));
     bad |= be_malloc((void **)&e->d_st, sdr_engine::kMaxChan * sizeof(ChanState));
     bad |= be_host_alloc((void **)&e->h_cd, (size_t)sdr_engine::kRing * sdr_engine::kMaxChan * sizeof(ChanDyn));
     bad |= be_malloc((void **)&e->d_group, sdr_engine::kMaxChan * sizeof(int));
@@ -580,6 +588,9 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
         CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CUDA_TRY(cudaStreamCreateWithPriority(&e->stream_dc, cudaStreamNonBlocking, hi));
     }
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_tail, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&e->ev_front_done, cudaEventDisableTiming));
+    for (int b = 0; b < 2; ++b) CUDA_TRY(cudaEventCreateWithFlags(&e->ev_tail_done[b], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_input, cudaEventDisableTiming));
     for (int b = 0; b < 2; ++b) {
         CUDA_TRY(cudaEventCreateWithFlags(&e->ev_dc_done[b], cudaEventDisableTiming));
@@ -626,12 +637,15 @@ extern "C" int sdr_engine_destroy(sdr_engine *e) {
     be_free(e->d_raw); be_free(e->d_blkbuf[0]); be_free(e->d_blkbuf[1]); be_free(e->d_rawbuf); be_free(e->d_scratch); be_host_free(e->h_stage);
     be_free(e->d_tile_sum); be_free(e->d_tile_carry2[0]); be_free(e->d_tile_carry2[1]); be_free(e->d_dc_state);
     be_free(e->d_seg_in); be_free(e->d_seg_out); be_free(e->d_fstate); be_free(e->d_fixups); be_free(e->d_apow); be_free(e->d_nco);
-    be_free(e->d_cs); be_free(e->d_cd); be_free(e->d_st); be_host_free(e->h_cd); be_free(e->d_group); be_host_free(e->h_group);
+    be_free(e->d_cs); be_free(e->d_cd2[0]); be_free(e->d_cd2[1]); be_free(e->d_st); be_host_free(e->h_cd); be_free(e->d_group); be_host_free(e->h_group);
     be_free(e->d_taps); be_free(e->d_results); be_host_free(e->h_results);
 #ifndef SDR_EMU
     for (int i = 0; i < sdr_engine::kRing; ++i) cudaEventDestroy(e->ring_ev[i]);
     if (e->stream2) { cudaStreamSynchronize(e->stream2); cudaStreamDestroy(e->stream2); }
     if (e->stream_dc) { cudaStreamSynchronize(e->stream_dc); cudaStreamDestroy(e->stream_dc); }
+    if (e->stream_tail) { cudaStreamSynchronize(e->stream_tail); cudaStreamDestroy(e->stream_tail); }
+    if (e->ev_front_done) cudaEventDestroy(e->ev_front_done);
+    for (int b = 0; b < 2; ++b) if (e->ev_tail_done[b]) cudaEventDestroy(e->ev_tail_done[b]);
     if (e->ev_input) cudaEventDestroy(e->ev_input);
     for (int b = 0; b < 2; ++b) { if (e->ev_dc_done[b]) cudaEventDestroy(e->ev_dc_done[b]); if (e->ev_consumed[b]) cudaEventDestroy(e->ev_consumed[b]); }
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
@@ -692,6 +706,7 @@ extern "C" int sdr_engine_set_timing(sdr_engine *e, int enable) {
         for (int i = 0; i < sdr_engine::kTimeSets; ++i) for (int k = 0; k < 5; ++k) CUDA_TRY(cudaEventCreate(&e->tev[i][k]));
         for (int i = 0; i < sdr_engine::kTimeSets; ++i) for (int k = 0; k < 2; ++k) CUDA_TRY(cudaEventCreate(&e->tev_spec[i][k]));
         for (int i = 0; i < sdr_engine::kTimeSets; ++i) for (int k = 0; k < 2; ++k) CUDA_TRY(cudaEventCreate(&e->tev_dc[i][k]));
+        for (int i = 0; i < sdr_engine::kTimeSets; ++i) for (int k = 0; k < 2; ++k) CUDA_TRY(cudaEventCreate(&e->tev_tail[i][k]));
         e->tev_made = true;
     }
 #endif
@@ -720,6 +735,14 @@ static int add_halfband_taps(sdr_engine *e, int m) {
 }
 
 static int rebuild(sdr_engine *e);
+static void sync_all(sdr_engine *e) {
+    be_sync(e->stream);
+#ifndef SDR_EMU
+    cudaStreamSynchronize(e->stream_tail);
+    cudaStreamSynchronize(e->stream_dc);
+    cudaStreamSynchronize(e->stream2);
+#endif
+}
 
 static int chan_create_impl(sdr_engine *e, const char *modem, long long sample_rate, long long bandwidth, int audio_rate,
                             unsigned inject_cap, sdr_chan **out) {
@@ -795,6 +818,7 @@ static int chan_create_impl(sdr_engine *e, const char *modem, long long sample_r
     c->standalone = inject_cap != 0;
     c->inject_cap = inject_cap;
     for (int j = 0; j <= cs.n_tail; ++j) cs.lvl_off[j] = take(2 * (kHist + (nb >> (cs.K1 + j)) + 4));
+    cs.lvl0_alt_off = take(2 * (kHist + (nb >> cs.K1) + 4));
     const size_t cap_z = (nb >> cs.S) + 4;
     const size_t cap_iq = (size_t)std::ceil((double)cap_z * (double)c->iq_plan.rate_arb) + 8;
     cs.iq_off = take(2 * (kHist + cap_iq));
@@ -867,14 +891,14 @@ extern "C" int sdr_modem_demodulate(sdr_chan *c, const sdr_cf32 *iq, unsigned n,
     sdr_engine *e = c->eng;
     std::lock_guard<std::mutex> lk(e->mu);
     if (e->dirty) { int r = rebuild(e); if (r) return r; }
-    be_sync(e->stream);                                                 // h_dyn / h_slot are reused call to call
+    sync_all(e);                                                        // h_dyn / h_slot are reused call to call
     float *d_iq = c->cs.arena + c->cs.iq_off + 2 * kHist;
     be_h2d(d_iq, iq, (size_t)n * sizeof(sdr_cf32), e->stream);
     memset(c->h_dyn, 0, sizeof(ChanDyn));
     c->h_dyn->valid = 1; c->h_dyn->active = 1; c->h_dyn->inject_n = (int)n;
-    be_h2d(e->d_cd + c->index, c->h_dyn, sizeof(ChanDyn), e->stream);
+    be_h2d(e->d_cd2[0] + c->index, c->h_dyn, sizeof(ChanDyn), e->stream);
     TailArgs ta;
-    ta.cs = e->d_cs; ta.cd = e->d_cd; ta.st = e->d_st; ta.taps = e->d_taps; ta.nco = e->d_nco;
+    ta.cs = e->d_cs; ta.cd = e->d_cd2[0]; ta.st = e->d_st; ta.taps = e->d_taps; ta.nco = e->d_nco;
     ta.results = e->d_results; ta.n = 0; ta.first = c->index;
     launch_tail(ta, 1, e->stream, e->launches);
     be_d2h(c->h_slot, e->d_results + c->cs.res_off, c->slot_bytes, e->stream);
@@ -892,7 +916,7 @@ extern "C" int sdr_chan_destroy(sdr_chan *c) {
     if (!c) return SDR_OK;
     sdr_engine *e = c->eng;
     std::lock_guard<std::mutex> lk(e->mu);
-    be_sync(e->stream);
+    sync_all(e);
     e->chans[c->index] = nullptr;
     be_free(c->d_arena);
     be_free(c->d_priv_hist);
@@ -1035,7 +1059,7 @@ static void schedule_frames(sdr_spectrum *s, unsigned n, long long sample_rate, 
 // submit
 // ---------------------------------------------------------------------------------------------------------------------
 static int rebuild(sdr_engine *e) {
-    be_sync(e->stream);
+    sync_all(e);
     size_t total = 0;
     for (auto *c : e->chans) if (c) { c->cs.res_off = (long long)total; total += c->slot_bytes; }
     if (total > e->results_bytes) {
@@ -1192,6 +1216,12 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
     if (n_slots == 0) {
         { int r = run_spectra(); if (r) return r; }
         time_mark(e, 3); time_mark(e, 4);
+#ifndef SDR_EMU
+        if (e->timing && e->time_pending < sdr_engine::kTimeSets) {
+            cudaEventRecord(e->tev_tail[e->time_pending][0], e->stream);
+            cudaEventRecord(e->tev_tail[e->time_pending][1], e->stream);
+        }
+#endif
         if (e->timing && e->time_pending < sdr_engine::kTimeSets) e->time_pending++;
 #ifndef SDR_EMU
         CUDA_TRY(cudaEventRecord(e->ring_ev[slot], e->stream));
@@ -1225,12 +1255,19 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         d.dir = dir; d.dir_prev = c->dir_prev;
         d.hist = c->priv_valid ? c->d_priv_hist + kBlkHist : nullptr;
         c->priv_valid = false;
+        d.lvl0_sel = c->lvl0_sel;                                       // consecutive processed blocks alternate level-0 buffers
+        c->lvl0_sel ^= 1;
         if (dir) c->theta += (unsigned)n * c->dtheta;                   // mix_block advances the phase by n steps
         c->dtheta_prev = c->dtheta; c->dir_prev = dir;
         c->consumed += n;
         by_k[c->cs.K1].push_back(i);
     }
-    be_h2d(e->d_cd, h_cd, (size_t)n_slots * sizeof(ChanDyn), e->stream);
+    ChanDyn *d_cd = e->d_cd2[p];
+#ifndef SDR_EMU
+    // d_cd2[p] and the level-0 buffers this block's front kernel writes were last read by the tail of two blocks ago
+    CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_tail_done[p], 0));
+#endif
+    be_h2d(d_cd, h_cd, (size_t)n_slots * sizeof(ChanDyn), e->stream);
     int goff = 0;
     float h3[6];
     halfband_branch_taps(3, 65.0f, h3);
@@ -1240,7 +1277,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         memcpy(h_group + goff, by_k[K].data(), cg * sizeof(int));
         be_h2d(e->d_group + goff, h_group + goff, cg * sizeof(int), e->stream);
         FrontArgs fa;
-        fa.x = blk; fa.n = (int)n; fa.nco = e->d_nco; fa.cs = e->d_cs; fa.cd = e->d_cd; fa.group = e->d_group + goff; fa.cg = cg;
+        fa.x = blk; fa.n = (int)n; fa.nco = e->d_nco; fa.cs = e->d_cs; fa.cd = d_cd; fa.group = e->d_group + goff; fa.cg = cg;
         const int n_chunks = (cg + 31) / 32;
         const long long nq = ((long long)n >> K) + 1;
         int n_span = std::max(1, (148 * kFrontWarps) / n_chunks);       // jobs <= 16 warps on each of the 148 SMs
@@ -1257,21 +1294,31 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
     }
     { int r = run_spectra(); if (r) return r; }                     // side stream, after the front kernel got the SMs
     TailArgs ta;
-    ta.cs = e->d_cs; ta.cd = e->d_cd; ta.st = e->d_st; ta.taps = e->d_taps; ta.nco = e->d_nco;
+    ta.cs = e->d_cs; ta.cd = d_cd; ta.st = e->d_st; ta.taps = e->d_taps; ta.nco = e->d_nco;
     ta.results = e->d_results; ta.n = (int)n; ta.first = 0;
     // the tail indexes channels by slot; free slots carry valid = 0 and are not touched
+    time_mark(e, 3);
+    // the channel tail (and the results' D2H) go to their own stream: they overlap the next block's front kernel
+    sdr_stream_t ts = e->stream;
 #ifndef SDR_EMU
     CUDA_TRY(cudaEventRecord(e->ring_ev[slot], e->stream));
+    CUDA_TRY(cudaEventRecord(e->ev_front_done, e->stream));
+    ts = e->stream_tail;
+    CUDA_TRY(cudaStreamWaitEvent(ts, e->ev_front_done, 0));
+    if (e->timing && e->time_pending < sdr_engine::kTimeSets) cudaEventRecord(e->tev_tail[e->time_pending][0], ts);
 #endif
-    time_mark(e, 3);
-    launch_tail(ta, n_slots, e->stream, e->launches);
-    time_mark(e, 4);
-    if (e->timing && e->time_pending < sdr_engine::kTimeSets) e->time_pending++;
+    launch_tail(ta, n_slots, ts, e->launches);
     if (to_host && e->results_bytes) {
         size_t total = 0;
         for (auto *c : e->chans) if (c) total = std::max(total, (size_t)c->cs.res_off + c->slot_bytes);
-        be_d2h(e->h_results, e->d_results, total, e->stream);
+        be_d2h(e->h_results, e->d_results, total, ts);
     }
+#ifndef SDR_EMU
+    if (e->timing && e->time_pending < sdr_engine::kTimeSets) cudaEventRecord(e->tev_tail[e->time_pending][1], ts);
+    CUDA_TRY(cudaEventRecord(e->ev_tail_done[p], ts));
+#endif
+    time_mark(e, 4);
+    if (e->timing && e->time_pending < sdr_engine::kTimeSets) e->time_pending++;
     return join_side();
 }
 
@@ -1306,6 +1353,7 @@ extern "C" int sdr_engine_wait(sdr_engine *e) {
     if (!e) return fail(SDR_ERR_ARG, "null engine");
     if (be_sync(e->stream)) return fail(SDR_ERR_CUDA, std::string("stream sync failed: ") + be_last_error());
 #ifndef SDR_EMU
+    if (cudaStreamSynchronize(e->stream_tail) != cudaSuccess) return fail(SDR_ERR_CUDA, std::string("tail stream sync failed: ") + be_last_error());
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(SDR_ERR_CUDA, std::string("kernel error: ") + cudaGetErrorString(err));
 #endif
