@@ -78,7 +78,7 @@ constexpr int kFrontSmemBytes = kFrontSmemTab + kFrontWarps * 2 * 32 * (int)size
 constexpr int kDcLaneBatch = 32;   // steps per batch
 constexpr int kDcLaneRing = 4;     // batches in flight
 __global__ void __launch_bounds__(32) k_dc_exact(DcExactArgs a) {
-    __shared__ float2 sx[kDcLaneRing][kDcLaneBatch][32];
+    __shared__ float2 sx[kDcLaneRing][kDcLaneBatch][33];         // [batch][step][segment], padded: conflict-free both ways
     const int lane = threadIdx.x;
     const int s = blockIdx.x * 32 + lane;
     const bool live = s < a.n_seg;
@@ -99,18 +99,22 @@ __global__ void __launch_bounds__(32) k_dc_exact(DcExactArgs a) {
     t_begin = (t_begin / kDcLaneBatch - 1) * kDcLaneBatch;       // batch grid anchored at t = 0 (t_begin < 0)
     const int nb = (t_end - t_begin + kDcLaneBatch - 1) / kDcLaneBatch;
     const float c = a.c;
-    const float2 *const xs = a.xraw + p0;                        // this lane's stream, indexed by t
     const int own_end = p1 - p0;
-    const unsigned sx_lane = (unsigned)__cvta_generic_to_shared(&sx[0][0][0]) + (unsigned)lane * 8u;
+    // Fetch: the warp copies segment q's next 32 samples with ONE coalesced 256-byte cp.async (lane i takes step i) and
+    // drops them transposed at sx[.][i][q]; the chain then reads sx[.][j][lane].  32 such copies per batch.
+    const unsigned sx_base = (unsigned)__cvta_generic_to_shared(&sx[0][0][0]) + (unsigned)lane * (33u * 8u);
+    const float2 *const blk_base = a.xraw + (long long)blockIdx.x * 32 * a.seg_len + lane;   // + q * seg_len + t
     int ft = t_begin, fk = 0;                                    // fetch cursor
     auto fetch = [&]() {
         if (fk < nb) {
-            const unsigned dst = sx_lane + (unsigned)(fk & (kDcLaneRing - 1)) * (kDcLaneBatch * 32 * 8u);
+            const unsigned dst = sx_base + (unsigned)(fk & (kDcLaneRing - 1)) * (kDcLaneBatch * 33u * 8u);
+            const int t = ft + lane;                             // the step this lane copies for every segment
 #pragma unroll 8
-            for (int j = 0; j < kDcLaneBatch; ++j) {
-                const int t = ft + j;
-                if (t >= t_own && t < own_end)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (unsigned)j * 256u), "l"(xs + t));
+            for (int q = 0; q < 32; ++q) {
+                const int q_own = __shfl_sync(0xffffffffu, t_own, q), q_end = __shfl_sync(0xffffffffu, own_end, q);
+                if (t >= q_own && t < q_end)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (unsigned)q * 8u),
+                                 "l"(blk_base + (long long)q * a.seg_len + ft));
             }
         }
         asm volatile("cp.async.commit_group;");
@@ -124,7 +128,7 @@ __global__ void __launch_bounds__(32) k_dc_exact(DcExactArgs a) {
         asm volatile("cp.async.wait_group %0;" ::"n"(kDcLaneRing - 2) : "memory");
         __syncwarp();
         fetch();
-        const float2(*b)[32] = sx[k & (kDcLaneRing - 1)];
+        const float2(*b)[33] = sx[k & (kDcLaneRing - 1)];
         if (t0 >= t_own && t0 + kDcLaneBatch <= 0) {
             // whole batch is warm-up for this lane
 #pragma unroll
