@@ -38,7 +38,9 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 // ---------------------------------------------------------------------------------------------------------------------
 // kernels (GPU) / serial replays (test-only emulator)
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kDcReservedSms = 8;    // SMs the channel front kernel leaves to the DC blocker's warps (ceil(251 / 32) = 8 at 61.44 MSps)
+constexpr int kDcReservedSms = 16;   // SMs the channel front kernel leaves free: the bit-exact DC blocker's serial chains (one warp
+                                     // per segment, ~125 warps per 61 MSps block) run there at full speed instead of fighting the
+                                     // front warps for issue slots
 constexpr int kFrontWarps = 15;      // warps per CTA of the channel front kernel (one CTA per SM); 15 x 32 x 128 registers leave room for one
                                      // warp of the bit-exact DC blocker on every SM, which then runs underneath the front kernel
 #ifndef SDR_EMU
@@ -69,96 +71,73 @@ constexpr int kFrontSmemTab = 1024 * 16 * (int)sizeof(float2);                  
 constexpr int kFrontSmemBytes = kFrontSmemTab + kFrontWarps * 2 * 32 * (int)sizeof(float4);   // + 16384
 // Bit-exact DC blocker: one warp per segment.  All lanes run the (strictly serial) chain redundantly; the warp as a whole
 // prefetches the raw samples three 32-sample batches ahead into shared memory and stores the outputs coalesced.
-// Bit-exact DC blocker, lane-parallel form: every LANE replays its own segment (32 segments per warp), so the whole
-// block needs only ceil(n_seg / 32) warps (8 at 61.44 MSps).  A serial FMUL -> FADD chain is latency-bound and collapses
-// when it has to share a scheduler with the channel-front warps, so these few warps get SMs of their own: the front
-// kernel leaves kDcReservedSms SMs free (launch_front_k) and each DC warp runs alone at ~9 cycles per step, entirely
-// underneath the previous block's channel kernels.
-// Samples reach shared memory through a per-lane cp.async ring laid out [batch][step][lane] (conflict-free reads).
-constexpr int kDcLaneBatch = 32;   // steps per batch
-constexpr int kDcLaneRing = 4;     // batches in flight
+constexpr int kDcBatch = 64;     // samples per cp.async batch (two 8-byte copies per lane)
+constexpr int kDcRing = 4;       // batches in flight: ~1700 cycles of lead over the serial chain
 __global__ void __launch_bounds__(32) k_dc_exact(DcExactArgs a) {
-    __shared__ float2 sx[kDcLaneRing][kDcLaneBatch][33];         // [batch][step][segment], padded: conflict-free both ways
-    const int lane = threadIdx.x;
-    const int s = blockIdx.x * 32 + lane;
-    const bool live = s < a.n_seg;
-    int i0 = 0;
-    float2 v = make_float2(0.f, 0.f);
-    if (live) dc_exact_plan(a, s, i0, v);
-    const int p0 = live ? s * a.seg_len : 0;
-    int p1 = p0 + (live ? a.seg_len : 0);
+    __shared__ __align__(16) float2 sx[kDcRing][kDcBatch];
+    __shared__ float2 sy[kDcBatch];
+    const int s = blockIdx.x, lane = threadIdx.x;
+    int i0;
+    float2 v;
+    dc_exact_plan(a, s, i0, v);
+    const int p0 = s * a.seg_len;
+    int p1 = p0 + a.seg_len;
     if (p1 > a.n) p1 = a.n;
-    // all lanes walk the same step counter t (sample index = p0 + t); a lane joins when t reaches its own warm-up start
-    const int t_own = i0 - p0;                                   // <= 0
-    int t_begin = t_own, t_end = p1 - p0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        t_begin = min(t_begin, __shfl_xor_sync(0xffffffffu, t_begin, o));
-        t_end = max(t_end, __shfl_xor_sync(0xffffffffu, t_end, o));
-    }
-    t_begin = (t_begin / kDcLaneBatch - 1) * kDcLaneBatch;       // batch grid anchored at t = 0 (t_begin < 0)
-    const int nb = (t_end - t_begin + kDcLaneBatch - 1) / kDcLaneBatch;
+    const int nb = (p1 - i0 + kDcBatch - 1) / kDcBatch;
     const float c = a.c;
-    const int own_end = p1 - p0;
-    // Fetch: the warp copies segment q's next 32 samples with ONE coalesced 256-byte cp.async (lane i takes step i) and
-    // drops them transposed at sx[.][i][q]; the chain then reads sx[.][j][lane].  32 such copies per batch.
-    const unsigned sx_base = (unsigned)__cvta_generic_to_shared(&sx[0][0][0]) + (unsigned)lane * (33u * 8u);
-    const float2 *const blk_base = a.xraw + (long long)blockIdx.x * 32 * a.seg_len + lane;   // + q * seg_len + t
-    int ft = t_begin, fk = 0;                                    // fetch cursor
+    float2 *const y_out = a.y;
+    // cp.async ring: the global -> shared copy of batch k + kDcRing - 1 is issued before batch k is consumed, so the
+    // serial chain never waits on memory.  `src` / `fidx` walk ahead of the chain by kDcRing - 1 batches.
+    const float2 *src = a.xraw + i0 + lane;
+    int fidx = i0 + lane;
+    const unsigned sx_base = (unsigned)__cvta_generic_to_shared(&sx[0][0]) + (unsigned)lane * 8u;
+    int fk = 0;
     auto fetch = [&]() {
-        if (fk < nb) {
-            const unsigned dst = sx_base + (unsigned)(fk & (kDcLaneRing - 1)) * (kDcLaneBatch * 33u * 8u);
-            const int t = ft + lane;                             // the step this lane copies for every segment
-#pragma unroll 8
-            for (int q = 0; q < 32; ++q) {
-                const int q_own = __shfl_sync(0xffffffffu, t_own, q), q_end = __shfl_sync(0xffffffffu, own_end, q);
-                if (t >= q_own && t < q_end)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (unsigned)q * 8u),
-                                 "l"(blk_base + (long long)q * a.seg_len + ft));
-            }
-        }
+        const unsigned dst = sx_base + (unsigned)(fk & (kDcRing - 1)) * (kDcBatch * 8u);
+        if (fidx < p1) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src));
+        if (fidx + 32 < p1) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 256u), "l"(src + 32));
         asm volatile("cp.async.commit_group;");
-        ft += kDcLaneBatch; ++fk;
+        src += kDcBatch; fidx += kDcBatch; ++fk;
     };
 #pragma unroll
-    for (int k = 0; k < kDcLaneRing - 1; ++k) fetch();
+    for (int k = 0; k < kDcRing - 1; ++k) fetch();
     float2 v_in = v, y;
-    int t0 = t_begin;
-    for (int k = 0; k < nb; ++k, t0 += kDcLaneBatch) {
-        asm volatile("cp.async.wait_group %0;" ::"n"(kDcLaneRing - 2) : "memory");
-        __syncwarp();
+    int base = i0;
+    for (int k = 0; k < nb; ++k, base += kDcBatch) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kDcRing - 2) : "memory");   // batch k has landed (for this lane)
+        __syncwarp();                                          // ... and for every lane; batch k-1 is fully consumed
         fetch();
-        const float2(*b)[33] = sx[k & (kDcLaneRing - 1)];
-        if (t0 >= t_own && t0 + kDcLaneBatch <= 0) {
-            // whole batch is warm-up for this lane
+        const float2 *b = sx[k & (kDcRing - 1)];
+        if (base + kDcBatch <= p0) {
+            // pure warm-up batch: nothing but the chain
 #pragma unroll
-            for (int j = 0; j < kDcLaneBatch; ++j) dc_ref_step(c, b[j][lane], v, y);
-        } else if (t0 >= 0 && t0 + kDcLaneBatch <= own_end) {
-            // whole batch is output: four outputs (32 bytes, one sector) at a time
-            if (t0 == 0) v_in = v;
-            float4 *dst = reinterpret_cast<float4 *>(a.y + p0 + t0);
+            for (int j = 0; j < kDcBatch; ++j) dc_ref_step(c, b[j], v, y);
+            if (base + kDcBatch == p0) v_in = v;
+        } else if (base >= p0 && base + kDcBatch <= p1) {
+            // pure output batch
+            if (base == p0) v_in = v;
 #pragma unroll
-            for (int j = 0; j < kDcLaneBatch; j += 4) {
-                float2 y0, y1, y2, y3;
-                dc_ref_step(c, b[j][lane], v, y0); dc_ref_step(c, b[j + 1][lane], v, y1);
-                dc_ref_step(c, b[j + 2][lane], v, y2); dc_ref_step(c, b[j + 3][lane], v, y3);
-                dst[j / 2] = make_float4(y0.x, y0.y, y1.x, y1.y);
-                dst[j / 2 + 1] = make_float4(y2.x, y2.y, y3.x, y3.y);
+            for (int j = 0; j < kDcBatch; ++j) {
+                dc_ref_step(c, b[j], v, y);
+                if (lane == 0) sy[j] = y;
             }
+            __syncwarp();
+            y_out[base + lane] = sy[lane];
+            y_out[base + 32 + lane] = sy[32 + lane];
         } else {
-            // ragged batch: this lane's warm-up starts or its segment ends inside it (or it is not this lane's turn yet)
-            for (int j = 0; j < kDcLaneBatch; ++j) {
-                const int t = t0 + j;
-                if (t >= t_own && t < own_end) {
-                    if (t == 0) v_in = v;
-                    dc_ref_step(c, b[j][lane], v, y);
-                    if (t >= 0) a.y[p0 + t] = y;
+            // boundary batch (segment start not aligned to the batch grid, or the end of the block)
+            for (int j = 0; j < kDcBatch; ++j) {
+                const int idx = base + j;
+                if (idx < p1) {
+                    if (idx == p0) v_in = v;
+                    dc_ref_step(c, b[j], v, y);
+                    if (idx >= p0 && lane == 0) y_out[idx] = y;
                 }
             }
         }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    if (live) { a.seg_in[s] = v_in; a.seg_out[s] = v; }
+    if (lane == 0) { a.seg_in[s] = v_in; a.seg_out[s] = v; }
 }
 __global__ void k_dc_verify(DcExactArgs a) {
     if (threadIdx.x == 0 && blockIdx.x == 0) dc_exact_verify(a);
@@ -240,7 +219,7 @@ __global__ void __launch_bounds__(kSpecThreads) k_spec_points(SpecArgs a) {
 
 static void launch_dc_exact(const DcExactArgs &a, sdr_stream_t s, unsigned long long &launches) {
 #ifndef SDR_EMU
-    k_dc_exact<<<(a.n_seg + 31) / 32, 32, 0, s>>>(a);
+    k_dc_exact<<<a.n_seg, 32, 0, s>>>(a);
     k_dc_verify<<<1, 32, 0, s>>>(a);
 #else
     (void)s;
