@@ -38,8 +38,8 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 // ---------------------------------------------------------------------------------------------------------------------
 // kernels (GPU) / serial replays (test-only emulator)
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kDcReservedSms = 16;   // SMs the channel front kernel leaves free: the bit-exact DC blocker's serial chains (one warp
-                                     // per segment, ~125 warps per 61 MSps block) run there at full speed instead of fighting the
+constexpr int kDcReservedSms = 8;    // SMs the channel front kernel leaves free: the bit-exact DC blocker's serial chains (one warp
+                                     // per segment, 63 warps per 61 MSps block) run there at full speed instead of fighting the
                                      // front warps for issue slots
 constexpr int kFrontWarps = 15;      // warps per CTA of the channel front kernel (one CTA per SM); 15 x 32 x 128 registers leave room for one
                                      // warp of the bit-exact DC blocker on every SM, which then runs underneath the front kernel
