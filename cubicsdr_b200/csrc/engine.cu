@@ -75,7 +75,6 @@ constexpr int kDcBatch = 64;     // samples per cp.async batch (two 8-byte copie
 constexpr int kDcRing = 4;       // batches in flight: ~1700 cycles of lead over the serial chain
 __global__ void __launch_bounds__(32) k_dc_exact(DcExactArgs a) {
     __shared__ __align__(16) float2 sx[kDcRing][kDcBatch];
-    __shared__ float2 sy[kDcBatch];
     const int s = blockIdx.x, lane = threadIdx.x;
     int i0;
     float2 v;
@@ -116,14 +115,21 @@ __global__ void __launch_bounds__(32) k_dc_exact(DcExactArgs a) {
         } else if (base >= p0 && base + kDcBatch <= p1) {
             // pure output batch
             if (base == p0) v_in = v;
+            // every lane runs the chain; lane l keeps outputs l and l + 32 in registers (selects, off the chain), so
+            // the batch is stored coalesced without a shared-memory round trip between the steps
+            float2 k0 = make_float2(0.f, 0.f), k1 = k0;
 #pragma unroll
-            for (int j = 0; j < kDcBatch; ++j) {
+            for (int j = 0; j < 32; ++j) {
                 dc_ref_step(c, b[j], v, y);
-                if (lane == 0) sy[j] = y;
+                if (lane == j) k0 = y;
             }
-            __syncwarp();
-            y_out[base + lane] = sy[lane];
-            y_out[base + 32 + lane] = sy[32 + lane];
+#pragma unroll
+            for (int j = 32; j < kDcBatch; ++j) {
+                dc_ref_step(c, b[j], v, y);
+                if (lane == j - 32) k1 = y;
+            }
+            y_out[base + lane] = k0;
+            y_out[base + 32 + lane] = k1;
         } else {
             // boundary batch (segment start not aligned to the batch grid, or the end of the block)
             for (int j = 0; j < kDcBatch; ++j) {
@@ -568,7 +574,7 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
     const int tiles = (max_block + kDcTile - 1) / kDcTile;
     bad |= be_malloc((void **)&e->d_tile_sum, tiles * sizeof(double2));
     for (int b = 0; b < 2; ++b) bad |= be_malloc((void **)&e->d_tile_carry2[b], tiles * sizeof(double2));
-    const int max_seg = (int)(max_block / kDcSegLen) + 2;
+    const int max_seg = (int)(max_block / kDcSegLenLight) + 2;
     bad |= be_malloc((void **)&e->d_seg_in, max_seg * sizeof(float2));
     bad |= be_malloc((void **)&e->d_seg_out, max_seg * sizeof(float2));
     bad |= be_malloc((void **)&e->d_fstate, sizeof(float2));
@@ -1127,14 +1133,19 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
     launch_dc(dc, !e->exact_dc, dcs, e->launches);
     if (e->exact_dc) {
         DcExactArgs xa;
-        xa.xraw = raw; xa.y = blk; xa.n = (int)n; xa.seg_len = kDcSegLen; xa.warm = kDcWarm;
+        // few, long segments when the channel front kernel owns the SMs (the replay's warps must fit on the reserved
+        // ones); many short ones when the GPU is otherwise idle and only the replay's own latency matters
+        size_t live = 0;
+        for (auto *c : e->chans) live += c != nullptr;
+        const unsigned seg = live >= 64 ? kDcSegLen : kDcSegLenLight;
+        xa.xraw = raw; xa.y = blk; xa.n = (int)n; xa.seg_len = (int)seg; xa.warm = kDcWarm;
         xa.c = (float)e->dc_a;
         xa.tile_carry = e->d_tile_carry2[p]; xa.prev_tile_carry = e->d_tile_carry2[p ^ 1];
         xa.prev_n = e->have_block ? (int)e->last_n : 0;
         xa.seg_in = e->d_seg_in; xa.seg_out = e->d_seg_out; xa.fstate = e->d_fstate; xa.fixups = e->d_fixups;
         // speculate only when there is parallelism to gain and the warm-up region lies inside the data we hold
-        const bool spec = n >= 4u * kDcSegLen && (!e->have_block || e->last_n >= (unsigned)(kDcWarm + kDcTile));
-        xa.n_seg = spec ? (int)((n + kDcSegLen - 1) / kDcSegLen) : 1;
+        const bool spec = n >= 4u * seg && (!e->have_block || e->last_n >= (unsigned)(kDcWarm + kDcTile));
+        xa.n_seg = spec ? (int)((n + seg - 1) / seg) : 1;
         if (!spec) xa.seg_len = (int)n;
         launch_dc_exact(xa, dcs, e->launches);
     }
