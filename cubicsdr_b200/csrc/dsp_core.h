@@ -235,8 +235,7 @@ SDR_HD inline void dc_apply_phase(int ph, const DcArgs &a, int bid, int tid, DcS
 //     from the true carried state of segment 0, that every output is the reference's; a failing junction (rare) is
 //     replayed serially by dc_exact_verify.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kDcSegLen = 16384;     // segment length of the speculative replay under a heavy channel load ...
-constexpr int kDcSegLenLight = 4096; // ... and when the GPU is otherwise idle
+constexpr int kDcSegLenLight = 4096; // segment length of the speculative replay (longer under a heavy channel load: engine.cu)
 constexpr int kDcWarm = 24576;      // P(junction not coalesced) ~ 1.5e-4: a serial fix-up every dozen blocks at 61 MSps
 
 struct DcExactArgs {

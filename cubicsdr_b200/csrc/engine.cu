@@ -41,6 +41,7 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 constexpr int kDcReservedSms = 8;    // SMs the channel front kernel leaves free: the bit-exact DC blocker's serial chains (one warp
                                      // per segment, 63 warps per 61 MSps block) run there at full speed instead of fighting the
                                      // front warps for issue slots
+constexpr int kDcWarpsPerCta = 8;    // segments (warps) per CTA of the bit-exact DC replay under a heavy channel load
 constexpr int kFrontWarps = 15;      // warps per CTA of the channel front kernel (one CTA per SM); 15 x 32 x 128 registers leave room for one
                                      // warp of the bit-exact DC blocker on every SM, which then runs underneath the front kernel
 #ifndef SDR_EMU
@@ -70,12 +71,19 @@ __global__ void __launch_bounds__(kDcThreads) k_dc_apply(DcArgs a) {
 constexpr int kFrontSmemTab = 1024 * 16 * (int)sizeof(float2);                    // 131072
 constexpr int kFrontSmemBytes = kFrontSmemTab + kFrontWarps * 2 * 32 * (int)sizeof(float4);   // + 16384
 // Bit-exact DC blocker: one warp per segment.  All lanes run the (strictly serial) chain redundantly; the warp as a whole
-// prefetches the raw samples three 32-sample batches ahead into shared memory and stores the outputs coalesced.
+// prefetches the raw samples three batches ahead into shared memory and stores the outputs coalesced.  A CTA holds up to
+// kDcWarpsPerCta segments.  Under a heavy channel load the launch also asks for kDcExclusiveSmem bytes of dynamic shared
+// memory it never touches: with that request a DC CTA cannot share an SM with a channel-front CTA (143 KB), so the block
+// scheduler puts the replay on the SMs the front kernel leaves free, whichever of the two kernels starts first.
 constexpr int kDcBatch = 64;     // samples per cp.async batch (two 8-byte copies per lane)
 constexpr int kDcRing = 4;       // batches in flight: ~1700 cycles of lead over the serial chain
-__global__ void __launch_bounds__(32) k_dc_exact(DcExactArgs a) {
-    __shared__ __align__(16) float2 sx[kDcRing][kDcBatch];
-    const int s = blockIdx.x, lane = threadIdx.x;
+constexpr int kDcExclusiveSmem = 90 * 1024;
+__global__ void __launch_bounds__(32 * kDcWarpsPerCta) k_dc_exact(DcExactArgs a) {
+    __shared__ __align__(16) float2 sx_all[kDcWarpsPerCta][kDcRing][kDcBatch];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (s >= a.n_seg) return;
+    float2 (*sx)[kDcBatch] = sx_all[warp];
     int i0;
     float2 v;
     dc_exact_plan(a, s, i0, v);
@@ -223,12 +231,18 @@ __global__ void __launch_bounds__(kSpecThreads) k_spec_points(SpecArgs a) {
 }
 #endif
 
-static void launch_dc_exact(const DcExactArgs &a, sdr_stream_t s, unsigned long long &launches) {
+static void launch_dc_exact(const DcExactArgs &a, bool exclusive, sdr_stream_t s, unsigned long long &launches) {
 #ifndef SDR_EMU
-    k_dc_exact<<<a.n_seg, 32, 0, s>>>(a);
+    if (exclusive) {
+        static bool attr_set = false;
+        if (!attr_set) { cudaFuncSetAttribute(k_dc_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, kDcExclusiveSmem); attr_set = true; }
+        k_dc_exact<<<(a.n_seg + kDcWarpsPerCta - 1) / kDcWarpsPerCta, 32 * kDcWarpsPerCta, kDcExclusiveSmem, s>>>(a);
+    } else {
+        k_dc_exact<<<a.n_seg, 32, 0, s>>>(a);
+    }
     k_dc_verify<<<1, 32, 0, s>>>(a);
 #else
-    (void)s;
+    (void)s; (void)exclusive;
     for (int g = 0; g < a.n_seg; ++g) dc_exact_segment_serial(a, g, false, make_float2(0.f, 0.f));
     dc_exact_verify(a);
 #endif
@@ -1137,7 +1151,14 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         // ones); many short ones when the GPU is otherwise idle and only the replay's own latency matters
         size_t live = 0;
         for (auto *c : e->chans) live += c != nullptr;
-        const unsigned seg = live >= 64 ? kDcSegLen : kDcSegLenLight;
+        const bool heavy = live >= 256;
+        unsigned seg = kDcSegLenLight;
+        if (heavy) {                                           // at most one warp per scheduler slot pair on the reserved SMs
+            const unsigned cap = kDcReservedSms * kDcWarpsPerCta;
+            seg = (unsigned)((n + cap - 1) / cap);
+            seg = (seg + 63u) & ~63u;
+            if (seg < kDcSegLenLight) seg = kDcSegLenLight;
+        }
         xa.xraw = raw; xa.y = blk; xa.n = (int)n; xa.seg_len = (int)seg; xa.warm = kDcWarm;
         xa.c = (float)e->dc_a;
         xa.tile_carry = e->d_tile_carry2[p]; xa.prev_tile_carry = e->d_tile_carry2[p ^ 1];
@@ -1147,7 +1168,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         const bool spec = n >= 4u * seg && (!e->have_block || e->last_n >= (unsigned)(kDcWarm + kDcTile));
         xa.n_seg = spec ? (int)((n + seg - 1) / seg) : 1;
         if (!spec) xa.seg_len = (int)n;
-        launch_dc_exact(xa, dcs, e->launches);
+        launch_dc_exact(xa, heavy && spec, dcs, e->launches);
     }
     // history in front of the block: the tail of the previous block, which lives in the other buffer
     size_t need = kBlkHist;
