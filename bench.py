@@ -242,30 +242,28 @@ def main():
     # end to end: pinned host block -> H2D (copy stream, overlapped with the previous block's kernels) -> (broadcast) ->
     # kernels -> D2H of every result -> batched fetch into host arrays.  Public API only: submit_device / wait / fetch.
     copy_stream = torch.cuda.Stream(device=dev)
-    stages = [torch.empty(N, dtype=torch.complex64, device=dev) for _ in range(2)]
-    h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
+    stages = [torch.empty(N, dtype=torch.complex64, device=dev) for _ in range(3)]
+    h2d_done = [torch.cuda.Event() for _ in range(3)]
 
     def h2d(i):
         if rank == 0:
             with torch.cuda.stream(copy_stream):
-                stages[i & 1].copy_(host_blocks[i & 1], non_blocking=True)
-                h2d_done[i & 1].record(copy_stream)
+                stages[i % 3].copy_(host_blocks[i & 1], non_blocking=True)
+                h2d_done[i % 3].record(copy_stream)
 
-    def step_e2e(i, first):
-        if first:
-            h2d(i)
-        buf = stages[i & 1]
-        ev = h2d_done[i & 1]
+    def submit_e2e(i):
+        buf = stages[i % 3]
+        ev = h2d_done[i % 3]
         if world > 1:
             with torch.cuda.stream(side):
                 if rank == 0:
-                    side.wait_event(h2d_done[i & 1])
+                    side.wait_event(h2d_done[i % 3])
                 dist.broadcast(buf, src=0)
                 bc_done[i & 3].record(side)
             ev = bc_done[i & 3]
         eng.submit_device_async(buf.data_ptr(), N, CENTER, fs, fetch_to_host=True, ready_event=ev.cuda_event if (rank == 0 or world > 1) else None)
-        h2d(i + 1)                                             # next block's copy overlaps this block's kernels
-        eng.wait()
+
+    def fetch_e2e():
         nbytes = 0
         if cobjs:
             audio, n_audio, _, _ = eng.fetch_audio_batch(cobjs, 1024)
@@ -274,6 +272,15 @@ def main():
             pts, lines, cf = spec.fetch_all(64)
             nbytes += pts.nbytes + lines.nbytes
         return nbytes
+
+    # One block in flight, like the reference's thread pipeline: per step, submit block i+1, start the H2D of block i+2
+    # (its stage buffer was last read by block i-1, whose results were already waited for), then wait for and fetch the
+    # results of block i.  Every step still costs one H2D, one pass of the path and one D2H + fetch.
+    def step_e2e(i):
+        submit_e2e(i + 1)
+        h2d(i + 2)
+        eng.wait_block(1)
+        return fetch_e2e()
 
     # ---- warm-up ------------------------------------------------------------------------------------------------------
     for i in range(args.warmup):
@@ -310,14 +317,18 @@ def main():
     value = N * args.steps / (ms * 1e-3) / 1e6
 
     # ---- timed: end to end through host buffers -------------------------------------------------------------------------
+    h2d(0)
+    submit_e2e(0)
+    h2d(1)
     for i in range(3):
-        step_e2e(i, i == 0)
+        step_e2e(i)
     torch.cuda.synchronize()
     barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     d2h = 0
     for i in range(args.steps):
-        d2h = step_e2e(3 + i, False)
+        d2h = step_e2e(3 + i)
+    eng.wait()                                                  # drain the block still in flight (submitted, not yet fetched)
     torch.cuda.synchronize(); barrier()
     t_e2e = time.perf_counter() - t0
     if dist is not None:

@@ -16,6 +16,7 @@ SYMBOLS = [
     "sdr_last_error", "sdr_version", "sdr_is_device_build",
     "sdr_engine_create", "sdr_engine_destroy", "sdr_engine_submit", "sdr_engine_submit_device", "sdr_engine_submit_device_async",
     "sdr_engine_wait",
+    "sdr_engine_wait_block",
     "sdr_engine_fetch_block", "sdr_engine_launch_count", "sdr_engine_set_timing", "sdr_engine_get_timing",
     "sdr_chan_create", "sdr_chan_destroy", "sdr_chan_set_frequency", "sdr_chan_get_bandwidth", "sdr_chan_want_iq",
     "sdr_chan_fetch_audio", "sdr_chan_fetch_iq", "sdr_engine_fetch_audio_batch",
@@ -49,6 +50,7 @@ class Lib:
         L.sdr_engine_submit_device.argtypes = [vp, vp, u, ll, ll, i]
         L.sdr_engine_submit_device_async.argtypes = [vp, vp, u, ll, ll, i, vp]
         L.sdr_engine_wait.argtypes = [vp]
+        L.sdr_engine_wait_block.argtypes = [vp, C.c_int]
         L.sdr_engine_fetch_block.argtypes = [vp, vp, u, P(u)]
         L.sdr_engine_launch_count.argtypes = [vp]
         L.sdr_engine_launch_count.restype = C.c_ulonglong
@@ -132,6 +134,10 @@ class Engine:
 
     def wait(self):
         self.lib.check(self.lib.L.sdr_engine_wait(self.h))
+
+    def wait_block(self, lag=0):
+        """Wait for the host results of the latest (lag=0) or previous (lag=1) block only; fetches then read that block."""
+        self.lib.check(self.lib.L.sdr_engine_wait_block(self.h, int(lag)))
 
     def fetch_block(self, n):
         out = np.zeros(n, np.complex64)

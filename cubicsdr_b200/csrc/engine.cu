@@ -418,6 +418,10 @@ struct sdr_spectrum {
     float *h_points = nullptr; unsigned char *h_lines = nullptr; double2 *h_cf = nullptr; int *h_frame_start = nullptr;
     float *h_dbg = nullptr;
     unsigned f_max = 0, frames_last = 0;
+    unsigned frames_buf[2] = {0, 0};   // frames of the blocks whose results sit in host buffer 0 / 1
+    float *hp(int q) const { return h_points + (size_t)q * f_max * fft_size; }
+    unsigned char *hl(int q) const { return h_lines + (size_t)q * f_max * fft_size; }
+    double2 *hc(int q) const { return h_cf + (size_t)q * f_max; }
 };
 
 struct sdr_engine {
@@ -464,6 +468,14 @@ struct sdr_engine {
     unsigned char *d_results = nullptr, *h_results = nullptr; size_t results_bytes = 0;
     bool dirty = true;
     bool results_on_host = false;
+    // host results are double-buffered so that a caller may fetch block b while block b+1 is in flight (sdr_engine_wait_block)
+    int res_sel = 0, fetch_sel = 0;
+    bool res_on_host[2] = {false, false};
+    unsigned char *hres(int q) const { return h_results + (size_t)q * results_bytes; }
+#ifndef SDR_EMU
+    cudaEvent_t ev_res_tail[2] = {nullptr, nullptr}, ev_res_spec[2] = {nullptr, nullptr};
+    bool res_tail_rec[2] = {false, false}, res_spec_rec[2] = {false, false};
+#endif
     std::vector<sdr_spectrum *> spectra;
     // optional per-stage device timing (CUDA events on the engine stream): 0 dc, 1 spectrum, 2 front, 3 tail
     bool timing = false;
@@ -622,6 +634,10 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
     }
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+    for (int b = 0; b < 2; ++b) {
+        CUDA_TRY(cudaEventCreateWithFlags(&e->ev_res_tail[b], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&e->ev_res_spec[b], cudaEventDisableTiming));
+    }
 #endif
     e->taps_cap = 4u << 20;   // floats
     bad |= be_malloc((void **)&e->d_taps, e->taps_cap * sizeof(float));
@@ -674,6 +690,7 @@ extern "C" int sdr_engine_destroy(sdr_engine *e) {
     for (int b = 0; b < 2; ++b) { if (e->ev_dc_done[b]) cudaEventDestroy(e->ev_dc_done[b]); if (e->ev_consumed[b]) cudaEventDestroy(e->ev_consumed[b]); }
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
+    for (int b = 0; b < 2; ++b) { if (e->ev_res_tail[b]) cudaEventDestroy(e->ev_res_tail[b]); if (e->ev_res_spec[b]) cudaEventDestroy(e->ev_res_spec[b]); }
     if (e->own_stream) cudaStreamDestroy(e->stream);
 #endif
     delete e;
@@ -1004,9 +1021,9 @@ extern "C" int sdr_spectrum_create(sdr_engine *e, unsigned fft_size, unsigned lp
     bad |= be_malloc((void **)&s->d_points, F * fft_size * sizeof(float));
     bad |= be_malloc((void **)&s->d_lines, F * fft_size);
     bad |= be_malloc((void **)&s->d_frame_start, F * sizeof(int));
-    bad |= be_host_alloc((void **)&s->h_points, F * fft_size * sizeof(float));
-    bad |= be_host_alloc((void **)&s->h_lines, F * fft_size);
-    bad |= be_host_alloc((void **)&s->h_cf, F * sizeof(double2));
+    bad |= be_host_alloc((void **)&s->h_points, 2 * F * fft_size * sizeof(float));
+    bad |= be_host_alloc((void **)&s->h_lines, 2 * F * fft_size);
+    bad |= be_host_alloc((void **)&s->h_cf, 2 * F * sizeof(double2));
     bad |= be_host_alloc((void **)&s->h_frame_start, (size_t)sdr_engine::kRing * F * sizeof(int));
     bad |= be_host_alloc((void **)&s->h_dbg, 2 * N * sizeof(float));
     if (bad) { spectrum_free(s); delete s; return fail(SDR_ERR_NOMEM, "sdr_spectrum_create: allocation failed"); }
@@ -1089,9 +1106,10 @@ static int rebuild(sdr_engine *e) {
     if (total > e->results_bytes) {
         be_free(e->d_results); be_host_free(e->h_results);
         e->d_results = nullptr; e->h_results = nullptr;
-        if (be_malloc((void **)&e->d_results, total) || be_host_alloc((void **)&e->h_results, total))
+        if (be_malloc((void **)&e->d_results, total) || be_host_alloc((void **)&e->h_results, 2 * total))
             return fail(SDR_ERR_NOMEM, "results buffer");
         e->results_bytes = total;
+        e->res_on_host[0] = e->res_on_host[1] = false;
     }
     for (auto *c : e->chans) if (c) be_h2d(e->d_cs + c->index, &c->cs, sizeof(ChanStatic), e->stream);
     if (e->taps_host.size() > e->taps_uploaded) {
@@ -1188,6 +1206,12 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
     e->parity = p;
     e->last_n = n; e->have_block = true;
     e->results_on_host = to_host;
+    const int q = (e->res_sel ^= 1);                            // host result buffer of this block
+    e->res_on_host[q] = to_host;
+    e->fetch_sel = q;
+#ifndef SDR_EMU
+    e->res_tail_rec[q] = e->res_spec_rec[q] = false;
+#endif
 
     // 3. spectra.  Frame scheduling and the (tiny) frame-start upload happen here; the kernels are enqueued on the side
     //    stream AFTER the channel front kernel has been launched (run_spectra below), so that the front kernel's single
@@ -1197,6 +1221,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
     for (auto *s : e->spectra) {
         schedule_frames(s, n, rate, starts);
         s->frames_last = (unsigned)std::min<size_t>(starts.size(), s->f_max);
+        s->frames_buf[q] = s->frames_last;
         if (!s->frames_last) continue;
         int *h_fs = s->h_frame_start + (size_t)slot * s->f_max;
         memcpy(h_fs, starts.data(), s->frames_last * sizeof(int));
@@ -1225,14 +1250,15 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
             int r = launch_spectrum(job.second, sps, e->launches);
             if (r) return r;
             if (to_host) {
-                be_d2h(s->h_points, s->d_points, (size_t)s->frames_last * s->fft_size * sizeof(float), sps);
-                be_d2h(s->h_lines, s->d_lines, (size_t)s->frames_last * s->fft_size, sps);
-                be_d2h(s->h_cf, s->d_frame_cf_maa, (size_t)s->frames_last * sizeof(double2), sps);
+                be_d2h(s->hp(q), s->d_points, (size_t)s->frames_last * s->fft_size * sizeof(float), sps);
+                be_d2h(s->hl(q), s->d_lines, (size_t)s->frames_last * s->fft_size, sps);
+                be_d2h(s->hc(q), s->d_frame_cf_maa, (size_t)s->frames_last * sizeof(double2), sps);
             }
         }
 #ifndef SDR_EMU
         if (e->timing && e->time_pending < sdr_engine::kTimeSets) cudaEventRecord(e->tev_spec[e->time_pending][1], sps);
         if (forked) CUDA_TRY(cudaEventRecord(e->ev_join, e->stream2));
+        if (to_host && !spec_jobs.empty()) { CUDA_TRY(cudaEventRecord(e->ev_res_spec[q], sps)); e->res_spec_rec[q] = true; }
 #endif
         return SDR_OK;
     };
@@ -1347,7 +1373,10 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
     if (to_host && e->results_bytes) {
         size_t total = 0;
         for (auto *c : e->chans) if (c) total = std::max(total, (size_t)c->cs.res_off + c->slot_bytes);
-        be_d2h(e->h_results, e->d_results, total, ts);
+        be_d2h(e->hres(q), e->d_results, total, ts);
+#ifndef SDR_EMU
+        CUDA_TRY(cudaEventRecord(e->ev_res_tail[q], ts)); e->res_tail_rec[q] = true;
+#endif
     }
 #ifndef SDR_EMU
     if (e->timing && e->time_pending < sdr_engine::kTimeSets) cudaEventRecord(e->tev_tail[e->time_pending][1], ts);
@@ -1395,8 +1424,29 @@ extern "C" int sdr_engine_wait(sdr_engine *e) {
 #endif
     {
         std::lock_guard<std::mutex> lk(e->mu);
+        e->fetch_sel = e->res_sel;
         time_collect(e);
     }
+    return SDR_OK;
+}
+
+// Wait only until the results of the latest (lag = 0) or the previous (lag = 1) submitted block are on the host, and make
+// the fetch calls read that block.  With lag = 1 the caller keeps one block in flight: submit(b+1), wait_block(1), fetch b.
+extern "C" int sdr_engine_wait_block(sdr_engine *e, int lag) {
+    if (!e) return fail(SDR_ERR_ARG, "null engine");
+    if (lag < 0 || lag > 1) return fail(SDR_ERR_ARG, "sdr_engine_wait_block: lag must be 0 or 1");
+    int q;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        q = lag ? (e->res_sel ^ 1) : e->res_sel;
+        if (!e->res_on_host[q]) return fail(SDR_ERR_STATE, "sdr_engine_wait_block: that block was not submitted with host results");
+    }
+#ifndef SDR_EMU
+    if (e->res_tail_rec[q] && cudaEventSynchronize(e->ev_res_tail[q]) != cudaSuccess) return fail(SDR_ERR_CUDA, std::string("result wait failed: ") + be_last_error());
+    if (e->res_spec_rec[q] && cudaEventSynchronize(e->ev_res_spec[q]) != cudaSuccess) return fail(SDR_ERR_CUDA, std::string("result wait failed: ") + be_last_error());
+#endif
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->fetch_sel = q;
     return SDR_OK;
 }
 
@@ -1414,8 +1464,8 @@ extern "C" int sdr_chan_fetch_audio(sdr_chan *c, float *audio, unsigned cap, uns
     if (!c) return fail(SDR_ERR_ARG, "null channel");
     sdr_engine *e = c->eng;
     std::lock_guard<std::mutex> lk(e->mu);
-    if (!e->results_on_host || !e->h_results) return fail(SDR_ERR_STATE, "no host results for the last block");
-    const unsigned char *slot = e->h_results + c->cs.res_off;
+    if (!e->res_on_host[e->fetch_sel] || !e->h_results) return fail(SDR_ERR_STATE, "no host results for the last block");
+    const unsigned char *slot = e->hres(e->fetch_sel) + c->cs.res_off;
     const ChanResultHeader *h = reinterpret_cast<const ChanResultHeader *>(slot);
     unsigned m = std::min(cap, std::min(h->n_audio, (unsigned)c->cs.res_audio_cap));
     if (audio) memcpy(audio, slot + 32, (size_t)m * sizeof(float));
@@ -1430,11 +1480,11 @@ extern "C" int sdr_engine_fetch_audio_batch(sdr_engine *e, sdr_chan *const *chan
                                             unsigned *n_audio, double *level_db, float *peak) {
     if (!e || !chans) return fail(SDR_ERR_ARG, "null argument");
     std::lock_guard<std::mutex> lk(e->mu);
-    if (!e->results_on_host || !e->h_results) return fail(SDR_ERR_STATE, "no host results for the last block");
+    if (!e->res_on_host[e->fetch_sel] || !e->h_results) return fail(SDR_ERR_STATE, "no host results for the last block");
     for (unsigned i = 0; i < n_chan; ++i) {
         const sdr_chan *c = chans[i];
         if (!c || c->eng != e) return fail(SDR_ERR_ARG, "channel does not belong to this engine");
-        const unsigned char *slot = e->h_results + c->cs.res_off;
+        const unsigned char *slot = e->hres(e->fetch_sel) + c->cs.res_off;
         const ChanResultHeader *h = reinterpret_cast<const ChanResultHeader *>(slot);
         unsigned m = std::min(stride, std::min(h->n_audio, (unsigned)c->cs.res_audio_cap));
         if (audio) memcpy(audio + (size_t)i * stride, slot + 32, (size_t)m * sizeof(float));
@@ -1449,9 +1499,9 @@ extern "C" int sdr_chan_fetch_iq(sdr_chan *c, sdr_cf32 *iq, unsigned cap, unsign
     if (!c) return fail(SDR_ERR_ARG, "null channel");
     sdr_engine *e = c->eng;
     std::lock_guard<std::mutex> lk(e->mu);
-    if (!e->results_on_host || !e->h_results) return fail(SDR_ERR_STATE, "no host results for the last block");
+    if (!e->res_on_host[e->fetch_sel] || !e->h_results) return fail(SDR_ERR_STATE, "no host results for the last block");
     if (!c->cs.want_iq) return fail(SDR_ERR_STATE, "sdr_chan_want_iq was not enabled");
-    const unsigned char *slot = e->h_results + c->cs.res_off;
+    const unsigned char *slot = e->hres(e->fetch_sel) + c->cs.res_off;
     const ChanResultHeader *h = reinterpret_cast<const ChanResultHeader *>(slot);
     unsigned m = std::min(cap, std::min(h->n_iq, (unsigned)c->cs.res_iq_cap));
     if (iq) memcpy(iq, slot + 32 + (size_t)c->cs.res_audio_cap * 4, (size_t)m * sizeof(sdr_cf32));
@@ -1461,30 +1511,32 @@ extern "C" int sdr_chan_fetch_iq(sdr_chan *c, sdr_cf32 *iq, unsigned cap, unsign
 
 extern "C" int sdr_spectrum_frames(sdr_spectrum *s, unsigned *n) {
     if (!s || !n) return fail(SDR_ERR_ARG, "null argument");
-    *n = s->frames_last;
+    *n = s->frames_buf[s->eng->fetch_sel];
     return SDR_OK;
 }
 
 extern "C" int sdr_spectrum_fetch(sdr_spectrum *s, unsigned idx, float *points_y, uint8_t *line, double *cf) {
     if (!s) return fail(SDR_ERR_ARG, "null spectrum");
     std::lock_guard<std::mutex> lk(s->eng->mu);
-    if (idx >= s->frames_last) return fail(SDR_ERR_ARG, "frame index out of range");
-    if (!s->eng->results_on_host) return fail(SDR_ERR_STATE, "no host results for the last block");
-    if (points_y) memcpy(points_y, s->h_points + (size_t)idx * s->fft_size, s->fft_size * sizeof(float));
-    if (line) memcpy(line, s->h_lines + (size_t)idx * s->fft_size, s->fft_size);
-    if (cf) { cf[0] = s->h_cf[idx].x; cf[1] = s->h_cf[idx].y; }
+    const int q = s->eng->fetch_sel;
+    if (idx >= s->frames_buf[q]) return fail(SDR_ERR_ARG, "frame index out of range");
+    if (!s->eng->res_on_host[q]) return fail(SDR_ERR_STATE, "no host results for the last block");
+    if (points_y) memcpy(points_y, s->hp(q) + (size_t)idx * s->fft_size, s->fft_size * sizeof(float));
+    if (line) memcpy(line, s->hl(q) + (size_t)idx * s->fft_size, s->fft_size);
+    if (cf) { cf[0] = s->hc(q)[idx].x; cf[1] = s->hc(q)[idx].y; }
     return SDR_OK;
 }
 
 extern "C" int sdr_spectrum_fetch_all(sdr_spectrum *s, unsigned cap_frames, float *points_y, uint8_t *lines, double *cf, unsigned *n_frames) {
     if (!s) return fail(SDR_ERR_ARG, "null spectrum");
     std::lock_guard<std::mutex> lk(s->eng->mu);
-    if (!s->eng->results_on_host) return fail(SDR_ERR_STATE, "no host results for the last block");
-    const unsigned m = std::min(cap_frames, s->frames_last);
-    if (points_y) memcpy(points_y, s->h_points, (size_t)m * s->fft_size * sizeof(float));
-    if (lines) memcpy(lines, s->h_lines, (size_t)m * s->fft_size);
-    if (cf) for (unsigned f = 0; f < m; ++f) { cf[2 * f] = s->h_cf[f].x; cf[2 * f + 1] = s->h_cf[f].y; }
-    if (n_frames) *n_frames = s->frames_last;
+    const int q = s->eng->fetch_sel;
+    if (!s->eng->res_on_host[q]) return fail(SDR_ERR_STATE, "no host results for the last block");
+    const unsigned m = std::min(cap_frames, s->frames_buf[q]);
+    if (points_y) memcpy(points_y, s->hp(q), (size_t)m * s->fft_size * sizeof(float));
+    if (lines) memcpy(lines, s->hl(q), (size_t)m * s->fft_size);
+    if (cf) for (unsigned f = 0; f < m; ++f) { cf[2 * f] = s->hc(q)[f].x; cf[2 * f + 1] = s->hc(q)[f].y; }
+    if (n_frames) *n_frames = s->frames_buf[q];
     return SDR_OK;
 }
 

@@ -205,6 +205,19 @@ public:
                               data_in.frequency, data_in.sampleRate) != SDR_OK) return false;
         return sdr_engine_wait(eng_->get()) == SDR_OK;
     }
+    // Pipelined variant: submits the block and returns once the PREVIOUS block's results are on the host (false for the
+    // very first block: nothing to fetch yet).  Mirrors the one-block lag the reference's queues between SDRPostThread
+    // and the demodulator threads introduce anyway; fetchAudio / getFrame then read that previous block.
+    bool runSingleCHPipelined(const DemodulatorThreadIQData &data_in, bool *have_results) {
+        if (have_results) *have_results = false;
+        if (data_in.data.empty()) return true;
+        if (sdr_engine_submit(eng_->get(), reinterpret_cast<const sdr_cf32 *>(data_in.data.data()), (unsigned)data_in.data.size(),
+                              data_in.frequency, data_in.sampleRate) != SDR_OK) return false;
+        if (!primed_) { primed_ = true; return true; }
+        if (sdr_engine_wait_block(eng_->get(), 1) != SDR_OK) return false;
+        if (have_results) *have_results = true;
+        return true;
+    }
     // the DC-corrected block that runSingleCH pushes to the visual queues and the demodulator pipes (:284-298)
     bool fetchDemodDataOut(DemodulatorThreadIQData &out, long long frequency, long long sampleRate, size_t n) {
         out.frequency = frequency; out.sampleRate = sampleRate; out.data.resize(n);
@@ -215,6 +228,7 @@ public:
     }
 private:
     std::shared_ptr<Engine> eng_;
+    bool primed_ = false;
 };
 
 // ---- DemodulatorPreThread's DSP (demod/DemodulatorPreThread.cpp:154-220) + DemodulatorThread's (DemodulatorThread.cpp:120-233)

@@ -75,3 +75,7 @@ def test_dc_blocker_bit_exact_including_speculative_segments(emu_lib, ref):
     fix, mode = C.c_uint(), C.c_int()
     emu_lib.L.sdr_engine_debug_dc_fixups(eng.h, C.byref(fix), C.byref(mode))
     assert mode.value == 1 and fix.value == 0
+
+
+def test_pipelined_fetch_returns_previous_block(emu_lib):
+    parity.check_pipelined_fetch(emu_lib)

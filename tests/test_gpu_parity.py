@@ -129,3 +129,7 @@ def test_dc_blocker_bit_exact_at_full_block_size(gpu_lib, ref):
     gpu_lib.L.sdr_engine_debug_dc_fixups(eng.h, C.byref(fix), C.byref(mode))
     assert mode.value == 1
     assert fix.value <= 2          # a junction that has not coalesced is replayed serially; it must stay rare
+
+
+def test_pipelined_fetch_returns_previous_block(gpu_lib):
+    parity.check_pipelined_fetch(gpu_lib)
