@@ -276,11 +276,19 @@ def main():
     # One block in flight, like the reference's thread pipeline: per step, submit block i+1, start the H2D of block i+2
     # (its stage buffer was last read by block i-1, whose results were already waited for), then wait for and fetch the
     # results of block i.  Every step still costs one H2D, one pass of the path and one D2H + fetch.
+    host_split = [0.0, 0.0, 0.0]                                # host seconds in submit+h2d / wait / fetch (diagnostic, stderr)
+
     def step_e2e(i):
+        t_a = time.perf_counter()
         submit_e2e(i + 1)
         h2d(i + 2)
+        t_b = time.perf_counter()
         eng.wait_block(1)
-        return fetch_e2e()
+        t_c = time.perf_counter()
+        nb = fetch_e2e()
+        t_d = time.perf_counter()
+        host_split[0] += t_b - t_a; host_split[1] += t_c - t_b; host_split[2] += t_d - t_c
+        return nb
 
     # ---- warm-up ------------------------------------------------------------------------------------------------------
     for i in range(args.warmup):
@@ -331,6 +339,8 @@ def main():
     eng.wait()                                                  # drain the block still in flight (submitted, not yet fetched)
     torch.cuda.synchronize(); barrier()
     t_e2e = time.perf_counter() - t0
+    if rank == 0:
+        print("e2e host split per step (ms): submit+h2d %.3f  wait %.3f  fetch %.3f" % tuple(1e3 * v / (args.steps + 3) for v in host_split), file=sys.stderr)
     if dist is not None:
         tt = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
