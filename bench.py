@@ -242,22 +242,22 @@ def main():
     # end to end: pinned host block -> H2D (copy stream, overlapped with the previous block's kernels) -> (broadcast) ->
     # kernels -> D2H of every result -> batched fetch into host arrays.  Public API only: submit_device / wait / fetch.
     copy_stream = torch.cuda.Stream(device=dev)
-    stages = [torch.empty(N, dtype=torch.complex64, device=dev) for _ in range(3)]
-    h2d_done = [torch.cuda.Event() for _ in range(3)]
+    stages = [torch.empty(N, dtype=torch.complex64, device=dev) for _ in range(4)]
+    h2d_done = [torch.cuda.Event() for _ in range(4)]
 
     def h2d(i):
         if rank == 0:
             with torch.cuda.stream(copy_stream):
-                stages[i % 3].copy_(host_blocks[i & 1], non_blocking=True)
-                h2d_done[i % 3].record(copy_stream)
+                stages[i % 4].copy_(host_blocks[i & 1], non_blocking=True)
+                h2d_done[i % 4].record(copy_stream)
 
     def submit_e2e(i):
-        buf = stages[i % 3]
-        ev = h2d_done[i % 3]
+        buf = stages[i % 4]
+        ev = h2d_done[i % 4]
         if world > 1:
             with torch.cuda.stream(side):
                 if rank == 0:
-                    side.wait_event(h2d_done[i % 3])
+                    side.wait_event(h2d_done[i % 4])
                 dist.broadcast(buf, src=0)
                 bc_done[i & 3].record(side)
             ev = bc_done[i & 3]
@@ -273,17 +273,17 @@ def main():
             nbytes += pts.nbytes + lines.nbytes
         return nbytes
 
-    # One block in flight, like the reference's thread pipeline: per step, submit block i+1, start the H2D of block i+2
-    # (its stage buffer was last read by block i-1, whose results were already waited for), then wait for and fetch the
-    # results of block i.  Every step still costs one H2D, one pass of the path and one D2H + fetch.
+    # Two blocks in flight, like the reference's thread pipeline (queues between its threads): per step, submit block i+2,
+    # start the H2D of block i+3 (its stage buffer was last read by block i-1, whose results were already waited for), then
+    # wait for and fetch the results of block i.  Every step still costs one H2D, one pass of the path and one D2H + fetch.
     host_split = [0.0, 0.0, 0.0]                                # host seconds in submit+h2d / wait / fetch (diagnostic, stderr)
 
     def step_e2e(i):
         t_a = time.perf_counter()
-        submit_e2e(i + 1)
-        h2d(i + 2)
+        submit_e2e(i + 2)
+        h2d(i + 3)
         t_b = time.perf_counter()
-        eng.wait_block(1)
+        eng.wait_block(2)
         t_c = time.perf_counter()
         nb = fetch_e2e()
         t_d = time.perf_counter()
@@ -328,6 +328,8 @@ def main():
     h2d(0)
     submit_e2e(0)
     h2d(1)
+    submit_e2e(1)
+    h2d(2)
     for i in range(3):
         step_e2e(i)
     torch.cuda.synchronize()
@@ -336,7 +338,7 @@ def main():
     d2h = 0
     for i in range(args.steps):
         d2h = step_e2e(3 + i)
-    eng.wait()                                                  # drain the block still in flight (submitted, not yet fetched)
+    eng.wait()                                                  # drain the blocks still in flight (submitted, not yet fetched)
     torch.cuda.synchronize(); barrier()
     t_e2e = time.perf_counter() - t0
     if rank == 0:

@@ -41,6 +41,7 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 constexpr int kDcReservedSms = 8;    // SMs the channel front kernel leaves free: the bit-exact DC blocker's serial chains (one warp
                                      // per segment, 63 warps per 61 MSps block) run there at full speed instead of fighting the
                                      // front warps for issue slots
+constexpr int kResBuf = 3;           // host result buffers (ring): blocks a pipelined consumer may keep in flight + 1
 constexpr int kDcWarpsPerCta = 8;    // segments (warps) per CTA of the bit-exact DC replay under a heavy channel load
 constexpr int kFrontWarps = 15;      // warps per CTA of the channel front kernel (one CTA per SM); 15 x 32 x 128 registers leave room for one
                                      // warp of the bit-exact DC blocker on every SM, which then runs underneath the front kernel
@@ -418,7 +419,7 @@ struct sdr_spectrum {
     float *h_points = nullptr; unsigned char *h_lines = nullptr; double2 *h_cf = nullptr; int *h_frame_start = nullptr;
     float *h_dbg = nullptr;
     unsigned f_max = 0, frames_last = 0;
-    unsigned frames_buf[2] = {0, 0};   // frames of the blocks whose results sit in host buffer 0 / 1
+    unsigned frames_buf[kResBuf] = {0, 0, 0};   // frames of the blocks whose results sit in each host buffer
     float *hp(int q) const { return h_points + (size_t)q * f_max * fft_size; }
     unsigned char *hl(int q) const { return h_lines + (size_t)q * f_max * fft_size; }
     double2 *hc(int q) const { return h_cf + (size_t)q * f_max; }
@@ -468,13 +469,14 @@ struct sdr_engine {
     unsigned char *d_results = nullptr, *h_results = nullptr; size_t results_bytes = 0;
     bool dirty = true;
     bool results_on_host = false;
-    // host results are double-buffered so that a caller may fetch block b while block b+1 is in flight (sdr_engine_wait_block)
+    // host results live in a ring of kResBuf buffers so that a caller may fetch block b while up to kResBuf - 1 newer
+    // blocks are in flight (sdr_engine_wait_block)
     int res_sel = 0, fetch_sel = 0;
-    bool res_on_host[2] = {false, false};
+    bool res_on_host[kResBuf] = {false, false, false};
     unsigned char *hres(int q) const { return h_results + (size_t)q * results_bytes; }
 #ifndef SDR_EMU
-    cudaEvent_t ev_res_tail[2] = {nullptr, nullptr}, ev_res_spec[2] = {nullptr, nullptr};
-    bool res_tail_rec[2] = {false, false}, res_spec_rec[2] = {false, false};
+    cudaEvent_t ev_res_tail[kResBuf] = {nullptr, nullptr, nullptr}, ev_res_spec[kResBuf] = {nullptr, nullptr, nullptr};
+    bool res_tail_rec[kResBuf] = {false, false, false}, res_spec_rec[kResBuf] = {false, false, false};
 #endif
     std::vector<sdr_spectrum *> spectra;
     // optional per-stage device timing (CUDA events on the engine stream): 0 dc, 1 spectrum, 2 front, 3 tail
@@ -634,7 +636,7 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
     }
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kResBuf; ++b) {
         CUDA_TRY(cudaEventCreateWithFlags(&e->ev_res_tail[b], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&e->ev_res_spec[b], cudaEventDisableTiming));
     }
@@ -690,7 +692,7 @@ extern "C" int sdr_engine_destroy(sdr_engine *e) {
     for (int b = 0; b < 2; ++b) { if (e->ev_dc_done[b]) cudaEventDestroy(e->ev_dc_done[b]); if (e->ev_consumed[b]) cudaEventDestroy(e->ev_consumed[b]); }
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
-    for (int b = 0; b < 2; ++b) { if (e->ev_res_tail[b]) cudaEventDestroy(e->ev_res_tail[b]); if (e->ev_res_spec[b]) cudaEventDestroy(e->ev_res_spec[b]); }
+    for (int b = 0; b < kResBuf; ++b) { if (e->ev_res_tail[b]) cudaEventDestroy(e->ev_res_tail[b]); if (e->ev_res_spec[b]) cudaEventDestroy(e->ev_res_spec[b]); }
     if (e->own_stream) cudaStreamDestroy(e->stream);
 #endif
     delete e;
@@ -1021,9 +1023,9 @@ extern "C" int sdr_spectrum_create(sdr_engine *e, unsigned fft_size, unsigned lp
     bad |= be_malloc((void **)&s->d_points, F * fft_size * sizeof(float));
     bad |= be_malloc((void **)&s->d_lines, F * fft_size);
     bad |= be_malloc((void **)&s->d_frame_start, F * sizeof(int));
-    bad |= be_host_alloc((void **)&s->h_points, 2 * F * fft_size * sizeof(float));
-    bad |= be_host_alloc((void **)&s->h_lines, 2 * F * fft_size);
-    bad |= be_host_alloc((void **)&s->h_cf, 2 * F * sizeof(double2));
+    bad |= be_host_alloc((void **)&s->h_points, kResBuf * F * fft_size * sizeof(float));
+    bad |= be_host_alloc((void **)&s->h_lines, kResBuf * F * fft_size);
+    bad |= be_host_alloc((void **)&s->h_cf, kResBuf * F * sizeof(double2));
     bad |= be_host_alloc((void **)&s->h_frame_start, (size_t)sdr_engine::kRing * F * sizeof(int));
     bad |= be_host_alloc((void **)&s->h_dbg, 2 * N * sizeof(float));
     if (bad) { spectrum_free(s); delete s; return fail(SDR_ERR_NOMEM, "sdr_spectrum_create: allocation failed"); }
@@ -1106,10 +1108,10 @@ static int rebuild(sdr_engine *e) {
     if (total > e->results_bytes) {
         be_free(e->d_results); be_host_free(e->h_results);
         e->d_results = nullptr; e->h_results = nullptr;
-        if (be_malloc((void **)&e->d_results, total) || be_host_alloc((void **)&e->h_results, 2 * total))
+        if (be_malloc((void **)&e->d_results, total) || be_host_alloc((void **)&e->h_results, kResBuf * total))
             return fail(SDR_ERR_NOMEM, "results buffer");
         e->results_bytes = total;
-        e->res_on_host[0] = e->res_on_host[1] = false;
+        for (int b = 0; b < kResBuf; ++b) e->res_on_host[b] = false;
     }
     for (auto *c : e->chans) if (c) be_h2d(e->d_cs + c->index, &c->cs, sizeof(ChanStatic), e->stream);
     if (e->taps_host.size() > e->taps_uploaded) {
@@ -1206,7 +1208,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
     e->parity = p;
     e->last_n = n; e->have_block = true;
     e->results_on_host = to_host;
-    const int q = (e->res_sel ^= 1);                            // host result buffer of this block
+    const int q = e->res_sel = (e->res_sel + 1) % kResBuf;     // host result buffer of this block
     e->res_on_host[q] = to_host;
     e->fetch_sel = q;
 #ifndef SDR_EMU
@@ -1430,15 +1432,16 @@ extern "C" int sdr_engine_wait(sdr_engine *e) {
     return SDR_OK;
 }
 
-// Wait only until the results of the latest (lag = 0) or the previous (lag = 1) submitted block are on the host, and make
-// the fetch calls read that block.  With lag = 1 the caller keeps one block in flight: submit(b+1), wait_block(1), fetch b.
+// Wait only until the results of the block submitted `lag` submits ago (0 = latest, up to kResBuf - 1) are on the host, and
+// make the fetch calls read that block.  With lag = 2 the caller keeps two blocks in flight: submit(b+2), wait_block(2),
+// fetch b -- the GPU then never idles while the host copies results out.
 extern "C" int sdr_engine_wait_block(sdr_engine *e, int lag) {
     if (!e) return fail(SDR_ERR_ARG, "null engine");
-    if (lag < 0 || lag > 1) return fail(SDR_ERR_ARG, "sdr_engine_wait_block: lag must be 0 or 1");
+    if (lag < 0 || lag >= kResBuf) return fail(SDR_ERR_ARG, "sdr_engine_wait_block: lag must be 0, 1 or 2");
     int q;
     {
         std::lock_guard<std::mutex> lk(e->mu);
-        q = lag ? (e->res_sel ^ 1) : e->res_sel;
+        q = (e->res_sel - lag + kResBuf) % kResBuf;
         if (!e->res_on_host[q]) return fail(SDR_ERR_STATE, "sdr_engine_wait_block: that block was not submitted with host results");
     }
 #ifndef SDR_EMU

@@ -52,10 +52,11 @@ int sdr_engine_submit_device(sdr_engine *eng, const void *d_iq, unsigned n, long
 int sdr_engine_submit_device_async(sdr_engine *eng, const void *d_iq, unsigned n, long long center_freq, long long sample_rate,
                                    int fetch_to_host, void *ready_event);
 int sdr_engine_wait(sdr_engine *eng);
-/* Pipelined consumer (the reference's threads run one block apart, ThreadBlockingQueue between SDRPostThread.cpp:294-298
- * and DemodulatorPreThread.cpp:53): wait only until the host results of the latest (lag 0) or the previous (lag 1)
- * submitted block have landed, and point the fetch calls at that block.  submit(b+1); wait_block(1); fetch = block b,
- * while b+1 is still on the GPU.  Host results are double-buffered; at most one newer block may be in flight. */
+/* Pipelined consumer (the reference's threads run blocks apart, ThreadBlockingQueue between SDRPostThread.cpp:294-298
+ * and DemodulatorPreThread.cpp:53): wait only until the host results of the block submitted `lag` submits ago (0 = the
+ * latest, 1, or 2) have landed, and point the fetch calls at that block.  submit(b+2); wait_block(2); fetch = block b,
+ * while b+1 and b+2 are still on the GPU.  Host results sit in a ring of three buffers, so at most two newer blocks may
+ * be in flight when a block is fetched. */
 int sdr_engine_wait_block(sdr_engine *eng, int lag);
 /* DC-blocked block of the last submit (what runSingleCH pushes to the visual queues / demod pipes), host copy.    */
 int sdr_engine_fetch_block(sdr_engine *eng, sdr_cf32 *out, unsigned cap, unsigned *n);

@@ -128,8 +128,8 @@ def run_spectrum(lib, ref, fs, fft_size, n_blocks, chans, lps=0, block=None, see
     return worst
 
 
-def check_pipelined_fetch(lib, fs=2400000, n_blocks=5, fft_size=1024, device=0):
-    """submit(b+1); wait_block(1); fetch must return exactly block b's results (double-buffered host results)."""
+def check_pipelined_fetch(lib, fs=2400000, n_blocks=6, fft_size=1024, device=0):
+    """submit(b+lag); wait_block(lag); fetch must return exactly block b's results (ring of host result buffers)."""
     chans = [("FM", 200000, 300000), ("NBFM", 12500, -412500), ("AM", 6000, 150000), ("USB", 5400, -250000)]
     N = synth.block_size(fs)
     blocks = [synth.wideband(fs, N, chans, seed=77, t0=b * N) for b in range(n_blocks)]
@@ -149,16 +149,22 @@ def check_pipelined_fetch(lib, fs=2400000, n_blocks=5, fft_size=1024, device=0):
         eng.wait()
         want.append(grab(cs, sp))
     eng.close()
-    eng, cs, sp = make()
-    got = []
-    eng.submit(blocks[0], CENTER, fs)
-    for b in range(1, n_blocks):
-        eng.submit(blocks[b], CENTER, fs)
-        eng.wait_block(1)
-        got.append(grab(cs, sp))
-    eng.wait_block(0)
-    got.append(grab(cs, sp))
-    eng.close()
+    for lag in (1, 2):
+        eng, cs, sp = make()
+        got = []
+        for b in range(n_blocks):
+            eng.submit(blocks[b], CENTER, fs)
+            if b >= lag:
+                eng.wait_block(lag)
+                got.append(grab(cs, sp))
+        for k in range(lag - 1, -1, -1):                        # drain
+            eng.wait_block(k)
+            got.append(grab(cs, sp))
+        eng.close()
+        _same_results(want, got, n_blocks)
+
+
+def _same_results(want, got, n_blocks):
     for b in range(n_blocks):
         (wa, wf), (ga, gf) = want[b], got[b]
         for (a0, l0, p0, s0), (a1, l1, p1, s1) in zip(wa, ga):
