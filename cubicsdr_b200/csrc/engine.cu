@@ -497,6 +497,9 @@ struct sdr_engine {
     // the DC blocker of block b+1 runs on its own stream underneath the channel kernels of block b
     // the channel tail of block b runs on its own stream underneath the front kernel of block b+1
     cudaStream_t stream_tail = nullptr;
+    cudaStream_t stream_res = nullptr;   // device -> host copies of results, off the compute streams
+    cudaEvent_t ev_spec_k = nullptr, ev_tail_k = nullptr;   // spectrum / tail kernels of the current block are done
+    int last_res_q = -1;                 // host buffer of the previous to_host block (its D2H reads d_points / d_results)
     cudaEvent_t ev_front_done = nullptr, ev_tail_done[2] = {nullptr, nullptr};
     cudaEvent_t tev_tail[kTimeSets][2];
     cudaStream_t stream_dc = nullptr;
@@ -627,6 +630,9 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
         CUDA_TRY(cudaStreamCreateWithPriority(&e->stream_dc, cudaStreamNonBlocking, hi));
     }
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_tail, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_res, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&e->ev_spec_k, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&e->ev_tail_k, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_front_done, cudaEventDisableTiming));
     for (int b = 0; b < 2; ++b) CUDA_TRY(cudaEventCreateWithFlags(&e->ev_tail_done[b], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_input, cudaEventDisableTiming));
@@ -686,6 +692,9 @@ extern "C" int sdr_engine_destroy(sdr_engine *e) {
     if (e->stream2) { cudaStreamSynchronize(e->stream2); cudaStreamDestroy(e->stream2); }
     if (e->stream_dc) { cudaStreamSynchronize(e->stream_dc); cudaStreamDestroy(e->stream_dc); }
     if (e->stream_tail) { cudaStreamSynchronize(e->stream_tail); cudaStreamDestroy(e->stream_tail); }
+    if (e->stream_res) { cudaStreamSynchronize(e->stream_res); cudaStreamDestroy(e->stream_res); }
+    if (e->ev_spec_k) cudaEventDestroy(e->ev_spec_k);
+    if (e->ev_tail_k) cudaEventDestroy(e->ev_tail_k);
     if (e->ev_front_done) cudaEventDestroy(e->ev_front_done);
     for (int b = 0; b < 2; ++b) if (e->ev_tail_done[b]) cudaEventDestroy(e->ev_tail_done[b]);
     if (e->ev_input) cudaEventDestroy(e->ev_input);
@@ -782,6 +791,7 @@ static void sync_all(sdr_engine *e) {
     be_sync(e->stream);
 #ifndef SDR_EMU
     cudaStreamSynchronize(e->stream_tail);
+    cudaStreamSynchronize(e->stream_res);
     cudaStreamSynchronize(e->stream_dc);
     cudaStreamSynchronize(e->stream2);
 #endif
@@ -1208,7 +1218,10 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
     e->parity = p;
     e->last_n = n; e->have_block = true;
     e->results_on_host = to_host;
+    const int prev_q = e->last_res_q;
     const int q = e->res_sel = (e->res_sel + 1) % kResBuf;     // host result buffer of this block
+    e->last_res_q = to_host ? q : -1;
+    (void)prev_q;
     e->res_on_host[q] = to_host;
     e->fetch_sel = q;
 #ifndef SDR_EMU
@@ -1247,21 +1260,37 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         }
         if (e->timing && e->time_pending < sdr_engine::kTimeSets) cudaEventRecord(e->tev_spec[e->time_pending][0], sps);
 #endif
+#ifndef SDR_EMU
+        // the previous block's D2H (result stream) still reads the device outputs these kernels overwrite
+        if (!spec_jobs.empty() && prev_q >= 0 && e->res_spec_rec[prev_q]) CUDA_TRY(cudaStreamWaitEvent(sps, e->ev_res_spec[prev_q], 0));
+#endif
         for (auto &job : spec_jobs) {
-            sdr_spectrum *s = job.first;
             int r = launch_spectrum(job.second, sps, e->launches);
             if (r) return r;
-            if (to_host) {
-                be_d2h(s->hp(q), s->d_points, (size_t)s->frames_last * s->fft_size * sizeof(float), sps);
-                be_d2h(s->hl(q), s->d_lines, (size_t)s->frames_last * s->fft_size, sps);
-                be_d2h(s->hc(q), s->d_frame_cf_maa, (size_t)s->frames_last * sizeof(double2), sps);
-            }
         }
 #ifndef SDR_EMU
         if (e->timing && e->time_pending < sdr_engine::kTimeSets) cudaEventRecord(e->tev_spec[e->time_pending][1], sps);
         if (forked) CUDA_TRY(cudaEventRecord(e->ev_join, e->stream2));
-        if (to_host && !spec_jobs.empty()) { CUDA_TRY(cudaEventRecord(e->ev_res_spec[q], sps)); e->res_spec_rec[q] = true; }
 #endif
+        if (to_host && !spec_jobs.empty()) {
+            sdr_stream_t rs = sps;
+#ifndef SDR_EMU
+            // results leave on their own stream: the compute streams (and the next block's front kernel behind the
+            // join) do not wait for PCIe
+            CUDA_TRY(cudaEventRecord(e->ev_spec_k, sps));
+            rs = e->stream_res;
+            CUDA_TRY(cudaStreamWaitEvent(rs, e->ev_spec_k, 0));
+#endif
+            for (auto &job : spec_jobs) {
+                sdr_spectrum *s = job.first;
+                be_d2h(s->hp(q), s->d_points, (size_t)s->frames_last * s->fft_size * sizeof(float), rs);
+                be_d2h(s->hl(q), s->d_lines, (size_t)s->frames_last * s->fft_size, rs);
+                be_d2h(s->hc(q), s->d_frame_cf_maa, (size_t)s->frames_last * sizeof(double2), rs);
+            }
+#ifndef SDR_EMU
+            CUDA_TRY(cudaEventRecord(e->ev_res_spec[q], rs)); e->res_spec_rec[q] = true;
+#endif
+        }
         return SDR_OK;
     };
     // everything enqueued after this submit on the main stream (next block's history slide, DC blocker) must wait for the
@@ -1371,13 +1400,22 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
     CUDA_TRY(cudaStreamWaitEvent(ts, e->ev_front_done, 0));
     if (e->timing && e->time_pending < sdr_engine::kTimeSets) cudaEventRecord(e->tev_tail[e->time_pending][0], ts);
 #endif
+#ifndef SDR_EMU
+    if (prev_q >= 0 && e->res_tail_rec[prev_q]) CUDA_TRY(cudaStreamWaitEvent(ts, e->ev_res_tail[prev_q], 0));   // its D2H reads d_results
+#endif
     launch_tail(ta, n_slots, ts, e->launches);
     if (to_host && e->results_bytes) {
         size_t total = 0;
         for (auto *c : e->chans) if (c) total = std::max(total, (size_t)c->cs.res_off + c->slot_bytes);
-        be_d2h(e->hres(q), e->d_results, total, ts);
+        sdr_stream_t rs = ts;
 #ifndef SDR_EMU
-        CUDA_TRY(cudaEventRecord(e->ev_res_tail[q], ts)); e->res_tail_rec[q] = true;
+        CUDA_TRY(cudaEventRecord(e->ev_tail_k, ts));
+        rs = e->stream_res;
+        CUDA_TRY(cudaStreamWaitEvent(rs, e->ev_tail_k, 0));
+#endif
+        be_d2h(e->hres(q), e->d_results, total, rs);
+#ifndef SDR_EMU
+        CUDA_TRY(cudaEventRecord(e->ev_res_tail[q], rs)); e->res_tail_rec[q] = true;
 #endif
     }
 #ifndef SDR_EMU
@@ -1421,6 +1459,8 @@ extern "C" int sdr_engine_wait(sdr_engine *e) {
     if (be_sync(e->stream)) return fail(SDR_ERR_CUDA, std::string("stream sync failed: ") + be_last_error());
 #ifndef SDR_EMU
     if (cudaStreamSynchronize(e->stream_tail) != cudaSuccess) return fail(SDR_ERR_CUDA, std::string("tail stream sync failed: ") + be_last_error());
+    if (cudaStreamSynchronize(e->stream2) != cudaSuccess) return fail(SDR_ERR_CUDA, std::string("side stream sync failed: ") + be_last_error());
+    if (cudaStreamSynchronize(e->stream_res) != cudaSuccess) return fail(SDR_ERR_CUDA, std::string("result stream sync failed: ") + be_last_error());
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(SDR_ERR_CUDA, std::string("kernel error: ") + cudaGetErrorString(err));
 #endif
