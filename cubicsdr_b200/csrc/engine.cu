@@ -472,6 +472,7 @@ struct sdr_engine {
     // host results live in a ring of kResBuf buffers so that a caller may fetch block b while up to kResBuf - 1 newer
     // blocks are in flight (sdr_engine_wait_block)
     int res_sel = 0, fetch_sel = 0;
+    int last_res_q = -1;                 // host buffer of the previous to_host block (its D2H reads d_points / d_results)
     bool res_on_host[kResBuf] = {false, false, false};
     unsigned char *hres(int q) const { return h_results + (size_t)q * results_bytes; }
 #ifndef SDR_EMU
@@ -499,7 +500,6 @@ struct sdr_engine {
     cudaStream_t stream_tail = nullptr;
     cudaStream_t stream_res = nullptr;   // device -> host copies of results, off the compute streams
     cudaEvent_t ev_spec_k = nullptr, ev_tail_k = nullptr;   // spectrum / tail kernels of the current block are done
-    int last_res_q = -1;                 // host buffer of the previous to_host block (its D2H reads d_points / d_results)
     cudaEvent_t ev_front_done = nullptr, ev_tail_done[2] = {nullptr, nullptr};
     cudaEvent_t tev_tail[kTimeSets][2];
     cudaStream_t stream_dc = nullptr;
