@@ -24,6 +24,7 @@ struct TailArgs {
     unsigned char *results;
     int n;                        // wideband block length
     int first;                    // channel slot handled by CTA 0
+    unsigned long long *dbg;      // diagnostics: per-phase end times of the first 64 channels (null = off)
 };
 
 struct TailShared {

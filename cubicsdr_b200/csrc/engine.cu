@@ -205,9 +205,12 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 1) k_chan_front(FrontArgs a,
 }
 __global__ void __launch_bounds__(kTailThreads) k_chan_tail(TailArgs a) {
     __shared__ TailShared sm;
+    const bool dbg = a.dbg && threadIdx.x == 0 && blockIdx.x < 64;
+    if (dbg) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.dbg[blockIdx.x * 64 + 63] = t; }
     for (int ph = 0; ph < TP_COUNT; ++ph) {
         tail_phase(ph, a, a.first + blockIdx.x, threadIdx.x, blockDim.x, &sm);
         __syncthreads();
+        if (dbg) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.dbg[blockIdx.x * 64 + ph] = t; }
     }
 }
 __global__ void __launch_bounds__(kFftThreads) k_spec_fft(SpecArgs a, int phases) {
@@ -738,15 +741,28 @@ extern "C" int sdr_engine_debug_front_timeline(sdr_engine *e, int enable, unsign
     std::lock_guard<std::mutex> lk(e->mu);
     be_sync(e->stream);
     if (enable && !e->d_front_dbg) {
-        if (be_malloc((void **)&e->d_front_dbg, 4 * 1024 * sizeof(unsigned long long))) return SDR_ERR_NOMEM;
-        be_memset(e->d_front_dbg, 0, 4 * 1024 * sizeof(unsigned long long), e->stream);
+        if (be_malloc((void **)&e->d_front_dbg, (4 * 1024 + 64 * 64) * sizeof(unsigned long long))) return SDR_ERR_NOMEM;
+        be_memset(e->d_front_dbg, 0, (4 * 1024 + 64 * 64) * sizeof(unsigned long long), e->stream);
     }
     if (out && e->d_front_dbg) {
         be_d2h(out, e->d_front_dbg, (size_t)4 * std::min(max_ctas, 1024u) * sizeof(unsigned long long), e->stream);
         be_sync(e->stream);
-        be_memset(e->d_front_dbg, 0, 4 * 1024 * sizeof(unsigned long long), e->stream);
+        be_memset(e->d_front_dbg, 0, (4 * 1024 + 64 * 64) * sizeof(unsigned long long), e->stream);
     }
     if (!enable && e->d_front_dbg) { be_free(e->d_front_dbg); e->d_front_dbg = nullptr; }
+    return SDR_OK;
+}
+
+static void sync_all(sdr_engine *e);
+// diagnostics: globaltimer at the end of every tail-kernel phase for the first 64 channels ([64][64], slot 63 = start);
+// enabled together with sdr_engine_debug_front_timeline(e, 1, ...)
+extern "C" int sdr_engine_debug_tail_phases(sdr_engine *e, unsigned long long *out, int *n_phases) {
+    if (!e || !out || !e->d_front_dbg) return SDR_ERR_ARG;
+    std::lock_guard<std::mutex> lk(e->mu);
+    sync_all(e);
+    be_d2h(out, e->d_front_dbg + 4 * 1024, (size_t)64 * 64 * sizeof(unsigned long long), e->stream);
+    be_sync(e->stream);
+    if (n_phases) *n_phases = TP_COUNT;
     return SDR_OK;
 }
 
@@ -952,7 +968,7 @@ extern "C" int sdr_modem_demodulate(sdr_chan *c, const sdr_cf32 *iq, unsigned n,
     be_h2d(e->d_cd2[0] + c->index, c->h_dyn, sizeof(ChanDyn), e->stream);
     TailArgs ta;
     ta.cs = e->d_cs; ta.cd = e->d_cd2[0]; ta.st = e->d_st; ta.taps = e->d_taps; ta.nco = e->d_nco;
-    ta.results = e->d_results; ta.n = 0; ta.first = c->index;
+    ta.results = e->d_results; ta.n = 0; ta.first = c->index; ta.dbg = nullptr;
     launch_tail(ta, 1, e->stream, e->launches);
     be_d2h(c->h_slot, e->d_results + c->cs.res_off, c->slot_bytes, e->stream);
     if (be_sync(e->stream)) return fail(SDR_ERR_CUDA, std::string("sdr_modem_demodulate: ") + be_last_error());
@@ -1388,7 +1404,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
     { int r = run_spectra(); if (r) return r; }                     // side stream, after the front kernel got the SMs
     TailArgs ta;
     ta.cs = e->d_cs; ta.cd = d_cd; ta.st = e->d_st; ta.taps = e->d_taps; ta.nco = e->d_nco;
-    ta.results = e->d_results; ta.n = (int)n; ta.first = 0;
+    ta.results = e->d_results; ta.n = (int)n; ta.first = 0; ta.dbg = e->d_front_dbg ? e->d_front_dbg + 4 * 1024 : nullptr;
     // the tail indexes channels by slot; free slots carry valid = 0 and are not touched
     time_mark(e, 3);
     // the channel tail (and the results' D2H) go to their own stream: they overlap the next block's front kernel
