@@ -73,42 +73,146 @@ SDR_HD inline float2 *chan_lvl(const TailArgs &a, const ChanStatic &cs, const Ch
     return chan_cbuf(a, cs, (j == 0 && cd.lvl0_sel) ? cs.lvl0_alt_off : cs.lvl_off[j]);
 }
 
-// generic decimate-by-2 half-band over a [kHist | new] complex stream, parallel over outputs
-SDR_HD inline void hb_decim_c(const float2 *in, long long in_g0, float2 *out, long long out_g0, int n_out, int m,
-                              const float *h1, int tid, int nt) {
-    for (int r = tid; r < n_out; r += nt) {
-        const long long k = out_g0 + r;
-        const int base = (int)(2 * k - in_g0) + kHist;       // buffer position of in[2k]
-        float2 acc = in[base - 2 * m + 1];                    // delay branch: in[2k - 2m + 1]
-        const float2 *p = in + base - 4 * m + 2;              // filtered branch: in[2k - 4m + 2 + 2t]
-        for (int t = 0; t < 2 * m; ++t) acc = cf_fma(sdr_ldg(h1 + t), p[2 * t], acc);
+// Decimate-by-2 half-band over a [kHist | new] stream, parallel over outputs.  One output is a chain of 2m+1 dependent
+// multiply-adds fed by 2m+1 loads; a thread working on one output at a time spends its life waiting for memory, so every
+// thread carries kTailIlp outputs at once (independent accumulators, loads of all of them in flight) and the semi-length is
+// a template parameter (liquid's msresamp2 only uses m = 3, 5, 10) so that the tap loop unrolls with the taps in registers.
+// The order of the additions per output is the reference's (delay branch first, then taps 0..2m-1).  `in` was written by
+// an earlier phase of the same launch, so it is read with ordinary (coherent) loads, never through the read-only path.
+constexpr int kTailIlp = 4;
+SDR_HD SDR_FORCEINLINE float tap_fma(float h, float x, float acc) { return fmaf(h, x, acc); }
+SDR_HD SDR_FORCEINLINE float2 tap_fma(float h, float2 x, float2 acc) { return cf_fma(h, x, acc); }
+
+template <int M, typename T>
+SDR_HD inline void hb_decim_t(const T *in, long long in_g0, T *out, long long out_g0, int n_out,
+                              const float *__restrict__ h1, int tid, int nt) {
+    float h[2 * M];
+#pragma unroll
+    for (int t = 0; t < 2 * M; ++t) h[t] = sdr_ldg(h1 + t);
+    const int base0 = (int)(2 * out_g0 - in_g0) + kHist;        // buffer position of in[2 * out_g0]
+    int r = tid;
+    for (; r + (kTailIlp - 1) * nt < n_out; r += kTailIlp * nt) {
+        T acc[kTailIlp];
+        const T *p[kTailIlp];
+#pragma unroll
+        for (int u = 0; u < kTailIlp; ++u) {
+            const int base = base0 + 2 * (r + u * nt);
+            acc[u] = in[base - 2 * M + 1];                       // delay branch: in[2k - 2m + 1]
+            p[u] = in + base - 4 * M + 2;                        // filtered branch: in[2k - 4m + 2 + 2t]
+        }
+#pragma unroll
+        for (int t = 0; t < 2 * M; ++t) {
+#pragma unroll
+            for (int u = 0; u < kTailIlp; ++u) acc[u] = tap_fma(h[t], p[u][2 * t], acc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < kTailIlp; ++u) out[kHist + r + u * nt] = acc[u];
+    }
+    for (; r < n_out; r += nt) {
+        const int base = base0 + 2 * r;
+        T acc = in[base - 2 * M + 1];
+        const T *q = in + base - 4 * M + 2;
+#pragma unroll
+        for (int t = 0; t < 2 * M; ++t) acc = tap_fma(h[t], q[2 * t], acc);
         out[kHist + r] = acc;
     }
+}
+template <typename T>
+SDR_HD inline void hb_decim_any(const T *in, long long in_g0, T *out, long long out_g0, int n_out, int m, const float *h1, int tid, int nt) {
+    if (m == 3) hb_decim_t<3, T>(in, in_g0, out, out_g0, n_out, h1, tid, nt);
+    else if (m == 5) hb_decim_t<5, T>(in, in_g0, out, out_g0, n_out, h1, tid, nt);
+    else if (m == 10) hb_decim_t<10, T>(in, in_g0, out, out_g0, n_out, h1, tid, nt);
+    else {                                                       // not produced by the design code; kept for completeness
+        for (int r = tid; r < n_out; r += nt) {
+            const int base = (int)(2 * (out_g0 + r) - in_g0) + kHist;
+            T acc = in[base - 2 * m + 1];
+            const T *p = in + base - 4 * m + 2;
+            for (int t = 0; t < 2 * m; ++t) acc = tap_fma(sdr_ldg(h1 + t), p[2 * t], acc);
+            out[kHist + r] = acc;
+        }
+    }
+}
+SDR_HD inline void hb_decim_c(const float2 *in, long long in_g0, float2 *out, long long out_g0, int n_out, int m,
+                              const float *h1, int tid, int nt) {
+    hb_decim_any<float2>(in, in_g0, out, out_g0, n_out, m, h1, tid, nt);
 }
 SDR_HD inline void hb_decim_r(const float *in, long long in_g0, float *out, long long out_g0, int n_out, int m,
                               const float *h1, int tid, int nt) {
-    for (int r = tid; r < n_out; r += nt) {
-        const long long k = out_g0 + r;
-        const int base = (int)(2 * k - in_g0) + kHist;
-        float acc = in[base - 2 * m + 1];
-        const float *p = in + base - 4 * m + 2;
-        for (int t = 0; t < 2 * m; ++t) acc = fmaf(sdr_ldg(h1 + t), p[2 * t], acc);
-        out[kHist + r] = acc;
-    }
+    hb_decim_any<float>(in, in_g0, out, out_g0, n_out, m, h1, tid, nt);
 }
 // interpolate-by-2 half-band (resamp2 interp_execute): Y[2k] = X[k-m], Y[2k+1] = sum h1[t] X[k-2m+1+t]
-SDR_HD inline void hb_interp_r(const float *in, int n_in, float *out, int m, const float *h1, int tid, int nt) {
-    for (int r = tid; r < 2 * n_in; r += nt) {
-        const int k = r >> 1;
-        float v;
-        if ((r & 1) == 0) v = in[kHist + k - m];
-        else {
-            const float *p = in + kHist + k - 2 * m + 1;
-            v = 0.f;
-            for (int t = 0; t < 2 * m; ++t) v = fmaf(sdr_ldg(h1 + t), p[t], v);
+// (thread r handles input k = r: both outputs of the pair, kTailIlp pairs at a time)
+template <int M>
+SDR_HD inline void hb_interp_t(const float *in, int n_in, float *out, const float *__restrict__ h1, int tid, int nt) {
+    float h[2 * M];
+#pragma unroll
+    for (int t = 0; t < 2 * M; ++t) h[t] = sdr_ldg(h1 + t);
+    int k = tid;
+    for (; k + (kTailIlp - 1) * nt < n_in; k += kTailIlp * nt) {
+        float v[kTailIlp], e[kTailIlp];
+#pragma unroll
+        for (int u = 0; u < kTailIlp; ++u) { v[u] = 0.f; e[u] = in[kHist + k + u * nt - M]; }
+#pragma unroll
+        for (int t = 0; t < 2 * M; ++t) {
+#pragma unroll
+            for (int u = 0; u < kTailIlp; ++u) v[u] = fmaf(h[t], in[kHist + k + u * nt - 2 * M + 1 + t], v[u]);
         }
-        out[kHist + r] = v;
+#pragma unroll
+        for (int u = 0; u < kTailIlp; ++u) { out[kHist + 2 * (k + u * nt)] = e[u]; out[kHist + 2 * (k + u * nt) + 1] = v[u]; }
     }
+    for (; k < n_in; k += nt) {
+        float v = 0.f;
+#pragma unroll
+        for (int t = 0; t < 2 * M; ++t) v = fmaf(h[t], in[kHist + k - 2 * M + 1 + t], v);
+        out[kHist + 2 * k] = in[kHist + k - M];
+        out[kHist + 2 * k + 1] = v;
+    }
+}
+SDR_HD inline void hb_interp_r(const float *in, int n_in, float *out, int m, const float *h1, int tid, int nt) {
+    if (m == 3) hb_interp_t<3>(in, n_in, out, h1, tid, nt);
+    else if (m == 5) hb_interp_t<5>(in, n_in, out, h1, tid, nt);
+    else if (m == 10) hb_interp_t<10>(in, n_in, out, h1, tid, nt);
+    else {
+        for (int r = tid; r < 2 * n_in; r += nt) {
+            const int k = r >> 1;
+            float v;
+            if ((r & 1) == 0) v = in[kHist + k - m];
+            else {
+                const float *p = in + kHist + k - 2 * m + 1;
+                v = 0.f;
+                for (int t = 0; t < 2 * m; ++t) v = fmaf(sdr_ldg(h1 + t), p[t], v);
+            }
+            out[kHist + r] = v;
+        }
+    }
+}
+
+// kTailIlp outputs of the real 256-arm polyphase stage (audio resampler), loads of all of them in flight
+SDR_HD SDR_FORCEINLINE void arb_r_group(const float *z, const float *pfb, unsigned long long ph0, unsigned step, int r0, int stride,
+                                        float *acc) {
+    const float *zq[kTailIlp];
+    const float *h[kTailIlp];
+#pragma unroll
+    for (int u = 0; u < kTailIlp; ++u) {
+        const unsigned long long psi = ph0 + (unsigned long long)(r0 + u * stride) * step;
+        zq[u] = z + (int)(psi >> 24);
+        h[u] = pfb + ((psi >> 16) & 255u) * kPfbTaps;
+        acc[u] = 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < kPfbTaps; ++t) {
+#pragma unroll
+        for (int u = 0; u < kTailIlp; ++u) acc[u] = fmaf(sdr_ldg(h[u] + t), zq[u][-t], acc[u]);
+    }
+}
+SDR_HD SDR_FORCEINLINE float arb_r_one(const float *z, const float *pfb, unsigned long long ph0, unsigned step, int r) {
+    const unsigned long long psi = ph0 + (unsigned long long)r * step;
+    const float *zq = z + (int)(psi >> 24);
+    const float *h = pfb + ((psi >> 16) & 255u) * kPfbTaps;
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < kPfbTaps; ++t) acc = fmaf(sdr_ldg(h + t), zq[-t], acc);
+    return acc;
 }
 
 SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt, TailShared *sm) {
@@ -169,15 +273,43 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
         float2 *iq = chan_cbuf(a, cs, cs.iq_off) + kHist;
         const float *pfb = a.taps + cs.pfb_off;
         const unsigned long long ph0 = st.arb_phase;
-        for (int r = tid; r < sm->n_iq; r += nt) {
+        const float zeta = cs.zeta;
+        const int n_iq = sm->n_iq;
+        const bool keep = cs.want_iq != 0;
+        int r = tid;
+        for (; r + (kTailIlp - 1) * nt < n_iq; r += kTailIlp * nt) {       // kTailIlp outputs in flight per thread
+            float2 acc[kTailIlp];
+            const float2 *zq[kTailIlp];
+            const float *h[kTailIlp];
+#pragma unroll
+            for (int u = 0; u < kTailIlp; ++u) {
+                const unsigned long long psi = ph0 + (unsigned long long)(r + u * nt) * cs.arb_step;
+                zq[u] = z + (int)(psi >> 24);
+                h[u] = pfb + ((psi >> 16) & 255u) * kPfbTaps;
+                acc[u] = make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int t = 0; t < kPfbTaps; ++t) {
+#pragma unroll
+                for (int u = 0; u < kTailIlp; ++u) acc[u] = cf_fma(sdr_ldg(h[u] + t), zq[u][-t], acc[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < kTailIlp; ++u) {
+                const float2 y = cf_scale(zeta, acc[u]);
+                iq[r + u * nt] = y;
+                if (keep && r + u * nt < cs.res_iq_cap) res_iq[r + u * nt] = y;
+            }
+        }
+        for (; r < n_iq; r += nt) {
             const unsigned long long psi = ph0 + (unsigned long long)r * cs.arb_step;
             const int q = (int)(psi >> 24);
             const float *h = pfb + ((psi >> 16) & 255u) * kPfbTaps;
             float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
             for (int t = 0; t < kPfbTaps; ++t) acc = cf_fma(sdr_ldg(h + t), z[q - t], acc);
-            acc = cf_scale(cs.zeta, acc);
+            acc = cf_scale(zeta, acc);
             iq[r] = acc;
-            if (cs.want_iq && r < cs.res_iq_cap) res_iq[r] = acc;
+            if (keep && r < cs.res_iq_cap) res_iq[r] = acc;
         }
         return;
     }
@@ -287,12 +419,16 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
                 const float *z = ((cs.a_S == 0) ? chan_rbuf(a, cs, cs.d_off) : chan_rbuf(a, cs, cs.al_off[cs.a_S])) + kHist;
                 const float *pfb = a.taps + cs.a_pfb_off;
                 const unsigned long long ph0 = st.a_phase;
-                for (int r = tid; r < sm->n_audio; r += nt) {
-                    const unsigned long long psi = ph0 + (unsigned long long)r * cs.a_step;
-                    const int q = (int)(psi >> 24);
-                    const float *h = pfb + ((psi >> 16) & 255u) * kPfbTaps;
-                    float acc = 0.f;
-                    for (int t = 0; t < kPfbTaps; ++t) acc = fmaf(sdr_ldg(h + t), z[q - t], acc);
+                const int na = sm->n_audio;
+                int r = tid;
+                for (; r + (kTailIlp - 1) * nt < na; r += kTailIlp * nt) {
+                    float acc[kTailIlp];
+                    arb_r_group(z, pfb, ph0, cs.a_step, r, nt, acc);
+#pragma unroll
+                    for (int u = 0; u < kTailIlp; ++u) if (r + u * nt < cs.res_audio_cap) res_audio[r + u * nt] = acc[u] * cs.a_zeta;
+                }
+                for (; r < na; r += nt) {
+                    const float acc = arb_r_one(z, pfb, ph0, cs.a_step, r);
                     if (r < cs.res_audio_cap) res_audio[r] = acc * cs.a_zeta;
                 }
             }
@@ -304,12 +440,17 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
                 const float *pfb = a.taps + cs.a_pfb_off;
                 const unsigned long long ph0 = st.a_phase;
                 const int nb = sm->a_n[0];
-                for (int r = tid; r < nb; r += nt) {
-                    const unsigned long long psi = ph0 + (unsigned long long)r * cs.a_step;
-                    const int q = (int)(psi >> 24);
-                    const float *h = pfb + ((psi >> 16) & 255u) * kPfbTaps;
-                    float acc = 0.f;
-                    for (int t = 0; t < kPfbTaps; ++t) acc = fmaf(sdr_ldg(h + t), z[q - t], acc);
+                int r = tid;
+                for (; r + (kTailIlp - 1) * nt < nb; r += kTailIlp * nt) {
+                    float acc[kTailIlp];
+                    arb_r_group(z, pfb, ph0, cs.a_step, r, nt, acc);
+#pragma unroll
+                    for (int u = 0; u < kTailIlp; ++u) {
+                        if (out) out[r + u * nt] = acc[u]; else if (r + u * nt < cs.res_audio_cap) res_audio[r + u * nt] = acc[u];
+                    }
+                }
+                for (; r < nb; r += nt) {
+                    const float acc = arb_r_one(z, pfb, ph0, cs.a_step, r);
                     if (out) out[r] = acc; else if (r < cs.res_audio_cap) res_audio[r] = acc;
                 }
             } else if (j <= cs.a_S) {
@@ -319,7 +460,10 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
                 hb_interp_r(in, sm->a_n[j - 1], out, cs.a_m[g], a.taps + cs.a_h1[g], tid, nt);
                 if (j == cs.a_S) {
                     // final level: also the audio result (each thread copies what it just wrote)
-                    for (int r = tid; r < sm->n_audio && r < cs.res_audio_cap; r += nt) res_audio[r] = out[kHist + r];
+                    for (int k = tid; k < sm->a_n[j - 1]; k += nt) {      // thread k wrote outputs 2k and 2k + 1
+                        for (int r = 2 * k; r < 2 * k + 2; ++r)
+                            if (r < sm->n_audio && r < cs.res_audio_cap) res_audio[r] = out[kHist + r];
+                    }
                 }
             }
         }

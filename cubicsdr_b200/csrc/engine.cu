@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 1) k_chan_front(FrontArgs a,
         atomicMax(a.dbg + 4 * blockIdx.x + 3, t2);
     }
 }
-__global__ void __launch_bounds__(kTailThreads) k_chan_tail(TailArgs a) {
+__global__ void __launch_bounds__(kTailThreads, 4) k_chan_tail(TailArgs a) {
     __shared__ TailShared sm;
     const bool dbg = a.dbg && threadIdx.x == 0 && blockIdx.x < 64;
     if (dbg) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.dbg[blockIdx.x * 64 + 63] = t; }
