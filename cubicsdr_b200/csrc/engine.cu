@@ -38,9 +38,17 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 // ---------------------------------------------------------------------------------------------------------------------
 // kernels (GPU) / serial replays (test-only emulator)
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kDcReservedSms = 8;    // SMs the channel front kernel leaves free: the bit-exact DC blocker's serial chains (one warp
-                                     // per segment, 63 warps per 61 MSps block) run there at full speed instead of fighting the
-                                     // front warps for issue slots
+// SMs the channel front kernel leaves free under a heavy channel load: the bit-exact DC blocker's serial chains (one warp
+// per segment) run there instead of fighting the front warps for issue slots.  The split follows the channel count:
+//   >= 384 channels: 8 SMs x 8 warps (the front kernel is long, the replay hides underneath even at 2 warps / scheduler)
+//   128 .. 383     : 16 SMs x 4 warps (one warp per scheduler = full chain speed; the front kernel is short)
+//   < 128          : none -- the front kernel is negligible, the replay spreads over the whole GPU in short segments
+struct DcSplit { int reserved_sms; int warps_per_cta; };
+static inline DcSplit dc_split_for(size_t live_channels) {
+    if (live_channels >= 384) return DcSplit{8, 8};
+    if (live_channels >= 128) return DcSplit{16, 4};
+    return DcSplit{0, 1};
+}
 constexpr int kResBuf = 3;           // host result buffers (ring): blocks a pipelined consumer may keep in flight + 1
 constexpr int kDcWarpsPerCta = 8;    // segments (warps) per CTA of the bit-exact DC replay under a heavy channel load
 constexpr int kFrontWarps = 15;      // warps per CTA of the channel front kernel (one CTA per SM); 15 x 32 x 128 registers leave room for one
@@ -235,18 +243,18 @@ __global__ void __launch_bounds__(kSpecThreads) k_spec_points(SpecArgs a) {
 }
 #endif
 
-static void launch_dc_exact(const DcExactArgs &a, bool exclusive, sdr_stream_t s, unsigned long long &launches) {
+static void launch_dc_exact(const DcExactArgs &a, int warps_per_cta, sdr_stream_t s, unsigned long long &launches) {
 #ifndef SDR_EMU
-    if (exclusive) {
+    if (warps_per_cta > 1) {                                   // exclusive CTAs on the SMs the front kernel leaves free
         static bool attr_set = false;
         if (!attr_set) { cudaFuncSetAttribute(k_dc_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, kDcExclusiveSmem); attr_set = true; }
-        k_dc_exact<<<(a.n_seg + kDcWarpsPerCta - 1) / kDcWarpsPerCta, 32 * kDcWarpsPerCta, kDcExclusiveSmem, s>>>(a);
+        k_dc_exact<<<(a.n_seg + warps_per_cta - 1) / warps_per_cta, 32 * warps_per_cta, kDcExclusiveSmem, s>>>(a);
     } else {
         k_dc_exact<<<a.n_seg, 32, 0, s>>>(a);
     }
     k_dc_verify<<<1, 32, 0, s>>>(a);
 #else
-    (void)s; (void)exclusive;
+    (void)s; (void)warps_per_cta;
     for (int g = 0; g < a.n_seg; ++g) dc_exact_segment_serial(a, g, false, make_float2(0.f, 0.f));
     dc_exact_verify(a);
 #endif
@@ -281,34 +289,34 @@ static void launch_dc(const DcArgs &a, bool apply, sdr_stream_t s, unsigned long
 }
 
 template <int K>
-static int launch_front_k(const FrontArgs &a, int jobs, sdr_stream_t s) {
+static int launch_front_k(const FrontArgs &a, int jobs, int reserved_sms, sdr_stream_t s) {
 #ifndef SDR_EMU
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(k_chan_front<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrontSmemBytes));
         attr_set = true;
     }
-    // one CTA per SM while the jobs fit; kDcReservedSms SMs stay free for the DC blocker's serial chains
-    const int sms = 148 - kDcReservedSms;
+    // one CTA per SM while the jobs fit; reserved_sms SMs stay free for the DC blocker's serial chains
+    const int sms = 148 - reserved_sms;
     int n_cta = (jobs + kFrontWarps - 1) / kFrontWarps;
     if (jobs <= sms * kFrontWarps) n_cta = jobs < sms ? jobs : sms;
     k_chan_front<K><<<n_cta, kFrontWarps * 32, kFrontSmemBytes, s>>>(a, jobs);
 #else
-    (void)s;
+    (void)s; (void)reserved_sms;
     for (int j = 0; j < jobs; ++j) for (int l = 0; l < 32; ++l) front_thread<K>(a, j, l);
 #endif
     return 0;
 }
-static int launch_front(int K, const FrontArgs &a, int jobs, sdr_stream_t s, unsigned long long &launches) {
+static int launch_front(int K, const FrontArgs &a, int jobs, int reserved_sms, sdr_stream_t s, unsigned long long &launches) {
     launches += 1;
     switch (K) {
-    case 0: return launch_front_k<0>(a, jobs, s);
-    case 1: return launch_front_k<1>(a, jobs, s);
-    case 2: return launch_front_k<2>(a, jobs, s);
-    case 3: return launch_front_k<3>(a, jobs, s);
-    case 4: return launch_front_k<4>(a, jobs, s);
-    case 5: return launch_front_k<5>(a, jobs, s);
-    default: return launch_front_k<6>(a, jobs, s);
+    case 0: return launch_front_k<0>(a, jobs, reserved_sms, s);
+    case 1: return launch_front_k<1>(a, jobs, reserved_sms, s);
+    case 2: return launch_front_k<2>(a, jobs, reserved_sms, s);
+    case 3: return launch_front_k<3>(a, jobs, reserved_sms, s);
+    case 4: return launch_front_k<4>(a, jobs, reserved_sms, s);
+    case 5: return launch_front_k<5>(a, jobs, reserved_sms, s);
+    default: return launch_front_k<6>(a, jobs, reserved_sms, s);
     }
 }
 
@@ -1197,10 +1205,11 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         // ones); many short ones when the GPU is otherwise idle and only the replay's own latency matters
         size_t live = 0;
         for (auto *c : e->chans) live += c != nullptr;
-        const bool heavy = live >= 256;
+        const DcSplit split = dc_split_for(live);
+        const bool heavy = split.reserved_sms > 0;
         unsigned seg = kDcSegLenLight;
-        if (heavy) {                                           // at most one warp per scheduler slot pair on the reserved SMs
-            const unsigned cap = kDcReservedSms * kDcWarpsPerCta;
+        if (heavy) {                                           // exactly as many segments as warp slots on the reserved SMs
+            const unsigned cap = (unsigned)(split.reserved_sms * split.warps_per_cta);
             seg = (unsigned)((n + cap - 1) / cap);
             seg = (seg + 63u) & ~63u;
             if (seg < kDcSegLenLight) seg = kDcSegLenLight;
@@ -1214,7 +1223,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         const bool spec = n >= 4u * seg && (!e->have_block || e->last_n >= (unsigned)(kDcWarm + kDcTile));
         xa.n_seg = spec ? (int)((n + seg - 1) / seg) : 1;
         if (!spec) xa.seg_len = (int)n;
-        launch_dc_exact(xa, heavy && spec, dcs, e->launches);
+        launch_dc_exact(xa, (heavy && spec) ? split.warps_per_cta : 1, dcs, e->launches);
     }
     // history in front of the block: the tail of the previous block, which lives in the other buffer
     size_t need = kBlkHist;
@@ -1338,6 +1347,9 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         return join_side();
     }
     std::vector<int> by_k[kFrontMaxK + 1];
+    size_t live_now = 0;
+    for (auto *c : e->chans) live_now += c != nullptr;
+    const int front_reserved = e->exact_dc ? dc_split_for(live_now).reserved_sms : 0;
     for (int i = 0; i < n_slots; ++i) {
         sdr_chan *c = e->chans[i];
         ChanDyn &d = h_cd[i];
@@ -1389,7 +1401,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         fa.x = blk; fa.n = (int)n; fa.nco = e->d_nco; fa.cs = e->d_cs; fa.cd = d_cd; fa.group = e->d_group + goff; fa.cg = cg;
         const int n_chunks = (cg + 31) / 32;
         const long long nq = ((long long)n >> K) + 1;
-        int n_span = std::max(1, ((148 - kDcReservedSms) * kFrontWarps) / n_chunks);   // one wave of CTAs on the SMs the front uses
+        int n_span = std::max(1, ((148 - front_reserved) * kFrontWarps) / n_chunks);   // one wave of CTAs on the SMs the front uses
         // every span pays kFrontWarm warm-up super-steps; with few channels, parallelism is worth more than the overhead
         const long long min_span = (K == 0) ? 256 : kFrontWarm;
         if ((long long)n_span * min_span > nq) n_span = (int)std::max<long long>(1, nq / min_span);
@@ -1397,7 +1409,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         fa.span = (int)((nq + n_span - 1) / n_span);
         fa.c0 = h3[0]; fa.c1 = h3[1]; fa.c2 = h3[2];
         fa.dbg = e->d_front_dbg;
-        int fr = launch_front(K, fa, n_chunks * n_span, e->stream, e->launches);
+        int fr = launch_front(K, fa, n_chunks * n_span, front_reserved, e->stream, e->launches);
         if (fr) return fr;
         goff += cg;
     }
