@@ -161,7 +161,26 @@ def run_reference(args, wl, chans, rank):
             "cpu_baseline": {"value": val, "unit": "MSamples/s", "cores": threads, "kind": "reference",
                              "sample": "1 block (1/60 s of IQ) per step after 1 untimed block, all channels + spectrum, liquid-dsp %s" % ver},
             "e2e": {"value": val, "unit": "MSamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
+
+
+# The contract is ONE JSON line on stdout.  Libraries underneath (NCCL's version banner, for one) also write to fd 1, so
+# the real stdout is kept aside and fd 1 is pointed at stderr for the duration of the run.
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -174,6 +193,7 @@ def main():
     ap.add_argument("--ring", type=int, default=16, help="distinct input blocks rotated through (ring * block > L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    capture_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -406,7 +426,7 @@ def main():
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 

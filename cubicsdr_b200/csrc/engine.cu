@@ -82,11 +82,12 @@ constexpr int kFrontSmemBytes = kFrontSmemTab + kFrontWarps * 2 * 32 * (int)size
 // Bit-exact DC blocker: one warp per segment.  All lanes run the (strictly serial) chain redundantly; the warp as a whole
 // prefetches the raw samples three batches ahead into shared memory and stores the outputs coalesced.  A CTA holds up to
 // kDcWarpsPerCta segments.  Under a heavy channel load the launch also asks for kDcExclusiveSmem bytes of dynamic shared
-// memory it never touches: with that request a DC CTA cannot share an SM with a channel-front CTA (143 KB), so the block
-// scheduler puts the replay on the SMs the front kernel leaves free, whichever of the two kernels starts first.
+// memory it never touches: with that request a DC CTA shares its SM with nothing (not the channel front, 143 KB, nor the
+// tail or FFT CTAs that would steal its issue slots), so the block scheduler puts the replay on the SMs the front kernel
+// leaves free, whichever kernel starts first, and the serial chains run at their isolated speed.
 constexpr int kDcBatch = 64;     // samples per cp.async batch (two 8-byte copies per lane)
 constexpr int kDcRing = 4;       // batches in flight: ~1700 cycles of lead over the serial chain
-constexpr int kDcExclusiveSmem = 90 * 1024;
+constexpr int kDcExclusiveSmem = 200 * 1024;
 __global__ void __launch_bounds__(32 * kDcWarpsPerCta) k_dc_exact(DcExactArgs a) {
     __shared__ __align__(16) float2 sx_all[kDcWarpsPerCta][kDcRing][kDcBatch];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
