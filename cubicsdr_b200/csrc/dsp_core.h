@@ -31,6 +31,13 @@ SDR_HD SDR_FORCEINLINE float2 cf_make(float a, float b) { return make_float2(a, 
 SDR_HD SDR_FORCEINLINE float2 cf_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 SDR_HD SDR_FORCEINLINE float2 cf_fma(float h, float2 x, float2 acc) { return make_float2(fmaf(h, x.x, acc.x), fmaf(h, x.y, acc.y)); }
 SDR_HD SDR_FORCEINLINE float2 cf_scale(float h, float2 x) { return make_float2(h * x.x, h * x.y); }
+SDR_HD SDR_FORCEINLINE float flip_sign(float v, unsigned mask) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(__float_as_uint(v) ^ mask);
+#else
+    uint32_t u; memcpy(&u, &v, 4); u ^= mask; memcpy(&v, &u, 4); return v;
+#endif
+}
 // x * (c + j s)
 SDR_HD SDR_FORCEINLINE float2 cf_rot(float2 x, float c, float s) {
     return make_float2(fmaf(x.x, c, -(x.y * s)), fmaf(x.x, s, x.y * c));
@@ -524,7 +531,9 @@ SDR_HD inline void front_span(const FrontArgs &a, int ch, int span_idx, bool sto
     const float2 *hx = cd.hist ? cd.hist : a.x;
     // table oscillator: entry = (theta + 2^21) >> 22; mixing down conjugates (sign on the sine); no mixing = constant
     // entry 0 = (1, 0).  The *_prev values describe the block whose tail forms the history in front of this one.
-    const float sg = cd.dir < 0 ? -1.0f : 1.0f, sg_prev = cd.dir_prev < 0 ? -1.0f : 1.0f;
+    // the conjugation is a sign flip of the sine: done as an integer XOR (bit-identical to multiplying by -1.0f, and it
+    // runs on the integer pipe instead of the FP32 pipe the kernel is bound by)
+    const unsigned sg = cd.dir < 0 ? 0x80000000u : 0u, sg_prev = cd.dir_prev < 0 ? 0x80000000u : 0u;
     const unsigned dth = cd.dir ? cd.dtheta : 0u, dth_prev = cd.dir_prev ? cd.dtheta_prev : 0u;
     const unsigned thb = (cd.dir ? cd.theta0 : 0u) + 0x200000u;          // biased phase at sample 0 of the block
     const unsigned thb_prev = (cd.dir_prev ? cd.theta0 : 0u) + 0x200000u;
@@ -533,7 +542,7 @@ SDR_HD inline void front_span(const FrontArgs &a, int ch, int span_idx, bool sto
         for (long long q = q_lo; q < q_hi; ++q) {
             const int i = (int)(q - g0);
             const float2 w = tabf.get(thb + (unsigned)i * dth);
-            if (store) out[q - qa] = cf_rot(sdr_ldg(a.x + i), w.x, w.y * sg);
+            if (store) out[q - qa] = cf_rot(sdr_ldg(a.x + i), w.x, flip_sign(w.y, sg));
         }
         return;
     }
@@ -558,13 +567,13 @@ SDR_HD inline void front_span(const FrontArgs &a, int ch, int span_idx, bool sto
             prefetched = (q + 1 < q_hi) && (in_block || (i0 + 2 * M <= 0));
             if (prefetched) xs.prefetch(src + M);
             const unsigned step = in_block ? dth : dth_prev;
-            const float s_sign = in_block ? sg : sg_prev;
+            const unsigned s_sign = in_block ? sg : sg_prev;
             unsigned th = in_block ? thb + (unsigned)i0 * dth : thb_prev - (unsigned)(-i0) * dth_prev;
 #pragma unroll
             for (int t = 0; t < M; ++t) {
                 const float2 w = tabf.get(th);
                 th += step;
-                const float2 y = front_feed<K>(hb, t, cf_rot(xs.get(t), w.x, w.y * s_sign), c0, c1, c2);
+                const float2 y = front_feed<K>(hb, t, cf_rot(xs.get(t), w.x, flip_sign(w.y, s_sign)), c0, c1, c2);
                 if (t == 0 && store && q >= q_lo) out[q - qa] = y;
             }
         } else {
@@ -578,10 +587,10 @@ SDR_HD inline void front_span(const FrontArgs &a, int ch, int span_idx, bool sto
                 if (gq + t >= 0 && i >= -kBlkHist) {
                     if (i >= 0) {
                         const float2 w = tabf.get(thb + (unsigned)i * dth);
-                        u = cf_rot(sdr_ldg(a.x + i), w.x, w.y * sg);
+                        u = cf_rot(sdr_ldg(a.x + i), w.x, flip_sign(w.y, sg));
                     } else {
                         const float2 w = tabf.get(thb_prev - (unsigned)(-i) * dth_prev);
-                        u = cf_rot(sdr_ldg(hx + i), w.x, w.y * sg_prev);
+                        u = cf_rot(sdr_ldg(hx + i), w.x, flip_sign(w.y, sg_prev));
                     }
                 }
                 const float2 y = front_feed_dyn<K>(hb, t, u, c0, c1, c2);
