@@ -51,8 +51,8 @@ static inline DcSplit dc_split_for(size_t live_channels) {
 }
 constexpr int kResBuf = 3;           // host result buffers (ring): blocks a pipelined consumer may keep in flight + 1
 constexpr int kDcWarpsPerCta = 8;    // segments (warps) per CTA of the bit-exact DC replay under a heavy channel load
-constexpr int kFrontWarps = 15;      // warps per CTA of the channel front kernel (one CTA per SM); 15 x 32 x 128 registers leave room for one
-                                     // warp of the bit-exact DC blocker on every SM, which then runs underneath the front kernel
+constexpr int kFrontWarps = 16;      // warps per CTA of the channel front kernel (one CTA per SM): 16 x 32 x 128 registers = the whole
+                                     // register file; the bit-exact DC replay has its own SMs (dc_split_for)
 #ifndef SDR_EMU
 __global__ void __launch_bounds__(kDcThreads) k_dc_tile_sum(DcArgs a) {
     __shared__ DcShared sm;
