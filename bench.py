@@ -354,6 +354,7 @@ def main():
         step_e2e(i)
     torch.cuda.synchronize()
     barrier(); torch.cuda.synchronize()
+    eng.set_timing(True)                                        # stage times of the first 64 e2e blocks (stderr diagnostic)
     t0 = time.perf_counter()
     d2h = 0
     for i in range(args.steps):
@@ -361,7 +362,10 @@ def main():
     eng.wait()                                                  # drain the blocks still in flight (submitted, not yet fetched)
     torch.cuda.synchronize(); barrier()
     t_e2e = time.perf_counter() - t0
+    e2e_stage_ms, e2e_stage_blocks = eng.get_timing()
+    eng.set_timing(False)
     if rank == 0:
+        print("e2e device stages per block (ms): %s" % {k: round(v / max(1, e2e_stage_blocks), 3) for k, v in e2e_stage_ms.items()}, file=sys.stderr)
         print("e2e host split per step (ms): submit+h2d %.3f  wait %.3f  fetch %.3f" % tuple(1e3 * v / (args.steps + 3) for v in host_split), file=sys.stderr)
     if dist is not None:
         tt = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
