@@ -83,6 +83,27 @@ int main(int argc, char **argv) {
             if (b == 1 && f + 1 == spec.framesReady()) for (unsigned i = 0; i < 256; ++i) pts.push_back(d.spectrum_points[2 * i + 1]);
         }
     }
+    // ---- pipelined ingress: the block just submitted stays on the GPU while the previous one is fetched; the audio of
+    // blocks 0,1 re-run through a fresh channel must equal what the blocking loop produced (block 1 is drained at the end)
+    {
+        auto eng2 = std::make_shared<Engine>(0, 1u << 17);       // fresh engine: the DC blocker starts from rest, as above
+        SDRPostB200 post2(eng2);
+        DemodulatorB200 fm2(eng2, "FM", 2400000, 200000, 48000, false);
+        fm2.setFrequency(100000000 + 300000);
+        std::vector<float> audio2;
+        for (int b = 0; b < 2; ++b) {
+            DemodulatorThreadIQData blk;
+            blk.frequency = 100000000; blk.sampleRate = 2400000;
+            blk.data = slurp<liquid_float_complex>(dir + "/wide_" + std::to_string(b) + ".bin");
+            bool have = false;
+            if (!post2.runSingleCHPipelined(blk, &have)) { std::cerr << sdr_last_error() << "\n"; return 13; }
+            if (have != (b > 0)) return 14;
+            if (have) { AudioThreadInput a; if (!fm2.fetchAudio(a, nullptr)) return 15; audio2.insert(audio2.end(), a.data.begin(), a.data.end()); }
+        }
+        if (sdr_engine_wait_block(eng2->get(), 0) != SDR_OK) return 16;
+        { AudioThreadInput a; if (!fm2.fetchAudio(a, nullptr)) return 17; audio2.insert(audio2.end(), a.data.begin(), a.data.end()); }
+        dump(dir + "/audio_chan_FM_pipelined.bin", audio2);
+    }
     dump(dir + "/audio_chan_FM.bin", audio);
     dump(dir + "/postiq_chan_FM.bin", postiq);
     dump(dir + "/spec_last_points.bin", pts);

@@ -24,12 +24,17 @@ def relrms(a, b):
     return float(np.linalg.norm(a - b) / nb) if nb > 0 else float(np.linalg.norm(a))
 
 
-def run_channels(lib, ref, fs, chans, n_blocks, block=None, seed=1234, device=0, want_iq=True, retune=None, signal=None):
+def run_channels(lib, ref, fs, chans, n_blocks, block=None, seed=1234, device=0, want_iq=True, retune=None, signal=None,
+                 resident=None, spectrum=0):
     """Stream n_blocks through engine and oracle.  chans: [(modem, bw, offset_hz)].
     Returns per-channel dict with concatenated audio / iq of both sides and per-block count equality."""
     N = block or synth.block_size(fs)
     eng = Engine(lib, device=device, max_block=N)
     cs = [Channel(eng, m, fs, bw, 48000, frequency=CENTER + off, want_iq=want_iq) for m, bw, off in chans]
+    # `resident`: further channels (and a spectrum) attached to the same engine but not compared -- they put the engine in
+    # the configuration the full-size workload runs in (grid sizes, DC replay placement, stream overlap)
+    extra = [Channel(eng, m, fs, bw, 48000, frequency=CENTER + off) for m, bw, off in (resident or [])]
+    sp = Spectrum(eng, spectrum, 0) if spectrum else None
     rcs = [RefChan(ref, m, fs, bw) for m, bw, off in chans]
     ing = RefIngress(ref)
     out = [dict(modem=m, audio=[], ref_audio=[], iq=[], ref_iq=[], counts_ok=True, lvl=[], ref_lvl=[], peak=[], ref_peak=[],
@@ -63,8 +68,10 @@ def run_channels(lib, ref, fs, chans, n_blocks, block=None, seed=1234, device=0,
     for o in out:
         for k in ("audio", "ref_audio", "iq", "ref_iq"):
             o[k] = np.concatenate(o[k]) if len(o[k]) else np.zeros(0)
-    for c in cs:
+    for c in cs + extra:
         c.close()
+    if sp is not None:
+        sp.close()
     for rc in rcs:
         rc.close()
     ing.close()

@@ -133,3 +133,19 @@ def test_dc_blocker_bit_exact_at_full_block_size(gpu_lib, ref):
 
 def test_pipelined_fetch_returns_previous_block(gpu_lib):
     parity.check_pipelined_fetch(gpu_lib)
+
+
+def test_cfg5_full_configuration_slice(gpu_lib, ref):
+    """configs[4] exactly as bench.py runs it: 512 mixed channels + the 16384-point spectrum attached at 61.44 MSps (16-warp
+    front kernel on 140 SMs, DC replay in 8 x 8-warp SM-exclusive CTAs, tail / spectrum / result streams).  Twelve of the
+    channels (three per modem) are compared with the oracle over two blocks; the DC-blocked block must be bit-exact."""
+    fs = 61440000
+    chans = synth.channel_plan("mixed", fs, 512)
+    pick = list(range(0, 512, 43))[:12]
+    sub = [chans[i] for i in pick]
+    rest = [c for i, c in enumerate(chans) if i not in pick]
+    out, dc_err, _ = parity.run_channels(gpu_lib, ref, fs, sub, n_blocks=2, signal=chans[::16] + sub, resident=rest,
+                                         spectrum=16384, want_iq=False)
+    assert max(dc_err) == 0.0
+    assert sorted({o["modem"] for o in out}) == ["AM", "FM", "LSB", "USB"]
+    parity.check_channels(out)

@@ -53,6 +53,8 @@ def _run(lib, ref, tmp):
     got = np.fromfile(os.path.join(tmp, "audio_chan_FM.bin"), np.float32)
     want = np.concatenate(want_audio["FM"][:2])
     assert len(got) == len(want) and relrms(got, want) <= TOL
+    piped = np.fromfile(os.path.join(tmp, "audio_chan_FM_pipelined.bin"), np.float32)
+    assert np.array_equal(piped, got), "pipelined ingress (runSingleCHPipelined) must return the same audio, one block late"
     got = np.fromfile(os.path.join(tmp, "postiq_chan_FM.bin"), np.complex64)
     assert len(got) == sum(len(q) for q in fm_iq) and relrms(got, np.concatenate(fm_iq)) <= TOL
     pts = np.fromfile(os.path.join(tmp, "spec_last_points.bin"), np.float32)
