@@ -15,6 +15,8 @@ when N > 1 the raw block is broadcast from rank 0 over NCCL inside the timed reg
            engine's stream inside the timed region.
 `cpu_baseline` / `--impl reference`: the reference's own liquid-dsp binary + CubicSDR glue (oracle/_ref) on the host cores.
 """
+import os
+os.environ.setdefault("OMP_NUM_THREADS", "1")   # no spinning OpenMP pool next to the reference's own threads (cpu_baseline / --impl reference)
 import argparse
 import json
 import os
@@ -192,6 +194,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ring", type=int, default=16, help="distinct input blocks rotated through (ring * block > L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--channels", type=int, default=0, help="diagnostic only: override the workload's channel count (not a contract line)")
     args = ap.parse_args()
     capture_stdout()
     rank = int(os.environ.get("RANK", "0"))
@@ -201,6 +204,8 @@ def main():
     from cubicsdr_b200 import synth
     fs = wl["fs"]
     N = synth.block_size(fs)
+    if args.channels > 0 and wl["n_chan"]:
+        wl = dict(wl, n_chan=args.channels, desc=wl["desc"] + " [DIAGNOSTIC: %d channels]" % args.channels)
     chans = synth.channel_plan(wl["plan"], fs, wl["n_chan"]) if wl["n_chan"] else []
 
     if args.impl == "reference":

@@ -41,12 +41,14 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 // SMs the channel front kernel leaves free under a heavy channel load: the bit-exact DC blocker's serial chains (one warp
 // per segment) run there instead of fighting the front warps for issue slots.  The split follows the channel count:
 //   >= 384 channels: 8 SMs x 8 warps (the front kernel is long, the replay hides underneath even at 2 warps / scheduler)
-//   192 .. 383     : 16 SMs x 4 warps (one warp per scheduler = full chain speed; the front kernel is short)
-//   < 192          : none -- the front kernel is negligible, the replay spreads over the whole GPU in short segments
+//   96 .. 383      : 16 SMs x 4 warps (one warp per scheduler = full chain speed; the front kernel is short)
+//   1 .. 95        : 32 SMs x 4 warps (the replay's latency is the block period: more, shorter segments)
+//   0              : none -- nothing else runs but the spectrum; the replay spreads over the whole GPU in short segments
 struct DcSplit { int reserved_sms; int warps_per_cta; };
 static inline DcSplit dc_split_for(size_t live_channels) {
     if (live_channels >= 384) return DcSplit{8, 8};
-    if (live_channels >= 192) return DcSplit{16, 4};
+    if (live_channels >= 96) return DcSplit{16, 4};
+    if (live_channels >= 1) return DcSplit{32, 4};
     return DcSplit{0, 1};
 }
 constexpr int kResBuf = 3;           // host result buffers (ring): blocks a pipelined consumer may keep in flight + 1
