@@ -224,6 +224,17 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     lib = cubicsdr_b200.lib()
+
+    def print_timeline(tag):                                    # stderr diagnostic: device timeline of a few steady-state blocks
+        try:
+            import ctypes as C
+            tl = np.zeros((16, 8), np.float32); ntl = C.c_int()
+            lib.L.sdr_engine_debug_timeline(eng.h, tl.ctypes.data_as(C.c_void_p), C.byref(ntl))
+            print("%s timeline (ms) dc_start dc_end | front_start front_end tail_end | spec_start spec_end tail_start" % tag, file=sys.stderr)
+            for r in range(8, min(13, ntl.value)):
+                print("  blk %2d " % r + " ".join("%7.3f" % v for v in tl[r]), file=sys.stderr)
+        except Exception as ex:
+            print("timeline unavailable: %r" % (ex,), file=sys.stderr)
     # a dedicated (non-default) stream shared by torch and the engine: torch.cuda.Event timing then sees the kernels
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
@@ -341,6 +352,8 @@ def main():
     ms = e0.elapsed_time(e1)
     eng.wait()
     stage_ms, stage_blocks = eng.get_timing()
+    if rank == 0:
+        print_timeline("device")
     eng.set_timing(False)
     launches = eng.launch_count - launches0
     if dist is not None:
@@ -370,6 +383,7 @@ def main():
     e2e_stage_ms, e2e_stage_blocks = eng.get_timing()
     eng.set_timing(False)
     if rank == 0:
+        print_timeline("e2e")
         print("e2e device stages per block (ms): %s" % {k: round(v / max(1, e2e_stage_blocks), 3) for k, v in e2e_stage_ms.items()}, file=sys.stderr)
         print("e2e host split per step (ms): submit+h2d %.3f  wait %.3f  fetch %.3f" % tuple(1e3 * v / (args.steps + 3) for v in host_split), file=sys.stderr)
     if dist is not None:

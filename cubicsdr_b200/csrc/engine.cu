@@ -509,7 +509,7 @@ struct sdr_engine {
     static const int kTimeSets = 64;
     int time_pending = 0;
     double stage_ms[4] = {0, 0, 0, 0};
-    float timeline[16][5];
+    float timeline[16][8];
     int timeline_n = 0;
     unsigned long long stage_count = 0;
 #ifndef SDR_EMU
@@ -544,13 +544,17 @@ static void time_collect(sdr_engine *e) {
     // diagnostics: absolute timeline (ms since the first block's DC start) of the first 16 blocks of this batch
     e->timeline_n = 0;
     for (int i = 0; i < e->time_pending && i < 16; ++i) {
-        float t[5] = {0, 0, 0, 0, 0};
+        float t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         cudaEventElapsedTime(&t[0], e->tev_dc[0][0], e->tev_dc[i][0]);
         cudaEventElapsedTime(&t[1], e->tev_dc[0][0], e->tev_dc[i][1]);
         cudaEventElapsedTime(&t[2], e->tev_dc[0][0], e->tev[i][2]);
         cudaEventElapsedTime(&t[3], e->tev_dc[0][0], e->tev[i][3]);
         cudaEventElapsedTime(&t[4], e->tev_dc[0][0], e->tev_tail[i][1]);
-        for (int k = 0; k < 5; ++k) e->timeline[i][k] = t[k];
+        cudaEventElapsedTime(&t[5], e->tev_dc[0][0], e->tev_spec[i][0]);     // may fail when no spectrum is attached: stays 0
+        cudaEventElapsedTime(&t[6], e->tev_dc[0][0], e->tev_spec[i][1]);
+        cudaEventElapsedTime(&t[7], e->tev_dc[0][0], e->tev_tail[i][0]);
+        cudaGetLastError();
+        for (int k = 0; k < 8; ++k) e->timeline[i][k] = t[k];
         e->timeline_n = i + 1;
     }
     for (int i = 0; i < e->time_pending; ++i) {
@@ -735,7 +739,8 @@ extern "C" int sdr_engine_destroy(sdr_engine *e) {
 extern "C" unsigned long long sdr_engine_launch_count(sdr_engine *e) { return e ? e->launches : 0; }
 
 // diagnostics: {dc_start, dc_end, front_start, front_end, tail_end} in ms for up to 16 blocks of the last timed batch
-extern "C" int sdr_engine_debug_timeline(sdr_engine *e, float *out80, int *n_blocks) {
+extern "C" int sdr_engine_debug_timeline(sdr_engine *e, float *out128, int *n_blocks) {   // [16][8], see time_collect
+    float *out80 = out128;
     if (!e || !out80) return SDR_ERR_ARG;
     std::lock_guard<std::mutex> lk(e->mu);
     memcpy(out80, e->timeline, sizeof e->timeline);

@@ -22,8 +22,8 @@ eng.set_timing(True)
 for i in range(8):
     eng.submit_device_async(xs[i % 4].data_ptr(), N, bench.CENTER, fs, fetch_to_host=False)
 eng.wait()
-out = np.zeros((16, 5), np.float32); n = C.c_int()
+out = np.zeros((16, 8), np.float32); n = C.c_int()
 lib.L.sdr_engine_debug_timeline(eng.h, out.ctypes.data_as(C.c_void_p), C.byref(n))
-print("block: dc_start dc_end | front_start front_end tail_end   (ms)")
+print("block: dc_start dc_end | front_start front_end tail_end | spec_start spec_end tail_start   (ms)")
 for i in range(n.value):
     print(i, " ".join("%7.3f" % v for v in out[i]))
