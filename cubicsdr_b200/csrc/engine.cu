@@ -256,6 +256,28 @@ __global__ void __launch_bounds__(kSpecThreads) k_spec_points(SpecArgs a) {
 }
 #endif
 
+// Per-block parameter blocks (a few KB: channel descriptors, group lists, frame offsets) are pulled from their pinned,
+// device-visible host slots by a tiny kernel instead of cudaMemcpyAsync: a memcpy would queue on the host-to-device copy
+// engine behind the caller's multi-megabyte input transfers and stall the compute stream that waits for it.
+#ifndef SDR_EMU
+__global__ void k_upload_words(const unsigned *__restrict__ src_host, unsigned *__restrict__ dst, unsigned n_words) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += gridDim.x * blockDim.x) dst[i] = src_host[i];
+}
+#endif
+static void upload_params(void *dst, const void *src_pinned, size_t bytes, sdr_stream_t s, unsigned long long &launches) {
+    if (!bytes) return;
+#ifndef SDR_EMU
+    const unsigned words = (unsigned)((bytes + 3) / 4);          // all parameter blocks are arrays of 4-byte-aligned structs
+    unsigned blocks = (words + 255u) / 256u;
+    if (blocks > 64u) blocks = 64u;
+    k_upload_words<<<blocks, 256, 0, s>>>(reinterpret_cast<const unsigned *>(src_pinned), reinterpret_cast<unsigned *>(dst), words);
+    launches += 1;
+#else
+    (void)s; (void)launches;
+    memcpy(dst, src_pinned, bytes);
+#endif
+}
+
 static void launch_dc_exact(const DcExactArgs &a, int warps_per_cta, sdr_stream_t s, unsigned long long &launches) {
 #ifndef SDR_EMU
     if (warps_per_cta > 1) {                                   // exclusive CTAs on the SMs the front kernel leaves free
@@ -1283,7 +1305,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         if (!s->frames_last) continue;
         int *h_fs = s->h_frame_start + (size_t)slot * s->f_max;
         memcpy(h_fs, starts.data(), s->frames_last * sizeof(int));
-        be_h2d(s->d_frame_start, h_fs, s->frames_last * sizeof(int), e->stream);
+        upload_params(s->d_frame_start, h_fs, s->frames_last * sizeof(int), e->stream, e->launches);
         SpecArgs a;
         a.x = blk; a.frame_start = s->d_frame_start; a.F = (int)s->frames_last; a.N = (int)s->N; a.fft_size = (int)s->fft_size;
         a.P = s->P; a.nsub = s->nsub; a.log_nsub = s->log_nsub; a.tw = s->d_tw; a.mags = s->d_mags; a.maa_f = s->d_maa; a.ema = s->d_ema;
@@ -1406,7 +1428,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
     // d_cd2[p] and the level-0 buffers this block's front kernel writes were last read by the tail of two blocks ago
     CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_tail_done[p], 0));
 #endif
-    be_h2d(d_cd, h_cd, (size_t)n_slots * sizeof(ChanDyn), e->stream);
+    upload_params(d_cd, h_cd, (size_t)n_slots * sizeof(ChanDyn), e->stream, e->launches);
     int goff = 0;
     float h3[6];
     halfband_branch_taps(3, 65.0f, h3);
@@ -1414,7 +1436,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         const int cg = (int)by_k[K].size();
         if (!cg) continue;
         memcpy(h_group + goff, by_k[K].data(), cg * sizeof(int));
-        be_h2d(e->d_group + goff, h_group + goff, cg * sizeof(int), e->stream);
+        upload_params(e->d_group + goff, h_group + goff, cg * sizeof(int), e->stream, e->launches);
         FrontArgs fa;
         fa.x = blk; fa.n = (int)n; fa.nco = e->d_nco; fa.cs = e->d_cs; fa.cd = d_cd; fa.group = e->d_group + goff; fa.cg = cg;
         const int n_chunks = (cg + 31) / 32;
