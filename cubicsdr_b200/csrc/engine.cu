@@ -550,6 +550,7 @@ struct sdr_engine {
     cudaEvent_t tev_tail[kTimeSets][2];
     cudaStream_t stream_dc = nullptr;
     cudaEvent_t ev_input = nullptr, ev_dc_done[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+    cudaEvent_t ev_params[2] = {nullptr, nullptr};   // per-block parameter blocks of this parity are on the device
     cudaEvent_t tev_dc[kTimeSets][2];
 #endif
 };
@@ -669,7 +670,7 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
     for (int b = 0; b < 2; ++b) bad |= be_malloc((void **)&e->d_cd2[b], sdr_engine::kMaxChan * sizeof(ChanDyn));
     bad |= be_malloc((void **)&e->d_st, sdr_engine::kMaxChan * sizeof(ChanState));
     bad |= be_host_alloc((void **)&e->h_cd, (size_t)sdr_engine::kRing * sdr_engine::kMaxChan * sizeof(ChanDyn));
-    bad |= be_malloc((void **)&e->d_group, sdr_engine::kMaxChan * sizeof(int));
+    bad |= be_malloc((void **)&e->d_group, 2 * sdr_engine::kMaxChan * sizeof(int));   // double-buffered by block parity
     bad |= be_host_alloc((void **)&e->h_group, (size_t)sdr_engine::kRing * sdr_engine::kMaxChan * sizeof(int));
 #ifndef SDR_EMU
     for (int i = 0; i < sdr_engine::kRing; ++i) CUDA_TRY(cudaEventCreateWithFlags(&e->ring_ev[i], cudaEventDisableTiming));
@@ -688,6 +689,7 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_input, cudaEventDisableTiming));
     for (int b = 0; b < 2; ++b) {
         CUDA_TRY(cudaEventCreateWithFlags(&e->ev_dc_done[b], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&e->ev_params[b], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&e->ev_consumed[b], cudaEventDisableTiming));
     }
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
@@ -748,7 +750,7 @@ extern "C" int sdr_engine_destroy(sdr_engine *e) {
     if (e->ev_front_done) cudaEventDestroy(e->ev_front_done);
     for (int b = 0; b < 2; ++b) if (e->ev_tail_done[b]) cudaEventDestroy(e->ev_tail_done[b]);
     if (e->ev_input) cudaEventDestroy(e->ev_input);
-    for (int b = 0; b < 2; ++b) { if (e->ev_dc_done[b]) cudaEventDestroy(e->ev_dc_done[b]); if (e->ev_consumed[b]) cudaEventDestroy(e->ev_consumed[b]); }
+    for (int b = 0; b < 2; ++b) { if (e->ev_dc_done[b]) cudaEventDestroy(e->ev_dc_done[b]); if (e->ev_consumed[b]) cudaEventDestroy(e->ev_consumed[b]); if (e->ev_params[b]) cudaEventDestroy(e->ev_params[b]); }
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
     for (int b = 0; b < kResBuf; ++b) { if (e->ev_res_tail[b]) cudaEventDestroy(e->ev_res_tail[b]); if (e->ev_res_spec[b]) cudaEventDestroy(e->ev_res_spec[b]); }
@@ -1096,7 +1098,7 @@ extern "C" int sdr_spectrum_create(sdr_engine *e, unsigned fft_size, unsigned lp
     bad |= be_malloc((void **)&s->d_frame_cf_maa, F * sizeof(double2));
     bad |= be_malloc((void **)&s->d_points, F * fft_size * sizeof(float));
     bad |= be_malloc((void **)&s->d_lines, F * fft_size);
-    bad |= be_malloc((void **)&s->d_frame_start, F * sizeof(int));
+    bad |= be_malloc((void **)&s->d_frame_start, 2 * F * sizeof(int));   // double-buffered by block parity
     bad |= be_host_alloc((void **)&s->h_points, kResBuf * F * fft_size * sizeof(float));
     bad |= be_host_alloc((void **)&s->h_lines, kResBuf * F * fft_size);
     bad |= be_host_alloc((void **)&s->h_cf, kResBuf * F * sizeof(double2));
@@ -1280,6 +1282,17 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
 #endif
     time_mark(e, 0);
     time_mark(e, 1);
+    // Per-block parameter blocks are uploaded on the DC stream, behind the replay: that stream runs a block ahead on its own
+    // SMs, so the upload kernels never wait for a free SM slot right in front of the channel front kernel (the main stream
+    // just waits for the event).  Their device buffers are double-buffered by block parity.
+    sdr_stream_t par_stream = dcs;
+    auto params_ready = [&]() -> int {
+#ifndef SDR_EMU
+        CUDA_TRY(cudaEventRecord(e->ev_params[p], par_stream));
+        CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_params[p], 0));
+#endif
+        return SDR_OK;
+    };
     e->parity = p;
     e->last_n = n; e->have_block = true;
     e->results_on_host = to_host;
@@ -1305,9 +1318,10 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         if (!s->frames_last) continue;
         int *h_fs = s->h_frame_start + (size_t)slot * s->f_max;
         memcpy(h_fs, starts.data(), s->frames_last * sizeof(int));
-        upload_params(s->d_frame_start, h_fs, s->frames_last * sizeof(int), e->stream, e->launches);
+        int *d_fs = s->d_frame_start + (size_t)p * s->f_max;
+        upload_params(d_fs, h_fs, s->frames_last * sizeof(int), par_stream, e->launches);
         SpecArgs a;
-        a.x = blk; a.frame_start = s->d_frame_start; a.F = (int)s->frames_last; a.N = (int)s->N; a.fft_size = (int)s->fft_size;
+        a.x = blk; a.frame_start = d_fs; a.F = (int)s->frames_last; a.N = (int)s->N; a.fft_size = (int)s->fft_size;
         a.P = s->P; a.nsub = s->nsub; a.log_nsub = s->log_nsub; a.tw = s->d_tw; a.mags = s->d_mags; a.maa_f = s->d_maa; a.ema = s->d_ema;
         a.rate = (double)s->average_rate; a.frame_cf = s->d_frame_cf; a.scalars = s->d_scalars; a.frame_cf_maa = s->d_frame_cf_maa;
         a.points = s->d_points; a.lines = s->d_lines; a.scale_factor = s->scale_factor;
@@ -1372,6 +1386,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
     // 4. channels: per-block oscillator bookkeeping (DemodulatorPreThread.cpp:154-163, 186-195)
     int n_slots = (int)e->chans.size();
     if (n_slots == 0) {
+        { int r = params_ready(); if (r) return r; }
         { int r = run_spectra(); if (r) return r; }
         time_mark(e, 3); time_mark(e, 4);
 #ifndef SDR_EMU
@@ -1428,17 +1443,29 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
     // d_cd2[p] and the level-0 buffers this block's front kernel writes were last read by the tail of two blocks ago
     CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_tail_done[p], 0));
 #endif
-    upload_params(d_cd, h_cd, (size_t)n_slots * sizeof(ChanDyn), e->stream, e->launches);
+#ifndef SDR_EMU
+    CUDA_TRY(cudaStreamWaitEvent(par_stream, e->ev_tail_done[p], 0));   // d_cd2[p] was last read by the tail of two blocks ago
+#endif
+    upload_params(d_cd, h_cd, (size_t)n_slots * sizeof(ChanDyn), par_stream, e->launches);
     int goff = 0;
     float h3[6];
     halfband_branch_taps(3, 65.0f, h3);
+    struct FrontGroup { int K, cg; int *d_grp; };
+    std::vector<FrontGroup> groups;
     for (int K = 0; K <= kFrontMaxK; ++K) {
         const int cg = (int)by_k[K].size();
         if (!cg) continue;
         memcpy(h_group + goff, by_k[K].data(), cg * sizeof(int));
-        upload_params(e->d_group + goff, h_group + goff, cg * sizeof(int), e->stream, e->launches);
+        int *d_grp = e->d_group + (size_t)p * sdr_engine::kMaxChan + goff;
+        upload_params(d_grp, h_group + goff, cg * sizeof(int), par_stream, e->launches);
+        groups.push_back(FrontGroup{K, cg, d_grp});
+        goff += cg;
+    }
+    { int r = params_ready(); if (r) return r; }
+    for (const FrontGroup &g : groups) {
+        const int K = g.K, cg = g.cg;
         FrontArgs fa;
-        fa.x = blk; fa.n = (int)n; fa.nco = e->d_nco; fa.cs = e->d_cs; fa.cd = d_cd; fa.group = e->d_group + goff; fa.cg = cg;
+        fa.x = blk; fa.n = (int)n; fa.nco = e->d_nco; fa.cs = e->d_cs; fa.cd = d_cd; fa.group = g.d_grp; fa.cg = cg;
         const int n_chunks = (cg + 31) / 32;
         const long long nq = ((long long)n >> K) + 1;
         int n_span = std::max(1, ((148 - front_reserved) * kFrontWarps) / n_chunks);   // one wave of CTAs on the SMs the front uses
@@ -1451,7 +1478,6 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         fa.dbg = e->d_front_dbg;
         int fr = launch_front(K, fa, n_chunks * n_span, front_reserved, e->stream, e->launches);
         if (fr) return fr;
-        goff += cg;
     }
     { int r = run_spectra(); if (r) return r; }                     // side stream, after the front kernel got the SMs
     TailArgs ta;
