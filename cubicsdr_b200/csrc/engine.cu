@@ -674,11 +674,13 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
     bad |= be_host_alloc((void **)&e->h_group, (size_t)sdr_engine::kRing * sdr_engine::kMaxChan * sizeof(int));
 #ifndef SDR_EMU
     for (int i = 0; i < sdr_engine::kRing; ++i) CUDA_TRY(cudaEventCreateWithFlags(&e->ring_ev[i], cudaEventDisableTiming));
-    CUDA_TRY(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
-    {   // highest priority: the DC blocker's one-warp CTAs should slot in the moment any SM has room
+    {   // highest priority: the DC replay's CTAs should slot in the moment an SM is free.  Next: the spectrum, which the
+        // next block's front kernel waits for (join): its FFT CTAs must get their SMs before the 512 tail CTAs that become
+        // runnable at the same instant fill the GPU (nothing waits for the tail until a block later)
         int lo = 0, hi = 0;
         CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CUDA_TRY(cudaStreamCreateWithPriority(&e->stream_dc, cudaStreamNonBlocking, hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&e->stream2, cudaStreamNonBlocking, hi < lo ? hi + 1 : hi));
     }
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_tail, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_res, cudaStreamNonBlocking));
