@@ -415,7 +415,9 @@ def main():
             traffic = json.load(open(tp)).get(args.workload, {}).get(dom)
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_chan_front (NCO mix + half-band cascade)" if c_local else "spectrum kernels",
+    roofline = {"bound": "hbm", "note": "contract figure (algorithmic bytes / kernel time / measured HBM peak); with hundreds of channels in "
+                                        "single-channel mode the kernel is FP32-pipe bound, see the fp32 object" if c_local else
+                                        "contract figure (algorithmic bytes / kernel time / measured HBM peak)", "kernel": "k_chan_front (NCO mix + half-band cascade)" if c_local else "spectrum kernels",
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "alg_bytes_per_sample": b_alg, "kernel_ms_per_block": t_dom_ms,
                 "stage_ms_per_block": {k: v / max(1, stage_blocks) for k, v in stage_ms.items()}}
