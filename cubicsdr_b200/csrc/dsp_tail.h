@@ -390,7 +390,9 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
         return;
     }
     if (ph == TP_AGC_B) {
-        if (!is_fm && tid == 0) {
+        // a block that yields no decimated samples never reaches buildAudioOutput (`if (!bufSize) return;`,
+        // ModemAM.cpp:35, ModemUSB/LSB likewise): the ceiling averages must not advance
+        if (!is_fm && tid == 0 && sm->n_iq > 0) {
             float mx = 0.f;
             for (int t = 0; t < nt; ++t) mx = fmaxf(mx, sm->red_f[t]);
             float ma = st.agc_ma + (st.agc_ceil - st.agc_ma) * 0.025f;

@@ -135,6 +135,49 @@ def run_spectrum(lib, ref, fs, fft_size, n_blocks, chans, lps=0, block=None, see
     return worst
 
 
+def check_add_remove_mid_stream(lib, ref, fs=2400000, n_blocks=6, device=0):
+    """Demodulators come and go while the stream runs (DemodulatorMgr::newThread / deleteThread between blocks): a channel
+    attached after block 1 starts from rest with that block's successor, a channel removed after block 3 frees its slot,
+    which the next newcomer reuses; everybody else's state must be untouched.  Every channel is compared with its own
+    oracle instance over exactly the blocks it lived through."""
+    plan = {  # name: (modem, bw, offset, first block, last block exclusive)
+        "a": ("FM", 200000, 300000, 0, n_blocks),
+        "b": ("AM", 6000, -450000, 0, 4),
+        "c": ("NBFM", 12500, 150000, 2, n_blocks),
+        "d": ("USB", 5400, -600000, 4, n_blocks),       # takes over b's slot
+    }
+    signal = [(m, bw, off) for m, bw, off, _, _ in plan.values()]
+    N = synth.block_size(fs)
+    eng = Engine(lib, device=device, max_block=N)
+    ing = RefIngress(ref)
+    live, refs = {}, {}
+    got = {k: [] for k in plan}
+    want = {k: [] for k in plan}
+    for b in range(n_blocks):
+        for k, (m, bw, off, b0, b1) in plan.items():
+            if b == b1 and k in live:
+                live.pop(k).close(); refs.pop(k).close()
+        for k, (m, bw, off, b0, b1) in plan.items():
+            if b == b0:
+                live[k] = Channel(eng, m, fs, bw, 48000, frequency=CENTER + off)
+                refs[k] = RefChan(ref, m, fs, bw)
+        x = synth.wideband(fs, N, signal, seed=4321, t0=b * N)
+        eng.submit(x, CENTER, fs)
+        eng.wait()
+        y = ing.block(x)
+        for k in live:
+            a, lvl, pk, sk = live[k].fetch_audio()
+            r = refs[k].process(y, plan[k][2])
+            assert len(a) == len(r["audio"]), "%s block %d: audio count %d vs %d" % (k, b, len(a), len(r["audio"]))
+            got[k].append(a); want[k].append(r["audio"])
+    for k in list(live):
+        live.pop(k).close(); refs.pop(k).close()
+    ing.close(); eng.close()
+    for k in plan:
+        e = relrms(np.concatenate(got[k]), np.concatenate(want[k]))
+        assert e <= TOL, "channel %s (%s): audio relative RMS error %.3g" % (k, plan[k][0], e)
+
+
 def check_pipelined_fetch(lib, fs=2400000, n_blocks=6, fft_size=1024, device=0):
     """submit(b+lag); wait_block(lag); fetch must return exactly block b's results (ring of host result buffers)."""
     chans = [("FM", 200000, 300000), ("NBFM", 12500, -412500), ("AM", 6000, 150000), ("USB", 5400, -250000)]

@@ -79,3 +79,17 @@ def test_dc_blocker_bit_exact_including_speculative_segments(emu_lib, ref):
 
 def test_pipelined_fetch_returns_previous_block(emu_lib):
     parity.check_pipelined_fetch(emu_lib)
+
+
+def test_channels_added_and_removed_mid_stream(emu_lib, ref):
+    parity.check_add_remove_mid_stream(emu_lib, ref)
+
+
+def test_tiny_blocks(emu_lib, ref):
+    """Blocks far shorter than any filter history (257 and 33 samples): outputs per block are 0..few samples, every carry
+    path and the exact per-block output counts are exercised dozens of times."""
+    out, dc_err, _ = parity.run_channels(emu_lib, ref, 2400000, [FIVE[0], FIVE[2], FIVE[4]], n_blocks=60, block=257)
+    assert max(dc_err) == 0.0
+    parity.check_channels(out)
+    out, _, _ = parity.run_channels(emu_lib, ref, 2400000, [FIVE[0], FIVE[1]], n_blocks=150, block=33, want_iq=False)
+    parity.check_channels(out)

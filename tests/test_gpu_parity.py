@@ -149,3 +149,13 @@ def test_cfg5_full_configuration_slice(gpu_lib, ref):
     assert max(dc_err) == 0.0
     assert sorted({o["modem"] for o in out}) == ["AM", "FM", "LSB", "USB"]
     parity.check_channels(out)
+
+
+def test_channels_added_and_removed_mid_stream(gpu_lib, ref):
+    parity.check_add_remove_mid_stream(gpu_lib, ref)
+
+
+def test_tiny_blocks(gpu_lib, ref):
+    out, dc_err, _ = parity.run_channels(gpu_lib, ref, 2400000, [FIVE[0], FIVE[2], FIVE[4]], n_blocks=60, block=257)
+    assert max(dc_err) == 0.0
+    parity.check_channels(out)
