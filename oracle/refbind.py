@@ -144,6 +144,9 @@ class RefSpectrum:
         self.ref, self.fft_size = ref, fft_size
         self.h = C.c_void_p(ref.L.ref_spectrum_create(fft_size))
 
+    def set_average_rate(self, r):
+        self.ref.L.ref_spectrum_set_average_rate(self.h, C.c_float(r))
+
     def frame(self, frame):
         frame = np.ascontiguousarray(frame, np.complex64)
         N = 2 * self.fft_size

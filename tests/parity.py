@@ -25,17 +25,17 @@ def relrms(a, b):
 
 
 def run_channels(lib, ref, fs, chans, n_blocks, block=None, seed=1234, device=0, want_iq=True, retune=None, signal=None,
-                 resident=None, spectrum=0):
+                 resident=None, spectrum=0, audio_rate=48000):
     """Stream n_blocks through engine and oracle.  chans: [(modem, bw, offset_hz)].
     Returns per-channel dict with concatenated audio / iq of both sides and per-block count equality."""
     N = block or synth.block_size(fs)
     eng = Engine(lib, device=device, max_block=N)
-    cs = [Channel(eng, m, fs, bw, 48000, frequency=CENTER + off, want_iq=want_iq) for m, bw, off in chans]
+    cs = [Channel(eng, m, fs, bw, audio_rate, frequency=CENTER + off, want_iq=want_iq) for m, bw, off in chans]
     # `resident`: further channels (and a spectrum) attached to the same engine but not compared -- they put the engine in
     # the configuration the full-size workload runs in (grid sizes, DC replay placement, stream overlap)
     extra = [Channel(eng, m, fs, bw, 48000, frequency=CENTER + off) for m, bw, off in (resident or [])]
     sp = Spectrum(eng, spectrum, 0) if spectrum else None
-    rcs = [RefChan(ref, m, fs, bw) for m, bw, off in chans]
+    rcs = [RefChan(ref, m, fs, bw, audio_rate) for m, bw, off in chans]
     ing = RefIngress(ref)
     out = [dict(modem=m, audio=[], ref_audio=[], iq=[], ref_iq=[], counts_ok=True, lvl=[], ref_lvl=[], peak=[], ref_peak=[],
                 skipped=[], ref_skipped=[]) for m, _, _ in chans]
@@ -94,7 +94,7 @@ def check_channels(out, tol=TOL):
         assert np.allclose(o["peak"], o["ref_peak"], rtol=1e-4, atol=1e-6), "%s: peak differs" % o["modem"]
 
 
-def run_spectrum(lib, ref, fs, fft_size, n_blocks, chans, lps=0, block=None, seed=1234, device=0):
+def run_spectrum(lib, ref, fs, fft_size, n_blocks, chans, lps=0, block=None, seed=1234, device=0, avg_rate=None):
     """Returns worst-case errors over all frames: magnitudes, maa, points, ceil/floor, u8 mismatch fraction."""
     N = block or synth.block_size(fs)
     eng = Engine(lib, device=device, max_block=N)
@@ -102,6 +102,8 @@ def run_spectrum(lib, ref, fs, fft_size, n_blocks, chans, lps=0, block=None, see
     ing = RefIngress(ref)
     rsp = RefSpectrum(ref, fft_size)
     rd = RefDistrib(ref, 2 * fft_size, lps if lps else 100000000)
+    if avg_rate is not None:                                    # SpectrumVisualProcessor::setFFTAverageRate (:76-78)
+        sp.set_average_rate(avg_rate); rsp.set_average_rate(avg_rate)
     worst = dict(mags=0.0, maa=0.0, points=0.0, cf=0.0)
     n_frames = 0
     u8_bad = 0

@@ -93,3 +93,33 @@ def test_tiny_blocks(emu_lib, ref):
     parity.check_channels(out)
     out, _, _ = parity.run_channels(emu_lib, ref, 2400000, [FIVE[0], FIVE[1]], n_blocks=150, block=33, want_iq=False)
     parity.check_channels(out)
+
+
+def test_rate_and_bandwidth_sweep(emu_lib, ref):
+    """Audio rates other than 48 kHz (decimating and interpolating audio resamplers), wideband rates with zero to a few
+    half-band stages, bandwidths that are not the modems' defaults, and the exact edge of the 0.75 fs skip rule."""
+    three = [("FM", 200000, 300000), ("AM", 6000, -450000), ("USB", 5400, 600000)]
+    for ar in (44100, 96000, 8000):
+        out, _, _ = parity.run_channels(emu_lib, ref, 2400000, three, n_blocks=3, audio_rate=ar, want_iq=False)
+        parity.check_channels(out)
+    out, _, _ = parity.run_channels(emu_lib, ref, 250000, [("FM", 200000, 0), ("AM", 6000, 50000), ("NBFM", 12500, -60000)],
+                                    n_blocks=4, block=20000)
+    parity.check_channels(out)
+    out, _, _ = parity.run_channels(emu_lib, ref, 1000000, [("FM", 200000, 100000), ("LSB", 5400, -250000)], n_blocks=3)
+    parity.check_channels(out)
+    odd = [("FM", 150000, 300000), ("FM", 31000, -450000), ("AM", 10000, 600000), ("USB", 2700, -100000), ("NBFM", 25000, 40000)]
+    out, _, _ = parity.run_channels(emu_lib, ref, 2400000, odd, n_blocks=3)
+    parity.check_channels(out)
+    lim = int((2400000 / 2) * 1.5)
+    out, _, _ = parity.run_channels(emu_lib, ref, 2400000, [("AM", 6000, lim), ("AM", 6000, lim + 1), ("AM", 6000, -lim)], n_blocks=2,
+                                    signal=[("AM", 6000, 300000)], want_iq=False)
+    parity.check_channels(out)
+    assert out[0]["skipped"] == [False, False] and out[1]["skipped"] == [True, True] and out[2]["skipped"] == [False, False]
+
+
+def test_spectrum_average_rates(emu_lib, ref):
+    """setFFTAverageRate: a slow average (0.2) and no averaging at all (1.0, what the waterfall thread uses)."""
+    chans = synth.channel_plan("mixed", 2400000, 8)
+    for r in (0.2, 1.0):
+        w = parity.run_spectrum(emu_lib, ref, 2400000, 512, n_blocks=2, chans=chans, avg_rate=r)
+        assert w["frames"] > 50 and w["mags"] <= parity.TOL and w["maa"] <= parity.TOL and w["points"] <= parity.TOL, (r, w)
