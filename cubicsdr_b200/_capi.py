@@ -23,6 +23,7 @@ SYMBOLS = [
     "sdr_modem_check_sample_rate", "sdr_modem_create", "sdr_modem_demodulate",
     "sdr_spectrum_create", "sdr_spectrum_destroy", "sdr_spectrum_set_average_rate", "sdr_spectrum_frames",
     "sdr_spectrum_fetch", "sdr_spectrum_fetch_all", "sdr_spectrum_fetch_debug",
+    "sdr_pfb_optimal_channel_count", "sdr_pfb_create", "sdr_pfb_destroy", "sdr_pfb_reset", "sdr_pfb_execute", "sdr_pfb_execute_device",
     "sdr_design_kaiser", "sdr_design_nco_table", "sdr_design_nco_step", "sdr_design_resampler",
     "sdr_design_halfband_branch", "sdr_design_am_dc_block", "sdr_design_hilbert_q", "sdr_design_butter6_sos",
 ]
@@ -73,6 +74,12 @@ class Lib:
         L.sdr_spectrum_frames.argtypes = [vp, P(u)]
         L.sdr_spectrum_fetch.argtypes = [vp, u, vp, vp, vp]
         L.sdr_spectrum_fetch_debug.argtypes = [vp, u, vp, vp]
+        L.sdr_pfb_optimal_channel_count.argtypes = [C.c_longlong]
+        L.sdr_pfb_create.argtypes = [vp, u, u, C.c_float, u, C.POINTER(vp)]
+        L.sdr_pfb_destroy.argtypes = [vp]
+        L.sdr_pfb_reset.argtypes = [vp]
+        L.sdr_pfb_execute.argtypes = [vp, vp, u, vp]
+        L.sdr_pfb_execute_device.argtypes = [vp, vp, u, vp]
         L.sdr_spectrum_fetch_all.argtypes = [vp, u, vp, vp, vp, P(u)]
         L.sdr_design_kaiser.argtypes = [u, f, f, f, vp]
         L.sdr_design_nco_table.argtypes = [vp]
@@ -262,3 +269,38 @@ class Spectrum:
         if self.h:
             self.lib.L.sdr_spectrum_destroy(self.h)
             self.h = None
+
+
+class Channelizer:
+    """sdr_pfb: SDRPostThread::initPFBCH / runPFBCH -- firpfbch_crcf_create_kaiser(LIQUID_ANALYZER, M, 4, 60) + one
+    analyzer_execute per M input samples (src/sdr/SDRPostThread.cpp:401-455)."""
+
+    def __init__(self, engine, num_channels, max_frames, m=4, as_db=60.0):
+        self.engine, self.lib = engine, engine.lib
+        self.M, self.max_frames = int(num_channels), int(max_frames)
+        h = C.c_void_p()
+        self.lib.check(self.lib.L.sdr_pfb_create(engine.h, self.M, int(m), C.c_float(as_db), self.max_frames, C.byref(h)))
+        self.h = h
+
+    @staticmethod
+    def optimal_channel_count(lib, sample_rate):
+        return int(lib.L.sdr_pfb_optimal_channel_count(int(sample_rate)))
+
+    def execute(self, x):
+        """x: complex64[n], n a multiple of M -> complex64[n / M, M] (one row per input frame, M channel samples)."""
+        x = np.ascontiguousarray(x, np.complex64)
+        y = np.zeros(x.size, np.complex64)
+        self.lib.check(self.lib.L.sdr_pfb_execute(self.h, _ptr(x), x.size, _ptr(y)))
+        return y.reshape(-1, self.M)
+
+    def execute_device(self, d_in, n, d_out):
+        self.lib.check(self.lib.L.sdr_pfb_execute_device(self.h, C.c_void_p(d_in), int(n), C.c_void_p(d_out)))
+
+    def reset(self):
+        self.lib.check(self.lib.L.sdr_pfb_reset(self.h))
+
+    def close(self):
+        if self.h:
+            self.lib.L.sdr_pfb_destroy(self.h)
+            self.h = None
+

@@ -230,4 +230,28 @@ void butterworth_lowpass_sos(unsigned order, float fc, std::vector<Sos> &sos) {
     }
 }
 
+
+void pfb_analysis_tables(unsigned M, unsigned m, float as_db, std::vector<float> &hq, std::vector<float> &tw_re_im) {
+    const unsigned p = 2 * m, h_len = 2 * M * m + 1;
+    std::vector<float> h(h_len);
+    kaiser_lowpass(h_len, 0.5f / (float)M, as_db, 0.0f, h.data());
+    hq.assign((size_t)M * p, 0.f);
+    for (unsigned c = 0; c < M; ++c)
+        for (unsigned q = 0; q < p; ++q) hq[(size_t)c * p + q] = h[(M - 1 - c) + q * M];
+    tw_re_im.assign((size_t)2 * M, 0.f);
+    for (unsigned n = 0; n < M; ++n) {
+        const double ph = -2.0 * 3.14159265358979323846 * (double)n / (double)M;
+        tw_re_im[2 * n] = (float)cos(ph);
+        tw_re_im[2 * n + 1] = (float)sin(ph);
+    }
+}
+
+int optimal_channel_count(long long sample_rate) {
+    if (sample_rate <= 500000) return 1;
+    int count = (int)ceil((double)sample_rate / 500000.0);
+    if (count % 2 == 1) count--;
+    if (count < 2) count = 2;
+    return count;
+}
+
 }  // namespace sdrb200

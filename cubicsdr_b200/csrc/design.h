@@ -14,6 +14,11 @@ namespace sdrb200 {
 float kaiser_beta_for_atten(float as_db);                       // Vaidyanathan fit, used by every Kaiser design below
 unsigned filter_len_estimate(float df, float as_db);            // (As-7.95)/(14.26 df), truncated
 void kaiser_lowpass(unsigned n, float fc, float as_db, float mu, float *h);   // sinc(2 fc t) * kaiser, centre tap 1
+// firpfbch_crcf_create_kaiser(LIQUID_ANALYZER, M, m, As): branch filters of the analysis channelizer and its DFT twiddles.
+// hq[c * 2m + q] = h[(M - 1 - c) + q M] with h = kaiser_lowpass(2 M m + 1, 0.5 / M, As, 0);  tw[n] = exp(-j 2 pi n / M)
+void pfb_analysis_tables(unsigned M, unsigned m, float as_db, std::vector<float> &hq, std::vector<float> &tw_re_im);
+// SDRThread::getOptimalChannelCount (src/sdr/SoapySDRThread.cpp:676-693), CHANNELIZER_RATE_MAX = 500000
+int optimal_channel_count(long long sample_rate);
 
 // 1024-entry sine table of the table-driven oscillator (nco_crcf: DemodulatorPreThread.cpp:22, ModemUSB.cpp:9)
 void nco_sine_table(float *tab1024);

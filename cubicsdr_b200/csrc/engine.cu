@@ -17,6 +17,7 @@
 #include "design.h"
 #include "dsp_core.h"
 #include "dsp_spec.h"
+#include "dsp_pfb.h"
 #include "dsp_tail.h"
 
 using namespace sdrb200;
@@ -253,6 +254,13 @@ __global__ void k_spec_scalar(SpecArgs a) {
 }
 __global__ void __launch_bounds__(kSpecThreads) k_spec_points(SpecArgs a) {
     spec_points_thread(a, (long long)blockIdx.x * blockDim.x + threadIdx.x);
+}
+__global__ void __launch_bounds__(kPfbThreads) k_pfb_analyze(PfbArgs a) {
+    extern __shared__ float2 pfb_sm[];
+    for (int ph = 0; ph < 3; ++ph) {
+        pfb_phase(ph, a, blockIdx.x, threadIdx.x, blockDim.x, pfb_sm);
+        __syncthreads();
+    }
 }
 #endif
 
@@ -1689,6 +1697,122 @@ extern "C" int sdr_spectrum_fetch_debug(sdr_spectrum *s, unsigned idx, float *ma
     if (mags) memcpy(mags, s->h_dbg, s->N * sizeof(float));
     if (maa) memcpy(maa, s->h_dbg + s->N, s->N * sizeof(float));
     return SDR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// polyphase filterbank channelizer: SDRPostThread::initPFBCH / runPFBCH, SDRPostThread.cpp:401-455
+// ---------------------------------------------------------------------------------------------------------------------
+struct sdr_pfb {
+    sdr_engine *eng = nullptr;
+    unsigned M = 0, p = 0, max_frames = 0;
+    float *d_hq = nullptr; float2 *d_tw = nullptr;
+    float2 *d_x = nullptr;       // [(p-1) M history | max_frames M new]
+    float2 *d_y = nullptr;       // [max_frames M]
+    float2 *d_scr = nullptr;     // [(p-1) M] history slide scratch
+    float2 *h_io = nullptr;      // pinned staging, max_frames M
+};
+
+static void pfb_free(sdr_pfb *p) {
+    be_free(p->d_hq); be_free(p->d_tw); be_free(p->d_x); be_free(p->d_y); be_free(p->d_scr); be_host_free(p->h_io);
+}
+
+extern "C" int sdr_pfb_optimal_channel_count(long long sample_rate) { return optimal_channel_count(sample_rate); }
+
+extern "C" int sdr_pfb_create(sdr_engine *e, unsigned num_channels, unsigned m, float as_db, unsigned max_frames, sdr_pfb **out) {
+    if (!e || !out) return fail(SDR_ERR_ARG, "sdr_pfb_create: null argument");
+    if (num_channels < 2 || (num_channels & 1u) || num_channels > (unsigned)kPfbMaxChannels || m < 1 || m > 8 || max_frames < 1)
+        return fail(SDR_ERR_ARG, "sdr_pfb_create: num_channels must be even and in [2, 256], m in [1, 8]");
+    std::lock_guard<std::mutex> lk(e->mu);
+    auto *p = new sdr_pfb();
+    p->eng = e; p->M = num_channels; p->p = 2 * m; p->max_frames = max_frames;
+    std::vector<float> hq, tw;
+    pfb_analysis_tables(num_channels, m, as_db, hq, tw);
+    const size_t hist = (size_t)(p->p - 1) * p->M, cap = (size_t)max_frames * p->M;
+    int bad = 0;
+    bad |= be_malloc((void **)&p->d_hq, hq.size() * sizeof(float));
+    bad |= be_malloc((void **)&p->d_tw, tw.size() * sizeof(float));
+    bad |= be_malloc((void **)&p->d_x, (hist + cap) * sizeof(float2));
+    bad |= be_malloc((void **)&p->d_y, cap * sizeof(float2));
+    bad |= be_malloc((void **)&p->d_scr, hist * sizeof(float2));
+    bad |= be_host_alloc((void **)&p->h_io, cap * sizeof(float2));
+    if (bad) { pfb_free(p); delete p; return fail(SDR_ERR_NOMEM, "sdr_pfb_create: allocation failed"); }
+    be_h2d(p->d_hq, hq.data(), hq.size() * sizeof(float), e->stream);
+    be_h2d(p->d_tw, tw.data(), tw.size() * sizeof(float), e->stream);
+    be_memset(p->d_x, 0, hist * sizeof(float2), e->stream);      // firpfbch_crcf_reset: empty windows
+    be_sync(e->stream);
+    *out = p;
+    return SDR_OK;
+}
+
+extern "C" int sdr_pfb_destroy(sdr_pfb *p) {
+    if (!p) return SDR_OK;
+    { std::lock_guard<std::mutex> lk(p->eng->mu); be_sync(p->eng->stream); pfb_free(p); }
+    delete p;
+    return SDR_OK;
+}
+
+extern "C" int sdr_pfb_reset(sdr_pfb *p) {
+    if (!p) return fail(SDR_ERR_ARG, "null channelizer");
+    std::lock_guard<std::mutex> lk(p->eng->mu);
+    be_memset(p->d_x, 0, (size_t)(p->p - 1) * p->M * sizeof(float2), p->eng->stream);
+    be_sync(p->eng->stream);
+    return SDR_OK;
+}
+
+// device-resident form: d_in / d_out hold n = frames * M samples; history is carried inside the object
+static int pfb_run(sdr_pfb *p, const float2 *d_in, unsigned n, float2 *d_out) {
+    sdr_engine *e = p->eng;
+    const unsigned F = n / p->M;
+    const size_t hist = (size_t)(p->p - 1) * p->M;
+    float2 *xnew = p->d_x + hist;
+    be_d2d(xnew, d_in, (size_t)n * sizeof(float2), e->stream);
+    PfbArgs a;
+    a.x = xnew; a.y = d_out; a.hq = p->d_hq; a.tw = p->d_tw; a.M = (int)p->M; a.p = (int)p->p; a.F = (int)F;
+    const int tiles = ((int)F + kPfbTileFrames - 1) / kPfbTileFrames;
+#ifndef SDR_EMU
+    const size_t smem = pfb_smem_elems(a.M, a.p) * sizeof(float2);
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) { CUDA_TRY(cudaFuncSetAttribute(k_pfb_analyze, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; }
+    k_pfb_analyze<<<tiles, kPfbThreads, smem, e->stream>>>(a);
+#else
+    std::vector<float2> sm(pfb_smem_elems(a.M, a.p));
+    for (int t = 0; t < tiles; ++t)
+        for (int ph = 0; ph < 3; ++ph) for (int th = 0; th < kPfbThreads; ++th) pfb_phase(ph, a, t, th, kPfbThreads, sm.data());
+#endif
+    e->launches += 1;
+    // slide: the last p-1 frames of [history | new] become the history of the next call (through scratch: the ranges overlap
+    // when the call was shorter than the history)
+    be_d2d(p->d_scr, p->d_x + (size_t)n, hist * sizeof(float2), e->stream);
+    be_d2d(p->d_x, p->d_scr, hist * sizeof(float2), e->stream);
+    return SDR_OK;
+}
+
+extern "C" int sdr_pfb_execute(sdr_pfb *p, const sdr_cf32 *iq, unsigned n, sdr_cf32 *out) {
+    if (!p || !iq || !out) return fail(SDR_ERR_ARG, "sdr_pfb_execute: null argument");
+    if (n == 0 || n % p->M != 0 || n / p->M > p->max_frames)
+        return fail(SDR_ERR_ARG, "sdr_pfb_execute: n must be a non-zero multiple of num_channels within max_frames (SoapySDRThread.cpp:668-674)");
+    sdr_engine *e = p->eng;
+    std::lock_guard<std::mutex> lk(e->mu);
+    memcpy(p->h_io, iq, (size_t)n * sizeof(sdr_cf32));
+    be_h2d(p->d_y, p->h_io, (size_t)n * sizeof(float2), e->stream);          // d_y doubles as the input landing buffer
+    be_sync(e->stream);
+    // input must not alias the output: run from a private copy inside d_x (pfb_run copies d_in there first)
+    int r = pfb_run(p, p->d_y, n, p->d_y);
+    if (r) return r;
+    be_d2h(p->h_io, p->d_y, (size_t)n * sizeof(float2), e->stream);
+    if (be_sync(e->stream)) return fail(SDR_ERR_CUDA, std::string("sdr_pfb_execute: ") + be_last_error());
+#ifndef SDR_EMU
+    { cudaError_t err = cudaGetLastError(); if (err != cudaSuccess) return fail(SDR_ERR_CUDA, std::string("sdr_pfb_execute: ") + cudaGetErrorString(err)); }
+#endif
+    memcpy(out, p->h_io, (size_t)n * sizeof(sdr_cf32));
+    return SDR_OK;
+}
+
+extern "C" int sdr_pfb_execute_device(sdr_pfb *p, const void *d_iq, unsigned n, void *d_out) {
+    if (!p || !d_iq || !d_out) return fail(SDR_ERR_ARG, "sdr_pfb_execute_device: null argument");
+    if (n == 0 || n % p->M != 0 || n / p->M > p->max_frames) return fail(SDR_ERR_ARG, "sdr_pfb_execute_device: bad length");
+    std::lock_guard<std::mutex> lk(p->eng->mu);
+    return pfb_run(p, (const float2 *)d_iq, n, (float2 *)d_out);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -122,6 +122,19 @@ int sdr_spectrum_fetch_all(sdr_spectrum *sp, unsigned cap_frames, float *points_
 /* diagnostics for parity tests: linear fftshifted magnitudes and float(maa) of frame idx (2 * fft_size floats each) */
 int sdr_spectrum_fetch_debug(sdr_spectrum *sp, unsigned idx, float *mags, float *maa);
 
+/* ---- polyphase filterbank channelizer -----------------------------------------------------------
+ * Replaces firpfbch_crcf_create_kaiser(LIQUID_ANALYZER, numChannels, 4, 60) (src/sdr/SDRPostThread.cpp:406) and the
+ * per-numChannels-samples firpfbch_crcf_analyzer_execute loop of SDRPostThread::runPFBCH (:447-451).  Output layout is
+ * liquid's: numChannels interleaved channel samples per input frame, which runDemodChannels de-interleaves (:366-382).
+ * n must be a multiple of num_channels (SDRThread::getOptimalElementCount, src/sdr/SoapySDRThread.cpp:668-674). */
+typedef struct sdr_pfb sdr_pfb;
+int sdr_pfb_optimal_channel_count(long long sample_rate);     /* SDRThread::getOptimalChannelCount, SoapySDRThread.cpp:676-693 */
+int sdr_pfb_create(sdr_engine *eng, unsigned num_channels, unsigned m, float as_db, unsigned max_frames, sdr_pfb **out);
+int sdr_pfb_destroy(sdr_pfb *pfb);
+int sdr_pfb_reset(sdr_pfb *pfb);                                /* firpfbch_crcf_reset */
+int sdr_pfb_execute(sdr_pfb *pfb, const sdr_cf32 *iq, unsigned n, sdr_cf32 *out);              /* host buffers */
+int sdr_pfb_execute_device(sdr_pfb *pfb, const void *d_iq, unsigned n, void *d_out);           /* device buffers, engine stream */
+
 /* ---- design introspection (host only; used by the tests to pin filter tables against the reference) ---------------- */
 int sdr_design_kaiser(unsigned n, float fc, float as_db, float mu, float *h);
 int sdr_design_nco_table(float *sintab1024);

@@ -94,7 +94,15 @@ LQ fftplan fft_create_plan(unsigned int n, lq_cf *x, lq_cf *y, int dir, int flag
 LQ int fft_destroy_plan(fftplan p);
 LQ int fft_execute(fftplan p);
 
+/* polyphase filterbank channelizer (SDRPostThread.cpp:401-455: firpfbch_crcf analyzer; LIQUID_ANALYZER = 0) */
+typedef struct firpfbch_crcf_s *firpfbch_crcf;
+LQ firpfbch_crcf firpfbch_crcf_create_kaiser(int type, unsigned int M, unsigned int m, float As);
+LQ int firpfbch_crcf_destroy(firpfbch_crcf q);
+LQ int firpfbch_crcf_reset(firpfbch_crcf q);
+LQ int firpfbch_crcf_analyzer_execute(firpfbch_crcf q, lq_cf *x, lq_cf *y);
+
 #ifdef __cplusplus
 }
 #endif
+
 #endif

@@ -104,6 +104,33 @@ API void ref_ingress_block(void *h, lq_cf *in, unsigned n, lq_cf *out) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// SDRPostThread::runPFBCH channelizer       src/sdr/SDRPostThread.cpp:401-455
+//   initPFBCH :401-414  firpfbch_crcf_create_kaiser(LIQUID_ANALYZER, numChannels, 4, 60)
+//   runPFBCH  :447-451  one analyzer_execute per numChannels input samples -> numChannels interleaved outputs
+// ---------------------------------------------------------------------------------------------------------
+struct RefPfb { firpfbch_crcf q; unsigned M; };
+API void *ref_pfb_create(unsigned num_channels, unsigned m, float as_db) {
+    auto *p = new RefPfb; p->M = num_channels;
+    p->q = firpfbch_crcf_create_kaiser(0 /* LIQUID_ANALYZER */, num_channels, m, as_db);
+    return p;
+}
+API void ref_pfb_destroy(void *h) { auto *p = (RefPfb *)h; firpfbch_crcf_destroy(p->q); delete p; }
+// n must be a multiple of num_channels (SDRThread::getOptimalElementCount guarantees it, SoapySDRThread.cpp:668-674)
+API void ref_pfb_execute(void *h, lq_cf *in, unsigned n, lq_cf *out) {
+    auto *p = (RefPfb *)h;
+    for (unsigned i = 0; i + p->M <= n; i += p->M) firpfbch_crcf_analyzer_execute(p->q, in + i, out + i);
+}
+// SDRThread::getOptimalChannelCount          src/sdr/SoapySDRThread.cpp:676-693  (CHANNELIZER_RATE_MAX = 500000, CubicSDRDefs.h:63)
+API int ref_optimal_channel_count(long long sampleRate_in) {
+    if (sampleRate_in <= 500000) return 1;
+    int optimal_rate = 500000;
+    int optimal_count = int(ceil(double(sampleRate_in) / double(optimal_rate)));
+    if (optimal_count % 2 == 1) optimal_count--;
+    if (optimal_count < 2) optimal_count = 2;
+    return optimal_count;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // one demodulator channel: DemodulatorPreThread + Modem + DemodulatorThread metering
 // ---------------------------------------------------------------------------------------------------------
 enum { M_FM = 0, M_NBFM = 1, M_AM = 2, M_USB = 3, M_LSB = 4 };

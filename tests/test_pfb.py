@@ -1,0 +1,67 @@
+"""Polyphase filterbank channelizer (SDRPostThread::runPFBCH) against the reference binary's
+firpfbch_crcf analyzer.  Emulator tier on CPU, the same checks on the device in the GPU tier."""
+import numpy as np
+import pytest
+
+from cubicsdr_b200 import Channelizer, Engine, synth
+from oracle.refbind import RefPfb
+from tests.parity import TOL, relrms
+
+
+def _stream(lib, ref, M, frames_per_call, seed=7, device=0):
+    """Several calls of different lengths through engine and oracle: state (2m - 1 frames of history) must carry."""
+    rng = np.random.default_rng(seed)
+    eng = Engine(lib, device=device, max_block=4096)
+    ch = Channelizer(eng, M, max(frames_per_call))
+    rp = RefPfb(ref, M)
+    worst = 0.0
+    for F in frames_per_call:
+        x = (rng.standard_normal(F * M) + 1j * rng.standard_normal(F * M)).astype(np.complex64)
+        x += np.exp(2j * np.pi * 0.123 * np.arange(F * M)).astype(np.complex64) * 3           # a strong tone: one hot channel
+        got, want = ch.execute(x), rp.execute(x)
+        assert got.shape == want.shape == (F, M)
+        worst = max(worst, relrms(got, want))
+    ch.close(); rp.close(); eng.close()
+    return worst
+
+
+CASES = [(2, [5, 1, 9, 40]), (8, [3, 16, 1, 1, 33]), (40, [7, 2, 50]), (122, [20, 3, 41])]
+
+
+@pytest.mark.parametrize("M,calls", CASES)
+def test_channelizer_matches_reference_binary_emulator(emu_lib, ref, M, calls):
+    assert _stream(emu_lib, ref, M, calls) <= TOL
+
+
+def test_optimal_channel_count_rule(emu_lib, ref):
+    """SDRThread::getOptimalChannelCount and the block-size rule that makes every block a whole number of frames."""
+    ref.L.ref_optimal_channel_count.argtypes = [__import__("ctypes").c_longlong]
+    for fs in (250000, 500000, 500001, 1000000, 2400000, 10000000, 20000000, 30720000, 40000000, 61440000):
+        want = ref.L.ref_optimal_channel_count(fs)
+        assert Channelizer.optimal_channel_count(emu_lib, fs) == want
+        if want > 1:
+            assert synth.block_size(fs) % want == 0
+    assert Channelizer.optimal_channel_count(emu_lib, 61440000) == 122
+
+
+def test_reset_and_bad_lengths(emu_lib, ref):
+    from cubicsdr_b200 import SdrError
+    eng = Engine(emu_lib, max_block=4096)
+    ch = Channelizer(eng, 8, 16)
+    x = (np.arange(64) + 1j).astype(np.complex64)
+    a = ch.execute(x)
+    ch.reset()
+    assert np.array_equal(ch.execute(x), a)                      # reset = empty windows again
+    with pytest.raises(SdrError):
+        ch.execute(x[:63])                                         # not a whole number of frames
+    with pytest.raises(SdrError):
+        ch.execute(np.zeros(8 * 17, np.complex64))                 # more frames than the object was sized for
+    with pytest.raises(SdrError):
+        Channelizer(eng, 7, 16)                                    # the reference only ever makes even counts
+    ch.close(); eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,calls", CASES + [(122, [8394])])
+def test_channelizer_matches_reference_binary_gpu(gpu_lib, ref, M, calls):
+    assert _stream(gpu_lib, ref, M, calls) <= TOL
