@@ -38,6 +38,9 @@ WORKLOADS = {
                  desc="cfg5: 512 mixed FM/AM/USB/LSB demod channels + 16384-pt spectrum/waterfall on 61.44 MSps IQ"),
     "cfg3": dict(fs=20000000, plan="nbfm64", n_chan=64, fft=0, desc="cfg3: 64 NBFM channels @12.5 kHz from 20 MSps IQ"),
     "cfg2": dict(fs=10000000, plan="mixed", n_chan=0, fft=8192, desc="cfg2: 8192-pt spectrum FFT + waterfall on 10 MSps IQ"),
+    # SURVEY.md 8(f) row 1 (not a BASELINE config): the reference's channelizer for rates above 500 kSps, on its own
+    "pfb": dict(fs=61440000, plan="mixed", n_chan=0, fft=0,
+                desc="pfb: firpfbch analysis channelizer (SDRPostThread::runPFBCH), 122 channels on 61.44 MSps IQ"),
 }
 FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12    # non-tensor FP32 issue peak of a B200 at max clock
 
@@ -166,6 +169,76 @@ def run_reference(args, wl, chans, rank):
     emit(line)
 
 
+def run_pfb(args, wl):
+    """--workload pfb: the polyphase analysis channelizer alone, device-resident and through host
+    buffers, next to the reference binary's firpfbch_crcf on one host core (the reference runs it on one thread)."""
+    import ctypes as C
+    import torch
+    import cubicsdr_b200
+    from cubicsdr_b200 import Channelizer, Engine, synth
+    fs = wl["fs"]
+    N = synth.block_size(fs)
+    lib = cubicsdr_b200.lib()
+    M = Channelizer.optimal_channel_count(lib, fs)
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    eng = Engine(lib, device=0, max_block=N, stream=stream.cuda_stream)
+    ch = Channelizer(eng, M, N // M)
+    carriers = synth.channel_plan("mixed", fs, 16)
+    ring = [torch_wideband(torch, fs, N, carriers, r * N, dev, 1) for r in range(args.ring)]
+    outs = [torch.empty(N, dtype=torch.complex64, device=dev) for _ in range(2)]
+    sampler = ClockSampler(0)
+    sampler.start()
+    for i in range(max(args.warmup, 3) + 200):
+        ch.execute_device(ring[i % args.ring].data_ptr(), N, outs[i & 1].data_ptr())
+    torch.cuda.synchronize()
+    launches0 = eng.launch_count
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        ch.execute_device(ring[i % args.ring].data_ptr(), N, outs[i & 1].data_ptr())
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count - launches0
+    value = N * args.steps / (ms * 1e-3) / 1e6
+    host_in = ring[0].cpu().numpy()
+    for _ in range(3):
+        ch.execute(host_in)
+    t0 = time.perf_counter()
+    for _ in range(max(1, args.steps // 10)):
+        out_host = ch.execute(host_in)
+    t_e2e = (time.perf_counter() - t0) / max(1, args.steps // 10)
+    clocks = sampler.stop()
+    peak, peak_src = measured_peaks()
+    achieved = 16.0 * N / (ms / args.steps * 1e-3) / 1e9
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle.refbind import Ref, RefPfb
+        rp = RefPfb(Ref(), M)
+        rp.execute(host_in)
+        t0 = time.perf_counter(); rp.execute(host_in); secs = time.perf_counter() - t0
+        cpu = {"value": N / secs / 1e6, "unit": "MSamples/s", "cores": 1, "kind": "reference",
+               "sample": "1 block (%d samples) after 1 untimed block, reference liquid-dsp firpfbch_crcf analyzer, one thread as in SDRPostThread" % N}
+    line = {"metric": "IQ MSamples/s through the analysis channelizer", "value": value, "unit": "MSamples/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "fs": fs, "block": N, "pfb_channels": M,
+                       "l2": "%d distinct %.1f MB input blocks rotate" % (args.ring, N * 8 / 1e6)},
+            "clocks": clocks,
+            "e2e": {"value": N / t_e2e / 1e6, "unit": "MSamples/s", "h2d_bytes_per_step": N * 8, "d2h_bytes_per_step": N * 8,
+                    "note": "blocking sdr_pfb_execute with pageable host arrays (staging memcpy + H2D + kernel + D2H + memcpy)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_pfb_analyze", "achieved": achieved, "peak": peak, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "alg_bytes_per_sample": 16.0,
+                         "kernel_ms_per_block": ms / args.steps},
+            "cpu_baseline": cpu}
+    ch.close(); eng.close()
+    emit(line)
+
+
 # The contract is ONE JSON line on stdout.  Libraries underneath (NCCL's version banner, for one) also write to fd 1, so
 # the real stdout is kept aside and fd 1 is pointed at stderr for the duration of the run.
 _REAL_STDOUT = None
@@ -208,6 +281,10 @@ def main():
         wl = dict(wl, n_chan=args.channels, desc=wl["desc"] + " [DIAGNOSTIC: %d channels]" % args.channels)
     chans = synth.channel_plan(wl["plan"], fs, wl["n_chan"]) if wl["n_chan"] else []
 
+    if args.workload == "pfb":
+        if rank == 0 and args.impl != "reference":
+            run_pfb(args, wl)
+        return
     if args.impl == "reference":
         run_reference(args, wl, chans, rank)
         return
