@@ -11,9 +11,11 @@
 //
 // GPU form: a CTA owns a tile of kPfbTileFrames frames.  Phase 0 stages the tile's input (plus 2m-1 frames of history)
 // in shared memory with coalesced loads; phase 1 runs the branch filters (one thread per (frame, branch), 2m multiply-adds
-// from shared memory); phase 2 evaluates the M-point DFT of every frame directly from a shared twiddle table (M is even
-// but rarely a power of two -- 122 at 61.44 MSps -- and M^2 work per frame is small next to the per-channel demodulators).
-// HBM traffic: 8 B in + 8 B out per sample.
+// from shared memory); phase 2 is one radix-2 decimation-in-frequency step (M is always even: getOptimalChannelCount),
+//     A[c] = X[c] + X[c + M/2],   B[c] = (X[c] - X[c + M/2]) exp(-j 2 pi c / M),      y[2r] = DFT_{M/2}(A)[r],  y[2r+1] = DFT_{M/2}(B)[r]
+// and phase 3 evaluates the two M/2-point DFTs directly from the shared twiddle table, four frames per thread so that every
+// twiddle fetched is used four times (M/2 is 61 at 61.44 MSps: prime, so no further cheap split; M^2/2 multiply-adds per
+// frame are small next to the per-channel demodulators).  HBM traffic: 8 B in + 8 B out per sample.
 #pragma once
 #include "dsp_core.h"
 
@@ -57,21 +59,47 @@ SDR_HD inline void pfb_phase(int ph, const PfbArgs &a, int tile, int tid, int nt
             for (int q = 0; q < p; ++q) acc = cf_fma(sdr_ldg(h + q), xc[-(long long)q * M], acc);
             su[o] = acc;
         }
+    } else if (ph == 2) {
+        const int H = M >> 1;
+        for (int o = tid; o < T * H; o += nt) {
+            const int fl = o / H, c = o - fl * H;
+            float2 *u = su + (size_t)fl * M;
+            const float2 x0 = u[c], x1 = u[c + H], w = stw[c];
+            const float dr = x0.x - x1.x, di = x0.y - x1.y;
+            u[c] = make_float2(x0.x + x1.x, x0.y + x1.y);
+            u[c + H] = make_float2(dr * w.x - di * w.y, dr * w.y + di * w.x);
+        }
     } else {
-        for (int o = tid; o < T * M; o += nt) {
-            const int fl = o / M, k = o - fl * M;
-            const float2 *u = su + (size_t)fl * M;
-            float re = 0.f, im = 0.f;
-            int idx = 0;                                                    // (c * k) mod M, kept incrementally
-            for (int c = 0; c < M; ++c) {
-                const float2 w = stw[idx], v = u[c];
-                re = fmaf(v.x, w.x, re); re = fmaf(-v.y, w.y, re);
-                im = fmaf(v.x, w.y, im); im = fmaf(v.y, w.x, im);
-                idx += k; if (idx >= M) idx -= M;
+        const int H = M >> 1;
+        const int groups = (T + 3) >> 2;                                    // four frames per work item
+        for (int o = tid; o < groups * M; o += nt) {
+            const int g = o / M, k = o - g * M;
+            const int r = k >> 1;
+            const int fl0 = g * 4;
+            const float2 *u0 = su + (size_t)fl0 * M + ((k & 1) ? H : 0);
+            const bool v1 = fl0 + 1 < T, v2 = fl0 + 2 < T, v3 = fl0 + 3 < T;
+            const float2 *u1 = v1 ? u0 + M : u0, *u2 = v2 ? u0 + 2 * M : u0, *u3 = v3 ? u0 + 3 * M : u0;
+            float re0 = 0.f, im0 = 0.f, re1 = 0.f, im1 = 0.f, re2 = 0.f, im2 = 0.f, re3 = 0.f, im3 = 0.f;
+            int idx = 0;                                                    // (2 c r) mod M, kept incrementally
+            const int step = 2 * r;                                         // < M
+            for (int c = 0; c < H; ++c) {
+                const float2 w = stw[idx];
+                const float2 a0 = u0[c], a1 = u1[c], a2 = u2[c], a3 = u3[c];
+                re0 = fmaf(a0.x, w.x, re0); re0 = fmaf(-a0.y, w.y, re0); im0 = fmaf(a0.x, w.y, im0); im0 = fmaf(a0.y, w.x, im0);
+                re1 = fmaf(a1.x, w.x, re1); re1 = fmaf(-a1.y, w.y, re1); im1 = fmaf(a1.x, w.y, im1); im1 = fmaf(a1.y, w.x, im1);
+                re2 = fmaf(a2.x, w.x, re2); re2 = fmaf(-a2.y, w.y, re2); im2 = fmaf(a2.x, w.y, im2); im2 = fmaf(a2.y, w.x, im2);
+                re3 = fmaf(a3.x, w.x, re3); re3 = fmaf(-a3.y, w.y, re3); im3 = fmaf(a3.x, w.y, im3); im3 = fmaf(a3.y, w.x, im3);
+                idx += step; if (idx >= M) idx -= M;
             }
-            a.y[(size_t)(f0 + fl) * M + k] = make_float2(re, im);
+            float2 *y = a.y + (size_t)(f0 + fl0) * M + k;
+            y[0] = make_float2(re0, im0);
+            if (v1) y[M] = make_float2(re1, im1);
+            if (v2) y[2 * M] = make_float2(re2, im2);
+            if (v3) y[3 * M] = make_float2(re3, im3);
         }
     }
 }
+
+constexpr int kPfbPhases = 4;
 
 }  // namespace sdrb200

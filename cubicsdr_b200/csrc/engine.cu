@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(kSpecThreads) k_spec_points(SpecArgs a) {
 }
 __global__ void __launch_bounds__(kPfbThreads) k_pfb_analyze(PfbArgs a) {
     extern __shared__ float2 pfb_sm[];
-    for (int ph = 0; ph < 3; ++ph) {
+    for (int ph = 0; ph < kPfbPhases; ++ph) {
         pfb_phase(ph, a, blockIdx.x, threadIdx.x, blockDim.x, pfb_sm);
         __syncthreads();
     }
@@ -1777,7 +1777,7 @@ static int pfb_run(sdr_pfb *p, const float2 *d_in, unsigned n, float2 *d_out) {
 #else
     std::vector<float2> sm(pfb_smem_elems(a.M, a.p));
     for (int t = 0; t < tiles; ++t)
-        for (int ph = 0; ph < 3; ++ph) for (int th = 0; th < kPfbThreads; ++th) pfb_phase(ph, a, t, th, kPfbThreads, sm.data());
+        for (int ph = 0; ph < kPfbPhases; ++ph) for (int th = 0; th < kPfbThreads; ++th) pfb_phase(ph, a, t, th, kPfbThreads, sm.data());
 #endif
     e->launches += 1;
     // slide: the last p-1 frames of [history | new] become the history of the next call (through scratch: the ranges overlap
