@@ -374,6 +374,8 @@ struct ChanDyn {                  // written by the host for every block
     int pad0;
     const float2 *hist;           // non-null: history for samples i < 0 is hist[i] (the channel skipped the previous block(s),
                                   // so its delay lines must see the tail of the last block it DID consume)
+    const float2 *xin;            // non-null: this channel's own input stream (channelizer mode: the samples of its filterbank
+                                  // channel, xin[0] = first sample of the block, history at negative indices) instead of FrontArgs::x
 };
 
 struct ChanState {                // device-resident, advanced by the tail kernel
@@ -528,7 +530,8 @@ SDR_HD inline void front_span(const FrontArgs &a, int ch, int span_idx, bool sto
     if (span_idx == a.n_span - 1 || q_hi > qb) q_hi = qb;
     if (q_lo >= q_hi) return;
     float2 *out = reinterpret_cast<float2 *>(cs.arena + (cd.lvl0_sel ? cs.lvl0_alt_off : cs.lvl_off[0])) + kHist;
-    const float2 *hx = cd.hist ? cd.hist : a.x;
+    const float2 *xb = cd.xin ? cd.xin : a.x;             // the block this channel reads: the shared wideband block, or its own stream
+    const float2 *hx = cd.hist ? cd.hist : xb;
     // table oscillator: entry = (theta + 2^21) >> 22; mixing down conjugates (sign on the sine); no mixing = constant
     // entry 0 = (1, 0).  The *_prev values describe the block whose tail forms the history in front of this one.
     // the conjugation is a sign flip of the sine: done as an integer XOR (bit-identical to multiplying by -1.0f, and it
@@ -542,7 +545,7 @@ SDR_HD inline void front_span(const FrontArgs &a, int ch, int span_idx, bool sto
         for (long long q = q_lo; q < q_hi; ++q) {
             const int i = (int)(q - g0);
             const float2 w = tabf.get(thb + (unsigned)i * dth);
-            if (store) out[q - qa] = cf_rot(sdr_ldg(a.x + i), w.x, flip_sign(w.y, sg));
+            if (store) out[q - qa] = cf_rot(sdr_ldg(xb + i), w.x, flip_sign(w.y, sg));
         }
         return;
     }
@@ -560,7 +563,7 @@ SDR_HD inline void front_span(const FrontArgs &a, int ch, int span_idx, bool sto
         // block (i0 >= 0) or the history in front of it (i0 + M <= 0), and the channel already existed (gq >= 0)
         const bool in_block = i0 >= 0, in_hist = (i0 + M <= 0) && (i0 >= -kBlkHist);
         if ((in_block || in_hist) && gq >= 0) {
-            const float2 *src = (in_block ? a.x : hx) + i0;
+            const float2 *src = (in_block ? xb : hx) + i0;
             if (!prefetched) xs.prefetch(src);
             xs.commit(src);
             // the next super-step can be prefetched only if it is whole and comes from the same buffer
@@ -587,7 +590,7 @@ SDR_HD inline void front_span(const FrontArgs &a, int ch, int span_idx, bool sto
                 if (gq + t >= 0 && i >= -kBlkHist) {
                     if (i >= 0) {
                         const float2 w = tabf.get(thb + (unsigned)i * dth);
-                        u = cf_rot(sdr_ldg(a.x + i), w.x, flip_sign(w.y, sg));
+                        u = cf_rot(sdr_ldg(xb + i), w.x, flip_sign(w.y, sg));
                     } else {
                         const float2 w = tabf.get(thb_prev - (unsigned)(-i) * dth_prev);
                         u = cf_rot(sdr_ldg(hx + i), w.x, flip_sign(w.y, sg_prev));

@@ -205,7 +205,10 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 1) k_chan_front(FrontArgs a,
         if (!real) ci = a.cg - 1;                              // padding lanes shadow the last channel, without stores
         const int ch = a.group[ci];
         const long long g0 = a.cd[ch].g0;
-        const bool lock_step = __all_sync(0xffffffffu, g0 == __shfl_sync(0xffffffffu, g0, 0));
+        // warp-staged samples need every lane to read the same samples: same position in the same stream
+        const unsigned long long xin = (unsigned long long)a.cd[ch].xin;
+        const bool lock_step = __all_sync(0xffffffffu, g0 == __shfl_sync(0xffffffffu, g0, 0)) &&
+                               __all_sync(0xffffffffu, xin == __shfl_sync(0xffffffffu, xin, 0)) && xin == 0ull;
         TabRep16 tab;
         tab.base = reinterpret_cast<const char *>(front_sm);
         tab.lane_off = (unsigned)(lane & 15) * 8u;
