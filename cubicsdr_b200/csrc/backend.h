@@ -50,6 +50,10 @@ inline int be_h2d(void *d, const void *h, size_t n, sdr_stream_t) { memcpy(d, h,
 inline int be_d2h(void *h, const void *d, size_t n, sdr_stream_t) { memcpy(h, d, n); return 0; }
 inline int be_d2d(void *d, const void *s, size_t n, sdr_stream_t) { memmove(d, s, n); return 0; }
 inline int be_sync(sdr_stream_t) { return 0; }
+inline int be_d2d_2d(void *d, size_t dpitch, const void *s_, size_t spitch, size_t width, size_t height, sdr_stream_t) {
+    for (size_t r = 0; r < height; ++r) memmove((char *)d + r * dpitch, (const char *)s_ + r * spitch, width);
+    return 0;
+}
 inline const char *be_last_error() { return "emu"; }
 #else
 inline int be_malloc(void **p, size_t n) { return cudaMalloc(p, n ? n : 1) != cudaSuccess; }
@@ -61,6 +65,9 @@ inline int be_h2d(void *d, const void *h, size_t n, sdr_stream_t s) { return cud
 inline int be_d2h(void *h, const void *d, size_t n, sdr_stream_t s) { return cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s) != cudaSuccess; }
 inline int be_d2d(void *d, const void *s_, size_t n, sdr_stream_t s) { return cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, s) != cudaSuccess; }
 inline int be_sync(sdr_stream_t s) { return cudaStreamSynchronize(s) != cudaSuccess; }
+inline int be_d2d_2d(void *d, size_t dpitch, const void *s_, size_t spitch, size_t width, size_t height, sdr_stream_t s) {
+    return cudaMemcpy2DAsync(d, dpitch, s_, spitch, width, height, cudaMemcpyDeviceToDevice, s) != cudaSuccess;
+}
 inline const char *be_last_error() { return cudaGetErrorString(cudaGetLastError()); }
 #endif
 

@@ -31,6 +31,7 @@ struct PfbArgs {
     const float *hq;       // [M][p]: hq[c*p + q] = h[(M-1-c) + q*M]
     const float2 *tw;      // [M]: exp(-j 2 pi n / M)
     int M, p, F;
+    long long chan_stride; // 0: y is frame-major [F][M] (liquid's layout); else channel-major: y[k * chan_stride + f]
 };
 
 // shared memory layout (float2): sx[(T + p - 1) * M] | su[T * M] | stw[M]
@@ -91,15 +92,26 @@ SDR_HD inline void pfb_phase(int ph, const PfbArgs &a, int tile, int tid, int nt
                 re3 = fmaf(a3.x, w.x, re3); re3 = fmaf(-a3.y, w.y, re3); im3 = fmaf(a3.x, w.y, im3); im3 = fmaf(a3.y, w.x, im3);
                 idx += step; if (idx >= M) idx -= M;
             }
-            float2 *y = a.y + (size_t)(f0 + fl0) * M + k;
+            // frame-major: M apart; channel-major (engine channelizer mode): the four frames of a channel are adjacent
+            const long long fs = a.chan_stride ? 1 : M;
+            float2 *y = a.chan_stride ? a.y + (long long)k * a.chan_stride + (f0 + fl0) : a.y + (size_t)(f0 + fl0) * M + k;
             y[0] = make_float2(re0, im0);
-            if (v1) y[M] = make_float2(re1, im1);
-            if (v2) y[2 * M] = make_float2(re2, im2);
-            if (v3) y[3 * M] = make_float2(re3, im3);
+            if (v1) y[fs] = make_float2(re1, im1);
+            if (v2) y[2 * fs] = make_float2(re2, im2);
+            if (v3) y[3 * fs] = make_float2(re3, im3);
         }
     }
 }
 
 constexpr int kPfbPhases = 4;
+
+// Channel 0 of the filterbank sits on the tuner's centre frequency and gets the DC blocker in channelizer mode
+// (SDRPostThread::runDemodChannels, SDRPostThread.cpp:363-375): the same float recurrence as the wideband one, at the
+// channel rate, so short enough to run serially (n = block / M samples).
+SDR_HD inline void pfb_dc0_serial(const float2 *in, float2 *out, int n, float c, float2 *state) {
+    float2 v = state[0], y;
+    for (int i = 0; i < n; ++i) { dc_ref_step(c, in[i], v, y); out[i] = y; }
+    state[0] = v;
+}
 
 }  // namespace sdrb200

@@ -258,6 +258,21 @@ __global__ void k_spec_scalar(SpecArgs a) {
 __global__ void __launch_bounds__(kSpecThreads) k_spec_points(SpecArgs a) {
     spec_points_thread(a, (long long)blockIdx.x * blockDim.x + threadIdx.x);
 }
+// serial float recurrence; the warp stages 256 samples at a time in shared memory so that the chain never waits on HBM
+__global__ void __launch_bounds__(32) k_pfb_dc0(const float2 *in, float2 *out, int n, float c, float2 *state) {
+    __shared__ float2 si[256], so[256];
+    float2 v = state[0], y;
+    for (int base = 0; base < n; base += 256) {
+        const int m = n - base < 256 ? n - base : 256;
+        for (int i = threadIdx.x; i < m; i += 32) si[i] = in[base + i];
+        __syncwarp();
+        for (int i = 0; i < m; ++i) { dc_ref_step(c, si[i], v, y); if (threadIdx.x == 0) so[i] = y; }
+        __syncwarp();
+        for (int i = threadIdx.x; i < m; i += 32) out[base + i] = so[i];
+        __syncwarp();
+    }
+    if (threadIdx.x == 0) state[0] = v;
+}
 __global__ void __launch_bounds__(kPfbThreads) k_pfb_analyze(PfbArgs a) {
     extern __shared__ float2 pfb_sm[];
     for (int ph = 0; ph < kPfbPhases; ++ph) {
@@ -451,6 +466,7 @@ struct sdr_chan {
     unsigned char *h_slot = nullptr; // pinned result slot, standalone only
     float2 *d_priv_hist = nullptr;  // tail of the last consumed block, kept while the channel skips blocks
     bool priv_valid = false;
+    int pfb_slot_prev = -1;         // channelizer mode: stream slot this channel read in the last block it consumed
     // DemodulatorPreThread state
     long long frequency = 0;
     long long shift_frequency = 0;  // last applied shift (starts at 0 like the reference member)
@@ -494,6 +510,13 @@ struct sdr_engine {
     float2 *d_raw = nullptr, *d_scratch = nullptr;
     float2 *d_blkbuf[2] = {nullptr, nullptr};   // DC-blocked stream, double-buffered: [hist_cap | max_block] each
     float2 *d_rawbuf = nullptr;                 // raw stream [hist_cap | max_block] (the bit-exact DC replay warms up on history)
+    // channelizer mode (SDRPostThread::runPFBCH): filterbank tables for the current channel count, the channel streams
+    // [2 parities][M + 1 slots][kBlkHist history | frames] (slot M = DC-corrected channel 0) and the channel-0 DC state
+    int chan_mode = 0;                          // 0: runSingleCH for every rate; 1: runPFBCH when the rate gives more than one channel
+    int pfb_M = 0; float *d_pfb_hq = nullptr; float2 *d_pfb_tw = nullptr;
+    float2 *d_pfb_streams[2] = {nullptr, nullptr}; size_t pfb_stride = 0; size_t pfb_slots = 0;
+    float2 *d_pfb_dc_state = nullptr;
+    unsigned pfb_last_frames = 0; bool pfb_have_block = false;
     int parity = 0;                             // buffer holding the block submitted last
     bool exact_dc = true;                       // bit-exact replay of the reference's float DC blocker (SDR_B200_DC=scan disables)
     double2 *d_tile_carry2[2] = {nullptr, nullptr};
@@ -747,6 +770,7 @@ extern "C" int sdr_engine_destroy(sdr_engine *e) {
     be_sync(e->stream);
     for (auto *c : e->chans) if (c) { be_free(c->d_arena); be_free(c->d_priv_hist); be_host_free(c->h_dyn); be_host_free(c->h_slot); delete c; }
     for (auto *s : e->spectra) if (s) { spectrum_free(s); delete s; }
+    be_free(e->d_pfb_hq); be_free(e->d_pfb_tw); be_free(e->d_pfb_streams[0]); be_free(e->d_pfb_streams[1]); be_free(e->d_pfb_dc_state);
     be_free(e->d_raw); be_free(e->d_blkbuf[0]); be_free(e->d_blkbuf[1]); be_free(e->d_rawbuf); be_free(e->d_scratch); be_host_free(e->h_stage);
     be_free(e->d_tile_sum); be_free(e->d_tile_carry2[0]); be_free(e->d_tile_carry2[1]); be_free(e->d_dc_state);
     be_free(e->d_seg_in); be_free(e->d_seg_out); be_free(e->d_fstate); be_free(e->d_fixups); be_free(e->d_apow); be_free(e->d_nco);
@@ -1215,6 +1239,34 @@ static int rebuild(sdr_engine *e) {
 // ready: 0 = the block becomes ready when the engine's main stream reaches this point (conservative),
 //        1 = the block is ready now (resident data, or a host block that submit copies on the DC stream itself),
 //        2 = the block is ready when `ready_event` fires
+// channelizer mode: (re)build the filterbank tables and the channel-stream buffers when the channel count changes
+// (SDRPostThread::initPFBCH, SDRPostThread.cpp:401-414: a new count means a new channelizer, i.e. empty windows)
+static int pfb_prepare(sdr_engine *e, int M) {
+    if (e->pfb_M == M && e->d_pfb_streams[0]) return SDR_OK;
+    sync_all(e);
+    be_free(e->d_pfb_hq); be_free(e->d_pfb_tw); be_free(e->d_pfb_streams[0]); be_free(e->d_pfb_streams[1]); be_free(e->d_pfb_dc_state);
+    e->d_pfb_hq = nullptr; e->d_pfb_tw = nullptr; e->d_pfb_streams[0] = e->d_pfb_streams[1] = nullptr; e->d_pfb_dc_state = nullptr;
+    std::vector<float> hq, tw;
+    pfb_analysis_tables((unsigned)M, 4, 60.0f, hq, tw);                       // firpfbch_crcf_create_kaiser(LIQUID_ANALYZER, M, 4, 60)
+    e->pfb_slots = (size_t)M + 1;                                            // M channels + the DC-corrected copy of channel 0
+    e->pfb_stride = ((size_t)kBlkHist + e->max_block / (size_t)M + 8 + 1) & ~(size_t)1;
+    const size_t bytes = e->pfb_slots * e->pfb_stride * sizeof(float2);
+    int bad = 0;
+    bad |= be_malloc((void **)&e->d_pfb_hq, hq.size() * sizeof(float));
+    bad |= be_malloc((void **)&e->d_pfb_tw, tw.size() * sizeof(float));
+    for (int b = 0; b < 2; ++b) bad |= be_malloc((void **)&e->d_pfb_streams[b], bytes);
+    bad |= be_malloc((void **)&e->d_pfb_dc_state, sizeof(float2));
+    if (bad) return fail(SDR_ERR_NOMEM, "channelizer buffers");
+    be_h2d(e->d_pfb_hq, hq.data(), hq.size() * sizeof(float), e->stream);
+    be_h2d(e->d_pfb_tw, tw.data(), tw.size() * sizeof(float), e->stream);
+    for (int b = 0; b < 2; ++b) be_memset(e->d_pfb_streams[b], 0, bytes, e->stream);
+    be_memset(e->d_pfb_dc_state, 0, sizeof(float2), e->stream);
+    be_sync(e->stream);
+    e->pfb_M = M; e->pfb_have_block = false; e->pfb_last_frames = 0;
+    for (auto *c : e->chans) if (c) c->pfb_slot_prev = -1;
+    return SDR_OK;
+}
+
 static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_src, unsigned n, long long center, long long rate,
                          bool to_host, int ready, void *ready_event) {
     if (e->dirty) { int r = rebuild(e); if (r) return r; }
@@ -1227,6 +1279,20 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
 #endif
     ChanDyn *h_cd = e->h_cd + (size_t)slot * sdr_engine::kMaxChan;
     int *h_group = e->h_group + (size_t)slot * sdr_engine::kMaxChan;
+
+    // SDRPostThread::run dispatch (SDRPostThread.cpp:178-187): blocks that come with more than one channel go through the
+    // channelizer; the count is SDRThread::getOptimalChannelCount of the rate (SoapySDRThread.cpp:513,676-693)
+    const int pfb_M = (e->chan_mode == 1) ? optimal_channel_count(rate) : 1;
+    const bool pfb = pfb_M > 1;
+    if (pfb) {
+        if (pfb_M > kPfbMaxChannels) return fail(SDR_ERR_UNSUPPORTED, "channelizer mode: sample rate needs more channels than supported");
+        if (n % (unsigned)pfb_M) return fail(SDR_ERR_ARG, "channelizer mode: block length must be a multiple of the channel count (SoapySDRThread.cpp:668-674)");
+        if ((size_t)(2 * 4 - 1) * pfb_M > (size_t)kBlkHist) return fail(SDR_ERR_UNSUPPORTED, "channelizer history");
+        int r = pfb_prepare(e, pfb_M);
+        if (r) return r;
+    }
+    const unsigned n_ch = pfb ? n / (unsigned)pfb_M : n;          // samples every demodulator sees this block
+    const long long rate_ch = pfb ? rate / pfb_M : rate;          // chanBw = sampleRate / numChannels (SDRPostThread.cpp:408)
 
     // 1+2. DC blocker (SDRPostThread.cpp:284) on its own stream, so that it runs underneath the channel kernels of the
     //      previous block: raw history slide -> copy the block in -> double-precision scan -> bit-exact float replay
@@ -1243,42 +1309,49 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
     CUDA_TRY(cudaStreamWaitEvent(dcs, e->ev_consumed[p], 0));  // the kernels of two blocks ago are done with this buffer
     if (e->timing && e->time_pending < sdr_engine::kTimeSets) cudaEventRecord(e->tev_dc[e->time_pending][0], dcs);
 #endif
-    const size_t need_raw = std::min(e->hist_cap, (size_t)kDcWarm + 2 * kDcTile);
-    if (e->have_block && e->last_n > 0) {
-        be_d2d(e->d_scratch, raw + (long long)e->last_n - (long long)need_raw, need_raw * sizeof(float2), dcs);
-        be_d2d(raw - need_raw, e->d_scratch, need_raw * sizeof(float2), dcs);
-    }
-    if (h_src) be_h2d(raw, h_src, (size_t)n * sizeof(float2), dcs);   // host block: straight into the raw stream buffer
-    else be_d2d(raw, d_src, (size_t)n * sizeof(float2), dcs);
-    DcArgs dc;
-    dc.x = raw; dc.y = blk; dc.n = (int)n; dc.a = e->dc_a; dc.tile_sum = e->d_tile_sum; dc.tile_carry = e->d_tile_carry2[p];
-    dc.state = e->d_dc_state; dc.apow = e->d_apow;
-    launch_dc(dc, !e->exact_dc, dcs, e->launches);
-    if (e->exact_dc) {
-        DcExactArgs xa;
-        // few, long segments when the channel front kernel owns the SMs (the replay's warps must fit on the reserved
-        // ones); many short ones when the GPU is otherwise idle and only the replay's own latency matters
-        size_t live = 0;
-        for (auto *c : e->chans) live += c != nullptr;
-        const DcSplit split = dc_split_for(live);
-        const bool heavy = split.reserved_sms > 0;
-        unsigned seg = kDcSegLenLight;
-        if (heavy) {                                           // exactly as many segments as warp slots on the reserved SMs
-            const unsigned cap = (unsigned)(split.reserved_sms * split.warps_per_cta);
-            seg = (unsigned)((n + cap - 1) / cap);
-            seg = (seg + 63u) & ~63u;
-            if (seg < kDcSegLenLight) seg = kDcSegLenLight;
+    if (pfb) {
+        // channelizer mode has no wideband DC blocker (runPFBCH pushes the block as it came to the visual queues and to the
+        // filterbank, SDRPostThread.cpp:432-451): the block goes straight into the stream buffer
+        if (h_src) be_h2d(blk, h_src, (size_t)n * sizeof(float2), dcs);
+        else be_d2d(blk, d_src, (size_t)n * sizeof(float2), dcs);
+    } else {
+        const size_t need_raw = std::min(e->hist_cap, (size_t)kDcWarm + 2 * kDcTile);
+        if (e->have_block && e->last_n > 0) {
+            be_d2d(e->d_scratch, raw + (long long)e->last_n - (long long)need_raw, need_raw * sizeof(float2), dcs);
+            be_d2d(raw - need_raw, e->d_scratch, need_raw * sizeof(float2), dcs);
         }
-        xa.xraw = raw; xa.y = blk; xa.n = (int)n; xa.seg_len = (int)seg; xa.warm = kDcWarm;
-        xa.c = (float)e->dc_a;
-        xa.tile_carry = e->d_tile_carry2[p]; xa.prev_tile_carry = e->d_tile_carry2[p ^ 1];
-        xa.prev_n = e->have_block ? (int)e->last_n : 0;
-        xa.seg_in = e->d_seg_in; xa.seg_out = e->d_seg_out; xa.fstate = e->d_fstate; xa.fixups = e->d_fixups;
-        // speculate only when there is parallelism to gain and the warm-up region lies inside the data we hold
-        const bool spec = n >= 4u * seg && (!e->have_block || e->last_n >= (unsigned)(kDcWarm + kDcTile));
-        xa.n_seg = spec ? (int)((n + seg - 1) / seg) : 1;
-        if (!spec) xa.seg_len = (int)n;
-        launch_dc_exact(xa, (heavy && spec) ? split.warps_per_cta : 1, dcs, e->launches);
+        if (h_src) be_h2d(raw, h_src, (size_t)n * sizeof(float2), dcs);   // host block: straight into the raw stream buffer
+        else be_d2d(raw, d_src, (size_t)n * sizeof(float2), dcs);
+        DcArgs dc;
+        dc.x = raw; dc.y = blk; dc.n = (int)n; dc.a = e->dc_a; dc.tile_sum = e->d_tile_sum; dc.tile_carry = e->d_tile_carry2[p];
+        dc.state = e->d_dc_state; dc.apow = e->d_apow;
+        launch_dc(dc, !e->exact_dc, dcs, e->launches);
+        if (e->exact_dc) {
+            DcExactArgs xa;
+            // few, long segments when the channel front kernel owns the SMs (the replay's warps must fit on the reserved
+            // ones); many short ones when the GPU is otherwise idle and only the replay's own latency matters
+            size_t live = 0;
+            for (auto *c : e->chans) live += c != nullptr;
+            const DcSplit split = dc_split_for(live);
+            const bool heavy = split.reserved_sms > 0;
+            unsigned seg = kDcSegLenLight;
+            if (heavy) {                                           // exactly as many segments as warp slots on the reserved SMs
+                const unsigned cap = (unsigned)(split.reserved_sms * split.warps_per_cta);
+                seg = (unsigned)((n + cap - 1) / cap);
+                seg = (seg + 63u) & ~63u;
+                if (seg < kDcSegLenLight) seg = kDcSegLenLight;
+            }
+            xa.xraw = raw; xa.y = blk; xa.n = (int)n; xa.seg_len = (int)seg; xa.warm = kDcWarm;
+            xa.c = (float)e->dc_a;
+            xa.tile_carry = e->d_tile_carry2[p]; xa.prev_tile_carry = e->d_tile_carry2[p ^ 1];
+            xa.prev_n = e->have_block ? (int)e->last_n : 0;
+            xa.seg_in = e->d_seg_in; xa.seg_out = e->d_seg_out; xa.fstate = e->d_fstate; xa.fixups = e->d_fixups;
+            // speculate only when there is parallelism to gain and the warm-up region lies inside the data we hold
+            const bool spec = n >= 4u * seg && (!e->have_block || e->last_n >= (unsigned)(kDcWarm + kDcTile));
+            xa.n_seg = spec ? (int)((n + seg - 1) / seg) : 1;
+            if (!spec) xa.seg_len = (int)n;
+            launch_dc_exact(xa, (heavy && spec) ? split.warps_per_cta : 1, dcs, e->launches);
+        }
     }
     // history in front of the block: the tail of the previous block, which lives in the other buffer
     size_t need = kBlkHist;
@@ -1287,6 +1360,37 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
     if (e->have_block && e->last_n > 0) {
         const float2 *prev = e->d_blkbuf[p ^ 1] + e->hist_cap;
         be_d2d(blk - need, prev + (long long)e->last_n - (long long)need, need * sizeof(float2), dcs);
+    }
+    float2 *pfb_streams = nullptr;
+    if (pfb) {
+        // filterbank -> channel-major streams [slot][kBlkHist history | n_ch new]; history = tail of the previous block's
+        // streams (other parity); slot M = channel 0 after the DC blocker (runDemodChannels, SDRPostThread.cpp:363-375)
+        pfb_streams = e->d_pfb_streams[p];
+        const size_t stride = e->pfb_stride;
+        if (e->pfb_have_block)
+            be_d2d_2d(pfb_streams, stride * sizeof(float2), e->d_pfb_streams[p ^ 1] + e->pfb_last_frames, stride * sizeof(float2),
+                      (size_t)kBlkHist * sizeof(float2), e->pfb_slots, dcs);
+        PfbArgs pa;
+        pa.x = blk; pa.y = pfb_streams + kBlkHist; pa.hq = e->d_pfb_hq; pa.tw = e->d_pfb_tw; pa.M = pfb_M; pa.p = 8; pa.F = (int)n_ch;
+        pa.chan_stride = (long long)stride;
+        const int tiles = ((int)n_ch + kPfbTileFrames - 1) / kPfbTileFrames;
+        float2 *ch0 = pfb_streams + kBlkHist, *ch0_dc = pfb_streams + (size_t)pfb_M * stride + kBlkHist;
+#ifndef SDR_EMU
+        const size_t smem = pfb_smem_elems(pa.M, pa.p) * sizeof(float2);
+        static size_t attr_smem_e = 0;
+        if (smem > attr_smem_e) { CUDA_TRY(cudaFuncSetAttribute(k_pfb_analyze, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem_e = smem; }
+        k_pfb_analyze<<<tiles, kPfbThreads, smem, dcs>>>(pa);
+        k_pfb_dc0<<<1, 32, 0, dcs>>>(ch0, ch0_dc, (int)n_ch, (float)e->dc_a, e->d_pfb_dc_state);
+#else
+        {
+            std::vector<float2> sm(pfb_smem_elems(pa.M, pa.p));
+            for (int t = 0; t < tiles; ++t)
+                for (int ph = 0; ph < kPfbPhases; ++ph) for (int th = 0; th < kPfbThreads; ++th) pfb_phase(ph, pa, t, th, kPfbThreads, sm.data());
+            pfb_dc0_serial(ch0, ch0_dc, (int)n_ch, (float)e->dc_a, e->d_pfb_dc_state);
+        }
+#endif
+        e->launches += 2;
+        e->pfb_last_frames = n_ch; e->pfb_have_block = true;
     }
 #ifndef SDR_EMU
     if (e->timing && e->time_pending < sdr_engine::kTimeSets) cudaEventRecord(e->tev_dc[e->time_pending][1], dcs);
@@ -1417,7 +1521,19 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
     std::vector<int> by_k[kFrontMaxK + 1];
     size_t live_now = 0;
     for (auto *c : e->chans) live_now += c != nullptr;
-    const int front_reserved = e->exact_dc ? dc_split_for(live_now).reserved_sms : 0;
+    const int front_reserved = (e->exact_dc && !pfb) ? dc_split_for(live_now).reserved_sms : 0;
+    // channelizer mode: channel centre frequencies (SDRPostThread::updateChannels, SDRPostThread.cpp:115-124)
+    std::vector<long long> chan_centers;
+    if (pfb) {
+        chan_centers.assign((size_t)pfb_M + 1, 0);
+        const long long chan_bw = rate / pfb_M;
+        for (int i = 0; i < pfb_M / 2; ++i) {
+            const int ofs = (int)(chan_bw * i);
+            chan_centers[i] = center + ofs;
+            chan_centers[i + pfb_M / 2] = center - (rate / 2) + ofs;
+        }
+        chan_centers[pfb_M] = center + (rate / 2);
+    }
     for (int i = 0; i < n_slots; ++i) {
         sdr_chan *c = e->chans[i];
         ChanDyn &d = h_cd[i];
@@ -1425,18 +1541,36 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         if (!c || c->standalone) continue;
         d.valid = 1;
         // a channel that sits this block out keeps the tail of the last block it consumed (its filters do not advance)
+        // (in channelizer mode the tail lives in the stream the channel last read: the history region of that slot)
         auto keep_tail = [&]() {
             if (!c->priv_valid && c->consumed > 0) {
-                be_d2d(c->d_priv_hist, blk - kBlkHist, kBlkHist * sizeof(float2), e->stream);
-                c->priv_valid = true;
+                const float2 *src = blk - kBlkHist;
+                if (pfb) src = c->pfb_slot_prev >= 0 ? pfb_streams + (size_t)c->pfb_slot_prev * e->pfb_stride : nullptr;
+                if (src) { be_d2d(c->d_priv_hist, src, kBlkHist * sizeof(float2), e->stream); c->priv_valid = true; }
             }
         };
-        if (c->sample_rate != rate) { keep_tail(); continue; }                     // `inp->sampleRate == currentSampleRate` (:167)
-        const long long shift = c->frequency - center;
-        const long long lim = (long long)(int)((double)(rate / 2) * 1.5);
+        if (c->sample_rate != rate_ch) { keep_tail(); continue; }                  // `inp->sampleRate == currentSampleRate` (:167)
+        long long in_freq = center;                                                 // inp->frequency
+        int stream_slot = -1;
+        if (pfb) {
+            // SDRPostThread::getChannelAt (SDRPostThread.cpp:127-139): nearest centre, first one wins a tie
+            int ci = -1;
+            long long min_delta = rate;
+            for (int k = 0; k <= pfb_M; ++k) {
+                const long long fd = std::llabs(c->frequency - chan_centers[k]);
+                if (fd < min_delta) { min_delta = fd; ci = k; }
+            }
+            if (ci < 0) { keep_tail(); continue; }                                  // no channel: the demodulator gets no data this block
+            in_freq = chan_centers[ci];
+            // channel 0 is read after its DC blocker; the extra channel wraps onto numChannels/2 (:357-361)
+            stream_slot = ci == 0 ? pfb_M : (ci == pfb_M ? pfb_M / 2 : ci);
+            if (c->pfb_slot_prev >= 0 && c->pfb_slot_prev != stream_slot) keep_tail();   // it hops to another stream: remember the old one's tail
+        }
+        const long long shift = c->frequency - in_freq;
+        const long long lim = (long long)(int)((double)(rate_ch / 2) * 1.5);
         if (shift != c->shift_frequency) {
             c->shift_frequency = shift;
-            if (std::llabs(shift) <= lim) c->dtheta = nco_phase_step(nco_shift_word_arg(shift, rate));
+            if (std::llabs(shift) <= lim) c->dtheta = nco_phase_step(nco_shift_word_arg(shift, rate_ch));
         }
         if (std::llabs(c->shift_frequency) > lim) { keep_tail(); continue; }   // block skipped for this channel (:161-164)
         const int dir = c->shift_frequency < 0 ? +1 : (c->shift_frequency > 0 ? -1 : 0);
@@ -1444,11 +1578,12 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         d.dir = dir; d.dir_prev = c->dir_prev;
         d.hist = c->priv_valid ? c->d_priv_hist + kBlkHist : nullptr;
         c->priv_valid = false;
+        if (pfb) { d.xin = pfb_streams + (size_t)stream_slot * e->pfb_stride + kBlkHist; c->pfb_slot_prev = stream_slot; }
         d.lvl0_sel = c->lvl0_sel;                                       // consecutive processed blocks alternate level-0 buffers
         c->lvl0_sel ^= 1;
-        if (dir) c->theta += (unsigned)n * c->dtheta;                   // mix_block advances the phase by n steps
+        if (dir) c->theta += n_ch * c->dtheta;                          // mix_block advances the phase by one step per input sample
         c->dtheta_prev = c->dtheta; c->dir_prev = dir;
-        c->consumed += n;
+        c->consumed += n_ch;
         by_k[c->cs.K1].push_back(i);
     }
     ChanDyn *d_cd = e->d_cd2[p];
@@ -1478,9 +1613,9 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
     for (const FrontGroup &g : groups) {
         const int K = g.K, cg = g.cg;
         FrontArgs fa;
-        fa.x = blk; fa.n = (int)n; fa.nco = e->d_nco; fa.cs = e->d_cs; fa.cd = d_cd; fa.group = g.d_grp; fa.cg = cg;
+        fa.x = blk; fa.n = (int)n_ch; fa.nco = e->d_nco; fa.cs = e->d_cs; fa.cd = d_cd; fa.group = g.d_grp; fa.cg = cg;
         const int n_chunks = (cg + 31) / 32;
-        const long long nq = ((long long)n >> K) + 1;
+        const long long nq = ((long long)n_ch >> K) + 1;
         int n_span = std::max(1, ((148 - front_reserved) * kFrontWarps) / n_chunks);   // one wave of CTAs on the SMs the front uses
         // every span pays kFrontWarm warm-up super-steps; with few channels, parallelism is worth more than the overhead
         const long long min_span = (K == 0) ? 256 : kFrontWarm;
@@ -1495,7 +1630,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
     { int r = run_spectra(); if (r) return r; }                     // side stream, after the front kernel got the SMs
     TailArgs ta;
     ta.cs = e->d_cs; ta.cd = d_cd; ta.st = e->d_st; ta.taps = e->d_taps; ta.nco = e->d_nco;
-    ta.results = e->d_results; ta.n = (int)n; ta.first = 0; ta.dbg = e->d_front_dbg ? e->d_front_dbg + 4 * 1024 : nullptr;
+    ta.results = e->d_results; ta.n = (int)n_ch; ta.first = 0; ta.dbg = e->d_front_dbg ? e->d_front_dbg + 4 * 1024 : nullptr;
     // the tail indexes channels by slot; free slots carry valid = 0 and are not touched
     time_mark(e, 3);
     // the channel tail (and the results' D2H) go to their own stream: they overlap the next block's front kernel
@@ -1559,6 +1694,26 @@ extern "C" int sdr_engine_submit_device_async(sdr_engine *e, const void *d_iq, u
     if (n == 0 || n > e->max_block) return fail(SDR_ERR_ARG, "sdr_engine_submit_device_async: block size out of range");
     std::lock_guard<std::mutex> lk(e->mu);
     return submit_common(e, (const float2 *)d_iq, nullptr, n, center, rate, to_host != 0, ready_event ? 2 : 1, ready_event);
+}
+
+// SDRPostThread::setChannelizerType (SDRPostThread.cpp:142-144), restricted to what is built: 0 = every block through
+// runSingleCH (default), 1 = SDRPostPFBCH: blocks whose rate gives more than one channel go through the analysis filterbank
+// and every demodulator reads its filterbank channel at sampleRate / numChannels.  Set before the first block.
+extern "C" int sdr_engine_set_channelizer(sdr_engine *e, int mode) {
+    if (!e) return fail(SDR_ERR_ARG, "null engine");
+    if (mode != 0 && mode != 1) return fail(SDR_ERR_UNSUPPORTED, "sdr_engine_set_channelizer: mode must be 0 (single channel) or 1 (PFBCH)");
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (e->have_block && mode != e->chan_mode) return fail(SDR_ERR_STATE, "sdr_engine_set_channelizer: set the mode before the first block");
+    e->chan_mode = mode;
+    return SDR_OK;
+}
+
+// what the demodulators of a channelizer-mode engine must be created with: numChannels and chanBw = rate / numChannels
+extern "C" int sdr_engine_channel_plan(long long sample_rate, int *num_channels, long long *channel_rate) {
+    const int m = optimal_channel_count(sample_rate);
+    if (num_channels) *num_channels = m;
+    if (channel_rate) *channel_rate = sample_rate / m;
+    return SDR_OK;
 }
 
 extern "C" int sdr_engine_wait(sdr_engine *e) {
@@ -1770,7 +1925,7 @@ static int pfb_run(sdr_pfb *p, const float2 *d_in, unsigned n, float2 *d_out) {
     float2 *xnew = p->d_x + hist;
     be_d2d(xnew, d_in, (size_t)n * sizeof(float2), e->stream);
     PfbArgs a;
-    a.x = xnew; a.y = d_out; a.hq = p->d_hq; a.tw = p->d_tw; a.M = (int)p->M; a.p = (int)p->p; a.F = (int)F;
+    a.x = xnew; a.y = d_out; a.hq = p->d_hq; a.tw = p->d_tw; a.M = (int)p->M; a.p = (int)p->p; a.F = (int)F; a.chan_stride = 0;
     const int tiles = ((int)F + kPfbTileFrames - 1) / kPfbTileFrames;
 #ifndef SDR_EMU
     const size_t smem = pfb_smem_elems(a.M, a.p) * sizeof(float2);

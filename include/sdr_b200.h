@@ -127,6 +127,14 @@ int sdr_spectrum_fetch_debug(sdr_spectrum *sp, unsigned idx, float *mags, float 
  * per-numChannels-samples firpfbch_crcf_analyzer_execute loop of SDRPostThread::runPFBCH (:447-451).  Output layout is
  * liquid's: numChannels interleaved channel samples per input frame, which runDemodChannels de-interleaves (:366-382).
  * n must be a multiple of num_channels (SDRThread::getOptimalElementCount, src/sdr/SoapySDRThread.cpp:668-674). */
+/* Channelizer mode of the engine: SDRPostThread::setChannelizerType / the dispatch of SDRPostThread::run (:142-148,
+ * :178-187).  mode 0 (default) = runSingleCH for every block; mode 1 = SDRPostPFBCH: a block whose rate gives
+ * numChannels > 1 goes through the analysis filterbank (no wideband DC blocker, :432-451), demodulators are routed to
+ * the nearest channel centre (updateChannels / getChannelAt / runDemodChannels, :115-139, :303-398; channel 0 gets the DC
+ * blocker, the extra channel wraps onto numChannels/2) and must have been created with sample_rate = channel_rate of
+ * sdr_engine_channel_plan (what DemodulatorPreThread sees as inp->sampleRate).  Spectra see the raw block, as there. */
+int sdr_engine_set_channelizer(sdr_engine *eng, int mode);
+int sdr_engine_channel_plan(long long sample_rate, int *num_channels, long long *channel_rate);
 typedef struct sdr_pfb sdr_pfb;
 int sdr_pfb_optimal_channel_count(long long sample_rate);     /* SDRThread::getOptimalChannelCount, SoapySDRThread.cpp:676-693 */
 int sdr_pfb_create(sdr_engine *eng, unsigned num_channels, unsigned m, float as_db, unsigned max_frames, sdr_pfb **out);

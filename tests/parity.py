@@ -250,3 +250,101 @@ def check_against_golden(lib, device=0):
     eng.close()
     assert worst <= TOL, worst
     return worst
+
+
+class RefChannelizerPath:
+    """Oracle for channelizer mode: the reference binary's firpfbch_crcf + a restatement of the routing around it.
+      SDRPostThread::runPFBCH            src/sdr/SDRPostThread.cpp:416-455  (no wideband DC blocker; one analyzer_execute per frame)
+      SDRPostThread::updateChannels      :115-124   channel centre frequencies (integer arithmetic as there)
+      SDRPostThread::getChannelAt        :127-139   nearest centre, first minimum wins
+      SDRPostThread::runDemodChannels    :303-398   de-interleave, channel 0 through the DC blocker, extra channel = numChannels/2
+    Every demodulator then runs DemodulatorPreThread + Modem at the channel rate (RefChan with sample_rate = chanBw)."""
+
+    def __init__(self, ref, fs, chans, audio_rate=48000):
+        from oracle.refbind import RefPfb
+        self.ref, self.fs = ref, fs
+        ref.L.ref_optimal_channel_count.argtypes = [__import__("ctypes").c_longlong]
+        self.M = ref.L.ref_optimal_channel_count(fs)
+        self.chan_bw = fs // self.M
+        self.pfb = RefPfb(ref, self.M)
+        self.dc = RefIngress(ref)                               # dcFilter: the same iirfilt DC blocker object type (:29)
+        self.demods = [RefChan(ref, m, self.chan_bw, bw, audio_rate) for m, bw, _ in chans]
+
+    def centers(self, frequency):
+        M, c = self.M, [0] * (self.M + 1)
+        for i in range(M // 2):
+            ofs = int(self.chan_bw * i)
+            c[i] = frequency + ofs
+            c[i + M // 2] = frequency - (self.fs // 2) + ofs
+        c[M] = frequency + (self.fs // 2)
+        return c
+
+    def channel_at(self, centers, f):
+        chan, min_delta = -1, self.fs
+        for i in range(self.M + 1):
+            d = abs(f - centers[i])
+            if d < min_delta:
+                min_delta, chan = d, i
+        return chan
+
+    def block(self, x, frequency, demod_freqs):
+        """-> list of RefChan.process results (or None when a demodulator got no data), and the chosen channel per demod."""
+        y = self.pfb.execute(x)                                 # [frames, M]
+        centers = self.centers(frequency)
+        picks = [self.channel_at(centers, f) for f in demod_freqs]
+        ch0 = self.dc.block(np.ascontiguousarray(y[:, 0])) if 0 in picks else None
+        out = []
+        for d, f, ci in zip(self.demods, demod_freqs, picks):
+            if ci < 0:
+                out.append(None); continue
+            data = ch0 if ci == 0 else np.ascontiguousarray(y[:, self.M // 2 if ci == self.M else ci])
+            out.append(d.process(data, f - centers[ci]))
+        return out, picks
+
+    def close(self):
+        self.pfb.close(); self.dc.close()
+        for d in self.demods:
+            d.close()
+
+
+def check_channelizer_mode(lib, ref, fs, chans, n_blocks, retune=None, device=0, seed=2024):
+    """Engine in channelizer mode against RefChannelizerPath.  chans: [(modem, bw, offset)].  Returns the set of filterbank
+    channels that were exercised."""
+    N = synth.block_size(fs)
+    eng = Engine(lib, device=device, max_block=N)
+    eng.set_channelizer(1)
+    M, chan_rate = eng.channel_plan(fs)
+    oracle = RefChannelizerPath(ref, fs, chans)
+    assert (M, chan_rate) == (oracle.M, oracle.chan_bw) and N % M == 0
+    cs = [Channel(eng, m, chan_rate, bw, 48000, frequency=CENTER + off) for m, bw, off in chans]
+    freqs = [CENTER + off for _, _, off in chans]
+    got = [[] for _ in chans]; want = [[] for _ in chans]
+    used = set()
+    signal = list(chans)
+    for b in sorted(retune or {}):
+        signal += [(chans[i][0], chans[i][1], off) for i, off in retune[b].items()]
+    for b in range(n_blocks):
+        if retune and b in retune:
+            for i, off in retune[b].items():
+                freqs[i] = CENTER + off
+                cs[i].set_frequency(freqs[i])
+        x = synth.wideband(fs, N, signal, seed=seed, t0=b * N) + np.complex64(0.02 + 0.01j)     # a DC offset: channel 0's blocker matters
+        eng.submit(x, CENTER, fs)
+        eng.wait()
+        res, picks = oracle.block(x, CENTER, freqs)
+        used.update(picks)
+        for i, (c, r) in enumerate(zip(cs, res)):
+            a, lvl, pk, sk = c.fetch_audio()
+            if r is None or r["skipped"]:
+                assert sk or len(a) == 0, "demod %d block %d: engine produced audio where the reference had none" % (i, b)
+                continue
+            assert not sk, "demod %d block %d: engine skipped a block the reference processed" % (i, b)
+            assert len(a) == len(r["audio"]), "demod %d block %d: %d audio samples vs %d" % (i, b, len(a), len(r["audio"]))
+            got[i].append(a); want[i].append(r["audio"])
+    for c in cs:
+        c.close()
+    oracle.close(); eng.close()
+    for i, (m, bw, off) in enumerate(chans):
+        e = relrms(np.concatenate(got[i]), np.concatenate(want[i]))
+        assert e <= TOL, "demod %d (%s @ %+d Hz): audio relative RMS error %.3g" % (i, m, off, e)
+    return used

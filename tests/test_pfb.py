@@ -65,3 +65,45 @@ def test_reset_and_bad_lengths(emu_lib, ref):
 @pytest.mark.parametrize("M,calls", CASES + [(122, [8394])])
 def test_channelizer_matches_reference_binary_gpu(gpu_lib, ref, M, calls):
     assert _stream(gpu_lib, ref, M, calls) <= TOL
+
+
+def test_engine_channelizer_mode_emulator(emu_lib, ref):
+    """SDRPostThread::runPFBCH end to end at 2.4 MSps (4 channels of 600 kHz; 5 streams with the wrap channel):
+    demodulators on channel 0 (DC-corrected), on an ordinary channel, on the wrap channel, and one that hops between
+    channels mid-stream."""
+    from tests import parity
+    fs = 2400000
+    chans = [("FM", 200000, 40000), ("AM", 6000, -650000), ("NBFM", 12500, 1150000), ("USB", 5400, 560000), ("FM", 200000, -1100000)]
+    used = parity.check_channelizer_mode(emu_lib, ref, fs, chans, n_blocks=5, retune={2: {3: -90000}, 3: {1: 700000}})
+    assert {0, 4}.issubset(used) and len(used) >= 4          # channel 0, the extra (wrap) channel and ordinary ones
+
+
+def test_engine_channelizer_mode_20_channels_emulator(emu_lib, ref):
+    """10 MSps: 20 filterbank channels of 500 kHz, demodulators spread over both halves of the band."""
+    from tests import parity
+    fs = 10000000
+    chans = [("FM", 200000, 1480000), ("NBFM", 12500, -2260000), ("AM", 6000, 4890000), ("LSB", 5400, -4990000), ("FM", 150000, -130000)]
+    used = parity.check_channelizer_mode(emu_lib, ref, fs, chans, n_blocks=3)
+    assert len(used) == 5
+
+
+@pytest.mark.gpu
+def test_engine_channelizer_mode_gpu(gpu_lib, ref):
+    from tests import parity
+    fs = 2400000
+    chans = [("FM", 200000, 40000), ("AM", 6000, -650000), ("NBFM", 12500, 1150000), ("USB", 5400, 560000), ("FM", 200000, -1100000)]
+    used = parity.check_channelizer_mode(gpu_lib, ref, fs, chans, n_blocks=5, retune={2: {3: -90000}, 3: {1: 700000}})
+    assert {0, 4}.issubset(used)
+
+
+@pytest.mark.gpu
+def test_engine_channelizer_mode_122_channels_gpu(gpu_lib, ref):
+    """The BASELINE rate: 61.44 MSps = 122 channels of 503 606 Hz, twelve demodulators across the band, two blocks."""
+    from tests import parity
+    fs = 61440000
+    offs = [-30500000, -21000000, -12345678, -5000000, -250000, 60000, 3000000, 9876543, 15000000, 22222222, 28000000, 30600000]
+    modems = ["FM", "AM", "USB", "LSB", "NBFM", "FM"]
+    bws = {"FM": 200000, "AM": 6000, "USB": 5400, "LSB": 5400, "NBFM": 12500}
+    chans = [(modems[i % 6], bws[modems[i % 6]], o) for i, o in enumerate(offs)]
+    used = parity.check_channelizer_mode(gpu_lib, ref, fs, chans, n_blocks=2)
+    assert 0 in used and 122 in used and len(used) >= 10
