@@ -267,6 +267,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ring", type=int, default=16, help="distinct input blocks rotated through (ring * block > L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--channelizer", action="store_true",
+                    help="diagnostic: run the engine in channelizer mode (SDRPostThread::runPFBCH, SURVEY.md 8(f) row 1) -- not a contract line")
     ap.add_argument("--channels", type=int, default=0, help="diagnostic only: override the workload's channel count (not a contract line)")
     args = ap.parse_args()
     capture_stdout()
@@ -318,7 +320,13 @@ def main():
     assert stream.cuda_stream != 0
     eng = Engine(lib, device=local_rank, max_block=N, stream=stream.cuda_stream)
     mine = chans[rank::world]                                  # channel sharding
-    cobjs = [Channel(eng, m, fs, bw, 48000, frequency=CENTER + off) for m, bw, off in mine]
+    chan_fs = fs
+    if args.channelizer:
+        eng.set_channelizer(1)
+        n_pfb, chan_fs = eng.channel_plan(fs)
+        wl = dict(wl, desc=wl["desc"] + " [DIAGNOSTIC: channelizer mode, %d filterbank channels of %d Hz]" % (n_pfb, chan_fs))
+        args.no_cpu_baseline = True                              # the reference arm below times runSingleCH, not runPFBCH
+    cobjs = [Channel(eng, m, chan_fs, bw, 48000, frequency=CENTER + off) for m, bw, off in mine]
     spec = Spectrum(eng, wl["fft"], 0) if (wl["fft"] and rank == 0) else None
 
     # ---- inputs: ring of distinct blocks resident in HBM on rank 0 (ring * block bytes > 126 MB L2) -----------------
