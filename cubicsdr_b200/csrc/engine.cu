@@ -1239,6 +1239,17 @@ static int rebuild(sdr_engine *e) {
 // ready: 0 = the block becomes ready when the engine's main stream reaches this point (conservative),
 //        1 = the block is ready now (resident data, or a host block that submit copies on the DC stream itself),
 //        2 = the block is ready when `ready_event` fires
+#ifndef SDR_EMU
+// the filterbank kernel's dynamic shared memory grows with the channel count: raise the opt-in limit monotonically
+static int pfb_allow_smem(size_t bytes) {
+    static size_t allowed = 48 * 1024;
+    if (bytes > allowed) {
+        CUDA_TRY(cudaFuncSetAttribute(k_pfb_analyze, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        allowed = bytes;
+    }
+    return SDR_OK;
+}
+#endif
 // channelizer mode: (re)build the filterbank tables and the channel-stream buffers when the channel count changes
 // (SDRPostThread::initPFBCH, SDRPostThread.cpp:401-414: a new count means a new channelizer, i.e. empty windows)
 static int pfb_prepare(sdr_engine *e, int M) {
@@ -1377,8 +1388,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         float2 *ch0 = pfb_streams + kBlkHist, *ch0_dc = pfb_streams + (size_t)pfb_M * stride + kBlkHist;
 #ifndef SDR_EMU
         const size_t smem = pfb_smem_elems(pa.M, pa.p) * sizeof(float2);
-        static size_t attr_smem_e = 0;
-        if (smem > attr_smem_e) { CUDA_TRY(cudaFuncSetAttribute(k_pfb_analyze, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem_e = smem; }
+        { int r = pfb_allow_smem(smem); if (r) return r; }
         k_pfb_analyze<<<tiles, kPfbThreads, smem, dcs>>>(pa);
         k_pfb_dc0<<<1, 32, 0, dcs>>>(ch0, ch0_dc, (int)n_ch, (float)e->dc_a, e->d_pfb_dc_state);
 #else
@@ -1929,8 +1939,7 @@ static int pfb_run(sdr_pfb *p, const float2 *d_in, unsigned n, float2 *d_out) {
     const int tiles = ((int)F + kPfbTileFrames - 1) / kPfbTileFrames;
 #ifndef SDR_EMU
     const size_t smem = pfb_smem_elems(a.M, a.p) * sizeof(float2);
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) { CUDA_TRY(cudaFuncSetAttribute(k_pfb_analyze, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; }
+    { int r = pfb_allow_smem(smem); if (r) return r; }
     k_pfb_analyze<<<tiles, kPfbThreads, smem, e->stream>>>(a);
 #else
     std::vector<float2> sm(pfb_smem_elems(a.M, a.p));
