@@ -205,6 +205,13 @@ public:
                               data_in.frequency, data_in.sampleRate) != SDR_OK) return false;
         return sdr_engine_wait(eng_->get()) == SDR_OK;
     }
+    // SDRPostThread::setChannelizerType (SDRPostThread.cpp:142-144): SDRPostPFBCH (1) makes blocks above 500 kSps take the
+    // runPFBCH path; demodulators must then be created with the channel rate of channelPlan().  Call before the first block.
+    bool setChannelizerType(int chType) { return sdr_engine_set_channelizer(eng_->get(), chType) == SDR_OK; }
+    // numChannels (SDRThread::getOptimalChannelCount) and chanBw = sampleRate / numChannels (:408) for a wideband rate
+    static void channelPlan(long long sampleRate, int &numChannels, long long &chanBw) {
+        sdr_engine_channel_plan(sampleRate, &numChannels, &chanBw);
+    }
     // Pipelined variant: submits the block and returns once the PREVIOUS block's results are on the host (false for the
     // very first block: nothing to fetch yet).  Mirrors the one-block lag the reference's queues between SDRPostThread
     // and the demodulator threads introduce anyway; fetchAudio / getFrame then read that previous block.

@@ -100,6 +100,10 @@ LQ firpfbch_crcf firpfbch_crcf_create_kaiser(int type, unsigned int M, unsigned 
 LQ int firpfbch_crcf_destroy(firpfbch_crcf q);
 LQ int firpfbch_crcf_reset(firpfbch_crcf q);
 LQ int firpfbch_crcf_analyzer_execute(firpfbch_crcf q, lq_cf *x, lq_cf *y);
+typedef struct firpfbch2_crcf_s *firpfbch2_crcf;
+LQ firpfbch2_crcf firpfbch2_crcf_create_kaiser(int type, unsigned int M, unsigned int m, float As);
+LQ int firpfbch2_crcf_destroy(firpfbch2_crcf q);
+LQ int firpfbch2_crcf_execute(firpfbch2_crcf q, lq_cf *x, lq_cf *y);
 
 #ifdef __cplusplus
 }

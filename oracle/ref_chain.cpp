@@ -120,6 +120,22 @@ API void ref_pfb_execute(void *h, lq_cf *in, unsigned n, lq_cf *out) {
     auto *p = (RefPfb *)h;
     for (unsigned i = 0; i + p->M <= n; i += p->M) firpfbch_crcf_analyzer_execute(p->q, in + i, out + i);
 }
+// SDRPostThread::runPFBCH2 channelizer      src/sdr/SDRPostThread.cpp:457-511
+//   initPFBCH2 :457-470  firpfbch2_crcf_create_kaiser(LIQUID_ANALYZER, numChannels, 4, 60)
+//   runPFBCH2  :503-506  one execute per numChannels/2 input samples -> numChannels interleaved outputs
+struct RefPfb2 { firpfbch2_crcf q; unsigned M; };
+API void *ref_pfb2_create(unsigned num_channels, unsigned m, float as_db) {
+    auto *p = new RefPfb2; p->M = num_channels;
+    p->q = firpfbch2_crcf_create_kaiser(0 /* LIQUID_ANALYZER */, num_channels, m, as_db);
+    return p;
+}
+API void ref_pfb2_destroy(void *h) { auto *p = (RefPfb2 *)h; firpfbch2_crcf_destroy(p->q); delete p; }
+// n must be a multiple of num_channels / 2; out receives 2 n samples
+API void ref_pfb2_execute(void *h, lq_cf *in, unsigned n, lq_cf *out) {
+    auto *p = (RefPfb2 *)h;
+    const unsigned M2 = p->M / 2;
+    for (unsigned i = 0; i + M2 <= n; i += M2) firpfbch2_crcf_execute(p->q, in + i, out + 2 * i);
+}
 // SDRThread::getOptimalChannelCount          src/sdr/SoapySDRThread.cpp:676-693  (CHANNELIZER_RATE_MAX = 500000, CubicSDRDefs.h:63)
 API int ref_optimal_channel_count(long long sampleRate_in) {
     if (sampleRate_in <= 500000) return 1;

@@ -98,6 +98,28 @@ class RefPfb:
         self.ref.L.ref_pfb_destroy(self.h)
 
 
+class RefPfb2:
+    """SDRPostThread::runPFBCH2 channelizer: the reference binary's firpfbch2_crcf analyzer (SDRPostThread.cpp:457-511)."""
+
+    def __init__(self, ref, num_channels, m=4, as_db=60.0):
+        self.ref, self.M = ref, num_channels
+        ref.L.ref_pfb2_create.restype = C.c_void_p
+        ref.L.ref_pfb2_create.argtypes = [C.c_uint, C.c_uint, C.c_float]
+        ref.L.ref_pfb2_execute.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]
+        ref.L.ref_pfb2_destroy.argtypes = [C.c_void_p]
+        self.h = C.c_void_p(ref.L.ref_pfb2_create(num_channels, m, as_db))
+
+    def execute(self, x):
+        x = np.ascontiguousarray(x, np.complex64)
+        assert x.size % (self.M // 2) == 0
+        y = np.zeros(2 * x.size, np.complex64)
+        self.ref.L.ref_pfb2_execute(self.h, _p(x), x.size, _p(y))
+        return y.reshape(-1, self.M)
+
+    def close(self):
+        self.ref.L.ref_pfb2_destroy(self.h)
+
+
 class RefIngress:
     """SDRPostThread::runSingleCH DC blocker (src/sdr/SDRPostThread.cpp:29,284)."""
 
