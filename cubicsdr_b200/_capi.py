@@ -24,7 +24,7 @@ SYMBOLS = [
     "sdr_spectrum_create", "sdr_spectrum_destroy", "sdr_spectrum_set_average_rate", "sdr_spectrum_frames",
     "sdr_spectrum_fetch", "sdr_spectrum_fetch_all", "sdr_spectrum_fetch_debug",
     "sdr_engine_set_channelizer", "sdr_engine_channel_plan",
-    "sdr_pfb_optimal_channel_count", "sdr_pfb_create", "sdr_pfb_destroy", "sdr_pfb_reset", "sdr_pfb_execute", "sdr_pfb_execute_device",
+    "sdr_pfb_optimal_channel_count", "sdr_pfb_create", "sdr_pfb2_create", "sdr_pfb_destroy", "sdr_pfb_reset", "sdr_pfb_execute", "sdr_pfb_execute_device",
     "sdr_design_kaiser", "sdr_design_nco_table", "sdr_design_nco_step", "sdr_design_resampler",
     "sdr_design_halfband_branch", "sdr_design_am_dc_block", "sdr_design_hilbert_q", "sdr_design_butter6_sos",
 ]
@@ -79,6 +79,7 @@ class Lib:
         L.sdr_engine_channel_plan.argtypes = [C.c_longlong, vp, vp]
         L.sdr_pfb_optimal_channel_count.argtypes = [C.c_longlong]
         L.sdr_pfb_create.argtypes = [vp, u, u, C.c_float, u, C.POINTER(vp)]
+        L.sdr_pfb2_create.argtypes = [vp, u, u, C.c_float, u, C.POINTER(vp)]
         L.sdr_pfb_destroy.argtypes = [vp]
         L.sdr_pfb_reset.argtypes = [vp]
         L.sdr_pfb_execute.argtypes = [vp, vp, u, vp]
@@ -288,11 +289,13 @@ class Channelizer:
     """sdr_pfb: SDRPostThread::initPFBCH / runPFBCH -- firpfbch_crcf_create_kaiser(LIQUID_ANALYZER, M, 4, 60) + one
     analyzer_execute per M input samples (src/sdr/SDRPostThread.cpp:401-455)."""
 
-    def __init__(self, engine, num_channels, max_frames, m=4, as_db=60.0):
+    def __init__(self, engine, num_channels, max_frames, m=4, as_db=60.0, oversampled=False):
+        """oversampled=True: firpfbch2_crcf (runPFBCH2): one output frame per num_channels / 2 input samples."""
         self.engine, self.lib = engine, engine.lib
-        self.M, self.max_frames = int(num_channels), int(max_frames)
+        self.M, self.max_frames, self.osf = int(num_channels), int(max_frames), 2 if oversampled else 1
         h = C.c_void_p()
-        self.lib.check(self.lib.L.sdr_pfb_create(engine.h, self.M, int(m), C.c_float(as_db), self.max_frames, C.byref(h)))
+        create = self.lib.L.sdr_pfb2_create if oversampled else self.lib.L.sdr_pfb_create
+        self.lib.check(create(engine.h, self.M, int(m), C.c_float(as_db), self.max_frames, C.byref(h)))
         self.h = h
 
     @staticmethod
@@ -302,7 +305,7 @@ class Channelizer:
     def execute(self, x):
         """x: complex64[n], n a multiple of M -> complex64[n / M, M] (one row per input frame, M channel samples)."""
         x = np.ascontiguousarray(x, np.complex64)
-        y = np.zeros(x.size, np.complex64)
+        y = np.zeros(x.size * self.osf, np.complex64)
         self.lib.check(self.lib.L.sdr_pfb_execute(self.h, _ptr(x), x.size, _ptr(y)))
         return y.reshape(-1, self.M)
 

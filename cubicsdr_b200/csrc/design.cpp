@@ -246,6 +246,24 @@ void pfb_analysis_tables(unsigned M, unsigned m, float as_db, std::vector<float>
     }
 }
 
+void pfb2_analysis_tables(unsigned M, unsigned m, float as_db, std::vector<float> &hq, std::vector<float> &tw_re_im) {
+    const unsigned D = M / 2, taps = 4 * m, h_len = 2 * M * m + 1;
+    std::vector<float> h(h_len);
+    kaiser_lowpass(h_len, 1.0f / (float)M, as_db, 0.0f, h.data());
+    // liquid normalises the prototype to M / sum(h) and scales the transform by 1 / M: folded into one factor here
+    double sum = 0.0;
+    for (float v : h) sum += (double)v;
+    hq.assign((size_t)D * taps, 0.f);
+    for (unsigned cm = 0; cm < D; ++cm)
+        for (unsigned d = 0; d < taps; ++d) hq[(size_t)cm * taps + d] = (float)((double)h[cm + D * d] / sum);
+    tw_re_im.assign((size_t)2 * M, 0.f);
+    for (unsigned n = 0; n < M; ++n) {
+        const double ph = 2.0 * 3.14159265358979323846 * (double)n / (double)M;
+        tw_re_im[2 * n] = (float)cos(ph);
+        tw_re_im[2 * n + 1] = (float)sin(ph);
+    }
+}
+
 int optimal_channel_count(long long sample_rate) {
     if (sample_rate <= 500000) return 1;
     int count = (int)ceil((double)sample_rate / 500000.0);

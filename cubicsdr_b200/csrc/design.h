@@ -17,6 +17,9 @@ void kaiser_lowpass(unsigned n, float fc, float as_db, float mu, float *h);   //
 // firpfbch_crcf_create_kaiser(LIQUID_ANALYZER, M, m, As): branch filters of the analysis channelizer and its DFT twiddles.
 // hq[c * 2m + q] = h[(M - 1 - c) + q M] with h = kaiser_lowpass(2 M m + 1, 0.5 / M, As, 0);  tw[n] = exp(-j 2 pi n / M)
 void pfb_analysis_tables(unsigned M, unsigned m, float as_db, std::vector<float> &hq, std::vector<float> &tw_re_im);
+// firpfbch2_crcf_create_kaiser(LIQUID_ANALYZER, M, m, As): hq[cm * 4m + d] = g[cm + (M/2) d], g = h / sum(h),
+// h = kaiser_lowpass(2 M m + 1, 1 / M, As, 0);  tw[n] = exp(+j 2 pi n / M) (the analyzer ends in an inverse DFT scaled by 1/M)
+void pfb2_analysis_tables(unsigned M, unsigned m, float as_db, std::vector<float> &hq, std::vector<float> &tw_re_im);
 // SDRThread::getOptimalChannelCount (src/sdr/SoapySDRThread.cpp:676-693), CHANNELIZER_RATE_MAX = 500000
 int optimal_channel_count(long long sample_rate);
 

@@ -31,6 +31,8 @@ struct PfbArgs {
     const float *hq;       // [M][p]: hq[c*p + q] = h[(M-1-c) + q*M]
     const float2 *tw;      // [M]: exp(-j 2 pi n / M)
     int M, p, F;
+    int osf;               // 1: firpfbch (critically sampled, one frame per M inputs); 2: firpfbch2 (one frame per M/2 inputs)
+    long long frame_base;  // osf 2: index of this call's first output frame since reset (its parity selects the branch phase)
     long long chan_stride; // 0: y is frame-major [F][M] (liquid's layout); else channel-major: y[k * chan_stride + f]
 };
 
@@ -47,10 +49,27 @@ SDR_HD inline void pfb_phase(int ph, const PfbArgs &a, int tile, int tid, int nt
     float2 *su = sm + (size_t)(kPfbTileFrames + p - 1) * M;
     float2 *stw = su + (size_t)kPfbTileFrames * M;
     if (ph == 0) {
-        const float2 *src = a.x + (long long)(f0 - (p - 1)) * M;           // history frames first
-        const int n = (T + p - 1) * M;
+        // input tile: osf 1 -> frames of M samples, p-1 frames of history; osf 2 -> half-frames of M/2 samples, 2p-1 of history
+        const int D = a.osf == 2 ? M / 2 : M, hist = a.osf == 2 ? 2 * p - 1 : p - 1;
+        const float2 *src = a.x + (long long)(f0 - hist) * D;
+        const int n = (T + hist) * D;
         for (int i = tid; i < n; i += nt) sx[i] = src[i];
         for (int i = tid; i < M; i += nt) stw[i] = a.tw[i];
+    } else if (ph == 1 && a.osf == 2) {
+        // firpfbch2 (liquid 1.5.0, pinned against the binary): with D = M/2, frame n, branch c (cm = c mod D, pc = c >= D):
+        //   X[c] = sum_{q=0}^{2m-1} g[cm + D d] x[(n - d) D + (D-1-cm)],  d = ((n + pc) & 1) + 2q,   g = h / sum(h), fc = 1/M
+        // (a sample pushed in half-frame e only ever feeds branches of parity e; the output transform is the inverse DFT / M)
+        const int D = M / 2, hist = 2 * p - 1;
+        for (int o = tid; o < T * M; o += nt) {
+            const int fl = o / M, c = o - fl * M;
+            const int cm = c >= D ? c - D : c, pc = c >= D ? 1 : 0;
+            const int d0 = (int)((a.frame_base + f0 + fl + pc) & 1);
+            const float *h = a.hq + (size_t)cm * (2 * p) + d0;             // hq[cm][d], d = d0 + 2q
+            const float2 *xc = sx + (size_t)(fl + hist - d0) * D + (D - 1 - cm);   // x[(n - d0) D + ...]; next tap 2 D earlier
+            float2 acc = make_float2(0.f, 0.f);
+            for (int q = 0; q < p; ++q) acc = cf_fma(sdr_ldg(h + 2 * q), xc[-(long long)(2 * q) * D], acc);
+            su[o] = acc;
+        }
     } else if (ph == 1) {
         for (int o = tid; o < T * M; o += nt) {
             const int fl = o / M, c = o - fl * M;

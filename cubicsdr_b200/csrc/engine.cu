@@ -513,7 +513,7 @@ struct sdr_engine {
     // channelizer mode (SDRPostThread::runPFBCH): filterbank tables for the current channel count, the channel streams
     // [2 parities][M + 1 slots][kBlkHist history | frames] (slot M = DC-corrected channel 0) and the channel-0 DC state
     int chan_mode = 0;                          // 0: runSingleCH for every rate; 1: runPFBCH when the rate gives more than one channel
-    int pfb_M = 0; float *d_pfb_hq = nullptr; float2 *d_pfb_tw = nullptr;
+    int pfb_M = 0, pfb_osf = 0; long long pfb_frame_base = 0; float *d_pfb_hq = nullptr; float2 *d_pfb_tw = nullptr;
     float2 *d_pfb_streams[2] = {nullptr, nullptr}; size_t pfb_stride = 0; size_t pfb_slots = 0;
     float2 *d_pfb_dc_state = nullptr;
     unsigned pfb_last_frames = 0; bool pfb_have_block = false;
@@ -1252,15 +1252,16 @@ static int pfb_allow_smem(size_t bytes) {
 #endif
 // channelizer mode: (re)build the filterbank tables and the channel-stream buffers when the channel count changes
 // (SDRPostThread::initPFBCH, SDRPostThread.cpp:401-414: a new count means a new channelizer, i.e. empty windows)
-static int pfb_prepare(sdr_engine *e, int M) {
-    if (e->pfb_M == M && e->d_pfb_streams[0]) return SDR_OK;
+static int pfb_prepare(sdr_engine *e, int M, int osf) {
+    if (e->pfb_M == M && e->pfb_osf == osf && e->d_pfb_streams[0]) return SDR_OK;
     sync_all(e);
     be_free(e->d_pfb_hq); be_free(e->d_pfb_tw); be_free(e->d_pfb_streams[0]); be_free(e->d_pfb_streams[1]); be_free(e->d_pfb_dc_state);
     e->d_pfb_hq = nullptr; e->d_pfb_tw = nullptr; e->d_pfb_streams[0] = e->d_pfb_streams[1] = nullptr; e->d_pfb_dc_state = nullptr;
     std::vector<float> hq, tw;
-    pfb_analysis_tables((unsigned)M, 4, 60.0f, hq, tw);                       // firpfbch_crcf_create_kaiser(LIQUID_ANALYZER, M, 4, 60)
+    if (osf == 2) pfb2_analysis_tables((unsigned)M, 4, 60.0f, hq, tw);       // firpfbch2_crcf_create_kaiser(LIQUID_ANALYZER, M, 4, 60)
+    else pfb_analysis_tables((unsigned)M, 4, 60.0f, hq, tw);                  // firpfbch_crcf_create_kaiser(LIQUID_ANALYZER, M, 4, 60)
     e->pfb_slots = (size_t)M + 1;                                            // M channels + the DC-corrected copy of channel 0
-    e->pfb_stride = ((size_t)kBlkHist + e->max_block / (size_t)M + 8 + 1) & ~(size_t)1;
+    e->pfb_stride = ((size_t)kBlkHist + (size_t)osf * (e->max_block / (size_t)M) + 8 + 1) & ~(size_t)1;
     const size_t bytes = e->pfb_slots * e->pfb_stride * sizeof(float2);
     int bad = 0;
     bad |= be_malloc((void **)&e->d_pfb_hq, hq.size() * sizeof(float));
@@ -1273,7 +1274,7 @@ static int pfb_prepare(sdr_engine *e, int M) {
     for (int b = 0; b < 2; ++b) be_memset(e->d_pfb_streams[b], 0, bytes, e->stream);
     be_memset(e->d_pfb_dc_state, 0, sizeof(float2), e->stream);
     be_sync(e->stream);
-    e->pfb_M = M; e->pfb_have_block = false; e->pfb_last_frames = 0;
+    e->pfb_M = M; e->pfb_osf = osf; e->pfb_frame_base = 0; e->pfb_have_block = false; e->pfb_last_frames = 0;
     for (auto *c : e->chans) if (c) c->pfb_slot_prev = -1;
     return SDR_OK;
 }
@@ -1293,17 +1294,20 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
 
     // SDRPostThread::run dispatch (SDRPostThread.cpp:178-187): blocks that come with more than one channel go through the
     // channelizer; the count is SDRThread::getOptimalChannelCount of the rate (SoapySDRThread.cpp:513,676-693)
-    const int pfb_M = (e->chan_mode == 1) ? optimal_channel_count(rate) : 1;
+    const int pfb_M = (e->chan_mode != 0) ? optimal_channel_count(rate) : 1;
+    const int pfb_osf = e->chan_mode == 2 ? 2 : 1;                // SDRPostPFBCH2: firpfbch2, two output frames per numChannels inputs
     const bool pfb = pfb_M > 1;
     if (pfb) {
         if (pfb_M > kPfbMaxChannels) return fail(SDR_ERR_UNSUPPORTED, "channelizer mode: sample rate needs more channels than supported");
         if (n % (unsigned)pfb_M) return fail(SDR_ERR_ARG, "channelizer mode: block length must be a multiple of the channel count (SoapySDRThread.cpp:668-674)");
-        if ((size_t)(2 * 4 - 1) * pfb_M > (size_t)kBlkHist) return fail(SDR_ERR_UNSUPPORTED, "channelizer history");
-        int r = pfb_prepare(e, pfb_M);
+        if ((size_t)(2 * 8 - 1) * pfb_M > (size_t)kBlkHist) return fail(SDR_ERR_UNSUPPORTED, "channelizer history");
+        int r = pfb_prepare(e, pfb_M, pfb_osf);
         if (r) return r;
     }
-    const unsigned n_ch = pfb ? n / (unsigned)pfb_M : n;          // samples every demodulator sees this block
-    const long long rate_ch = pfb ? rate / pfb_M : rate;          // chanBw = sampleRate / numChannels (SDRPostThread.cpp:408)
+    // samples every demodulator sees this block, and at which rate: chanBw = sampleRate / numChannels (SDRPostThread.cpp:408),
+    // twice that for the oversampled channelizer (runDemodChannels(chanBw * 2), :510)
+    const unsigned n_ch = pfb ? (unsigned)pfb_osf * (n / (unsigned)pfb_M) : n;
+    const long long rate_ch = pfb ? (long long)pfb_osf * (rate / pfb_M) : rate;
 
     // 1+2. DC blocker (SDRPostThread.cpp:284) on its own stream, so that it runs underneath the channel kernels of the
     //      previous block: raw history slide -> copy the block in -> double-precision scan -> bit-exact float replay
@@ -1383,7 +1387,8 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
                       (size_t)kBlkHist * sizeof(float2), e->pfb_slots, dcs);
         PfbArgs pa;
         pa.x = blk; pa.y = pfb_streams + kBlkHist; pa.hq = e->d_pfb_hq; pa.tw = e->d_pfb_tw; pa.M = pfb_M; pa.p = 8; pa.F = (int)n_ch;
-        pa.chan_stride = (long long)stride;
+        pa.chan_stride = (long long)stride; pa.osf = pfb_osf; pa.frame_base = e->pfb_frame_base;
+        e->pfb_frame_base += n_ch;
         const int tiles = ((int)n_ch + kPfbTileFrames - 1) / kPfbTileFrames;
         float2 *ch0 = pfb_streams + kBlkHist, *ch0_dc = pfb_streams + (size_t)pfb_M * stride + kBlkHist;
 #ifndef SDR_EMU
@@ -1711,7 +1716,7 @@ extern "C" int sdr_engine_submit_device_async(sdr_engine *e, const void *d_iq, u
 // and every demodulator reads its filterbank channel at sampleRate / numChannels.  Set before the first block.
 extern "C" int sdr_engine_set_channelizer(sdr_engine *e, int mode) {
     if (!e) return fail(SDR_ERR_ARG, "null engine");
-    if (mode != 0 && mode != 1) return fail(SDR_ERR_UNSUPPORTED, "sdr_engine_set_channelizer: mode must be 0 (single channel) or 1 (PFBCH)");
+    if (mode < 0 || mode > 2) return fail(SDR_ERR_UNSUPPORTED, "sdr_engine_set_channelizer: mode must be 0 (single channel), 1 (PFBCH) or 2 (PFBCH2)");
     std::lock_guard<std::mutex> lk(e->mu);
     if (e->have_block && mode != e->chan_mode) return fail(SDR_ERR_STATE, "sdr_engine_set_channelizer: set the mode before the first block");
     e->chan_mode = mode;
@@ -1873,6 +1878,10 @@ extern "C" int sdr_spectrum_fetch_debug(sdr_spectrum *s, unsigned idx, float *ma
 struct sdr_pfb {
     sdr_engine *eng = nullptr;
     unsigned M = 0, p = 0, max_frames = 0;
+    int osf = 1;                 // 1: firpfbch_crcf, 2: firpfbch2_crcf (one output frame per M/2 inputs)
+    long long frame_base = 0;    // output frames produced since reset (osf 2: branch phase)
+    size_t hist() const { return osf == 2 ? (size_t)(2 * p - 1) * (M / 2) : (size_t)(p - 1) * M; }
+    unsigned step() const { return osf == 2 ? M / 2 : M; }      // input samples per output frame
     float *d_hq = nullptr; float2 *d_tw = nullptr;
     float2 *d_x = nullptr;       // [(p-1) M history | max_frames M new]
     float2 *d_y = nullptr;       // [max_frames M]
@@ -1886,16 +1895,26 @@ static void pfb_free(sdr_pfb *p) {
 
 extern "C" int sdr_pfb_optimal_channel_count(long long sample_rate) { return optimal_channel_count(sample_rate); }
 
+static int pfb_create_impl(sdr_engine *e, int osf, unsigned num_channels, unsigned m, float as_db, unsigned max_frames, sdr_pfb **out);
 extern "C" int sdr_pfb_create(sdr_engine *e, unsigned num_channels, unsigned m, float as_db, unsigned max_frames, sdr_pfb **out) {
+    return pfb_create_impl(e, 1, num_channels, m, as_db, max_frames, out);
+}
+// firpfbch2_crcf_create_kaiser(LIQUID_ANALYZER, M, m, As) (SDRPostThread::initPFBCH2, SDRPostThread.cpp:457-470): one output
+// frame of M samples per M/2 inputs; max_frames counts OUTPUT frames
+extern "C" int sdr_pfb2_create(sdr_engine *e, unsigned num_channels, unsigned m, float as_db, unsigned max_frames, sdr_pfb **out) {
+    return pfb_create_impl(e, 2, num_channels, m, as_db, max_frames, out);
+}
+static int pfb_create_impl(sdr_engine *e, int osf, unsigned num_channels, unsigned m, float as_db, unsigned max_frames, sdr_pfb **out) {
     if (!e || !out) return fail(SDR_ERR_ARG, "sdr_pfb_create: null argument");
     if (num_channels < 2 || (num_channels & 1u) || num_channels > (unsigned)kPfbMaxChannels || m < 1 || m > 8 || max_frames < 1)
         return fail(SDR_ERR_ARG, "sdr_pfb_create: num_channels must be even and in [2, 256], m in [1, 8]");
     std::lock_guard<std::mutex> lk(e->mu);
     auto *p = new sdr_pfb();
-    p->eng = e; p->M = num_channels; p->p = 2 * m; p->max_frames = max_frames;
+    p->eng = e; p->M = num_channels; p->p = 2 * m; p->max_frames = max_frames; p->osf = osf;
     std::vector<float> hq, tw;
-    pfb_analysis_tables(num_channels, m, as_db, hq, tw);
-    const size_t hist = (size_t)(p->p - 1) * p->M, cap = (size_t)max_frames * p->M;
+    if (osf == 2) pfb2_analysis_tables(num_channels, m, as_db, hq, tw);
+    else pfb_analysis_tables(num_channels, m, as_db, hq, tw);
+    const size_t hist = p->hist(), cap = (size_t)max_frames * p->M;
     int bad = 0;
     bad |= be_malloc((void **)&p->d_hq, hq.size() * sizeof(float));
     bad |= be_malloc((void **)&p->d_tw, tw.size() * sizeof(float));
@@ -1922,20 +1941,23 @@ extern "C" int sdr_pfb_destroy(sdr_pfb *p) {
 extern "C" int sdr_pfb_reset(sdr_pfb *p) {
     if (!p) return fail(SDR_ERR_ARG, "null channelizer");
     std::lock_guard<std::mutex> lk(p->eng->mu);
-    be_memset(p->d_x, 0, (size_t)(p->p - 1) * p->M * sizeof(float2), p->eng->stream);
+    be_memset(p->d_x, 0, p->hist() * sizeof(float2), p->eng->stream);
     be_sync(p->eng->stream);
+    p->frame_base = 0;
     return SDR_OK;
 }
 
 // device-resident form: d_in / d_out hold n = frames * M samples; history is carried inside the object
 static int pfb_run(sdr_pfb *p, const float2 *d_in, unsigned n, float2 *d_out) {
     sdr_engine *e = p->eng;
-    const unsigned F = n / p->M;
-    const size_t hist = (size_t)(p->p - 1) * p->M;
+    const unsigned F = n / p->step();
+    const size_t hist = p->hist();
     float2 *xnew = p->d_x + hist;
     be_d2d(xnew, d_in, (size_t)n * sizeof(float2), e->stream);
     PfbArgs a;
     a.x = xnew; a.y = d_out; a.hq = p->d_hq; a.tw = p->d_tw; a.M = (int)p->M; a.p = (int)p->p; a.F = (int)F; a.chan_stride = 0;
+    a.osf = p->osf; a.frame_base = p->frame_base;
+    p->frame_base += F;
     const int tiles = ((int)F + kPfbTileFrames - 1) / kPfbTileFrames;
 #ifndef SDR_EMU
     const size_t smem = pfb_smem_elems(a.M, a.p) * sizeof(float2);
@@ -1956,8 +1978,8 @@ static int pfb_run(sdr_pfb *p, const float2 *d_in, unsigned n, float2 *d_out) {
 
 extern "C" int sdr_pfb_execute(sdr_pfb *p, const sdr_cf32 *iq, unsigned n, sdr_cf32 *out) {
     if (!p || !iq || !out) return fail(SDR_ERR_ARG, "sdr_pfb_execute: null argument");
-    if (n == 0 || n % p->M != 0 || n / p->M > p->max_frames)
-        return fail(SDR_ERR_ARG, "sdr_pfb_execute: n must be a non-zero multiple of num_channels within max_frames (SoapySDRThread.cpp:668-674)");
+    if (n == 0 || n % p->step() != 0 || n / p->step() > p->max_frames)
+        return fail(SDR_ERR_ARG, "sdr_pfb_execute: n must be a non-zero multiple of num_channels (half of it for firpfbch2) within max_frames (SoapySDRThread.cpp:668-674)");
     sdr_engine *e = p->eng;
     std::lock_guard<std::mutex> lk(e->mu);
     memcpy(p->h_io, iq, (size_t)n * sizeof(sdr_cf32));
@@ -1966,18 +1988,19 @@ extern "C" int sdr_pfb_execute(sdr_pfb *p, const sdr_cf32 *iq, unsigned n, sdr_c
     // input must not alias the output: run from a private copy inside d_x (pfb_run copies d_in there first)
     int r = pfb_run(p, p->d_y, n, p->d_y);
     if (r) return r;
-    be_d2h(p->h_io, p->d_y, (size_t)n * sizeof(float2), e->stream);
+    const size_t n_out = (size_t)n * (size_t)p->osf;                      // firpfbch2 is oversampled by two
+    be_d2h(p->h_io, p->d_y, n_out * sizeof(float2), e->stream);
     if (be_sync(e->stream)) return fail(SDR_ERR_CUDA, std::string("sdr_pfb_execute: ") + be_last_error());
 #ifndef SDR_EMU
     { cudaError_t err = cudaGetLastError(); if (err != cudaSuccess) return fail(SDR_ERR_CUDA, std::string("sdr_pfb_execute: ") + cudaGetErrorString(err)); }
 #endif
-    memcpy(out, p->h_io, (size_t)n * sizeof(sdr_cf32));
+    memcpy(out, p->h_io, n_out * sizeof(sdr_cf32));
     return SDR_OK;
 }
 
 extern "C" int sdr_pfb_execute_device(sdr_pfb *p, const void *d_iq, unsigned n, void *d_out) {
     if (!p || !d_iq || !d_out) return fail(SDR_ERR_ARG, "sdr_pfb_execute_device: null argument");
-    if (n == 0 || n % p->M != 0 || n / p->M > p->max_frames) return fail(SDR_ERR_ARG, "sdr_pfb_execute_device: bad length");
+    if (n == 0 || n % p->step() != 0 || n / p->step() > p->max_frames) return fail(SDR_ERR_ARG, "sdr_pfb_execute_device: bad length");
     std::lock_guard<std::mutex> lk(p->eng->mu);
     return pfb_run(p, (const float2 *)d_iq, n, (float2 *)d_out);
 }

@@ -128,7 +128,8 @@ int sdr_spectrum_fetch_debug(sdr_spectrum *sp, unsigned idx, float *mags, float 
  * liquid's: numChannels interleaved channel samples per input frame, which runDemodChannels de-interleaves (:366-382).
  * n must be a multiple of num_channels (SDRThread::getOptimalElementCount, src/sdr/SoapySDRThread.cpp:668-674). */
 /* Channelizer mode of the engine: SDRPostThread::setChannelizerType / the dispatch of SDRPostThread::run (:142-148,
- * :178-187).  mode 0 (default) = runSingleCH for every block; mode 1 = SDRPostPFBCH: a block whose rate gives
+ * :178-187).  mode 0 (default) = runSingleCH for every block; mode 2 = SDRPostPFBCH2 (as mode 1 with firpfbch2: the
+ * demodulators run at twice the channel rate); mode 1 = SDRPostPFBCH: a block whose rate gives
  * numChannels > 1 goes through the analysis filterbank (no wideband DC blocker, :432-451), demodulators are routed to
  * the nearest channel centre (updateChannels / getChannelAt / runDemodChannels, :115-139, :303-398; channel 0 gets the DC
  * blocker, the extra channel wraps onto numChannels/2) and must have been created with sample_rate = channel_rate of
@@ -138,6 +139,10 @@ int sdr_engine_channel_plan(long long sample_rate, int *num_channels, long long 
 typedef struct sdr_pfb sdr_pfb;
 int sdr_pfb_optimal_channel_count(long long sample_rate);     /* SDRThread::getOptimalChannelCount, SoapySDRThread.cpp:676-693 */
 int sdr_pfb_create(sdr_engine *eng, unsigned num_channels, unsigned m, float as_db, unsigned max_frames, sdr_pfb **out);
+/* firpfbch2_crcf_create_kaiser(LIQUID_ANALYZER, numChannels, 4, 60) + firpfbch2_crcf_execute per numChannels/2 samples
+ * (SDRPostThread::initPFBCH2 / runPFBCH2, SDRPostThread.cpp:457-511): 2 n output samples for n inputs; max_frames counts
+ * output frames.  Same execute / reset / destroy calls. */
+int sdr_pfb2_create(sdr_engine *eng, unsigned num_channels, unsigned m, float as_db, unsigned max_frames, sdr_pfb **out);
 int sdr_pfb_destroy(sdr_pfb *pfb);
 int sdr_pfb_reset(sdr_pfb *pfb);                                /* firpfbch_crcf_reset */
 int sdr_pfb_execute(sdr_pfb *pfb, const sdr_cf32 *iq, unsigned n, sdr_cf32 *out);              /* host buffers */

@@ -260,15 +260,17 @@ class RefChannelizerPath:
       SDRPostThread::runDemodChannels    :303-398   de-interleave, channel 0 through the DC blocker, extra channel = numChannels/2
     Every demodulator then runs DemodulatorPreThread + Modem at the channel rate (RefChan with sample_rate = chanBw)."""
 
-    def __init__(self, ref, fs, chans, audio_rate=48000):
-        from oracle.refbind import RefPfb
-        self.ref, self.fs = ref, fs
+    def __init__(self, ref, fs, chans, audio_rate=48000, mode=1):
+        from oracle.refbind import RefPfb, RefPfb2
+        self.ref, self.fs, self.mode = ref, fs, mode
         ref.L.ref_optimal_channel_count.argtypes = [__import__("ctypes").c_longlong]
         self.M = ref.L.ref_optimal_channel_count(fs)
         self.chan_bw = fs // self.M
-        self.pfb = RefPfb(ref, self.M)
+        # runPFBCH2 (:472-511): firpfbch2, and runDemodChannels(chanBw * 2) -- the demodulators see twice the channel rate
+        self.pfb = RefPfb2(ref, self.M) if mode == 2 else RefPfb(ref, self.M)
+        self.demod_rate = self.chan_bw * (2 if mode == 2 else 1)
         self.dc = RefIngress(ref)                               # dcFilter: the same iirfilt DC blocker object type (:29)
-        self.demods = [RefChan(ref, m, self.chan_bw, bw, audio_rate) for m, bw, _ in chans]
+        self.demods = [RefChan(ref, m, self.demod_rate, bw, audio_rate) for m, bw, _ in chans]
 
     def centers(self, frequency):
         M, c = self.M, [0] * (self.M + 1)
@@ -307,15 +309,16 @@ class RefChannelizerPath:
             d.close()
 
 
-def check_channelizer_mode(lib, ref, fs, chans, n_blocks, retune=None, device=0, seed=2024):
+def check_channelizer_mode(lib, ref, fs, chans, n_blocks, retune=None, device=0, seed=2024, mode=1):
     """Engine in channelizer mode against RefChannelizerPath.  chans: [(modem, bw, offset)].  Returns the set of filterbank
     channels that were exercised."""
     N = synth.block_size(fs)
     eng = Engine(lib, device=device, max_block=N)
-    eng.set_channelizer(1)
+    eng.set_channelizer(mode)
     M, chan_rate = eng.channel_plan(fs)
-    oracle = RefChannelizerPath(ref, fs, chans)
+    oracle = RefChannelizerPath(ref, fs, chans, mode=mode)
     assert (M, chan_rate) == (oracle.M, oracle.chan_bw) and N % M == 0
+    chan_rate = oracle.demod_rate
     cs = [Channel(eng, m, chan_rate, bw, 48000, frequency=CENTER + off) for m, bw, off in chans]
     freqs = [CENTER + off for _, _, off in chans]
     got = [[] for _ in chans]; want = [[] for _ in chans]

@@ -4,25 +4,28 @@ import numpy as np
 import pytest
 
 from cubicsdr_b200 import Channelizer, Engine, synth
-from oracle.refbind import RefPfb
+from oracle.refbind import RefPfb, RefPfb2
 from tests.parity import TOL, relrms
 
 
-def _stream(lib, ref, M, frames_per_call, seed=7, device=0):
-    """Several calls of different lengths through engine and oracle: state (2m - 1 frames of history) must carry."""
+def _stream(lib, ref, M, frames_per_call, seed=7, device=0, oversampled=False):
+    """Several calls of different lengths through engine and oracle: state (the filter windows) must carry.  With
+    oversampled=True (firpfbch2) a frame consumes M / 2 samples, and odd frame counts exercise the alternating branch phase."""
     rng = np.random.default_rng(seed)
     eng = Engine(lib, device=device, max_block=4096)
-    ch = Channelizer(eng, M, max(frames_per_call))
-    rp = RefPfb(ref, M)
-    worst = 0.0
+    ch = Channelizer(eng, M, max(frames_per_call), oversampled=oversampled)
+    rp = RefPfb2(ref, M) if oversampled else RefPfb(ref, M)
+    step = M // 2 if oversampled else M
+    gots, wants = [], []
     for F in frames_per_call:
-        x = (rng.standard_normal(F * M) + 1j * rng.standard_normal(F * M)).astype(np.complex64)
-        x += np.exp(2j * np.pi * 0.123 * np.arange(F * M)).astype(np.complex64) * 3           # a strong tone: one hot channel
+        x = (rng.standard_normal(F * step) + 1j * rng.standard_normal(F * step)).astype(np.complex64)
+        x += np.exp(2j * np.pi * 0.123 * np.arange(F * step)).astype(np.complex64) * 3        # a strong tone: one hot channel
         got, want = ch.execute(x), rp.execute(x)
         assert got.shape == want.shape == (F, M)
-        worst = max(worst, relrms(got, want))
+        gots.append(got); wants.append(want)
     ch.close(); rp.close(); eng.close()
-    return worst
+    # over the whole stream: the first frames of a 2-channel bank are numerically zero on both sides (sinc prototype)
+    return relrms(np.concatenate(gots), np.concatenate(wants))
 
 
 CASES = [(2, [5, 1, 9, 40]), (8, [3, 16, 1, 1, 33]), (40, [7, 2, 50]), (122, [20, 3, 41])]
@@ -107,3 +110,30 @@ def test_engine_channelizer_mode_122_channels_gpu(gpu_lib, ref):
     chans = [(modems[i % 6], bws[modems[i % 6]], o) for i, o in enumerate(offs)]
     used = parity.check_channelizer_mode(gpu_lib, ref, fs, chans, n_blocks=2)
     assert 0 in used and 122 in used and len(used) >= 10
+
+
+@pytest.mark.parametrize("M,calls", [(2, [5, 1, 9, 40]), (8, [3, 16, 1, 1, 33]), (40, [7, 2, 50]), (122, [21, 3, 40])])
+def test_oversampled_channelizer_matches_reference_binary_emulator(emu_lib, ref, M, calls):
+    assert _stream(emu_lib, ref, M, calls, oversampled=True) <= TOL
+
+
+def test_engine_oversampled_channelizer_mode_emulator(emu_lib, ref):
+    """SDRPostThread::runPFBCH2: demodulators at twice the channel rate behind firpfbch2."""
+    from tests import parity
+    chans = [("FM", 200000, 40000), ("AM", 6000, -650000), ("NBFM", 12500, 1150000), ("USB", 5400, 560000)]
+    used = parity.check_channelizer_mode(emu_lib, ref, 2400000, chans, n_blocks=4, retune={2: {3: -90000}}, mode=2)
+    assert {0, 4}.issubset(used)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,calls", [(8, [3, 16, 1, 1, 33]), (122, [21, 3, 40])])
+def test_oversampled_channelizer_matches_reference_binary_gpu(gpu_lib, ref, M, calls):
+    assert _stream(gpu_lib, ref, M, calls, oversampled=True) <= TOL
+
+
+@pytest.mark.gpu
+def test_engine_oversampled_channelizer_mode_gpu(gpu_lib, ref):
+    from tests import parity
+    chans = [("FM", 200000, 40000), ("AM", 6000, -650000), ("NBFM", 12500, 1150000), ("USB", 5400, 560000)]
+    used = parity.check_channelizer_mode(gpu_lib, ref, 2400000, chans, n_blocks=4, retune={2: {3: -90000}}, mode=2)
+    assert {0, 4}.issubset(used)
