@@ -104,6 +104,29 @@ int main(int argc, char **argv) {
         { AudioThreadInput a; if (!fm2.fetchAudio(a, nullptr)) return 17; audio2.insert(audio2.end(), a.data.begin(), a.data.end()); }
         dump(dir + "/audio_chan_FM_pipelined.bin", audio2);
     }
+    // ---- channelizer mode (SDRPostThread::setChannelizerType(SDRPostPFBCH) -> runPFBCH): the demodulator is created with
+    // the channel rate and keeps its absolute frequency; the engine routes it to its filterbank channel
+    {
+        auto eng3 = std::make_shared<Engine>(0, 1u << 17);
+        SDRPostB200 post3(eng3);
+        if (!post3.setChannelizerType(1)) return 18;
+        int numChannels = 0; long long chanBw = 0;
+        SDRPostB200::channelPlan(2400000, numChannels, chanBw);
+        if (numChannels != 4 || chanBw != 600000) return 19;
+        DemodulatorB200 fm3(eng3, "FM", chanBw, 200000, 48000, false);
+        fm3.setFrequency(100000000 + 300000);
+        std::vector<float> audio3;
+        for (int b = 0; b < 2; ++b) {
+            DemodulatorThreadIQData blk;
+            blk.frequency = 100000000; blk.sampleRate = 2400000;
+            blk.data = slurp<liquid_float_complex>(dir + "/wide_" + std::to_string(b) + ".bin");
+            if (!post3.runSingleCH(blk)) { std::cerr << sdr_last_error() << "\n"; return 20; }   // the engine dispatches by mode
+            AudioThreadInput a;
+            if (!fm3.fetchAudio(a, nullptr)) return 21;
+            audio3.insert(audio3.end(), a.data.begin(), a.data.end());
+        }
+        dump(dir + "/audio_chan_FM_channelizer.bin", audio3);
+    }
     dump(dir + "/audio_chan_FM.bin", audio);
     dump(dir + "/postiq_chan_FM.bin", postiq);
     dump(dir + "/spec_last_points.bin", pts);

@@ -41,6 +41,14 @@ def _run(lib, ref, tmp):
             want_audio[FIVE[i][0]].append(r["audio"])
             if i == 0 and b < 2:
                 fm_iq.append(r["iq"])
+    # channelizer mode: the same two wideband blocks through the reference's runPFBCH path (tests/parity.RefChannelizerPath)
+    from tests.parity import CENTER, RefChannelizerPath
+    pfb_path = RefChannelizerPath(ref, fs, [FIVE[0]])
+    want_pfb = []
+    for b in range(2):
+        res, _ = pfb_path.block(synth.wideband(fs, N, FIVE, t0=b * N), CENTER, [CENTER + FIVE[0][2]])
+        want_pfb.append(res[0]["audio"])
+    pfb_path.close()
     exe = os.path.join(tmp, "host_adapter_test")
     _build(lib.path, exe)
     out = subprocess.run([exe, tmp], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
@@ -53,6 +61,9 @@ def _run(lib, ref, tmp):
     got = np.fromfile(os.path.join(tmp, "audio_chan_FM.bin"), np.float32)
     want = np.concatenate(want_audio["FM"][:2])
     assert len(got) == len(want) and relrms(got, want) <= TOL
+    chz = np.fromfile(os.path.join(tmp, "audio_chan_FM_channelizer.bin"), np.float32)
+    want_chz = np.concatenate(want_pfb)
+    assert len(chz) == len(want_chz) and relrms(chz, want_chz) <= TOL, "channelizer mode through the C++ adapters"
     piped = np.fromfile(os.path.join(tmp, "audio_chan_FM_pipelined.bin"), np.float32)
     assert np.array_equal(piped, got), "pipelined ingress (runSingleCHPipelined) must return the same audio, one block late"
     got = np.fromfile(os.path.join(tmp, "postiq_chan_FM.bin"), np.complex64)
