@@ -132,8 +132,9 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_run(wl, chans, iq_host, threads, blocks):
-    """Time the reference CPU path (oracle/_ref: reference liquid-dsp binary + CubicSDR glue) on `blocks` blocks."""
+def cpu_reference_run(wl, chans, iq_host, threads, blocks, channelizer=0):
+    """Time the reference CPU path (oracle/_ref: reference liquid-dsp binary + CubicSDR glue) on `blocks` blocks.
+    channelizer = 1 / 2: through SDRPostThread::runPFBCH / runPFBCH2 instead of runSingleCH."""
     import ctypes as C
     from oracle.refbind import Ref
     ref = Ref()
@@ -143,6 +144,16 @@ def cpu_reference_run(wl, chans, iq_host, threads, blocks):
     shifts = (C.c_longlong * max(1, n_chan))(*[off for _, _, off in chans])
     chk = C.c_double()
     iq = np.ascontiguousarray(iq_host, np.complex64)
+    if channelizer:
+        freqs = (C.c_longlong * max(1, n_chan))(*[CENTER + off for _, _, off in chans])
+        ref.L.ref_bench_pfb_path.restype = C.c_double
+        ref.L.ref_bench_pfb_path.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_longlong, C.c_longlong, C.c_int, C.c_uint,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_uint, C.c_void_p]
+        secs = ref.L.ref_bench_pfb_path(iq.ctypes.data_as(C.c_void_p), iq.size, 1, blocks, wl["fs"], CENTER, int(channelizer), n_chan,
+                                        names, bws, freqs, 48000, wl["fft"], threads, C.byref(chk))
+        if secs < 0:
+            raise RuntimeError("reference channelizer path: block length is not a multiple of the channel count")
+        return secs, ref.version()
     secs = ref.L.ref_bench_path(iq.ctypes.data_as(C.c_void_p), iq.size, 1, blocks, wl["fs"], n_chan, names, bws, shifts, 48000,
                                 wl["fft"], threads, C.byref(chk))      # 1 untimed block first (page faults, cold filters)
     return secs, ref.version()
@@ -156,7 +167,7 @@ def run_reference(args, wl, chans, rank):
     N = synth.block_size(wl["fs"])
     iq = synth.wideband(wl["fs"], N, chans[:: max(1, len(chans) // 32)] if chans else [], t0=0)   # carriers: a 32-channel subset keeps generation quick
     threads = os.cpu_count() or 1
-    secs, ver = cpu_reference_run(wl, chans, iq, threads, args.steps)
+    secs, ver = cpu_reference_run(wl, chans, iq, threads, args.steps, channelizer=1 if args.channelizer else 0)
     t_tot = secs
     val = N * args.steps / t_tot / 1e6
     line = {"impl": "reference", "metric": "IQ MSamples/s through spectrum+demod chain", "value": val, "unit": "MSamples/s",
@@ -288,6 +299,8 @@ def main():
             run_pfb(args, wl)
         return
     if args.impl == "reference":
+        if args.channelizer:
+            wl = dict(wl, desc=wl["desc"] + " [DIAGNOSTIC: channelizer mode (SDRPostThread::runPFBCH)]")
         run_reference(args, wl, chans, rank)
         return
 
@@ -325,7 +338,6 @@ def main():
         eng.set_channelizer(1)
         n_pfb, chan_fs = eng.channel_plan(fs)
         wl = dict(wl, desc=wl["desc"] + " [DIAGNOSTIC: channelizer mode, %d filterbank channels of %d Hz]" % (n_pfb, chan_fs))
-        args.no_cpu_baseline = True                              # the reference arm below times runSingleCH, not runPFBCH
     cobjs = [Channel(eng, m, chan_fs, bw, 48000, frequency=CENTER + off) for m, bw, off in mine]
     spec = Spectrum(eng, wl["fft"], 0) if (wl["fft"] and rank == 0) else None
 
@@ -517,7 +529,7 @@ def main():
         try:
             threads = os.cpu_count() or 1
             iq_host = ring[0].cpu().numpy()
-            secs, ver = cpu_reference_run(wl, chans, iq_host, threads, 1)
+            secs, ver = cpu_reference_run(wl, chans, iq_host, threads, 1, channelizer=1 if args.channelizer else 0)
             cpu = {"value": N / secs / 1e6, "unit": "MSamples/s", "cores": threads, "kind": "reference",
                    "sample": "1 block (%d samples = 1/60 s), all %d channels%s, reference liquid-dsp %s binary + CubicSDR glue" % (
                        N, len(chans), " + spectrum" if wl["fft"] else "", ver)}

@@ -557,3 +557,96 @@ API double ref_bench_path(const lq_cf *iq, unsigned n, unsigned warm_blocks, uns
     if (spec) { ref_spectrum_destroy(spec); ref_distrib_destroy(dist); }
     return std::chrono::duration<double>(t1 - t0).count();
 }
+
+// The same benchmark through the reference's channelizer path (SDRPostThread::runPFBCH + runDemodChannels, mode 1, or
+// runPFBCH2, mode 2): the filterbank runs on the calling thread like SDRPostThread, the spectrum sees the raw block, every
+// demodulator (created at the channel rate) reads its de-interleaved channel; channel 0 goes through the DC blocker.
+// freqs are absolute demodulator frequencies, `center` the tuner frequency.
+API double ref_bench_pfb_path(const lq_cf *iq, unsigned n, unsigned warm_blocks, unsigned blocks, long long sampleRate, long long center,
+                              int mode, unsigned n_chan, const char *const *modem_names, const long long *bandwidths,
+                              const long long *freqs, int audioRate, unsigned fftSize, unsigned threads, double *audio_checksum) {
+    const int M = ref_optimal_channel_count(sampleRate);
+    if (M < 2 || n % (unsigned)M) return -1.0;
+    const long long chanBw = sampleRate / M;
+    const int osf = mode == 2 ? 2 : 1;
+    const long long demodRate = chanBw * osf;
+    std::vector<void *> chans(n_chan);
+    for (unsigned c = 0; c < n_chan; c++) chans[c] = ref_chan_create(modem_names[c], demodRate, bandwidths[c], audioRate);
+    void *pfb = osf == 2 ? ref_pfb2_create((unsigned)M, 4, 60.0f) : ref_pfb_create((unsigned)M, 4, 60.0f);
+    void *dcf = ref_ingress_create();
+    void *spec = fftSize ? ref_spectrum_create(fftSize) : nullptr;
+    void *dist = fftSize ? ref_distrib_create(fftSize * 2, 1000000) : nullptr;
+    // updateChannels (:115-124) and getChannelAt (:127-139)
+    std::vector<long long> centers((size_t)M + 1);
+    for (int i = 0; i < M / 2; i++) { int ofs = (int)(chanBw * i); centers[i] = center + ofs; centers[i + M / 2] = center - (sampleRate / 2) + ofs; }
+    centers[M] = center + (sampleRate / 2);
+    std::vector<int> pick(n_chan, -1);
+    for (unsigned c = 0; c < n_chan; c++) {
+        long long minDelta = sampleRate;
+        for (int i = 0; i < M + 1; i++) { long long fd = std::llabs(freqs[c] - centers[i]); if (fd < minDelta) { minDelta = fd; pick[c] = i; } }
+    }
+    const size_t chanDataSize = (size_t)osf * n / M;
+    std::vector<lq_cf> dataOut((size_t)osf * n);
+    std::vector<std::vector<lq_cf>> chanData((size_t)M + 1);
+    std::vector<char> active((size_t)M + 1, 0);
+    for (unsigned c = 0; c < n_chan; c++) if (pick[c] >= 0) active[pick[c]] = 1;
+    std::vector<lq_cf> dcBuf(chanDataSize), frames;
+    unsigned cap_frames = fftSize ? (n / (fftSize * 2) + 2) : 0;
+    if (fftSize) frames.resize((size_t)cap_frames * fftSize * 2);
+    std::vector<float> pts(fftSize ? fftSize : 1);
+    std::vector<unsigned char> line(fftSize ? fftSize : 1);
+    if (threads < 1) threads = 1;
+    std::vector<double> sums(threads, 0.0);
+    auto t0 = std::chrono::steady_clock::now();
+    for (unsigned b = 0; b < warm_blocks + blocks; b++) {
+        if (b == warm_blocks) t0 = std::chrono::steady_clock::now();
+        if (osf == 2) ref_pfb2_execute(pfb, const_cast<lq_cf *>(iq), n, dataOut.data());
+        else ref_pfb_execute(pfb, const_cast<lq_cf *>(iq), n, dataOut.data());
+        for (int i = 0; i < M + 1; i++) {                                   // runDemodChannels :333-397
+            if (!active[i]) continue;
+            chanData[i].resize(chanDataSize);
+            int idx = (i == M) ? M / 2 : i;
+            if (i == 0) {
+                for (size_t j = 0; j < chanDataSize; j++) { dcBuf[j] = dataOut[idx]; idx += M; }
+                ref_ingress_block(dcf, dcBuf.data(), (unsigned)chanDataSize, chanData[i].data());
+            } else {
+                for (size_t j = 0; j < chanDataSize; j++) { chanData[i][j] = dataOut[idx]; idx += M; }
+            }
+        }
+        std::atomic<unsigned> next(0);
+        auto work = [&](unsigned tid) {
+            std::vector<float> audio(8192);
+            for (;;) {
+                unsigned c = next.fetch_add(1);
+                if (c >= n_chan) break;
+                if (pick[c] < 0) continue;
+                auto *rc = (RefChan *)chans[c];
+                size_t need = (size_t)ceil((double)chanDataSize * rc->iqResampleRatio * rc->audioResampleRatio) + 2048;
+                if (audio.size() < need) audio.resize(need);
+                unsigned na = 0;
+                ref_chan_process(chans[c], chanData[pick[c]].data(), (unsigned)chanDataSize, freqs[c] - centers[pick[c]], nullptr, nullptr,
+                                 nullptr, audio.data(), &na, nullptr, nullptr);
+                double s = 0; for (unsigned i = 0; i < na; i++) s += audio[i];
+                sums[tid] += s;
+            }
+        };
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < threads; t++) pool.emplace_back(work, t);
+        if (spec) {
+            unsigned nf = ref_distrib_push(dist, const_cast<lq_cf *>(iq), n, sampleRate, frames.data(), cap_frames);
+            for (unsigned f = 0; f < nf && f < cap_frames; f++)
+                ref_spectrum_frame(spec, frames.data() + (size_t)f * fftSize * 2, fftSize * 2, pts.data(), line.data(), nullptr, nullptr, nullptr);
+        }
+        work(0);
+        for (auto &t : pool) t.join();
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    double tot = 0; for (double s : sums) tot += s;
+    if (audio_checksum) *audio_checksum = tot;
+    for (auto c : chans) ref_chan_destroy(c);
+    if (osf == 2) ref_pfb2_destroy(pfb); else ref_pfb_destroy(pfb);
+    ref_ingress_destroy(dcf);
+    if (spec) { ref_spectrum_destroy(spec); ref_distrib_destroy(dist); }
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
