@@ -337,6 +337,7 @@ def main():
     if args.channelizer:
         eng.set_channelizer(1)
         n_pfb, chan_fs = eng.channel_plan(fs)
+        eng.set_channel_block_max(N // n_pfb)
         wl = dict(wl, desc=wl["desc"] + " [DIAGNOSTIC: channelizer mode, %d filterbank channels of %d Hz]" % (n_pfb, chan_fs))
     cobjs = [Channel(eng, m, chan_fs, bw, 48000, frequency=CENTER + off) for m, bw, off in mine]
     spec = Spectrum(eng, wl["fft"], 0) if (wl["fft"] and rank == 0) else None

@@ -23,7 +23,7 @@ SYMBOLS = [
     "sdr_modem_check_sample_rate", "sdr_modem_create", "sdr_modem_demodulate",
     "sdr_spectrum_create", "sdr_spectrum_destroy", "sdr_spectrum_set_average_rate", "sdr_spectrum_frames",
     "sdr_spectrum_fetch", "sdr_spectrum_fetch_all", "sdr_spectrum_fetch_debug",
-    "sdr_engine_set_channelizer", "sdr_engine_channel_plan",
+    "sdr_engine_set_channelizer", "sdr_engine_channel_plan", "sdr_engine_set_channel_block_max",
     "sdr_pfb_optimal_channel_count", "sdr_pfb_create", "sdr_pfb2_create", "sdr_pfb_destroy", "sdr_pfb_reset", "sdr_pfb_execute", "sdr_pfb_execute_device",
     "sdr_design_kaiser", "sdr_design_nco_table", "sdr_design_nco_step", "sdr_design_resampler",
     "sdr_design_halfband_branch", "sdr_design_am_dc_block", "sdr_design_hilbert_q", "sdr_design_butter6_sos",
@@ -77,6 +77,7 @@ class Lib:
         L.sdr_spectrum_fetch_debug.argtypes = [vp, u, vp, vp]
         L.sdr_engine_set_channelizer.argtypes = [vp, C.c_int]
         L.sdr_engine_channel_plan.argtypes = [C.c_longlong, vp, vp]
+        L.sdr_engine_set_channel_block_max.argtypes = [vp, u]
         L.sdr_pfb_optimal_channel_count.argtypes = [C.c_longlong]
         L.sdr_pfb_create.argtypes = [vp, u, u, C.c_float, u, C.POINTER(vp)]
         L.sdr_pfb2_create.argtypes = [vp, u, u, C.c_float, u, C.POINTER(vp)]
@@ -146,6 +147,10 @@ class Engine:
     def set_channelizer(self, mode):
         """0: SDRPostThread::runSingleCH for every block; 1: runPFBCH when the rate gives more than one channel."""
         self.lib.check(self.lib.L.sdr_engine_set_channelizer(self.h, int(mode)))
+
+    def set_channel_block_max(self, n):
+        """Most samples a demodulator gets per block (channelizer mode: block / numChannels); before creating channels."""
+        self.lib.check(self.lib.L.sdr_engine_set_channel_block_max(self.h, int(n)))
 
     def channel_plan(self, sample_rate):
         """(numChannels, channel rate) of channelizer mode for this wideband rate."""

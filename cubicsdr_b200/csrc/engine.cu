@@ -258,20 +258,31 @@ __global__ void k_spec_scalar(SpecArgs a) {
 __global__ void __launch_bounds__(kSpecThreads) k_spec_points(SpecArgs a) {
     spec_points_thread(a, (long long)blockIdx.x * blockDim.x + threadIdx.x);
 }
-// serial float recurrence; the warp stages 256 samples at a time in shared memory so that the chain never waits on HBM
+// serial float recurrence at the channel rate.  The warp stages 256 samples at a time in shared memory; every lane runs the
+// chain (fully unrolled 32 steps, inputs fetched ahead of it) and lane l keeps output l, so a batch is stored coalesced and
+// the chain runs at its latency (~10 cycles a step) instead of waiting for shared memory every step.
 __global__ void __launch_bounds__(32) k_pfb_dc0(const float2 *in, float2 *out, int n, float c, float2 *state) {
-    __shared__ float2 si[256], so[256];
+    __shared__ float2 si[256];
+    const int lane = threadIdx.x;
     float2 v = state[0], y;
     for (int base = 0; base < n; base += 256) {
         const int m = n - base < 256 ? n - base : 256;
-        for (int i = threadIdx.x; i < m; i += 32) si[i] = in[base + i];
+        for (int i = lane; i < m; i += 32) si[i] = in[base + i];
         __syncwarp();
-        for (int i = 0; i < m; ++i) { dc_ref_step(c, si[i], v, y); if (threadIdx.x == 0) so[i] = y; }
-        __syncwarp();
-        for (int i = threadIdx.x; i < m; i += 32) out[base + i] = so[i];
+        int b = 0;
+        for (; b + 32 <= m; b += 32) {
+            float2 keep = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                dc_ref_step(c, si[b + j], v, y);
+                if (lane == j) keep = y;
+            }
+            out[base + b + lane] = keep;
+        }
+        for (; b < m; ++b) { dc_ref_step(c, si[b], v, y); if (lane == 0) out[base + b] = y; }
         __syncwarp();
     }
-    if (threadIdx.x == 0) state[0] = v;
+    if (lane == 0) state[0] = v;
 }
 __global__ void __launch_bounds__(kPfbThreads) k_pfb_analyze(PfbArgs a) {
     extern __shared__ float2 pfb_sm[];
@@ -503,6 +514,7 @@ struct sdr_engine {
     sdr_stream_t stream = nullptr;
     bool own_stream = false;
     unsigned max_block = 0;
+    unsigned chan_block_max = 0;                // most samples one demodulator receives per block (= max_block unless the channelizer divides it)
     std::mutex mu;
     unsigned long long launches = 0;
     // wideband buffers
@@ -674,6 +686,7 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
     sdr_engine *e = new sdr_engine();
     e->device = device;
     e->max_block = max_block;
+    e->chan_block_max = max_block;
 #ifndef SDR_EMU
     if (stream) { e->stream = (cudaStream_t)stream; e->own_stream = false; }
     else { CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)); e->own_stream = true; }
@@ -970,7 +983,7 @@ static int chan_create_impl(sdr_engine *e, const char *modem, long long sample_r
     // ---- arena layout (floats)
     size_t off = 0;
     auto take = [&](size_t floats) { size_t o = off; off += (floats + 3) & ~size_t(3); return (int)o; };
-    const size_t nb = inject_cap ? inject_cap : e->max_block;
+    const size_t nb = inject_cap ? inject_cap : e->chan_block_max;
     c->standalone = inject_cap != 0;
     c->inject_cap = inject_cap;
     for (int j = 0; j <= cs.n_tail; ++j) cs.lvl_off[j] = take(2 * (kHist + (nb >> (cs.K1 + j)) + 4));
@@ -1308,6 +1321,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
     // twice that for the oversampled channelizer (runDemodChannels(chanBw * 2), :510)
     const unsigned n_ch = pfb ? (unsigned)pfb_osf * (n / (unsigned)pfb_M) : n;
     const long long rate_ch = pfb ? (long long)pfb_osf * (rate / pfb_M) : rate;
+    if (n_ch > e->chan_block_max) return fail(SDR_ERR_ARG, "block exceeds sdr_engine_set_channel_block_max");
 
     // 1+2. DC blocker (SDRPostThread.cpp:284) on its own stream, so that it runs underneath the channel kernels of the
     //      previous block: raw history slide -> copy the block in -> double-precision scan -> bit-exact float replay
@@ -1720,6 +1734,16 @@ extern "C" int sdr_engine_set_channelizer(sdr_engine *e, int mode) {
     std::lock_guard<std::mutex> lk(e->mu);
     if (e->have_block && mode != e->chan_mode) return fail(SDR_ERR_STATE, "sdr_engine_set_channelizer: set the mode before the first block");
     e->chan_mode = mode;
+    return SDR_OK;
+}
+
+// Channelizer mode hands every demodulator block / numChannels samples (twice that for PFBCH2), not the whole block: tell the
+// engine before creating channels so that their buffers and result slots are sized for that (default: max_block).
+extern "C" int sdr_engine_set_channel_block_max(sdr_engine *e, unsigned n) {
+    if (!e || n == 0) return fail(SDR_ERR_ARG, "sdr_engine_set_channel_block_max: bad argument");
+    std::lock_guard<std::mutex> lk(e->mu);
+    for (auto *c : e->chans) if (c) return fail(SDR_ERR_STATE, "sdr_engine_set_channel_block_max: call before creating channels");
+    e->chan_block_max = n < e->max_block ? n : e->max_block;
     return SDR_OK;
 }
 

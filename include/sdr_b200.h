@@ -136,6 +136,9 @@ int sdr_spectrum_fetch_debug(sdr_spectrum *sp, unsigned idx, float *mags, float 
  * sdr_engine_channel_plan (what DemodulatorPreThread sees as inp->sampleRate).  Spectra see the raw block, as there. */
 int sdr_engine_set_channelizer(sdr_engine *eng, int mode);
 int sdr_engine_channel_plan(long long sample_rate, int *num_channels, long long *channel_rate);
+/* Most samples one demodulator receives per block (channelizer mode: block / num_channels, twice that in mode 2); sizes the
+ * channels' buffers and result slots.  Default max_block; call before creating channels. */
+int sdr_engine_set_channel_block_max(sdr_engine *eng, unsigned n);
 typedef struct sdr_pfb sdr_pfb;
 int sdr_pfb_optimal_channel_count(long long sample_rate);     /* SDRThread::getOptimalChannelCount, SoapySDRThread.cpp:676-693 */
 int sdr_pfb_create(sdr_engine *eng, unsigned num_channels, unsigned m, float as_db, unsigned max_frames, sdr_pfb **out);

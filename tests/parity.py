@@ -319,6 +319,7 @@ def check_channelizer_mode(lib, ref, fs, chans, n_blocks, retune=None, device=0,
     oracle = RefChannelizerPath(ref, fs, chans, mode=mode)
     assert (M, chan_rate) == (oracle.M, oracle.chan_bw) and N % M == 0
     chan_rate = oracle.demod_rate
+    eng.set_channel_block_max((2 if mode == 2 else 1) * (N // M))
     cs = [Channel(eng, m, chan_rate, bw, 48000, frequency=CENTER + off) for m, bw, off in chans]
     freqs = [CENTER + off for _, _, off in chans]
     got = [[] for _ in chans]; want = [[] for _ in chans]
