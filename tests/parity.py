@@ -309,7 +309,7 @@ class RefChannelizerPath:
             d.close()
 
 
-def check_channelizer_mode(lib, ref, fs, chans, n_blocks, retune=None, device=0, seed=2024, mode=1):
+def check_channelizer_mode(lib, ref, fs, chans, n_blocks, retune=None, device=0, seed=2024, mode=1, center_by_block=None):
     """Engine in channelizer mode against RefChannelizerPath.  chans: [(modem, bw, offset)].  Returns the set of filterbank
     channels that were exercised."""
     N = synth.block_size(fs)
@@ -327,15 +327,17 @@ def check_channelizer_mode(lib, ref, fs, chans, n_blocks, retune=None, device=0,
     signal = list(chans)
     for b in sorted(retune or {}):
         signal += [(chans[i][0], chans[i][1], off) for i, off in retune[b].items()]
+    center = CENTER
     for b in range(n_blocks):
         if retune and b in retune:
             for i, off in retune[b].items():
                 freqs[i] = CENTER + off
                 cs[i].set_frequency(freqs[i])
         x = synth.wideband(fs, N, signal, seed=seed, t0=b * N) + np.complex64(0.02 + 0.01j)     # a DC offset: channel 0's blocker matters
-        eng.submit(x, CENTER, fs)
+        center = (center_by_block or {}).get(b, center) if b else (center_by_block or {}).get(0, CENTER)   # the tuner moves: every centre moves
+        eng.submit(x, center, fs)
         eng.wait()
-        res, picks = oracle.block(x, CENTER, freqs)
+        res, picks = oracle.block(x, center, freqs)
         used.update(picks)
         for i, (c, r) in enumerate(zip(cs, res)):
             a, lvl, pk, sk = c.fetch_audio()

@@ -137,3 +137,24 @@ def test_engine_oversampled_channelizer_mode_gpu(gpu_lib, ref):
     chans = [("FM", 200000, 40000), ("AM", 6000, -650000), ("NBFM", 12500, 1150000), ("USB", 5400, 560000)]
     used = parity.check_channelizer_mode(gpu_lib, ref, 2400000, chans, n_blocks=4, retune={2: {3: -90000}}, mode=2)
     assert {0, 4}.issubset(used)
+
+
+def test_engine_channelizer_mode_ties_and_band_edges_emulator(emu_lib, ref):
+    """getChannelAt corner cases: a demodulator exactly half-way between two channel centres (the first minimum wins), one
+    on the lower band edge (channel numChannels/2) and one on the upper edge (the extra channel that wraps onto it)."""
+    from tests import parity
+    fs = 2400000                                             # 4 channels of 600 kHz: centres 0, +600k, -1200k, -600k, (+1200k)
+    chans = [("AM", 6000, 300000), ("AM", 6000, -300000), ("FM", 200000, -1200000), ("FM", 200000, 1200000), ("NBFM", 12500, 900000)]
+    used = parity.check_channelizer_mode(emu_lib, ref, fs, chans, n_blocks=3)
+    assert {0, 2, 4}.issubset(used)
+
+
+def test_engine_channelizer_mode_tuner_moves_emulator(emu_lib, ref):
+    """The tuner frequency changes between blocks (SDRPostThread::runPFBCH :425-429: updateChannels): every channel centre
+    moves, demodulators keep their absolute frequency, so their shifts change and some hop to another filterbank channel."""
+    from tests import parity
+    fs = 2400000
+    chans = [("AM", 6000, 250000), ("USB", 5400, -700000), ("LSB", 5400, 950000), ("AM", 10000, -80000)]
+    moves = {2: parity.CENTER + 400000, 4: parity.CENTER - 350000}
+    used = parity.check_channelizer_mode(emu_lib, ref, fs, chans, n_blocks=6, center_by_block=moves)
+    assert len(used) >= 4
