@@ -13,7 +13,7 @@ CHANS = [("FM", 200000, 300000), ("NBFM", 12500, -150000), ("AM", 6000, 450000),
 FS, NB = 2400000, 3
 
 
-def _run_rank(rank, world, port, emu_path, out_dir):
+def _run_rank(rank, world, port, emu_path, out_dir, mode=0):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -25,8 +25,13 @@ def _run_rank(rank, world, port, emu_path, out_dir):
     lib = Lib(emu_path)
     N = synth.block_size(FS)
     eng = Engine(lib, max_block=N)
+    chan_fs = FS
+    if mode:                                                     # channelizer mode: every rank runs the filterbank on the block
+        eng.set_channelizer(mode)
+        n_pfb, chan_fs = eng.channel_plan(FS)
+        eng.set_channel_block_max(N // n_pfb)
     mine = shard_channels(list(enumerate(CHANS)), rank, world)
-    cs = [(idx, Channel(eng, m, FS, bw, 48000, frequency=100000000 + off)) for idx, (m, bw, off) in mine]
+    cs = [(idx, Channel(eng, m, chan_fs, bw, 48000, frequency=100000000 + off)) for idx, (m, bw, off) in mine]
     res = {idx: [] for idx, _ in cs}
     for b in range(NB):
         blk = torch.zeros(N, dtype=torch.complex64)
@@ -42,15 +47,21 @@ def _run_rank(rank, world, port, emu_path, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_ranks_equal_single_rank(emu_lib, tmp_path):
+@pytest.mark.parametrize("mode", [0, 1])
+def test_two_ranks_equal_single_rank(emu_lib, tmp_path, mode):
     import torch.multiprocessing as mp
     from cubicsdr_b200 import Channel, Engine, synth
     from cubicsdr_b200.parallel import owner_of
-    port = 29500 + (os.getpid() % 500)
-    mp.spawn(_run_rank, args=(2, port, emu_lib.path, str(tmp_path)), nprocs=2, join=True)
+    port = 29500 + (os.getpid() % 500) + 7 * mode
+    mp.spawn(_run_rank, args=(2, port, emu_lib.path, str(tmp_path), mode), nprocs=2, join=True)
     N = synth.block_size(FS)
     eng = Engine(emu_lib, max_block=N)
-    cs = [Channel(eng, m, FS, bw, 48000, frequency=100000000 + off) for m, bw, off in CHANS]
+    chan_fs = FS
+    if mode:
+        eng.set_channelizer(mode)
+        n_pfb, chan_fs = eng.channel_plan(FS)
+        eng.set_channel_block_max(N // n_pfb)
+    cs = [Channel(eng, m, chan_fs, bw, 48000, frequency=100000000 + off) for m, bw, off in CHANS]
     single = [[] for _ in cs]
     for b in range(NB):
         eng.submit(synth.wideband(FS, N, CHANS, t0=b * N), 100000000, FS)
