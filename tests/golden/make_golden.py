@@ -45,6 +45,33 @@ def main():
                 out["spec_line_b%d_f%d" % (b, f)] = r["line"]
     np.savez_compressed(os.path.join(HERE, "chain_2p4msps.npz"), **out)
     print("wrote chain_2p4msps.npz with", len(out), "arrays")
+    channelizer_golden(ref)
+
+
+def channelizer_golden(ref):
+    """SDRPostThread::runPFBCH / runPFBCH2 (SURVEY.md 8(f) row 1): the reference binary's firpfbch / firpfbch2 on a seeded
+    block, and the audio of two demodulators fed through the channelizer path (tests/parity.RefChannelizerPath)."""
+    from oracle.refbind import RefPfb, RefPfb2
+    from tests.parity import CENTER, RefChannelizerPath
+    out = {}
+    rng = np.random.default_rng(20260922)
+    for M in (8, 122):
+        x = (rng.standard_normal(M * 24) + 1j * rng.standard_normal(M * 24)).astype(np.complex64)
+        out["pfb_in_M%d" % M] = x
+        out["pfb_out_M%d" % M] = RefPfb(ref, M).execute(x)
+        out["pfb2_out_M%d" % M] = RefPfb2(ref, M).execute(x)
+    fs, N = 2400000, synth.block_size(2400000)
+    chans = [("FM", 200000, 40000), ("AM", 6000, -650000)]
+    for mode in (1, 2):
+        path = RefChannelizerPath(ref, fs, chans, mode=mode)
+        for b in range(2):
+            x = synth.wideband(fs, N, chans, seed=77, t0=b * N)
+            res, picks = path.block(x, CENTER, [CENTER + off for _, _, off in chans])
+            for (m, _, _), r in zip(chans, res):
+                out["mode%d_audio_%s_b%d" % (mode, m, b)] = r["audio"]
+        path.close()
+    np.savez_compressed(os.path.join(HERE, "channelizer.npz"), **out)
+    print("wrote channelizer.npz with", len(out), "arrays")
 
 
 if __name__ == "__main__":

@@ -158,3 +158,49 @@ def test_engine_channelizer_mode_tuner_moves_emulator(emu_lib, ref):
     moves = {2: parity.CENTER + 400000, 4: parity.CENTER - 350000}
     used = parity.check_channelizer_mode(emu_lib, ref, fs, chans, n_blocks=6, center_by_block=moves)
     assert len(used) >= 4
+
+
+def _check_channelizer_golden(lib, ref, device=0):
+    """Committed golden vectors (tests/golden/channelizer.npz, written by the reference binary): they pin the oracle (a
+    transplant that broke would stop reproducing them) and the engine."""
+    import os
+    from cubicsdr_b200 import Channel
+    from tests import parity
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "channelizer.npz"))
+    eng = Engine(lib, device=device, max_block=4096)
+    for M in (8, 122):
+        x = g["pfb_in_M%d" % M]
+        for key, cls, over in (("pfb_out_M%d", RefPfb, False), ("pfb2_out_M%d", RefPfb2, True)):
+            want = g[key % M]
+            rp = cls(ref, M)
+            assert np.array_equal(rp.execute(x), want), "oracle no longer reproduces its golden vector (%s)" % (key % M)
+            rp.close()
+            ch = Channelizer(eng, M, want.shape[0], oversampled=over)
+            assert relrms(ch.execute(x), want) <= TOL
+            ch.close()
+    eng.close()
+    fs, N = 2400000, synth.block_size(2400000)
+    chans = [("FM", 200000, 40000), ("AM", 6000, -650000)]
+    for mode in (1, 2):
+        eng = Engine(lib, device=device, max_block=N)
+        eng.set_channelizer(mode)
+        M, chan_rate = eng.channel_plan(fs)
+        eng.set_channel_block_max(mode * (N // M))
+        cs = [Channel(eng, m, chan_rate * mode, bw, 48000, frequency=parity.CENTER + off) for m, bw, off in chans]
+        for b in range(2):
+            eng.submit(synth.wideband(fs, N, chans, seed=77, t0=b * N), parity.CENTER, fs)
+            eng.wait()
+            for (m, _, _), c in zip(chans, cs):
+                want = g["mode%d_audio_%s_b%d" % (mode, m, b)]
+                a = c.fetch_audio()[0]
+                assert len(a) == len(want) and relrms(a, want) <= TOL, (mode, m, b)
+        eng.close()
+
+
+def test_channelizer_golden_vectors_emulator(emu_lib, ref):
+    _check_channelizer_golden(emu_lib, ref)
+
+
+@pytest.mark.gpu
+def test_channelizer_golden_vectors_gpu(gpu_lib, ref):
+    _check_channelizer_golden(gpu_lib, ref)
