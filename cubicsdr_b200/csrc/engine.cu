@@ -1322,6 +1322,34 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
     const unsigned n_ch = pfb ? (unsigned)pfb_osf * (n / (unsigned)pfb_M) : n;
     const long long rate_ch = pfb ? (long long)pfb_osf * (rate / pfb_M) : rate;
     if (n_ch > e->chan_block_max) return fail(SDR_ERR_ARG, "block exceeds sdr_engine_set_channel_block_max");
+    // channelizer mode: channel centre frequencies (SDRPostThread::updateChannels, SDRPostThread.cpp:115-124) and the channel
+    // every attached demodulator lands on (getChannelAt, :127-139: nearest centre, the first one wins a tie).  Channel 0's DC
+    // blocker only runs on blocks in which some demodulator sits on channel 0 (runDemodChannels skips idle channels,
+    // :333-339), so its state must not advance on the others.
+    std::vector<long long> chan_centers;
+    std::vector<int> pfb_pick;
+    bool pfb_ch0_active = false;
+    if (pfb) {
+        chan_centers.assign((size_t)pfb_M + 1, 0);
+        const long long chan_bw = rate / pfb_M;
+        for (int i = 0; i < pfb_M / 2; ++i) {
+            const int ofs = (int)(chan_bw * i);
+            chan_centers[i] = center + ofs;
+            chan_centers[i + pfb_M / 2] = center - (rate / 2) + ofs;
+        }
+        chan_centers[pfb_M] = center + (rate / 2);
+        pfb_pick.assign(e->chans.size(), -1);
+        for (size_t i = 0; i < e->chans.size(); ++i) {
+            const sdr_chan *c = e->chans[i];
+            if (!c || c->standalone) continue;
+            long long min_delta = rate;
+            for (int k = 0; k <= pfb_M; ++k) {
+                const long long fd = std::llabs(c->frequency - chan_centers[k]);
+                if (fd < min_delta) { min_delta = fd; pfb_pick[i] = k; }
+            }
+            if (pfb_pick[i] == 0) pfb_ch0_active = true;
+        }
+    }
 
     // 1+2. DC blocker (SDRPostThread.cpp:284) on its own stream, so that it runs underneath the channel kernels of the
     //      previous block: raw history slide -> copy the block in -> double-precision scan -> bit-exact float replay
@@ -1409,16 +1437,16 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         const size_t smem = pfb_smem_elems(pa.M, pa.p) * sizeof(float2);
         { int r = pfb_allow_smem(smem); if (r) return r; }
         k_pfb_analyze<<<tiles, kPfbThreads, smem, dcs>>>(pa);
-        k_pfb_dc0<<<1, 32, 0, dcs>>>(ch0, ch0_dc, (int)n_ch, (float)e->dc_a, e->d_pfb_dc_state);
+        if (pfb_ch0_active) k_pfb_dc0<<<1, 32, 0, dcs>>>(ch0, ch0_dc, (int)n_ch, (float)e->dc_a, e->d_pfb_dc_state);
 #else
         {
             std::vector<float2> sm(pfb_smem_elems(pa.M, pa.p));
             for (int t = 0; t < tiles; ++t)
                 for (int ph = 0; ph < kPfbPhases; ++ph) for (int th = 0; th < kPfbThreads; ++th) pfb_phase(ph, pa, t, th, kPfbThreads, sm.data());
-            pfb_dc0_serial(ch0, ch0_dc, (int)n_ch, (float)e->dc_a, e->d_pfb_dc_state);
+            if (pfb_ch0_active) pfb_dc0_serial(ch0, ch0_dc, (int)n_ch, (float)e->dc_a, e->d_pfb_dc_state);
         }
 #endif
-        e->launches += 2;
+        e->launches += pfb_ch0_active ? 2 : 1;
         e->pfb_last_frames = n_ch; e->pfb_have_block = true;
     }
 #ifndef SDR_EMU
@@ -1551,18 +1579,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
     size_t live_now = 0;
     for (auto *c : e->chans) live_now += c != nullptr;
     const int front_reserved = (e->exact_dc && !pfb) ? dc_split_for(live_now).reserved_sms : 0;
-    // channelizer mode: channel centre frequencies (SDRPostThread::updateChannels, SDRPostThread.cpp:115-124)
-    std::vector<long long> chan_centers;
-    if (pfb) {
-        chan_centers.assign((size_t)pfb_M + 1, 0);
-        const long long chan_bw = rate / pfb_M;
-        for (int i = 0; i < pfb_M / 2; ++i) {
-            const int ofs = (int)(chan_bw * i);
-            chan_centers[i] = center + ofs;
-            chan_centers[i + pfb_M / 2] = center - (rate / 2) + ofs;
-        }
-        chan_centers[pfb_M] = center + (rate / 2);
-    }
+
     for (int i = 0; i < n_slots; ++i) {
         sdr_chan *c = e->chans[i];
         ChanDyn &d = h_cd[i];
@@ -1582,13 +1599,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         long long in_freq = center;                                                 // inp->frequency
         int stream_slot = -1;
         if (pfb) {
-            // SDRPostThread::getChannelAt (SDRPostThread.cpp:127-139): nearest centre, first one wins a tie
-            int ci = -1;
-            long long min_delta = rate;
-            for (int k = 0; k <= pfb_M; ++k) {
-                const long long fd = std::llabs(c->frequency - chan_centers[k]);
-                if (fd < min_delta) { min_delta = fd; ci = k; }
-            }
+            const int ci = pfb_pick[i];                                             // SDRPostThread::getChannelAt, computed above
             if (ci < 0) { keep_tail(); continue; }                                  // no channel: the demodulator gets no data this block
             in_freq = chan_centers[ci];
             // channel 0 is read after its DC blocker; the extra channel wraps onto numChannels/2 (:357-361)

@@ -93,3 +93,80 @@ def test_random_configurations_emulator(emu_lib, ref, seed0):
 def test_random_configurations_gpu(gpu_lib, ref):
     for seed in range(7000, 7040):
         _case(gpu_lib, ref, seed)
+
+
+CH_MODEMS = {"FM": [200000, 150000, 120000, 80000], "NBFM": [12500, 25000, 16000], "AM": [6000, 10000, 4000], "USB": [5400, 2700],
+             "LSB": [5400, 3000]}
+
+
+def _channelizer_case(lib, ref, seed):
+    """Channelizer mode (runPFBCH / runPFBCH2): random rate, 1-4 demodulators anywhere in (and slightly beyond) the band,
+    retunes and tuner moves between blocks -- i.e. demodulators hopping between filterbank channels, onto and off channel 0
+    (whose DC blocker only advances while it is in use) and onto the wrap channel."""
+    from tests.parity import RefChannelizerPath
+    rng = np.random.default_rng(seed)
+    fs = int(rng.choice([1000000, 2000000, 2400000, 3200000, 5000000, 10000000]))
+    mode = int(rng.choice([1, 1, 2]))
+    chans = []
+    for _ in range(int(rng.integers(1, 5))):
+        m = str(rng.choice(list(CH_MODEMS)))
+        chans.append((m, int(rng.choice(CH_MODEMS[m])), int(rng.integers(-fs // 2 - 100000, fs // 2 + 100000))))
+    nb = int(rng.integers(2, 6))
+    N = synth.block_size(fs)
+    eng = Engine(lib, max_block=N)
+    eng.set_channelizer(mode)
+    M, _ = eng.channel_plan(fs)
+    oracle = RefChannelizerPath(ref, fs, chans, mode=mode)
+    eng.set_channel_block_max(mode * (N // M))
+    cs = [Channel(eng, m, oracle.demod_rate, bw, 48000, frequency=CENTER + off, want_iq=True) for m, bw, off in chans]
+    freqs = [CENTER + off for _, _, off in chans]
+    retune, centers = {}, {}
+    for b in range(1, nb):
+        if rng.random() < 0.4:
+            retune.setdefault(b, {})[int(rng.integers(0, len(chans)))] = int(rng.integers(-fs // 2, fs // 2))
+        if rng.random() < 0.2:
+            centers[b] = CENTER + int(rng.integers(-500000, 500000))
+    signal = list(chans) + [(chans[i][0], chans[i][1], o) for b in retune for i, o in retune[b].items()]
+    got = [[] for _ in chans]; want = [[] for _ in chans]
+    center = CENTER
+    for b in range(nb):
+        for i, o in retune.get(b, {}).items():
+            freqs[i] = CENTER + o
+            cs[i].set_frequency(freqs[i])
+        center = centers.get(b, center)
+        x = synth.wideband(fs, N, signal, seed=seed, t0=b * N) + np.complex64(0.02 + 0.01j)
+        eng.submit(x, center, fs)
+        eng.wait()
+        res, _ = oracle.block(x, center, freqs)
+        for i, (c, r) in enumerate(zip(cs, res)):
+            a, _, _, sk = c.fetch_audio()
+            if r is None or r["skipped"]:
+                assert sk or len(a) == 0, "seed %d demod %d block %d: audio where the reference had none" % (seed, i, b)
+                continue
+            assert not sk and len(a) == len(r["audio"]), "seed %d demod %d block %d: counts" % (seed, i, b)
+            if chans[i][0] in ("FM", "NBFM"):
+                q = c.fetch_iq()
+                assert len(q) == len(r["iq"])
+                got[i].append(q.view(np.float32)); want[i].append(r["iq"].view(np.float32))
+            else:
+                got[i].append(a); want[i].append(r["audio"])
+    for c in cs:
+        c.close()
+    oracle.close(); eng.close()
+    for i in range(len(chans)):
+        if got[i]:
+            g, w = np.concatenate(got[i]), np.concatenate(want[i])
+            if np.linalg.norm(w) > 0:
+                e = relrms(g, w)
+                assert e <= TOL, "seed %d demod %d %s: relative RMS error %.3g" % (seed, i, chans[i], e)
+
+
+def test_random_channelizer_configurations_emulator(emu_lib, ref):
+    for seed in range(100, 160):
+        _channelizer_case(emu_lib, ref, seed)
+
+
+@pytest.mark.gpu
+def test_random_channelizer_configurations_gpu(gpu_lib, ref):
+    for seed in range(300, 330):
+        _channelizer_case(gpu_lib, ref, seed)
