@@ -603,6 +603,44 @@ SDR_HD inline void front_span(const FrontArgs &a, int ch, int span_idx, bool sto
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Rare path: history that spans more than one oscillator setting.  The front kernel rebuilds its delay lines at a block
+// start from up to kFrontWarm * 2^K history samples, re-mixed with ONE setting (that of the previous block).  When the blocks
+// are shorter than that window and the channel was retuned within it, the host instead has the history mixed sample by
+// sample with the settings that were actually in effect (this function, one thread per sample) into the channel's private
+// history, and tells the front kernel that the history needs no mixing (dir_prev = 0: table entry 0 = (1, 0) is exact).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kPremixSegs = 8;
+struct PremixSeg { int n; unsigned dtheta; int dir; };          // newest block first: length, phase step, +1 up / -1 down / 0 none
+struct PremixArgs {
+    const float2 *x;              // raw stream of the channel: x[0] = first sample of the new block, history at negative indices
+    float2 *out;                  // out[-count .. -1] receive the mixed history
+    const float2 *nco;            // [1024] {cos, sin}
+    unsigned theta0;              // oscillator phase at x[0]
+    int count, nseg;
+    PremixSeg seg[kPremixSegs];
+};
+SDR_HD inline void premix_thread(const PremixArgs &a, int i) {      // i = 1 .. count: sample x[-i]
+    if (i < 1 || i > a.count) return;
+    unsigned theta = a.theta0;
+    int rem = i, dir = 0;
+    bool found = false;
+    for (int k = 0; k < a.nseg && !found; ++k) {
+        const PremixSeg sg = a.seg[k];
+        if (rem <= sg.n) {                                           // x[-i] is the rem-th sample from the end of block k
+            if (sg.dir) theta -= (unsigned)rem * sg.dtheta;          // mix_block steps once per sample; an unmixed block does not step
+            dir = sg.dir; found = true;
+        } else {
+            if (sg.dir) theta -= (unsigned)sg.n * sg.dtheta;
+            rem -= sg.n;
+        }
+    }
+    const float2 x = a.x[-i];
+    if (!found || dir == 0) { a.out[-i] = x; return; }              // older than every tracked block, or never mixed
+    const float2 w = a.nco[(theta + 0x200000u) >> 22];
+    a.out[-i] = cf_rot(x, w.x, flip_sign(w.y, dir < 0 ? 0x80000000u : 0u));
+}
+
 // job -> (span, channel chunk): jobs are dealt round-robin over the CTAs so that a small job count still lands on
 // every SM (job = cta + n_cta * warp_in_cta)
 SDR_HD SDR_FORCEINLINE void front_job(const FrontArgs &a, int job, int &span_idx, int &chunk) {

@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 1) k_chan_front(FrontArgs a,
         atomicMax(a.dbg + 4 * blockIdx.x + 3, t2);
     }
 }
+__global__ void k_premix_hist(PremixArgs a) { premix_thread(a, 1 + (int)(blockIdx.x * blockDim.x + threadIdx.x)); }
 __global__ void __launch_bounds__(kTailThreads, 4) k_chan_tail(TailArgs a) {
     __shared__ TailShared sm;
     const bool dbg = a.dbg && threadIdx.x == 0 && blockIdx.x < 64;
@@ -484,6 +485,7 @@ struct sdr_chan {
     unsigned theta = 0, dtheta = 0, dtheta_prev = 0;
     int dir_prev = 0;
     long long consumed = 0;         // wideband samples consumed
+    std::vector<PremixSeg> recent;  // oscillator settings of the last consumed blocks, newest first (rare-path history mixing)
     size_t slot_bytes = 0;
 };
 
@@ -1618,12 +1620,43 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         d.dir = dir; d.dir_prev = c->dir_prev;
         d.hist = c->priv_valid ? c->d_priv_hist + kBlkHist : nullptr;
         c->priv_valid = false;
+        const bool hopped = pfb && c->pfb_slot_prev >= 0 && c->pfb_slot_prev != stream_slot;
         if (pfb) { d.xin = pfb_streams + (size_t)stream_slot * e->pfb_stride + kBlkHist; c->pfb_slot_prev = stream_slot; }
+        // Rare path (dsp_core.h, premix_thread): the history window of the front kernel reaches back over more than one
+        // oscillator setting -- blocks shorter than kFrontWarm * 2^K samples around a retune.  Mix the history with the
+        // settings that were in effect and hand it over as "already mixed".
+        if (!d.hist && !hopped && c->cs.K1 > 0 && !c->recent.empty()) {
+            const int window = (kFrontWarm + 1) << c->cs.K1;
+            int covered = 0;
+            bool mixed_settings = false;
+            for (const PremixSeg &sg : c->recent) {
+                if (covered >= window) break;
+                if (sg.dir != c->recent[0].dir || (sg.dir && sg.dtheta != c->recent[0].dtheta)) mixed_settings = true;
+                covered += sg.n;
+            }
+            if (mixed_settings) {
+                PremixArgs pm;
+                pm.x = pfb ? d.xin : blk; pm.out = c->d_priv_hist + kBlkHist; pm.nco = e->d_nco; pm.theta0 = c->theta;
+                pm.count = std::min<int>(kBlkHist, std::min<long long>(c->consumed, (long long)window + 64));
+                pm.nseg = (int)std::min<size_t>(c->recent.size(), (size_t)kPremixSegs);
+                for (int k = 0; k < pm.nseg; ++k) pm.seg[k] = c->recent[k];
+#ifndef SDR_EMU
+                k_premix_hist<<<(pm.count + 127) / 128, 128, 0, e->stream>>>(pm);
+#else
+                for (int t = 1; t <= pm.count; ++t) premix_thread(pm, t);
+#endif
+                e->launches += 1;
+                d.hist = c->d_priv_hist + kBlkHist;
+                d.dir_prev = 0; d.dtheta_prev = 0;                       // the history is mixed already: read it through table entry 0
+            }
+        }
         d.lvl0_sel = c->lvl0_sel;                                       // consecutive processed blocks alternate level-0 buffers
         c->lvl0_sel ^= 1;
         if (dir) c->theta += n_ch * c->dtheta;                          // mix_block advances the phase by one step per input sample
         c->dtheta_prev = c->dtheta; c->dir_prev = dir;
         c->consumed += n_ch;
+        c->recent.insert(c->recent.begin(), PremixSeg{(int)n_ch, dir ? c->dtheta : 0u, dir});
+        if (c->recent.size() > (size_t)kPremixSegs) c->recent.pop_back();
         by_k[c->cs.K1].push_back(i);
     }
     ChanDyn *d_cd = e->d_cd2[p];
