@@ -206,9 +206,11 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 1) k_chan_front(FrontArgs a,
         const int ch = a.group[ci];
         const long long g0 = a.cd[ch].g0;
         // warp-staged samples need every lane to read the same samples: same position in the same stream
-        const unsigned long long xin = (unsigned long long)a.cd[ch].xin;
+        // (a lane with a private history -- a channel that skipped blocks, or whose history was pre-mixed -- reads other
+        // samples than its neighbours for i < 0, so such a warp takes the per-lane path as well)
+        const unsigned long long xin = (unsigned long long)a.cd[ch].xin, hst = (unsigned long long)a.cd[ch].hist;
         const bool lock_step = __all_sync(0xffffffffu, g0 == __shfl_sync(0xffffffffu, g0, 0)) &&
-                               __all_sync(0xffffffffu, xin == __shfl_sync(0xffffffffu, xin, 0)) && xin == 0ull;
+                               __all_sync(0xffffffffu, xin == 0ull) && __all_sync(0xffffffffu, hst == 0ull);
         TabRep16 tab;
         tab.base = reinterpret_cast<const char *>(front_sm);
         tab.lane_off = (unsigned)(lane & 15) * 8u;

@@ -98,12 +98,6 @@ def test_random_configurations_with_short_blocks_emulator(emu_lib, ref):
         _case(emu_lib, ref, seed, tiny=True)
 
 
-@pytest.mark.gpu
-def test_random_configurations_gpu(gpu_lib, ref):
-    for seed in range(7000, 7040):
-        _case(gpu_lib, ref, seed)
-
-
 CH_MODEMS = {"FM": [200000, 150000, 120000, 80000], "NBFM": [12500, 25000, 16000], "AM": [6000, 10000, 4000], "USB": [5400, 2700],
              "LSB": [5400, 3000]}
 
@@ -173,9 +167,3 @@ def _channelizer_case(lib, ref, seed):
 def test_random_channelizer_configurations_emulator(emu_lib, ref):
     for seed in range(100, 160):
         _channelizer_case(emu_lib, ref, seed)
-
-
-@pytest.mark.gpu
-def test_random_channelizer_configurations_gpu(gpu_lib, ref):
-    for seed in range(300, 330):
-        _channelizer_case(gpu_lib, ref, seed)
