@@ -480,6 +480,8 @@ struct sdr_chan {
     unsigned char *h_slot = nullptr; // pinned result slot, standalone only
     float2 *d_priv_hist = nullptr;  // tail of the last consumed block, kept while the channel skips blocks
     bool priv_valid = false;
+    int roll_pending = 0;           // > 0: the last consumed block was this short and read its history from d_priv_hist: the
+                                    // private tail must be extended by that block before it is used again
     int pfb_slot_prev = -1;         // channelizer mode: stream slot this channel read in the last block it consumed
     // DemodulatorPreThread state
     long long frequency = 0;
@@ -1013,7 +1015,8 @@ static int chan_create_impl(sdr_engine *e, const char *modem, long long sample_r
     if (be_malloc((void **)&c->d_arena, off * sizeof(float))) { delete c; return fail(SDR_ERR_NOMEM, "sdr_chan_create: arena"); }
     be_memset(c->d_arena, 0, off * sizeof(float), e->stream);
     cs.arena = c->d_arena;
-    if (be_malloc((void **)&c->d_priv_hist, kBlkHist * sizeof(float2))) { be_free(c->d_arena); delete c; return fail(SDR_ERR_NOMEM, "sdr_chan_create: history"); }
+    // [raw tail of the consumed stream | the same, mixed (rare path) | scratch for rolling the raw tail]
+    if (be_malloc((void **)&c->d_priv_hist, 3 * (size_t)kBlkHist * sizeof(float2))) { be_free(c->d_arena); delete c; return fail(SDR_ERR_NOMEM, "sdr_chan_create: history"); }
     c->slot_bytes = 32 + (size_t)cs.res_audio_cap * 4 + (size_t)cs.res_iq_cap * 8;
     c->slot_bytes = (c->slot_bytes + 31) & ~size_t(31);
     ChanState st;
@@ -1590,6 +1593,23 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         memset(&d, 0, sizeof d);
         if (!c || c->standalone) continue;
         d.valid = 1;
+        // Consumed history that is not contiguous in the stream (a skipped block inside the front kernel's history window,
+        // only possible with blocks shorter than that window): keep extending the private raw tail block by block until a
+        // consumed block is long enough to hold the whole window again.
+        if (c && !c->standalone && c->roll_pending > 0) {
+            const int n2 = c->roll_pending;
+            const float2 *prev_tail = nullptr;                    // the n2 samples of the previous block = end of the stream history
+            if (!pfb) prev_tail = blk - n2;
+            else if (c->pfb_slot_prev >= 0) prev_tail = pfb_streams + (size_t)c->pfb_slot_prev * e->pfb_stride + kBlkHist - n2;
+            if (prev_tail) {
+                float2 *scr = c->d_priv_hist + 2 * (size_t)kBlkHist;
+                be_d2d(scr, c->d_priv_hist + n2, (size_t)(kBlkHist - n2) * sizeof(float2), e->stream);
+                be_d2d(c->d_priv_hist, scr, (size_t)(kBlkHist - n2) * sizeof(float2), e->stream);
+                be_d2d(c->d_priv_hist + (kBlkHist - n2), prev_tail, (size_t)n2 * sizeof(float2), e->stream);
+                c->priv_valid = true;
+            }
+            c->roll_pending = 0;
+        }
         // a channel that sits this block out keeps the tail of the last block it consumed (its filters do not advance)
         // (in channelizer mode the tail lives in the stream the channel last read: the history region of that slot)
         auto keep_tail = [&]() {
@@ -1627,7 +1647,8 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         // Rare path (dsp_core.h, premix_thread): the history window of the front kernel reaches back over more than one
         // oscillator setting -- blocks shorter than kFrontWarm * 2^K samples around a retune.  Mix the history with the
         // settings that were in effect and hand it over as "already mixed".
-        if (!d.hist && !hopped && c->cs.K1 > 0 && !c->recent.empty()) {
+        const bool hist_private_raw = d.hist != nullptr;
+        if (!hopped && c->cs.K1 > 0 && !c->recent.empty()) {
             const int window = (kFrontWarm + 1) << c->cs.K1;
             int covered = 0;
             bool mixed_settings = false;
@@ -1638,7 +1659,8 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
             }
             if (mixed_settings) {
                 PremixArgs pm;
-                pm.x = pfb ? d.xin : blk; pm.out = c->d_priv_hist + kBlkHist; pm.nco = e->d_nco; pm.theta0 = c->theta;
+                pm.x = d.hist ? d.hist : (pfb ? d.xin : blk);       // private raw tail if the stream history is not the consumed one
+                pm.out = c->d_priv_hist + 2 * (size_t)kBlkHist; pm.nco = e->d_nco; pm.theta0 = c->theta;
                 pm.count = std::min<int>(kBlkHist, std::min<long long>(c->consumed, (long long)window + 64));
                 pm.nseg = (int)std::min<size_t>(c->recent.size(), (size_t)kPremixSegs);
                 for (int k = 0; k < pm.nseg; ++k) pm.seg[k] = c->recent[k];
@@ -1648,7 +1670,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
                 for (int t = 1; t <= pm.count; ++t) premix_thread(pm, t);
 #endif
                 e->launches += 1;
-                d.hist = c->d_priv_hist + kBlkHist;
+                d.hist = c->d_priv_hist + 2 * (size_t)kBlkHist;
                 d.dir_prev = 0; d.dtheta_prev = 0;                       // the history is mixed already: read it through table entry 0
             }
         }
@@ -1656,6 +1678,8 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         c->lvl0_sel ^= 1;
         if (dir) c->theta += n_ch * c->dtheta;                          // mix_block advances the phase by one step per input sample
         c->dtheta_prev = c->dtheta; c->dir_prev = dir;
+        // the next block's window may reach back before this block: if this block's own history was private, it stays private
+        if (hist_private_raw && (int)n_ch < ((kFrontWarm + 2) << kFrontMaxK)) c->roll_pending = (int)n_ch;
         c->consumed += n_ch;
         c->recent.insert(c->recent.begin(), PremixSeg{(int)n_ch, dir ? c->dtheta : 0u, dir});
         if (c->recent.size() > (size_t)kPremixSegs) c->recent.pop_back();

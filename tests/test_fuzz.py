@@ -4,10 +4,11 @@ onto 0 Hz and beyond the 0.75 fs skip rule).  FM / NBFM channels are judged on t
 amplifies 1e-6 IQ differences without bound wherever a retune or start-up transient takes the amplitude through zero);
 AM / SSB channels on the audio.  The DC-blocked block must be bit-exact in every block.
 
-Blocks shorter than the front kernel's history window (13 x 2^K <= 832 samples) around a retune take the rare path that
-mixes the history with every setting that was in effect (dsp_core.h premix_thread): the `tiny` variant of the generator.
-Known limit, kept out of the generator: such short blocks combined with a block SKIPPED by the 0.75 fs rule inside the
-window (the consumed history is then not contiguous in the stream).  CubicSDR's blocks are 1/60 s (>= 4167 samples)."""
+Blocks shorter than the front kernel's history window (13 x 2^K <= 832 samples) take the rare paths: around a retune the
+history is mixed with every oscillator setting that was in effect (dsp_core.h premix_thread); next to a block skipped by
+the 0.75 fs rule the consumed history is not contiguous in the stream and is kept in a rolling private tail
+(engine.cu, roll_pending).  The `tiny` variant of the generator exercises both.  CubicSDR's own blocks are 1/60 s
+(>= 4167 samples), so the reference never gets there."""
 import numpy as np
 import pytest
 
@@ -38,7 +39,7 @@ def _case(lib, ref, seed, tiny=False):
         if rng.random() < 0.4:
             i = int(rng.integers(0, len(chans)))
             r = rng.random()
-            if r < 0.15 and not tiny:
+            if r < 0.15:
                 new = int(fs * 0.8) * (1 if rng.random() < 0.5 else -1)          # beyond 0.75 fs: the block is skipped
             elif r < 0.3:
                 new = 0
