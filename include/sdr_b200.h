@@ -72,7 +72,9 @@ int sdr_engine_get_timing(sdr_engine *eng, double *stage_ms4, unsigned long long
 /* modem: "FM" "NBFM" "AM" "USB" "LSB" (Modem::addModemFactory names, src/CubicSDR.cpp:305-311).
  * bandwidth is passed through Modem::checkSampleRate (ModemAnalog.cpp:14-19, ModemUSB.cpp:29-37).
  * Builds what DemodulatorWorkerThread builds (src/demod/DemodulatorWorkerThread.cpp:63-101): msresamp_crcf(bw/fs, 60),
- * the modem, and its kit msresamp_rrrf(audio_rate/bw, 60) (ModemAnalog.cpp:21-33).                                  */
+ * the modem, and its kit msresamp_rrrf(audio_rate/bw, 60) (ModemAnalog.cpp:21-33).
+ * Creating or destroying a channel re-plans the result buffers at the next submit: fetch the results of blocks already
+ * submitted (sdr_engine_wait / sdr_engine_wait_block) before changing the channel set.                              */
 int sdr_chan_create(sdr_engine *eng, const char *modem, long long sample_rate, long long bandwidth, int audio_rate,
                     sdr_chan **out);
 int sdr_chan_destroy(sdr_chan *ch);

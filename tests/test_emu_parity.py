@@ -123,3 +123,35 @@ def test_spectrum_average_rates(emu_lib, ref):
     for r in (0.2, 1.0):
         w = parity.run_spectrum(emu_lib, ref, 2400000, 512, n_blocks=2, chans=chans, avg_rate=r)
         assert w["frames"] > 50 and w["mags"] <= parity.TOL and w["maa"] <= parity.TOL and w["points"] <= parity.TOL, (r, w)
+
+
+def test_several_spectra_and_a_channel_on_one_engine(emu_lib, ref):
+    """The reference runs a spectrum processor and a waterfall processor (different FFT sizes, the waterfall rate-limited)
+    off the same block queue, next to the demodulators: three spectra + one channel on one engine, each against its oracle."""
+    from cubicsdr_b200 import Channel, Engine, Spectrum
+    from oracle.refbind import RefChan, RefDistrib, RefIngress, RefSpectrum
+    fs, N = 2400000, synth.block_size(2400000)
+    eng = Engine(emu_lib, max_block=N)
+    cfgs = [(1024, 0), (512, 30), (4096, 0)]
+    sps = [Spectrum(eng, f, l) for f, l in cfgs]
+    rsp = [RefSpectrum(ref, f) for f, _ in cfgs]
+    rds = [RefDistrib(ref, 2 * f, l if l else 100000000) for f, l in cfgs]
+    ch = Channel(eng, "FM", fs, 200000, 48000, frequency=parity.CENTER + 300000)
+    rc = RefChan(ref, "FM", fs, 200000)
+    ing = RefIngress(ref)
+    chans = synth.channel_plan("mixed", fs, 6) + [("FM", 200000, 300000)]
+    frames_seen = 0
+    for b in range(3):
+        x = synth.wideband(fs, N, chans, t0=b * N)
+        eng.submit(x, parity.CENTER, fs)
+        eng.wait()
+        y = ing.block(x)
+        for sp, rs, rd in zip(sps, rsp, rds):
+            frames = rd.push(y, fs)
+            assert sp.frames == len(frames)
+            for k in range(sp.frames):
+                pts, line, cf = sp.fetch(k)
+                assert parity.relrms(pts, rs.frame(frames[k])["points"]) <= parity.TOL
+                frames_seen += 1
+        assert parity.relrms(ch.fetch_audio()[0], rc.process(y, 300000)["audio"]) <= parity.TOL
+    assert frames_seen > 60
