@@ -1,10 +1,17 @@
 // cubicsdr_b200/csrc/engine.cu -- engine object, kernel launches and the C-ABI of include/sdr_b200.h.
 //
-// One engine per GPU.  A submit does, on one CUDA stream:
-//   slide wideband history -> (H2D) -> DC-blocker scan -> spectrum kernels -> front kernel(s) -> tail kernel -> (D2H)
+// One engine per GPU.  A submit enqueues, without any host synchronisation, on five streams tied together by events:
+//   dc    (highest priority)  history slides -> block copy-in -> DC blocker (double-precision scan + bit-exact float replay)
+//                             or, in channelizer mode, the analysis filterbank -> upload of the block's parameter lists;
+//                             runs one block ahead of the channel kernels (double-buffered block)
+//   main                      channel front kernel(s): oscillator mix + first half-band stages
+//   side  (high priority)     spectrum: FFT / averaging / waterfall line, forked after the front launch, joined before the next
+//   tail                      per-channel low-rate chain (remaining half-bands, polyphase arm, demodulator, audio, metering)
+//   res                       every device -> host result copy (ring of three pinned result buffers: sdr_engine_wait_block)
 // Host-side logic that the reference keeps in its threads is restated here next to the launch it controls:
 //   DemodulatorPreThread shift / skip rule      src/demod/DemodulatorPreThread.cpp:154-163
 //   FFTDataDistributor framing / line limiter   src/process/FFTDataDistributor.cpp:28-144
+//   SDRPostThread channelizer dispatch, channel centres, demodulator routing   src/sdr/SDRPostThread.cpp:115-139,178-187,303-455
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
