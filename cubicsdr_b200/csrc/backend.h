@@ -50,6 +50,8 @@ inline int be_h2d(void *d, const void *h, size_t n, sdr_stream_t) { memcpy(d, h,
 inline int be_d2h(void *h, const void *d, size_t n, sdr_stream_t) { memcpy(h, d, n); return 0; }
 inline int be_d2d(void *d, const void *s, size_t n, sdr_stream_t) { memmove(d, s, n); return 0; }
 inline int be_sync(sdr_stream_t) { return 0; }
+inline int be_malloc_async(void **p, size_t n, sdr_stream_t) { return be_malloc(p, n); }
+inline void be_free_async(void *p, sdr_stream_t) { free(p); }
 inline int be_d2d_2d(void *d, size_t dpitch, const void *s_, size_t spitch, size_t width, size_t height, sdr_stream_t) {
     for (size_t r = 0; r < height; ++r) memmove((char *)d + r * dpitch, (const char *)s_ + r * spitch, width);
     return 0;
@@ -65,6 +67,9 @@ inline int be_h2d(void *d, const void *h, size_t n, sdr_stream_t s) { return cud
 inline int be_d2h(void *h, const void *d, size_t n, sdr_stream_t s) { return cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s) != cudaSuccess; }
 inline int be_d2d(void *d, const void *s_, size_t n, sdr_stream_t s) { return cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, s) != cudaSuccess; }
 inline int be_sync(sdr_stream_t s) { return cudaStreamSynchronize(s) != cudaSuccess; }
+// stream-ordered allocation: unlike cudaMalloc / cudaFree these never wait for the other streams of the device
+inline int be_malloc_async(void **p, size_t n, sdr_stream_t s) { return cudaMallocAsync(p, n ? n : 1, s) != cudaSuccess; }
+inline void be_free_async(void *p, sdr_stream_t s) { if (p) cudaFreeAsync(p, s); }
 inline int be_d2d_2d(void *d, size_t dpitch, const void *s_, size_t spitch, size_t width, size_t height, sdr_stream_t s) {
     return cudaMemcpy2DAsync(d, dpitch, s_, spitch, width, height, cudaMemcpyDeviceToDevice, s) != cudaSuccess;
 }

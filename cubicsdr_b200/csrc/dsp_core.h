@@ -242,8 +242,8 @@ SDR_HD inline void dc_apply_phase(int ph, const DcArgs &a, int bid, int tid, DcS
 //     from the true carried state of segment 0, that every output is the reference's; a failing junction (rare) is
 //     replayed serially by dc_exact_verify.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kDcSegLenLight = 4096; // segment length of the speculative replay (longer under a heavy channel load: engine.cu)
-constexpr int kDcWarm = 24576;      // P(junction not coalesced) ~ 1.5e-4: a serial fix-up every dozen blocks at 61 MSps
+constexpr int kDcWarm = 24576;      // warm-up samples (a multiple of kDcTile); P(junction not coalesced) ~ 1.5e-4
+constexpr int kDcMinSpec = 32768;   // blocks shorter than this are replayed serially (the warm-up alone is 24576 steps)
 
 struct DcExactArgs {
     const float2 *xraw;              // raw stream: xraw[0] = first sample of the block, history at negative indices
@@ -254,6 +254,8 @@ struct DcExactArgs {
     const double2 *tile_carry;       // exact state entering tile t of the current block (kDcTile samples per tile)
     const double2 *prev_tile_carry;  // same for the previous block
     int prev_n;                      // length of the previous block, 0 if there was none
+    int raw_hist;                    // samples of raw history readable in front of xraw[0] (GPU staging bound)
+    long long raw_end;               // samples readable from xraw[0] on (block + padding)
     float2 *seg_in, *seg_out;        // [n_seg] warmed-up state entering / true-candidate state leaving each segment
     float2 *fstate;                  // [1] the reference's float state carried across blocks
     unsigned *fixups;                // [1] junctions that had to be replayed (diagnostic)
@@ -273,20 +275,29 @@ SDR_HD SDR_FORCEINLINE void dc_ref_step(float c, float2 x, float2 &v, float2 &y)
     v = make_float2(nr, ni);
 }
 
-// where segment s starts its warm-up (index relative to the block start, possibly negative) and from which state
+// Where segment s starts its warm-up (index relative to the block start, possibly negative) and from which state.
+// seg_len and warm are multiples of kDcTile, so d = s * seg_len - warm is a tile boundary of this block when it is >= 0;
+// when it reaches back into the previous block, the warm-up starts at that block's first tile boundary at or after d
+// (its tile grid is anchored at ITS start), or at this block's start if there is none.  Every lane of the GPU kernel
+// therefore starts at an index in [d, d + kDcTile).
 SDR_HD inline void dc_exact_plan(const DcExactArgs &a, int s, int &i_start, float2 &v0) {
     if (s == 0) { i_start = 0; v0 = a.fstate[0]; return; }
-    const int d = s * a.seg_len - a.warm;
+    const long long d = (long long)s * a.seg_len - a.warm;
     if (d >= 0) {
-        const int t = d / kDcTile;
+        const int t = (int)(d / kDcTile);
         i_start = t * kDcTile;
         v0 = make_float2((float)a.tile_carry[t].x, (float)a.tile_carry[t].y);
     } else if (a.prev_n > 0) {
-        int pos = a.prev_n + d;                              // position inside the previous block
+        long long pos = (long long)a.prev_n + d;             // position inside the previous block
         if (pos < 0) pos = 0;
-        const int t = pos / kDcTile;
-        i_start = t * kDcTile - a.prev_n;
-        v0 = make_float2((float)a.prev_tile_carry[t].x, (float)a.prev_tile_carry[t].y);
+        const int t = (int)((pos + kDcTile - 1) / kDcTile);
+        if ((long long)t * kDcTile >= a.prev_n) {            // no boundary left in the previous block: start with this one
+            i_start = 0;
+            v0 = make_float2((float)a.tile_carry[0].x, (float)a.tile_carry[0].y);
+        } else {
+            i_start = t * kDcTile - a.prev_n;
+            v0 = make_float2((float)a.prev_tile_carry[t].x, (float)a.prev_tile_carry[t].y);
+        }
     } else {
         i_start = 0;                                         // first block of the stream: everything before it is zero
         v0 = make_float2(0.f, 0.f);

@@ -46,21 +46,20 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 // ---------------------------------------------------------------------------------------------------------------------
 // kernels (GPU) / serial replays (test-only emulator)
 // ---------------------------------------------------------------------------------------------------------------------
-// SMs the channel front kernel leaves free under a heavy channel load: the bit-exact DC blocker's serial chains (one warp
-// per segment) run there instead of fighting the front warps for issue slots.  The split follows the channel count:
-//   >= 384 channels: 8 SMs x 8 warps (the front kernel is long, the replay hides underneath even at 2 warps / scheduler)
-//   96 .. 383      : 16 SMs x 4 warps (one warp per scheduler = full chain speed; the front kernel is short)
-//   1 .. 95        : 32 SMs x 4 warps (the replay's latency is the block period: more, shorter segments)
-//   0              : none -- nothing else runs but the spectrum; the replay spreads over the whole GPU in short segments
-struct DcSplit { int reserved_sms; int warps_per_cta; };
-static inline DcSplit dc_split_for(size_t live_channels) {
-    if (live_channels >= 384) return DcSplit{8, 8};
-    if (live_channels >= 96) return DcSplit{16, 4};
-    if (live_channels >= 1) return DcSplit{32, 4};
-    return DcSplit{0, 1};
+// SMs the channel front kernel leaves free for the bit-exact DC blocker (k_dc_lanes: one lane per segment, four warps per
+// SM-exclusive CTA, i.e. one serial-chain warp per scheduler).  The replay's latency is the warm-up (24576 steps) plus one
+// segment; fewer SMs mean fewer, longer segments:
+//   >= 384 channels: 4 SMs (512 lanes; the front kernel is long and wants every SM it can get, the replay hides underneath)
+//   otherwise      : 8 SMs (1024 lanes: 1024-sample segments at 61.44 MSps)
+// SDR_B200_DC_SMS overrides (experiments).
+static inline int dc_reserved_sms(size_t live_channels) {
+    static int forced = -1;
+    if (forced < 0) { const char *v = getenv("SDR_B200_DC_SMS"); forced = v ? atoi(v) : 0; }
+    if (forced > 0) return forced > 32 ? 32 : forced;
+    return live_channels >= 384 ? 4 : 8;
 }
 constexpr int kResBuf = 3;           // host result buffers (ring): blocks a pipelined consumer may keep in flight + 1
-constexpr int kDcWarpsPerCta = 8;    // segments (warps) per CTA of the bit-exact DC replay under a heavy channel load
+constexpr unsigned kDlWarpsHost = 4;   // warps per CTA of k_dc_lanes (one per scheduler)
 constexpr int kFrontWarps = 16;      // warps per CTA of the channel front kernel (one CTA per SM): 16 x 32 x 128 registers = the whole
                                      // register file; the bit-exact DC replay has its own SMs (dc_split_for)
 #ifndef SDR_EMU
@@ -89,21 +88,16 @@ __global__ void __launch_bounds__(kDcThreads) k_dc_apply(DcArgs a) {
 // warp's private double-buffered slot for the wideband samples of the super-step it is working on (XWarpStage).
 constexpr int kFrontSmemTab = 1024 * 16 * (int)sizeof(float2);                    // 131072
 constexpr int kFrontSmemBytes = kFrontSmemTab + kFrontWarps * 2 * 32 * (int)sizeof(float4);   // + 16384
-// Bit-exact DC blocker: one warp per segment.  All lanes run the (strictly serial) chain redundantly; the warp as a whole
-// prefetches the raw samples three batches ahead into shared memory and stores the outputs coalesced.  A CTA holds up to
-// kDcWarpsPerCta segments.  Under a heavy channel load the launch also asks for kDcExclusiveSmem bytes of dynamic shared
-// memory it never touches: with that request a DC CTA shares its SM with nothing (not the channel front, 143 KB, nor the
-// tail or FFT CTAs that would steal its issue slots), so the block scheduler puts the replay on the SMs the front kernel
-// leaves free, whichever kernel starts first, and the serial chains run at their isolated speed.
+// Bit-exact DC blocker, serial form (short blocks, or no usable history for a warm-up): one warp, every lane runs the
+// (strictly serial) chain redundantly; the warp prefetches the raw samples three batches ahead into shared memory and
+// stores the outputs coalesced.
 constexpr int kDcBatch = 64;     // samples per cp.async batch (two 8-byte copies per lane)
 constexpr int kDcRing = 4;       // batches in flight: ~1700 cycles of lead over the serial chain
-constexpr int kDcExclusiveSmem = 200 * 1024;
-__global__ void __launch_bounds__(32 * kDcWarpsPerCta) k_dc_exact(DcExactArgs a) {
-    __shared__ __align__(16) float2 sx_all[kDcWarpsPerCta][kDcRing][kDcBatch];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int s = blockIdx.x * (blockDim.x >> 5) + warp;
+__global__ void __launch_bounds__(32) k_dc_exact(DcExactArgs a) {
+    __shared__ __align__(16) float2 sx[kDcRing][kDcBatch];
+    const int lane = threadIdx.x & 31;
+    const int s = blockIdx.x;
     if (s >= a.n_seg) return;
-    float2 (*sx)[kDcBatch] = sx_all[warp];
     int i0;
     float2 v;
     dc_exact_plan(a, s, i0, v);
@@ -172,6 +166,140 @@ __global__ void __launch_bounds__(32 * kDcWarpsPerCta) k_dc_exact(DcExactArgs a)
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (lane == 0) { a.seg_in[s] = v_in; a.seg_out[s] = v; }
+}
+
+// Bit-exact DC blocker, speculative form: ONE LANE PER SEGMENT.  The chain of a segment is strictly serial (FMUL -> FADD,
+// ~9 cycles a step) but segments are independent once each has been warmed up from the exact state, so a warp advances 32
+// segments in lock step -- lane l of warp w owns segment 32 w + l and walks the W + L samples [s L - W, (s + 1) L) of its
+// own stream -- instead of 32 lanes repeating one chain.  A 61.44 MSps block is ~1000 segments of 1024 samples = 32 warps
+// on 8 SMs (one warp per scheduler: nothing else competes for its issue slots), and the latency of the whole replay is
+// W + L = 25600 steps instead of W + block / 64.
+// Staging: the 32 streams of a warp are 8 L bytes apart, so every batch of 32 steps is moved through shared memory
+// transposed: half a warp copies 32 consecutive samples of one stream with 16-byte cp.async (coalesced 256 B), five
+// batches in flight; rows are 34 float2 apart, which keeps rows 16-byte aligned and makes the per-lane 128-bit reads down
+// a column conflict-free (quarter-warp word offsets 68 l mod 32 = 4 l).  Outputs leave the same way in reverse.
+constexpr int kDlBatch = 32;
+constexpr int kDlRing = 5;
+constexpr int kDlRow = 34;
+constexpr int kDlWarps = 4;
+constexpr int kDlSmemWarp = (kDlRing + 1) * 32 * kDlRow * (int)sizeof(float2);     // input ring + one output tile: 52224 B
+constexpr int kDlSmem = kDlWarps * kDlSmemWarp;                                    // 208896 B: the CTA owns its SM
+__global__ void __launch_bounds__(32 * kDlWarps, 1) k_dc_lanes(DcExactArgs a) {
+    extern __shared__ __align__(16) unsigned char dl_sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s0 = (blockIdx.x * kDlWarps + warp) * 32;              // first segment of this warp
+    if (s0 >= a.n_seg) return;
+    float2 *ring = reinterpret_cast<float2 *>(dl_sm + (size_t)warp * kDlSmemWarp);   // [kDlRing][32][kDlRow]
+    float2 *so = ring + kDlRing * 32 * kDlRow;                                        // [32][kDlRow]
+    const int L = a.seg_len, W = a.warm, n = a.n;
+    const int s = s0 + lane;
+    int i_begin = 0x7fffffff;                                        // lanes past the last segment never become active
+    float2 v = make_float2(0.f, 0.f);
+    if (s < a.n_seg) dc_exact_plan(a, s, i_begin, v);
+    const int p0 = s * L;                                            // first output sample of this lane
+    const int p1 = (s < a.n_seg) ? ((p0 + L < n) ? p0 + L : n) : p0;
+    const int d = p0 - W;                                            // this lane's sample at step 0
+    const int d0 = s0 * L - W;                                       // same for lane 0 (streams are L apart)
+    const int nb = (W + L) / kDlBatch;
+    const long long lo = -(long long)a.raw_hist, hi = a.raw_end;     // readable extent of the raw stream: [lo, hi)
+    const float c = a.c;
+    // transposed copies: lanes 0-15 move stream 2 it, lanes 16-31 stream 2 it + 1, two samples (16 bytes) each
+    const int fj = lane >> 4, ft = (lane & 15) * 2;
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
+    int fk = 0;
+    auto fetch = [&]() {
+        if (fk < nb) {
+            const unsigned dst0 = ring_s + (unsigned)(((fk % kDlRing) * 32 + fj) * kDlRow + ft) * 8u;
+            const int i00 = d0 + fk * kDlBatch;                      // lane 0's first sample of this batch
+            const float2 *src0 = a.xraw + i00 + fj * L + ft;
+            // the engine pads the raw buffer so that the streams of lanes past the end of the block stay readable (their
+            // samples are never used): normally every tile takes the unguarded path
+            if (i00 >= lo && (long long)i00 + 31ll * L + kDlBatch <= hi) {
+#pragma unroll
+                for (int it = 0; it < 16; ++it)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (unsigned)(it * 2 * kDlRow * 8)),
+                                 "l"(src0 + (size_t)it * 2 * L));
+            } else {
+                for (int it = 0; it < 16; ++it) {
+                    const long long idx = (long long)i00 + (long long)(2 * it + fj) * L + ft;
+                    if (idx >= lo && idx + 2 <= hi)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (unsigned)(it * 2 * kDlRow * 8)),
+                                     "l"(src0 + (size_t)it * 2 * L));
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;");
+        ++fk;
+    };
+#pragma unroll
+    for (int k = 0; k < kDlRing - 1; ++k) fetch();
+    float2 v_in = v, y;
+    const int kw = W / kDlBatch;                                     // batches [0, kw) warm up, [kw, nb) produce output
+    for (int k = 0; k < nb; ++k) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kDlRing - 2) : "memory");   // batch k has landed (this lane's copies)
+        __syncwarp();                                                // ... and every lane's; batch k - 1 and its outputs are consumed
+        fetch();
+        const float4 *row = reinterpret_cast<const float4 *>(ring + ((k % kDlRing) * 32 + lane) * kDlRow);
+        const int base = d + k * kDlBatch;
+        // A lane is `on` (all 32 steps count), `off` (none does: it has not started, has finished, or owns no segment) or
+        // partial.  Without partial lanes the warp runs the unrolled chain on a copy of the state, which off lanes discard.
+        if (k < kw) {
+            const bool on = base >= i_begin, off = (long long)base + kDlBatch <= (long long)i_begin;
+            if (__all_sync(0xffffffffu, on || off)) {
+                float2 vv = v;
+#pragma unroll
+                for (int t = 0; t < kDlBatch / 2; ++t) {
+                    const float4 q = row[t];
+                    dc_ref_step(c, make_float2(q.x, q.y), vv, y);
+                    dc_ref_step(c, make_float2(q.z, q.w), vv, y);
+                }
+                if (on) v = vv;
+            } else {                                                 // a lane starts inside this batch (previous block's tile grid)
+                for (int t = 0; t < kDlBatch / 2; ++t) {
+                    const float4 q = row[t];
+                    if (base + 2 * t >= i_begin) dc_ref_step(c, make_float2(q.x, q.y), v, y);
+                    if (base + 2 * t + 1 >= i_begin) dc_ref_step(c, make_float2(q.z, q.w), v, y);
+                }
+            }
+            if (k == kw - 1) v_in = v;
+        } else {
+            float4 *orow = reinterpret_cast<float4 *>(so + lane * kDlRow);
+            const bool on = base + kDlBatch <= p1, off = base >= p1;
+            if (__all_sync(0xffffffffu, on || off)) {
+                float2 vv = v;
+#pragma unroll
+                for (int t = 0; t < kDlBatch / 2; ++t) {
+                    const float4 q = row[t];
+                    float2 y0, y1;
+                    dc_ref_step(c, make_float2(q.x, q.y), vv, y0);
+                    dc_ref_step(c, make_float2(q.z, q.w), vv, y1);
+                    orow[t] = make_float4(y0.x, y0.y, y1.x, y1.y);
+                }
+                if (on) v = vv;
+            } else {                                                 // the block ends inside this batch
+                for (int t = 0; t < kDlBatch / 2; ++t) {
+                    const float4 q = row[t];
+                    float2 y0 = make_float2(0.f, 0.f), y1 = y0;
+                    if (base + 2 * t < p1) dc_ref_step(c, make_float2(q.x, q.y), v, y0);
+                    if (base + 2 * t + 1 < p1) dc_ref_step(c, make_float2(q.z, q.w), v, y1);
+                    orow[t] = make_float4(y0.x, y0.y, y1.x, y1.y);
+                }
+            }
+            __syncwarp();
+            // transposed store: half a warp writes 32 consecutive outputs of one stream (nothing at or past the block end)
+            const int ob = (k - kw) * kDlBatch + ft;                  // offset of this lane's pair inside its stream's segment
+#pragma unroll 4
+            for (int it = 0; it < 16; ++it) {
+                const int j = 2 * it + fj;
+                const long long idx = (long long)(s0 + j) * L + ob;
+                const float4 q = *reinterpret_cast<const float4 *>(so + j * kDlRow + ft);
+                if (idx + 2 <= n) *reinterpret_cast<float4 *>(a.y + idx) = q;
+                else if (idx < n) a.y[idx] = make_float2(q.x, q.y);
+            }
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (s < a.n_seg) { a.seg_in[s] = v_in; a.seg_out[s] = v; }
 }
 // All junctions are compared in parallel; only when one of them fails (rare) does thread 0 walk them serially and replay.
 __global__ void __launch_bounds__(256) k_dc_verify(DcExactArgs a) {
@@ -325,18 +453,19 @@ static void upload_params(void *dst, const void *src_pinned, size_t bytes, sdr_s
 #endif
 }
 
-static void launch_dc_exact(const DcExactArgs &a, int warps_per_cta, sdr_stream_t s, unsigned long long &launches) {
+static void launch_dc_exact(const DcExactArgs &a, sdr_stream_t s, unsigned long long &launches) {
 #ifndef SDR_EMU
-    if (warps_per_cta > 1) {                                   // exclusive CTAs on the SMs the front kernel leaves free
+    if (a.n_seg > 1) {                                          // one lane per segment, SM-exclusive CTAs of four warps
         static bool attr_set = false;
-        if (!attr_set) { cudaFuncSetAttribute(k_dc_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, kDcExclusiveSmem); attr_set = true; }
-        k_dc_exact<<<(a.n_seg + warps_per_cta - 1) / warps_per_cta, 32 * warps_per_cta, kDcExclusiveSmem, s>>>(a);
+        if (!attr_set) { cudaFuncSetAttribute(k_dc_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, kDlSmem); attr_set = true; }
+        const int warps = (a.n_seg + 31) / 32;
+        k_dc_lanes<<<(warps + kDlWarps - 1) / kDlWarps, 32 * kDlWarps, kDlSmem, s>>>(a);
     } else {
-        k_dc_exact<<<a.n_seg, 32, 0, s>>>(a);
+        k_dc_exact<<<1, 32, 0, s>>>(a);
     }
     k_dc_verify<<<1, 256, 0, s>>>(a);
 #else
-    (void)s; (void)warps_per_cta;
+    (void)s;
     for (int g = 0; g < a.n_seg; ++g) dc_exact_segment_serial(a, g, false, make_float2(0.f, 0.f));
     dc_exact_verify(a);
 #endif
@@ -498,6 +627,14 @@ struct sdr_chan {
     long long consumed = 0;         // wideband samples consumed
     std::vector<PremixSeg> recent;  // oscillator settings of the last consumed blocks, newest first (rare-path history mixing)
     size_t slot_bytes = 0;
+    // lifecycle (see "channels" below): device memory comes from the stream-ordered allocator on the engine's admin stream
+    bool fresh = true;              // the first submit that sees the channel makes its main stream wait for ev_ready
+    bool cs_dirty = false;          // descriptor changed after creation (sdr_chan_want_iq): re-uploaded with the next block
+    bool async_mem = false;         // arena / history came from be_malloc_async
+#ifndef SDR_EMU
+    cudaEvent_t ev_ready = nullptr; // arena cleared, descriptor / state / filter taps on the device
+    cudaEvent_t ev_dead = nullptr;  // destroyed: every block that could still touch the channel's memory has drained
+#endif
 };
 
 struct sdr_spectrum {
@@ -506,7 +643,7 @@ struct sdr_spectrum {
     int P = 1, nsub = 0, log_nsub = 0;
     float average_rate = 0.65f, scale_factor = 1.0f;
     // framing state (FFTDataDistributor)
-    long long buffered = 0, last_rate = 0;
+    long long buffered = 0, last_rate = 0, last_center = 0;
     double line_accum = 0.0;
     // device
     float2 *d_tw = nullptr; float *d_mags = nullptr, *d_maa = nullptr; double2 *d_ema = nullptr; double *d_scalars = nullptr;
@@ -531,7 +668,7 @@ struct sdr_engine {
     std::mutex mu;
     unsigned long long launches = 0;
     // wideband buffers
-    size_t hist_cap = 0;
+    size_t hist_cap = 0, raw_pad = 0;
     float2 *d_raw = nullptr, *d_scratch = nullptr;
     float2 *d_blkbuf[2] = {nullptr, nullptr};   // DC-blocked stream, double-buffered: [hist_cap | max_block] each
     float2 *d_rawbuf = nullptr;                 // raw stream [hist_cap | max_block] (the bit-exact DC replay warms up on history)
@@ -572,7 +709,20 @@ struct sdr_engine {
     std::vector<float> taps_host; float *d_taps = nullptr; size_t taps_cap = 0, taps_uploaded = 0;
     std::map<std::string, int> taps_cache;
     unsigned char *d_results = nullptr, *h_results = nullptr; size_t results_bytes = 0;
-    bool dirty = true;
+    // Channel lifecycle: sdr_chan_create / sdr_chan_destroy run on other threads than the submitter (DemodulatorWorkerThread,
+    // DemodulatorMgr) and must never make it wait (SDRPostThread only try_push()es, SDRPostThread.cpp:238-298).  `mu` (the
+    // submit lock) is therefore only ever taken for a few host instructions by them; allocations, uploads and frees go
+    // through the stream-ordered allocator on `stream_admin` under `mu_cfg`, and a destroyed channel's memory, slot and
+    // result region are recycled only after an event proves that the blocks in flight at destroy time have drained.
+    std::mutex mu_cfg;                  // taps pool, slot / result-region allocators, graveyard; never held across a device sync
+    std::vector<char> slot_used;        // by slot: owned by a live or not-yet-reaped channel
+    std::vector<std::pair<size_t, size_t>> res_free;   // free extents (offset, bytes) of the result buffer below res_hwm
+    size_t res_hwm = 0;                 // layout high-water mark; the buffers grow (the one remaining sync) if it passes results_bytes
+    std::vector<sdr_chan *> graveyard;
+    ChanStatic *h_cs_stage = nullptr;   // pinned [kMaxChan]: descriptors re-uploaded by the submitter (cs_dirty)
+#ifndef SDR_EMU
+    cudaStream_t stream_admin = nullptr;
+#endif
     bool results_on_host = false;
     // host results live in a ring of kResBuf buffers so that a caller may fetch block b while up to kResBuf - 1 newer
     // blocks are in flight (sdr_engine_wait_block)
@@ -710,13 +860,15 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
     int bad = 0;
     bad |= be_malloc((void **)&e->d_raw, (size_t)max_block * sizeof(float2));
     for (int b = 0; b < 2; ++b) bad |= be_malloc((void **)&e->d_blkbuf[b], (e->hist_cap + max_block) * sizeof(float2));
-    bad |= be_malloc((void **)&e->d_rawbuf, (e->hist_cap + max_block) * sizeof(float2));
+    // the DC replay's lanes past the end of a block still stage (unused) samples of their streams: pad instead of guarding
+    e->raw_pad = (size_t)max_block / 8 + 2 * 65536;
+    bad |= be_malloc((void **)&e->d_rawbuf, (e->hist_cap + max_block + e->raw_pad) * sizeof(float2));
     bad |= be_malloc((void **)&e->d_scratch, e->hist_cap * sizeof(float2));
     bad |= be_host_alloc((void **)&e->h_stage, (size_t)max_block * sizeof(sdr_cf32));
     const int tiles = (max_block + kDcTile - 1) / kDcTile;
     bad |= be_malloc((void **)&e->d_tile_sum, tiles * sizeof(double2));
     for (int b = 0; b < 2; ++b) bad |= be_malloc((void **)&e->d_tile_carry2[b], tiles * sizeof(double2));
-    const int max_seg = (int)(max_block / kDcSegLenLight) + 2;
+    const int max_seg = (int)(max_block / kDcTile) + 2;
     bad |= be_malloc((void **)&e->d_seg_in, max_seg * sizeof(float2));
     bad |= be_malloc((void **)&e->d_seg_out, max_seg * sizeof(float2));
     bad |= be_malloc((void **)&e->d_fstate, sizeof(float2));
@@ -744,6 +896,14 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
     }
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_tail, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_res, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_admin, cudaStreamNonBlocking));
+    {   // channel memory comes from the stream-ordered pool: keep what is freed cached instead of returning it to the driver
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_spec_k, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_tail_k, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_front_done, cudaEventDisableTiming));
@@ -763,9 +923,14 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
 #endif
     e->taps_cap = 4u << 20;   // floats
     bad |= be_malloc((void **)&e->d_taps, e->taps_cap * sizeof(float));
+    e->slot_used.assign(sdr_engine::kMaxChan, 0);
+    bad |= be_host_alloc((void **)&e->h_cs_stage, (size_t)sdr_engine::kMaxChan * sizeof(ChanStatic));
+    e->results_bytes = (size_t)16 << 20;                        // grows (ensure_results) if a layout ever needs more
+    bad |= be_malloc((void **)&e->d_results, e->results_bytes);
+    bad |= be_host_alloc((void **)&e->h_results, kResBuf * e->results_bytes);
     if (bad) { delete e; return fail(SDR_ERR_NOMEM, "sdr_engine_create: allocation failed"); }
     for (int b = 0; b < 2; ++b) be_memset(e->d_blkbuf[b], 0, (e->hist_cap + max_block) * sizeof(float2), e->stream);
-    be_memset(e->d_rawbuf, 0, (e->hist_cap + max_block) * sizeof(float2), e->stream);
+    be_memset(e->d_rawbuf, 0, (e->hist_cap + max_block + e->raw_pad) * sizeof(float2), e->stream);
     be_memset(e->d_fstate, 0, sizeof(float2), e->stream);
     be_memset(e->d_fixups, 0, sizeof(unsigned), e->stream);
     be_memset(e->d_dc_state, 0, sizeof(double2), e->stream);
@@ -790,11 +955,30 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
 }
 
 static void spectrum_free(sdr_spectrum *sp);
+static void sync_all(sdr_engine *e);
+static void reap_graveyard(sdr_engine *e, bool wait);
+static void chan_release_memory(sdr_engine *e, sdr_chan *c, sdr_stream_t s);
+static sdr_stream_t admin_stream(sdr_engine *e);
 
 extern "C" int sdr_engine_destroy(sdr_engine *e) {
     if (!e) return SDR_OK;
-    be_sync(e->stream);
-    for (auto *c : e->chans) if (c) { be_free(c->d_arena); be_free(c->d_priv_hist); be_host_free(c->h_dyn); be_host_free(c->h_slot); delete c; }
+#ifndef SDR_EMU
+    cudaSetDevice(e->device);
+#endif
+    sync_all(e);
+#ifndef SDR_EMU
+    if (e->stream_admin) cudaStreamSynchronize(e->stream_admin);
+#endif
+    reap_graveyard(e, true);
+    for (auto *c : e->chans) if (c) {
+        chan_release_memory(e, c, admin_stream(e));
+        be_host_free(c->h_dyn); be_host_free(c->h_slot);
+#ifndef SDR_EMU
+        if (c->ev_ready) cudaEventDestroy(c->ev_ready);
+#endif
+        delete c;
+    }
+    be_host_free(e->h_cs_stage);
     for (auto *s : e->spectra) if (s) { spectrum_free(s); delete s; }
     be_free(e->d_pfb_hq); be_free(e->d_pfb_tw); be_free(e->d_pfb_streams[0]); be_free(e->d_pfb_streams[1]); be_free(e->d_pfb_dc_state);
     be_free(e->d_raw); be_free(e->d_blkbuf[0]); be_free(e->d_blkbuf[1]); be_free(e->d_rawbuf); be_free(e->d_scratch); be_host_free(e->h_stage);
@@ -808,6 +992,7 @@ extern "C" int sdr_engine_destroy(sdr_engine *e) {
     if (e->stream_dc) { cudaStreamSynchronize(e->stream_dc); cudaStreamDestroy(e->stream_dc); }
     if (e->stream_tail) { cudaStreamSynchronize(e->stream_tail); cudaStreamDestroy(e->stream_tail); }
     if (e->stream_res) { cudaStreamSynchronize(e->stream_res); cudaStreamDestroy(e->stream_res); }
+    if (e->stream_admin) { cudaStreamSynchronize(e->stream_admin); cudaStreamDestroy(e->stream_admin); }
     if (e->ev_spec_k) cudaEventDestroy(e->ev_spec_k);
     if (e->ev_tail_k) cudaEventDestroy(e->ev_tail_k);
     if (e->ev_front_done) cudaEventDestroy(e->ev_front_done);
@@ -915,7 +1100,7 @@ static int add_halfband_taps(sdr_engine *e, int m) {
     return pool_add(e, fkey("hb", (float)m), h1, 2 * m);
 }
 
-static int rebuild(sdr_engine *e);
+static int ensure_results(sdr_engine *e);
 static void sync_all(sdr_engine *e) {
     be_sync(e->stream);
 #ifndef SDR_EMU
@@ -926,21 +1111,76 @@ static void sync_all(sdr_engine *e) {
 #endif
 }
 
+// ---- allocators of the configuration side (all under e->mu_cfg) --------------------------------------------------------------
+static sdr_stream_t admin_stream(sdr_engine *e) {
+#ifndef SDR_EMU
+    return e->stream_admin;
+#else
+    return e->stream;
+#endif
+}
+static void chan_release_memory(sdr_engine *e, sdr_chan *c, sdr_stream_t s) {
+    if (c->async_mem) { be_free_async(c->d_arena, s); be_free_async(c->d_priv_hist, s); }
+    else { be_free(c->d_arena); be_free(c->d_priv_hist); }
+    c->d_arena = nullptr; c->d_priv_hist = nullptr;
+    (void)e;
+}
+// result-buffer regions: first fit over the free extents, else extend the high-water mark
+static size_t res_region_take(sdr_engine *e, size_t bytes) {
+    for (size_t k = 0; k < e->res_free.size(); ++k) {
+        if (e->res_free[k].second >= bytes) {
+            const size_t off = e->res_free[k].first;
+            e->res_free[k].first += bytes; e->res_free[k].second -= bytes;
+            if (!e->res_free[k].second) e->res_free.erase(e->res_free.begin() + (long)k);
+            return off;
+        }
+    }
+    const size_t off = e->res_hwm;
+    e->res_hwm += bytes;
+    return off;
+}
+static void res_region_give(sdr_engine *e, size_t off, size_t bytes) {
+    auto it = e->res_free.begin();
+    while (it != e->res_free.end() && it->first < off) ++it;
+    it = e->res_free.insert(it, std::make_pair(off, bytes));
+    if (it + 1 != e->res_free.end() && it->first + it->second == (it + 1)->first) { it->second += (it + 1)->second; e->res_free.erase(it + 1); }
+    if (it != e->res_free.begin() && (it - 1)->first + (it - 1)->second == it->first) { (it - 1)->second += it->second; it = e->res_free.erase(it) - 1; }
+    if (it->first + it->second == e->res_hwm) { e->res_hwm = it->first; e->res_free.erase(it); }
+}
+// recycle what destroyed channels held once their event has fired (never waits)
+static void reap_graveyard(sdr_engine *e, bool wait) {
+    for (size_t k = 0; k < e->graveyard.size();) {
+        sdr_chan *g = e->graveyard[k];
+        bool done = true;
+#ifndef SDR_EMU
+        if (g->ev_dead) {
+            if (wait) cudaEventSynchronize(g->ev_dead);
+            done = cudaEventQuery(g->ev_dead) == cudaSuccess;
+        }
+#endif
+        (void)wait;
+        if (!done) { ++k; continue; }
+        if (g->index >= 0 && (size_t)g->index < e->slot_used.size()) e->slot_used[(size_t)g->index] = 0;
+        if (g->slot_bytes) res_region_give(e, (size_t)g->cs.res_off, g->slot_bytes);
+#ifndef SDR_EMU
+        if (g->ev_dead) cudaEventDestroy(g->ev_dead);
+        if (g->ev_ready) cudaEventDestroy(g->ev_ready);
+#endif
+        delete g;
+        e->graveyard.erase(e->graveyard.begin() + (long)k);
+    }
+}
+
+// DemodulatorWorkerThread builds the resampler for a new demodulator off the hot threads (DemodulatorWorkerThread.cpp:63-108);
+// so does this: design and layout without any lock, allocation / clearing / uploads on the admin stream under mu_cfg, and the
+// submit lock only to publish the finished channel.
 static int chan_create_impl(sdr_engine *e, const char *modem, long long sample_rate, long long bandwidth, int audio_rate,
                             unsigned inject_cap, sdr_chan **out) {
     if (!e || !out || sample_rate <= 0 || audio_rate <= 0) return fail(SDR_ERR_ARG, "sdr_chan_create: bad arguments");
     const int mk = modem_from_name(modem);
     if (mk < 0) return fail(SDR_ERR_UNSUPPORTED, std::string("sdr_chan_create: unknown modem '") + (modem ? modem : "") + "'");
-    std::lock_guard<std::mutex> lk(e->mu);
-    int slot = -1;
-    for (size_t i = 0; i < e->chans.size(); ++i) if (!e->chans[i]) { slot = (int)i; break; }
-    if (slot < 0) {
-        if ((int)e->chans.size() >= sdr_engine::kMaxChan) return fail(SDR_ERR_STATE, "sdr_chan_create: too many channels");
-        slot = (int)e->chans.size();
-        e->chans.push_back(nullptr);
-    }
     sdr_chan *c = new sdr_chan();
-    c->eng = e; c->index = slot; c->modem = mk; c->sample_rate = sample_rate;
+    c->eng = e; c->index = -1; c->modem = mk; c->sample_rate = sample_rate;
     c->bandwidth = check_sample_rate(mk, bandwidth);
     c->audio_rate = audio_rate;
     const float As = 60.0f;                                             // DemodulatorWorkerThread.cpp:95, ModemAnalog.cpp:25
@@ -960,39 +1200,19 @@ static int chan_create_impl(sdr_engine *e, const char *modem, long long sample_r
     cs.K1 = std::max(0, std::min(cs.S - 2, kFrontMaxK));               // only the m = 3 stages can be fused
     cs.n_tail = cs.S - cs.K1;
     if (cs.n_tail > kMaxTailHb) { delete c; return fail(SDR_ERR_UNSUPPORTED, "sdr_chan_create: too many tail stages"); }
-    for (int j = 0; j < cs.n_tail; ++j) {
-        const int g = cs.S - cs.K1 - 1 - j;                             // cascade position executed at tail step j
-        cs.tail_m[j] = c->iq_plan.hb.m[g];
-        cs.tail_h1[j] = add_halfband_taps(e, cs.tail_m[j]);
-        if (cs.tail_h1[j] < 0) { delete c; return fail(SDR_ERR_UNSUPPORTED, "half-band prototype not available"); }
-    }
     for (int g = cs.S - cs.K1; g < cs.S; ++g)
         if (c->iq_plan.hb.m[g] != 3) { delete c; return fail(SDR_ERR_STATE, "front stage is not m = 3"); }
     cs.zeta = c->iq_plan.zeta;
     cs.arb_step = c->iq_plan.arb_step;
-    cs.pfb_off = pool_add(e, fkey("pfb", c->iq_plan.rate_arb), c->iq_plan.pfb.data(), c->iq_plan.pfb.size());
     cs.a_interp = c->audio_plan.interp ? 1 : 0;
     cs.a_S = c->audio_plan.num_halfband;
-    for (int g = 0; g < cs.a_S; ++g) {
-        cs.a_m[g] = c->audio_plan.hb.m[g];
-        cs.a_h1[g] = add_halfband_taps(e, cs.a_m[g]);
-        if (cs.a_h1[g] < 0) { delete c; return fail(SDR_ERR_UNSUPPORTED, "half-band prototype not available"); }
-    }
     cs.a_zeta = c->audio_plan.interp ? 1.0f : c->audio_plan.zeta;
     cs.a_step = c->audio_plan.arb_step;
-    cs.a_pfb_off = pool_add(e, fkey("pfb", c->audio_plan.rate_arb), c->audio_plan.pfb.data(), c->audio_plan.pfb.size());
-    {
-        float am[51]; am_dc_block_taps(25, 30.0f, am);                  // ModemAM.cpp:9
-        // firfilt runs y[t] = sum h[k] x[t-k]; the filter is symmetric so no reversal is needed
-        cs.am_taps_off = pool_add(e, "am51", am, 51);
-        float hq[10]; hilbert_quadrature_taps(5, 90.0f, hq);            // ModemUSB.cpp:11
-        cs.hq_off = pool_add(e, "hq10", hq, 10);
-        std::vector<Sos> sos; butterworth_lowpass_sos(6, 0.25f, sos);   // ModemUSB.cpp:8
-        float flat[15];
-        for (int s = 0; s < 3; ++s) { flat[5 * s] = sos[s].b[0]; flat[5 * s + 1] = sos[s].b[1]; flat[5 * s + 2] = sos[s].b[2]; flat[5 * s + 3] = sos[s].a[1]; flat[5 * s + 4] = sos[s].a[2]; }
-        cs.sos_off = pool_add(e, "sos6", flat, 15);
-    }
-    if (e->taps_host.size() > e->taps_cap) { delete c; return fail(SDR_ERR_NOMEM, "taps pool exhausted"); }
+    float am[51]; am_dc_block_taps(25, 30.0f, am);                      // ModemAM.cpp:9
+    float hq[10]; hilbert_quadrature_taps(5, 90.0f, hq);                // ModemUSB.cpp:11
+    std::vector<Sos> sos; butterworth_lowpass_sos(6, 0.25f, sos);       // ModemUSB.cpp:8
+    float flat[15];
+    for (int k = 0; k < 3; ++k) { flat[5 * k] = sos[k].b[0]; flat[5 * k + 1] = sos[k].b[1]; flat[5 * k + 2] = sos[k].b[2]; flat[5 * k + 3] = sos[k].a[1]; flat[5 * k + 4] = sos[k].a[2]; }
     // ---- arena layout (floats)
     size_t off = 0;
     auto take = [&](size_t floats) { size_t o = off; off += (floats + 3) & ~size_t(3); return (int)o; };
@@ -1019,26 +1239,84 @@ static int chan_create_impl(sdr_engine *e, const char *modem, long long sample_r
     cs.res_iq_cap = (int)cap_iq;
     cs.want_iq = 0;
     c->arena_floats = off;
-    if (be_malloc((void **)&c->d_arena, off * sizeof(float))) { delete c; return fail(SDR_ERR_NOMEM, "sdr_chan_create: arena"); }
-    be_memset(c->d_arena, 0, off * sizeof(float), e->stream);
-    cs.arena = c->d_arena;
-    // [raw tail of the consumed stream | the same, mixed (rare path) | scratch for rolling the raw tail]
-    if (be_malloc((void **)&c->d_priv_hist, 3 * (size_t)kBlkHist * sizeof(float2))) { be_free(c->d_arena); delete c; return fail(SDR_ERR_NOMEM, "sdr_chan_create: history"); }
     c->slot_bytes = 32 + (size_t)cs.res_audio_cap * 4 + (size_t)cs.res_iq_cap * 8;
     c->slot_bytes = (c->slot_bytes + 31) & ~size_t(31);
     ChanState st;
     memset(&st, 0, sizeof st);
     st.agc_ceil = st.agc_ma = st.agc_maa = 1.0f;                        // ModemAnalog.cpp:6
-    be_h2d(e->d_st + slot, &st, sizeof st, e->stream);
-    be_sync(e->stream);
     if (c->standalone) {
         if (be_host_alloc((void **)&c->h_dyn, sizeof(ChanDyn)) || be_host_alloc((void **)&c->h_slot, c->slot_bytes)) {
-            be_free(c->d_arena); be_free(c->d_priv_hist); delete c;
+            be_host_free(c->h_dyn); be_host_free(c->h_slot); delete c;
             return fail(SDR_ERR_NOMEM, "sdr_modem_create: host buffers");
         }
     }
-    e->chans[slot] = c;
-    e->dirty = true;
+    // ---- configuration lock: filter taps, slot, result region, device memory and uploads (admin stream; no device-wide sync)
+    {
+        std::lock_guard<std::mutex> lk(e->mu_cfg);
+#ifndef SDR_EMU
+        cudaSetDevice(e->device);                                       // DemodulatorWorkerThread is not the thread that made the engine
+#endif
+        reap_graveyard(e, false);
+        sdr_stream_t as = admin_stream(e);
+        auto bail = [&](int code, const char *msg) {
+            chan_release_memory(e, c, as);
+            if (c->index >= 0) e->slot_used[(size_t)c->index] = 0;
+            be_host_free(c->h_dyn); be_host_free(c->h_slot);
+#ifndef SDR_EMU
+            if (c->ev_ready) cudaEventDestroy(c->ev_ready);
+#endif
+            delete c;
+            return fail(code, msg);
+        };
+        for (int j = 0; j < cs.n_tail; ++j) {
+            const int g = cs.S - cs.K1 - 1 - j;                         // cascade position executed at tail step j
+            cs.tail_m[j] = c->iq_plan.hb.m[g];
+            cs.tail_h1[j] = add_halfband_taps(e, cs.tail_m[j]);
+            if (cs.tail_h1[j] < 0) return bail(SDR_ERR_UNSUPPORTED, "half-band prototype not available");
+        }
+        cs.pfb_off = pool_add(e, fkey("pfb", c->iq_plan.rate_arb), c->iq_plan.pfb.data(), c->iq_plan.pfb.size());
+        for (int g = 0; g < cs.a_S; ++g) {
+            cs.a_m[g] = c->audio_plan.hb.m[g];
+            cs.a_h1[g] = add_halfband_taps(e, cs.a_m[g]);
+            if (cs.a_h1[g] < 0) return bail(SDR_ERR_UNSUPPORTED, "half-band prototype not available");
+        }
+        cs.a_pfb_off = pool_add(e, fkey("pfb", c->audio_plan.rate_arb), c->audio_plan.pfb.data(), c->audio_plan.pfb.size());
+        // firfilt runs y[t] = sum h[k] x[t-k]; the AM notch is symmetric so no reversal is needed
+        cs.am_taps_off = pool_add(e, "am51", am, 51);
+        cs.hq_off = pool_add(e, "hq10", hq, 10);
+        cs.sos_off = pool_add(e, "sos6", flat, 15);
+        if (e->taps_host.size() > e->taps_cap) return bail(SDR_ERR_NOMEM, "taps pool exhausted");
+        int slot = -1;
+        for (size_t i = 0; i < e->slot_used.size(); ++i) if (!e->slot_used[i]) { slot = (int)i; break; }
+        if (slot < 0) return bail(SDR_ERR_STATE, "sdr_chan_create: too many channels");
+        e->slot_used[(size_t)slot] = 1;
+        c->index = slot;
+        c->async_mem = true;
+        if (be_malloc_async((void **)&c->d_arena, off * sizeof(float), as)) return bail(SDR_ERR_NOMEM, "sdr_chan_create: arena");
+        // [raw tail of the consumed stream | the same, mixed (rare path) | scratch for rolling the raw tail]
+        if (be_malloc_async((void **)&c->d_priv_hist, 3 * (size_t)kBlkHist * sizeof(float2), as)) return bail(SDR_ERR_NOMEM, "sdr_chan_create: history");
+        be_memset(c->d_arena, 0, off * sizeof(float), as);
+        cs.arena = c->d_arena;
+        cs.res_off = (long long)res_region_take(e, c->slot_bytes);
+        // pageable sources: the runtime stages them before returning, so the locals may go out of scope
+        be_h2d(e->d_st + slot, &st, sizeof st, as);
+        be_h2d(e->d_cs + slot, &cs, sizeof cs, as);
+        if (e->taps_host.size() > e->taps_uploaded) {
+            be_h2d(e->d_taps + e->taps_uploaded, e->taps_host.data() + e->taps_uploaded,
+                   (e->taps_host.size() - e->taps_uploaded) * sizeof(float), as);
+            e->taps_uploaded = e->taps_host.size();
+        }
+#ifndef SDR_EMU
+        if (cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming) != cudaSuccess) return bail(SDR_ERR_CUDA, "sdr_chan_create: event");
+        cudaEventRecord(c->ev_ready, as);
+        if (c->standalone) cudaEventSynchronize(c->ev_ready);           // sdr_modem_*: the caller's own thread, nobody else waits
+#endif
+    }
+    {   // publish: the submitter sees the channel from its next block on
+        std::lock_guard<std::mutex> lk(e->mu);
+        if ((size_t)c->index >= e->chans.size()) e->chans.resize((size_t)c->index + 1, nullptr);
+        e->chans[(size_t)c->index] = c;
+    }
     *out = c;
     return SDR_OK;
 }
@@ -1073,7 +1351,7 @@ extern "C" int sdr_modem_demodulate(sdr_chan *c, const sdr_cf32 *iq, unsigned n,
     if (!iq || n > c->inject_cap) return fail(SDR_ERR_ARG, "sdr_modem_demodulate: bad buffer / too many samples");
     sdr_engine *e = c->eng;
     std::lock_guard<std::mutex> lk(e->mu);
-    if (e->dirty) { int r = rebuild(e); if (r) return r; }
+    { int r = ensure_results(e); if (r) return r; }
     sync_all(e);                                                        // h_dyn / h_slot are reused call to call
     float *d_iq = c->cs.arena + c->cs.iq_off + 2 * kHist;
     be_h2d(d_iq, iq, (size_t)n * sizeof(sdr_cf32), e->stream);
@@ -1095,18 +1373,46 @@ extern "C" int sdr_modem_demodulate(sdr_chan *c, const sdr_cf32 *iq, unsigned n,
     return SDR_OK;
 }
 
+// DemodulatorMgr::deleteThread happens while blocks are in flight.  The channel disappears from the submitter's list at once
+// (a few host instructions under the submit lock); its memory is handed back on the admin stream once events recorded on
+// every engine stream at this moment have fired, and its slot / result region are recycled when that is known to have happened.
 extern "C" int sdr_chan_destroy(sdr_chan *c) {
     if (!c) return SDR_OK;
     sdr_engine *e = c->eng;
-    std::lock_guard<std::mutex> lk(e->mu);
-    sync_all(e);
-    e->chans[c->index] = nullptr;
-    be_free(c->d_arena);
-    be_free(c->d_priv_hist);
-    be_host_free(c->h_dyn);
-    be_host_free(c->h_slot);
-    e->dirty = true;
-    delete c;
+#ifndef SDR_EMU
+    cudaSetDevice(e->device);
+    cudaEvent_t fence[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (auto &f : fence) cudaEventCreateWithFlags(&f, cudaEventDisableTiming);
+#endif
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        if (c->index >= 0 && (size_t)c->index < e->chans.size() && e->chans[(size_t)c->index] == c) e->chans[(size_t)c->index] = nullptr;
+#ifndef SDR_EMU
+        // everything already enqueued may still touch the channel; nothing enqueued later will
+        cudaStream_t ss[5] = {e->stream, e->stream_tail, e->stream_res, e->stream_dc, e->stream2};
+        for (int k = 0; k < 5; ++k) if (fence[k]) cudaEventRecord(fence[k], ss[k]);
+#endif
+    }
+    {
+        std::lock_guard<std::mutex> lk(e->mu_cfg);
+        sdr_stream_t as = admin_stream(e);
+#ifndef SDR_EMU
+        for (int k = 0; k < 5; ++k) if (fence[k]) cudaStreamWaitEvent(as, fence[k], 0);
+        if (c->ev_ready) cudaStreamWaitEvent(as, c->ev_ready, 0);
+#endif
+        chan_release_memory(e, c, as);
+#ifndef SDR_EMU
+        if (cudaEventCreateWithFlags(&c->ev_dead, cudaEventDisableTiming) == cudaSuccess) cudaEventRecord(c->ev_dead, as);
+        if (c->standalone && c->ev_dead) cudaEventSynchronize(c->ev_dead);   // pinned host buffers go now: the caller's own thread waits
+#endif
+        be_host_free(c->h_dyn); be_host_free(c->h_slot);
+        c->h_dyn = nullptr; c->h_slot = nullptr;
+        e->graveyard.push_back(c);
+        reap_graveyard(e, false);
+    }
+#ifndef SDR_EMU
+    for (auto &f : fence) if (f) cudaEventDestroy(f);                   // a recorded event may be destroyed: the wait stays valid
+#endif
     return SDR_OK;
 }
 
@@ -1125,7 +1431,7 @@ extern "C" int sdr_chan_want_iq(sdr_chan *c, int enable) {
     if (!c) return fail(SDR_ERR_ARG, "null channel");
     std::lock_guard<std::mutex> lk(c->eng->mu);
     c->cs.want_iq = enable ? 1 : 0;
-    c->eng->dirty = true;
+    c->cs_dirty = true;                                                 // re-uploaded with the next block's parameters
     return SDR_OK;
 }
 
@@ -1188,7 +1494,7 @@ extern "C" int sdr_spectrum_destroy(sdr_spectrum *s) {
     if (!s) return SDR_OK;
     sdr_engine *e = s->eng;
     std::lock_guard<std::mutex> lk(e->mu);
-    be_sync(e->stream);
+    sync_all(e);                                                        // the side / result streams may still use its buffers
     e->spectra.erase(std::remove(e->spectra.begin(), e->spectra.end(), s), e->spectra.end());
     spectrum_free(s);
     delete s;
@@ -1204,9 +1510,11 @@ extern "C" int sdr_spectrum_set_average_rate(sdr_spectrum *s, float r) {
 
 // FFTDataDistributor::process restated for frames that are transformed immediately (src/process/FFTDataDistributor.cpp:
 // 41-53 reset on rate change, :89-97 line-rate step, :100-142 emit loop).  Returns frame starts relative to the block.
-static void schedule_frames(sdr_spectrum *s, unsigned n, long long sample_rate, std::vector<int> &starts) {
+static void schedule_frames(sdr_spectrum *s, unsigned n, long long sample_rate, long long center, std::vector<int> &starts) {
     starts.clear();
-    if (s->last_rate != sample_rate) { s->buffered = 0; s->last_rate = sample_rate; }
+    // "Settings have changed ... dump all previous samples" (:41-53): a new rate OR a new tuner frequency empties the buffer;
+    // lineRateAccum is left alone, as there
+    if (s->last_rate != sample_rate || s->last_center != center) { s->buffered = 0; s->last_rate = sample_rate; s->last_center = center; }
     const long long before = s->buffered, N = s->N;
     s->buffered += n;
     if (s->buffered < N) return;
@@ -1241,25 +1549,23 @@ static void schedule_frames(sdr_spectrum *s, unsigned n, long long sample_rate, 
 // ---------------------------------------------------------------------------------------------------------------------
 // submit
 // ---------------------------------------------------------------------------------------------------------------------
-static int rebuild(sdr_engine *e) {
+// The result buffers (device + a ring of pinned host copies) are sized generously at engine creation; only when the layout
+// outgrows them does the engine stop, once, to enlarge them.
+static int ensure_results(sdr_engine *e) {
+    size_t need;
+    { std::lock_guard<std::mutex> lk(e->mu_cfg); need = e->res_hwm; }
+    if (need <= e->results_bytes) return SDR_OK;
     sync_all(e);
-    size_t total = 0;
-    for (auto *c : e->chans) if (c) { c->cs.res_off = (long long)total; total += c->slot_bytes; }
-    if (total > e->results_bytes) {
-        be_free(e->d_results); be_host_free(e->h_results);
-        e->d_results = nullptr; e->h_results = nullptr;
-        if (be_malloc((void **)&e->d_results, total) || be_host_alloc((void **)&e->h_results, kResBuf * total))
-            return fail(SDR_ERR_NOMEM, "results buffer");
-        e->results_bytes = total;
-        for (int b = 0; b < kResBuf; ++b) e->res_on_host[b] = false;
+    size_t total = std::max<size_t>(need * 2, (size_t)16 << 20);
+    unsigned char *d_new = nullptr, *h_new = nullptr;
+    if (be_malloc((void **)&d_new, total) || be_host_alloc((void **)&h_new, kResBuf * total)) {
+        be_free(d_new); be_host_free(h_new);
+        return fail(SDR_ERR_NOMEM, "results buffer");
     }
-    for (auto *c : e->chans) if (c) be_h2d(e->d_cs + c->index, &c->cs, sizeof(ChanStatic), e->stream);
-    if (e->taps_host.size() > e->taps_uploaded) {
-        be_h2d(e->d_taps, e->taps_host.data(), e->taps_host.size() * sizeof(float), e->stream);
-        e->taps_uploaded = e->taps_host.size();
-    }
-    be_sync(e->stream);
-    e->dirty = false;
+    be_free(e->d_results); be_host_free(e->h_results);
+    e->d_results = d_new; e->h_results = h_new;
+    e->results_bytes = total;
+    for (int b = 0; b < kResBuf; ++b) e->res_on_host[b] = false;
     return SDR_OK;
 }
 
@@ -1308,7 +1614,7 @@ static int pfb_prepare(sdr_engine *e, int M, int osf) {
 
 static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_src, unsigned n, long long center, long long rate,
                          bool to_host, int ready, void *ready_event) {
-    if (e->dirty) { int r = rebuild(e); if (r) return r; }
+    { int r = ensure_results(e); if (r) return r; }
     const int p = e->parity ^ 1;                               // this block's buffer; the other one holds the previous block
     float2 *blk = e->d_blkbuf[p] + e->hist_cap;
     float2 *raw = e->d_rawbuf + e->hist_cap;
@@ -1399,29 +1705,24 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         launch_dc(dc, !e->exact_dc, dcs, e->launches);
         if (e->exact_dc) {
             DcExactArgs xa;
-            // few, long segments when the channel front kernel owns the SMs (the replay's warps must fit on the reserved
-            // ones); many short ones when the GPU is otherwise idle and only the replay's own latency matters
+            // one lane per segment on the SMs the channel front kernel leaves free: as many segments (multiples of the scan
+            // tile) as those SMs hold lanes, each warmed up over kDcWarm samples
             size_t live = 0;
             for (auto *c : e->chans) live += c != nullptr;
-            const DcSplit split = dc_split_for(live);
-            const bool heavy = split.reserved_sms > 0;
-            unsigned seg = kDcSegLenLight;
-            if (heavy) {                                           // exactly as many segments as warp slots on the reserved SMs
-                const unsigned cap = (unsigned)(split.reserved_sms * split.warps_per_cta);
-                seg = (unsigned)((n + cap - 1) / cap);
-                seg = (seg + 63u) & ~63u;
-                if (seg < kDcSegLenLight) seg = kDcSegLenLight;
-            }
+            const unsigned lanes = (unsigned)dc_reserved_sms(live) * kDlWarpsHost * 32u;
+            const unsigned tiles_n = (n + kDcTile - 1) / kDcTile;
+            const unsigned seg = kDcTile * ((tiles_n + lanes - 1) / lanes);
             xa.xraw = raw; xa.y = blk; xa.n = (int)n; xa.seg_len = (int)seg; xa.warm = kDcWarm;
+            xa.raw_hist = (int)need_raw; xa.raw_end = (long long)e->max_block + (long long)e->raw_pad;
             xa.c = (float)e->dc_a;
             xa.tile_carry = e->d_tile_carry2[p]; xa.prev_tile_carry = e->d_tile_carry2[p ^ 1];
             xa.prev_n = e->have_block ? (int)e->last_n : 0;
             xa.seg_in = e->d_seg_in; xa.seg_out = e->d_seg_out; xa.fstate = e->d_fstate; xa.fixups = e->d_fixups;
             // speculate only when there is parallelism to gain and the warm-up region lies inside the data we hold
-            const bool spec = n >= 4u * seg && (!e->have_block || e->last_n >= (unsigned)(kDcWarm + kDcTile));
+            const bool spec = n >= (unsigned)kDcMinSpec && n > seg && (!e->have_block || e->last_n >= (unsigned)(kDcWarm + kDcTile));
             xa.n_seg = spec ? (int)((n + seg - 1) / seg) : 1;
             if (!spec) xa.seg_len = (int)n;
-            launch_dc_exact(xa, (heavy && spec) ? split.warps_per_cta : 1, dcs, e->launches);
+            launch_dc_exact(xa, dcs, e->launches);
         }
     }
     // history in front of the block: the tail of the previous block, which lives in the other buffer
@@ -1500,7 +1801,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
     std::vector<int> starts;
     std::vector<std::pair<sdr_spectrum *, SpecArgs>> spec_jobs;
     for (auto *s : e->spectra) {
-        schedule_frames(s, n, rate, starts);
+        schedule_frames(s, n, rate, center, starts);
         s->frames_last = (unsigned)std::min<size_t>(starts.size(), s->f_max);
         s->frames_buf[q] = s->frames_last;
         if (!s->frames_last) continue;
@@ -1592,7 +1893,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
     std::vector<int> by_k[kFrontMaxK + 1];
     size_t live_now = 0;
     for (auto *c : e->chans) live_now += c != nullptr;
-    const int front_reserved = (e->exact_dc && !pfb) ? dc_split_for(live_now).reserved_sms : 0;
+    const int front_reserved = (e->exact_dc && !pfb) ? dc_reserved_sms(live_now) : 0;
 
     for (int i = 0; i < n_slots; ++i) {
         sdr_chan *c = e->chans[i];
@@ -1600,6 +1901,17 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         memset(&d, 0, sizeof d);
         if (!c || c->standalone) continue;
         d.valid = 1;
+        if (c->fresh) {                                          // created since the last block: its memory is being prepared on
+            c->fresh = false;                                    // the admin stream -- a device-side wait, the host never blocks
+#ifndef SDR_EMU
+            if (c->ev_ready) CUDA_TRY(cudaStreamWaitEvent(e->stream, c->ev_ready, 0));
+#endif
+        }
+        if (c->cs_dirty) {                                       // sdr_chan_want_iq on a live channel: only that flag differs
+            c->cs_dirty = false;
+            e->h_cs_stage[i] = c->cs;
+            upload_params(e->d_cs + i, e->h_cs_stage + i, sizeof(ChanStatic), par_stream, e->launches);
+        }
         // Consumed history that is not contiguous in the stream (a skipped block inside the front kernel's history window,
         // only possible with blocks shorter than that window): keep extending the private raw tail block by block until a
         // consumed block is long enough to hold the whole window again.

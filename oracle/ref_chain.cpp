@@ -359,7 +359,7 @@ API int ref_chan_process(void *h, const lq_cf *block, unsigned n, long long shif
 // ---------------------------------------------------------------------------------------------------------
 struct RefDistrib {
     unsigned fftSize; unsigned linesPerSecond; double lineRateAccum;
-    std::vector<lq_cf> buf; size_t bufferMax, bufferOffset, bufferedItems; long long sampleRate;
+    std::vector<lq_cf> buf; size_t bufferMax, bufferOffset, bufferedItems; long long sampleRate; long long frequency = 0;
 };
 API void *ref_distrib_create(unsigned fftSize, unsigned lps) {
     auto *d = new RefDistrib(); d->fftSize = fftSize; d->linesPerSecond = lps; d->lineRateAccum = 0;
@@ -367,10 +367,11 @@ API void *ref_distrib_create(unsigned fftSize, unsigned lps) {
 }
 API void ref_distrib_destroy(void *h) { delete (RefDistrib *)h; }
 // returns number of frames written to frames_out (each fftSize samples)
-API unsigned ref_distrib_push(void *h, const lq_cf *in, unsigned n, long long sampleRate, lq_cf *frames_out, unsigned cap_frames) {
+API unsigned ref_distrib_push(void *h, const lq_cf *in, unsigned n, long long sampleRate, long long frequency, lq_cf *frames_out, unsigned cap_frames) {
     auto *d = (RefDistrib *)h;
     unsigned nf = 0;
-    if (d->sampleRate != sampleRate) {                                      // :41-53
+    if (d->sampleRate != sampleRate || d->frequency != frequency) {         // :41-53
+        d->frequency = frequency;
         d->bufferMax = std::max((size_t)(sampleRate * 0.250), (size_t)(1.2 * d->fftSize));
         d->bufferOffset = 0; d->bufferedItems = 0; d->sampleRate = sampleRate; d->buf.resize(d->bufferMax);
     }
@@ -542,7 +543,7 @@ API double ref_bench_path(const lq_cf *iq, unsigned n, unsigned warm_blocks, uns
         std::vector<std::thread> pool;
         for (unsigned t = 1; t < threads; t++) pool.emplace_back(work, t);
         if (spec) {   // the spectrum thread's work rides on the calling thread, then it joins the channel pool
-            unsigned nf = ref_distrib_push(dist, dc.data(), n, sampleRate, frames.data(), cap_frames);
+            unsigned nf = ref_distrib_push(dist, dc.data(), n, sampleRate, 0, frames.data(), cap_frames);
             for (unsigned f = 0; f < nf && f < cap_frames; f++)
                 ref_spectrum_frame(spec, frames.data() + (size_t)f * fftSize * 2, fftSize * 2, pts.data(), line.data(), nullptr, nullptr, nullptr);
         }
@@ -633,7 +634,7 @@ API double ref_bench_pfb_path(const lq_cf *iq, unsigned n, unsigned warm_blocks,
         std::vector<std::thread> pool;
         for (unsigned t = 1; t < threads; t++) pool.emplace_back(work, t);
         if (spec) {
-            unsigned nf = ref_distrib_push(dist, const_cast<lq_cf *>(iq), n, sampleRate, frames.data(), cap_frames);
+            unsigned nf = ref_distrib_push(dist, const_cast<lq_cf *>(iq), n, sampleRate, center, frames.data(), cap_frames);
             for (unsigned f = 0; f < nf && f < cap_frames; f++)
                 ref_spectrum_frame(spec, frames.data() + (size_t)f * fftSize * 2, fftSize * 2, pts.data(), line.data(), nullptr, nullptr, nullptr);
         }

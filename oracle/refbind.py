@@ -64,7 +64,7 @@ class Ref:
         L.ref_chan_process.argtypes = [vp, vp, u, ll, vp, vp, vp, vp, vp, vp, vp]
         L.ref_distrib_create.restype = vp; L.ref_distrib_create.argtypes = [u, u]
         L.ref_distrib_destroy.argtypes = [vp]
-        L.ref_distrib_push.restype = u; L.ref_distrib_push.argtypes = [vp, vp, u, ll, vp, u]
+        L.ref_distrib_push.restype = u; L.ref_distrib_push.argtypes = [vp, vp, u, ll, ll, vp, u]
         L.ref_spectrum_create.restype = vp; L.ref_spectrum_create.argtypes = [u]
         L.ref_spectrum_destroy.argtypes = [vp]
         L.ref_spectrum_set_average_rate.argtypes = [vp, f]
@@ -170,11 +170,11 @@ class RefDistrib:
         self.ref, self.n = ref, frame_len
         self.h = C.c_void_p(ref.L.ref_distrib_create(frame_len, lps))
 
-    def push(self, block, sample_rate):
+    def push(self, block, sample_rate, frequency=0):
         block = np.ascontiguousarray(block, np.complex64)
         cap = block.size // self.n + 4
         out = np.zeros(cap * self.n, np.complex64)
-        nf = self.ref.L.ref_distrib_push(self.h, _p(block), block.size, int(sample_rate), _p(out), cap)
+        nf = self.ref.L.ref_distrib_push(self.h, _p(block), block.size, int(sample_rate), int(frequency), _p(out), cap)
         return out[:nf * self.n].reshape(nf, self.n)
 
     def close(self):

@@ -54,6 +54,16 @@ def test_spectrum_split_transform_and_line_limiter(emu_lib, ref):
     assert 1 <= w["frames"] <= 6 and w["mags"] <= parity.TOL
 
 
+def test_spectrum_moving_tuner(emu_lib, ref):
+    """The tuner moves between blocks: FFTDataDistributor dumps what it had buffered (FFTDataDistributor.cpp:41-53), so the
+    frame grid restarts at the first block with the new frequency.  Block length is not a multiple of the frame length,
+    so a dropped remainder shifts every later frame."""
+    chans = synth.channel_plan("mixed", 2400000, 4)
+    w = parity.run_spectrum(emu_lib, ref, 2400000, 1024, n_blocks=6, chans=chans, block=40003,
+                            center_by_block={2: parity.CENTER + 250000, 3: parity.CENTER + 250000, 4: parity.CENTER - 100000})
+    assert w["frames"] > 100 and w["mags"] <= parity.TOL and w["points"] <= parity.TOL
+
+
 def test_against_golden_vectors(emu_lib):
     parity.check_against_golden(emu_lib)
 

@@ -79,6 +79,14 @@ def test_line_limiter(gpu_lib, ref):
     assert 1 <= w["frames"] <= 6 and w["mags"] <= parity.TOL
 
 
+def test_spectrum_moving_tuner(gpu_lib, ref):
+    """Retunes between blocks: the distributor's buffered remainder is dumped (FFTDataDistributor.cpp:41-53)."""
+    chans = synth.channel_plan("mixed", 2400000, 4)
+    w = parity.run_spectrum(gpu_lib, ref, 2400000, 1024, n_blocks=6, chans=chans, block=40003,
+                            center_by_block={2: parity.CENTER + 250000, 3: parity.CENTER + 250000, 4: parity.CENTER - 100000})
+    assert w["frames"] > 100 and w["mags"] <= parity.TOL and w["points"] <= parity.TOL
+
+
 def test_block_partition_invariance_full_size(gpu_lib):
     """Size-independent property at BASELINE size (61.44 MSps block): streaming the same samples as one block or as
     three ragged pieces yields bit-identical audio (all state is carried exactly)."""

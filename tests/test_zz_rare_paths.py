@@ -7,9 +7,6 @@ from tests.test_fuzz import _case, _channelizer_case
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first device run (last GPU minute of round 1) failed: a warp whose lanes had different history "
-                                        "pointers still took the warp-staged sample path; fixed in k_chan_front right after, device "
-                                        "re-validation pending (the emulator tier covers the logic)")
 def test_short_blocks_around_retunes_gpu(gpu_lib, ref):
     for seed in range(9100, 9130):
         _case(gpu_lib, ref, seed, tiny=True)
