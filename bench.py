@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py -- IQ MSamples/s through the spectrum + demodulator chain (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg5|cfg3|cfg2] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg5|cfg4|cfg3|cfg2|cfg1] [--impl ours|reference]
   N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 A step = one reference-sized IQ block (fs/60 samples, SoapySDRThread.cpp:668-674) through the whole hot path:
@@ -9,17 +9,24 @@ DC blocker -> spectrum FFT / EMA / waterfall line (rank 0) -> NCO mix + multi-st
 resampling for every channel of this rank.  Channels are sharded over the ranks (strong scaling: the job is fixed);
 when N > 1 the raw block is broadcast from rank 0 over NCCL inside the timed region.
 
-`value`   device-resident inputs (a ring of distinct blocks larger than L2), results left in HBM.
-`e2e`     the same through host buffers: pinned host block -> H2D -> (broadcast) -> kernels -> D2H -> batched audio fetch.
-`roofline` for the dominant kernel (channel front: oscillator mix + half-band cascade), timed with CUDA events on the
-           engine's stream inside the timed region.
-`cpu_baseline` / `--impl reference`: the reference's own liquid-dsp binary + CubicSDR glue (oracle/_ref) on the host cores.
+`value`    device-resident inputs (a ring of distinct blocks larger than L2), results left in HBM.  The K steps are timed
+           with CUDA events between a barrier + synchronize on both sides; that region is repeated until at least a
+           second has been measured and the median repetition is reported (`reps`).
+`e2e`      the same through the C-ABI call a CubicSDR thread makes: sdr_engine_submit(host pointer) on pinned host blocks
+           (H2D inside), sdr_engine_wait_block, batched audio / spectrum fetch into host arrays (D2H inside).
+`roofline` for the dominant kernel (channel front: oscillator mix + half-band cascade; FP32-issue bound with many channels,
+           so the bound is "fp32" and the HBM contract figure sits in roofline.hbm), timed with CUDA events on the engine's
+           streams inside the timed region.
+`cpu_baseline` / `--impl reference`: the reference's own liquid-dsp binary + CubicSDR glue (oracle/_ref) on the host cores
+           the process may really use (affinity and cgroup quota), single-channel glue as `value`, the reference's stock
+           channelizer path (what SDRPostThread runs above 500 kSps) as `cpu_baseline_channelizer`.
+`configs`  (N = 1) the other BASELINE.json configurations, each with its own device / e2e / roofline / CPU figures.
 """
 import os
 os.environ.setdefault("OMP_NUM_THREADS", "1")   # no spinning OpenMP pool next to the reference's own threads (cpu_baseline / --impl reference)
 import argparse
 import json
-import os
+import math
 import subprocess
 import sys
 import threading
@@ -36,23 +43,67 @@ WORKLOADS = {
     # BASELINE.json configs[4] (the metric's own config: spectrum + demod chain), run as a fixed job sharded over N GPUs
     "cfg5": dict(fs=61440000, plan="mixed", n_chan=512, fft=16384,
                  desc="cfg5: 512 mixed FM/AM/USB/LSB demod channels + 16384-pt spectrum/waterfall on 61.44 MSps IQ"),
+    "cfg4": dict(fs=40000000, plan="mixed", n_chan=256, fft=0,
+                 desc="cfg4: 256 mixed FM/AM/USB/LSB demod channels from 40 MSps IQ"),
     "cfg3": dict(fs=20000000, plan="nbfm64", n_chan=64, fft=0, desc="cfg3: 64 NBFM channels @12.5 kHz from 20 MSps IQ"),
     "cfg2": dict(fs=10000000, plan="mixed", n_chan=0, fft=8192, desc="cfg2: 8192-pt spectrum FFT + waterfall on 10 MSps IQ"),
+    "cfg1": dict(fs=2400000, plan="wbfm1", n_chan=1, fft=0, desc="cfg1: 1x WBFM demod, 2.4 MSps IQ, 200 kHz -> 48 kHz audio"),
     # SURVEY.md 8(f) row 1 (not a BASELINE config): the reference's channelizer for rates above 500 kSps, on its own
     "pfb": dict(fs=61440000, plan="mixed", n_chan=0, fft=0,
                 desc="pfb: firpfbch analysis channelizer (SDRPostThread::runPFBCH), 122 channels on 61.44 MSps IQ"),
 }
 FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12    # non-tensor FP32 issue peak of a B200 at max clock
+L2_BYTES = 126e6
 
 
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
-            return float(json.load(open(p))["hbm_gbs"]), "measured"
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
         except Exception:
             pass
-    return 6650.0, "fallback"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_cores():
+    """Host cores this process may really use: scheduler affinity, capped by the cgroup CPU quota (os.cpu_count() sees the
+    whole machine even inside a container with a quota)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    quota = None
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(p)
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0 and p > 0:
+                quota = q / p
+        except Exception:
+            pass
+    if quota is not None:
+        n = max(1, min(n, int(math.floor(quota + 1e-9)) or 1))
+    return max(1, n)
+
+
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def config_of(wl, N, n_chan):
+    """The `config` object: identical keys and values on both arms."""
+    return {"workload": wl["desc"], "fs": wl["fs"], "block": N, "channels": n_chan, "fft_size": wl["fft"]}
 
 
 def torch_wideband(torch, fs, n, chans, t0, device, seed):
@@ -128,12 +179,17 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+        # the median over the samples taken while the GPU was clocked up (idle samples before / after the loops read low)
+        load = [v for v in sm if mx and v >= 0.6 * max(mx)] or sm
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ---------------------------------------------------------------------------------------------------------------------------
+# CPU reference legs (oracle/_ref: the reference's own liquid-dsp binary + a restatement of the CubicSDR glue around it)
+# ---------------------------------------------------------------------------------------------------------------------------
 def cpu_reference_run(wl, chans, iq_host, threads, blocks, channelizer=0):
-    """Time the reference CPU path (oracle/_ref: reference liquid-dsp binary + CubicSDR glue) on `blocks` blocks.
+    """Time the reference CPU path on `blocks` blocks after one untimed block.
     channelizer = 1 / 2: through SDRPostThread::runPFBCH / runPFBCH2 instead of runSingleCH."""
     import ctypes as C
     from oracle.refbind import Ref
@@ -159,6 +215,28 @@ def cpu_reference_run(wl, chans, iq_host, threads, blocks, channelizer=0):
     return secs, ref.version()
 
 
+def cpu_baselines(wl, chans, iq_host, threads, blocks=1):
+    """(cpu_baseline, cpu_baseline_channelizer): the glue that matches the engine's default mode (runSingleCH) and the
+    reference's stock path for this rate (runPFBCH above 500 kSps; identical to runSingleCH below)."""
+    N = len(iq_host)
+    what = "%d block(s) of %d samples (1/60 s each) after 1 untimed block, all %d channels%s" % (
+        blocks, N, len(chans), " + spectrum" if wl["fft"] else "")
+    out = []
+    for mode in (0, 1):
+        try:
+            if mode == 1 and wl["fs"] <= 500000:
+                out.append(None); continue
+            secs, ver = cpu_reference_run(wl, chans, iq_host, threads, blocks, channelizer=mode)
+            out.append({"value": N * blocks / secs / 1e6, "unit": "MSamples/s", "cores": threads, "kind": "reference",
+                        "cpu": cpu_model(),
+                        "path": "SDRPostThread::runPFBCH + runDemodChannels (the stock path above 500 kSps)" if mode else
+                                "SDRPostThread::runSingleCH (DC blocker + every demodulator at the full rate: the engine's default mode)",
+                        "sample": what + ", reference liquid-dsp %s binary + CubicSDR glue" % ver})
+        except Exception as ex:        # the oracle is a checker; its absence must not hide the GPU number
+            out.append({"value": None, "unit": "MSamples/s", "cores": 0, "kind": "reference", "sample": "unavailable: %r" % (ex,)})
+    return out[0], out[1]
+
+
 def run_reference(args, wl, chans, rank):
     """--impl reference: the reference's own CPU implementation on the host cores, same config / metric / unit."""
     from cubicsdr_b200 import synth
@@ -166,16 +244,25 @@ def run_reference(args, wl, chans, rank):
         return
     N = synth.block_size(wl["fs"])
     iq = synth.wideband(wl["fs"], N, chans[:: max(1, len(chans) // 32)] if chans else [], t0=0)   # carriers: a 32-channel subset keeps generation quick
-    threads = os.cpu_count() or 1
+    threads = cpu_cores()
     secs, ver = cpu_reference_run(wl, chans, iq, threads, args.steps, channelizer=1 if args.channelizer else 0)
-    t_tot = secs
-    val = N * args.steps / t_tot / 1e6
+    val = N * args.steps / secs / 1e6
+    stock = None
+    if not args.channelizer and wl["fs"] > 500000:
+        try:
+            s2, _ = cpu_reference_run(wl, chans, iq, threads, max(1, min(args.steps, 4)), channelizer=1)
+            stock = {"value": N * max(1, min(args.steps, 4)) / s2 / 1e6, "unit": "MSamples/s", "cores": threads, "kind": "reference",
+                     "path": "SDRPostThread::runPFBCH + runDemodChannels (the stock path above 500 kSps)"}
+        except Exception as ex:
+            stock = {"value": None, "sample": "unavailable: %r" % (ex,)}
     line = {"impl": "reference", "metric": "IQ MSamples/s through spectrum+demod chain", "value": val, "unit": "MSamples/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "fs": wl["fs"], "block": N, "channels": len(chans), "fft_size": wl["fft"]},
-            "cpu_baseline": {"value": val, "unit": "MSamples/s", "cores": threads, "kind": "reference",
+            "config": config_of(wl, N, len(chans)),
+            "cpu_baseline": {"value": val, "unit": "MSamples/s", "cores": threads, "kind": "reference", "cpu": cpu_model(),
+                             "path": "SDRPostThread::runPFBCH" if args.channelizer else "SDRPostThread::runSingleCH (the mode the engine arm runs)",
                              "sample": "1 block (1/60 s of IQ) per step after 1 untimed block, all channels + spectrum, liquid-dsp %s" % ver},
+            "cpu_baseline_channelizer": stock,
             "e2e": {"value": val, "unit": "MSamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -183,7 +270,6 @@ def run_reference(args, wl, chans, rank):
 def run_pfb(args, wl):
     """--workload pfb: the polyphase analysis channelizer alone, device-resident and through host
     buffers, next to the reference binary's firpfbch_crcf on one host core (the reference runs it on one thread)."""
-    import ctypes as C
     import torch
     import cubicsdr_b200
     from cubicsdr_b200 import Channelizer, Engine, synth
@@ -220,7 +306,7 @@ def run_pfb(args, wl):
         ch.execute(host_in)
     t0 = time.perf_counter()
     for _ in range(max(1, args.steps // 10)):
-        out_host = ch.execute(host_in)
+        ch.execute(host_in)
     t_e2e = (time.perf_counter() - t0) / max(1, args.steps // 10)
     clocks = sampler.stop()
     peak, peak_src = measured_peaks()
@@ -269,15 +355,294 @@ def emit(line):
     out.flush()
 
 
+# ---------------------------------------------------------------------------------------------------------------------------
+# the engine arm
+# ---------------------------------------------------------------------------------------------------------------------------
+class Ctx:
+    """torch / library / process-group handles shared by the workloads of one bench run"""
+    pass
+
+
+def run_engine_workload(cx, wl, chans, steps, warmup, min_seconds, channelizer=False, want_cpu=True, want_timeline=False):
+    """One workload on this rank's GPU (channels sharded over the ranks).  Returns the dict of measured figures on rank 0,
+    None elsewhere."""
+    torch, lib, dist, dev = cx.torch, cx.lib, cx.dist, cx.dev
+    rank, world = cx.rank, cx.world
+    from cubicsdr_b200 import Channel, Engine, Spectrum, synth
+    fs = wl["fs"]
+    N = synth.block_size(fs)
+    stream = torch.cuda.Stream(device=dev)          # a dedicated (non-default) stream shared by torch and the engine
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    eng = Engine(lib, device=cx.local_rank, max_block=N, stream=stream.cuda_stream)
+    mine = chans[rank::world]                                  # channel sharding (SURVEY.md 8e)
+    chan_fs = fs
+    desc = wl["desc"]
+    if channelizer:
+        eng.set_channelizer(1)
+        n_pfb, chan_fs = eng.channel_plan(fs)
+        eng.set_channel_block_max(N // n_pfb)
+        desc += " [DIAGNOSTIC: channelizer mode, %d filterbank channels of %d Hz]" % (n_pfb, chan_fs)
+    cobjs = [Channel(eng, m, chan_fs, bw, 48000, frequency=CENTER + off) for m, bw, off in mine]
+    spec = Spectrum(eng, wl["fft"], 0) if (wl["fft"] and rank == 0) else None
+
+    def print_timeline(tag):                                    # stderr diagnostic: device timeline of a few steady-state blocks
+        try:
+            import ctypes as C
+            tl = np.zeros((16, 8), np.float32); ntl = C.c_int()
+            lib.L.sdr_engine_debug_timeline(eng.h, tl.ctypes.data_as(C.c_void_p), C.byref(ntl))
+            print("%s timeline (ms) dc_start dc_end | front_start front_end tail_end | spec_start spec_end tail_start" % tag, file=sys.stderr)
+            for r in range(8, min(13, ntl.value)):
+                print("  blk %2d " % r + " ".join("%7.3f" % v for v in tl[r]), file=sys.stderr)
+        except Exception as ex:
+            print("timeline unavailable: %r" % (ex,), file=sys.stderr)
+
+    # ---- inputs: ring of distinct blocks resident in HBM on rank 0, larger than the 126 MB L2 in total ------------------
+    n_ring = max(cx.args.ring, int(math.ceil(1.1 * L2_BYTES / (N * 8.0))))
+    ring = []
+    carriers = chans if chans else synth.channel_plan("mixed", fs, 16)
+    if rank == 0:
+        base = [torch_wideband(torch, fs, N, carriers, r * N, dev, 1234) for r in range(min(n_ring, 16))]
+        ring = list(base)
+        g = torch.Generator(device=dev); g.manual_seed(77)
+        while len(ring) < n_ring:                             # further distinct blocks: an earlier one plus fresh noise (cheap)
+            b = base[len(ring) % len(base)]
+            ring.append(b + 0.002 * torch.view_as_complex(torch.randn(N, 2, device=dev, generator=g)))
+    recvs = [torch.empty(N, dtype=torch.complex64, device=dev) for _ in range(4)] if world > 1 else None
+    # host side of the e2e: four pinned blocks from the C-ABI's own allocator
+    host_blocks = []
+    if rank == 0:
+        for k in range(4):
+            a, addr = lib.host_alloc(N)
+            a[:] = ring[k % len(ring)].cpu().numpy()
+            host_blocks.append((a, addr))
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    side = torch.cuda.Stream(device=dev)                       # input production (NCCL broadcast) off the engine's stream
+    bc_done = [torch.cuda.Event() for _ in range(4)]
+
+    def step_device(i):
+        buf = ring[i % n_ring] if rank == 0 else recvs[i & 3]
+        ev = None
+        if world > 1:
+            with torch.cuda.stream(side):
+                dist.broadcast(buf, src=0)                        # the path's one exchange step (raw IQ over NVLink)
+                bc_done[i & 3].record(side)
+            ev = bc_done[i & 3].cuda_event
+        # resident block (or ready at `ev`): the DC blocker of this block overlaps the previous block's channel kernels
+        eng.submit_device_async(buf.data_ptr(), N, CENTER, fs, fetch_to_host=False, ready_event=ev)
+
+    # ---- end to end.  One GPU: exactly the host entry a CubicSDR thread calls -- sdr_engine_submit on a pinned host block
+    # (the engine's DMA stream and device ring inside), sdr_engine_wait_block(2), batched fetch.  Several GPUs: rank 0 copies
+    # the pinned block to its GPU, the raw block is broadcast over NCCL, every rank submits the resident copy.
+    copy_stream = torch.cuda.Stream(device=dev)
+    stages = [torch.empty(N, dtype=torch.complex64, device=dev) for _ in range(4)] if world > 1 else None
+    h2d_done = [torch.cuda.Event() for _ in range(4)]
+    host_t = [torch.from_numpy(a) for a, _ in host_blocks] if (world > 1 and rank == 0) else None
+
+    def h2d(i):
+        if world > 1 and rank == 0:
+            with torch.cuda.stream(copy_stream):
+                stages[i % 4].copy_(host_t[i % 4], non_blocking=True)
+                h2d_done[i % 4].record(copy_stream)
+
+    def submit_e2e(i):
+        if world == 1:
+            eng.submit_ptr(host_blocks[i % 4][1], N, CENTER, fs)
+            return
+        buf = stages[i % 4]
+        with torch.cuda.stream(side):
+            if rank == 0:
+                side.wait_event(h2d_done[i % 4])
+            dist.broadcast(buf, src=0)
+            bc_done[i & 3].record(side)
+        eng.submit_device_async(buf.data_ptr(), N, CENTER, fs, fetch_to_host=True, ready_event=bc_done[i & 3].cuda_event)
+
+    def fetch_e2e():
+        nbytes = 0
+        if cobjs:
+            audio, n_audio, _, _ = eng.fetch_audio_batch(cobjs, 1024)
+            nbytes += int(n_audio.sum()) * 4
+        if spec is not None:
+            pts, lines, cf = spec.fetch_all(64)
+            nbytes += pts.nbytes + lines.nbytes
+        return nbytes
+
+    # Two blocks in flight, like the reference's thread pipeline (queues between its threads): per step, submit block i+2,
+    # then wait for and fetch the results of block i.  Every step costs one H2D, one pass of the path and one D2H + fetch.
+    host_split = [0.0, 0.0, 0.0]                                # host seconds in submit / wait / fetch (diagnostic, stderr)
+
+    def step_e2e(i):
+        t_a = time.perf_counter()
+        submit_e2e(i + 2)
+        h2d(i + 3)
+        t_b = time.perf_counter()
+        eng.wait_block(2)
+        t_c = time.perf_counter()
+        nb = fetch_e2e()
+        t_d = time.perf_counter()
+        host_split[0] += t_b - t_a; host_split[1] += t_c - t_b; host_split[2] += t_d - t_c
+        return nb
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        tt = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    # ---- warm-up ------------------------------------------------------------------------------------------------------
+    for i in range(max(3, warmup)):
+        step_device(i)
+    eng.wait()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(32):                                         # also the estimate that sizes the repetitions
+        step_device(i)
+    eng.wait(); torch.cuda.synchronize()
+    est = max_over_ranks((time.perf_counter() - t0) / 32)
+    reps = int(min(400, max(1, math.ceil(min_seconds / max(1e-6, est * steps)))))
+
+    # stage times (CUDA events on the engine's streams, at most 64 blocks per collection): a pass of its own
+    eng.set_timing(True)
+    for i in range(min(60, max(steps, 16))):
+        step_device(i)
+    eng.wait()
+    stage_ms, stage_blocks = eng.get_timing()
+    if rank == 0 and want_timeline:
+        print_timeline("device")
+    eng.set_timing(False)
+
+    # ---- timed: device-resident.  K steps between barrier + synchronize, repeated `reps` times; the median is reported ----
+    launches0 = eng.launch_count
+    rep_ms = []
+    k = 0
+    for r in range(reps):
+        barrier(); torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            step_device(k); k += 1
+        eng.wait()                                              # every stream of the engine has drained (device-side work only)
+        e1.record(stream)
+        torch.cuda.synchronize(); barrier()
+        rep_ms.append(max_over_ranks(e0.elapsed_time(e1)))
+    launches = (eng.launch_count - launches0) // reps
+    ms = float(np.median(rep_ms))
+    value = N * steps / (ms * 1e-3) / 1e6
+
+    # ---- timed: end to end through host buffers -------------------------------------------------------------------------
+    h2d(0); submit_e2e(0); h2d(1); submit_e2e(1); h2d(2)
+    for i in range(3):
+        step_e2e(i)
+    eng.wait(); torch.cuda.synchronize()
+    e2e_reps = int(min(200, max(1, math.ceil(min_seconds / max(1e-6, 1.3 * est * steps)))))
+    rep_s = []
+    d2h = 0
+    k = 3
+    for r in range(e2e_reps):
+        # prime two blocks, then K timed steps each of which submits one block and fetches one
+        barrier(); torch.cuda.synchronize()
+        if r == 0 and rank == 0 and want_timeline:
+            eng.set_timing(True)
+        t0 = time.perf_counter()
+        for i in range(steps):
+            d2h = step_e2e(k); k += 1
+        torch.cuda.synchronize(); barrier()
+        rep_s.append(max_over_ranks(time.perf_counter() - t0))
+        if r == 0 and rank == 0 and want_timeline:
+            eng.wait()
+            e2e_stage_ms, e2e_stage_blocks = eng.get_timing()
+            eng.set_timing(False)
+            print_timeline("e2e")
+            print("e2e device stages per block (ms): %s" % {kk: round(v / max(1, e2e_stage_blocks), 3) for kk, v in e2e_stage_ms.items()}, file=sys.stderr)
+    eng.wait()                                                  # drain the blocks still in flight (submitted, not yet fetched)
+    t_e2e = float(np.median(rep_s))
+    if rank == 0 and want_timeline:
+        tot = max(1, e2e_reps * steps + 3)
+        print("e2e host split per step (ms): submit %.3f  wait %.3f  fetch %.3f" % tuple(1e3 * v / tot for v in host_split), file=sys.stderr)
+    if dist is not None:
+        dd = torch.tensor([d2h], device=dev, dtype=torch.float64)
+        dist.all_reduce(dd, op=dist.ReduceOp.SUM)
+        d2h = int(dd.item())
+    e2e_value = N * steps / t_e2e / 1e6
+
+    res = None
+    if rank == 0:
+        # ---- roofline of the dominant kernel ---------------------------------------------------------------------------------
+        peak, peak_src = measured_peaks()
+        c_local = len(mine)
+        b_alg = 8.0 + c_local * 4.0 * 48000.0 / fs + (2.5 if spec is not None else 0.0)     # SURVEY.md 8(d): bytes / wideband sample / GPU
+        per_block = {kk: v / max(1, stage_blocks) for kk, v in stage_ms.items()}
+        dom = "front" if c_local else "spectrum"
+        if c_local and per_block.get("dc", 0.0) > per_block.get("front", 0.0) and not channelizer:
+            dom = "dc"                                            # few channels: the bit-exact DC replay's latency is the longest stage
+        t_dom_ms = per_block[dom]
+        hbm_gbs = (N * b_alg / (t_dom_ms * 1e-3)) / 1e9 if t_dom_ms > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(cx.args.workload if wl is WORKLOADS.get(cx.args.workload) else "", {}).get(dom)
+            except Exception:
+                traffic = None
+        names = {"front": "k_chan_front (NCO mix + half-band cascade)", "spectrum": "spectrum kernels (k_spec_*)",
+                 "dc": "k_dc_lanes (bit-exact DC blocker replay: serial float recurrence, latency bound)"}
+        hbm = {"achieved": hbm_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": hbm_gbs / peak,
+               "alg_bytes_per_sample": b_alg,
+               "note": "contract figure: algorithmic bytes per launch / kernel time / measured HBM copy peak"}
+        if c_local and dom == "front" and c_local >= 32:
+            flops = 30.0 * c_local * N / (per_block["front"] * 1e-3) / 1e12
+            fpk = cx.fp32_peak or FP32_NOMINAL_TFLOPS
+            roofline = {"bound": "fp32", "kernel": names[dom], "achieved": flops, "peak": fpk,
+                        "peak_source": "measured FFMA issue rate (sdr_debug_fp32_peak)" if cx.fp32_peak else "nominal 148 SM x 128 lanes x 2 x 1.965 GHz",
+                        "unit": "TFLOP/s", "frac": flops / fpk, "traffic": traffic,
+                        "flop_per_sample_per_channel": 30.0,
+                        "note": "per-channel mixing replays the reference's table oscillator sample by sample: ~30 flop / sample / channel "
+                                "(SURVEY.md 8d); FP32 issue, not HBM, binds with hundreds of channels in single-channel mode",
+                        "hbm": hbm}
+        else:
+            roofline = dict(hbm, bound="hbm", kernel=names[dom], traffic=traffic)
+        roofline["kernel_ms_per_block"] = t_dom_ms
+        roofline["stage_ms_per_block"] = per_block
+        res = {"value": value, "ms_per_step": ms / steps, "reps": reps, "rep_ms_min_max": [min(rep_ms), max(rep_ms)],
+               "e2e": {"value": e2e_value, "unit": "MSamples/s", "h2d_bytes_per_step": N * 8, "d2h_bytes_per_step": d2h,
+                       "reps": e2e_reps,
+                       "api": "sdr_engine_submit(pinned host block) + sdr_engine_wait_block(2) + sdr_engine_fetch_audio_batch / sdr_spectrum_fetch_all"
+                              if world == 1 else "pinned host block -> H2D -> ncclBroadcast -> sdr_engine_submit_device_async + wait_block(2) + batched fetch"},
+               "gpu_launches": int(launches), "roofline": roofline, "N": N, "c_local": c_local, "desc": desc,
+               "l2": "%d distinct %.1f MB input blocks rotate (%.0f MB > 126 MB L2)" % (n_ring, N * 8 / 1e6, n_ring * N * 8 / 1e6),
+               "realtime_factor": value * 1e6 / fs}
+        if want_cpu:
+            iq_host = host_blocks[0][0].copy()
+            res["cpu_baseline"], res["cpu_baseline_channelizer"] = cpu_baselines(wl, chans, iq_host, cpu_cores())
+    for c in cobjs:
+        c.close()
+    if spec is not None:
+        spec.close()
+    eng.close()
+    for _, addr in host_blocks:
+        lib.host_free(addr)
+    del ring
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ring", type=int, default=16, help="distinct input blocks rotated through (ring * block > L2)")
+    ap.add_argument("--ring", type=int, default=16, help="least number of distinct input blocks rotated through (ring * block > L2 is enforced)")
+    ap.add_argument("--min-seconds", type=float, default=1.0, help="the timed K-step region is repeated until this much has been measured")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE.json configurations (configs sub-object)")
     ap.add_argument("--channelizer", action="store_true",
                     help="diagnostic: run the engine in channelizer mode (SDRPostThread::runPFBCH, SURVEY.md 8(f) row 1) -- not a contract line")
     ap.add_argument("--channels", type=int, default=0, help="diagnostic only: override the workload's channel count (not a contract line)")
@@ -306,252 +671,76 @@ def main():
 
     import torch
     import cubicsdr_b200
-    from cubicsdr_b200 import Channel, Engine, Spectrum
     if args.warmup < 3:
         args.warmup = 3
+    cx = Ctx()
+    cx.args, cx.torch, cx.rank, cx.world, cx.local_rank = args, torch, rank, world, local_rank
     torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
+    cx.dev = torch.device("cuda", local_rank)
+    cx.dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-    lib = cubicsdr_b200.lib()
+        dist.init_process_group("nccl", device_id=cx.dev)
+        cx.dist = dist
+    cx.lib = cubicsdr_b200.lib()
+    cx.fp32_peak = None
+    try:
+        import ctypes as C
+        tf = C.c_double()
+        cx.lib.L.sdr_debug_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+        if cx.lib.L.sdr_debug_fp32_peak(local_rank, C.byref(tf)) == 0 and tf.value > 1.0:
+            cx.fp32_peak = tf.value
+    except Exception:
+        pass
 
-    def print_timeline(tag):                                    # stderr diagnostic: device timeline of a few steady-state blocks
-        try:
-            import ctypes as C
-            tl = np.zeros((16, 8), np.float32); ntl = C.c_int()
-            lib.L.sdr_engine_debug_timeline(eng.h, tl.ctypes.data_as(C.c_void_p), C.byref(ntl))
-            print("%s timeline (ms) dc_start dc_end | front_start front_end tail_end | spec_start spec_end tail_start" % tag, file=sys.stderr)
-            for r in range(8, min(13, ntl.value)):
-                print("  blk %2d " % r + " ".join("%7.3f" % v for v in tl[r]), file=sys.stderr)
-        except Exception as ex:
-            print("timeline unavailable: %r" % (ex,), file=sys.stderr)
-    # a dedicated (non-default) stream shared by torch and the engine: torch.cuda.Event timing then sees the kernels
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
-    assert stream.cuda_stream != 0
-    eng = Engine(lib, device=local_rank, max_block=N, stream=stream.cuda_stream)
-    mine = chans[rank::world]                                  # channel sharding
-    chan_fs = fs
-    if args.channelizer:
-        eng.set_channelizer(1)
-        n_pfb, chan_fs = eng.channel_plan(fs)
-        eng.set_channel_block_max(N // n_pfb)
-        wl = dict(wl, desc=wl["desc"] + " [DIAGNOSTIC: channelizer mode, %d filterbank channels of %d Hz]" % (n_pfb, chan_fs))
-    cobjs = [Channel(eng, m, chan_fs, bw, 48000, frequency=CENTER + off) for m, bw, off in mine]
-    spec = Spectrum(eng, wl["fft"], 0) if (wl["fft"] and rank == 0) else None
-
-    # ---- inputs: ring of distinct blocks resident in HBM on rank 0 (ring * block bytes > 126 MB L2) -----------------
-    ring = []
-    carriers = chans if chans else synth.channel_plan("mixed", fs, 16)
-    if rank == 0:
-        for r in range(args.ring):
-            ring.append(torch_wideband(torch, fs, N, carriers, r * N, dev, 1234))
-    recvs = [torch.empty(N, dtype=torch.complex64, device=dev) for _ in range(4)] if world > 1 else None
-    host_blocks = None
-    if rank == 0:
-        host_blocks = [torch.empty(N, dtype=torch.complex64).pin_memory() for _ in range(2)]
-        host_blocks[0].copy_(ring[0]); host_blocks[1].copy_(ring[1 % args.ring])
-    torch.cuda.synchronize()
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-
-    side = torch.cuda.Stream(device=dev)                       # input production (NCCL broadcast) off the engine's stream
-    bc_done = [torch.cuda.Event() for _ in range(4)]
-
-    def step_device(i):
-        buf = ring[i % args.ring] if rank == 0 else recvs[i & 3]
-        ev = None
-        if world > 1:
-            with torch.cuda.stream(side):
-                dist.broadcast(buf, src=0)                        # the path's one exchange step (raw IQ over NVLink)
-                bc_done[i & 3].record(side)
-            ev = bc_done[i & 3].cuda_event
-        # resident block (or ready at `ev`): the DC blocker of this block overlaps the previous block's channel kernels
-        eng.submit_device_async(buf.data_ptr(), N, CENTER, fs, fetch_to_host=False, ready_event=ev)
-
-    # end to end: pinned host block -> H2D (copy stream, overlapped with the previous block's kernels) -> (broadcast) ->
-    # kernels -> D2H of every result -> batched fetch into host arrays.  Public API only: submit_device / wait / fetch.
-    copy_stream = torch.cuda.Stream(device=dev)
-    stages = [torch.empty(N, dtype=torch.complex64, device=dev) for _ in range(4)]
-    h2d_done = [torch.cuda.Event() for _ in range(4)]
-
-    def h2d(i):
-        if rank == 0:
-            with torch.cuda.stream(copy_stream):
-                stages[i % 4].copy_(host_blocks[i & 1], non_blocking=True)
-                h2d_done[i % 4].record(copy_stream)
-
-    def submit_e2e(i):
-        buf = stages[i % 4]
-        ev = h2d_done[i % 4]
-        if world > 1:
-            with torch.cuda.stream(side):
-                if rank == 0:
-                    side.wait_event(h2d_done[i % 4])
-                dist.broadcast(buf, src=0)
-                bc_done[i & 3].record(side)
-            ev = bc_done[i & 3]
-        eng.submit_device_async(buf.data_ptr(), N, CENTER, fs, fetch_to_host=True, ready_event=ev.cuda_event if (rank == 0 or world > 1) else None)
-
-    def fetch_e2e():
-        nbytes = 0
-        if cobjs:
-            audio, n_audio, _, _ = eng.fetch_audio_batch(cobjs, 1024)
-            nbytes += int(n_audio.sum()) * 4
-        if spec is not None:
-            pts, lines, cf = spec.fetch_all(64)
-            nbytes += pts.nbytes + lines.nbytes
-        return nbytes
-
-    # Two blocks in flight, like the reference's thread pipeline (queues between its threads): per step, submit block i+2,
-    # start the H2D of block i+3 (its stage buffer was last read by block i-1, whose results were already waited for), then
-    # wait for and fetch the results of block i.  Every step still costs one H2D, one pass of the path and one D2H + fetch.
-    host_split = [0.0, 0.0, 0.0]                                # host seconds in submit+h2d / wait / fetch (diagnostic, stderr)
-
-    def step_e2e(i):
-        t_a = time.perf_counter()
-        submit_e2e(i + 2)
-        h2d(i + 3)
-        t_b = time.perf_counter()
-        eng.wait_block(2)
-        t_c = time.perf_counter()
-        nb = fetch_e2e()
-        t_d = time.perf_counter()
-        host_split[0] += t_b - t_a; host_split[1] += t_c - t_b; host_split[2] += t_d - t_c
-        return nb
-
-    # ---- warm-up ------------------------------------------------------------------------------------------------------
-    for i in range(args.warmup):
-        step_device(i)
-    eng.wait()
-    torch.cuda.synchronize()
-
-    # ---- timed: device-resident -----------------------------------------------------------------------------------------
-    # clocks / throttle reasons are sampled from just before the timed region until the end of the e2e region
-    # (nvidia-smi cannot sample faster than ~10 Hz, and the device-resident region alone lasts a fraction of a second)
+    # clocks / throttle reasons are sampled over the whole measured part of the run
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for i in range(60):                                         # ~50 ms of the same work so the first samples see load
-        step_device(i)
-    eng.wait()
-    eng.set_timing(True)
-    launches0 = eng.launch_count
-    barrier(); torch.cuda.synchronize()
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for i in range(args.steps):
-        step_device(args.warmup + i)
-    e1.record(stream)
-    torch.cuda.synchronize(); barrier()
-    ms = e0.elapsed_time(e1)
-    eng.wait()
-    stage_ms, stage_blocks = eng.get_timing()
-    if rank == 0:
-        print_timeline("device")
-    eng.set_timing(False)
-    launches = eng.launch_count - launches0
-    if dist is not None:
-        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt.item())
-    value = N * args.steps / (ms * 1e-3) / 1e6
-
-    # ---- timed: end to end through host buffers -------------------------------------------------------------------------
-    h2d(0)
-    submit_e2e(0)
-    h2d(1)
-    submit_e2e(1)
-    h2d(2)
-    for i in range(3):
-        step_e2e(i)
-    torch.cuda.synchronize()
-    barrier(); torch.cuda.synchronize()
-    eng.set_timing(True)                                        # stage times of the first 64 e2e blocks (stderr diagnostic)
-    t0 = time.perf_counter()
-    d2h = 0
-    for i in range(args.steps):
-        d2h = step_e2e(3 + i)
-    eng.wait()                                                  # drain the blocks still in flight (submitted, not yet fetched)
-    torch.cuda.synchronize(); barrier()
-    t_e2e = time.perf_counter() - t0
-    e2e_stage_ms, e2e_stage_blocks = eng.get_timing()
-    eng.set_timing(False)
-    if rank == 0:
-        print_timeline("e2e")
-        print("e2e device stages per block (ms): %s" % {k: round(v / max(1, e2e_stage_blocks), 3) for k, v in e2e_stage_ms.items()}, file=sys.stderr)
-        print("e2e host split per step (ms): submit+h2d %.3f  wait %.3f  fetch %.3f" % tuple(1e3 * v / (args.steps + 3) for v in host_split), file=sys.stderr)
-    if dist is not None:
-        tt = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_e2e = float(tt.item())
-        dd = torch.tensor([d2h], device=dev, dtype=torch.float64)
-        dist.all_reduce(dd, op=dist.ReduceOp.SUM)
-        d2h = int(dd.item())
-    e2e_value = N * args.steps / t_e2e / 1e6
+    main_res = run_engine_workload(cx, wl, chans, args.steps, args.warmup, args.min_seconds, channelizer=args.channelizer,
+                                   want_cpu=not args.no_cpu_baseline, want_timeline=True)
     clocks = sampler.stop()
 
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
+    # the other BASELINE.json configurations (one GPU; shorter runs), reported inside the same line
+    configs = None
+    if world == 1 and not args.no_configs and args.workload == "cfg5" and not args.channelizer and not args.channels:
+        configs = {}
+        for name in ("cfg1", "cfg2", "cfg3", "cfg4"):
+            w2 = WORKLOADS[name]
+            c2 = synth.channel_plan(w2["plan"], w2["fs"], w2["n_chan"]) if w2["n_chan"] else []
+            try:
+                r2 = run_engine_workload(cx, w2, c2, max(20, min(args.steps, 100)), 3, min(0.5, args.min_seconds), want_cpu=not args.no_cpu_baseline)
+                configs[name] = {"config": config_of(w2, r2["N"], len(c2)), "value": r2["value"], "unit": "MSamples/s",
+                                 "ms_per_step": r2["ms_per_step"], "reps": r2["reps"], "e2e": r2["e2e"], "roofline": r2["roofline"],
+                                 "gpu_launches_per_step": r2["gpu_launches"] / max(1, max(20, min(args.steps, 100))),
+                                 "realtime_factor": r2["realtime_factor"], "cpu_baseline": r2.get("cpu_baseline"),
+                                 "cpu_baseline_channelizer": r2.get("cpu_baseline_channelizer"),
+                                 "note": "cfg4 is specified on 4 GPUs: this is the whole 256-channel job on one" if name == "cfg4" else None}
+            except Exception as ex:
+                configs[name] = {"error": repr(ex)}
 
-    # ---- roofline of the dominant kernel ---------------------------------------------------------------------------------
-    peak, peak_src = measured_peaks()
-    c_local = len(mine)
-    b_alg = 8.0 + c_local * 4.0 * 48000.0 / fs + (2.5 if spec is not None else 0.0)     # bytes / wideband sample / GPU
-    dom = "front" if c_local else "spectrum"
-    t_dom_ms = stage_ms[dom] / max(1, stage_blocks)
-    achieved = (N * b_alg / (t_dom_ms * 1e-3)) / 1e9 if t_dom_ms > 0 else 0.0
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get(args.workload, {}).get(dom)
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "note": "contract figure (algorithmic bytes / kernel time / measured HBM peak); with hundreds of channels in "
-                                        "single-channel mode the kernel is FP32-pipe bound, see the fp32 object" if c_local else
-                                        "contract figure (algorithmic bytes / kernel time / measured HBM peak)", "kernel": "k_chan_front (NCO mix + half-band cascade)" if c_local else "spectrum kernels",
-                "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "alg_bytes_per_sample": b_alg, "kernel_ms_per_block": t_dom_ms,
-                "stage_ms_per_block": {k: v / max(1, stage_blocks) for k, v in stage_ms.items()}}
-    if c_local:
-        flops = 30.0 * c_local * N / (t_dom_ms * 1e-3) / 1e12
-        roofline["fp32"] = {"note": "many-channel single-channel-mode is FP32-issue bound (SURVEY.md 8d): ~30 flop / sample / channel",
-                            "achieved_tflops": flops, "nominal_peak_tflops": FP32_NOMINAL_TFLOPS, "frac": flops / FP32_NOMINAL_TFLOPS}
-
-    # ---- CPU baseline (bounded sample: one block, all channels) -------------------------------------------------------------
-    cpu = None
-    if not args.no_cpu_baseline:
-        try:
-            threads = os.cpu_count() or 1
-            iq_host = ring[0].cpu().numpy()
-            secs, ver = cpu_reference_run(wl, chans, iq_host, threads, 1, channelizer=1 if args.channelizer else 0)
-            cpu = {"value": N / secs / 1e6, "unit": "MSamples/s", "cores": threads, "kind": "reference",
-                   "sample": "1 block (%d samples = 1/60 s), all %d channels%s, reference liquid-dsp %s binary + CubicSDR glue" % (
-                       N, len(chans), " + spectrum" if wl["fft"] else "", ver)}
-        except Exception as ex:        # the oracle is a checker; its absence must not hide the GPU number
-            cpu = {"value": None, "unit": "MSamples/s", "cores": 0, "kind": "reference", "sample": "unavailable: %r" % (ex,)}
-
-    line = {"metric": "IQ MSamples/s through spectrum+demod chain", "value": value, "unit": "MSamples/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "fs": fs, "block": N, "channels": len(chans), "channels_per_gpu": c_local,
-                       "fft_size": wl["fft"], "l2": "%d distinct %.1f MB input blocks rotate (%.0f MB > 126 MB L2)" % (
-                           args.ring, N * 8 / 1e6, args.ring * N * 8 / 1e6),
-                       "realtime_factor": value * 1e6 / fs},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "MSamples/s", "h2d_bytes_per_step": N * 8, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches,
-            "roofline": roofline,
-            "cpu_baseline": cpu}
-    emit(line)
-    if dist is not None:
-        dist.destroy_process_group()
+    if rank == 0:
+        r = main_res
+        line = {"metric": "IQ MSamples/s through spectrum+demod chain", "value": r["value"], "unit": "MSamples/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config_of(dict(wl, desc=r["desc"]), r["N"], len(chans)),
+                "notes": {"channels_per_gpu": r["c_local"], "l2": r["l2"], "realtime_factor": r["realtime_factor"],
+                          "timing": "K steps between barrier+synchronize, CUDA events, max over ranks; repeated %d times (>= %.1f s measured), "
+                                    "median repetition reported; repetitions ranged %.3f .. %.3f ms" % (
+                                        r["reps"], args.min_seconds, r["rep_ms_min_max"][0], r["rep_ms_min_max"][1]),
+                          "host_cores_usable": cpu_cores(), "host_cpu": cpu_model()},
+                "reps": r["reps"],
+                "clocks": clocks,
+                "e2e": r["e2e"],
+                "gpu_launches": r["gpu_launches"],
+                "roofline": r["roofline"],
+                "cpu_baseline": r.get("cpu_baseline"),
+                "cpu_baseline_channelizer": r.get("cpu_baseline_channelizer")}
+        if configs is not None:
+            line["configs"] = configs
+        emit(line)
+    if cx.dist is not None:
+        cx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -14,6 +14,7 @@ PRODUCT_LIB = os.path.join(_HERE, "libsdr_b200.so")
 # every symbol include/sdr_b200.h declares (tests/test_abi.py checks the header against this list and the .so)
 SYMBOLS = [
     "sdr_last_error", "sdr_version", "sdr_is_device_build",
+    "sdr_host_alloc", "sdr_host_free", "sdr_engine_host_buffer", "sdr_chan_result_caps",
     "sdr_engine_create", "sdr_engine_destroy", "sdr_engine_submit", "sdr_engine_submit_device", "sdr_engine_submit_device_async",
     "sdr_engine_wait",
     "sdr_engine_wait_block",
@@ -49,6 +50,10 @@ class Lib:
         L.sdr_engine_create.argtypes = [i, u, vp, P(vp)]
         L.sdr_engine_destroy.argtypes = [vp]
         L.sdr_engine_submit.argtypes = [vp, vp, u, ll, ll]
+        L.sdr_host_alloc.argtypes = [C.c_size_t, P(vp)]
+        L.sdr_host_free.argtypes = [vp]
+        L.sdr_engine_host_buffer.argtypes = [vp, P(vp), P(u)]
+        L.sdr_chan_result_caps.argtypes = [vp, P(u), P(u)]
         L.sdr_engine_submit_device.argtypes = [vp, vp, u, ll, ll, i]
         L.sdr_engine_submit_device_async.argtypes = [vp, vp, u, ll, ll, i, vp]
         L.sdr_engine_wait.argtypes = [vp]
@@ -96,6 +101,17 @@ class Lib:
         L.sdr_design_hilbert_q.argtypes = [vp]
         L.sdr_design_butter6_sos.argtypes = [vp]
 
+    def host_alloc(self, n_complex):
+        """Pinned complex64 array of n samples (sdr_host_alloc); keep the returned array alive while it is in use."""
+        p = C.c_void_p()
+        self.check(self.L.sdr_host_alloc(int(n_complex) * 8, C.byref(p)))
+        buf = (C.c_float * (2 * int(n_complex))).from_address(p.value)
+        a = np.frombuffer(buf, dtype=np.complex64)
+        return a, p.value
+
+    def host_free(self, addr):
+        self.L.sdr_host_free(C.c_void_p(addr))
+
     def check(self, rc):
         if rc != 0:
             raise SdrError("sdr_b200 error %d: %s" % (rc, self.L.sdr_last_error().decode()))
@@ -133,6 +149,17 @@ class Engine:
     def submit(self, iq, center_freq, sample_rate):
         iq = np.ascontiguousarray(iq, dtype=np.complex64)
         self.lib.check(self.lib.L.sdr_engine_submit(self.h, _ptr(iq), iq.size, int(center_freq), int(sample_rate)))
+
+    def submit_ptr(self, host_ptr, n, center_freq, sample_rate):
+        """sdr_engine_submit on a raw host address (e.g. pinned memory from Lib.host_alloc)."""
+        self.lib.check(self.lib.L.sdr_engine_submit(self.h, C.c_void_p(host_ptr), int(n), int(center_freq), int(sample_rate)))
+
+    def host_buffer(self):
+        """The pinned buffer the next submit takes without a staging copy, as a complex64 numpy view."""
+        p, cap = C.c_void_p(), C.c_uint()
+        self.lib.check(self.lib.L.sdr_engine_host_buffer(self.h, C.byref(p), C.byref(cap)))
+        buf = (C.c_float * (2 * cap.value)).from_address(p.value)
+        return np.frombuffer(buf, dtype=np.complex64)
 
     def submit_device(self, dev_ptr, n, center_freq, sample_rate, fetch_to_host=True):
         self.lib.check(self.lib.L.sdr_engine_submit_device(self.h, C.c_void_p(dev_ptr), n, int(center_freq), int(sample_rate),
@@ -178,7 +205,7 @@ class Engine:
     def fetch_audio_batch(self, chans, stride=1024):
         """(audio[n_chan, stride], n_audio[n_chan], level_db[n_chan], peak[n_chan]) for a list of Channel objects."""
         n = len(chans)
-        key = (id(chans), n, stride)
+        key = (tuple(c.h.value for c in chans), stride)
         if getattr(self, "_batch_key", None) != key:
             self._batch_key = key
             self._batch_h = (C.c_void_p * n)(*[c.h for c in chans])

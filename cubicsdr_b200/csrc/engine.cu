@@ -684,7 +684,13 @@ struct sdr_engine {
     double2 *d_tile_carry2[2] = {nullptr, nullptr};
     float2 *d_seg_in = nullptr, *d_seg_out = nullptr, *d_fstate = nullptr;
     unsigned *d_fixups = nullptr;
-    sdr_cf32 *h_stage = nullptr;        // pinned staging for H2D
+    // host blocks: ring of pinned staging buffers -> DMA on stream_h2d -> ring of device buffers -> the DC stream
+    static const int kInRing = 3;
+    sdr_cf32 *h_in[kInRing] = {nullptr, nullptr, nullptr};
+    float2 *d_in[kInRing] = {nullptr, nullptr, nullptr};
+    bool in_rec[kInRing] = {false, false, false};
+    int in_sel = 0;
+    bool poisoned = false;              // a CUDA error after host-side state had advanced: the engine refuses further blocks
     unsigned last_n = 0;
     bool have_block = false;
     // DC blocker
@@ -722,6 +728,8 @@ struct sdr_engine {
     ChanStatic *h_cs_stage = nullptr;   // pinned [kMaxChan]: descriptors re-uploaded by the submitter (cs_dirty)
 #ifndef SDR_EMU
     cudaStream_t stream_admin = nullptr;
+    cudaStream_t stream_h2d = nullptr;
+    cudaEvent_t ev_h2d[kInRing] = {nullptr, nullptr, nullptr}, ev_in_free[kInRing] = {nullptr, nullptr, nullptr};
 #endif
     bool results_on_host = false;
     // host results live in a ring of kResBuf buffers so that a caller may fetch block b while up to kResBuf - 1 newer
@@ -864,7 +872,12 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
     e->raw_pad = (size_t)max_block / 8 + 2 * 65536;
     bad |= be_malloc((void **)&e->d_rawbuf, (e->hist_cap + max_block + e->raw_pad) * sizeof(float2));
     bad |= be_malloc((void **)&e->d_scratch, e->hist_cap * sizeof(float2));
-    bad |= be_host_alloc((void **)&e->h_stage, (size_t)max_block * sizeof(sdr_cf32));
+    for (int k = 0; k < sdr_engine::kInRing; ++k) {
+        bad |= be_host_alloc((void **)&e->h_in[k], (size_t)max_block * sizeof(sdr_cf32));
+#ifndef SDR_EMU
+        bad |= be_malloc((void **)&e->d_in[k], (size_t)max_block * sizeof(float2));
+#endif
+    }
     const int tiles = (max_block + kDcTile - 1) / kDcTile;
     bad |= be_malloc((void **)&e->d_tile_sum, tiles * sizeof(double2));
     for (int b = 0; b < 2; ++b) bad |= be_malloc((void **)&e->d_tile_carry2[b], tiles * sizeof(double2));
@@ -897,6 +910,11 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_tail, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_res, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_admin, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_h2d, cudaStreamNonBlocking));
+    for (int k = 0; k < sdr_engine::kInRing; ++k) {
+        CUDA_TRY(cudaEventCreateWithFlags(&e->ev_h2d[k], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&e->ev_in_free[k], cudaEventDisableTiming));
+    }
     {   // channel memory comes from the stream-ordered pool: keep what is freed cached instead of returning it to the driver
         cudaMemPool_t pool = nullptr;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
@@ -981,7 +999,8 @@ extern "C" int sdr_engine_destroy(sdr_engine *e) {
     be_host_free(e->h_cs_stage);
     for (auto *s : e->spectra) if (s) { spectrum_free(s); delete s; }
     be_free(e->d_pfb_hq); be_free(e->d_pfb_tw); be_free(e->d_pfb_streams[0]); be_free(e->d_pfb_streams[1]); be_free(e->d_pfb_dc_state);
-    be_free(e->d_raw); be_free(e->d_blkbuf[0]); be_free(e->d_blkbuf[1]); be_free(e->d_rawbuf); be_free(e->d_scratch); be_host_free(e->h_stage);
+    be_free(e->d_raw); be_free(e->d_blkbuf[0]); be_free(e->d_blkbuf[1]); be_free(e->d_rawbuf); be_free(e->d_scratch);
+    for (int k = 0; k < sdr_engine::kInRing; ++k) { be_host_free(e->h_in[k]); be_free(e->d_in[k]); }
     be_free(e->d_tile_sum); be_free(e->d_tile_carry2[0]); be_free(e->d_tile_carry2[1]); be_free(e->d_dc_state);
     be_free(e->d_seg_in); be_free(e->d_seg_out); be_free(e->d_fstate); be_free(e->d_fixups); be_free(e->d_apow); be_free(e->d_nco);
     be_free(e->d_cs); be_free(e->d_cd2[0]); be_free(e->d_cd2[1]); be_free(e->d_st); be_host_free(e->h_cd); be_free(e->d_group); be_host_free(e->h_group);
@@ -993,6 +1012,8 @@ extern "C" int sdr_engine_destroy(sdr_engine *e) {
     if (e->stream_tail) { cudaStreamSynchronize(e->stream_tail); cudaStreamDestroy(e->stream_tail); }
     if (e->stream_res) { cudaStreamSynchronize(e->stream_res); cudaStreamDestroy(e->stream_res); }
     if (e->stream_admin) { cudaStreamSynchronize(e->stream_admin); cudaStreamDestroy(e->stream_admin); }
+    if (e->stream_h2d) { cudaStreamSynchronize(e->stream_h2d); cudaStreamDestroy(e->stream_h2d); }
+    for (int k = 0; k < sdr_engine::kInRing; ++k) { if (e->ev_h2d[k]) cudaEventDestroy(e->ev_h2d[k]); if (e->ev_in_free[k]) cudaEventDestroy(e->ev_in_free[k]); }
     if (e->ev_spec_k) cudaEventDestroy(e->ev_spec_k);
     if (e->ev_tail_k) cudaEventDestroy(e->ev_tail_k);
     if (e->ev_front_done) cudaEventDestroy(e->ev_front_done);
@@ -1108,6 +1129,7 @@ static void sync_all(sdr_engine *e) {
     cudaStreamSynchronize(e->stream_res);
     cudaStreamSynchronize(e->stream_dc);
     cudaStreamSynchronize(e->stream2);
+    if (e->stream_h2d) cudaStreamSynchronize(e->stream_h2d);
 #endif
 }
 
@@ -1427,6 +1449,12 @@ extern "C" int sdr_chan_get_bandwidth(sdr_chan *c, int *bw) {
     *bw = c->bandwidth;
     return SDR_OK;
 }
+extern "C" int sdr_chan_result_caps(sdr_chan *c, unsigned *audio_cap, unsigned *iq_cap) {
+    if (!c) return fail(SDR_ERR_ARG, "null channel");
+    if (audio_cap) *audio_cap = (unsigned)c->cs.res_audio_cap;
+    if (iq_cap) *iq_cap = (unsigned)c->cs.res_iq_cap;
+    return SDR_OK;
+}
 extern "C" int sdr_chan_want_iq(sdr_chan *c, int enable) {
     if (!c) return fail(SDR_ERR_ARG, "null channel");
     std::lock_guard<std::mutex> lk(c->eng->mu);
@@ -1613,17 +1641,17 @@ static int pfb_prepare(sdr_engine *e, int M, int osf) {
 }
 
 static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_src, unsigned n, long long center, long long rate,
-                         bool to_host, int ready, void *ready_event) {
+                         bool to_host, int ready, void *ready_event, void *consumed_event = nullptr) {
+    if (e->poisoned) return fail(SDR_ERR_STATE, "engine is in a failed state after a CUDA error: destroy it");
+#ifndef SDR_EMU
+    cudaSetDevice(e->device);
+#else
+    (void)consumed_event;
+#endif
     { int r = ensure_results(e); if (r) return r; }
     const int p = e->parity ^ 1;                               // this block's buffer; the other one holds the previous block
     float2 *blk = e->d_blkbuf[p] + e->hist_cap;
     float2 *raw = e->d_rawbuf + e->hist_cap;
-    const int slot = (int)(e->ring_seq++ % sdr_engine::kRing);
-#ifndef SDR_EMU
-    CUDA_TRY(cudaEventSynchronize(e->ring_ev[slot]));      // the copies that last used this parameter slot are done
-#endif
-    ChanDyn *h_cd = e->h_cd + (size_t)slot * sdr_engine::kMaxChan;
-    int *h_group = e->h_group + (size_t)slot * sdr_engine::kMaxChan;
 
     // SDRPostThread::run dispatch (SDRPostThread.cpp:178-187): blocks that come with more than one channel go through the
     // channelizer; the count is SDRThread::getOptimalChannelCount of the rate (SoapySDRThread.cpp:513,676-693)
@@ -1642,6 +1670,14 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
     const unsigned n_ch = pfb ? (unsigned)pfb_osf * (n / (unsigned)pfb_M) : n;
     const long long rate_ch = pfb ? (long long)pfb_osf * (rate / pfb_M) : rate;
     if (n_ch > e->chan_block_max) return fail(SDR_ERR_ARG, "block exceeds sdr_engine_set_channel_block_max");
+    // ---- the arguments are fine: from here on host-side state advances, so any failure below (a CUDA error) leaves the
+    //      engine unusable (the C-ABI wrappers drain the streams and refuse further blocks)
+    const int slot = (int)(e->ring_seq++ % sdr_engine::kRing);
+#ifndef SDR_EMU
+    CUDA_TRY(cudaEventSynchronize(e->ring_ev[slot]));      // the copies that last used this parameter slot are done
+#endif
+    ChanDyn *h_cd = e->h_cd + (size_t)slot * sdr_engine::kMaxChan;
+    int *h_group = e->h_group + (size_t)slot * sdr_engine::kMaxChan;
     // channelizer mode: channel centre frequencies (SDRPostThread::updateChannels, SDRPostThread.cpp:115-124) and the channel
     // every attached demodulator lands on (getChannelAt, :127-139: nearest centre, the first one wins a tie).  Channel 0's DC
     // blocker only runs on blocks in which some demodulator sits on channel 0 (runDemodChannels skips idle channels,
@@ -1691,6 +1727,9 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         // filterbank, SDRPostThread.cpp:432-451): the block goes straight into the stream buffer
         if (h_src) be_h2d(blk, h_src, (size_t)n * sizeof(float2), dcs);
         else be_d2d(blk, d_src, (size_t)n * sizeof(float2), dcs);
+#ifndef SDR_EMU
+        if (consumed_event) CUDA_TRY(cudaEventRecord((cudaEvent_t)consumed_event, dcs));
+#endif
     } else {
         const size_t need_raw = std::min(e->hist_cap, (size_t)kDcWarm + 2 * kDcTile);
         if (e->have_block && e->last_n > 0) {
@@ -1699,6 +1738,9 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         }
         if (h_src) be_h2d(raw, h_src, (size_t)n * sizeof(float2), dcs);   // host block: straight into the raw stream buffer
         else be_d2d(raw, d_src, (size_t)n * sizeof(float2), dcs);
+#ifndef SDR_EMU
+        if (consumed_event) CUDA_TRY(cudaEventRecord((cudaEvent_t)consumed_event, dcs));   // the caller's buffer may be refilled
+#endif
         DcArgs dc;
         dc.x = raw; dc.y = blk; dc.n = (int)n; dc.a = e->dc_a; dc.tile_sum = e->d_tile_sum; dc.tile_carry = e->d_tile_carry2[p];
         dc.state = e->d_dc_state; dc.apow = e->d_apow;
@@ -2087,23 +2129,84 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
     return join_side();
 }
 
+// a failed submit after the argument checks means a CUDA error with host-side state already advanced: drain and refuse
+static int submit_guard(sdr_engine *e, int r) {
+    if (r == SDR_ERR_CUDA) {
+        const std::string keep = g_err;
+        sync_all(e);
+#ifndef SDR_EMU
+        cudaGetLastError();
+#endif
+        e->poisoned = true;
+        g_err = keep;
+    }
+    return r;
+}
+
+// Pinned memory for the host side of the boundary (input blocks the producer fills, result arrays): a block submitted from
+// such memory is copied by DMA straight from where it lies.
+extern "C" int sdr_host_alloc(size_t bytes, void **out) {
+    if (!out) return fail(SDR_ERR_ARG, "sdr_host_alloc: null argument");
+    *out = nullptr;
+    if (be_host_alloc(out, bytes)) return fail(SDR_ERR_NOMEM, "sdr_host_alloc: pinned allocation failed");
+    return SDR_OK;
+}
+extern "C" int sdr_host_free(void *p) { be_host_free(p); return SDR_OK; }
+
+// The engine's own pinned input ring: the buffer the NEXT sdr_engine_submit will use.  A producer that fills it in place
+// (SDRThread::readStream writes its samples there instead of into a std::vector) saves the staging copy; the buffer is
+// free to write as soon as this call returns.
+extern "C" int sdr_engine_host_buffer(sdr_engine *e, sdr_cf32 **buf, unsigned *cap) {
+    if (!e || !buf) return fail(SDR_ERR_ARG, "sdr_engine_host_buffer: null argument");
+    std::lock_guard<std::mutex> lk(e->mu);
+    const int k = e->in_sel % sdr_engine::kInRing;
+#ifndef SDR_EMU
+    if (e->in_rec[k] && cudaEventSynchronize(e->ev_h2d[k]) != cudaSuccess) return fail(SDR_ERR_CUDA, "sdr_engine_host_buffer: wait failed");
+#endif
+    *buf = e->h_in[k];
+    if (cap) *cap = e->max_block;
+    return SDR_OK;
+}
+
+// SDRPostThread::run hands one block to the path (SDRPostThread.cpp:178-187).  Never waits for the GPU in steady state: the
+// block is staged through a ring of pinned buffers (skipped when `iq` already is pinned memory: the engine's own ring
+// buffer, sdr_host_alloc memory or anything cudaHostRegister'ed), copied by DMA on a dedicated stream into a ring of device
+// buffers, and the DC stream picks it up from there.  A pinned source must stay untouched until two further blocks have been
+// submitted or sdr_engine_wait / sdr_engine_wait_block(0) has returned for this one.
 extern "C" int sdr_engine_submit(sdr_engine *e, const sdr_cf32 *iq, unsigned n, long long center, long long rate) {
     if (!e || !iq) return fail(SDR_ERR_ARG, "sdr_engine_submit: null argument");
     if (n == 0 || n > e->max_block) return fail(SDR_ERR_ARG, "sdr_engine_submit: block size out of range");
     std::lock_guard<std::mutex> lk(e->mu);
-    // the pinned staging buffer is reused every block: wait for the previous block's H2D (on the DC stream) first
 #ifndef SDR_EMU
-    be_sync(e->stream_dc);
+    if (e->poisoned) return fail(SDR_ERR_STATE, "engine is in a failed state after a CUDA error: destroy it");
+    cudaSetDevice(e->device);
+    const int k = e->in_sel++ % sdr_engine::kInRing;
+    // this slot's previous H2D (three submits ago) must have left the pinned buffer; in steady state it finished long ago
+    if (e->in_rec[k]) CUDA_TRY(cudaEventSynchronize(e->ev_h2d[k]));
+    const sdr_cf32 *src = iq;
+    bool pinned = iq == e->h_in[k];
+    if (!pinned) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, iq) == cudaSuccess) pinned = pa.type == cudaMemoryTypeHost;
+        else cudaGetLastError();
+    }
+    if (!pinned) { memcpy(e->h_in[k], iq, (size_t)n * sizeof(sdr_cf32)); src = e->h_in[k]; }
+    // the device buffer of this slot was read by the DC stream three blocks ago
+    if (e->in_rec[k]) CUDA_TRY(cudaStreamWaitEvent(e->stream_h2d, e->ev_in_free[k], 0));
+    CUDA_TRY(cudaMemcpyAsync(e->d_in[k], src, (size_t)n * sizeof(sdr_cf32), cudaMemcpyHostToDevice, e->stream_h2d));
+    CUDA_TRY(cudaEventRecord(e->ev_h2d[k], e->stream_h2d));
+    e->in_rec[k] = true;
+    return submit_guard(e, submit_common(e, e->d_in[k], nullptr, n, center, rate, true, 2, e->ev_h2d[k], e->ev_in_free[k]));
+#else
+    return submit_common(e, nullptr, iq, n, center, rate, true, 1, nullptr);
 #endif
-    memcpy(e->h_stage, iq, (size_t)n * sizeof(sdr_cf32));
-    return submit_common(e, nullptr, e->h_stage, n, center, rate, true, 1, nullptr);
 }
 
 extern "C" int sdr_engine_submit_device(sdr_engine *e, const void *d_iq, unsigned n, long long center, long long rate, int to_host) {
     if (!e || !d_iq) return fail(SDR_ERR_ARG, "sdr_engine_submit_device: null argument");
     if (n == 0 || n > e->max_block) return fail(SDR_ERR_ARG, "sdr_engine_submit_device: block size out of range");
     std::lock_guard<std::mutex> lk(e->mu);
-    return submit_common(e, (const float2 *)d_iq, nullptr, n, center, rate, to_host != 0, 0, nullptr);
+    return submit_guard(e, submit_common(e, (const float2 *)d_iq, nullptr, n, center, rate, to_host != 0, 0, nullptr));
 }
 
 extern "C" int sdr_engine_submit_device_async(sdr_engine *e, const void *d_iq, unsigned n, long long center, long long rate,
@@ -2111,7 +2214,7 @@ extern "C" int sdr_engine_submit_device_async(sdr_engine *e, const void *d_iq, u
     if (!e || !d_iq) return fail(SDR_ERR_ARG, "sdr_engine_submit_device_async: null argument");
     if (n == 0 || n > e->max_block) return fail(SDR_ERR_ARG, "sdr_engine_submit_device_async: block size out of range");
     std::lock_guard<std::mutex> lk(e->mu);
-    return submit_common(e, (const float2 *)d_iq, nullptr, n, center, rate, to_host != 0, ready_event ? 2 : 1, ready_event);
+    return submit_guard(e, submit_common(e, (const float2 *)d_iq, nullptr, n, center, rate, to_host != 0, ready_event ? 2 : 1, ready_event));
 }
 
 // SDRPostThread::setChannelizerType (SDRPostThread.cpp:142-144), restricted to what is built: 0 = every block through
@@ -2416,6 +2519,55 @@ extern "C" int sdr_pfb_execute_device(sdr_pfb *p, const void *d_iq, unsigned n, 
     if (n == 0 || n % p->step() != 0 || n / p->step() > p->max_frames) return fail(SDR_ERR_ARG, "sdr_pfb_execute_device: bad length");
     std::lock_guard<std::mutex> lk(p->eng->mu);
     return pfb_run(p, (const float2 *)d_iq, n, (float2 *)d_out);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// diagnostics: measured non-tensor FP32 issue peak of the device (bench.py's roofline denominator for the FP32-bound channel
+// front kernel; MEASURED_PEAKS.json only carries HBM and tensor figures).  Eight independent FFMA chains per thread, 16 CTAs
+// of 256 threads per SM, best of five launches timed with CUDA events.  Not part of the public header.
+// ---------------------------------------------------------------------------------------------------------------------
+#ifndef SDR_EMU
+__global__ void __launch_bounds__(256) k_fp32_peak(float *out, int iters, float b, float c) {
+    float a0 = threadIdx.x, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+            a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+#endif
+extern "C" int sdr_debug_fp32_peak(int device, double *tflops) {
+    if (!tflops) return SDR_ERR_ARG;
+#ifndef SDR_EMU
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const int ctas = prop.multiProcessorCount * 16, iters = 2048;
+    float *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, (size_t)ctas * 256 * sizeof(float)));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int r = 0; r < 6; ++r) {
+        cudaEventRecord(e0, 0);
+        k_fp32_peak<<<ctas, 256>>>(d, iters, 0.999f, 0.001f);
+        cudaEventRecord(e1, 0);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double tf = (double)ctas * 256.0 * iters * 16.0 * 8.0 * 2.0 / (ms * 1e-3) / 1e12;
+        if (r > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *tflops = best;
+    return SDR_OK;
+#else
+    (void)device; *tflops = 0.0;
+    return SDR_ERR_UNSUPPORTED;
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

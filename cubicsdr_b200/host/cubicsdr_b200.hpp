@@ -248,6 +248,7 @@ public:
         if (sdr_chan_create(e->get(), modemName.c_str(), sampleRate, bandwidth, audioSampleRate, &ch_) != SDR_OK)
             throw std::runtime_error(sdr_last_error());
         sdr_chan_get_bandwidth(ch_, &bandwidth_);
+        sdr_chan_result_caps(ch_, &audioCap_, &iqCap_);          // most samples one block can yield: the fetch buffers' size
         if (wantIQ) sdr_chan_want_iq(ch_, 1);
     }
     ~DemodulatorB200() { if (ch_) sdr_chan_destroy(ch_); }
@@ -258,7 +259,7 @@ public:
     // after SDRPostB200::runSingleCH: what DemodulatorThread would push to the audio queue for this block.
     // Returns false when the block was skipped for this channel (|shift| > 0.75 fs) or on error.
     bool fetchAudio(AudioThreadInput &ati, double *signalLevelDb = nullptr) {
-        ati.data.resize(8192);
+        ati.data.resize(audioCap_);
         unsigned n = 0; double lvl = 0; float pk = 0; int skipped = 0;
         if (sdr_chan_fetch_audio(ch_, ati.data.data(), (unsigned)ati.data.size(), &n, &lvl, &pk, &skipped) != SDR_OK) { ati.data.clear(); return false; }
         ati.data.resize(n);
@@ -267,7 +268,7 @@ public:
         return !skipped;
     }
     bool fetchPostIQ(DemodulatorThreadPostIQData &out) {                    // DemodulatorPreThread.cpp:211-217
-        out.data.resize(65536);
+        out.data.resize(iqCap_);
         unsigned n = 0;
         if (sdr_chan_fetch_iq(ch_, reinterpret_cast<sdr_cf32 *>(out.data.data()), (unsigned)out.data.size(), &n) != SDR_OK) { out.data.clear(); return false; }
         out.data.resize(n);
@@ -279,6 +280,7 @@ private:
     sdr_chan *ch_;
     std::string name_;
     int bandwidth_ = 0, audioRate_;
+    unsigned audioCap_ = 0, iqCap_ = 0;
 };
 
 // ---- SpectrumVisualProcessor (process/SpectrumVisualProcessor.h:14-23) ---------------------------------------------------------

@@ -12,6 +12,7 @@
  */
 #ifndef SDR_B200_H
 #define SDR_B200_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -39,9 +40,20 @@ int sdr_engine_destroy(sdr_engine *eng);
 
 /* Replaces SDRPostThread::runSingleCH (src/sdr/SDRPostThread.cpp:248-299): takes one block of raw IQ, applies the
  * DC blocker (:284), and runs every attached spectrum and channel on it.  Asynchronous: returns once the work is
- * enqueued; results are fetched per channel / spectrum after sdr_engine_wait().  center_freq / sample_rate are the
- * SDRThreadIQData fields (src/sdr/SoapySDRThread.h:20-39).  iq is host memory.                                    */
+ * enqueued; results are fetched per channel / spectrum after sdr_engine_wait() / sdr_engine_wait_block().  center_freq /
+ * sample_rate are the SDRThreadIQData fields (src/sdr/SoapySDRThread.h:20-39).  iq is host memory.
+ * Like the reference's post thread, which only try_push()es (:238-298), the call never waits for the GPU in steady state:
+ * a pageable block is copied once into a ring of three pinned buffers; a block that already lies in pinned memory (the
+ * engine's own ring buffer from sdr_engine_host_buffer, sdr_host_alloc memory, anything cudaHostRegister'ed) is sent by
+ * DMA from where it lies and must then stay untouched until two further blocks have been submitted or a wait call has
+ * returned for it.                                                                                                    */
 int sdr_engine_submit(sdr_engine *eng, const sdr_cf32 *iq, unsigned n, long long center_freq, long long sample_rate);
+/* The pinned buffer the NEXT sdr_engine_submit takes without a staging copy (capacity max_block samples): what a producer
+ * fills in place of SDRThreadIQData::data (SDRThread::readStream appends the stream to that vector, src/sdr/SoapySDRThread.cpp:195-380).   */
+int sdr_engine_host_buffer(sdr_engine *eng, sdr_cf32 **buf, unsigned *cap);
+/* Pinned host memory for blocks and result arrays that live on the host side of the boundary. */
+int sdr_host_alloc(size_t bytes, void **out);
+int sdr_host_free(void *p);
 /* Same, for a block that already lives in this GPU's memory (e.g. after an NCCL broadcast).  No host copy is made;
  * with fetch_to_host = 0 results stay in device memory (throughput measurement), otherwise they are copied back.  */
 int sdr_engine_submit_device(sdr_engine *eng, const void *d_iq, unsigned n, long long center_freq, long long sample_rate,
@@ -73,8 +85,10 @@ int sdr_engine_get_timing(sdr_engine *eng, double *stage_ms4, unsigned long long
  * bandwidth is passed through Modem::checkSampleRate (ModemAnalog.cpp:14-19, ModemUSB.cpp:29-37).
  * Builds what DemodulatorWorkerThread builds (src/demod/DemodulatorWorkerThread.cpp:63-101): msresamp_crcf(bw/fs, 60),
  * the modem, and its kit msresamp_rrrf(audio_rate/bw, 60) (ModemAnalog.cpp:21-33).
- * Creating or destroying a channel re-plans the result buffers at the next submit: fetch the results of blocks already
- * submitted (sdr_engine_wait / sdr_engine_wait_block) before changing the channel set.                              */
+ * Like DemodulatorWorkerThread, create / destroy may run on any thread while another one submits blocks: they never make
+ * the submitter wait (device memory comes from the stream-ordered allocator; a new channel joins with the next block, a
+ * destroyed one is recycled once the blocks in flight have drained).  A destroyed handle must not be used again, and
+ * results of blocks submitted before the destroy can no longer be fetched for it.                                      */
 int sdr_chan_create(sdr_engine *eng, const char *modem, long long sample_rate, long long bandwidth, int audio_rate,
                     sdr_chan **out);
 int sdr_chan_destroy(sdr_chan *ch);
@@ -82,6 +96,8 @@ int sdr_chan_destroy(sdr_chan *ch);
  * DemodulatorPreThread.cpp:154-163 does, including abs(), the up/down choice and the 0.75 fs skip rule.            */
 int sdr_chan_set_frequency(sdr_chan *ch, long long frequency);
 int sdr_chan_get_bandwidth(sdr_chan *ch, int *bandwidth);
+/* most audio samples / decimated IQ samples one block can yield for this channel (size the fetch buffers with these) */
+int sdr_chan_result_caps(sdr_chan *ch, unsigned *audio_cap, unsigned *iq_cap);
 /* also return the decimated IQ of each block (DemodulatorThreadPostIQData::data, src/demod/DemodDefs.h:43-59) */
 int sdr_chan_want_iq(sdr_chan *ch, int enable);
 /* Results of the last submitted block (after sdr_engine_wait): audio = AudioThreadInput::data

@@ -25,7 +25,7 @@ def relrms(a, b):
 
 
 def run_channels(lib, ref, fs, chans, n_blocks, block=None, seed=1234, device=0, want_iq=True, retune=None, signal=None,
-                 resident=None, spectrum=0, audio_rate=48000):
+                 resident=None, spectrum=0, audio_rate=48000, spec_out=None):
     """Stream n_blocks through engine and oracle.  chans: [(modem, bw, offset_hz)].
     Returns per-channel dict with concatenated audio / iq of both sides and per-block count equality."""
     N = block or synth.block_size(fs)
@@ -35,6 +35,12 @@ def run_channels(lib, ref, fs, chans, n_blocks, block=None, seed=1234, device=0,
     # the configuration the full-size workload runs in (grid sizes, DC replay placement, stream overlap)
     extra = [Channel(eng, m, fs, bw, 48000, frequency=CENTER + off) for m, bw, off in (resident or [])]
     sp = Spectrum(eng, spectrum, 0) if spectrum else None
+    # spec_out (a dict): also compare the attached spectrum, frame by frame, with the reference's (same streams overlapping
+    # as in the full workload); filled with the worst relative errors
+    rsp = RefSpectrum(ref, spectrum) if (spectrum and spec_out is not None) else None
+    rdist = RefDistrib(ref, 2 * spectrum, 100000000) if rsp else None
+    if rsp:
+        spec_out.update(mags=0.0, points=0.0, frames=0, u8_bad_far=0)
     rcs = [RefChan(ref, m, fs, bw, audio_rate) for m, bw, off in chans]
     ing = RefIngress(ref)
     out = [dict(modem=m, audio=[], ref_audio=[], iq=[], ref_iq=[], counts_ok=True, lvl=[], ref_lvl=[], peak=[], ref_peak=[],
@@ -51,6 +57,19 @@ def run_channels(lib, ref, fs, chans, n_blocks, block=None, seed=1234, device=0,
         eng.wait()
         y = ing.block(x)
         dc_err.append(relrms(eng.fetch_block(N), y))
+        if rsp:
+            frames = rdist.push(y, fs, CENTER)
+            assert sp.frames == len(frames), "frame count %d vs reference %d in block %d" % (sp.frames, len(frames), b)
+            for f in range(sp.frames):
+                r = rsp.frame(frames[f])
+                pts, line, cf = sp.fetch(f)
+                mags, _ = sp.fetch_debug(f)
+                spec_out["mags"] = max(spec_out["mags"], relrms(mags, r["fft_result"]))
+                spec_out["points"] = max(spec_out["points"], relrms(pts, r["points"]))
+                bad = line.astype(np.int32) != r["line"].astype(np.int32)
+                v = np.clip(r["points"].astype(np.float64), 0, 0.99) * 255.0
+                spec_out["u8_bad_far"] += int((bad & ~(np.abs(v - np.round(v)) < 255.0 * 1e-5)).sum())
+                spec_out["frames"] += 1
         for i, (c, rc) in enumerate(zip(cs, rcs)):
             r = rc.process(y, offs[i])
             a, lvl, pk, sk = c.fetch_audio()
@@ -72,6 +91,8 @@ def run_channels(lib, ref, fs, chans, n_blocks, block=None, seed=1234, device=0,
         c.close()
     if sp is not None:
         sp.close()
+    if rsp:
+        rsp.close(); rdist.close()
     for rc in rcs:
         rc.close()
     ing.close()

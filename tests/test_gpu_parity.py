@@ -152,10 +152,32 @@ def test_cfg5_full_configuration_slice(gpu_lib, ref):
     pick = list(range(0, 512, 43))[:12]
     sub = [chans[i] for i in pick]
     rest = [c for i, c in enumerate(chans) if i not in pick]
+    spec = {}
     out, dc_err, _ = parity.run_channels(gpu_lib, ref, fs, sub, n_blocks=2, signal=chans[::16] + sub, resident=rest,
-                                         spectrum=16384, want_iq=False)
+                                         spectrum=16384, want_iq=False, spec_out=spec)
     assert max(dc_err) == 0.0
     assert sorted({o["modem"] for o in out}) == ["AM", "FM", "LSB", "USB"]
+    parity.check_channels(out)
+    # the 16384-point spectrum computed next to the 512 channels (side stream under the channel tail) matches too
+    assert spec["frames"] >= 60 and spec["mags"] <= parity.TOL and spec["points"] <= parity.TOL and spec["u8_bad_far"] == 0, spec
+
+
+def test_cfg3_all_64_channels(gpu_lib, ref):
+    """configs[2] in full: every one of the 64 NBFM channels at 20 MSps against the oracle."""
+    fs = 20000000
+    chans = synth.channel_plan("nbfm64", fs, 64)
+    out, dc_err, _ = parity.run_channels(gpu_lib, ref, fs, chans, n_blocks=2, want_iq=False)
+    assert max(dc_err) == 0.0 and len(out) == 64
+    parity.check_channels(out)
+
+
+def test_cfg4_all_256_channels(gpu_lib, ref):
+    """configs[3] in full: all 256 mixed FM / AM / USB / LSB channels at 40 MSps against the oracle (one GPU holds the
+    whole job here; the sharded form is covered by tests/test_group.py)."""
+    fs = 40000000
+    chans = synth.channel_plan("mixed", fs, 256)
+    out, dc_err, _ = parity.run_channels(gpu_lib, ref, fs, chans, n_blocks=2, want_iq=False, signal=chans[::8])
+    assert max(dc_err) == 0.0 and len(out) == 256
     parity.check_channels(out)
 
 
