@@ -374,17 +374,36 @@ def run_engine_workload(cx, wl, chans, steps, warmup, min_seconds, channelizer=F
     stream = torch.cuda.Stream(device=dev)          # a dedicated (non-default) stream shared by torch and the engine
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
-    eng = Engine(lib, device=cx.local_rank, max_block=N, stream=stream.cuda_stream)
-    mine = chans[rank::world]                                  # channel sharding
-    chan_fs = fs
     desc = wl["desc"]
-    if channelizer:
-        eng.set_channelizer(1)
-        n_pfb, chan_fs = eng.channel_plan(fs)
-        eng.set_channel_block_max(N // n_pfb)
-        desc += " [DIAGNOSTIC: channelizer mode, %d filterbank channels of %d Hz]" % (n_pfb, chan_fs)
-    cobjs = [Channel(eng, m, chan_fs, bw, 48000, frequency=CENTER + off) for m, bw, off in mine]
-    spec = Spectrum(eng, wl["fft"], 0) if (wl["fft"] and rank == 0) else None
+    chan_fs = fs
+    grp = None
+    if world > 1:
+        # several GPUs: the product's group API in its one-process-per-GPU form (sdr_group_create_rank): channel c on rank
+        # c mod N, spectrum on rank 0, the raw block moved by the group's own ncclBroadcast.  torch.distributed only carries
+        # the 128-byte NCCL id and the timing barriers.
+        from cubicsdr_b200 import Group
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(Group.unique_id(lib)), dtype=torch.uint8))
+        dist.broadcast(idt, src=0)
+        grp = Group(lib, max_block=N, device=cx.local_rank, rank=rank, world=world, nccl_id=bytes(idt.cpu().numpy().tobytes()))
+        assert grp.transport == 1 and grp.total == world
+        eng = grp.engines[0]
+        made = [grp.channel(m, chan_fs, bw, 48000, frequency=CENTER + off) for m, bw, off in chans]
+        cobjs = [c for c in made if c is not None]
+        mine = [ch for ch, c in zip(chans, made) if c is not None]
+        assert mine == chans[rank::world]
+        spec = grp.spectrum(wl["fft"], 0) if wl["fft"] else None
+    else:
+        eng = Engine(lib, device=cx.local_rank, max_block=N, stream=stream.cuda_stream)
+        mine = chans
+        if channelizer:
+            eng.set_channelizer(1)
+            n_pfb, chan_fs = eng.channel_plan(fs)
+            eng.set_channel_block_max(N // n_pfb)
+            desc += " [DIAGNOSTIC: channelizer mode, %d filterbank channels of %d Hz]" % (n_pfb, chan_fs)
+        cobjs = [Channel(eng, m, chan_fs, bw, 48000, frequency=CENTER + off) for m, bw, off in mine]
+        spec = Spectrum(eng, wl["fft"], 0) if wl["fft"] else None
 
     def print_timeline(tag):                                    # stderr diagnostic: device timeline of a few steady-state blocks
         try:
@@ -408,7 +427,6 @@ def run_engine_workload(cx, wl, chans, steps, warmup, min_seconds, channelizer=F
         while len(ring) < n_ring:                             # further distinct blocks: an earlier one plus fresh noise (cheap)
             b = base[len(ring) % len(base)]
             ring.append(b + 0.002 * torch.view_as_complex(torch.randn(N, 2, device=dev, generator=g)))
-    recvs = [torch.empty(N, dtype=torch.complex64, device=dev) for _ in range(4)] if world > 1 else None
     # host side of the e2e: four pinned blocks from the C-ABI's own allocator
     host_blocks = []
     if rank == 0:
@@ -422,45 +440,24 @@ def run_engine_workload(cx, wl, chans, steps, warmup, min_seconds, channelizer=F
         if dist is not None:
             dist.barrier()
 
-    side = torch.cuda.Stream(device=dev)                       # input production (NCCL broadcast) off the engine's stream
-    bc_done = [torch.cuda.Event() for _ in range(4)]
-
     def step_device(i):
-        buf = ring[i % n_ring] if rank == 0 else recvs[i & 3]
-        ev = None
-        if world > 1:
-            with torch.cuda.stream(side):
-                dist.broadcast(buf, src=0)                        # the path's one exchange step (raw IQ over NVLink)
-                bc_done[i & 3].record(side)
-            ev = bc_done[i & 3].cuda_event
-        # resident block (or ready at `ev`): the DC blocker of this block overlaps the previous block's channel kernels
-        eng.submit_device_async(buf.data_ptr(), N, CENTER, fs, fetch_to_host=False, ready_event=ev)
+        if grp is not None:
+            # the resident block of rank 0 goes to every rank by the group's one exchange step (raw IQ over NVLink)
+            grp.submit(ring[i % n_ring].data_ptr() if rank == 0 else None, CENTER, fs, n=N)
+            return
+        # resident block: the DC blocker of this block overlaps the previous block's channel kernels
+        eng.submit_device_async(ring[i % n_ring].data_ptr(), N, CENTER, fs, fetch_to_host=False, ready_event=None)
 
-    # ---- end to end.  One GPU: exactly the host entry a CubicSDR thread calls -- sdr_engine_submit on a pinned host block
-    # (the engine's DMA stream and device ring inside), sdr_engine_wait_block(2), batched fetch.  Several GPUs: rank 0 copies
-    # the pinned block to its GPU, the raw block is broadcast over NCCL, every rank submits the resident copy.
-    copy_stream = torch.cuda.Stream(device=dev)
-    stages = [torch.empty(N, dtype=torch.complex64, device=dev) for _ in range(4)] if world > 1 else None
-    h2d_done = [torch.cuda.Event() for _ in range(4)]
-    host_t = [torch.from_numpy(a) for a, _ in host_blocks] if (world > 1 and rank == 0) else None
-
+    # ---- end to end: exactly the host entry a CubicSDR thread calls -- sdr_engine_submit (one GPU) / sdr_group_submit (several)
+    # on a pinned host block (DMA to the GPU, the broadcast to the other ranks), sdr_*_wait_block(2), batched fetch.
     def h2d(i):
-        if world > 1 and rank == 0:
-            with torch.cuda.stream(copy_stream):
-                stages[i % 4].copy_(host_t[i % 4], non_blocking=True)
-                h2d_done[i % 4].record(copy_stream)
+        pass
 
     def submit_e2e(i):
-        if world == 1:
+        if grp is not None:
+            grp.submit(host_blocks[i % 4][1] if rank == 0 else None, CENTER, fs, n=N)
+        else:
             eng.submit_ptr(host_blocks[i % 4][1], N, CENTER, fs)
-            return
-        buf = stages[i % 4]
-        with torch.cuda.stream(side):
-            if rank == 0:
-                side.wait_event(h2d_done[i % 4])
-            dist.broadcast(buf, src=0)
-            bc_done[i & 3].record(side)
-        eng.submit_device_async(buf.data_ptr(), N, CENTER, fs, fetch_to_host=True, ready_event=bc_done[i & 3].cuda_event)
 
     def fetch_e2e():
         nbytes = 0
@@ -496,6 +493,8 @@ def run_engine_workload(cx, wl, chans, steps, warmup, min_seconds, channelizer=F
         return float(tt.item())
 
     # ---- warm-up ------------------------------------------------------------------------------------------------------
+    if grp is not None:
+        grp.set_host_results(False)                             # device-resident measurement: results stay in HBM
     for i in range(max(3, warmup)):
         step_device(i)
     eng.wait()
@@ -536,6 +535,8 @@ def run_engine_workload(cx, wl, chans, steps, warmup, min_seconds, channelizer=F
     value = N * steps / (ms * 1e-3) / 1e6
 
     # ---- timed: end to end through host buffers -------------------------------------------------------------------------
+    if grp is not None:
+        grp.set_host_results(True)
     h2d(0); submit_e2e(0); h2d(1); submit_e2e(1); h2d(2)
     for i in range(3):
         step_e2e(i)
@@ -613,7 +614,7 @@ def run_engine_workload(cx, wl, chans, steps, warmup, min_seconds, channelizer=F
                "e2e": {"value": e2e_value, "unit": "MSamples/s", "h2d_bytes_per_step": N * 8, "d2h_bytes_per_step": d2h,
                        "reps": e2e_reps,
                        "api": "sdr_engine_submit(pinned host block) + sdr_engine_wait_block(2) + sdr_engine_fetch_audio_batch / sdr_spectrum_fetch_all"
-                              if world == 1 else "pinned host block -> H2D -> ncclBroadcast -> sdr_engine_submit_device_async + wait_block(2) + batched fetch"},
+                              if world == 1 else "sdr_group_submit(pinned host block on rank 0: DMA + one ncclBroadcast inside) + sdr_engine_wait_block(2) + batched fetch"},
                "gpu_launches": int(launches), "roofline": roofline, "N": N, "c_local": c_local, "desc": desc,
                "l2": "%d distinct %.1f MB input blocks rotate (%.0f MB > 126 MB L2)" % (n_ring, N * 8 / 1e6, n_ring * N * 8 / 1e6),
                "realtime_factor": value * 1e6 / fs}
@@ -624,7 +625,10 @@ def run_engine_workload(cx, wl, chans, steps, warmup, min_seconds, channelizer=F
         c.close()
     if spec is not None:
         spec.close()
-    eng.close()
+    if grp is not None:
+        grp.close()
+    else:
+        eng.close()
     for _, addr in host_blocks:
         lib.host_free(addr)
     del ring

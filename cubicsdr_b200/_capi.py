@@ -14,7 +14,7 @@ PRODUCT_LIB = os.path.join(_HERE, "libsdr_b200.so")
 # every symbol include/sdr_b200.h declares (tests/test_abi.py checks the header against this list and the .so)
 SYMBOLS = [
     "sdr_last_error", "sdr_version", "sdr_is_device_build",
-    "sdr_host_alloc", "sdr_host_free", "sdr_engine_host_buffer", "sdr_chan_result_caps",
+    "sdr_host_alloc", "sdr_host_free", "sdr_engine_host_buffer", "sdr_chan_result_caps", "sdr_chan_audio_channels", "sdr_modem_check_sample_rate2", "sdr_chan_set_squelch", "sdr_chan_fetch_meter",
     "sdr_engine_create", "sdr_engine_destroy", "sdr_engine_submit", "sdr_engine_submit_device", "sdr_engine_submit_device_async",
     "sdr_engine_wait",
     "sdr_engine_wait_block",
@@ -26,6 +26,8 @@ SYMBOLS = [
     "sdr_spectrum_fetch", "sdr_spectrum_fetch_all", "sdr_spectrum_fetch_debug",
     "sdr_engine_set_channelizer", "sdr_engine_channel_plan", "sdr_engine_set_channel_block_max",
     "sdr_pfb_optimal_channel_count", "sdr_pfb_create", "sdr_pfb2_create", "sdr_pfb_destroy", "sdr_pfb_reset", "sdr_pfb_execute", "sdr_pfb_execute_device",
+    "sdr_group_create", "sdr_group_create_rank", "sdr_group_unique_id", "sdr_group_destroy", "sdr_group_info", "sdr_group_engine",
+    "sdr_group_chan_create", "sdr_group_spectrum_create", "sdr_group_submit", "sdr_group_wait", "sdr_group_wait_block", "sdr_group_set_host_results",
     "sdr_design_kaiser", "sdr_design_nco_table", "sdr_design_nco_step", "sdr_design_resampler",
     "sdr_design_halfband_branch", "sdr_design_am_dc_block", "sdr_design_hilbert_q", "sdr_design_butter6_sos",
 ]
@@ -54,6 +56,10 @@ class Lib:
         L.sdr_host_free.argtypes = [vp]
         L.sdr_engine_host_buffer.argtypes = [vp, P(vp), P(u)]
         L.sdr_chan_result_caps.argtypes = [vp, P(u), P(u)]
+        L.sdr_chan_audio_channels.argtypes = [vp, P(i)]
+        L.sdr_modem_check_sample_rate2.argtypes = [C.c_char_p, ll, i]
+        L.sdr_chan_set_squelch.argtypes = [vp, i, f]
+        L.sdr_chan_fetch_meter.argtypes = [vp, P(f), P(f), P(f), P(i)]
         L.sdr_engine_submit_device.argtypes = [vp, vp, u, ll, ll, i]
         L.sdr_engine_submit_device_async.argtypes = [vp, vp, u, ll, ll, i, vp]
         L.sdr_engine_wait.argtypes = [vp]
@@ -91,6 +97,18 @@ class Lib:
         L.sdr_pfb_execute.argtypes = [vp, vp, u, vp]
         L.sdr_pfb_execute_device.argtypes = [vp, vp, u, vp]
         L.sdr_spectrum_fetch_all.argtypes = [vp, u, vp, vp, vp, P(u)]
+        L.sdr_group_create.argtypes = [vp, i, u, P(vp)]
+        L.sdr_group_create_rank.argtypes = [i, i, i, vp, u, P(vp)]
+        L.sdr_group_unique_id.argtypes = [vp]
+        L.sdr_group_destroy.argtypes = [vp]
+        L.sdr_group_info.argtypes = [vp, P(i), P(i), P(i)]
+        L.sdr_group_engine.argtypes = [vp, i, P(vp)]
+        L.sdr_group_chan_create.argtypes = [vp, C.c_char_p, ll, ll, i, P(vp)]
+        L.sdr_group_spectrum_create.argtypes = [vp, u, u, P(vp)]
+        L.sdr_group_submit.argtypes = [vp, vp, u, ll, ll]
+        L.sdr_group_wait.argtypes = [vp]
+        L.sdr_group_wait_block.argtypes = [vp, i]
+        L.sdr_group_set_host_results.argtypes = [vp, i]
         L.sdr_design_kaiser.argtypes = [u, f, f, f, vp]
         L.sdr_design_nco_table.argtypes = [vp]
         L.sdr_design_nco_step.argtypes = [f]
@@ -128,17 +146,19 @@ def _ptr(a):
 class Engine:
     """One engine per GPU (sdr_engine).  submit() replaces SDRPostThread::runSingleCH (SDRPostThread.cpp:248-299)."""
 
-    def __init__(self, lib, device=0, max_block=1 << 20, stream=None):
+    def __init__(self, lib, device=0, max_block=1 << 20, stream=None, handle=None):
         self.lib = lib
-        h = C.c_void_p()
-        lib.check(lib.L.sdr_engine_create(device, max_block, C.c_void_p(stream) if stream else None, C.byref(h)))
-        self.h = h
+        self.owned = handle is None
+        if handle is None:
+            handle = C.c_void_p()
+            lib.check(lib.L.sdr_engine_create(device, max_block, C.c_void_p(stream) if stream else None, C.byref(handle)))
+        self.h = handle
         self.max_block = max_block
 
     def close(self):
-        if self.h:
+        if self.h and self.owned:
             self.lib.L.sdr_engine_destroy(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:
@@ -231,10 +251,12 @@ class Engine:
 class Channel:
     """sdr_chan: DemodulatorPreThread + Modem + DemodulatorThread metering for one demodulator."""
 
-    def __init__(self, engine, modem, sample_rate, bandwidth, audio_rate=48000, frequency=0, want_iq=False):
+    def __init__(self, engine, modem, sample_rate, bandwidth, audio_rate=48000, frequency=0, want_iq=False, handle=None):
         self.engine, self.lib = engine, engine.lib
-        h = C.c_void_p()
-        self.lib.check(self.lib.L.sdr_chan_create(engine.h, modem.encode(), int(sample_rate), int(bandwidth), int(audio_rate), C.byref(h)))
+        h = handle
+        if h is None:
+            h = C.c_void_p()
+            self.lib.check(self.lib.L.sdr_chan_create(engine.h, modem.encode(), int(sample_rate), int(bandwidth), int(audio_rate), C.byref(h)))
         self.h = h
         self.modem = modem
         bw = C.c_int()
@@ -243,8 +265,10 @@ class Channel:
         self.set_frequency(frequency)
         if want_iq:
             self.lib.check(self.lib.L.sdr_chan_want_iq(h, 1))
-        self._audio = np.zeros(int(engine.max_block * (audio_rate / float(sample_rate)) * 1.5) + 4096, np.float32)
-        self._iq = np.zeros(int(engine.max_block * (self.bandwidth / float(sample_rate)) * 1.5) + 4096, np.complex64)
+        ca, ci = C.c_uint(), C.c_uint()
+        self.lib.check(self.lib.L.sdr_chan_result_caps(h, C.byref(ca), C.byref(ci)))
+        self._audio = np.zeros(ca.value + 16, np.float32)
+        self._iq = np.zeros(ci.value + 16, np.complex64)
 
     def set_frequency(self, f):
         self.lib.check(self.lib.L.sdr_chan_set_frequency(self.h, int(f)))
@@ -254,6 +278,15 @@ class Channel:
         self.lib.check(self.lib.L.sdr_chan_fetch_audio(self.h, _ptr(self._audio), self._audio.size, C.byref(n), C.byref(lvl),
                                                        C.byref(pk), C.byref(sk)))
         return self._audio[:n.value].copy(), lvl.value, pk.value, bool(sk.value)
+
+    def set_squelch(self, enabled, level_db):
+        self.lib.check(self.lib.L.sdr_chan_set_squelch(self.h, 1 if enabled else 0, C.c_float(level_db)))
+
+    def fetch_meter(self):
+        """(signal_level, signal_floor, signal_ceil, squelched) after the fetched block."""
+        a, b, c_, s = C.c_float(), C.c_float(), C.c_float(), C.c_int()
+        self.lib.check(self.lib.L.sdr_chan_fetch_meter(self.h, C.byref(a), C.byref(b), C.byref(c_), C.byref(s)))
+        return a.value, b.value, c_.value, bool(s.value)
 
     def fetch_iq(self):
         n = C.c_uint()
@@ -269,10 +302,12 @@ class Channel:
 class Spectrum:
     """sdr_spectrum: FFTDataDistributor framing + SpectrumVisualProcessor (non-view) + WaterfallPanel::step."""
 
-    def __init__(self, engine, fft_size, lines_per_second=0):
+    def __init__(self, engine, fft_size, lines_per_second=0, handle=None):
         self.engine, self.lib = engine, engine.lib
-        h = C.c_void_p()
-        self.lib.check(self.lib.L.sdr_spectrum_create(engine.h, fft_size, lines_per_second, C.byref(h)))
+        h = handle
+        if h is None:
+            h = C.c_void_p()
+            self.lib.check(self.lib.L.sdr_spectrum_create(engine.h, fft_size, lines_per_second, C.byref(h)))
         self.h = h
         self.fft_size = fft_size
 
@@ -314,6 +349,82 @@ class Spectrum:
     def close(self):
         if self.h:
             self.lib.L.sdr_spectrum_destroy(self.h)
+            self.h = None
+
+
+class Group:
+    """sdr_group: several GPUs behind the same boundary.  Group(lib, devices=[0, 1, ...]) is the one-process form;
+    Group(lib, device=d, rank=r, world=w, nccl_id=bytes) the one-process-per-GPU form (nccl_id from Group.unique_id on rank 0)."""
+
+    def __init__(self, lib, devices=None, max_block=1 << 20, device=0, rank=0, world=1, nccl_id=None):
+        self.lib, self.max_block = lib, max_block
+        h = C.c_void_p()
+        if world > 1:
+            idbuf = (C.c_char * 128).from_buffer_copy(nccl_id) if nccl_id is not None else None
+            lib.check(lib.L.sdr_group_create_rank(int(device), int(rank), int(world), idbuf, max_block, C.byref(h)))
+        else:
+            devs = list(devices if devices is not None else [device])
+            arr = (C.c_int * len(devs))(*devs)
+            lib.check(lib.L.sdr_group_create(arr, len(devs), max_block, C.byref(h)))
+        self.h = h
+        nl, tot, tr = C.c_int(), C.c_int(), C.c_int()
+        lib.check(lib.L.sdr_group_info(h, C.byref(nl), C.byref(tot), C.byref(tr)))
+        self.n_local, self.total, self.transport = nl.value, tot.value, tr.value
+        self.rank, self.world = (rank, world) if world > 1 else (0, 1)
+        self._next = 0
+        self.engines = []
+        for k in range(self.n_local):
+            eh = C.c_void_p()
+            lib.check(lib.L.sdr_group_engine(h, k, C.byref(eh)))
+            self.engines.append(Engine(lib, max_block=max_block, handle=eh))
+
+    @staticmethod
+    def unique_id(lib):
+        buf = (C.c_char * 128)()
+        lib.check(lib.L.sdr_group_unique_id(buf))
+        return bytes(buf)
+
+    def channel(self, modem, sample_rate, bandwidth, audio_rate=48000, frequency=0, want_iq=False):
+        """Next channel of the group (placed on member c mod N); None if it lives on another rank."""
+        ch = C.c_void_p()
+        self.lib.check(self.lib.L.sdr_group_chan_create(self.h, modem.encode(), int(sample_rate), int(bandwidth), int(audio_rate), C.byref(ch)))
+        owner = self._next % self.total
+        self._next += 1
+        if not ch.value:
+            return None
+        eng = self.engines[0] if self.world > 1 else self.engines[owner]
+        return Channel(eng, modem, sample_rate, bandwidth, audio_rate, frequency, want_iq, handle=ch)
+
+    def spectrum(self, fft_size, lines_per_second=0):
+        sp = C.c_void_p()
+        self.lib.check(self.lib.L.sdr_group_spectrum_create(self.h, fft_size, lines_per_second, C.byref(sp)))
+        return Spectrum(self.engines[0], fft_size, lines_per_second, handle=sp) if sp.value else None
+
+    def submit(self, iq, center_freq, sample_rate, n=None):
+        """iq: complex64 array, a raw host address (int), or None on ranks that receive the block by broadcast."""
+        if iq is None:
+            ptr = None
+        elif isinstance(iq, int):
+            ptr = C.c_void_p(iq)
+        else:
+            iq = np.ascontiguousarray(iq, dtype=np.complex64)
+            ptr, n = _ptr(iq), iq.size
+        self.lib.check(self.lib.L.sdr_group_submit(self.h, ptr, int(n), int(center_freq), int(sample_rate)))
+
+    def set_host_results(self, on=True):
+        self.lib.check(self.lib.L.sdr_group_set_host_results(self.h, 1 if on else 0))
+
+    def wait(self):
+        self.lib.check(self.lib.L.sdr_group_wait(self.h))
+
+    def wait_block(self, lag=0):
+        self.lib.check(self.lib.L.sdr_group_wait_block(self.h, int(lag)))
+
+    def close(self):
+        if self.h:
+            for e in self.engines:
+                e.h = None
+            self.lib.L.sdr_group_destroy(self.h)
             self.h = None
 
 

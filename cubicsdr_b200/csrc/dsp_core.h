@@ -24,7 +24,7 @@ constexpr int kMaxAudioHb = 8;
 constexpr int kPfbTaps = 14;      // 2 * m of the arbitrary resampler (m = 7)
 constexpr int kTailThreads = 256;
 
-enum ModemKind { MODEM_FM = 0, MODEM_NBFM = 1, MODEM_AM = 2, MODEM_USB = 3, MODEM_LSB = 4 };
+enum ModemKind { MODEM_FM = 0, MODEM_NBFM = 1, MODEM_AM = 2, MODEM_USB = 3, MODEM_LSB = 4, MODEM_IQ = 5 };
 
 // ---- small complex helpers ------------------------------------------------------------------------------------------
 SDR_HD SDR_FORCEINLINE float2 cf_make(float a, float b) { return make_float2(a, b); }
@@ -368,6 +368,7 @@ struct ChanStatic {
     int d_off;                    // real: demodulated samples (after auto-gain) feeding the audio resampler
     int al_off[kMaxAudioHb + 1];  // real: audio resampler level buffers (decim: after each half-band; interp: arb out, then each half-band)
     int want_iq;                  // copy decimated IQ into the result slot
+    int bandwidth;                // modem rate (DemodulatorThreadPostIQData::sampleRate): sampleTime of a block = n_iq / bandwidth
     int res_audio_cap, res_iq_cap;
     long long res_off;            // byte offset of the result slot in the results buffer
 };
@@ -382,6 +383,8 @@ struct ChanDyn {                  // written by the host for every block
     int inject_n;                 // > 0: the decimated IQ of this call was uploaded by the host (Modem::demodulate seam):
                                   //      skip the IQ resampler and demodulate inject_n samples
     int lvl0_sel;                 // which level-0 buffer this block uses (0: lvl_off[0], 1: lvl0_alt_off)
+    int squelch_enabled;          // DemodulatorThread::squelchEnabled for this block
+    float squelch_level;          // DemodulatorThread::squelchLevel (dB)
     int pad0;
     const float2 *hist;           // non-null: history for samples i < 0 is hist[i] (the channel skipped the previous block(s),
                                   // so its delay lines must see the tail of the last block it DID consume)
@@ -397,7 +400,7 @@ struct ChanState {                // device-resident, advanced by the tail kerne
     unsigned ssb_theta;               // SSB quarter-rate oscillator phase
     float sos_v[3][2][2];             // [section][v1,v2][re,im]
     float agc_ceil, agc_ma, agc_maa;  // ModemAnalog.cpp:6,70-72
-    int pad;
+    float sig_level, sig_floor, sig_ceil;   // DemodulatorThread::signalLevel / signalFloor / signalCeil (std::atomic<float>)
 };
 
 struct ChanResultHeader {
@@ -405,7 +408,10 @@ struct ChanResultHeader {
     float peak;
     int skipped;
     double level_db;
+    float sig_level, sig_floor, sig_ceil;   // after this block (DemodulatorThread.cpp:165-196)
+    int squelched;                          // AudioThreadInput::is_squelch_active (:198, :235-238)
 };
+constexpr int kResHdrBytes = 64;            // the header's room in front of a result slot's audio samples
 
 // =====================================================================================================================
 // 3. Front kernel: table-oscillator mix + K half-band (m = 3) decimators, one thread per (channel, time span)

@@ -15,6 +15,22 @@ namespace sdrb200 {
 
 constexpr int kTailStreams = kMaxTailHb + 1 + 3 + kMaxAudioHb + 1;   // complex levels, iq, w, d, audio levels
 
+// singly rounded arithmetic for the few host-side expressions that are replayed on the device (the compiler may not fuse
+// them: the host evaluates them with one rounding per operation)
+#if defined(__CUDA_ARCH__) && !defined(SDR_EMU)
+SDR_DEV SDR_FORCEINLINE double d_add(double a, double b) { return __dadd_rn(a, b); }
+SDR_DEV SDR_FORCEINLINE double d_sub(double a, double b) { return __dsub_rn(a, b); }
+SDR_DEV SDR_FORCEINLINE double d_mul(double a, double b) { return __dmul_rn(a, b); }
+SDR_DEV SDR_FORCEINLINE double d_div(double a, double b) { return __ddiv_rn(a, b); }
+SDR_DEV SDR_FORCEINLINE float f_add(float a, float b) { return __fadd_rn(a, b); }
+#else
+SDR_HD SDR_FORCEINLINE double d_add(double a, double b) { return a + b; }
+SDR_HD SDR_FORCEINLINE double d_sub(double a, double b) { return a - b; }
+SDR_HD SDR_FORCEINLINE double d_mul(double a, double b) { return a * b; }
+SDR_HD SDR_FORCEINLINE double d_div(double a, double b) { return a / b; }
+SDR_HD SDR_FORCEINLINE float f_add(float a, float b) { return a + b; }
+#endif
+
 struct TailArgs {
     const ChanStatic *cs;
     const ChanDyn *cd;
@@ -221,14 +237,23 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
     if (!cd.valid) return;
     ChanState &st = a.st[ch];
     ChanResultHeader *hdr = reinterpret_cast<ChanResultHeader *>(a.results + cs.res_off);
-    float *res_audio = reinterpret_cast<float *>(a.results + cs.res_off + 32);
+    float *res_audio = reinterpret_cast<float *>(a.results + cs.res_off + kResHdrBytes);
     float2 *res_iq = reinterpret_cast<float2 *>(res_audio + cs.res_audio_cap);
     if (!cd.active) {
-        if (ph == TP_SETUP && tid == 0) { hdr->n_audio = 0; hdr->n_iq = 0; hdr->peak = 0.f; hdr->skipped = 1; hdr->level_db = 0.0; }
+        if (ph == TP_SETUP && tid == 0) {
+            hdr->n_audio = 0; hdr->n_iq = 0; hdr->peak = 0.f; hdr->skipped = 1; hdr->level_db = 0.0;
+            hdr->sig_level = st.sig_level; hdr->sig_floor = st.sig_floor; hdr->sig_ceil = st.sig_ceil;   // no block reached DemodulatorThread
+            hdr->squelched = (cd.squelch_enabled && st.sig_level < cd.squelch_level) ? 1 : 0;
+        }
         return;
     }
     const bool is_fm = (cs.modem == MODEM_FM || cs.modem == MODEM_NBFM);
     const bool is_ssb = (cs.modem == MODEM_USB || cs.modem == MODEM_LSB);
+    // "I/Q" (analog/ModemIQ.cpp:39-56): no demodulator, no audio resampler -- the decimated IQ itself leaves as two-channel
+    // audio {imag, real}; the level is metered on the IQ like FM's (useSignalOutput stays false)
+    const bool is_iq = cs.modem == MODEM_IQ;
+    const bool has_agc = !is_fm && !is_iq;                  // ModemAM / USB / LSB pass autoGain = true to buildAudioOutput
+    const bool lvl_from_iq = is_fm || is_iq;
 
     if (ph == TP_SETUP) {
         if (tid == 0) {
@@ -246,7 +271,11 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
             }
             // audio resampler bookkeeping: its input is the demodulated stream, one sample per decimated IQ sample
             const long long d0 = (long long)st.iq_count, d1 = d0 + sm->n_iq;
-            if (!cs.a_interp) {
+            if (is_iq) {
+                for (int j = 0; j <= cs.a_S; ++j) { sm->a_g0[j] = 0; sm->a_n[j] = 0; }
+                sm->n_audio = 2 * sm->n_iq;
+                sm->a_phase_after = st.a_phase;
+            } else if (!cs.a_interp) {
                 for (int j = 0; j <= cs.a_S; ++j) { sm->a_g0[j] = d0 >> j; sm->a_n[j] = (int)((d1 >> j) - (d0 >> j)); }
                 sm->n_audio = arb_count(cs.a_step, st.a_phase, sm->a_n[cs.a_S], &sm->a_phase_after);
             } else {
@@ -319,7 +348,12 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
 
     if (ph == TP_DEMOD_A) {
         const int n = sm->n_iq;
-        if (is_fm) {
+        if (is_iq) {
+            for (int i = tid; i < n; i += nt) {
+                const float2 x = iq[i];
+                if (2 * i + 1 < cs.res_audio_cap) { res_audio[2 * i] = x.y; res_audio[2 * i + 1] = x.x; }
+            }
+        } else if (is_fm) {
             const float ref = 0.31830987f;                       // (float)(1 / (2 pi kf)), kf = 0.5  (freqdem_create(0.5))
             for (int i = tid; i < n; i += nt) {
                 float2 x = iq[i], p = iq[i - 1];
@@ -382,7 +416,7 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
 
     // ---- block auto-gain (AM / SSB): ModemAnalog.cpp:70-86 ------------------------------------------------------------
     if (ph == TP_AGC_A) {
-        if (!is_fm) {
+        if (has_agc) {
             float mx = 0.f;
             for (int i = tid; i < sm->n_iq; i += nt) mx = fmaxf(mx, d[i]);
             sm->red_f[tid] = mx;
@@ -392,7 +426,7 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
     if (ph == TP_AGC_B) {
         // a block that yields no decimated samples never reaches buildAudioOutput (`if (!bufSize) return;`,
         // ModemAM.cpp:35, ModemUSB/LSB likewise): the ceiling averages must not advance
-        if (!is_fm && tid == 0 && sm->n_iq > 0) {
+        if (has_agc && tid == 0 && sm->n_iq > 0) {
             float mx = 0.f;
             for (int t = 0; t < nt; ++t) mx = fmaxf(mx, sm->red_f[t]);
             float ma = st.agc_ma + (st.agc_ceil - st.agc_ma) * 0.025f;
@@ -403,13 +437,14 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
         return;
     }
     if (ph == TP_AGC_C) {
-        if (!is_fm) { const float g = sm->gain; for (int i = tid; i < sm->n_iq; i += nt) d[i] *= g; }
+        if (has_agc) { const float g = sm->gain; for (int i = tid; i < sm->n_iq; i += nt) d[i] *= g; }
         return;
     }
 
     // ---- audio resampler msresamp_rrrf ---------------------------------------------------------------------------------
     if (ph >= TP_AUD0 && ph < TP_AUD0 + kMaxAudioHb + 1) {
         const int j = ph - TP_AUD0;
+        if (is_iq) return;
         if (!cs.a_interp) {
             // decimator: a_S half-bands (cascade position g = a_S-1-j for phase j), then the arbitrary stage
             if (j < cs.a_S) {
@@ -477,8 +512,8 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
         const int na = sm->n_audio < cs.res_audio_cap ? sm->n_audio : cs.res_audio_cap;
         float pk = 0.f;
         double acc = 0.0;
-        for (int i = tid; i < na; i += nt) { float v = fabsf(res_audio[i]); pk = fmaxf(pk, v); if (!is_fm) acc += (double)v; }
-        if (is_fm) for (int i = tid; i < sm->n_iq; i += nt) { double re = iq[i].x, im = iq[i].y; acc += sqrt(re * re + im * im); }
+        for (int i = tid; i < na; i += nt) { float v = fabsf(res_audio[i]); pk = fmaxf(pk, v); if (!lvl_from_iq) acc += (double)v; }
+        if (lvl_from_iq) for (int i = tid; i < sm->n_iq; i += nt) { double re = iq[i].x, im = iq[i].y; acc += sqrt(re * re + im * im); }
         sm->red_f[tid] = pk;
         sm->red_d[tid] = acc;
         return;
@@ -488,7 +523,7 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
             float pk = 0.f;
             double acc = 0.0;
             for (int t = 0; t < nt; ++t) { pk = fmaxf(pk, sm->red_f[t]); acc += sm->red_d[t]; }
-            const int cnt = is_fm ? sm->n_iq : sm->n_audio;
+            const int cnt = lvl_from_iq ? sm->n_iq : sm->n_audio;
             double lvl = 0.0;
             if (sm->n_audio > 0 && cnt > 0) {
                 double lin = acc / (double)cnt;
@@ -496,6 +531,31 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
                 lvl = 20.0 * log10(lin);
             }
             hdr->n_audio = (unsigned)sm->n_audio; hdr->n_iq = (unsigned)sm->n_iq; hdr->peak = pk; hdr->skipped = 0; hdr->level_db = lvl;
+            // Floor / ceiling trackers, smoothed level and the squelch decision, DemodulatorThread.cpp:142-198.  The members
+            // are std::atomic<float>, the expressions mix float and double exactly as written there; every operation is
+            // issued singly rounded (no contraction into fused multiply-adds) so that the doubles match the host's.
+            // A block without decimated samples never gets this far in the reference (`if (!bufSize) continue`, :96-99).
+            if (sm->n_iq > 0) {
+                const double csl = lvl;                                  // 0 when the block gave no audio (:142, :145)
+                const double sample_time = d_div((double)sm->n_iq, (double)cs.bandwidth);        // :143
+                if (sm->n_audio > 0) {
+                    float sf = st.sig_floor, sc = st.sig_ceil;
+                    const float sl = cd.squelch_level;
+                    if (csl > (double)sc) sc = (float)csl;
+                    if (csl < (double)sf) sf = (float)csl;
+                    if (f_add(sl, 1.0f) > sc) sc = f_add(sl, 1.0f);
+                    if (f_add(sf, 2.0f) > sc) sc = f_add(sf, 2.0f);
+                    // sc -= (sc - (csl + 2.0f)) * sampleTime * 0.05f;   sf += ((csl - 5.0f) - sf) * sampleTime * 0.15f;
+                    sc = (float)d_sub((double)sc, d_mul(d_mul(d_sub((double)sc, d_add(csl, 2.0)), sample_time), (double)0.05f));
+                    sf = (float)d_add((double)sf, d_mul(d_mul(d_sub(d_sub(csl, 5.0), (double)sf), sample_time), (double)0.15f));
+                    st.sig_floor = sf; st.sig_ceil = sc;
+                }
+                const double slv = (double)st.sig_level;
+                if (csl > slv) st.sig_level = (float)d_add(slv, d_mul(d_sub(csl, slv), 0.5));                             // :192-193
+                else st.sig_level = (float)d_add(slv, d_mul(d_mul(d_mul(d_sub(csl, slv), 0.05), sample_time), 30.0));      // :195
+            }
+            hdr->sig_level = st.sig_level; hdr->sig_floor = st.sig_floor; hdr->sig_ceil = st.sig_ceil;
+            hdr->squelched = (cd.squelch_enabled && st.sig_level < cd.squelch_level) ? 1 : 0;                             // :198
         }
         return;
     }

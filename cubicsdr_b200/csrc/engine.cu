@@ -589,6 +589,7 @@ static int modem_from_name(const char *n) {
     if (s == "AM") return MODEM_AM;
     if (s == "USB") return MODEM_USB;
     if (s == "LSB") return MODEM_LSB;
+    if (s == "I/Q") return MODEM_IQ;
     return -1;
 }
 
@@ -628,6 +629,8 @@ struct sdr_chan {
     std::vector<PremixSeg> recent;  // oscillator settings of the last consumed blocks, newest first (rare-path history mixing)
     size_t slot_bytes = 0;
     // lifecycle (see "channels" below): device memory comes from the stream-ordered allocator on the engine's admin stream
+    bool squelch_enabled = false;   // DemodulatorThread::squelchEnabled / squelchLevel (DemodulatorThread.cpp:25-26, 384-397)
+    float squelch_level = -100.f;
     bool fresh = true;              // the first submit that sees the channel makes its main stream wait for ev_ready
     bool cs_dirty = false;          // descriptor changed after creation (sdr_chan_want_iq): re-uploaded with the next block
     bool async_mem = false;         // arena / history came from be_malloc_async
@@ -771,6 +774,16 @@ struct sdr_engine {
     cudaEvent_t tev_dc[kTimeSets][2];
 #endif
 };
+
+// several engines of one process may sit on different GPUs (sdr_group): every entry point that issues CUDA work first makes
+// its engine's device current
+static inline void use_device(const sdr_engine *e) {
+#ifndef SDR_EMU
+    cudaSetDevice(e->device);
+#else
+    (void)e;
+#endif
+}
 
 static void time_mark(sdr_engine *e, int which) {
 #ifndef SDR_EMU
@@ -1045,6 +1058,7 @@ extern "C" int sdr_engine_debug_timeline(sdr_engine *e, float *out128, int *n_bl
 extern "C" int sdr_engine_debug_dc_fixups(sdr_engine *e, unsigned *fixups, int *exact_mode) {
     if (!e) return SDR_ERR_ARG;
     std::lock_guard<std::mutex> lk(e->mu);
+    use_device(e);
     be_sync(e->stream);
     unsigned v = 0;
     be_d2h(&v, e->d_fixups, sizeof v, e->stream);
@@ -1058,6 +1072,7 @@ extern "C" int sdr_engine_debug_dc_fixups(sdr_engine *e, unsigned *fixups, int *
 extern "C" int sdr_engine_debug_front_timeline(sdr_engine *e, int enable, unsigned long long *out, unsigned max_ctas) {
     if (!e) return SDR_ERR_ARG;
     std::lock_guard<std::mutex> lk(e->mu);
+    use_device(e);
     be_sync(e->stream);
     if (enable && !e->d_front_dbg) {
         if (be_malloc((void **)&e->d_front_dbg, (4 * 1024 + 64 * 64) * sizeof(unsigned long long))) return SDR_ERR_NOMEM;
@@ -1078,6 +1093,7 @@ static void sync_all(sdr_engine *e);
 extern "C" int sdr_engine_debug_tail_phases(sdr_engine *e, unsigned long long *out, int *n_phases) {
     if (!e || !out || !e->d_front_dbg) return SDR_ERR_ARG;
     std::lock_guard<std::mutex> lk(e->mu);
+    use_device(e);
     sync_all(e);
     be_d2h(out, e->d_front_dbg + 4 * 1024, (size_t)64 * 64 * sizeof(unsigned long long), e->stream);
     be_sync(e->stream);
@@ -1088,6 +1104,7 @@ extern "C" int sdr_engine_debug_tail_phases(sdr_engine *e, unsigned long long *o
 extern "C" int sdr_engine_set_timing(sdr_engine *e, int enable) {
     if (!e) return fail(SDR_ERR_ARG, "null engine");
     std::lock_guard<std::mutex> lk(e->mu);
+    use_device(e);
 #ifndef SDR_EMU
     if (enable && !e->tev_made) {
         for (int i = 0; i < sdr_engine::kTimeSets; ++i) for (int k = 0; k < 5; ++k) CUDA_TRY(cudaEventCreate(&e->tev[i][k]));
@@ -1204,6 +1221,7 @@ static int chan_create_impl(sdr_engine *e, const char *modem, long long sample_r
     sdr_chan *c = new sdr_chan();
     c->eng = e; c->index = -1; c->modem = mk; c->sample_rate = sample_rate;
     c->bandwidth = check_sample_rate(mk, bandwidth);
+    if (mk == MODEM_IQ) c->bandwidth = audio_rate;                      // ModemIQ::checkSampleRate returns audioSampleRate (ModemIQ.cpp:31-33)
     c->audio_rate = audio_rate;
     const float As = 60.0f;                                             // DemodulatorWorkerThread.cpp:95, ModemAnalog.cpp:25
     const double iq_ratio = (double)c->bandwidth / (double)sample_rate; // :97-100
@@ -1257,15 +1275,18 @@ static int chan_create_impl(sdr_engine *e, const char *modem, long long sample_r
         for (int j = 0; j <= cs.a_S; ++j) cs.al_off[j] = take(kHist + (cap_b << j) + 4);
         cap_audio = cap_b << cs.a_S;
     }
+    if (mk == MODEM_IQ) cap_audio = 2 * cap_iq;                         // two-channel output, one {imag, real} pair per decimated sample
     cs.res_audio_cap = (int)((cap_audio + 3) & ~size_t(3));
     cs.res_iq_cap = (int)cap_iq;
     cs.want_iq = 0;
+    cs.bandwidth = c->bandwidth;
     c->arena_floats = off;
-    c->slot_bytes = 32 + (size_t)cs.res_audio_cap * 4 + (size_t)cs.res_iq_cap * 8;
+    c->slot_bytes = kResHdrBytes + (size_t)cs.res_audio_cap * 4 + (size_t)cs.res_iq_cap * 8;
     c->slot_bytes = (c->slot_bytes + 31) & ~size_t(31);
     ChanState st;
     memset(&st, 0, sizeof st);
     st.agc_ceil = st.agc_ma = st.agc_maa = 1.0f;                        // ModemAnalog.cpp:6
+    st.sig_level = -100.f; st.sig_floor = -30.f; st.sig_ceil = 30.f;    // DemodulatorThread.cpp:25-26
     if (c->standalone) {
         if (be_host_alloc((void **)&c->h_dyn, sizeof(ChanDyn)) || be_host_alloc((void **)&c->h_slot, c->slot_bytes)) {
             be_host_free(c->h_dyn); be_host_free(c->h_slot); delete c;
@@ -1354,6 +1375,12 @@ extern "C" int sdr_modem_check_sample_rate(const char *modem, long long sample_r
     if (mk < 0) return fail(SDR_ERR_UNSUPPORTED, "unknown modem");
     return check_sample_rate(mk, sample_rate);
 }
+// the two-argument form of Modem::checkSampleRate(sampleRate, audioSampleRate): "I/Q" answers with the audio rate
+extern "C" int sdr_modem_check_sample_rate2(const char *modem, long long sample_rate, int audio_rate) {
+    const int mk = modem_from_name(modem);
+    if (mk < 0) return fail(SDR_ERR_UNSUPPORTED, "unknown modem");
+    return mk == MODEM_IQ ? audio_rate : check_sample_rate(mk, sample_rate);
+}
 
 extern "C" int sdr_modem_create(sdr_engine *e, const char *modem, long long sample_rate, int audio_rate, unsigned max_samples,
                                 sdr_chan **out) {
@@ -1373,6 +1400,7 @@ extern "C" int sdr_modem_demodulate(sdr_chan *c, const sdr_cf32 *iq, unsigned n,
     if (!iq || n > c->inject_cap) return fail(SDR_ERR_ARG, "sdr_modem_demodulate: bad buffer / too many samples");
     sdr_engine *e = c->eng;
     std::lock_guard<std::mutex> lk(e->mu);
+    use_device(e);
     { int r = ensure_results(e); if (r) return r; }
     sync_all(e);                                                        // h_dyn / h_slot are reused call to call
     float *d_iq = c->cs.arena + c->cs.iq_off + 2 * kHist;
@@ -1388,7 +1416,7 @@ extern "C" int sdr_modem_demodulate(sdr_chan *c, const sdr_cf32 *iq, unsigned n,
     if (be_sync(e->stream)) return fail(SDR_ERR_CUDA, std::string("sdr_modem_demodulate: ") + be_last_error());
     const ChanResultHeader *h = reinterpret_cast<const ChanResultHeader *>(c->h_slot);
     unsigned m = std::min(cap, std::min(h->n_audio, (unsigned)c->cs.res_audio_cap));
-    if (audio) memcpy(audio, c->h_slot + 32, (size_t)m * sizeof(float));
+    if (audio) memcpy(audio, c->h_slot + kResHdrBytes, (size_t)m * sizeof(float));
     if (n_audio) *n_audio = h->n_audio;
     if (level_db) *level_db = h->level_db;
     if (peak) *peak = h->peak;
@@ -1449,6 +1477,20 @@ extern "C" int sdr_chan_get_bandwidth(sdr_chan *c, int *bw) {
     *bw = c->bandwidth;
     return SDR_OK;
 }
+// DemodulatorThread::setSquelchEnabled / setSquelchLevel (src/demod/DemodulatorThread.cpp:384-397): takes effect with the next block
+extern "C" int sdr_chan_set_squelch(sdr_chan *c, int enabled, float level_db) {
+    if (!c) return fail(SDR_ERR_ARG, "null channel");
+    std::lock_guard<std::mutex> lk(c->eng->mu);
+    c->squelch_enabled = enabled != 0;
+    c->squelch_level = level_db;
+    return SDR_OK;
+}
+// AudioThreadInput::channels of this channel's output: 2 for "I/Q" (interleaved {imag, real}, ModemIQ.cpp:46-55), else 1
+extern "C" int sdr_chan_audio_channels(sdr_chan *c, int *channels) {
+    if (!c || !channels) return fail(SDR_ERR_ARG, "null argument");
+    *channels = c->modem == MODEM_IQ ? 2 : 1;
+    return SDR_OK;
+}
 extern "C" int sdr_chan_result_caps(sdr_chan *c, unsigned *audio_cap, unsigned *iq_cap) {
     if (!c) return fail(SDR_ERR_ARG, "null channel");
     if (audio_cap) *audio_cap = (unsigned)c->cs.res_audio_cap;
@@ -1477,6 +1519,7 @@ extern "C" int sdr_spectrum_create(sdr_engine *e, unsigned fft_size, unsigned lp
     if (fft_size < 16 || (fft_size & (fft_size - 1)) || fft_size > 32768)
         return fail(SDR_ERR_UNSUPPORTED, "sdr_spectrum_create: fft_size must be a power of two in [16, 32768]");
     std::lock_guard<std::mutex> lk(e->mu);
+    use_device(e);
     sdr_spectrum *s = new sdr_spectrum();
     s->eng = e; s->fft_size = fft_size; s->N = 2 * fft_size; s->lps = lps;     // SPECTRUM_VZM = 2 (SpectrumVisualProcessor.cpp:145)
     s->P = 1;
@@ -1522,6 +1565,7 @@ extern "C" int sdr_spectrum_destroy(sdr_spectrum *s) {
     if (!s) return SDR_OK;
     sdr_engine *e = s->eng;
     std::lock_guard<std::mutex> lk(e->mu);
+    use_device(e);
     sync_all(e);                                                        // the side / result streams may still use its buffers
     e->spectra.erase(std::remove(e->spectra.begin(), e->spectra.end(), s), e->spectra.end());
     spectrum_free(s);
@@ -1999,6 +2043,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         }
         if (std::llabs(c->shift_frequency) > lim) { keep_tail(); continue; }   // block skipped for this channel (:161-164)
         const int dir = c->shift_frequency < 0 ? +1 : (c->shift_frequency > 0 ? -1 : 0);
+        d.squelch_enabled = c->squelch_enabled ? 1 : 0; d.squelch_level = c->squelch_level;
         d.active = 1; d.g0 = c->consumed; d.theta0 = c->theta; d.dtheta = c->dtheta; d.dtheta_prev = c->dtheta_prev;
         d.dir = dir; d.dir_prev = c->dir_prev;
         d.hist = c->priv_valid ? c->d_priv_hist + kBlkHist : nullptr;
@@ -2249,6 +2294,7 @@ extern "C" int sdr_engine_channel_plan(long long sample_rate, int *num_channels,
 
 extern "C" int sdr_engine_wait(sdr_engine *e) {
     if (!e) return fail(SDR_ERR_ARG, "null engine");
+    use_device(e);
     if (be_sync(e->stream)) return fail(SDR_ERR_CUDA, std::string("stream sync failed: ") + be_last_error());
 #ifndef SDR_EMU
     if (cudaStreamSynchronize(e->stream_tail) != cudaSuccess) return fail(SDR_ERR_CUDA, std::string("tail stream sync failed: ") + be_last_error());
@@ -2289,6 +2335,7 @@ extern "C" int sdr_engine_wait_block(sdr_engine *e, int lag) {
 extern "C" int sdr_engine_fetch_block(sdr_engine *e, sdr_cf32 *out, unsigned cap, unsigned *n) {
     if (!e || !out) return fail(SDR_ERR_ARG, "null argument");
     std::lock_guard<std::mutex> lk(e->mu);
+    use_device(e);
     unsigned m = std::min(cap, e->last_n);
     be_d2h(out, e->d_blkbuf[e->parity] + e->hist_cap, (size_t)m * sizeof(sdr_cf32), e->stream);
     be_sync(e->stream);
@@ -2304,11 +2351,26 @@ extern "C" int sdr_chan_fetch_audio(sdr_chan *c, float *audio, unsigned cap, uns
     const unsigned char *slot = e->hres(e->fetch_sel) + c->cs.res_off;
     const ChanResultHeader *h = reinterpret_cast<const ChanResultHeader *>(slot);
     unsigned m = std::min(cap, std::min(h->n_audio, (unsigned)c->cs.res_audio_cap));
-    if (audio) memcpy(audio, slot + 32, (size_t)m * sizeof(float));
+    if (audio) memcpy(audio, slot + kResHdrBytes, (size_t)m * sizeof(float));
     if (n_audio) *n_audio = h->n_audio;
     if (level_db) *level_db = h->level_db;
     if (peak) *peak = h->peak;
     if (skipped) *skipped = h->skipped;
+    return SDR_OK;
+}
+
+// getSignalLevel / getSignalFloor / getSignalCeil (DemodulatorThread.cpp:372-382) after the fetched block, and the block's
+// AudioThreadInput::is_squelch_active (:198, :235-238)
+extern "C" int sdr_chan_fetch_meter(sdr_chan *c, float *signal_level, float *signal_floor, float *signal_ceil, int *squelched) {
+    if (!c) return fail(SDR_ERR_ARG, "null channel");
+    sdr_engine *e = c->eng;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!e->res_on_host[e->fetch_sel] || !e->h_results) return fail(SDR_ERR_STATE, "no host results for the last block");
+    const ChanResultHeader *h = reinterpret_cast<const ChanResultHeader *>(e->hres(e->fetch_sel) + c->cs.res_off);
+    if (signal_level) *signal_level = h->sig_level;
+    if (signal_floor) *signal_floor = h->sig_floor;
+    if (signal_ceil) *signal_ceil = h->sig_ceil;
+    if (squelched) *squelched = h->squelched;
     return SDR_OK;
 }
 
@@ -2323,7 +2385,7 @@ extern "C" int sdr_engine_fetch_audio_batch(sdr_engine *e, sdr_chan *const *chan
         const unsigned char *slot = e->hres(e->fetch_sel) + c->cs.res_off;
         const ChanResultHeader *h = reinterpret_cast<const ChanResultHeader *>(slot);
         unsigned m = std::min(stride, std::min(h->n_audio, (unsigned)c->cs.res_audio_cap));
-        if (audio) memcpy(audio + (size_t)i * stride, slot + 32, (size_t)m * sizeof(float));
+        if (audio) memcpy(audio + (size_t)i * stride, slot + kResHdrBytes, (size_t)m * sizeof(float));
         if (n_audio) n_audio[i] = h->n_audio;
         if (level_db) level_db[i] = h->level_db;
         if (peak) peak[i] = h->peak;
@@ -2340,7 +2402,7 @@ extern "C" int sdr_chan_fetch_iq(sdr_chan *c, sdr_cf32 *iq, unsigned cap, unsign
     const unsigned char *slot = e->hres(e->fetch_sel) + c->cs.res_off;
     const ChanResultHeader *h = reinterpret_cast<const ChanResultHeader *>(slot);
     unsigned m = std::min(cap, std::min(h->n_iq, (unsigned)c->cs.res_iq_cap));
-    if (iq) memcpy(iq, slot + 32 + (size_t)c->cs.res_audio_cap * 4, (size_t)m * sizeof(sdr_cf32));
+    if (iq) memcpy(iq, slot + kResHdrBytes + (size_t)c->cs.res_audio_cap * 4, (size_t)m * sizeof(sdr_cf32));
     if (n_iq) *n_iq = h->n_iq;
     return SDR_OK;
 }
@@ -2379,6 +2441,7 @@ extern "C" int sdr_spectrum_fetch_all(sdr_spectrum *s, unsigned cap_frames, floa
 extern "C" int sdr_spectrum_fetch_debug(sdr_spectrum *s, unsigned idx, float *mags, float *maa) {
     if (!s) return fail(SDR_ERR_ARG, "null spectrum");
     std::lock_guard<std::mutex> lk(s->eng->mu);
+    use_device(s->eng);
     if (idx >= s->frames_last) return fail(SDR_ERR_ARG, "frame index out of range");
     be_d2h(s->h_dbg, s->d_mags + (size_t)idx * s->N, s->N * sizeof(float), s->eng->stream);
     be_d2h(s->h_dbg + s->N, s->d_maa + (size_t)idx * s->N, s->N * sizeof(float), s->eng->stream);
@@ -2425,6 +2488,7 @@ static int pfb_create_impl(sdr_engine *e, int osf, unsigned num_channels, unsign
     if (num_channels < 2 || (num_channels & 1u) || num_channels > (unsigned)kPfbMaxChannels || m < 1 || m > 8 || max_frames < 1)
         return fail(SDR_ERR_ARG, "sdr_pfb_create: num_channels must be even and in [2, 256], m in [1, 8]");
     std::lock_guard<std::mutex> lk(e->mu);
+    use_device(e);
     auto *p = new sdr_pfb();
     p->eng = e; p->M = num_channels; p->p = 2 * m; p->max_frames = max_frames; p->osf = osf;
     std::vector<float> hq, tw;
@@ -2449,7 +2513,7 @@ static int pfb_create_impl(sdr_engine *e, int osf, unsigned num_channels, unsign
 
 extern "C" int sdr_pfb_destroy(sdr_pfb *p) {
     if (!p) return SDR_OK;
-    { std::lock_guard<std::mutex> lk(p->eng->mu); be_sync(p->eng->stream); pfb_free(p); }
+    { std::lock_guard<std::mutex> lk(p->eng->mu); use_device(p->eng); be_sync(p->eng->stream); pfb_free(p); }
     delete p;
     return SDR_OK;
 }
@@ -2457,6 +2521,7 @@ extern "C" int sdr_pfb_destroy(sdr_pfb *p) {
 extern "C" int sdr_pfb_reset(sdr_pfb *p) {
     if (!p) return fail(SDR_ERR_ARG, "null channelizer");
     std::lock_guard<std::mutex> lk(p->eng->mu);
+    use_device(p->eng);
     be_memset(p->d_x, 0, p->hist() * sizeof(float2), p->eng->stream);
     be_sync(p->eng->stream);
     p->frame_base = 0;
@@ -2498,6 +2563,7 @@ extern "C" int sdr_pfb_execute(sdr_pfb *p, const sdr_cf32 *iq, unsigned n, sdr_c
         return fail(SDR_ERR_ARG, "sdr_pfb_execute: n must be a non-zero multiple of num_channels (half of it for firpfbch2) within max_frames (SoapySDRThread.cpp:668-674)");
     sdr_engine *e = p->eng;
     std::lock_guard<std::mutex> lk(e->mu);
+    use_device(e);
     memcpy(p->h_io, iq, (size_t)n * sizeof(sdr_cf32));
     be_h2d(p->d_y, p->h_io, (size_t)n * sizeof(float2), e->stream);          // d_y doubles as the input landing buffer
     be_sync(e->stream);
@@ -2518,6 +2584,7 @@ extern "C" int sdr_pfb_execute_device(sdr_pfb *p, const void *d_iq, unsigned n, 
     if (!p || !d_iq || !d_out) return fail(SDR_ERR_ARG, "sdr_pfb_execute_device: null argument");
     if (n == 0 || n % p->step() != 0 || n / p->step() > p->max_frames) return fail(SDR_ERR_ARG, "sdr_pfb_execute_device: bad length");
     std::lock_guard<std::mutex> lk(p->eng->mu);
+    use_device(p->eng);
     return pfb_run(p, (const float2 *)d_iq, n, (float2 *)d_out);
 }
 
@@ -2592,3 +2659,8 @@ extern "C" int sdr_design_butter6_sos(float *o) {
     for (int i = 0; i < 3; ++i) { memcpy(o + 6 * i, s[i].b, 12); memcpy(o + 6 * i + 3, s[i].a, 12); }
     return SDR_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// several GPUs behind the same boundary
+// ---------------------------------------------------------------------------------------------------------------------
+#include "group.h"

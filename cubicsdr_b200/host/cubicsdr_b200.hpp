@@ -249,6 +249,7 @@ public:
             throw std::runtime_error(sdr_last_error());
         sdr_chan_get_bandwidth(ch_, &bandwidth_);
         sdr_chan_result_caps(ch_, &audioCap_, &iqCap_);          // most samples one block can yield: the fetch buffers' size
+        sdr_chan_audio_channels(ch_, &channels_);                // 2 for "I/Q" (ModemIQ.cpp:46), else 1
         if (wantIQ) sdr_chan_want_iq(ch_, 1);
     }
     ~DemodulatorB200() { if (ch_) sdr_chan_destroy(ch_); }
@@ -263,10 +264,27 @@ public:
         unsigned n = 0; double lvl = 0; float pk = 0; int skipped = 0;
         if (sdr_chan_fetch_audio(ch_, ati.data.data(), (unsigned)ati.data.size(), &n, &lvl, &pk, &skipped) != SDR_OK) { ati.data.clear(); return false; }
         ati.data.resize(n);
-        ati.channels = 1; ati.sampleRate = audioRate_; ati.inputRate = bandwidth_; ati.peak = pk;
+        ati.channels = channels_; ati.sampleRate = audioRate_; ati.inputRate = bandwidth_; ati.peak = pk;
         if (signalLevelDb) *signalLevelDb = lvl;
+        int squelched = 0;                                       // DemodulatorThread.cpp:198, 235-238
+        sdr_chan_fetch_meter(ch_, &signalLevel_, &signalFloor_, &signalCeil_, &squelched);
+        ati.is_squelch_active = squelched != 0;
+        // squelchBreak bookkeeping (:200-220); the visual cue / solo-mode lock that hang off it stay with the GUI host
+        if (squelchEnabled_) {
+            if (!squelched && !squelchBreak_) squelchBreak_ = true;
+            else if (squelched && squelchBreak_) squelchBreak_ = false;
+        }
         return !skipped;
     }
+    // DemodulatorThread::setSquelchEnabled / setSquelchLevel / get* (DemodulatorThread.cpp:372-404)
+    void setSquelchEnabled(bool on) { squelchEnabled_ = on; sdr_chan_set_squelch(ch_, on ? 1 : 0, squelchLevel_); }
+    void setSquelchLevel(float db) { squelchEnabled_ = true; squelchLevel_ = db; sdr_chan_set_squelch(ch_, 1, db); }
+    bool isSquelchEnabled() const { return squelchEnabled_; }
+    float getSquelchLevel() const { return squelchLevel_; }
+    float getSignalLevel() const { return signalLevel_; }
+    float getSignalFloor() const { return signalFloor_; }
+    float getSignalCeil() const { return signalCeil_; }
+    bool getSquelchBreak() const { return squelchBreak_; }
     bool fetchPostIQ(DemodulatorThreadPostIQData &out) {                    // DemodulatorPreThread.cpp:211-217
         out.data.resize(iqCap_);
         unsigned n = 0;
@@ -279,8 +297,10 @@ private:
     std::shared_ptr<Engine> eng_;
     sdr_chan *ch_;
     std::string name_;
-    int bandwidth_ = 0, audioRate_;
+    int bandwidth_ = 0, audioRate_, channels_ = 1;
     unsigned audioCap_ = 0, iqCap_ = 0;
+    bool squelchEnabled_ = false, squelchBreak_ = false;
+    float squelchLevel_ = -100.f, signalLevel_ = -100.f, signalFloor_ = -30.f, signalCeil_ = 30.f;
 };
 
 // ---- SpectrumVisualProcessor (process/SpectrumVisualProcessor.h:14-23) ---------------------------------------------------------

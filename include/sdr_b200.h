@@ -81,7 +81,7 @@ int sdr_engine_set_timing(sdr_engine *eng, int enable);
 int sdr_engine_get_timing(sdr_engine *eng, double *stage_ms4, unsigned long long *blocks);
 
 /* ---- channel: DemodulatorPreThread + Modem + DemodulatorThread metering --------------------------------------------- */
-/* modem: "FM" "NBFM" "AM" "USB" "LSB" (Modem::addModemFactory names, src/CubicSDR.cpp:305-311).
+/* modem: "FM" "NBFM" "AM" "USB" "LSB" "I/Q" (Modem::addModemFactory names, src/CubicSDR.cpp:305-313).
  * bandwidth is passed through Modem::checkSampleRate (ModemAnalog.cpp:14-19, ModemUSB.cpp:29-37).
  * Builds what DemodulatorWorkerThread builds (src/demod/DemodulatorWorkerThread.cpp:63-101): msresamp_crcf(bw/fs, 60),
  * the modem, and its kit msresamp_rrrf(audio_rate/bw, 60) (ModemAnalog.cpp:21-33).
@@ -96,6 +96,8 @@ int sdr_chan_destroy(sdr_chan *ch);
  * DemodulatorPreThread.cpp:154-163 does, including abs(), the up/down choice and the 0.75 fs skip rule.            */
 int sdr_chan_set_frequency(sdr_chan *ch, long long frequency);
 int sdr_chan_get_bandwidth(sdr_chan *ch, int *bandwidth);
+/* AudioThreadInput::channels: 2 for "I/Q" (audio = interleaved {imag, real} of the decimated IQ, ModemIQ.cpp:46-55), else 1 */
+int sdr_chan_audio_channels(sdr_chan *ch, int *channels);
 /* most audio samples / decimated IQ samples one block can yield for this channel (size the fetch buffers with these) */
 int sdr_chan_result_caps(sdr_chan *ch, unsigned *audio_cap, unsigned *iq_cap);
 /* also return the decimated IQ of each block (DemodulatorThreadPostIQData::data, src/demod/DemodDefs.h:43-59) */
@@ -106,6 +108,13 @@ int sdr_chan_want_iq(sdr_chan *ch, int enable);
 int sdr_chan_fetch_audio(sdr_chan *ch, float *audio, unsigned cap, unsigned *n_audio, double *level_db, float *peak,
                          int *skipped);
 int sdr_chan_fetch_iq(sdr_chan *ch, sdr_cf32 *iq, unsigned cap, unsigned *n_iq);
+/* DemodulatorThread's squelch (src/demod/DemodulatorThread.cpp:165-198, 384-397): the floor / ceiling trackers, the
+ * smoothed signal level and the squelch decision are advanced on the device with every block the channel processes.
+ * sdr_chan_set_squelch = setSquelchEnabled + setSquelchLevel (dB), effective from the next block.  sdr_chan_fetch_meter
+ * returns getSignalLevel / getSignalFloor / getSignalCeil as they stand after the fetched block and that block's
+ * AudioThreadInput::is_squelch_active (the host drops the audio of a squelched block, :318).                         */
+int sdr_chan_set_squelch(sdr_chan *ch, int enabled, float level_db);
+int sdr_chan_fetch_meter(sdr_chan *ch, float *signal_level, float *signal_floor, float *signal_ceil, int *squelched);
 /* One call for many channels (what a host with hundreds of demodulators uses instead of n_chan fetches): audio of
  * channel i lands at audio + i * stride (at most stride samples); the other arrays have n_chan entries and may be NULL. */
 int sdr_engine_fetch_audio_batch(sdr_engine *eng, sdr_chan *const *chans, unsigned n_chan, float *audio, unsigned stride,
@@ -114,6 +123,8 @@ int sdr_engine_fetch_audio_batch(sdr_engine *eng, sdr_chan *const *chans, unsign
 /* ---- Modem plugin seam: one call = Modem::demodulate(kit, input, audioOut) (src/modules/modem/Modem.h:148-153) -------- */
 /* Modem::checkSampleRate for `modem` (ModemAnalog.cpp:14-19, ModemUSB.cpp:29-37); negative on unknown modem.       */
 int sdr_modem_check_sample_rate(const char *modem, long long sample_rate);
+/* both arguments of Modem::checkSampleRate(sampleRate, audioSampleRate): "I/Q" returns the audio rate (ModemIQ.cpp:31-33) */
+int sdr_modem_check_sample_rate2(const char *modem, long long sample_rate, int audio_rate);
 /* Modem factory + buildKit(sample_rate, audio_rate) (Modem.cpp:40-55, ModemAnalog.cpp:21-33).  The handle is an sdr_chan
  * without the pre-demod stage: sdr_engine_submit ignores it; destroy it with sdr_chan_destroy (= disposeKit + delete). */
 int sdr_modem_create(sdr_engine *eng, const char *modem, long long sample_rate, int audio_rate, unsigned max_samples,
@@ -180,6 +191,36 @@ int sdr_design_halfband_branch(int m, float as_db, float *h1 /* 2m */);
 int sdr_design_am_dc_block(float *h51);
 int sdr_design_hilbert_q(float *hq10);
 int sdr_design_butter6_sos(float *sos18 /* 3 x {b0,b1,b2,a0,a1,a2} */);
+
+/* ---- group: several GPUs behind the same boundary -------------------------------------------------------
+ * The reference hands every block to every demodulator (src/sdr/SDRPostThread.cpp:294-298); channels are independent given
+ * the block.  A group places channel c (in creation order) on member c mod N, keeps spectra on member 0 and moves the raw
+ * block to every member with ONE ncclBroadcast over NVLink per block; every member runs its own (bit-identical) DC blocker
+ * and returns its own channels' results -- sdr_chan_* / sdr_spectrum_* calls work on a group's handles unchanged.
+ * sdr_group_create: one process drives n GPUs (CubicSDR is one process, src/CubicSDR.cpp:340-397); devices[0] takes the
+ * host block.  sdr_group_create_rank: one process per GPU (torch.distributed.run); nccl_id = the 128 bytes rank 0 got from
+ * sdr_group_unique_id, handed to the other ranks by the launcher; NULL = the caller moves the block itself and passes it
+ * to sdr_group_submit on every rank.  In that form every rank makes the same sdr_group_chan_create /
+ * sdr_group_spectrum_create calls in the same order and receives *out = NULL for objects that live on another rank.      */
+typedef struct sdr_group sdr_group;
+int sdr_group_create(const int *devices, int n, unsigned max_block, sdr_group **out);
+int sdr_group_create_rank(int device, int rank, int world, const void *nccl_id, unsigned max_block, sdr_group **out);
+int sdr_group_unique_id(void *id128);
+int sdr_group_destroy(sdr_group *g);
+/* n_local members in this process, total members of the group, transport (0 none, 1 NCCL broadcast, 2 peer copies) */
+int sdr_group_info(sdr_group *g, int *n_local, int *total, int *transport);
+int sdr_group_engine(sdr_group *g, int i, sdr_engine **eng);
+int sdr_group_chan_create(sdr_group *g, const char *modem, long long sample_rate, long long bandwidth, int audio_rate,
+                          sdr_chan **out);
+int sdr_group_spectrum_create(sdr_group *g, unsigned fft_size, unsigned lines_per_second, sdr_spectrum **out);
+/* One block for the whole group (SDRPostThread::run, src/sdr/SDRPostThread.cpp:178-187): iq is host memory on the root
+ * (rank 0; pinned memory is sent by DMA from where it lies, a device pointer is accepted for resident blocks).  Enqueues only: DMA to GPU 0, the broadcast, one pass of the
+ * path per member.  sdr_group_wait / sdr_group_wait_block are sdr_engine_wait / sdr_engine_wait_block on every member.    */
+int sdr_group_submit(sdr_group *g, const sdr_cf32 *iq, unsigned n, long long center_freq, long long sample_rate);
+int sdr_group_wait(sdr_group *g);
+int sdr_group_wait_block(sdr_group *g, int lag);
+/* 0: leave results in device memory (throughput measurements with resident blocks); default 1 */
+int sdr_group_set_host_results(sdr_group *g, int on);
 
 #ifdef __cplusplus
 }

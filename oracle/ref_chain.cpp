@@ -149,7 +149,7 @@ API int ref_optimal_channel_count(long long sampleRate_in) {
 // ---------------------------------------------------------------------------------------------------------
 // one demodulator channel: DemodulatorPreThread + Modem + DemodulatorThread metering
 // ---------------------------------------------------------------------------------------------------------
-enum { M_FM = 0, M_NBFM = 1, M_AM = 2, M_USB = 3, M_LSB = 4 };
+enum { M_FM = 0, M_NBFM = 1, M_AM = 2, M_USB = 3, M_LSB = 4, M_IQ = 5 };
 
 struct RefChan {
     int modem;
@@ -173,6 +173,10 @@ struct RefChan {
     firhilbf c2rFilt;
     std::vector<lq_cf> in_buf, out_buf, resampled;
     std::vector<float> demodOut, audioOut;
+    // DemodulatorThread members (src/demod/DemodulatorThread.cpp:25-26): squelchLevel(-100), signalLevel(-100),
+    // signalFloor(-30), signalCeil(30), squelchEnabled(false)
+    float squelchLevel = -100, signalLevel = -100, signalFloor = -30, signalCeil = 30;
+    bool squelchEnabled = false, squelched = false;
 };
 
 static int modem_from_name(const char *n) {
@@ -182,6 +186,7 @@ static int modem_from_name(const char *n) {
     if (s == "AM") return M_AM;
     if (s == "USB") return M_USB;
     if (s == "LSB") return M_LSB;
+    if (s == "I/Q") return M_IQ;
     return -1;
 }
 
@@ -201,6 +206,7 @@ API void *ref_chan_create(const char *modem, long long sampleRate, long long ban
     c->modem = m;
     c->sampleRate = sampleRate;
     c->bandwidth = ref_modem_check_sample_rate(modem, bandwidth);
+    if (m == M_IQ) c->bandwidth = audioRate;                               // ModemIQ::checkSampleRate (ModemIQ.cpp:31-33)
     c->audioRate = audioRate;
     c->freqShifter = nco_crcf_create(0);                                   // DemodulatorPreThread.cpp:22
     c->shiftFrequency = 0;
@@ -238,6 +244,46 @@ API void ref_chan_destroy(void *h) {
 }
 
 API int ref_chan_bandwidth(void *h) { return ((RefChan *)h)->bandwidth; }
+
+// --- DemodulatorThread.cpp:142-163 (level) and :223-233 (peak); abMagnitude :49-58, linearToDb :60-67; then :165-198:
+// floor / ceiling trackers, smoothed level, squelch decision.  The members are std::atomic<float>; the arithmetic is the
+// reference's mixed float / double expressions, statement by statement.  c->audioOut holds the block's audio, c->resampled
+// the decimated IQ the modem was given.
+static int ref_chan_meter_block(RefChan *c, unsigned numAudioWritten, size_t bufSize, bool useSignalOutput, double *level_db, float *peak) {
+    const lq_cf *d = c->resampled.data();
+    double currentSignalLevel = 0;
+    double sampleTime = double(bufSize) / double(c->bandwidth);                              // :143 (inp->sampleRate = the modem rate)
+    if (numAudioWritten) {                                                                    // :145 `!ati->data.empty()`
+        double accum = 0;
+        if (useSignalOutput) {
+            for (unsigned i = 0; i < numAudioWritten; i++) { double v = (double)c->audioOut[i]; accum += sqrt(v * v + 0.0); }
+            accum /= double(numAudioWritten);
+        } else {
+            for (size_t i = 0; i < bufSize; i++) { double a = d[i].real, b = d[i].imag; accum += sqrt(a * a + b * b); }
+            accum /= double(bufSize);
+        }
+        if (accum <= 1e-20) accum = 1e-20;
+        currentSignalLevel = 20.0 * log10(accum);
+        float sf = c->signalFloor, sc = c->signalCeil, sl = c->squelchLevel;                 // :165
+        if (currentSignalLevel > sc) sc = currentSignalLevel;
+        if (currentSignalLevel < sf) sf = currentSignalLevel;
+        if (sl + 1.0f > sc) sc = sl + 1.0f;
+        if ((sf + 2.0f) > sc) sc = sf + 2.0f;
+        sc -= (sc - (currentSignalLevel + 2.0f)) * sampleTime * 0.05f;                        // :185
+        sf += ((currentSignalLevel - 5.0f) - sf) * sampleTime * 0.15f;                        // :186
+        c->signalFloor = sf; c->signalCeil = sc;
+    }
+    if (level_db) *level_db = currentSignalLevel;
+    if (currentSignalLevel > c->signalLevel) c->signalLevel = c->signalLevel + (currentSignalLevel - c->signalLevel) * 0.5;     // :192-196
+    else c->signalLevel = c->signalLevel + (currentSignalLevel - c->signalLevel) * 0.05 * sampleTime * 30.0;
+    c->squelched = c->squelchEnabled && (c->signalLevel < c->squelchLevel);                   // :198
+    if (peak) {                                                                               // :223-233
+        float p = 0;
+        for (unsigned i = 0; i < numAudioWritten; i++) { float a = fabs(c->audioOut[i]); if (a > p) p = a; }
+        *peak = p;
+    }
+    return 0;
+}
 
 // One block through the channel.  shift = demod frequency - block centre frequency.
 // Returns 0, or 1 if the block was skipped by the |shift| > 0.75 fs rule.
@@ -278,6 +324,13 @@ API int ref_chan_process(void *h, const lq_cf *block, unsigned n, long long shif
     // --- DemodulatorThread.cpp:120-140 -> Modem::demodulate
     size_t bufSize = numWritten;                                            // ModemAnalog::initOutputBuffers :42-65
     if (!bufSize) return 0;
+    if (c->modem == M_IQ) {                                                 // ModemIQ::demodulate (ModemIQ.cpp:39-56): channels = 2
+        c->audioOut.resize(bufSize * 2);
+        for (size_t i = 0; i < bufSize; i++) { c->audioOut[i * 2] = c->resampled[i].imag; c->audioOut[i * 2 + 1] = c->resampled[i].real; }
+        if (audio_out) memcpy(audio_out, c->audioOut.data(), bufSize * 2 * sizeof(float));
+        if (n_audio) *n_audio = (unsigned)(bufSize * 2);
+        return ref_chan_meter_block(c, (unsigned)(bufSize * 2), bufSize, false, level_db, peak);
+    }
     size_t audio_out_size = (size_t)ceil((double)bufSize * c->audioResampleRatio) + 512;
     c->demodOut.resize(bufSize);
     c->audioOut.resize(audio_out_size);
@@ -333,25 +386,20 @@ API int ref_chan_process(void *h, const lq_cf *block, unsigned n, long long shif
     if (audio_out) memcpy(audio_out, c->audioOut.data(), numAudioWritten * sizeof(float));
     if (n_audio) *n_audio = numAudioWritten;
 
-    // --- DemodulatorThread.cpp:142-163 (level) and :223-233 (peak); abMagnitude :49-58, linearToDb :60-67
-    if (numAudioWritten) {
-        double accum = 0;
-        if (useSignalOutput) {
-            for (unsigned i = 0; i < numAudioWritten; i++) { double v = (double)c->audioOut[i]; accum += sqrt(v * v + 0.0); }
-            accum /= double(numAudioWritten);
-        } else {
-            for (size_t i = 0; i < bufSize; i++) { double a = d[i].real, b = d[i].imag; accum += sqrt(a * a + b * b); }
-            accum /= double(bufSize);
-        }
-        if (accum <= 1e-20) accum = 1e-20;
-        if (level_db) *level_db = 20.0 * log10(accum);
-    } else if (level_db) *level_db = 0;
-    if (peak) {
-        float p = 0;
-        for (unsigned i = 0; i < numAudioWritten; i++) { float a = fabs(c->audioOut[i]); if (a > p) p = a; }
-        *peak = p;
-    }
-    return 0;
+    return ref_chan_meter_block(c, numAudioWritten, bufSize, useSignalOutput, level_db, peak);
+}
+
+// DemodulatorThread::setSquelchEnabled / setSquelchLevel (:384-397: setting a level switches the squelch on)
+API void ref_chan_set_squelch(void *h, int enabled, float level) {
+    auto *c = (RefChan *)h;
+    c->squelchEnabled = enabled != 0;
+    c->squelchLevel = level;
+}
+// getSignalLevel / getSignalFloor / getSignalCeil (:372-382) and AudioThreadInput::is_squelch_active of the last block (:235-238)
+API void ref_chan_meter(void *h, float *level_floor_ceil3, int *squelched) {
+    auto *c = (RefChan *)h;
+    if (level_floor_ceil3) { level_floor_ceil3[0] = c->signalLevel; level_floor_ceil3[1] = c->signalFloor; level_floor_ceil3[2] = c->signalCeil; }
+    if (squelched) *squelched = c->squelched ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -61,6 +61,8 @@ class Ref:
         L.ref_chan_create.restype = vp; L.ref_chan_create.argtypes = [C.c_char_p, ll, ll, i]
         L.ref_chan_destroy.argtypes = [vp]
         L.ref_chan_bandwidth.argtypes = [vp]
+        L.ref_chan_meter.argtypes = [vp, vp, vp]; L.ref_chan_meter.restype = None
+        L.ref_chan_set_squelch.argtypes = [vp, C.c_int, C.c_float]; L.ref_chan_set_squelch.restype = None
         L.ref_chan_process.argtypes = [vp, vp, u, ll, vp, vp, vp, vp, vp, vp, vp]
         L.ref_distrib_create.restype = vp; L.ref_distrib_create.argtypes = [u, u]
         L.ref_distrib_destroy.argtypes = [vp]
@@ -151,13 +153,19 @@ class RefChan:
         block = np.ascontiguousarray(block, np.complex64)
         n = block.size
         cap_iq = int(n * self.bandwidth / self.sample_rate) + 1024
-        cap_a = int(n * self.audio_rate / self.sample_rate) + 2048
+        cap_a = 2 * int(n * self.audio_rate / self.sample_rate) + 4096      # "I/Q" yields two floats per decimated sample
         iq = np.zeros(cap_iq, np.complex64); dm = np.zeros(cap_iq, np.float32); au = np.zeros(cap_a, np.float32)
         niq, na, lvl, pk = C.c_uint(), C.c_uint(), C.c_double(), C.c_float()
         skipped = self.ref.L.ref_chan_process(self.h, _p(block), n, int(shift), _p(iq), C.byref(niq), _p(dm), _p(au), C.byref(na),
                                               C.byref(lvl), C.byref(pk))
+        m3 = (C.c_float * 3)(); sq = C.c_int()
+        self.ref.L.ref_chan_meter(self.h, m3, C.byref(sq))
         return dict(skipped=bool(skipped), iq=iq[:niq.value].copy(), demod=dm[:niq.value].copy(), audio=au[:na.value].copy(),
-                    level_db=lvl.value, peak=pk.value)
+                    level_db=lvl.value, peak=pk.value, signal_level=m3[0], signal_floor=m3[1], signal_ceil=m3[2], squelched=bool(sq.value))
+
+    def set_squelch(self, enabled, level_db):
+        """DemodulatorThread::setSquelchEnabled / setSquelchLevel."""
+        self.ref.L.ref_chan_set_squelch(self.h, 1 if enabled else 0, C.c_float(level_db))
 
     def close(self):
         self.ref.L.ref_chan_destroy(self.h)

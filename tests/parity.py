@@ -25,7 +25,7 @@ def relrms(a, b):
 
 
 def run_channels(lib, ref, fs, chans, n_blocks, block=None, seed=1234, device=0, want_iq=True, retune=None, signal=None,
-                 resident=None, spectrum=0, audio_rate=48000, spec_out=None):
+                 resident=None, spectrum=0, audio_rate=48000, spec_out=None, squelch=None):
     """Stream n_blocks through engine and oracle.  chans: [(modem, bw, offset_hz)].
     Returns per-channel dict with concatenated audio / iq of both sides and per-block count equality."""
     N = block or synth.block_size(fs)
@@ -44,7 +44,10 @@ def run_channels(lib, ref, fs, chans, n_blocks, block=None, seed=1234, device=0,
     rcs = [RefChan(ref, m, fs, bw, audio_rate) for m, bw, off in chans]
     ing = RefIngress(ref)
     out = [dict(modem=m, audio=[], ref_audio=[], iq=[], ref_iq=[], counts_ok=True, lvl=[], ref_lvl=[], peak=[], ref_peak=[],
-                skipped=[], ref_skipped=[]) for m, _, _ in chans]
+                skipped=[], ref_skipped=[], meter=[], ref_meter=[], squelched=[], ref_squelched=[]) for m, _, _ in chans]
+    # squelch: {channel index: level in dB} -- DemodulatorThread::setSquelchLevel on both sides before the first block
+    for i, lvl_db in (squelch or {}).items():
+        cs[i].set_squelch(True, lvl_db); rcs[i].set_squelch(True, lvl_db)
     dc_err = []
     offs = [off for _, _, off in chans]
     for b in range(n_blocks):
@@ -84,6 +87,9 @@ def run_channels(lib, ref, fs, chans, n_blocks, block=None, seed=1234, device=0,
                     o["counts_ok"] = False
                 o["iq"].append(q); o["ref_iq"].append(r["iq"])
             o["lvl"].append(lvl); o["ref_lvl"].append(r["level_db"]); o["peak"].append(pk); o["ref_peak"].append(r["peak"])
+            m = c.fetch_meter()
+            o["meter"].append(m[:3]); o["ref_meter"].append((r["signal_level"], r["signal_floor"], r["signal_ceil"]))
+            o["squelched"].append(m[3]); o["ref_squelched"].append(r["squelched"])
     for o in out:
         for k in ("audio", "ref_audio", "iq", "ref_iq"):
             o[k] = np.concatenate(o[k]) if len(o[k]) else np.zeros(0)
@@ -113,6 +119,10 @@ def check_channels(out, tol=TOL):
             assert e <= tol, "%s: decimated IQ relative RMS error %.3g > %.1g" % (o["modem"], e, tol)
         assert np.allclose(o["lvl"], o["ref_lvl"], atol=2e-4), "%s: level metering differs" % o["modem"]
         assert np.allclose(o["peak"], o["ref_peak"], rtol=1e-4, atol=1e-6), "%s: peak differs" % o["modem"]
+        # DemodulatorThread's signalLevel / signalFloor / signalCeil trackers (float members) and the squelch decision
+        assert np.allclose(o["meter"], o["ref_meter"], rtol=0, atol=2e-4), "%s: squelch trackers differ: %r vs %r" % (
+            o["modem"], o["meter"][-1], o["ref_meter"][-1])
+        assert o["squelched"] == o["ref_squelched"], "%s: squelch decision differs" % o["modem"]
 
 
 def run_spectrum(lib, ref, fs, fft_size, n_blocks, chans, lps=0, block=None, seed=1234, device=0, avg_rate=None,

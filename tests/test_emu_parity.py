@@ -34,6 +34,30 @@ def test_retune_zero_shift_and_skip_rule(emu_lib, ref):
     assert any(out[2]["skipped"])
 
 
+def test_iq_modem(emu_lib, ref):
+    """ModemIQ ("I/Q", analog/ModemIQ.cpp): bandwidth = the audio rate, output = interleaved {imag, real} of the decimated IQ,
+    two channels, level metered on the IQ."""
+    import ctypes as C
+    chans = [("I/Q", 48000, 300000), ("FM", 200000, -250000), ("I/Q", 12345, -700000)]      # the requested bandwidth is ignored
+    out, _, _ = parity.run_channels(emu_lib, ref, 2400000, chans, n_blocks=5, signal=[("FM", 200000, 300000), ("FM", 200000, -250000), ("AM", 6000, -700000)])
+    parity.check_channels(out)
+    assert len(out[0]["audio"]) == 2 * len(out[0]["iq"]) > 0
+    assert np.array_equal(out[0]["audio"][0::2], out[0]["iq"].imag) and np.array_equal(out[0]["audio"][1::2], out[0]["iq"].real)
+    assert emu_lib.L.sdr_modem_check_sample_rate2(b"I/Q", 200000, 44100) == 44100
+
+
+def test_squelch_trackers_and_decision(emu_lib, ref):
+    """DemodulatorThread's floor / ceiling trackers, smoothed level and squelch gate (DemodulatorThread.cpp:165-198) with the
+    squelch set at different levels: some channels stay shut, some open as the smoothed level climbs from -100 dB."""
+    chans = [("FM", 200000, 300000), ("NBFM", 12500, -150000), ("AM", 6000, 450000), ("USB", 5400, -600000), ("FM", 200000, -800000)]
+    out, _, _ = parity.run_channels(emu_lib, ref, 2400000, chans, n_blocks=10, want_iq=False,
+                                    squelch={0: -25.0, 1: -5.0, 2: -40.0, 3: -70.0, 4: 10.0})
+    parity.check_channels(out)
+    sq = [o["squelched"] for o in out]
+    assert any(any(s) for s in sq) and any(not all(s) for s in sq)          # both outcomes occur
+    assert any(s[0] and not s[-1] for s in sq)                               # a squelch opens as the level rises
+
+
 def test_spectrum_small(emu_lib, ref):
     chans = synth.channel_plan("mixed", 2400000, 8)
     w = parity.run_spectrum(emu_lib, ref, 2400000, 1024, n_blocks=3, chans=chans)

@@ -23,6 +23,25 @@ def test_five_modems(gpu_lib, ref):
     parity.check_channels(out)
 
 
+def test_iq_modem(gpu_lib, ref):
+    """ModemIQ ("I/Q"): two-channel {imag, real} output of the decimated IQ at the audio rate."""
+    chans = [("I/Q", 48000, 300000), ("FM", 200000, -250000), ("I/Q", 12345, -700000)]
+    out, _, _ = parity.run_channels(gpu_lib, ref, 2400000, chans, n_blocks=5,
+                                    signal=[("FM", 200000, 300000), ("FM", 200000, -250000), ("AM", 6000, -700000)])
+    parity.check_channels(out)
+    assert len(out[0]["audio"]) == 2 * len(out[0]["iq"]) > 0
+
+
+def test_squelch_trackers_and_decision(gpu_lib, ref):
+    """DemodulatorThread.cpp:165-198 on the device: trackers and squelch decision equal the reference's, block by block."""
+    chans = [("FM", 200000, 300000), ("NBFM", 12500, -150000), ("AM", 6000, 450000), ("USB", 5400, -600000), ("FM", 200000, -800000)]
+    out, _, _ = parity.run_channels(gpu_lib, ref, 2400000, chans, n_blocks=10, want_iq=False,
+                                    squelch={0: -25.0, 1: -5.0, 2: -40.0, 3: -70.0, 4: 10.0})
+    parity.check_channels(out)
+    sq = [o["squelched"] for o in out]
+    assert any(any(s) for s in sq) and any(not all(s) for s in sq)
+
+
 def test_ragged_blocks_and_carry(gpu_lib, ref):
     out, _, _ = parity.run_channels(gpu_lib, ref, 2400000, FIVE[:3], n_blocks=5, block=40003)
     parity.check_channels(out)

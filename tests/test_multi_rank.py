@@ -1,6 +1,8 @@
 """world_size-2 test of the sharded path on CPU (gloo): rank 0 owns the raw block, broadcasts it, every rank runs its
 channel shard (kernel phases replayed by the test-only emulator), and the union of the shards equals the single-rank
-result bit for bit."""
+result bit for bit.  Mode 0 goes through the product's group API in its one-process-per-GPU form (sdr_group_create_rank
+without an NCCL id: gloo moves the block, the group does placement and submission); the channelizer modes drive the
+engines directly."""
 import os
 import sys
 
@@ -24,6 +26,27 @@ def _run_rank(rank, world, port, emu_path, out_dir, mode=0):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     lib = Lib(emu_path)
     N = synth.block_size(FS)
+    if mode == 0:
+        from cubicsdr_b200 import Group
+        g = Group(lib, max_block=N, rank=rank, world=world, nccl_id=None)
+        assert (g.n_local, g.total, g.transport) == (1, world, 0)
+        cs = [(idx, g.channel(m, FS, bw, 48000, frequency=100000000 + off)) for idx, (m, bw, off) in enumerate(CHANS)]
+        assert [c is not None for _, c in cs] == [idx % world == rank for idx, _ in cs]      # placement: channel c on rank c mod N
+        cs = [(idx, c) for idx, c in cs if c is not None]
+        res = {idx: [] for idx, _ in cs}
+        for b in range(NB):
+            blk = torch.zeros(N, dtype=torch.complex64)
+            if rank == 0:
+                blk = torch.from_numpy(synth.wideband(FS, N, CHANS, t0=b * N))
+            broadcast_block(dist, blk, src=0)
+            g.submit(blk.numpy(), 100000000, FS)
+            g.wait()
+            for idx, c in cs:
+                res[idx].append(c.fetch_audio()[0])
+        np.savez(os.path.join(out_dir, "rank%d.npz" % rank), **{str(k): np.concatenate(v) for k, v in res.items()})
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     eng = Engine(lib, max_block=N)
     chan_fs = FS
     if mode:                                                     # channelizer mode: every rank runs the filterbank on the block
