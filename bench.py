@@ -421,7 +421,12 @@ def run_engine_workload(cx, wl, chans, steps, warmup, min_seconds, channelizer=F
     ring = []
     carriers = chans if chans else synth.channel_plan("mixed", fs, 16)
     if rank == 0:
-        base = [torch_wideband(torch, fs, N, carriers, r * N, dev, 1234) for r in range(min(n_ring, 16))]
+        if cx.args.noise_inputs:                               # profiling runs: skip the per-carrier synthesis (thousands of launches)
+            gq = torch.Generator(device=dev); gq.manual_seed(5)
+            base = [(0.05 * torch.view_as_complex(torch.randn(N, 2, device=dev, generator=gq)) + complex(0.01, -0.02)).to(torch.complex64)
+                    for r in range(min(n_ring, 16))]
+        else:
+            base = [torch_wideband(torch, fs, N, carriers, r * N, dev, 1234) for r in range(min(n_ring, 16))]
         ring = list(base)
         g = torch.Generator(device=dev); g.manual_seed(77)
         while len(ring) < n_ring:                             # further distinct blocks: an earlier one plus fresh noise (cheap)
@@ -646,6 +651,7 @@ def main():
     ap.add_argument("--ring", type=int, default=16, help="least number of distinct input blocks rotated through (ring * block > L2 is enforced)")
     ap.add_argument("--min-seconds", type=float, default=1.0, help="the timed K-step region is repeated until this much has been measured")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--noise-inputs", action="store_true", help="profiling aid: noise-only input blocks (no per-carrier synthesis); not a contract line")
     ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE.json configurations (configs sub-object)")
     ap.add_argument("--channelizer", action="store_true",
                     help="diagnostic: run the engine in channelizer mode (SDRPostThread::runPFBCH, SURVEY.md 8(f) row 1) -- not a contract line")

@@ -20,6 +20,9 @@
 #include <string>
 #include <vector>
 
+#ifndef SDR_EMU
+#include <cuda.h>          // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, nothing links libcuda)
+#endif
 #include "../../include/sdr_b200.h"
 #include "design.h"
 #include "dsp_core.h"
@@ -301,6 +304,162 @@ __global__ void __launch_bounds__(32 * kDlWarps, 1) k_dc_lanes(DcExactArgs a) {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (s < a.n_seg) { a.seg_in[s] = v_in; a.seg_out[s] = v; }
 }
+// ---- TMA + mbarrier helpers (cp.async.bulk.tensor: SASS UTMALDG / UTMASTG; mbarrier: SYNCS) -----------------------------------
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap *map, int c0, int c1, unsigned bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int c1, unsigned src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(src) : "memory");
+}
+
+// The same replay fed by TMA.  The raw stream (from sample -W on) is described to the copy engine as a 2-D tensor of rows of
+// L samples: the lanes of a warp walk 32 consecutive rows in lock step, so ONE cp.async.bulk.tensor instruction per 16 steps
+// brings the next 16 samples of all 32 segments into a shared-memory box of 32 rows x 128 B; completion is counted on an
+// mbarrier per ring slot.  The 128-byte swizzle of the tensor map
+// (16-byte chunk index XOR row mod 8) is what makes the per-lane row reads conflict-free: lane l reads chunk c of its row at
+// l * 128 + ((c ^ (l & 7)) << 4).  Results leave the same way: a swizzled box per 16 steps, one cp.async.bulk.tensor store
+// issued by lane 0; rows past the last segment are clipped by the tensor's bounds.  Compared with k_dc_lanes the warp spends
+// no issue slots on copies or address arithmetic: ~0.7 instructions per step next to the four of the chain.
+constexpr int kDtBox = 16;                                    // samples per box row (128 B)
+constexpr int kDtBoxBytes = 32 * kDtBox * (int)sizeof(float2);   // 4096
+constexpr int kDtBatch = 2 * kDtBox;                          // steps per ring slot (two boxes)
+constexpr int kDtRing = 5;
+constexpr int kDtSmemWarp = (kDtRing + 1) * 2 * kDtBoxBytes;  // input ring + one output batch: 49152 B
+constexpr int kDtSmem = kDlWarps * kDtSmemWarp + 1024 + 256;  // + alignment slack + mbarriers
+__global__ void __launch_bounds__(32 * kDlWarps, 1)
+k_dc_lanes_tma(DcExactArgs a, const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map) {
+    extern __shared__ unsigned char dt_sm_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s0 = (blockIdx.x * kDlWarps + warp) * 32;              // first segment (tensor row) of this warp
+    if (s0 >= a.n_seg) return;
+    // swizzled boxes must sit on 1024-byte boundaries of the shared window
+    const unsigned raw_s = (unsigned)__cvta_generic_to_shared(dt_sm_raw);
+    const unsigned pad = (1024u - (raw_s & 1023u)) & 1023u;
+    unsigned char *wsm = dt_sm_raw + pad + (size_t)warp * kDtSmemWarp;
+    const unsigned ring_s = raw_s + pad + (unsigned)warp * kDtSmemWarp;                // [kDtRing][2 boxes][4096 B]
+    const unsigned out_s = ring_s + kDtRing * 2 * kDtBoxBytes;                         // [2 boxes][4096 B]
+    const unsigned bar_s = raw_s + pad + kDlWarps * kDtSmemWarp + (unsigned)warp * 64u;   // [kDtRing] mbarriers
+    const unsigned swz = (unsigned)(lane & 7) << 4;
+    const unsigned char *my_in = wsm + lane * 128;
+    unsigned char *my_out = wsm + kDtRing * 2 * kDtBoxBytes + lane * 128;
+    if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < kDtRing; ++r) mbar_init(bar_s + 8u * r, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const int L = a.seg_len, W = a.warm, n = a.n;
+    const int s = s0 + lane;
+    int i_begin = 0x7fffffff;                                        // lanes past the last segment never become active
+    float2 v = make_float2(0.f, 0.f);
+    if (s < a.n_seg) dc_exact_plan(a, s, i_begin, v);
+    const int p0 = s * L;
+    const int p1 = (s < a.n_seg) ? ((p0 + L < n) ? p0 + L : n) : p0;
+    const int d = p0 - W;                                            // this lane's sample at step 0 (= column 0 of its tensor row)
+    const int nb = (W + L) / kDtBatch;
+    const float c = a.c;
+    int fk = 0;
+    auto fetch = [&]() {
+        if (fk < nb && lane == 0) {
+            const int slot = fk % kDtRing;
+            const unsigned bar = bar_s + 8u * slot, dst = ring_s + (unsigned)(slot * 2 * kDtBoxBytes);
+            mbar_expect_tx(bar, 2u * kDtBoxBytes);
+            // step j of segment r is sample r L - W + j = element (row r + j / L, column j mod L) of the stream viewed as rows
+            // of L samples starting at sample -W; a 16-sample box never straddles rows (L is a multiple of 1024)
+            const int j0 = fk * kDtBatch, jr = j0 / L, jc = j0 - jr * L;
+            tma_load_2d(dst, &in_map, 2 * jc, s0 + jr, bar);                               // columns are floats: 2 per sample
+            tma_load_2d(dst + kDtBoxBytes, &in_map, 2 * (jc + kDtBox), s0 + jr, bar);
+        }
+        ++fk;
+    };
+#pragma unroll 1
+    for (int k = 0; k < kDtRing - 1; ++k) fetch();
+    float2 v_in = v, y;
+    const int kw = W / kDtBatch;                                     // batches [0, kw) warm up, [kw, nb) produce output
+#pragma unroll 1
+    for (int k = 0; k < nb; ++k) {
+        const int slot = k % kDtRing;
+        mbar_wait(bar_s + 8u * slot, (unsigned)((k / kDtRing) & 1));  // both boxes of batch k have landed
+        __syncwarp();                                                // every lane is done with batch k - 1: its slot may be refilled
+        fetch();
+        const unsigned char *row = my_in + slot * 2 * kDtBoxBytes;
+        const int base = d + k * kDtBatch;
+        // A lane is `on` (all 32 steps count), `off` (none does: it has not started, has finished, or owns no segment) or
+        // partial.  Without partial lanes the warp runs the unrolled chain on a copy of the state, which off lanes discard.
+        if (k < kw) {
+            const bool on = base >= i_begin, off = (long long)base + kDtBatch <= (long long)i_begin;
+            if (__all_sync(0xffffffffu, on || off)) {
+                float2 vv = v;
+#pragma unroll
+                for (int t = 0; t < kDtBatch / 2; ++t) {
+                    const float4 q = *reinterpret_cast<const float4 *>(row + (t >> 3) * kDtBoxBytes + (((unsigned)(t & 7) << 4) ^ swz));
+                    dc_ref_step(c, make_float2(q.x, q.y), vv, y);
+                    dc_ref_step(c, make_float2(q.z, q.w), vv, y);
+                }
+                if (on) v = vv;
+            } else {                                                 // a lane starts inside this batch (previous block's tile grid)
+                for (int t = 0; t < kDtBatch / 2; ++t) {
+                    const float4 q = *reinterpret_cast<const float4 *>(row + (t >> 3) * kDtBoxBytes + (((unsigned)(t & 7) << 4) ^ swz));
+                    if (base + 2 * t >= i_begin) dc_ref_step(c, make_float2(q.x, q.y), v, y);
+                    if (base + 2 * t + 1 >= i_begin) dc_ref_step(c, make_float2(q.z, q.w), v, y);
+                }
+            }
+            if (k == kw - 1) v_in = v;
+        } else {
+            const bool on = base + kDtBatch <= p1, off = base >= p1;
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous batch's results have left the tile
+            __syncwarp();
+            if (__all_sync(0xffffffffu, on || off)) {
+                float2 vv = v;
+#pragma unroll
+                for (int t = 0; t < kDtBatch / 2; ++t) {
+                    const unsigned o = (unsigned)(t >> 3) * kDtBoxBytes + (((unsigned)(t & 7) << 4) ^ swz);
+                    const float4 q = *reinterpret_cast<const float4 *>(row + o);
+                    float2 y0, y1;
+                    dc_ref_step(c, make_float2(q.x, q.y), vv, y0);
+                    dc_ref_step(c, make_float2(q.z, q.w), vv, y1);
+                    *reinterpret_cast<float4 *>(my_out + o) = make_float4(y0.x, y0.y, y1.x, y1.y);
+                }
+                if (on) v = vv;
+            } else {                                                 // the block ends inside this batch
+                for (int t = 0; t < kDtBatch / 2; ++t) {
+                    const unsigned o = (unsigned)(t >> 3) * kDtBoxBytes + (((unsigned)(t & 7) << 4) ^ swz);
+                    const float4 q = *reinterpret_cast<const float4 *>(row + o);
+                    float2 y0 = make_float2(0.f, 0.f), y1 = y0;
+                    if (base + 2 * t < p1) dc_ref_step(c, make_float2(q.x, q.y), v, y0);
+                    if (base + 2 * t + 1 < p1) dc_ref_step(c, make_float2(q.z, q.w), v, y1);
+                    *reinterpret_cast<float4 *>(my_out + o) = make_float4(y0.x, y0.y, y1.x, y1.y);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the tile was written through the generic proxy
+            __syncwarp();
+            if (lane == 0) {
+                const int col = 2 * ((k - kw) * kDtBatch);             // float column inside the segment
+                tma_store_2d(&out_map, col, s0, out_s);
+                tma_store_2d(&out_map, col + 2 * kDtBox, s0, out_s + kDtBoxBytes);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
+    if (s < a.n_seg) { a.seg_in[s] = v_in; a.seg_out[s] = v; }
+}
 // All junctions are compared in parallel; only when one of them fails (rare) does thread 0 walk them serially and replay.
 __global__ void __launch_bounds__(256) k_dc_verify(DcExactArgs a) {
     int bad = 0;
@@ -453,23 +612,68 @@ static void upload_params(void *dst, const void *src_pinned, size_t bytes, sdr_s
 #endif
 }
 
-static void launch_dc_exact(const DcExactArgs &a, sdr_stream_t s, unsigned long long &launches) {
+#ifndef SDR_EMU
+// cuTensorMapEncodeTiled is the one driver-API call the library needs: fetched through the runtime, nothing links libcuda
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tma_encoder() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        else cudaGetLastError();
+    }
+    return fn;
+}
+// rows of `row_samples` complex samples (as pairs of floats) starting at `base`; boxes of 16 samples x 32 rows, 128-byte swizzle
+static bool tma_rows_map(CUtensorMap *m, float2 *base, unsigned row_samples, unsigned long long rows) {
+    EncodeTiledFn enc = tma_encoder();
+    if (!enc || rows == 0) return false;
+    const cuuint64_t gdim[2] = {2ull * row_samples, rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)row_samples * sizeof(float2)};
+    const cuuint32_t box[2] = {2u * kDtBox, 32u};
+    const cuuint32_t estr[2] = {1u, 1u};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+#endif
+
+// tma_rows: samples readable from xraw[-warm] on (rows of the input tensor = that / seg_len); 0 = use the cp.async kernel
+static int launch_dc_exact(const DcExactArgs &a, unsigned long long tma_rows, sdr_stream_t s, unsigned long long &launches) {
 #ifndef SDR_EMU
     if (a.n_seg > 1) {                                          // one lane per segment, SM-exclusive CTAs of four warps
-        static bool attr_set = false;
-        if (!attr_set) { cudaFuncSetAttribute(k_dc_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, kDlSmem); attr_set = true; }
         const int warps = (a.n_seg + 31) / 32;
-        k_dc_lanes<<<(warps + kDlWarps - 1) / kDlWarps, 32 * kDlWarps, kDlSmem, s>>>(a);
+        static int use_tma = -1;
+        if (use_tma < 0) { const char *v = getenv("SDR_B200_DC_TMA"); use_tma = (v && v[0] == '0') ? 0 : 1; }
+        CUtensorMap in_map, out_map;
+        if (use_tma && tma_rows) {
+            if (!tma_rows_map(&in_map, const_cast<float2 *>(a.xraw) - a.warm, (unsigned)a.seg_len, tma_rows / (unsigned)a.seg_len) ||
+                !tma_rows_map(&out_map, a.y, (unsigned)a.seg_len, (unsigned long long)a.n_seg))
+                return fail(SDR_ERR_CUDA, "cuTensorMapEncodeTiled failed for the DC replay's stream tensors");
+            static bool attr_set = false;
+            if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(k_dc_lanes_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kDtSmem)); attr_set = true; }
+            k_dc_lanes_tma<<<(warps + kDlWarps - 1) / kDlWarps, 32 * kDlWarps, kDtSmem, s>>>(a, in_map, out_map);
+        } else {
+            static bool attr_set = false;
+            if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(k_dc_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, kDlSmem)); attr_set = true; }
+            k_dc_lanes<<<(warps + kDlWarps - 1) / kDlWarps, 32 * kDlWarps, kDlSmem, s>>>(a);
+        }
     } else {
         k_dc_exact<<<1, 32, 0, s>>>(a);
     }
     k_dc_verify<<<1, 256, 0, s>>>(a);
 #else
-    (void)s;
+    (void)s; (void)tma_rows;
     for (int g = 0; g < a.n_seg; ++g) dc_exact_segment_serial(a, g, false, make_float2(0.f, 0.f));
     dc_exact_verify(a);
 #endif
     launches += 2;
+    return SDR_OK;
 }
 
 // double-precision scan of the recurrence: tile sums + carries always (they seed the bit-exact replay), and the direct
@@ -880,7 +1084,9 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
     e->hist_cap = 65536 + kBlkHist;
     int bad = 0;
     bad |= be_malloc((void **)&e->d_raw, (size_t)max_block * sizeof(float2));
-    for (int b = 0; b < 2; ++b) bad |= be_malloc((void **)&e->d_blkbuf[b], (e->hist_cap + max_block) * sizeof(float2));
+    e->raw_pad = (size_t)max_block / 8 + 2 * 65536;
+    // (padded like the raw buffer: the TMA store of the DC replay writes the last, partial segment as a whole row)
+    for (int b = 0; b < 2; ++b) bad |= be_malloc((void **)&e->d_blkbuf[b], (e->hist_cap + max_block + e->raw_pad) * sizeof(float2));
     // the DC replay's lanes past the end of a block still stage (unused) samples of their streams: pad instead of guarding
     e->raw_pad = (size_t)max_block / 8 + 2 * 65536;
     bad |= be_malloc((void **)&e->d_rawbuf, (e->hist_cap + max_block + e->raw_pad) * sizeof(float2));
@@ -960,7 +1166,7 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
     bad |= be_malloc((void **)&e->d_results, e->results_bytes);
     bad |= be_host_alloc((void **)&e->h_results, kResBuf * e->results_bytes);
     if (bad) { delete e; return fail(SDR_ERR_NOMEM, "sdr_engine_create: allocation failed"); }
-    for (int b = 0; b < 2; ++b) be_memset(e->d_blkbuf[b], 0, (e->hist_cap + max_block) * sizeof(float2), e->stream);
+    for (int b = 0; b < 2; ++b) be_memset(e->d_blkbuf[b], 0, (e->hist_cap + max_block + e->raw_pad) * sizeof(float2), e->stream);
     be_memset(e->d_rawbuf, 0, (e->hist_cap + max_block + e->raw_pad) * sizeof(float2), e->stream);
     be_memset(e->d_fstate, 0, sizeof(float2), e->stream);
     be_memset(e->d_fixups, 0, sizeof(unsigned), e->stream);
@@ -1808,7 +2014,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
             const bool spec = n >= (unsigned)kDcMinSpec && n > seg && (!e->have_block || e->last_n >= (unsigned)(kDcWarm + kDcTile));
             xa.n_seg = spec ? (int)((n + seg - 1) / seg) : 1;
             if (!spec) xa.seg_len = (int)n;
-            launch_dc_exact(xa, dcs, e->launches);
+            { int r = launch_dc_exact(xa, (unsigned long long)kDcWarm + e->max_block + e->raw_pad, dcs, e->launches); if (r) return r; }
         }
     }
     // history in front of the block: the tail of the previous block, which lives in the other buffer
