@@ -465,12 +465,14 @@ def run_engine_workload(cx, wl, chans, steps, warmup, min_seconds, channelizer=F
             eng.submit_ptr(host_blocks[i % 4][1], N, CENTER, fs)
 
     def fetch_e2e():
+        # the block's results were DMA'd to the engine's pinned host buffer; the batch "view" calls hand out pointers, counts,
+        # levels and peaks for every channel (what the host's audio sink consumes) without another copy
         nbytes = 0
         if cobjs:
-            audio, n_audio, _, _ = eng.fetch_audio_batch(cobjs, 1024)
+            ptrs, n_audio, _, _ = eng.view_audio_batch(cobjs)
             nbytes += int(n_audio.sum()) * 4
         if spec is not None:
-            pts, lines, cf = spec.fetch_all(64)
+            pts, lines = spec.view()
             nbytes += pts.nbytes + lines.nbytes
         return nbytes
 
@@ -618,7 +620,7 @@ def run_engine_workload(cx, wl, chans, steps, warmup, min_seconds, channelizer=F
         res = {"value": value, "ms_per_step": ms / steps, "reps": reps, "rep_ms_min_max": [min(rep_ms), max(rep_ms)],
                "e2e": {"value": e2e_value, "unit": "MSamples/s", "h2d_bytes_per_step": N * 8, "d2h_bytes_per_step": d2h,
                        "reps": e2e_reps,
-                       "api": "sdr_engine_submit(pinned host block) + sdr_engine_wait_block(2) + sdr_engine_fetch_audio_batch / sdr_spectrum_fetch_all"
+                       "api": "sdr_engine_submit(pinned host block) + sdr_engine_wait_block(2) + sdr_engine_view_audio_batch / sdr_spectrum_view (results DMA'd to pinned host memory)"
                               if world == 1 else "sdr_group_submit(pinned host block on rank 0: DMA + one ncclBroadcast inside) + sdr_engine_wait_block(2) + batched fetch"},
                "gpu_launches": int(launches), "roofline": roofline, "N": N, "c_local": c_local, "desc": desc,
                "l2": "%d distinct %.1f MB input blocks rotate (%.0f MB > 126 MB L2)" % (n_ring, N * 8 / 1e6, n_ring * N * 8 / 1e6),

@@ -20,7 +20,7 @@ SYMBOLS = [
     "sdr_engine_wait_block",
     "sdr_engine_fetch_block", "sdr_engine_launch_count", "sdr_engine_set_timing", "sdr_engine_get_timing",
     "sdr_chan_create", "sdr_chan_destroy", "sdr_chan_set_frequency", "sdr_chan_get_bandwidth", "sdr_chan_want_iq",
-    "sdr_chan_fetch_audio", "sdr_chan_fetch_iq", "sdr_engine_fetch_audio_batch",
+    "sdr_chan_fetch_audio", "sdr_chan_fetch_iq", "sdr_engine_fetch_audio_batch", "sdr_engine_view_audio_batch", "sdr_spectrum_view",
     "sdr_modem_check_sample_rate", "sdr_modem_create", "sdr_modem_demodulate",
     "sdr_spectrum_create", "sdr_spectrum_destroy", "sdr_spectrum_set_average_rate", "sdr_spectrum_frames",
     "sdr_spectrum_fetch", "sdr_spectrum_fetch_all", "sdr_spectrum_fetch_debug",
@@ -77,6 +77,8 @@ class Lib:
         L.sdr_chan_fetch_audio.argtypes = [vp, vp, u, P(u), P(d), P(f), P(i)]
         L.sdr_chan_fetch_iq.argtypes = [vp, vp, u, P(u)]
         L.sdr_engine_fetch_audio_batch.argtypes = [vp, vp, u, vp, u, vp, vp, vp]
+        L.sdr_engine_view_audio_batch.argtypes = [vp, vp, u, vp, vp, vp, vp]
+        L.sdr_spectrum_view.argtypes = [vp, P(vp), P(vp), P(u)]
         L.sdr_modem_check_sample_rate.argtypes = [C.c_char_p, ll]
         L.sdr_modem_create.argtypes = [vp, C.c_char_p, ll, i, u, P(vp)]
         L.sdr_modem_demodulate.argtypes = [vp, vp, u, vp, u, P(u), P(d), P(f)]
@@ -237,6 +239,27 @@ class Engine:
                                                                _ptr(self._batch_n), _ptr(self._batch_lvl), _ptr(self._batch_pk)))
         return self._batch_audio, self._batch_n, self._batch_lvl, self._batch_pk
 
+    def view_audio_batch(self, chans):
+        """Zero-copy batch fetch: (pointers[n_chan] as uint64, n_audio[n_chan], level_db[n_chan], peak[n_chan]); the audio stays in
+        the engine's pinned result buffer (valid until two further blocks have been submitted)."""
+        n = len(chans)
+        key = (tuple(c.h.value for c in chans),)
+        if getattr(self, "_view_key", None) != key:
+            self._view_key = key
+            self._view_h = (C.c_void_p * n)(*[c.h for c in chans])
+            self._view_ptr = np.zeros(n, np.uint64)
+            self._view_n = np.zeros(n, np.uint32)
+            self._view_lvl = np.zeros(n, np.float64)
+            self._view_pk = np.zeros(n, np.float32)
+        self.lib.check(self.lib.L.sdr_engine_view_audio_batch(self.h, self._view_h, n, _ptr(self._view_ptr), _ptr(self._view_n),
+                                                              _ptr(self._view_lvl), _ptr(self._view_pk)))
+        return self._view_ptr, self._view_n, self._view_lvl, self._view_pk
+
+    @staticmethod
+    def audio_at(ptr, n):
+        """numpy view of n floats at a pointer returned by view_audio_batch"""
+        return np.frombuffer((C.c_float * int(n)).from_address(int(ptr)), dtype=np.float32)
+
     def set_timing(self, on=True):
         self.lib.check(self.lib.L.sdr_engine_set_timing(self.h, 1 if on else 0))
 
@@ -339,6 +362,16 @@ class Spectrum:
                                                          _ptr(self._all_cf), C.byref(n)))
         m = min(n.value, cap_frames)
         return self._all_pts[:m], self._all_lines[:m], self._all_cf[:m]
+
+    def view(self):
+        """Zero-copy: (points[n_frames, fft_size] float32, lines[n_frames, fft_size] uint8) views of the pinned result buffer."""
+        pp, pl, n = C.c_void_p(), C.c_void_p(), C.c_uint()
+        self.lib.check(self.lib.L.sdr_spectrum_view(self.h, C.byref(pp), C.byref(pl), C.byref(n)))
+        if not n.value:
+            return np.zeros((0, self.fft_size), np.float32), np.zeros((0, self.fft_size), np.uint8)
+        pts = np.frombuffer((C.c_float * (n.value * self.fft_size)).from_address(pp.value), dtype=np.float32).reshape(n.value, self.fft_size)
+        lines = np.frombuffer((C.c_ubyte * (n.value * self.fft_size)).from_address(pl.value), dtype=np.uint8).reshape(n.value, self.fft_size)
+        return pts, lines
 
     def fetch_debug(self, idx):
         mags = np.zeros(2 * self.fft_size, np.float32)

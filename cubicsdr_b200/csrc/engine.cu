@@ -327,20 +327,45 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int
                  ::"l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(src) : "memory");
 }
 
+__device__ __forceinline__ unsigned mbar_test(unsigned bar, unsigned parity) {       // non-blocking probe
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
+
 // The same replay fed by TMA.  The raw stream (from sample -W on) is described to the copy engine as a 2-D tensor of rows of
 // L samples: the lanes of a warp walk 32 consecutive rows in lock step, so ONE cp.async.bulk.tensor instruction per 16 steps
 // brings the next 16 samples of all 32 segments into a shared-memory box of 32 rows x 128 B; completion is counted on an
-// mbarrier per ring slot.  The 128-byte swizzle of the tensor map
+// mbarrier per ring slot (a slot = 64 steps = four boxes; three slots in flight).  The 128-byte swizzle of the tensor map
 // (16-byte chunk index XOR row mod 8) is what makes the per-lane row reads conflict-free: lane l reads chunk c of its row at
-// l * 128 + ((c ^ (l & 7)) << 4).  Results leave the same way: a swizzled box per 16 steps, one cp.async.bulk.tensor store
-// issued by lane 0; rows past the last segment are clipped by the tensor's bounds.  Compared with k_dc_lanes the warp spends
-// no issue slots on copies or address arithmetic: ~0.7 instructions per step next to the four of the chain.
+// l * 128 + ((c ^ (l & 7)) << 4).  Results leave the same way: swizzled boxes, cp.async.bulk.tensor stores issued by lane 0;
+// rows past the last segment are clipped by the tensor's bounds.  The serial chain is the only thing the warp really does:
+// per 64 steps it spends a few dozen instructions on the ring (no divisions, no per-sample copies), the barrier of the next
+// slot is probed while the current one is being consumed, and the first samples of the next slot are loaded before the
+// current chain ends.
 constexpr int kDtBox = 16;                                    // samples per box row (128 B)
 constexpr int kDtBoxBytes = 32 * kDtBox * (int)sizeof(float2);   // 4096
-constexpr int kDtBatch = 2 * kDtBox;                          // steps per ring slot (two boxes)
-constexpr int kDtRing = 5;
-constexpr int kDtSmemWarp = (kDtRing + 1) * 2 * kDtBoxBytes;  // input ring + one output batch: 49152 B
-constexpr int kDtSmem = kDlWarps * kDtSmemWarp + 1024 + 256;  // + alignment slack + mbarriers
+constexpr int kDtBoxes = 4;                                   // boxes per ring slot
+constexpr int kDtBatch = kDtBoxes * kDtBox;                   // 64 steps per slot
+constexpr int kDtSlotBytes = kDtBoxes * kDtBoxBytes;          // 16384
+constexpr int kDtRing = 3;
+constexpr int kDtSmemWarp = kDtRing * kDtSlotBytes + 2 * kDtBoxBytes;   // input ring + an output tile of 32 steps: 57344 B
+constexpr int kDtSmem = kDlWarps * kDtSmemWarp + 1024 + 256;  // + alignment slack + mbarriers = 230656 B
+// 32 steps (two boxes at `row`) of the chain for one lane; `first` = its first two float4 (already loaded)
+template <bool kStore>
+__device__ __forceinline__ void dt_half(const unsigned char *row, unsigned char *out, unsigned swz, float c, float2 &v,
+                                        float4 q0, float4 q1) {
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+        const unsigned o = (unsigned)(t >> 3) * kDtBoxBytes + (((unsigned)(t & 7) << 4) ^ swz);
+        const float4 q = t == 0 ? q0 : (t == 1 ? q1 : *reinterpret_cast<const float4 *>(row + o));
+        float2 y0, y1;
+        dc_ref_step(c, make_float2(q.x, q.y), v, y0);
+        dc_ref_step(c, make_float2(q.z, q.w), v, y1);
+        if (kStore) *reinterpret_cast<float4 *>(out + o) = make_float4(y0.x, y0.y, y1.x, y1.y);
+    }
+}
 __global__ void __launch_bounds__(32 * kDlWarps, 1)
 k_dc_lanes_tma(DcExactArgs a, const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map) {
     extern __shared__ unsigned char dt_sm_raw[];
@@ -351,12 +376,12 @@ k_dc_lanes_tma(DcExactArgs a, const __grid_constant__ CUtensorMap in_map, const 
     const unsigned raw_s = (unsigned)__cvta_generic_to_shared(dt_sm_raw);
     const unsigned pad = (1024u - (raw_s & 1023u)) & 1023u;
     unsigned char *wsm = dt_sm_raw + pad + (size_t)warp * kDtSmemWarp;
-    const unsigned ring_s = raw_s + pad + (unsigned)warp * kDtSmemWarp;                // [kDtRing][2 boxes][4096 B]
-    const unsigned out_s = ring_s + kDtRing * 2 * kDtBoxBytes;                         // [2 boxes][4096 B]
+    const unsigned ring_s = raw_s + pad + (unsigned)warp * kDtSmemWarp;                // [kDtRing][4 boxes][4096 B]
+    const unsigned out_s = ring_s + kDtRing * kDtSlotBytes;                            // [2 boxes][4096 B]
     const unsigned bar_s = raw_s + pad + kDlWarps * kDtSmemWarp + (unsigned)warp * 64u;   // [kDtRing] mbarriers
     const unsigned swz = (unsigned)(lane & 7) << 4;
     const unsigned char *my_in = wsm + lane * 128;
-    unsigned char *my_out = wsm + kDtRing * 2 * kDtBoxBytes + lane * 128;
+    unsigned char *my_out = wsm + kDtRing * kDtSlotBytes + lane * 128;
     if (lane == 0) {
 #pragma unroll
         for (int r = 0; r < kDtRing; ++r) mbar_init(bar_s + 8u * r, 1u);
@@ -370,49 +395,66 @@ k_dc_lanes_tma(DcExactArgs a, const __grid_constant__ CUtensorMap in_map, const 
     if (s < a.n_seg) dc_exact_plan(a, s, i_begin, v);
     const int p0 = s * L;
     const int p1 = (s < a.n_seg) ? ((p0 + L < n) ? p0 + L : n) : p0;
-    const int d = p0 - W;                                            // this lane's sample at step 0 (= column 0 of its tensor row)
+    const int d = p0 - W;                                            // this lane's sample at step 0
     const int nb = (W + L) / kDtBatch;
+    const int kw = W / kDtBatch;                                     // batches [0, kw) warm up, [kw, nb) produce output
     const float c = a.c;
-    int fk = 0;
+    // ---- producer side (lane 0 issues; the running coordinates are warp-uniform): step j of segment r is sample r L - W + j =
+    //      element (row r + j / L, column j mod L) of the stream viewed as rows of L samples starting at sample -W; a box never
+    //      straddles rows (L is a multiple of 1024)
+    int fk = 0, f_slot = 0, f_col = 0, f_row = s0;
     auto fetch = [&]() {
         if (fk < nb && lane == 0) {
-            const int slot = fk % kDtRing;
-            const unsigned bar = bar_s + 8u * slot, dst = ring_s + (unsigned)(slot * 2 * kDtBoxBytes);
-            mbar_expect_tx(bar, 2u * kDtBoxBytes);
-            // step j of segment r is sample r L - W + j = element (row r + j / L, column j mod L) of the stream viewed as rows
-            // of L samples starting at sample -W; a 16-sample box never straddles rows (L is a multiple of 1024)
-            const int j0 = fk * kDtBatch, jr = j0 / L, jc = j0 - jr * L;
-            tma_load_2d(dst, &in_map, 2 * jc, s0 + jr, bar);                               // columns are floats: 2 per sample
-            tma_load_2d(dst + kDtBoxBytes, &in_map, 2 * (jc + kDtBox), s0 + jr, bar);
+            const unsigned bar = bar_s + 8u * (unsigned)f_slot, dst = ring_s + (unsigned)(f_slot * kDtSlotBytes);
+            mbar_expect_tx(bar, (unsigned)kDtSlotBytes);
+#pragma unroll
+            for (int b = 0; b < kDtBoxes; ++b) tma_load_2d(dst + b * kDtBoxBytes, &in_map, 2 * (f_col + b * kDtBox), f_row, bar);   // columns are floats
         }
         ++fk;
+        f_col += kDtBatch;
+        if (f_col >= L) { f_col = 0; ++f_row; }
+        f_slot = (f_slot + 1 == kDtRing) ? 0 : f_slot + 1;
     };
 #pragma unroll 1
     for (int k = 0; k < kDtRing - 1; ++k) fetch();
-    float2 v_in = v, y;
-    const int kw = W / kDtBatch;                                     // batches [0, kw) warm up, [kw, nb) produce output
+    // ---- consumer side
+    float2 v_in = v;
+    int c_slot = 0;
+    unsigned c_par = 0, ready = 0;
+    float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
+    bool have_q = false;
 #pragma unroll 1
     for (int k = 0; k < nb; ++k) {
-        const int slot = k % kDtRing;
-        mbar_wait(bar_s + 8u * slot, (unsigned)((k / kDtRing) & 1));  // both boxes of batch k have landed
+        const unsigned bar = bar_s + 8u * (unsigned)c_slot;
+        while (!ready) {                                             // normally known already from the probe of the previous round
+            mbar_wait(bar, c_par);
+            ready = 1;
+        }
         __syncwarp();                                                // every lane is done with batch k - 1: its slot may be refilled
         fetch();
-        const unsigned char *row = my_in + slot * 2 * kDtBoxBytes;
+        const int n_slot = (c_slot + 1 == kDtRing) ? 0 : c_slot + 1;
+        const unsigned n_par = n_slot == 0 ? (c_par ^ 1u) : c_par;
+        // probe the next slot now; the answer is needed only after this batch's chain
+        unsigned ready_next = (k + 1 < nb) ? mbar_test(bar_s + 8u * (unsigned)n_slot, n_par) : 0u;
+        const unsigned char *row = my_in + c_slot * kDtSlotBytes;
+        if (!have_q) {
+            q0 = *reinterpret_cast<const float4 *>(row + swz);
+            q1 = *reinterpret_cast<const float4 *>(row + (16u ^ swz));
+        }
         const int base = d + k * kDtBatch;
-        // A lane is `on` (all 32 steps count), `off` (none does: it has not started, has finished, or owns no segment) or
+        // A lane is `on` (all 64 steps count), `off` (none does: it has not started, has finished, or owns no segment) or
         // partial.  Without partial lanes the warp runs the unrolled chain on a copy of the state, which off lanes discard.
         if (k < kw) {
             const bool on = base >= i_begin, off = (long long)base + kDtBatch <= (long long)i_begin;
             if (__all_sync(0xffffffffu, on || off)) {
                 float2 vv = v;
-#pragma unroll
-                for (int t = 0; t < kDtBatch / 2; ++t) {
-                    const float4 q = *reinterpret_cast<const float4 *>(row + (t >> 3) * kDtBoxBytes + (((unsigned)(t & 7) << 4) ^ swz));
-                    dc_ref_step(c, make_float2(q.x, q.y), vv, y);
-                    dc_ref_step(c, make_float2(q.z, q.w), vv, y);
-                }
+                dt_half<false>(row, nullptr, swz, c, vv, q0, q1);
+                const unsigned char *row2 = row + 2 * kDtBoxBytes;
+                dt_half<false>(row2, nullptr, swz, c, vv, *reinterpret_cast<const float4 *>(row2 + swz),
+                               *reinterpret_cast<const float4 *>(row2 + (16u ^ swz)));
                 if (on) v = vv;
             } else {                                                 // a lane starts inside this batch (previous block's tile grid)
+                float2 y;
                 for (int t = 0; t < kDtBatch / 2; ++t) {
                     const float4 q = *reinterpret_cast<const float4 *>(row + (t >> 3) * kDtBoxBytes + (((unsigned)(t & 7) << 4) ^ swz));
                     if (base + 2 * t >= i_begin) dc_ref_step(c, make_float2(q.x, q.y), v, y);
@@ -421,40 +463,48 @@ k_dc_lanes_tma(DcExactArgs a, const __grid_constant__ CUtensorMap in_map, const 
             }
             if (k == kw - 1) v_in = v;
         } else {
-            const bool on = base + kDtBatch <= p1, off = base >= p1;
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous batch's results have left the tile
-            __syncwarp();
-            if (__all_sync(0xffffffffu, on || off)) {
-                float2 vv = v;
-#pragma unroll
-                for (int t = 0; t < kDtBatch / 2; ++t) {
-                    const unsigned o = (unsigned)(t >> 3) * kDtBoxBytes + (((unsigned)(t & 7) << 4) ^ swz);
-                    const float4 q = *reinterpret_cast<const float4 *>(row + o);
-                    float2 y0, y1;
-                    dc_ref_step(c, make_float2(q.x, q.y), vv, y0);
-                    dc_ref_step(c, make_float2(q.z, q.w), vv, y1);
-                    *reinterpret_cast<float4 *>(my_out + o) = make_float4(y0.x, y0.y, y1.x, y1.y);
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {                            // the output tile holds 32 steps: two rounds per slot
+                const int hb = base + h * (kDtBatch / 2);
+                const unsigned char *rowh = row + h * 2 * kDtBoxBytes;
+                const bool on = hb + kDtBatch / 2 <= p1, off = hb >= p1;
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous results have left the tile
+                __syncwarp();
+                if (__all_sync(0xffffffffu, on || off)) {
+                    float2 vv = v;
+                    dt_half<true>(rowh, my_out, swz, c, vv, *reinterpret_cast<const float4 *>(rowh + swz),
+                                  *reinterpret_cast<const float4 *>(rowh + (16u ^ swz)));
+                    if (on) v = vv;
+                } else {                                             // the block ends inside these 32 steps
+                    for (int t = 0; t < kDtBatch / 4; ++t) {
+                        const unsigned o = (unsigned)(t >> 3) * kDtBoxBytes + (((unsigned)(t & 7) << 4) ^ swz);
+                        const float4 q = *reinterpret_cast<const float4 *>(rowh + o);
+                        float2 y0 = make_float2(0.f, 0.f), y1 = y0;
+                        if (hb + 2 * t < p1) dc_ref_step(c, make_float2(q.x, q.y), v, y0);
+                        if (hb + 2 * t + 1 < p1) dc_ref_step(c, make_float2(q.z, q.w), v, y1);
+                        *reinterpret_cast<float4 *>(my_out + o) = make_float4(y0.x, y0.y, y1.x, y1.y);
+                    }
                 }
-                if (on) v = vv;
-            } else {                                                 // the block ends inside this batch
-                for (int t = 0; t < kDtBatch / 2; ++t) {
-                    const unsigned o = (unsigned)(t >> 3) * kDtBoxBytes + (((unsigned)(t & 7) << 4) ^ swz);
-                    const float4 q = *reinterpret_cast<const float4 *>(row + o);
-                    float2 y0 = make_float2(0.f, 0.f), y1 = y0;
-                    if (base + 2 * t < p1) dc_ref_step(c, make_float2(q.x, q.y), v, y0);
-                    if (base + 2 * t + 1 < p1) dc_ref_step(c, make_float2(q.z, q.w), v, y1);
-                    *reinterpret_cast<float4 *>(my_out + o) = make_float4(y0.x, y0.y, y1.x, y1.y);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the tile was written through the generic proxy
+                __syncwarp();
+                if (lane == 0) {
+                    const int col = 2 * ((k - kw) * kDtBatch + h * (kDtBatch / 2));   // float column inside the segment
+                    tma_store_2d(&out_map, col, s0, out_s);
+                    tma_store_2d(&out_map, col + 2 * kDtBox, s0, out_s + kDtBoxBytes);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the tile was written through the generic proxy
-            __syncwarp();
-            if (lane == 0) {
-                const int col = 2 * ((k - kw) * kDtBatch);             // float column inside the segment
-                tma_store_2d(&out_map, col, s0, out_s);
-                tma_store_2d(&out_map, col + 2 * kDtBox, s0, out_s + kDtBoxBytes);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         }
+        // the first samples of the next slot, if it is known to have landed (else the top of the loop waits and loads them)
+        have_q = false;
+        if (ready_next) {
+            const unsigned char *nrow = my_in + n_slot * kDtSlotBytes;
+            q0 = *reinterpret_cast<const float4 *>(nrow + swz);
+            q1 = *reinterpret_cast<const float4 *>(nrow + (16u ^ swz));
+            have_q = true;
+        }
+        ready = ready_next;
+        c_slot = n_slot; c_par = n_par;
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     __syncwarp();
@@ -2599,6 +2649,27 @@ extern "C" int sdr_engine_fetch_audio_batch(sdr_engine *e, sdr_chan *const *chan
     return SDR_OK;
 }
 
+// Zero-copy form of the batch fetch: pointers into the pinned host buffer the block's results were DMA'd to.  They stay valid
+// until two further blocks have been submitted (the ring of three result buffers); a host that hands the samples on at once
+// (AudioThread mixes them into its own buffer, src/audio/AudioThread.cpp:88-243) needs no intermediate copy.
+extern "C" int sdr_engine_view_audio_batch(sdr_engine *e, sdr_chan *const *chans, unsigned n_chan, const float **audio,
+                                           unsigned *n_audio, double *level_db, float *peak) {
+    if (!e || !chans) return fail(SDR_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!e->res_on_host[e->fetch_sel] || !e->h_results) return fail(SDR_ERR_STATE, "no host results for the last block");
+    for (unsigned i = 0; i < n_chan; ++i) {
+        const sdr_chan *c = chans[i];
+        if (!c || c->eng != e) return fail(SDR_ERR_ARG, "channel does not belong to this engine");
+        const unsigned char *slot = e->hres(e->fetch_sel) + c->cs.res_off;
+        const ChanResultHeader *h = reinterpret_cast<const ChanResultHeader *>(slot);
+        if (audio) audio[i] = reinterpret_cast<const float *>(slot + kResHdrBytes);
+        if (n_audio) n_audio[i] = std::min(h->n_audio, (unsigned)c->cs.res_audio_cap);
+        if (level_db) level_db[i] = h->level_db;
+        if (peak) peak[i] = h->peak;
+    }
+    return SDR_OK;
+}
+
 extern "C" int sdr_chan_fetch_iq(sdr_chan *c, sdr_cf32 *iq, unsigned cap, unsigned *n_iq) {
     if (!c) return fail(SDR_ERR_ARG, "null channel");
     sdr_engine *e = c->eng;
@@ -2640,6 +2711,18 @@ extern "C" int sdr_spectrum_fetch_all(sdr_spectrum *s, unsigned cap_frames, floa
     if (points_y) memcpy(points_y, s->hp(q), (size_t)m * s->fft_size * sizeof(float));
     if (lines) memcpy(lines, s->hl(q), (size_t)m * s->fft_size);
     if (cf) for (unsigned f = 0; f < m; ++f) { cf[2 * f] = s->hc(q)[f].x; cf[2 * f + 1] = s->hc(q)[f].y; }
+    if (n_frames) *n_frames = s->frames_buf[q];
+    return SDR_OK;
+}
+
+// zero-copy form: the frames of the fetched block where the DMA left them ([n_frames][fft_size] each), same lifetime as above
+extern "C" int sdr_spectrum_view(sdr_spectrum *s, const float **points_y, const uint8_t **lines, unsigned *n_frames) {
+    if (!s) return fail(SDR_ERR_ARG, "null spectrum");
+    std::lock_guard<std::mutex> lk(s->eng->mu);
+    const int q = s->eng->fetch_sel;
+    if (!s->eng->res_on_host[q]) return fail(SDR_ERR_STATE, "no host results for the last block");
+    if (points_y) *points_y = s->hp(q);
+    if (lines) *lines = s->hl(q);
     if (n_frames) *n_frames = s->frames_buf[q];
     return SDR_OK;
 }

@@ -120,6 +120,11 @@ int sdr_chan_fetch_meter(sdr_chan *ch, float *signal_level, float *signal_floor,
 int sdr_engine_fetch_audio_batch(sdr_engine *eng, sdr_chan *const *chans, unsigned n_chan, float *audio, unsigned stride,
                                  unsigned *n_audio, double *level_db, float *peak);
 
+/* Zero-copy form: audio[i] points into the pinned host buffer the block's results were DMA'd to (n_audio[i] floats).  The
+ * pointers stay valid until two further blocks have been submitted.  For hosts that pass the samples on at once.         */
+int sdr_engine_view_audio_batch(sdr_engine *eng, sdr_chan *const *chans, unsigned n_chan, const float **audio,
+                                unsigned *n_audio, double *level_db, float *peak);
+
 /* ---- Modem plugin seam: one call = Modem::demodulate(kit, input, audioOut) (src/modules/modem/Modem.h:148-153) -------- */
 /* Modem::checkSampleRate for `modem` (ModemAnalog.cpp:14-19, ModemUSB.cpp:29-37); negative on unknown modem.       */
 int sdr_modem_check_sample_rate(const char *modem, long long sample_rate);
@@ -145,6 +150,8 @@ int sdr_spectrum_frames(sdr_spectrum *sp, unsigned *n_frames);
 /* frame `idx` of the last block: points_y = SpectrumVisualData::spectrum_points y values (fft_size floats),
  * line = the u8 waterfall line, ceil_floor = {fft_ceil_maa, fft_floor_maa}.  Any pointer may be NULL.            */
 int sdr_spectrum_fetch(sdr_spectrum *sp, unsigned idx, float *points_y, uint8_t *line, double *ceil_floor);
+/* zero-copy: all frames of the fetched block, [n_frames][fft_size] each, in the pinned result buffer (same lifetime as above) */
+int sdr_spectrum_view(sdr_spectrum *sp, const float **points_y, const uint8_t **lines, unsigned *n_frames);
 /* every frame of the last block in one call: points_y [cap_frames][fft_size], lines likewise, ceil_floor [cap_frames][2] */
 int sdr_spectrum_fetch_all(sdr_spectrum *sp, unsigned cap_frames, float *points_y, uint8_t *lines, double *ceil_floor,
                            unsigned *n_frames);

@@ -189,3 +189,25 @@ def test_several_spectra_and_a_channel_on_one_engine(emu_lib, ref):
                 frames_seen += 1
         assert parity.relrms(ch.fetch_audio()[0], rc.process(y, 300000)["audio"]) <= parity.TOL
     assert frames_seen > 60
+
+
+def test_zero_copy_views_equal_the_copying_fetches(emu_lib):
+    """sdr_engine_view_audio_batch / sdr_spectrum_view hand out the pinned result buffer itself: same samples as the copies."""
+    from cubicsdr_b200 import Channel, Engine, Spectrum
+    fs, N = 2400000, synth.block_size(2400000)
+    eng = Engine(emu_lib, max_block=N)
+    cs = [Channel(eng, m, fs, bw, 48000, frequency=parity.CENTER + off) for m, bw, off in FIVE]
+    sp = Spectrum(eng, 512, 0)
+    for b in range(3):
+        eng.submit(synth.wideband(fs, N, FIVE, t0=b * N), parity.CENTER, fs)
+        eng.wait()
+        ptrs, n_audio, lvl, pk = eng.view_audio_batch(cs)
+        for i, c in enumerate(cs):
+            a, l, p, _ = c.fetch_audio()
+            assert n_audio[i] == len(a) and np.array_equal(Engine.audio_at(ptrs[i], n_audio[i]), a) and lvl[i] == l and pk[i] == p
+        pts, lines = sp.view()
+        assert pts.shape[0] == sp.frames
+        for f in range(sp.frames):
+            p1, l1, _ = sp.fetch(f)
+            assert np.array_equal(pts[f], p1) and np.array_equal(lines[f], l1)
+    eng.close()
