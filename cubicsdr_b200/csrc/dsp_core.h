@@ -251,6 +251,7 @@ struct DcExactArgs {
     int n, n_seg;
     int seg_len, warm;
     float c;                         // feedback coefficient as the reference holds it (float)
+    float one;                       // 1.0f, opaque to the compiler (k_dc_lanes_tma's FMA form of x + t)
     const double2 *tile_carry;       // exact state entering tile t of the current block (kDcTile samples per tile)
     const double2 *prev_tile_carry;  // same for the previous block
     int prev_n;                      // length of the previous block, 0 if there was none

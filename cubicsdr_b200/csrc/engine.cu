@@ -352,24 +352,47 @@ constexpr int kDtSlotBytes = kDtBoxes * kDtBoxBytes;          // 16384
 constexpr int kDtRing = 3;
 constexpr int kDtSmemWarp = kDtRing * kDtSlotBytes + 2 * kDtBoxBytes;   // input ring + an output tile of 32 steps: 57344 B
 constexpr int kDtSmem = kDlWarps * kDtSmemWarp + 1024 + 256;  // + alignment slack + mbarriers = 230656 B
-// 32 steps (two boxes at `row`) of the chain for one lane; `first` = its first two float4 (already loaded)
-template <bool kStore>
-__device__ __forceinline__ void dt_half(const unsigned char *row, unsigned char *out, unsigned swz, float c, float2 &v,
+__device__ __forceinline__ bool elect_one() {                  // one lane of the (converged) warp; the compiler treats what it guards as uniform
+    unsigned p;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+    return p != 0;
+}
+// One step of the recurrence for the replay kernels.  FORM 0: FMUL, FADD.  FORM 1: FMUL, then x * one + t as a fused multiply-add
+// with one = 1.0f read from the argument block (an exact identity: the same single rounding of x + t; it keeps both operations
+// of the chain on the FMA pipe, and `one` must be opaque to the compiler or it folds the operation back into an FADD).
+template <int FORM>
+__device__ __forceinline__ void dt_step(float c, float one, float2 x, float2 &v, float2 &y) {
+    const float tr = __fmul_rn(c, v.x), ti = __fmul_rn(c, v.y);
+    float nr, ni;
+    if (FORM == 1) {
+        asm("fma.rn.f32 %0, %1, %2, %3;" : "=f"(nr) : "f"(x.x), "f"(one), "f"(tr));
+        asm("fma.rn.f32 %0, %1, %2, %3;" : "=f"(ni) : "f"(x.y), "f"(one), "f"(ti));
+    } else {
+        nr = __fadd_rn(x.x, tr); ni = __fadd_rn(x.y, ti);
+    }
+    y = make_float2(__fsub_rn(nr, v.x), __fsub_rn(ni, v.y));
+    v = make_float2(nr, ni);
+}
+// 32 steps (two boxes at `row`) of the chain for one lane; q0, q1 = its first two float4 (already loaded)
+template <bool kStore, int FORM>
+__device__ __forceinline__ void dt_half(const unsigned char *row, unsigned char *out, unsigned swz, float c, float one, float2 &v,
                                         float4 q0, float4 q1) {
 #pragma unroll
     for (int t = 0; t < 16; ++t) {
         const unsigned o = (unsigned)(t >> 3) * kDtBoxBytes + (((unsigned)(t & 7) << 4) ^ swz);
         const float4 q = t == 0 ? q0 : (t == 1 ? q1 : *reinterpret_cast<const float4 *>(row + o));
         float2 y0, y1;
-        dc_ref_step(c, make_float2(q.x, q.y), v, y0);
-        dc_ref_step(c, make_float2(q.z, q.w), v, y1);
+        dt_step<FORM>(c, one, make_float2(q.x, q.y), v, y0);
+        dt_step<FORM>(c, one, make_float2(q.z, q.w), v, y1);
         if (kStore) *reinterpret_cast<float4 *>(out + o) = make_float4(y0.x, y0.y, y1.x, y1.y);
     }
 }
+template <int FORM>
 __global__ void __launch_bounds__(32 * kDlWarps, 1)
 k_dc_lanes_tma(DcExactArgs a, const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map) {
     extern __shared__ unsigned char dt_sm_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform also in the compiler's eyes
+    const int lane = threadIdx.x & 31;
     const int s0 = (blockIdx.x * kDlWarps + warp) * 32;              // first segment (tensor row) of this warp
     if (s0 >= a.n_seg) return;
     // swizzled boxes must sit on 1024-byte boundaries of the shared window
@@ -388,23 +411,32 @@ k_dc_lanes_tma(DcExactArgs a, const __grid_constant__ CUtensorMap in_map, const 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
+    const bool leader = elect_one();                                 // the one lane that issues every TMA operation and owns their groups
     const int L = a.seg_len, W = a.warm, n = a.n;
     const int s = s0 + lane;
+    const bool live = s < a.n_seg;
     int i_begin = 0x7fffffff;                                        // lanes past the last segment never become active
     float2 v = make_float2(0.f, 0.f);
-    if (s < a.n_seg) dc_exact_plan(a, s, i_begin, v);
+    if (live) dc_exact_plan(a, s, i_begin, v);
     const int p0 = s * L;
-    const int p1 = (s < a.n_seg) ? ((p0 + L < n) ? p0 + L : n) : p0;
+    const int p1 = live ? ((p0 + L < n) ? p0 + L : n) : p0;
     const int d = p0 - W;                                            // this lane's sample at step 0
     const int nb = (W + L) / kDtBatch;
     const int kw = W / kDtBatch;                                     // batches [0, kw) warm up, [kw, nb) produce output
-    const float c = a.c;
-    // ---- producer side (lane 0 issues; the running coordinates are warp-uniform): step j of segment r is sample r L - W + j =
-    //      element (row r + j / L, column j mod L) of the stream viewed as rows of L samples starting at sample -W; a box never
-    //      straddles rows (L is a multiple of 1024)
+    const float c = a.c, one = a.one;
+    // A lane starts at i_begin.  Lanes whose warm-up begins in the previous block start at one of ITS tile boundaries, less than a
+    // tile after step 0 and anywhere inside a batch: the first k1 batches test every step.  Every other start (tile boundaries
+    // of this block, the block start) falls on a batch boundary: from batch k1 on a lane is simply on from batch k_on.
+    const int k1 = kw < kDcTile / kDtBatch ? kw : kDcTile / kDtBatch;
+    const int k_on = live ? (int)(((long long)i_begin - d + kDtBatch - 1) / kDtBatch) : 0x7fffffff;
+    // only the block's last segment can end inside a batch
+    const bool warp_partial = __any_sync(0xffffffffu, live && ((p1 - p0) % (kDtBatch / 2)) != 0);
+    // ---- producer side (one elected lane issues; the running coordinates are warp-uniform): step j of segment r is sample
+    //      r L - W + j = element (row r + j / L, column j mod L) of the stream viewed as rows of L samples starting at sample -W;
+    //      a box never straddles rows (L is a multiple of 1024)
     int fk = 0, f_slot = 0, f_col = 0, f_row = s0;
     auto fetch = [&]() {
-        if (fk < nb && lane == 0) {
+        if (fk < nb && leader) {
             const unsigned bar = bar_s + 8u * (unsigned)f_slot, dst = ring_s + (unsigned)(f_slot * kDtSlotBytes);
             mbar_expect_tx(bar, (unsigned)kDtSlotBytes);
 #pragma unroll
@@ -417,87 +449,29 @@ k_dc_lanes_tma(DcExactArgs a, const __grid_constant__ CUtensorMap in_map, const 
     };
 #pragma unroll 1
     for (int k = 0; k < kDtRing - 1; ++k) fetch();
-    // ---- consumer side
-    float2 v_in = v;
-    int c_slot = 0;
-    unsigned c_par = 0, ready = 0;
+    // ---- consumer side: per batch -- make sure it has landed, let the producer refill the slot consumed last, probe the next
+    //      slot's barrier (the answer is needed only after this batch's chain), run the chain, load the next slot's first samples
+    int c_slot = 0, n_slot = 0;
+    unsigned c_par = 0, n_par = 0, ready = 0, ready_next = 0;
     float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
     bool have_q = false;
-#pragma unroll 1
-    for (int k = 0; k < nb; ++k) {
-        const unsigned bar = bar_s + 8u * (unsigned)c_slot;
-        while (!ready) {                                             // normally known already from the probe of the previous round
-            mbar_wait(bar, c_par);
-            ready = 1;
-        }
+    const unsigned char *row = my_in;
+    auto begin_batch = [&](int k) {
+        if (!ready) mbar_wait(bar_s + 8u * (unsigned)c_slot, c_par);
         __syncwarp();                                                // every lane is done with batch k - 1: its slot may be refilled
         fetch();
-        const int n_slot = (c_slot + 1 == kDtRing) ? 0 : c_slot + 1;
-        const unsigned n_par = n_slot == 0 ? (c_par ^ 1u) : c_par;
-        // probe the next slot now; the answer is needed only after this batch's chain
-        unsigned ready_next = (k + 1 < nb) ? mbar_test(bar_s + 8u * (unsigned)n_slot, n_par) : 0u;
-        const unsigned char *row = my_in + c_slot * kDtSlotBytes;
+        n_slot = (c_slot + 1 == kDtRing) ? 0 : c_slot + 1;
+        n_par = n_slot == 0 ? (c_par ^ 1u) : c_par;
+        ready_next = (k + 1 < nb) ? mbar_test(bar_s + 8u * (unsigned)n_slot, n_par) : 0u;
+        row = my_in + c_slot * kDtSlotBytes;
         if (!have_q) {
             q0 = *reinterpret_cast<const float4 *>(row + swz);
             q1 = *reinterpret_cast<const float4 *>(row + (16u ^ swz));
         }
-        const int base = d + k * kDtBatch;
-        // A lane is `on` (all 64 steps count), `off` (none does: it has not started, has finished, or owns no segment) or
-        // partial.  Without partial lanes the warp runs the unrolled chain on a copy of the state, which off lanes discard.
-        if (k < kw) {
-            const bool on = base >= i_begin, off = (long long)base + kDtBatch <= (long long)i_begin;
-            if (__all_sync(0xffffffffu, on || off)) {
-                float2 vv = v;
-                dt_half<false>(row, nullptr, swz, c, vv, q0, q1);
-                const unsigned char *row2 = row + 2 * kDtBoxBytes;
-                dt_half<false>(row2, nullptr, swz, c, vv, *reinterpret_cast<const float4 *>(row2 + swz),
-                               *reinterpret_cast<const float4 *>(row2 + (16u ^ swz)));
-                if (on) v = vv;
-            } else {                                                 // a lane starts inside this batch (previous block's tile grid)
-                float2 y;
-                for (int t = 0; t < kDtBatch / 2; ++t) {
-                    const float4 q = *reinterpret_cast<const float4 *>(row + (t >> 3) * kDtBoxBytes + (((unsigned)(t & 7) << 4) ^ swz));
-                    if (base + 2 * t >= i_begin) dc_ref_step(c, make_float2(q.x, q.y), v, y);
-                    if (base + 2 * t + 1 >= i_begin) dc_ref_step(c, make_float2(q.z, q.w), v, y);
-                }
-            }
-            if (k == kw - 1) v_in = v;
-        } else {
-#pragma unroll 1
-            for (int h = 0; h < 2; ++h) {                            // the output tile holds 32 steps: two rounds per slot
-                const int hb = base + h * (kDtBatch / 2);
-                const unsigned char *rowh = row + h * 2 * kDtBoxBytes;
-                const bool on = hb + kDtBatch / 2 <= p1, off = hb >= p1;
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous results have left the tile
-                __syncwarp();
-                if (__all_sync(0xffffffffu, on || off)) {
-                    float2 vv = v;
-                    dt_half<true>(rowh, my_out, swz, c, vv, *reinterpret_cast<const float4 *>(rowh + swz),
-                                  *reinterpret_cast<const float4 *>(rowh + (16u ^ swz)));
-                    if (on) v = vv;
-                } else {                                             // the block ends inside these 32 steps
-                    for (int t = 0; t < kDtBatch / 4; ++t) {
-                        const unsigned o = (unsigned)(t >> 3) * kDtBoxBytes + (((unsigned)(t & 7) << 4) ^ swz);
-                        const float4 q = *reinterpret_cast<const float4 *>(rowh + o);
-                        float2 y0 = make_float2(0.f, 0.f), y1 = y0;
-                        if (hb + 2 * t < p1) dc_ref_step(c, make_float2(q.x, q.y), v, y0);
-                        if (hb + 2 * t + 1 < p1) dc_ref_step(c, make_float2(q.z, q.w), v, y1);
-                        *reinterpret_cast<float4 *>(my_out + o) = make_float4(y0.x, y0.y, y1.x, y1.y);
-                    }
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the tile was written through the generic proxy
-                __syncwarp();
-                if (lane == 0) {
-                    const int col = 2 * ((k - kw) * kDtBatch + h * (kDtBatch / 2));   // float column inside the segment
-                    tma_store_2d(&out_map, col, s0, out_s);
-                    tma_store_2d(&out_map, col + 2 * kDtBox, s0, out_s + kDtBoxBytes);
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-            }
-        }
-        // the first samples of the next slot, if it is known to have landed (else the top of the loop waits and loads them)
+    };
+    auto end_batch = [&]() {
         have_q = false;
-        if (ready_next) {
+        if (ready_next) {                                            // known to have landed: its first samples, ahead of the chain
             const unsigned char *nrow = my_in + n_slot * kDtSlotBytes;
             q0 = *reinterpret_cast<const float4 *>(nrow + swz);
             q1 = *reinterpret_cast<const float4 *>(nrow + (16u ^ swz));
@@ -505,10 +479,86 @@ k_dc_lanes_tma(DcExactArgs a, const __grid_constant__ CUtensorMap in_map, const 
         }
         ready = ready_next;
         c_slot = n_slot; c_par = n_par;
+    };
+    int k = 0;
+    // ---- warm-up, first tile: starts may fall anywhere
+#pragma unroll 1
+    for (; k < k1; ++k) {
+        begin_batch(k);
+        const int base = d + k * kDtBatch;
+        const bool on = base >= i_begin, off = (long long)base + kDtBatch <= (long long)i_begin;
+        if (__all_sync(0xffffffffu, on || off)) {
+            float2 vv = v;
+            dt_half<false, FORM>(row, nullptr, swz, c, one, vv, q0, q1);
+            const unsigned char *row2 = row + 2 * kDtBoxBytes;
+            dt_half<false, FORM>(row2, nullptr, swz, c, one, vv, *reinterpret_cast<const float4 *>(row2 + swz),
+                                 *reinterpret_cast<const float4 *>(row2 + (16u ^ swz)));
+            if (on) v = vv;
+        } else {
+            float2 y;
+            for (int t = 0; t < kDtBatch / 2; ++t) {
+                const float4 q = *reinterpret_cast<const float4 *>(row + (t >> 3) * kDtBoxBytes + (((unsigned)(t & 7) << 4) ^ swz));
+                if (base + 2 * t >= i_begin) dt_step<FORM>(c, one, make_float2(q.x, q.y), v, y);
+                if (base + 2 * t + 1 >= i_begin) dt_step<FORM>(c, one, make_float2(q.z, q.w), v, y);
+            }
+        }
+        end_batch();
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    // ---- warm-up, steady state: nothing but the ring and the chain; a lane that has not started discards its batch
+#pragma unroll 1
+    for (; k < kw; ++k) {
+        begin_batch(k);
+        float2 vv = v;
+        dt_half<false, FORM>(row, nullptr, swz, c, one, vv, q0, q1);
+        const unsigned char *row2 = row + 2 * kDtBoxBytes;
+        dt_half<false, FORM>(row2, nullptr, swz, c, one, vv, *reinterpret_cast<const float4 *>(row2 + swz),
+                             *reinterpret_cast<const float4 *>(row2 + (16u ^ swz)));
+        if (k >= k_on) v = vv;
+        end_batch();
+    }
+    const float2 v_in = v;
+    // ---- output: the tile holds 32 steps, two rounds per slot
+#pragma unroll 1
+    for (; k < nb; ++k) {
+        begin_batch(k);
+        const int base = d + k * kDtBatch;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const int hb = base + h * (kDtBatch / 2);
+            const unsigned char *rowh = row + h * 2 * kDtBoxBytes;
+            const bool on = hb + kDtBatch / 2 <= p1;
+            if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous results have left the tile
+            __syncwarp();
+            if (!warp_partial || __all_sync(0xffffffffu, on || hb >= p1)) {
+                float2 vv = v;
+                const float4 a0 = h == 0 ? q0 : *reinterpret_cast<const float4 *>(rowh + swz);
+                const float4 a1 = h == 0 ? q1 : *reinterpret_cast<const float4 *>(rowh + (16u ^ swz));
+                dt_half<true, FORM>(rowh, my_out, swz, c, one, vv, a0, a1);
+                if (on) v = vv;
+            } else {                                                 // the block ends inside these 32 steps
+                for (int t = 0; t < kDtBatch / 4; ++t) {
+                    const unsigned o = (unsigned)(t >> 3) * kDtBoxBytes + (((unsigned)(t & 7) << 4) ^ swz);
+                    const float4 q = *reinterpret_cast<const float4 *>(rowh + o);
+                    float2 y0 = make_float2(0.f, 0.f), y1 = y0;
+                    if (hb + 2 * t < p1) dt_step<FORM>(c, one, make_float2(q.x, q.y), v, y0);
+                    if (hb + 2 * t + 1 < p1) dt_step<FORM>(c, one, make_float2(q.z, q.w), v, y1);
+                    *reinterpret_cast<float4 *>(my_out + o) = make_float4(y0.x, y0.y, y1.x, y1.y);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the tile was written through the generic proxy
+            __syncwarp();
+            if (leader) {
+                const int col = 2 * ((k - kw) * kDtBatch + h * (kDtBatch / 2));   // float column inside the segment
+                tma_store_2d(&out_map, col, s0, out_s);
+                tma_store_2d(&out_map, col + 2 * kDtBox, s0, out_s + kDtBoxBytes);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+        end_batch();
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");          // (a no-op for the lanes that issued nothing)
     __syncwarp();
-    if (s < a.n_seg) { a.seg_in[s] = v_in; a.seg_out[s] = v; }
+    if (live) { a.seg_in[s] = v_in; a.seg_out[s] = v; }
 }
 // All junctions are compared in parallel; only when one of them fails (rare) does thread 0 walk them serially and replay.
 __global__ void __launch_bounds__(256) k_dc_verify(DcExactArgs a) {
@@ -706,8 +756,16 @@ static int launch_dc_exact(const DcExactArgs &a, unsigned long long tma_rows, sd
                 !tma_rows_map(&out_map, a.y, (unsigned)a.seg_len, (unsigned long long)a.n_seg))
                 return fail(SDR_ERR_CUDA, "cuTensorMapEncodeTiled failed for the DC replay's stream tensors");
             static bool attr_set = false;
-            if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(k_dc_lanes_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kDtSmem)); attr_set = true; }
-            k_dc_lanes_tma<<<(warps + kDlWarps - 1) / kDlWarps, 32 * kDlWarps, kDtSmem, s>>>(a, in_map, out_map);
+            static int form = -1;
+            if (!attr_set) {
+                CUDA_TRY(cudaFuncSetAttribute(k_dc_lanes_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDtSmem));
+                CUDA_TRY(cudaFuncSetAttribute(k_dc_lanes_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDtSmem));
+                const char *f = getenv("SDR_B200_DC_FORM");
+                form = (f && f[0] == '0') ? 0 : 1;
+                attr_set = true;
+            }
+            if (form) k_dc_lanes_tma<1><<<(warps + kDlWarps - 1) / kDlWarps, 32 * kDlWarps, kDtSmem, s>>>(a, in_map, out_map);
+            else k_dc_lanes_tma<0><<<(warps + kDlWarps - 1) / kDlWarps, 32 * kDlWarps, kDtSmem, s>>>(a, in_map, out_map);
         } else {
             static bool attr_set = false;
             if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(k_dc_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, kDlSmem)); attr_set = true; }
@@ -2056,7 +2114,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
             const unsigned seg = kDcTile * ((tiles_n + lanes - 1) / lanes);
             xa.xraw = raw; xa.y = blk; xa.n = (int)n; xa.seg_len = (int)seg; xa.warm = kDcWarm;
             xa.raw_hist = (int)need_raw; xa.raw_end = (long long)e->max_block + (long long)e->raw_pad;
-            xa.c = (float)e->dc_a;
+            xa.c = (float)e->dc_a; xa.one = 1.0f;
             xa.tile_carry = e->d_tile_carry2[p]; xa.prev_tile_carry = e->d_tile_carry2[p ^ 1];
             xa.prev_n = e->have_block ? (int)e->last_n : 0;
             xa.seg_in = e->d_seg_in; xa.seg_out = e->d_seg_out; xa.fstate = e->d_fstate; xa.fixups = e->d_fixups;

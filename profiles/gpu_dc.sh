@@ -4,9 +4,10 @@ tag=${1:-dc}
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_parity.py -q -x -k "dc_blocker or five_modems or tiny_blocks or ragged or cfg5_full" > gpurun_out/pytest_$tag.log 2>&1
 echo "pytest rc=$?"; tail -15 gpurun_out/pytest_$tag.log
+./profiles/micro/dc_chain_forms.bin > gpurun_out/chain_forms_$tag.txt 2>&1; cat gpurun_out/chain_forms_$tag.txt
 for v in 1 0; do
-  SDR_B200_DC_TMA=$v timeout 300 python bench.py --steps 50 --no-configs --no-cpu-baseline --noise-inputs --min-seconds 0.3 > gpurun_out/bench_${tag}_tma$v.json 2> gpurun_out/bench_${tag}_tma$v.err
-  echo "bench tma=$v rc=$?"; python - <<PY
+  SDR_B200_DC_FORM=$v timeout 300 python bench.py --steps 50 --no-configs --no-cpu-baseline --noise-inputs --min-seconds 0.3 > gpurun_out/bench_${tag}_tma$v.json 2> gpurun_out/bench_${tag}_tma$v.err
+  echo "bench form=$v rc=$?"; python - <<PY
 import json
 try:
     l=json.load(open("gpurun_out/bench_${tag}_tma$v.json"))
