@@ -97,6 +97,7 @@ struct DcArgs {
     double2 *tile_carry;  // [tiles]  state entering each tile
     double2 *state;       // [1]      v[-1] carried across blocks
     const double *apow;   // [kDcTile + 1] a^k
+    float2 *copy_to;      // non-null: the tile-sum pass also copies x there (the block's way into the raw stream buffer)
 };
 
 // phase 0 of kernel A: each thread folds 4 consecutive samples, writes partial to shared; phase 1: thread 0 combines.
@@ -123,6 +124,15 @@ SDR_HD inline void dc_tile_sum_phase(int ph, const DcArgs &a, int bid, int tid, 
         double vr = 0.0, vi = 0.0;
         float2 s[kDcPer];
         dc_load(a.x, base, a.n, s);
+        if (a.copy_to) {
+            if (base + kDcPer <= a.n && ((reinterpret_cast<size_t>(a.copy_to + base) & 15) == 0)) {
+                float4 *p = reinterpret_cast<float4 *>(a.copy_to + base);
+#pragma unroll
+                for (int k = 0; k < kDcPer / 2; ++k) p[k] = make_float4(s[2 * k].x, s[2 * k].y, s[2 * k + 1].x, s[2 * k + 1].y);
+            } else {
+                for (int k = 0; k < per; ++k) if (base + k < a.n) a.copy_to[base + k] = s[k];
+            }
+        }
         for (int k = 0; k < per; ++k)      // beyond the block end the recurrence is simply not advanced
             if (base + k < a.n) { vr = fma(a.a, vr, (double)s[k].x); vi = fma(a.a, vi, (double)s[k].y); }
         sm->part[tid] = make_double2(vr, vi);

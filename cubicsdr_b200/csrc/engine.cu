@@ -373,18 +373,30 @@ __device__ __forceinline__ void dt_step(float c, float one, float2 x, float2 &v,
     y = make_float2(__fsub_rn(nr, v.x), __fsub_rn(ni, v.y));
     v = make_float2(nr, ni);
 }
-// 32 steps (two boxes at `row`) of the chain for one lane; q0, q1 = its first two float4 (already loaded)
+// 16 steps (the box at `row`) of the chain for one lane; q0, q1 = its first two float4 (already loaded)
 template <bool kStore, int FORM>
-__device__ __forceinline__ void dt_half(const unsigned char *row, unsigned char *out, unsigned swz, float c, float one, float2 &v,
-                                        float4 q0, float4 q1) {
+__device__ __forceinline__ void dt_box(const unsigned char *row, unsigned char *out, unsigned swz, float c, float one, float2 &v,
+                                       float4 q0, float4 q1) {
 #pragma unroll
-    for (int t = 0; t < 16; ++t) {
-        const unsigned o = (unsigned)(t >> 3) * kDtBoxBytes + (((unsigned)(t & 7) << 4) ^ swz);
+    for (int t = 0; t < 8; ++t) {
+        const unsigned o = ((unsigned)t << 4) ^ swz;
         const float4 q = t == 0 ? q0 : (t == 1 ? q1 : *reinterpret_cast<const float4 *>(row + o));
         float2 y0, y1;
         dt_step<FORM>(c, one, make_float2(q.x, q.y), v, y0);
         dt_step<FORM>(c, one, make_float2(q.z, q.w), v, y1);
         if (kStore) *reinterpret_cast<float4 *>(out + o) = make_float4(y0.x, y0.y, y1.x, y1.y);
+    }
+}
+// 64 steps (a whole ring slot) without output
+template <int FORM>
+__device__ __forceinline__ void dt_slot(const unsigned char *row, unsigned swz, float c, float one, float2 &v, float4 q0, float4 q1) {
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+        const unsigned o = (unsigned)(t >> 3) * kDtBoxBytes + (((unsigned)(t & 7) << 4) ^ swz);
+        const float4 q = t == 0 ? q0 : (t == 1 ? q1 : *reinterpret_cast<const float4 *>(row + o));
+        float2 y;
+        dt_step<FORM>(c, one, make_float2(q.x, q.y), v, y);
+        dt_step<FORM>(c, one, make_float2(q.z, q.w), v, y);
     }
 }
 template <int FORM>
@@ -400,7 +412,7 @@ k_dc_lanes_tma(DcExactArgs a, const __grid_constant__ CUtensorMap in_map, const 
     const unsigned pad = (1024u - (raw_s & 1023u)) & 1023u;
     unsigned char *wsm = dt_sm_raw + pad + (size_t)warp * kDtSmemWarp;
     const unsigned ring_s = raw_s + pad + (unsigned)warp * kDtSmemWarp;                // [kDtRing][4 boxes][4096 B]
-    const unsigned out_s = ring_s + kDtRing * kDtSlotBytes;                            // [2 boxes][4096 B]
+    const unsigned out_s = ring_s + kDtRing * kDtSlotBytes;                            // [2 tiles][one box of 4096 B]
     const unsigned bar_s = raw_s + pad + kDlWarps * kDtSmemWarp + (unsigned)warp * 64u;   // [kDtRing] mbarriers
     const unsigned swz = (unsigned)(lane & 7) << 4;
     const unsigned char *my_in = wsm + lane * 128;
@@ -429,8 +441,8 @@ k_dc_lanes_tma(DcExactArgs a, const __grid_constant__ CUtensorMap in_map, const 
     // of this block, the block start) falls on a batch boundary: from batch k1 on a lane is simply on from batch k_on.
     const int k1 = kw < kDcTile / kDtBatch ? kw : kDcTile / kDtBatch;
     const int k_on = live ? (int)(((long long)i_begin - d + kDtBatch - 1) / kDtBatch) : 0x7fffffff;
-    // only the block's last segment can end inside a batch
-    const bool warp_partial = __any_sync(0xffffffffu, live && ((p1 - p0) % (kDtBatch / 2)) != 0);
+    // only the block's last segment can end inside a box
+    const bool warp_partial = __any_sync(0xffffffffu, live && ((p1 - p0) % kDtBox) != 0);
     // ---- producer side (one elected lane issues; the running coordinates are warp-uniform): step j of segment r is sample
     //      r L - W + j = element (row r + j / L, column j mod L) of the stream viewed as rows of L samples starting at sample -W;
     //      a box never straddles rows (L is a multiple of 1024)
@@ -489,10 +501,7 @@ k_dc_lanes_tma(DcExactArgs a, const __grid_constant__ CUtensorMap in_map, const 
         const bool on = base >= i_begin, off = (long long)base + kDtBatch <= (long long)i_begin;
         if (__all_sync(0xffffffffu, on || off)) {
             float2 vv = v;
-            dt_half<false, FORM>(row, nullptr, swz, c, one, vv, q0, q1);
-            const unsigned char *row2 = row + 2 * kDtBoxBytes;
-            dt_half<false, FORM>(row2, nullptr, swz, c, one, vv, *reinterpret_cast<const float4 *>(row2 + swz),
-                                 *reinterpret_cast<const float4 *>(row2 + (16u ^ swz)));
+            dt_slot<FORM>(row, swz, c, one, vv, q0, q1);
             if (on) v = vv;
         } else {
             float2 y;
@@ -509,50 +518,49 @@ k_dc_lanes_tma(DcExactArgs a, const __grid_constant__ CUtensorMap in_map, const 
     for (; k < kw; ++k) {
         begin_batch(k);
         float2 vv = v;
-        dt_half<false, FORM>(row, nullptr, swz, c, one, vv, q0, q1);
-        const unsigned char *row2 = row + 2 * kDtBoxBytes;
-        dt_half<false, FORM>(row2, nullptr, swz, c, one, vv, *reinterpret_cast<const float4 *>(row2 + swz),
-                             *reinterpret_cast<const float4 *>(row2 + (16u ^ swz)));
+        dt_slot<FORM>(row, swz, c, one, vv, q0, q1);
         if (k >= k_on) v = vv;
         end_batch();
     }
     const float2 v_in = v;
-    // ---- output: the tile holds 32 steps, two rounds per slot
+    // ---- output: one box (16 steps) at a time through two alternating tiles, so that the store of one box drains while the
+    //      next is being computed (the leader only ever waits for the store issued two boxes ago)
+    int o_sel = 0;
 #pragma unroll 1
     for (; k < nb; ++k) {
         begin_batch(k);
         const int base = d + k * kDtBatch;
 #pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-            const int hb = base + h * (kDtBatch / 2);
-            const unsigned char *rowh = row + h * 2 * kDtBoxBytes;
-            const bool on = hb + kDtBatch / 2 <= p1;
-            if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous results have left the tile
+        for (int h = 0; h < kDtBoxes; ++h) {
+            const int hb = base + h * kDtBox;
+            const unsigned char *rowh = row + h * kDtBoxBytes;
+            unsigned char *outh = my_out + o_sel * kDtBoxBytes;
+            const bool on = hb + kDtBox <= p1;
+            if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the box stored from this tile two rounds ago has left it
             __syncwarp();
             if (!warp_partial || __all_sync(0xffffffffu, on || hb >= p1)) {
                 float2 vv = v;
                 const float4 a0 = h == 0 ? q0 : *reinterpret_cast<const float4 *>(rowh + swz);
                 const float4 a1 = h == 0 ? q1 : *reinterpret_cast<const float4 *>(rowh + (16u ^ swz));
-                dt_half<true, FORM>(rowh, my_out, swz, c, one, vv, a0, a1);
+                dt_box<true, FORM>(rowh, outh, swz, c, one, vv, a0, a1);
                 if (on) v = vv;
-            } else {                                                 // the block ends inside these 32 steps
-                for (int t = 0; t < kDtBatch / 4; ++t) {
-                    const unsigned o = (unsigned)(t >> 3) * kDtBoxBytes + (((unsigned)(t & 7) << 4) ^ swz);
+            } else {                                                 // the block ends inside these 16 steps
+                for (int t = 0; t < kDtBox / 2; ++t) {
+                    const unsigned o = ((unsigned)t << 4) ^ swz;
                     const float4 q = *reinterpret_cast<const float4 *>(rowh + o);
                     float2 y0 = make_float2(0.f, 0.f), y1 = y0;
                     if (hb + 2 * t < p1) dt_step<FORM>(c, one, make_float2(q.x, q.y), v, y0);
                     if (hb + 2 * t + 1 < p1) dt_step<FORM>(c, one, make_float2(q.z, q.w), v, y1);
-                    *reinterpret_cast<float4 *>(my_out + o) = make_float4(y0.x, y0.y, y1.x, y1.y);
+                    *reinterpret_cast<float4 *>(outh + o) = make_float4(y0.x, y0.y, y1.x, y1.y);
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the tile was written through the generic proxy
             __syncwarp();
             if (leader) {
-                const int col = 2 * ((k - kw) * kDtBatch + h * (kDtBatch / 2));   // float column inside the segment
-                tma_store_2d(&out_map, col, s0, out_s);
-                tma_store_2d(&out_map, col + 2 * kDtBox, s0, out_s + kDtBoxBytes);
+                tma_store_2d(&out_map, 2 * ((k - kw) * kDtBatch + h * kDtBox), s0, out_s + (unsigned)(o_sel * kDtBoxBytes));   // float column inside the segment
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
+            o_sel ^= 1;
         }
         end_batch();
     }
@@ -2094,15 +2102,17 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
             be_d2d(e->d_scratch, raw + (long long)e->last_n - (long long)need_raw, need_raw * sizeof(float2), dcs);
             be_d2d(raw - need_raw, e->d_scratch, need_raw * sizeof(float2), dcs);
         }
-        if (h_src) be_h2d(raw, h_src, (size_t)n * sizeof(float2), dcs);   // host block: straight into the raw stream buffer
+        DcArgs dc;
+        dc.x = raw; dc.y = blk; dc.n = (int)n; dc.a = e->dc_a; dc.tile_sum = e->d_tile_sum; dc.tile_carry = e->d_tile_carry2[p];
+        dc.state = e->d_dc_state; dc.apow = e->d_apow; dc.copy_to = nullptr;
+        if (h_src) be_h2d(raw, h_src, (size_t)n * sizeof(float2), dcs);   // host block (emulator): straight into the raw stream buffer
+        else if (e->exact_dc) { dc.x = d_src; dc.copy_to = raw; }         // the tile-sum pass of the scan brings the block in as it reads it
         else be_d2d(raw, d_src, (size_t)n * sizeof(float2), dcs);
+        launch_dc(dc, !e->exact_dc, dcs, e->launches);
+        dc.x = raw;
 #ifndef SDR_EMU
         if (consumed_event) CUDA_TRY(cudaEventRecord((cudaEvent_t)consumed_event, dcs));   // the caller's buffer may be refilled
 #endif
-        DcArgs dc;
-        dc.x = raw; dc.y = blk; dc.n = (int)n; dc.a = e->dc_a; dc.tile_sum = e->d_tile_sum; dc.tile_carry = e->d_tile_carry2[p];
-        dc.state = e->d_dc_state; dc.apow = e->d_apow;
-        launch_dc(dc, !e->exact_dc, dcs, e->launches);
         if (e->exact_dc) {
             DcExactArgs xa;
             // one lane per segment on the SMs the channel front kernel leaves free: as many segments (multiples of the scan
