@@ -322,11 +322,6 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap *map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int c1, unsigned src) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
-                 ::"l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(src) : "memory");
-}
-
 __device__ __forceinline__ unsigned mbar_test(unsigned bar, unsigned parity) {       // non-blocking probe
     unsigned ok;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -339,8 +334,8 @@ __device__ __forceinline__ unsigned mbar_test(unsigned bar, unsigned parity) {  
 // brings the next 16 samples of all 32 segments into a shared-memory box of 32 rows x 128 B; completion is counted on an
 // mbarrier per ring slot (a slot = 64 steps = four boxes; three slots in flight).  The 128-byte swizzle of the tensor map
 // (16-byte chunk index XOR row mod 8) is what makes the per-lane row reads conflict-free: lane l reads chunk c of its row at
-// l * 128 + ((c ^ (l & 7)) << 4).  Results leave the same way: swizzled boxes, cp.async.bulk.tensor stores issued by lane 0;
-// rows past the last segment are clipped by the tensor's bounds.  The serial chain is the only thing the warp really does:
+// l * 128 + ((c ^ (l & 7)) << 4).  Results leave through a small padded tile as full 128-byte lines.  The serial chain is
+// the only thing the warp really does:
 // per 64 steps it spends a few dozen instructions on the ring (no divisions, no per-sample copies), the barrier of the next
 // slot is probed while the current one is being consumed, and the first samples of the next slot are loaded before the
 // current chain ends.
@@ -373,20 +368,6 @@ __device__ __forceinline__ void dt_step(float c, float one, float2 x, float2 &v,
     y = make_float2(__fsub_rn(nr, v.x), __fsub_rn(ni, v.y));
     v = make_float2(nr, ni);
 }
-// 16 steps (the box at `row`) of the chain for one lane; q0, q1 = its first two float4 (already loaded)
-template <bool kStore, int FORM>
-__device__ __forceinline__ void dt_box(const unsigned char *row, unsigned char *out, unsigned swz, float c, float one, float2 &v,
-                                       float4 q0, float4 q1) {
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        const unsigned o = ((unsigned)t << 4) ^ swz;
-        const float4 q = t == 0 ? q0 : (t == 1 ? q1 : *reinterpret_cast<const float4 *>(row + o));
-        float2 y0, y1;
-        dt_step<FORM>(c, one, make_float2(q.x, q.y), v, y0);
-        dt_step<FORM>(c, one, make_float2(q.z, q.w), v, y1);
-        if (kStore) *reinterpret_cast<float4 *>(out + o) = make_float4(y0.x, y0.y, y1.x, y1.y);
-    }
-}
 // 64 steps (a whole ring slot) without output
 template <int FORM>
 __device__ __forceinline__ void dt_slot(const unsigned char *row, unsigned swz, float c, float one, float2 &v, float4 q0, float4 q1) {
@@ -401,7 +382,7 @@ __device__ __forceinline__ void dt_slot(const unsigned char *row, unsigned swz, 
 }
 template <int FORM>
 __global__ void __launch_bounds__(32 * kDlWarps, 1)
-k_dc_lanes_tma(DcExactArgs a, const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map) {
+k_dc_lanes_tma(DcExactArgs a, const __grid_constant__ CUtensorMap in_map) {
     extern __shared__ unsigned char dt_sm_raw[];
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform also in the compiler's eyes
     const int lane = threadIdx.x & 31;
@@ -412,11 +393,11 @@ k_dc_lanes_tma(DcExactArgs a, const __grid_constant__ CUtensorMap in_map, const 
     const unsigned pad = (1024u - (raw_s & 1023u)) & 1023u;
     unsigned char *wsm = dt_sm_raw + pad + (size_t)warp * kDtSmemWarp;
     const unsigned ring_s = raw_s + pad + (unsigned)warp * kDtSmemWarp;                // [kDtRing][4 boxes][4096 B]
-    const unsigned out_s = ring_s + kDtRing * kDtSlotBytes;                            // [2 tiles][one box of 4096 B]
     const unsigned bar_s = raw_s + pad + kDlWarps * kDtSmemWarp + (unsigned)warp * 64u;   // [kDtRing] mbarriers
     const unsigned swz = (unsigned)(lane & 7) << 4;
     const unsigned char *my_in = wsm + lane * 128;
-    unsigned char *my_out = wsm + kDtRing * kDtSlotBytes + lane * 128;
+    unsigned char *out_p = wsm + kDtRing * kDtSlotBytes;              // output tile [32 rows][144 B]
+    unsigned char *my_out_p = out_p + lane * 144;
     if (lane == 0) {
 #pragma unroll
         for (int r = 0; r < kDtRing; ++r) mbar_init(bar_s + 8u * r, 1u);
@@ -523,9 +504,11 @@ k_dc_lanes_tma(DcExactArgs a, const __grid_constant__ CUtensorMap in_map, const 
         end_batch();
     }
     const float2 v_in = v;
-    // ---- output: one box (16 steps) at a time through two alternating tiles, so that the store of one box drains while the
-    //      next is being computed (the leader only ever waits for the store issued two boxes ago)
-    int o_sel = 0;
+    // ---- output: 16 steps at a time through a padded tile (rows 144 B apart: the per-lane 16-byte writes of a quarter warp and
+    //      the transposed reads -- eight lanes per row -- are both conflict-free); every row leaves as one full 128-byte line.
+    //      (A TMA store per box was measured slower here: the proxy fence and the read-wait cost ~800 cycles per round.)
+    constexpr int kORow = 144;
+    const int orow = lane >> 3, ochunk = lane & 7;
 #pragma unroll 1
     for (; k < nb; ++k) {
         begin_batch(k);
@@ -534,38 +517,44 @@ k_dc_lanes_tma(DcExactArgs a, const __grid_constant__ CUtensorMap in_map, const 
         for (int h = 0; h < kDtBoxes; ++h) {
             const int hb = base + h * kDtBox;
             const unsigned char *rowh = row + h * kDtBoxBytes;
-            unsigned char *outh = my_out + o_sel * kDtBoxBytes;
             const bool on = hb + kDtBox <= p1;
-            if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the box stored from this tile two rounds ago has left it
-            __syncwarp();
+            __syncwarp();                                            // the previous round's rows have been read
             if (!warp_partial || __all_sync(0xffffffffu, on || hb >= p1)) {
                 float2 vv = v;
-                const float4 a0 = h == 0 ? q0 : *reinterpret_cast<const float4 *>(rowh + swz);
-                const float4 a1 = h == 0 ? q1 : *reinterpret_cast<const float4 *>(rowh + (16u ^ swz));
-                dt_box<true, FORM>(rowh, outh, swz, c, one, vv, a0, a1);
+                float4 q = h == 0 ? q0 : *reinterpret_cast<const float4 *>(rowh + swz);
+                float4 qn = h == 0 ? q1 : *reinterpret_cast<const float4 *>(rowh + (16u ^ swz));
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    float2 y0, y1;
+                    dt_step<FORM>(c, one, make_float2(q.x, q.y), vv, y0);
+                    dt_step<FORM>(c, one, make_float2(q.z, q.w), vv, y1);
+                    *reinterpret_cast<float4 *>(my_out_p + t * 16) = make_float4(y0.x, y0.y, y1.x, y1.y);
+                    q = qn;
+                    if (t + 2 < 8) qn = *reinterpret_cast<const float4 *>(rowh + (((unsigned)(t + 2) << 4) ^ swz));
+                }
                 if (on) v = vv;
             } else {                                                 // the block ends inside these 16 steps
                 for (int t = 0; t < kDtBox / 2; ++t) {
-                    const unsigned o = ((unsigned)t << 4) ^ swz;
-                    const float4 q = *reinterpret_cast<const float4 *>(rowh + o);
+                    const float4 q = *reinterpret_cast<const float4 *>(rowh + (((unsigned)t << 4) ^ swz));
                     float2 y0 = make_float2(0.f, 0.f), y1 = y0;
                     if (hb + 2 * t < p1) dt_step<FORM>(c, one, make_float2(q.x, q.y), v, y0);
                     if (hb + 2 * t + 1 < p1) dt_step<FORM>(c, one, make_float2(q.z, q.w), v, y1);
-                    *reinterpret_cast<float4 *>(outh + o) = make_float4(y0.x, y0.y, y1.x, y1.y);
+                    *reinterpret_cast<float4 *>(my_out_p + t * 16) = make_float4(y0.x, y0.y, y1.x, y1.y);
                 }
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the tile was written through the generic proxy
             __syncwarp();
-            if (leader) {
-                tma_store_2d(&out_map, 2 * ((k - kw) * kDtBatch + h * kDtBox), s0, out_s + (unsigned)(o_sel * kDtBoxBytes));   // float column inside the segment
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            const int ob = (k - kw) * kDtBatch + h * kDtBox + 2 * ochunk;     // this lane's pair inside the segment of its row
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int r = 4 * it + orow;
+                const long long idx = (long long)(s0 + r) * L + ob;
+                const float4 q = *reinterpret_cast<const float4 *>(out_p + r * kORow + ochunk * 16);
+                if (idx + 2 <= n) *reinterpret_cast<float4 *>(a.y + idx) = q;
+                else if (idx < n) a.y[idx] = make_float2(q.x, q.y);
             }
-            o_sel ^= 1;
         }
         end_batch();
     }
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");          // (a no-op for the lanes that issued nothing)
-    __syncwarp();
     if (live) { a.seg_in[s] = v_in; a.seg_out[s] = v; }
 }
 // All junctions are compared in parallel; only when one of them fails (rare) does thread 0 walk them serially and replay.
@@ -758,10 +747,9 @@ static int launch_dc_exact(const DcExactArgs &a, unsigned long long tma_rows, sd
         const int warps = (a.n_seg + 31) / 32;
         static int use_tma = -1;
         if (use_tma < 0) { const char *v = getenv("SDR_B200_DC_TMA"); use_tma = (v && v[0] == '0') ? 0 : 1; }
-        CUtensorMap in_map, out_map;
+        CUtensorMap in_map;
         if (use_tma && tma_rows) {
-            if (!tma_rows_map(&in_map, const_cast<float2 *>(a.xraw) - a.warm, (unsigned)a.seg_len, tma_rows / (unsigned)a.seg_len) ||
-                !tma_rows_map(&out_map, a.y, (unsigned)a.seg_len, (unsigned long long)a.n_seg))
+            if (!tma_rows_map(&in_map, const_cast<float2 *>(a.xraw) - a.warm, (unsigned)a.seg_len, tma_rows / (unsigned)a.seg_len))
                 return fail(SDR_ERR_CUDA, "cuTensorMapEncodeTiled failed for the DC replay's stream tensors");
             static bool attr_set = false;
             static int form = -1;
@@ -772,8 +760,8 @@ static int launch_dc_exact(const DcExactArgs &a, unsigned long long tma_rows, sd
                 form = (f && f[0] == '0') ? 0 : 1;
                 attr_set = true;
             }
-            if (form) k_dc_lanes_tma<1><<<(warps + kDlWarps - 1) / kDlWarps, 32 * kDlWarps, kDtSmem, s>>>(a, in_map, out_map);
-            else k_dc_lanes_tma<0><<<(warps + kDlWarps - 1) / kDlWarps, 32 * kDlWarps, kDtSmem, s>>>(a, in_map, out_map);
+            if (form) k_dc_lanes_tma<1><<<(warps + kDlWarps - 1) / kDlWarps, 32 * kDlWarps, kDtSmem, s>>>(a, in_map);
+            else k_dc_lanes_tma<0><<<(warps + kDlWarps - 1) / kDlWarps, 32 * kDlWarps, kDtSmem, s>>>(a, in_map);
         } else {
             static bool attr_set = false;
             if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(k_dc_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, kDlSmem)); attr_set = true; }
