@@ -509,6 +509,7 @@ k_dc_lanes_tma(DcExactArgs a, const __grid_constant__ CUtensorMap in_map) {
     //      (A TMA store per box was measured slower here: the proxy fence and the read-wait cost ~800 cycles per round.)
     constexpr int kORow = 144;
     const int orow = lane >> 3, ochunk = lane & 7;
+    float2 *const y_lane = a.y + (long long)(s0 + orow) * L;          // segment start of this lane's first row of a tile
 #pragma unroll 1
     for (; k < nb; ++k) {
         begin_batch(k);
@@ -544,13 +545,19 @@ k_dc_lanes_tma(DcExactArgs a, const __grid_constant__ CUtensorMap in_map) {
             }
             __syncwarp();
             const int ob = (k - kw) * kDtBatch + h * kDtBox + 2 * ochunk;     // this lane's pair inside the segment of its row
+            const float4 *tp = reinterpret_cast<const float4 *>(out_p + orow * kORow + ochunk * 16);
+            if ((long long)(s0 + 31) * L + (k - kw) * kDtBatch + (h + 1) * kDtBox <= (long long)n) {   // the whole tile lies inside the block
+                float4 *gp = reinterpret_cast<float4 *>(y_lane + ob);
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int r = 4 * it + orow;
-                const long long idx = (long long)(s0 + r) * L + ob;
-                const float4 q = *reinterpret_cast<const float4 *>(out_p + r * kORow + ochunk * 16);
-                if (idx + 2 <= n) *reinterpret_cast<float4 *>(a.y + idx) = q;
-                else if (idx < n) a.y[idx] = make_float2(q.x, q.y);
+                for (int it = 0; it < 8; ++it) { *gp = tp[it * (4 * kORow / 16)]; gp += 2 * (size_t)L; }   // four rows down: 4 L samples = 2 L float4
+            } else {
+#pragma unroll 1
+                for (int it = 0; it < 8; ++it) {
+                    const long long idx = (long long)(s0 + 4 * it + orow) * L + ob;
+                    const float4 q = tp[it * (4 * kORow / 16)];
+                    if (idx + 2 <= n) *reinterpret_cast<float4 *>(a.y + idx) = q;
+                    else if (idx < n) a.y[idx] = make_float2(q.x, q.y);
+                }
             }
         }
         end_batch();
