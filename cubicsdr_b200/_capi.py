@@ -22,7 +22,7 @@ SYMBOLS = [
     "sdr_chan_create", "sdr_chan_destroy", "sdr_chan_set_frequency", "sdr_chan_get_bandwidth", "sdr_chan_want_iq",
     "sdr_chan_fetch_audio", "sdr_chan_fetch_iq", "sdr_engine_fetch_audio_batch", "sdr_engine_view_audio_batch", "sdr_spectrum_view",
     "sdr_modem_check_sample_rate", "sdr_modem_create", "sdr_modem_demodulate",
-    "sdr_spectrum_create", "sdr_spectrum_destroy", "sdr_spectrum_set_average_rate", "sdr_spectrum_frames",
+    "sdr_spectrum_create", "sdr_spectrum_destroy", "sdr_spectrum_set_average_rate", "sdr_spectrum_set_view", "sdr_spectrum_desired_input", "sdr_spectrum_frames",
     "sdr_spectrum_fetch", "sdr_spectrum_fetch_all", "sdr_spectrum_fetch_debug",
     "sdr_engine_set_channelizer", "sdr_engine_channel_plan", "sdr_engine_set_channel_block_max",
     "sdr_pfb_optimal_channel_count", "sdr_pfb_create", "sdr_pfb2_create", "sdr_pfb_destroy", "sdr_pfb_reset", "sdr_pfb_execute", "sdr_pfb_execute_device",
@@ -85,6 +85,8 @@ class Lib:
         L.sdr_spectrum_create.argtypes = [vp, u, u, P(vp)]
         L.sdr_spectrum_destroy.argtypes = [vp]
         L.sdr_spectrum_set_average_rate.argtypes = [vp, f]
+        L.sdr_spectrum_set_view.argtypes = [vp, i, ll, C.c_long]
+        L.sdr_spectrum_desired_input.argtypes = [vp, ll, P(u)]
         L.sdr_spectrum_frames.argtypes = [vp, P(u)]
         L.sdr_spectrum_fetch.argtypes = [vp, u, vp, vp, vp]
         L.sdr_spectrum_fetch_debug.argtypes = [vp, u, vp, vp]
@@ -336,6 +338,15 @@ class Spectrum:
 
     def set_average_rate(self, r):
         self.lib.check(self.lib.L.sdr_spectrum_set_average_rate(self.h, r))
+
+    def set_view(self, is_view, center_freq=0, bandwidth=0):
+        """SpectrumVisualProcessor::setView(bView, centerFreq, bandwidth): zoomed view from the next block on."""
+        self.lib.check(self.lib.L.sdr_spectrum_set_view(self.h, 1 if is_view else 0, int(center_freq), int(bandwidth)))
+
+    def desired_input(self, sample_rate):
+        n = C.c_uint()
+        self.lib.check(self.lib.L.sdr_spectrum_desired_input(self.h, int(sample_rate), C.byref(n)))
+        return n.value
 
     @property
     def frames(self):

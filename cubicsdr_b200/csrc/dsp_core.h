@@ -24,7 +24,8 @@ constexpr int kMaxAudioHb = 8;
 constexpr int kPfbTaps = 14;      // 2 * m of the arbitrary resampler (m = 7)
 constexpr int kTailThreads = 256;
 
-enum ModemKind { MODEM_FM = 0, MODEM_NBFM = 1, MODEM_AM = 2, MODEM_USB = 3, MODEM_LSB = 4, MODEM_IQ = 5 };
+enum ModemKind { MODEM_FM = 0, MODEM_NBFM = 1, MODEM_AM = 2, MODEM_USB = 3, MODEM_LSB = 4, MODEM_IQ = 5,
+                 MODEM_NONE = 6 };   // no modem: the decimated IQ is the product (the zoomed spectrum view's hidden channel)
 
 // ---- small complex helpers ------------------------------------------------------------------------------------------
 SDR_HD SDR_FORCEINLINE float2 cf_make(float a, float b) { return make_float2(a, b); }
@@ -396,7 +397,8 @@ struct ChanDyn {                  // written by the host for every block
     int lvl0_sel;                 // which level-0 buffer this block uses (0: lvl_off[0], 1: lvl0_alt_off)
     int squelch_enabled;          // DemodulatorThread::squelchEnabled for this block
     float squelch_level;          // DemodulatorThread::squelchLevel (dB)
-    int pad0;
+    int view;                     // 1: hidden channel of a zoomed spectrum view -- processed by that spectrum's own tail launch
+                                  //    (its level-0 stream is written by the view mixer, its block length is the frames' total)
     const float2 *hist;           // non-null: history for samples i < 0 is hist[i] (the channel skipped the previous block(s),
                                   // so its delay lines must see the tail of the last block it DID consume)
     const float2 *xin;            // non-null: this channel's own input stream (channelizer mode: the samples of its filterbank

@@ -25,6 +25,7 @@ constexpr int kSpecThreads = 256;
 struct SpecArgs {
     const float2 *x;          // wideband stream, x[0] = first sample of the current block (history at negative indices)
     const int *frame_start;   // [F] first sample of each frame relative to x
+    int frame_stride;         // > 0: frame f starts at f * frame_stride instead (zoomed view: the hidden channel's decimated stream)
     int F;
     int N;                    // transform length (2 * fft_size)
     int fft_size;             // display points
@@ -41,7 +42,59 @@ struct SpecArgs {
     float *points;            // [F][fft_size]
     unsigned char *lines;     // [F][fft_size]
     float scale_factor;
+    // bins merged into display point x: round(visual_start + i) for i = pt_i0[x] .. pt_i0[x] + pt_cnt[x] - 1
+    // (the reference's visualAccum loop, :538-556, evaluated once on the host for the current view)
+    const int *pt_i0, *pt_cnt;
+    double visual_start;
+    // zoomed view, applied to {ma, maa} before the first frame of the block: rebin < 0 / > 0 = zoomed in / out (:454-492),
+    // shift = bins the averages move by after the view's centre moved (> 0: towards lower indices, :317-329)
+    int rebin, shift;
+    double2 *ema_tmp;         // [N] scratch for the two moves above
 };
+
+// ---- zoomed view (SpectrumVisualProcessor.cpp:283-386): the frames handed to the view are mixed down by the view's oscillator
+//      (nco_crcf_mix_block_up / _down over each frame, the phase running on from frame to frame) straight into the level-0
+//      stream of the view's hidden channel, whose resampler (msresamp_crcf(resampleBw / sampleRate)) is the channel tail's
+struct ViewMixArgs {
+    const float2 *x;          // block stream (history at negative indices)
+    const int *frame_start;   // [F]
+    int F, D;                 // frames this block, samples per frame
+    const float2 *nco;        // [1024] {cos, sin}
+    unsigned theta0, dtheta;  // oscillator phase at the first sample, phase step
+    int dir;                  // +1 mix up, -1 mix down, 0 copy (:347)
+    float2 *out;              // level-0 stream of the hidden channel: out[0 .. F D)
+};
+SDR_HD inline void view_mix_thread(const ViewMixArgs &a, long long g) {
+    if (g >= (long long)a.F * a.D) return;
+    const int f = (int)(g / a.D), i = (int)(g - (long long)f * a.D);
+    const float2 v = a.x[a.frame_start[f] + i];
+    if (!a.dir) { a.out[g] = v; return; }
+    const float2 w = a.nco[(a.theta0 + (unsigned)g * a.dtheta + 0x200000u) >> 22];
+    a.out[g] = cf_rot(v, w.x, a.dir < 0 ? -w.y : w.y);
+}
+// the two re-arrangements of the running averages; phase 0 copies into the scratch, phase 1 writes back (grid-wide barrier
+// between them = two launches)
+SDR_HD inline void view_ema_move_thread(const SpecArgs &a, int ph, int i) {
+    if (i >= a.N) return;
+    if (ph == 0) { a.ema_tmp[i] = a.ema[i]; return; }
+    const int N = a.N;
+    double2 v = a.ema_tmp[i];
+    if (a.shift > 0) { if (i + a.shift < N) v = a.ema_tmp[i + a.shift]; }             // memmove(&ma[0], &ma[numShift], N - numShift)
+    else if (a.shift < 0) { if (i + a.shift >= 0) v = a.ema_tmp[i + a.shift]; }       // memmove(&ma[numShift], &ma[0], N - numShift)
+    if (a.rebin) {
+        // the shift (in process(): before the transform) and the re-binning (after it) compose: rebin reads the shifted array
+        auto shifted = [&](int k) -> double2 {
+            double2 u = a.ema_tmp[k];
+            if (a.shift > 0) { if (k + a.shift < N) u = a.ema_tmp[k + a.shift]; }
+            else if (a.shift < 0) { if (k + a.shift >= 0) u = a.ema_tmp[k + a.shift]; }
+            return u;
+        };
+        if (a.rebin < 0) v = shifted((N / 4) + (i / 2));
+        else if (i < N / 4 || i >= N - N / 4) v = make_double2(0.0, 0.0);
+        else v = shifted((i - N / 4) * 2);
+    }
+    a.ema[i] = v;
+}
 
 // position p in the in-place DIF result holds X[k]; stages are: one radix-2 (if log_nsub odd) then radix-4's
 SDR_HD inline int dif_output_index(int p, int log_n) {
@@ -77,7 +130,7 @@ SDR_HD inline int fft_phase_count(int log_nsub) { return 1 + (log_nsub & 1) + (l
 SDR_HD inline void spec_fft_phase(int ph, const SpecArgs &a, int bid, int tid, int nt, float2 *sm) {
     const int f = bid / a.P, psub = bid - f * a.P;
     const int nsub = a.nsub, N = a.N;
-    const float2 *x = a.x + a.frame_start[f];
+    const float2 *x = a.x + (a.frame_stride > 0 ? f * a.frame_stride : a.frame_start[f]);
     const int n_r2 = a.log_nsub & 1, n_r4 = a.log_nsub >> 1;
     if (ph == 0) {
         // load with the radix-P decimation-in-frequency first stage: y_p[n] = (sum_r x[n + r N/P] W_P^{r p}) W_N^{n p}
@@ -195,12 +248,14 @@ SDR_HD inline void spec_points_thread(const SpecArgs &a, long long gid) {
     const int f = (int)(gid / a.fft_size), xp = (int)(gid - (long long)f * a.fft_size);
     const float *m = a.maa_f + (size_t)f * a.N;
     const double point_ceil = a.frame_cf_maa[f].x, point_floor = a.frame_cf_maa[f].y;
-    // bandwidth == sample rate: two bins per point; bin 0 is replaced by the floor (idx > 0 test, :546-556)
+    // bins of this point (:538-556): out-of-range bins -- and bin 0 -- count as the floor (`idx > 0 && idx < fftSizeInternal`)
     double acc = 0.0;
-    const int i0 = 2 * xp;
-    acc += (i0 > 0) ? (double)m[i0] : point_floor;
-    acc += (double)m[i0 + 1];
-    const double num = log10((acc / 2.0) + 0.25 - (point_floor - 0.75));
+    const int i0 = a.pt_i0[xp], cnt = a.pt_cnt[xp];
+    for (int j = 0; j < cnt; ++j) {
+        const unsigned idx = (unsigned)round(a.visual_start + (double)(i0 + j));
+        acc += (idx > 0 && idx < (unsigned)a.N) ? (double)m[idx] : point_floor;
+    }
+    const double num = log10((acc / (double)cnt) + 0.25 - (point_floor - 0.75));
     const double den = log10((point_ceil + 0.25) - (point_floor - 0.75));
     const float y = (float)((num / den) * (double)a.scale_factor);
     a.points[gid] = y;

@@ -40,6 +40,7 @@ struct TailArgs {
     unsigned char *results;
     int n;                        // wideband block length
     int first;                    // channel slot handled by CTA 0
+    int view_pass;                // 0: the block's channels; 1: the launch of a zoomed view's hidden channel (ChanDyn::view)
     unsigned long long *dbg;      // diagnostics: per-phase end times of the first 64 channels (null = off)
 };
 
@@ -234,7 +235,7 @@ SDR_HD SDR_FORCEINLINE float arb_r_one(const float *z, const float *pfb, unsigne
 SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt, TailShared *sm) {
     const ChanStatic &cs = a.cs[ch];
     const ChanDyn &cd = a.cd[ch];
-    if (!cd.valid) return;
+    if (!cd.valid || cd.view != a.view_pass) return;
     ChanState &st = a.st[ch];
     ChanResultHeader *hdr = reinterpret_cast<ChanResultHeader *>(a.results + cs.res_off);
     float *res_audio = reinterpret_cast<float *>(a.results + cs.res_off + kResHdrBytes);
@@ -252,8 +253,9 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
     // "I/Q" (analog/ModemIQ.cpp:39-56): no demodulator, no audio resampler -- the decimated IQ itself leaves as two-channel
     // audio {imag, real}; the level is metered on the IQ like FM's (useSignalOutput stays false)
     const bool is_iq = cs.modem == MODEM_IQ;
-    const bool has_agc = !is_fm && !is_iq;                  // ModemAM / USB / LSB pass autoGain = true to buildAudioOutput
-    const bool lvl_from_iq = is_fm || is_iq;
+    const bool is_none = cs.modem == MODEM_NONE;             // resampler only (zoomed spectrum view): nothing after the IQ stage
+    const bool has_agc = !is_fm && !is_iq && !is_none;      // ModemAM / USB / LSB pass autoGain = true to buildAudioOutput
+    const bool lvl_from_iq = is_fm || is_iq || is_none;
 
     if (ph == TP_SETUP) {
         if (tid == 0) {
@@ -271,9 +273,9 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
             }
             // audio resampler bookkeeping: its input is the demodulated stream, one sample per decimated IQ sample
             const long long d0 = (long long)st.iq_count, d1 = d0 + sm->n_iq;
-            if (is_iq) {
+            if (is_iq || is_none) {
                 for (int j = 0; j <= cs.a_S; ++j) { sm->a_g0[j] = 0; sm->a_n[j] = 0; }
-                sm->n_audio = 2 * sm->n_iq;
+                sm->n_audio = is_iq ? 2 * sm->n_iq : 0;
                 sm->a_phase_after = st.a_phase;
             } else if (!cs.a_interp) {
                 for (int j = 0; j <= cs.a_S; ++j) { sm->a_g0[j] = d0 >> j; sm->a_n[j] = (int)((d1 >> j) - (d0 >> j)); }
@@ -348,7 +350,8 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
 
     if (ph == TP_DEMOD_A) {
         const int n = sm->n_iq;
-        if (is_iq) {
+        if (is_none) {
+        } else if (is_iq) {
             for (int i = tid; i < n; i += nt) {
                 const float2 x = iq[i];
                 if (2 * i + 1 < cs.res_audio_cap) { res_audio[2 * i] = x.y; res_audio[2 * i + 1] = x.x; }
@@ -401,7 +404,7 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
     }
 
     if (ph == TP_DEMOD_B) {
-        if (is_ssb) {                                            // firhilbf c2r, 21 taps
+        if (is_ssb && !is_none) {                                // firhilbf c2r, 21 taps
             const float2 *w = chan_cbuf(a, cs, cs.w_off) + kHist;
             const float *hq = a.taps + cs.hq_off;
             const float sgn = (cs.modem == MODEM_USB) ? -1.0f : 1.0f;   // usb = yi - yq, lsb = yi + yq
@@ -444,7 +447,7 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
     // ---- audio resampler msresamp_rrrf ---------------------------------------------------------------------------------
     if (ph >= TP_AUD0 && ph < TP_AUD0 + kMaxAudioHb + 1) {
         const int j = ph - TP_AUD0;
-        if (is_iq) return;
+        if (is_iq || is_none) return;
         if (!cs.a_interp) {
             // decimator: a_S half-bands (cascade position g = a_S-1-j for phase j), then the arbitrary stage
             if (j < cs.a_S) {
@@ -509,6 +512,7 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
 
     // ---- metering: DemodulatorThread.cpp:142-163 (level), 223-233 (peak) ---------------------------------------------
     if (ph == TP_METER_A) {
+        if (is_none) { sm->red_f[tid] = 0.f; sm->red_d[tid] = 0.0; return; }
         const int na = sm->n_audio < cs.res_audio_cap ? sm->n_audio : cs.res_audio_cap;
         float pk = 0.f;
         double acc = 0.0;

@@ -659,6 +659,13 @@ __global__ void k_spec_scalar(SpecArgs a) {
 __global__ void __launch_bounds__(kSpecThreads) k_spec_points(SpecArgs a) {
     spec_points_thread(a, (long long)blockIdx.x * blockDim.x + threadIdx.x);
 }
+__global__ void __launch_bounds__(256) k_view_mix(ViewMixArgs a) {
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < (long long)a.F * a.D; g += (long long)gridDim.x * blockDim.x)
+        view_mix_thread(a, g);
+}
+__global__ void __launch_bounds__(kSpecThreads) k_view_ema_move(SpecArgs a, int ph) {
+    view_ema_move_thread(a, ph, blockIdx.x * blockDim.x + threadIdx.x);
+}
 // serial float recurrence at the channel rate.  The warp stages 256 samples at a time in shared memory; every lane runs the
 // chain (fully unrolled 32 steps, inputs fetched ahead of it) and lane l keeps output l, so a batch is stored coalesced and
 // the chain runs at its latency (~10 cycles a step) instead of waiting for shared memory every step.
@@ -871,6 +878,11 @@ static int launch_spectrum(const SpecArgs &a, sdr_stream_t s, unsigned long long
         attr_set = true;
     }
     k_spec_fft<<<a.F * a.P, kFftThreads, smem, s>>>(a, phases);
+    if (a.rebin || a.shift) {
+        k_view_ema_move<<<(a.N + kSpecThreads - 1) / kSpecThreads, kSpecThreads, 0, s>>>(a, 0);
+        k_view_ema_move<<<(a.N + kSpecThreads - 1) / kSpecThreads, kSpecThreads, 0, s>>>(a, 1);
+        launches += 2;
+    }
     k_spec_ema<<<(a.N + kSpecThreads - 1) / kSpecThreads, kSpecThreads, 0, s>>>(a);
     k_spec_minmax<<<a.F, kSpecThreads, 0, s>>>(a);
     k_spec_scalar<<<1, 32, 0, s>>>(a);
@@ -881,6 +893,7 @@ static int launch_spectrum(const SpecArgs &a, sdr_stream_t s, unsigned long long
     std::vector<float2> sm(a.nsub);
     for (int b = 0; b < a.F * a.P; ++b)
         for (int ph = 0; ph < phases; ++ph) for (int t = 0; t < kFftThreads; ++t) spec_fft_phase(ph, a, b, t, kFftThreads, sm.data());
+    if (a.rebin || a.shift) for (int ph = 0; ph < 2; ++ph) for (int i = 0; i < a.N; ++i) view_ema_move_thread(a, ph, i);
     for (int i = 0; i < a.N; ++i) spec_ema_thread(a, i);
     for (int f = 0; f < a.F; ++f) {
         SpecRedShared rs;
@@ -963,6 +976,15 @@ struct sdr_spectrum {
     // framing state (FFTDataDistributor)
     long long buffered = 0, last_rate = 0, last_center = 0;
     double line_accum = 0.0;
+    // zoomed view (SpectrumVisualProcessor::setView, .cpp:57-75, process() :283-386): members as in the reference
+    bool is_view = false, last_view = false;
+    long long view_center = 0; long view_bw = 0;
+    long shift_frequency = 0, last_bandwidth = 0, last_input_bw = 0;
+    unsigned nco_theta = 0, nco_dtheta = 0;         // freqShifter
+    sdr_chan *vchan = nullptr;                      // the view's msresamp_crcf (a hidden, modem-less channel)
+    double visual_ratio = 1.0;                      // bandwidth / resampleBw of the point table on the device
+    int *d_pt = nullptr, *h_pt = nullptr;           // [2][fft_size]: first bin offset and bin count of every display point
+    double2 *d_ema_tmp = nullptr;
     // device
     float2 *d_tw = nullptr; float *d_mags = nullptr, *d_maa = nullptr; double2 *d_ema = nullptr; double *d_scalars = nullptr;
     float2 *d_frame_cf = nullptr; double2 *d_frame_cf_maa = nullptr; float *d_points = nullptr; unsigned char *d_lines = nullptr;
@@ -1192,7 +1214,8 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
 #else
     (void)stream;
 #endif
-    e->hist_cap = 65536 + kBlkHist;
+    // history kept in front of the block: the DC replay's warm-up, and a zoomed spectrum view's frame (up to one block long)
+    e->hist_cap = (std::max<size_t>(65536, max_block) + kBlkHist + 1) & ~(size_t)1;
     int bad = 0;
     bad |= be_malloc((void **)&e->d_raw, (size_t)max_block * sizeof(float2));
     e->raw_pad = (size_t)max_block / 8 + 2 * 65536;
@@ -1530,14 +1553,18 @@ static void reap_graveyard(sdr_engine *e, bool wait) {
 // DemodulatorWorkerThread builds the resampler for a new demodulator off the hot threads (DemodulatorWorkerThread.cpp:63-108);
 // so does this: design and layout without any lock, allocation / clearing / uploads on the admin stream under mu_cfg, and the
 // submit lock only to publish the finished channel.
+// view_cap != 0: the hidden channel of a zoomed spectrum view (SpectrumVisualProcessor's own msresamp_crcf): no modem, every
+// half-band stage in the tail kernel (its level-0 stream is written by the view mixer, not by the front kernel), buffers for
+// view_cap samples per block; called from a submit, i.e. with e->mu already held.
 static int chan_create_impl(sdr_engine *e, const char *modem, long long sample_rate, long long bandwidth, int audio_rate,
-                            unsigned inject_cap, sdr_chan **out) {
+                            unsigned inject_cap, sdr_chan **out, unsigned view_cap = 0) {
     if (!e || !out || sample_rate <= 0 || audio_rate <= 0) return fail(SDR_ERR_ARG, "sdr_chan_create: bad arguments");
-    const int mk = modem_from_name(modem);
+    const int mk = view_cap ? (int)MODEM_NONE : modem_from_name(modem);
     if (mk < 0) return fail(SDR_ERR_UNSUPPORTED, std::string("sdr_chan_create: unknown modem '") + (modem ? modem : "") + "'");
     sdr_chan *c = new sdr_chan();
     c->eng = e; c->index = -1; c->modem = mk; c->sample_rate = sample_rate;
     c->bandwidth = check_sample_rate(mk, bandwidth);
+    if (view_cap) c->bandwidth = (int)bandwidth;                        // a power-of-two fraction of the rate, as it comes
     if (mk == MODEM_IQ) c->bandwidth = audio_rate;                      // ModemIQ::checkSampleRate returns audioSampleRate (ModemIQ.cpp:31-33)
     c->audio_rate = audio_rate;
     const float As = 60.0f;                                             // DemodulatorWorkerThread.cpp:95, ModemAnalog.cpp:25
@@ -1555,6 +1582,7 @@ static int chan_create_impl(sdr_engine *e, const char *modem, long long sample_r
     cs.modem = mk;
     cs.S = c->iq_plan.num_halfband;
     cs.K1 = std::max(0, std::min(cs.S - 2, kFrontMaxK));               // only the m = 3 stages can be fused
+    if (view_cap) cs.K1 = 0;
     cs.n_tail = cs.S - cs.K1;
     if (cs.n_tail > kMaxTailHb) { delete c; return fail(SDR_ERR_UNSUPPORTED, "sdr_chan_create: too many tail stages"); }
     for (int g = cs.S - cs.K1; g < cs.S; ++g)
@@ -1573,8 +1601,8 @@ static int chan_create_impl(sdr_engine *e, const char *modem, long long sample_r
     // ---- arena layout (floats)
     size_t off = 0;
     auto take = [&](size_t floats) { size_t o = off; off += (floats + 3) & ~size_t(3); return (int)o; };
-    const size_t nb = inject_cap ? inject_cap : e->chan_block_max;
-    c->standalone = inject_cap != 0;
+    const size_t nb = view_cap ? view_cap : (inject_cap ? inject_cap : e->chan_block_max);
+    c->standalone = inject_cap != 0 || view_cap != 0;                   // neither is part of the block's channel set
     c->inject_cap = inject_cap;
     for (int j = 0; j <= cs.n_tail; ++j) cs.lvl_off[j] = take(2 * (kHist + (nb >> (cs.K1 + j)) + 4));
     cs.lvl0_alt_off = take(2 * (kHist + (nb >> cs.K1) + 4));
@@ -1604,7 +1632,7 @@ static int chan_create_impl(sdr_engine *e, const char *modem, long long sample_r
     memset(&st, 0, sizeof st);
     st.agc_ceil = st.agc_ma = st.agc_maa = 1.0f;                        // ModemAnalog.cpp:6
     st.sig_level = -100.f; st.sig_floor = -30.f; st.sig_ceil = 30.f;    // DemodulatorThread.cpp:25-26
-    if (c->standalone) {
+    if (inject_cap) {
         if (be_host_alloc((void **)&c->h_dyn, sizeof(ChanDyn)) || be_host_alloc((void **)&c->h_slot, c->slot_bytes)) {
             be_host_free(c->h_dyn); be_host_free(c->h_slot); delete c;
             return fail(SDR_ERR_NOMEM, "sdr_modem_create: host buffers");
@@ -1669,10 +1697,13 @@ static int chan_create_impl(sdr_engine *e, const char *modem, long long sample_r
 #ifndef SDR_EMU
         if (cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming) != cudaSuccess) return bail(SDR_ERR_CUDA, "sdr_chan_create: event");
         cudaEventRecord(c->ev_ready, as);
-        if (c->standalone) cudaEventSynchronize(c->ev_ready);           // sdr_modem_*: the caller's own thread, nobody else waits
+        if (inject_cap) cudaEventSynchronize(c->ev_ready);              // sdr_modem_*: the caller's own thread, nobody else waits
 #endif
     }
-    {   // publish: the submitter sees the channel from its next block on
+    if (view_cap) {                                                     // e->mu is held by the submit that makes the view
+        if ((size_t)c->index >= e->chans.size()) e->chans.resize((size_t)c->index + 1, nullptr);
+        e->chans[(size_t)c->index] = c;
+    } else {   // publish: the submitter sees the channel from its next block on
         std::lock_guard<std::mutex> lk(e->mu);
         if ((size_t)c->index >= e->chans.size()) e->chans.resize((size_t)c->index + 1, nullptr);
         e->chans[(size_t)c->index] = c;
@@ -1727,7 +1758,7 @@ extern "C" int sdr_modem_demodulate(sdr_chan *c, const sdr_cf32 *iq, unsigned n,
     be_h2d(e->d_cd2[0] + c->index, c->h_dyn, sizeof(ChanDyn), e->stream);
     TailArgs ta;
     ta.cs = e->d_cs; ta.cd = e->d_cd2[0]; ta.st = e->d_st; ta.taps = e->d_taps; ta.nco = e->d_nco;
-    ta.results = e->d_results; ta.n = 0; ta.first = c->index; ta.dbg = nullptr;
+    ta.results = e->d_results; ta.n = 0; ta.first = c->index; ta.view_pass = 0; ta.dbg = nullptr;
     launch_tail(ta, 1, e->stream, e->launches);
     be_d2h(c->h_slot, e->d_results + c->cs.res_off, c->slot_bytes, e->stream);
     if (be_sync(e->stream)) return fail(SDR_ERR_CUDA, std::string("sdr_modem_demodulate: ") + be_last_error());
@@ -1743,8 +1774,7 @@ extern "C" int sdr_modem_demodulate(sdr_chan *c, const sdr_cf32 *iq, unsigned n,
 // DemodulatorMgr::deleteThread happens while blocks are in flight.  The channel disappears from the submitter's list at once
 // (a few host instructions under the submit lock); its memory is handed back on the admin stream once events recorded on
 // every engine stream at this moment have fired, and its slot / result region are recycled when that is known to have happened.
-extern "C" int sdr_chan_destroy(sdr_chan *c) {
-    if (!c) return SDR_OK;
+static void chan_destroy_core(sdr_chan *c, bool have_mu) {
     sdr_engine *e = c->eng;
 #ifndef SDR_EMU
     cudaSetDevice(e->device);
@@ -1752,7 +1782,8 @@ extern "C" int sdr_chan_destroy(sdr_chan *c) {
     for (auto &f : fence) cudaEventCreateWithFlags(&f, cudaEventDisableTiming);
 #endif
     {
-        std::lock_guard<std::mutex> lk(e->mu);
+        std::unique_lock<std::mutex> lk(e->mu, std::defer_lock);
+        if (!have_mu) lk.lock();
         if (c->index >= 0 && (size_t)c->index < e->chans.size() && e->chans[(size_t)c->index] == c) e->chans[(size_t)c->index] = nullptr;
 #ifndef SDR_EMU
         // everything already enqueued may still touch the channel; nothing enqueued later will
@@ -1770,7 +1801,7 @@ extern "C" int sdr_chan_destroy(sdr_chan *c) {
         chan_release_memory(e, c, as);
 #ifndef SDR_EMU
         if (cudaEventCreateWithFlags(&c->ev_dead, cudaEventDisableTiming) == cudaSuccess) cudaEventRecord(c->ev_dead, as);
-        if (c->standalone && c->ev_dead) cudaEventSynchronize(c->ev_dead);   // pinned host buffers go now: the caller's own thread waits
+        if (c->h_dyn && c->ev_dead) cudaEventSynchronize(c->ev_dead);   // sdr_modem_*: pinned host buffers go now, the caller's own thread waits
 #endif
         be_host_free(c->h_dyn); be_host_free(c->h_slot);
         c->h_dyn = nullptr; c->h_slot = nullptr;
@@ -1780,6 +1811,15 @@ extern "C" int sdr_chan_destroy(sdr_chan *c) {
 #ifndef SDR_EMU
     for (auto &f : fence) if (f) cudaEventDestroy(f);                   // a recorded event may be destroyed: the wait stays valid
 #endif
+}
+static void chan_destroy_locked(sdr_chan *c) { chan_destroy_core(c, true); }
+
+// DemodulatorMgr::deleteThread happens while blocks are in flight.  The channel disappears from the submitter's list at once
+// (a few host instructions under the submit lock); its memory is handed back on the admin stream once events recorded on
+// every engine stream at this moment have fired, and its slot / result region are recycled when that is known to have happened.
+extern "C" int sdr_chan_destroy(sdr_chan *c) {
+    if (!c) return SDR_OK;
+    chan_destroy_core(c, false);
     return SDR_OK;
 }
 
@@ -1825,7 +1865,23 @@ extern "C" int sdr_chan_want_iq(sdr_chan *c, int enable) {
 // ---------------------------------------------------------------------------------------------------------------------
 // spectrum
 // ---------------------------------------------------------------------------------------------------------------------
+// The reference's point loop (SpectrumVisualProcessor.cpp:532-556) decides with a running double accumulator how many bins merge
+// into each display point; the same loop, run once on the host for a view ratio, gives every point its first bin offset and
+// bin count (the device then does the sums).
+static void spectrum_point_table(sdr_spectrum *s, double visualRatio) {
+    double visualAccum = 0, i = 0;
+    for (unsigned x = 0; x < s->fft_size; ++x) {
+        visualAccum += visualRatio * double(2);                               // SPECTRUM_VZM
+        int cnt = 0;
+        const int i0 = (int)i;
+        while (visualAccum >= 1.0) { cnt++; visualAccum -= 1.0; i++; }
+        s->h_pt[x] = i0; s->h_pt[s->fft_size + x] = cnt < 1 ? 1 : cnt;
+    }
+    s->visual_ratio = visualRatio;
+}
+static void chan_destroy_locked(sdr_chan *c);
 static void spectrum_free(sdr_spectrum *s) {
+    be_free(s->d_pt); be_host_free(s->h_pt); be_free(s->d_ema_tmp);
     be_free(s->d_tw); be_free(s->d_mags); be_free(s->d_maa); be_free(s->d_ema); be_free(s->d_scalars); be_free(s->d_frame_cf);
     be_free(s->d_frame_cf_maa); be_free(s->d_points); be_free(s->d_lines); be_free(s->d_frame_start);
     be_host_free(s->h_points); be_host_free(s->h_lines); be_host_free(s->h_cf); be_host_free(s->h_frame_start); be_host_free(s->h_dbg);
@@ -1862,6 +1918,9 @@ extern "C" int sdr_spectrum_create(sdr_engine *e, unsigned fft_size, unsigned lp
     bad |= be_host_alloc((void **)&s->h_cf, kResBuf * F * sizeof(double2));
     bad |= be_host_alloc((void **)&s->h_frame_start, (size_t)sdr_engine::kRing * F * sizeof(int));
     bad |= be_host_alloc((void **)&s->h_dbg, 2 * N * sizeof(float));
+    bad |= be_malloc((void **)&s->d_pt, 2 * (size_t)fft_size * sizeof(int));
+    bad |= be_host_alloc((void **)&s->h_pt, (size_t)(1 + sdr_engine::kRing) * 2 * (size_t)fft_size * sizeof(int));   // [table | one upload slot per parameter-ring entry]
+    bad |= be_malloc((void **)&s->d_ema_tmp, N * sizeof(double2));
     if (bad) { spectrum_free(s); delete s; return fail(SDR_ERR_NOMEM, "sdr_spectrum_create: allocation failed"); }
     std::vector<float2> tw(N);
     for (size_t k = 0; k < N; ++k) {
@@ -1872,6 +1931,8 @@ extern "C" int sdr_spectrum_create(sdr_engine *e, unsigned fft_size, unsigned lp
     be_memset(s->d_ema, 0, N * sizeof(double2), e->stream);                      // vectors resized to zeros (:252-264)
     const double sc[4] = {100.0, 100.0, 0.0, 0.0};                                 // fft_ceil_ma/maa, fft_floor_ma/maa (:32-33)
     be_h2d(s->d_scalars, sc, sizeof sc, e->stream);
+    spectrum_point_table(s, 1.0);
+    be_h2d(s->d_pt, s->h_pt, 2 * (size_t)fft_size * sizeof(int), e->stream);
     be_sync(e->stream);
     e->spectra.push_back(s);
     *out = s;
@@ -1884,12 +1945,32 @@ extern "C" int sdr_spectrum_destroy(sdr_spectrum *s) {
     std::lock_guard<std::mutex> lk(e->mu);
     use_device(e);
     sync_all(e);                                                        // the side / result streams may still use its buffers
+    if (s->vchan) { chan_destroy_locked(s->vchan); s->vchan = nullptr; }
     e->spectra.erase(std::remove(e->spectra.begin(), e->spectra.end(), s), e->spectra.end());
     spectrum_free(s);
     delete s;
     return SDR_OK;
 }
 
+// SpectrumVisualProcessor::setView(bView, centerFreq, bandwidth) (:64-71); setCenterFrequency / setBandwidth are the same call
+// with one argument changed.  Effective from the next block.
+extern "C" int sdr_spectrum_set_view(sdr_spectrum *s, int is_view, long long center_freq, long bandwidth) {
+    if (!s) return fail(SDR_ERR_ARG, "null spectrum");
+    if (is_view && bandwidth <= 0) return fail(SDR_ERR_ARG, "sdr_spectrum_set_view: bandwidth must be positive");
+    std::lock_guard<std::mutex> lk(s->eng->mu);
+    s->is_view = is_view != 0; s->view_center = center_freq; s->view_bw = bandwidth;
+    return SDR_OK;
+}
+// getDesiredInputSize (:134-138) for a sample rate: the frame length the view asks of the distributor
+extern "C" int sdr_spectrum_desired_input(sdr_spectrum *s, long long sample_rate, unsigned *n) {
+    if (!s || !n || sample_rate <= 0) return fail(SDR_ERR_ARG, "sdr_spectrum_desired_input: bad arguments");
+    std::lock_guard<std::mutex> lk(s->eng->mu);
+    if (!s->is_view) { *n = s->N; return SDR_OK; }
+    long rb = (long)sample_rate;
+    while (rb / 2 >= s->view_bw) rb /= 2;
+    *n = (unsigned)(size_t)((double)s->N / ((double)rb / (double)sample_rate));
+    return SDR_OK;
+}
 extern "C" int sdr_spectrum_set_average_rate(sdr_spectrum *s, float r) {
     if (!s) return fail(SDR_ERR_ARG, "null spectrum");
     std::lock_guard<std::mutex> lk(s->eng->mu);
@@ -1899,12 +1980,12 @@ extern "C" int sdr_spectrum_set_average_rate(sdr_spectrum *s, float r) {
 
 // FFTDataDistributor::process restated for frames that are transformed immediately (src/process/FFTDataDistributor.cpp:
 // 41-53 reset on rate change, :89-97 line-rate step, :100-142 emit loop).  Returns frame starts relative to the block.
-static void schedule_frames(sdr_spectrum *s, unsigned n, long long sample_rate, long long center, std::vector<int> &starts) {
+static void schedule_frames(sdr_spectrum *s, long long frame_len, unsigned n, long long sample_rate, long long center, std::vector<int> &starts) {
     starts.clear();
     // "Settings have changed ... dump all previous samples" (:41-53): a new rate OR a new tuner frequency empties the buffer;
     // lineRateAccum is left alone, as there
     if (s->last_rate != sample_rate || s->last_center != center) { s->buffered = 0; s->last_rate = sample_rate; s->last_center = center; }
-    const long long before = s->buffered, N = s->N;
+    const long long before = s->buffered, N = frame_len;
     s->buffered += n;
     if (s->buffered < N) return;
     if (s->lps == 0) {                                  // full coverage: every non-overlapping frame
@@ -2132,7 +2213,11 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
     }
     // history in front of the block: the tail of the previous block, which lives in the other buffer
     size_t need = kBlkHist;
-    for (auto *s : e->spectra) need = std::max(need, (size_t)s->N + 16);
+    for (auto *s : e->spectra) {
+        size_t fl = s->N;
+        if (s->is_view && s->view_bw > 0) { long rb = (long)rate; while (rb / 2 >= s->view_bw) rb /= 2; fl = (size_t)((double)s->N / ((double)rb / (double)rate)); }
+        need = std::max(need, fl + 16);
+    }
     if (need > e->hist_cap) need = e->hist_cap;
     if (e->have_block && e->last_n > 0) {
         const float2 *prev = e->d_blkbuf[p ^ 1] + e->hist_cap;
@@ -2204,9 +2289,19 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
     //    stream AFTER the channel front kernel has been launched (run_spectra below), so that the front kernel's single
     //    wave of 148 CTAs gets the SMs first and the spectrum fills in underneath the channel tail.
     std::vector<int> starts;
-    std::vector<std::pair<sdr_spectrum *, SpecArgs>> spec_jobs;
+    struct SpecJob { sdr_spectrum *s; SpecArgs a; bool view; ViewMixArgs mix; sdr_chan *vc; int n_view; bool wait_ready; };
+    std::vector<SpecJob> spec_jobs;
+    std::vector<std::pair<int, ChanDyn>> view_dyn;             // per-block parameters of the views' hidden channels (patched in below)
     for (auto *s : e->spectra) {
-        schedule_frames(s, n, rate, center, starts);
+        // frame length: the transform's, or what a zoomed view needs to end up with it after its resampler (:283-297)
+        long resample_bw = (long)rate;
+        long long D = s->N;
+        if (s->is_view) {
+            while (resample_bw / 2 >= s->view_bw) resample_bw /= 2;          // SPECTRUM_VZM = 2
+            D = (long long)(size_t)((double)s->N / ((double)resample_bw / (double)rate));
+            if ((size_t)D + 16 > e->hist_cap) return fail(SDR_ERR_UNSUPPORTED, "zoomed view: a frame of the view is longer than the engine's stream history (one block)");
+        }
+        schedule_frames(s, D, n, rate, center, starts);
         s->frames_last = (unsigned)std::min<size_t>(starts.size(), s->f_max);
         s->frames_buf[q] = s->frames_last;
         if (!s->frames_last) continue;
@@ -2214,12 +2309,76 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         memcpy(h_fs, starts.data(), s->frames_last * sizeof(int));
         int *d_fs = s->d_frame_start + (size_t)p * s->f_max;
         upload_params(d_fs, h_fs, s->frames_last * sizeof(int), par_stream, e->launches);
-        SpecArgs a;
-        a.x = blk; a.frame_start = d_fs; a.F = (int)s->frames_last; a.N = (int)s->N; a.fft_size = (int)s->fft_size;
+        SpecJob job;
+        job.s = s; job.view = false; job.vc = nullptr; job.n_view = 0; job.wait_ready = false;
+        SpecArgs &a = job.a;
+        a.x = blk; a.frame_start = d_fs; a.frame_stride = 0; a.F = (int)s->frames_last; a.N = (int)s->N; a.fft_size = (int)s->fft_size;
         a.P = s->P; a.nsub = s->nsub; a.log_nsub = s->log_nsub; a.tw = s->d_tw; a.mags = s->d_mags; a.maa_f = s->d_maa; a.ema = s->d_ema;
         a.rate = (double)s->average_rate; a.frame_cf = s->d_frame_cf; a.scalars = s->d_scalars; a.frame_cf_maa = s->d_frame_cf_maa;
         a.points = s->d_points; a.lines = s->d_lines; a.scale_factor = s->scale_factor;
-        spec_jobs.emplace_back(s, a);
+        a.rebin = 0; a.shift = 0; a.ema_tmp = s->d_ema_tmp;
+        double visual_ratio = 1.0;
+        if (s->is_view) {
+            // ---- SpectrumVisualProcessor::process, view branch, once for the block's frames (only its first frame can change anything)
+            const long long N = s->N;
+            bool mixing = false;
+            if (s->view_center != center) {                                             // :304-347
+                if ((s->view_center - center) != (long long)s->shift_frequency || s->last_input_bw != (long)rate) {
+                    if (std::llabs(center - s->view_center) < (rate / 2)) {
+                        const long last_shift = s->shift_frequency;
+                        s->shift_frequency = (long)(s->view_center - center);
+                        s->nco_dtheta = nco_phase_step(nco_shift_word_arg(s->shift_frequency, rate));
+                        const long freq_diff = s->shift_frequency - last_shift;
+                        if (s->last_bandwidth != 0) {                                   // the averages follow the view
+                            const double bin_per_hz = double(s->last_bandwidth) / double(N);
+                            const unsigned num_shift = (unsigned)std::floor(double(std::labs(freq_diff)) / bin_per_hz);
+                            if (num_shift < (unsigned)(N / 2) && num_shift) a.shift = freq_diff > 0 ? (int)num_shift : -(int)num_shift;
+                        }
+                    }
+                }
+                mixing = true;
+            }
+            long bw_diff = 0;
+            bool new_resampler = false;
+            if (!s->vchan || resample_bw != s->last_bandwidth || s->last_input_bw != (long)rate) {   // :354-368
+                if (s->vchan) { chan_destroy_locked(s->vchan); s->vchan = nullptr; }
+                const unsigned cap = (unsigned)std::min<size_t>(2 * (size_t)e->max_block + 64, 0x7fffff00u);
+                int r = chan_create_impl(e, nullptr, rate, resample_bw, 48000, 0, &s->vchan, cap);
+                if (r) return r;
+                bw_diff = resample_bw - s->last_bandwidth;
+                s->last_bandwidth = resample_bw; s->last_input_bw = (long)rate;
+                new_resampler = true;
+            }
+            if (new_resampler && s->last_view) a.rebin = bw_diff < 0 ? -1 : 1;           // :454
+            visual_ratio = double(s->view_bw) / double(resample_bw);                    // :532
+            sdr_chan *vc = s->vchan;
+            const int n_view = (int)(s->frames_last * D);
+            job.view = true; job.vc = vc; job.n_view = n_view; job.wait_ready = vc->fresh; vc->fresh = false;
+            job.mix.x = blk; job.mix.frame_start = d_fs; job.mix.F = (int)s->frames_last; job.mix.D = (int)D; job.mix.nco = e->d_nco;
+            job.mix.theta0 = s->nco_theta; job.mix.dtheta = s->nco_dtheta;
+            job.mix.dir = mixing ? (s->shift_frequency < 0 ? +1 : -1) : 0;                // mix_block_up if shiftFrequency < 0 (:340-344)
+            job.mix.out = reinterpret_cast<float2 *>(vc->cs.arena + (vc->lvl0_sel ? vc->cs.lvl0_alt_off : vc->cs.lvl_off[0])) + kHist;
+            if (mixing) s->nco_theta += (unsigned)n_view * s->nco_dtheta;
+            ChanDyn vd;
+            memset(&vd, 0, sizeof vd);
+            vd.valid = 1; vd.active = 1; vd.view = 1; vd.g0 = vc->consumed; vd.lvl0_sel = vc->lvl0_sel;
+            vc->lvl0_sel ^= 1; vc->consumed += n_view;
+            view_dyn.emplace_back(vc->index, vd);
+            // every frame yields exactly N resampled samples (power-of-two ratio, frame = N / ratio): the transforms read the
+            // hidden channel's decimated stream, frame f at f N
+            a.x = reinterpret_cast<const float2 *>(vc->cs.arena + vc->cs.iq_off) + kHist;
+            a.frame_stride = (int)N;
+        }
+        if (visual_ratio != s->visual_ratio) {                   // bins per display point for this view (the host-side loop, uploaded)
+            spectrum_point_table(s, visual_ratio);
+            int *h_tab = s->h_pt + (size_t)(1 + slot) * 2 * s->fft_size;
+            memcpy(h_tab, s->h_pt, 2 * (size_t)s->fft_size * sizeof(int));
+            upload_params(s->d_pt, h_tab, 2 * (size_t)s->fft_size * sizeof(int), par_stream, e->launches);
+        }
+        a.pt_i0 = s->d_pt; a.pt_cnt = s->d_pt + s->fft_size;
+        a.visual_start = (double(s->N) / 2.0) - (double(s->N) * (visual_ratio / 2.0));
+        s->last_view = s->is_view;                               // :636
+        spec_jobs.push_back(job);
     }
     bool forked = false;
     auto run_spectra = [&]() -> int {
@@ -2238,7 +2397,23 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         if (!spec_jobs.empty() && prev_q >= 0 && e->res_spec_rec[prev_q]) CUDA_TRY(cudaStreamWaitEvent(sps, e->ev_res_spec[prev_q], 0));
 #endif
         for (auto &job : spec_jobs) {
-            int r = launch_spectrum(job.second, sps, e->launches);
+            if (job.view) {
+                // zoomed view: its frames -> oscillator mix into the hidden channel's level-0 stream -> that channel's half-bands
+                // and polyphase arm (the tail kernel, on its own slot) -> the transforms read its decimated stream
+#ifndef SDR_EMU
+                if (job.wait_ready && job.vc->ev_ready) CUDA_TRY(cudaStreamWaitEvent(sps, job.vc->ev_ready, 0));
+                const long long tot = (long long)job.mix.F * job.mix.D;
+                k_view_mix<<<(unsigned)std::min<long long>((tot + 255) / 256, 2048), 256, 0, sps>>>(job.mix);
+#else
+                for (long long g = 0; g < (long long)job.mix.F * job.mix.D; ++g) view_mix_thread(job.mix, g);
+#endif
+                e->launches += 1;
+                TailArgs tv;
+                tv.cs = e->d_cs; tv.cd = e->d_cd2[p]; tv.st = e->d_st; tv.taps = e->d_taps; tv.nco = e->d_nco;
+                tv.results = e->d_results; tv.n = job.n_view; tv.first = job.vc->index; tv.view_pass = 1; tv.dbg = nullptr;
+                launch_tail(tv, 1, sps, e->launches);
+            }
+            int r = launch_spectrum(job.a, sps, e->launches);
             if (r) return r;
         }
 #ifndef SDR_EMU
@@ -2255,7 +2430,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
             CUDA_TRY(cudaStreamWaitEvent(rs, e->ev_spec_k, 0));
 #endif
             for (auto &job : spec_jobs) {
-                sdr_spectrum *s = job.first;
+                sdr_spectrum *s = job.s;
                 be_d2h(s->hp(q), s->d_points, (size_t)s->frames_last * s->fft_size * sizeof(float), rs);
                 be_d2h(s->hl(q), s->d_lines, (size_t)s->frames_last * s->fft_size, rs);
                 be_d2h(s->hc(q), s->d_frame_cf_maa, (size_t)s->frames_last * sizeof(double2), rs);
@@ -2410,6 +2585,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         if (c->recent.size() > (size_t)kPremixSegs) c->recent.pop_back();
         by_k[c->cs.K1].push_back(i);
     }
+    for (auto &vd : view_dyn) h_cd[vd.first] = vd.second;       // the zoomed views' hidden channels (their own tail launch)
     ChanDyn *d_cd = e->d_cd2[p];
 #ifndef SDR_EMU
     // d_cd2[p] and the level-0 buffers this block's front kernel writes were last read by the tail of two blocks ago
@@ -2454,7 +2630,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
     { int r = run_spectra(); if (r) return r; }                     // side stream, after the front kernel got the SMs
     TailArgs ta;
     ta.cs = e->d_cs; ta.cd = d_cd; ta.st = e->d_st; ta.taps = e->d_taps; ta.nco = e->d_nco;
-    ta.results = e->d_results; ta.n = (int)n_ch; ta.first = 0; ta.dbg = e->d_front_dbg ? e->d_front_dbg + 4 * 1024 : nullptr;
+    ta.results = e->d_results; ta.n = (int)n_ch; ta.first = 0; ta.view_pass = 0; ta.dbg = e->d_front_dbg ? e->d_front_dbg + 4 * 1024 : nullptr;
     // the tail indexes channels by slot; free slots carry valid = 0 and are not touched
     time_mark(e, 3);
     // the channel tail (and the results' D2H) go to their own stream: they overlap the next block's front kernel

@@ -145,6 +145,15 @@ int sdr_modem_demodulate(sdr_chan *modem, const sdr_cf32 *iq, unsigned n, float 
 int sdr_spectrum_create(sdr_engine *eng, unsigned fft_size, unsigned lines_per_second, sdr_spectrum **out);
 int sdr_spectrum_destroy(sdr_spectrum *sp);
 int sdr_spectrum_set_average_rate(sdr_spectrum *sp, float rate);      /* setFFTAverageRate, default 0.65 (:36) */
+/* Zoomed view: SpectrumVisualProcessor::setView(bView, centerFreq, bandwidth) (src/process/SpectrumVisualProcessor.cpp:57-75;
+ * setCenterFrequency / setBandwidth :87-110 are the same call with one argument changed).  In view mode every frame is
+ * shifted by the view's oscillator and decimated by msresamp_crcf(resampleBw / sampleRate) -- resampleBw = the smallest
+ * power-of-two fraction of the rate that still holds the bandwidth -- before the transform (:283-386); on a zoom step or a
+ * pan the running averages are re-binned / moved (:317-329, :454-492) and the display points span bandwidth / resampleBw of
+ * the bins (:532-556).  Effective from the next block.  A frame of the view is fft_size * 2 * sampleRate / resampleBw
+ * samples (sdr_spectrum_desired_input = getDesiredInputSize) and must fit the engine's stream history (one block).     */
+int sdr_spectrum_set_view(sdr_spectrum *sp, int is_view, long long center_freq, long bandwidth);
+int sdr_spectrum_desired_input(sdr_spectrum *sp, long long sample_rate, unsigned *n);
 /* frames produced by the last submitted block */
 int sdr_spectrum_frames(sdr_spectrum *sp, unsigned *n_frames);
 /* frame `idx` of the last block: points_y = SpectrumVisualData::spectrum_points y values (fft_size floats),

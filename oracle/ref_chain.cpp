@@ -414,6 +414,7 @@ API void *ref_distrib_create(unsigned fftSize, unsigned lps) {
     d->bufferMax = d->bufferOffset = d->bufferedItems = 0; d->sampleRate = 0; return d;
 }
 API void ref_distrib_destroy(void *h) { delete (RefDistrib *)h; }
+API void ref_distrib_set_fft_size(void *h, unsigned fftSize) { ((RefDistrib *)h)->fftSize = fftSize; }   // FFTDataDistributor.cpp:15-18
 // returns number of frames written to frames_out (each fftSize samples)
 API unsigned ref_distrib_push(void *h, const lq_cf *in, unsigned n, long long sampleRate, long long frequency, lq_cf *frames_out, unsigned cap_frames) {
     auto *d = (RefDistrib *)h;
@@ -468,7 +469,15 @@ struct RefSpectrum {
     fftplan plan;
     double fft_ceil_ma, fft_ceil_maa, fft_floor_ma, fft_floor_maa;
     float fft_average_rate, scaleFactor;
-    std::vector<double> fft_result, fft_result_ma, fft_result_maa;
+    std::vector<double> fft_result, fft_result_ma, fft_result_maa, fft_result_temp;
+    // view (zoom) state: SpectrumVisualProcessor.cpp:10-41 constructor values
+    bool is_view = false, lastView = false;
+    long long centerFreq = 0; long bandwidth = 0;
+    nco_crcf freqShifter = nullptr; long shiftFrequency = 0;
+    long lastInputBandwidth = 0, lastBandwidth = 0;
+    msresamp_crcf resampler = nullptr; double resamplerRatio = 0;
+    unsigned lastDataSize = 0, desiredInputSize = 0;
+    std::vector<lq_cf> fftInData, fftLastData, shiftBuffer, resampleBuffer;
 };
 API void *ref_spectrum_create(unsigned fftSize) {
     auto *s = new RefSpectrum();
@@ -479,20 +488,39 @@ API void *ref_spectrum_create(unsigned fftSize) {
     s->fft_average_rate = 0.65f; s->scaleFactor = 1.0f;                                           // :36-37
     s->fft_result.assign(s->fftSizeInternal, 0.0); s->fft_result_ma.assign(s->fftSizeInternal, 0.0);
     s->fft_result_maa.assign(s->fftSizeInternal, 0.0);                                            // :252-264
+    s->fft_result_temp.assign(s->fftSizeInternal, 0.0);
+    s->freqShifter = nco_crcf_create(0);                                                          // :28
+    s->fftInData.assign(s->fftSizeInternal, lq_cf{0, 0}); s->fftLastData.assign(s->fftSizeInternal, lq_cf{0, 0});   // setup() :166-175
     return s;
 }
-API void ref_spectrum_destroy(void *h) { auto *s = (RefSpectrum *)h; fft_destroy_plan(s->plan); delete s; }
+API void ref_spectrum_destroy(void *h) {
+    auto *s = (RefSpectrum *)h;
+    fft_destroy_plan(s->plan); nco_crcf_destroy(s->freqShifter);
+    if (s->resampler) msresamp_crcf_destroy(s->resampler);
+    delete s;
+}
+// setView(bView, centerFreq, bandwidth) :64-71
+API void ref_spectrum_set_view(void *h, int is_view, long long centerFreq, long bandwidth) {
+    auto *s = (RefSpectrum *)h;
+    s->is_view = is_view != 0; s->centerFreq = centerFreq; s->bandwidth = bandwidth;
+}
+// the frame length FFTVisualDataThread gives the distributor for this view (:283-297, FFTVisualDataThread.cpp:55-61)
+API unsigned ref_spectrum_desired_input(void *h, long long sampleRate) {
+    auto *s = (RefSpectrum *)h;
+    if (!s->is_view) return s->fftSizeInternal;
+    long resampleBw = sampleRate;
+    while (resampleBw / 2 >= (long)s->bandwidth) resampleBw /= 2;
+    double ratio = (double)(resampleBw) / (double)sampleRate;
+    return (unsigned)(size_t)(s->fftSizeInternal / ratio);
+}
 API void ref_spectrum_set_average_rate(void *h, float r) { ((RefSpectrum *)h)->fft_average_rate = r; }
 
-// frame: >= fftSizeInternal samples (n given); outputs: points_y[fftSize], u8 line[fftSize], optional copies of
-// fft_result (linear magnitudes, fftshifted) and fft_result_maa, and the ceil/floor pair used for this frame.
-API void ref_spectrum_frame(void *h, const lq_cf *frame, unsigned n, float *points_y, unsigned char *wf_line,
-                            double *fft_result_out, double *fft_maa_out, double *ceil_floor_out) {
-    auto *s = (RefSpectrum *)h;
+// FFT + magnitudes + averaging + points for the frame in s->fftInput (SpectrumVisualProcessor.cpp:437-576).  `rebin` != 0:
+// a new resampler was made in view mode (zoom step, :454-492), with bwDiff's sign in it.  visualRatio = bandwidth / resampleBw
+// (:532; 1 when not in view mode).
+static void ref_spectrum_execute(RefSpectrum *s, int rebin, double visualRatio, float *points_y, unsigned char *wf_line,
+                                 double *fft_result_out, double *fft_maa_out, double *ceil_floor_out) {
     const unsigned N = s->fftSizeInternal;
-    // :388-403 (non-view): copy first N samples, zero-pad a short frame (priming path not modelled: n >= N expected)
-    if (n < N) { memcpy(s->fftInput.data(), frame, n * sizeof(lq_cf)); memset(&s->fftInput[n], 0, (N - n) * sizeof(lq_cf)); }
-    else memcpy(s->fftInput.data(), frame, N * sizeof(lq_cf));
     float fft_ceil = 0, fft_floor = 1;                                      // :437
     fft_execute(s->plan);                                                   // :439
     for (int i = 0, iMax = N / 2; i < iMax; i++) {                          // :441-452
@@ -502,6 +530,23 @@ API void ref_spectrum_frame(void *h, const lq_cf *frame, unsigned n, float *poin
         float z = sqrt(x * x + y * y);
         s->fft_result[i] = (z);
         s->fft_result[N / 2 + i] = (c);
+    }
+    if (rebin) {                                                            // :454-492 (newResampler && lastView)
+        std::vector<double> &ma = s->fft_result_ma, &maa = s->fft_result_maa, &tmp = s->fft_result_temp;
+        if (rebin < 0) {                                                    // zoomed in: every old bin of the middle half becomes two
+            for (unsigned i = 0; i < N; i++) tmp[i] = ma[(N / 4) + (i / 2)];
+            for (unsigned i = 0; i < N; i++) { ma[i] = tmp[i]; tmp[i] = maa[(N / 4) + (i / 2)]; }
+            for (unsigned i = 0; i < N; i++) maa[i] = tmp[i];
+        } else {                                                            // zoomed out: every second old bin, zeros outside
+            for (size_t i = 0; i < N; i++) {
+                if (i < N / 4) tmp[i] = 0; else if (i >= N - N / 4) tmp[i] = 0; else tmp[i] = ma[(i - N / 4) * 2];
+            }
+            for (unsigned i = 0; i < N; i++) {
+                ma[i] = tmp[i];
+                if (i < N / 4) tmp[i] = 0; else if (i >= N - N / 4) tmp[i] = 0; else tmp[i] = maa[(i - N / 4) * 2];
+            }
+            for (unsigned i = 0; i < N; i++) maa[i] = tmp[i];
+        }
     }
     for (int i = 0, iMax = N; i < iMax; i++) {                              // :494-511
         if (s->fft_result_maa[i] != s->fft_result_maa[i]) s->fft_result_maa[i] = s->fft_result[i];
@@ -520,8 +565,7 @@ API void ref_spectrum_frame(void *h, const lq_cf *frame, unsigned n, float *poin
     if (s->fft_floor_maa != s->fft_floor_maa) s->fft_floor_maa = fft_floor;
     s->fft_floor_maa = s->fft_floor_maa + (s->fft_floor_ma - s->fft_floor_maa) * 0.05;
 
-    float sf = s->scaleFactor;                                              // :532-576 with bandwidth == resampleBw
-    double visualRatio = 1.0;
+    float sf = s->scaleFactor;                                              // :532-576
     double visualStart = (double(N) / 2.0) - (double(N) * (visualRatio / 2.0));
     double visualAccum = 0, acc = 0, accCount = 0, i = 0;
     double point_ceil = s->fft_ceil_maa, point_floor = s->fft_floor_maa;
@@ -546,6 +590,105 @@ API void ref_spectrum_frame(void *h, const lq_cf *frame, unsigned n, float *poin
     if (fft_result_out) memcpy(fft_result_out, s->fft_result.data(), N * sizeof(double));
     if (fft_maa_out) memcpy(fft_maa_out, s->fft_result_maa.data(), N * sizeof(double));
     if (ceil_floor_out) { ceil_floor_out[0] = point_ceil; ceil_floor_out[1] = point_floor; }
+}
+
+// Non-view frame: >= fftSizeInternal samples (n given); outputs: points_y[fftSize], u8 line[fftSize], optional copies of
+// fft_result (linear magnitudes, fftshifted) and fft_result_maa, and the ceil/floor pair used for this frame.
+API void ref_spectrum_frame(void *h, const lq_cf *frame, unsigned n, float *points_y, unsigned char *wf_line,
+                            double *fft_result_out, double *fft_maa_out, double *ceil_floor_out) {
+    auto *s = (RefSpectrum *)h;
+    const unsigned N = s->fftSizeInternal;
+    // :388-403 (non-view): copy first N samples, zero-pad a short frame (priming path not modelled: n >= N expected)
+    if (n < N) { memcpy(s->fftInput.data(), frame, n * sizeof(lq_cf)); memset(&s->fftInput[n], 0, (N - n) * sizeof(lq_cf)); }
+    else memcpy(s->fftInput.data(), frame, N * sizeof(lq_cf));
+    ref_spectrum_execute(s, 0, 1.0, points_y, wf_line, fft_result_out, fft_maa_out, ceil_floor_out);
+    s->lastView = false;                                                    // :636
+}
+
+// One SpectrumVisualProcessor::process() call in view mode (:283-386, :400-420, :437-636): `frame` is what the distributor
+// handed over (n samples taken at centre `frequency`, rate `sampleRate`).  Returns 1 if a transform was executed.
+API int ref_spectrum_view_frame(void *h, const lq_cf *frame, unsigned n, long long frequency, long long sampleRate, float *points_y,
+                                unsigned char *wf_line, double *fft_result_out, double *fft_maa_out, double *ceil_floor_out) {
+    auto *s = (RefSpectrum *)h;
+    const unsigned N = s->fftSizeInternal;
+    if (!s->is_view || !sampleRate || !n) return 0;
+    unsigned int num_written;
+    long resampleBw = sampleRate;
+    bool newResampler = false;
+    int bwDiff = 0;
+    while (resampleBw / 2 >= (long)s->bandwidth) resampleBw /= 2;            // :289-291 (SPECTRUM_VZM = 2)
+    s->resamplerRatio = (double)(resampleBw) / (double)sampleRate;
+    size_t desired_input_size = N / s->resamplerRatio;
+    s->desiredInputSize = desired_input_size;
+    if (n < desired_input_size) desired_input_size = n;                     // :299-302
+    if (s->centerFreq != frequency) {                                       // :304-347
+        if ((s->centerFreq - frequency) != s->shiftFrequency || s->lastInputBandwidth != sampleRate) {
+            if (std::llabs(frequency - s->centerFreq) < (sampleRate / 2)) {  // wxGetApp().getSampleRate(): the device rate
+                long lastShiftFrequency = s->shiftFrequency;
+                s->shiftFrequency = s->centerFreq - frequency;
+                nco_crcf_set_frequency(s->freqShifter, (2.0 * M_PI) * (((double)labs(s->shiftFrequency)) / ((double)sampleRate)));
+                long freqDiff = s->shiftFrequency - lastShiftFrequency;
+                if (s->lastBandwidth != 0) {
+                    double binPerHz = double(s->lastBandwidth) / double(N);
+                    unsigned int numShift = floor(double(labs(freqDiff)) / binPerHz);
+                    if (numShift < N / 2 && numShift) {
+                        if (freqDiff > 0) {
+                            memmove(&s->fft_result_ma[0], &s->fft_result_ma[numShift], (N - numShift) * sizeof(double));
+                            memmove(&s->fft_result_maa[0], &s->fft_result_maa[numShift], (N - numShift) * sizeof(double));
+                        } else {
+                            memmove(&s->fft_result_ma[numShift], &s->fft_result_ma[0], (N - numShift) * sizeof(double));
+                            memmove(&s->fft_result_maa[numShift], &s->fft_result_maa[0], (N - numShift) * sizeof(double));
+                        }
+                    }
+                }
+            }
+        }
+        s->shiftBuffer.resize(desired_input_size);
+        std::vector<lq_cf> in(frame, frame + desired_input_size);
+        if (s->shiftFrequency < 0) nco_crcf_mix_block_up(s->freqShifter, in.data(), s->shiftBuffer.data(), (unsigned)desired_input_size);
+        else nco_crcf_mix_block_down(s->freqShifter, in.data(), s->shiftBuffer.data(), (unsigned)desired_input_size);
+    } else {
+        s->shiftBuffer.assign(frame, frame + desired_input_size);
+    }
+    if (!s->resampler || resampleBw != s->lastBandwidth || s->lastInputBandwidth != sampleRate) {   // :354-368
+        if (s->resampler) msresamp_crcf_destroy(s->resampler);
+        s->resampler = msresamp_crcf_create((float)s->resamplerRatio, 60.0f);
+        bwDiff = resampleBw - s->lastBandwidth;
+        s->lastBandwidth = resampleBw;
+        s->lastInputBandwidth = sampleRate;
+        newResampler = true;
+    }
+    unsigned int out_size = ceil((double)(desired_input_size)*s->resamplerRatio) + 512;
+    s->resampleBuffer.resize(out_size);
+    msresamp_crcf_execute(s->resampler, s->shiftBuffer.data(), (unsigned)desired_input_size, s->resampleBuffer.data(), &num_written);
+    lq_cf *fftInData = s->fftInData.data(), *fftLastData = s->fftLastData.data(), *fftInput = s->fftInput.data();
+    if (num_written < N) {                                                  // :380-385
+        memcpy(fftInData, s->resampleBuffer.data(), num_written * sizeof(lq_cf));
+        memset(&(fftInData[num_written]), 0, (N - num_written) * sizeof(lq_cf));
+    } else memcpy(fftInData, s->resampleBuffer.data(), N * sizeof(lq_cf));
+    bool execute = false;                                                   // :398-420
+    if (num_written >= N) {
+        execute = true;
+        memcpy(fftInput, fftInData, N * sizeof(lq_cf));
+        memcpy(fftLastData, fftInput, N * sizeof(lq_cf));
+    } else {
+        if (s->lastDataSize + num_written < N) {                            // priming
+            unsigned int num_copy = N - s->lastDataSize;
+            if (num_written > num_copy) num_copy = num_written;
+            memcpy(fftLastData, fftInData, num_copy * sizeof(lq_cf));
+            s->lastDataSize += num_copy;
+        } else {
+            unsigned int num_last = (N - num_written);
+            memcpy(fftInput, fftLastData + (s->lastDataSize - num_last), num_last * sizeof(lq_cf));
+            memcpy(fftInput + num_last, fftInData, num_written * sizeof(lq_cf));
+            memcpy(fftLastData, fftInput, N * sizeof(lq_cf));
+            execute = true;
+        }
+    }
+    if (execute) ref_spectrum_execute(s, (newResampler && s->lastView) ? (bwDiff < 0 ? -1 : 1) : 0, (double(s->bandwidth) / double(resampleBw)), points_y, wf_line,
+                                      fft_result_out, fft_maa_out, ceil_floor_out);
+    s->lastView = s->is_view;                                               // :636
+    return execute ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------

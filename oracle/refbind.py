@@ -185,6 +185,11 @@ class RefDistrib:
         nf = self.ref.L.ref_distrib_push(self.h, _p(block), block.size, int(sample_rate), int(frequency), _p(out), cap)
         return out[:nf * self.n].reshape(nf, self.n)
 
+    def set_frame_len(self, n):
+        """FFTDataDistributor::setFFTSize: only the frame length changes; buffered samples and the line accumulator stay."""
+        self.ref.L.ref_distrib_set_fft_size(self.h, int(n))
+        self.n = int(n)
+
     def close(self):
         self.ref.L.ref_distrib_destroy(self.h)
 
@@ -206,6 +211,26 @@ class RefSpectrum:
         res = np.zeros(N, np.float64); maa = np.zeros(N, np.float64); cf = np.zeros(2, np.float64)
         self.ref.L.ref_spectrum_frame(self.h, _p(frame), frame.size, _p(pts), _p(line), _p(res), _p(maa), _p(cf))
         return dict(points=pts, line=line, fft_result=res, maa=maa, ceil_floor=cf)
+
+    def set_view(self, is_view, center_freq, bandwidth):
+        """SpectrumVisualProcessor::setView(bView, centerFreq, bandwidth)."""
+        self.ref.L.ref_spectrum_set_view.argtypes = [C.c_void_p, C.c_int, C.c_longlong, C.c_long]
+        self.ref.L.ref_spectrum_set_view(self.h, 1 if is_view else 0, int(center_freq), int(bandwidth))
+
+    def desired_input(self, sample_rate):
+        self.ref.L.ref_spectrum_desired_input.argtypes = [C.c_void_p, C.c_longlong]
+        self.ref.L.ref_spectrum_desired_input.restype = C.c_uint
+        return int(self.ref.L.ref_spectrum_desired_input(self.h, int(sample_rate)))
+
+    def view_frame(self, frame, frequency, sample_rate):
+        """One process() call of the view branch on the frame the distributor handed over; None if no transform ran."""
+        frame = np.ascontiguousarray(frame, np.complex64)
+        N = 2 * self.fft_size
+        pts = np.zeros(self.fft_size, np.float32); line = np.zeros(self.fft_size, np.uint8)
+        res = np.zeros(N, np.float64); maa = np.zeros(N, np.float64); cf = np.zeros(2, np.float64)
+        self.ref.L.ref_spectrum_view_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_longlong, C.c_longlong] + [C.c_void_p] * 5
+        ok = self.ref.L.ref_spectrum_view_frame(self.h, _p(frame), frame.size, int(frequency), int(sample_rate), _p(pts), _p(line), _p(res), _p(maa), _p(cf))
+        return dict(points=pts, line=line, fft_result=res, maa=maa, ceil_floor=cf) if ok else None
 
     def close(self):
         self.ref.L.ref_spectrum_destroy(self.h)

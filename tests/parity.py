@@ -126,9 +126,11 @@ def check_channels(out, tol=TOL):
 
 
 def run_spectrum(lib, ref, fs, fft_size, n_blocks, chans, lps=0, block=None, seed=1234, device=0, avg_rate=None,
-                 center_by_block=None):
+                 center_by_block=None, view_by_block=None):
     """Returns worst-case errors over all frames: magnitudes, maa, points, ceil/floor, u8 mismatch fraction.
-    center_by_block: {block index: tuner frequency} -- the tuner moves (FFTDataDistributor dumps its buffer, :41-53)."""
+    center_by_block: {block index: tuner frequency} -- the tuner moves (FFTDataDistributor dumps its buffer, :41-53).
+    view_by_block: {block index: (is_view, centre frequency, bandwidth)} -- SpectrumVisualProcessor::setView before that block
+    (zoomed view: the distributor then hands out frames of getDesiredInputSize samples, FFTVisualDataThread.cpp:55-61)."""
     N = block or synth.block_size(fs)
     eng = Engine(lib, device=device, max_block=N)
     sp = Spectrum(eng, fft_size, lps)
@@ -142,15 +144,26 @@ def run_spectrum(lib, ref, fs, fft_size, n_blocks, chans, lps=0, block=None, see
     u8_bad = 0
     u8_bad_far = 0
     center = CENTER
+    view = None
     for b in range(n_blocks):
         x = synth.wideband(fs, N, chans, seed=seed, t0=b * N)
         center = (center_by_block or {}).get(b, center) if b else (center_by_block or {}).get(0, CENTER)
+        if view_by_block and b in view_by_block:
+            view = view_by_block[b]
+            sp.set_view(*view); rsp.set_view(*view)
+            # the processor's desired input size becomes the distributor's frame length (FFTVisualDataThread.cpp:55-61);
+            # what the distributor had buffered stays (its carried remainder), its line accumulator too
+            want = rsp.desired_input(fs)
+            assert sp.desired_input(fs) == want
+            if want != rd.n:
+                rd.set_frame_len(want)
         eng.submit(x, center, fs)
         eng.wait()
         frames = rd.push(ing.block(x), fs, center)
         assert sp.frames == len(frames), "frame count %d vs reference %d in block %d" % (sp.frames, len(frames), b)
         for f in range(sp.frames):
-            r = rsp.frame(frames[f])
+            r = rsp.view_frame(frames[f], center, fs) if view and view[0] else rsp.frame(frames[f])
+            assert r is not None
             pts, line, cf = sp.fetch(f)
             mags, maa = sp.fetch_debug(f)
             worst["mags"] = max(worst["mags"], relrms(mags, r["fft_result"]))

@@ -211,3 +211,31 @@ def test_zero_copy_views_equal_the_copying_fetches(emu_lib):
             p1, l1, _ = sp.fetch(f)
             assert np.array_equal(pts[f], p1) and np.array_equal(lines[f], l1)
     eng.close()
+
+
+def test_zoomed_view_static(emu_lib, ref):
+    """SpectrumVisualProcessor's view branch (.cpp:283-386): frames of getDesiredInputSize samples, shifted by the view's
+    oscillator and decimated by msresamp_crcf before the transform; display points cover bandwidth / resampleBw of the bins."""
+    chans = synth.channel_plan("mixed", 2400000, 8)
+    w = parity.run_spectrum(emu_lib, ref, 2400000, 512, n_blocks=4, chans=chans,
+                            view_by_block={0: (True, parity.CENTER + 210000, 500000)})     # resampleBw = fs / 4, ratio 0.25
+    assert w["frames"] >= 30 and w["mags"] <= parity.TOL and w["maa"] <= parity.TOL and w["points"] <= parity.TOL and w["cf"] <= 1e-6
+    # a view centred on the tuner frequency: no shift at all (:347), and one wide enough that the resampler runs at ratio 1
+    w = parity.run_spectrum(emu_lib, ref, 2400000, 256, n_blocks=3, chans=chans, view_by_block={0: (True, parity.CENTER, 1500000)})
+    assert w["frames"] >= 100 and w["mags"] <= parity.TOL and w["points"] <= parity.TOL
+
+
+def test_zoomed_view_zoom_pan_and_back(emu_lib, ref):
+    """Zoom in, pan, zoom out, leave the view and come back: new resamplers, the running averages re-binned (:454-492) and
+    moved (:317-329), the line limiter running through it all."""
+    chans = synth.channel_plan("mixed", 2400000, 8)
+    C0 = parity.CENTER
+    views = {0: (True, C0 + 100000, 1000000),     # resampleBw fs/2
+             2: (True, C0 + 100000, 400000),      # zoom in two steps: fs/4 ... rebin
+             3: (True, C0 + 160000, 400000),      # pan up: averages move down
+             4: (True, C0 - 50000, 400000),       # pan down across the centre: the mix direction flips
+             5: (True, C0 - 50000, 1100000),      # zoom out
+             7: (False, 0, 0),                    # plain spectrum again
+             8: (True, C0 - 50000, 1100000)}      # and back into the same view (its resampler is still there)
+    w = parity.run_spectrum(emu_lib, ref, 2400000, 512, n_blocks=10, chans=chans, view_by_block=views, lps=400)
+    assert w["frames"] >= 40 and w["mags"] <= parity.TOL and w["maa"] <= parity.TOL and w["points"] <= parity.TOL

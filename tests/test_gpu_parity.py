@@ -208,3 +208,20 @@ def test_tiny_blocks(gpu_lib, ref):
     out, dc_err, _ = parity.run_channels(gpu_lib, ref, 2400000, [FIVE[0], FIVE[2], FIVE[4]], n_blocks=60, block=257)
     assert max(dc_err) == 0.0
     parity.check_channels(out)
+
+
+def test_zoomed_view(gpu_lib, ref):
+    """SpectrumVisualProcessor's view branch on the device: static view, then zoom / pan / leave / return with the line limiter."""
+    chans = synth.channel_plan("mixed", 2400000, 8)
+    w = parity.run_spectrum(gpu_lib, ref, 2400000, 512, n_blocks=4, chans=chans,
+                            view_by_block={0: (True, parity.CENTER + 210000, 500000)})
+    assert w["frames"] >= 30 and w["mags"] <= parity.TOL and w["maa"] <= parity.TOL and w["points"] <= parity.TOL and w["cf"] <= 1e-6
+    C0 = parity.CENTER
+    views = {0: (True, C0 + 100000, 1000000), 2: (True, C0 + 100000, 400000), 3: (True, C0 + 160000, 400000),
+             4: (True, C0 - 50000, 400000), 5: (True, C0 - 50000, 1100000), 7: (False, 0, 0), 8: (True, C0 - 50000, 1100000)}
+    w = parity.run_spectrum(gpu_lib, ref, 2400000, 512, n_blocks=10, chans=chans, view_by_block=views, lps=400)
+    assert w["frames"] >= 40 and w["mags"] <= parity.TOL and w["maa"] <= parity.TOL and w["points"] <= parity.TOL
+    # a deep zoom at a high rate: 10 MSps, 8192-point display, view of 600 kHz (resampleBw = fs / 16, frames of 262144 samples)
+    w = parity.run_spectrum(gpu_lib, ref, 10000000, 8192, n_blocks=6, chans=synth.channel_plan("mixed", 10000000, 16),
+                            view_by_block={0: (True, C0 + 450000, 600000)})
+    assert w["frames"] >= 3 and w["mags"] <= parity.TOL and w["points"] <= parity.TOL
