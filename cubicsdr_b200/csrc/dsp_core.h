@@ -25,7 +25,8 @@ constexpr int kPfbTaps = 14;      // 2 * m of the arbitrary resampler (m = 7)
 constexpr int kTailThreads = 256;
 
 enum ModemKind { MODEM_FM = 0, MODEM_NBFM = 1, MODEM_AM = 2, MODEM_USB = 3, MODEM_LSB = 4, MODEM_IQ = 5,
-                 MODEM_NONE = 6 };   // no modem: the decimated IQ is the product (the zoomed spectrum view's hidden channel)
+                 MODEM_NONE = 6,    // no modem: the decimated IQ is the product (the zoomed spectrum view's hidden channel)
+                 MODEM_DSB = 7, MODEM_CW = 8 };
 
 // ---- small complex helpers ------------------------------------------------------------------------------------------
 SDR_HD SDR_FORCEINLINE float2 cf_make(float a, float b) { return make_float2(a, b); }
@@ -370,6 +371,9 @@ struct ChanStatic {
     int am_taps_off;              // 51 taps
     int hq_off;                   // 10 Hilbert quadrature taps
     int sos_off;                  // 3 x {b0,b1,b2,a1,a2}
+    int cw_hq_off;                // CW: quadrature taps of firhilbf_create(5, 60) (ModemCW.cpp:23)
+    unsigned cw_dtheta;           // CW: phase step of the beat oscillator, 2 pi 650 / audio rate (ModemCW.cpp:176)
+    int cw_w_off;                 // CW: complex stream after the beat mixer, at the audio rate ([kHist | new])
     // stream buffers inside the channel arena (offsets in floats); each is [kHist | data]
     float *arena;                 // this channel's arena in HBM
     int lvl_off[kMaxTailHb + 1];  // complex level buffers: level 0 = front output, level j = output of tail stage j-1
@@ -414,6 +418,7 @@ struct ChanState {                // device-resident, advanced by the tail kerne
     float sos_v[3][2][2];             // [section][v1,v2][re,im]
     float agc_ceil, agc_ma, agc_maa;  // ModemAnalog.cpp:6,70-72
     float sig_level, sig_floor, sig_ceil;   // DemodulatorThread::signalLevel / signalFloor / signalCeil (std::atomic<float>)
+    unsigned dsb_theta, dsb_dtheta;         // ampmodem's Costas-loop oscillator (nco_crcf theta / d_theta), ModemDSB
 };
 
 struct ChanResultHeader {

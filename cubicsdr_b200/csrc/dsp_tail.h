@@ -30,6 +30,21 @@ SDR_HD SDR_FORCEINLINE double d_mul(double a, double b) { return a * b; }
 SDR_HD SDR_FORCEINLINE double d_div(double a, double b) { return a / b; }
 SDR_HD SDR_FORCEINLINE float f_add(float a, float b) { return a + b; }
 #endif
+#if defined(__CUDA_ARCH__) && !defined(SDR_EMU)
+SDR_DEV SDR_FORCEINLINE float f_sub(float a, float b) { return __fsub_rn(a, b); }
+SDR_DEV SDR_FORCEINLINE float f_mul(float a, float b) { return __fmul_rn(a, b); }
+#else
+SDR_HD SDR_FORCEINLINE float f_sub(float a, float b) { return a - b; }
+SDR_HD SDR_FORCEINLINE float f_mul(float a, float b) { return a * b; }
+#endif
+// nco_crcf_pll_step's phase / frequency increment (liquid 1.5.0: the float argument goes through double for the division by
+// 2 pi, back to float, loses its integer part towards zero, wraps into [0, 1) and is scaled to the 32-bit phase word)
+SDR_HD SDR_FORCEINLINE unsigned pll_word(float z) {
+    float x = (float)d_mul((double)z, 0.15915494309189535);
+    x = f_sub(x, truncf(x));
+    if (x < 0.0f) x = f_add(x, 1.0f);
+    return (unsigned)(long long)f_mul(x, 4294967296.0f);
+}
 
 struct TailArgs {
     const ChanStatic *cs;
@@ -75,7 +90,9 @@ enum TailPhase {
     TP_DEMOD_B,                                   // SSB Hilbert stage
     TP_AGC_A, TP_AGC_B, TP_AGC_C,
     TP_AUD0,                                      // audio: stage phases (kMaxAudioHb + 1)
-    TP_METER_A = TP_AUD0 + kMaxAudioHb + 1,
+    TP_CW_A = TP_AUD0 + kMaxAudioHb + 1,           // CW: beat mixer, Hilbert c2r, block gain (after the complex interpolator)
+    TP_CW_B, TP_CW_C, TP_CW_D, TP_CW_E,
+    TP_METER_A,
     TP_METER_B,
     TP_HIST_A, TP_HIST_B,
     TP_COUNT
@@ -159,36 +176,45 @@ SDR_HD inline void hb_decim_r(const float *in, long long in_g0, float *out, long
 }
 // interpolate-by-2 half-band (resamp2 interp_execute): Y[2k] = X[k-m], Y[2k+1] = sum h1[t] X[k-2m+1+t]
 // (thread r handles input k = r: both outputs of the pair, kTailIlp pairs at a time)
-template <int M>
-SDR_HD inline void hb_interp_t(const float *in, int n_in, float *out, const float *__restrict__ h1, int tid, int nt) {
+SDR_HD SDR_FORCEINLINE void t_zero(float &v) { v = 0.f; }
+SDR_HD SDR_FORCEINLINE void t_zero(float2 &v) { v = make_float2(0.f, 0.f); }
+template <int M, typename T>
+SDR_HD inline void hb_interp_t(const T *in, int n_in, T *out, const float *__restrict__ h1, int tid, int nt) {
     float h[2 * M];
 #pragma unroll
     for (int t = 0; t < 2 * M; ++t) h[t] = sdr_ldg(h1 + t);
     int k = tid;
     for (; k + (kTailIlp - 1) * nt < n_in; k += kTailIlp * nt) {
-        float v[kTailIlp], e[kTailIlp];
+        T v[kTailIlp], e[kTailIlp];
 #pragma unroll
-        for (int u = 0; u < kTailIlp; ++u) { v[u] = 0.f; e[u] = in[kHist + k + u * nt - M]; }
+        for (int u = 0; u < kTailIlp; ++u) { t_zero(v[u]); e[u] = in[kHist + k + u * nt - M]; }
 #pragma unroll
         for (int t = 0; t < 2 * M; ++t) {
 #pragma unroll
-            for (int u = 0; u < kTailIlp; ++u) v[u] = fmaf(h[t], in[kHist + k + u * nt - 2 * M + 1 + t], v[u]);
+            for (int u = 0; u < kTailIlp; ++u) v[u] = tap_fma(h[t], in[kHist + k + u * nt - 2 * M + 1 + t], v[u]);
         }
 #pragma unroll
         for (int u = 0; u < kTailIlp; ++u) { out[kHist + 2 * (k + u * nt)] = e[u]; out[kHist + 2 * (k + u * nt) + 1] = v[u]; }
     }
     for (; k < n_in; k += nt) {
-        float v = 0.f;
+        T v;
+        t_zero(v);
 #pragma unroll
-        for (int t = 0; t < 2 * M; ++t) v = fmaf(h[t], in[kHist + k - 2 * M + 1 + t], v);
+        for (int t = 0; t < 2 * M; ++t) v = tap_fma(h[t], in[kHist + k - 2 * M + 1 + t], v);
         out[kHist + 2 * k] = in[kHist + k - M];
         out[kHist + 2 * k + 1] = v;
     }
 }
+// complex samples (msresamp_cccf's half-band interpolators, ModemCW.cpp:158): the design only produces m = 3, 5, 10
+SDR_HD inline void hb_interp_c(const float2 *in, int n_in, float2 *out, int m, const float *h1, int tid, int nt) {
+    if (m == 3) hb_interp_t<3, float2>(in, n_in, out, h1, tid, nt);
+    else if (m == 5) hb_interp_t<5, float2>(in, n_in, out, h1, tid, nt);
+    else hb_interp_t<10, float2>(in, n_in, out, h1, tid, nt);
+}
 SDR_HD inline void hb_interp_r(const float *in, int n_in, float *out, int m, const float *h1, int tid, int nt) {
-    if (m == 3) hb_interp_t<3>(in, n_in, out, h1, tid, nt);
-    else if (m == 5) hb_interp_t<5>(in, n_in, out, h1, tid, nt);
-    else if (m == 10) hb_interp_t<10>(in, n_in, out, h1, tid, nt);
+    if (m == 3) hb_interp_t<3, float>(in, n_in, out, h1, tid, nt);
+    else if (m == 5) hb_interp_t<5, float>(in, n_in, out, h1, tid, nt);
+    else if (m == 10) hb_interp_t<10, float>(in, n_in, out, h1, tid, nt);
     else {
         for (int r = tid; r < 2 * n_in; r += nt) {
             const int k = r >> 1;
@@ -232,6 +258,16 @@ SDR_HD SDR_FORCEINLINE float arb_r_one(const float *z, const float *pfb, unsigne
     return acc;
 }
 
+SDR_HD SDR_FORCEINLINE float2 arb_c_one(const float2 *z, const float *pfb, unsigned long long ph0, unsigned step, int r) {
+    const unsigned long long psi = ph0 + (unsigned long long)r * step;
+    const float2 *zq = z + (int)(psi >> 24);
+    const float *h = pfb + ((psi >> 16) & 255u) * kPfbTaps;
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < kPfbTaps; ++t) acc = cf_fma(sdr_ldg(h + t), zq[-t], acc);
+    return acc;
+}
+
 SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt, TailShared *sm) {
     const ChanStatic &cs = a.cs[ch];
     const ChanDyn &cd = a.cd[ch];
@@ -254,7 +290,10 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
     // audio {imag, real}; the level is metered on the IQ like FM's (useSignalOutput stays false)
     const bool is_iq = cs.modem == MODEM_IQ;
     const bool is_none = cs.modem == MODEM_NONE;             // resampler only (zoomed spectrum view): nothing after the IQ stage
-    const bool has_agc = !is_fm && !is_iq && !is_none;      // ModemAM / USB / LSB pass autoGain = true to buildAudioOutput
+    // CW (analog/ModemCW.cpp:155-209): the decimated IQ is interpolated to the audio rate as complex samples (msresamp_cccf),
+    // mixed up by the beat oscillator, made real by firhilbf(5, 60) and scaled by its own block gain; no audio resampler after
+    const bool is_cw = cs.modem == MODEM_CW;
+    const bool has_agc = !is_fm && !is_iq && !is_none && !is_cw;   // ModemAM / USB / LSB / DSB pass autoGain = true to buildAudioOutput
     const bool lvl_from_iq = is_fm || is_iq || is_none;
 
     if (ph == TP_SETUP) {
@@ -350,7 +389,7 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
 
     if (ph == TP_DEMOD_A) {
         const int n = sm->n_iq;
-        if (is_none) {
+        if (is_none || is_cw) {
         } else if (is_iq) {
             for (int i = tid; i < n; i += nt) {
                 const float2 x = iq[i];
@@ -373,6 +412,31 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
                     acc = fmaf(sdr_ldg(h + k), sqrtf(x.x * x.x + x.y * x.y), acc);
                 }
                 d[i] = acc;
+            }
+        } else if (cs.modem == MODEM_DSB) {
+            // ampmodem_demod_dsb_pll_costas (liquid 1.5.0 binary, read from its disassembly): per sample
+            //   v = x * conj(osc)                       nco_crcf_mix_down, table oscillator, four products and two sums, no fusing
+            //   e = Re v > 0 ? Im v : -Im v             hard-limited Costas error
+            //   d_theta += w(alpha e), theta += w(beta e)   nco_crcf_pll_step, alpha = 0.001f, beta = sqrtf(alpha),
+            //                                           w(z) = (uint32)(int64)(frac((float)((double)z / 2 pi)) * 2^32)
+            //   theta += d_theta                        nco_crcf_step
+            //   y = Re v / 0.5                          mod_index
+            // A feedback loop through a quantised oscillator: strictly serial, one thread.
+            if (tid == 0) {
+                unsigned th = st.dsb_theta, dth = st.dsb_dtheta;
+                const float alpha = 0.001f, beta = 0.0316227786f;    // sqrtf(0.001f) = 0x3d0186e3 (nco_crcf_pll_set_bandwidth)
+                for (int i = 0; i < n; ++i) {
+                    const float2 w = nco_lookup(a.nco, th);
+                    const float2 x = iq[i];
+                    const float vr = f_add(f_mul(x.x, w.x), f_mul(x.y, w.y));
+                    const float vi = f_sub(f_mul(x.y, w.x), f_mul(x.x, w.y));
+                    const float e = vr > 0.0f ? vi : -vi;
+                    dth += pll_word(f_mul(alpha, e));
+                    th += pll_word(f_mul(e, beta));
+                    th += dth;
+                    d[i] = vr / 0.5f;
+                }
+                st.dsb_theta = th; st.dsb_dtheta = dth;
             }
         } else if (tid == 0) {                                   // SSB: quarter-rate shift, Butterworth-6, shift back
             float2 *w = chan_cbuf(a, cs, cs.w_off) + kHist;
@@ -448,6 +512,19 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
     if (ph >= TP_AUD0 && ph < TP_AUD0 + kMaxAudioHb + 1) {
         const int j = ph - TP_AUD0;
         if (is_iq || is_none) return;
+        if (is_cw) {                                             // msresamp_cccf interpolator: arbitrary stage, then a_S half-bands (:158)
+            if (j == 0) {
+                const float2 *z = iq;
+                float2 *out = chan_cbuf(a, cs, cs.al_off[0]) + kHist;
+                const float *pfb = a.taps + cs.a_pfb_off;
+                const unsigned long long ph0 = st.a_phase;
+                for (int r = tid; r < sm->a_n[0]; r += nt) out[r] = arb_c_one(z, pfb, ph0, cs.a_step, r);
+            } else if (j <= cs.a_S) {
+                hb_interp_c(chan_cbuf(a, cs, cs.al_off[j - 1]), sm->a_n[j - 1], chan_cbuf(a, cs, cs.al_off[j]), cs.a_m[j - 1],
+                            a.taps + cs.a_h1[j - 1], tid, nt);
+            }
+            return;
+        }
         if (!cs.a_interp) {
             // decimator: a_S half-bands (cascade position g = a_S-1-j for phase j), then the arbitrary stage
             if (j < cs.a_S) {
@@ -506,6 +583,47 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
                     }
                 }
             }
+        }
+        return;
+    }
+
+    // ---- CW back end (ModemCW.cpp:176-208) -----------------------------------------------------------------------------
+    if (ph >= TP_CW_A && ph <= TP_CW_E) {
+        if (!is_cw) return;
+        const int na = sm->n_audio < cs.res_audio_cap ? sm->n_audio : cs.res_audio_cap;
+        float2 *w = chan_cbuf(a, cs, cs.cw_w_off) + kHist;
+        if (ph == TP_CW_A) {                                     // nco_crcf_mix_up with the current phase, then step (:181-182)
+            const float2 *x = chan_cbuf(a, cs, cs.al_off[cs.a_S]) + kHist;
+            const unsigned th0 = st.ssb_theta;
+            for (int i = tid; i < na; i += nt) {
+                const float2 o = nco_lookup(a.nco, th0 + (unsigned)i * cs.cw_dtheta);
+                w[i] = cf_rot(x[i], o.x, o.y);
+            }
+        } else if (ph == TP_CW_B) {                              // firhilbf_c2r_execute(mToReal, sig, &lsb, &out): out = the usb branch (:183)
+            const float *hq = a.taps + cs.cw_hq_off;
+            for (int i = tid; i < na; i += nt) {
+                float yq = 0.f;
+                for (int j = 0; j < 10; ++j) yq = fmaf(sdr_ldg(hq + j), w[i - 19 + 2 * j].y, yq);
+                res_audio[i] = w[i - 10].x - yq;
+            }
+        } else if (ph == TP_CW_C) {                              // :187-197 aOutputCeil = max over the block (positive peaks)
+            float mx = 0.f;
+            for (int i = tid; i < na; i += nt) mx = fmaxf(mx, res_audio[i]);
+            sm->red_f[tid] = mx;
+        } else if (ph == TP_CW_D) {
+            if (tid == 0 && na > 0) {
+                float mx = 0.f;
+                for (int t = 0; t < nt; ++t) mx = fmaxf(mx, sm->red_f[t]);
+                const float ma = st.agc_ma + (st.agc_ceil - st.agc_ma) * 0.025f;
+                const float maa = st.agc_maa + (ma - st.agc_maa) * 0.025f;
+                st.agc_ma = ma; st.agc_maa = maa; st.agc_ceil = mx;
+                const float gain_db = 10.0f * log10f(0.5f / maa);            // mGain (:199)
+                sm->gain = powf(10.0f, gain_db / 10.0f);                     // :204
+                st.ssb_theta += (unsigned)sm->n_audio * cs.cw_dtheta;
+            }
+        } else {
+            const float g = sm->gain;
+            for (int i = tid; i < na; i += nt) res_audio[i] *= g;
         }
         return;
     }
@@ -582,6 +700,10 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
             float2 *b = chan_cbuf(a, cs, cs.w_off);
             if (tid < kHist) { if (ph == TP_HIST_A) sm->hist_tmp[s][tid] = b[sm->n_iq + tid]; else b[tid] = sm->hist_tmp[s][tid]; }
         }
+        if (is_cw) {                                             // the beat mixer's stream feeds the 21-tap Hilbert filter at the audio rate
+            float2 *b = chan_cbuf(a, cs, cs.cw_w_off);
+            if (tid < kHist) { if (ph == TP_HIST_A) sm->hist_tmp[s][tid] = b[sm->n_audio + tid]; else b[tid] = sm->hist_tmp[s][tid]; }
+        }
         ++s;
         {
             float *b = chan_rbuf(a, cs, cs.d_off);
@@ -593,6 +715,11 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
             if (!cs.a_interp && j == 0) continue;               // decimator level 0 is the d stream itself
             if (cs.a_interp && j == cs.a_S && cs.a_S > 0) continue;   // final interpolator level feeds nothing
             if (cs.a_interp && cs.a_S == 0) continue;
+            if (is_cw) {                                          // complex levels
+                float2 *bc = chan_cbuf(a, cs, cs.al_off[j]);
+                if (tid < kHist) { if (ph == TP_HIST_A) sm->hist_tmp[s][tid] = bc[sm->a_n[j] + tid]; else bc[tid] = sm->hist_tmp[s][tid]; }
+                continue;
+            }
             float *b = chan_rbuf(a, cs, cs.al_off[j]);
             if (tid < kHist) { if (ph == TP_HIST_A) sm->hist_tmp[s][tid].x = b[sm->a_n[j] + tid]; else b[tid] = sm->hist_tmp[s][tid].x; }
         }

@@ -918,6 +918,8 @@ static int modem_from_name(const char *n) {
     if (s == "USB") return MODEM_USB;
     if (s == "LSB") return MODEM_LSB;
     if (s == "I/Q") return MODEM_IQ;
+    if (s == "DSB") return MODEM_DSB;
+    if (s == "CW") return MODEM_CW;
     return -1;
 }
 
@@ -1574,6 +1576,7 @@ static int chan_create_impl(sdr_engine *e, const char *modem, long long sample_r
     const double a_ratio = double(audio_rate) / double(c->bandwidth);   // ModemAnalog.cpp:29-30
     c->audio_plan = make_resampler_plan((float)a_ratio, As);
     if (c->iq_plan.interp) { delete c; return fail(SDR_ERR_UNSUPPORTED, "sdr_chan_create: bandwidth above the sample rate"); }
+    if (mk == MODEM_CW && !c->audio_plan.interp) { delete c; return fail(SDR_ERR_UNSUPPORTED, "sdr_chan_create: CW bandwidth above the audio rate"); }
     if (c->iq_plan.num_halfband > kMaxTailHb + kFrontMaxK || c->audio_plan.num_halfband > kMaxAudioHb) {
         delete c; return fail(SDR_ERR_UNSUPPORTED, "sdr_chan_create: too many half-band stages");
     }
@@ -1595,6 +1598,7 @@ static int chan_create_impl(sdr_engine *e, const char *modem, long long sample_r
     cs.a_step = c->audio_plan.arb_step;
     float am[51]; am_dc_block_taps(25, 30.0f, am);                      // ModemAM.cpp:9
     float hq[10]; hilbert_quadrature_taps(5, 90.0f, hq);                // ModemUSB.cpp:11
+    float hq_cw[10]; hilbert_quadrature_taps(5, 60.0f, hq_cw);          // ModemCW.cpp:23
     std::vector<Sos> sos; butterworth_lowpass_sos(6, 0.25f, sos);       // ModemUSB.cpp:8
     float flat[15];
     for (int k = 0; k < 3; ++k) { flat[5 * k] = sos[k].b[0]; flat[5 * k + 1] = sos[k].b[1]; flat[5 * k + 2] = sos[k].b[2]; flat[5 * k + 3] = sos[k].a[1]; flat[5 * k + 4] = sos[k].a[2]; }
@@ -1617,8 +1621,14 @@ static int chan_create_impl(sdr_engine *e, const char *modem, long long sample_r
         cap_audio = (size_t)std::ceil((double)((cap_iq >> cs.a_S) + 4) * (double)c->audio_plan.rate_arb) + 8;
     } else {
         const size_t cap_b = (size_t)std::ceil((double)cap_iq * (double)c->audio_plan.rate_arb) + 8;
-        for (int j = 0; j <= cs.a_S; ++j) cs.al_off[j] = take(kHist + (cap_b << j) + 4);
+        const size_t width = mk == MODEM_CW ? 2 : 1;                    // CW interpolates complex samples (msresamp_cccf)
+        for (int j = 0; j <= cs.a_S; ++j) cs.al_off[j] = take(width * (kHist + (cap_b << j) + 4));
         cap_audio = cap_b << cs.a_S;
+    }
+    if (mk == MODEM_CW) {
+        cs.cw_w_off = take(2 * (kHist + cap_audio + 4));
+        // nco_crcf_set_frequency(mLO, 2.0f * (float)M_PI * mBeepFrequency / kit->audioSampleRate), mBeepFrequency = 650 (ModemCW.cpp:17,176)
+        cs.cw_dtheta = nco_phase_step(2.0f * (float)3.14159265358979323846 * 650.0f / (float)audio_rate);
     }
     if (mk == MODEM_IQ) cap_audio = 2 * cap_iq;                         // two-channel output, one {imag, real} pair per decimated sample
     cs.res_audio_cap = (int)((cap_audio + 3) & ~size_t(3));
@@ -1673,6 +1683,7 @@ static int chan_create_impl(sdr_engine *e, const char *modem, long long sample_r
         cs.am_taps_off = pool_add(e, "am51", am, 51);
         cs.hq_off = pool_add(e, "hq10", hq, 10);
         cs.sos_off = pool_add(e, "sos6", flat, 15);
+        cs.cw_hq_off = pool_add(e, "hq10_60", hq_cw, 10);
         if (e->taps_host.size() > e->taps_cap) return bail(SDR_ERR_NOMEM, "taps pool exhausted");
         int slot = -1;
         for (size_t i = 0; i < e->slot_used.size(); ++i) if (!e->slot_used[i]) { slot = (int)i; break; }

@@ -181,6 +181,9 @@ CUBICSDR_B200_MODEM(ModemNBFM, "NBFM", 12500)     // analog/ModemNBFM.cpp:18-24
 CUBICSDR_B200_MODEM(ModemAM, "AM", 6000)          // analog/ModemAM.cpp:21-27
 CUBICSDR_B200_MODEM(ModemUSB, "USB", 5400)        // analog/ModemUSB.cpp:19-41
 CUBICSDR_B200_MODEM(ModemLSB, "LSB", 5400)        // analog/ModemLSB.cpp:19-41
+CUBICSDR_B200_MODEM(ModemDSB, "DSB", 5400)        // analog/ModemDSB.cpp:15-25
+CUBICSDR_B200_MODEM(ModemCW, "CW", 500)           // analog/ModemCW.cpp:99-112
+CUBICSDR_B200_MODEM(ModemIQ, "I/Q", 48000)        // analog/ModemIQ.cpp:12-37
 #undef CUBICSDR_B200_MODEM
 
 // what CubicSDR::OnInit does at CubicSDR.cpp:305-311
@@ -191,6 +194,9 @@ inline void registerModems(const std::shared_ptr<Engine> &e) {
     Modem::addModemFactory(ModemAM::factory, "AM", 6000);
     Modem::addModemFactory(ModemLSB::factory, "LSB", 5400);
     Modem::addModemFactory(ModemUSB::factory, "USB", 5400);
+    Modem::addModemFactory(ModemCW::factory, "CW", 500);
+    Modem::addModemFactory(ModemDSB::factory, "DSB", 5400);
+    Modem::addModemFactory(ModemIQ::factory, "I/Q", 48000);
 }
 
 // ---- SDRPostThread::runSingleCH (sdr/SDRPostThread.cpp:248-299): one block in, DC-blocked block + all attached work out ----

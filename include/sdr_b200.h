@@ -81,7 +81,7 @@ int sdr_engine_set_timing(sdr_engine *eng, int enable);
 int sdr_engine_get_timing(sdr_engine *eng, double *stage_ms4, unsigned long long *blocks);
 
 /* ---- channel: DemodulatorPreThread + Modem + DemodulatorThread metering --------------------------------------------- */
-/* modem: "FM" "NBFM" "AM" "USB" "LSB" "I/Q" (Modem::addModemFactory names, src/CubicSDR.cpp:305-313).
+/* modem: "FM" "NBFM" "AM" "CW" "USB" "LSB" "DSB" "I/Q" (Modem::addModemFactory names, src/CubicSDR.cpp:305-313).
  * bandwidth is passed through Modem::checkSampleRate (ModemAnalog.cpp:14-19, ModemUSB.cpp:29-37).
  * Builds what DemodulatorWorkerThread builds (src/demod/DemodulatorWorkerThread.cpp:63-101): msresamp_crcf(bw/fs, 60),
  * the modem, and its kit msresamp_rrrf(audio_rate/bw, 60) (ModemAnalog.cpp:21-33).

@@ -61,6 +61,12 @@ LQ int msresamp_rrrf_destroy(msresamp_rrrf q);
 LQ float msresamp_rrrf_get_delay(msresamp_rrrf q);
 LQ int msresamp_rrrf_execute(msresamp_rrrf q, float *x, unsigned int nx, float *y, unsigned int *ny);
 
+/* msresamp_cccf (ModemCW.cpp:125,158): complex samples, complex taps */
+typedef struct msresamp_cccf_s *msresamp_cccf;
+LQ msresamp_cccf msresamp_cccf_create(float r, float as);
+LQ int msresamp_cccf_destroy(msresamp_cccf q);
+LQ int msresamp_cccf_execute(msresamp_cccf q, lq_cf *x, unsigned int nx, lq_cf *y, unsigned int *ny);
+
 /* freqdem, liquid.h:8247-8275 */
 typedef struct freqdem_s *freqdem;
 LQ freqdem freqdem_create(float kf);
@@ -87,6 +93,12 @@ typedef struct firhilbf_s *firhilbf;
 LQ firhilbf firhilbf_create(unsigned int m, float as);
 LQ int firhilbf_destroy(firhilbf q);
 LQ int firhilbf_c2r_execute(firhilbf q, lq_cf x, float *y0_lsb, float *y1_usb);
+
+/* ampmodem, liquid.h:8283-8324 (ModemDSB.cpp:7,38: ampmodem_create(0.5, LIQUID_AMPMODEM_DSB = 0, 1) + ampmodem_demodulate) */
+typedef struct ampmodem_s *ampmodem;
+LQ ampmodem ampmodem_create(float mod_index, int type, int suppressed_carrier);
+LQ int ampmodem_destroy(ampmodem q);
+LQ int ampmodem_demodulate(ampmodem q, lq_cf y, float *x);
 
 /* fft, liquid.h:1531, 1582, 1609 */
 typedef struct fftplan_s *fftplan;

@@ -149,7 +149,7 @@ API int ref_optimal_channel_count(long long sampleRate_in) {
 // ---------------------------------------------------------------------------------------------------------
 // one demodulator channel: DemodulatorPreThread + Modem + DemodulatorThread metering
 // ---------------------------------------------------------------------------------------------------------
-enum { M_FM = 0, M_NBFM = 1, M_AM = 2, M_USB = 3, M_LSB = 4, M_IQ = 5 };
+enum { M_FM = 0, M_NBFM = 1, M_AM = 2, M_USB = 3, M_LSB = 4, M_IQ = 5, M_DSB = 7, M_CW = 8 };
 
 struct RefChan {
     int modem;
@@ -171,6 +171,11 @@ struct RefChan {
     iirfilt_crcf ssbFilt;
     nco_crcf ssbShift;
     firhilbf c2rFilt;
+    ampmodem demodAM_DSB = nullptr;                                            // ModemDSB.cpp:7
+    // ModemCW members (ModemCW.cpp:15-25) and its kit's msresamp_cccf (:117-127)
+    msresamp_cccf cwInputResampler = nullptr; nco_crcf cwLO = nullptr; firhilbf cwToReal = nullptr;
+    float cwBeepFrequency = 650.0f, cwGain = 15.0f;
+    std::vector<lq_cf> cwInput;
     std::vector<lq_cf> in_buf, out_buf, resampled;
     std::vector<float> demodOut, audioOut;
     // DemodulatorThread members (src/demod/DemodulatorThread.cpp:25-26): squelchLevel(-100), signalLevel(-100),
@@ -187,6 +192,8 @@ static int modem_from_name(const char *n) {
     if (s == "USB") return M_USB;
     if (s == "LSB") return M_LSB;
     if (s == "I/Q") return M_IQ;
+    if (s == "DSB") return M_DSB;
+    if (s == "CW") return M_CW;
     return -1;
 }
 
@@ -221,6 +228,12 @@ API void *ref_chan_create(const char *modem, long long sampleRate, long long ban
     c->demodFM = nullptr; c->mDCBlock = nullptr; c->ssbFilt = nullptr; c->ssbShift = nullptr; c->c2rFilt = nullptr;
     if (m == M_FM || m == M_NBFM) c->demodFM = freqdem_create(0.5f);       // ModemFM.cpp:7
     if (m == M_AM) c->mDCBlock = firfilt_rrrf_create_dc_blocker(25, 30.0f); // ModemAM.cpp:9
+    if (m == M_DSB) c->demodAM_DSB = ampmodem_create(0.5f, 0 /* LIQUID_AMPMODEM_DSB */, 1);   // ModemDSB.cpp:7
+    if (m == M_CW) {                                                       // ModemCW.cpp:21-23, 117-127
+        c->cwLO = nco_crcf_create(0);
+        c->cwToReal = firhilbf_create(5, 60.0f);
+        c->cwInputResampler = msresamp_cccf_create((float)c->audioResampleRatio, 60.0f);
+    }
     if (m == M_USB || m == M_LSB) {                                        // ModemUSB.cpp:8-11
         c->ssbFilt = iirfilt_crcf_create_lowpass(6, 0.25);
         c->ssbShift = nco_crcf_create(0);
@@ -240,6 +253,10 @@ API void ref_chan_destroy(void *h) {
     if (c->ssbFilt) iirfilt_crcf_destroy(c->ssbFilt);
     if (c->ssbShift) nco_crcf_destroy(c->ssbShift);
     if (c->c2rFilt) firhilbf_destroy(c->c2rFilt);
+    if (c->demodAM_DSB) ampmodem_destroy(c->demodAM_DSB);
+    if (c->cwLO) nco_crcf_destroy(c->cwLO);
+    if (c->cwToReal) firhilbf_destroy(c->cwToReal);
+    if (c->cwInputResampler) msresamp_cccf_destroy(c->cwInputResampler);
     delete c;
 }
 
@@ -324,6 +341,30 @@ API int ref_chan_process(void *h, const lq_cf *block, unsigned n, long long shif
     // --- DemodulatorThread.cpp:120-140 -> Modem::demodulate
     size_t bufSize = numWritten;                                            // ModemAnalog::initOutputBuffers :42-65
     if (!bufSize) return 0;
+    if (c->modem == M_CW) {                                                 // ModemCW::demodulate (ModemCW.cpp:155-209)
+        size_t audio_out_size = (size_t)ceil((double)(bufSize)*c->audioResampleRatio) + 512;
+        c->cwInput.resize(audio_out_size);
+        unsigned int outSize = 0;
+        msresamp_cccf_execute(c->cwInputResampler, c->resampled.data(), (unsigned int)bufSize, c->cwInput.data(), &outSize);
+        c->demodOut.resize(outSize);
+        nco_crcf_set_frequency(c->cwLO, 2.0f * (float)M_PI * c->cwBeepFrequency / c->audioRate);
+        for (unsigned int i = 0; i < outSize; i++) {
+            lq_cf sig; float lsb;
+            nco_crcf_mix_up(c->cwLO, c->cwInput[i], &sig);
+            nco_crcf_step(c->cwLO);
+            firhilbf_c2r_execute(c->cwToReal, sig, &lsb, &c->demodOut[i]);
+        }
+        c->aOutputCeilMA = c->aOutputCeilMA + (c->aOutputCeil - c->aOutputCeilMA) * 0.025f;    // mAutoGain (:187-199)
+        c->aOutputCeilMAA = c->aOutputCeilMAA + (c->aOutputCeilMA - c->aOutputCeilMAA) * 0.025f;
+        c->aOutputCeil = 0;
+        for (size_t i = 0; i < outSize; i++) if (c->demodOut[i] > c->aOutputCeil) c->aOutputCeil = c->demodOut[i];
+        c->cwGain = 10.0f * std::log10(0.5f / c->aOutputCeilMAA);
+        for (size_t i = 0; i < outSize; i++) c->demodOut[i] *= std::pow(10.0f, c->cwGain / 10.0f);
+        c->audioOut.assign(c->demodOut.begin(), c->demodOut.end());
+        if (audio_out) memcpy(audio_out, c->audioOut.data(), outSize * sizeof(float));
+        if (n_audio) *n_audio = outSize;
+        return ref_chan_meter_block(c, outSize, bufSize, true, level_db, peak);
+    }
     if (c->modem == M_IQ) {                                                 // ModemIQ::demodulate (ModemIQ.cpp:39-56): channels = 2
         c->audioOut.resize(bufSize * 2);
         for (size_t i = 0; i < bufSize; i++) { c->audioOut[i * 2] = c->resampled[i].imag; c->audioOut[i * 2 + 1] = c->resampled[i].real; }
@@ -357,6 +398,10 @@ API int ref_chan_process(void *h, const lq_cf *block, unsigned n, long long shif
             nco_crcf_mix_up(c->ssbShift, y, &x);
             firhilbf_c2r_execute(c->c2rFilt, x, &discard, &c->demodOut[i]);
         }
+        autoGain = true; useSignalOutput = true;
+        break;
+    case M_DSB:                                                             // ModemDSB.cpp:27-41
+        for (size_t i = 0; i < bufSize; i++) ampmodem_demodulate(c->demodAM_DSB, d[i], &c->demodOut[i]);
         autoGain = true; useSignalOutput = true;
         break;
     case M_LSB:                                                             // ModemLSB.cpp:43-64

@@ -239,3 +239,23 @@ def test_zoomed_view_zoom_pan_and_back(emu_lib, ref):
              8: (True, C0 - 50000, 1100000)}      # and back into the same view (its resampler is still there)
     w = parity.run_spectrum(emu_lib, ref, 2400000, 512, n_blocks=10, chans=chans, view_by_block=views, lps=400)
     assert w["frames"] >= 40 and w["mags"] <= parity.TOL and w["maa"] <= parity.TOL and w["points"] <= parity.TOL
+
+
+def test_dsb_modem_costas_loop(emu_lib, ref):
+    """ModemDSB: liquid's ampmodem(0.5, DSB, suppressed carrier) -- a hard-limited Costas loop through the table oscillator
+    (ampmodem_demod_dsb_pll_costas + nco_crcf_pll_step, replayed operation by operation) -- then the AM-style audio path."""
+    chans = [("DSB", 5400, 300000), ("DSB", 5400, -450000), ("AM", 6000, 600000)]
+    signal = [("USB", 5400, 300000), ("LSB", 5400, 300000), ("AM", 6000, -450000), ("AM", 6000, 600000)]   # a suppressed-carrier DSB signal, an AM one
+    out, _, _ = parity.run_channels(emu_lib, ref, 2400000, chans, n_blocks=12, signal=signal)
+    parity.check_channels(out)
+    assert len(out[0]["audio"]) > 9000
+
+
+def test_cw_modem(emu_lib, ref):
+    """ModemCW (analog/ModemCW.cpp:155-209): complex interpolation to the audio rate (msresamp_cccf), 650 Hz beat oscillator,
+    firhilbf(5, 60) to real, block gain through log10 / pow; the audio leaves without a further resampler."""
+    chans = [("CW", 500, 300000), ("CW", 1500, -450123), ("AM", 6000, 600000)]
+    signal = [("USB", 5400, 300000 - 600), ("USB", 5400, -450123 - 400), ("AM", 6000, 600000)]      # carriers a few hundred Hz off: audible beats
+    out, _, _ = parity.run_channels(emu_lib, ref, 2400000, chans, n_blocks=30, signal=signal)
+    parity.check_channels(out)
+    assert len(out[0]["audio"]) == 30 * 800

@@ -225,3 +225,21 @@ def test_zoomed_view(gpu_lib, ref):
     w = parity.run_spectrum(gpu_lib, ref, 10000000, 8192, n_blocks=6, chans=synth.channel_plan("mixed", 10000000, 16),
                             view_by_block={0: (True, C0 + 450000, 600000)})
     assert w["frames"] >= 3 and w["mags"] <= parity.TOL and w["points"] <= parity.TOL
+
+
+def test_dsb_modem_costas_loop(gpu_lib, ref):
+    """ModemDSB on the device: the Costas loop's oscillator must track the reference's word for word."""
+    chans = [("DSB", 5400, 300000), ("DSB", 5400, -450000), ("AM", 6000, 600000)]
+    signal = [("USB", 5400, 300000), ("LSB", 5400, 300000), ("AM", 6000, -450000), ("AM", 6000, 600000)]
+    out, _, _ = parity.run_channels(gpu_lib, ref, 2400000, chans, n_blocks=12, signal=signal)
+    parity.check_channels(out)
+
+
+def test_cw_modem(gpu_lib, ref):
+    """ModemCW (analog/ModemCW.cpp:155-209): complex interpolation to the audio rate (msresamp_cccf), 650 Hz beat oscillator,
+    firhilbf(5, 60) to real, block gain through log10 / pow; the audio leaves without a further resampler."""
+    chans = [("CW", 500, 300000), ("CW", 1500, -450123), ("AM", 6000, 600000)]
+    signal = [("USB", 5400, 300000 - 600), ("USB", 5400, -450123 - 400), ("AM", 6000, 600000)]      # carriers a few hundred Hz off: audible beats
+    out, _, _ = parity.run_channels(gpu_lib, ref, 2400000, chans, n_blocks=30, signal=signal)
+    parity.check_channels(out)
+    assert len(out[0]["audio"]) == 30 * 800
