@@ -56,7 +56,8 @@ int main(int argc, char **argv) {
         modem->disposeKit(kit);
         delete modem;
     }
-    if (Modem::makeModem("DSB") != nullptr) return 7;           // not registered -> nullptr, like Modem::makeModem
+    if (Modem::makeModem("FMS") != nullptr) return 7;           // not registered -> nullptr, like Modem::makeModem
+    { Modem *d = Modem::makeModem("DSB"); if (!d || d->getName() != "DSB") return 7; delete d; }
 
     // ---- S3 + S2: block ingress, pre-demod + demod batched, spectrum ----------------------------------------------------
     SDRPostB200 post(eng);
