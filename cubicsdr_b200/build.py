@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = [os.path.join(HERE, "csrc", "engine.cu"), os.path.join(HERE, "csrc", "design.cpp")]
-HDR = [os.path.join(HERE, "csrc", f) for f in ("backend.h", "design.h", "dsp_core.h", "dsp_tail.h", "dsp_spec.h", "dsp_pfb.h")] + [
+HDR = [os.path.join(HERE, "csrc", f) for f in ("backend.h", "design.h", "dsp_core.h", "dsp_tail.h", "dsp_spec.h", "dsp_pfb.h", "group.h")] + [
     os.path.join(ROOT, "include", "sdr_b200.h")]
 OUT = os.path.join(HERE, "libsdr_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
