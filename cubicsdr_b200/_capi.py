@@ -24,7 +24,7 @@ SYMBOLS = [
     "sdr_modem_check_sample_rate", "sdr_modem_create", "sdr_modem_demodulate",
     "sdr_spectrum_create", "sdr_spectrum_destroy", "sdr_spectrum_set_average_rate", "sdr_spectrum_set_view", "sdr_spectrum_desired_input", "sdr_spectrum_frames",
     "sdr_spectrum_fetch", "sdr_spectrum_fetch_all", "sdr_spectrum_fetch_debug",
-    "sdr_engine_set_channelizer", "sdr_engine_channel_plan", "sdr_engine_set_channel_block_max",
+    "sdr_engine_set_channelizer", "sdr_engine_set_dc_window", "sdr_engine_channel_plan", "sdr_engine_set_channel_block_max",
     "sdr_pfb_optimal_channel_count", "sdr_pfb_create", "sdr_pfb2_create", "sdr_pfb_destroy", "sdr_pfb_reset", "sdr_pfb_execute", "sdr_pfb_execute_device",
     "sdr_group_create", "sdr_group_create_rank", "sdr_group_unique_id", "sdr_group_destroy", "sdr_group_info", "sdr_group_engine",
     "sdr_group_chan_create", "sdr_group_spectrum_create", "sdr_group_submit", "sdr_group_wait", "sdr_group_wait_block", "sdr_group_set_host_results",
@@ -91,6 +91,8 @@ class Lib:
         L.sdr_spectrum_fetch.argtypes = [vp, u, vp, vp, vp]
         L.sdr_spectrum_fetch_debug.argtypes = [vp, u, vp, vp]
         L.sdr_engine_set_channelizer.argtypes = [vp, C.c_int]
+        L.sdr_engine_set_dc_window.argtypes = [vp, C.c_int]
+        L.sdr_engine_debug_dc_window.argtypes = [vp, C.POINTER(C.c_uint), C.POINTER(C.c_ulonglong)]
         L.sdr_engine_channel_plan.argtypes = [C.c_longlong, vp, vp]
         L.sdr_engine_set_channel_block_max.argtypes = [vp, u]
         L.sdr_pfb_optimal_channel_count.argtypes = [C.c_longlong]
@@ -198,6 +200,16 @@ class Engine:
     def set_channelizer(self, mode):
         """0: SDRPostThread::runSingleCH for every block; 1: runPFBCH when the rate gives more than one channel."""
         self.lib.check(self.lib.L.sdr_engine_set_channelizer(self.h, int(mode)))
+
+    def set_dc_window(self, mode):
+        """DC blocker replay: 1 candidate windows, 0 warmed-up segments, -1 automatic (by channel load).  Same samples either way."""
+        self.lib.check(self.lib.L.sdr_engine_set_dc_window(self.h, int(mode)))
+
+    def dc_window_stats(self):
+        """(stretches the window walker had to run serially, blocks that took the window path) so far"""
+        s, b = C.c_uint(), C.c_ulonglong()
+        self.lib.check(self.lib.L.sdr_engine_debug_dc_window(self.h, C.byref(s), C.byref(b)))
+        return s.value, b.value
 
     def set_channel_block_max(self, n):
         """Most samples a demodulator gets per block (channelizer mode: block / numChannels); before creating channels."""

@@ -272,6 +272,7 @@ struct DcExactArgs {
     float2 *seg_in, *seg_out;        // [n_seg] warmed-up state entering / true-candidate state leaving each segment
     float2 *fstate;                  // [1] the reference's float state carried across blocks
     unsigned *fixups;                // [1] junctions that had to be replayed (diagnostic)
+    const float2 *start;             // non-null: the true state entering every segment is known (dsp_dcwin.h), no warm-up
 };
 
 // one step of the reference recurrence for both components; no fused multiply-add allowed
@@ -295,6 +296,7 @@ SDR_HD SDR_FORCEINLINE void dc_ref_step(float c, float2 x, float2 &v, float2 &y)
 // therefore starts at an index in [d, d + kDcTile).
 SDR_HD inline void dc_exact_plan(const DcExactArgs &a, int s, int &i_start, float2 &v0) {
     if (s == 0) { i_start = 0; v0 = a.fstate[0]; return; }
+    if (a.start) { i_start = s * a.seg_len; v0 = a.start[s]; return; }
     const long long d = (long long)s * a.seg_len - a.warm;
     if (d >= 0) {
         const int t = (int)(d / kDcTile);

@@ -26,6 +26,7 @@
 #include "../../include/sdr_b200.h"
 #include "design.h"
 #include "dsp_core.h"
+#include "dsp_dcwin.h"
 #include "dsp_spec.h"
 #include "dsp_pfb.h"
 #include "dsp_tail.h"
@@ -578,6 +579,73 @@ __global__ void __launch_bounds__(256) k_dc_verify(DcExactArgs a) {
     }
 }
 
+// ---- bit-exact DC blocker without a warm-up (dsp_dcwin.h): candidate windows, chunk composition, walk + gather --------------
+// pass 1: CTA = (boundary b, component k), thread = candidate.  The tile's samples of that component sit in shared memory (one
+// LDS.128 per four steps, broadcast); the chain is two dependent FP32 operations a step and eight warps a CTA / eight CTAs an SM
+// keep the issue slots busy: this is throughput work spread over the whole chip, not a latency chain on a few SMs.
+__global__ void __launch_bounds__(kDwCand) k_dc_window(DcWinArgs a) {
+    __shared__ __align__(16) float sx[kDcTile];
+    const int b = (int)(blockIdx.x >> 1), k = (int)(blockIdx.x & 1), i = (int)threadIdx.x;
+    if (!dw_good(a, b, k)) return;                                   // uniform: the run of an earlier boundary covers this tile
+    float v = dw_unord(dw_ord(dw_center(a, b, k)) + i - kDwHalf);
+    const float c = a.c;
+    const float *xk = reinterpret_cast<const float *>(a.xraw) + k;
+    for (int p = b; p < a.tiles;) {
+        const int i0 = p * kDcTile;
+        int len = a.n - i0; if (len > kDcTile) len = kDcTile;
+        __syncthreads();                                             // the previous tile has been consumed
+        for (int j = i; j < len; j += kDwCand) sx[j] = __ldg(xk + 2 * (size_t)(i0 + j));
+        __syncthreads();
+        if (len == kDcTile) {
+            const float4 *s4 = reinterpret_cast<const float4 *>(sx);
+#pragma unroll 8
+            for (int j = 0; j < kDcTile / 4; ++j) {
+                const float4 q = s4[j];
+                v = __fadd_rn(q.x, __fmul_rn(c, v));
+                v = __fadd_rn(q.y, __fmul_rn(c, v));
+                v = __fadd_rn(q.z, __fmul_rn(c, v));
+                v = __fadd_rn(q.w, __fmul_rn(c, v));
+            }
+        } else {
+            for (int j = 0; j < len; ++j) v = __fadd_rn(sx[j], __fmul_rn(c, v));
+        }
+        ++p;
+        if (p >= a.tiles) break;
+        dw_row(a.st, p, k)[i] = v;
+        if (dw_good(a, p, k)) break;                                 // uniform
+    }
+}
+// pass 2: CTA = (chunk, component): the chunk's table rows in shared memory, thread = candidate at the chunk's entry
+__global__ void __launch_bounds__(kDwCand) k_dc_compose(DcWinArgs a) {
+    __shared__ float rows[kDwChunk * kDwCand];
+    __shared__ DwChunkInfo ci;
+    const int c = (int)(blockIdx.x >> 1), k = (int)(blockIdx.x & 1), i = (int)threadIdx.x;
+    if (i < kDwChunk) dw_chunk_info(a, c, k, i, &ci);
+    __syncthreads();
+    for (int j = 0; j < ci.n; ++j) rows[j * kDwCand + i] = dw_row(a.st, c * kDwChunk + 1 + j, k)[i];
+    __syncthreads();
+    dw_compose_thread(a, c, k, i, rows, &ci);
+}
+// pass 3: the chunk maps in shared memory, one thread per component walks them (two warps: no divergence between the
+// components), then everybody gathers the true state of every boundary
+__global__ void __launch_bounds__(1024) k_dc_resolve(DcWinArgs a, int gmap_in_smem) {
+    extern __shared__ __align__(16) unsigned char rs_sm[];
+    short *sg = reinterpret_cast<short *>(rs_sm);
+    const int chunks = (a.tiles - 1 + kDwChunk - 1) / kDwChunk;
+    const short *gm = a.gmap;
+    if (gmap_in_smem) {
+        const int words = chunks * kDwCand;                          // 2 components x kDwCand shorts = kDwCand 32-bit words a chunk
+        for (int w = (int)threadIdx.x; w < words; w += (int)blockDim.x)
+            reinterpret_cast<unsigned *>(sg)[w] = reinterpret_cast<const unsigned *>(a.gmap)[w];
+        gm = sg;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) dw_walk(a, 0, gm);
+    else if (threadIdx.x == 32) dw_walk(a, 1, gm);
+    __syncthreads();
+    for (int p = 1 + (int)threadIdx.x; p < a.tiles; p += (int)blockDim.x) dw_gather_thread(a, p);
+}
+
 template <int K>
 __global__ void __launch_bounds__(kFrontWarps * 32, 1) k_chan_front(FrontArgs a, int jobs) {
     extern __shared__ __align__(16) unsigned char front_sm[];
@@ -753,6 +821,34 @@ static bool tma_rows_map(CUtensorMap *m, float2 *base, unsigned row_samples, uns
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 #endif
+
+// candidate windows -> chunk maps -> walk + gather: the true state entering every tile lands in a.seg_in (dsp_dcwin.h)
+static int launch_dc_window(const DcWinArgs &a, sdr_stream_t s, unsigned long long &launches) {
+    const int chunks = (a.tiles - 1 + kDwChunk - 1) / kDwChunk;
+#ifndef SDR_EMU
+    k_dc_window<<<2 * a.tiles, kDwCand, 0, s>>>(a);
+    k_dc_compose<<<2 * chunks, kDwCand, 0, s>>>(a);
+    const size_t gbytes = (size_t)chunks * 2 * kDwCand * sizeof(short);
+    const bool in_smem = gbytes <= 200 * 1024;
+    static bool attr_set = false;
+    if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(k_dc_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+    k_dc_resolve<<<1, 1024, in_smem ? gbytes : 0, s>>>(a, in_smem ? 1 : 0);
+#else
+    (void)s;
+    for (int b = 0; b < a.tiles; ++b) for (int k = 0; k < 2; ++k) for (int i = 0; i < kDwCand; ++i) dw_window_thread(a, b, k, i);
+    for (int c = 0; c < chunks; ++c) for (int k = 0; k < 2; ++k) {
+        DwChunkInfo ci;
+        std::vector<float> rows((size_t)kDwChunk * kDwCand);
+        for (int j = 0; j < kDwChunk; ++j) dw_chunk_info(a, c, k, j, &ci);
+        for (int j = 0; j < ci.n; ++j) for (int i = 0; i < kDwCand; ++i) rows[(size_t)j * kDwCand + i] = dw_row(a.st, c * kDwChunk + 1 + j, k)[i];
+        for (int i = 0; i < kDwCand; ++i) dw_compose_thread(a, c, k, i, rows.data(), &ci);
+    }
+    dw_walk(a, 0, a.gmap); dw_walk(a, 1, a.gmap);
+    for (int p = 1; p < a.tiles; ++p) dw_gather_thread(a, p);
+#endif
+    launches += 3;
+    return SDR_OK;
+}
 
 // tma_rows: samples readable from xraw[-warm] on (rows of the input tensor = that / seg_len); 0 = use the cp.async kernel
 static int launch_dc_exact(const DcExactArgs &a, unsigned long long tma_rows, sdr_stream_t s, unsigned long long &launches) {
@@ -1026,6 +1122,13 @@ struct sdr_engine {
     double2 *d_tile_carry2[2] = {nullptr, nullptr};
     float2 *d_seg_in = nullptr, *d_seg_out = nullptr, *d_fstate = nullptr;
     unsigned *d_fixups = nullptr;
+    // candidate-window DC replay (dsp_dcwin.h): tables and walker outputs; dc_window: -1 auto (by channel load), 0 off, 1 on
+    float *d_dw_st = nullptr, *d_dw_pst = nullptr;
+    short *d_dw_gmap = nullptr;
+    int *d_dw_entry = nullptr;
+    unsigned *d_dw_stats = nullptr;
+    int dc_window = -1;
+    unsigned long long dw_blocks = 0;
     // host blocks: ring of pinned staging buffers -> DMA on stream_h2d -> ring of device buffers -> the DC stream
     static const int kInRing = 3;
     sdr_cf32 *h_in[kInRing] = {nullptr, nullptr, nullptr};
@@ -1217,7 +1320,9 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
     (void)stream;
 #endif
     // history kept in front of the block: the DC replay's warm-up, and a zoomed spectrum view's frame (up to one block long)
-    e->hist_cap = (std::max<size_t>(65536, max_block) + kBlkHist + 1) & ~(size_t)1;
+    // history kept in front of a block: the spectrum frames that straddle blocks; a zoomed view's frames are the transform length
+    // times its decimation (262144 samples for a 16384-point transform zoomed 16x), however short the blocks are
+    e->hist_cap = (std::max<size_t>((size_t)1 << 19, max_block) + kBlkHist + 1) & ~(size_t)1;
     int bad = 0;
     bad |= be_malloc((void **)&e->d_raw, (size_t)max_block * sizeof(float2));
     e->raw_pad = (size_t)max_block / 8 + 2 * 65536;
@@ -1241,6 +1346,17 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
     bad |= be_malloc((void **)&e->d_seg_out, max_seg * sizeof(float2));
     bad |= be_malloc((void **)&e->d_fstate, sizeof(float2));
     bad |= be_malloc((void **)&e->d_fixups, sizeof(unsigned));
+    {
+        const size_t rows = (size_t)max_seg * 2 * kDwCand;
+        const size_t chunks = (size_t)max_seg / kDwChunk + 2;
+        bad |= be_malloc((void **)&e->d_dw_st, rows * sizeof(float));
+        bad |= be_malloc((void **)&e->d_dw_pst, rows * sizeof(float));
+        bad |= be_malloc((void **)&e->d_dw_gmap, chunks * 2 * kDwCand * sizeof(short));
+        bad |= be_malloc((void **)&e->d_dw_entry, chunks * 2 * sizeof(int));
+        bad |= be_malloc((void **)&e->d_dw_stats, 4 * sizeof(unsigned));
+        const char *w = getenv("SDR_B200_DC_WINDOW");
+        if (w) e->dc_window = atoi(w) ? 1 : 0;
+    }
     { const char *m = getenv("SDR_B200_DC"); if (m && std::string(m) == "scan") e->exact_dc = false; }
     bad |= be_malloc((void **)&e->d_dc_state, sizeof(double2));
     bad |= be_malloc((void **)&e->d_apow, (kDcTile + 1) * sizeof(double));
@@ -1306,6 +1422,7 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
     be_memset(e->d_rawbuf, 0, (e->hist_cap + max_block + e->raw_pad) * sizeof(float2), e->stream);
     be_memset(e->d_fstate, 0, sizeof(float2), e->stream);
     be_memset(e->d_fixups, 0, sizeof(unsigned), e->stream);
+    if (!bad) be_memset(e->d_dw_stats, 0, 4 * sizeof(unsigned), e->stream);
     be_memset(e->d_dc_state, 0, sizeof(double2), e->stream);
     // DC blocker coefficient: a = -(-1 + alpha) with alpha = 0.0005f, evaluated in float as the reference does
     const float a_f = 1.0f - 0.0005f;
@@ -1357,6 +1474,7 @@ extern "C" int sdr_engine_destroy(sdr_engine *e) {
     be_free(e->d_raw); be_free(e->d_blkbuf[0]); be_free(e->d_blkbuf[1]); be_free(e->d_rawbuf); be_free(e->d_scratch);
     for (int k = 0; k < sdr_engine::kInRing; ++k) { be_host_free(e->h_in[k]); be_free(e->d_in[k]); }
     be_free(e->d_tile_sum); be_free(e->d_tile_carry2[0]); be_free(e->d_tile_carry2[1]); be_free(e->d_dc_state);
+    be_free(e->d_dw_st); be_free(e->d_dw_pst); be_free(e->d_dw_gmap); be_free(e->d_dw_entry); be_free(e->d_dw_stats);
     be_free(e->d_seg_in); be_free(e->d_seg_out); be_free(e->d_fstate); be_free(e->d_fixups); be_free(e->d_apow); be_free(e->d_nco);
     be_free(e->d_cs); be_free(e->d_cd2[0]); be_free(e->d_cd2[1]); be_free(e->d_st); be_host_free(e->h_cd); be_free(e->d_group); be_host_free(e->h_group);
     be_free(e->d_taps); be_free(e->d_results); be_host_free(e->h_results);
@@ -1407,6 +1525,26 @@ extern "C" int sdr_engine_debug_dc_fixups(sdr_engine *e, unsigned *fixups, int *
     be_sync(e->stream);
     if (fixups) *fixups = v;
     if (exact_mode) *exact_mode = e->exact_dc ? 1 : 0;
+    return SDR_OK;
+}
+// diagnostics: candidate-window replay -- stretches its walker had to run serially so far; blocks that took the window path
+extern "C" int sdr_engine_debug_dc_window(sdr_engine *e, unsigned *serial_stretches, unsigned long long *window_blocks) {
+    if (!e) return SDR_ERR_ARG;
+    std::lock_guard<std::mutex> lk(e->mu);
+    use_device(e);
+    be_sync(e->stream);
+    unsigned v = 0;
+    be_d2h(&v, e->d_dw_stats, sizeof v, e->stream);
+    be_sync(e->stream);
+    if (serial_stretches) *serial_stretches = v;
+    if (window_blocks) *window_blocks = e->dw_blocks;
+    return SDR_OK;
+}
+// select the DC replay: -1 automatic (windows unless the channel load hides a warm-up replay), 0 warm-up replay, 1 windows
+extern "C" int sdr_engine_set_dc_window(sdr_engine *e, int mode) {
+    if (!e) return SDR_ERR_ARG;
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->dc_window = mode < 0 ? -1 : (mode ? 1 : 0);
     return SDR_OK;
 }
 
@@ -2185,7 +2323,13 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
 #endif
     } else {
         const size_t need_raw = std::min(e->hist_cap, (size_t)kDcWarm + 2 * kDcTile);
-        if (e->have_block && e->last_n > 0) {
+        // which replay: candidate windows (no warm-up: a few dozen microseconds of chip-wide throughput work) unless enough
+        // channels are attached for a warm-up replay on a few reserved SMs to hide under the channel front kernel
+        size_t live = 0;
+        for (auto *c : e->chans) live += c != nullptr;
+        const unsigned tiles_n = (n + kDcTile - 1) / kDcTile;
+        const bool window = e->exact_dc && tiles_n >= (unsigned)kDwMinTiles && (e->dc_window < 0 ? live < 256 : e->dc_window == 1);
+        if (e->have_block && e->last_n > 0 && !window) {
             be_d2d(e->d_scratch, raw + (long long)e->last_n - (long long)need_raw, need_raw * sizeof(float2), dcs);
             be_d2d(raw - need_raw, e->d_scratch, need_raw * sizeof(float2), dcs);
         }
@@ -2204,22 +2348,29 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
             DcExactArgs xa;
             // one lane per segment on the SMs the channel front kernel leaves free: as many segments (multiples of the scan
             // tile) as those SMs hold lanes, each warmed up over kDcWarm samples
-            size_t live = 0;
-            for (auto *c : e->chans) live += c != nullptr;
             const unsigned lanes = (unsigned)dc_reserved_sms(live) * kDlWarpsHost * 32u;
-            const unsigned tiles_n = (n + kDcTile - 1) / kDcTile;
-            const unsigned seg = kDcTile * ((tiles_n + lanes - 1) / lanes);
-            xa.xraw = raw; xa.y = blk; xa.n = (int)n; xa.seg_len = (int)seg; xa.warm = kDcWarm;
+            const unsigned seg = window ? (unsigned)kDcTile : kDcTile * ((tiles_n + lanes - 1) / lanes);
+            xa.xraw = raw; xa.y = blk; xa.n = (int)n; xa.seg_len = (int)seg; xa.warm = window ? 0 : kDcWarm;
+            xa.start = nullptr;
             xa.raw_hist = (int)need_raw; xa.raw_end = (long long)e->max_block + (long long)e->raw_pad;
             xa.c = (float)e->dc_a; xa.one = 1.0f;
             xa.tile_carry = e->d_tile_carry2[p]; xa.prev_tile_carry = e->d_tile_carry2[p ^ 1];
             xa.prev_n = e->have_block ? (int)e->last_n : 0;
             xa.seg_in = e->d_seg_in; xa.seg_out = e->d_seg_out; xa.fstate = e->d_fstate; xa.fixups = e->d_fixups;
             // speculate only when there is parallelism to gain and the warm-up region lies inside the data we hold
-            const bool spec = n >= (unsigned)kDcMinSpec && n > seg && (!e->have_block || e->last_n >= (unsigned)(kDcWarm + kDcTile));
+            const bool spec = window || (n >= (unsigned)kDcMinSpec && n > seg && (!e->have_block || e->last_n >= (unsigned)(kDcWarm + kDcTile)));
             xa.n_seg = spec ? (int)((n + seg - 1) / seg) : 1;
             if (!spec) xa.seg_len = (int)n;
-            { int r = launch_dc_exact(xa, (unsigned long long)kDcWarm + e->max_block + e->raw_pad, dcs, e->launches); if (r) return r; }
+            if (window) {
+                DcWinArgs wa;
+                wa.xraw = raw; wa.n = (int)n; wa.tiles = (int)tiles_n; wa.c = xa.c; wa.tile_carry = e->d_tile_carry2[p]; wa.fstate = e->d_fstate;
+                wa.st = e->d_dw_st; wa.pst = e->d_dw_pst; wa.gmap = e->d_dw_gmap; wa.entry = e->d_dw_entry; wa.seg_in = e->d_seg_in;
+                wa.stats = e->d_dw_stats;
+                { int r = launch_dc_window(wa, dcs, e->launches); if (r) return r; }
+                xa.start = e->d_seg_in;
+                e->dw_blocks += 1;
+            }
+            { int r = launch_dc_exact(xa, (unsigned long long)xa.warm + e->max_block + e->raw_pad, dcs, e->launches); if (r) return r; }
         }
     }
     // history in front of the block: the tail of the previous block, which lives in the other buffer
@@ -2310,7 +2461,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         if (s->is_view) {
             while (resample_bw / 2 >= s->view_bw) resample_bw /= 2;          // SPECTRUM_VZM = 2
             D = (long long)(size_t)((double)s->N / ((double)resample_bw / (double)rate));
-            if ((size_t)D + 16 > e->hist_cap) return fail(SDR_ERR_UNSUPPORTED, "zoomed view: a frame of the view is longer than the engine's stream history (one block)");
+            if ((size_t)D + 16 > e->hist_cap) return fail(SDR_ERR_UNSUPPORTED, "zoomed view: a frame of the view is longer than the engine's stream history (max(524288, max_block) samples)");
         }
         schedule_frames(s, D, n, rate, center, starts);
         s->frames_last = (unsigned)std::min<size_t>(starts.size(), s->f_max);

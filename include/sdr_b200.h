@@ -181,6 +181,11 @@ int sdr_spectrum_fetch_debug(sdr_spectrum *sp, unsigned idx, float *mags, float 
  * sdr_engine_channel_plan (what DemodulatorPreThread sees as inp->sampleRate).  Spectra see the raw block, as there. */
 int sdr_engine_set_channelizer(sdr_engine *eng, int mode);
 int sdr_engine_channel_plan(long long sample_rate, int *num_channels, long long *channel_rate);
+/* The wideband DC blocker (iirfilt_crcf_execute_block, src/sdr/SDRPostThread.cpp:284) is replayed bit for bit in one of two
+ * ways: 1 = candidate windows (no warm-up: the lowest latency, some chip-wide work), 0 = warmed-up segments on a few reserved
+ * SMs (hides under a long channel front kernel), -1 (default) = chosen per block from the number of attached channels.
+ * Both give identical samples; this only moves time around.  Environment: SDR_B200_DC_WINDOW=0|1. */
+int sdr_engine_set_dc_window(sdr_engine *eng, int mode);
 /* Most samples one demodulator receives per block (channelizer mode: block / num_channels, twice that in mode 2); sizes the
  * channels' buffers and result slots.  Default max_block; call before creating channels. */
 int sdr_engine_set_channel_block_max(sdr_engine *eng, unsigned n);

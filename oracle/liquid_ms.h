@@ -40,6 +40,10 @@ LQ int nco_crcf_mix_up(nco_crcf q, lq_cf x, lq_cf *y);
 LQ int nco_crcf_mix_down(nco_crcf q, lq_cf x, lq_cf *y);
 LQ int nco_crcf_mix_block_up(nco_crcf q, lq_cf *x, lq_cf *y, unsigned int n);
 LQ int nco_crcf_mix_block_down(nco_crcf q, lq_cf *x, lq_cf *y, unsigned int n);
+/* phase-locked-loop entry points used by ModemFMStereo.cpp:143-145, 239-250 */
+LQ int nco_crcf_cexpf(nco_crcf q, lq_cf *y);
+LQ int nco_crcf_pll_set_bandwidth(nco_crcf q, float bw);
+LQ int nco_crcf_pll_step(nco_crcf q, float dphi);
 
 /* resamp2 / resamp / msresamp2 / msresamp, liquid.h:4214, 4294, 4513, 4600, 4663, 4736-4780 */
 typedef struct resamp2_crcf_s *resamp2_crcf;
@@ -76,6 +80,7 @@ LQ int freqdem_demodulate_block(freqdem q, lq_cf *r, unsigned int n, float *m);
 /* firfilt_rrrf, liquid.h:2825, 2873, 2888 */
 typedef struct firfilt_rrrf_s *firfilt_rrrf;
 LQ firfilt_rrrf firfilt_rrrf_create_dc_blocker(unsigned int m, float as);
+LQ firfilt_rrrf firfilt_rrrf_create(float *h, unsigned int n);          /* ModemFMStereo.cpp:122-123 */
 LQ int firfilt_rrrf_destroy(firfilt_rrrf q);
 LQ int firfilt_rrrf_push(firfilt_rrrf q, float x);
 LQ int firfilt_rrrf_execute(firfilt_rrrf q, float *y);
@@ -84,7 +89,21 @@ LQ int firfilt_rrrf_execute(firfilt_rrrf q, float *y);
 typedef struct iirfilt_crcf_s *iirfilt_crcf;
 LQ iirfilt_crcf iirfilt_crcf_create_lowpass(unsigned int order, float fc);
 LQ iirfilt_crcf iirfilt_crcf_create_dc_blocker(float alpha);
+/* liquid.h:3387 (ModemFMStereo.cpp:136): ftype CHEBY2 = 2, btype BANDPASS = 2, format SOS = 0 */
+LQ iirfilt_crcf iirfilt_crcf_create_prototype(int ftype, int btype, int format, unsigned int order, float fc, float f0, float ap, float as);
 LQ int iirfilt_crcf_destroy(iirfilt_crcf q);
+/* iirfilt_rrrf (ModemFMStereo.cpp:158-159, 268-269): first-order de-emphasis sections */
+typedef struct iirfilt_rrrf_s *iirfilt_rrrf;
+LQ iirfilt_rrrf iirfilt_rrrf_create(float *b, unsigned int nb, float *a, unsigned int na);
+LQ int iirfilt_rrrf_destroy(iirfilt_rrrf q);
+LQ int iirfilt_rrrf_execute(iirfilt_rrrf q, float x, float *y);
+/* design entry point, for pinning the product's host-side design (liquid.h:2466) */
+LQ int cheby2_azpkf(unsigned int n, float es, lq_cf *z, lq_cf *p, lq_cf *k);
+LQ float iirdes_freqprewarp(int btype, float fc, float f0);
+LQ int bilinear_zpkf(lq_cf *za, unsigned int nza, lq_cf *pa, unsigned int npa, lq_cf ka, float m, lq_cf *zd, lq_cf *pd, lq_cf *kd);
+LQ int iirdes_dzpk_lp2bp(lq_cf *zd, lq_cf *pd, unsigned int n, float f0, lq_cf *zdt, lq_cf *pdt);
+LQ int iirdes_dzpk2sosf(lq_cf *zd, lq_cf *pd, unsigned int n, lq_cf kd, float *b, float *a);
+LQ int liquid_iirdes(int ftype, int btype, int format, unsigned int n, float fc, float f0, float ap, float as, float *b, float *a);
 LQ int iirfilt_crcf_execute(iirfilt_crcf q, lq_cf x, lq_cf *y);
 LQ int iirfilt_crcf_execute_block(iirfilt_crcf q, lq_cf *x, unsigned int n, lq_cf *y);
 
@@ -93,6 +112,7 @@ typedef struct firhilbf_s *firhilbf;
 LQ firhilbf firhilbf_create(unsigned int m, float as);
 LQ int firhilbf_destroy(firhilbf q);
 LQ int firhilbf_c2r_execute(firhilbf q, lq_cf x, float *y0_lsb, float *y1_usb);
+LQ int firhilbf_r2c_execute(firhilbf q, float x, lq_cf *y);             /* ModemFMStereo.cpp:232 */
 
 /* ampmodem, liquid.h:8283-8324 (ModemDSB.cpp:7,38: ampmodem_create(0.5, LIQUID_AMPMODEM_DSB = 0, 1) + ampmodem_demodulate) */
 typedef struct ampmodem_s *ampmodem;

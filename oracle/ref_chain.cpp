@@ -87,6 +87,41 @@ API void ref_firhilb_destroy(void *q) { firhilbf_destroy((firhilbf)q); }
 API void ref_firhilb_c2r_block(void *q, lq_cf *x, unsigned n, float *lsb, float *usb) {
     for (unsigned i = 0; i < n; i++) firhilbf_c2r_execute((firhilbf)q, x[i], lsb + i, usb + i);
 }
+API void ref_firhilb_r2c_block(void *q, float *x, unsigned n, lq_cf *y) {
+    for (unsigned i = 0; i < n; i++) firhilbf_r2c_execute((firhilbf)q, x[i], y + i);
+}
+API int ref_iirdes(int ftype, int btype, int format, unsigned n, float fc, float f0, float ap, float as, float *b, float *a) {
+    return liquid_iirdes(ftype, btype, format, n, fc, f0, ap, as, b, a);
+}
+// the stages of liquid_iirdes, one by one (pins for the product's host-side restatement, csrc/design.cpp)
+API void ref_cheby2_azpk(unsigned n, float es, lq_cf *z, lq_cf *p, lq_cf *k) { cheby2_azpkf(n, es, z, p, k); }
+API float ref_iirdes_freqprewarp(int btype, float fc, float f0) { return iirdes_freqprewarp(btype, fc, f0); }
+API void ref_bilinear_zpk(lq_cf *za, unsigned nza, lq_cf *pa, unsigned npa, const lq_cf *ka, float m, lq_cf *zd, lq_cf *pd, lq_cf *kd) {
+    bilinear_zpkf(za, nza, pa, npa, *ka, m, zd, pd, kd);
+}
+API void ref_dzpk_lp2bp(lq_cf *zd, lq_cf *pd, unsigned n, float f0, lq_cf *zdt, lq_cf *pdt) { iirdes_dzpk_lp2bp(zd, pd, n, f0, zdt, pdt); }
+API void ref_dzpk2sos(lq_cf *zd, lq_cf *pd, unsigned n, const lq_cf *kd, float *b, float *a) { iirdes_dzpk2sosf(zd, pd, n, *kd, b, a); }
+API void *ref_iirfilt_prototype_create(int ftype, int btype, int format, unsigned order, float fc, float f0, float ap, float as) {
+    return iirfilt_crcf_create_prototype(ftype, btype, format, order, fc, f0, ap, as);
+}
+API void *ref_firfilt_create(float *h, unsigned n) { return firfilt_rrrf_create(h, n); }
+API void *ref_iirfilt_rrrf_create(float *b, unsigned nb, float *a, unsigned na) { return iirfilt_rrrf_create(b, nb, a, na); }
+API void ref_iirfilt_rrrf_destroy(void *q) { iirfilt_rrrf_destroy((iirfilt_rrrf)q); }
+API void ref_iirfilt_rrrf_block(void *q, float *x, unsigned n, float *y) {
+    for (unsigned i = 0; i < n; i++) iirfilt_rrrf_execute((iirfilt_rrrf)q, x[i], y + i);
+}
+// nco_crcf phase-locked loop: bandwidth, then one pll_step per phase error; raw phase / frequency words after each
+API void ref_nco_pll_run(float bw, const float *dphi, unsigned n, uint32_t *theta, uint32_t *dtheta) {
+    nco_crcf q = nco_crcf_create(1 /* LIQUID_VCO */);
+    nco_crcf_reset(q);
+    nco_crcf_pll_set_bandwidth(q, bw);
+    for (unsigned i = 0; i < n; i++) {
+        nco_crcf_pll_step(q, dphi[i]);
+        nco_crcf_step(q);
+        theta[i] = ref_nco_raw_theta(q); dtheta[i] = ref_nco_raw_dtheta(q);
+    }
+    nco_crcf_destroy(q);
+}
 API void ref_fft_forward(lq_cf *x, lq_cf *y, unsigned n) {
     fftplan p = fft_create_plan(n, x, y, +1 /*LIQUID_FFT_FORWARD*/, 0);
     fft_execute(p);
@@ -149,7 +184,7 @@ API int ref_optimal_channel_count(long long sampleRate_in) {
 // ---------------------------------------------------------------------------------------------------------
 // one demodulator channel: DemodulatorPreThread + Modem + DemodulatorThread metering
 // ---------------------------------------------------------------------------------------------------------
-enum { M_FM = 0, M_NBFM = 1, M_AM = 2, M_USB = 3, M_LSB = 4, M_IQ = 5, M_DSB = 7, M_CW = 8 };
+enum { M_FM = 0, M_NBFM = 1, M_AM = 2, M_USB = 3, M_LSB = 4, M_IQ = 5, M_DSB = 7, M_CW = 8, M_FMS = 9 };
 
 struct RefChan {
     int modem;
@@ -176,6 +211,15 @@ struct RefChan {
     msresamp_cccf cwInputResampler = nullptr; nco_crcf cwLO = nullptr; firhilbf cwToReal = nullptr;
     float cwBeepFrequency = 650.0f, cwGain = 15.0f;
     std::vector<lq_cf> cwInput;
+    // ModemKitFMStereo (ModemFMStereo.h:7-32) and ModemFMStereo's buffers (:55-58)
+    msresamp_rrrf stereoResampler = nullptr;
+    firfilt_rrrf firStereoLeft = nullptr, firStereoRight = nullptr;
+    iirfilt_crcf iirStereoPilot = nullptr;
+    int demph = 75;
+    iirfilt_rrrf iirDemphR = nullptr, iirDemphL = nullptr;
+    firhilbf firStereoR2C = nullptr, firStereoC2R = nullptr;
+    nco_crcf stereoPilot = nullptr;
+    std::vector<float> demodStereoData, resampledStereoData;
     std::vector<lq_cf> in_buf, out_buf, resampled;
     std::vector<float> demodOut, audioOut;
     // DemodulatorThread members (src/demod/DemodulatorThread.cpp:25-26): squelchLevel(-100), signalLevel(-100),
@@ -194,6 +238,7 @@ static int modem_from_name(const char *n) {
     if (s == "I/Q") return M_IQ;
     if (s == "DSB") return M_DSB;
     if (s == "CW") return M_CW;
+    if (s == "FMS") return M_FMS;
     return -1;
 }
 
@@ -201,6 +246,7 @@ static int modem_from_name(const char *n) {
 API int ref_modem_check_sample_rate(const char *name, long long bw) {
     int m = modem_from_name(name);
     if (m < 0) return -1;
+    if (m == M_FMS) return bw < 100000 ? 100000 : (int)bw;                  // ModemFMStereo.cpp:27-35
     if (bw < 500) return 500;
     if ((m == M_USB || m == M_LSB) && (bw % 2)) return (int)(bw + 1);
     return (int)bw;
@@ -234,6 +280,42 @@ API void *ref_chan_create(const char *modem, long long sampleRate, long long ban
         c->cwToReal = firhilbf_create(5, 60.0f);
         c->cwInputResampler = msresamp_cccf_create((float)c->audioResampleRatio, 60.0f);
     }
+    if (m == M_FMS) {                                                      // ModemFMStereo.cpp:6-9, 89-167 (buildKit)
+        c->demodFM = freqdem_create(0.5f);
+        c->stereoResampler = msresamp_rrrf_create((float)c->audioResampleRatio, As);
+        float firStereoCutoff = 16000.0f / float(audioRate);
+        float ft = 1000.0f / float(audioRate);
+        float mu = 0.0f;
+        if (firStereoCutoff < 0) firStereoCutoff = 0;
+        if (firStereoCutoff > 0.5) firStereoCutoff = 0.5;
+        unsigned int h_len = estimate_req_filter_len(ft, As);
+        std::vector<float> h(h_len);
+        liquid_firdes_kaiser(h_len, firStereoCutoff, As, mu, h.data());
+        c->firStereoLeft = firfilt_rrrf_create(h.data(), h_len);
+        c->firStereoRight = firfilt_rrrf_create(h.data(), h_len);
+        float bw = float(c->bandwidth);
+        if (bw < 100000.0) bw = 100000.0;
+        unsigned int order = 5;
+        float f0 = ((float)19000 / bw);
+        float fc = ((float)19500 / bw);
+        float Ap = 1.0f;
+        c->iirStereoPilot = iirfilt_crcf_create_prototype(2 /* CHEBY2 */, 2 /* BANDPASS */, 0 /* SOS */, order, fc, f0, Ap, As);
+        c->firStereoR2C = firhilbf_create(5, 60.0f);
+        c->firStereoC2R = firhilbf_create(5, 60.0f);
+        c->stereoPilot = nco_crcf_create(1 /* LIQUID_VCO */);
+        nco_crcf_reset(c->stereoPilot);
+        nco_crcf_pll_set_bandwidth(c->stereoPilot, 0.25f);
+        if (c->demph) {                                                     // :149-166, _demph = 75 (:8)
+            double f = (1.0 / (2.0 * M_PI * double(c->demph) * 1e-6));
+            double t = 1.0 / (2.0 * M_PI * f);
+            t = 1.0 / (2.0 * double(audioRate) * tan(1.0 / (2.0 * double(audioRate) * t)));
+            double tb = (1.0 + 2.0 * t * double(audioRate));
+            float b_demph[2] = {(float)(1.0 / tb), (float)(1.0 / tb)};
+            float a_demph[2] = {1.0, (float)((1.0 - 2.0 * t * double(audioRate)) / tb)};
+            c->iirDemphL = iirfilt_rrrf_create(b_demph, 2, a_demph, 2);
+            c->iirDemphR = iirfilt_rrrf_create(b_demph, 2, a_demph, 2);
+        }
+    }
     if (m == M_USB || m == M_LSB) {                                        // ModemUSB.cpp:8-11
         c->ssbFilt = iirfilt_crcf_create_lowpass(6, 0.25);
         c->ssbShift = nco_crcf_create(0);
@@ -257,6 +339,15 @@ API void ref_chan_destroy(void *h) {
     if (c->cwLO) nco_crcf_destroy(c->cwLO);
     if (c->cwToReal) firhilbf_destroy(c->cwToReal);
     if (c->cwInputResampler) msresamp_cccf_destroy(c->cwInputResampler);
+    if (c->stereoResampler) msresamp_rrrf_destroy(c->stereoResampler);
+    if (c->firStereoLeft) firfilt_rrrf_destroy(c->firStereoLeft);
+    if (c->firStereoRight) firfilt_rrrf_destroy(c->firStereoRight);
+    if (c->iirStereoPilot) iirfilt_crcf_destroy(c->iirStereoPilot);
+    if (c->iirDemphL) iirfilt_rrrf_destroy(c->iirDemphL);
+    if (c->iirDemphR) iirfilt_rrrf_destroy(c->iirDemphR);
+    if (c->firStereoR2C) firhilbf_destroy(c->firStereoR2C);
+    if (c->firStereoC2R) firhilbf_destroy(c->firStereoC2R);
+    if (c->stereoPilot) nco_crcf_destroy(c->stereoPilot);
     delete c;
 }
 
@@ -364,6 +455,57 @@ API int ref_chan_process(void *h, const lq_cf *block, unsigned n, long long shif
         if (audio_out) memcpy(audio_out, c->audioOut.data(), outSize * sizeof(float));
         if (n_audio) *n_audio = outSize;
         return ref_chan_meter_block(c, outSize, bufSize, true, level_db, peak);
+    }
+    if (c->modem == M_FMS) {                                                // ModemFMStereo::demodulate (ModemFMStereo.cpp:186-287)
+        size_t audio_out_size = (size_t)ceil((double)(bufSize)*c->audioResampleRatio) + 512;
+        c->demodOut.resize(bufSize);
+        freqdem_demodulate_block(c->demodFM, c->resampled.data(), (int)bufSize, c->demodOut.data());
+        std::vector<float> resampledOutputData(audio_out_size);
+        unsigned int numAudioWritten = 0;
+        msresamp_rrrf_execute(c->audioResampler, c->demodOut.data(), (int)bufSize, resampledOutputData.data(), &numAudioWritten);
+        c->demodStereoData.resize(bufSize);
+        float phase_error = 0;
+        for (size_t i = 0; i < bufSize; i++) {
+            lq_cf u, v, w, x, y;
+            firhilbf_r2c_execute(c->firStereoR2C, c->demodOut[i], &x);                  // real -> complex
+            iirfilt_crcf_execute(c->iirStereoPilot, x, &v);                              // 19 kHz pilot band-pass
+            nco_crcf_cexpf(c->stereoPilot, &w);
+            w.imag = -w.imag;
+            u.real = v.real * w.real - v.imag * w.imag;
+            u.imag = v.real * w.imag + v.imag * w.real;
+            phase_error = atan2f(u.imag, u.real);
+            nco_crcf_pll_step(c->stereoPilot, phase_error);
+            nco_crcf_step(c->stereoPilot);
+            nco_crcf_mix_down(c->stereoPilot, x, &y);                                   // 38 kHz down-mix
+            nco_crcf_mix_down(c->stereoPilot, y, &x);
+            float usb_discard;
+            firhilbf_c2r_execute(c->firStereoC2R, x, &c->demodStereoData[i], &usb_discard);
+        }
+        c->resampledStereoData.resize(audio_out_size);
+        msresamp_rrrf_execute(c->stereoResampler, c->demodStereoData.data(), (int)bufSize, c->resampledStereoData.data(), &numAudioWritten);
+        c->audioOut.resize(numAudioWritten * 2);
+        for (size_t i = 0; i < numAudioWritten; i++) {
+            float l, r, ld, rd;
+            if (c->demph) {
+                iirfilt_rrrf_execute(c->iirDemphL, 0.568f * (resampledOutputData[i] - (c->resampledStereoData[i])), &ld);
+                iirfilt_rrrf_execute(c->iirDemphR, 0.568f * (resampledOutputData[i] + (c->resampledStereoData[i])), &rd);
+                firfilt_rrrf_push(c->firStereoLeft, ld);
+                firfilt_rrrf_execute(c->firStereoLeft, &l);
+                firfilt_rrrf_push(c->firStereoRight, rd);
+                firfilt_rrrf_execute(c->firStereoRight, &r);
+            } else {
+                firfilt_rrrf_push(c->firStereoLeft, 0.568f * (resampledOutputData[i] - (c->resampledStereoData[i])));
+                firfilt_rrrf_execute(c->firStereoLeft, &l);
+                firfilt_rrrf_push(c->firStereoRight, 0.568f * (resampledOutputData[i] + (c->resampledStereoData[i])));
+                firfilt_rrrf_execute(c->firStereoRight, &r);
+            }
+            c->audioOut[i * 2] = l;
+            c->audioOut[i * 2 + 1] = r;
+        }
+        if (demod_out) memcpy(demod_out, c->demodStereoData.data(), bufSize * sizeof(float));   // the 38 kHz difference signal, for localisation
+        if (audio_out) memcpy(audio_out, c->audioOut.data(), numAudioWritten * 2 * sizeof(float));
+        if (n_audio) *n_audio = numAudioWritten * 2;
+        return ref_chan_meter_block(c, numAudioWritten * 2, bufSize, false, level_db, peak);
     }
     if (c->modem == M_IQ) {                                                 // ModemIQ::demodulate (ModemIQ.cpp:39-56): channels = 2
         c->audioOut.resize(bufSize * 2);

@@ -15,7 +15,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 
   python bench.py --steps 4 --warmup 3 --no-configs --no-cpu-baseline --min-seconds 0 --noise-inputs > gpurun_out/ncu_launch_$tag.log 2>&1
 echo "ncu launches rc=$?"
 # full captures of the top kernels
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_dc_lanes|k_chan_front|k_chan_tail|k_spec_fft' -s 60 -c 8 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_dc_lanes|k_dc_window|k_dc_compose|k_dc_resolve|k_chan_front|k_chan_tail|k_spec_fft' -s 60 -c 8 \
   -o gpurun_out/prof_$tag python bench.py --steps 4 --warmup 3 --no-configs --no-cpu-baseline --min-seconds 0 --noise-inputs > gpurun_out/ncu_full_$tag.log 2>&1
 echo "ncu full rc=$?"
 ls -la gpurun_out | tail -20

@@ -402,3 +402,65 @@ def check_channelizer_mode(lib, ref, fs, chans, n_blocks, retune=None, device=0,
         e = relrms(np.concatenate(got[i]), np.concatenate(want[i]))
         assert e <= TOL, "demod %d (%s @ %+d Hz): audio relative RMS error %.3g" % (i, m, off, e)
     return used
+
+
+def dc_window_case(lib, ref, fs, blocks, make_block, modes=(1,), max_block=None):
+    """Stream the blocks through the engine's DC blocker with the given replay mode per block and compare every sample, bit for
+    bit, with the reference's iirfilt_crcf_execute_block."""
+    from cubicsdr_b200 import Engine
+    from oracle.refbind import RefIngress
+    eng = Engine(lib, max_block=max_block or max(blocks))
+    ing = RefIngress(ref)
+    t0 = 0
+    for b, n in enumerate(blocks):
+        eng.set_dc_window(modes[b % len(modes)])
+        x = make_block(t0, n).astype(np.complex64)
+        t0 += n
+        eng.submit(x, CENTER, fs); eng.wait()
+        got, want = eng.fetch_block(n).view(np.float32), ing.block(x).view(np.float32)
+        assert np.array_equal(got, want), "block %d: %d samples differ" % (b, int(np.count_nonzero(got != want)))
+    stats = eng.dc_window_stats()
+    eng.close()
+    return stats
+
+
+def check_dc_window(lib, ref, big=False):
+    """The candidate-window replay (dsp_dcwin.h) on the inputs that stress it: a DC offset (every boundary enumerable), zero-mean
+    noise and a carrier next to 0 Hz (the state keeps crossing zero: runs of boundaries without a window), silence, ragged block
+    lengths (partial last tile, blocks below the window path's minimum), and switching between the two replays block by block."""
+    rng = np.random.default_rng(7)
+
+    def noise_dc(t0, n):
+        return 0.05 * (rng.standard_normal(n) + 1j * rng.standard_normal(n)) + (0.01 - 0.02j)
+
+    def noise_zero_mean(t0, n):
+        return 0.05 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+
+    def carrier_near_dc(t0, n):
+        t = np.arange(t0, t0 + n)
+        return 0.02 * np.exp(1j * 0.0056 * t) + 0.3 * np.exp(1j * 0.31 * t) + 0.007 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+
+    def silence_then_burst(t0, n):
+        x = np.zeros(n, np.complex64)
+        x[n // 3: n // 3 + 5000] = 0.4 * (rng.standard_normal(min(5000, n - n // 3)) + 0.3)
+        return x
+
+    s, blocks = dc_window_case(lib, ref, 2400000, [40000] * 4, noise_dc)
+    assert blocks == 4 and s == 0
+    s, blocks = dc_window_case(lib, ref, 2400000, [40000] * 5, noise_zero_mean)
+    assert blocks == 5
+    s, blocks = dc_window_case(lib, ref, 2400000, [40000] * 5, carrier_near_dc)
+    assert blocks == 5
+    dc_window_case(lib, ref, 2400000, [30000] * 3, silence_then_burst)
+    # ragged lengths: partial last tile, exactly one tile more, below the minimum (serial replay), then long again
+    s, blocks = dc_window_case(lib, ref, 2400000, [40000, 3073, 33333, 1500, 1024 * 7, 2049, 40000], noise_zero_mean, max_block=40000)
+    assert blocks == 6                  # all but the 1500-sample block (two tiles: serial replay)
+    # the two replays alternate on one stream (the warm-up replay reads the raw history the window replay does not need)
+    s, blocks = dc_window_case(lib, ref, 20000000, [333360] * 4, carrier_near_dc, modes=(1, 0, 0, 1))
+    assert blocks == 2
+    if big:
+        # full-size blocks (61.44 MSps: 1001 tiles, 32 chunks), zero-mean and with an offset
+        s, blocks = dc_window_case(lib, ref, 61440000, [1024068] * 3, noise_zero_mean)
+        assert blocks == 3
+        s, blocks = dc_window_case(lib, ref, 61440000, [1024068] * 2, noise_dc)
+        assert blocks == 2 and s == 0

@@ -259,3 +259,7 @@ def test_cw_modem(emu_lib, ref):
     out, _, _ = parity.run_channels(emu_lib, ref, 2400000, chans, n_blocks=30, signal=signal)
     parity.check_channels(out)
     assert len(out[0]["audio"]) == 30 * 800
+
+
+def test_dc_window_replay_bit_exact(emu_lib, ref):
+    parity.check_dc_window(emu_lib, ref)

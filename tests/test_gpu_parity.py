@@ -243,3 +243,10 @@ def test_cw_modem(gpu_lib, ref):
     out, _, _ = parity.run_channels(gpu_lib, ref, 2400000, chans, n_blocks=30, signal=signal)
     parity.check_channels(out)
     assert len(out[0]["audio"]) == 30 * 800
+
+
+def test_dc_window_replay_bit_exact_gpu(gpu_lib, ref):
+    """The candidate-window DC replay (k_dc_window / k_dc_compose / k_dc_resolve + the tile replay) on the device: bit for bit
+    against the reference binary on offset, zero-mean, near-DC-carrier, silent and ragged inputs, both replays alternating, and
+    full 61.44 MSps blocks."""
+    parity.check_dc_window(gpu_lib, ref, big=True)
