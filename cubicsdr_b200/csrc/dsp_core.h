@@ -273,6 +273,7 @@ struct DcExactArgs {
     float2 *fstate;                  // [1] the reference's float state carried across blocks
     unsigned *fixups;                // [1] junctions that had to be replayed (diagnostic)
     const float2 *start;             // non-null: the true state entering every segment is known (dsp_dcwin.h), no warm-up
+    unsigned *junction_bad;          // with `start`: set by a segment whose end state is not the next segment's start (k_dc_verify then runs)
 };
 
 // one step of the reference recurrence for both components; no fused multiply-add allowed
@@ -295,8 +296,8 @@ SDR_HD SDR_FORCEINLINE void dc_ref_step(float c, float2 x, float2 &v, float2 &y)
 // (its tile grid is anchored at ITS start), or at this block's start if there is none.  Every lane of the GPU kernel
 // therefore starts at an index in [d, d + kDcTile).
 SDR_HD inline void dc_exact_plan(const DcExactArgs &a, int s, int &i_start, float2 &v0) {
+    if (a.start) { i_start = s * a.seg_len; v0 = a.start[s]; return; }       // (segment 0: the walker put the carried state there)
     if (s == 0) { i_start = 0; v0 = a.fstate[0]; return; }
-    if (a.start) { i_start = s * a.seg_len; v0 = a.start[s]; return; }
     const long long d = (long long)s * a.seg_len - a.warm;
     if (d >= 0) {
         const int t = (int)(d / kDcTile);
@@ -319,6 +320,17 @@ SDR_HD inline void dc_exact_plan(const DcExactArgs &a, int s, int &i_start, floa
     }
 }
 
+// end of a segment's replay: record the states; with known start states also prove the junction on the spot and, for the
+// last segment, publish the carried state (k_dc_verify then has nothing to do)
+SDR_HD SDR_FORCEINLINE void dc_segment_done(const DcExactArgs &a, int s, float2 v_in, float2 v_out) {
+    a.seg_in[s] = v_in; a.seg_out[s] = v_out;
+    if (a.start) {
+        if (s + 1 < a.n_seg) {
+            const float2 nx = a.start[s + 1];
+            if (nx.x != v_out.x || nx.y != v_out.y) a.junction_bad[0] = 1u;
+        } else a.fstate[0] = v_out;
+    }
+}
 // plain serial form of one segment (emulator; also the replay used by dc_exact_verify)
 SDR_HD inline void dc_exact_segment_serial(const DcExactArgs &a, int s, bool use_v, float2 v_in) {
     int i; float2 v;
@@ -335,7 +347,7 @@ SDR_HD inline void dc_exact_segment_serial(const DcExactArgs &a, int s, bool use
 
 // single thread: prove the junctions, replay what does not match, publish the carried state
 SDR_HD inline void dc_exact_verify(const DcExactArgs &a) {
-    float2 truth = a.fstate[0];
+    float2 truth = a.start ? a.start[0] : a.fstate[0];      // (with known starts the last segment has already overwritten fstate)
     for (int s = 0; s < a.n_seg; ++s) {
         if (s > 0) {
             const float2 w = a.seg_in[s];

@@ -38,6 +38,7 @@ struct SpecArgs {
     double rate;              // (double)(float)fft_average_rate
     float2 *frame_cf;         // [F] {ceil, floor} of the frame (float, as the reference's locals)
     double *scalars;          // [4] ceil_ma, ceil_maa, floor_ma, floor_maa  (persistent)
+    double *scalars_out;      // fused tail (k_spec_points2): the four averages after this block go here (the other half of a pair)
     double2 *frame_cf_maa;    // [F] {ceil_maa, floor_maa} after the frame's scalar update
     float *points;            // [F][fft_size]
     unsigned char *lines;     // [F][fft_size]
@@ -198,6 +199,193 @@ SDR_HD inline void spec_fft_phase(int ph, const SpecArgs &a, int bid, int tid, i
     }
 }
 
+
+// =====================================================================================================================
+// Spectrum transform, second form: Stockham autosort passes with the butterflies in registers.
+//   A frame of N points is split P ways by a radix-P decimation-in-frequency stage applied while the samples are read from
+//   global memory (P = N / nsub, nsub <= 8192); one CTA transforms one sub-sequence of nsub = r0 r1 r2 points in up to three
+//   passes of radix 16 / 16 / {2..32}.  In a pass thread j reads its r inputs x[j + t n / r] (consecutive threads, consecutive
+//   addresses), multiplies by exp(-2 pi i t k / (s r)), k = j mod s, transforms them in registers and writes them back to
+//   y[(j - k) r + k + t s]; every thread has read before anyone writes (one buffer, two barriers per pass).  The stride-r0 writes
+//   of the first pass are skewed by one element per r0 so that the 32 lanes of a warp fall on distinct banks (a' = a + a / r0); the
+//   later passes write runs of >= 16 consecutive elements.  The last pass writes |X| straight to global memory, fftshifted.
+// =====================================================================================================================
+constexpr int kFft2MaxSub = 8192;
+constexpr int kFft2Threads = 512;
+constexpr int kFft2SmemElems = kFft2MaxSub + kFft2MaxSub / 16;
+
+SDR_HD SDR_FORCEINLINE float2 w32_const(int m) {          // exp(-2 pi i m / 32); m is a compile-time constant after unrolling
+    switch (m & 31) {
+        case 0: return make_float2(1.000000000e+00f, 0.0f);
+        case 1: return make_float2(9.807852804e-01f, -1.950903220e-01f);
+        case 2: return make_float2(9.238795325e-01f, -3.826834324e-01f);
+        case 3: return make_float2(8.314696123e-01f, -5.555702330e-01f);
+        case 4: return make_float2(7.071067812e-01f, -7.071067812e-01f);
+        case 5: return make_float2(5.555702330e-01f, -8.314696123e-01f);
+        case 6: return make_float2(3.826834324e-01f, -9.238795325e-01f);
+        case 7: return make_float2(1.950903220e-01f, -9.807852804e-01f);
+        case 8: return make_float2(0.0f, -1.000000000e+00f);
+        case 9: return make_float2(-1.950903220e-01f, -9.807852804e-01f);
+        case 10: return make_float2(-3.826834324e-01f, -9.238795325e-01f);
+        case 11: return make_float2(-5.555702330e-01f, -8.314696123e-01f);
+        case 12: return make_float2(-7.071067812e-01f, -7.071067812e-01f);
+        case 13: return make_float2(-8.314696123e-01f, -5.555702330e-01f);
+        case 14: return make_float2(-9.238795325e-01f, -3.826834324e-01f);
+        case 15: return make_float2(-9.807852804e-01f, -1.950903220e-01f);
+        case 16: return make_float2(-1.000000000e+00f, 0.0f);
+        case 17: return make_float2(-9.807852804e-01f, 1.950903220e-01f);
+        case 18: return make_float2(-9.238795325e-01f, 3.826834324e-01f);
+        case 19: return make_float2(-8.314696123e-01f, 5.555702330e-01f);
+        case 20: return make_float2(-7.071067812e-01f, 7.071067812e-01f);
+        case 21: return make_float2(-5.555702330e-01f, 8.314696123e-01f);
+        case 22: return make_float2(-3.826834324e-01f, 9.238795325e-01f);
+        case 23: return make_float2(-1.950903220e-01f, 9.807852804e-01f);
+        case 24: return make_float2(0.0f, 1.000000000e+00f);
+        case 25: return make_float2(1.950903220e-01f, 9.807852804e-01f);
+        case 26: return make_float2(3.826834324e-01f, 9.238795325e-01f);
+        case 27: return make_float2(5.555702330e-01f, 8.314696123e-01f);
+        case 28: return make_float2(7.071067812e-01f, 7.071067812e-01f);
+        case 29: return make_float2(8.314696123e-01f, 5.555702330e-01f);
+        case 30: return make_float2(9.238795325e-01f, 3.826834324e-01f);
+        case 31: return make_float2(9.807852804e-01f, 1.950903220e-01f);
+    }
+    return make_float2(1.0f, 0.0f);
+}
+template <int R> SDR_HD SDR_FORCEINLINE int bitrev_r(int i) {
+    int o = 0;
+    for (int b = 1; b < R; b <<= 1) { o = (o << 1) | (i & 1); i >>= 1; }
+    return o;
+}
+// in-register decimation-in-frequency transform of R points: X[bitrev_r<R>(i)] = u[i] afterwards
+template <int R> SDR_HD SDR_FORCEINLINE void reg_fft(float2 (&u)[R]) {
+#pragma unroll
+    for (int len = R; len >= 2; len >>= 1) {
+        const int half = len >> 1;
+#pragma unroll
+        for (int blk = 0; blk < R; blk += len) {
+#pragma unroll
+            for (int j = 0; j < half; ++j) {
+                const float2 p = u[blk + j], q = u[blk + j + half];
+                u[blk + j] = make_float2(p.x + q.x, p.y + q.y);
+                const float2 d = make_float2(p.x - q.x, p.y - q.y);
+                const int m = j * (32 / len);                     // W_len^j = W_32^(j 32 / len)
+                if (m == 0) u[blk + j + half] = d;
+                else if (m == 8) u[blk + j + half] = make_float2(d.y, -d.x);          // times -j
+                else u[blk + j + half] = cmul(d, w32_const(m));
+            }
+        }
+    }
+}
+SDR_HD SDR_FORCEINLINE int fft2_pad(int a, int pr) { return pr ? a + a / pr : a; }
+
+// the radices of the passes for a sub-sequence of n points (n a power of two, 2 <= n <= kFft2MaxSub)
+struct Fft2Plan { int passes; int r[3]; };
+SDR_HD inline Fft2Plan fft2_plan(int n) {
+    Fft2Plan p; p.passes = 0; p.r[0] = p.r[1] = p.r[2] = 1;
+    int rem = n;
+    while (rem > 32) { p.r[p.passes++] = 16; rem /= 16; }
+    if (rem > 1 || p.passes == 0) p.r[p.passes++] = rem;
+    return p;
+}
+
+// sample n of sub-sequence psub of frame x (radix-P DIF stage on load): (sum_r x[n + r nsub] W_P^(r psub)) W_N^(n psub)
+SDR_HD SDR_FORCEINLINE float2 fft2_split_load(const SpecArgs &a, const float2 *x, int psub, int n) {
+    if (a.P == 1) return x[n];
+    const int nsub = a.nsub, N = a.N;
+    float2 v;
+    if (a.P == 2) {
+        const float2 x0 = x[n], x1 = x[n + nsub];
+        v = psub == 0 ? make_float2(x0.x + x1.x, x0.y + x1.y) : make_float2(x0.x - x1.x, x0.y - x1.y);
+    } else if (a.P == 4) {
+        const float2 x0 = x[n], x1 = x[n + nsub], x2 = x[n + 2 * nsub], x3 = x[n + 3 * nsub];
+        const float2 s02 = make_float2(x0.x + x2.x, x0.y + x2.y), d02 = make_float2(x0.x - x2.x, x0.y - x2.y);
+        const float2 s13 = make_float2(x1.x + x3.x, x1.y + x3.y), d13 = make_float2(x1.x - x3.x, x1.y - x3.y);
+        if (psub == 0) v = make_float2(s02.x + s13.x, s02.y + s13.y);
+        else if (psub == 1) v = make_float2(d02.x + d13.y, d02.y - d13.x);      // d02 - j d13
+        else if (psub == 2) v = make_float2(s02.x - s13.x, s02.y - s13.y);
+        else v = make_float2(d02.x - d13.y, d02.y + d13.x);                      // d02 + j d13
+    } else {                                                                     // any power of two: direct sum
+        v = x[n];
+        for (int r = 1; r < a.P; ++r) {
+            const float2 w = sdr_ldg(a.tw + (((long long)r * psub) % a.P) * (N / a.P));
+            const float2 t = cmul(x[n + r * nsub], w);
+            v.x += t.x; v.y += t.y;
+        }
+    }
+    if (psub) v = cmul(v, sdr_ldg(a.tw + ((long long)n * psub) % N));
+    return v;
+}
+
+// one pass for butterfly j: read + twiddle + transform into u (FIRST: inputs come from global memory through the split stage)
+template <int R, bool FIRST>
+SDR_HD SDR_FORCEINLINE void fft2_pass_load(const SpecArgs &a, const float2 *x, int psub, const float2 *buf, int pr_in, int s, int j, float2 (&u)[R]) {
+    const int n = a.nsub, q = n / R;
+#pragma unroll
+    for (int t = 0; t < R; ++t) u[t] = FIRST ? fft2_split_load(a, x, psub, j + t * q) : buf[fft2_pad(j + t * q, pr_in)];
+    if (!FIRST) {
+        const int k = j & (s - 1);
+        const int tstep = k * (a.N / (s * R));                   // exp(-2 pi i t k / (s R)) = tw[t k N / (s R)]
+#pragma unroll
+        for (int t = 1; t < R; ++t) u[t] = cmul(u[t], sdr_ldg(a.tw + t * tstep));
+    }
+    reg_fft<R>(u);
+}
+template <int R>
+SDR_HD SDR_FORCEINLINE void fft2_pass_store(float2 *buf, int pr_out, int s, int j, const float2 (&u)[R]) {
+    const int k = j & (s - 1), base = (j - k) * R + k;
+#pragma unroll
+    for (int i = 0; i < R; ++i) buf[fft2_pad(base + bitrev_r<R>(i) * s, pr_out)] = u[i];
+}
+// last pass: |X[k]| fftshifted straight to global memory: result[i] = |X[(i + N/2) mod N]|   (SpectrumVisualProcessor.cpp:441-452)
+template <int R>
+SDR_HD SDR_FORCEINLINE void fft2_pass_store_mags(const SpecArgs &a, int f, int psub, int s, int j, const float2 (&u)[R]) {
+    const int k = j & (s - 1), base = (j - k) * R + k, N = a.N;
+    float *out = a.mags + (size_t)f * N;
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        const int ks = base + bitrev_r<R>(i) * s;               // index inside the sub-sequence's transform
+        const int kk = ks * a.P + psub;                          // bin of the frame
+        out[(kk + N / 2) & (N - 1)] = sqrtf(u[i].x * u[i].x + u[i].y * u[i].y);
+    }
+}
+// The whole transform of one (frame, sub-sequence) for thread tid, as a sequence of half-phases separated by barriers:
+//   hp = 2 i     : pass i reads (+ transforms) into the thread's registers `u`
+//   hp = 2 i + 1 : pass i writes
+// (the GPU kernel keeps `u` in registers across the barrier; the emulator keeps one array per thread)
+struct Fft2Regs { float2 u[32]; };
+template <int R>
+SDR_HD SDR_FORCEINLINE void fft2_half(const SpecArgs &a, const float2 *x, int f, int psub, float2 *buf, int pass, int passes, int s, int pr_prev,
+                                      int pr_this, bool write_half, int j, Fft2Regs &rg) {
+    float2 (&u)[R] = reinterpret_cast<float2 (&)[R]>(rg.u);
+    if (j >= a.nsub / R) return;
+    if (!write_half) {
+        if (pass == 0) fft2_pass_load<R, true>(a, x, psub, buf, 0, s, j, u);
+        else fft2_pass_load<R, false>(a, x, psub, buf, pr_prev, s, j, u);
+    } else {
+        if (pass == passes - 1) fft2_pass_store_mags<R>(a, f, psub, s, j, u);
+        else fft2_pass_store<R>(buf, pr_this, s, j, u);
+    }
+}
+SDR_HD inline void spec_fft2_half(int hp, const SpecArgs &a, int bid, int tid, float2 *buf, Fft2Regs &rg) {
+    const int f = bid / a.P, psub = bid - f * a.P;
+    const float2 *x = a.x + (a.frame_stride > 0 ? f * a.frame_stride : a.frame_start[f]);
+    const Fft2Plan pl = fft2_plan(a.nsub);
+    const int pass = hp >> 1;
+    if (pass >= pl.passes) return;
+    int s = 1;
+    for (int i = 0; i < pass; ++i) s *= pl.r[i];
+    // layout of the buffer: skewed by r0 after pass 0 (stride-r0 writes), plain after pass 1
+    const int pr_prev = (pass == 1) ? pl.r[0] : 0, pr_this = (pass == 0) ? pl.r[0] : 0;
+    const bool wh = (hp & 1) != 0;
+    switch (pl.r[pass]) {
+        case 32: fft2_half<32>(a, x, f, psub, buf, pass, pl.passes, s, pr_prev, pr_this, wh, tid, rg); break;
+        case 16: fft2_half<16>(a, x, f, psub, buf, pass, pl.passes, s, pr_prev, pr_this, wh, tid, rg); break;
+        case 8: fft2_half<8>(a, x, f, psub, buf, pass, pl.passes, s, pr_prev, pr_this, wh, tid, rg); break;
+        case 4: fft2_half<4>(a, x, f, psub, buf, pass, pl.passes, s, pr_prev, pr_this, wh, tid, rg); break;
+        default: fft2_half<2>(a, x, f, psub, buf, pass, pl.passes, s, pr_prev, pr_this, wh, tid, rg); break;
+    }
+}
+
 // one thread per bin
 SDR_HD inline void spec_ema_thread(const SpecArgs &a, int i) {
     if (i >= a.N) return;
@@ -258,6 +446,62 @@ SDR_HD inline void spec_points_thread(const SpecArgs &a, long long gid) {
     const double num = log10((acc / (double)cnt) + 0.25 - (point_floor - 0.75));
     const double den = log10((point_ceil + 0.25) - (point_floor - 0.75));
     const float y = (float)((num / den) * (double)a.scale_factor);
+    a.points[gid] = y;
+    const float wv = y < 0 ? 0.f : (y > 0.99 ? (float)0.99 : y);
+    a.lines[gid] = (unsigned char)floor((double)wv * 255.0);
+}
+
+
+// ---- fused tail of the spectrum path -------------------------------------------------------------------------------------
+// (1) per-bin averages over the block's frames and the frames' ceil / floor in one pass: every thread owns a bin and walks the
+//     frames in order (:494-497); the ceil / floor of float(maa) (:499-504: ceil starts at 0, floor at 1) are folded per warp and
+//     merged with one atomic max / min per warp and frame (non-negative floats order like their bit patterns).
+//     frame_cf must hold {0, 1} per frame on entry (the transform kernel's CTA 0 sees to that).
+SDR_HD SDR_FORCEINLINE void spec_ema2_step(const SpecArgs &a, int f, int i, double &ma, double &maa, float &out) {
+    const double xv = (double)a.mags[(size_t)f * a.N + i];
+    maa += (ma - maa) * a.rate;                 // uses the OLD ma (:496)
+    ma += (xv - ma) * a.rate;
+    out = (float)maa;
+    a.maa_f[(size_t)f * a.N + i] = out;
+}
+SDR_HD inline void spec_ema2_thread_serial(const SpecArgs &a, int i) {          // emulator form
+    if (i >= a.N) return;
+    double ma = a.ema[i].x, maa = a.ema[i].y;
+    for (int f = 0; f < a.F; ++f) {
+        float v;
+        spec_ema2_step(a, f, i, ma, maa, v);
+        if (v > a.frame_cf[f].x) a.frame_cf[f].x = v;
+        if (v < a.frame_cf[f].y) a.frame_cf[f].y = v;
+    }
+    a.ema[i] = make_double2(ma, maa);
+}
+// (2) scalar averages up to and including frame f (:513-521), from the block's entry values
+SDR_HD inline double2 spec_scalar_upto(const SpecArgs &a, int f, double *after /* [4] or null */) {
+    double cma = a.scalars[0], cmaa = a.scalars[1], fma_ = a.scalars[2], fmaa = a.scalars[3];
+    for (int g = 0; g <= f; ++g) {
+        const double c = (double)a.frame_cf[g].x, fl = (double)a.frame_cf[g].y;
+        cma = cma + (c - cma) * 0.05;
+        cmaa = cmaa + (cma - cmaa) * 0.05;
+        fma_ = fma_ + (fl - fma_) * 0.05;
+        fmaa = fmaa + (fma_ - fmaa) * 0.05;
+    }
+    if (after) { after[0] = cma; after[1] = cmaa; after[2] = fma_; after[3] = fmaa; }
+    return make_double2(cmaa, fmaa);
+}
+//     display point xp of frame f (:532-576, WaterfallPanel.cpp:64-70)
+SDR_HD inline void spec_points2_thread(const SpecArgs &a, int f, int xp, double point_ceil, double point_floor) {
+    if (xp >= a.fft_size) return;
+    const float *m = a.maa_f + (size_t)f * a.N;
+    double acc = 0.0;
+    const int i0 = a.pt_i0[xp], cnt = a.pt_cnt[xp];
+    for (int j = 0; j < cnt; ++j) {
+        const unsigned idx = (unsigned)round(a.visual_start + (double)(i0 + j));
+        acc += (idx > 0 && idx < (unsigned)a.N) ? (double)m[idx] : point_floor;
+    }
+    const double num = log10((acc / (double)cnt) + 0.25 - (point_floor - 0.75));
+    const double den = log10((point_ceil + 0.25) - (point_floor - 0.75));
+    const float y = (float)((num / den) * (double)a.scale_factor);
+    const size_t gid = (size_t)f * a.fft_size + xp;
     a.points[gid] = y;
     const float wv = y < 0 ? 0.f : (y > 0.99 ? (float)0.99 : y);
     a.lines[gid] = (unsigned char)floor((double)wv * 255.0);

@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(32) k_dc_exact(DcExactArgs a) {
         }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    if (lane == 0) { a.seg_in[s] = v_in; a.seg_out[s] = v; }
+    if (lane == 0) dc_segment_done(a, s, v_in, v);
 }
 
 // Bit-exact DC blocker, speculative form: ONE LANE PER SEGMENT.  The chain of a segment is strictly serial (FMUL -> FADD,
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(32 * kDlWarps, 1) k_dc_lanes(DcExactArgs a) {
         }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    if (s < a.n_seg) { a.seg_in[s] = v_in; a.seg_out[s] = v; }
+    if (s < a.n_seg) dc_segment_done(a, s, v_in, v);
 }
 // ---- TMA + mbarrier helpers (cp.async.bulk.tensor: SASS UTMALDG / UTMASTG; mbarrier: SYNCS) -----------------------------------
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -563,10 +563,15 @@ k_dc_lanes_tma(DcExactArgs a, const __grid_constant__ CUtensorMap in_map) {
         }
         end_batch();
     }
-    if (live) { a.seg_in[s] = v_in; a.seg_out[s] = v; }
+    if (live) dc_segment_done(a, s, v_in, v);
 }
 // All junctions are compared in parallel; only when one of them fails (rare) does thread 0 walk them serially and replay.
 __global__ void __launch_bounds__(256) k_dc_verify(DcExactArgs a) {
+    if (a.start) {                                                   // every segment has checked its own junction (dc_segment_done)
+        if (a.junction_bad[0] == 0u) return;
+        __syncthreads();
+        if (threadIdx.x == 0) a.junction_bad[0] = 0u;
+    }
     int bad = 0;
     for (int s = 1 + (int)threadIdx.x; s < a.n_seg; s += (int)blockDim.x) {
         const float2 w = a.seg_in[s], t = a.seg_out[s - 1];
@@ -713,6 +718,58 @@ __global__ void __launch_bounds__(kFftThreads) k_spec_fft(SpecArgs a, int phases
         spec_fft_phase(ph, a, blockIdx.x, threadIdx.x, blockDim.x, fft_sm);
         __syncthreads();
     }
+}
+// Spectrum transform, Stockham passes with register butterflies (dsp_spec.h, second form).  CTA = (frame, sub-sequence).
+__global__ void __launch_bounds__(kFft2Threads) k_spec_fft2(SpecArgs a) {
+    extern __shared__ __align__(16) unsigned char fft2_sm[];
+    float2 *buf = reinterpret_cast<float2 *>(fft2_sm);
+    if (blockIdx.x == 0) for (int f = (int)threadIdx.x; f < a.F; f += (int)blockDim.x) a.frame_cf[f] = make_float2(0.f, 1.f);
+    const Fft2Plan pl = fft2_plan(a.nsub);
+    Fft2Regs rg;
+    for (int pass = 0; pass < pl.passes; ++pass) {
+        spec_fft2_half(2 * pass, a, (int)blockIdx.x, (int)threadIdx.x, buf, rg);
+        __syncthreads();                                            // everybody has read
+        spec_fft2_half(2 * pass + 1, a, (int)blockIdx.x, (int)threadIdx.x, buf, rg);
+        __syncthreads();
+    }
+}
+// averages + frame ceil / floor (fused): one thread per bin, frames in order, one atomic pair per warp and frame
+__global__ void __launch_bounds__(kSpecThreads) k_spec_ema2(SpecArgs a) {
+    const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const bool live = i < a.N;
+    double ma = 0.0, maa = 0.0;
+    if (live) { ma = a.ema[i].x; maa = a.ema[i].y; }
+    unsigned *cf = reinterpret_cast<unsigned *>(a.frame_cf);
+    for (int f = 0; f < a.F; ++f) {
+        float v = 0.f;
+        if (live) spec_ema2_step(a, f, i, ma, maa, v);
+        float mx = live ? v : 0.f, mn = live ? v : 1.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMax(cf + 2 * f, __float_as_uint(mx));
+            atomicMin(cf + 2 * f + 1, __float_as_uint(mn));
+        }
+    }
+    if (live) a.ema[i] = make_double2(ma, maa);
+}
+// scalar averages + display points + waterfall line (fused): CTA = (256 points, frame); thread 0 replays the scalar averages up to
+// its frame (a few dozen dependent operations), everybody then maps its point
+__global__ void __launch_bounds__(kSpecThreads) k_spec_points2(SpecArgs a) {
+    __shared__ double2 cfm;
+    const int f = (int)blockIdx.y, xp = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (threadIdx.x == 0) {
+        const bool last = f == a.F - 1 && blockIdx.x == 0;
+        double after[4];
+        cfm = spec_scalar_upto(a, f, after);
+        if (blockIdx.x == 0) a.frame_cf_maa[f] = cfm;
+        if (last) { a.scalars_out[0] = after[0]; a.scalars_out[1] = after[1]; a.scalars_out[2] = after[2]; a.scalars_out[3] = after[3]; }
+    }
+    __syncthreads();
+    spec_points2_thread(a, f, xp, cfm.x, cfm.y);
 }
 __global__ void __launch_bounds__(kSpecThreads) k_spec_ema(SpecArgs a) { spec_ema_thread(a, blockIdx.x * blockDim.x + threadIdx.x); }
 __global__ void __launch_bounds__(kSpecThreads) k_spec_minmax(SpecArgs a) {
@@ -965,40 +1022,43 @@ static void launch_tail(const TailArgs &a, int n_chan, sdr_stream_t s, unsigned 
 
 static int launch_spectrum(const SpecArgs &a, sdr_stream_t s, unsigned long long &launches) {
     if (a.F == 0) return 0;
-    const int phases = fft_phase_count(a.log_nsub);
 #ifndef SDR_EMU
-    const size_t smem = (size_t)a.nsub * sizeof(float2);
+    const Fft2Plan pl = fft2_plan(a.nsub);
+    const size_t smem = pl.passes > 1 ? (size_t)(a.nsub + a.nsub / pl.r[0]) * sizeof(float2) : 0;
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(k_spec_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, kFftMaxSub * (int)sizeof(float2)));
+        CUDA_TRY(cudaFuncSetAttribute(k_spec_fft2, cudaFuncAttributeMaxDynamicSharedMemorySize, kFft2SmemElems * (int)sizeof(float2)));
         attr_set = true;
     }
-    k_spec_fft<<<a.F * a.P, kFftThreads, smem, s>>>(a, phases);
+    k_spec_fft2<<<a.F * a.P, kFft2Threads, smem, s>>>(a);
     if (a.rebin || a.shift) {
         k_view_ema_move<<<(a.N + kSpecThreads - 1) / kSpecThreads, kSpecThreads, 0, s>>>(a, 0);
         k_view_ema_move<<<(a.N + kSpecThreads - 1) / kSpecThreads, kSpecThreads, 0, s>>>(a, 1);
         launches += 2;
     }
-    k_spec_ema<<<(a.N + kSpecThreads - 1) / kSpecThreads, kSpecThreads, 0, s>>>(a);
-    k_spec_minmax<<<a.F, kSpecThreads, 0, s>>>(a);
-    k_spec_scalar<<<1, 32, 0, s>>>(a);
-    const long long pts = (long long)a.F * a.fft_size;
-    k_spec_points<<<(unsigned)((pts + kSpecThreads - 1) / kSpecThreads), kSpecThreads, 0, s>>>(a);
+    k_spec_ema2<<<(a.N + kSpecThreads - 1) / kSpecThreads, kSpecThreads, 0, s>>>(a);
+    k_spec_points2<<<dim3((unsigned)((a.fft_size + kSpecThreads - 1) / kSpecThreads), (unsigned)a.F), kSpecThreads, 0, s>>>(a);
 #else
     (void)s;
-    std::vector<float2> sm(a.nsub);
-    for (int b = 0; b < a.F * a.P; ++b)
-        for (int ph = 0; ph < phases; ++ph) for (int t = 0; t < kFftThreads; ++t) spec_fft_phase(ph, a, b, t, kFftThreads, sm.data());
-    if (a.rebin || a.shift) for (int ph = 0; ph < 2; ++ph) for (int i = 0; i < a.N; ++i) view_ema_move_thread(a, ph, i);
-    for (int i = 0; i < a.N; ++i) spec_ema_thread(a, i);
-    for (int f = 0; f < a.F; ++f) {
-        SpecRedShared rs;
-        for (int ph = 0; ph < 2; ++ph) for (int t = 0; t < kSpecThreads; ++t) spec_minmax_phase(ph, a, f, t, kSpecThreads, &rs);
+    {
+        const Fft2Plan pl = fft2_plan(a.nsub);
+        std::vector<float2> buf((size_t)a.nsub + a.nsub / 2 + 16);
+        std::vector<Fft2Regs> regs(kFft2Threads);
+        for (int f = 0; f < a.F; ++f) a.frame_cf[f] = make_float2(0.f, 1.f);
+        for (int b = 0; b < a.F * a.P; ++b)
+            for (int hp = 0; hp < 2 * pl.passes; ++hp) for (int t = 0; t < kFft2Threads; ++t) spec_fft2_half(hp, a, b, t, buf.data(), regs[t]);
     }
-    spec_scalar_thread(a);
-    for (long long g = 0; g < (long long)a.F * a.fft_size; ++g) spec_points_thread(a, g);
+    if (a.rebin || a.shift) for (int ph = 0; ph < 2; ++ph) for (int i = 0; i < a.N; ++i) view_ema_move_thread(a, ph, i);
+    for (int i = 0; i < a.N; ++i) spec_ema2_thread_serial(a, i);
+    for (int f = 0; f < a.F; ++f) {
+        double after[4];
+        const double2 cfm = spec_scalar_upto(a, f, after);
+        a.frame_cf_maa[f] = cfm;
+        for (int xp = 0; xp < a.fft_size; ++xp) spec_points2_thread(a, f, xp, cfm.x, cfm.y);
+        if (f == a.F - 1) for (int k = 0; k < 4; ++k) a.scalars_out[k] = after[k];
+    }
 #endif
-    launches += 5;
+    launches += 3;
     return 0;
 }
 
@@ -1070,6 +1130,7 @@ struct sdr_spectrum {
     sdr_engine *eng = nullptr;
     unsigned fft_size = 0, N = 0, lps = 0;
     int P = 1, nsub = 0, log_nsub = 0;
+    int scalar_sel = 0;                          // which half of d_scalars holds the current scalar averages
     float average_rate = 0.65f, scale_factor = 1.0f;
     // framing state (FFTDataDistributor)
     long long buffered = 0, last_rate = 0, last_center = 0;
@@ -2044,8 +2105,14 @@ extern "C" int sdr_spectrum_create(sdr_engine *e, unsigned fft_size, unsigned lp
     use_device(e);
     sdr_spectrum *s = new sdr_spectrum();
     s->eng = e; s->fft_size = fft_size; s->N = 2 * fft_size; s->lps = lps;     // SPECTRUM_VZM = 2 (SpectrumVisualProcessor.cpp:145)
+    // sub-sequences per frame: at most kFft2MaxSub points per CTA, and more, shorter ones (down to 2048 points) while a block's
+    // frames would not fill the GPU otherwise
     s->P = 1;
-    while ((int)(s->N / s->P) > kFftMaxSub) s->P *= 2;
+    while ((int)(s->N / s->P) > kFft2MaxSub) s->P *= 2;
+    {
+        const long frames = (long)(e->max_block / s->N) + 1;
+        while (s->P < 8 && (int)(s->N / (s->P * 2)) >= 2048 && frames * s->P < 96) s->P *= 2;
+    }
     s->nsub = s->N / s->P;
     s->log_nsub = 0;
     while ((1 << s->log_nsub) < s->nsub) ++s->log_nsub;
@@ -2056,7 +2123,7 @@ extern "C" int sdr_spectrum_create(sdr_engine *e, unsigned fft_size, unsigned lp
     bad |= be_malloc((void **)&s->d_mags, F * N * sizeof(float));
     bad |= be_malloc((void **)&s->d_maa, F * N * sizeof(float));
     bad |= be_malloc((void **)&s->d_ema, N * sizeof(double2));
-    bad |= be_malloc((void **)&s->d_scalars, 4 * sizeof(double));
+    bad |= be_malloc((void **)&s->d_scalars, 8 * sizeof(double));          // two sets: a block reads one and writes the other
     bad |= be_malloc((void **)&s->d_frame_cf, F * sizeof(float2));
     bad |= be_malloc((void **)&s->d_frame_cf_maa, F * sizeof(double2));
     bad |= be_malloc((void **)&s->d_points, F * fft_size * sizeof(float));
@@ -2351,7 +2418,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
             const unsigned lanes = (unsigned)dc_reserved_sms(live) * kDlWarpsHost * 32u;
             const unsigned seg = window ? (unsigned)kDcTile : kDcTile * ((tiles_n + lanes - 1) / lanes);
             xa.xraw = raw; xa.y = blk; xa.n = (int)n; xa.seg_len = (int)seg; xa.warm = window ? 0 : kDcWarm;
-            xa.start = nullptr;
+            xa.start = nullptr; xa.junction_bad = e->d_dw_stats + 1;
             xa.raw_hist = (int)need_raw; xa.raw_end = (long long)e->max_block + (long long)e->raw_pad;
             xa.c = (float)e->dc_a; xa.one = 1.0f;
             xa.tile_carry = e->d_tile_carry2[p]; xa.prev_tile_carry = e->d_tile_carry2[p ^ 1];
@@ -2476,7 +2543,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         SpecArgs &a = job.a;
         a.x = blk; a.frame_start = d_fs; a.frame_stride = 0; a.F = (int)s->frames_last; a.N = (int)s->N; a.fft_size = (int)s->fft_size;
         a.P = s->P; a.nsub = s->nsub; a.log_nsub = s->log_nsub; a.tw = s->d_tw; a.mags = s->d_mags; a.maa_f = s->d_maa; a.ema = s->d_ema;
-        a.rate = (double)s->average_rate; a.frame_cf = s->d_frame_cf; a.scalars = s->d_scalars; a.frame_cf_maa = s->d_frame_cf_maa;
+        a.rate = (double)s->average_rate; a.frame_cf = s->d_frame_cf; a.scalars = s->d_scalars + 4 * s->scalar_sel; a.scalars_out = s->d_scalars + 4 * (s->scalar_sel ^ 1); s->scalar_sel ^= 1; a.frame_cf_maa = s->d_frame_cf_maa;
         a.points = s->d_points; a.lines = s->d_lines; a.scale_factor = s->scale_factor;
         a.rebin = 0; a.shift = 0; a.ema_tmp = s->d_ema_tmp;
         double visual_ratio = 1.0;
