@@ -29,7 +29,7 @@ SYMBOLS = [
     "sdr_group_create", "sdr_group_create_rank", "sdr_group_unique_id", "sdr_group_destroy", "sdr_group_info", "sdr_group_engine",
     "sdr_group_chan_create", "sdr_group_spectrum_create", "sdr_group_submit", "sdr_group_wait", "sdr_group_wait_block", "sdr_group_set_host_results",
     "sdr_design_kaiser", "sdr_design_nco_table", "sdr_design_nco_step", "sdr_design_resampler",
-    "sdr_design_halfband_branch", "sdr_design_am_dc_block", "sdr_design_hilbert_q", "sdr_design_butter6_sos",
+    "sdr_design_halfband_branch", "sdr_design_am_dc_block", "sdr_design_hilbert_q", "sdr_design_butter6_sos", "sdr_design_cheby2_bp5_sos", "sdr_design_hilbert_q_as",
 ]
 
 
@@ -124,6 +124,8 @@ class Lib:
         L.sdr_design_am_dc_block.argtypes = [vp]
         L.sdr_design_hilbert_q.argtypes = [vp]
         L.sdr_design_butter6_sos.argtypes = [vp]
+        L.sdr_design_cheby2_bp5_sos.argtypes = [C.c_float, C.c_float, vp]
+        L.sdr_design_hilbert_q_as.argtypes = [C.c_float, vp]
 
     def host_alloc(self, n_complex):
         """Pinned complex64 array of n samples (sdr_host_alloc); keep the returned array alive while it is in use."""

@@ -231,6 +231,141 @@ void butterworth_lowpass_sos(unsigned order, float fc, std::vector<Sos> &sos) {
 }
 
 
+// ---- Chebyshev-II band-pass, order 5 (liquid_iirdes as iirfilt_crcf_create_prototype calls it, ModemFMStereo.cpp:136) --------
+namespace {
+struct cf { float re, im; };
+inline float bits_f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+// cheby2_azpkf(5, 10^(-60/20)): analog zeros and poles of the prototype (its gain is not used).  Independent of the rates, so carried as the bit
+// patterns the reference computes (as the half-band prototypes are).
+const uint32_t kCheby2Za[4][2] = {{0x00000000u, 0x3f869650u}, {0x80000000u, 0xbf869650u}, {0x00000000u, 0x3fd9c440u}, {0x80000000u, 0xbfd9c440u}};
+const uint32_t kCheby2Pa[5][2] = {{0xbdf46b57u, 0x3ecebecbu}, {0xbdf46b57u, 0xbecebecbu}, {0xbeb15f7fu, 0x3e8dac18u}, {0xbeb15f7fu, 0xbe8dac18u},
+                                  {0xbeeb0b3bu, 0x00000000u}};
+
+// liquid_cplxpair(z, n, 1e-6, p): conjugate pairs first (in order of discovery), then the real values; then
+// liquid_cplxpair_cleanup: exact conjugates with the negative imaginary part first, pairs sorted by real part, reals sorted
+void cplxpair(const cf *z, unsigned n, float tol, cf *p) {
+    std::vector<unsigned char> paired(n, 0);
+    unsigned k = 0, num_pairs = 0;
+    for (unsigned i = 0; i < n; ++i) {
+        if (paired[i] || fabsf(z[i].im) < tol) continue;
+        for (unsigned j = 0; j < n; ++j) {
+            if (j == i || paired[j] || fabsf(z[j].im) < tol) continue;
+            if (fabsf(z[i].im + z[j].im) < tol && fabsf(z[i].re - z[j].re) < tol) {
+                p[k++] = z[i]; p[k++] = z[j];
+                paired[i] = paired[j] = 1;
+                ++num_pairs;
+                break;
+            }
+        }
+    }
+    for (unsigned i = 0; i < n; ++i) if (!paired[i]) { p[k++] = z[i]; paired[i] = 1; }
+    for (unsigned i = 0; i < num_pairs; ++i) {
+        if (!(p[2 * i].im < 0)) p[2 * i].im = -p[2 * i].im;
+        p[2 * i + 1].re = p[2 * i].re; p[2 * i + 1].im = -p[2 * i].im;
+    }
+    for (unsigned i = 0; i < num_pairs; ++i)
+        for (unsigned j = num_pairs - 1; j > i; --j)
+            if (p[2 * j].re < p[2 * (j - 1)].re) { std::swap(p[2 * j], p[2 * (j - 1)]); std::swap(p[2 * j + 1], p[2 * (j - 1) + 1]); }
+    for (unsigned i = 2 * num_pairs; i < n; ++i)
+        for (unsigned j = n - 1; j > i; --j)
+            if (p[j].re < p[j - 1].re) std::swap(p[j], p[j - 1]);
+}
+}  // namespace
+
+void cheby2_bandpass5_sos(float fc, float f0, std::vector<Sos> &sos) {
+    const unsigned n = 5, nza = 4;
+    cf za[5], pa[5];
+    for (unsigned i = 0; i < nza; ++i) { za[i].re = bits_f(kCheby2Za[i][0]); za[i].im = bits_f(kCheby2Za[i][1]); }
+    for (unsigned i = 0; i < n; ++i) { pa[i].re = bits_f(kCheby2Pa[i][0]); pa[i].im = bits_f(kCheby2Pa[i][1]); }
+    // iirdes_freqprewarp(BANDPASS): |(cos(2 pi fc) - cos(2 pi f0)) / sin(2 pi fc)|, the angles narrowed to float first
+    const double two_pi = 6.283185307179586;
+    float sn, cs;
+    sincosf((float)((double)fc * two_pi), &sn, &cs);
+    volatile float c0 = cosf((float)((double)f0 * two_pi));
+    volatile float num = cs - c0;
+    volatile float mq = num / sn;
+    const float m = fabsf(mq);
+    // bilinear_zpkf: zd = (1 + m za) / (1 - m za) and the same for the poles, evaluated in double from the float products and
+    // narrowed; the gain G *= (1 - pd) / (1 - zd) in double from the narrowed values, G itself kept in float between factors
+    cf zd[10], pd[10];
+    float Gr = 1.0f, Gi = 0.0f;                                      // liquid_iirdes hands the transform its nominal gain k0 = 1, not ka
+    for (unsigned i = 0; i < n; ++i) {
+        if (i < nza) {
+            volatile float zmr = za[i].re * m, zmi = za[i].im * m;
+            const double zr = (double)zmr, zi = (double)zmi;
+            const double dr = 1.0 - zr, nr = zr + 1.0, zi2 = zi * zi;
+            const double den = dr * dr + zi2;
+            zd[i].re = (float)((nr * dr - zi2) / den);
+            zd[i].im = (float)((zi + zi) / den);
+        } else { zd[i].re = -1.0f; zd[i].im = 0.0f; }
+        {
+            volatile float pmr = pa[i].re * m, pmi = pa[i].im * m;
+            const double pr = (double)pmr, pi = (double)pmi;
+            const double dr = 1.0 - pr, nr = pr + 1.0, pi2 = pi * pi;
+            const double den = dr * dr + pi2;
+            pd[i].re = (float)((nr * dr - pi2) / den);
+            pd[i].im = (float)((pi + pi) / den);
+        }
+        const double zr = (double)zd[i].re, zi = (double)zd[i].im, pr = (double)pd[i].re, pi = (double)pd[i].im;
+        const double omz = 1.0 - zr, den = omz * omz + zi * zi;
+        const double qr = ((1.0 - pr) * omz + pi * zi) / den;
+        const double qi = ((zr - 1.0) * pi - (pr - 1.0) * zi) / den;
+        const double gr = (double)Gr, gi = (double)Gi;
+        Gr = (float)(gr * qr - gi * qi);
+        Gi = (float)(gi * qr + gr * qi);
+    }
+    // iirdes_dzpk_lp2bp: every zero / pole z becomes 0.5 (c0 (1 + z) +- csqrt(c0^2 (1 + z)^2 - 4 z)), all in float
+    const float cc = cosf((float)((double)f0 * two_pi));
+    volatile float cc2 = cc * cc;
+    cf zt[10], pt[10];
+    for (int which = 0; which < 2; ++which) {
+        const cf *src = which ? pd : zd;
+        cf *dst = which ? pt : zt;
+        for (unsigned i = 0; i < n; ++i) {
+            const float zr = src[i].re, zi = src[i].im;
+            volatile float t0r = zr + 1.0f;
+            volatile float a = cc2 * t0r, b = cc2 * zi;              // c0^2 t0
+            volatile float ar = a * t0r, bz = b * zi, az = a * zi, tb = t0r * b;
+            volatile float re2 = ar - bz, im2 = az + tb;             // c0^2 t0^2
+            volatile float fzr = 4.0f * zr, fzi = 4.0f * zi;
+            volatile float argr = re2 - fzr, argi = im2 - fzi;
+            const std::complex<float> sq = std::sqrt(std::complex<float>(argr, argi));
+            volatile float hr = cc * t0r, hi = zi * cc;
+            volatile float s1r = sq.real() + hr, s1i = sq.imag() + hi, s2r = hr - sq.real(), s2i = hi - sq.imag();
+            dst[2 * i].re = s1r * 0.5f; dst[2 * i].im = s1i * 0.5f;
+            dst[2 * i + 1].re = s2r * 0.5f; dst[2 * i + 1].im = s2i * 0.5f;
+        }
+    }
+    // iirdes_dzpk2sosf: pair, then per pair  a = {1, -(re0 + re1), re0 re1 - im0 im1}, the same for the zeros, and the gain
+    // kd^(1 / sections) on every numerator
+    cf zp[10], pp[10];
+    cplxpair(zt, 2 * n, 1e-6f, zp);
+    cplxpair(pt, 2 * n, 1e-6f, pp);
+    const unsigned L = n;
+    volatile float inv_l = 1.0f / (float)L;
+    const float k = (float)pow((double)Gr, (double)inv_l);
+    sos.clear();
+    for (unsigned i = 0; i < L; ++i) {
+        Sos s;
+        volatile float sp = pp[2 * i].re + pp[2 * i + 1].re, pr = pp[2 * i].re * pp[2 * i + 1].re, pi = pp[2 * i + 1].im * pp[2 * i].im;
+        volatile float sz = zp[2 * i].re + zp[2 * i + 1].re, zr = zp[2 * i].re * zp[2 * i + 1].re, zi = zp[2 * i + 1].im * zp[2 * i].im;
+        volatile float a2 = pr - pi, b2 = zr - zi;
+        s.a[0] = 1.0f; s.a[1] = -sp; s.a[2] = a2;
+        volatile float b0 = 1.0f * k, b1 = -sz * k, b2k = b2 * k;
+        s.b[0] = b0; s.b[1] = b1; s.b[2] = b2k;
+        sos.push_back(s);
+    }
+}
+
+void fm_deemphasis(int tau_us, int audio_rate, float *b2, float *a1) {
+    const double f = (1.0 / (2.0 * kPi * double(tau_us) * 1e-6));
+    double t = 1.0 / (2.0 * kPi * f);
+    t = 1.0 / (2.0 * double(audio_rate) * tan(1.0 / (2.0 * double(audio_rate) * t)));
+    const double tb = (1.0 + 2.0 * t * double(audio_rate));
+    b2[0] = (float)(1.0 / tb); b2[1] = (float)(1.0 / tb);
+    *a1 = (float)((1.0 - 2.0 * t * double(audio_rate)) / tb);
+}
+
 void pfb_analysis_tables(unsigned M, unsigned m, float as_db, std::vector<float> &hq, std::vector<float> &tw_re_im) {
     const unsigned p = 2 * m, h_len = 2 * M * m + 1;
     std::vector<float> h(h_len);

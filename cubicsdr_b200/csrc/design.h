@@ -67,5 +67,12 @@ void am_dc_block_taps(unsigned m, float as_db, float *h /*2m+1*/);          // f
 void hilbert_quadrature_taps(unsigned m, float as_db, float *hq /*2m*/);    // firhilbf_create(5,90): ModemUSB.cpp:11
 struct Sos { float b[3]; float a[3]; };
 void butterworth_lowpass_sos(unsigned order, float fc, std::vector<Sos> &sos);   // iirfilt_crcf_create_lowpass(6,0.25): ModemUSB.cpp:8
+// iirfilt_crcf_create_prototype(LIQUID_IIRDES_CHEBY2, LIQUID_IIRDES_BANDPASS, LIQUID_IIRDES_SOS, 5, fc, f0, 1, 60): the 19 kHz pilot
+// band-pass of ModemFMStereo.cpp:130-136 as five second-order sections.  The poles sit 0.002 inside the unit circle, so the sections
+// must be the reference's to the last bit: the arithmetic below follows liquid 1.5.0's iirdes stage by stage (analog prototype as
+// constants, bilinear_zpkf in double, iirdes_dzpk_lp2bp and iirdes_dzpk2sosf in float) and is pinned against the binary.
+void cheby2_bandpass5_sos(float fc, float f0, std::vector<Sos> &sos);
+// ModemFMStereo.cpp:149-159: first-order de-emphasis section {b0, b1, a1} for a time constant in microseconds
+void fm_deemphasis(int tau_us, int audio_rate, float *b2, float *a1);
 
 }  // namespace sdrb200

@@ -276,7 +276,7 @@ template <int R> SDR_HD SDR_FORCEINLINE void reg_fft(float2 (&u)[R]) {
         }
     }
 }
-SDR_HD SDR_FORCEINLINE int fft2_pad(int a, int pr) { return pr ? a + a / pr : a; }
+SDR_HD SDR_FORCEINLINE int fft2_pad(int a, int lpr) { return lpr ? a + (a >> lpr) : a; }        // lpr = log2 of the skew period, 0 = plain
 
 // the radices of the passes for a sub-sequence of n points (n a power of two, 2 <= n <= kFft2MaxSub)
 struct Fft2Plan { int passes; int r[3]; };
@@ -307,12 +307,12 @@ SDR_HD SDR_FORCEINLINE float2 fft2_split_load(const SpecArgs &a, const float2 *x
     } else {                                                                     // any power of two: direct sum
         v = x[n];
         for (int r = 1; r < a.P; ++r) {
-            const float2 w = sdr_ldg(a.tw + (((long long)r * psub) % a.P) * (N / a.P));
+            const float2 w = sdr_ldg(a.tw + ((r * psub) & (a.P - 1)) * nsub);       // W_P^(r psub) = W_N^(r psub N / P), N / P = nsub
             const float2 t = cmul(x[n + r * nsub], w);
             v.x += t.x; v.y += t.y;
         }
     }
-    if (psub) v = cmul(v, sdr_ldg(a.tw + ((long long)n * psub) % N));
+    if (psub) v = cmul(v, sdr_ldg(a.tw + ((n * psub) & (N - 1))));
     return v;
 }
 
@@ -375,7 +375,9 @@ SDR_HD inline void spec_fft2_half(int hp, const SpecArgs &a, int bid, int tid, f
     int s = 1;
     for (int i = 0; i < pass; ++i) s *= pl.r[i];
     // layout of the buffer: skewed by r0 after pass 0 (stride-r0 writes), plain after pass 1
-    const int pr_prev = (pass == 1) ? pl.r[0] : 0, pr_this = (pass == 0) ? pl.r[0] : 0;
+    int lr0 = 0;
+    while ((1 << lr0) < pl.r[0]) ++lr0;
+    const int pr_prev = (pass == 1) ? lr0 : 0, pr_this = (pass == 0) ? lr0 : 0;
     const bool wh = (hp & 1) != 0;
     switch (pl.r[pass]) {
         case 32: fft2_half<32>(a, x, f, psub, buf, pass, pl.passes, s, pr_prev, pr_this, wh, tid, rg); break;

@@ -910,7 +910,11 @@ static int launch_dc_window(const DcWinArgs &a, sdr_stream_t s, unsigned long lo
 // tma_rows: samples readable from xraw[-warm] on (rows of the input tensor = that / seg_len); 0 = use the cp.async kernel
 static int launch_dc_exact(const DcExactArgs &a, unsigned long long tma_rows, sdr_stream_t s, unsigned long long &launches) {
 #ifndef SDR_EMU
-    if (a.n_seg > 1) {                                          // one lane per segment, SM-exclusive CTAs of four warps
+    if (a.start) {
+        // the true state entering every tile is known (candidate windows): one warp per tile, every lane runs the 1024-step chain
+        // and keeps two outputs per batch -- a few hundred light CTAs anywhere on the chip, no warm-up, no staging kernel
+        k_dc_exact<<<a.n_seg, 32, 0, s>>>(a);
+    } else if (a.n_seg > 1) {                                   // one lane per segment, SM-exclusive CTAs of four warps
         const int warps = (a.n_seg + 31) / 32;
         static int use_tma = -1;
         if (use_tma < 0) { const char *v = getenv("SDR_B200_DC_TMA"); use_tma = (v && v[0] == '0') ? 0 : 1; }
@@ -2105,14 +2109,10 @@ extern "C" int sdr_spectrum_create(sdr_engine *e, unsigned fft_size, unsigned lp
     use_device(e);
     sdr_spectrum *s = new sdr_spectrum();
     s->eng = e; s->fft_size = fft_size; s->N = 2 * fft_size; s->lps = lps;     // SPECTRUM_VZM = 2 (SpectrumVisualProcessor.cpp:145)
-    // sub-sequences per frame: at most kFft2MaxSub points per CTA, and more, shorter ones (down to 2048 points) while a block's
-    // frames would not fill the GPU otherwise
+    // sub-sequences per frame: at most kFft2MaxSub points per CTA (a CTA's transform takes a few microseconds: frames are not
+    // split further just to occupy more SMs)
     s->P = 1;
     while ((int)(s->N / s->P) > kFft2MaxSub) s->P *= 2;
-    {
-        const long frames = (long)(e->max_block / s->N) + 1;
-        while (s->P < 8 && (int)(s->N / (s->P * 2)) >= 2048 && frames * s->P < 96) s->P *= 2;
-    }
     s->nsub = s->N / s->P;
     s->log_nsub = 0;
     while ((1 << s->log_nsub) < s->nsub) ++s->log_nsub;
@@ -3416,6 +3416,14 @@ extern "C" int sdr_design_butter6_sos(float *o) {
     for (int i = 0; i < 3; ++i) { memcpy(o + 6 * i, s[i].b, 12); memcpy(o + 6 * i + 3, s[i].a, 12); }
     return SDR_OK;
 }
+
+extern "C" int sdr_design_cheby2_bp5_sos(float fc, float f0, float *o) {
+    if (!o) return SDR_ERR_ARG;
+    std::vector<Sos> s; cheby2_bandpass5_sos(fc, f0, s);
+    for (int i = 0; i < 5; ++i) { memcpy(o + 6 * i, s[i].b, 12); memcpy(o + 6 * i + 3, s[i].a, 12); }
+    return SDR_OK;
+}
+extern "C" int sdr_design_hilbert_q_as(float as_db, float *hq) { if (!hq) return SDR_ERR_ARG; hilbert_quadrature_taps(5, as_db, hq); return SDR_OK; }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // several GPUs behind the same boundary

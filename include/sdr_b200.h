@@ -212,6 +212,9 @@ int sdr_design_halfband_branch(int m, float as_db, float *h1 /* 2m */);
 int sdr_design_am_dc_block(float *h51);
 int sdr_design_hilbert_q(float *hq10);
 int sdr_design_butter6_sos(float *sos18 /* 3 x {b0,b1,b2,a0,a1,a2} */);
+/* iirfilt_crcf_create_prototype(CHEBY2, BANDPASS, SOS, 5, fc, f0, 1, 60), ModemFMStereo.cpp:136: 5 x {b0,b1,b2,a0,a1,a2} */
+int sdr_design_cheby2_bp5_sos(float fc, float f0, float *sos30);
+int sdr_design_hilbert_q_as(float as_db, float *hq10);         /* firhilbf_create(5, as): ModemFMStereo.cpp:138, ModemCW.cpp:22 */
 
 /* ---- group: several GPUs behind the same boundary -------------------------------------------------------
  * The reference hands every block to every demodulator (src/sdr/SDRPostThread.cpp:294-298); channels are independent given

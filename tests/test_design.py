@@ -92,3 +92,25 @@ def test_demod_filters(product_lib, ref):
     yy = sosfilt(s.reshape(3, 6).astype(np.float64), x.real.astype(np.float64))
     assert np.abs(yy - y.real).max() < 1e-6
     assert abs(y.real[0] - 0.0295882113) < 1e-7        # SURVEY.md A.8 probe
+
+
+def test_fm_stereo_pilot_bandpass_is_the_reference_design_bit_for_bit(ref, product_lib):
+    """iirfilt_crcf_create_prototype(CHEBY2, BANDPASS, SOS, 5, 19500 / bw, 19000 / bw, 1, 60) (ModemFMStereo.cpp:130-136): poles
+    0.002 inside the unit circle, so the product's host-side design must give the reference's sections to the last bit -- over the
+    whole range of modem rates -- and the Hilbert taps of firhilbf_create(5, 60)."""
+    vp, f, u = C.c_void_p, C.c_float, C.c_uint
+    ref.L.ref_iirdes.argtypes = [C.c_int, C.c_int, C.c_int, u, f, f, f, f, vp, vp]
+    for bw in list(range(100000, 400001, 2477)) + [200000, 250000, 192000, 150000, 100000, 256000]:
+        b = np.zeros(30, np.float32); a = np.zeros(30, np.float32)
+        f0 = np.float32(19000) / np.float32(bw); fc = np.float32(19500) / np.float32(bw)
+        assert ref.L.ref_iirdes(2, 2, 0, 5, fc, f0, 1.0, 60.0, _p(b), _p(a)) == 0
+        o = np.zeros(30, np.float32)
+        assert product_lib.L.sdr_design_cheby2_bp5_sos(fc, f0, _p(o)) == 0
+        want = np.concatenate([np.concatenate([b[3 * i:3 * i + 3], a[3 * i:3 * i + 3]]) for i in range(5)])
+        assert np.array_equal(want.view(np.uint32), o.view(np.uint32)), bw
+    ref.L.ref_firhilb_r2c_block.argtypes = [vp, vp, u, vp]
+    hb = C.c_void_p(ref.L.ref_firhilb_create(5, 60.0))
+    x = np.zeros(24, np.float32); x[0] = 1; y = np.zeros(24, np.complex64)
+    ref.L.ref_firhilb_r2c_block(hb, _p(x), 24, _p(y)); ref.L.ref_firhilb_destroy(hb)
+    hq = np.zeros(10, np.float32); product_lib.L.sdr_design_hilbert_q_as(60.0, _p(hq))
+    assert np.abs(y.imag[1:20:2] - hq[::-1]).max() < 1e-6 and y.real[10] == 1.0
