@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <complex>
+#include <xmmintrin.h>
 #include <cstring>
 
 namespace sdrb200 {
@@ -355,6 +356,23 @@ void cheby2_bandpass5_sos(float fc, float f0, std::vector<Sos> &sos) {
         s.b[0] = b0; s.b[1] = b1; s.b[2] = b2k;
         sos.push_back(s);
     }
+}
+
+// iirfiltsos_crcf_create (what iirfilt_crcf_create_sos builds each section with) normalises {b0, b1} by a reciprocal of a0 that the
+// reference's binary takes from the SSE approximation instruction plus one Newton step, x = 2 x0 - a0 x0 x0 with x0 = rcpps(a0);
+// b2, a1 and a2 are divided exactly.  For a0 = 1 that reciprocal is one ulp short of 1 on the CPUs at hand, which moves b0 and b1
+// down by an ulp -- visible through a filter whose poles sit 0.002 inside the unit circle.  The same instruction is used here.
+void sos_section_object(Sos &s) {
+    const float a0 = s.a[0];
+    float x0 = _mm_cvtss_f32(_mm_rcp_ps(_mm_set1_ps(a0)));
+    volatile float ax = a0 * x0;
+    volatile float axx = ax * x0;
+    volatile float two = x0 + x0;
+    volatile float r = two - axx;
+    volatile float b0 = r * s.b[0], b1 = r * s.b[1];
+    volatile float inv = 1.0f / a0;
+    volatile float b2 = s.b[2] * inv, a1 = s.a[1] * inv, a2 = inv * s.a[2];
+    s.b[0] = b0; s.b[1] = b1; s.b[2] = b2; s.a[0] = 1.0f; s.a[1] = a1; s.a[2] = a2;
 }
 
 void fm_deemphasis(int tau_us, int audio_rate, float *b2, float *a1) {

@@ -72,6 +72,7 @@ void butterworth_lowpass_sos(unsigned order, float fc, std::vector<Sos> &sos);  
 // must be the reference's to the last bit: the arithmetic below follows liquid 1.5.0's iirdes stage by stage (analog prototype as
 // constants, bilinear_zpkf in double, iirdes_dzpk_lp2bp and iirdes_dzpk2sosf in float) and is pinned against the binary.
 void cheby2_bandpass5_sos(float fc, float f0, std::vector<Sos> &sos);
+void sos_section_object(Sos &s);   // the coefficients as iirfiltsos_crcf_create stores them (see design.cpp)
 // ModemFMStereo.cpp:149-159: first-order de-emphasis section {b0, b1, a1} for a time constant in microseconds
 void fm_deemphasis(int tau_us, int audio_rate, float *b2, float *a1);
 

@@ -26,7 +26,10 @@ constexpr int kTailThreads = 256;
 
 enum ModemKind { MODEM_FM = 0, MODEM_NBFM = 1, MODEM_AM = 2, MODEM_USB = 3, MODEM_LSB = 4, MODEM_IQ = 5,
                  MODEM_NONE = 6,    // no modem: the decimated IQ is the product (the zoomed spectrum view's hidden channel)
-                 MODEM_DSB = 7, MODEM_CW = 8 };
+                 MODEM_DSB = 7, MODEM_CW = 8,
+                 MODEM_FMS = 9 };   // FM stereo (analog/ModemFMStereo.cpp): two-channel audio {left, right}
+constexpr int kFmsFirMax = 256;   // most taps of the stereo low-pass pair (firfilt_rrrf, estimate_req_filter_len(1000 / audio rate, 60))
+constexpr int kFmsFirHist = 256;  // history kept in front of its two input streams
 
 // ---- small complex helpers ------------------------------------------------------------------------------------------
 SDR_HD SDR_FORCEINLINE float2 cf_make(float a, float b) { return make_float2(a, b); }
@@ -388,6 +391,14 @@ struct ChanStatic {
     int cw_hq_off;                // CW: quadrature taps of firhilbf_create(5, 60) (ModemCW.cpp:23)
     unsigned cw_dtheta;           // CW: phase step of the beat oscillator, 2 pi 650 / audio rate (ModemCW.cpp:176)
     int cw_w_off;                 // CW: complex stream after the beat mixer, at the audio rate ([kHist | new])
+    // FM stereo (ModemFMStereo.cpp:89-167): pilot band-pass sections 5 x {b0,b1,b2,a1,a2}, the low-pass pair's taps, de-emphasis
+    int fms_sos_off, fms_fir_off, fms_fir_n, fms_demph;
+    float fms_db0, fms_db1, fms_da1;
+    int fms_x2_off;               // complex [kHist | new]: the pilot-squared down-mix feeding firhilbf c2r
+    int fms_ds_off;               // real [kHist | new]: the difference signal at the modem rate (demodStereoData)
+    int fms_al_off[kMaxAudioHb + 1];   // its audio-resampler levels (stereoResampler)
+    int fms_am_off, fms_as_off;   // real: sum / difference signal at the audio rate (resampledOutputData / resampledStereoData)
+    int fms_ld_off, fms_rd_off;   // real [kFmsFirHist | new]: de-emphasised left / right feeding the low-pass pair
     // stream buffers inside the channel arena (offsets in floats); each is [kHist | data]
     float *arena;                 // this channel's arena in HBM
     int lvl_off[kMaxTailHb + 1];  // complex level buffers: level 0 = front output, level j = output of tail stage j-1
@@ -433,6 +444,9 @@ struct ChanState {                // device-resident, advanced by the tail kerne
     float agc_ceil, agc_ma, agc_maa;  // ModemAnalog.cpp:6,70-72
     float sig_level, sig_floor, sig_ceil;   // DemodulatorThread::signalLevel / signalFloor / signalCeil (std::atomic<float>)
     unsigned dsb_theta, dsb_dtheta;         // ampmodem's Costas-loop oscillator (nco_crcf theta / d_theta), ModemDSB
+    unsigned fms_theta, fms_dtheta;         // FM stereo: the pilot's phase-locked oscillator (stereoPilot)
+    float fms_sos_v[5][2][2];               // pilot band-pass [section][v1,v2][re,im]
+    float fms_dl, fms_dr;                   // de-emphasis delay elements (iirDemphL / iirDemphR)
 };
 
 struct ChanResultHeader {

@@ -284,7 +284,11 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
         }
         return;
     }
-    const bool is_fm = (cs.modem == MODEM_FM || cs.modem == MODEM_NBFM);
+    // FM stereo (analog/ModemFMStereo.cpp:186-287) shares the discriminator and the metering of FM; its own stages reuse phases that
+    // FM leaves empty: TP_DEMOD_B real -> complex, TP_AGC_A pilot band-pass + phase-locked loop + 38 kHz down-mix (serial),
+    // TP_AGC_B complex -> real, the audio phases run both resamplers, TP_CW_A de-emphasis, TP_CW_B low-pass pair, TP_CW_C/D histories
+    const bool is_fms = cs.modem == MODEM_FMS;
+    const bool is_fm = (cs.modem == MODEM_FM || cs.modem == MODEM_NBFM || is_fms);
     const bool is_ssb = (cs.modem == MODEM_USB || cs.modem == MODEM_LSB);
     // "I/Q" (analog/ModemIQ.cpp:39-56): no demodulator, no audio resampler -- the decimated IQ itself leaves as two-channel
     // audio {imag, real}; the level is metered on the IQ like FM's (useSignalOutput stays false)
@@ -468,6 +472,16 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
     }
 
     if (ph == TP_DEMOD_B) {
+        if (is_fms) {                                            // firhilbf_r2c_execute (:232): {x[i - 10], sum hq x[i - 19 + 2 j]}
+            float2 *w = chan_cbuf(a, cs, cs.w_off) + kHist;
+            const float *hq = a.taps + cs.cw_hq_off;             // firhilbf_create(5, 60): the taps CW uses
+            for (int i = tid; i < sm->n_iq; i += nt) {
+                float yq = 0.f;
+                for (int j = 0; j < 10; ++j) yq = fmaf(sdr_ldg(hq + j), d[i - 19 + 2 * j], yq);
+                w[i] = make_float2(d[i - 10], yq);
+            }
+            return;
+        }
         if (is_ssb && !is_none) {                                // firhilbf c2r, 21 taps
             const float2 *w = chan_cbuf(a, cs, cs.w_off) + kHist;
             const float *hq = a.taps + cs.hq_off;
@@ -482,6 +496,62 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
     }
 
     // ---- block auto-gain (AM / SSB): ModemAnalog.cpp:70-86 ------------------------------------------------------------
+    if (ph == TP_AGC_A && is_fms) {
+        // :231-255, one sample after the other: 19 kHz pilot band-pass (five second-order sections; liquid 1.5.0's
+        // iirfiltsos_execute_df2 as its binary evaluates it: v0 = x - (a1 v1 + a2 v2), y = (b1 v1 + b2 v2) + b0 v0, every
+        // operation singly rounded -- the poles sit 0.002 inside the unit circle), phase detector against the loop oscillator
+        // (table oscillator: nco_crcf ignores its LIQUID_VCO type), nco_crcf_pll_step with bandwidth 0.25 (alpha = 0.25,
+        // beta = sqrtf(alpha) = 0.5), one oscillator step, two mix-downs by the stepped phase.
+        if (tid == 0) {
+            const float2 *w = chan_cbuf(a, cs, cs.w_off) + kHist;
+            float2 *x2 = chan_cbuf(a, cs, cs.fms_x2_off) + kHist;
+            const float *sos = a.taps + cs.fms_sos_off;
+            float c[5][5], v[5][2][2];
+            for (int q = 0; q < 5; ++q) {
+                for (int k = 0; k < 5; ++k) c[q][k] = sos[5 * q + k];
+                for (int k = 0; k < 2; ++k) { v[q][k][0] = st.fms_sos_v[q][k][0]; v[q][k][1] = st.fms_sos_v[q][k][1]; }
+            }
+            unsigned th = st.fms_theta, dth = st.fms_dtheta;
+            const int n = sm->n_iq;
+            for (int i = 0; i < n; ++i) {
+                const float2 x = w[i];
+                float yr = x.x, yi = x.y;
+                for (int q = 0; q < 5; ++q) {
+                    const float v0r = f_sub(yr, f_add(f_mul(c[q][3], v[q][0][0]), f_mul(v[q][1][0], c[q][4])));
+                    const float v0i = f_sub(yi, f_add(f_mul(c[q][3], v[q][0][1]), f_mul(c[q][4], v[q][1][1])));
+                    yr = f_add(f_add(f_mul(c[q][1], v[q][0][0]), f_mul(v[q][1][0], c[q][2])), f_mul(v0r, c[q][0]));
+                    yi = f_add(f_add(f_mul(c[q][1], v[q][0][1]), f_mul(c[q][2], v[q][1][1])), f_mul(c[q][0], v0i));
+                    v[q][1][0] = v[q][0][0]; v[q][1][1] = v[q][0][1];
+                    v[q][0][0] = v0r; v[q][0][1] = v0i;
+                }
+                const float2 o = nco_lookup(a.nco, th);          // nco_crcf_cexpf: {cos, sin}
+                const float wi = -o.y;                            // conjf(w)
+                const float ur = f_sub(f_mul(yr, o.x), f_mul(yi, wi));
+                const float ui = f_add(f_mul(yr, wi), f_mul(yi, o.x));
+                const float e = atan2f(ui, ur);
+                dth += pll_word(f_mul(e, 0.25f));
+                th += pll_word(f_mul(e, 0.5f));
+                th += dth;                                        // nco_crcf_step
+                const float2 p = nco_lookup(a.nco, th);
+                const float y1r = f_add(f_mul(x.x, p.x), f_mul(x.y, p.y)), y1i = f_sub(f_mul(x.y, p.x), f_mul(x.x, p.y));   // nco_crcf_mix_down
+                x2[i] = make_float2(f_add(f_mul(y1r, p.x), f_mul(y1i, p.y)), f_sub(f_mul(y1i, p.x), f_mul(y1r, p.y)));
+            }
+            st.fms_theta = th; st.fms_dtheta = dth;
+            for (int q = 0; q < 5; ++q) for (int k = 0; k < 2; ++k) { st.fms_sos_v[q][k][0] = v[q][k][0]; st.fms_sos_v[q][k][1] = v[q][k][1]; }
+        }
+        return;
+    }
+    if (ph == TP_AGC_B && is_fms) {                              // firhilbf_c2r_execute (:258): the lower-sideband output
+        const float2 *x2 = chan_cbuf(a, cs, cs.fms_x2_off) + kHist;
+        float *ds = chan_rbuf(a, cs, cs.fms_ds_off) + kHist;
+        const float *hq = a.taps + cs.cw_hq_off;
+        for (int i = tid; i < sm->n_iq; i += nt) {
+            float yq = 0.f;
+            for (int j = 0; j < 10; ++j) yq = fmaf(sdr_ldg(hq + j), x2[i - 19 + 2 * j].y, yq);
+            ds[i] = x2[i - 10].x + yq;
+        }
+        return;
+    }
     if (ph == TP_AGC_A) {
         if (has_agc) {
             float mx = 0.f;
@@ -526,27 +596,35 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
             return;
         }
         if (!cs.a_interp) {
-            // decimator: a_S half-bands (cascade position g = a_S-1-j for phase j), then the arbitrary stage
-            if (j < cs.a_S) {
-                const int g = cs.a_S - 1 - j;
-                const float *in = (j == 0) ? chan_rbuf(a, cs, cs.d_off) : chan_rbuf(a, cs, cs.al_off[j]);
-                hb_decim_r(in, sm->a_g0[j], chan_rbuf(a, cs, cs.al_off[j + 1]), sm->a_g0[j + 1], sm->a_n[j + 1], cs.a_m[g],
-                           a.taps + cs.a_h1[g], tid, nt);
-            } else if (j == cs.a_S) {
-                const float *z = ((cs.a_S == 0) ? chan_rbuf(a, cs, cs.d_off) : chan_rbuf(a, cs, cs.al_off[cs.a_S])) + kHist;
-                const float *pfb = a.taps + cs.a_pfb_off;
-                const unsigned long long ph0 = st.a_phase;
-                const int na = sm->n_audio;
-                int r = tid;
-                for (; r + (kTailIlp - 1) * nt < na; r += kTailIlp * nt) {
-                    float acc[kTailIlp];
-                    arb_r_group(z, pfb, ph0, cs.a_step, r, nt, acc);
+            // decimator: a_S half-bands (cascade position g = a_S-1-j for phase j), then the arbitrary stage.  FM stereo runs
+            // two of them in lock step (audioResampler on the sum signal, stereoResampler on the difference signal: same ratio,
+            // same input counts, hence the same phases) and keeps both outputs for its back end.
+            for (int strm = 0; strm < (is_fms ? 2 : 1); ++strm) {
+                const int s_d = strm ? cs.fms_ds_off : cs.d_off;
+                const int *s_al = strm ? cs.fms_al_off : cs.al_off;
+                if (j < cs.a_S) {
+                    const int g = cs.a_S - 1 - j;
+                    const float *in = (j == 0) ? chan_rbuf(a, cs, s_d) : chan_rbuf(a, cs, s_al[j]);
+                    hb_decim_r(in, sm->a_g0[j], chan_rbuf(a, cs, s_al[j + 1]), sm->a_g0[j + 1], sm->a_n[j + 1], cs.a_m[g],
+                               a.taps + cs.a_h1[g], tid, nt);
+                } else if (j == cs.a_S) {
+                    const float *z = ((cs.a_S == 0) ? chan_rbuf(a, cs, s_d) : chan_rbuf(a, cs, s_al[cs.a_S])) + kHist;
+                    const float *pfb = a.taps + cs.a_pfb_off;
+                    const unsigned long long ph0 = st.a_phase;
+                    const int na = sm->n_audio;
+                    float *dst = is_fms ? chan_rbuf(a, cs, strm ? cs.fms_as_off : cs.fms_am_off) : res_audio;
+                    const int cap = is_fms ? 0x7fffffff : cs.res_audio_cap;
+                    int r = tid;
+                    for (; r + (kTailIlp - 1) * nt < na; r += kTailIlp * nt) {
+                        float acc[kTailIlp];
+                        arb_r_group(z, pfb, ph0, cs.a_step, r, nt, acc);
 #pragma unroll
-                    for (int u = 0; u < kTailIlp; ++u) if (r + u * nt < cs.res_audio_cap) res_audio[r + u * nt] = acc[u] * cs.a_zeta;
-                }
-                for (; r < na; r += nt) {
-                    const float acc = arb_r_one(z, pfb, ph0, cs.a_step, r);
-                    if (r < cs.res_audio_cap) res_audio[r] = acc * cs.a_zeta;
+                        for (int u = 0; u < kTailIlp; ++u) if (r + u * nt < cap) dst[r + u * nt] = acc[u] * cs.a_zeta;
+                    }
+                    for (; r < na; r += nt) {
+                        const float acc = arb_r_one(z, pfb, ph0, cs.a_step, r);
+                        if (r < cap) dst[r] = acc * cs.a_zeta;
+                    }
                 }
             }
         } else {
@@ -588,6 +666,65 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
     }
 
     // ---- CW back end (ModemCW.cpp:176-208) -----------------------------------------------------------------------------
+    if (ph >= TP_CW_A && ph <= TP_CW_E && is_fms) {
+        // ---- FM stereo back end (ModemFMStereo.cpp:262-286) at the audio rate ------------------------------------------------
+        const int na = sm->n_audio;                              // samples per channel (doubled for the result header in TP_CW_E)
+        float *ld = chan_rbuf(a, cs, cs.fms_ld_off) + kFmsFirHist, *rd = chan_rbuf(a, cs, cs.fms_rd_off) + kFmsFirHist;
+        if (ph == TP_CW_A) {
+            // 0.568 (sum -+ difference), then iirfilt_rrrf {b0, b1} / {1, a1}: v0 = x - a1 v1, y = b0 v0 + b1 v1 (two serial
+            // chains: thread 0 left, thread 32 right)
+            if (tid == 0 || tid == 32) {
+                const bool right = tid == 32;
+                const float *m = chan_rbuf(a, cs, cs.fms_am_off), *sd = chan_rbuf(a, cs, cs.fms_as_off);
+                float *out = right ? rd : ld;
+                float v1 = right ? st.fms_dr : st.fms_dl;
+                for (int i = 0; i < na; ++i) {
+                    const float x = f_mul(0.568f, right ? f_add(m[i], sd[i]) : f_sub(m[i], sd[i]));
+                    if (cs.fms_demph) {
+                        const float v0 = f_sub(x, f_mul(cs.fms_da1, v1));
+                        out[i] = f_add(f_mul(cs.fms_db0, v0), f_mul(cs.fms_db1, v1));
+                        v1 = v0;
+                    } else out[i] = x;
+                }
+                if (right) st.fms_dr = v1; else st.fms_dl = v1;
+            }
+        } else if (ph == TP_CW_B) {                              // firfilt_rrrf_push + execute on both: y[t] = sum h[k] x[t - k]
+            const float *h = a.taps + cs.fms_fir_off;
+            const int nh = cs.fms_fir_n;
+            for (int r = tid; r < 2 * na; r += nt) {
+                const int i = r >> 1;
+                const float *x = (r & 1) ? rd : ld;
+                float acc = 0.f;
+                for (int k = 0; k < nh; ++k) acc = fmaf(sdr_ldg(h + k), x[i - k], acc);
+                if (r < cs.res_audio_cap) res_audio[r] = acc;   // interleaved {left, right} (:284-285)
+            }
+        } else if (ph == TP_CW_C || ph == TP_CW_D) {
+            // histories of the streams only this modem has; staged through the shared scratch like the common ones
+            float *scr = reinterpret_cast<float *>(&sm->hist_tmp[0][0]);       // kTailStreams * kHist float2 >= 2 * 256 + 128 + 64 * 10
+            const bool save = ph == TP_CW_C;
+            for (int t = tid; t < kFmsFirHist; t += nt) {
+                if (save) { scr[t] = ld[na - kFmsFirHist + t]; scr[kFmsFirHist + t] = rd[na - kFmsFirHist + t]; }
+                else { ld[t - kFmsFirHist] = scr[t]; rd[t - kFmsFirHist] = scr[kFmsFirHist + t]; }
+            }
+            float *q = scr + 2 * kFmsFirHist;
+            if (tid < kHist) {
+                float2 *x2b = chan_cbuf(a, cs, cs.fms_x2_off);
+                float2 *q2 = reinterpret_cast<float2 *>(q);
+                if (save) q2[tid] = x2b[sm->n_iq + tid]; else x2b[tid] = q2[tid];
+                float *dsb = chan_rbuf(a, cs, cs.fms_ds_off);
+                float *q3 = q + 2 * kHist;
+                if (save) q3[tid] = dsb[sm->n_iq + tid]; else dsb[tid] = q3[tid];
+                for (int j = 1; j <= cs.a_S; ++j) {                       // the difference signal's decimator levels
+                    float *b = chan_rbuf(a, cs, cs.fms_al_off[j]);
+                    float *qj = q + 3 * kHist + (j - 1) * kHist;
+                    if (save) qj[tid] = b[sm->a_n[j] + tid]; else b[tid] = qj[tid];
+                }
+            }
+        } else if (tid == 0) {
+            sm->n_audio = 2 * na;                                 // audioOut->channels = 2 (:264): the header counts floats
+        }
+        return;
+    }
     if (ph >= TP_CW_A && ph <= TP_CW_E) {
         if (!is_cw) return;
         const int na = sm->n_audio < cs.res_audio_cap ? sm->n_audio : cs.res_audio_cap;

@@ -1080,11 +1080,13 @@ static int modem_from_name(const char *n) {
     if (s == "I/Q") return MODEM_IQ;
     if (s == "DSB") return MODEM_DSB;
     if (s == "CW") return MODEM_CW;
+    if (s == "FMS") return MODEM_FMS;
     return -1;
 }
 
 // Modem::checkSampleRate: ModemAnalog.cpp:14-19 (MIN_BANDWIDTH 500), ModemUSB.cpp:29-37 / ModemLSB.cpp:29-37
 static int check_sample_rate(int modem, long long bw) {
+    if (modem == MODEM_FMS) return bw < 100000 ? 100000 : (int)bw;      // ModemFMStereo.cpp:27-35
     if (bw < 500) return 500;
     if ((modem == MODEM_USB || modem == MODEM_LSB) && (bw % 2)) return (int)(bw + 1);
     return (int)bw;
@@ -1780,6 +1782,7 @@ static int chan_create_impl(sdr_engine *e, const char *modem, long long sample_r
     c->audio_plan = make_resampler_plan((float)a_ratio, As);
     if (c->iq_plan.interp) { delete c; return fail(SDR_ERR_UNSUPPORTED, "sdr_chan_create: bandwidth above the sample rate"); }
     if (mk == MODEM_CW && !c->audio_plan.interp) { delete c; return fail(SDR_ERR_UNSUPPORTED, "sdr_chan_create: CW bandwidth above the audio rate"); }
+    if (mk == MODEM_FMS && c->audio_plan.interp) { delete c; return fail(SDR_ERR_UNSUPPORTED, "sdr_chan_create: FM stereo with an audio rate above the modem rate"); }
     if (c->iq_plan.num_halfband > kMaxTailHb + kFrontMaxK || c->audio_plan.num_halfband > kMaxAudioHb) {
         delete c; return fail(SDR_ERR_UNSUPPORTED, "sdr_chan_create: too many half-band stages");
     }
@@ -1832,6 +1835,39 @@ static int chan_create_impl(sdr_engine *e, const char *modem, long long sample_r
         cs.cw_w_off = take(2 * (kHist + cap_audio + 4));
         // nco_crcf_set_frequency(mLO, 2.0f * (float)M_PI * mBeepFrequency / kit->audioSampleRate), mBeepFrequency = 650 (ModemCW.cpp:17,176)
         cs.cw_dtheta = nco_phase_step(2.0f * (float)3.14159265358979323846 * 650.0f / (float)audio_rate);
+    }
+    // FM stereo (ModemFMStereo.cpp:89-167): the second resampler's levels, the streams between its stages, the filters
+    std::vector<float> fms_fir;
+    float fms_sos_flat[25];
+    if (mk == MODEM_FMS) {
+        cs.fms_x2_off = take(2 * (kHist + cap_iq));
+        cs.fms_ds_off = take(kHist + cap_iq);
+        for (int j = 1; j <= cs.a_S; ++j) cs.fms_al_off[j] = take(kHist + (cap_iq >> j) + 4);
+        cs.fms_am_off = take(cap_audio + 4);
+        cs.fms_as_off = take(cap_audio + 4);
+        cs.fms_ld_off = take(kFmsFirHist + cap_audio + 4);
+        cs.fms_rd_off = take(kFmsFirHist + cap_audio + 4);
+        float cutoff = 16000.0f / float(audio_rate);                   // :103-115
+        const float ft = 1000.0f / float(audio_rate);
+        if (cutoff < 0) cutoff = 0;
+        if (cutoff > 0.5f) cutoff = 0.5f;
+        const unsigned h_len = filter_len_estimate(ft, As);            // estimate_req_filter_len (:117)
+        if (h_len < 1 || h_len > (unsigned)kFmsFirMax) { delete c; return fail(SDR_ERR_UNSUPPORTED, "sdr_chan_create: FM stereo low-pass too long for this audio rate"); }
+        fms_fir.resize(h_len);
+        kaiser_lowpass(h_len, cutoff, As, 0.0f, fms_fir.data());       // liquid_firdes_kaiser (:119)
+        cs.fms_fir_n = (int)h_len;
+        float bwf = float(c->bandwidth);                                // :126-136
+        if (bwf < 100000.0) bwf = 100000.0;
+        std::vector<Sos> ps;
+        cheby2_bandpass5_sos((float)19500 / bwf, (float)19000 / bwf, ps);
+        for (auto &sec : ps) sos_section_object(sec);                   // iirfilt_crcf_create_sos -> iirfiltsos_crcf_create
+        for (int k = 0; k < 5; ++k) { fms_sos_flat[5 * k] = ps[k].b[0]; fms_sos_flat[5 * k + 1] = ps[k].b[1]; fms_sos_flat[5 * k + 2] = ps[k].b[2];
+                                      fms_sos_flat[5 * k + 3] = ps[k].a[1]; fms_sos_flat[5 * k + 4] = ps[k].a[2]; }
+        cs.fms_demph = 75;                                              // _demph = 75 (:8); other settings are a writeSetting away (:78-83)
+        float b2[2], a1;
+        fm_deemphasis(cs.fms_demph, audio_rate, b2, &a1);               // :149-159
+        cs.fms_db0 = b2[0]; cs.fms_db1 = b2[1]; cs.fms_da1 = a1;
+        cap_audio *= 2;                                                 // two-channel output {left, right}
     }
     if (mk == MODEM_IQ) cap_audio = 2 * cap_iq;                         // two-channel output, one {imag, real} pair per decimated sample
     cs.res_audio_cap = (int)((cap_audio + 3) & ~size_t(3));
@@ -1887,6 +1923,10 @@ static int chan_create_impl(sdr_engine *e, const char *modem, long long sample_r
         cs.hq_off = pool_add(e, "hq10", hq, 10);
         cs.sos_off = pool_add(e, "sos6", flat, 15);
         cs.cw_hq_off = pool_add(e, "hq10_60", hq_cw, 10);
+        if (mk == MODEM_FMS) {
+            cs.fms_sos_off = pool_add(e, fkey("fms_sos", (float)c->bandwidth), fms_sos_flat, 25);
+            cs.fms_fir_off = pool_add(e, fkey("fms_fir", (float)audio_rate), fms_fir.data(), fms_fir.size());
+        }
         if (e->taps_host.size() > e->taps_cap) return bail(SDR_ERR_NOMEM, "taps pool exhausted");
         int slot = -1;
         for (size_t i = 0; i < e->slot_used.size(); ++i) if (!e->slot_used[i]) { slot = (int)i; break; }
@@ -2059,7 +2099,7 @@ extern "C" int sdr_chan_set_squelch(sdr_chan *c, int enabled, float level_db) {
 // AudioThreadInput::channels of this channel's output: 2 for "I/Q" (interleaved {imag, real}, ModemIQ.cpp:46-55), else 1
 extern "C" int sdr_chan_audio_channels(sdr_chan *c, int *channels) {
     if (!c || !channels) return fail(SDR_ERR_ARG, "null argument");
-    *channels = c->modem == MODEM_IQ ? 2 : 1;
+    *channels = (c->modem == MODEM_IQ || c->modem == MODEM_FMS) ? 2 : 1;
     return SDR_OK;
 }
 extern "C" int sdr_chan_result_caps(sdr_chan *c, unsigned *audio_cap, unsigned *iq_cap) {

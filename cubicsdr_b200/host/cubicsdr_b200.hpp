@@ -123,7 +123,7 @@ public:
         const size_t bufSize = input->data.size();
         if (!bufSize) return;                                // ModemAnalog::initOutputBuffers: `if (!bufSize) return`
         const double ratio = double(kit->audioSampleRate) / double(kit->sampleRate);
-        const size_t audio_out_size = (size_t)std::ceil((double)bufSize * ratio) + 512;       // ModemAnalog.cpp:51
+        const size_t audio_out_size = 2 * ((size_t)std::ceil((double)bufSize * ratio) + 512);   // ModemAnalog.cpp:51 (x 2: FM stereo's two channels)
         resampledOutputData.resize(audio_out_size);
         unsigned numAudioWritten = 0;
         double level = 0.0;
@@ -133,7 +133,7 @@ public:
             audioOut->data.clear();
             return;
         }
-        audioOut->channels = 1;                              // ModemAnalog.cpp:90-92
+        audioOut->channels = (getName() == "FMS" || getName() == "I/Q") ? 2 : 1;   // ModemAnalog.cpp:90-92; ModemFMStereo.cpp:264, ModemIQ.cpp:46
         audioOut->sampleRate = kit->audioSampleRate;
         audioOut->data.assign(resampledOutputData.begin(), resampledOutputData.begin() + numAudioWritten);
         audioOut->peak = peak;                               // DemodulatorThread.cpp:223-233 computes the same value
@@ -184,6 +184,7 @@ CUBICSDR_B200_MODEM(ModemLSB, "LSB", 5400)        // analog/ModemLSB.cpp:19-41
 CUBICSDR_B200_MODEM(ModemDSB, "DSB", 5400)        // analog/ModemDSB.cpp:15-25
 CUBICSDR_B200_MODEM(ModemCW, "CW", 500)           // analog/ModemCW.cpp:99-112
 CUBICSDR_B200_MODEM(ModemIQ, "I/Q", 48000)        // analog/ModemIQ.cpp:12-37
+CUBICSDR_B200_MODEM(ModemFMStereo, "FMS", 200000) // analog/ModemFMStereo.cpp:15-40
 #undef CUBICSDR_B200_MODEM
 
 // what CubicSDR::OnInit does at CubicSDR.cpp:305-311
@@ -197,6 +198,7 @@ inline void registerModems(const std::shared_ptr<Engine> &e) {
     Modem::addModemFactory(ModemCW::factory, "CW", 500);
     Modem::addModemFactory(ModemDSB::factory, "DSB", 5400);
     Modem::addModemFactory(ModemIQ::factory, "I/Q", 48000);
+    Modem::addModemFactory(ModemFMStereo::factory, "FMS", 200000);
 }
 
 // ---- SDRPostThread::runSingleCH (sdr/SDRPostThread.cpp:248-299): one block in, DC-blocked block + all attached work out ----
@@ -255,7 +257,7 @@ public:
             throw std::runtime_error(sdr_last_error());
         sdr_chan_get_bandwidth(ch_, &bandwidth_);
         sdr_chan_result_caps(ch_, &audioCap_, &iqCap_);          // most samples one block can yield: the fetch buffers' size
-        sdr_chan_audio_channels(ch_, &channels_);                // 2 for "I/Q" (ModemIQ.cpp:46), else 1
+        sdr_chan_audio_channels(ch_, &channels_);                // 2 for "I/Q" (ModemIQ.cpp:46) and "FMS" (ModemFMStereo.cpp:264), else 1
         if (wantIQ) sdr_chan_want_iq(ch_, 1);
     }
     ~DemodulatorB200() { if (ch_) sdr_chan_destroy(ch_); }

@@ -6,7 +6,7 @@ Philox generator from `seed`, so the oracle and the engine see identical bytes.
 """
 import numpy as np
 
-MODEM_DEFAULT_BW = {"FM": 200000, "NBFM": 12500, "AM": 6000, "USB": 5400, "LSB": 5400}
+MODEM_DEFAULT_BW = {"FM": 200000, "NBFM": 12500, "AM": 6000, "USB": 5400, "LSB": 5400, "FMS": 200000}
 
 
 def block_size(sample_rate):
@@ -54,7 +54,16 @@ def wideband(sample_rate, n_samples, chans, seed=1234, t0=0, dtype=np.complex64)
     amp = 0.5 / max(1.0, np.sqrt(len(chans)) * 1.5) if chans else 0.0
     for k, (modem, bw, off) in enumerate(chans):
         tone = 1000.0 + (400.0 if (k & 1) else 0.0)
-        if modem in ("FM", "NBFM"):
+        if modem == "FMS":
+            # FM stereo multiplex: 0.45 (L + R) + 0.1 pilot + 0.45 (L - R) sin(2 wp t), L = sin(w1 t), R = 0.7 sin(w2 t), 75 kHz
+            # deviation; the phase is the closed-form integral, so blocks generated separately join up
+            w1, w2, wp = 2 * np.pi * tone, 2 * np.pi * (tone + 1650.0), 2 * np.pi * 19000.0
+            A, P, g = 0.45, 0.1, 0.7
+            integ = A * (-np.cos(w1 * t) / w1 - g * np.cos(w2 * t) / w2) - P * np.cos(wp * t) / wp
+            for wk, gk in ((w1, 1.0), (w2, -g)):
+                integ += A * gk * 0.5 * (np.sin((2 * wp - wk) * t) / (2 * wp - wk) - np.sin((2 * wp + wk) * t) / (2 * wp + wk))
+            x += amp * np.exp(1j * (2 * np.pi * off * t + 2 * np.pi * 75000.0 * integ))
+        elif modem in ("FM", "NBFM"):
             dev = 75000.0 if modem == "FM" else 2500.0
             ph = 2 * np.pi * off * t + (dev / tone) * np.sin(2 * np.pi * tone * t)
             x += amp * np.exp(1j * ph)

@@ -220,6 +220,7 @@ struct RefChan {
     firhilbf firStereoR2C = nullptr, firStereoC2R = nullptr;
     nco_crcf stereoPilot = nullptr;
     std::vector<float> demodStereoData, resampledStereoData;
+    std::vector<lq_cf> dbg_x, dbg_v, dbg_x2;          // test instrumentation: the loop's intermediates of the last block
     std::vector<lq_cf> in_buf, out_buf, resampled;
     std::vector<float> demodOut, audioOut;
     // DemodulatorThread members (src/demod/DemodulatorThread.cpp:25-26): squelchLevel(-100), signalLevel(-100),
@@ -467,8 +468,11 @@ API int ref_chan_process(void *h, const lq_cf *block, unsigned n, long long shif
         float phase_error = 0;
         for (size_t i = 0; i < bufSize; i++) {
             lq_cf u, v, w, x, y;
+            if (i == 0) { c->dbg_x.resize(bufSize); c->dbg_v.resize(bufSize); c->dbg_x2.resize(bufSize); }
             firhilbf_r2c_execute(c->firStereoR2C, c->demodOut[i], &x);                  // real -> complex
+            c->dbg_x[i] = x;
             iirfilt_crcf_execute(c->iirStereoPilot, x, &v);                              // 19 kHz pilot band-pass
+            c->dbg_v[i] = v;
             nco_crcf_cexpf(c->stereoPilot, &w);
             w.imag = -w.imag;
             u.real = v.real * w.real - v.imag * w.imag;
@@ -478,6 +482,7 @@ API int ref_chan_process(void *h, const lq_cf *block, unsigned n, long long shif
             nco_crcf_step(c->stereoPilot);
             nco_crcf_mix_down(c->stereoPilot, x, &y);                                   // 38 kHz down-mix
             nco_crcf_mix_down(c->stereoPilot, y, &x);
+            c->dbg_x2[i] = x;
             float usb_discard;
             firhilbf_c2r_execute(c->firStereoC2R, x, &c->demodStereoData[i], &usb_discard);
         }
@@ -576,6 +581,14 @@ API int ref_chan_process(void *h, const lq_cf *block, unsigned n, long long shif
     return ref_chan_meter_block(c, numAudioWritten, bufSize, useSignalOutput, level_db, peak);
 }
 
+// test instrumentation: intermediates of the FM stereo loop of the last block (which: 0 real->complex, 1 pilot filter, 2 down-mix)
+API unsigned ref_chan_fms_debug(void *h, int which, lq_cf *out, unsigned cap) {
+    auto *c = (RefChan *)h;
+    const std::vector<lq_cf> &v = which == 0 ? c->dbg_x : (which == 1 ? c->dbg_v : c->dbg_x2);
+    unsigned n = (unsigned)std::min<size_t>(cap, v.size());
+    memcpy(out, v.data(), n * sizeof(lq_cf));
+    return n;
+}
 // DemodulatorThread::setSquelchEnabled / setSquelchLevel (:384-397: setting a level switches the squelch on)
 API void ref_chan_set_squelch(void *h, int enabled, float level) {
     auto *c = (RefChan *)h;

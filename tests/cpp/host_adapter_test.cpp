@@ -56,8 +56,9 @@ int main(int argc, char **argv) {
         modem->disposeKit(kit);
         delete modem;
     }
-    if (Modem::makeModem("FMS") != nullptr) return 7;           // not registered -> nullptr, like Modem::makeModem
+    if (Modem::makeModem("QAM") != nullptr) return 7;           // not registered (a digital modem) -> nullptr, like Modem::makeModem
     { Modem *d = Modem::makeModem("DSB"); if (!d || d->getName() != "DSB") return 7; delete d; }
+    { Modem *d = Modem::makeModem("FMS"); if (!d || d->getName() != "FMS" || d->checkSampleRate(50000, 48000) != 100000) return 8; delete d; }
 
     // ---- S3 + S2: block ingress, pre-demod + demod batched, spectrum ----------------------------------------------------
     SDRPostB200 post(eng);

@@ -464,3 +464,51 @@ def check_dc_window(lib, ref, big=False):
         assert blocks == 3
         s, blocks = dc_window_case(lib, ref, 61440000, [1024068] * 2, noise_dc)
         assert blocks == 2 and s == 0
+
+
+def fm_stereo_floor(ref, fs, chan, signal, n_blocks, eps=1e-7, seed=1234):
+    """How far the reference's own FM stereo output moves when its input moves by `eps` (relative, white): the loop's oscillator is
+    a 1024-entry table (nco_crcf ignores LIQUID_VCO), so a phase that moves by 1e-7 rad now and then lands in the neighbouring
+    table entry, the phase detector sees 6e-3 rad more or less, and the loop (bandwidth 0.25) carries the kick on.  Differences of
+    1e-7 at the loop's input therefore surface as ~1e-3 in the difference channel -- for ANY second implementation, the reference
+    binary on another libm included.  Returns the relative RMS change of (sum, difference)."""
+    m, bw, off = chan
+    N = synth.block_size(fs)
+    rng = np.random.default_rng(99)
+    a, b = RefChan(ref, m, fs, bw), RefChan(ref, m, fs, bw)
+    ing = RefIngress(ref)
+    A, B = [], []
+    for k in range(n_blocks):
+        y = ing.block(synth.wideband(fs, N, signal, seed=seed, t0=k * N))
+        y2 = (y * (1.0 + eps * rng.standard_normal(N))).astype(np.complex64)
+        A.append(a.process(y, off)["audio"]); B.append(b.process(y2, off)["audio"])
+    a.close(); b.close(); ing.close()
+    A, B = np.concatenate(A).reshape(-1, 2), np.concatenate(B).reshape(-1, 2)
+    return relrms(B.sum(1), A.sum(1)), relrms(B[:, 1] - B[:, 0], A[:, 1] - A[:, 0])
+
+
+def check_fm_stereo(lib, ref, n_blocks=10):
+    """ModemFMStereo against the reference: exact per-block counts, the sum channel (discriminator, resampler, de-emphasis, low-pass:
+    no feedback) to the usual 1e-5, the difference channel (through the pilot loop) to within a small multiple of the reference's
+    own sensitivity to 1e-7 input noise (fm_stereo_floor) -- the tightest bar that means anything for this loop."""
+    fs = 2400000
+    chans = [("FMS", 200000, 300000), ("FMS", 250000, -500000), ("FMS", 200000, 700000), ("FM", 200000, 700000)]
+    signal = [("FMS", 200000, 300000), ("FMS", 250000, -500000), ("FM", 200000, 700000)]
+    out, _, _ = run_channels(lib, ref, fs, chans, n_blocks=n_blocks, signal=signal)
+    check_channels([o for o in out if o["modem"] != "FMS"])
+    res = []
+    for o, ch in zip(out, chans):
+        if o["modem"] != "FMS":
+            continue
+        assert o["counts_ok"] and o["skipped"] == o["ref_skipped"]
+        a, r = o["audio"].reshape(-1, 2), o["ref_audio"].reshape(-1, 2)
+        e_sum, e_diff = relrms(a.sum(1), r.sum(1)), relrms(a[:, 1] - a[:, 0], r[:, 1] - r[:, 0])
+        f_sum, f_diff = fm_stereo_floor(ref, fs, ch, signal, n_blocks)
+        assert e_sum <= TOL, "FM stereo sum channel: %.3g" % e_sum
+        assert e_diff <= max(4.0 * f_diff, 2e-4), "FM stereo difference channel: %.3g (reference's own sensitivity %.3g)" % (e_diff, f_diff)
+        assert relrms(o["iq"], o["ref_iq"]) <= TOL
+        res.append((e_sum, e_diff, f_sum, f_diff))
+    assert len(out[0]["audio"]) == n_blocks * 1600                # 800 frames of {left, right} per block
+    a = out[0]["audio"].reshape(-1, 2)[4000:]
+    assert np.std(a[:, 0]) > 0.05 and np.std(a[:, 1]) > 0.05 and np.std(a[:, 0] - a[:, 1]) > 0.05    # two different programmes came out
+    return res

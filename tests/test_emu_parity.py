@@ -261,5 +261,14 @@ def test_cw_modem(emu_lib, ref):
     assert len(out[0]["audio"]) == 30 * 800
 
 
+def test_fm_stereo_modem(emu_lib, ref):
+    """ModemFMStereo (analog/ModemFMStereo.cpp:186-287) on a stereo multiplex with a 19 kHz pilot: discriminator, both audio
+    resamplers, real -> complex, pilot band-pass (reference design bit for bit, sections replayed operation by operation),
+    phase-locked oscillator, 38 kHz down-mix, complex -> real, de-emphasis, low-pass pair; two-channel audio {left, right}.
+    Also a 250 kHz modem rate (other pilot-filter design, other resampler plan) and a plain FM carrier (no pilot: the loop idles)."""
+    res = parity.check_fm_stereo(emu_lib, ref)
+    print("FM stereo (sum err, difference err, reference sensitivity sum, difference):", res)
+
+
 def test_dc_window_replay_bit_exact(emu_lib, ref):
     parity.check_dc_window(emu_lib, ref)

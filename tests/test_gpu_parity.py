@@ -250,3 +250,9 @@ def test_dc_window_replay_bit_exact_gpu(gpu_lib, ref):
     against the reference binary on offset, zero-mean, near-DC-carrier, silent and ragged inputs, both replays alternating, and
     full 61.44 MSps blocks."""
     parity.check_dc_window(gpu_lib, ref, big=True)
+
+
+def test_fm_stereo_modem_gpu(gpu_lib, ref):
+    """ModemFMStereo on the device (see tests/parity.py check_fm_stereo for what can and cannot be asked of the pilot loop)."""
+    res = parity.check_fm_stereo(gpu_lib, ref)
+    print("FM stereo (sum err, difference err, reference sensitivity sum, difference):", res)
