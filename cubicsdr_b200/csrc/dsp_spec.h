@@ -316,17 +316,27 @@ SDR_HD SDR_FORCEINLINE float2 fft2_split_load(const SpecArgs &a, const float2 *x
     return v;
 }
 
-// one pass for butterfly j: read + twiddle + transform into u (FIRST: inputs come from global memory through the split stage)
-template <int R, bool FIRST>
-SDR_HD SDR_FORCEINLINE void fft2_pass_load(const SpecArgs &a, const float2 *x, int psub, const float2 *buf, int pr_in, int s, int j, float2 (&u)[R]) {
+// one pass for butterfly j: read + twiddle + transform into u
+template <int R>
+SDR_HD SDR_FORCEINLINE void fft2_pass_load(const SpecArgs &a, const float2 *buf, int pr_in, int s, int j, float2 (&u)[R]) {
     const int n = a.nsub, q = n / R;
 #pragma unroll
-    for (int t = 0; t < R; ++t) u[t] = FIRST ? fft2_split_load(a, x, psub, j + t * q) : buf[fft2_pad(j + t * q, pr_in)];
-    if (!FIRST) {
+    for (int t = 0; t < R; ++t) u[t] = buf[fft2_pad(j + t * q, pr_in)];
+    if (s > 1) {
+        // exp(-2 pi i t k / (s R)) = tw[t k N / (s R)], t = 1 .. R - 1.  The table is read only at t = 1, 2, 4, .. (the reads of a
+        // warp are scattered: k differs per lane), the other powers are products of at most log2 R of those (<= 3e-7 off)
         const int k = j & (s - 1);
-        const int tstep = k * (a.N / (s * R));                   // exp(-2 pi i t k / (s R)) = tw[t k N / (s R)]
+        const int tstep = k * (a.N / (s * R));
+        float2 w[R];
 #pragma unroll
-        for (int t = 1; t < R; ++t) u[t] = cmul(u[t], sdr_ldg(a.tw + t * tstep));
+        for (int b = 1; b < R; b <<= 1) w[b] = sdr_ldg(a.tw + b * tstep);
+#pragma unroll
+        for (int t = 3; t < R; ++t) {
+            const int low = t & (-t);
+            if (low != t) w[t] = cmul(w[t - low], w[low]);
+        }
+#pragma unroll
+        for (int t = 1; t < R; ++t) u[t] = cmul(u[t], w[t]);
     }
     reg_fft<R>(u);
 }
@@ -354,21 +364,27 @@ SDR_HD SDR_FORCEINLINE void fft2_pass_store_mags(const SpecArgs &a, int f, int p
 // (the GPU kernel keeps `u` in registers across the barrier; the emulator keeps one array per thread)
 struct Fft2Regs { float2 u[32]; };
 template <int R>
-SDR_HD SDR_FORCEINLINE void fft2_half(const SpecArgs &a, const float2 *x, int f, int psub, float2 *buf, int pass, int passes, int s, int pr_prev,
+SDR_HD SDR_FORCEINLINE void fft2_half(const SpecArgs &a, int f, int psub, float2 *buf, int pass, int passes, int s, int pr_prev,
                                       int pr_this, bool write_half, int j, Fft2Regs &rg) {
     float2 (&u)[R] = reinterpret_cast<float2 (&)[R]>(rg.u);
     if (j >= a.nsub / R) return;
     if (!write_half) {
-        if (pass == 0) fft2_pass_load<R, true>(a, x, psub, buf, 0, s, j, u);
-        else fft2_pass_load<R, false>(a, x, psub, buf, pr_prev, s, j, u);
+        fft2_pass_load<R>(a, buf, pr_prev, s, j, u);
     } else {
         if (pass == passes - 1) fft2_pass_store_mags<R>(a, f, psub, s, j, u);
         else fft2_pass_store<R>(buf, pr_this, s, j, u);
     }
 }
-SDR_HD inline void spec_fft2_half(int hp, const SpecArgs &a, int bid, int tid, float2 *buf, Fft2Regs &rg) {
+// load phase: the sub-sequence (radix-P stage applied) into the work buffer, plain layout; nt threads, a few elements each with
+// their loads independent of one another (the passes then never wait on global memory)
+SDR_HD inline void spec_fft2_load(const SpecArgs &a, int bid, int tid, int nt, float2 *buf) {
     const int f = bid / a.P, psub = bid - f * a.P;
     const float2 *x = a.x + (a.frame_stride > 0 ? f * a.frame_stride : a.frame_start[f]);
+#pragma unroll 4
+    for (int n = tid; n < a.nsub; n += nt) buf[n] = fft2_split_load(a, x, psub, n);
+}
+SDR_HD inline void spec_fft2_half(int hp, const SpecArgs &a, int bid, int tid, float2 *buf, Fft2Regs &rg) {
+    const int f = bid / a.P, psub = bid - f * a.P;
     const Fft2Plan pl = fft2_plan(a.nsub);
     const int pass = hp >> 1;
     if (pass >= pl.passes) return;
@@ -380,11 +396,11 @@ SDR_HD inline void spec_fft2_half(int hp, const SpecArgs &a, int bid, int tid, f
     const int pr_prev = (pass == 1) ? lr0 : 0, pr_this = (pass == 0) ? lr0 : 0;
     const bool wh = (hp & 1) != 0;
     switch (pl.r[pass]) {
-        case 32: fft2_half<32>(a, x, f, psub, buf, pass, pl.passes, s, pr_prev, pr_this, wh, tid, rg); break;
-        case 16: fft2_half<16>(a, x, f, psub, buf, pass, pl.passes, s, pr_prev, pr_this, wh, tid, rg); break;
-        case 8: fft2_half<8>(a, x, f, psub, buf, pass, pl.passes, s, pr_prev, pr_this, wh, tid, rg); break;
-        case 4: fft2_half<4>(a, x, f, psub, buf, pass, pl.passes, s, pr_prev, pr_this, wh, tid, rg); break;
-        default: fft2_half<2>(a, x, f, psub, buf, pass, pl.passes, s, pr_prev, pr_this, wh, tid, rg); break;
+        case 32: fft2_half<32>(a, f, psub, buf, pass, pl.passes, s, pr_prev, pr_this, wh, tid, rg); break;
+        case 16: fft2_half<16>(a, f, psub, buf, pass, pl.passes, s, pr_prev, pr_this, wh, tid, rg); break;
+        case 8: fft2_half<8>(a, f, psub, buf, pass, pl.passes, s, pr_prev, pr_this, wh, tid, rg); break;
+        case 4: fft2_half<4>(a, f, psub, buf, pass, pl.passes, s, pr_prev, pr_this, wh, tid, rg); break;
+        default: fft2_half<2>(a, f, psub, buf, pass, pl.passes, s, pr_prev, pr_this, wh, tid, rg); break;
     }
 }
 

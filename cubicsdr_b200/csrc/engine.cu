@@ -726,6 +726,8 @@ __global__ void __launch_bounds__(kFft2Threads) k_spec_fft2(SpecArgs a) {
     if (blockIdx.x == 0) for (int f = (int)threadIdx.x; f < a.F; f += (int)blockDim.x) a.frame_cf[f] = make_float2(0.f, 1.f);
     const Fft2Plan pl = fft2_plan(a.nsub);
     Fft2Regs rg;
+    spec_fft2_load(a, (int)blockIdx.x, (int)threadIdx.x, (int)blockDim.x, buf);
+    __syncthreads();
     for (int pass = 0; pass < pl.passes; ++pass) {
         spec_fft2_half(2 * pass, a, (int)blockIdx.x, (int)threadIdx.x, buf, rg);
         __syncthreads();                                            // everybody has read
@@ -1028,7 +1030,7 @@ static int launch_spectrum(const SpecArgs &a, sdr_stream_t s, unsigned long long
     if (a.F == 0) return 0;
 #ifndef SDR_EMU
     const Fft2Plan pl = fft2_plan(a.nsub);
-    const size_t smem = pl.passes > 1 ? (size_t)(a.nsub + a.nsub / pl.r[0]) * sizeof(float2) : 0;
+    const size_t smem = (size_t)(a.nsub + a.nsub / pl.r[0]) * sizeof(float2);
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(k_spec_fft2, cudaFuncAttributeMaxDynamicSharedMemorySize, kFft2SmemElems * (int)sizeof(float2)));
@@ -1049,8 +1051,10 @@ static int launch_spectrum(const SpecArgs &a, sdr_stream_t s, unsigned long long
         std::vector<float2> buf((size_t)a.nsub + a.nsub / 2 + 16);
         std::vector<Fft2Regs> regs(kFft2Threads);
         for (int f = 0; f < a.F; ++f) a.frame_cf[f] = make_float2(0.f, 1.f);
-        for (int b = 0; b < a.F * a.P; ++b)
+        for (int b = 0; b < a.F * a.P; ++b) {
+            for (int t = 0; t < kFft2Threads; ++t) spec_fft2_load(a, b, t, kFft2Threads, buf.data());
             for (int hp = 0; hp < 2 * pl.passes; ++hp) for (int t = 0; t < kFft2Threads; ++t) spec_fft2_half(hp, a, b, t, buf.data(), regs[t]);
+        }
     }
     if (a.rebin || a.shift) for (int ph = 0; ph < 2; ++ph) for (int i = 0; i < a.N; ++i) view_ema_move_thread(a, ph, i);
     for (int i = 0; i < a.N; ++i) spec_ema2_thread_serial(a, i);
