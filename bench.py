@@ -729,6 +729,18 @@ def main():
                                  "note": "cfg4 is specified on 4 GPUs: this is the whole 256-channel job on one" if name == "cfg4" else None}
             except Exception as ex:
                 configs[name] = {"error": repr(ex)}
+        # the same cfg5 job the way the reference's stock dispatch runs it at this rate (SDRPostThread::runPFBCH: analysis
+        # filterbank, demodulators at the channel rate); parity of that mode: tests/test_pfb.py
+        try:
+            r3 = run_engine_workload(cx, wl, chans, max(20, min(args.steps, 100)), 3, min(0.5, args.min_seconds), channelizer=True, want_cpu=False)
+            configs["cfg5_channelizer"] = {"config": config_of(dict(wl, desc=r3["desc"]), r3["N"], len(chans)), "value": r3["value"], "unit": "MSamples/s",
+                                           "ms_per_step": r3["ms_per_step"], "reps": r3["reps"], "e2e": r3["e2e"],
+                                           "stage_ms_per_block": r3["roofline"]["stage_ms_per_block"],
+                                           "gpu_launches_per_step": r3["gpu_launches"] / max(1, max(20, min(args.steps, 100))),
+                                           "realtime_factor": r3["realtime_factor"],
+                                           "note": "engine in channelizer mode (sdr_engine_set_channelizer(1)); compare with cpu_baseline_channelizer of the main line"}
+        except Exception as ex:
+            configs["cfg5_channelizer"] = {"error": repr(ex)}
 
     if rank == 0:
         r = main_res

@@ -5,7 +5,7 @@ thin Python host side used by the tests and bench.py: ctypes bindings plus class
 interfaces for the path (cubicsdr_b200.host).  There is no CPU fallback: `lib()` raises if the CUDA library is
 missing, and engine creation fails if no GPU is present.
 """
-from ._capi import Channel, Channelizer, Engine, Group, Lib, PRODUCT_LIB, SdrError, Spectrum, SYMBOLS  # noqa: F401
+from ._capi import Channel, Channelizer, Engine, Group, Lib, Mixer, PRODUCT_LIB, Scope, SdrError, Spectrum, SYMBOLS, fetch_pcm16  # noqa: F401
 from . import synth  # noqa: F401
 
 _lib = None

@@ -30,6 +30,8 @@ SYMBOLS = [
     "sdr_group_chan_create", "sdr_group_spectrum_create", "sdr_group_submit", "sdr_group_wait", "sdr_group_wait_block", "sdr_group_set_host_results",
     "sdr_design_kaiser", "sdr_design_nco_table", "sdr_design_nco_step", "sdr_design_resampler",
     "sdr_design_halfband_branch", "sdr_design_am_dc_block", "sdr_design_hilbert_q", "sdr_design_butter6_sos", "sdr_design_cheby2_bp5_sos", "sdr_design_hilbert_q_as",
+    "sdr_mixer_create", "sdr_mixer_destroy", "sdr_mixer_bind", "sdr_mixer_add_source", "sdr_mixer_set_gain", "sdr_mixer_set_active",
+    "sdr_mixer_push", "sdr_mixer_render", "sdr_chan_fetch_pcm16", "sdr_scope_create", "sdr_scope_destroy", "sdr_scope_process",
 ]
 
 
@@ -124,6 +126,18 @@ class Lib:
         L.sdr_design_am_dc_block.argtypes = [vp]
         L.sdr_design_hilbert_q.argtypes = [vp]
         L.sdr_design_butter6_sos.argtypes = [vp]
+        L.sdr_mixer_create.argtypes = [vp, C.c_int, C.c_uint, C.POINTER(vp)]
+        L.sdr_mixer_destroy.argtypes = [vp]
+        L.sdr_mixer_bind.argtypes = [vp, vp, C.c_float, C.POINTER(C.c_int)]
+        L.sdr_mixer_add_source.argtypes = [vp, C.c_float, C.POINTER(C.c_int)]
+        L.sdr_mixer_set_gain.argtypes = [vp, C.c_int, C.c_float]
+        L.sdr_mixer_set_active.argtypes = [vp, C.c_int, C.c_int]
+        L.sdr_mixer_push.argtypes = [vp, C.c_int, vp, C.c_uint, C.c_int, C.c_float, C.c_int]
+        L.sdr_mixer_render.argtypes = [vp, C.c_uint, vp]
+        L.sdr_chan_fetch_pcm16.argtypes = [vp, vp, C.c_uint, C.POINTER(C.c_uint)]
+        L.sdr_scope_create.argtypes = [vp, vp, C.c_uint, C.c_uint, C.POINTER(vp)]
+        L.sdr_scope_destroy.argtypes = [vp]
+        L.sdr_scope_process.argtypes = [vp, vp, C.POINTER(C.c_uint), vp, C.POINTER(C.c_uint), vp]
         L.sdr_design_cheby2_bp5_sos.argtypes = [C.c_float, C.c_float, vp]
         L.sdr_design_hilbert_q_as.argtypes = [C.c_float, vp]
 
@@ -521,3 +535,74 @@ class Channelizer:
             self.lib.L.sdr_pfb_destroy(self.h)
             self.h = None
 
+
+
+class Mixer:
+    """audioCallback of the reference (src/audio/AudioThread.cpp:88-243) on the device: bound demodulators' audio is queued after every
+    block without leaving the GPU; render(n) is one callback for n stereo frames."""
+
+    def __init__(self, eng, sample_rate=48000, max_frames=4096):
+        self.lib, self.eng = eng.lib, eng
+        h = C.c_void_p()
+        self.lib.check(self.lib.L.sdr_mixer_create(eng.h, int(sample_rate), int(max_frames), C.byref(h)))
+        self.h = h
+
+    def bind(self, chan, gain=1.0):
+        i = C.c_int()
+        self.lib.check(self.lib.L.sdr_mixer_bind(self.h, chan.h, float(gain), C.byref(i)))
+        return i.value
+
+    def add_source(self, gain=1.0):
+        i = C.c_int()
+        self.lib.check(self.lib.L.sdr_mixer_add_source(self.h, float(gain), C.byref(i)))
+        return i.value
+
+    def set_gain(self, source, gain):
+        self.lib.check(self.lib.L.sdr_mixer_set_gain(self.h, int(source), float(gain)))
+
+    def set_active(self, source, active):
+        self.lib.check(self.lib.L.sdr_mixer_set_active(self.h, int(source), 1 if active else 0))
+
+    def push(self, source, data, channels=1, peak=0.0, sample_rate=48000):
+        d = np.ascontiguousarray(data, np.float32)
+        self.lib.check(self.lib.L.sdr_mixer_push(self.h, int(source), _ptr(d), d.size, int(channels), float(peak), int(sample_rate)))
+
+    def render(self, n_frames):
+        out = np.zeros(2 * n_frames, np.float32)
+        self.lib.check(self.lib.L.sdr_mixer_render(self.h, int(n_frames), _ptr(out)))
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.L.sdr_mixer_destroy(self.h)
+            self.h = None
+
+
+class Scope:
+    """ScopeVisualProcessor (src/process/ScopeVisualProcessor.cpp) on a channel's audio: waveform points and audio spectrum."""
+
+    def __init__(self, eng, chan, fft_size=1024, max_samples=1024):
+        self.lib, self.fft_size, self.max_samples = eng.lib, fft_size, max_samples
+        h = C.c_void_p()
+        self.lib.check(self.lib.L.sdr_scope_create(eng.h, chan.h, int(fft_size), int(max_samples), C.byref(h)))
+        self.h = h
+
+    def process(self):
+        wave = np.zeros(2 * self.max_samples, np.float32); spec = np.zeros(self.fft_size, np.float32)
+        nw, ns = C.c_uint(), C.c_uint()
+        fc = np.zeros(2, np.float64)
+        self.lib.check(self.lib.L.sdr_scope_process(self.h, _ptr(wave), C.byref(nw), _ptr(spec), C.byref(ns), _ptr(fc)))
+        return wave[:2 * nw.value].copy(), spec[:2 * ns.value].copy(), fc
+
+    def close(self):
+        if self.h:
+            self.lib.L.sdr_scope_destroy(self.h)
+            self.h = None
+
+
+def fetch_pcm16(chan, cap=1 << 16):
+    """AudioFileWAV::writePayloadToFileStream's 16-bit words for the channel's last block."""
+    out = np.zeros(cap, np.int16)
+    n = C.c_uint()
+    chan.lib.check(chan.lib.L.sdr_chan_fetch_pcm16(chan.h, _ptr(out), cap, C.byref(n)))
+    return out[:n.value].copy()

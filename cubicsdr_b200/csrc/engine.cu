@@ -30,6 +30,7 @@
 #include "dsp_spec.h"
 #include "dsp_pfb.h"
 #include "dsp_tail.h"
+#include "dsp_sink.h"
 
 using namespace sdrb200;
 
@@ -651,6 +652,62 @@ __global__ void __launch_bounds__(1024) k_dc_resolve(DcWinArgs a, int gmap_in_sm
     for (int p = 1 + (int)threadIdx.x; p < a.tiles; p += (int)blockDim.x) dw_gather_thread(a, p);
 }
 
+// ---- audio-side consumers (dsp_sink.h) ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_mix_feed(MixArgs a) { mix_feed_thread(a, (int)(blockIdx.x * blockDim.x + threadIdx.x)); }
+__global__ void __launch_bounds__(128) k_mix_walk(MixArgs a) { mix_walk_thread(a, (int)(blockIdx.x * blockDim.x + threadIdx.x)); }
+__global__ void __launch_bounds__(256) k_mix_sum(MixArgs a) { mix_sum_thread(a, (int)(blockIdx.x * blockDim.x + threadIdx.x)); }
+__global__ void __launch_bounds__(256) k_mix_scale(MixArgs a) {
+    __shared__ float sc;
+    if (threadIdx.x == 0) sc = mix_scale(a);
+    __syncthreads();
+    const int k = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (k < 2 * a.n_frames && sc != 1.0f) a.out[k] = __fmul_rn(a.out[k], sc);
+}
+// a host-fed AudioThreadInput (tests, or audio that does not come from this engine): samples staged in `data`
+__global__ void k_mix_push(MixArgs a, int j, const float *data, int n, int channels, float peak, int rate) {
+    MixSource &s = a.src[j];
+    if (s.q_count == kMixEntries || n > s.ring_cap) return;
+    int w = s.w;
+    if (w + n > s.ring_cap) w = 0;
+    float *ring = a.rings + s.ring_off;
+    for (int i = (int)threadIdx.x; i < n; i += (int)blockDim.x) ring[w + i] = data[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        MixEntry e; e.start = w; e.n = n; e.channels = channels; e.rate = rate; e.peak = peak;
+        s.ent[(s.q_head + s.q_count) % kMixEntries] = e; s.q_count += 1; s.w = w + n;
+    }
+}
+__global__ void __launch_bounds__(256) k_pcm16(PcmArgs a) { pcm16_thread(a, (int)(blockIdx.x * blockDim.x + threadIdx.x)); }
+__global__ void __launch_bounds__(256) k_scope_prepare(ScopeArgs a) {
+    __shared__ float pk;
+    if (threadIdx.x == 0) pk = scope_wave_peak_serial(a);          // <= max_samples comparisons; every CTA repeats them
+    __syncthreads();
+    scope_prepare_thread(a, (int)(blockIdx.x * blockDim.x + threadIdx.x), pk);
+}
+// averages, ceil / floor, scalar averages and points of the audio spectrum: one CTA (fft_size / 2 <= 4096 bins)
+__global__ void __launch_bounds__(1024) k_scope_finish(ScopeArgs a) {
+    __shared__ double smx[32], smn[32];
+    double mx = 0.0, mn = 1.0;
+    for (int i = (int)threadIdx.x; i < a.fft_size / 2; i += (int)blockDim.x) {
+        const double maa = scope_ema_bin(a, i);
+        if (maa > mx) mx = maa;
+        if (maa < mn) mn = maa;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ox = __shfl_xor_sync(0xffffffffu, mx, o), on = __shfl_xor_sync(0xffffffffu, mn, o);
+        if (ox > mx) mx = ox;
+        if (on < mn) mn = on;
+    }
+    if ((threadIdx.x & 31) == 0) { smx[threadIdx.x >> 5] = mx; smn[threadIdx.x >> 5] = mn; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { if (smx[w] > mx) mx = smx[w]; if (smn[w] < mn) mn = smn[w]; }
+        scope_finish_serial(a, mx, mn);
+    }
+    __syncthreads();
+    for (int i = (int)threadIdx.x; i < a.fft_size / 2; i += (int)blockDim.x) scope_points_thread(a, i);
+}
+
 template <int K>
 __global__ void __launch_bounds__(kFrontWarps * 32, 1) k_chan_front(FrontArgs a, int jobs) {
     extern __shared__ __align__(16) unsigned char front_sm[];
@@ -882,6 +939,8 @@ static bool tma_rows_map(CUtensorMap *m, float2 *base, unsigned row_samples, uns
 #endif
 
 // candidate windows -> chunk maps -> walk + gather: the true state entering every tile lands in a.seg_in (dsp_dcwin.h)
+struct sdr_engine;
+static void mixers_feed(sdr_engine *e, sdr_stream_t ts);
 static int launch_dc_window(const DcWinArgs &a, sdr_stream_t s, unsigned long long &launches) {
     const int chunks = (a.tiles - 1 + kDwChunk - 1) / kDwChunk;
 #ifndef SDR_EMU
@@ -1199,6 +1258,7 @@ struct sdr_engine {
     int *d_dw_entry = nullptr;
     unsigned *d_dw_stats = nullptr;
     int dc_window = -1;
+    std::vector<struct sdr_mixer *> mixers;   // device-side audio mixers fed after every block (dsp_sink.h)
     unsigned long long dw_blocks = 0;
     // host blocks: ring of pinned staging buffers -> DMA on stream_h2d -> ring of device buffers -> the DC stream
     static const int kInRing = 3;
@@ -2919,6 +2979,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
     if (prev_q >= 0 && e->res_tail_rec[prev_q]) CUDA_TRY(cudaStreamWaitEvent(ts, e->ev_res_tail[prev_q], 0));   // its D2H reads d_results
 #endif
     launch_tail(ta, n_slots, ts, e->launches);
+    mixers_feed(e, ts);                                            // bound channels' audio joins their mixer queues (device side)
     if (to_host && e->results_bytes) {
         size_t total = 0;
         for (auto *c : e->chans) if (c) total = std::max(total, (size_t)c->cs.res_off + c->slot_bytes);
@@ -3441,6 +3502,314 @@ extern "C" int sdr_debug_fp32_peak(int device, double *tflops) {
 // ---------------------------------------------------------------------------------------------------------------------
 // design introspection
 // ---------------------------------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------------------
+// audio-side consumers on the device (dsp_sink.h)
+// ---------------------------------------------------------------------------------------------------------------------
+struct sdr_mixer {
+    sdr_engine *eng = nullptr;
+    int rate = 0;
+    unsigned max_frames = 0;
+    int n_src = 0;
+    MixSource *d_src = nullptr;
+    float *d_rings = nullptr;
+    size_t ring_floats = 0, ring_cap_total = 0;
+    int *d_map = nullptr;
+    double *d_peak = nullptr;
+    float *d_out = nullptr, *h_out = nullptr;
+    float *d_stage = nullptr, *h_stage = nullptr;
+    static const int kRing = 32768;          // floats per source: several blocks of audio
+    static const int kStage = 65536;
+};
+static MixArgs mixer_args(sdr_mixer *m) {
+    MixArgs a;
+    a.src = m->d_src; a.n_src = m->n_src; a.rings = m->d_rings; a.rate = m->rate; a.cs = m->eng->d_cs; a.results = m->eng->d_results;
+    a.n_frames = 0; a.map = m->d_map; a.mix_peak = m->d_peak; a.out = m->d_out;
+    return a;
+}
+static void mixers_feed(sdr_engine *e, sdr_stream_t ts) {
+    for (sdr_mixer *m : e->mixers) {
+        if (!m->n_src) continue;
+        MixArgs a = mixer_args(m);
+#ifndef SDR_EMU
+        k_mix_feed<<<(m->n_src + 127) / 128, 128, 0, ts>>>(a);
+#else
+        (void)ts;
+        for (int j = 0; j < m->n_src; ++j) mix_feed_thread(a, j);
+#endif
+        e->launches += 1;
+    }
+}
+static sdr_stream_t sink_stream(sdr_engine *e) {
+#ifndef SDR_EMU
+    return e->stream_tail;
+#else
+    return e->stream;
+#endif
+}
+extern "C" int sdr_mixer_create(sdr_engine *e, int sample_rate, unsigned max_frames, sdr_mixer **out) {
+    if (!e || !out || sample_rate <= 0 || !max_frames) return fail(SDR_ERR_ARG, "sdr_mixer_create: bad arguments");
+    std::lock_guard<std::mutex> lk(e->mu);
+    use_device(e);
+    sdr_mixer *m = new sdr_mixer();
+    m->eng = e; m->rate = sample_rate; m->max_frames = max_frames;
+    m->ring_cap_total = (size_t)kMixMaxSources * sdr_mixer::kRing;
+    int bad = 0;
+    bad |= be_malloc((void **)&m->d_src, kMixMaxSources * sizeof(MixSource));
+    bad |= be_malloc((void **)&m->d_rings, m->ring_cap_total * sizeof(float));
+    bad |= be_malloc((void **)&m->d_map, (size_t)kMixMaxSources * 2 * max_frames * sizeof(int));
+    bad |= be_malloc((void **)&m->d_peak, kMixMaxSources * sizeof(double));
+    bad |= be_malloc((void **)&m->d_out, 2 * (size_t)max_frames * sizeof(float));
+    bad |= be_host_alloc((void **)&m->h_out, 2 * (size_t)max_frames * sizeof(float));
+    bad |= be_malloc((void **)&m->d_stage, sdr_mixer::kStage * sizeof(float));
+    bad |= be_host_alloc((void **)&m->h_stage, sdr_mixer::kStage * sizeof(float));
+    if (bad) {
+        be_free(m->d_src); be_free(m->d_rings); be_free(m->d_map); be_free(m->d_peak); be_free(m->d_out); be_host_free(m->h_out);
+        be_free(m->d_stage); be_host_free(m->h_stage); delete m;
+        return fail(SDR_ERR_NOMEM, "sdr_mixer_create: allocation failed");
+    }
+    be_memset(m->d_src, 0, kMixMaxSources * sizeof(MixSource), sink_stream(e));
+    e->mixers.push_back(m);
+    *out = m;
+    return SDR_OK;
+}
+extern "C" int sdr_mixer_destroy(sdr_mixer *m) {
+    if (!m) return SDR_OK;
+    sdr_engine *e = m->eng;
+    std::lock_guard<std::mutex> lk(e->mu);
+    use_device(e);
+    be_sync(sink_stream(e));
+    e->mixers.erase(std::remove(e->mixers.begin(), e->mixers.end(), m), e->mixers.end());
+    be_free(m->d_src); be_free(m->d_rings); be_free(m->d_map); be_free(m->d_peak); be_free(m->d_out); be_host_free(m->h_out);
+    be_free(m->d_stage); be_host_free(m->h_stage);
+    delete m;
+    return SDR_OK;
+}
+static int mixer_add(sdr_mixer *m, int chan_slot, int feed_rate, float gain, int *index) {
+    if (m->n_src >= kMixMaxSources) return fail(SDR_ERR_STATE, "sdr_mixer: too many sources");
+    MixSource s;
+    memset(&s, 0, sizeof s);
+    s.chan = chan_slot; s.feed_rate = feed_rate; s.gain = gain; s.active = 1;
+    s.ring_off = (int)((size_t)m->n_src * sdr_mixer::kRing); s.ring_cap = sdr_mixer::kRing;
+    sdr_stream_t ss = sink_stream(m->eng);
+    be_sync(ss);                                                  // (binding is rare; the copy below reads a stack object)
+    be_h2d(m->d_src + m->n_src, &s, sizeof s, ss);
+    be_sync(ss);
+    if (index) *index = m->n_src;
+    m->n_src += 1;
+    return SDR_OK;
+}
+// AudioThread::bindThread (src/audio/AudioThread.cpp:62-72): the channel's audio of every block joins this source's queue
+extern "C" int sdr_mixer_bind(sdr_mixer *m, sdr_chan *c, float gain, int *source_index) {
+    if (!m || !c || c->eng != m->eng || c->index < 0) return fail(SDR_ERR_ARG, "sdr_mixer_bind: bad arguments");
+    std::lock_guard<std::mutex> lk(m->eng->mu);
+    use_device(m->eng);
+    return mixer_add(m, c->index, c->audio_rate, gain, source_index);
+}
+extern "C" int sdr_mixer_add_source(sdr_mixer *m, float gain, int *source_index) {
+    if (!m) return fail(SDR_ERR_ARG, "sdr_mixer_add_source: null mixer");
+    std::lock_guard<std::mutex> lk(m->eng->mu);
+    use_device(m->eng);
+    return mixer_add(m, -1, 0, gain, source_index);
+}
+static int mixer_poke(sdr_mixer *m, int source, size_t field_off, const void *v, size_t bytes) {
+    if (!m || source < 0 || source >= m->n_src) return fail(SDR_ERR_ARG, "sdr_mixer: bad source");
+    std::lock_guard<std::mutex> lk(m->eng->mu);
+    use_device(m->eng);
+    sdr_stream_t ss = sink_stream(m->eng);
+    be_h2d(reinterpret_cast<char *>(m->d_src + source) + field_off, v, bytes, ss);
+    be_sync(ss);
+    return SDR_OK;
+}
+extern "C" int sdr_mixer_set_gain(sdr_mixer *m, int source, float gain) { return mixer_poke(m, source, offsetof(MixSource, gain), &gain, sizeof gain); }     // AudioThread::setGain
+extern "C" int sdr_mixer_set_active(sdr_mixer *m, int source, int active) { return mixer_poke(m, source, offsetof(MixSource, active), &active, sizeof active); }   // AudioThread::setActive
+// one AudioThreadInput pushed by the host (what DemodulatorThread does with audioOutputQueue->try_push, for audio from elsewhere)
+extern "C" int sdr_mixer_push(sdr_mixer *m, int source, const float *data, unsigned n, int channels, float peak, int sample_rate) {
+    if (!m || source < 0 || source >= m->n_src || (n && !data) || n > (unsigned)sdr_mixer::kStage) return fail(SDR_ERR_ARG, "sdr_mixer_push: bad arguments");
+    sdr_engine *e = m->eng;
+    std::lock_guard<std::mutex> lk(e->mu);
+    use_device(e);
+    sdr_stream_t ss = sink_stream(e);
+    be_sync(ss);
+    if (n) memcpy(m->h_stage, data, n * sizeof(float));
+    be_h2d(m->d_stage, m->h_stage, n * sizeof(float), ss);
+    MixArgs a = mixer_args(m);
+#ifndef SDR_EMU
+    k_mix_push<<<1, 256, 0, ss>>>(a, source, m->d_stage, (int)n, channels, peak, sample_rate);
+#else
+    {
+        MixSource &s = a.src[source];
+        if (s.q_count != kMixEntries && (int)n <= s.ring_cap) {
+            int w = s.w; if (w + (int)n > s.ring_cap) w = 0;
+            for (unsigned i = 0; i < n; ++i) a.rings[s.ring_off + w + i] = m->d_stage[i];
+            MixEntry en; en.start = w; en.n = (int)n; en.channels = channels; en.rate = sample_rate; en.peak = peak;
+            s.ent[(s.q_head + s.q_count) % kMixEntries] = en; s.q_count += 1; s.w = w + (int)n;
+        }
+    }
+#endif
+    e->launches += 1;
+    be_sync(ss);
+    return SDR_OK;
+}
+// audioCallback (src/audio/AudioThread.cpp:88-243): n_frames interleaved stereo frames of the mix into out[2 n_frames]
+extern "C" int sdr_mixer_render(sdr_mixer *m, unsigned n_frames, float *out) {
+    if (!m || !out || !n_frames || n_frames > m->max_frames) return fail(SDR_ERR_ARG, "sdr_mixer_render: bad arguments");
+    sdr_engine *e = m->eng;
+    sdr_stream_t ss;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        use_device(e);
+        ss = sink_stream(e);
+        MixArgs a = mixer_args(m);
+        a.n_frames = (int)n_frames;
+#ifndef SDR_EMU
+        if (m->n_src) k_mix_walk<<<(m->n_src + 127) / 128, 128, 0, ss>>>(a);
+        k_mix_sum<<<(2 * n_frames + 255) / 256, 256, 0, ss>>>(a);
+        k_mix_scale<<<(2 * n_frames + 255) / 256, 256, 0, ss>>>(a);
+#else
+        for (int j = 0; j < m->n_src; ++j) mix_walk_thread(a, j);
+        for (unsigned k = 0; k < 2 * n_frames; ++k) mix_sum_thread(a, (int)k);
+        { const float sc = mix_scale(a); if (sc != 1.0f) for (unsigned k = 0; k < 2 * n_frames; ++k) a.out[k] = a.out[k] * sc; }
+#endif
+        e->launches += 3;
+        be_d2h(m->h_out, m->d_out, 2 * (size_t)n_frames * sizeof(float), ss);
+        if (be_sync(ss)) return fail(SDR_ERR_CUDA, "sdr_mixer_render: stream sync failed");
+        memcpy(out, m->h_out, 2 * (size_t)n_frames * sizeof(float));
+    }
+    return SDR_OK;
+}
+// AudioFileWAV::writePayloadToFileStream (src/audio/AudioFileWAV.cpp:143-165): the last block's audio of a channel as the 16-bit words
+// a recording receives (clipping prevented through the block's peak); two-channel audio in whole {left, right} pairs
+extern "C" int sdr_chan_fetch_pcm16(sdr_chan *c, short *out, unsigned cap, unsigned *n) {
+    if (!c || !out || !n || c->index < 0) return fail(SDR_ERR_ARG, "sdr_chan_fetch_pcm16: bad arguments");
+    sdr_engine *e = c->eng;
+    std::lock_guard<std::mutex> lk(e->mu);
+    use_device(e);
+    sdr_stream_t ss = sink_stream(e);
+    const unsigned room = std::min<unsigned>(cap, (unsigned)c->cs.res_audio_cap);
+    short *d_out = nullptr; int *d_n = nullptr;
+    if (be_malloc((void **)&d_out, ((size_t)room + 2) * sizeof(short)) || be_malloc((void **)&d_n, sizeof(int))) { be_free(d_out); return fail(SDR_ERR_NOMEM, "sdr_chan_fetch_pcm16"); }
+    PcmArgs a;
+    a.cs = e->d_cs; a.results = e->d_results; a.chan = c->index; a.channels = (c->modem == MODEM_IQ || c->modem == MODEM_FMS) ? 2 : 1;
+    a.out = d_out; a.cap = (int)room; a.n_out = d_n;
+#ifndef SDR_EMU
+    k_pcm16<<<(room + 255) / 256 + 1, 256, 0, ss>>>(a);
+#else
+    for (unsigned i = 0; i < room + 1; ++i) pcm16_thread(a, (int)i);
+#endif
+    e->launches += 1;
+    int hn = 0;
+    be_d2h(&hn, d_n, sizeof hn, ss);
+    be_sync(ss);
+    if (hn > 0) { be_d2h(out, d_out, (size_t)hn * sizeof(short), ss); be_sync(ss); }
+    *n = (unsigned)hn;
+    be_free(d_out); be_free(d_n);
+    return SDR_OK;
+}
+// ScopeVisualProcessor (src/process/ScopeVisualProcessor.cpp:14-217) on the audio of one channel
+struct sdr_scope {
+    sdr_engine *eng = nullptr; sdr_chan *chan = nullptr;
+    int fft_size = 0, max_samples = 0;
+    float2 *d_in = nullptr, *d_tw = nullptr; float *d_mags = nullptr; double2 *d_ema = nullptr; double *d_scalars = nullptr;
+    float *d_wave = nullptr, *d_spec = nullptr; int *d_counts = nullptr; double *d_fc = nullptr; float2 *d_cf = nullptr; int *d_fs = nullptr;
+};
+extern "C" int sdr_scope_destroy(sdr_scope *s) {
+    if (!s) return SDR_OK;
+    std::lock_guard<std::mutex> lk(s->eng->mu);
+    use_device(s->eng);
+    be_sync(sink_stream(s->eng));
+    be_free(s->d_in); be_free(s->d_tw); be_free(s->d_mags); be_free(s->d_ema); be_free(s->d_scalars); be_free(s->d_wave); be_free(s->d_spec);
+    be_free(s->d_counts); be_free(s->d_fc); be_free(s->d_cf); be_free(s->d_fs);
+    delete s;
+    return SDR_OK;
+}
+extern "C" int sdr_scope_create(sdr_engine *e, sdr_chan *c, unsigned fft_size, unsigned max_samples, sdr_scope **out) {
+    if (!e || !c || !out || c->eng != e) return fail(SDR_ERR_ARG, "sdr_scope_create: bad arguments");
+    if (fft_size < 64 || (fft_size & (fft_size - 1)) || fft_size > (unsigned)kFft2MaxSub || !max_samples)
+        return fail(SDR_ERR_UNSUPPORTED, "sdr_scope_create: fft_size must be a power of two in [64, 8192]");
+    std::lock_guard<std::mutex> lk(e->mu);
+    use_device(e);
+    sdr_scope *s = new sdr_scope();
+    s->eng = e; s->chan = c; s->fft_size = (int)fft_size; s->max_samples = (int)max_samples;
+    int bad = 0;
+    bad |= be_malloc((void **)&s->d_in, fft_size * sizeof(float2));
+    bad |= be_malloc((void **)&s->d_tw, fft_size * sizeof(float2));
+    bad |= be_malloc((void **)&s->d_mags, fft_size * sizeof(float));
+    bad |= be_malloc((void **)&s->d_ema, (fft_size / 2) * sizeof(double2));
+    bad |= be_malloc((void **)&s->d_scalars, 4 * sizeof(double));
+    bad |= be_malloc((void **)&s->d_wave, 2 * (size_t)max_samples * sizeof(float));
+    bad |= be_malloc((void **)&s->d_spec, fft_size * sizeof(float));
+    bad |= be_malloc((void **)&s->d_counts, 2 * sizeof(int));
+    bad |= be_malloc((void **)&s->d_fc, 2 * sizeof(double));
+    bad |= be_malloc((void **)&s->d_cf, sizeof(float2));
+    bad |= be_malloc((void **)&s->d_fs, sizeof(int));
+    if (bad) { std::string msg = "sdr_scope_create: allocation failed"; (void)msg; e->mu.unlock(); sdr_scope_destroy(s); e->mu.lock(); return fail(SDR_ERR_NOMEM, "sdr_scope_create: allocation failed"); }
+    std::vector<float2> tw(fft_size);
+    for (unsigned k = 0; k < fft_size; ++k) { const double ang = -2.0 * 3.14159265358979323846 * (double)k / (double)fft_size; tw[k] = make_float2((float)std::cos(ang), (float)std::sin(ang)); }
+    sdr_stream_t ss = sink_stream(e);
+    be_h2d(s->d_tw, tw.data(), fft_size * sizeof(float2), ss);
+    be_memset(s->d_ema, 0, (fft_size / 2) * sizeof(double2), ss);
+    be_memset(s->d_scalars, 0, 4 * sizeof(double), ss);                       // fft_ceil_ma = fft_ceil_maa = fft_floor_ma = fft_floor_maa = 0 (:11-12)
+    be_memset(s->d_fs, 0, sizeof(int), ss);
+    be_sync(ss);
+    *out = s;
+    return SDR_OK;
+}
+// process() on the channel's last block: waveform points {x, y} (n_wave of them) and audio-spectrum points {x, y} (n_spec), floor / ceil
+extern "C" int sdr_scope_process(sdr_scope *s, float *wave_xy, unsigned *n_wave, float *spec_xy, unsigned *n_spec, double *floor_ceil) {
+    if (!s || !wave_xy || !spec_xy || !n_wave || !n_spec) return fail(SDR_ERR_ARG, "sdr_scope_process: null argument");
+    sdr_engine *e = s->eng;
+    std::lock_guard<std::mutex> lk(e->mu);
+    use_device(e);
+    sdr_stream_t ss = sink_stream(e);
+    ScopeArgs a;
+    a.cs = e->d_cs; a.results = e->d_results; a.chan = s->chan->index;
+    a.channels = (s->chan->modem == MODEM_IQ || s->chan->modem == MODEM_FMS) ? 2 : 1;
+    a.sample_rate = s->chan->audio_rate; a.input_rate = s->chan->bandwidth;
+    a.fft_size = s->fft_size; a.max_samples = s->max_samples; a.fft_in = s->d_in; a.mags = s->d_mags; a.ema = s->d_ema; a.scalars = s->d_scalars;
+    a.rate = (double)0.65f; a.wave_xy = s->d_wave; a.spec_xy = s->d_spec; a.counts = s->d_counts; a.floor_ceil = s->d_fc; a.red = nullptr;
+    SpecArgs f;
+    memset(&f, 0, sizeof f);
+    f.x = s->d_in; f.frame_start = s->d_fs; f.frame_stride = 0; f.F = 1; f.N = s->fft_size; f.fft_size = s->fft_size / 2; f.P = 1; f.nsub = s->fft_size;
+    f.tw = s->d_tw; f.mags = s->d_mags; f.frame_cf = s->d_cf;
+    const int work = std::max(s->fft_size, s->max_samples);
+#ifndef SDR_EMU
+    k_scope_prepare<<<(work + 255) / 256, 256, 0, ss>>>(a);
+    {
+        const Fft2Plan pl = fft2_plan(f.nsub);
+        const size_t smem = (size_t)(f.nsub + f.nsub / pl.r[0]) * sizeof(float2);
+        CUDA_TRY(cudaFuncSetAttribute(k_spec_fft2, cudaFuncAttributeMaxDynamicSharedMemorySize, kFft2SmemElems * (int)sizeof(float2)));
+        k_spec_fft2<<<1, kFft2Threads, smem, ss>>>(f);
+    }
+    k_scope_finish<<<1, 1024, 0, ss>>>(a);
+#else
+    {
+        const float pk = scope_wave_peak_serial(a);
+        for (int i = 0; i < work; ++i) scope_prepare_thread(a, i, pk);
+        const Fft2Plan pl = fft2_plan(f.nsub);
+        std::vector<float2> buf((size_t)f.nsub + f.nsub / 2 + 16);
+        std::vector<Fft2Regs> regs(kFft2Threads);
+        for (int t = 0; t < kFft2Threads; ++t) spec_fft2_load(f, 0, t, kFft2Threads, buf.data());
+        for (int hp = 0; hp < 2 * pl.passes; ++hp) for (int t = 0; t < kFft2Threads; ++t) spec_fft2_half(hp, f, 0, t, buf.data(), regs[t]);
+        double mx = 0.0, mn = 1.0;
+        for (int i = 0; i < a.fft_size / 2; ++i) { const double maa = scope_ema_bin(a, i); if (maa > mx) mx = maa; if (maa < mn) mn = maa; }
+        scope_finish_serial(a, mx, mn);
+        for (int i = 0; i < a.fft_size / 2; ++i) scope_points_thread(a, i);
+    }
+#endif
+    e->launches += 3;
+    int counts[2] = {0, 0};
+    double fc[2] = {0, 0};
+    be_d2h(counts, s->d_counts, sizeof counts, ss);
+    be_d2h(fc, s->d_fc, sizeof fc, ss);
+    if (be_sync(ss)) return fail(SDR_ERR_CUDA, "sdr_scope_process: stream sync failed");
+    if (counts[0] > 0) be_d2h(wave_xy, s->d_wave, 2 * (size_t)counts[0] * sizeof(float), ss);
+    if (counts[1] > 0) be_d2h(spec_xy, s->d_spec, 2 * (size_t)counts[1] * sizeof(float), ss);
+    be_sync(ss);
+    *n_wave = (unsigned)counts[0]; *n_spec = (unsigned)counts[1];
+    if (floor_ceil) { floor_ceil[0] = fc[0]; floor_ceil[1] = fc[1]; }
+    return SDR_OK;
+}
+
 extern "C" int sdr_design_kaiser(unsigned n, float fc, float as_db, float mu, float *h) { if (!h) return SDR_ERR_ARG; kaiser_lowpass(n, fc, as_db, mu, h); return SDR_OK; }
 extern "C" int sdr_design_nco_table(float *t) { if (!t) return SDR_ERR_ARG; nco_sine_table(t); return SDR_OK; }
 extern "C" uint32_t sdr_design_nco_step(float d) { return nco_phase_step(d); }

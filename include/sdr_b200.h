@@ -201,6 +201,30 @@ int sdr_pfb_reset(sdr_pfb *pfb);                                /* firpfbch_crcf
 int sdr_pfb_execute(sdr_pfb *pfb, const sdr_cf32 *iq, unsigned n, sdr_cf32 *out);              /* host buffers */
 int sdr_pfb_execute_device(sdr_pfb *pfb, const void *d_iq, unsigned n, void *d_out);           /* device buffers, engine stream */
 
+/* ---- audio-side consumers kept on the device ------------------------------------------------------
+ * Mixer = the RtAudio callback of the reference, audioCallback (src/audio/AudioThread.cpp:88-243): every bound source is one
+ * AudioThread (inputQueue of per-block AudioThreadInput entries, currentInput, audioQueuePtr, gain, active -- all in HBM).
+ * sdr_mixer_bind = AudioThread::bindThread for a demodulator of this engine: after every block its audio, peak and channel count
+ * join the source's queue without leaving the GPU.  sdr_mixer_render(n) = one callback for n frames: interleaved stereo, sources
+ * summed in binding order, the peak normalisation of :231-238.  sdr_mixer_push queues an AudioThreadInput from the host. */
+typedef struct sdr_mixer sdr_mixer;
+int sdr_mixer_create(sdr_engine *eng, int sample_rate, unsigned max_frames, sdr_mixer **out);
+int sdr_mixer_destroy(sdr_mixer *m);
+int sdr_mixer_bind(sdr_mixer *m, sdr_chan *chan, float gain, int *source_index);
+int sdr_mixer_add_source(sdr_mixer *m, float gain, int *source_index);
+int sdr_mixer_set_gain(sdr_mixer *m, int source, float gain);                  /* AudioThread::setGain */
+int sdr_mixer_set_active(sdr_mixer *m, int source, int active);                /* AudioThread::setActive */
+int sdr_mixer_push(sdr_mixer *m, int source, const float *data, unsigned n, int channels, float peak, int sample_rate);
+int sdr_mixer_render(sdr_mixer *m, unsigned n_frames, float *out_stereo /* 2 n_frames */);
+/* AudioFileWAV::writePayloadToFileStream (src/audio/AudioFileWAV.cpp:143-165): the channel's last block as 16-bit PCM words */
+int sdr_chan_fetch_pcm16(sdr_chan *chan, short *out, unsigned cap, unsigned *n);
+/* ScopeVisualProcessor (src/process/ScopeVisualProcessor.cpp:14-217) on a channel's audio: waveform points {x, y} and the audio
+ * spectrum's points {x, y} with its running averages; floor_ceil = {fft_floor_maa, fft_ceil_maa} */
+typedef struct sdr_scope sdr_scope;
+int sdr_scope_create(sdr_engine *eng, sdr_chan *chan, unsigned fft_size, unsigned max_samples, sdr_scope **out);
+int sdr_scope_destroy(sdr_scope *s);
+int sdr_scope_process(sdr_scope *s, float *wave_xy, unsigned *n_wave, float *spec_xy, unsigned *n_spec, double *floor_ceil);
+
 /* ---- design introspection (host only; used by the tests to pin filter tables against the reference) ---------------- */
 int sdr_design_kaiser(unsigned n, float fc, float as_db, float mu, float *h);
 int sdr_design_nco_table(float *sintab1024);

@@ -602,6 +602,175 @@ API void ref_chan_meter(void *h, float *level_floor_ceil3, int *squelched) {
     if (squelched) *squelched = c->squelched ? 1 : 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Audio-side consumers
+//   audioCallback                         src/audio/AudioThread.cpp:88-243   (the mix of every bound AudioThread)
+//   AudioFileWAV::writePayloadToFileStream src/audio/AudioFileWAV.cpp:143-165 (16-bit PCM)
+//   ScopeVisualProcessor::process         src/process/ScopeVisualProcessor.cpp:60-217 (waveform + audio spectrum)
+// ---------------------------------------------------------------------------------------------------------
+struct RefAudioInput { int sampleRate, channels; float peak; std::vector<float> data; };
+struct RefMixSource {                                   // the members of a bound AudioThread the callback touches
+    std::vector<RefAudioInput *> queue;                 // inputQueue (front = oldest)
+    RefAudioInput *currentInput = nullptr;
+    size_t audioQueuePtr = 0;
+    float gain = 1.0f;
+    bool active = true;
+    bool try_pop() { if (queue.empty()) { return false; } delete currentInput; currentInput = queue.front(); queue.erase(queue.begin()); return true; }
+};
+struct RefMixer { int sampleRate; std::vector<RefMixSource *> bound; };
+API void *ref_mixer_create(int sampleRate) { auto *m = new RefMixer; m->sampleRate = sampleRate; return m; }
+API void ref_mixer_destroy(void *h) {
+    auto *m = (RefMixer *)h;
+    for (auto *s : m->bound) { for (auto *q : s->queue) delete q; delete s->currentInput; delete s; }
+    delete m;
+}
+API int ref_mixer_add_source(void *h, float gain) { auto *m = (RefMixer *)h; auto *s = new RefMixSource; s->gain = gain; m->bound.push_back(s); return (int)m->bound.size() - 1; }
+API void ref_mixer_set_gain(void *h, int idx, float gain) { ((RefMixer *)h)->bound[(size_t)idx]->gain = gain; }
+API void ref_mixer_push(void *h, int idx, const float *data, unsigned n, int channels, float peak, int sampleRate) {
+    auto *in = new RefAudioInput; in->sampleRate = sampleRate; in->channels = channels; in->peak = peak; in->data.assign(data, data + n);
+    ((RefMixer *)h)->bound[(size_t)idx]->queue.push_back(in);
+}
+// audioCallback (AudioThread.cpp:88-243), statement by statement; `src` = the controller, `srcmix` = a bound thread
+API void ref_mixer_callback(void *h, float *out, unsigned nBufferFrames) {
+    auto *src = (RefMixer *)h;
+    memset(out, 0, nBufferFrames * 2 * sizeof(float));
+    double peak = 0.0;
+    for (size_t j = 0; j < src->bound.size(); j++) {
+        RefMixSource *srcmix = src->bound[j];
+        if (srcmix->queue.empty() || !srcmix->active) continue;                       // :122 (an empty inputQueue skips the thread, whatever currentInput still holds)
+        if (!srcmix->currentInput) {                                                  // :126-134
+            srcmix->audioQueuePtr = 0;
+            srcmix->try_pop();
+            continue;
+        }
+        if (srcmix->currentInput->sampleRate != src->sampleRate) {                    // :136-155
+            while (srcmix->try_pop()) {
+                if (srcmix->currentInput && srcmix->currentInput->sampleRate == src->sampleRate) break;
+                delete srcmix->currentInput; srcmix->currentInput = nullptr;
+            }
+            srcmix->audioQueuePtr = 0;
+            if (!srcmix->currentInput) continue;
+        }
+        if (srcmix->currentInput->channels == 0 || srcmix->currentInput->data.empty()) {   // :158-171
+            if (!srcmix->queue.empty()) {
+                srcmix->audioQueuePtr = 0;
+                delete srcmix->currentInput; srcmix->currentInput = nullptr;
+                if (!srcmix->try_pop()) continue;
+            }
+            continue;
+        }
+        double mixPeak = srcmix->currentInput->peak * srcmix->gain;                   // :173
+        if (srcmix->currentInput->channels == 1) {                                    // :175-202
+            for (unsigned int i = 0; i < nBufferFrames; i++) {
+                if (srcmix->audioQueuePtr >= srcmix->currentInput->data.size()) {
+                    srcmix->audioQueuePtr = 0;
+                    delete srcmix->currentInput; srcmix->currentInput = nullptr;
+                    if (!srcmix->try_pop()) break;
+                    double srcPeak = srcmix->currentInput->peak * srcmix->gain;
+                    if (mixPeak < srcPeak) mixPeak = srcPeak;
+                }
+                if (srcmix->currentInput && !srcmix->currentInput->data.empty()) {
+                    float v = srcmix->currentInput->data[srcmix->audioQueuePtr] * srcmix->gain;
+                    out[i * 2] += v;
+                    out[i * 2 + 1] += v;
+                }
+                srcmix->audioQueuePtr++;
+            }
+        } else {                                                                      // :203-226
+            for (unsigned int i = 0, iMax = srcmix->currentInput->channels * nBufferFrames; i < iMax; i++) {
+                if (srcmix->audioQueuePtr >= srcmix->currentInput->data.size()) {
+                    srcmix->audioQueuePtr = 0;
+                    delete srcmix->currentInput; srcmix->currentInput = nullptr;
+                    if (!srcmix->try_pop()) break;
+                    double srcPeak = srcmix->currentInput->peak * srcmix->gain;
+                    if (mixPeak < srcPeak) mixPeak = srcPeak;
+                }
+                if (srcmix->currentInput && !srcmix->currentInput->data.empty())
+                    out[i] = out[i] + srcmix->currentInput->data[srcmix->audioQueuePtr] * srcmix->gain;
+                srcmix->audioQueuePtr++;
+            }
+        }
+        peak += mixPeak;                                                              // :228
+    }
+    if (peak > 1.0) {                                                                 // :231-238
+        float invPeak = (float)(1.0 / peak);
+        for (unsigned int i = 0; i < nBufferFrames * 2; i++) out[i] *= invPeak;
+    }
+}
+// AudioFileWAV::writePayloadToFileStream (:143-165): the 16-bit little-endian words it writes for data[start, end)
+API unsigned ref_wav_payload(const float *data, unsigned start, unsigned end, int channels, float peak, short *out) {
+    float intScale = (peak < 1.0) ? 32767.0f : (32767.0f / peak);
+    unsigned k = 0;
+    if (channels == 1) {
+        for (size_t i = start, iMax = end; i < iMax; i++) out[k++] = (short)int(data[i] * intScale);
+    } else if (channels == 2) {
+        for (size_t i = start, iMax = end / 2; i < iMax; i++) { out[k++] = (short)int(data[i * 2] * intScale); out[k++] = (short)int(data[i * 2 + 1] * intScale); }
+    }
+    return k;
+}
+// ScopeVisualProcessor (:14-217): waveform (type 0, SCOPE_MODE_Y) and the audio spectrum with its running averages
+struct RefScope {
+    unsigned fftSize = 0, maxScopeSamples = 1024;
+    double fft_average_rate = 0.65f, fft_ceil_ma = 0, fft_ceil_maa = 0, fft_floor_ma = 0, fft_floor_maa = 0;
+    std::vector<lq_cf> fftInData, fftOutput;
+    std::vector<double> fft_result, fft_result_ma, fft_result_maa;
+    fftplan fftPlan = nullptr;
+};
+API void *ref_scope_create(unsigned fftSize, unsigned maxScopeSamples) {
+    auto *s = new RefScope; s->fftSize = fftSize; s->maxScopeSamples = maxScopeSamples;
+    s->fftInData.resize(fftSize); s->fftOutput.resize(fftSize);
+    s->fftPlan = fft_create_plan(fftSize, s->fftInData.data(), s->fftOutput.data(), +1, 0);      // :23-34
+    return s;
+}
+API void ref_scope_destroy(void *h) { auto *s = (RefScope *)h; if (s->fftPlan) fft_destroy_plan(s->fftPlan); delete s; }
+// one AudioThreadInput through process(): waveform points (x, y interleaved; returns their count / 2) and spectrum points
+API unsigned ref_scope_process(void *h, const float *data, unsigned n, int channels, int sampleRate, int inputRate,
+                               float *waveform_xy, float *spectrum_xy, unsigned *n_spec, double *floor_ceil2) {
+    auto *s = (RefScope *)h;
+    size_t i, iMax = n;
+    if (iMax > s->maxScopeSamples) iMax = s->maxScopeSamples;                                    // :73-76
+    float peak = 1.0f;
+    for (i = 0; i < iMax; i++) { float p = fabs(data[i]); if (p > peak) peak = p; }              // :87-94
+    for (i = 0; i < iMax; i++) {                                                                  // :119-122 (type 0)
+        waveform_xy[i * 2] = (float)((((double)i / (double)iMax) - 0.5) * 2.0);
+        waveform_xy[i * 2 + 1] = data[i] / peak;
+    }
+    const unsigned n_wave = (unsigned)iMax;
+    const unsigned fftSize = s->fftSize;
+    iMax = n;
+    if (channels == 1) {                                                                          // :133-142
+        for (i = 0; i < fftSize; i++) { s->fftInData[i].real = i < iMax ? data[i] : 0; s->fftInData[i].imag = 0; }
+    } else {                                                                                      // :143-153
+        iMax = iMax / 2;
+        for (i = 0; i < fftSize; i++) { s->fftInData[i].real = i < iMax ? data[i] + data[iMax + i] : 0; s->fftInData[i].imag = 0; }
+    }
+    double fft_ceil = 0, fft_floor = 1;
+    if (s->fft_result.size() < (fftSize / 2)) { s->fft_result.resize(fftSize / 2); s->fft_result_ma.resize(fftSize / 2); s->fft_result_maa.resize(fftSize / 2); }
+    fft_execute(s->fftPlan);
+    for (i = 0; i < (fftSize / 2); i++) { double a = (double)s->fftOutput[i].real, b = (double)s->fftOutput[i].imag; s->fft_result[i] = sqrt(a * a + b * b); }
+    for (i = 0; i < (fftSize / 2); i++) {                                                         // :182-192
+        s->fft_result_ma[i] += (s->fft_result[i] - s->fft_result_ma[i]) * s->fft_average_rate;
+        s->fft_result_maa[i] += (s->fft_result_ma[i] - s->fft_result_maa[i]) * s->fft_average_rate;
+        if (s->fft_result_maa[i] > fft_ceil) fft_ceil = s->fft_result_maa[i];
+        if (s->fft_result_maa[i] < fft_floor) fft_floor = s->fft_result_maa[i];
+    }
+    s->fft_ceil_ma = s->fft_ceil_ma + (fft_ceil - s->fft_ceil_ma) * 0.05;
+    s->fft_ceil_maa = s->fft_ceil_maa + (s->fft_ceil_ma - s->fft_ceil_maa) * 0.05;
+    s->fft_floor_ma = s->fft_floor_ma + (fft_floor - s->fft_floor_ma) * 0.05;
+    s->fft_floor_maa = s->fft_floor_maa + (s->fft_floor_ma - s->fft_floor_maa) * 0.05;
+    unsigned int outSize = fftSize / 2;
+    if (sampleRate != inputRate) outSize = (int)floor((float)outSize * ((float)sampleRate / (float)inputRate));
+    for (i = 0; i < outSize; i++) {                                                               // :207-211
+        float v = (log10(s->fft_result_maa[i] + 0.25 - (s->fft_floor_maa - 0.75)) / log10((s->fft_ceil_maa + 0.25) - (s->fft_floor_maa - 0.75)));
+        spectrum_xy[i * 2] = (float)((double)i / (double)(outSize));
+        spectrum_xy[i * 2 + 1] = v;
+    }
+    if (n_spec) *n_spec = outSize;
+    if (floor_ceil2) { floor_ceil2[0] = s->fft_floor_maa; floor_ceil2[1] = s->fft_ceil_maa; }
+    return n_wave;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // FFTDataDistributor framing             src/process/FFTDataDistributor.cpp:28-144
 // ---------------------------------------------------------------------------------------------------------

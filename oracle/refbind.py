@@ -234,3 +234,68 @@ class RefSpectrum:
 
     def close(self):
         self.ref.L.ref_spectrum_destroy(self.h)
+
+
+class RefMixer:
+    """audioCallback (src/audio/AudioThread.cpp:88-243) restated in oracle/ref_chain.cpp."""
+
+    def __init__(self, ref, sample_rate=48000):
+        L = self.L = ref.L
+        L.ref_mixer_create.restype = C.c_void_p; L.ref_mixer_create.argtypes = [C.c_int]
+        L.ref_mixer_destroy.argtypes = [C.c_void_p]
+        L.ref_mixer_add_source.argtypes = [C.c_void_p, C.c_float]
+        L.ref_mixer_set_gain.argtypes = [C.c_void_p, C.c_int, C.c_float]
+        L.ref_mixer_push.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint, C.c_int, C.c_float, C.c_int]
+        L.ref_mixer_callback.argtypes = [C.c_void_p, C.c_void_p, C.c_uint]
+        self.h = C.c_void_p(L.ref_mixer_create(int(sample_rate)))
+
+    def add_source(self, gain=1.0):
+        return self.L.ref_mixer_add_source(self.h, float(gain))
+
+    def set_gain(self, i, gain):
+        self.L.ref_mixer_set_gain(self.h, int(i), float(gain))
+
+    def push(self, i, data, channels=1, peak=0.0, sample_rate=48000):
+        d = np.ascontiguousarray(data, np.float32)
+        self.L.ref_mixer_push(self.h, int(i), _p(d), d.size, int(channels), float(peak), int(sample_rate))
+
+    def callback(self, n_frames):
+        out = np.zeros(2 * n_frames, np.float32)
+        self.L.ref_mixer_callback(self.h, _p(out), int(n_frames))
+        return out
+
+    def close(self):
+        self.L.ref_mixer_destroy(self.h)
+
+
+class RefScope:
+    """ScopeVisualProcessor (src/process/ScopeVisualProcessor.cpp:14-217) restated in oracle/ref_chain.cpp."""
+
+    def __init__(self, ref, fft_size=1024, max_samples=1024):
+        L = self.L = ref.L
+        L.ref_scope_create.restype = C.c_void_p; L.ref_scope_create.argtypes = [C.c_uint, C.c_uint]
+        L.ref_scope_destroy.argtypes = [C.c_void_p]
+        L.ref_scope_process.restype = C.c_uint
+        L.ref_scope_process.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        self.fft_size, self.max_samples = fft_size, max_samples
+        self.h = C.c_void_p(L.ref_scope_create(fft_size, max_samples))
+
+    def process(self, data, channels, sample_rate, input_rate):
+        d = np.ascontiguousarray(data, np.float32)
+        wave = np.zeros(2 * max(self.max_samples, 1), np.float32); spec = np.zeros(self.fft_size, np.float32)
+        ns = C.c_uint(); fc = np.zeros(2, np.float64)
+        nw = self.L.ref_scope_process(self.h, _p(d), d.size, int(channels), int(sample_rate), int(input_rate), _p(wave), _p(spec), C.byref(ns), _p(fc))
+        return wave[:2 * nw].copy(), spec[:2 * ns.value].copy(), fc
+
+    def close(self):
+        self.L.ref_scope_destroy(self.h)
+
+
+def ref_wav_payload(ref, data, channels, peak):
+    """AudioFileWAV::writePayloadToFileStream's 16-bit words for data[0, len)."""
+    d = np.ascontiguousarray(data, np.float32)
+    out = np.zeros(d.size + 2, np.int16)
+    ref.L.ref_wav_payload.restype = C.c_uint
+    ref.L.ref_wav_payload.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_int, C.c_float, C.c_void_p]
+    n = ref.L.ref_wav_payload(_p(d), 0, d.size, int(channels), float(peak), _p(out))
+    return out[:n].copy()

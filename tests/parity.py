@@ -512,3 +512,76 @@ def check_fm_stereo(lib, ref, n_blocks=10):
     a = out[0]["audio"].reshape(-1, 2)[4000:]
     assert np.std(a[:, 0]) > 0.05 and np.std(a[:, 1]) > 0.05 and np.std(a[:, 0] - a[:, 1]) > 0.05    # two different programmes came out
     return res
+
+
+def check_audio_sinks(lib, ref, n_blocks=8):
+    """SURVEY.md 8(f) row 4 on the device against the reference's code restated in the oracle: the audio mix of several demodulators
+    (audioCallback: sources summed in binding order, queue / currentInput / audioQueuePtr bookkeeping over callbacks of 512 frames that
+    do not line up with the 800-sample blocks, a two-channel source, gains, the peak normalisation), host-fed sources that exercise the
+    callback's other branches (empty input, foreign sample rate, inactive source), 16-bit PCM words, scope waveform + audio spectrum."""
+    from cubicsdr_b200 import Mixer, Scope, fetch_pcm16
+    from oracle.refbind import RefMixer, RefScope, ref_wav_payload
+    fs = 2400000
+    chans = [("FM", 200000, 300000), ("AM", 6000, -450000), ("USB", 5400, 600000), ("FMS", 200000, 900000), ("NBFM", 12500, -150000)]
+    signal = [("FM", 200000, 300000), ("AM", 6000, -450000), ("USB", 5400, 600000), ("FMS", 200000, 900000), ("NBFM", 12500, -150000)]
+    gains = [0.9, 0.6, 1.3, 0.5, 0.8]
+    N = synth.block_size(fs)
+    eng = Engine(lib, max_block=N)
+    cs = [Channel(eng, m, fs, bw, 48000, frequency=CENTER + off) for m, bw, off in chans]
+    mix, rmix = Mixer(eng, 48000, 2048), RefMixer(ref, 48000)
+    for c, g in zip(cs, gains):
+        mix.bind(c, g); rmix.add_source(g)
+    extra = mix.add_source(0.7); rmix.add_source(0.7)            # a host-fed source for the callback's rarer branches
+    scope, rscope = Scope(eng, cs[0], 1024, 1024), RefScope(ref, 1024, 1024)
+    scope2, rscope2 = Scope(eng, cs[3], 512, 600), RefScope(ref, 512, 600)        # two-channel input, truncated waveform
+    rng = np.random.default_rng(11)
+    worst = dict(mix=0.0, wave=0.0, spec=0.0, pcm=0)
+    for b in range(n_blocks):
+        x = synth.wideband(fs, N, signal, t0=b * N)
+        eng.submit(x, CENTER, fs); eng.wait()
+        # the reference side queues the ENGINE's audio (the mixer is what is under test here; the demodulators have their own tests)
+        for i, c in enumerate(cs):
+            a, lvl, pk, sk = c.fetch_audio()
+            if len(a):
+                rmix.push(i, a, channels=2 if chans[i][0] == "FMS" else 1, peak=pk, sample_rate=48000)
+            words = fetch_pcm16(c)
+            want = ref_wav_payload(ref, a, 2 if chans[i][0] == "FMS" else 1, pk)
+            worst["pcm"] += int(np.count_nonzero(words != want)) if len(words) == len(want) else 10 ** 6
+            if i == 0:
+                w, s_, fc = scope.process(); rw, rs, rfc = rscope.process(a, 1, 48000, cs[0].bandwidth)
+                assert len(w) == len(rw) and len(s_) == len(rs)
+                worst["wave"] = max(worst["wave"], float(np.abs(w - rw).max())); worst["spec"] = max(worst["spec"], relrms(s_[1::2], rs[1::2]))
+                assert np.allclose(fc, rfc, rtol=1e-5, atol=1e-9)
+            if i == 3:
+                w, s_, fc = scope2.process(); rw, rs, rfc = rscope2.process(a, 2, 48000, cs[3].bandwidth)
+                assert len(w) == len(rw) and len(s_) == len(rs)
+                worst["wave"] = max(worst["wave"], float(np.abs(w - rw).max())); worst["spec"] = max(worst["spec"], relrms(s_[1::2], rs[1::2]))
+        # host-fed source: ordinary data, an empty input, a foreign rate, a pause
+        if b % 4 == 0:
+            d = (0.2 * rng.standard_normal(700)).astype(np.float32)
+            mix.push(extra, d, 1, 0.6, 48000); rmix.push(extra, d, 1, 0.6, 48000)
+        elif b % 4 == 1:
+            e0 = np.zeros(0, np.float32)
+            mix.push(extra, e0, 1, 0.0, 48000); rmix.push(extra, e0, 1, 0.0, 48000)
+            d = (0.2 * rng.standard_normal(300)).astype(np.float32)
+            mix.push(extra, d, 2, 0.5, 48000); rmix.push(extra, d, 2, 0.5, 48000)
+        elif b % 4 == 2:
+            d = (0.2 * rng.standard_normal(400)).astype(np.float32)
+            mix.push(extra, d, 1, 0.4, 44100); rmix.push(extra, d, 1, 0.4, 44100)
+            mix.push(extra, d, 1, 0.4, 48000); rmix.push(extra, d, 1, 0.4, 48000)
+        if b == 5:
+            mix.set_gain(1, 2.5); rmix.set_gain(1, 2.5)
+        for cb in range(2 if b % 3 else 1):                       # 512-frame callbacks, sometimes one, sometimes two per block
+            got, want = mix.render(512), rmix.callback(512)
+            worst["mix"] = max(worst["mix"], float(np.abs(want).max()))
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), "block %d callback %d: %d of %d mixed samples differ (max %.3g)" % (
+                b, cb, int(np.count_nonzero(got != want)), got.size, float(np.abs(got - want).max()))
+    assert worst["mix"] > 0.05                                       # the callbacks did carry audio
+    assert worst["pcm"] == 0 and worst["wave"] <= 1e-6 and worst["spec"] <= TOL, worst
+    for o in (mix, scope, scope2):
+        o.close()
+    rmix.close(); rscope.close(); rscope2.close()
+    for c in cs:
+        c.close()
+    eng.close()
+    return worst

@@ -272,3 +272,7 @@ def test_fm_stereo_modem(emu_lib, ref):
 
 def test_dc_window_replay_bit_exact(emu_lib, ref):
     parity.check_dc_window(emu_lib, ref)
+
+
+def test_audio_side_consumers(emu_lib, ref):
+    print(parity.check_audio_sinks(emu_lib, ref))

@@ -256,3 +256,8 @@ def test_fm_stereo_modem_gpu(gpu_lib, ref):
     """ModemFMStereo on the device (see tests/parity.py check_fm_stereo for what can and cannot be asked of the pilot loop)."""
     res = parity.check_fm_stereo(gpu_lib, ref)
     print("FM stereo (sum err, difference err, reference sensitivity sum, difference):", res)
+
+
+def test_audio_side_consumers_gpu(gpu_lib, ref):
+    """Mixer (audioCallback), 16-bit PCM (AudioFileWAV) and scope (ScopeVisualProcessor) on the device, against the oracle's restatement."""
+    print(parity.check_audio_sinks(gpu_lib, ref))
