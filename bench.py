@@ -658,6 +658,7 @@ def main():
     ap.add_argument("--channelizer", action="store_true",
                     help="diagnostic: run the engine in channelizer mode (SDRPostThread::runPFBCH, SURVEY.md 8(f) row 1) -- not a contract line")
     ap.add_argument("--channels", type=int, default=0, help="diagnostic only: override the workload's channel count (not a contract line)")
+    ap.add_argument("--fft", type=int, default=-1, help="diagnostic only: override the workload's spectrum size (0 = no spectrum; not a contract line)")
     args = ap.parse_args()
     capture_stdout()
     rank = int(os.environ.get("RANK", "0"))
@@ -669,6 +670,8 @@ def main():
     N = synth.block_size(fs)
     if args.channels > 0 and wl["n_chan"]:
         wl = dict(wl, n_chan=args.channels, desc=wl["desc"] + " [DIAGNOSTIC: %d channels]" % args.channels)
+    if args.fft >= 0:
+        wl = dict(wl, fft=args.fft, desc=wl["desc"] + " [DIAGNOSTIC: spectrum size %d]" % args.fft)
     chans = synth.channel_plan(wl["plan"], fs, wl["n_chan"]) if wl["n_chan"] else []
 
     if args.workload == "pfb":

@@ -792,13 +792,16 @@ __global__ void __launch_bounds__(kFft2Threads) k_spec_fft2(SpecArgs a) {
         __syncthreads();
     }
 }
-// averages + frame ceil / floor (fused): one thread per bin, frames in order, one atomic pair per warp and frame
+// averages + frame ceil / floor (fused): one thread per bin, frames in order; the frame's ceil / floor are folded per warp, then per
+// CTA through shared memory (double-buffered by frame parity: one barrier per frame), and merged with one atomic pair per CTA and frame
 __global__ void __launch_bounds__(kSpecThreads) k_spec_ema2(SpecArgs a) {
+    __shared__ float s_mx[2][kSpecThreads / 32], s_mn[2][kSpecThreads / 32];
     const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     const bool live = i < a.N;
     double ma = 0.0, maa = 0.0;
     if (live) { ma = a.ema[i].x; maa = a.ema[i].y; }
     unsigned *cf = reinterpret_cast<unsigned *>(a.frame_cf);
+    const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
     for (int f = 0; f < a.F; ++f) {
         float v = 0.f;
         if (live) spec_ema2_step(a, f, i, ma, maa, v);
@@ -808,9 +811,14 @@ __global__ void __launch_bounds__(kSpecThreads) k_spec_ema2(SpecArgs a) {
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
         }
-        if ((threadIdx.x & 31) == 0) {
-            atomicMax(cf + 2 * f, __float_as_uint(mx));
-            atomicMin(cf + 2 * f + 1, __float_as_uint(mn));
+        if (lane == 0) { s_mx[f & 1][warp] = mx; s_mn[f & 1][warp] = mn; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float cx = 0.f, cn = 1.f;
+#pragma unroll
+            for (int w = 0; w < kSpecThreads / 32; ++w) { cx = fmaxf(cx, s_mx[f & 1][w]); cn = fminf(cn, s_mn[f & 1][w]); }
+            atomicMax(cf + 2 * f, __float_as_uint(cx));
+            atomicMin(cf + 2 * f + 1, __float_as_uint(cn));
         }
     }
     if (live) a.ema[i] = make_double2(ma, maa);
