@@ -51,17 +51,17 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 // ---------------------------------------------------------------------------------------------------------------------
 // kernels (GPU) / serial replays (test-only emulator)
 // ---------------------------------------------------------------------------------------------------------------------
-// SMs the channel front kernel leaves free for the bit-exact DC blocker (k_dc_lanes: one lane per segment, four warps per
-// SM-exclusive CTA, i.e. one serial-chain warp per scheduler).  The replay's latency is the warm-up (24576 steps) plus one
-// segment; fewer SMs mean fewer, longer segments:
-//   >= 384 channels: 4 SMs (512 lanes; the front kernel is long and wants every SM it can get, the replay hides underneath)
-//   otherwise      : 8 SMs (1024 lanes: 1024-sample segments at 61.44 MSps)
-// SDR_B200_DC_SMS overrides (experiments).
+// SMs the channel front kernel leaves free for the DC blocker of the next block (the front CTAs take a whole SM's registers, so
+// nothing else runs next to them): 8.  The warm-up replay puts 1024 lanes there (1024-sample segments at 61.44 MSps), the scan's
+// small CTAs and the candidate-window kernels start there and spread out when the front kernel ends.  Measured at 512 channels:
+// 4 SMs give the front kernel 3 % more room but stretch the DC stage to 0.55 ms (its scan CTAs queue on four SMs), which then
+// is the block period and costs the host entry 12 %; 8 SMs: DC 0.33 ms, hidden.  SDR_B200_DC_SMS overrides (experiments).
 static inline int dc_reserved_sms(size_t live_channels) {
     static int forced = -1;
     if (forced < 0) { const char *v = getenv("SDR_B200_DC_SMS"); forced = v ? atoi(v) : 0; }
     if (forced > 0) return forced > 32 ? 32 : forced;
-    return live_channels >= 384 ? 4 : 8;
+    (void)live_channels;
+    return 8;
 }
 constexpr int kResBuf = 3;           // host result buffers (ring): blocks a pipelined consumer may keep in flight + 1
 constexpr unsigned kDlWarpsHost = 4;   // warps per CTA of k_dc_lanes (one per scheduler)
