@@ -946,6 +946,18 @@ static bool tma_rows_map(CUtensorMap *m, float2 *base, unsigned row_samples, uns
 }
 #endif
 
+#ifndef SDR_EMU
+// cudaFuncSetAttribute is per device: a process that drives several GPUs (sdr_group_create) must raise the shared-memory limit of a
+// kernel on every one of them.  `flags` is the caller's static table; returns true the first time on the current device.
+static inline bool first_on_device(bool (&flags)[64]) {
+    int d = 0;
+    cudaGetDevice(&d);
+    d &= 63;
+    if (flags[d]) return false;
+    flags[d] = true;
+    return true;
+}
+#endif
 // candidate windows -> chunk maps -> walk + gather: the true state entering every tile lands in a.seg_in (dsp_dcwin.h)
 struct sdr_engine;
 static void mixers_feed(sdr_engine *e, sdr_stream_t ts);
@@ -956,8 +968,8 @@ static int launch_dc_window(const DcWinArgs &a, sdr_stream_t s, unsigned long lo
     k_dc_compose<<<2 * chunks, kDwCand, 0, s>>>(a);
     const size_t gbytes = (size_t)chunks * 2 * kDwCand * sizeof(short);
     const bool in_smem = gbytes <= 200 * 1024;
-    static bool attr_set = false;
-    if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(k_dc_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+    static bool attr_set[64];
+    if (first_on_device(attr_set)) CUDA_TRY(cudaFuncSetAttribute(k_dc_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     k_dc_resolve<<<1, 1024, in_smem ? gbytes : 0, s>>>(a, in_smem ? 1 : 0);
 #else
     (void)s;
@@ -991,20 +1003,18 @@ static int launch_dc_exact(const DcExactArgs &a, unsigned long long tma_rows, sd
         if (use_tma && tma_rows) {
             if (!tma_rows_map(&in_map, const_cast<float2 *>(a.xraw) - a.warm, (unsigned)a.seg_len, tma_rows / (unsigned)a.seg_len))
                 return fail(SDR_ERR_CUDA, "cuTensorMapEncodeTiled failed for the DC replay's stream tensors");
-            static bool attr_set = false;
+            static bool attr_set[64];
             static int form = -1;
-            if (!attr_set) {
+            if (first_on_device(attr_set)) {
                 CUDA_TRY(cudaFuncSetAttribute(k_dc_lanes_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDtSmem));
                 CUDA_TRY(cudaFuncSetAttribute(k_dc_lanes_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDtSmem));
-                const char *f = getenv("SDR_B200_DC_FORM");
-                form = (f && f[0] == '0') ? 0 : 1;
-                attr_set = true;
             }
+            if (form < 0) { const char *f = getenv("SDR_B200_DC_FORM"); form = (f && f[0] == '0') ? 0 : 1; }
             if (form) k_dc_lanes_tma<1><<<(warps + kDlWarps - 1) / kDlWarps, 32 * kDlWarps, kDtSmem, s>>>(a, in_map);
             else k_dc_lanes_tma<0><<<(warps + kDlWarps - 1) / kDlWarps, 32 * kDlWarps, kDtSmem, s>>>(a, in_map);
         } else {
-            static bool attr_set = false;
-            if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(k_dc_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, kDlSmem)); attr_set = true; }
+            static bool attr_set[64];
+            if (first_on_device(attr_set)) CUDA_TRY(cudaFuncSetAttribute(k_dc_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, kDlSmem));
             k_dc_lanes<<<(warps + kDlWarps - 1) / kDlWarps, 32 * kDlWarps, kDlSmem, s>>>(a);
         }
     } else {
@@ -1050,11 +1060,8 @@ static void launch_dc(const DcArgs &a, bool apply, sdr_stream_t s, unsigned long
 template <int K>
 static int launch_front_k(const FrontArgs &a, int jobs, int reserved_sms, sdr_stream_t s) {
 #ifndef SDR_EMU
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(k_chan_front<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrontSmemBytes));
-        attr_set = true;
-    }
+    static bool attr_set[64];
+    if (first_on_device(attr_set)) CUDA_TRY(cudaFuncSetAttribute(k_chan_front<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrontSmemBytes));
     // one CTA per SM while the jobs fit; reserved_sms SMs stay free for the DC blocker's serial chains
     const int sms = 148 - reserved_sms;
     int n_cta = (jobs + kFrontWarps - 1) / kFrontWarps;
@@ -1098,11 +1105,8 @@ static int launch_spectrum(const SpecArgs &a, sdr_stream_t s, unsigned long long
 #ifndef SDR_EMU
     const Fft2Plan pl = fft2_plan(a.nsub);
     const size_t smem = (size_t)(a.nsub + a.nsub / pl.r[0]) * sizeof(float2);
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(k_spec_fft2, cudaFuncAttributeMaxDynamicSharedMemorySize, kFft2SmemElems * (int)sizeof(float2)));
-        attr_set = true;
-    }
+    static bool attr_set[64];
+    if (first_on_device(attr_set)) CUDA_TRY(cudaFuncSetAttribute(k_spec_fft2, cudaFuncAttributeMaxDynamicSharedMemorySize, kFft2SmemElems * (int)sizeof(float2)));
     k_spec_fft2<<<a.F * a.P, kFft2Threads, smem, s>>>(a);
     if (a.rebin || a.shift) {
         k_view_ema_move<<<(a.N + kSpecThreads - 1) / kSpecThreads, kSpecThreads, 0, s>>>(a, 0);
@@ -2373,10 +2377,13 @@ static int ensure_results(sdr_engine *e) {
 #ifndef SDR_EMU
 // the filterbank kernel's dynamic shared memory grows with the channel count: raise the opt-in limit monotonically
 static int pfb_allow_smem(size_t bytes) {
-    static size_t allowed = 48 * 1024;
-    if (bytes > allowed) {
+    static size_t allowed[64];                                     // per device (zero-initialised: anything above 48 KB asks once)
+    int d = 0;
+    cudaGetDevice(&d);
+    d &= 63;
+    if (bytes > 48 * 1024 && bytes > allowed[d]) {
         CUDA_TRY(cudaFuncSetAttribute(k_pfb_analyze, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        allowed = bytes;
+        allowed[d] = bytes;
     }
     return SDR_OK;
 }
@@ -3008,6 +3015,12 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
 #endif
     time_mark(e, 4);
     if (e->timing && e->time_pending < sdr_engine::kTimeSets) e->time_pending++;
+#ifndef SDR_EMU
+    {   // a kernel that could not be launched (shared-memory limit, bad configuration) must not pass silently
+        const cudaError_t le = cudaGetLastError();
+        if (le != cudaSuccess) return fail(SDR_ERR_CUDA, std::string("kernel launch failed in submit: ") + cudaGetErrorString(le));
+    }
+#endif
     return join_side();
 }
 
