@@ -2590,7 +2590,17 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         const size_t smem = pfb_smem_elems(pa.M, pa.p) * sizeof(float2);
         { int r = pfb_allow_smem(smem); if (r) return r; }
         k_pfb_analyze<<<tiles, kPfbThreads, smem, dcs>>>(pa);
-        if (pfb_ch0_active) k_pfb_dc0<<<1, 32, 0, dcs>>>(ch0, ch0_dc, (int)n_ch, (float)e->dc_a, e->d_pfb_dc_state);
+        if (pfb_ch0_active) {
+            // channel 0's DC blocker (runDemodChannels, SDRPostThread.cpp:363-375): the same float recurrence at the channel rate,
+            // one warp with the samples prefetched three batches ahead (k_dc_exact), the carried state published by k_dc_verify
+            DcExactArgs xa;
+            memset(&xa, 0, sizeof xa);
+            xa.xraw = ch0; xa.y = ch0_dc; xa.n = (int)n_ch; xa.n_seg = 1; xa.seg_len = (int)n_ch; xa.warm = 0;
+            xa.c = (float)e->dc_a; xa.one = 1.0f; xa.seg_in = e->d_seg_in; xa.seg_out = e->d_seg_out; xa.fstate = e->d_pfb_dc_state;
+            xa.fixups = e->d_fixups; xa.start = nullptr; xa.junction_bad = e->d_dw_stats + 1;
+            k_dc_exact<<<1, 32, 0, dcs>>>(xa);
+            k_dc_verify<<<1, 256, 0, dcs>>>(xa);
+        }
 #else
         {
             std::vector<float2> sm(pfb_smem_elems(pa.M, pa.p));
@@ -2599,7 +2609,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
             if (pfb_ch0_active) pfb_dc0_serial(ch0, ch0_dc, (int)n_ch, (float)e->dc_a, e->d_pfb_dc_state);
         }
 #endif
-        e->launches += pfb_ch0_active ? 2 : 1;
+        e->launches += pfb_ch0_active ? 3 : 1;
         e->pfb_last_frames = n_ch; e->pfb_have_block = true;
     }
 #ifndef SDR_EMU
