@@ -599,7 +599,8 @@ def run_engine_workload(cx, wl, chans, steps, warmup, min_seconds, channelizer=F
             except Exception:
                 traffic = None
         names = {"front": "k_chan_front (NCO mix + half-band cascade)", "spectrum": "spectrum kernels (k_spec_*)",
-                 "dc": "k_dc_lanes (bit-exact DC blocker replay: serial float recurrence, latency bound)"}
+                 "dc": "DC blocker stage (double-precision scan + bit-exact float replay: candidate windows k_dc_window / k_dc_compose / k_dc_resolve / k_dc_exact, "
+                       "or warmed-up segments k_dc_lanes_tma at >= 256 channels; latency bound)"}
         hbm = {"achieved": hbm_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": hbm_gbs / peak,
                "alg_bytes_per_sample": b_alg,
                "note": "contract figure: algorithmic bytes per launch / kernel time / measured HBM copy peak"}
