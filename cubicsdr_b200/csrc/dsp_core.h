@@ -257,7 +257,8 @@ SDR_HD inline void dc_apply_phase(int ph, const DcArgs &a, int bid, int tid, DcS
 //     from the true carried state of segment 0, that every output is the reference's; a failing junction (rare) is
 //     replayed serially by dc_exact_verify.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kDcWarm = 24576;      // warm-up samples (a multiple of kDcTile); P(junction not coalesced) ~ 1.5e-4
+constexpr int kDcWarm = 12288;      // warm-up samples (a multiple of kDcTile); P(junction not coalesced) ~ 7 % (1.5e-4 at 24576): the
+                                    // tiles whose warmed-up state turns out wrong are re-run in parallel from their neighbour's end state
 constexpr int kDcMinSpec = 32768;   // blocks shorter than this are replayed serially (the warm-up alone is 24576 steps)
 
 struct DcExactArgs {
@@ -277,6 +278,9 @@ struct DcExactArgs {
     unsigned *fixups;                // [1] junctions that had to be replayed (diagnostic)
     const float2 *start;             // non-null: the true state entering every segment is known (dsp_dcwin.h), no warm-up
     unsigned *junction_bad;          // with `start`: set by a segment whose end state is not the next segment's start (k_dc_verify then runs)
+    int states_only;                 // warm-up kernels: leave the warmed-up state in seg_in[s] and stop (the tiles are replayed by k_dc_exact)
+    int no_publish;                  // with `start`: candidates, not proven states -- record seg_in / seg_out only
+    const int *fix_mask;             // non-null: re-run only segments s with fix_mask[s] != 0, each from seg_out[s - 1]
 };
 
 // one step of the reference recurrence for both components; no fused multiply-add allowed
@@ -299,6 +303,7 @@ SDR_HD SDR_FORCEINLINE void dc_ref_step(float c, float2 x, float2 &v, float2 &y)
 // (its tile grid is anchored at ITS start), or at this block's start if there is none.  Every lane of the GPU kernel
 // therefore starts at an index in [d, d + kDcTile).
 SDR_HD inline void dc_exact_plan(const DcExactArgs &a, int s, int &i_start, float2 &v0) {
+    if (a.fix_mask) { i_start = s * a.seg_len; v0 = a.seg_out[s > 0 ? s - 1 : 0]; return; }
     if (a.start) { i_start = s * a.seg_len; v0 = a.start[s]; return; }       // (segment 0: the walker put the carried state there)
     if (s == 0) { i_start = 0; v0 = a.fstate[0]; return; }
     const long long d = (long long)s * a.seg_len - a.warm;
@@ -327,7 +332,7 @@ SDR_HD inline void dc_exact_plan(const DcExactArgs &a, int s, int &i_start, floa
 // last segment, publish the carried state (k_dc_verify then has nothing to do)
 SDR_HD SDR_FORCEINLINE void dc_segment_done(const DcExactArgs &a, int s, float2 v_in, float2 v_out) {
     a.seg_in[s] = v_in; a.seg_out[s] = v_out;
-    if (a.start) {
+    if (a.start && !a.no_publish) {
         if (s + 1 < a.n_seg) {
             const float2 nx = a.start[s + 1];
             if (nx.x != v_out.x || nx.y != v_out.y) a.junction_bad[0] = 1u;

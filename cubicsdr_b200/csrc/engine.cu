@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(32) k_dc_exact(DcExactArgs a) {
     const int lane = threadIdx.x & 31;
     const int s = blockIdx.x;
     if (s >= a.n_seg) return;
+    if (a.fix_mask && !a.fix_mask[s]) return;                        // fix-up round: only the tiles whose start state was wrong
     int i0;
     float2 v;
     dc_exact_plan(a, s, i0, v);
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(32 * kDlWarps, 1) k_dc_lanes(DcExactArgs a) {
     const int p1 = (s < a.n_seg) ? ((p0 + L < n) ? p0 + L : n) : p0;
     const int d = p0 - W;                                            // this lane's sample at step 0
     const int d0 = s0 * L - W;                                       // same for lane 0 (streams are L apart)
-    const int nb = (W + L) / kDlBatch;
+    const int nb = a.states_only ? W / kDlBatch : (W + L) / kDlBatch;
     const long long lo = -(long long)a.raw_hist, hi = a.raw_end;     // readable extent of the raw stream: [lo, hi)
     const float c = a.c;
     // transposed copies: lanes 0-15 move stream 2 it, lanes 16-31 stream 2 it + 1, two samples (16 bytes) each
@@ -304,6 +305,7 @@ __global__ void __launch_bounds__(32 * kDlWarps, 1) k_dc_lanes(DcExactArgs a) {
         }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (a.states_only) { if (s < a.n_seg) a.seg_in[s] = v_in; return; }
     if (s < a.n_seg) dc_segment_done(a, s, v_in, v);
 }
 // ---- TMA + mbarrier helpers (cp.async.bulk.tensor: SASS UTMALDG / UTMASTG; mbarrier: SYNCS) -----------------------------------
@@ -416,8 +418,8 @@ k_dc_lanes_tma(DcExactArgs a, const __grid_constant__ CUtensorMap in_map) {
     const int p0 = s * L;
     const int p1 = live ? ((p0 + L < n) ? p0 + L : n) : p0;
     const int d = p0 - W;                                            // this lane's sample at step 0
-    const int nb = (W + L) / kDtBatch;
     const int kw = W / kDtBatch;                                     // batches [0, kw) warm up, [kw, nb) produce output
+    const int nb = a.states_only ? kw : (W + L) / kDtBatch;
     const float c = a.c, one = a.one;
     // A lane starts at i_begin.  Lanes whose warm-up begins in the previous block start at one of ITS tile boundaries, less than a
     // tile after step 0 and anywhere inside a batch: the first k1 batches test every step.  Every other start (tile boundaries
@@ -506,6 +508,7 @@ k_dc_lanes_tma(DcExactArgs a, const __grid_constant__ CUtensorMap in_map) {
         end_batch();
     }
     const float2 v_in = v;
+    if (a.states_only) { if (live) a.seg_in[s] = v_in; return; }    // the tiles themselves are replayed one warp each (k_dc_exact)
     // ---- output: 16 steps at a time through a padded tile (rows 144 B apart: the per-lane 16-byte writes of a quarter warp and
     //      the transposed reads -- eight lanes per row -- are both conflict-free); every row leaves as one full 128-byte line.
     //      (A TMA store per box was measured slower here: the proxy fence and the read-wait cost ~800 cycles per round.)
@@ -565,6 +568,15 @@ k_dc_lanes_tma(DcExactArgs a, const __grid_constant__ CUtensorMap in_map) {
         end_batch();
     }
     if (live) dc_segment_done(a, s, v_in, v);
+}
+// which tiles started from a state that is not their neighbour's end state (stats[2] counts them: parallel re-runs)
+__global__ void __launch_bounds__(256) k_dc_mark(DcExactArgs a, int *mask, unsigned *stats) {
+    const int s = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (s >= a.n_seg) return;
+    int bad = 0;
+    if (s > 0) { const float2 w = a.seg_in[s], t = a.seg_out[s - 1]; bad = (w.x != t.x) | (w.y != t.y); }
+    mask[s] = bad;
+    if (bad) atomicAdd(stats + 2, 1u);
 }
 // All junctions are compared in parallel; only when one of them fails (rare) does thread 0 walk them serially and replay.
 __global__ void __launch_bounds__(256) k_dc_verify(DcExactArgs a) {
@@ -989,13 +1001,20 @@ static int launch_dc_window(const DcWinArgs &a, sdr_stream_t s, unsigned long lo
 }
 
 // tma_rows: samples readable from xraw[-warm] on (rows of the input tensor = that / seg_len); 0 = use the cp.async kernel
-static int launch_dc_exact(const DcExactArgs &a, unsigned long long tma_rows, sdr_stream_t s, unsigned long long &launches) {
+static int launch_dc_exact(const DcExactArgs &a, unsigned long long tma_rows, sdr_stream_t s, unsigned long long &launches, int *fix_mask, unsigned *stats) {
 #ifndef SDR_EMU
     if (a.start) {
         // the true state entering every tile is known (candidate windows): one warp per tile, every lane runs the 1024-step chain
         // and keeps two outputs per batch -- a few hundred light CTAs anywhere on the chip, no warm-up, no staging kernel
         k_dc_exact<<<a.n_seg, 32, 0, s>>>(a);
-    } else if (a.n_seg > 1) {                                   // one lane per segment, SM-exclusive CTAs of four warps
+    } else if (a.n_seg > 1) {
+        // Warm-up form: one lane per tile (SM-exclusive CTAs of four warps on the SMs the front kernel leaves free) runs the
+        // chain over the kDcWarm samples in front of its tile from the exact state and leaves a CANDIDATE start state; the tiles
+        // are then replayed one warp each; tiles whose candidate was not their neighbour's end state (a few per cent) are re-run
+        // from it, in parallel, up to three rounds (a run of consecutive wrong candidates needs one round per member);
+        // k_dc_verify proves every junction and replays serially whatever is left.
+        DcExactArgs w = a;
+        w.states_only = 1;
         const int warps = (a.n_seg + 31) / 32;
         static int use_tma = -1;
         if (use_tma < 0) { const char *v = getenv("SDR_B200_DC_TMA"); use_tma = (v && v[0] == '0') ? 0 : 1; }
@@ -1010,19 +1029,29 @@ static int launch_dc_exact(const DcExactArgs &a, unsigned long long tma_rows, sd
                 CUDA_TRY(cudaFuncSetAttribute(k_dc_lanes_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDtSmem));
             }
             if (form < 0) { const char *f = getenv("SDR_B200_DC_FORM"); form = (f && f[0] == '0') ? 0 : 1; }
-            if (form) k_dc_lanes_tma<1><<<(warps + kDlWarps - 1) / kDlWarps, 32 * kDlWarps, kDtSmem, s>>>(a, in_map);
-            else k_dc_lanes_tma<0><<<(warps + kDlWarps - 1) / kDlWarps, 32 * kDlWarps, kDtSmem, s>>>(a, in_map);
+            if (form) k_dc_lanes_tma<1><<<(warps + kDlWarps - 1) / kDlWarps, 32 * kDlWarps, kDtSmem, s>>>(w, in_map);
+            else k_dc_lanes_tma<0><<<(warps + kDlWarps - 1) / kDlWarps, 32 * kDlWarps, kDtSmem, s>>>(w, in_map);
         } else {
             static bool attr_set[64];
             if (first_on_device(attr_set)) CUDA_TRY(cudaFuncSetAttribute(k_dc_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, kDlSmem));
-            k_dc_lanes<<<(warps + kDlWarps - 1) / kDlWarps, 32 * kDlWarps, kDlSmem, s>>>(a);
+            k_dc_lanes<<<(warps + kDlWarps - 1) / kDlWarps, 32 * kDlWarps, kDlSmem, s>>>(w);
         }
+        DcExactArgs r = a;                                           // every tile from its candidate
+        r.start = a.seg_in; r.no_publish = 1;
+        k_dc_exact<<<a.n_seg, 32, 0, s>>>(r);
+        DcExactArgs f = a;                                           // wrong candidates: from the neighbour's end state
+        f.fix_mask = fix_mask;
+        for (int round = 0; round < 3; ++round) {
+            k_dc_mark<<<(a.n_seg + 255) / 256, 256, 0, s>>>(a, fix_mask, stats);
+            k_dc_exact<<<a.n_seg, 32, 0, s>>>(f);
+        }
+        launches += 7;
     } else {
         k_dc_exact<<<1, 32, 0, s>>>(a);
     }
     k_dc_verify<<<1, 256, 0, s>>>(a);
 #else
-    (void)s; (void)tma_rows;
+    (void)s; (void)tma_rows; (void)fix_mask; (void)stats;
     for (int g = 0; g < a.n_seg; ++g) dc_exact_segment_serial(a, g, false, make_float2(0.f, 0.f));
     dc_exact_verify(a);
 #endif
@@ -1269,6 +1298,7 @@ struct sdr_engine {
     short *d_dw_gmap = nullptr;
     int *d_dw_entry = nullptr;
     unsigned *d_dw_stats = nullptr;
+    int *d_dc_fix_mask = nullptr;            // warm-up replay: tiles to re-run in a fix-up round
     int dc_window = -1;
     std::vector<struct sdr_mixer *> mixers;   // device-side audio mixers fed after every block (dsp_sink.h)
     unsigned long long dw_blocks = 0;
@@ -1497,6 +1527,7 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
         bad |= be_malloc((void **)&e->d_dw_gmap, chunks * 2 * kDwCand * sizeof(short));
         bad |= be_malloc((void **)&e->d_dw_entry, chunks * 2 * sizeof(int));
         bad |= be_malloc((void **)&e->d_dw_stats, 4 * sizeof(unsigned));
+        bad |= be_malloc((void **)&e->d_dc_fix_mask, (size_t)max_seg * sizeof(int));
         const char *w = getenv("SDR_B200_DC_WINDOW");
         if (w) e->dc_window = atoi(w) ? 1 : 0;
     }
@@ -1617,6 +1648,7 @@ extern "C" int sdr_engine_destroy(sdr_engine *e) {
     be_free(e->d_raw); be_free(e->d_blkbuf[0]); be_free(e->d_blkbuf[1]); be_free(e->d_rawbuf); be_free(e->d_scratch);
     for (int k = 0; k < sdr_engine::kInRing; ++k) { be_host_free(e->h_in[k]); be_free(e->d_in[k]); }
     be_free(e->d_tile_sum); be_free(e->d_tile_carry2[0]); be_free(e->d_tile_carry2[1]); be_free(e->d_dc_state);
+    be_free(e->d_dc_fix_mask);
     be_free(e->d_dw_st); be_free(e->d_dw_pst); be_free(e->d_dw_gmap); be_free(e->d_dw_entry); be_free(e->d_dw_stats);
     be_free(e->d_seg_in); be_free(e->d_seg_out); be_free(e->d_fstate); be_free(e->d_fixups); be_free(e->d_apow); be_free(e->d_nco);
     be_free(e->d_cs); be_free(e->d_cd2[0]); be_free(e->d_cd2[1]); be_free(e->d_st); be_host_free(e->h_cd); be_free(e->d_group); be_host_free(e->h_group);
@@ -1671,6 +1703,18 @@ extern "C" int sdr_engine_debug_dc_fixups(sdr_engine *e, unsigned *fixups, int *
     return SDR_OK;
 }
 // diagnostics: candidate-window replay -- stretches its walker had to run serially so far; blocks that took the window path
+// diagnostics: tiles the warm-up replay re-ran in its parallel fix-up rounds so far
+extern "C" int sdr_engine_debug_dc_reruns(sdr_engine *e, unsigned *reruns) {
+    if (!e || !reruns) return SDR_ERR_ARG;
+    std::lock_guard<std::mutex> lk(e->mu);
+    use_device(e);
+    be_sync(e->stream);
+    unsigned v[4] = {0, 0, 0, 0};
+    be_d2h(v, e->d_dw_stats, sizeof v, e->stream);
+    be_sync(e->stream);
+    *reruns = v[2];
+    return SDR_OK;
+}
 extern "C" int sdr_engine_debug_dc_window(sdr_engine *e, unsigned *serial_stretches, unsigned long long *window_blocks) {
     if (!e) return SDR_ERR_ARG;
     std::lock_guard<std::mutex> lk(e->mu);
@@ -2514,7 +2558,10 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         size_t live = 0;
         for (auto *c : e->chans) live += c != nullptr;
         const unsigned tiles_n = (n + kDcTile - 1) / kDcTile;
-        const bool window = e->exact_dc && tiles_n >= (unsigned)kDwMinTiles && (e->dc_window < 0 ? live < 256 : e->dc_window == 1);
+        // automatic choice: the windows' table pass is chip-wide work that competes with a long front kernel, the warm-up replay is
+        // ~0.2 ms of latency on the reserved SMs: windows for few channels or short blocks, the warm-up replay otherwise
+        const bool window = e->exact_dc && tiles_n >= (unsigned)kDwMinTiles &&
+                            (e->dc_window < 0 ? (live < 32 || (live < 256 && n <= 500000u)) : e->dc_window == 1);
         if (e->have_block && e->last_n > 0 && !window) {
             be_d2d(e->d_scratch, raw + (long long)e->last_n - (long long)need_raw, need_raw * sizeof(float2), dcs);
             be_d2d(raw - need_raw, e->d_scratch, need_raw * sizeof(float2), dcs);
@@ -2534,10 +2581,9 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
             DcExactArgs xa;
             // one lane per segment on the SMs the channel front kernel leaves free: as many segments (multiples of the scan
             // tile) as those SMs hold lanes, each warmed up over kDcWarm samples
-            const unsigned lanes = (unsigned)dc_reserved_sms(live) * kDlWarpsHost * 32u;
-            const unsigned seg = window ? (unsigned)kDcTile : kDcTile * ((tiles_n + lanes - 1) / lanes);
+            const unsigned seg = (unsigned)kDcTile;                 // both replays work tile by tile
             xa.xraw = raw; xa.y = blk; xa.n = (int)n; xa.seg_len = (int)seg; xa.warm = window ? 0 : kDcWarm;
-            xa.start = nullptr; xa.junction_bad = e->d_dw_stats + 1;
+            xa.start = nullptr; xa.junction_bad = e->d_dw_stats + 1; xa.states_only = 0; xa.no_publish = 0; xa.fix_mask = nullptr;
             xa.raw_hist = (int)need_raw; xa.raw_end = (long long)e->max_block + (long long)e->raw_pad;
             xa.c = (float)e->dc_a; xa.one = 1.0f;
             xa.tile_carry = e->d_tile_carry2[p]; xa.prev_tile_carry = e->d_tile_carry2[p ^ 1];
@@ -2556,7 +2602,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
                 xa.start = e->d_seg_in;
                 e->dw_blocks += 1;
             }
-            { int r = launch_dc_exact(xa, (unsigned long long)xa.warm + e->max_block + e->raw_pad, dcs, e->launches); if (r) return r; }
+            { int r = launch_dc_exact(xa, (unsigned long long)xa.warm + e->max_block + e->raw_pad, dcs, e->launches, e->d_dc_fix_mask, e->d_dw_stats); if (r) return r; }
         }
     }
     // history in front of the block: the tail of the previous block, which lives in the other buffer
