@@ -257,8 +257,9 @@ SDR_HD inline void dc_apply_phase(int ph, const DcArgs &a, int bid, int tid, DcS
 //     from the true carried state of segment 0, that every output is the reference's; a failing junction (rare) is
 //     replayed serially by dc_exact_verify.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kDcWarm = 12288;      // warm-up samples (a multiple of kDcTile); P(junction not coalesced) ~ 7 % (1.5e-4 at 24576): the
-                                    // tiles whose warmed-up state turns out wrong are re-run in parallel from their neighbour's end state
+constexpr int kDcWarm = 24576;      // warm-up samples (a multiple of kDcTile); P(candidate not merged with the true trajectory) ~ 1.5e-4.
+                                    // (12288 was measured: 2.8 % wrong candidates, and they come in runs -- chains that pass a region
+                                    // where merging is slow are all late -- so a parallel fix-up needs one round per run member.)
 constexpr int kDcMinSpec = 32768;   // blocks shorter than this are replayed serially (the warm-up alone is 24576 steps)
 
 struct DcExactArgs {

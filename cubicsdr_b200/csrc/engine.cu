@@ -1010,9 +1010,9 @@ static int launch_dc_exact(const DcExactArgs &a, unsigned long long tma_rows, sd
     } else if (a.n_seg > 1) {
         // Warm-up form: one lane per tile (SM-exclusive CTAs of four warps on the SMs the front kernel leaves free) runs the
         // chain over the kDcWarm samples in front of its tile from the exact state and leaves a CANDIDATE start state; the tiles
-        // are then replayed one warp each; tiles whose candidate was not their neighbour's end state (a few per cent) are re-run
-        // from it, in parallel, up to three rounds (a run of consecutive wrong candidates needs one round per member);
-        // k_dc_verify proves every junction and replays serially whatever is left.
+        // are then replayed one warp each; tiles whose candidate was not their neighbour's end state (1.5e-4 of them) are re-run
+        // from it in one parallel round; k_dc_verify proves every junction and replays serially whatever is left (a run of
+        // consecutive wrong candidates).
         DcExactArgs w = a;
         w.states_only = 1;
         const int warps = (a.n_seg + 31) / 32;
@@ -1041,11 +1041,9 @@ static int launch_dc_exact(const DcExactArgs &a, unsigned long long tma_rows, sd
         k_dc_exact<<<a.n_seg, 32, 0, s>>>(r);
         DcExactArgs f = a;                                           // wrong candidates: from the neighbour's end state
         f.fix_mask = fix_mask;
-        for (int round = 0; round < 3; ++round) {
-            k_dc_mark<<<(a.n_seg + 255) / 256, 256, 0, s>>>(a, fix_mask, stats);
-            k_dc_exact<<<a.n_seg, 32, 0, s>>>(f);
-        }
-        launches += 7;
+        k_dc_mark<<<(a.n_seg + 255) / 256, 256, 0, s>>>(a, fix_mask, stats);
+        k_dc_exact<<<a.n_seg, 32, 0, s>>>(f);
+        launches += 4;
     } else {
         k_dc_exact<<<1, 32, 0, s>>>(a);
     }
@@ -2558,10 +2556,9 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         size_t live = 0;
         for (auto *c : e->chans) live += c != nullptr;
         const unsigned tiles_n = (n + kDcTile - 1) / kDcTile;
-        // automatic choice: the windows' table pass is chip-wide work that competes with a long front kernel, the warm-up replay is
-        // ~0.2 ms of latency on the reserved SMs: windows for few channels or short blocks, the warm-up replay otherwise
-        const bool window = e->exact_dc && tiles_n >= (unsigned)kDwMinTiles &&
-                            (e->dc_window < 0 ? (live < 32 || (live < 256 && n <= 500000u)) : e->dc_window == 1);
+        // automatic choice (measured, profiles/README.md): the windows' table pass is chip-wide work that competes with a long
+        // front kernel -- at 256 channels and more the warm-up replay on the reserved SMs is the faster block period
+        const bool window = e->exact_dc && tiles_n >= (unsigned)kDwMinTiles && (e->dc_window < 0 ? live < 256 : e->dc_window == 1);
         if (e->have_block && e->last_n > 0 && !window) {
             be_d2d(e->d_scratch, raw + (long long)e->last_n - (long long)need_raw, need_raw * sizeof(float2), dcs);
             be_d2d(raw - need_raw, e->d_scratch, need_raw * sizeof(float2), dcs);

@@ -95,7 +95,7 @@ def test_against_golden_vectors(emu_lib):
 def test_dc_blocker_bit_exact_including_speculative_segments(emu_lib, ref):
     """The warm-up replay (the one used next to a long channel front kernel; selected explicitly here): 326 tiles per block at
     20 MSps, each warmed up from the exact state.  Every sample of the DC-blocked block must equal the reference's -- tiles whose
-    warmed-up state had not yet merged with the true trajectory (a few per cent with a 12288-sample warm-up) are replayed."""
+    warmed-up state had not yet merged with the true trajectory (1.5e-4 of them) are replayed."""
     import ctypes as C
     from cubicsdr_b200 import Engine
     from oracle.refbind import RefIngress
@@ -110,7 +110,7 @@ def test_dc_blocker_bit_exact_including_speculative_segments(emu_lib, ref):
         assert np.array_equal(eng.fetch_block(N).view(np.float32), ing.block(x).view(np.float32)), b
     fix, mode = C.c_uint(), C.c_int()
     emu_lib.L.sdr_engine_debug_dc_fixups(eng.h, C.byref(fix), C.byref(mode))
-    assert mode.value == 1 and fix.value < 3 * 326 // 4          # (the emulator replays them serially and counts them here)
+    assert mode.value == 1 and fix.value <= 2                    # (the emulator replays them serially and counts them here)
     assert eng.dc_window_stats()[1] == 0
 
 
