@@ -56,12 +56,18 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 // small CTAs and the candidate-window kernels start there and spread out when the front kernel ends.  Measured at 512 channels:
 // 4 SMs give the front kernel 3 % more room but stretch the DC stage to 0.55 ms (its scan CTAs queue on four SMs), which then
 // is the block period and costs the host entry 12 %; 8 SMs: DC 0.33 ms, hidden.  SDR_B200_DC_SMS overrides (experiments).
+// With fewer channels more SMs are left free (below).
 static inline int dc_reserved_sms(size_t live_channels) {
     static int forced = -1;
     if (forced < 0) { const char *v = getenv("SDR_B200_DC_SMS"); forced = v ? atoi(v) : 0; }
-    if (forced > 0) return forced > 32 ? 32 : forced;
-    (void)live_channels;
-    return 8;
+    if (forced > 0) return forced > 100 ? 100 : forced;
+    // fewer channels: the front kernel has less work than SMs, and everything else of the block (DC tables and replay, tail,
+    // spectrum) is queued behind its SM-exclusive CTAs -- give those more room (measured on 61.44 MSps blocks, profiles/gpu_exp5.sh:
+    // 64 channels 3973 -> 4265 MS/s with 74 SMs, 128 channels 3106 -> 3416 with 32, 256 channels 2578 -> 2624 with 16)
+    if (live_channels >= 384) return 8;
+    if (live_channels >= 192) return 16;
+    if (live_channels >= 96) return 32;
+    return 74;
 }
 constexpr int kResBuf = 3;           // host result buffers (ring): blocks a pipelined consumer may keep in flight + 1
 constexpr unsigned kDlWarpsHost = 4;   // warps per CTA of k_dc_lanes (one per scheduler)
