@@ -787,13 +787,6 @@ __global__ void __launch_bounds__(kTailThreads, 4) k_chan_tail(TailArgs a) {
         if (dbg) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.dbg[blockIdx.x * 64 + ph] = t; }
     }
 }
-__global__ void __launch_bounds__(kFftThreads) k_spec_fft(SpecArgs a, int phases) {
-    extern __shared__ float2 fft_sm[];
-    for (int ph = 0; ph < phases; ++ph) {
-        spec_fft_phase(ph, a, blockIdx.x, threadIdx.x, blockDim.x, fft_sm);
-        __syncthreads();
-    }
-}
 // Spectrum transform, Stockham passes with register butterflies (dsp_spec.h, second form).  CTA = (frame, sub-sequence).
 __global__ void __launch_bounds__(kFft2Threads) k_spec_fft2(SpecArgs a) {
     extern __shared__ __align__(16) unsigned char fft2_sm[];
@@ -856,19 +849,6 @@ __global__ void __launch_bounds__(kSpecThreads) k_spec_points2(SpecArgs a) {
     __syncthreads();
     spec_points2_thread(a, f, xp, cfm.x, cfm.y);
 }
-__global__ void __launch_bounds__(kSpecThreads) k_spec_ema(SpecArgs a) { spec_ema_thread(a, blockIdx.x * blockDim.x + threadIdx.x); }
-__global__ void __launch_bounds__(kSpecThreads) k_spec_minmax(SpecArgs a) {
-    __shared__ SpecRedShared sm;
-    spec_minmax_phase(0, a, blockIdx.x, threadIdx.x, blockDim.x, &sm);
-    __syncthreads();
-    spec_minmax_phase(1, a, blockIdx.x, threadIdx.x, blockDim.x, &sm);
-}
-__global__ void k_spec_scalar(SpecArgs a) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) spec_scalar_thread(a);
-}
-__global__ void __launch_bounds__(kSpecThreads) k_spec_points(SpecArgs a) {
-    spec_points_thread(a, (long long)blockIdx.x * blockDim.x + threadIdx.x);
-}
 __global__ void __launch_bounds__(256) k_view_mix(ViewMixArgs a) {
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < (long long)a.F * a.D; g += (long long)gridDim.x * blockDim.x)
         view_mix_thread(a, g);
@@ -879,29 +859,6 @@ __global__ void __launch_bounds__(kSpecThreads) k_view_ema_move(SpecArgs a, int 
 // serial float recurrence at the channel rate.  The warp stages 256 samples at a time in shared memory; every lane runs the
 // chain (fully unrolled 32 steps, inputs fetched ahead of it) and lane l keeps output l, so a batch is stored coalesced and
 // the chain runs at its latency (~10 cycles a step) instead of waiting for shared memory every step.
-__global__ void __launch_bounds__(32) k_pfb_dc0(const float2 *in, float2 *out, int n, float c, float2 *state) {
-    __shared__ float2 si[256];
-    const int lane = threadIdx.x;
-    float2 v = state[0], y;
-    for (int base = 0; base < n; base += 256) {
-        const int m = n - base < 256 ? n - base : 256;
-        for (int i = lane; i < m; i += 32) si[i] = in[base + i];
-        __syncwarp();
-        int b = 0;
-        for (; b + 32 <= m; b += 32) {
-            float2 keep = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                dc_ref_step(c, si[b + j], v, y);
-                if (lane == j) keep = y;
-            }
-            out[base + b + lane] = keep;
-        }
-        for (; b < m; ++b) { dc_ref_step(c, si[b], v, y); if (lane == 0) out[base + b] = y; }
-        __syncwarp();
-    }
-    if (lane == 0) state[0] = v;
-}
 __global__ void __launch_bounds__(kPfbThreads) k_pfb_analyze(PfbArgs a) {
     extern __shared__ float2 pfb_sm[];
     for (int ph = 0; ph < kPfbPhases; ++ph) {
