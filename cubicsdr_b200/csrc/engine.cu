@@ -2109,6 +2109,7 @@ extern "C" int sdr_modem_demodulate(sdr_chan *c, const sdr_cf32 *iq, unsigned n,
 // DemodulatorMgr::deleteThread happens while blocks are in flight.  The channel disappears from the submitter's list at once
 // (a few host instructions under the submit lock); its memory is handed back on the admin stream once events recorded on
 // every engine stream at this moment have fired, and its slot / result region are recycled when that is known to have happened.
+static void mixers_forget_chan(sdr_engine *e, int index);
 static void chan_destroy_core(sdr_chan *c, bool have_mu) {
     sdr_engine *e = c->eng;
 #ifndef SDR_EMU
@@ -2120,6 +2121,7 @@ static void chan_destroy_core(sdr_chan *c, bool have_mu) {
         std::unique_lock<std::mutex> lk(e->mu, std::defer_lock);
         if (!have_mu) lk.lock();
         if (c->index >= 0 && (size_t)c->index < e->chans.size() && e->chans[(size_t)c->index] == c) e->chans[(size_t)c->index] = nullptr;
+        if (c->index >= 0) mixers_forget_chan(e, c->index);      // a mixer source bound to it keeps what it has queued and is fed no more
 #ifndef SDR_EMU
         // everything already enqueued may still touch the channel; nothing enqueued later will
         cudaStream_t ss[5] = {e->stream, e->stream_tail, e->stream_res, e->stream_dc, e->stream2};
@@ -3554,6 +3556,7 @@ struct sdr_mixer {
     double *d_peak = nullptr;
     float *d_out = nullptr, *h_out = nullptr;
     float *d_stage = nullptr, *h_stage = nullptr;
+    std::vector<int> src_chan;               // host shadow of MixSource::chan
     static const int kRing = 32768;          // floats per source: several blocks of audio
     static const int kStage = 65536;
 };
@@ -3633,7 +3636,18 @@ static int mixer_add(sdr_mixer *m, int chan_slot, int feed_rate, float gain, int
     be_sync(ss);
     if (index) *index = m->n_src;
     m->n_src += 1;
+    m->src_chan.push_back(chan_slot);
     return SDR_OK;
+}
+// the channel in slot `index` is being destroyed (engine lock held): its slot may be reused, so no source may read it any more
+static void mixers_forget_chan(sdr_engine *e, int index) {
+    static const int none = -1;
+    for (sdr_mixer *m : e->mixers)
+        for (size_t j = 0; j < m->src_chan.size(); ++j)
+            if (m->src_chan[j] == index) {
+                m->src_chan[j] = -1;
+                be_h2d(reinterpret_cast<char *>(m->d_src + j) + offsetof(MixSource, chan), &none, sizeof none, sink_stream(e));
+            }
 }
 // AudioThread::bindThread (src/audio/AudioThread.cpp:62-72): the channel's audio of every block joins this source's queue
 extern "C" int sdr_mixer_bind(sdr_mixer *m, sdr_chan *c, float gain, int *source_index) {

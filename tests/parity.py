@@ -576,6 +576,19 @@ def check_audio_sinks(lib, ref, n_blocks=8):
             worst["mix"] = max(worst["mix"], float(np.abs(want).max()))
             assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), "block %d callback %d: %d of %d mixed samples differ (max %.3g)" % (
                 b, cb, int(np.count_nonzero(got != want)), got.size, float(np.abs(got - want).max()))
+    # a bound demodulator goes away: its source keeps what it has queued and is fed no more (the slot may be reused)
+    cs[4].close()
+    for b in range(n_blocks, n_blocks + 2):
+        x = synth.wideband(fs, N, signal, t0=b * N)
+        eng.submit(x, CENTER, fs); eng.wait()
+        for i, c in enumerate(cs[:4]):
+            a, lvl, pk, sk = c.fetch_audio()
+            if len(a):
+                rmix.push(i, a, channels=2 if chans[i][0] == "FMS" else 1, peak=pk, sample_rate=48000)
+        for cb in range(2):
+            got, want = mix.render(512), rmix.callback(512)
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), "after a channel was destroyed: block %d callback %d" % (b, cb)
+    cs = cs[:4]
     assert worst["mix"] > 0.05                                       # the callbacks did carry audio
     assert worst["pcm"] == 0 and worst["wave"] <= 1e-6 and worst["spec"] <= TOL, worst
     for o in (mix, scope, scope2):
