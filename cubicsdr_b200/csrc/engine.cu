@@ -3557,6 +3557,9 @@ struct sdr_mixer {
     float *d_out = nullptr, *h_out = nullptr;
     float *d_stage = nullptr, *h_stage = nullptr;
     std::vector<int> src_chan;               // host shadow of MixSource::chan
+#ifndef SDR_EMU
+    cudaEvent_t ev_done = nullptr;           // end of the last render's device work
+#endif
     static const int kRing = 32768;          // floats per source: several blocks of audio
     static const int kStage = 65536;
 };
@@ -3619,6 +3622,9 @@ extern "C" int sdr_mixer_destroy(sdr_mixer *m) {
     use_device(e);
     be_sync(sink_stream(e));
     e->mixers.erase(std::remove(e->mixers.begin(), e->mixers.end(), m), e->mixers.end());
+#ifndef SDR_EMU
+    if (m->ev_done) cudaEventDestroy(m->ev_done);
+#endif
     be_free(m->d_src); be_free(m->d_rings); be_free(m->d_map); be_free(m->d_peak); be_free(m->d_out); be_host_free(m->h_out);
     be_free(m->d_stage); be_host_free(m->h_stage);
     delete m;
@@ -3705,11 +3711,12 @@ extern "C" int sdr_mixer_push(sdr_mixer *m, int source, const float *data, unsig
 extern "C" int sdr_mixer_render(sdr_mixer *m, unsigned n_frames, float *out) {
     if (!m || !out || !n_frames || n_frames > m->max_frames) return fail(SDR_ERR_ARG, "sdr_mixer_render: bad arguments");
     sdr_engine *e = m->eng;
-    sdr_stream_t ss;
     {
+        // the engine lock is held only while the kernels are enqueued: the audio thread waits for its own event afterwards, so a
+        // callback never stands between SDRPostThread and its next submit
         std::lock_guard<std::mutex> lk(e->mu);
         use_device(e);
-        ss = sink_stream(e);
+        sdr_stream_t ss = sink_stream(e);
         MixArgs a = mixer_args(m);
         a.n_frames = (int)n_frames;
 #ifndef SDR_EMU
@@ -3723,9 +3730,15 @@ extern "C" int sdr_mixer_render(sdr_mixer *m, unsigned n_frames, float *out) {
 #endif
         e->launches += 3;
         be_d2h(m->h_out, m->d_out, 2 * (size_t)n_frames * sizeof(float), ss);
-        if (be_sync(ss)) return fail(SDR_ERR_CUDA, "sdr_mixer_render: stream sync failed");
-        memcpy(out, m->h_out, 2 * (size_t)n_frames * sizeof(float));
+#ifndef SDR_EMU
+        if (!m->ev_done && cudaEventCreateWithFlags(&m->ev_done, cudaEventDisableTiming) != cudaSuccess) return fail(SDR_ERR_CUDA, "sdr_mixer_render: event");
+        CUDA_TRY(cudaEventRecord(m->ev_done, ss));
+#endif
     }
+#ifndef SDR_EMU
+    if (cudaEventSynchronize(m->ev_done) != cudaSuccess) return fail(SDR_ERR_CUDA, "sdr_mixer_render: wait failed");
+#endif
+    memcpy(out, m->h_out, 2 * (size_t)n_frames * sizeof(float));
     return SDR_OK;
 }
 // AudioFileWAV::writePayloadToFileStream (src/audio/AudioFileWAV.cpp:143-165): the last block's audio of a channel as the 16-bit words
