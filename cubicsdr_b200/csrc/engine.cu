@@ -1262,6 +1262,12 @@ struct sdr_engine {
     int *d_dc_fix_mask = nullptr;            // warm-up replay: tiles to re-run in a fix-up round
     int dc_window = -1;
     std::vector<struct sdr_mixer *> mixers;   // device-side audio mixers fed after every block (dsp_sink.h)
+    std::mutex mu_pcm;                        // sdr_chan_fetch_pcm16 calls, one at a time
+    short *d_pcm = nullptr, *h_pcm = nullptr; // its staging: [count | words]
+    size_t pcm_cap = 0;
+#ifndef SDR_EMU
+    cudaEvent_t ev_pcm = nullptr;
+#endif
     unsigned long long dw_blocks = 0;
     // host blocks: ring of pinned staging buffers -> DMA on stream_h2d -> ring of device buffers -> the DC stream
     static const int kInRing = 3;
@@ -1610,6 +1616,10 @@ extern "C" int sdr_engine_destroy(sdr_engine *e) {
     for (int k = 0; k < sdr_engine::kInRing; ++k) { be_host_free(e->h_in[k]); be_free(e->d_in[k]); }
     be_free(e->d_tile_sum); be_free(e->d_tile_carry2[0]); be_free(e->d_tile_carry2[1]); be_free(e->d_dc_state);
     be_free(e->d_dc_fix_mask);
+    be_free(e->d_pcm); be_host_free(e->h_pcm);
+#ifndef SDR_EMU
+    if (e->ev_pcm) cudaEventDestroy(e->ev_pcm);
+#endif
     be_free(e->d_dw_st); be_free(e->d_dw_pst); be_free(e->d_dw_gmap); be_free(e->d_dw_entry); be_free(e->d_dw_stats);
     be_free(e->d_seg_in); be_free(e->d_seg_out); be_free(e->d_fstate); be_free(e->d_fixups); be_free(e->d_apow); be_free(e->d_nco);
     be_free(e->d_cs); be_free(e->d_cd2[0]); be_free(e->d_cd2[1]); be_free(e->d_st); be_host_free(e->h_cd); be_free(e->d_group); be_host_free(e->h_group);
@@ -3746,27 +3756,44 @@ extern "C" int sdr_mixer_render(sdr_mixer *m, unsigned n_frames, float *out) {
 extern "C" int sdr_chan_fetch_pcm16(sdr_chan *c, short *out, unsigned cap, unsigned *n) {
     if (!c || !out || !n || c->index < 0) return fail(SDR_ERR_ARG, "sdr_chan_fetch_pcm16: bad arguments");
     sdr_engine *e = c->eng;
-    std::lock_guard<std::mutex> lk(e->mu);
-    use_device(e);
-    sdr_stream_t ss = sink_stream(e);
+    std::lock_guard<std::mutex> call(e->mu_pcm);                 // one conversion at a time (they share the engine's staging buffers)
     const unsigned room = std::min<unsigned>(cap, (unsigned)c->cs.res_audio_cap);
-    short *d_out = nullptr; int *d_n = nullptr;
-    if (be_malloc((void **)&d_out, ((size_t)room + 2) * sizeof(short)) || be_malloc((void **)&d_n, sizeof(int))) { be_free(d_out); return fail(SDR_ERR_NOMEM, "sdr_chan_fetch_pcm16"); }
-    PcmArgs a;
-    a.cs = e->d_cs; a.results = e->d_results; a.chan = c->index; a.channels = (c->modem == MODEM_IQ || c->modem == MODEM_FMS) ? 2 : 1;
-    a.out = d_out; a.cap = (int)room; a.n_out = d_n;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);                   // held only while enqueueing (see sdr_mixer_render)
+        use_device(e);
+        sdr_stream_t ss = sink_stream(e);
+        if (room + 2 > e->pcm_cap) {                             // (rare: the first call, or a channel with a larger slot)
+            be_sync(ss);
+            be_free(e->d_pcm); be_host_free(e->h_pcm);
+            e->d_pcm = nullptr; e->h_pcm = nullptr; e->pcm_cap = 0;
+            if (be_malloc((void **)&e->d_pcm, ((size_t)room + 2 + 2) * sizeof(short)) || be_host_alloc((void **)&e->h_pcm, ((size_t)room + 2 + 2) * sizeof(short)))
+                return fail(SDR_ERR_NOMEM, "sdr_chan_fetch_pcm16");
+            e->pcm_cap = room + 2;
+        }
+        PcmArgs a;
+        a.cs = e->d_cs; a.results = e->d_results; a.chan = c->index; a.channels = (c->modem == MODEM_IQ || c->modem == MODEM_FMS) ? 2 : 1;
+        a.out = e->d_pcm + 2; a.cap = (int)room; a.n_out = reinterpret_cast<int *>(e->d_pcm);      // [count (one int) | words]
 #ifndef SDR_EMU
-    k_pcm16<<<(room + 255) / 256 + 1, 256, 0, ss>>>(a);
+        k_pcm16<<<(room + 255) / 256 + 1, 256, 0, ss>>>(a);
 #else
-    for (unsigned i = 0; i < room + 1; ++i) pcm16_thread(a, (int)i);
+        for (unsigned i = 0; i < room + 1; ++i) pcm16_thread(a, (int)i);
 #endif
-    e->launches += 1;
+        e->launches += 1;
+        be_d2h(e->h_pcm, e->d_pcm, ((size_t)room + 2) * sizeof(short), ss);
+#ifndef SDR_EMU
+        if (!e->ev_pcm && cudaEventCreateWithFlags(&e->ev_pcm, cudaEventDisableTiming) != cudaSuccess) return fail(SDR_ERR_CUDA, "sdr_chan_fetch_pcm16: event");
+        CUDA_TRY(cudaEventRecord(e->ev_pcm, ss));
+#endif
+    }
+#ifndef SDR_EMU
+    if (cudaEventSynchronize(e->ev_pcm) != cudaSuccess) return fail(SDR_ERR_CUDA, "sdr_chan_fetch_pcm16: wait failed");
+#endif
     int hn = 0;
-    be_d2h(&hn, d_n, sizeof hn, ss);
-    be_sync(ss);
-    if (hn > 0) { be_d2h(out, d_out, (size_t)hn * sizeof(short), ss); be_sync(ss); }
+    memcpy(&hn, e->h_pcm, sizeof hn);
+    if (hn < 0) hn = 0;
+    if ((unsigned)hn > room) hn = (int)room;
+    memcpy(out, e->h_pcm + 2, (size_t)hn * sizeof(short));
     *n = (unsigned)hn;
-    be_free(d_out); be_free(d_n);
     return SDR_OK;
 }
 // ScopeVisualProcessor (src/process/ScopeVisualProcessor.cpp:14-217) on the audio of one channel
@@ -3775,6 +3802,11 @@ struct sdr_scope {
     int fft_size = 0, max_samples = 0;
     float2 *d_in = nullptr, *d_tw = nullptr; float *d_mags = nullptr; double2 *d_ema = nullptr; double *d_scalars = nullptr;
     float *d_wave = nullptr, *d_spec = nullptr; int *d_counts = nullptr; double *d_fc = nullptr; float2 *d_cf = nullptr; int *d_fs = nullptr;
+    unsigned char *h_out = nullptr;          // pinned: [counts (2 int) | floor, ceil (2 double) | waveform | spectrum]
+    std::mutex mu_call;
+#ifndef SDR_EMU
+    cudaEvent_t ev_done = nullptr;
+#endif
 };
 extern "C" int sdr_scope_destroy(sdr_scope *s) {
     if (!s) return SDR_OK;
@@ -3782,7 +3814,10 @@ extern "C" int sdr_scope_destroy(sdr_scope *s) {
     use_device(s->eng);
     be_sync(sink_stream(s->eng));
     be_free(s->d_in); be_free(s->d_tw); be_free(s->d_mags); be_free(s->d_ema); be_free(s->d_scalars); be_free(s->d_wave); be_free(s->d_spec);
-    be_free(s->d_counts); be_free(s->d_fc); be_free(s->d_cf); be_free(s->d_fs);
+    be_free(s->d_counts); be_free(s->d_fc); be_free(s->d_cf); be_free(s->d_fs); be_host_free(s->h_out);
+#ifndef SDR_EMU
+    if (s->ev_done) cudaEventDestroy(s->ev_done);
+#endif
     delete s;
     return SDR_OK;
 }
@@ -3806,6 +3841,7 @@ extern "C" int sdr_scope_create(sdr_engine *e, sdr_chan *c, unsigned fft_size, u
     bad |= be_malloc((void **)&s->d_fc, 2 * sizeof(double));
     bad |= be_malloc((void **)&s->d_cf, sizeof(float2));
     bad |= be_malloc((void **)&s->d_fs, sizeof(int));
+    bad |= be_host_alloc((void **)&s->h_out, 32 + 2 * (size_t)max_samples * sizeof(float) + (size_t)fft_size * sizeof(float));
     if (bad) { std::string msg = "sdr_scope_create: allocation failed"; (void)msg; e->mu.unlock(); sdr_scope_destroy(s); e->mu.lock(); return fail(SDR_ERR_NOMEM, "sdr_scope_create: allocation failed"); }
     std::vector<float2> tw(fft_size);
     for (unsigned k = 0; k < fft_size; ++k) { const double ang = -2.0 * 3.14159265358979323846 * (double)k / (double)fft_size; tw[k] = make_float2((float)std::cos(ang), (float)std::sin(ang)); }
@@ -3822,7 +3858,8 @@ extern "C" int sdr_scope_create(sdr_engine *e, sdr_chan *c, unsigned fft_size, u
 extern "C" int sdr_scope_process(sdr_scope *s, float *wave_xy, unsigned *n_wave, float *spec_xy, unsigned *n_spec, double *floor_ceil) {
     if (!s || !wave_xy || !spec_xy || !n_wave || !n_spec) return fail(SDR_ERR_ARG, "sdr_scope_process: null argument");
     sdr_engine *e = s->eng;
-    std::lock_guard<std::mutex> lk(e->mu);
+    std::lock_guard<std::mutex> call(s->mu_call);
+    std::unique_lock<std::mutex> lk(e->mu);
     use_device(e);
     sdr_stream_t ss = sink_stream(e);
     ScopeArgs a;
@@ -3861,16 +3898,26 @@ extern "C" int sdr_scope_process(sdr_scope *s, float *wave_xy, unsigned *n_wave,
     }
 #endif
     e->launches += 3;
-    int counts[2] = {0, 0};
-    double fc[2] = {0, 0};
-    be_d2h(counts, s->d_counts, sizeof counts, ss);
-    be_d2h(fc, s->d_fc, sizeof fc, ss);
-    if (be_sync(ss)) return fail(SDR_ERR_CUDA, "sdr_scope_process: stream sync failed");
-    if (counts[0] > 0) be_d2h(wave_xy, s->d_wave, 2 * (size_t)counts[0] * sizeof(float), ss);
-    if (counts[1] > 0) be_d2h(spec_xy, s->d_spec, 2 * (size_t)counts[1] * sizeof(float), ss);
-    be_sync(ss);
-    *n_wave = (unsigned)counts[0]; *n_spec = (unsigned)counts[1];
-    if (floor_ceil) { floor_ceil[0] = fc[0]; floor_ceil[1] = fc[1]; }
+    // results to pinned host memory; the engine lock is released before the wait (see sdr_mixer_render)
+    int *h_counts = reinterpret_cast<int *>(s->h_out);
+    double *h_fc = reinterpret_cast<double *>(s->h_out + 16);
+    float *h_wave = reinterpret_cast<float *>(s->h_out + 32), *h_spec = h_wave + 2 * (size_t)s->max_samples;
+    be_d2h(h_counts, s->d_counts, 2 * sizeof(int), ss);
+    be_d2h(h_fc, s->d_fc, 2 * sizeof(double), ss);
+    be_d2h(h_wave, s->d_wave, 2 * (size_t)s->max_samples * sizeof(float), ss);
+    be_d2h(h_spec, s->d_spec, (size_t)s->fft_size * sizeof(float), ss);
+#ifndef SDR_EMU
+    if (!s->ev_done && cudaEventCreateWithFlags(&s->ev_done, cudaEventDisableTiming) != cudaSuccess) return fail(SDR_ERR_CUDA, "sdr_scope_process: event");
+    CUDA_TRY(cudaEventRecord(s->ev_done, ss));
+    lk.unlock();
+    if (cudaEventSynchronize(s->ev_done) != cudaSuccess) return fail(SDR_ERR_CUDA, "sdr_scope_process: wait failed");
+#endif
+    const int nw = h_counts[0] < 0 ? 0 : (h_counts[0] > s->max_samples ? s->max_samples : h_counts[0]);
+    const int nsp = h_counts[1] < 0 ? 0 : (h_counts[1] > s->fft_size / 2 ? s->fft_size / 2 : h_counts[1]);
+    memcpy(wave_xy, h_wave, 2 * (size_t)nw * sizeof(float));
+    memcpy(spec_xy, h_spec, 2 * (size_t)nsp * sizeof(float));
+    *n_wave = (unsigned)nw; *n_spec = (unsigned)nsp;
+    if (floor_ceil) { floor_ceil[0] = h_fc[0]; floor_ceil[1] = h_fc[1]; }
     return SDR_OK;
 }
 
