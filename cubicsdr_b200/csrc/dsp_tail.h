@@ -285,8 +285,8 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
         return;
     }
     // FM stereo (analog/ModemFMStereo.cpp:186-287) shares the discriminator and the metering of FM; its own stages reuse phases that
-    // FM leaves empty: TP_DEMOD_B real -> complex, TP_AGC_A pilot band-pass + phase-locked loop + 38 kHz down-mix (serial),
-    // TP_AGC_B complex -> real, the audio phases run both resamplers, TP_CW_A de-emphasis, TP_CW_B low-pass pair, TP_CW_C/D histories
+    // FM leaves empty: TP_DEMOD_B real -> complex, TP_AGC_A pilot band-pass (five sections as a systolic chain), TP_AGC_B phase-locked
+    // loop + 38 kHz down-mix (serial), TP_AGC_C complex -> real, the audio phases run both resamplers, TP_CW_A de-emphasis, TP_CW_B low-pass pair, TP_CW_C/D histories
     const bool is_fms = cs.modem == MODEM_FMS;
     const bool is_fm = (cs.modem == MODEM_FM || cs.modem == MODEM_NBFM || is_fms);
     const bool is_ssb = (cs.modem == MODEM_USB || cs.modem == MODEM_LSB);
@@ -497,25 +497,52 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
 
     // ---- block auto-gain (AM / SSB): ModemAnalog.cpp:70-86 ------------------------------------------------------------
     if (ph == TP_AGC_A && is_fms) {
-        // :231-255, one sample after the other: 19 kHz pilot band-pass (five second-order sections; liquid 1.5.0's
-        // iirfiltsos_execute_df2 as its binary evaluates it: v0 = x - (a1 v1 + a2 v2), y = (b1 v1 + b2 v2) + b0 v0, every
-        // operation singly rounded -- the poles sit 0.002 inside the unit circle), phase detector against the loop oscillator
-        // (table oscillator: nco_crcf ignores its LIQUID_VCO type), nco_crcf_pll_step with bandwidth 0.25 (alpha = 0.25,
-        // beta = sqrtf(alpha) = 0.5), one oscillator step, two mix-downs by the stepped phase.
+        // :234, the 19 kHz pilot band-pass over the block: five second-order sections; liquid 1.5.0's iirfiltsos_execute_df2 as its
+        // binary evaluates it -- v0 = x - (a1 v1 + a2 v2), y = (b1 v1 + b2 v2) + b0 v0, every operation singly rounded (the poles sit
+        // 0.002 inside the unit circle).  The filter does not depend on the loop behind it, so it runs ahead of it as a systolic
+        // chain: lane q of warp 0 is section q and works on sample t - q at step t (same arithmetic per section and sample as the
+        // serial form, five sections in flight); the result goes through the x2 stream, which the loop then overwrites in place.
+        const float2 *w = chan_cbuf(a, cs, cs.w_off) + kHist;
+        float2 *x2 = chan_cbuf(a, cs, cs.fms_x2_off) + kHist;
+        const float *sos = a.taps + cs.fms_sos_off;
+        const int n = sm->n_iq;
+#if defined(__CUDA_ARCH__) && !defined(SDR_EMU)
+        if (tid < 32) {
+            const int lane = tid, q = lane < 5 ? lane : 4;
+            const float b0 = sos[5 * q], b1 = sos[5 * q + 1], b2 = sos[5 * q + 2], a1 = sos[5 * q + 3], a2 = sos[5 * q + 4];
+            float v1r = st.fms_sos_v[q][0][0], v1i = st.fms_sos_v[q][0][1], v2r = st.fms_sos_v[q][1][0], v2i = st.fms_sos_v[q][1][1];
+            float2 out = make_float2(0.f, 0.f);
+            float2 chunk = lane < n ? w[lane] : make_float2(0.f, 0.f), next = chunk;
+            for (int t = 0; t < n + 4; ++t) {
+                if ((t & 31) == 0) {                             // 32 inputs at a time, the next 32 already on their way
+                    chunk = next;
+                    const int k = t + 32 + lane;
+                    next = k < n ? w[k] : make_float2(0.f, 0.f);
+                }
+                const float xr = __shfl_sync(0xffffffffu, chunk.x, t & 31), xi = __shfl_sync(0xffffffffu, chunk.y, t & 31);
+                const float ur = __shfl_up_sync(0xffffffffu, out.x, 1), ui = __shfl_up_sync(0xffffffffu, out.y, 1);
+                const int i = t - lane;
+                if (lane < 5 && i >= 0 && i < n) {
+                    const float yr0 = lane == 0 ? xr : ur, yi0 = lane == 0 ? xi : ui;
+                    const float v0r = f_sub(yr0, f_add(f_mul(a1, v1r), f_mul(v2r, a2)));
+                    const float v0i = f_sub(yi0, f_add(f_mul(a1, v1i), f_mul(a2, v2i)));
+                    out.x = f_add(f_add(f_mul(b1, v1r), f_mul(v2r, b2)), f_mul(v0r, b0));
+                    out.y = f_add(f_add(f_mul(b1, v1i), f_mul(b2, v2i)), f_mul(b0, v0i));
+                    v2r = v1r; v2i = v1i; v1r = v0r; v1i = v0i;
+                    if (lane == 4) x2[i] = out;
+                }
+            }
+            if (lane < 5) { st.fms_sos_v[q][0][0] = v1r; st.fms_sos_v[q][0][1] = v1i; st.fms_sos_v[q][1][0] = v2r; st.fms_sos_v[q][1][1] = v2i; }
+        }
+#else
         if (tid == 0) {
-            const float2 *w = chan_cbuf(a, cs, cs.w_off) + kHist;
-            float2 *x2 = chan_cbuf(a, cs, cs.fms_x2_off) + kHist;
-            const float *sos = a.taps + cs.fms_sos_off;
             float c[5][5], v[5][2][2];
             for (int q = 0; q < 5; ++q) {
                 for (int k = 0; k < 5; ++k) c[q][k] = sos[5 * q + k];
                 for (int k = 0; k < 2; ++k) { v[q][k][0] = st.fms_sos_v[q][k][0]; v[q][k][1] = st.fms_sos_v[q][k][1]; }
             }
-            unsigned th = st.fms_theta, dth = st.fms_dtheta;
-            const int n = sm->n_iq;
             for (int i = 0; i < n; ++i) {
-                const float2 x = w[i];
-                float yr = x.x, yi = x.y;
+                float yr = w[i].x, yi = w[i].y;
                 for (int q = 0; q < 5; ++q) {
                     const float v0r = f_sub(yr, f_add(f_mul(c[q][3], v[q][0][0]), f_mul(v[q][1][0], c[q][4])));
                     const float v0i = f_sub(yi, f_add(f_mul(c[q][3], v[q][0][1]), f_mul(c[q][4], v[q][1][1])));
@@ -524,6 +551,25 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
                     v[q][1][0] = v[q][0][0]; v[q][1][1] = v[q][0][1];
                     v[q][0][0] = v0r; v[q][0][1] = v0i;
                 }
+                x2[i] = make_float2(yr, yi);
+            }
+            for (int q = 0; q < 5; ++q) for (int k = 0; k < 2; ++k) { st.fms_sos_v[q][k][0] = v[q][k][0]; st.fms_sos_v[q][k][1] = v[q][k][1]; }
+        }
+#endif
+        return;
+    }
+    if (ph == TP_AGC_B && is_fms) {
+        // :235-255, one sample after the other: phase detector against the loop oscillator (table oscillator: nco_crcf ignores its
+        // LIQUID_VCO type), nco_crcf_pll_step with bandwidth 0.25 (alpha = 0.25, beta = sqrtf(alpha) = 0.5), one oscillator step, two
+        // mix-downs by the stepped phase.
+        if (tid == 0) {
+            const float2 *w = chan_cbuf(a, cs, cs.w_off) + kHist;
+            float2 *x2 = chan_cbuf(a, cs, cs.fms_x2_off) + kHist;
+            unsigned th = st.fms_theta, dth = st.fms_dtheta;
+            const int n = sm->n_iq;
+            for (int i = 0; i < n; ++i) {
+                const float2 x = w[i];
+                const float yr = x2[i].x, yi = x2[i].y;          // the pilot filter's output
                 const float2 o = nco_lookup(a.nco, th);          // nco_crcf_cexpf: {cos, sin}
                 const float wi = -o.y;                            // conjf(w)
                 const float ur = f_sub(f_mul(yr, o.x), f_mul(yi, wi));
@@ -537,11 +583,10 @@ SDR_HD inline void tail_phase(int ph, const TailArgs &a, int ch, int tid, int nt
                 x2[i] = make_float2(f_add(f_mul(y1r, p.x), f_mul(y1i, p.y)), f_sub(f_mul(y1i, p.x), f_mul(y1r, p.y)));
             }
             st.fms_theta = th; st.fms_dtheta = dth;
-            for (int q = 0; q < 5; ++q) for (int k = 0; k < 2; ++k) { st.fms_sos_v[q][k][0] = v[q][k][0]; st.fms_sos_v[q][k][1] = v[q][k][1]; }
         }
         return;
     }
-    if (ph == TP_AGC_B && is_fms) {                              // firhilbf_c2r_execute (:258): the lower-sideband output
+    if (ph == TP_AGC_C && is_fms) {                              // firhilbf_c2r_execute (:258): the lower-sideband output
         const float2 *x2 = chan_cbuf(a, cs, cs.fms_x2_off) + kHist;
         float *ds = chan_rbuf(a, cs, cs.fms_ds_off) + kHist;
         const float *hq = a.taps + cs.cw_hq_off;
