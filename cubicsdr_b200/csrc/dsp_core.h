@@ -23,7 +23,6 @@ constexpr int kMaxTailHb = 16;    // msresamp2 never has more than 16 stages
 constexpr int kMaxAudioHb = 8;
 constexpr int kPfbTaps = 14;      // 2 * m of the arbitrary resampler (m = 7)
 constexpr int kTailThreads = 256;
-constexpr int kTailThreadsHeavy = 512;   // CTAs of channels with thousands of low-rate samples a block (wide-band FM)
 
 enum ModemKind { MODEM_FM = 0, MODEM_NBFM = 1, MODEM_AM = 2, MODEM_USB = 3, MODEM_LSB = 4, MODEM_IQ = 5,
                  MODEM_NONE = 6,    // no modem: the decimated IQ is the product (the zoomed spectrum view's hidden channel)
@@ -415,7 +414,6 @@ struct ChanStatic {
     int w_off;                    // complex: SSB post-filter stream feeding the Hilbert stage
     int d_off;                    // real: demodulated samples (after auto-gain) feeding the audio resampler
     int al_off[kMaxAudioHb + 1];  // real: audio resampler level buffers (decim: after each half-band; interp: arb out, then each half-band)
-    int heavy;                    // thousands of decimated samples a block: the tail runs this channel with kTailThreadsHeavy threads
     int want_iq;                  // copy decimated IQ into the result slot
     int bandwidth;                // modem rate (DemodulatorThreadPostIQData::sampleRate): sampleTime of a block = n_iq / bandwidth
     int res_audio_cap, res_iq_cap;

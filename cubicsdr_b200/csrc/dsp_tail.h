@@ -56,7 +56,6 @@ struct TailArgs {
     int n;                        // wideband block length
     int first;                    // channel slot handled by CTA 0
     int view_pass;                // 0: the block's channels; 1: the launch of a zoomed view's hidden channel (ChanDyn::view)
-    int heavy_pass;               // 0: every channel; 1: only ChanStatic::heavy channels (kTailThreadsHeavy threads); 2: only the others
     unsigned long long *dbg;      // diagnostics: per-phase end times of the first 64 channels (null = off)
 };
 
@@ -70,8 +69,8 @@ struct TailShared {
     int n_audio;
     unsigned long long a_phase_after;
     float gain;
-    float red_f[kTailThreadsHeavy];
-    double red_d[kTailThreadsHeavy];
+    float red_f[kTailThreads];
+    double red_d[kTailThreads];
     float2 hist_tmp[kTailStreams][kHist];
 };
 

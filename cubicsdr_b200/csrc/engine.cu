@@ -777,18 +777,12 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 1) k_chan_front(FrontArgs a,
     }
 }
 __global__ void k_premix_hist(PremixArgs a) { premix_thread(a, 1 + (int)(blockIdx.x * blockDim.x + threadIdx.x)); }
-// Channel tail: one CTA per channel.  Channels with thousands of low-rate samples a block (wide-band FM: 3333 decimated samples, a
-// 16001-sample level-0 stream through 21- and 41-tap half-bands) are the long poles of this kernel; they run with 512 threads in a
-// launch of their own (on a second stream, next to the 256-thread launch of the other channels).
-template <int NT>
-__global__ void __launch_bounds__(NT, NT == kTailThreadsHeavy ? 2 : 4) k_chan_tail(TailArgs a) {
+__global__ void __launch_bounds__(kTailThreads, 4) k_chan_tail(TailArgs a) {
     __shared__ TailShared sm;
-    const int ch = a.first + (int)blockIdx.x;
-    if (a.heavy_pass) { const bool heavy = a.cs[ch].heavy != 0; if ((a.heavy_pass == 1) != heavy) return; }      // uniform per CTA
     const bool dbg = a.dbg && threadIdx.x == 0 && blockIdx.x < 64;
     if (dbg) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.dbg[blockIdx.x * 64 + 63] = t; }
     for (int ph = 0; ph < TP_COUNT; ++ph) {
-        tail_phase(ph, a, ch, threadIdx.x, blockDim.x, &sm);
+        tail_phase(ph, a, a.first + blockIdx.x, threadIdx.x, blockDim.x, &sm);
         __syncthreads();
         if (dbg) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.dbg[blockIdx.x * 64 + ph] = t; }
     }
@@ -1085,8 +1079,7 @@ static int launch_front(int K, const FrontArgs &a, int jobs, int reserved_sms, s
 static void launch_tail(const TailArgs &a, int n_chan, sdr_stream_t s, unsigned long long &launches) {
     if (n_chan == 0) return;
 #ifndef SDR_EMU
-    if (a.heavy_pass == 1) k_chan_tail<kTailThreadsHeavy><<<n_chan, kTailThreadsHeavy, 0, s>>>(a);
-    else k_chan_tail<kTailThreads><<<n_chan, kTailThreads, 0, s>>>(a);
+    k_chan_tail<<<n_chan, kTailThreads, 0, s>>>(a);
 #else
     (void)s;
     TailShared *sm = new TailShared;
@@ -1352,8 +1345,7 @@ struct sdr_engine {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // the DC blocker of block b+1 runs on its own stream underneath the channel kernels of block b
     // the channel tail of block b runs on its own stream underneath the front kernel of block b+1
-    cudaStream_t stream_tail = nullptr, stream_tail2 = nullptr;   // tail2: the 512-thread launch of the heavy channels
-    cudaEvent_t ev_tail2 = nullptr;
+    cudaStream_t stream_tail = nullptr;
     cudaStream_t stream_res = nullptr;   // device -> host copies of results, off the compute streams
     cudaEvent_t ev_spec_k = nullptr, ev_tail_k = nullptr;   // spectrum / tail kernels of the current block are done
     cudaEvent_t ev_front_done = nullptr, ev_tail_done[2] = {nullptr, nullptr};
@@ -1528,8 +1520,6 @@ extern "C" int sdr_engine_create(int device, unsigned max_block, void *stream, s
         CUDA_TRY(cudaStreamCreateWithPriority(&e->stream2, cudaStreamNonBlocking, hi < lo ? hi + 1 : hi));
     }
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_tail, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_tail2, cudaStreamNonBlocking));
-    CUDA_TRY(cudaEventCreateWithFlags(&e->ev_tail2, cudaEventDisableTiming));
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_res, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_admin, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_h2d, cudaStreamNonBlocking));
@@ -1639,8 +1629,6 @@ extern "C" int sdr_engine_destroy(sdr_engine *e) {
     if (e->stream2) { cudaStreamSynchronize(e->stream2); cudaStreamDestroy(e->stream2); }
     if (e->stream_dc) { cudaStreamSynchronize(e->stream_dc); cudaStreamDestroy(e->stream_dc); }
     if (e->stream_tail) { cudaStreamSynchronize(e->stream_tail); cudaStreamDestroy(e->stream_tail); }
-    if (e->stream_tail2) { cudaStreamSynchronize(e->stream_tail2); cudaStreamDestroy(e->stream_tail2); }
-    if (e->ev_tail2) cudaEventDestroy(e->ev_tail2);
     if (e->stream_res) { cudaStreamSynchronize(e->stream_res); cudaStreamDestroy(e->stream_res); }
     if (e->stream_admin) { cudaStreamSynchronize(e->stream_admin); cudaStreamDestroy(e->stream_admin); }
     if (e->stream_h2d) { cudaStreamSynchronize(e->stream_h2d); cudaStreamDestroy(e->stream_h2d); }
@@ -1975,7 +1963,6 @@ static int chan_create_impl(sdr_engine *e, const char *modem, long long sample_r
     if (mk == MODEM_IQ) cap_audio = 2 * cap_iq;                         // two-channel output, one {imag, real} pair per decimated sample
     cs.res_audio_cap = (int)((cap_audio + 3) & ~size_t(3));
     cs.res_iq_cap = (int)cap_iq;
-    cs.heavy = (!view_cap && cap_iq >= 2048) ? 1 : 0;                   // e.g. wide-band FM: 3333 decimated samples a block
     cs.want_iq = 0;
     cs.bandwidth = c->bandwidth;
     c->arena_floats = off;
@@ -2116,7 +2103,7 @@ extern "C" int sdr_modem_demodulate(sdr_chan *c, const sdr_cf32 *iq, unsigned n,
     be_h2d(e->d_cd2[0] + c->index, c->h_dyn, sizeof(ChanDyn), e->stream);
     TailArgs ta;
     ta.cs = e->d_cs; ta.cd = e->d_cd2[0]; ta.st = e->d_st; ta.taps = e->d_taps; ta.nco = e->d_nco;
-    ta.results = e->d_results; ta.n = 0; ta.first = c->index; ta.view_pass = 0; ta.heavy_pass = 0; ta.dbg = nullptr;
+    ta.results = e->d_results; ta.n = 0; ta.first = c->index; ta.view_pass = 0; ta.dbg = nullptr;
     launch_tail(ta, 1, e->stream, e->launches);
     be_d2h(c->h_slot, e->d_results + c->cs.res_off, c->slot_bytes, e->stream);
     if (be_sync(e->stream)) return fail(SDR_ERR_CUDA, std::string("sdr_modem_demodulate: ") + be_last_error());
@@ -2799,7 +2786,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
                 e->launches += 1;
                 TailArgs tv;
                 tv.cs = e->d_cs; tv.cd = e->d_cd2[p]; tv.st = e->d_st; tv.taps = e->d_taps; tv.nco = e->d_nco;
-                tv.results = e->d_results; tv.n = job.n_view; tv.first = job.vc->index; tv.view_pass = 1; tv.heavy_pass = 0; tv.dbg = nullptr;
+                tv.results = e->d_results; tv.n = job.n_view; tv.first = job.vc->index; tv.view_pass = 1; tv.dbg = nullptr;
                 launch_tail(tv, 1, sps, e->launches);
             }
             int r = launch_spectrum(job.a, sps, e->launches);
@@ -3034,30 +3021,7 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
 #ifndef SDR_EMU
     if (prev_q >= 0 && e->res_tail_rec[prev_q]) CUDA_TRY(cudaStreamWaitEvent(ts, e->ev_res_tail[prev_q], 0));   // its D2H reads d_results
 #endif
-    ta.heavy_pass = 0;
-#ifndef SDR_EMU
-    {
-        // heavy channels (512 threads each) on a second stream next to the others; both classes present: two launches that join
-        // again on the tail stream (a launch whose class is absent is skipped)
-        int n_heavy = 0, n_live = 0;
-        for (auto *c : e->chans) if (c && !c->standalone) { ++n_live; n_heavy += c->cs.heavy; }
-        if (n_heavy > 0) {
-            cudaStream_t t2 = e->stream_tail2;
-            CUDA_TRY(cudaStreamWaitEvent(t2, e->ev_front_done, 0));
-            if (prev_q >= 0 && e->res_tail_rec[prev_q]) CUDA_TRY(cudaStreamWaitEvent(t2, e->ev_res_tail[prev_q], 0));
-            CUDA_TRY(cudaStreamWaitEvent(t2, e->ev_tail_done[p ^ 1], 0));      // (the previous block's tail: per-channel state is carried)
-            TailArgs th = ta;
-            th.heavy_pass = 1; th.dbg = nullptr;
-            launch_tail(th, n_slots, t2, e->launches);
-            CUDA_TRY(cudaEventRecord(e->ev_tail2, t2));
-            ta.heavy_pass = n_heavy < n_live ? 2 : -1;
-        }
-    }
-    if (ta.heavy_pass >= 0) launch_tail(ta, n_slots, ts, e->launches);
-    if (ta.heavy_pass != 0) CUDA_TRY(cudaStreamWaitEvent(ts, e->ev_tail2, 0));
-#else
     launch_tail(ta, n_slots, ts, e->launches);
-#endif
     mixers_feed(e, ts);                                            // bound channels' audio joins their mixer queues (device side)
     if (to_host && e->results_bytes) {
         size_t total = 0;
