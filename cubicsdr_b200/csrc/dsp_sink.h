@@ -53,6 +53,27 @@ SDR_HD SDR_FORCEINLINE bool mix_try_pop(MixSource &s) {
     s.q_head = (s.q_head + 1) % kMixEntries; s.q_count -= 1;
     return true;
 }
+// Room for an entry of n samples in a source's ring: entries are contiguous (one never wraps), live data runs from the oldest
+// entry still referenced (currentInput, else the head of the queue) to the write position.  Returns the start, or -1 when the
+// new entry would run into live data (the block is dropped, as DemodulatorThread's try_push on a full queue drops it).
+SDR_HD inline int mix_ring_take(const MixSource &s, int n) {
+    if (n > s.ring_cap || s.q_count == kMixEntries) return -1;
+    int oldest = -1;
+    if (s.has_cur && s.cur.n > 0) oldest = s.cur.start;
+    else if (s.q_count > 0) { for (int k = 0; k < s.q_count && oldest < 0; ++k) { const MixEntry &e = s.ent[(s.q_head + k) % kMixEntries]; if (e.n > 0) oldest = e.start; } }
+    const int w = s.w;
+    if (oldest < 0) return w + n <= s.ring_cap ? w : 0;                       // nothing live
+    if (w > oldest) { if (w + n <= s.ring_cap) return w; return n < oldest ? 0 : -1; }
+    if (w < oldest) return w + n < oldest ? w : -1;
+    return -1;                                                                // w == oldest with live data: the ring is full
+}
+SDR_HD inline void mix_queue_push(MixSource &s, int start, int n, int channels, int rate, float peak) {
+    MixEntry e;
+    e.start = start; e.n = n; e.channels = channels; e.rate = rate; e.peak = peak;
+    s.ent[(s.q_head + s.q_count) % kMixEntries] = e;
+    s.q_count += 1;
+    s.w = start + n;
+}
 // after a block: the channel's audio becomes one queued AudioThreadInput (thread j = source j)
 SDR_HD inline void mix_feed_thread(const MixArgs &a, int j) {
     if (j >= a.n_src) return;
@@ -63,16 +84,12 @@ SDR_HD inline void mix_feed_thread(const MixArgs &a, int j) {
     const float *audio = reinterpret_cast<const float *>(a.results + cs.res_off + kResHdrBytes);
     int n = (int)hdr->n_audio;
     if (n > cs.res_audio_cap) n = cs.res_audio_cap;
-    if (hdr->skipped || n <= 0 || n > s.ring_cap || s.q_count == kMixEntries) return;
+    if (hdr->skipped || n <= 0) return;
+    const int w = mix_ring_take(s, n);
+    if (w < 0) return;
     float *ring = a.rings + s.ring_off;
-    int w = s.w;
-    if (w + n > s.ring_cap) w = 0;                        // an entry never wraps: it restarts at the ring's base
     for (int i = 0; i < n; ++i) ring[w + i] = audio[i];
-    MixEntry e;
-    e.start = w; e.n = n; e.channels = (cs.modem == MODEM_IQ || cs.modem == MODEM_FMS) ? 2 : 1; e.rate = s.feed_rate; e.peak = hdr->peak;
-    s.ent[(s.q_head + s.q_count) % kMixEntries] = e;
-    s.q_count += 1;
-    s.w = w + n;
+    mix_queue_push(s, w, n, (cs.modem == MODEM_IQ || cs.modem == MODEM_FMS) ? 2 : 1, s.feed_rate, hdr->peak);
 }
 // phase A of the callback for source j (AudioThread.cpp:113-228)
 SDR_HD inline void mix_walk_thread(const MixArgs &a, int j) {

@@ -683,17 +683,16 @@ __global__ void __launch_bounds__(256) k_mix_scale(MixArgs a) {
 }
 // a host-fed AudioThreadInput (tests, or audio that does not come from this engine): samples staged in `data`
 __global__ void k_mix_push(MixArgs a, int j, const float *data, int n, int channels, float peak, int rate) {
+    __shared__ int w_s;
     MixSource &s = a.src[j];
-    if (s.q_count == kMixEntries || n > s.ring_cap) return;
-    int w = s.w;
-    if (w + n > s.ring_cap) w = 0;
+    if (threadIdx.x == 0) w_s = mix_ring_take(s, n);
+    __syncthreads();
+    const int w = w_s;
+    if (w < 0) return;
     float *ring = a.rings + s.ring_off;
     for (int i = (int)threadIdx.x; i < n; i += (int)blockDim.x) ring[w + i] = data[i];
     __syncthreads();
-    if (threadIdx.x == 0) {
-        MixEntry e; e.start = w; e.n = n; e.channels = channels; e.rate = rate; e.peak = peak;
-        s.ent[(s.q_head + s.q_count) % kMixEntries] = e; s.q_count += 1; s.w = w + n;
-    }
+    if (threadIdx.x == 0) mix_queue_push(s, w, n, channels, rate, peak);
 }
 __global__ void __launch_bounds__(256) k_pcm16(PcmArgs a) { pcm16_thread(a, (int)(blockIdx.x * blockDim.x + threadIdx.x)); }
 __global__ void __launch_bounds__(256) k_scope_prepare(ScopeArgs a) {
@@ -3705,11 +3704,10 @@ extern "C" int sdr_mixer_push(sdr_mixer *m, int source, const float *data, unsig
 #else
     {
         MixSource &s = a.src[source];
-        if (s.q_count != kMixEntries && (int)n <= s.ring_cap) {
-            int w = s.w; if (w + (int)n > s.ring_cap) w = 0;
+        const int w = mix_ring_take(s, (int)n);
+        if (w >= 0) {
             for (unsigned i = 0; i < n; ++i) a.rings[s.ring_off + w + i] = m->d_stage[i];
-            MixEntry en; en.start = w; en.n = (int)n; en.channels = channels; en.rate = sample_rate; en.peak = peak;
-            s.ent[(s.q_head + s.q_count) % kMixEntries] = en; s.q_count += 1; s.w = w + (int)n;
+            mix_queue_push(s, w, (int)n, channels, sample_rate, peak);
         }
     }
 #endif

@@ -589,6 +589,19 @@ def check_audio_sinks(lib, ref, n_blocks=8):
             got, want = mix.render(512), rmix.callback(512)
             assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), "after a channel was destroyed: block %d callback %d" % (b, cb)
     cs = cs[:4]
+    # a consumer that lags: far more blocks queued than a source's ring and queue hold -- the surplus is dropped (like a full
+    # inputQueue's try_push), nothing that is still queued is overwritten, and the mix stays finite and plays what was kept in order
+    lag = Mixer(eng, 48000, 1024)
+    src = lag.add_source(1.0)
+    for k in range(100):
+        lag.push(src, np.full(1600, float(k + 1), np.float32), 2, 0.5, 48000)
+    played = []
+    for k in range(80):
+        o = lag.render(800)
+        assert np.all(np.isfinite(o))
+        played.extend(np.unique(o[o != 0]).tolist())
+    assert played == sorted(played) and len(played) >= 10 and played[0] == 1.0, played[:12]
+    lag.close()
     assert worst["mix"] > 0.05                                       # the callbacks did carry audio
     assert worst["pcm"] == 0 and worst["wave"] <= 1e-6 and worst["spec"] <= TOL, worst
     for o in (mix, scope, scope2):
