@@ -165,7 +165,16 @@ SDR_HD inline void dw_walk(const DcWinArgs &a, int k, const short *gmap /* may b
             if (dw_good(a, p, k)) {
                 const int q = dw_ord(s) - dw_ord(dw_center(a, p, k)) + kDwHalf;
                 if (q >= 0 && q < kDwCand) { idx = q; indexed = true; }
-                else { if (indexed) a.stats[0] += 1u; indexed = false; }
+                else {
+                    if (indexed) {
+#if defined(__CUDA_ARCH__) && !defined(SDR_EMU)
+                        atomicAdd(a.stats, 1u);                      // (the two components walk concurrently)
+#else
+                        a.stats[0] += 1u;
+#endif
+                    }
+                    indexed = false;
+                }
             }
         }
     }
