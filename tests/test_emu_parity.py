@@ -279,3 +279,16 @@ def test_dc_window_replay_bit_exact(emu_lib, ref):
 
 def test_audio_side_consumers(emu_lib, ref):
     print(parity.check_audio_sinks(emu_lib, ref))
+
+
+def test_two_second_run(emu_lib, ref):
+    """SURVEY.md 8(d)'s parity protocol: 2 s (120 blocks) without a warm-up, five modems and a spectrum attached -- phase
+    accumulators, resampler phases, gain and tracker states must not drift away from the reference's over a long run."""
+    w = {}
+    out, dc_err, _ = parity.run_channels(emu_lib, ref, 2400000, FIVE, n_blocks=120, spectrum=512, spec_out=w)
+    assert max(dc_err) == 0.0
+    parity.check_channels(out)
+    assert w["frames"] > 0 and w["mags"] < 1e-5 and w["points"] < 1e-5 and w["u8_bad_far"] == 0
+    for o in out:                                   # the last half second on its own
+        n = len(o["ref_audio"]) // 4
+        assert parity.relrms(o["audio"][-n:], o["ref_audio"][-n:]) < 1e-5, o["modem"]

@@ -268,3 +268,17 @@ def test_fm_stereo_modem_gpu(gpu_lib, ref):
 def test_audio_side_consumers_gpu(gpu_lib, ref):
     """Mixer (audioCallback), 16-bit PCM (AudioFileWAV) and scope (ScopeVisualProcessor) on the device, against the oracle's restatement."""
     print(parity.check_audio_sinks(gpu_lib, ref))
+
+
+def test_two_second_run(gpu_lib, ref):
+    """SURVEY.md 8(d)'s parity protocol: 2 s (120 blocks) without a warm-up, five modems and a spectrum attached -- phase
+    accumulators, resampler phases, gain and tracker states must not drift away from the reference's over a long run."""
+    w = {}
+    out, dc_err, _ = parity.run_channels(gpu_lib, ref, 2400000, FIVE, n_blocks=120, spectrum=512, spec_out=w)
+    assert max(dc_err) == 0.0
+    parity.check_channels(out)
+    assert w["frames"] > 0 and w["mags"] < 1e-5 and w["points"] < 1e-5 and w["u8_bad_far"] == 0
+    # the last half second on its own: the errors of the early blocks must not be what keeps the whole-run figure small
+    for o in out:
+        n = len(o["ref_audio"]) // 4
+        assert parity.relrms(o["audio"][-n:], o["ref_audio"][-n:]) < 1e-5, o["modem"]
