@@ -84,4 +84,5 @@ def test_create_destroy_while_streaming_gpu(gpu_lib):
     lat1 = np.sort(lat1[5:])
     print("submit latency ms: undisturbed median %.3f max %.3f | with churn median %.3f p99 %.3f max %.3f (%d channels made)" % (
         1e3 * np.median(lat0[5:]), 1e3 * lat0[5:].max(), 1e3 * np.median(lat1), 1e3 * lat1[int(0.99 * len(lat1)) - 1], 1e3 * lat1[-1], made))
-    assert lat1[int(0.99 * len(lat1)) - 1] < 5e-3 and lat1[-1] < 25e-3
+    # (bounds leave room for the interpreter's 5 ms thread switch interval: the churn thread is Python too)
+    assert np.median(lat1) < 1.5e-3 and lat1[int(0.99 * len(lat1)) - 1] < 10e-3 and lat1[-1] < 50e-3
