@@ -18,6 +18,11 @@ where it lies and writes only into oracle/_ref/ (git-ignored, but shipped to the
   5. compile the CubicSDR glue restatement (oracle/ref_chain.cpp) and link everything into
      oracle/_ref/libsdr_ref.so
 
+  6. compile the reference's own, unmodified modem sources (src/modules/modem/Modem.cpp, ModemAnalog.cpp,
+     analog/Modem*.cpp) from where they lie, their liquid calls renamed to System V forwarders
+     (oracle/modem_abi.h, oracle/ref_modem_abi.c), with the C entry points of oracle/ref_modems.cpp, into
+     oracle/_ref/libmodems_ref.so (pins ref_chain.cpp's modem restatement: tests/test_oracle_modems.py)
+
 If /root/reference is absent (GPU box) and oracle/_ref/libsdr_ref.so already exists, nothing is done.
 """
 import os
@@ -30,6 +35,10 @@ REF_AR = "/root/reference/external/liquid-dsp/gcc/64/libliquid.a"
 OUT = os.path.join(HERE, "_ref")
 OBJ = os.path.join(OUT, "obj")
 LIB = os.path.join(OUT, "libsdr_ref.so")
+MODEMS_LIB = os.path.join(OUT, "libmodems_ref.so")
+REF_SRC = "/root/reference/src"
+REF_MODEM_SRCS = ["Modem.cpp", "ModemAnalog.cpp"] + ["analog/Modem%s.cpp" % m for m in
+                                                     ("FM", "NBFM", "FMStereo", "AM", "CW", "LSB", "USB", "DSB", "IQ")]
 
 # archive-undefined minus archive-defined (functions); these become ms_<name> shims
 IMPORT_FUNCS = """___chkstk_ms __mingw_vfprintf __mingw_vfscanf __mingw_vsprintf atan2f calloc ccosf cos cosf
@@ -138,8 +147,41 @@ def build(force=False):
     return LIB
 
 
+def build_modems(force=False):
+    """oracle/_ref/libmodems_ref.so: the reference's unmodified modem classes over its own liquid binary."""
+    if not os.path.exists(REF_SRC):
+        if os.path.exists(MODEMS_LIB):
+            return MODEMS_LIB
+        raise SystemExit("oracle/_ref/libmodems_ref.so missing and /root/reference absent")
+    lib = build(force)
+    mine = [os.path.join(HERE, f) for f in ("modem_abi.h", "ref_modem_abi.c", "ref_modems.cpp")] + [os.path.abspath(__file__)]
+    if (not force) and os.path.exists(MODEMS_LIB) and all(os.path.getmtime(MODEMS_LIB) >= os.path.getmtime(s) for s in mine + [lib]):
+        return MODEMS_LIB
+    mdir = os.path.join(OUT, "modem_obj")
+    os.makedirs(mdir, exist_ok=True)
+    mod = os.path.join(REF_SRC, "modules", "modem")
+    inc = []
+    for d in (REF_SRC, os.path.join(REF_SRC, "util"), os.path.join(REF_SRC, "audio"), os.path.join(REF_SRC, "demod"), mod,
+              os.path.join(mod, "analog"), "/root/reference/external/liquid-dsp/include", "/root/reference/external/rtaudio"):
+        inc += ["-I", d]
+    cxx = ["g++", "-std=c++17", "-O2", "-fPIC", "-pthread", "-w", "-include", os.path.join(HERE, "modem_abi.h")] + inc
+    objs = []
+    for src in REF_MODEM_SRCS:                                   # compiled where they lie, objects only into oracle/_ref/
+        o = os.path.join(mdir, os.path.basename(src)[:-4] + ".o")
+        run(cxx + ["-c", os.path.join(mod, src), "-o", o])
+        objs.append(o)
+    drv = os.path.join(mdir, "ref_modems.o")
+    run(cxx + ["-c", os.path.join(HERE, "ref_modems.cpp"), "-o", drv])
+    abi = os.path.join(mdir, "ref_modem_abi.o")
+    run(["gcc", "-O2", "-fPIC", "-c", os.path.join(HERE, "ref_modem_abi.c"), "-o", abi])
+    run(["g++", "-shared", "-o", MODEMS_LIB, drv, abi] + objs +
+        ["-L", OUT, "-l:libsdr_ref.so", "-Wl,-rpath,$ORIGIN", "-lm", "-pthread", "-Wl,--no-undefined"])
+    return MODEMS_LIB
+
+
 if __name__ == "__main__":
     if "--clean" in sys.argv and os.path.exists(REF_AR) and os.path.isdir(OBJ):
         import shutil
         shutil.rmtree(OBJ)      # our own build products only; re-extracted from the reference archive below
     print(build(force="--force" in sys.argv or "--clean" in sys.argv))
+    print(build_modems(force="--force" in sys.argv or "--clean" in sys.argv))

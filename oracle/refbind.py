@@ -1,7 +1,8 @@
 """oracle/refbind.py -- ctypes binding of oracle/_ref/libsdr_ref.so.  TEST INFRASTRUCTURE ONLY.
 
 The library is the reference's own liquid-dsp 1.5.0 binary plus the CubicSDR glue restated in oracle/ref_chain.cpp
-(see oracle/build_ref.py).  Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this.
+(see oracle/build_ref.py), and of oracle/_ref/libmodems_ref.so, the reference's own unmodified modem classes over that
+binary (RefModems / RefModem at the end).  Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this.
 """
 import ctypes as C
 import os
@@ -299,3 +300,70 @@ def ref_wav_payload(ref, data, channels, peak):
     ref.L.ref_wav_payload.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_int, C.c_float, C.c_void_p]
     n = ref.L.ref_wav_payload(_p(d), 0, d.size, int(channels), float(peak), _p(out))
     return out[:n].copy()
+
+
+MODEMS_LIB = os.path.join(_HERE, "_ref", "libmodems_ref.so")
+
+
+class RefModems:
+    """oracle/_ref/libmodems_ref.so: the reference's own, unmodified Modem classes (oracle/ref_modems.cpp)."""
+
+    def __init__(self, path=MODEMS_LIB):
+        if not os.path.exists(path):
+            import subprocess, sys
+            subprocess.check_call([sys.executable, os.path.join(_HERE, "build_ref.py")])
+        L = self.L = C.CDLL(path)
+        vp, u, i, ll = C.c_void_p, C.c_uint, C.c_int, C.c_longlong
+        L.refmodem_create.restype = vp; L.refmodem_create.argtypes = [C.c_char_p]
+        L.refmodem_default_rate.argtypes = [C.c_char_p]
+        L.refmodem_type.argtypes = [vp, C.c_char_p, i]
+        L.refmodem_check_sample_rate.argtypes = [vp, ll, i]
+        L.refmodem_write_setting.argtypes = [vp, C.c_char_p, C.c_char_p]; L.refmodem_write_setting.restype = None
+        L.refmodem_build_kit.argtypes = [vp, ll, i]
+        L.refmodem_should_rebuild_kit.argtypes = [vp]
+        L.refmodem_use_signal_output.argtypes = [vp]
+        L.refmodem_demodulate.argtypes = [vp, vp, u, ll, vp, u, vp, vp]
+        L.refmodem_destroy.argtypes = [vp]; L.refmodem_destroy.restype = None
+
+    def default_rate(self, name):
+        return self.L.refmodem_default_rate(name.encode())
+
+
+class RefModem:
+    """One Modem made by Modem::makeModem(name) with its kit (Modem.h:127-166)."""
+
+    def __init__(self, mods, name, sample_rate, audio_rate=48000):
+        self.L = mods.L
+        self.h = C.c_void_p(self.L.refmodem_create(name.encode()))
+        assert self.h.value, "unknown modem %r" % name
+        # DemodulatorWorkerThread.cpp:84-101: the kit is built at the rate checkSampleRate returns
+        self.sample_rate = self.L.refmodem_check_sample_rate(self.h, int(sample_rate), int(audio_rate))
+        self.audio_rate = audio_rate
+        assert self.L.refmodem_build_kit(self.h, self.sample_rate, int(audio_rate)) == 0
+
+    @property
+    def type(self):
+        buf = C.create_string_buffer(32)
+        self.L.refmodem_type(self.h, buf, 32)
+        return buf.value.decode()
+
+    @property
+    def use_signal_output(self):
+        return bool(self.L.refmodem_use_signal_output(self.h))
+
+    def write_setting(self, key, value):
+        self.L.refmodem_write_setting(self.h, key.encode(), str(value).encode())
+        if self.L.refmodem_should_rebuild_kit(self.h):
+            assert self.L.refmodem_build_kit(self.h, self.sample_rate, int(self.audio_rate)) == 0
+
+    def demodulate(self, iq):
+        iq = np.ascontiguousarray(iq, np.complex64)
+        cap = 4 * iq.size + 65536
+        au = np.zeros(cap, np.float32)
+        ch, rate = C.c_int(), C.c_int()
+        n = self.L.refmodem_demodulate(self.h, _p(iq), iq.size, self.sample_rate, _p(au), cap, C.byref(ch), C.byref(rate))
+        assert 0 <= n <= cap
+        return au[:n].copy(), ch.value, rate.value
+
+    def close(self):
+        self.L.refmodem_destroy(self.h)
