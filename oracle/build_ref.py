@@ -22,6 +22,9 @@ where it lies and writes only into oracle/_ref/ (git-ignored, but shipped to the
      analog/Modem*.cpp) from where they lie, their liquid calls renamed to System V forwarders
      (oracle/modem_abi.h, oracle/ref_modem_abi.c), with the C entry points of oracle/ref_modems.cpp, into
      oracle/_ref/libmodems_ref.so (pins ref_chain.cpp's modem restatement: tests/test_oracle_modems.py)
+  7. likewise src/process/FFTDataDistributor.cpp, SpectrumVisualProcessor.cpp and ScopeVisualProcessor.cpp, unmodified,
+     with the two headers that need wx (the application, the OpenGL panel) shadowed by oracle/shadow/, and the C entry
+     points of oracle/ref_visuals.cpp, into oracle/_ref/libvisuals_ref.so (tests/test_oracle_visuals.py)
 
 If /root/reference is absent (GPU box) and oracle/_ref/libsdr_ref.so already exists, nothing is done.
 """
@@ -36,7 +39,9 @@ OUT = os.path.join(HERE, "_ref")
 OBJ = os.path.join(OUT, "obj")
 LIB = os.path.join(OUT, "libsdr_ref.so")
 MODEMS_LIB = os.path.join(OUT, "libmodems_ref.so")
+VISUALS_LIB = os.path.join(OUT, "libvisuals_ref.so")
 REF_SRC = "/root/reference/src"
+REF_VISUAL_SRCS = ["FFTDataDistributor.cpp", "SpectrumVisualProcessor.cpp", "ScopeVisualProcessor.cpp"]
 REF_MODEM_SRCS = ["Modem.cpp", "ModemAnalog.cpp"] + ["analog/Modem%s.cpp" % m for m in
                                                      ("FM", "NBFM", "FMStereo", "AM", "CW", "LSB", "USB", "DSB", "IQ")]
 
@@ -179,9 +184,45 @@ def build_modems(force=False):
     return MODEMS_LIB
 
 
+def build_visuals(force=False):
+    """oracle/_ref/libvisuals_ref.so: the reference's unmodified FFTDataDistributor / SpectrumVisualProcessor /
+    ScopeVisualProcessor over its own liquid binary."""
+    if not os.path.exists(REF_SRC):
+        if os.path.exists(VISUALS_LIB):
+            return VISUALS_LIB
+        raise SystemExit("oracle/_ref/libvisuals_ref.so missing and /root/reference absent")
+    lib = build(force)
+    shadow = os.path.join(HERE, "shadow")
+    mine = [os.path.join(HERE, f) for f in ("modem_abi.h", "ref_modem_abi.c", "ref_visuals.cpp")] + \
+           [os.path.join(shadow, f) for f in ("CubicSDR.h", "ScopePanel.h")] + [os.path.abspath(__file__)]
+    if (not force) and os.path.exists(VISUALS_LIB) and all(os.path.getmtime(VISUALS_LIB) >= os.path.getmtime(s) for s in mine + [lib]):
+        return VISUALS_LIB
+    vdir = os.path.join(OUT, "visual_obj")
+    os.makedirs(vdir, exist_ok=True)
+    proc = os.path.join(REF_SRC, "process")
+    inc = []
+    for d in (shadow, REF_SRC, os.path.join(REF_SRC, "util"), os.path.join(REF_SRC, "audio"), os.path.join(REF_SRC, "demod"), proc,
+              os.path.join(REF_SRC, "modules", "modem"), "/root/reference/external/liquid-dsp/include", "/root/reference/external/rtaudio"):
+        inc += ["-I", d]
+    cxx = ["g++", "-std=c++17", "-O2", "-fPIC", "-pthread", "-w", "-include", os.path.join(HERE, "modem_abi.h")] + inc
+    objs = []
+    for src in REF_VISUAL_SRCS:                                  # compiled where they lie, objects only into oracle/_ref/
+        o = os.path.join(vdir, src[:-4] + ".o")
+        run(cxx + ["-c", os.path.join(proc, src), "-o", o])
+        objs.append(o)
+    drv = os.path.join(vdir, "ref_visuals.o")
+    run(cxx + ["-c", os.path.join(HERE, "ref_visuals.cpp"), "-o", drv])
+    abi = os.path.join(vdir, "ref_modem_abi.o")
+    run(["gcc", "-O2", "-fPIC", "-c", os.path.join(HERE, "ref_modem_abi.c"), "-o", abi])
+    run(["g++", "-shared", "-o", VISUALS_LIB, drv, abi] + objs +
+        ["-L", OUT, "-l:libsdr_ref.so", "-Wl,-rpath,$ORIGIN", "-lm", "-pthread", "-Wl,--no-undefined"])
+    return VISUALS_LIB
+
+
 if __name__ == "__main__":
     if "--clean" in sys.argv and os.path.exists(REF_AR) and os.path.isdir(OBJ):
         import shutil
         shutil.rmtree(OBJ)      # our own build products only; re-extracted from the reference archive below
     print(build(force="--force" in sys.argv or "--clean" in sys.argv))
     print(build_modems(force="--force" in sys.argv or "--clean" in sys.argv))
+    print(build_visuals(force="--force" in sys.argv or "--clean" in sys.argv))

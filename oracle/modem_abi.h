@@ -1,8 +1,9 @@
 /* oracle/modem_abi.h -- TEST INFRASTRUCTURE ONLY.
  *
- * Force-included (-include) in front of the reference's OWN, unmodified modem sources
- * (/root/reference/src/modules/modem/Modem.cpp, ModemAnalog.cpp, analog/Modem*.cpp) when oracle/build_ref.py compiles them
- * where they lie into oracle/_ref/libmodems_ref.so.  Those sources call liquid-dsp through liquid.h's System V
+ * Force-included (-include) in front of the reference's OWN, unmodified sources -- the modems
+ * (/root/reference/src/modules/modem/Modem.cpp, ModemAnalog.cpp, analog/Modem*.cpp) and the visual processors
+ * (src/process/FFTDataDistributor.cpp, SpectrumVisualProcessor.cpp, ScopeVisualProcessor.cpp) -- when oracle/build_ref.py
+ * compiles them where they lie into oracle/_ref/libmodems_ref.so / libvisuals_ref.so.  Those sources call liquid-dsp through liquid.h's System V
  * prototypes; the only liquid binary the reference ships is a MinGW archive whose functions use the Microsoft x64
  * convention (oracle/build_ref.py).  Every liquid entry point the modem sources use is therefore renamed here to a
  * System V forwarder sv_<name> (oracle/ref_modem_abi.c).  liquid.h builds its names by token pasting and the pasted
@@ -51,4 +52,13 @@
 #define nco_crcf_reset sv_nco_crcf_reset
 #define nco_crcf_set_frequency sv_nco_crcf_set_frequency
 #define nco_crcf_step sv_nco_crcf_step
+/* the visual processors (FFTDataDistributor needs none; SpectrumVisualProcessor.cpp, ScopeVisualProcessor.cpp) */
+#define fft_create_plan sv_fft_create_plan
+#define fft_execute sv_fft_execute
+#define fft_destroy_plan sv_fft_destroy_plan
+#define nco_crcf_mix_block_up sv_nco_crcf_mix_block_up
+#define nco_crcf_mix_block_down sv_nco_crcf_mix_block_down
+#define msresamp_crcf_create sv_msresamp_crcf_create
+#define msresamp_crcf_destroy sv_msresamp_crcf_destroy
+#define msresamp_crcf_execute sv_msresamp_crcf_execute
 #endif

@@ -56,3 +56,13 @@ FWD0(int, nco_crcf_pll_step, (obj q, float dphi), (q, dphi))
 FWD0(int, nco_crcf_reset, (obj q), (q))
 FWD0(int, nco_crcf_set_frequency, (obj q, float dtheta), (q, dtheta))
 FWD0(int, nco_crcf_step, (obj q), (q))
+
+/* the visual processors */
+FWD0(obj, fft_create_plan, (uint n, cf *x, cf *y, int dir, int flags), (n, x, y, dir, flags))
+FWD0(int, fft_execute, (obj p), (p))
+FWD0(int, fft_destroy_plan, (obj p), (p))
+FWD0(int, nco_crcf_mix_block_up, (obj q, cf *x, cf *y, uint n), (q, x, y, n))
+FWD0(int, nco_crcf_mix_block_down, (obj q, cf *x, cf *y, uint n), (q, x, y, n))
+FWD0(obj, msresamp_crcf_create, (float r, float as), (r, as))
+FWD0(int, msresamp_crcf_destroy, (obj q), (q))
+FWD0(int, msresamp_crcf_execute, (obj q, cf *x, uint nx, cf *y, uint *ny), (q, x, nx, y, ny))

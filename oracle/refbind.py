@@ -2,7 +2,8 @@
 
 The library is the reference's own liquid-dsp 1.5.0 binary plus the CubicSDR glue restated in oracle/ref_chain.cpp
 (see oracle/build_ref.py), and of oracle/_ref/libmodems_ref.so, the reference's own unmodified modem classes over that
-binary (RefModems / RefModem at the end).  Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this.
+binary (RefModems / RefModem at the end), and of oracle/_ref/libvisuals_ref.so, its unmodified FFTDataDistributor /
+SpectrumVisualProcessor / ScopeVisualProcessor (RefVisuals / SrcDistrib / SrcSpectrum / SrcScope).  Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this.
 """
 import ctypes as C
 import os
@@ -367,3 +368,113 @@ class RefModem:
 
     def close(self):
         self.L.refmodem_destroy(self.h)
+
+
+VISUALS_LIB = os.path.join(_HERE, "_ref", "libvisuals_ref.so")
+
+
+class RefVisuals:
+    """oracle/_ref/libvisuals_ref.so: the reference's own, unmodified FFTDataDistributor / SpectrumVisualProcessor /
+    ScopeVisualProcessor (oracle/ref_visuals.cpp)."""
+
+    def __init__(self, path=VISUALS_LIB):
+        if not os.path.exists(path):
+            import subprocess, sys
+            subprocess.check_call([sys.executable, os.path.join(_HERE, "build_ref.py")])
+        L = self.L = C.CDLL(path)
+        vp, u, i, ll, f = C.c_void_p, C.c_uint, C.c_int, C.c_longlong, C.c_float
+        L.refsrc_distrib_create.restype = vp; L.refsrc_distrib_create.argtypes = [u, u]
+        L.refsrc_distrib_set_fft_size.argtypes = [vp, u]; L.refsrc_distrib_set_fft_size.restype = None
+        L.refsrc_distrib_set_lines_per_second.argtypes = [vp, u]; L.refsrc_distrib_set_lines_per_second.restype = None
+        L.refsrc_distrib_push.restype = u; L.refsrc_distrib_push.argtypes = [vp, vp, u, ll, ll, vp, u, vp]
+        L.refsrc_distrib_destroy.argtypes = [vp]; L.refsrc_distrib_destroy.restype = None
+        L.refsrc_spectrum_create.restype = vp; L.refsrc_spectrum_create.argtypes = [u, ll]
+        L.refsrc_spectrum_set_view.argtypes = [vp, i, ll, C.c_long]; L.refsrc_spectrum_set_view.restype = None
+        L.refsrc_spectrum_set_average_rate.argtypes = [vp, f]; L.refsrc_spectrum_set_average_rate.restype = None
+        L.refsrc_spectrum_set_band.argtypes = [vp, ll, C.c_long]; L.refsrc_spectrum_set_band.restype = None
+        L.refsrc_spectrum_set_hide_dc.argtypes = [vp, i]; L.refsrc_spectrum_set_hide_dc.restype = None
+        L.refsrc_spectrum_desired_input.argtypes = [vp]
+        L.refsrc_spectrum_frame.argtypes = [vp, vp, u, ll, ll, vp, u, vp, vp, vp]
+        L.refsrc_spectrum_destroy.argtypes = [vp]; L.refsrc_spectrum_destroy.restype = None
+        L.refsrc_scope_create.restype = vp; L.refsrc_scope_create.argtypes = [i]
+        L.refsrc_scope_process.restype = u; L.refsrc_scope_process.argtypes = [vp, vp, u, i, i, i, i, vp, u, vp, u, vp, vp, vp]
+        L.refsrc_scope_destroy.argtypes = [vp]; L.refsrc_scope_destroy.restype = None
+
+
+class SrcDistrib:
+    """The reference's FFTDataDistributor object: setInput / attachOutput / setFFTSize / setLinesPerSecond, then per block
+    push + run() + drain (FFTVisualDataThread.cpp:40-84)."""
+
+    def __init__(self, vis, frame_len, lps):
+        self.L, self.n = vis.L, frame_len
+        self.h = C.c_void_p(self.L.refsrc_distrib_create(frame_len, lps))
+
+    def push(self, block, sample_rate, frequency=0):
+        block = np.ascontiguousarray(block, np.complex64)
+        out = np.zeros(block.size + 4 * self.n + 1048576, np.complex64)
+        ns = C.c_uint()
+        nf = self.L.refsrc_distrib_push(self.h, _p(block), block.size, int(sample_rate), int(frequency), _p(out), out.size, C.byref(ns))
+        assert ns.value <= out.size and ns.value == nf * self.n
+        return out[:ns.value].reshape(nf, self.n)
+
+    def set_frame_len(self, n):
+        self.L.refsrc_distrib_set_fft_size(self.h, int(n))
+        self.n = int(n)
+
+    def close(self):
+        self.L.refsrc_distrib_destroy(self.h)
+
+
+class SrcSpectrum:
+    """The reference's SpectrumVisualProcessor object."""
+
+    def __init__(self, vis, fft_size, device_sample_rate):
+        self.L, self.fft_size = vis.L, fft_size
+        self.h = C.c_void_p(self.L.refsrc_spectrum_create(fft_size, int(device_sample_rate)))
+
+    def set_average_rate(self, r):
+        self.L.refsrc_spectrum_set_average_rate(self.h, C.c_float(r))
+
+    def set_band(self, center_freq, bandwidth):
+        """Full-band display: setCenterFrequency(frequency) + setBandwidth(sampleRate), as AppFrame.cpp:1396-1399 does."""
+        self.L.refsrc_spectrum_set_band(self.h, int(center_freq), int(bandwidth))
+
+    def set_view(self, is_view, center_freq, bandwidth):
+        self.L.refsrc_spectrum_set_view(self.h, 1 if is_view else 0, int(center_freq), int(bandwidth))
+
+    def desired_input(self):
+        return int(self.L.refsrc_spectrum_desired_input(self.h))
+
+    def frame(self, frame, frequency, sample_rate):
+        """One process() call; None if the processor distributed nothing."""
+        frame = np.ascontiguousarray(frame, np.complex64)
+        pts = np.zeros(self.fft_size, np.float32); cf = np.zeros(2, np.float64)
+        center, bw = C.c_longlong(), C.c_int()
+        m = self.L.refsrc_spectrum_frame(self.h, _p(frame), frame.size, int(frequency), int(sample_rate), _p(pts), pts.size, _p(cf),
+                                         C.byref(center), C.byref(bw))
+        if not m:
+            return None
+        assert m == self.fft_size
+        return dict(points=pts, ceil_floor=cf, center=center.value, bandwidth=bw.value)
+
+    def close(self):
+        self.L.refsrc_spectrum_destroy(self.h)
+
+
+class SrcScope:
+    """The reference's ScopeVisualProcessor object (scope and spectrum both enabled, as constructed)."""
+
+    def __init__(self, vis, fft_size=1024):
+        self.L, self.fft_size = vis.L, fft_size
+        self.h = C.c_void_p(self.L.refsrc_scope_create(fft_size))
+
+    def process(self, data, channels, sample_rate, input_rate, type=0):
+        d = np.ascontiguousarray(data, np.float32)
+        wave = np.zeros(2 * d.size + 4096, np.float32); spec = np.zeros(2 * self.fft_size + 16, np.float32)
+        ns, mode = C.c_uint(), C.c_int(-1); fc = np.zeros(2, np.float64)
+        nw = self.L.refsrc_scope_process(self.h, _p(d), d.size, int(channels), int(sample_rate), int(input_rate), int(type),
+                                         _p(wave), wave.size, _p(spec), spec.size, C.byref(ns), _p(fc), C.byref(mode))
+        return wave[:nw].copy(), spec[:ns.value].copy(), fc, mode.value
+
+    def close(self):
+        self.L.refsrc_scope_destroy(self.h)
