@@ -9,7 +9,8 @@
 // audioQueuePtr live in HBM; the samples sit in a per-source ring the feed kernel fills from the channel's result slot after every
 // block.  Rendering n frames is the callback, statement by statement: a serial walk per source that decides which sample every
 // output slot takes (phase A, one thread per source), the sum over the sources IN BINDING ORDER per output slot (phase B: float
-// additions are not associative, the order is the reference's), the peak sum and the normalisation (phases C, D).
+// additions are not associative, the order is the reference's: MixArgs::order is the controller's boundThreads, which
+// AudioThread::setActive edits), the peak sum and the normalisation (phases C, D).
 #pragma once
 #include "dsp_core.h"
 
@@ -35,6 +36,8 @@ struct MixSource {
 struct MixArgs {
     MixSource *src;
     int n_src;
+    const int *order;              // the controller's boundThreads: source indices in binding order (inactive sources are not in it)
+    int n_order;
     float *rings;
     int rate;                      // the output device's sample rate (src->getSampleRate())
     // feed
@@ -142,7 +145,8 @@ SDR_HD inline void mix_sum_thread(const MixArgs &a, int k) {
     const int slots = 2 * a.n_frames;
     if (k >= slots) return;
     float acc = 0.f;
-    for (int j = 0; j < a.n_src; ++j) {
+    for (int o = 0; o < a.n_order; ++o) {
+        const int j = a.order[o];
         const int idx = a.map[(size_t)j * slots + k];
         if (idx >= 0) {
             const MixSource &s = a.src[j];
@@ -159,7 +163,7 @@ SDR_HD inline void mix_sum_thread(const MixArgs &a, int k) {
 // phases C + D: peak over the sources that mixed (:228), normalisation (:231-238); returns the scale (1 = none)
 SDR_HD inline float mix_scale(const MixArgs &a) {
     double peak = 0.0;
-    for (int j = 0; j < a.n_src; ++j) if (a.mix_peak[j] >= 0.0) peak += a.mix_peak[j];
+    for (int o = 0; o < a.n_order; ++o) { const int j = a.order[o]; if (a.mix_peak[j] >= 0.0) peak += a.mix_peak[j]; }
     return peak > 1.0 ? (float)(1.0 / peak) : 1.0f;
 }
 

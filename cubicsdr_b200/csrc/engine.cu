@@ -3566,6 +3566,9 @@ struct sdr_mixer {
     float *d_out = nullptr, *h_out = nullptr;
     float *d_stage = nullptr, *h_stage = nullptr;
     std::vector<int> src_chan;               // host shadow of MixSource::chan
+    std::vector<int> src_active;             // host shadow of MixSource::active
+    std::vector<int> order;                  // the controller's boundThreads: active sources in binding order
+    int *d_order = nullptr;
 #ifndef SDR_EMU
     cudaEvent_t ev_done = nullptr;           // end of the last render's device work
 #endif
@@ -3574,7 +3577,7 @@ struct sdr_mixer {
 };
 static MixArgs mixer_args(sdr_mixer *m) {
     MixArgs a;
-    a.src = m->d_src; a.n_src = m->n_src; a.rings = m->d_rings; a.rate = m->rate; a.cs = m->eng->d_cs; a.results = m->eng->d_results;
+    a.src = m->d_src; a.n_src = m->n_src; a.order = m->d_order; a.n_order = (int)m->order.size(); a.rings = m->d_rings; a.rate = m->rate; a.cs = m->eng->d_cs; a.results = m->eng->d_results;
     a.n_frames = 0; a.map = m->d_map; a.mix_peak = m->d_peak; a.out = m->d_out;
     return a;
 }
@@ -3610,12 +3613,13 @@ extern "C" int sdr_mixer_create(sdr_engine *e, int sample_rate, unsigned max_fra
     bad |= be_malloc((void **)&m->d_rings, m->ring_cap_total * sizeof(float));
     bad |= be_malloc((void **)&m->d_map, (size_t)kMixMaxSources * 2 * max_frames * sizeof(int));
     bad |= be_malloc((void **)&m->d_peak, kMixMaxSources * sizeof(double));
+    bad |= be_malloc((void **)&m->d_order, kMixMaxSources * sizeof(int));
     bad |= be_malloc((void **)&m->d_out, 2 * (size_t)max_frames * sizeof(float));
     bad |= be_host_alloc((void **)&m->h_out, 2 * (size_t)max_frames * sizeof(float));
     bad |= be_malloc((void **)&m->d_stage, sdr_mixer::kStage * sizeof(float));
     bad |= be_host_alloc((void **)&m->h_stage, sdr_mixer::kStage * sizeof(float));
     if (bad) {
-        be_free(m->d_src); be_free(m->d_rings); be_free(m->d_map); be_free(m->d_peak); be_free(m->d_out); be_host_free(m->h_out);
+        be_free(m->d_src); be_free(m->d_rings); be_free(m->d_map); be_free(m->d_peak); be_free(m->d_order); be_free(m->d_out); be_host_free(m->h_out);
         be_free(m->d_stage); be_host_free(m->h_stage); delete m;
         return fail(SDR_ERR_NOMEM, "sdr_mixer_create: allocation failed");
     }
@@ -3634,24 +3638,41 @@ extern "C" int sdr_mixer_destroy(sdr_mixer *m) {
 #ifndef SDR_EMU
     if (m->ev_done) cudaEventDestroy(m->ev_done);
 #endif
-    be_free(m->d_src); be_free(m->d_rings); be_free(m->d_map); be_free(m->d_peak); be_free(m->d_out); be_host_free(m->h_out);
+    be_free(m->d_src); be_free(m->d_rings); be_free(m->d_map); be_free(m->d_peak); be_free(m->d_order); be_free(m->d_out); be_host_free(m->h_out);
     be_free(m->d_stage); be_host_free(m->h_stage);
     delete m;
     return SDR_OK;
+}
+// AudioThread::setGain (src/audio/AudioThread.cpp:595-604): clamped to [0, 2]
+static float mixer_clamp_gain(float gain) {
+    if (gain < 0.0f) gain = 0.0f;
+    if (gain > 2.0f) gain = 2.0f;
+    return gain;
+}
+// the binding order changed: upload it (engine lock held; the sink stream is idle afterwards)
+static void mixer_upload_order(sdr_mixer *m) {
+    sdr_stream_t ss = sink_stream(m->eng);
+    be_sync(ss);
+    if (!m->order.empty()) be_h2d(m->d_order, m->order.data(), m->order.size() * sizeof(int), ss);
+    be_sync(ss);
 }
 static int mixer_add(sdr_mixer *m, int chan_slot, int feed_rate, float gain, int *index) {
     if (m->n_src >= kMixMaxSources) return fail(SDR_ERR_STATE, "sdr_mixer: too many sources");
     MixSource s;
     memset(&s, 0, sizeof s);
-    s.chan = chan_slot; s.feed_rate = feed_rate; s.gain = gain; s.active = 1;
+    // a demodulator's AudioThread: given its gain (setGain), then setActive(true), which binds it to the controller (:577-579)
+    s.chan = chan_slot; s.feed_rate = feed_rate; s.gain = mixer_clamp_gain(gain); s.active = 1;
     s.ring_off = (int)((size_t)m->n_src * sdr_mixer::kRing); s.ring_cap = sdr_mixer::kRing;
     sdr_stream_t ss = sink_stream(m->eng);
     be_sync(ss);                                                  // (binding is rare; the copy below reads a stack object)
     be_h2d(m->d_src + m->n_src, &s, sizeof s, ss);
     be_sync(ss);
     if (index) *index = m->n_src;
+    m->order.push_back(m->n_src);
     m->n_src += 1;
     m->src_chan.push_back(chan_slot);
+    m->src_active.push_back(1);
+    mixer_upload_order(m);
     return SDR_OK;
 }
 // the channel in slot `index` is being destroyed (engine lock held): its slot may be reused, so no source may read it any more
@@ -3686,8 +3707,36 @@ static int mixer_poke(sdr_mixer *m, int source, size_t field_off, const void *v,
     be_sync(ss);
     return SDR_OK;
 }
-extern "C" int sdr_mixer_set_gain(sdr_mixer *m, int source, float gain) { return mixer_poke(m, source, offsetof(MixSource, gain), &gain, sizeof gain); }     // AudioThread::setGain
-extern "C" int sdr_mixer_set_active(sdr_mixer *m, int source, int active) { return mixer_poke(m, source, offsetof(MixSource, active), &active, sizeof active); }   // AudioThread::setActive
+extern "C" int sdr_mixer_set_gain(sdr_mixer *m, int source, float gain) {               // AudioThread::setGain (:595-604)
+    gain = mixer_clamp_gain(gain);
+    return mixer_poke(m, source, offsetof(MixSource, gain), &gain, sizeof gain);
+}
+// AudioThread::setActive (:557-589): becoming active binds the thread to the controller -- APPENDED, so a source that was
+// inactive for a while is mixed last afterwards (float sums depend on the order); becoming inactive removes it; every call
+// flushes the inputQueue ("activity state changing, clear any inputs"); currentInput and audioQueuePtr stay.
+extern "C" int sdr_mixer_set_active(sdr_mixer *m, int source, int active) {
+    if (!m || source < 0 || source >= m->n_src) return fail(SDR_ERR_ARG, "sdr_mixer: bad source");
+    std::lock_guard<std::mutex> lk(m->eng->mu);
+    use_device(m->eng);
+    const int state = active ? 1 : 0;
+    bool order_changed = false;
+    if (state && !m->src_active[(size_t)source]) {
+        if (std::find(m->order.begin(), m->order.end(), source) == m->order.end()) { m->order.push_back(source); order_changed = true; }
+    } else if (!state && m->src_active[(size_t)source]) {
+        auto it = std::find(m->order.begin(), m->order.end(), source);
+        if (it != m->order.end()) { m->order.erase(it); order_changed = true; }
+    }
+    m->src_active[(size_t)source] = state;
+    sdr_stream_t ss = sink_stream(m->eng);
+    be_sync(ss);
+    static const int zero2[2] = {0, 0};
+    static_assert(offsetof(MixSource, q_count) == offsetof(MixSource, q_head) + sizeof(int), "q_head, q_count adjacent");
+    be_h2d(reinterpret_cast<char *>(m->d_src + source) + offsetof(MixSource, q_head), zero2, sizeof zero2, ss);
+    be_h2d(reinterpret_cast<char *>(m->d_src + source) + offsetof(MixSource, active), &state, sizeof state, ss);
+    be_sync(ss);
+    if (order_changed) mixer_upload_order(m);
+    return SDR_OK;
+}
 // one AudioThreadInput pushed by the host (what DemodulatorThread does with audioOutputQueue->try_push, for audio from elsewhere)
 extern "C" int sdr_mixer_push(sdr_mixer *m, int source, const float *data, unsigned n, int channels, float peak, int sample_rate) {
     if (!m || source < 0 || source >= m->n_src || (n && !data) || n > (unsigned)sdr_mixer::kStage) return fail(SDR_ERR_ARG, "sdr_mixer_push: bad arguments");

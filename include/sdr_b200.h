@@ -212,8 +212,10 @@ int sdr_mixer_create(sdr_engine *eng, int sample_rate, unsigned max_frames, sdr_
 int sdr_mixer_destroy(sdr_mixer *m);
 int sdr_mixer_bind(sdr_mixer *m, sdr_chan *chan, float gain, int *source_index);
 int sdr_mixer_add_source(sdr_mixer *m, float gain, int *source_index);
-int sdr_mixer_set_gain(sdr_mixer *m, int source, float gain);                  /* AudioThread::setGain */
-int sdr_mixer_set_active(sdr_mixer *m, int source, int active);                /* AudioThread::setActive */
+int sdr_mixer_set_gain(sdr_mixer *m, int source, float gain);                  /* AudioThread::setGain (:595-604): clamped to [0, 2] */
+/* AudioThread::setActive (:557-589): activation binds the source to the controller again -- at the END of the mix order;
+ * deactivation removes it; every call flushes the source's queue (currentInput and audioQueuePtr stay).            */
+int sdr_mixer_set_active(sdr_mixer *m, int source, int active);
 int sdr_mixer_push(sdr_mixer *m, int source, const float *data, unsigned n, int channels, float peak, int sample_rate);
 int sdr_mixer_render(sdr_mixer *m, unsigned n_frames, float *out_stereo /* 2 n_frames */);
 /* AudioFileWAV::writePayloadToFileStream (src/audio/AudioFileWAV.cpp:143-165): the channel's last block as 16-bit PCM words */

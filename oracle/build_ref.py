@@ -24,7 +24,9 @@ where it lies and writes only into oracle/_ref/ (git-ignored, but shipped to the
      oracle/_ref/libmodems_ref.so (pins ref_chain.cpp's modem restatement: tests/test_oracle_modems.py)
   7. likewise src/process/FFTDataDistributor.cpp, SpectrumVisualProcessor.cpp and ScopeVisualProcessor.cpp, unmodified,
      with the two headers that need wx (the application, the OpenGL panel) shadowed by oracle/shadow/, and the C entry
-     points of oracle/ref_visuals.cpp, into oracle/_ref/libvisuals_ref.so (tests/test_oracle_visuals.py)
+     points of oracle/ref_visuals.cpp, into oracle/_ref/libvisuals_ref.so (tests/test_oracle_visuals.py); the same library
+     holds the audio mixer: src/audio/AudioThread.cpp (its RtAudio callback) through oracle/ref_audio.cpp, with
+     src/IOThread.cpp, src/util/Timer.cpp and the reference's external/rtaudio/RtAudio.cpp (dummy API, no device)
 
 If /root/reference is absent (GPU box) and oracle/_ref/libsdr_ref.so already exists, nothing is done.
 """
@@ -193,8 +195,8 @@ def build_visuals(force=False):
         raise SystemExit("oracle/_ref/libvisuals_ref.so missing and /root/reference absent")
     lib = build(force)
     shadow = os.path.join(HERE, "shadow")
-    mine = [os.path.join(HERE, f) for f in ("modem_abi.h", "ref_modem_abi.c", "ref_visuals.cpp")] + \
-           [os.path.join(shadow, f) for f in ("CubicSDR.h", "ScopePanel.h")] + [os.path.abspath(__file__)]
+    mine = [os.path.join(HERE, f) for f in ("modem_abi.h", "ref_modem_abi.c", "ref_visuals.cpp", "ref_audio.cpp")] + \
+           [os.path.join(shadow, f) for f in ("CubicSDR.h", "ScopePanel.h", "DemodulatorInstance.h")] + [os.path.abspath(__file__)]
     if (not force) and os.path.exists(VISUALS_LIB) and all(os.path.getmtime(VISUALS_LIB) >= os.path.getmtime(s) for s in mine + [lib]):
         return VISUALS_LIB
     vdir = os.path.join(OUT, "visual_obj")
@@ -210,6 +212,17 @@ def build_visuals(force=False):
         o = os.path.join(vdir, src[:-4] + ".o")
         run(cxx + ["-c", os.path.join(proc, src), "-o", o])
         objs.append(o)
+    # the audio mixer: src/audio/AudioThread.cpp enters oracle/ref_audio.cpp's translation unit by #include (its callback is
+    # file-static); src/IOThread.cpp, src/util/Timer.cpp and the reference's RtAudio (no audio API compiled in: its dummy API)
+    # as they are
+    for src in (os.path.join(REF_SRC, "IOThread.cpp"), os.path.join(REF_SRC, "util", "Timer.cpp"),
+                "/root/reference/external/rtaudio/RtAudio.cpp"):
+        o = os.path.join(vdir, os.path.basename(src)[:-4] + ".o")
+        run(cxx + ["-c", src, "-o", o])
+        objs.append(o)
+    aud = os.path.join(vdir, "ref_audio.o")
+    run(cxx + ["-fno-access-control", "-c", os.path.join(HERE, "ref_audio.cpp"), "-o", aud])
+    objs.append(aud)
     drv = os.path.join(vdir, "ref_visuals.o")
     run(cxx + ["-c", os.path.join(HERE, "ref_visuals.cpp"), "-o", drv])
     abi = os.path.join(vdir, "ref_modem_abi.o")

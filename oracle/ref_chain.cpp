@@ -618,26 +618,59 @@ struct RefMixSource {                                   // the members of a boun
     bool active = true;
     bool try_pop() { if (queue.empty()) { return false; } delete currentInput; currentInput = queue.front(); queue.erase(queue.begin()); return true; }
 };
-struct RefMixer { int sampleRate; std::vector<RefMixSource *> bound; };
+struct RefMixer {
+    int sampleRate;
+    std::vector<RefMixSource *> all;                    // by source index (what the caller holds)
+    std::vector<RefMixSource *> boundThreads;           // the controller's list, in binding order (the callback's order)
+};
 API void *ref_mixer_create(int sampleRate) { auto *m = new RefMixer; m->sampleRate = sampleRate; return m; }
 API void ref_mixer_destroy(void *h) {
     auto *m = (RefMixer *)h;
-    for (auto *s : m->bound) { for (auto *q : s->queue) delete q; delete s->currentInput; delete s; }
+    for (auto *s : m->all) { for (auto *q : s->queue) delete q; delete s->currentInput; delete s; }
     delete m;
 }
-API int ref_mixer_add_source(void *h, float gain) { auto *m = (RefMixer *)h; auto *s = new RefMixSource; s->gain = gain; m->bound.push_back(s); return (int)m->bound.size() - 1; }
-API void ref_mixer_set_gain(void *h, int idx, float gain) { ((RefMixer *)h)->bound[(size_t)idx]->gain = gain; }
+// AudioThread::setGain (AudioThread.cpp:595-604): clamped to [0, 2]
+static float ref_mixer_clamp_gain(float gain_in) {
+    if (gain_in < 0.0) gain_in = 0.0;
+    if (gain_in > 2.0) gain_in = 2.0;
+    return gain_in;
+}
+// AudioThread::setActive (AudioThread.cpp:557-589): becoming active binds the thread to the controller (appended: a source
+// that was inactive for a while mixes LAST afterwards), becoming inactive removes it; every call flushes the inputQueue
+// (currentInput and audioQueuePtr stay)
+API void ref_mixer_set_active(void *h, int idx, int state_in) {
+    auto *m = (RefMixer *)h; RefMixSource *s = m->all[(size_t)idx];
+    const bool state = state_in != 0;
+    if (state && !s->active) {
+        if (std::find(m->boundThreads.begin(), m->boundThreads.end(), s) == m->boundThreads.end()) m->boundThreads.push_back(s);   // bindThread :56-63
+    } else if (!state && s->active) {
+        auto i = std::find(m->boundThreads.begin(), m->boundThreads.end(), s);                                                     // removeThread :65-74
+        if (i != m->boundThreads.end()) m->boundThreads.erase(i);
+    }
+    for (auto *q : s->queue) delete q;
+    s->queue.clear();
+    s->active = state;
+}
+// a demodulator's AudioThread: constructed inactive with gain 1 (:20-27), given its gain, then activated
+API int ref_mixer_add_source(void *h, float gain) {
+    auto *m = (RefMixer *)h; auto *s = new RefMixSource;
+    s->active = false; s->gain = ref_mixer_clamp_gain(gain);
+    m->all.push_back(s);
+    ref_mixer_set_active(h, (int)m->all.size() - 1, 1);
+    return (int)m->all.size() - 1;
+}
+API void ref_mixer_set_gain(void *h, int idx, float gain) { ((RefMixer *)h)->all[(size_t)idx]->gain = ref_mixer_clamp_gain(gain); }
 API void ref_mixer_push(void *h, int idx, const float *data, unsigned n, int channels, float peak, int sampleRate) {
     auto *in = new RefAudioInput; in->sampleRate = sampleRate; in->channels = channels; in->peak = peak; in->data.assign(data, data + n);
-    ((RefMixer *)h)->bound[(size_t)idx]->queue.push_back(in);
+    ((RefMixer *)h)->all[(size_t)idx]->queue.push_back(in);
 }
 // audioCallback (AudioThread.cpp:88-243), statement by statement; `src` = the controller, `srcmix` = a bound thread
 API void ref_mixer_callback(void *h, float *out, unsigned nBufferFrames) {
     auto *src = (RefMixer *)h;
     memset(out, 0, nBufferFrames * 2 * sizeof(float));
     double peak = 0.0;
-    for (size_t j = 0; j < src->bound.size(); j++) {
-        RefMixSource *srcmix = src->bound[j];
+    for (size_t j = 0; j < src->boundThreads.size(); j++) {
+        RefMixSource *srcmix = src->boundThreads[j];
         if (srcmix->queue.empty() || !srcmix->active) continue;                       // :122 (an empty inputQueue skips the thread, whatever currentInput still holds)
         if (!srcmix->currentInput) {                                                  // :126-134
             srcmix->audioQueuePtr = 0;

@@ -257,6 +257,10 @@ class RefMixer:
     def set_gain(self, i, gain):
         self.L.ref_mixer_set_gain(self.h, int(i), float(gain))
 
+    def set_active(self, i, active):
+        self.L.ref_mixer_set_active.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        self.L.ref_mixer_set_active(self.h, int(i), 1 if active else 0)
+
     def push(self, i, data, channels=1, peak=0.0, sample_rate=48000):
         d = np.ascontiguousarray(data, np.float32)
         self.L.ref_mixer_push(self.h, int(i), _p(d), d.size, int(channels), float(peak), int(sample_rate))
@@ -399,6 +403,13 @@ class RefVisuals:
         L.refsrc_scope_create.restype = vp; L.refsrc_scope_create.argtypes = [i]
         L.refsrc_scope_process.restype = u; L.refsrc_scope_process.argtypes = [vp, vp, u, i, i, i, i, vp, u, vp, u, vp, vp, vp]
         L.refsrc_scope_destroy.argtypes = [vp]; L.refsrc_scope_destroy.restype = None
+        L.refsrc_mixer_create.restype = vp; L.refsrc_mixer_create.argtypes = [i]
+        L.refsrc_mixer_add_source.argtypes = [vp, f]
+        L.refsrc_mixer_set_gain.argtypes = [vp, i, f]; L.refsrc_mixer_set_gain.restype = None
+        L.refsrc_mixer_set_active.argtypes = [vp, i, i]; L.refsrc_mixer_set_active.restype = None
+        L.refsrc_mixer_push.argtypes = [vp, i, vp, u, i, f, i]; L.refsrc_mixer_push.restype = None
+        L.refsrc_mixer_callback.argtypes = [vp, vp, u]
+        L.refsrc_mixer_destroy.argtypes = [vp]; L.refsrc_mixer_destroy.restype = None
 
 
 class SrcDistrib:
@@ -478,3 +489,32 @@ class SrcScope:
 
     def close(self):
         self.L.refsrc_scope_destroy(self.h)
+
+
+class SrcMixer:
+    """The reference's audioCallback (src/audio/AudioThread.cpp:88-243) on real AudioThread objects (oracle/ref_audio.cpp)."""
+
+    def __init__(self, vis, sample_rate=48000):
+        self.L = vis.L
+        self.h = C.c_void_p(self.L.refsrc_mixer_create(int(sample_rate)))
+
+    def add_source(self, gain=1.0):
+        return self.L.refsrc_mixer_add_source(self.h, float(gain))
+
+    def set_gain(self, i, gain):
+        self.L.refsrc_mixer_set_gain(self.h, int(i), float(gain))
+
+    def set_active(self, i, active):
+        self.L.refsrc_mixer_set_active(self.h, int(i), 1 if active else 0)
+
+    def push(self, i, data, channels=1, peak=0.0, sample_rate=48000):
+        d = np.ascontiguousarray(data, np.float32)
+        self.L.refsrc_mixer_push(self.h, int(i), _p(d), d.size, int(channels), float(peak), int(sample_rate))
+
+    def callback(self, n_frames):
+        out = np.full(2 * n_frames, np.nan, np.float32)          # the callback zeroes the buffer itself
+        assert self.L.refsrc_mixer_callback(self.h, _p(out), int(n_frames)) == 0
+        return out
+
+    def close(self):
+        self.L.refsrc_mixer_destroy(self.h)

@@ -570,7 +570,16 @@ def check_audio_sinks(lib, ref, n_blocks=8):
             mix.push(extra, d, 1, 0.4, 44100); rmix.push(extra, d, 1, 0.4, 44100)
             mix.push(extra, d, 1, 0.4, 48000); rmix.push(extra, d, 1, 0.4, 48000)
         if b == 5:
-            mix.set_gain(1, 2.5); rmix.set_gain(1, 2.5)
+            mix.set_gain(1, 2.5); rmix.set_gain(1, 2.5)           # AudioThread::setGain clamps to [0, 2]
+        # AudioThread::setActive: a demodulator is muted for a block and comes back -- its queue is flushed both times, it leaves the
+        # controller's list and re-enters it at the END (the float sums then run in another order)
+        if b == 2:
+            mix.set_active(0, False); rmix.set_active(0, False)
+        if b == 3:
+            mix.set_active(0, True); rmix.set_active(0, True)
+            mix.set_active(2, True); rmix.set_active(2, True)     # already active: only the flush happens
+        if b == 6:
+            mix.set_active(extra, False); rmix.set_active(extra, False)
         for cb in range(2 if b % 3 else 1):                       # 512-frame callbacks, sometimes one, sometimes two per block
             got, want = mix.render(512), rmix.callback(512)
             worst["mix"] = max(worst["mix"], float(np.abs(want).max()))
