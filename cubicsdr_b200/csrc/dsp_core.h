@@ -415,7 +415,7 @@ struct ChanStatic {
     int d_off;                    // real: demodulated samples (after auto-gain) feeding the audio resampler
     int al_off[kMaxAudioHb + 1];  // real: audio resampler level buffers (decim: after each half-band; interp: arb out, then each half-band)
     int want_iq;                  // copy decimated IQ into the result slot
-    int bandwidth;                // modem rate (DemodulatorThreadPostIQData::sampleRate): sampleTime of a block = n_iq / bandwidth
+    int bandwidth;                // DemodulatorThreadPostIQData::sampleRate (the bandwidth asked for): sampleTime of a block = n_iq / bandwidth
     int res_audio_cap, res_iq_cap;
     long long res_off;            // byte offset of the result slot in the results buffer
 };

@@ -1162,6 +1162,7 @@ struct sdr_chan {
     int modem = 0;
     long long sample_rate = 0;
     int bandwidth = 0, audio_rate = 0;
+    int asked_bandwidth = 0;        // what the caller asked for: DemodulatorThreadPostIQData::sampleRate (DemodulatorPreThread.cpp:222)
     ResamplerPlan iq_plan, audio_plan;
     ChanStatic cs;
     float *d_arena = nullptr;
@@ -1861,6 +1862,7 @@ static int chan_create_impl(sdr_engine *e, const char *modem, long long sample_r
     sdr_chan *c = new sdr_chan();
     c->eng = e; c->index = -1; c->modem = mk; c->sample_rate = sample_rate;
     c->bandwidth = check_sample_rate(mk, bandwidth);
+    c->asked_bandwidth = (int)bandwidth;
     if (view_cap) c->bandwidth = (int)bandwidth;                        // a power-of-two fraction of the rate, as it comes
     if (mk == MODEM_IQ) c->bandwidth = audio_rate;                      // ModemIQ::checkSampleRate returns audioSampleRate (ModemIQ.cpp:31-33)
     c->audio_rate = audio_rate;
@@ -1963,7 +1965,9 @@ static int chan_create_impl(sdr_engine *e, const char *modem, long long sample_r
     cs.res_audio_cap = (int)((cap_audio + 3) & ~size_t(3));
     cs.res_iq_cap = (int)cap_iq;
     cs.want_iq = 0;
-    cs.bandwidth = c->bandwidth;
+    // DemodulatorPreThread hands the demodulator thread `currentBandwidth` -- the bandwidth that was asked for, not what
+    // Modem::checkSampleRate made of it (:222) -- and DemodulatorThread's sampleTime divides by it (:143)
+    cs.bandwidth = c->asked_bandwidth > 0 ? c->asked_bandwidth : c->bandwidth;
     c->arena_floats = off;
     c->slot_bytes = kResHdrBytes + (size_t)cs.res_audio_cap * 4 + (size_t)cs.res_iq_cap * 8;
     c->slot_bytes = (c->slot_bytes + 31) & ~size_t(31);
@@ -3912,7 +3916,7 @@ extern "C" int sdr_scope_process(sdr_scope *s, float *wave_xy, unsigned *n_wave,
     ScopeArgs a;
     a.cs = e->d_cs; a.results = e->d_results; a.chan = s->chan->index;
     a.channels = (s->chan->modem == MODEM_IQ || s->chan->modem == MODEM_FMS) ? 2 : 1;
-    a.sample_rate = s->chan->audio_rate; a.input_rate = s->chan->bandwidth;
+    a.sample_rate = s->chan->audio_rate; a.input_rate = s->chan->asked_bandwidth > 0 ? s->chan->asked_bandwidth : s->chan->bandwidth;   // ati->inputRate = inp->sampleRate (DemodulatorThread.cpp:128)
     a.fft_size = s->fft_size; a.max_samples = s->max_samples; a.fft_in = s->d_in; a.mags = s->d_mags; a.ema = s->d_ema; a.scalars = s->d_scalars;
     a.rate = (double)0.65f; a.wave_xy = s->d_wave; a.spec_xy = s->d_spec; a.counts = s->d_counts; a.floor_ceil = s->d_fc; a.red = nullptr;
     SpecArgs f;

@@ -26,7 +26,11 @@ where it lies and writes only into oracle/_ref/ (git-ignored, but shipped to the
      with the two headers that need wx (the application, the OpenGL panel) shadowed by oracle/shadow/, and the C entry
      points of oracle/ref_visuals.cpp, into oracle/_ref/libvisuals_ref.so (tests/test_oracle_visuals.py); the same library
      holds the audio mixer: src/audio/AudioThread.cpp (its RtAudio callback) through oracle/ref_audio.cpp, with
-     src/IOThread.cpp, src/util/Timer.cpp and the reference's external/rtaudio/RtAudio.cpp (dummy API, no device)
+     src/IOThread.cpp, src/util/Timer.cpp and the reference's external/rtaudio/RtAudio.cpp (dummy API, no device), and the
+     WAV writer src/audio/AudioFile.cpp + AudioFileWAV.cpp
+  8. the whole demodulator: src/demod/DemodulatorInstance.cpp with its DemodulatorPreThread / DemodulatorWorkerThread /
+     DemodulatorThread, the audio thread and sinks, and the modems, unmodified, application header shadowed, with the C
+     entry points of oracle/ref_demod.cpp, into oracle/_ref/libdemod_ref.so (tests/test_oracle_demod.py)
 
 If /root/reference is absent (GPU box) and oracle/_ref/libsdr_ref.so already exists, nothing is done.
 """
@@ -44,6 +48,10 @@ MODEMS_LIB = os.path.join(OUT, "libmodems_ref.so")
 VISUALS_LIB = os.path.join(OUT, "libvisuals_ref.so")
 REF_SRC = "/root/reference/src"
 REF_VISUAL_SRCS = ["FFTDataDistributor.cpp", "SpectrumVisualProcessor.cpp", "ScopeVisualProcessor.cpp"]
+DEMOD_LIB = os.path.join(OUT, "libdemod_ref.so")
+REF_DEMOD_SRCS = ["demod/DemodulatorInstance.cpp", "demod/DemodulatorPreThread.cpp", "demod/DemodulatorWorkerThread.cpp",
+                  "demod/DemodulatorThread.cpp", "audio/AudioThread.cpp", "audio/AudioSinkThread.cpp", "audio/AudioSinkFileThread.cpp",
+                  "audio/AudioFile.cpp", "audio/AudioFileWAV.cpp", "IOThread.cpp", "util/Timer.cpp"]
 REF_MODEM_SRCS = ["Modem.cpp", "ModemAnalog.cpp"] + ["analog/Modem%s.cpp" % m for m in
                                                      ("FM", "NBFM", "FMStereo", "AM", "CW", "LSB", "USB", "DSB", "IQ")]
 
@@ -196,7 +204,7 @@ def build_visuals(force=False):
     lib = build(force)
     shadow = os.path.join(HERE, "shadow")
     mine = [os.path.join(HERE, f) for f in ("modem_abi.h", "ref_modem_abi.c", "ref_visuals.cpp", "ref_audio.cpp")] + \
-           [os.path.join(shadow, f) for f in ("CubicSDR.h", "ScopePanel.h", "DemodulatorInstance.h")] + [os.path.abspath(__file__)]
+           [os.path.join(shadow, f) for f in ("CubicSDR.h", "ScopePanel.h")] + [os.path.abspath(__file__)]
     if (not force) and os.path.exists(VISUALS_LIB) and all(os.path.getmtime(VISUALS_LIB) >= os.path.getmtime(s) for s in mine + [lib]):
         return VISUALS_LIB
     vdir = os.path.join(OUT, "visual_obj")
@@ -216,6 +224,7 @@ def build_visuals(force=False):
     # file-static); src/IOThread.cpp, src/util/Timer.cpp and the reference's RtAudio (no audio API compiled in: its dummy API)
     # as they are
     for src in (os.path.join(REF_SRC, "IOThread.cpp"), os.path.join(REF_SRC, "util", "Timer.cpp"),
+                os.path.join(REF_SRC, "audio", "AudioFile.cpp"), os.path.join(REF_SRC, "audio", "AudioFileWAV.cpp"),
                 "/root/reference/external/rtaudio/RtAudio.cpp"):
         o = os.path.join(vdir, os.path.basename(src)[:-4] + ".o")
         run(cxx + ["-c", src, "-o", o])
@@ -232,6 +241,44 @@ def build_visuals(force=False):
     return VISUALS_LIB
 
 
+def build_demod(force=False):
+    """oracle/_ref/libdemod_ref.so: the reference's unmodified DemodulatorInstance (pre-demod, worker and demodulator
+    threads, modems) over its own liquid binary."""
+    if not os.path.exists(REF_SRC):
+        if os.path.exists(DEMOD_LIB):
+            return DEMOD_LIB
+        raise SystemExit("oracle/_ref/libdemod_ref.so missing and /root/reference absent")
+    lib = build(force)
+    shadow = os.path.join(HERE, "shadow")
+    mine = [os.path.join(HERE, f) for f in ("modem_abi.h", "ref_modem_abi.c", "ref_demod.cpp")] + \
+           [os.path.join(shadow, "CubicSDR.h"), os.path.abspath(__file__)]
+    if (not force) and os.path.exists(DEMOD_LIB) and all(os.path.getmtime(DEMOD_LIB) >= os.path.getmtime(s) for s in mine + [lib]):
+        return DEMOD_LIB
+    ddir = os.path.join(OUT, "demod_obj")
+    os.makedirs(ddir, exist_ok=True)
+    mod = os.path.join(REF_SRC, "modules", "modem")
+    inc = []
+    for d in (shadow, REF_SRC, os.path.join(REF_SRC, "util"), os.path.join(REF_SRC, "audio"), os.path.join(REF_SRC, "demod"),
+              os.path.join(REF_SRC, "process"), mod, os.path.join(mod, "analog"), os.path.join(mod, "digital"),
+              "/root/reference/external/liquid-dsp/include", "/root/reference/external/rtaudio"):
+        inc += ["-I", d]
+    cxx = ["g++", "-std=c++17", "-O2", "-fPIC", "-pthread", "-w", "-include", os.path.join(HERE, "modem_abi.h")] + inc
+    objs = []
+    srcs = [os.path.join(REF_SRC, f) for f in REF_DEMOD_SRCS] + [os.path.join(mod, f) for f in REF_MODEM_SRCS] + \
+           ["/root/reference/external/rtaudio/RtAudio.cpp"]
+    for src in srcs:                                             # compiled where they lie, objects only into oracle/_ref/
+        o = os.path.join(ddir, os.path.basename(src)[:-4] + ".o")
+        run(cxx + ["-c", src, "-o", o])
+        objs.append(o)
+    drv = os.path.join(ddir, "ref_demod.o")
+    run(cxx + ["-fno-access-control", "-c", os.path.join(HERE, "ref_demod.cpp"), "-o", drv])
+    abi = os.path.join(ddir, "ref_modem_abi.o")
+    run(["gcc", "-O2", "-fPIC", "-c", os.path.join(HERE, "ref_modem_abi.c"), "-o", abi])
+    run(["g++", "-shared", "-o", DEMOD_LIB, drv, abi] + objs +
+        ["-L", OUT, "-l:libsdr_ref.so", "-Wl,-rpath,$ORIGIN", "-lm", "-pthread", "-Wl,--no-undefined"])
+    return DEMOD_LIB
+
+
 if __name__ == "__main__":
     if "--clean" in sys.argv and os.path.exists(REF_AR) and os.path.isdir(OBJ):
         import shutil
@@ -239,3 +286,4 @@ if __name__ == "__main__":
     print(build(force="--force" in sys.argv or "--clean" in sys.argv))
     print(build_modems(force="--force" in sys.argv or "--clean" in sys.argv))
     print(build_visuals(force="--force" in sys.argv or "--clean" in sys.argv))
+    print(build_demod(force="--force" in sys.argv or "--clean" in sys.argv))

@@ -11,6 +11,7 @@
 // tests/test_oracle_visuals.py pins the restated mixer of oracle/ref_chain.cpp (what the device mixer is compared against)
 // to it: same pushes and callbacks in, the same bits out.
 #include "AudioThread.cpp"                // /root/reference/src/audio, through the include path
+#include "AudioFileWAV.h"
 
 namespace {
 struct Mixer {
@@ -60,6 +61,29 @@ void refsrc_mixer_push(void *h, int i, const float *data, unsigned n, int channe
 int refsrc_mixer_callback(void *h, float *out, unsigned n_frames) {
     return audioCallback(out, nullptr, n_frames, 0.0, 0, &static_cast<Mixer *>(h)->controller);
 }
+// ---- AudioFileWAV (src/audio/AudioFileWAV.cpp, AudioFile.cpp: compiled unmodified next to this file) --------------------------
+// a recording in directory `dir` named `name`: every write is AudioFileWAV::writeToFile(input) (header on the first call, then
+// the 16-bit payload, :122-165); close fixes the chunk sizes (:102-120).  The test reads dir/name.wav back.
+void *refsrc_wav_open(const char *dir, const char *name) {
+    wxGetApp().getConfig()->recordingPath = dir;
+    AudioFileWAV *w = new AudioFileWAV;
+    w->setOutputFileName(name);
+    return w;
+}
+int refsrc_wav_write(void *h, const float *data, unsigned n, int channels, int sample_rate, float peak) {
+    auto a = std::make_shared<AudioThreadInput>();
+    a->channels = channels;
+    a->sampleRate = sample_rate;
+    a->peak = peak;
+    a->data.assign(data, data + n);
+    return static_cast<AudioFileWAV *>(h)->writeToFile(a) ? 0 : -1;
+}
+void refsrc_wav_close(void *h) {
+    AudioFileWAV *w = static_cast<AudioFileWAV *>(h);
+    w->closeFile();
+    delete w;
+}
+
 void refsrc_mixer_destroy(void *h) {
     Mixer *m = static_cast<Mixer *>(h);
     for (AudioThread *s : m->sources) { m->controller.removeThread(s); delete s; }

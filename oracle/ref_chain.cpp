@@ -190,6 +190,7 @@ struct RefChan {
     int modem;
     long long sampleRate;      // wideband rate
     int bandwidth;             // modem rate (after checkSampleRate)
+    int requestedBandwidth;    // what setBandwidth was given: DemodulatorThreadPostIQData::sampleRate (DemodulatorPreThread.cpp:222, currentBandwidth)
     int audioRate;
     // DemodulatorPreThread members (src/demod/DemodulatorPreThread.cpp:22, DemodulatorWorkerThread.cpp:95-101)
     nco_crcf freqShifter;
@@ -260,6 +261,7 @@ API void *ref_chan_create(const char *modem, long long sampleRate, long long ban
     c->modem = m;
     c->sampleRate = sampleRate;
     c->bandwidth = ref_modem_check_sample_rate(modem, bandwidth);
+    c->requestedBandwidth = (int)bandwidth;
     if (m == M_IQ) c->bandwidth = audioRate;                               // ModemIQ::checkSampleRate (ModemIQ.cpp:31-33)
     c->audioRate = audioRate;
     c->freqShifter = nco_crcf_create(0);                                   // DemodulatorPreThread.cpp:22
@@ -361,7 +363,7 @@ API int ref_chan_bandwidth(void *h) { return ((RefChan *)h)->bandwidth; }
 static int ref_chan_meter_block(RefChan *c, unsigned numAudioWritten, size_t bufSize, bool useSignalOutput, double *level_db, float *peak) {
     const lq_cf *d = c->resampled.data();
     double currentSignalLevel = 0;
-    double sampleTime = double(bufSize) / double(c->bandwidth);                              // :143 (inp->sampleRate = the modem rate)
+    double sampleTime = double(bufSize) / double(c->requestedBandwidth);                     // :143 (inp->sampleRate = the bandwidth that was ASKED for, not the one checkSampleRate made of it)
     if (numAudioWritten) {                                                                    // :145 `!ati->data.empty()`
         double accum = 0;
         if (useSignalOutput) {

@@ -3,7 +3,8 @@
 The library is the reference's own liquid-dsp 1.5.0 binary plus the CubicSDR glue restated in oracle/ref_chain.cpp
 (see oracle/build_ref.py), and of oracle/_ref/libmodems_ref.so, the reference's own unmodified modem classes over that
 binary (RefModems / RefModem at the end), and of oracle/_ref/libvisuals_ref.so, its unmodified FFTDataDistributor /
-SpectrumVisualProcessor / ScopeVisualProcessor (RefVisuals / SrcDistrib / SrcSpectrum / SrcScope).  Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this.
+SpectrumVisualProcessor / ScopeVisualProcessor / audioCallback / AudioFileWAV (RefVisuals / SrcDistrib / SrcSpectrum / SrcScope /
+SrcMixer / SrcWav), and of oracle/_ref/libdemod_ref.so, its whole DemodulatorInstance (RefDemodLib / SrcDemod).  Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this.
 """
 import ctypes as C
 import os
@@ -410,6 +411,9 @@ class RefVisuals:
         L.refsrc_mixer_push.argtypes = [vp, i, vp, u, i, f, i]; L.refsrc_mixer_push.restype = None
         L.refsrc_mixer_callback.argtypes = [vp, vp, u]
         L.refsrc_mixer_destroy.argtypes = [vp]; L.refsrc_mixer_destroy.restype = None
+        L.refsrc_wav_open.restype = vp; L.refsrc_wav_open.argtypes = [C.c_char_p, C.c_char_p]
+        L.refsrc_wav_write.argtypes = [vp, vp, u, i, i, f]
+        L.refsrc_wav_close.argtypes = [vp]; L.refsrc_wav_close.restype = None
 
 
 class SrcDistrib:
@@ -518,3 +522,76 @@ class SrcMixer:
 
     def close(self):
         self.L.refsrc_mixer_destroy(self.h)
+
+
+class SrcWav:
+    """The reference's AudioFileWAV object writing directory/name.wav (oracle/ref_audio.cpp)."""
+
+    def __init__(self, vis, directory, name):
+        self.L = vis.L
+        self.path = os.path.join(directory, name + ".wav")
+        self.h = C.c_void_p(self.L.refsrc_wav_open(str(directory).encode(), name.encode()))
+
+    def write(self, data, channels, sample_rate, peak):
+        d = np.ascontiguousarray(data, np.float32)
+        assert self.L.refsrc_wav_write(self.h, _p(d), d.size, int(channels), int(sample_rate), float(peak)) == 0
+
+    def close(self):
+        """Returns (header bytes, payload as int16)."""
+        self.L.refsrc_wav_close(self.h)
+        raw = open(self.path, "rb").read()
+        return raw[:44], np.frombuffer(raw[44:], np.int16).copy()
+
+
+DEMOD_LIB = os.path.join(_HERE, "_ref", "libdemod_ref.so")
+
+
+class RefDemodLib:
+    """oracle/_ref/libdemod_ref.so: the reference's own, unmodified DemodulatorInstance on its own threads (oracle/ref_demod.cpp)."""
+
+    def __init__(self, path=DEMOD_LIB):
+        if not os.path.exists(path):
+            import subprocess, sys
+            subprocess.check_call([sys.executable, os.path.join(_HERE, "build_ref.py")])
+        L = self.L = C.CDLL(path)
+        vp, u, i, ll, f = C.c_void_p, C.c_uint, C.c_int, C.c_longlong, C.c_float
+        L.refsrc_demod_create.restype = vp; L.refsrc_demod_create.argtypes = [C.c_char_p, ll, i, i, ll, ll]
+        L.refsrc_demod_set_frequency.argtypes = [vp, ll]; L.refsrc_demod_set_frequency.restype = None
+        L.refsrc_demod_set_squelch.argtypes = [vp, i, f]; L.refsrc_demod_set_squelch.restype = None
+        L.refsrc_demod_bandwidth.argtypes = [vp]
+        L.refsrc_demod_process.argtypes = [vp, vp, u, ll, vp, u, vp, vp, vp, vp, vp]
+        L.refsrc_demod_destroy.argtypes = [vp]; L.refsrc_demod_destroy.restype = None
+
+
+class SrcDemod:
+    """One real DemodulatorInstance: modem `modem` of `bandwidth` Hz at absolute frequency `frequency`, fed wideband blocks at
+    `sample_rate` whose tuner frequency is `center`."""
+
+    def __init__(self, lib, modem, sample_rate, bandwidth, frequency, center, audio_rate=48000):
+        self.L = lib.L
+        self.sample_rate, self.audio_rate = sample_rate, audio_rate
+        self.h = C.c_void_p(self.L.refsrc_demod_create(modem.encode(), int(sample_rate), int(bandwidth), int(audio_rate),
+                                                       int(frequency), int(center)))
+        assert self.h.value, "the reference's demodulator did not initialize"
+        self.bandwidth = self.L.refsrc_demod_bandwidth(self.h)
+
+    def set_frequency(self, frequency):
+        self.L.refsrc_demod_set_frequency(self.h, int(frequency))
+
+    def set_squelch(self, enabled, level_db):
+        self.L.refsrc_demod_set_squelch(self.h, 1 if enabled else 0, C.c_float(level_db))
+
+    def process(self, block, center):
+        block = np.ascontiguousarray(block, np.complex64)
+        cap = 2 * int(block.size * self.audio_rate / self.sample_rate) + 65536
+        au = np.zeros(cap, np.float32)
+        n, ch, pk, sq = C.c_uint(), C.c_int(), C.c_float(), C.c_int()
+        m3 = (C.c_float * 3)()
+        rc = self.L.refsrc_demod_process(self.h, _p(block), block.size, int(center), _p(au), cap, C.byref(n), C.byref(ch), C.byref(pk),
+                                         C.byref(sq), m3)
+        assert rc >= 0, "the reference's demodulator threads timed out"
+        return dict(skipped=bool(rc), audio=au[:n.value].copy(), channels=ch.value, peak=pk.value, squelched=bool(sq.value),
+                    signal_level=m3[0], signal_floor=m3[1], signal_ceil=m3[2])
+
+    def close(self):
+        self.L.refsrc_demod_destroy(self.h)

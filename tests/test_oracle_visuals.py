@@ -170,3 +170,26 @@ def test_audio_mixer_equals_the_reference_callback(ref, vis):
             n_cb += 1; n_nonzero += int(np.any(oa != 0))
     assert n_cb > 500 and n_nonzero > 300
     a.close(); b.close()
+
+
+def test_wav_words_equal_the_reference_writer(ref, vis, tmp_path):
+    """AudioFileWAV::writeToFile of the reference (header + 16-bit payload, AudioFileWAV.cpp:122-165) against the restated payload the
+    device's PCM words are compared with: one and two channels, peaks below and above 1 (the anti-clipping scale), odd lengths."""
+    import struct
+    rng = np.random.default_rng(5)
+    for channels in (1, 2):
+        w = refbind.SrcWav(vis, tmp_path, "rec%d" % channels)
+        want = []
+        for k in range(9):
+            n = int(rng.choice([800, 808, 1600, 33, 1])) * channels + (1 if (channels == 2 and k == 4) else 0)
+            data = (rng.standard_normal(n) * rng.choice([0.05, 0.4, 1.7])).astype(np.float32)
+            peak = float(np.abs(data).max())
+            w.write(data, channels, 48000, peak)
+            want.append(refbind.ref_wav_payload(ref, data, channels, peak))
+        header, words = w.close()
+        want = np.concatenate(want)
+        assert words.size == want.size and np.array_equal(words, want)
+        assert header[:4] == b"RIFF" and header[8:16] == b"WAVEfmt " and header[36:40] == b"data"
+        fmt = struct.unpack("<IHHIIHH", header[16:36])
+        assert fmt == (16, 1, channels, 48000, 48000 * 2 * channels, 2 * channels, 16)
+        assert struct.unpack("<I", header[40:44])[0] == 2 * words.size and struct.unpack("<I", header[4:8])[0] == 36 + 2 * words.size
