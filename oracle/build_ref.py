@@ -24,13 +24,14 @@ where it lies and writes only into oracle/_ref/ (git-ignored, but shipped to the
      oracle/_ref/libmodems_ref.so (pins ref_chain.cpp's modem restatement: tests/test_oracle_modems.py)
   7. likewise src/process/FFTDataDistributor.cpp, SpectrumVisualProcessor.cpp and ScopeVisualProcessor.cpp, unmodified,
      with the two headers that need wx (the application, the OpenGL panel) shadowed by oracle/shadow/, and the C entry
-     points of oracle/ref_visuals.cpp, into oracle/_ref/libvisuals_ref.so (tests/test_oracle_visuals.py); the same library
-     holds the audio mixer: src/audio/AudioThread.cpp (its RtAudio callback) through oracle/ref_audio.cpp, with
-     src/IOThread.cpp, src/util/Timer.cpp and the reference's external/rtaudio/RtAudio.cpp (dummy API, no device), and the
-     WAV writer src/audio/AudioFile.cpp + AudioFileWAV.cpp
+     points of oracle/ref_visuals.cpp, into oracle/_ref/libvisuals_ref.so (tests/test_oracle_visuals.py)
   8. the whole demodulator: src/demod/DemodulatorInstance.cpp with its DemodulatorPreThread / DemodulatorWorkerThread /
-     DemodulatorThread, the audio thread and sinks, and the modems, unmodified, application header shadowed, with the C
-     entry points of oracle/ref_demod.cpp, into oracle/_ref/libdemod_ref.so (tests/test_oracle_demod.py)
+     DemodulatorThread, the audio thread and sinks, and the modems -- and the ingress in front of them,
+     src/sdr/SDRPostThread.cpp (SoapySDR and AppConfig headers shadowed: only declarations need them) -- unmodified,
+     application header shadowed, with the C entry points of oracle/ref_demod.cpp, into oracle/_ref/libdemod_ref.so
+     (tests/test_oracle_demod.py); the same library exposes the audio mixer (the RtAudio callback of
+     src/audio/AudioThread.cpp, on the reference's RtAudio built with its dummy API: no device) and the WAV writer
+     (src/audio/AudioFile.cpp + AudioFileWAV.cpp) through oracle/ref_audio.cpp
 
 If /root/reference is absent (GPU box) and oracle/_ref/libsdr_ref.so already exists, nothing is done.
 """
@@ -50,8 +51,8 @@ REF_SRC = "/root/reference/src"
 REF_VISUAL_SRCS = ["FFTDataDistributor.cpp", "SpectrumVisualProcessor.cpp", "ScopeVisualProcessor.cpp"]
 DEMOD_LIB = os.path.join(OUT, "libdemod_ref.so")
 REF_DEMOD_SRCS = ["demod/DemodulatorInstance.cpp", "demod/DemodulatorPreThread.cpp", "demod/DemodulatorWorkerThread.cpp",
-                  "demod/DemodulatorThread.cpp", "audio/AudioThread.cpp", "audio/AudioSinkThread.cpp", "audio/AudioSinkFileThread.cpp",
-                  "audio/AudioFile.cpp", "audio/AudioFileWAV.cpp", "IOThread.cpp", "util/Timer.cpp"]
+                  "demod/DemodulatorThread.cpp", "audio/AudioSinkThread.cpp", "audio/AudioSinkFileThread.cpp",
+                  "audio/AudioFile.cpp", "audio/AudioFileWAV.cpp", "IOThread.cpp", "util/Timer.cpp", "sdr/SDRPostThread.cpp"]
 REF_MODEM_SRCS = ["Modem.cpp", "ModemAnalog.cpp"] + ["analog/Modem%s.cpp" % m for m in
                                                      ("FM", "NBFM", "FMStereo", "AM", "CW", "LSB", "USB", "DSB", "IQ")]
 
@@ -203,7 +204,7 @@ def build_visuals(force=False):
         raise SystemExit("oracle/_ref/libvisuals_ref.so missing and /root/reference absent")
     lib = build(force)
     shadow = os.path.join(HERE, "shadow")
-    mine = [os.path.join(HERE, f) for f in ("modem_abi.h", "ref_modem_abi.c", "ref_visuals.cpp", "ref_audio.cpp")] + \
+    mine = [os.path.join(HERE, f) for f in ("modem_abi.h", "ref_modem_abi.c", "ref_visuals.cpp")] + \
            [os.path.join(shadow, f) for f in ("CubicSDR.h", "ScopePanel.h")] + [os.path.abspath(__file__)]
     if (not force) and os.path.exists(VISUALS_LIB) and all(os.path.getmtime(VISUALS_LIB) >= os.path.getmtime(s) for s in mine + [lib]):
         return VISUALS_LIB
@@ -220,18 +221,6 @@ def build_visuals(force=False):
         o = os.path.join(vdir, src[:-4] + ".o")
         run(cxx + ["-c", os.path.join(proc, src), "-o", o])
         objs.append(o)
-    # the audio mixer: src/audio/AudioThread.cpp enters oracle/ref_audio.cpp's translation unit by #include (its callback is
-    # file-static); src/IOThread.cpp, src/util/Timer.cpp and the reference's RtAudio (no audio API compiled in: its dummy API)
-    # as they are
-    for src in (os.path.join(REF_SRC, "IOThread.cpp"), os.path.join(REF_SRC, "util", "Timer.cpp"),
-                os.path.join(REF_SRC, "audio", "AudioFile.cpp"), os.path.join(REF_SRC, "audio", "AudioFileWAV.cpp"),
-                "/root/reference/external/rtaudio/RtAudio.cpp"):
-        o = os.path.join(vdir, os.path.basename(src)[:-4] + ".o")
-        run(cxx + ["-c", src, "-o", o])
-        objs.append(o)
-    aud = os.path.join(vdir, "ref_audio.o")
-    run(cxx + ["-fno-access-control", "-c", os.path.join(HERE, "ref_audio.cpp"), "-o", aud])
-    objs.append(aud)
     drv = os.path.join(vdir, "ref_visuals.o")
     run(cxx + ["-c", os.path.join(HERE, "ref_visuals.cpp"), "-o", drv])
     abi = os.path.join(vdir, "ref_modem_abi.o")
@@ -250,8 +239,9 @@ def build_demod(force=False):
         raise SystemExit("oracle/_ref/libdemod_ref.so missing and /root/reference absent")
     lib = build(force)
     shadow = os.path.join(HERE, "shadow")
-    mine = [os.path.join(HERE, f) for f in ("modem_abi.h", "ref_modem_abi.c", "ref_demod.cpp")] + \
-           [os.path.join(shadow, "CubicSDR.h"), os.path.abspath(__file__)]
+    mine = [os.path.join(HERE, f) for f in ("modem_abi.h", "ref_modem_abi.c", "ref_demod.cpp", "ref_audio.cpp")] + \
+           [os.path.join(shadow, "CubicSDR.h"), os.path.join(shadow, "AppConfig.h"), os.path.join(shadow, "SoapySDR", "Types.hpp"),
+            os.path.abspath(__file__)]
     if (not force) and os.path.exists(DEMOD_LIB) and all(os.path.getmtime(DEMOD_LIB) >= os.path.getmtime(s) for s in mine + [lib]):
         return DEMOD_LIB
     ddir = os.path.join(OUT, "demod_obj")
@@ -259,7 +249,7 @@ def build_demod(force=False):
     mod = os.path.join(REF_SRC, "modules", "modem")
     inc = []
     for d in (shadow, REF_SRC, os.path.join(REF_SRC, "util"), os.path.join(REF_SRC, "audio"), os.path.join(REF_SRC, "demod"),
-              os.path.join(REF_SRC, "process"), mod, os.path.join(mod, "analog"), os.path.join(mod, "digital"),
+              os.path.join(REF_SRC, "sdr"), os.path.join(REF_SRC, "process"), mod, os.path.join(mod, "analog"), os.path.join(mod, "digital"),
               "/root/reference/external/liquid-dsp/include", "/root/reference/external/rtaudio"):
         inc += ["-I", d]
     cxx = ["g++", "-std=c++17", "-O2", "-fPIC", "-pthread", "-w", "-include", os.path.join(HERE, "modem_abi.h")] + inc
@@ -270,6 +260,10 @@ def build_demod(force=False):
         o = os.path.join(ddir, os.path.basename(src)[:-4] + ".o")
         run(cxx + ["-c", src, "-o", o])
         objs.append(o)
+    # src/audio/AudioThread.cpp enters oracle/ref_audio.cpp's translation unit by #include (its RtAudio callback is file-static)
+    aud = os.path.join(ddir, "ref_audio.o")
+    run(cxx + ["-fno-access-control", "-c", os.path.join(HERE, "ref_audio.cpp"), "-o", aud])
+    objs.append(aud)
     drv = os.path.join(ddir, "ref_demod.o")
     run(cxx + ["-fno-access-control", "-c", os.path.join(HERE, "ref_demod.cpp"), "-o", drv])
     abi = os.path.join(ddir, "ref_modem_abi.o")

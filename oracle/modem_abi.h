@@ -61,4 +61,13 @@
 #define msresamp_crcf_create sv_msresamp_crcf_create
 #define msresamp_crcf_destroy sv_msresamp_crcf_destroy
 #define msresamp_crcf_execute sv_msresamp_crcf_execute
+/* the ingress (src/sdr/SDRPostThread.cpp) */
+#define firpfbch2_crcf_create_kaiser sv_firpfbch2_crcf_create_kaiser
+#define firpfbch2_crcf_destroy sv_firpfbch2_crcf_destroy
+#define firpfbch2_crcf_execute sv_firpfbch2_crcf_execute
+#define firpfbch_crcf_analyzer_execute sv_firpfbch_crcf_analyzer_execute
+#define firpfbch_crcf_create_kaiser sv_firpfbch_crcf_create_kaiser
+#define firpfbch_crcf_destroy sv_firpfbch_crcf_destroy
+#define iirfilt_crcf_create_dc_blocker sv_iirfilt_crcf_create_dc_blocker
+#define iirfilt_crcf_execute_block sv_iirfilt_crcf_execute_block
 #endif

@@ -8,7 +8,7 @@
 // controller's private sampleRate without opening an audio device (setSampleRate of a controller opens the stream).
 // RtAudio is the reference's own external/rtaudio/RtAudio.cpp built with no audio API (its dummy API): no device is touched,
 // the callback is invoked by hand exactly as RtAudio would (outputBuffer, nBufferFrames, status 0, userData = controller).
-// tests/test_oracle_visuals.py pins the restated mixer of oracle/ref_chain.cpp (what the device mixer is compared against)
+// tests/test_oracle_demod.py pins the restated mixer of oracle/ref_chain.cpp (what the device mixer is compared against)
 // to it: same pushes and callbacks in, the same bits out.
 #include "AudioThread.cpp"                // /root/reference/src/audio, through the include path
 #include "AudioFileWAV.h"
@@ -22,7 +22,7 @@ struct Mixer {
 int g_next_device = 1000;
 }  // namespace
 
-// (wxGetApp() of the shadowed application header is defined in oracle/ref_visuals.cpp, same library)
+// (wxGetApp() of the shadowed application header is defined in oracle/ref_demod.cpp, same library: libdemod_ref.so)
 
 extern "C" {
 

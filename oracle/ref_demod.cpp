@@ -21,6 +21,7 @@
 #include "DemodulatorInstance.h"
 #include "DemodulatorPreThread.h"
 #include "DemodulatorThread.h"
+#include "SDRPostThread.h"
 #include "ModemFM.h"
 #include "ModemNBFM.h"
 #include "ModemFMStereo.h"
@@ -59,6 +60,7 @@ struct Chain {
     AudioThreadInputQueuePtr sink;         // the demodulator thread's "AudioSink" output: every block's AudioThreadInput
     DemodulatorThreadPostInputQueuePtr post;
     long long rate = 0;
+    long long last_center = 0;
 };
 template <class Q>
 bool wait_empty(const Q &q, int timeout_ms) {
@@ -110,6 +112,7 @@ void *refsrc_demod_create(const char *modem, long long sample_rate, int bandwidt
     std::call_once(g_registered, register_modems);
     Chain *c = new Chain;
     c->rate = sample_rate;
+    c->last_center = center;
     c->inst = new DemodulatorInstance();
     c->inst->audioThread->sampleRate = audio_rate;              // what AudioThread::setupDevice takes from the device
     c->inst->setDemodulatorType(modem);
@@ -142,15 +145,15 @@ int refsrc_demod_bandwidth(void *h) {                           // the rate the 
     ModemKit *k = c->inst->demodulatorPreThread->getModemKit();
     return k ? (int)k->sampleRate : 0;
 }
-// one wideband block through the chain.  Returns 0 when an AudioThreadInput came out (audio: up to cap floats, *n_audio its
-// size), 1 when the block produced none (the 0.75 fs skip rule, DemodulatorPreThread.cpp:161-164), -1 on a time-out.
-// meter = {signalLevel, signalFloor, signalCeil} after the block.
-int refsrc_demod_process(void *h, const float *iq, unsigned n, long long center, float *audio, unsigned cap, unsigned *n_audio,
-                         int *channels, float *peak, int *squelched, float *meter) {
-    Chain *c = static_cast<Chain *>(h);
+// wait until the demodulator has finished everything in its input pipe, then hand back what came out of its "AudioSink" tap.
+// The sentinels carry the rate and tuner frequency of the blocks the demodulator has been getting (a different rate would
+// make DemodulatorPreThread order new filters, :86-91).
+static int collect(Chain *c, float *audio, unsigned cap, unsigned *n_audio, int *channels, float *peak, int *squelched, float *meter) {
     auto in = c->inst->getIQInputDataPipe();
-    in->push(make_block(iq, n, c->rate, center));
-    in->push(make_block(nullptr, 0, c->rate, center));          // sentinel: popped only once the real block is done
+    DemodulatorPreThread *p = c->inst->demodulatorPreThread;
+    const long long rate = p->currentSampleRate ? (long long)p->currentSampleRate : c->rate;
+    const long long center = c->last_center;
+    in->push(make_block(nullptr, 0, rate, center));             // sentinel: popped only once the blocks before it are done
     if (!wait_empty(in, 20000)) return -1;
     c->post->push(std::make_shared<DemodulatorThreadPostIQData>());   // sentinel for DemodulatorThread (no samples: skipped)
     if (!wait_empty(c->post, 20000)) return -1;
@@ -173,6 +176,106 @@ int refsrc_demod_process(void *h, const float *iq, unsigned n, long long center,
     meter[2] = c->inst->getSignalCeil();
     return got;
 }
+// one wideband block through the chain.  Returns 0 when an AudioThreadInput came out (audio: up to cap floats, *n_audio its
+// size), 1 when the block produced none (the 0.75 fs skip rule, DemodulatorPreThread.cpp:161-164), -1 on a time-out.
+// meter = {signalLevel, signalFloor, signalCeil} after the block.
+int refsrc_demod_process(void *h, const float *iq, unsigned n, long long center, float *audio, unsigned cap, unsigned *n_audio,
+                         int *channels, float *peak, int *squelched, float *meter) {
+    Chain *c = static_cast<Chain *>(h);
+    c->last_center = center;
+    c->inst->getIQInputDataPipe()->push(make_block(iq, n, c->rate, center));
+    return collect(c, audio, cap, n_audio, channels, peak, squelched, meter);
+}
+// the same without feeding a block: for a demodulator that the application-level driver below feeds through SDRPostThread
+// (`center` = the frequency stamped on the blocks it gets: the tuner frequency, or its filterbank channel's centre)
+int refsrc_demod_collect(void *h, long long center, float *audio, unsigned cap, unsigned *n_audio, int *channels, float *peak,
+                         int *squelched, float *meter) {
+    Chain *c = static_cast<Chain *>(h);
+    c->last_center = center;
+    return collect(c, audio, cap, n_audio, channels, peak, squelched, meter);
+}
+
+// ---- the ingress: a real SDRPostThread on its own thread, feeding the demodulators registered with it -------------------------
+struct App {
+    SDRPostThread post;
+    std::thread *t = nullptr;
+    SDRThreadIQDataQueuePtr in;
+    DemodulatorThreadInputQueuePtr out, vis, active_vis;
+};
+// (SDRPostThread.cpp finds the demodulators through wxGetApp().getDemodMgr(): one application per process)
+void *refsrc_app_create(int channelizer_type /* 1: firpfbch, 2: firpfbch2; used when a block says numChannels > 1 */) {
+    App *a = new App;
+    a->in = std::make_shared<SDRThreadIQDataQueue>(); a->in->set_max_num_items(64);
+    a->out = std::make_shared<DemodulatorThreadInputQueue>(); a->out->set_max_num_items(1u << 16);
+    a->vis = std::make_shared<DemodulatorThreadInputQueue>(); a->vis->set_max_num_items(1);
+    a->active_vis = std::make_shared<DemodulatorThreadInputQueue>(); a->active_vis->set_max_num_items(1);
+    a->post.setInputQueue("IQDataInput", a->in);                // src/CubicSDR.cpp:372-386 wires these
+    a->post.setOutputQueue("IQDataOutput", a->out);
+    a->post.setOutputQueue("IQVisualDataOutput", a->vis);
+    a->post.setOutputQueue("IQActiveDemodVisualDataOutput", a->active_vis);
+    a->post.setChannelizerType((SDRPostThreadChannelizerType)channelizer_type);
+    wxGetApp().getDemodMgr().demods.clear();
+    wxGetApp().getDemodMgr().current = nullptr;
+    a->t = new std::thread(&SDRPostThread::threadMain, &a->post);
+    return a;
+}
+// DemodulatorMgr::newThread + CubicSDRApp::notifyDemodulatorsChanged: the demodulator joins the manager's list
+void refsrc_app_add_demod(void *ah, void *h) {
+    App *a = static_cast<App *>(ah);
+    Chain *c = static_cast<Chain *>(h);
+    wxGetApp().getDemodMgr().demods.push_back(DemodulatorInstancePtr(c->inst, [](DemodulatorInstance *) {}));   // (owned by its Chain)
+    a->post.notifyDemodulatorsChanged();
+}
+// one block from the device thread (SDRThreadIQData: frequency, sampleRate, numChannels, data).  Returns the number of samples
+// of the block SDRPostThread put on "IQDataOutput" (single channel: the DC-blocked block; channelizer modes: the block as it
+// came), copied to out; -1 on a time-out.
+int refsrc_app_block(void *ah, const float *iq, unsigned n, long long center, long long rate, int num_channels, float *out, unsigned cap) {
+    App *a = static_cast<App *>(ah);
+    wxGetApp().setFrequency(center);
+    auto b = std::make_shared<SDRThreadIQData>();
+    b->frequency = center; b->sampleRate = rate; b->numChannels = num_channels; b->dcCorrected = true;
+    b->data.resize(n);
+    if (n) std::memcpy(reinterpret_cast<void *>(b->data.data()), iq, (size_t)n * 2 * sizeof(float));
+    a->in->push(b);
+    auto s = std::make_shared<SDRThreadIQData>();               // sentinel: no samples (skipped, SDRPostThread.cpp:176)
+    s->frequency = center; s->sampleRate = rate; s->numChannels = num_channels;
+    a->in->push(s);
+    if (!wait_empty(a->in, 20000)) return -1;
+    a->in->push(std::make_shared<SDRThreadIQData>(*s));         // ... and a second one: the first is popped before it is done with
+    if (!wait_empty(a->in, 20000)) return -1;
+    a->vis->flush(); a->active_vis->flush();
+    int m = 0;
+    DemodulatorThreadIQDataPtr o;
+    while (a->out->try_pop(o)) {
+        if (!o) continue;
+        m = (int)o->data.size();
+        if (m) std::memcpy(out, o->data.data(), (size_t)((unsigned)m < cap ? (unsigned)m : cap) * 2 * sizeof(float));
+    }
+    return m;
+}
+// which filterbank channel SDRPostThread routed demodulator j of its run list to, its centre frequency and the channel rate
+int refsrc_app_route(void *ah, void *h, long long *channel_center, int *chan_bw) {
+    App *a = static_cast<App *>(ah);
+    Chain *c = static_cast<Chain *>(h);
+    for (size_t j = 0; j < a->post.runDemods.size(); ++j)
+        if (a->post.runDemods[j].get() == c->inst) {
+            const int ch = a->post.numChannels > 1 ? a->post.demodChannel[j] : 0;
+            if (channel_center) *channel_center = (a->post.numChannels > 1 && ch >= 0) ? a->post.chanCenters[(size_t)ch] : a->post.frequency;
+            if (chan_bw) *chan_bw = a->post.numChannels > 1 ? a->post.chanBw : (int)a->post.sampleRate;
+            return ch;
+        }
+    return -1;                                                  // not in the run list (inactive / out of range)
+}
+void refsrc_app_destroy(void *ah) {
+    App *a = static_cast<App *>(ah);
+    a->post.terminate();
+    a->t->join();
+    delete a->t;
+    wxGetApp().getDemodMgr().demods.clear();
+    wxGetApp().getDemodMgr().current = nullptr;
+    delete a;
+}
+
 // diagnostics: {sampleRateChanged, bandwidthChanged, audioSampleRateChanged, modemSettingsChanged, shouldRebuildKit, resampler id}
 void refsrc_demod_debug(void *h, long long *out) {
     Chain *c = static_cast<Chain *>(h);

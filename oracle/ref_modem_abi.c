@@ -66,3 +66,13 @@ FWD0(int, nco_crcf_mix_block_down, (obj q, cf *x, cf *y, uint n), (q, x, y, n))
 FWD0(obj, msresamp_crcf_create, (float r, float as), (r, as))
 FWD0(int, msresamp_crcf_destroy, (obj q), (q))
 FWD0(int, msresamp_crcf_execute, (obj q, cf *x, uint nx, cf *y, uint *ny), (q, x, nx, y, ny))
+
+/* the ingress */
+FWD0(obj, firpfbch2_crcf_create_kaiser, (int type, uint M, uint m, float as), (type, M, m, as))
+FWD0(int, firpfbch2_crcf_destroy, (obj q), (q))
+FWD0(int, firpfbch2_crcf_execute, (obj q, cf *x, cf *y), (q, x, y))
+FWD0(int, firpfbch_crcf_analyzer_execute, (obj q, cf *x, cf *y), (q, x, y))
+FWD0(obj, firpfbch_crcf_create_kaiser, (int type, uint M, uint m, float as), (type, M, m, as))
+FWD0(int, firpfbch_crcf_destroy, (obj q), (q))
+FWD0(obj, iirfilt_crcf_create_dc_blocker, (float alpha), (alpha))
+FWD0(int, iirfilt_crcf_execute_block, (obj q, cf *x, uint n, cf *y), (q, x, n, y))

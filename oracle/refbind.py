@@ -404,16 +404,6 @@ class RefVisuals:
         L.refsrc_scope_create.restype = vp; L.refsrc_scope_create.argtypes = [i]
         L.refsrc_scope_process.restype = u; L.refsrc_scope_process.argtypes = [vp, vp, u, i, i, i, i, vp, u, vp, u, vp, vp, vp]
         L.refsrc_scope_destroy.argtypes = [vp]; L.refsrc_scope_destroy.restype = None
-        L.refsrc_mixer_create.restype = vp; L.refsrc_mixer_create.argtypes = [i]
-        L.refsrc_mixer_add_source.argtypes = [vp, f]
-        L.refsrc_mixer_set_gain.argtypes = [vp, i, f]; L.refsrc_mixer_set_gain.restype = None
-        L.refsrc_mixer_set_active.argtypes = [vp, i, i]; L.refsrc_mixer_set_active.restype = None
-        L.refsrc_mixer_push.argtypes = [vp, i, vp, u, i, f, i]; L.refsrc_mixer_push.restype = None
-        L.refsrc_mixer_callback.argtypes = [vp, vp, u]
-        L.refsrc_mixer_destroy.argtypes = [vp]; L.refsrc_mixer_destroy.restype = None
-        L.refsrc_wav_open.restype = vp; L.refsrc_wav_open.argtypes = [C.c_char_p, C.c_char_p]
-        L.refsrc_wav_write.argtypes = [vp, vp, u, i, i, f]
-        L.refsrc_wav_close.argtypes = [vp]; L.refsrc_wav_close.restype = None
 
 
 class SrcDistrib:
@@ -496,10 +486,11 @@ class SrcScope:
 
 
 class SrcMixer:
-    """The reference's audioCallback (src/audio/AudioThread.cpp:88-243) on real AudioThread objects (oracle/ref_audio.cpp)."""
+    """The reference's audioCallback (src/audio/AudioThread.cpp:88-243) on real AudioThread objects (oracle/ref_audio.cpp, in
+    libdemod_ref.so: pass a RefDemodLib)."""
 
-    def __init__(self, vis, sample_rate=48000):
-        self.L = vis.L
+    def __init__(self, demod_lib, sample_rate=48000):
+        self.L = demod_lib.L
         self.h = C.c_void_p(self.L.refsrc_mixer_create(int(sample_rate)))
 
     def add_source(self, gain=1.0):
@@ -525,10 +516,10 @@ class SrcMixer:
 
 
 class SrcWav:
-    """The reference's AudioFileWAV object writing directory/name.wav (oracle/ref_audio.cpp)."""
+    """The reference's AudioFileWAV object writing directory/name.wav (oracle/ref_audio.cpp, in libdemod_ref.so)."""
 
-    def __init__(self, vis, directory, name):
-        self.L = vis.L
+    def __init__(self, demod_lib, directory, name):
+        self.L = demod_lib.L
         self.path = os.path.join(directory, name + ".wav")
         self.h = C.c_void_p(self.L.refsrc_wav_open(str(directory).encode(), name.encode()))
 
@@ -561,6 +552,16 @@ class RefDemodLib:
         L.refsrc_demod_bandwidth.argtypes = [vp]
         L.refsrc_demod_process.argtypes = [vp, vp, u, ll, vp, u, vp, vp, vp, vp, vp]
         L.refsrc_demod_destroy.argtypes = [vp]; L.refsrc_demod_destroy.restype = None
+        L.refsrc_mixer_create.restype = vp; L.refsrc_mixer_create.argtypes = [i]
+        L.refsrc_mixer_add_source.argtypes = [vp, f]
+        L.refsrc_mixer_set_gain.argtypes = [vp, i, f]; L.refsrc_mixer_set_gain.restype = None
+        L.refsrc_mixer_set_active.argtypes = [vp, i, i]; L.refsrc_mixer_set_active.restype = None
+        L.refsrc_mixer_push.argtypes = [vp, i, vp, u, i, f, i]; L.refsrc_mixer_push.restype = None
+        L.refsrc_mixer_callback.argtypes = [vp, vp, u]
+        L.refsrc_mixer_destroy.argtypes = [vp]; L.refsrc_mixer_destroy.restype = None
+        L.refsrc_wav_open.restype = vp; L.refsrc_wav_open.argtypes = [C.c_char_p, C.c_char_p]
+        L.refsrc_wav_write.argtypes = [vp, vp, u, i, i, f]
+        L.refsrc_wav_close.argtypes = [vp]; L.refsrc_wav_close.restype = None
 
 
 class SrcDemod:

@@ -14,12 +14,14 @@
 #include <cstring>
 #include "DemodulatorInstance.h"          // the reference's own (it compiles without the application)
 struct OracleDemodMgrStub {
-    // AudioThread.cpp:349 asks for the list of demodulators: there are none here
-    std::vector<DemodulatorInstancePtr> getDemodulators() { return {}; }
-    // DemodulatorThread.cpp:206-207, 320 (solo mode only, which is off here)
-    void setActiveDemodulator(DemodulatorInstancePtr) {}
+    std::vector<DemodulatorInstancePtr> demods;                  // filled by oracle/ref_demod.cpp's application-level driver
+    DemodulatorInstancePtr current;
+    // AudioThread.cpp:349, SDRPostThread.cpp:53,103: the list of demodulators
+    std::vector<DemodulatorInstancePtr> getDemodulators() { return demods; }
+    // SDRPostThread.cpp:70-86, 304: the demodulator the GUI has selected; DemodulatorThread.cpp:206-207, 320 (solo mode only, off here)
+    void setActiveDemodulator(DemodulatorInstancePtr d) { current = d; }
     void setActiveDemodulatorByRawPointer(DemodulatorInstance *, bool) {}
-    DemodulatorInstancePtr getCurrentModem() { return nullptr; }
+    DemodulatorInstancePtr getCurrentModem() { return current; }
     // DemodulatorInstance.cpp:327-328, 524: the manager remembers the last squelch / mute setting for new demodulators
     void setLastSquelchLevel(float) {}
     void setLastSquelchEnabled(bool) {}
@@ -51,7 +53,10 @@ struct OracleAppStub {
     OracleBookmarkMgrStub bookmarkMgr;
     OracleAppFrameStub appFrame;
     OracleConfigStub config;
+    long long frequency = 0;                                     // the tuner frequency (SDRPostThread.cpp:50, 79)
     long long getSampleRate() const { return sampleRate; }
+    long long getFrequency() const { return frequency; }
+    void setFrequency(long long f) { frequency = f; }
     bool getSoloMode() const { return false; }
     OracleDemodMgrStub &getDemodMgr() { return demodMgr; }
     OracleBookmarkMgrStub &getBookmarkMgr() { return bookmarkMgr; }

@@ -1,0 +1,3 @@
+// oracle/shadow/SoapySDR/Version.hpp -- TEST INFRASTRUCTURE ONLY: see Types.hpp (SoapySDR is not installed; nothing of it is used).
+#pragma once
+#include "Types.hpp"

@@ -2,8 +2,7 @@
 ScopeVisualProcessor.cpp -- compiled from where they lie into oracle/_ref/libvisuals_ref.so over the reference's own liquid-dsp
 binary, oracle/build_ref.py step 7) as the pin of the restated glue the parity tests compare against (oracle/ref_chain.cpp):
 same frames in, the SAME BITS out -- frames released by the distributor, display points, ceiling and floor of the spectrum in
-the full-band and in the zoomed-view branch (zoom, pan, back), waveform and audio spectrum of the scope, and the audio mix of the
-RtAudio callback (src/audio/AudioThread.cpp through oracle/ref_audio.cpp) over a long random sequence of pushes and callbacks."""
+the full-band and in the zoomed-view branch (zoom, pan, back), waveform and audio spectrum of the scope."""
 import os
 
 import numpy as np
@@ -133,63 +132,3 @@ def test_scope_equals_the_reference_class(ref, vis):
             assert mode == 0                                     # SCOPE_MODE_Y for ordinary demodulator audio (type 0)
         a.close(); b.close()
 
-
-def test_audio_mixer_equals_the_reference_callback(ref, vis):
-    """audioCallback (AudioThread.cpp:88-243) on real AudioThread objects against the restated mixer the device mixer is compared
-    with: a seeded random sequence of pushes (one and two channels, empty blocks, a foreign sample rate, peaks above 1), gain
-    changes, sources going inactive and coming back, and callbacks of several lengths that never line up with the blocks."""
-    rng = np.random.default_rng(2024)
-    a, b = refbind.RefMixer(ref, 48000), refbind.SrcMixer(vis, 48000)
-    gains = [0.9, 0.6, 1.3, 0.5, 1.0]
-    for g in gains:
-        assert a.add_source(g) == b.add_source(g)
-    n_cb = n_nonzero = 0
-    for step in range(1500):
-        r = rng.random()
-        i = int(rng.integers(len(gains)))
-        if r < 0.40:                                             # a demodulator hands over a block
-            channels = 2 if i == 3 else 1
-            n = int(rng.choice([800, 808, 768, 1600, 0, 33])) * channels if rng.random() < 0.9 else 0
-            data = (rng.standard_normal(n) * rng.choice([0.05, 0.3, 1.5])).astype(np.float32)
-            rate = 44100 if rng.random() < 0.05 else 48000
-            peak = float(np.abs(data).max()) if n else 0.0
-            if rng.random() < 0.05:
-                channels = 0                                     # AudioThreadInput with no channels: skipped by the callback
-            a.push(i, data, channels, peak, rate); b.push(i, data, channels, peak, rate)
-        elif r < 0.45:
-            g = float(rng.choice([0.0, 0.25, 1.0, 2.0, 3.5, -1.0]))          # setGain clamps to [0, 2]
-            a.set_gain(i, g); b.set_gain(i, g)
-        elif r < 0.50:
-            on = bool(rng.random() < 0.6)
-            a.set_active(i, on); b.set_active(i, on)
-        else:                                                    # the sound card asks for frames
-            n_frames = int(rng.choice([512, 256, 1024, 100]))
-            oa, ob = a.callback(n_frames), b.callback(n_frames)
-            assert np.array_equal(oa, ob), "callback %d: restated mixer differs from the reference's callback (max %g)" % (
-                n_cb, np.abs(oa - ob).max())
-            n_cb += 1; n_nonzero += int(np.any(oa != 0))
-    assert n_cb > 500 and n_nonzero > 300
-    a.close(); b.close()
-
-
-def test_wav_words_equal_the_reference_writer(ref, vis, tmp_path):
-    """AudioFileWAV::writeToFile of the reference (header + 16-bit payload, AudioFileWAV.cpp:122-165) against the restated payload the
-    device's PCM words are compared with: one and two channels, peaks below and above 1 (the anti-clipping scale), odd lengths."""
-    import struct
-    rng = np.random.default_rng(5)
-    for channels in (1, 2):
-        w = refbind.SrcWav(vis, tmp_path, "rec%d" % channels)
-        want = []
-        for k in range(9):
-            n = int(rng.choice([800, 808, 1600, 33, 1])) * channels + (1 if (channels == 2 and k == 4) else 0)
-            data = (rng.standard_normal(n) * rng.choice([0.05, 0.4, 1.7])).astype(np.float32)
-            peak = float(np.abs(data).max())
-            w.write(data, channels, 48000, peak)
-            want.append(refbind.ref_wav_payload(ref, data, channels, peak))
-        header, words = w.close()
-        want = np.concatenate(want)
-        assert words.size == want.size and np.array_equal(words, want)
-        assert header[:4] == b"RIFF" and header[8:16] == b"WAVEfmt " and header[36:40] == b"data"
-        fmt = struct.unpack("<IHHIIHH", header[16:36])
-        assert fmt == (16, 1, channels, 48000, 48000 * 2 * channels, 2 * channels, 16)
-        assert struct.unpack("<I", header[40:44])[0] == 2 * words.size and struct.unpack("<I", header[4:8])[0] == 36 + 2 * words.size
