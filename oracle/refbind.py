@@ -552,6 +552,12 @@ class RefDemodLib:
         L.refsrc_demod_bandwidth.argtypes = [vp]
         L.refsrc_demod_process.argtypes = [vp, vp, u, ll, vp, u, vp, vp, vp, vp, vp]
         L.refsrc_demod_destroy.argtypes = [vp]; L.refsrc_demod_destroy.restype = None
+        L.refsrc_demod_collect.argtypes = [vp, ll, vp, u, vp, vp, vp, vp, vp]
+        L.refsrc_app_create.restype = vp; L.refsrc_app_create.argtypes = [i]
+        L.refsrc_app_add_demod.argtypes = [vp, vp]; L.refsrc_app_add_demod.restype = None
+        L.refsrc_app_block.argtypes = [vp, vp, u, ll, ll, i, vp, u]
+        L.refsrc_app_route.argtypes = [vp, vp, vp, vp]
+        L.refsrc_app_destroy.argtypes = [vp]; L.refsrc_app_destroy.restype = None
         L.refsrc_mixer_create.restype = vp; L.refsrc_mixer_create.argtypes = [i]
         L.refsrc_mixer_add_source.argtypes = [vp, f]
         L.refsrc_mixer_set_gain.argtypes = [vp, i, f]; L.refsrc_mixer_set_gain.restype = None
@@ -594,5 +600,45 @@ class SrcDemod:
         return dict(skipped=bool(rc), audio=au[:n.value].copy(), channels=ch.value, peak=pk.value, squelched=bool(sq.value),
                     signal_level=m3[0], signal_floor=m3[1], signal_ceil=m3[2])
 
+    def collect(self, center):
+        """What came out for the blocks an SrcApp fed this demodulator (center: the frequency stamped on those blocks)."""
+        cap = 1 << 20
+        au = np.zeros(cap, np.float32)
+        n, ch, pk, sq = C.c_uint(), C.c_int(), C.c_float(), C.c_int()
+        m3 = (C.c_float * 3)()
+        rc = self.L.refsrc_demod_collect(self.h, int(center), _p(au), cap, C.byref(n), C.byref(ch), C.byref(pk), C.byref(sq), m3)
+        assert rc >= 0, "the reference's demodulator threads timed out"
+        return dict(skipped=bool(rc), audio=au[:n.value].copy(), channels=ch.value, peak=pk.value, squelched=bool(sq.value),
+                    signal_level=m3[0], signal_floor=m3[1], signal_ceil=m3[2])
+
     def close(self):
         self.L.refsrc_demod_destroy(self.h)
+
+
+class SrcApp:
+    """The reference's SDRPostThread on its own thread (oracle/ref_demod.cpp): blocks in as the device thread delivers them,
+    demodulators (SrcDemod) registered the way DemodulatorMgr holds them.  One per process at a time."""
+
+    def __init__(self, lib, channelizer_type=1):
+        self.L = lib.L
+        self.h = C.c_void_p(self.L.refsrc_app_create(int(channelizer_type)))
+
+    def add(self, demod):
+        self.L.refsrc_app_add_demod(self.h, demod.h)
+
+    def block(self, x, center, sample_rate, num_channels=1):
+        """Returns what SDRPostThread put on its "IQDataOutput" queue for this block."""
+        x = np.ascontiguousarray(x, np.complex64)
+        out = np.zeros(x.size, np.complex64)
+        m = self.L.refsrc_app_block(self.h, _p(x), x.size, int(center), int(sample_rate), int(num_channels), _p(out), out.size)
+        assert m >= 0, "the reference's SDRPostThread timed out"
+        return out[:m]
+
+    def route(self, demod):
+        """(filterbank channel or -1 when the demodulator is not in the run list, that channel's centre frequency, channel rate)."""
+        cc, bw = C.c_longlong(), C.c_int()
+        ch = self.L.refsrc_app_route(self.h, demod.h, C.byref(cc), C.byref(bw))
+        return ch, cc.value, bw.value
+
+    def close(self):
+        self.L.refsrc_app_destroy(self.h)

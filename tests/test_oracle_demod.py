@@ -150,3 +150,79 @@ def test_wav_words_equal_the_reference_writer(ref, demod_lib, tmp_path):
         fmt = struct.unpack("<IHHIIHH", header[16:36])
         assert fmt == (16, 1, channels, 48000, 48000 * 2 * channels, 2 * channels, 16)
         assert struct.unpack("<I", header[40:44])[0] == 2 * words.size and struct.unpack("<I", header[4:8])[0] == 36 + 2 * words.size
+
+
+# ---- the ingress in front of the demodulators: the reference's own SDRPostThread ------------------------------------------------
+def test_ingress_single_channel_equals_the_reference_post_thread(ref, demod_lib):
+    """SDRPostThread::runSingleCH (src/sdr/SDRPostThread.cpp:248-299) feeding three real DemodulatorInstances: the DC-blocked block
+    it publishes and every demodulator's audio against the restated ingress + chains, with the tuner moving and a retune on the way."""
+    chans = [("FM", 200000, 300000), ("AM", 6000, -450000), ("USB", 5400, 600000)]
+    N = synth.block_size(FS)
+    app = refbind.SrcApp(demod_lib, 1)
+    sds = [refbind.SrcDemod(demod_lib, m, FS, bw, CENTER + off, CENTER) for m, bw, off in chans]
+    for d in sds:
+        app.add(d)
+    rcs, ing = [refbind.RefChan(ref, m, FS, bw) for m, bw, _ in chans], refbind.RefIngress(ref)
+    freqs = [CENTER + off for _, _, off in chans]
+    center = CENTER
+    for b in range(10):
+        if b == 3:
+            center = CENTER + 100000                            # the tuner moves: every shift changes
+        if b == 6:
+            freqs[0] = CENTER - 350000; sds[0].set_frequency(freqs[0])
+        x = synth.wideband(FS, N, chans + [("FM", 200000, -350000)], seed=5, t0=b * N) + np.complex64(0.01 - 0.02j)
+        y, yr = app.block(x, center, FS, 1), ing.block(x)
+        assert np.array_equal(y.view(np.float32), yr.view(np.float32)), "block %d: DC-blocked block differs" % b
+        for d, rc, f in zip(sds, rcs, freqs):
+            assert app.route(d)[0] == 0
+            _same_block(rc.process(yr, f - center), d.collect(center), "block %d" % b)
+    for d in sds:
+        d.close()
+    for rc in rcs:
+        rc.close()
+    app.close(); ing.close()
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_ingress_channelizer_equals_the_reference_post_thread(ref, demod_lib, mode):
+    """SDRPostThread::runPFBCH / runPFBCH2 + runDemodChannels (:303-511): channel centres, nearest-channel routing, channel 0 through
+    the DC blocker, the wrap-around extra channel, the tuner moving and a demodulator hopping to another channel -- the restated
+    routing (tests/parity.py: RefChannelizerPath, what the engine's channelizer mode is compared with) against the real thread
+    feeding real DemodulatorInstances."""
+    from tests.parity import RefChannelizerPath
+    fs = 10000000
+    chans = [("NBFM", 12500, 10000), ("AM", 6000, 1262000), ("USB", 5400, -2490000), ("NBFM", 12500, 4990000), ("FM", 200000, -3730000)]
+    N = synth.block_size(fs)
+    oracle = RefChannelizerPath(ref, fs, chans, mode=mode)
+    M = oracle.M
+    assert N % M == 0
+    freqs = [CENTER + off for _, _, off in chans]
+    centers = oracle.centers(CENTER)
+    picks0 = [oracle.channel_at(centers, f) for f in freqs]
+    assert 0 in picks0 and M in picks0                          # channel 0 (DC-blocked) and the extra channel are exercised
+    app = refbind.SrcApp(demod_lib, mode)
+    sds = [refbind.SrcDemod(demod_lib, m, oracle.demod_rate, bw, f, centers[ci]) for (m, bw, _), f, ci in zip(chans, freqs, picks0)]
+    for d in sds:
+        app.add(d)
+    center, seen, routed = CENTER, set(), 0
+    for b in range(8):
+        if b == 3:
+            center = CENTER + 40000                             # the tuner moves: every channel centre moves
+        if b == 5:
+            freqs[1] = CENTER + 40000 + 2262000; sds[1].set_frequency(freqs[1])    # hops two channels up
+        x = synth.wideband(fs, N, chans + [("AM", 6000, 2302000)], seed=2024, t0=b * N) + np.complex64(0.02 + 0.01j)
+        raw = app.block(x, center, fs, M)
+        assert np.array_equal(raw.view(np.float32), x.view(np.float32))            # published as it came (getFullSampleRateIqData)
+        res, picks = oracle.block(x, center, freqs)
+        seen.update(picks)
+        for i, (d, r) in enumerate(zip(sds, res)):
+            want_center = oracle.centers(center)[picks[i]]
+            ch, cc, bw = app.route(d)
+            if ch >= 0:             # (-1 right after a refresh: updateActiveDemodulators ran again behind the block, :195-198)
+                assert ch == picks[i] and cc == want_center and bw == oracle.chan_bw, (b, i, ch, picks[i])
+                routed += 1
+            _same_block(r, d.collect(want_center), "mode %d block %d demodulator %d" % (mode, b, i))
+    assert len(seen) >= 5 and routed >= 20
+    for d in sds:
+        d.close()
+    oracle.close(); app.close()
