@@ -4,6 +4,15 @@
 // oracle/build_ref.py).  The arithmetic therefore IS the reference's; only the ~100 lines of C++ glue between
 // liquid calls are restated, each block citing the reference lines it follows (paths relative to
 // /root/reference/).  Exposed as a plain C API (SysV) for ctypes / bench.py.
+//
+// PINNED against the reference itself, run here: oracle/build_ref.py (steps 6-8) compiles the reference's own UNMODIFIED sources
+// -- SDRPostThread, DemodulatorInstance with its pre-demod / worker / demodulator threads, the nine analog modems,
+// FFTDataDistributor, SpectrumVisualProcessor, ScopeVisualProcessor, AudioThread's RtAudio callback, AudioFileWAV -- over the
+// same liquid binary (oracle/ref_modems.cpp, ref_visuals.cpp, ref_demod.cpp, ref_audio.cpp), and tests/test_oracle_modems.py,
+// test_oracle_visuals.py and test_oracle_demod.py assert that everything restated below returns the SAME BITS as those
+// objects do on the same inputs.  (Kept as a restatement rather than replaced by them because the reference's objects need
+// their threads, queues and ~20 ms of set-up per demodulator: too slow and too asynchronous for 512-channel parity runs and for
+// the timed CPU baseline.)
 #include <algorithm>
 #include <atomic>
 #include <chrono>
