@@ -226,3 +226,26 @@ def test_ingress_channelizer_equals_the_reference_post_thread(ref, demod_lib, mo
     for d in sds:
         d.close()
     oracle.close(); app.close()
+
+
+def test_seeded_fuzz_of_the_demodulator_chain(ref, demod_lib):
+    """Thirty seeded random demodulators (modem, bandwidth, offset, block length, retunes, squelch) through the reference's own
+    DemodulatorInstance and through the restated chain: the same bits every time."""
+    rng = np.random.default_rng(20260923)
+    ranges = {"FM": (60000, 400000), "NBFM": (4000, 40000), "AM": (2000, 20000), "USB": (1500, 12000), "LSB": (1500, 12000),
+              "DSB": (1500, 12000), "CW": (500, 2000), "I/Q": (8000, 100000), "FMS": (150000, 300000)}
+    on_air = {"FM": "FM", "NBFM": "NBFM", "AM": "AM", "USB": "USB", "LSB": "LSB", "DSB": "AM", "CW": "AM", "I/Q": "AM", "FMS": "FMS"}
+    names = list(ranges)
+    for case in range(30):
+        modem = names[case % len(names)]
+        lo, hi = ranges[modem]
+        bw = int(rng.integers(lo, hi + 1))
+        off = int(rng.integers(-1100000, 1100001))
+        block = int(rng.choice([synth.block_size(FS), 40003, 20000, 4099, 65536]))
+        n_blocks = 5 if block > 10000 else 12
+        retune = {int(b): int(rng.integers(-1150000, 1150001)) for b in rng.choice(np.arange(1, n_blocks), size=2, replace=False)} if rng.random() < 0.6 else None
+        if retune and rng.random() < 0.3:
+            retune[min(retune)] = int(rng.choice([0, 1900000, -1850000]))          # zero shift / beyond 0.75 fs
+        squelch = float(rng.uniform(-60, 0)) if rng.random() < 0.4 else None
+        signal = [(on_air[modem], 6000 if on_air[modem] == "AM" else min(bw, 250000), off)]
+        _run(ref, demod_lib, modem, bw, off, on_air[modem], n_blocks, block=block, squelch=squelch, retune=retune, signal=signal)

@@ -132,3 +132,38 @@ def test_scope_equals_the_reference_class(ref, vis):
             assert mode == 0                                     # SCOPE_MODE_Y for ordinary demodulator audio (type 0)
         a.close(); b.close()
 
+
+def test_seeded_fuzz_of_the_spectrum_processor(ref, vis):
+    """Eight seeded random sessions: display size, line rate, average rate, and a random walk of views (zoom levels, pans, leaving and
+    re-entering the view) -- the restated distributor + processor against the reference's objects, frame by frame."""
+    rng = np.random.default_rng(99)
+    for session in range(8):
+        fft_size = int(rng.choice([256, 512, 1024, 2048]))
+        lps = int(rng.choice([100000000, 60, 300, 1000]))
+        a, b = refbind.RefSpectrum(ref, fft_size), refbind.SrcSpectrum(vis, fft_size, FS)
+        b.set_band(CENTER, FS)
+        if rng.random() < 0.5:
+            r = float(rng.choice([0.1, 0.35, 0.9]))
+            a.set_average_rate(r); b.set_average_rate(r)
+        da, db = refbind.RefDistrib(ref, 2 * fft_size, lps), refbind.SrcDistrib(vis, 2 * fft_size, lps)
+        view, n = (False, CENTER, FS), 0
+        for k, x in enumerate(_blocks(10, seed=100 + session)):
+            if rng.random() < 0.45:
+                if rng.random() < 0.25:
+                    view = (False, CENTER, FS)
+                else:
+                    bw = int(rng.choice([1500000, 1100000, 700000, 400000, 250000, 120000]))
+                    view = (True, CENTER + int(rng.integers(-400000, 400001)), bw)
+                a.set_view(*view); b.set_view(*view)
+                want = a.desired_input(FS)
+                if want != da.n:
+                    da.set_frame_len(want); db.set_frame_len(want)
+            fa, fb = da.push(x, FS, CENTER), db.push(x, FS, CENTER)
+            assert fa.shape == fb.shape and np.array_equal(fa, fb), (session, k)
+            for f in fa:
+                ra = a.view_frame(f, CENTER, FS) if view[0] else a.frame(f)
+                assert ra is not None
+                _same_spectrum(ra, b.frame(f, CENTER, FS), "session %d block %d frame %d view %r" % (session, k, n, view))
+                n += 1
+        assert n > 0
+        a.close(); b.close(); da.close(); db.close()
