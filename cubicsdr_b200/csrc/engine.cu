@@ -2252,7 +2252,10 @@ extern "C" int sdr_spectrum_create(sdr_engine *e, unsigned fft_size, unsigned lp
     s->nsub = s->N / s->P;
     s->log_nsub = 0;
     while ((1 << s->log_nsub) < s->nsub) ++s->log_nsub;
-    s->f_max = e->max_block / s->N + 2;
+    // frames per block: the block's own, plus those that fit into what the distributor may still hold from earlier blocks -- less
+    // than one frame of the settings of THEN, and a zoomed view's frames are up to hist_cap samples long (leaving a view, or
+    // zooming out, turns that remainder into many short frames at once)
+    s->f_max = (unsigned)((e->max_block + e->hist_cap) / s->N + 2);
     const size_t N = s->N, F = s->f_max;
     int bad = 0;
     bad |= be_malloc((void **)&s->d_tw, N * sizeof(float2));
@@ -2586,6 +2589,10 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
         size_t fl = s->N;
         if (s->is_view && s->view_bw > 0) { long rb = (long)rate; while (rb / 2 >= s->view_bw) rb /= 2; fl = (size_t)((double)s->N / ((double)rb / (double)rate)); }
         need = std::max(need, fl + 16);
+        // what the distributor still holds from earlier blocks was buffered under the frame length of THEN: after a zoom-out (or
+        // on leaving a view) the frames get shorter and several whole frames start inside that remainder, further back than one
+        // new frame
+        if (s->buffered > 0) need = std::max(need, (size_t)s->buffered + 16);
     }
     if (need > e->hist_cap) need = e->hist_cap;
     if (e->have_block && e->last_n > 0) {
@@ -2721,7 +2728,8 @@ static int submit_common(sdr_engine *e, const float2 *d_src, const sdr_cf32 *h_s
             bool new_resampler = false;
             if (!s->vchan || resample_bw != s->last_bandwidth || s->last_input_bw != (long)rate) {   // :354-368
                 if (s->vchan) { chan_destroy_locked(s->vchan); s->vchan = nullptr; }
-                const unsigned cap = (unsigned)std::min<size_t>(2 * (size_t)e->max_block + 64, 0x7fffff00u);
+                // one block's frames of a view: the block plus the distributor's remainder (less than one frame of the previous settings)
+                const unsigned cap = (unsigned)std::min<size_t>(std::max<size_t>(2 * (size_t)e->max_block, (size_t)e->max_block + e->hist_cap) + 64, 0x7fffff00u);
                 int r = chan_create_impl(e, nullptr, rate, resample_bw, 48000, 0, &s->vchan, cap);
                 if (r) return r;
                 bw_diff = resample_bw - s->last_bandwidth;

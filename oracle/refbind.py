@@ -183,7 +183,7 @@ class RefDistrib:
 
     def push(self, block, sample_rate, frequency=0):
         block = np.ascontiguousarray(block, np.complex64)
-        cap = block.size // self.n + 4
+        cap = (block.size + (1 << 20)) // self.n + 4             # the block's frames + those in what is still buffered from before
         out = np.zeros(cap * self.n, np.complex64)
         nf = self.ref.L.ref_distrib_push(self.h, _p(block), block.size, int(sample_rate), int(frequency), _p(out), cap)
         return out[:nf * self.n].reshape(nf, self.n)

@@ -292,3 +292,29 @@ def test_two_second_run(emu_lib, ref):
     for o in out:                                   # the last half second on its own
         n = len(o["ref_audio"]) // 4
         assert parity.relrms(o["audio"][-n:], o["ref_audio"][-n:]) < 1e-5, o["modem"]
+
+
+def test_zoomed_view_seeded_random_sessions(emu_lib, ref):
+    """Random walks through the view settings (zoom in / out by several octaves at once, pans, leaving and re-entering the view) with
+    every frame transformed: after a zoom-out or on leaving a view the distributor's remainder -- buffered under the LONGER frames
+    of before -- turns into several short frames that start further back than one new frame (stream history, frame capacity and the
+    hidden resampler's block capacity all have to cover that).  Found by fuzzing against the oracle; the hand-written sequences
+    above had missed it."""
+    rng = np.random.default_rng(3)
+    chans = synth.channel_plan("mixed", 2400000, 8)
+    C0 = parity.CENTER
+    for session in range(6):
+        fft = int(rng.choice([256, 512, 1024]))
+        lps = int(rng.choice([0, 0, 400]))
+        views = {}
+        for k in range(8):
+            if rng.random() < 0.5:
+                views[k] = (False, 0, 0) if rng.random() < 0.25 else (
+                    True, C0 + int(rng.integers(-400000, 400001)), int(rng.choice([1500000, 1100000, 700000, 400000, 250000, 120000, 30000])))
+        w = parity.run_spectrum(emu_lib, ref, 2400000, fft, n_blocks=8, chans=chans, view_by_block=views, lps=lps, seed=100 + session)
+        assert w["frames"] > 0 and w["mags"] <= parity.TOL and w["maa"] <= parity.TOL and w["points"] <= parity.TOL and w["u8_bad_far"] == 0, (
+            session, fft, lps, views, w)
+    # the two transitions that failed, on their own: two octaves out at once, and out of a deep zoom into the plain spectrum
+    for views in ({0: (True, C0 + 10000, 250000), 2: (True, C0 + 10000, 1100000)}, {0: (True, C0 - 5000, 15000), 3: (False, 0, 0)}):
+        w = parity.run_spectrum(emu_lib, ref, 2400000, 512, n_blocks=5, chans=chans, view_by_block=views, lps=0, seed=102)
+        assert w["frames"] > 40 and w["mags"] <= parity.TOL and w["points"] <= parity.TOL, (views, w)
