@@ -318,3 +318,31 @@ def test_zoomed_view_seeded_random_sessions(emu_lib, ref):
     for views in ({0: (True, C0 + 10000, 250000), 2: (True, C0 + 10000, 1100000)}, {0: (True, C0 - 5000, 15000), 3: (False, 0, 0)}):
         w = parity.run_spectrum(emu_lib, ref, 2400000, 512, n_blocks=5, chans=chans, view_by_block=views, lps=0, seed=102)
         assert w["frames"] > 40 and w["mags"] <= parity.TOL and w["points"] <= parity.TOL, (views, w)
+
+
+def test_seeded_random_channel_sets(emu_lib, ref):
+    """Ten seeded random channel sets (one to four demodulators of any of eight modems, odd bandwidths, audio rates, block lengths
+    from 1000 samples to longer than a default block, retunes onto zero shift and beyond 0.75 fs, squelch levels)."""
+    rng = np.random.default_rng(2)
+    ranges = {"FM": (60000, 400000), "NBFM": (4000, 40000), "AM": (2000, 20000), "USB": (1500, 12000), "LSB": (1500, 12000),
+              "DSB": (1500, 12000), "CW": (500, 2000), "I/Q": (8000, 100000)}
+    on_air = {"FM": "FM", "NBFM": "NBFM", "AM": "AM", "USB": "USB", "LSB": "LSB", "DSB": "AM", "CW": "AM", "I/Q": "AM"}
+    names = list(ranges)
+    for case in range(10):
+        k = int(rng.integers(1, 5))
+        chans, sig = [], []
+        for _ in range(k):
+            m = names[int(rng.integers(len(names)))]
+            bw, off = int(rng.integers(ranges[m][0], ranges[m][1] + 1)), int(rng.integers(-1100000, 1100001))
+            chans.append((m, bw, off)); sig.append((on_air[m], 6000 if on_air[m] == "AM" else min(bw, 250000), off))
+        block = int(rng.choice([synth.block_size(2400000), 40003, 20000, 4099, 65536, 1000]))
+        nb = 5 if block > 10000 else 14
+        retune = {}
+        if rng.random() < 0.6:
+            for b in rng.choice(np.arange(1, nb), size=2, replace=False):
+                retune[int(b)] = {int(rng.integers(k)): int(rng.choice([int(rng.integers(-1150000, 1150001)), 0, 1900000, -1850000]))}
+        squelch = {int(rng.integers(k)): float(rng.uniform(-60, 0))} if rng.random() < 0.4 else None
+        out, dc_err, _ = parity.run_channels(emu_lib, ref, 2400000, chans, n_blocks=nb, block=block, retune=retune or None, signal=sig,
+                                             squelch=squelch, audio_rate=int(rng.choice([48000, 44100, 32000])))
+        assert max(dc_err) == 0.0, (case, chans)
+        parity.check_channels(out)
