@@ -16,7 +16,8 @@
 
 namespace sdrb200 {
 
-constexpr int kMixEntries = 32;            // AudioThreadInput descriptors queued per source (a full queue drops the new block, like try_push)
+constexpr int kMixEntries = 100;           // AudioThreadInput blocks queued per source: the reference's inputQueue holds 100 (pipeAudioData->
+                                           // set_max_num_items(100), DemodulatorInstance.cpp:72-73); a full queue drops the new block, like try_push
 constexpr int kMixMaxSources = 1024;
 
 struct MixEntry { int start, n, channels, rate; float peak; };

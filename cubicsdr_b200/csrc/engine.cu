@@ -3584,7 +3584,10 @@ struct sdr_mixer {
 #ifndef SDR_EMU
     cudaEvent_t ev_done = nullptr;           // end of the last render's device work
 #endif
-    static const int kRing = 32768;          // floats per source: several blocks of audio
+    // floats per source: the 100 queued blocks + currentInput of a two-channel 48 kHz demodulator at 60 blocks a second
+    // (1600 floats each) with room to spare; longer blocks fill the ring before the queue and are dropped from then on
+    static const int kRing = 196608;
+    int ring_sources = 0;                    // sources the ring pool has room for (grown by doubling, mixer_add)
     static const int kStage = 65536;
 };
 static MixArgs mixer_args(sdr_mixer *m) {
@@ -3619,7 +3622,8 @@ extern "C" int sdr_mixer_create(sdr_engine *e, int sample_rate, unsigned max_fra
     use_device(e);
     sdr_mixer *m = new sdr_mixer();
     m->eng = e; m->rate = sample_rate; m->max_frames = max_frames;
-    m->ring_cap_total = (size_t)kMixMaxSources * sdr_mixer::kRing;
+    m->ring_sources = 16;
+    m->ring_cap_total = (size_t)m->ring_sources * sdr_mixer::kRing;
     int bad = 0;
     bad |= be_malloc((void **)&m->d_src, kMixMaxSources * sizeof(MixSource));
     bad |= be_malloc((void **)&m->d_rings, m->ring_cap_total * sizeof(float));
@@ -3670,6 +3674,17 @@ static void mixer_upload_order(sdr_mixer *m) {
 }
 static int mixer_add(sdr_mixer *m, int chan_slot, int feed_rate, float gain, int *index) {
     if (m->n_src >= kMixMaxSources) return fail(SDR_ERR_STATE, "sdr_mixer: too many sources");
+    sdr_stream_t ss0 = sink_stream(m->eng);
+    if (m->n_src >= m->ring_sources) {                            // grow the ring pool (binding is rare: copy, swap, free)
+        const int grown = std::min(2 * m->ring_sources, (int)kMixMaxSources);
+        float *d_new = nullptr;
+        if (be_malloc((void **)&d_new, (size_t)grown * sdr_mixer::kRing * sizeof(float))) return fail(SDR_ERR_NOMEM, "sdr_mixer: ring pool");
+        be_sync(ss0);
+        be_d2d(d_new, m->d_rings, m->ring_cap_total * sizeof(float), ss0);
+        be_sync(ss0);
+        be_free(m->d_rings);
+        m->d_rings = d_new; m->ring_sources = grown; m->ring_cap_total = (size_t)grown * sdr_mixer::kRing;
+    }
     MixSource s;
     memset(&s, 0, sizeof s);
     // a demodulator's AudioThread: given its gain (setGain), then setActive(true), which binds it to the controller (:577-579)

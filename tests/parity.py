@@ -600,18 +600,38 @@ def check_audio_sinks(lib, ref, n_blocks=8):
             got, want = mix.render(512), rmix.callback(512)
             assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), "after a channel was destroyed: block %d callback %d" % (b, cb)
     cs = cs[:4]
-    # a consumer that lags: far more blocks queued than a source's ring and queue hold -- the surplus is dropped (like a full
-    # inputQueue's try_push), nothing that is still queued is overwritten, and the mix stays finite and plays what was kept in order
+    # a consumer that lags: more blocks queued than the reference's inputQueue holds (100, DemodulatorInstance.cpp:72-73) -- the
+    # surplus is dropped (try_push on a full queue), nothing that is still queued is overwritten, what was kept plays in order
     lag = Mixer(eng, 48000, 1024)
     src = lag.add_source(1.0)
-    for k in range(100):
+    for k in range(150):
         lag.push(src, np.full(1600, float(k + 1), np.float32), 2, 0.5, 48000)
     played = []
-    for k in range(80):
+    for k in range(210):
         o = lag.render(800)
         assert np.all(np.isfinite(o))
         played.extend(np.unique(o[o != 0]).tolist())
-    assert played == sorted(played) and len(played) >= 10 and played[0] == 1.0, played[:12]
+    assert played == [float(k + 1) for k in range(100)], played[:12]
+    # blocks too long for a source's ring are dropped before the queue is full; what was kept still plays in order
+    for k in range(40):
+        lag.push(src, np.full(30000, float(1000 + k), np.float32), 1, 0.5, 48000)
+    played = []
+    for k in range(400):
+        o = lag.render(1024)
+        played.extend(np.unique(o[o != 0]).tolist())
+    kept = sorted(set(played))
+    assert played == sorted(played) and 3 <= len(kept) < 40 and kept[0] == 1000.0, kept[:12]
+    # more sources than the ring pool starts with: it grows, the earlier sources' queued audio survives the move
+    many = Mixer(eng, 48000, 512)
+    first = many.add_source(1.0)
+    many.push(first, np.full(600, 0.25, np.float32), 1, 0.25, 48000)
+    others = [many.add_source(1.0) for _ in range(40)]
+    many.push(others[-1], np.full(600, 0.5, np.float32), 1, 0.5, 48000)
+    many.render(512)                                              # (the first callback only fetches currentInput, :126-134)
+    many.push(first, np.zeros(1, np.float32), 1, 0.0, 48000); many.push(others[-1], np.zeros(1, np.float32), 1, 0.0, 48000)
+    o = many.render(512)
+    assert np.all(o[:1000] == np.float32(0.75)), o[:8]
+    many.close()
     lag.close()
     assert worst["mix"] > 0.05                                       # the callbacks did carry audio
     assert worst["pcm"] == 0 and worst["wave"] <= 1e-6 and worst["spec"] <= TOL, worst

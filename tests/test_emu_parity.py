@@ -346,3 +346,44 @@ def test_seeded_random_channel_sets(emu_lib, ref):
                                              squelch=squelch, audio_rate=int(rng.choice([48000, 44100, 32000])))
         assert max(dc_err) == 0.0, (case, chans)
         parity.check_channels(out)
+
+
+def test_device_mixer_seeded_random_sessions(emu_lib, ref):
+    """Four seeded random sessions of pushes (one / two channels, empty blocks, a foreign rate, no channels), gain changes beyond the
+    clamp, sources going inactive and coming back, and callbacks of several lengths: the device mixer against the restated
+    callback (which tests/test_oracle_demod.py pins to the reference's own), bit for bit."""
+    from cubicsdr_b200 import Engine, Mixer
+    from oracle.refbind import RefMixer
+    eng = Engine(emu_lib, max_block=40000)
+    for seed in range(4):
+        rng = np.random.default_rng(seed)
+        a, b = RefMixer(ref, 48000), Mixer(eng, 48000, 2048)
+        for g in (0.9, 0.6, 1.3, 0.5, 1.0):
+            a.add_source(g); b.add_source(g)
+        n_cb = 0
+        for step in range(800):
+            r, i = rng.random(), int(rng.integers(5))
+            if r < 0.40:
+                channels = 2 if i == 3 else 1
+                n = int(rng.choice([800, 808, 768, 1600, 0, 33])) * channels if rng.random() < 0.9 else 0
+                data = (rng.standard_normal(n) * rng.choice([0.05, 0.3, 1.5])).astype(np.float32)
+                rate = 44100 if rng.random() < 0.05 else 48000
+                peak = float(np.abs(data).max()) if n else 0.0
+                if rng.random() < 0.05:
+                    channels = 0
+                a.push(i, data, channels, peak, rate); b.push(i, data, channels, peak, rate)
+            elif r < 0.45:
+                g = float(rng.choice([0.0, 0.25, 1.0, 2.0, 3.5, -1.0]))
+                a.set_gain(i, g); b.set_gain(i, g)
+            elif r < 0.50:
+                on = bool(rng.random() < 0.6)
+                a.set_active(i, on); b.set_active(i, on)
+            else:
+                nf = int(rng.choice([512, 256, 1024, 100]))
+                oa, ob = a.callback(nf), b.render(nf)
+                assert np.array_equal(oa.view(np.uint32), ob.view(np.uint32)), "seed %d step %d callback %d: max difference %g" % (
+                    seed, step, n_cb, np.abs(oa - ob).max())
+                n_cb += 1
+        assert n_cb > 300
+        a.close(); b.close()
+    eng.close()
