@@ -288,6 +288,9 @@ class RefScope:
         self.h = C.c_void_p(L.ref_scope_create(fft_size, max_samples))
 
     def process(self, data, channels, sample_rate, input_rate):
+        # with sampleRate > inputRate the reference reads past the end of its averages (ScopeVisualProcessor.cpp:194-203:
+        # outSize = fftSize / 2 * sampleRate / inputRate points out of fftSize / 2 bins); the restatement would do the same
+        assert sample_rate <= input_rate, "the reference's scope is undefined for an audio rate above the modem rate"
         d = np.ascontiguousarray(data, np.float32)
         wave = np.zeros(2 * max(self.max_samples, 1), np.float32); spec = np.zeros(self.fft_size, np.float32)
         ns = C.c_uint(); fc = np.zeros(2, np.float64)
