@@ -249,3 +249,44 @@ def test_seeded_fuzz_of_the_demodulator_chain(ref, demod_lib):
         squelch = float(rng.uniform(-60, 0)) if rng.random() < 0.4 else None
         signal = [(on_air[modem], 6000 if on_air[modem] == "AM" else min(bw, 250000), off)]
         _run(ref, demod_lib, modem, bw, off, on_air[modem], n_blocks, block=block, squelch=squelch, retune=retune, signal=signal)
+
+
+def test_engine_against_the_reference_application_directly(emu_lib, ref, demod_lib):
+    """No restatement in between: the same wideband blocks into sdr_engine_submit (kernel emulator here) and into the reference's
+    own SDRPostThread feeding its own DemodulatorInstances; the DC-blocked block bit for bit, every demodulator's audio within the
+    1e-5 relative RMS the north star grants, identical sample counts, peak and level trackers."""
+    from cubicsdr_b200 import Channel, Engine
+    from tests.parity import relrms, TOL
+    chans = [("FM", 200000, 300000), ("NBFM", 12500, -150000), ("AM", 6000, 450000), ("USB", 5401, -600000), ("LSB", 5400, 750000),
+             ("CW", 700, -250000), ("I/Q", 48000, 900000)]
+    on_air = [("FM", 200000, 300000), ("NBFM", 12500, -150000), ("AM", 6000, 450000), ("USB", 5400, -600000), ("LSB", 5400, 750000),
+              ("AM", 6000, -250000), ("AM", 6000, 900000)]
+    N = synth.block_size(FS)
+    eng = Engine(emu_lib, max_block=N)
+    cs = [Channel(eng, m, FS, bw, 48000, frequency=CENTER + off) for m, bw, off in chans]
+    app = refbind.SrcApp(demod_lib, 1)
+    sds = [refbind.SrcDemod(demod_lib, m, FS, bw, CENTER + off, CENTER) for m, bw, off in chans]
+    for d in sds:
+        app.add(d)
+    got, want = [[] for _ in chans], [[] for _ in chans]
+    for b in range(8):
+        x = synth.wideband(FS, N, on_air, seed=11, t0=b * N) + np.complex64(0.01 - 0.02j)
+        eng.submit(x, CENTER, FS); eng.wait()
+        y = app.block(x, CENTER, FS, 1)
+        assert np.array_equal(eng.fetch_block(N).view(np.float32), y.view(np.float32)), "block %d: DC-blocked block" % b
+        for i, (c, d) in enumerate(zip(cs, sds)):
+            a, lvl, pk, sk = c.fetch_audio()
+            s = d.collect(CENTER)
+            assert not sk and not s["skipped"] and len(a) == s["audio"].size, (b, chans[i], len(a), s["audio"].size)
+            assert abs(pk - s["peak"]) <= 1e-4 * max(s["peak"], 1e-3)
+            m = c.fetch_meter()
+            assert np.allclose(m[:3], (s["signal_level"], s["signal_floor"], s["signal_ceil"]), rtol=0, atol=2e-4), (b, chans[i], m, s)
+            got[i].append(a); want[i].append(s["audio"])
+    for i, ch in enumerate(chans):
+        e = relrms(np.concatenate(got[i]), np.concatenate(want[i]))
+        assert e <= TOL, "%r: audio relative RMS error %.3g against the reference application" % (ch, e)
+    for c in cs:
+        c.close()
+    for d in sds:
+        d.close()
+    app.close(); eng.close()

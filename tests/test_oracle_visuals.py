@@ -167,3 +167,37 @@ def test_seeded_fuzz_of_the_spectrum_processor(ref, vis):
                 n += 1
         assert n > 0
         a.close(); b.close(); da.close(); db.close()
+
+
+def test_engine_spectrum_against_the_reference_objects_directly(emu_lib, ref, vis):
+    """No restatement in between: the engine's spectrum (kernel emulator here) against the reference's own FFTDataDistributor and
+    SpectrumVisualProcessor objects on the same DC-blocked blocks -- frame counts, display points, ceiling and floor; full band, then
+    a zoomed view, then zoomed out by two octaves."""
+    from cubicsdr_b200 import Engine, Spectrum
+    from tests.parity import relrms, TOL
+    fft_size = 512
+    N = synth.block_size(FS)
+    eng = Engine(emu_lib, max_block=N)
+    sp = Spectrum(eng, fft_size, 0)
+    ing = refbind.RefIngress(ref)                                # (the DC blocker; pinned to SDRPostThread in test_oracle_demod.py)
+    d, p = refbind.SrcDistrib(vis, 2 * fft_size, 100000000), refbind.SrcSpectrum(vis, fft_size, FS)
+    p.set_band(CENTER, FS)
+    views = {3: (True, CENTER + 120000, 250000), 6: (True, CENTER + 120000, 1100000)}
+    n = 0
+    for b, x in enumerate(_blocks(9)):
+        if b in views:
+            sp.set_view(*views[b]); p.set_view(*views[b])
+            d.set_frame_len(sp.desired_input(FS))                # FFTVisualDataThread.cpp:55-61
+        eng.submit(x, CENTER, FS); eng.wait()
+        frames = d.push(ing.block(x), FS, CENTER)
+        assert sp.frames == len(frames), (b, sp.frames, len(frames))
+        for f in range(len(frames)):
+            r = p.frame(frames[f], CENTER, FS)
+            assert r is not None
+            pts, line, cf = sp.fetch(f)
+            assert relrms(pts, r["points"]) <= TOL, (b, f, relrms(pts, r["points"]))
+            assert np.abs(cf - r["ceil_floor"]).max() <= 1e-6 * np.abs(r["ceil_floor"]).max(), (b, f, cf, r["ceil_floor"])
+            n += 1
+        assert p.desired_input() == d.n
+    assert n > 150
+    sp.close(); eng.close(); d.close(); p.close(); ing.close()
